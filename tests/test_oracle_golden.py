@@ -1,0 +1,160 @@
+"""Pins the CPU oracle against every golden vector PCL's own tests hold for the ICP hot path
+(SURVEY.md §4 / §8c).  CPU-only."""
+import numpy as np
+import pytest
+
+
+def test_correspondences_bun0_bun4_397(golden, orc):
+    # test/registration/test_registration_api.cpp:83-104
+    tgt = orc.Index(orc.to_xyz1(golden["bun4"]))
+    c = tgt.correspondences(orc.to_xyz1(golden["bun0"]))
+    assert c.size == 397
+    assert np.array_equal(c["index_query"], np.arange(397))
+    assert np.array_equal(c["index_query"], golden["corr_original"][:, 0])
+    assert np.array_equal(c["index_match"], golden["corr_original"][:, 1])
+
+
+def test_reciprocal_correspondences_53(golden, orc):
+    # test/registration/test_registration_api.cpp:107-128
+    src = orc.to_xyz1(golden["bun0"])
+    tgt = orc.Index(orc.to_xyz1(golden["bun4"]))
+    c = tgt.correspondences_reciprocal(src, orc.Index(src))
+    assert c.size == 53
+    assert np.array_equal(c["index_query"], golden["corr_reciprocal"][:, 0])
+    assert np.array_equal(c["index_match"], golden["corr_reciprocal"][:, 1])
+
+
+def test_radius_search_3283_lists(golden, orc):
+    # test/kdtree/test_kdtree.cpp:292-328 + kdtree_unit_test_results.xml: exact count AND order
+    cloud = orc.to_xyz1(golden["sac_plane"])
+    offs, idx, d2 = orc.Index(cloud).radius(cloud, float(golden["radius_r"]))
+    assert np.array_equal(offs, golden["radius_offsets"])
+    assert np.array_equal(idx, golden["radius_indices"])
+    for i in (0, 1, 1000, 3282):
+        seg = d2[offs[i]:offs[i + 1]]
+        assert np.all(np.diff(seg) >= 0) and np.all(seg < np.float32(0.02 * 0.02))
+
+
+def test_knn10_known_answer(golden, orc):
+    # test/kdtree/test_kdtree.cpp:229-262
+    pts = orc.to_xyz1(golden["knn10_points"])
+    q = orc.to_xyz1(golden["knn10_query"][None])
+    idx, d2, keff = orc.Index(pts).knn(q, 10)
+    assert keff == 10
+    assert np.array_equal(idx[0], golden["knn10_indices"])
+    assert np.allclose(d2[0], golden["knn10_distances"], atol=0.1)
+    # rescaled representation alpha=(1,2,3) (:273-286) == scaling coordinates before indexing
+    a = np.array([1, 2, 3], np.float32)
+    idx, d2, _ = orc.Index(orc.to_xyz1(golden["knn10_points"] * a)).knn(orc.to_xyz1(golden["knn10_query"][None] * a), 10)
+    assert np.array_equal(idx[0], golden["knn10_rescaled_indices"])
+    assert np.allclose(d2[0], golden["knn10_rescaled_distances"], atol=0.1)
+    # k larger than the cloud is clamped (kdtree_flann.hpp:241-242)
+    idx, d2, keff = orc.Index(pts).knn(q, 12)
+    assert keff == 10 and np.all(idx[0, 10:] == -1)
+
+
+@pytest.mark.parametrize("scalar_is_double", [False, True])
+def test_icp_bun0_bun4_matrix(golden, orc, scalar_is_double):
+    # test/registration/test_registration.cpp:236-270
+    r = orc.icp_align(orc.to_xyz1(golden["bun0"]), orc.to_xyz1(golden["bun4"]), max_iterations=50,
+                      transformation_epsilon=1e-8, max_correspondence_distance=0.05,
+                      scalar_is_double=scalar_is_double)
+    T, G = r["final"], golden["icp_bun0_bun4"]
+    assert r["converged"]
+    tol = np.full((4, 4), 1e-3)
+    tol[0, 1] = 1e-2
+    tol[3, :] = 0.0
+    assert np.all(np.abs(T - G) <= tol), (T, r)
+
+
+def test_icp_translated(golden, orc):
+    # test/registration/test_registration.cpp:161-195
+    src = orc.to_xyz1(golden["bun0"])
+    tgt = src.copy()
+    tgt[:, 2] += np.float32(0.2)
+    r = orc.icp_align(src, tgt, max_iterations=50)
+    assert r["converged"]
+    T = r["final"]
+    assert orc.Index(tgt).fitness_score(src, T) < 1e-6
+    assert np.allclose(np.diag(T)[:3], 1.0, atol=2e-3)
+    assert np.allclose(T[:3, 3], [0, 0, 0.2], atol=2e-3)
+
+
+def test_fitness_score_indices(orc):
+    # test/registration/test_registration.cpp:198-233
+    src = orc.to_xyz1(np.array([[0, 0, 0], [0, 1, 0], [0, 0, 1], [10, 0, 0]], np.float32))
+    tgt = orc.to_xyz1(np.array([[0, 0, 0], [0, 1, 0], [0, 0, 1], [10, 0, 0.5]], np.float32))
+    t = orc.Index(tgt)
+    I = np.eye(4)
+    assert abs(t.fitness_score(src, I, max_range=1.0) - 0.0625) < 1e-4
+    assert abs(t.fitness_score(src, I, max_range=1.0, indices=[0, 1, 2]) - 0.0) < 1e-4
+
+
+def test_transformation_estimation_svd(golden, orc):
+    # test/registration/test_registration_api.cpp:383-423 (tolerance 1e-6 on quaternion / translation)
+    src = orc.to_xyz1(golden["bun4"])
+    Tref = golden["svd_Tref"]
+    tgt = orc.transform(src, Tref, mode=1)
+    for dbl in (False, True):
+        T = orc.estimate_svd(src, tgt, scalar_is_double=dbl)
+        assert np.allclose(T[:3, 3], Tref[:3, 3], atol=2e-6)
+        assert np.allclose(T[:3, :3], Tref[:3, :3], atol=2e-6)
+        corr = np.zeros(src.shape[0], dtype=orc.CORR_DTYPE)
+        corr["index_query"] = corr["index_match"] = np.arange(src.shape[0])
+        T2 = orc.estimate_svd(src, tgt, corr=corr, scalar_is_double=dbl)
+        assert np.array_equal(T, T2)
+
+
+def test_point_to_plane_lls_paraboloid(orc):
+    # test/registration/test_registration_api.cpp:469-518
+    xs = np.arange(-5.0, 5.0 + 1e-6, 0.5, dtype=np.float32)
+    X, Y = np.meshgrid(xs, xs, indexing="ij")
+    x, y = X.ravel(), Y.ravel()
+    z = np.float32(0.1) * x ** 2 + np.float32(0.2) * x * y - np.float32(0.3) * y + np.float32(1.0)
+    n = np.stack([-0.2 * x - 0.2, 0.6 * y - 0.2, np.ones_like(x)], 1).astype(np.float32)
+    n /= np.linalg.norm(n, axis=1, keepdims=True)
+    src = np.zeros((x.size, 12), np.float32)
+    src[:, 0], src[:, 1], src[:, 2], src[:, 3] = x, y, z, 1
+    src[:, 4:7] = n
+    G = np.array([[0.9938, 0.0988, 0.0517, 0.1], [-0.0997, 0.9949, 0.0149, -0.2],
+                  [-0.05, -0.02, 0.9986, 0.3], [0, 0, 0, 1]], np.float64)
+    tgt = orc.transform(src, G, mode=1, normal_off=4)
+    T, rc = orc.estimate_point_to_plane_lls(src, tgt)
+    assert rc == 0
+    assert np.all(np.abs(T - G) < 1e-2)
+
+
+def test_voxelgrid_bun0(golden, orc):
+    # test/filters/test_filters.cpp:566-603
+    cloud = orc.to_xyz1(golden["bun0"])
+    leaf = [0.02, 0.02, 0.02]
+    out = orc.voxelgrid(cloud, leaf)
+    assert out.shape[0] == int(golden["voxel_count_all"])
+    # the filter-field pass ("z" in [0.05, 0.1]) selects points before the grid: emulate with indices
+    z = cloud[:, 2]
+    # getMinMax3D with a filter field computes min/max over the SELECTED points; equivalent to
+    # running the grid on the selected subset (voxel_grid.hpp:614-617, 663-690)
+    sel = np.nonzero(~((z > np.float32(0.1)) | (z < np.float32(0.05))))[0].astype(np.int32)
+    out = orc.voxelgrid(cloud, leaf, indices=sel)
+    assert out.shape[0] == int(golden["voxel_count_z_005_01"])
+    assert np.allclose(out[0, :3], golden["voxel_z_first"], atol=1e-4)
+    assert np.allclose(out[13, :3], golden["voxel_z_last"], atol=1e-4)
+    neg = np.nonzero(~((z < np.float32(0.1)) & (z > np.float32(0.05))))[0].astype(np.int32)
+    out = orc.voxelgrid(cloud, leaf, indices=neg)
+    assert out.shape[0] == int(golden["voxel_count_z_negative"])
+    # overflow guard (voxel_grid.hpp:620-629)
+    assert orc.voxelgrid(cloud, [1e-5, 1e-5, 1e-5]) is None
+
+
+def test_normal_bun0(golden, orc):
+    # test/features/test_normal_estimation.cpp:98-163: indices = all points, k = all points
+    cloud = orc.to_xyz1(golden["bun0"])
+    g = golden["normal_bun0"]
+    n, ok = orc.point_normal(cloud, np.arange(cloud.shape[0]))
+    assert ok
+    assert np.allclose(np.abs(n[:3]), g[:3], atol=1e-4)
+    assert abs(n[3] - g[4]) < 1e-4
+    normals, dense = orc.Index(cloud).normals_knn(cloud, cloud.shape[0])
+    assert dense
+    assert np.allclose(normals[:, :3], -g[:3], atol=1e-4)
+    assert np.allclose(normals[:, 3], g[4], atol=1e-4)
