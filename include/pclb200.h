@@ -1,0 +1,252 @@
+/* pclb200.h — C-ABI of libpclb200.so: a B200-native (sm_100a) replacement for the ICP registration
+ * hot path of PointCloudLibrary/pcl 1.15.
+ *
+ * PCL has no C plugin ABI; its extension points are C++ virtual classes injected by shared_ptr
+ * (pcl::search::KdTree<PointT>, pcl::registration::CorrespondenceEstimationBase,
+ * pcl::registration::TransformationEstimation, pcl::Registration).  This header is what an FFI for
+ * that path binds: every entry point names the reference interface it replaces (file:line relative
+ * to the PCL source root).  The C++ facade in pcl_b200/pcl_compat/ re-creates the PCL classes on
+ * top of it; INTEGRATION.md shows the subclass a PCL maintainer would add.
+ *
+ * Conventions
+ *   - every function returns an int status: 0 = OK, < 0 = error (text via pclb200_last_error(),
+ *     thread-local); nothing throws across the boundary; there is NO CPU fallback — without a
+ *     CUDA device pclb200_create fails.
+ *   - point arrays are raw bytes + a stride: pcl::PointXYZ = 16, pcl::PointNormal = 48, packed
+ *     xyz = 12.  x,y,z are the first three floats of each record
+ *     (common/include/pcl/impl/point_types.hpp:205-322).  Normals, where needed, are passed as a
+ *     separate pointer to the first nx with their own stride (PointNormal: base + 16, stride 48).
+ *   - every `const void*` point/normal/index array may be HOST memory (pageable or pinned) or
+ *     DEVICE memory on the ctx's GPU; the library detects which (cudaPointerGetAttributes) and
+ *     skips the staging copy for device-resident data.  Output arrays follow the same rule.
+ *   - indices are int32 == pcl::index_t (common/include/pcl/types.h:112); distances are SQUARED,
+ *     fp32, computed as ((dx*dx)+dy*dy)+dz*dz without fma (flann::L2_Simple order); exact ties are
+ *     broken by the smaller original index.
+ *   - 4x4 transforms cross the boundary as 16 doubles, ROW-major (a float result is widened).
+ */
+#ifndef PCLB200_H_
+#define PCLB200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#if defined(__GNUC__)
+#define PCLB200_API __attribute__((visibility("default")))
+#else
+#define PCLB200_API
+#endif
+
+#define PCLB200_VERSION 100 /* 0.1.0 */
+
+/* status codes */
+#define PCLB200_OK 0
+#define PCLB200_ERR_CUDA -1          /* CUDA runtime error (no device, OOM, launch failure) */
+#define PCLB200_ERR_INVALID -2       /* bad argument (NULL, k < 0, stride < 12, ...) */
+#define PCLB200_ERR_EMPTY -3         /* empty cloud / no finite point: kdtree_flann.hpp:118-129 */
+#define PCLB200_ERR_LEAF_TOO_SMALL -4 /* VoxelGrid int32 overflow guard: voxel_grid.hpp:620-629 */
+#define PCLB200_ERR_INTERNAL -5      /* traversal stack overflow or other invariant violation */
+#define PCLB200_ERR_NCCL -6
+
+typedef struct pclb200_ctx pclb200_ctx;     /* one per GPU: stream, memory pool, optional NCCL comm */
+typedef struct pclb200_index pclb200_index; /* Morton-sorted LBVH over one cloud, resident in HBM */
+typedef struct pclb200_icp pclb200_icp;     /* one registration session (device-resident state) */
+
+/* pcl::Correspondence — common/include/pcl/correspondence.h:60-71 */
+typedef struct pclb200_corr {
+  int32_t index_query;
+  int32_t index_match;
+  float distance; /* squared */
+} pclb200_corr;
+
+PCLB200_API int pclb200_version(void);
+PCLB200_API const char* pclb200_last_error(void);
+
+/* ---- context ------------------------------------------------------------------------------- */
+PCLB200_API int pclb200_create(int device, pclb200_ctx** out);
+PCLB200_API int pclb200_destroy(pclb200_ctx* ctx);
+/* blocks until all work queued on the ctx's stream has finished */
+PCLB200_API int pclb200_synchronize(pclb200_ctx* ctx);
+/* number of kernels this library has launched on ctx since creation (bench.py's gpu_launches) */
+PCLB200_API int pclb200_launch_count(pclb200_ctx* ctx, uint64_t* out);
+/* raw cudaStream_t of the ctx (so callers can record CUDA events on the launching stream) */
+PCLB200_API int pclb200_stream(pclb200_ctx* ctx, void** out_stream);
+PCLB200_API void pclb200_free(void* host_ptr); /* frees arrays returned by pclb200_radius */
+
+/* ---- index: replaces pcl::KdTreeFLANN<PointT>::setInputCloud(cloud, indices) ------------------
+ * kdtree/include/pcl/kdtree/impl/kdtree_flann.hpp:100-136, 429-498 (reached through
+ * pcl::search::KdTree::setInputCloud, search/include/pcl/search/impl/kdtree.hpp:89-98).
+ * Non-finite points are dropped; results carry ORIGINAL cloud indices (index_mapping_).
+ * subset == NULL indexes the whole cloud.  Empty / all-NaN input => PCLB200_ERR_EMPTY. */
+PCLB200_API int pclb200_index_build(pclb200_ctx* ctx, const void* pts, size_t n, size_t stride,
+                                    const int32_t* subset, size_t n_subset, pclb200_index** out);
+PCLB200_API int pclb200_index_destroy(pclb200_index* idx);
+PCLB200_API int pclb200_index_size(const pclb200_index* idx, size_t* n_valid);
+/* build statistics: [0] leaves, [1] internal nodes, [2] bytes resident in HBM, [3] leaf size */
+PCLB200_API int pclb200_index_stats(const pclb200_index* idx, uint64_t out[4]);
+
+/* ---- k-NN: replaces pcl::KdTreeFLANN::nearestKSearch and the batch overload of
+ * pcl::search::Search (kdtree_flann.hpp:234-274; search/include/pcl/search/impl/search.hpp:111-137).
+ * Exact.  k is clamped to the number of indexed points (returned in *k_eff); outputs are nq rows
+ * of pitch k, ascending (d2, index); unused slots are (-1, +inf). */
+PCLB200_API int pclb200_knn(pclb200_ctx* ctx, const pclb200_index* idx, const void* queries,
+                            size_t nq, size_t stride, int k, int32_t* out_idx, float* out_d2,
+                            int* k_eff);
+
+/* ---- radius: replaces pcl::KdTreeFLANN::radiusSearch (kdtree_flann.hpp:372-414) and the batch
+ * overload search.hpp:157-194.  Neighbours with d2 < float(radius*radius) (strict, FLANN
+ * RadiusResultSet); max_nn == 0 or > N => unlimited, else the max_nn nearest; always returned
+ * ascending by (d2, index) (a sorted list is a valid answer for sorted == 0 too).
+ * out_offsets: caller array of nq+1; *out_idx / *out_d2: malloc'd host arrays of
+ * out_offsets[nq] entries, release with pclb200_free. */
+PCLB200_API int pclb200_radius(pclb200_ctx* ctx, const pclb200_index* idx, const void* queries,
+                               size_t nq, size_t stride, double radius, unsigned max_nn, int sorted,
+                               int64_t* out_offsets, int32_t** out_idx, float** out_d2);
+
+/* ---- correspondences: replaces CorrespondenceEstimation::determineCorrespondences and
+ * ::determineReciprocalCorrespondences (registration/include/pcl/registration/impl/
+ * correspondence_estimation.hpp:145-218, 220-311).
+ * src_indices == NULL => all points (PCLBase::initCompute identity indices).  is_dense == 0 skips
+ * non-finite source points (:173-174).  Pairs with d2 > max_dist*max_dist are dropped (:176).
+ * idx_src != NULL selects the reciprocal variant: idx_src must index the same `src` array and
+ * `tgt` must be the cloud idx_tgt was built from.  out: capacity n_idx (or n) records, ordered by
+ * index_query; *n_out receives the count. */
+PCLB200_API int pclb200_correspondences(pclb200_ctx* ctx, const pclb200_index* idx_tgt,
+                                        const pclb200_index* idx_src, const void* src, size_t n,
+                                        size_t stride, const int32_t* src_indices, size_t n_idx,
+                                        int is_dense, double max_dist, pclb200_corr* out,
+                                        size_t* n_out);
+
+/* ---- transformation estimation: replaces TransformationEstimationSVD::estimateRigidTransformation
+ * (impl/transformation_estimation_svd.hpp:50-181, Umeyama path, common/impl/eigen.hpp:675-734) and
+ * TransformationEstimationPointToPlaneLLS (impl/transformation_estimation_point_to_plane_lls.hpp
+ * :50-268).  corr == NULL pairs point i with point i.  Sums are accumulated in fp64 on the device;
+ * scalar_is_double selects the Scalar the 4x4 is rounded to. */
+PCLB200_API int pclb200_estimate_svd(pclb200_ctx* ctx, const void* src, size_t stride_s,
+                                     const void* tgt, size_t stride_t, const pclb200_corr* corr,
+                                     size_t n, int scalar_is_double, double T_out[16]);
+PCLB200_API int pclb200_estimate_point_to_plane_lls(pclb200_ctx* ctx, const void* src,
+                                                    size_t stride_s, const void* tgt,
+                                                    const void* tgt_normals, size_t stride_t,
+                                                    const pclb200_corr* corr, size_t n,
+                                                    int scalar_is_double, double T_out[16]);
+
+/* ---- ICP: replaces pcl::IterativeClosestPoint[WithNormals]::computeTransformation and the
+ * pcl::Registration state around it (impl/icp.hpp:113-268; impl/registration.hpp:45-221;
+ * default_convergence_criteria.h:64-326). */
+#define PCLB200_EST_SVD 0            /* TransformationEstimationSVD (default of IterativeClosestPoint) */
+#define PCLB200_EST_POINT_TO_PLANE_LLS 1 /* IterativeClosestPointWithNormals, non-symmetric */
+
+/* DefaultConvergenceCriteria::ConvergenceState — default_convergence_criteria.h:75-83 */
+#define PCLB200_CONV_NOT_CONVERGED 0
+#define PCLB200_CONV_ITERATIONS 1
+#define PCLB200_CONV_TRANSFORM 2
+#define PCLB200_CONV_ABS_MSE 3
+#define PCLB200_CONV_REL_MSE 4
+#define PCLB200_CONV_NO_CORRESPONDENCES 5
+#define PCLB200_CONV_FAILURE_AFTER_MAX_ITERATIONS 6
+
+typedef struct pclb200_icp_params {
+  int32_t max_iterations;         /* registration.h:566, default 10 */
+  int32_t use_reciprocal;         /* icp.h:265-280 setUseReciprocalCorrespondences */
+  int32_t estimator;              /* PCLB200_EST_* */
+  int32_t scalar_is_double;       /* the Scalar template argument */
+  int32_t with_normals_transform; /* 0: IterativeClosestPoint::transformCloud (icp.hpp:49-111);
+                                     1: ...WithNormals -> transformPointCloudWithNormals */
+  int32_t is_dense;               /* input_->is_dense: 0 => skip non-finite source points */
+  int32_t failure_after_max_iter; /* default_convergence_criteria.h:148-152 */
+  int32_t max_iterations_similar_transforms; /* :310, default 0 */
+  double max_correspondence_distance;     /* registration.h:117, default sqrt(DBL_MAX) */
+  double transformation_epsilon;          /* registration.h:588, default 0 */
+  double transformation_rotation_epsilon; /* default 0 = keep criteria default 0.99999 */
+  double euclidean_fitness_epsilon;       /* registration.h:116, default -DBL_MAX */
+  double mse_threshold_absolute;          /* default_convergence_criteria.h:307, default 1e-12 */
+} pclb200_icp_params;
+
+typedef struct pclb200_icp_stats {
+  int32_t converged;          /* Registration::hasConverged */
+  int32_t state;              /* PCLB200_CONV_* */
+  int32_t iterations;         /* nr_iterations_ */
+  int32_t reserved;
+  int64_t n_correspondences;  /* accepted pairs in the last evaluated iteration (all ranks) */
+  double mse;                 /* mean squared correspondence distance of that iteration */
+  double final_transformation[16];  /* row-major, rounded to Scalar */
+  double last_transformation[16];   /* getLastIncrementalTransformation */
+} pclb200_icp_stats;
+
+PCLB200_API void pclb200_icp_default_params(pclb200_icp_params* p);
+
+/* session API (the facade's IterativeClosestPoint holds one).
+ * set_target  : Registration::setInputTarget + initCompute's tree hand-over (registration.hpp:61-101);
+ *               tgt_normals (nullable) = first nx of the target normals, device copy kept for LLS.
+ * set_source  : Registration::setInputSource + align()'s prologue (registration.hpp:172-216,
+ *               icp.hpp:120-161): uploads the (indexed) source, applies `guess` (NULL = identity),
+ *               resets the iteration state.
+ * iterate     : runs up to max_steps iterations of the do-while at icp.hpp:164-241, stopping early
+ *               when the convergence criteria fire; *stats is refreshed after every call.
+ * get_cloud   : output = *input_ transformed by final_transformation_ (icp.hpp:265-267), written
+ *               with stride_out; normals (if the source had them) rotated into out_normals. */
+PCLB200_API int pclb200_icp_create(pclb200_ctx* ctx, const pclb200_icp_params* params,
+                                   pclb200_icp** out);
+PCLB200_API int pclb200_icp_destroy(pclb200_icp* icp);
+PCLB200_API int pclb200_icp_set_params(pclb200_icp* icp, const pclb200_icp_params* params);
+PCLB200_API int pclb200_icp_set_target(pclb200_icp* icp, const pclb200_index* idx_tgt,
+                                       const void* tgt_normals, size_t stride_n);
+PCLB200_API int pclb200_icp_set_source(pclb200_icp* icp, const void* src, size_t n, size_t stride,
+                                       const void* src_normals, size_t stride_n,
+                                       const int32_t* src_indices, size_t n_idx,
+                                       const double guess[16]);
+PCLB200_API int pclb200_icp_iterate(pclb200_icp* icp, int max_steps, pclb200_icp_stats* stats);
+PCLB200_API int pclb200_icp_get_cloud(pclb200_icp* icp, void* out_pts, size_t stride_out,
+                                      void* out_normals, size_t stride_n);
+
+/* one-call form: Registration::align(output, guess) (registration.hpp:172-221) */
+PCLB200_API int pclb200_icp_align(pclb200_ctx* ctx, const pclb200_icp_params* params,
+                                  const void* src, size_t n, size_t stride, const void* src_normals,
+                                  size_t stride_sn, const int32_t* src_indices, size_t n_idx,
+                                  const pclb200_index* idx_tgt, const void* tgt_normals,
+                                  size_t stride_tn, const double guess[16], void* out_cloud,
+                                  size_t stride_out, pclb200_icp_stats* stats);
+
+/* Registration::getFitnessScore(max_range, use_indices) — registration.hpp:134-168.
+ * Returns DBL_MAX in *score when no point is within max_range. */
+PCLB200_API int pclb200_fitness_score(pclb200_ctx* ctx, const pclb200_index* idx_tgt,
+                                      const void* src, size_t n, size_t stride,
+                                      const int32_t* src_indices, size_t n_idx, int is_dense,
+                                      const double T[16], int scalar_is_double, double max_range,
+                                      double* score);
+
+/* ---- normals: replaces NormalEstimation[OMP]::computeFeature with setKSearch(k)
+ * (features/include/pcl/features/impl/normal_3d.hpp:47-96; normal_3d.h:169-188,308-322;
+ * common/impl/centroid.hpp:578-652; features/impl/feature.hpp:65-92; common/impl/eigen.hpp:68-326).
+ * idx is the search surface; pts/indices are the query points.  out: n (or n_idx) records of
+ * 4 floats (nx, ny, nz, curvature); NaN rows where the reference writes NaN; *is_dense_out = 0
+ * if any. */
+PCLB200_API int pclb200_normals_knn(pclb200_ctx* ctx, const pclb200_index* idx, const void* pts,
+                                    size_t n, size_t stride, const int32_t* indices, size_t n_idx,
+                                    int is_dense, int k, const float viewpoint[3], float* out,
+                                    int* is_dense_out);
+
+/* ---- VoxelGrid: replaces pcl::VoxelGrid<PointT>::applyFilter (no filter field)
+ * (filters/include/pcl/filters/impl/voxel_grid.hpp:596-814).  out_xyz1: capacity n records
+ * {x,y,z,1}; ordered by voxel linear index.  PCLB200_ERR_LEAF_TOO_SMALL mirrors :620-629 (the
+ * caller then copies the input unfiltered, as the reference does). */
+PCLB200_API int pclb200_voxelgrid(pclb200_ctx* ctx, const void* pts, size_t n, size_t stride,
+                                  const int32_t* indices, size_t n_idx, int is_dense,
+                                  const float leaf[3], unsigned min_points_per_voxel,
+                                  float* out_xyz1, size_t* n_out);
+
+/* ---- multi-GPU: one process per GPU; every rank holds a replica of the target index and a
+ * shard of the source.  After comm_init, pclb200_icp_iterate all-reduces the 32 fp64 accumulators
+ * of each iteration across ranks, so every rank computes the identical transform.
+ * unique_id: 128 bytes from pclb200_comm_unique_id on rank 0, broadcast by the caller. */
+PCLB200_API int pclb200_comm_unique_id(void* out_128_bytes);
+PCLB200_API int pclb200_comm_init(pclb200_ctx* ctx, int rank, int nranks, const void* unique_id);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PCLB200_H_ */

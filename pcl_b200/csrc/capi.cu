@@ -1,0 +1,630 @@
+// capi.cu — the C boundary of libpclb200.so (include/pclb200.h).  No exception crosses it; there is no CPU
+// fallback: every entry point either runs the CUDA path or returns an error status.
+#include <cub/cub.cuh>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdlib>
+#include <limits>
+#include <memory>
+
+#include "internal.cuh"
+
+namespace pclb200 {
+// icp.cu
+struct Icp;
+Icp* icp_create(Ctx& c, const pclb200_icp_params& P);
+void icp_destroy(Icp* s);
+void icp_set_params(Icp& s, const pclb200_icp_params& P);
+void icp_set_target(Icp& s, const Index* idx, const void* tgt_normals, size_t stride_n);
+void icp_set_source(Icp& s, const void* src, size_t n, size_t stride, const void* src_normals, size_t stride_n,
+                    const int32_t* indices, size_t n_idx, const double* guess);
+void icp_iterate(Icp& s, int max_steps, pclb200_icp_stats* stats);
+void icp_get_cloud(Icp& s, void* out_pts, size_t stride_out, void* out_normals, size_t stride_n);
+void estimate_pairs(Ctx& c, int est, const void* src, size_t stride_s, const void* tgt, const void* tgt_normals,
+                    size_t stride_t, const pclb200_corr* corr, size_t n, int scalar_is_double, double* T_out);
+size_t correspondences(Ctx& c, const Index& tgt, const Index* src_index, const void* src, size_t n, size_t stride,
+                       const int32_t* indices, size_t n_idx, int is_dense, double max_dist, pclb200_corr* out);
+double fitness_score(Ctx& c, const Index& tgt, const void* src, size_t n, size_t stride, const int32_t* indices,
+                     size_t n_idx, const double* T, int scalar_is_double, double max_range);
+// search.cu
+void launch_normals(Ctx& c, const Index& idx, const float4* d_q, size_t nq, int k, const float vp[3], float4* d_out,
+                    int* d_not_dense);
+// voxel.cu
+size_t voxelgrid(Ctx& c, const void* pts, size_t n, size_t stride, const int32_t* indices, size_t n_idx, int is_dense,
+                 const float leaf[3], unsigned min_pts, float* out_xyz1);
+// comm.cu
+void comm_unique_id(void* out128);
+void comm_init(Ctx& c, int rank, int nranks, const void* unique_id);
+void comm_destroy(Ctx& c);
+
+static thread_local std::string g_last_error;
+
+template <typename F>
+static int guarded(F&& f)
+{
+  try {
+    f();
+    return PCLB200_OK;
+  }
+  catch (const Error& e) {
+    g_last_error = e.what();
+    return e.code;
+  }
+  catch (const std::bad_alloc&) {
+    g_last_error = "host allocation failed";
+    return PCLB200_ERR_INTERNAL;
+  }
+  catch (const std::exception& e) {
+    g_last_error = e.what();
+    return PCLB200_ERR_INTERNAL;
+  }
+}
+
+static void raise_if_device_error(Ctx& c)
+{
+  int h = 0;
+  PCLB_CUDA(cudaMemcpyAsync(&h, c.d_error, sizeof(int), cudaMemcpyDeviceToHost, c.stream));
+  PCLB_CUDA(cudaStreamSynchronize(c.stream));
+  if (h) {
+    PCLB_CUDA(cudaMemsetAsync(c.d_error, 0, sizeof(int), c.stream));
+    throw Error(PCLB200_ERR_INTERNAL, "LBVH traversal stack overflow (tree deeper than the per-query stack)");
+  }
+}
+
+static inline unsigned grid_for(size_t n, int block) { return (unsigned)((n + block - 1) / block); }
+
+__global__ void k_iota_slots(float4* q, size_t n)
+{
+  size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+  if (i < n)
+    q[i].w = __int_as_float((int)i);
+}
+
+__global__ void k_unpack_keys(const unsigned long long* __restrict__ keys, size_t n, int32_t* __restrict__ idx,
+                              float* __restrict__ d2)
+{
+  size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+  if (i < n) {
+    unsigned long long k = keys[i];
+    idx[i] = (int32_t)(unsigned)(k & 0xffffffffULL);
+    d2[i] = __uint_as_float((unsigned)(k >> 32));
+  }
+}
+
+// keep only the first max_nn entries of every (sorted) segment
+__global__ void k_truncate_segments(const unsigned long long* __restrict__ keys,
+                                    const unsigned long long* __restrict__ off_in,
+                                    const unsigned long long* __restrict__ off_out, size_t nq,
+                                    unsigned long long* __restrict__ out)
+{
+  size_t q = blockIdx.x;
+  if (q >= nq)
+    return;
+  const unsigned long long b = off_in[q], bo = off_out[q], len = off_out[q + 1] - off_out[q];
+  for (unsigned long long j = threadIdx.x; j < len; j += blockDim.x)
+    out[bo + j] = keys[b + j];
+}
+
+__global__ void k_clamp_counts(const unsigned long long* __restrict__ in, size_t n, unsigned long long cap,
+                               unsigned long long* __restrict__ out)
+{
+  size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+  if (i < n)
+    out[i] = in[i] < cap ? in[i] : cap;
+}
+
+}  // namespace pclb200
+
+using namespace pclb200;
+
+struct pclb200_ctx {
+  Ctx c;
+};
+struct pclb200_index {
+  Index* idx;
+};
+struct pclb200_icp {
+  Icp* s;
+  pclb200_ctx* ctx;
+};
+
+extern "C" {
+
+int pclb200_version(void) { return PCLB200_VERSION; }
+const char* pclb200_last_error(void) { return g_last_error.c_str(); }
+
+int pclb200_create(int device, pclb200_ctx** out)
+{
+  return guarded([&] {
+    PCLB_REQUIRE(out != nullptr, PCLB200_ERR_INVALID, "out == NULL");
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0) {
+      cudaGetLastError();
+      throw Error(PCLB200_ERR_CUDA, "no CUDA device available: libpclb200 has no CPU fallback");
+    }
+    PCLB_REQUIRE(device >= 0 && device < ndev, PCLB200_ERR_INVALID, "bad device ordinal");
+    PCLB_CUDA(cudaSetDevice(device));
+    std::unique_ptr<pclb200_ctx> h(new pclb200_ctx());
+    Ctx& c = h->c;
+    c.device = device;
+    cudaDeviceProp prop;
+    PCLB_CUDA(cudaGetDeviceProperties(&prop, device));
+    c.sm_count = prop.multiProcessorCount;
+    PCLB_CUDA(cudaStreamCreateWithFlags(&c.stream, cudaStreamNonBlocking));
+    cudaMemPool_t pool;
+    PCLB_CUDA(cudaDeviceGetDefaultMemPool(&pool, device));
+    uint64_t thr = UINT64_MAX;  // keep freed blocks cached: the ICP loop reuses the same sizes every call
+    PCLB_CUDA(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr));
+    c.pinned_bytes = 4096;
+    PCLB_CUDA(cudaMallocHost(&c.pinned, c.pinned_bytes));
+    PCLB_CUDA(cudaMalloc(reinterpret_cast<void**>(&c.d_error), sizeof(int)));
+    PCLB_CUDA(cudaMemsetAsync(c.d_error, 0, sizeof(int), c.stream));
+    PCLB_CUDA(cudaStreamSynchronize(c.stream));
+    *out = h.release();
+  });
+}
+
+int pclb200_destroy(pclb200_ctx* ctx)
+{
+  return guarded([&] {
+    if (!ctx)
+      return;
+    Ctx& c = ctx->c;
+    cudaSetDevice(c.device);
+    comm_destroy(c);
+    if (c.stream)
+      cudaStreamSynchronize(c.stream);
+    if (c.pinned)
+      cudaFreeHost(c.pinned);
+    if (c.d_error)
+      cudaFree(c.d_error);
+    if (c.stream)
+      cudaStreamDestroy(c.stream);
+    delete ctx;
+  });
+}
+
+int pclb200_synchronize(pclb200_ctx* ctx)
+{
+  return guarded([&] {
+    PCLB_REQUIRE(ctx, PCLB200_ERR_INVALID, "ctx == NULL");
+    PCLB_CUDA(cudaStreamSynchronize(ctx->c.stream));
+  });
+}
+
+int pclb200_launch_count(pclb200_ctx* ctx, uint64_t* out)
+{
+  return guarded([&] {
+    PCLB_REQUIRE(ctx && out, PCLB200_ERR_INVALID, "NULL argument");
+    *out = ctx->c.launches;
+  });
+}
+
+int pclb200_stream(pclb200_ctx* ctx, void** out_stream)
+{
+  return guarded([&] {
+    PCLB_REQUIRE(ctx && out_stream, PCLB200_ERR_INVALID, "NULL argument");
+    *out_stream = (void*)ctx->c.stream;
+  });
+}
+
+void pclb200_free(void* p) { free(p); }
+
+// ---- index -----------------------------------------------------------------------------------------------------
+int pclb200_index_build(pclb200_ctx* ctx, const void* pts, size_t n, size_t stride, const int32_t* subset,
+                        size_t n_subset, pclb200_index** out)
+{
+  return guarded([&] {
+    PCLB_REQUIRE(ctx && out, PCLB200_ERR_INVALID, "NULL argument");
+    PCLB_CUDA(cudaSetDevice(ctx->c.device));
+    Index* idx = build_index(ctx->c, pts, n, stride, subset, n_subset);
+    *out = new pclb200_index{idx};
+  });
+}
+
+int pclb200_index_destroy(pclb200_index* h)
+{
+  return guarded([&] {
+    if (!h)
+      return;
+    if (h->idx) {
+      cudaSetDevice(h->idx->ctx->device);
+      delete h->idx;
+    }
+    delete h;
+  });
+}
+
+int pclb200_index_size(const pclb200_index* h, size_t* n_valid)
+{
+  return guarded([&] {
+    PCLB_REQUIRE(h && h->idx && n_valid, PCLB200_ERR_INVALID, "NULL argument");
+    *n_valid = h->idx->n_valid;
+  });
+}
+
+int pclb200_index_stats(const pclb200_index* h, uint64_t out[4])
+{
+  return guarded([&] {
+    PCLB_REQUIRE(h && h->idx && out, PCLB200_ERR_INVALID, "NULL argument");
+    out[0] = (uint64_t)h->idx->n_leaves;
+    out[1] = (uint64_t)(h->idx->n_leaves > 0 ? h->idx->n_leaves - 1 : 0);
+    out[2] = (uint64_t)h->idx->bytes();
+    out[3] = (uint64_t)kLeafSize;
+  });
+}
+
+// ---- k-NN ---------------------------------------------------------------------------------------------------------
+int pclb200_knn(pclb200_ctx* ctx, const pclb200_index* h, const void* queries, size_t nq, size_t stride, int k,
+                int32_t* out_idx, float* out_d2, int* k_eff)
+{
+  return guarded([&] {
+    PCLB_REQUIRE(ctx && h && h->idx, PCLB200_ERR_INVALID, "NULL argument");
+    PCLB_REQUIRE(k >= 0, PCLB200_ERR_INVALID, "k < 0");
+    Ctx& c = ctx->c;
+    PCLB_CUDA(cudaSetDevice(c.device));
+    const Index& idx = *h->idx;
+    const int keff = (int)std::min<size_t>((size_t)k, idx.n_valid);  // kdtree_flann.hpp:241-242
+    if (k_eff)
+      *k_eff = keff;
+    if (k == 0 || nq == 0)
+      return;
+    PCLB_REQUIRE(queries && out_idx && out_d2, PCLB200_ERR_INVALID, "NULL argument");
+    cudaStream_t st = c.stream;
+    DevBuf<float4> dense;
+    dense.alloc(nq, st);
+    load_xyz_as_float4(c, queries, nq, stride, nullptr, 0, dense.p, st);
+    QueryBatch qb;
+    make_query_batch(c, idx, dense.p, nq, qb);
+    DevBuf<int32_t> d_idx;
+    DevBuf<float> d_d2;
+    const bool dev_out = is_device_ptr(out_idx) && is_device_ptr(out_d2);
+    int32_t* pi = out_idx;
+    float* pd = out_d2;
+    if (!dev_out) {
+      d_idx.alloc(nq * (size_t)k, st);
+      d_d2.alloc(nq * (size_t)k, st);
+      pi = d_idx.p;
+      pd = d_d2.p;
+    }
+    launch_knn(c, idx, qb.q.p, nq, k, std::numeric_limits<float>::infinity(), pi, pd);
+    if (!dev_out) {
+      PCLB_CUDA(cudaMemcpyAsync(out_idx, pi, nq * (size_t)k * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+      PCLB_CUDA(cudaMemcpyAsync(out_d2, pd, nq * (size_t)k * sizeof(float), cudaMemcpyDeviceToHost, st));
+    }
+    raise_if_device_error(c);
+  });
+}
+
+// ---- radius -------------------------------------------------------------------------------------------------------
+int pclb200_radius(pclb200_ctx* ctx, const pclb200_index* h, const void* queries, size_t nq, size_t stride,
+                   double radius, unsigned max_nn, int sorted, int64_t* out_offsets, int32_t** out_idx, float** out_d2)
+{
+  (void)sorted;
+  return guarded([&] {
+    PCLB_REQUIRE(ctx && h && h->idx && out_offsets && out_idx && out_d2, PCLB200_ERR_INVALID, "NULL argument");
+    Ctx& c = ctx->c;
+    PCLB_CUDA(cudaSetDevice(c.device));
+    const Index& idx = *h->idx;
+    *out_idx = nullptr;
+    *out_d2 = nullptr;
+    out_offsets[0] = 0;
+    if (nq == 0)
+      return;
+    cudaStream_t st = c.stream;
+    const float r2 = (float)(radius * radius);  // kdtree_flann.hpp:398
+    if (max_nn == 0 || (size_t)max_nn > idx.n_valid)
+      max_nn = (unsigned)idx.n_valid;            // :382-383
+    DevBuf<float4> dense;
+    dense.alloc(nq, st);
+    load_xyz_as_float4(c, queries, nq, stride, nullptr, 0, dense.p, st);
+    QueryBatch qb;
+    make_query_batch(c, idx, dense.p, nq, qb);
+    DevBuf<unsigned long long> counts, offsets;
+    counts.alloc(nq + 1, st);
+    offsets.alloc(nq + 1, st);
+    PCLB_CUDA(cudaMemsetAsync(counts.p, 0, (nq + 1) * sizeof(unsigned long long), st));
+    launch_radius_count(c, idx, qb.q.p, nq, r2, counts.p);
+    size_t tb = 0;
+    PCLB_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, tb, counts.p, offsets.p, (int)(nq + 1), st));
+    DevBuf<unsigned char> tmp;
+    tmp.alloc(tb, st);
+    PCLB_CUDA(cub::DeviceScan::ExclusiveSum(tmp.p, tb, counts.p, offsets.p, (int)(nq + 1), st));
+    ++c.launches;
+    unsigned long long total = 0;
+    PCLB_CUDA(cudaMemcpyAsync(&total, offsets.p + nq, sizeof(total), cudaMemcpyDeviceToHost, st));
+    PCLB_CUDA(cudaStreamSynchronize(st));
+    std::vector<unsigned long long> h_off(nq + 1, 0);
+    DevBuf<unsigned long long> keys, keys_sorted;
+    const unsigned long long* d_final_keys = nullptr;
+    const unsigned long long* d_final_off = offsets.p;
+    unsigned long long final_total = total;
+    DevBuf<unsigned long long> counts2, offsets2, keys_trunc;
+    if (total > 0) {
+      PCLB_REQUIRE(total < (unsigned long long)std::numeric_limits<int>::max(), PCLB200_ERR_INVALID,
+                   "radius search result exceeds 2^31 neighbours; lower the radius or set max_nn");
+      keys.alloc(total, st);
+      keys_sorted.alloc(total, st);
+      launch_radius_fill(c, idx, qb.q.p, nq, r2, offsets.p, keys.p);
+      // ascending (d2, index) inside every query's segment
+      size_t tb2 = 0;
+      PCLB_CUDA(cub::DeviceSegmentedSort::SortKeys(nullptr, tb2, keys.p, keys_sorted.p, (int)total, (int)nq, offsets.p,
+                                                   offsets.p + 1, st));
+      DevBuf<unsigned char> tmp2;
+      tmp2.alloc(tb2, st);
+      PCLB_CUDA(cub::DeviceSegmentedSort::SortKeys(tmp2.p, tb2, keys.p, keys_sorted.p, (int)total, (int)nq, offsets.p,
+                                                   offsets.p + 1, st));
+      c.launches += 3;
+      d_final_keys = keys_sorted.p;
+      if ((size_t)max_nn < idx.n_valid) {  // KNNRadius semantics: the max_nn nearest inside the ball
+        counts2.alloc(nq + 1, st);
+        offsets2.alloc(nq + 1, st);
+        PCLB_CUDA(cudaMemsetAsync(counts2.p, 0, (nq + 1) * sizeof(unsigned long long), st));
+        k_clamp_counts<<<grid_for(nq, 256), 256, 0, st>>>(counts.p, nq, (unsigned long long)max_nn, counts2.p);
+        PCLB_CUDA(cub::DeviceScan::ExclusiveSum(tmp.p, tb, counts2.p, offsets2.p, (int)(nq + 1), st));
+        PCLB_CUDA(cudaMemcpyAsync(&final_total, offsets2.p + nq, sizeof(final_total), cudaMemcpyDeviceToHost, st));
+        PCLB_CUDA(cudaStreamSynchronize(st));
+        keys_trunc.alloc(std::max<unsigned long long>(final_total, 1), st);
+        k_truncate_segments<<<(unsigned)nq, 64, 0, st>>>(keys_sorted.p, offsets.p, offsets2.p, nq, keys_trunc.p);
+        c.launches += 3;
+        d_final_keys = keys_trunc.p;
+        d_final_off = offsets2.p;
+      }
+    }
+    PCLB_CUDA(cudaMemcpyAsync(h_off.data(), d_final_off, (nq + 1) * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
+    PCLB_CUDA(cudaStreamSynchronize(st));
+    for (size_t i = 0; i <= nq; ++i)
+      out_offsets[i] = (int64_t)h_off[i];
+    int32_t* hi = static_cast<int32_t*>(malloc(std::max<size_t>(final_total, 1) * sizeof(int32_t)));
+    float* hd = static_cast<float*>(malloc(std::max<size_t>(final_total, 1) * sizeof(float)));
+    PCLB_REQUIRE(hi && hd, PCLB200_ERR_INTERNAL, "host allocation failed");
+    if (final_total > 0) {
+      DevBuf<int32_t> di;
+      DevBuf<float> dd;
+      di.alloc(final_total, st);
+      dd.alloc(final_total, st);
+      k_unpack_keys<<<grid_for(final_total, 256), 256, 0, st>>>(d_final_keys, final_total, di.p, dd.p);
+      ++c.launches;
+      PCLB_CUDA(cudaMemcpyAsync(hi, di.p, final_total * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+      PCLB_CUDA(cudaMemcpyAsync(hd, dd.p, final_total * sizeof(float), cudaMemcpyDeviceToHost, st));
+      PCLB_CUDA(cudaStreamSynchronize(st));
+    }
+    *out_idx = hi;
+    *out_d2 = hd;
+    raise_if_device_error(c);
+  });
+}
+
+// ---- correspondences -------------------------------------------------------------------------------------------------
+int pclb200_correspondences(pclb200_ctx* ctx, const pclb200_index* idx_tgt, const pclb200_index* idx_src,
+                            const void* src, size_t n, size_t stride, const int32_t* src_indices, size_t n_idx,
+                            int is_dense, double max_dist, pclb200_corr* out, size_t* n_out)
+{
+  return guarded([&] {
+    PCLB_REQUIRE(ctx && idx_tgt && idx_tgt->idx && n_out, PCLB200_ERR_INVALID, "NULL argument");
+    PCLB_CUDA(cudaSetDevice(ctx->c.device));
+    *n_out = correspondences(ctx->c, *idx_tgt->idx, idx_src ? idx_src->idx : nullptr, src, n, stride, src_indices, n_idx,
+                             is_dense, max_dist, out);
+  });
+}
+
+// ---- estimators ---------------------------------------------------------------------------------------------------------
+int pclb200_estimate_svd(pclb200_ctx* ctx, const void* src, size_t stride_s, const void* tgt, size_t stride_t,
+                         const pclb200_corr* corr, size_t n, int scalar_is_double, double T_out[16])
+{
+  return guarded([&] {
+    PCLB_REQUIRE(ctx && T_out, PCLB200_ERR_INVALID, "NULL argument");
+    PCLB_CUDA(cudaSetDevice(ctx->c.device));
+    estimate_pairs(ctx->c, PCLB200_EST_SVD, src, stride_s, tgt, nullptr, stride_t, corr, n, scalar_is_double, T_out);
+  });
+}
+
+int pclb200_estimate_point_to_plane_lls(pclb200_ctx* ctx, const void* src, size_t stride_s, const void* tgt,
+                                        const void* tgt_normals, size_t stride_t, const pclb200_corr* corr, size_t n,
+                                        int scalar_is_double, double T_out[16])
+{
+  return guarded([&] {
+    PCLB_REQUIRE(ctx && T_out, PCLB200_ERR_INVALID, "NULL argument");
+    PCLB_CUDA(cudaSetDevice(ctx->c.device));
+    estimate_pairs(ctx->c, PCLB200_EST_POINT_TO_PLANE_LLS, src, stride_s, tgt, tgt_normals, stride_t, corr, n,
+                   scalar_is_double, T_out);
+  });
+}
+
+// ---- ICP ------------------------------------------------------------------------------------------------------------------
+void pclb200_icp_default_params(pclb200_icp_params* p)
+{
+  if (!p)
+    return;
+  memset(p, 0, sizeof(*p));
+  p->max_iterations = 10;
+  p->estimator = PCLB200_EST_SVD;
+  p->is_dense = 1;
+  p->max_correspondence_distance = std::sqrt(std::numeric_limits<double>::max());
+  p->transformation_epsilon = 0.0;
+  p->transformation_rotation_epsilon = 0.0;
+  p->euclidean_fitness_epsilon = -std::numeric_limits<double>::max();
+  p->mse_threshold_absolute = 1e-12;
+}
+
+int pclb200_icp_create(pclb200_ctx* ctx, const pclb200_icp_params* params, pclb200_icp** out)
+{
+  return guarded([&] {
+    PCLB_REQUIRE(ctx && out, PCLB200_ERR_INVALID, "NULL argument");
+    PCLB_CUDA(cudaSetDevice(ctx->c.device));
+    pclb200_icp_params P;
+    if (params)
+      P = *params;
+    else
+      pclb200_icp_default_params(&P);
+    *out = new pclb200_icp{icp_create(ctx->c, P), ctx};
+  });
+}
+
+int pclb200_icp_destroy(pclb200_icp* icp)
+{
+  return guarded([&] {
+    if (!icp)
+      return;
+    cudaSetDevice(icp->ctx->c.device);
+    icp_destroy(icp->s);
+    delete icp;
+  });
+}
+
+int pclb200_icp_set_params(pclb200_icp* icp, const pclb200_icp_params* params)
+{
+  return guarded([&] {
+    PCLB_REQUIRE(icp && params, PCLB200_ERR_INVALID, "NULL argument");
+    icp_set_params(*icp->s, *params);
+  });
+}
+
+int pclb200_icp_set_target(pclb200_icp* icp, const pclb200_index* idx_tgt, const void* tgt_normals, size_t stride_n)
+{
+  return guarded([&] {
+    PCLB_REQUIRE(icp && idx_tgt && idx_tgt->idx, PCLB200_ERR_INVALID, "NULL argument");
+    PCLB_CUDA(cudaSetDevice(icp->ctx->c.device));
+    icp_set_target(*icp->s, idx_tgt->idx, tgt_normals, stride_n);
+  });
+}
+
+int pclb200_icp_set_source(pclb200_icp* icp, const void* src, size_t n, size_t stride, const void* src_normals,
+                           size_t stride_n, const int32_t* src_indices, size_t n_idx, const double guess[16])
+{
+  return guarded([&] {
+    PCLB_REQUIRE(icp, PCLB200_ERR_INVALID, "NULL argument");
+    PCLB_CUDA(cudaSetDevice(icp->ctx->c.device));
+    icp_set_source(*icp->s, src, n, stride, src_normals, stride_n, src_indices, n_idx, guess);
+  });
+}
+
+int pclb200_icp_iterate(pclb200_icp* icp, int max_steps, pclb200_icp_stats* stats)
+{
+  return guarded([&] {
+    PCLB_REQUIRE(icp, PCLB200_ERR_INVALID, "NULL argument");
+    PCLB_CUDA(cudaSetDevice(icp->ctx->c.device));
+    icp_iterate(*icp->s, max_steps, stats);
+  });
+}
+
+int pclb200_icp_get_cloud(pclb200_icp* icp, void* out_pts, size_t stride_out, void* out_normals, size_t stride_n)
+{
+  return guarded([&] {
+    PCLB_REQUIRE(icp && out_pts, PCLB200_ERR_INVALID, "NULL argument");
+    PCLB_CUDA(cudaSetDevice(icp->ctx->c.device));
+    icp_get_cloud(*icp->s, out_pts, stride_out, out_normals, stride_n);
+  });
+}
+
+int pclb200_icp_align(pclb200_ctx* ctx, const pclb200_icp_params* params, const void* src, size_t n, size_t stride,
+                      const void* src_normals, size_t stride_sn, const int32_t* src_indices, size_t n_idx,
+                      const pclb200_index* idx_tgt, const void* tgt_normals, size_t stride_tn, const double guess[16],
+                      void* out_cloud, size_t stride_out, pclb200_icp_stats* stats)
+{
+  return guarded([&] {
+    PCLB_REQUIRE(ctx && params && idx_tgt && idx_tgt->idx, PCLB200_ERR_INVALID, "NULL argument");
+    PCLB_CUDA(cudaSetDevice(ctx->c.device));
+    struct Guard {
+      Icp* s;
+      ~Guard() { icp_destroy(s); }
+    } g{icp_create(ctx->c, *params)};
+    icp_set_target(*g.s, idx_tgt->idx, tgt_normals, stride_tn);
+    icp_set_source(*g.s, src, n, stride, src_normals, stride_sn, src_indices, n_idx, guess);
+    icp_iterate(*g.s, std::numeric_limits<int>::max(), stats);
+    if (out_cloud) {
+      void* out_n = nullptr;
+      if (src_normals)  // normals live inside the same records, at the same offset as in the input
+        out_n = static_cast<unsigned char*>(out_cloud) +
+                (static_cast<const unsigned char*>(src_normals) - static_cast<const unsigned char*>(src));
+      icp_get_cloud(*g.s, out_cloud, stride_out, out_n, stride_sn);
+    }
+  });
+}
+
+int pclb200_fitness_score(pclb200_ctx* ctx, const pclb200_index* idx_tgt, const void* src, size_t n, size_t stride,
+                          const int32_t* src_indices, size_t n_idx, int is_dense, const double T[16],
+                          int scalar_is_double, double max_range, double* score)
+{
+  (void)is_dense;
+  return guarded([&] {
+    PCLB_REQUIRE(ctx && idx_tgt && idx_tgt->idx && T && score, PCLB200_ERR_INVALID, "NULL argument");
+    PCLB_CUDA(cudaSetDevice(ctx->c.device));
+    *score = fitness_score(ctx->c, *idx_tgt->idx, src, n, stride, src_indices, n_idx, T, scalar_is_double, max_range);
+  });
+}
+
+// ---- normals ----------------------------------------------------------------------------------------------------------------
+int pclb200_normals_knn(pclb200_ctx* ctx, const pclb200_index* h, const void* pts, size_t n, size_t stride,
+                        const int32_t* indices, size_t n_idx, int is_dense, int k, const float viewpoint[3], float* out,
+                        int* is_dense_out)
+{
+  (void)is_dense;
+  return guarded([&] {
+    PCLB_REQUIRE(ctx && h && h->idx && out && viewpoint, PCLB200_ERR_INVALID, "NULL argument");
+    PCLB_REQUIRE(k > 0, PCLB200_ERR_INVALID, "k must be positive (feature.hpp:135-176)");
+    Ctx& c = ctx->c;
+    PCLB_CUDA(cudaSetDevice(c.device));
+    cudaStream_t st = c.stream;
+    const size_t nq = indices ? n_idx : n;
+    if (is_dense_out)
+      *is_dense_out = 1;
+    if (!nq)
+      return;
+    DevBuf<float4> dense;
+    dense.alloc(nq, st);
+    load_xyz_as_float4(c, pts, n, stride, indices, n_idx, dense.p, st);
+    QueryBatch qb;
+    make_query_batch(c, *h->idx, dense.p, nq, qb);
+    DevBuf<float4> d_out;
+    DevBuf<int> d_flag;
+    d_flag.alloc(1, st);
+    PCLB_CUDA(cudaMemsetAsync(d_flag.p, 0, sizeof(int), st));
+    const bool dev_out = is_device_ptr(out);
+    float4* po = reinterpret_cast<float4*>(out);
+    if (!dev_out) {
+      d_out.alloc(nq, st);
+      po = d_out.p;
+    }
+    launch_normals(c, *h->idx, qb.q.p, nq, k, viewpoint, po, d_flag.p);
+    int flag = 0;
+    PCLB_CUDA(cudaMemcpyAsync(&flag, d_flag.p, sizeof(int), cudaMemcpyDeviceToHost, st));
+    if (!dev_out)
+      PCLB_CUDA(cudaMemcpyAsync(out, po, nq * sizeof(float4), cudaMemcpyDeviceToHost, st));
+    raise_if_device_error(c);
+    if (is_dense_out)
+      *is_dense_out = flag ? 0 : 1;
+  });
+}
+
+// ---- voxel grid ---------------------------------------------------------------------------------------------------------------
+int pclb200_voxelgrid(pclb200_ctx* ctx, const void* pts, size_t n, size_t stride, const int32_t* indices, size_t n_idx,
+                      int is_dense, const float leaf[3], unsigned min_points_per_voxel, float* out_xyz1, size_t* n_out)
+{
+  return guarded([&] {
+    PCLB_REQUIRE(ctx && leaf && out_xyz1 && n_out, PCLB200_ERR_INVALID, "NULL argument");
+    PCLB_CUDA(cudaSetDevice(ctx->c.device));
+    *n_out = voxelgrid(ctx->c, pts, n, stride, indices, n_idx, is_dense, leaf, min_points_per_voxel, out_xyz1);
+  });
+}
+
+// ---- multi-GPU ------------------------------------------------------------------------------------------------------------------
+int pclb200_comm_unique_id(void* out_128_bytes)
+{
+  return guarded([&] {
+    PCLB_REQUIRE(out_128_bytes, PCLB200_ERR_INVALID, "NULL argument");
+    comm_unique_id(out_128_bytes);
+  });
+}
+
+int pclb200_comm_init(pclb200_ctx* ctx, int rank, int nranks, const void* unique_id)
+{
+  return guarded([&] {
+    PCLB_REQUIRE(ctx && (nranks == 1 || unique_id), PCLB200_ERR_INVALID, "NULL argument");
+    comm_init(ctx->c, rank, nranks, unique_id);
+  });
+}
+
+}  // extern "C"

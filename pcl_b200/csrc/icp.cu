@@ -1,0 +1,1268 @@
+// icp.cu — the per-iteration hot loop of pcl::IterativeClosestPoint, device resident.
+//
+// Reference loop: registration/include/pcl/registration/impl/icp.hpp:164-241
+//   determineCorrespondences (impl/correspondence_estimation.hpp:145-218)  N_src x 1-NN + distance gate
+//   estimateRigidTransformation (impl/transformation_estimation_svd.hpp:137-155 -> Umeyama,
+//       common/impl/eigen.hpp:675-734; or impl/transformation_estimation_point_to_plane_lls.hpp:166-268)
+//   transformCloud (impl/icp.hpp:49-111) ; final = T_k * final (:223) ; convergence (:238)
+//
+// One iteration here = ONE streaming kernel over the Morton-ordered source:
+//   [apply the previous iteration's T_k to the point, in the reference's fp32 operation order, and
+//    write it back]  ->  exact 1-NN in the LBVH with the gate as the initial bound  ->  fp64 accumulation of
+//   the 17 (Umeyama) or 29 (point-to-plane) sums  ->  warp/block/grid reduction with a FIXED order
+//   (deterministic), last block folds the per-block partials
+// followed (after the cross-GPU all-reduce, if any) by a one-warp solve kernel that leaves T_k in
+// device memory for the next iteration.  The host only reads back ~200 bytes per iteration to run
+// DefaultConvergenceCriteria (default_convergence_criteria.hpp:49-140) in the caller's Scalar.
+#include <cub/cub.cuh>
+
+#include <algorithm>
+#include <cmath>
+#include <limits>
+#include <memory>
+
+#include "internal.cuh"
+#include "traverse.cuh"
+
+namespace pclb200 {
+
+void comm_allreduce_sum(Ctx& c, double* d_buf, int count);  // comm.cu (no-op without a communicator)
+bool comm_active(const Ctx& c);
+
+static inline unsigned grid_for(size_t n, int block) { return (unsigned)((n + block - 1) / block); }
+
+// accumulator slots (fp64)
+//   common : [0] accepted pairs, [1] sum of squared distances
+//   SVD    : [2..4] sum(p-o)  [5..7] sum(q-o)  [8..16] sum (q-o)(p-o)^T row-major
+//   LLS    : [2..22] upper triangle of A^T A (row-major order 0,1,..5,7,..), [23..28] A^T b
+constexpr int kAccSvd = 17;
+constexpr int kAccLls = 29;
+
+// transform left in device memory between iterations
+struct Pending {
+  float f[12];   // rows 0..2 of T_k, already rounded like the reference (cast<float>)
+  double d[12];  // same rows in double (Transformer<double> path)
+  int apply;     // 0 = identity / nothing to apply
+  int mode;      // 0: icp.hpp:49-111 order, 1: transforms.hpp SSE float order, 2: transforms.hpp double order
+};
+
+struct SolveOut {
+  double T[16];  // row-major, rounded to Scalar
+  double n;
+  double sum_d;
+  int ok;
+  int pad;
+};
+
+__device__ __forceinline__ void apply_pending(const Pending& P, float& x, float& y, float& z)
+{
+  const float px = x, py = y, pz = z;
+  if (P.mode == 0) {
+    x = ((P.f[0] * px + P.f[1] * py) + P.f[2] * pz) + P.f[3];
+    y = ((P.f[4] * px + P.f[5] * py) + P.f[6] * pz) + P.f[7];
+    z = ((P.f[8] * px + P.f[9] * py) + P.f[10] * pz) + P.f[11];
+  }
+  else if (P.mode == 1) {
+    x = P.f[0] * px + (P.f[1] * py + (P.f[2] * pz + P.f[3]));
+    y = P.f[4] * px + (P.f[5] * py + (P.f[6] * pz + P.f[7]));
+    z = P.f[8] * px + (P.f[9] * py + (P.f[10] * pz + P.f[11]));
+  }
+  else {
+    const double dx = px, dy = py, dz = pz;
+    x = (float)(((P.d[3] + dx * P.d[0]) + dy * P.d[1]) + dz * P.d[2]);
+    y = (float)(((P.d[7] + dx * P.d[4]) + dy * P.d[5]) + dz * P.d[6]);
+    z = (float)(((P.d[11] + dx * P.d[8]) + dy * P.d[9]) + dz * P.d[10]);
+  }
+}
+
+__device__ __forceinline__ void apply_pending_normal(const Pending& P, float& x, float& y, float& z)
+{
+  const float px = x, py = y, pz = z;
+  if (P.mode == 0) {
+    x = (P.f[0] * px + P.f[1] * py) + P.f[2] * pz;
+    y = (P.f[4] * px + P.f[5] * py) + P.f[6] * pz;
+    z = (P.f[8] * px + P.f[9] * py) + P.f[10] * pz;
+  }
+  else if (P.mode == 1) {
+    x = P.f[0] * px + (P.f[1] * py + P.f[2] * pz);
+    y = P.f[4] * px + (P.f[5] * py + P.f[6] * pz);
+    z = P.f[8] * px + (P.f[9] * py + P.f[10] * pz);
+  }
+  else {
+    const double dx = px, dy = py, dz = pz;
+    x = (float)((dx * P.d[0] + dy * P.d[1]) + dz * P.d[2]);
+    y = (float)((dx * P.d[4] + dy * P.d[5]) + dz * P.d[6]);
+    z = (float)((dx * P.d[8] + dy * P.d[9]) + dz * P.d[10]);
+  }
+}
+
+struct IterArgs {
+  const BvhNode* nodes;
+  const float4* pts;
+  int root;
+  const float4* tgt_normals;  // Morton order of the target (LLS only)
+  float4* cur;                // source, Morton order, w = slot
+  size_t n;
+  const Pending* pending;
+  float gate;
+  float ox, oy, oz;           // accumulation origin (target bbox centre)
+  double* partials;           // gridDim.x * kAccum
+  unsigned* counter;
+  double* accum;              // kAccum
+  int* d_error;
+  // reciprocal (optional)
+  const BvhNode* s_nodes;
+  const float4* s_pts;
+  int s_root;
+  const int32_t* src_orig;    // slot -> original source index (nullable = identity)
+};
+
+template <int NACC>
+__device__ __forceinline__ void block_reduce_and_publish(double* acc, const IterArgs& a)
+{
+  __shared__ double sm[8][NACC];
+  __shared__ bool is_last;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+  for (int t = 0; t < NACC; ++t) {
+    double v = acc[t];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1)
+      v += __shfl_down_sync(0xffffffffu, v, o);
+    if (lane == 0)
+      sm[warp][t] = v;
+  }
+  __syncthreads();
+  if (threadIdx.x < NACC) {
+    double v = 0.0;
+    for (int w = 0; w < (int)(blockDim.x >> 5); ++w)
+      v += sm[w][threadIdx.x];
+    a.partials[(size_t)blockIdx.x * kAccum + threadIdx.x] = v;
+  }
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    unsigned t = atomicAdd(a.counter, 1u);
+    is_last = (t == gridDim.x - 1);
+  }
+  __syncthreads();
+  if (is_last) {
+    __threadfence();
+    if (threadIdx.x < NACC) {
+      double v = 0.0;
+      for (unsigned b = 0; b < gridDim.x; ++b)  // fixed order => bitwise reproducible
+        v += __ldcg(&a.partials[(size_t)b * kAccum + threadIdx.x]);
+      a.accum[threadIdx.x] = v;
+    }
+    if (threadIdx.x >= NACC && threadIdx.x < kAccum)
+      a.accum[threadIdx.x] = 0.0;
+    if (threadIdx.x == 0)
+      *a.counter = 0;
+  }
+}
+
+template <int EST, bool RECIP>
+__global__ void __launch_bounds__(256)
+k_icp_iter(const IterArgs a)
+{
+  constexpr int NACC = EST == PCLB200_EST_SVD ? kAccSvd : kAccLls;
+  double acc[NACC];
+#pragma unroll
+  for (int t = 0; t < NACC; ++t)
+    acc[t] = 0.0;
+  const Pending P = *a.pending;
+  bool overflow = false;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < a.n; i += (size_t)gridDim.x * blockDim.x) {
+    float4 p = a.cur[i];
+    if (!(isfinite(p.x) && isfinite(p.y) && isfinite(p.z)))
+      continue;  // transformCloud leaves it untouched (icp.hpp:90-91); no correspondence (:173-174)
+    if (P.apply) {
+      apply_pending(P, p.x, p.y, p.z);
+      a.cur[i] = p;
+    }
+    Nearest1 v{p.x, p.y, p.z, a.gate, kSentinelIndex, -1};
+    if (!traverse(a.nodes, a.pts, a.root, p.x, p.y, p.z, v))
+      overflow = true;
+    if (v.best_pos < 0)
+      continue;  // distance[0] > max_dist_sqr (correspondence_estimation.hpp:176)
+    const float4 q = ldg4(a.pts + v.best_pos);
+    if (RECIP) {
+      // correspondence_estimation.hpp:259-269: 1-NN of the matched target point back into the source
+      Nearest1 b{q.x, q.y, q.z, a.gate, kSentinelIndex, -1};
+      if (!traverse(a.s_nodes, a.s_pts, a.s_root, q.x, q.y, q.z, b))
+        overflow = true;
+      const int slot = __float_as_int(p.w);
+      const int my_orig = a.src_orig ? a.src_orig[slot] : slot;
+      if (b.best_pos < 0 || b.best_idx != my_orig)
+        continue;
+    }
+    acc[0] += 1.0;
+    acc[1] += (double)v.best;
+    if (EST == PCLB200_EST_SVD) {
+      const double px = (double)p.x - (double)a.ox, py = (double)p.y - (double)a.oy, pz = (double)p.z - (double)a.oz;
+      const double qx = (double)q.x - (double)a.ox, qy = (double)q.y - (double)a.oy, qz = (double)q.z - (double)a.oz;
+      acc[2] += px; acc[3] += py; acc[4] += pz;
+      acc[5] += qx; acc[6] += qy; acc[7] += qz;
+      acc[8] += qx * px; acc[9] += qx * py; acc[10] += qx * pz;
+      acc[11] += qy * px; acc[12] += qy * py; acc[13] += qy * pz;
+      acc[14] += qz * px; acc[15] += qz * py; acc[16] += qz * pz;
+    }
+    else {
+      const float4 nn = ldg4(a.tgt_normals + v.best_pos);
+      if (!(isfinite(nn.x) && isfinite(nn.y) && isfinite(nn.z)))
+        continue;  // point_to_plane_lls.hpp:182-190 (pair skipped by the estimator, still a correspondence)
+      const float sx = p.x, sy = p.y, sz = p.z, dx = q.x, dy = q.y, dz = q.z, nx = nn.x, ny = nn.y, nz = nn.z;
+      // float expressions widened to double, exactly as :202-204 and :235 (no fma: -fmad=false)
+      const double A = (double)(nz * sy - ny * sz);
+      const double B = (double)(nx * sz - nz * sx);
+      const double C = (double)(ny * sx - nx * sy);
+      const double D = (double)(nx * dx + ny * dy + nz * dz - nx * sx - ny * sy - nz * sz);
+      acc[2] += A * A; acc[3] += A * B; acc[4] += A * C;
+      acc[5] += A * (double)nx; acc[6] += A * (double)ny; acc[7] += A * (double)nz;
+      acc[8] += B * B; acc[9] += B * C;
+      acc[10] += B * (double)nx; acc[11] += B * (double)ny; acc[12] += B * (double)nz;
+      acc[13] += C * C;
+      acc[14] += C * (double)nx; acc[15] += C * (double)ny; acc[16] += C * (double)nz;
+      acc[17] += (double)(nx * nx); acc[18] += (double)(nx * ny); acc[19] += (double)(nx * nz);
+      acc[20] += (double)(ny * ny); acc[21] += (double)(ny * nz);
+      acc[22] += (double)(nz * nz);
+      acc[23] += A * D; acc[24] += B * D; acc[25] += C * D;
+      acc[26] += (double)nx * D; acc[27] += (double)ny * D; acc[28] += (double)nz * D;
+    }
+  }
+  if (overflow)
+    atomicExch(a.d_error, 1);
+  block_reduce_and_publish<NACC>(acc, a);
+}
+
+// ---- accumulation over an explicit correspondence list (stand-alone estimators) ------------------------
+struct PairArgs {
+  const float4* src;          // dense, original order
+  const float4* tgt;          // dense, original order
+  const float4* tgt_normals;  // dense, original order (LLS)
+  const pclb200_corr* corr;   // nullable: pair i <-> i
+  size_t n;
+  float ox, oy, oz;
+  IterArgs pub;               // partials / counter / accum
+};
+
+template <int EST>
+__global__ void __launch_bounds__(256)
+k_accum_pairs(const PairArgs a)
+{
+  constexpr int NACC = EST == PCLB200_EST_SVD ? kAccSvd : kAccLls;
+  double acc[NACC];
+#pragma unroll
+  for (int t = 0; t < NACC; ++t)
+    acc[t] = 0.0;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < a.n; i += (size_t)gridDim.x * blockDim.x) {
+    const int qi = a.corr ? a.corr[i].index_query : (int)i;
+    const int mi = a.corr ? a.corr[i].index_match : (int)i;
+    const float4 p = ldg4(a.src + qi), q = ldg4(a.tgt + mi);
+    acc[0] += 1.0;
+    if (a.corr)
+      acc[1] += (double)a.corr[i].distance;
+    if (EST == PCLB200_EST_SVD) {
+      const double px = (double)p.x - (double)a.ox, py = (double)p.y - (double)a.oy, pz = (double)p.z - (double)a.oz;
+      const double qx = (double)q.x - (double)a.ox, qy = (double)q.y - (double)a.oy, qz = (double)q.z - (double)a.oz;
+      acc[2] += px; acc[3] += py; acc[4] += pz;
+      acc[5] += qx; acc[6] += qy; acc[7] += qz;
+      acc[8] += qx * px; acc[9] += qx * py; acc[10] += qx * pz;
+      acc[11] += qy * px; acc[12] += qy * py; acc[13] += qy * pz;
+      acc[14] += qz * px; acc[15] += qz * py; acc[16] += qz * pz;
+    }
+    else {
+      const float4 nn = ldg4(a.tgt_normals + mi);
+      if (!(isfinite(p.x) && isfinite(p.y) && isfinite(p.z) && isfinite(q.x) && isfinite(q.y) && isfinite(q.z) &&
+            isfinite(nn.x) && isfinite(nn.y) && isfinite(nn.z)))
+        continue;
+      const float sx = p.x, sy = p.y, sz = p.z, dx = q.x, dy = q.y, dz = q.z, nx = nn.x, ny = nn.y, nz = nn.z;
+      const double A = (double)(nz * sy - ny * sz);
+      const double B = (double)(nx * sz - nz * sx);
+      const double C = (double)(ny * sx - nx * sy);
+      const double D = (double)(nx * dx + ny * dy + nz * dz - nx * sx - ny * sy - nz * sz);
+      acc[2] += A * A; acc[3] += A * B; acc[4] += A * C;
+      acc[5] += A * (double)nx; acc[6] += A * (double)ny; acc[7] += A * (double)nz;
+      acc[8] += B * B; acc[9] += B * C;
+      acc[10] += B * (double)nx; acc[11] += B * (double)ny; acc[12] += B * (double)nz;
+      acc[13] += C * C;
+      acc[14] += C * (double)nx; acc[15] += C * (double)ny; acc[16] += C * (double)nz;
+      acc[17] += (double)(nx * nx); acc[18] += (double)(nx * ny); acc[19] += (double)(nx * nz);
+      acc[20] += (double)(ny * ny); acc[21] += (double)(ny * nz);
+      acc[22] += (double)(nz * nz);
+      acc[23] += A * D; acc[24] += B * D; acc[25] += C * D;
+      acc[26] += (double)nx * D; acc[27] += (double)ny * D; acc[28] += (double)nz * D;
+    }
+  }
+  block_reduce_and_publish<NACC>(acc, a.pub);
+}
+
+// ---- solve (one thread): accumulators -> T_k ------------------------------------------------------------
+__device__ double det3_dev(const double* m)
+{
+  return m[0] * (m[4] * m[8] - m[5] * m[7]) - m[1] * (m[3] * m[8] - m[5] * m[6]) + m[2] * (m[3] * m[7] - m[4] * m[6]);
+}
+
+// one-sided Jacobi SVD of a row-major 3x3 (stands in for Eigen::JacobiSVD inside Eigen::umeyama)
+__device__ void svd3_dev(const double* Ain, double* U, double* s, double* V)
+{
+  double A[9];
+  for (int i = 0; i < 9; ++i) {
+    A[i] = Ain[i];
+    V[i] = (i % 4 == 0) ? 1.0 : 0.0;
+  }
+  const double eps = 2.220446049250313e-16;
+  for (int sweep = 0; sweep < 60; ++sweep) {
+    bool rotated = false;
+    for (int p = 0; p < 2; ++p)
+      for (int q = p + 1; q < 3; ++q) {
+        double alpha = 0, beta = 0, gamma = 0;
+        for (int i = 0; i < 3; ++i) {
+          alpha += A[3 * i + p] * A[3 * i + p];
+          beta += A[3 * i + q] * A[3 * i + q];
+          gamma += A[3 * i + p] * A[3 * i + q];
+        }
+        if (gamma == 0.0 || fabs(gamma) <= eps * sqrt(alpha * beta))
+          continue;
+        rotated = true;
+        double zeta = (beta - alpha) / (2.0 * gamma);
+        double t = (zeta >= 0 ? 1.0 : -1.0) / (fabs(zeta) + sqrt(1.0 + zeta * zeta));
+        double c = 1.0 / sqrt(1.0 + t * t), sn = c * t;
+        for (int i = 0; i < 3; ++i) {
+          double ap = A[3 * i + p], aq = A[3 * i + q];
+          A[3 * i + p] = c * ap - sn * aq;
+          A[3 * i + q] = sn * ap + c * aq;
+          double vp = V[3 * i + p], vq = V[3 * i + q];
+          V[3 * i + p] = c * vp - sn * vq;
+          V[3 * i + q] = sn * vp + c * vq;
+        }
+      }
+    if (!rotated)
+      break;
+  }
+  double nrm[3];
+  for (int j = 0; j < 3; ++j)
+    nrm[j] = sqrt(A[j] * A[j] + A[3 + j] * A[3 + j] + A[6 + j] * A[6 + j]);
+  int ord[3] = {0, 1, 2};
+  for (int a = 0; a < 2; ++a)
+    for (int b = 0; b < 2 - a; ++b)
+      if (nrm[ord[b]] < nrm[ord[b + 1]]) {
+        int t = ord[b]; ord[b] = ord[b + 1]; ord[b + 1] = t;
+      }
+  double Vs[9];
+  for (int j = 0; j < 3; ++j) {
+    s[j] = nrm[ord[j]];
+    for (int i = 0; i < 3; ++i) {
+      Vs[3 * i + j] = V[3 * i + ord[j]];
+      U[3 * i + j] = s[j] > 0.0 ? A[3 * i + ord[j]] / s[j] : 0.0;
+    }
+  }
+  for (int i = 0; i < 9; ++i)
+    V[i] = Vs[i];
+  const double tiny = s[0] * eps * 8.0;
+  if (s[0] <= 0.0) {
+    for (int i = 0; i < 9; ++i)
+      U[i] = (i % 4 == 0) ? 1.0 : 0.0;
+    return;
+  }
+  if (s[1] <= tiny) {
+    double u0[3] = {U[0], U[3], U[6]};
+    int m = 0;
+    if (fabs(u0[1]) < fabs(u0[m])) m = 1;
+    if (fabs(u0[2]) < fabs(u0[m])) m = 2;
+    double e[3] = {0, 0, 0};
+    e[m] = 1.0;
+    double w[3] = {u0[1] * e[2] - u0[2] * e[1], u0[2] * e[0] - u0[0] * e[2], u0[0] * e[1] - u0[1] * e[0]};
+    double wn = sqrt(w[0] * w[0] + w[1] * w[1] + w[2] * w[2]);
+    for (int i = 0; i < 3; ++i)
+      U[3 * i + 1] = w[i] / wn;
+  }
+  if (s[2] <= tiny) {
+    double a[3] = {U[0], U[3], U[6]}, b[3] = {U[1], U[4], U[7]};
+    U[2] = a[1] * b[2] - a[2] * b[1];
+    U[5] = a[2] * b[0] - a[0] * b[2];
+    U[8] = a[0] * b[1] - a[1] * b[0];
+  }
+}
+
+__device__ bool solve6_dev(double (*A)[7], double* x)
+{
+  for (int c = 0; c < 6; ++c) {
+    int piv = c;
+    for (int r = c + 1; r < 6; ++r)
+      if (fabs(A[r][c]) > fabs(A[piv][c]))
+        piv = r;
+    if (A[piv][c] == 0.0)
+      return false;
+    if (piv != c)
+      for (int j = 0; j < 7; ++j) {
+        double t = A[piv][j]; A[piv][j] = A[c][j]; A[c][j] = t;
+      }
+    for (int r = c + 1; r < 6; ++r) {
+      double f = A[r][c] / A[c][c];
+      for (int j = c; j < 7; ++j)
+        A[r][j] -= f * A[c][j];
+    }
+  }
+  for (int r = 5; r >= 0; --r) {
+    double acc = A[r][6];
+    for (int j = r + 1; j < 6; ++j)
+      acc -= A[r][j] * x[j];
+    x[r] = acc / A[r][r];
+  }
+  return true;
+}
+
+__global__ void k_solve(const double* __restrict__ accum, int est, int scalar_is_double, int mode, double ox,
+                        double oy, double oz, int min_corr, Pending* pending, SolveOut* out)
+{
+  if (threadIdx.x != 0 || blockIdx.x != 0)
+    return;
+  const double n = accum[0];
+  out->n = n;
+  out->sum_d = accum[1];
+  double T[16];
+  for (int i = 0; i < 16; ++i)
+    T[i] = (i % 5 == 0) ? 1.0 : 0.0;
+  bool ok = n >= (double)min_corr;
+  if (ok && est == PCLB200_EST_SVD) {
+    const double inv_n = 1.0 / n;
+    const double mp[3] = {accum[2] * inv_n, accum[3] * inv_n, accum[4] * inv_n};
+    const double mq[3] = {accum[5] * inv_n, accum[6] * inv_n, accum[7] * inv_n};
+    double sig[9];
+    for (int r = 0; r < 3; ++r)
+      for (int c = 0; c < 3; ++c)
+        sig[3 * r + c] = accum[8 + 3 * r + c] * inv_n - mq[r] * mp[c];
+    double U[9], sv[3], V[9];
+    svd3_dev(sig, U, sv, V);
+    double S[3] = {1.0, 1.0, 1.0};
+    if (det3_dev(U) * det3_dev(V) < 0.0)
+      S[2] = -1.0;
+    double R[9];
+    for (int r = 0; r < 3; ++r)
+      for (int c = 0; c < 3; ++c) {
+        double a = 0.0;
+        for (int k = 0; k < 3; ++k)
+          a += U[3 * r + k] * S[k] * V[3 * c + k];
+        R[3 * r + c] = a;
+      }
+    const double o[3] = {ox, oy, oz};
+    for (int r = 0; r < 3; ++r) {
+      for (int c = 0; c < 3; ++c)
+        T[4 * r + c] = R[3 * r + c];
+      T[4 * r + 3] = (mq[r] + o[r]) - (R[3 * r] * (mp[0] + o[0]) + R[3 * r + 1] * (mp[1] + o[1]) +
+                                       R[3 * r + 2] * (mp[2] + o[2]));
+    }
+  }
+  else if (ok) {
+    double A[6][7];
+    int t = 2;
+    for (int r = 0; r < 6; ++r)
+      for (int c = r; c < 6; ++c) {
+        A[r][c] = accum[t];
+        A[c][r] = accum[t];
+        ++t;
+      }
+    for (int r = 0; r < 6; ++r)
+      A[r][6] = accum[23 + r];
+    double x[6];
+    if (!solve6_dev(A, x))
+      for (int i = 0; i < 6; ++i)
+        x[i] = __longlong_as_double(0x7ff8000000000000LL);
+    const double al = x[0], be = x[1], ga = x[2];
+    for (int i = 0; i < 16; ++i)
+      T[i] = 0.0;
+    T[0] = cos(ga) * cos(be);
+    T[1] = -sin(ga) * cos(al) + cos(ga) * sin(be) * sin(al);
+    T[2] = sin(ga) * sin(al) + cos(ga) * sin(be) * cos(al);
+    T[4] = sin(ga) * cos(be);
+    T[5] = cos(ga) * cos(al) + sin(ga) * sin(be) * sin(al);
+    T[6] = -cos(ga) * sin(al) + sin(ga) * sin(be) * cos(al);
+    T[8] = -sin(be);
+    T[9] = cos(be) * sin(al);
+    T[10] = cos(be) * cos(al);
+    T[3] = x[3];
+    T[7] = x[4];
+    T[11] = x[5];
+    T[15] = 1.0;
+  }
+  if (!scalar_is_double)
+    for (int i = 0; i < 16; ++i)
+      T[i] = (double)(float)T[i];
+  for (int i = 0; i < 16; ++i)
+    out->T[i] = T[i];
+  out->ok = ok ? 1 : 0;
+  if (pending) {
+    for (int i = 0; i < 12; ++i) {
+      pending->f[i] = (float)T[i];
+      pending->d[i] = T[i];
+    }
+    pending->apply = ok ? 1 : 0;
+    pending->mode = mode;
+  }
+}
+
+// ---- misc streaming kernels ------------------------------------------------------------------------------
+__global__ void k_apply_pending(float4* __restrict__ pts, size_t n, const Pending* __restrict__ pending,
+                                float4* __restrict__ normals /* nullable */)
+{
+  const Pending P = *pending;
+  if (!P.apply)
+    return;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+    float4 p = pts[i];
+    if (!(isfinite(p.x) && isfinite(p.y) && isfinite(p.z)))
+      continue;
+    apply_pending(P, p.x, p.y, p.z);
+    pts[i] = p;
+    if (normals) {
+      float4 m = normals[i];
+      if (P.mode == 0 && !(isfinite(m.x) && isfinite(m.y) && isfinite(m.z)))
+        continue;  // icp.hpp:97-98
+      apply_pending_normal(P, m.x, m.y, m.z);
+      normals[i] = m;
+    }
+  }
+}
+
+__global__ void k_clear_apply(Pending* p) { p->apply = 0; }
+
+// strided write-back of a dense float4 array: xyz into out + i*stride (+ optional w = 1 when stride >= 16)
+__global__ void k_scatter_xyz(const float4* __restrict__ src, size_t n, unsigned char* __restrict__ out, size_t stride,
+                              int write_w, float w)
+{
+  size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+  if (i >= n)
+    return;
+  float4 v = src[i];
+  float* o = reinterpret_cast<float*>(out + i * stride);
+  o[0] = v.x; o[1] = v.y; o[2] = v.z;
+  if (write_w)
+    o[3] = w;
+}
+
+// correspondences by slot: match = original target index or -1
+template <bool RECIP>
+__global__ void __launch_bounds__(128)
+k_corr(const BvhNode* __restrict__ nodes, const float4* __restrict__ pts, int root, const float4* __restrict__ q,
+       size_t nq, float gate, const BvhNode* __restrict__ s_nodes, const float4* __restrict__ s_pts, int s_root,
+       const int32_t* __restrict__ src_orig, pclb200_corr* __restrict__ out, int* __restrict__ d_error)
+{
+  size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+  if (i >= nq)
+    return;
+  const float4 p = __ldg(q + i);
+  const int slot = __float_as_int(p.w);
+  const int my_orig = src_orig ? src_orig[slot] : slot;
+  pclb200_corr r;
+  r.index_query = my_orig;
+  r.index_match = -1;
+  r.distance = 0.f;
+  if (isfinite(p.x) && isfinite(p.y) && isfinite(p.z)) {
+    Nearest1 v{p.x, p.y, p.z, gate, kSentinelIndex, -1};
+    if (!traverse(nodes, pts, root, p.x, p.y, p.z, v))
+      atomicExch(d_error, 1);
+    if (v.best_pos >= 0) {
+      bool keep = true;
+      if (RECIP) {
+        const float4 t = ldg4(pts + v.best_pos);
+        Nearest1 b{t.x, t.y, t.z, gate, kSentinelIndex, -1};
+        if (!traverse(s_nodes, s_pts, s_root, t.x, t.y, t.z, b))
+          atomicExch(d_error, 1);
+        keep = b.best_pos >= 0 && b.best_idx == my_orig;
+      }
+      if (keep) {
+        r.index_match = v.best_idx;
+        r.distance = v.best;
+      }
+    }
+  }
+  out[slot] = r;
+}
+
+struct CorrValid {
+  __host__ __device__ bool operator()(const pclb200_corr& c) const { return c.index_match >= 0; }
+};
+
+// fitness: sum of d2 <= max_range and count (registration.hpp:146-163)
+__global__ void __launch_bounds__(256)
+k_fitness(const BvhNode* __restrict__ nodes, const float4* __restrict__ pts, int root, const float4* __restrict__ q,
+          size_t nq, double max_range, IterArgs pub)
+{
+  double acc[2] = {0.0, 0.0};
+  bool overflow = false;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < nq; i += (size_t)gridDim.x * blockDim.x) {
+    const float4 p = __ldg(q + i);
+    if (!(isfinite(p.x) && isfinite(p.y) && isfinite(p.z)))
+      continue;
+    Nearest1 v{p.x, p.y, p.z, __int_as_float(0x7f800000), kSentinelIndex, -1};
+    if (!traverse(nodes, pts, root, p.x, p.y, p.z, v))
+      overflow = true;
+    if (v.best_pos >= 0 && (double)v.best <= max_range) {
+      acc[0] += 1.0;
+      acc[1] += (double)v.best;
+    }
+  }
+  if (overflow)
+    atomicExch(pub.d_error, 1);
+  block_reduce_and_publish<2>(acc, pub);
+}
+
+// =============================================================================================================
+// host side
+// =============================================================================================================
+float gate_from_max_dist(double max_dist)
+{
+  // d2 (float) is kept iff (double)d2 <= max_dist^2  <=>  d2 <= largest float <= max_dist^2
+  const double m2 = max_dist * max_dist;
+  if (!(m2 < (double)FLT_MAX))
+    return FLT_MAX;
+  float g = (float)m2;
+  if ((double)g > m2)
+    g = std::nextafter(g, -INFINITY);
+  return g;
+}
+
+// C = A*B row-major, Eigen coefficient order, in Scalar S (final = T_k * final, icp.hpp:223)
+template <typename S>
+static void mat4_mul(const S* A, const S* B, S* C)
+{
+  S R[16];
+  for (int r = 0; r < 4; ++r)
+    for (int c = 0; c < 4; ++c)
+      R[4 * r + c] = ((A[4 * r] * B[c] + A[4 * r + 1] * B[4 + c]) + A[4 * r + 2] * B[8 + c]) + A[4 * r + 3] * B[12 + c];
+  for (int i = 0; i < 16; ++i)
+    C[i] = R[i];
+}
+
+struct Reducer {  // scratch for block_reduce_and_publish
+  DevBuf<double> partials;
+  DevBuf<unsigned> counter;
+  DevBuf<double> accum;
+  unsigned max_blocks = 0;
+  void init(Ctx& c, unsigned blocks)
+  {
+    max_blocks = blocks;
+    partials.alloc((size_t)blocks * kAccum, c.stream);
+    counter.alloc(1, c.stream);
+    accum.alloc(kAccum, c.stream);
+    PCLB_CUDA(cudaMemsetAsync(counter.p, 0, sizeof(unsigned), c.stream));
+    PCLB_CUDA(cudaMemsetAsync(accum.p, 0, kAccum * sizeof(double), c.stream));
+  }
+};
+
+static unsigned persistent_grid(const Ctx& c, size_t n, int block, int per_sm)
+{
+  size_t want = (n + block - 1) / block;
+  size_t cap = (size_t)c.sm_count * per_sm;
+  return (unsigned)std::max<size_t>(1, std::min(want, cap));
+}
+
+struct Icp {
+  Ctx* ctx = nullptr;
+  pclb200_icp_params P;
+  const Index* tgt = nullptr;
+  DevBuf<float4> tgt_normals;   // Morton order of tgt
+  // source
+  size_t n_all = 0;             // records in the caller's source cloud
+  size_t n_q = 0;               // indexed source points (queries)
+  DevBuf<float4> src_all;       // original order, all records (for the output cloud)
+  DevBuf<float4> src_normals;   // original order (optional)
+  DevBuf<int32_t> src_orig;     // slot -> original source index (when indices were given)
+  DevBuf<float4> cur;           // Morton order, w = slot
+  DevBuf<int32_t> cur_label;    // Morton order: original source index of cur[i] (labels of the reciprocal tree)
+  bool have_src_normals = false;
+  // device state
+  DevBuf<Pending> pending;
+  DevBuf<SolveOut> solve_out;
+  Reducer red;
+  // host state (Scalar-typed values are kept in double; float mode rounds after every operation)
+  double final_T[16], last_T[16];
+  int iterations = 0;
+  int state = PCLB200_CONV_NOT_CONVERGED;
+  bool converged = false;
+  int64_t n_corr = 0;
+  double mse = 0.0;
+  // DefaultConvergenceCriteria state
+  double prev_mse = std::numeric_limits<double>::max();
+  int iterations_similar = 0;
+};
+
+static void set_identity(double* T)
+{
+  for (int i = 0; i < 16; ++i)
+    T[i] = (i % 5 == 0) ? 1.0 : 0.0;
+}
+
+static int transform_mode(const pclb200_icp_params& P)
+{
+  if (!P.with_normals_transform)
+    return 0;
+  return P.scalar_is_double ? 2 : 1;
+}
+
+static void upload_pending(Icp& s, const double* T, int apply)
+{
+  Pending h;
+  for (int i = 0; i < 12; ++i) {
+    h.f[i] = (float)T[i];
+    h.d[i] = T[i];
+  }
+  h.apply = apply;
+  h.mode = transform_mode(s.P);
+  PCLB_CUDA(cudaMemcpyAsync(s.pending.p, &h, sizeof(h), cudaMemcpyHostToDevice, s.ctx->stream));
+  PCLB_CUDA(cudaStreamSynchronize(s.ctx->stream));  // h is a stack object
+}
+
+Icp* icp_create(Ctx& c, const pclb200_icp_params& P)
+{
+  std::unique_ptr<Icp> s(new Icp());
+  s->ctx = &c;
+  s->P = P;
+  s->pending.alloc(1, c.stream);
+  s->solve_out.alloc(1, c.stream);
+  s->red.init(c, (unsigned)c.sm_count * 8);
+  set_identity(s->final_T);
+  set_identity(s->last_T);
+  upload_pending(*s, s->final_T, 0);
+  return s.release();
+}
+
+void icp_destroy(Icp* s) { delete s; }
+
+void icp_set_params(Icp& s, const pclb200_icp_params& P) { s.P = P; }
+
+__global__ void k_permute_normals(const float4* __restrict__ nrm_orig, const float4* __restrict__ pts, size_t n_padded,
+                                  float4* __restrict__ out)
+{
+  size_t j = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+  if (j >= n_padded)
+    return;
+  const int oi = __float_as_int(pts[j].w);
+  const float qn = __int_as_float(0x7fc00000);
+  out[j] = oi == kSentinelIndex ? make_float4(qn, qn, qn, 0.f) : nrm_orig[oi];
+}
+
+void icp_set_target(Icp& s, const Index* idx, const void* tgt_normals, size_t stride_n)
+{
+  Ctx& c = *s.ctx;
+  s.tgt = idx;
+  s.tgt_normals.release();
+  if (tgt_normals) {
+    DevBuf<float4> dense;
+    dense.alloc(idx->n_cloud, c.stream);
+    load_vec3_as_float4(c, tgt_normals, idx->n_cloud, stride_n, dense.p, c.stream);
+    s.tgt_normals.alloc(idx->pts.n, c.stream);
+    k_permute_normals<<<grid_for(idx->pts.n, 256), 256, 0, c.stream>>>(dense.p, idx->pts.p, idx->pts.n,
+                                                                      s.tgt_normals.p);
+    ++c.launches;
+    PCLB_CUDA(cudaGetLastError());
+  }
+}
+
+__global__ void k_cur_labels(const float4* __restrict__ cur, const int32_t* __restrict__ src_orig, size_t n,
+                             int32_t* __restrict__ label)
+{
+  size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+  if (i >= n)
+    return;
+  const int slot = __float_as_int(cur[i].w);
+  label[i] = src_orig ? src_orig[slot] : slot;
+}
+
+__global__ void k_gather_subset(const float4* __restrict__ all, const int32_t* __restrict__ sub, size_t n,
+                                float4* __restrict__ out)
+{
+  size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+  if (i < n)
+    out[i] = all[sub[i]];
+}
+
+void icp_reset_state(Icp& s, const double* guess)
+{
+  set_identity(s.last_T);
+  if (guess) {
+    for (int i = 0; i < 16; ++i)
+      s.final_T[i] = s.P.scalar_is_double ? guess[i] : (double)(float)guess[i];
+  }
+  else
+    set_identity(s.final_T);
+  s.iterations = 0;
+  s.state = PCLB200_CONV_NOT_CONVERGED;
+  s.converged = false;
+  s.n_corr = 0;
+  s.mse = 0.0;
+  s.prev_mse = std::numeric_limits<double>::max();
+  s.iterations_similar = 0;
+}
+
+void icp_set_source(Icp& s, const void* src, size_t n, size_t stride, const void* src_normals, size_t stride_n,
+                    const int32_t* indices, size_t n_idx, const double* guess)
+{
+  Ctx& c = *s.ctx;
+  cudaStream_t st = c.stream;
+  PCLB_REQUIRE(s.tgt != nullptr, PCLB200_ERR_INVALID, "icp: no target set (registration.hpp:77-81)");
+  PCLB_REQUIRE(src != nullptr && n > 0, PCLB200_ERR_INVALID, "icp: empty source");
+  s.n_all = n;
+  s.src_all.alloc(n, st);
+  load_xyz_as_float4(c, src, n, stride, nullptr, 0, s.src_all.p, st);
+  s.have_src_normals = src_normals != nullptr;
+  if (src_normals) {
+    s.src_normals.alloc(n, st);
+    load_vec3_as_float4(c, src_normals, n, stride_n, s.src_normals.p, st);
+  }
+  else
+    s.src_normals.release();
+  const float4* d_q = s.src_all.p;
+  DevBuf<float4> sub;
+  s.n_q = n;
+  s.src_orig.release();
+  if (indices) {
+    s.n_q = n_idx;
+    s.src_orig.alloc(n_idx, st);
+    PCLB_CUDA(cudaMemcpyAsync(s.src_orig.p, indices, n_idx * sizeof(int32_t),
+                              is_device_ptr(indices) ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, st));
+    sub.alloc(n_idx, st);
+    if (n_idx) {
+      k_gather_subset<<<grid_for(n_idx, 256), 256, 0, st>>>(s.src_all.p, s.src_orig.p, n_idx, sub.p);
+      ++c.launches;
+    }
+    d_q = sub.p;
+  }
+  QueryBatch qb;
+  make_query_batch(c, *s.tgt, d_q, s.n_q, qb);
+  s.cur = std::move(qb.q);
+  s.cur_label.alloc(s.n_q, st);
+  if (s.n_q) {
+    k_cur_labels<<<grid_for(s.n_q, 256), 256, 0, st>>>(s.cur.p, s.src_orig.p, s.n_q, s.cur_label.p);
+    ++c.launches;
+  }
+  icp_reset_state(s, guess);
+  // icp.hpp:125-134: a non-identity guess is applied once, before the first search
+  bool guess_identity = true;
+  if (guess)
+    for (int i = 0; i < 16; ++i)
+      if (s.final_T[i] != ((i % 5 == 0) ? 1.0 : 0.0))
+        guess_identity = false;
+  if (!guess_identity) {
+    upload_pending(s, s.final_T, 1);
+    k_apply_pending<<<persistent_grid(c, s.n_q, 256, 8), 256, 0, st>>>(s.cur.p, s.n_q, s.pending.p, nullptr);
+    ++c.launches;
+  }
+  upload_pending(s, s.last_T, 0);
+  PCLB_CUDA(cudaGetLastError());
+}
+
+static void check_device_error(Ctx& c)
+{
+  int h = 0;
+  PCLB_CUDA(cudaMemcpyAsync(&h, c.d_error, sizeof(int), cudaMemcpyDeviceToHost, c.stream));
+  PCLB_CUDA(cudaStreamSynchronize(c.stream));
+  if (h) {
+    PCLB_CUDA(cudaMemsetAsync(c.d_error, 0, sizeof(int), c.stream));
+    throw Error(PCLB200_ERR_INTERNAL, "LBVH traversal stack overflow (tree deeper than the per-query stack)");
+  }
+}
+
+// DefaultConvergenceCriteria::hasConverged — impl/default_convergence_criteria.hpp:49-140.
+// T is the current T_k in Scalar (stored as doubles; float mode: exactly representable floats).
+template <typename S>
+static bool has_converged(Icp& s, const double* Td)
+{
+  const pclb200_icp_params& P = s.P;
+  if (s.state != PCLB200_CONV_NOT_CONVERGED) {
+    s.iterations_similar = 0;
+    s.state = PCLB200_CONV_NOT_CONVERGED;
+  }
+  bool is_similar = false;
+  if (s.iterations >= P.max_iterations) {
+    if (!P.failure_after_max_iter) {
+      s.state = PCLB200_CONV_ITERATIONS;
+      return true;
+    }
+    s.state = PCLB200_CONV_FAILURE_AFTER_MAX_ITERATIONS;
+  }
+  S T[16];
+  for (int i = 0; i < 16; ++i)
+    T[i] = static_cast<S>(Td[i]);
+  const double rotation_threshold = P.transformation_rotation_epsilon > 0 ? P.transformation_rotation_epsilon : 0.99999;
+  const double translation_threshold = P.transformation_epsilon;
+  const double mse_threshold_relative = P.euclidean_fitness_epsilon;
+  const double mse_threshold_absolute = P.mse_threshold_absolute;
+  double cos_angle = 0.5 * (T[0] + T[5] + T[10] - 1);
+  double translation_sqr = T[3] * T[3] + T[7] * T[7] + T[11] * T[11];
+  if (cos_angle >= rotation_threshold && translation_sqr <= translation_threshold) {
+    if (s.iterations_similar >= P.max_iterations_similar_transforms) {
+      s.state = PCLB200_CONV_TRANSFORM;
+      return true;
+    }
+    is_similar = true;
+  }
+  const double cur_mse = s.mse;
+  if (std::abs(cur_mse - s.prev_mse) < mse_threshold_absolute) {
+    if (s.iterations_similar >= P.max_iterations_similar_transforms) {
+      s.state = PCLB200_CONV_ABS_MSE;
+      return true;
+    }
+    is_similar = true;
+  }
+  if (std::abs(cur_mse - s.prev_mse) / s.prev_mse < mse_threshold_relative) {
+    if (s.iterations_similar >= P.max_iterations_similar_transforms) {
+      s.state = PCLB200_CONV_REL_MSE;
+      return true;
+    }
+    is_similar = true;
+  }
+  if (is_similar)
+    ++s.iterations_similar;
+  else
+    s.iterations_similar = 0;
+  s.prev_mse = cur_mse;
+  return false;
+}
+
+static void fill_stats(const Icp& s, pclb200_icp_stats* st)
+{
+  if (!st)
+    return;
+  st->converged = s.converged ? 1 : 0;
+  st->state = s.state;
+  st->iterations = s.iterations;
+  st->reserved = 0;
+  st->n_correspondences = s.n_corr;
+  st->mse = s.mse;
+  for (int i = 0; i < 16; ++i) {
+    st->final_transformation[i] = s.final_T[i];
+    st->last_transformation[i] = s.last_T[i];
+  }
+}
+
+template <int EST, bool RECIP>
+static void launch_iter(Ctx& c, const IterArgs& a, unsigned grid)
+{
+  k_icp_iter<EST, RECIP><<<grid, 256, 0, c.stream>>>(a);
+  ++c.launches;
+}
+
+void icp_iterate(Icp& s, int max_steps, pclb200_icp_stats* stats)
+{
+  Ctx& c = *s.ctx;
+  cudaStream_t st = c.stream;
+  PCLB_REQUIRE(s.tgt && s.cur.p, PCLB200_ERR_INVALID, "icp: set_target and set_source must precede iterate");
+  PCLB_REQUIRE(s.P.estimator == PCLB200_EST_SVD || s.tgt_normals.p, PCLB200_ERR_INVALID,
+               "icp: point-to-plane needs target normals");
+  const Index& T = *s.tgt;
+  SolveOut* h_out = reinterpret_cast<SolveOut*>(c.pinned);
+  int steps = 0;
+  // the reference's do-while runs at least once per align(); a caller stepping one iteration at a time
+  // resumes a NOT_CONVERGED session, and a fresh session (iterations == 0) always enters.
+  while (steps < max_steps && (s.state == PCLB200_CONV_NOT_CONVERGED)) {
+    IterArgs a;
+    memset(&a, 0, sizeof(a));
+    a.nodes = T.nodes.p;
+    a.pts = T.pts.p;
+    a.root = T.root;
+    a.tgt_normals = s.tgt_normals.p;
+    a.cur = s.cur.p;
+    a.n = s.n_q;
+    a.pending = s.pending.p;
+    a.gate = gate_from_max_dist(s.P.max_correspondence_distance);
+    a.ox = 0.5f * (T.lo[0] + T.hi[0]);
+    a.oy = 0.5f * (T.lo[1] + T.hi[1]);
+    a.oz = 0.5f * (T.lo[2] + T.hi[2]);
+    a.partials = s.red.partials.p;
+    a.counter = s.red.counter.p;
+    a.accum = s.red.accum.p;
+    a.d_error = c.d_error;
+    a.src_orig = s.src_orig.p;
+    const unsigned grid = persistent_grid(c, s.n_q, 256, 8);
+    std::unique_ptr<Index> src_index;
+    if (s.P.use_reciprocal) {
+      // tree_reciprocal_ is rebuilt over the transformed source every iteration
+      // (correspondence_estimation.hpp:117-135 via setInputSource at icp.hpp:175)
+      k_apply_pending<<<grid, 256, 0, st>>>(s.cur.p, s.n_q, s.pending.p, nullptr);
+      k_clear_apply<<<1, 1, 0, st>>>(s.pending.p);
+      c.launches += 2;
+      src_index.reset(build_index_from_device(c, s.cur.p, s.n_q, s.cur_label.p));
+      a.s_nodes = src_index->nodes.p;
+      a.s_pts = src_index->pts.p;
+      a.s_root = src_index->root;
+    }
+    if (s.P.estimator == PCLB200_EST_SVD) {
+      if (s.P.use_reciprocal) launch_iter<PCLB200_EST_SVD, true>(c, a, grid);
+      else launch_iter<PCLB200_EST_SVD, false>(c, a, grid);
+    }
+    else {
+      if (s.P.use_reciprocal) launch_iter<PCLB200_EST_POINT_TO_PLANE_LLS, true>(c, a, grid);
+      else launch_iter<PCLB200_EST_POINT_TO_PLANE_LLS, false>(c, a, grid);
+    }
+    PCLB_CUDA(cudaGetLastError());
+    comm_allreduce_sum(c, s.red.accum.p, kAccum);
+    k_solve<<<1, 32, 0, st>>>(s.red.accum.p, s.P.estimator, s.P.scalar_is_double, transform_mode(s.P), (double)a.ox,
+                              (double)a.oy, (double)a.oz, 3, s.pending.p, s.solve_out.p);
+    ++c.launches;
+    PCLB_CUDA(cudaMemcpyAsync(h_out, s.solve_out.p, sizeof(SolveOut), cudaMemcpyDeviceToHost, st));
+    int h_err = 0;
+    PCLB_CUDA(cudaMemcpyAsync(&h_err, c.d_error, sizeof(int), cudaMemcpyDeviceToHost, st));
+    PCLB_CUDA(cudaStreamSynchronize(st));
+    if (h_err) {
+      PCLB_CUDA(cudaMemsetAsync(c.d_error, 0, sizeof(int), st));
+      throw Error(PCLB200_ERR_INTERNAL, "LBVH traversal stack overflow (tree deeper than the per-query stack)");
+    }
+    ++steps;
+    s.n_corr = (int64_t)h_out->n;
+    s.mse = h_out->n > 0 ? h_out->sum_d / h_out->n : 0.0;
+    if (!h_out->ok) {  // icp.hpp:204-213
+      s.state = PCLB200_CONV_NO_CORRESPONDENCES;
+      s.converged = false;
+      break;
+    }
+    for (int i = 0; i < 16; ++i)
+      s.last_T[i] = h_out->T[i];
+    if (s.P.scalar_is_double)
+      mat4_mul<double>(s.last_T, s.final_T, s.final_T);
+    else {
+      float A[16], B[16], C[16];
+      for (int i = 0; i < 16; ++i) {
+        A[i] = (float)s.last_T[i];
+        B[i] = (float)s.final_T[i];
+      }
+      mat4_mul<float>(A, B, C);
+      for (int i = 0; i < 16; ++i)
+        s.final_T[i] = C[i];
+    }
+    ++s.iterations;
+    s.converged = s.P.scalar_is_double ? has_converged<double>(s, s.last_T) : has_converged<float>(s, s.last_T);
+  }
+  fill_stats(s, stats);
+}
+
+// output = *input_ ; transformCloud(*input_, output, final_transformation_) — icp.hpp:265-267
+void icp_get_cloud(Icp& s, void* out_pts, size_t stride_out, void* out_normals, size_t stride_n)
+{
+  Ctx& c = *s.ctx;
+  cudaStream_t st = c.stream;
+  PCLB_REQUIRE(s.src_all.p, PCLB200_ERR_INVALID, "icp: no source");
+  DevBuf<float4> tmp, tmpn;
+  tmp.alloc(s.n_all, st);
+  PCLB_CUDA(cudaMemcpyAsync(tmp.p, s.src_all.p, s.n_all * sizeof(float4), cudaMemcpyDeviceToDevice, st));
+  const bool do_n = out_normals && s.have_src_normals;
+  if (do_n) {
+    tmpn.alloc(s.n_all, st);
+    PCLB_CUDA(cudaMemcpyAsync(tmpn.p, s.src_normals.p, s.n_all * sizeof(float4), cudaMemcpyDeviceToDevice, st));
+  }
+  DevBuf<Pending> pend;
+  pend.alloc(1, st);
+  Pending h;
+  for (int i = 0; i < 12; ++i) {
+    h.f[i] = (float)s.final_T[i];
+    h.d[i] = s.final_T[i];
+  }
+  h.apply = 1;
+  h.mode = transform_mode(s.P);
+  PCLB_CUDA(cudaMemcpyAsync(pend.p, &h, sizeof(h), cudaMemcpyHostToDevice, st));
+  k_apply_pending<<<persistent_grid(c, s.n_all, 256, 8), 256, 0, st>>>(tmp.p, s.n_all, pend.p, do_n ? tmpn.p : nullptr);
+  ++c.launches;
+  auto write_back = [&](const DevBuf<float4>& d, void* out, size_t stride, int write_w, float w) {
+    if (stride == 16 && write_w) {
+      PCLB_CUDA(cudaMemcpyAsync(out, d.p, s.n_all * 16, is_device_ptr(out) ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost, st));
+      return;
+    }
+    if (is_device_ptr(out)) {
+      k_scatter_xyz<<<grid_for(s.n_all, 256), 256, 0, st>>>(d.p, s.n_all, (unsigned char*)out, stride, write_w, w);
+      ++c.launches;
+    }
+    else {
+      // host strided output: only x,y,z (and w) of each record may be touched
+      std::vector<float4> hbuf(s.n_all);
+      PCLB_CUDA(cudaMemcpyAsync(hbuf.data(), d.p, s.n_all * 16, cudaMemcpyDeviceToHost, st));
+      PCLB_CUDA(cudaStreamSynchronize(st));
+      unsigned char* o = static_cast<unsigned char*>(out);
+      for (size_t i = 0; i < s.n_all; ++i) {
+        float* f = reinterpret_cast<float*>(o + i * stride);
+        f[0] = hbuf[i].x; f[1] = hbuf[i].y; f[2] = hbuf[i].z;
+        if (write_w)
+          f[3] = w;
+      }
+    }
+  };
+  // src_all keeps the caller's w (PointXYZ: 1.0 after align(), registration.hpp:213-216)
+  write_back(tmp, out_pts, stride_out, stride_out >= 16 ? 1 : 0, 1.0f);
+  if (do_n)
+    write_back(tmpn, out_normals, stride_n, 0, 0.f);
+  PCLB_CUDA(cudaStreamSynchronize(st));
+}
+
+// ---- stand-alone estimators ----------------------------------------------------------------------------------
+void estimate_pairs(Ctx& c, int est, const void* src, size_t stride_s, const void* tgt, const void* tgt_normals,
+                    size_t stride_t, const pclb200_corr* corr, size_t n, int scalar_is_double, double* T_out)
+{
+  cudaStream_t st = c.stream;
+  PCLB_REQUIRE(src && tgt && n > 0, PCLB200_ERR_INVALID, "estimate: empty input");
+  // the caller's arrays are indexed by corr[].index_*; without their sizes we need the max index
+  size_t n_src = n, n_tgt = n;
+  DevBuf<pclb200_corr> d_corr;
+  if (corr) {
+    std::vector<pclb200_corr> hc;
+    const pclb200_corr* hcorr = corr;
+    if (is_device_ptr(corr)) {
+      hc.resize(n);
+      PCLB_CUDA(cudaMemcpy(hc.data(), corr, n * sizeof(pclb200_corr), cudaMemcpyDeviceToHost));
+      hcorr = hc.data();
+    }
+    int mq = 0, mm = 0;
+    for (size_t i = 0; i < n; ++i) {
+      PCLB_REQUIRE(hcorr[i].index_query >= 0 && hcorr[i].index_match >= 0, PCLB200_ERR_INVALID, "negative index");
+      mq = std::max(mq, hcorr[i].index_query);
+      mm = std::max(mm, hcorr[i].index_match);
+    }
+    n_src = (size_t)mq + 1;
+    n_tgt = (size_t)mm + 1;
+    d_corr.alloc(n, st);
+    PCLB_CUDA(cudaMemcpyAsync(d_corr.p, hcorr, n * sizeof(pclb200_corr), cudaMemcpyHostToDevice, st));
+    PCLB_CUDA(cudaStreamSynchronize(st));
+  }
+  DevBuf<float4> ds, dt, dn;
+  ds.alloc(n_src, st);
+  dt.alloc(n_tgt, st);
+  load_xyz_as_float4(c, src, n_src, stride_s, nullptr, 0, ds.p, st);
+  load_xyz_as_float4(c, tgt, n_tgt, stride_t, nullptr, 0, dt.p, st);
+  if (est == PCLB200_EST_POINT_TO_PLANE_LLS) {
+    PCLB_REQUIRE(tgt_normals, PCLB200_ERR_INVALID, "point-to-plane needs target normals");
+    dn.alloc(n_tgt, st);
+    load_vec3_as_float4(c, tgt_normals, n_tgt, stride_t, dn.p, st);
+  }
+  Reducer red;
+  const unsigned grid = persistent_grid(c, n, 256, 4);
+  red.init(c, grid);
+  DevBuf<SolveOut> so;
+  so.alloc(1, st);
+  PairArgs a;
+  memset(&a, 0, sizeof(a));
+  a.src = ds.p;
+  a.tgt = dt.p;
+  a.tgt_normals = dn.p;
+  a.corr = d_corr.p;
+  a.n = n;
+  a.ox = a.oy = a.oz = 0.f;
+  a.pub.partials = red.partials.p;
+  a.pub.counter = red.counter.p;
+  a.pub.accum = red.accum.p;
+  if (est == PCLB200_EST_SVD) {
+    // shift by the first target point to keep the fp64 sums small
+    float4 first;
+    PCLB_CUDA(cudaMemcpyAsync(&first, dt.p, sizeof(float4), cudaMemcpyDeviceToHost, st));
+    PCLB_CUDA(cudaStreamSynchronize(st));
+    if (std::isfinite(first.x) && std::isfinite(first.y) && std::isfinite(first.z)) {
+      a.ox = first.x; a.oy = first.y; a.oz = first.z;
+    }
+    k_accum_pairs<PCLB200_EST_SVD><<<grid, 256, 0, st>>>(a);
+  }
+  else
+    k_accum_pairs<PCLB200_EST_POINT_TO_PLANE_LLS><<<grid, 256, 0, st>>>(a);
+  k_solve<<<1, 32, 0, st>>>(red.accum.p, est, scalar_is_double, 0, (double)a.ox, (double)a.oy, (double)a.oz, 1, nullptr,
+                            so.p);
+  c.launches += 2;
+  SolveOut h;
+  PCLB_CUDA(cudaMemcpyAsync(&h, so.p, sizeof(h), cudaMemcpyDeviceToHost, st));
+  PCLB_CUDA(cudaStreamSynchronize(st));
+  for (int i = 0; i < 16; ++i)
+    T_out[i] = h.T[i];
+}
+
+// ---- correspondences (materialised) -----------------------------------------------------------------------------
+size_t correspondences(Ctx& c, const Index& tgt, const Index* src_index, const void* src, size_t n, size_t stride,
+                       const int32_t* indices, size_t n_idx, int is_dense, double max_dist, pclb200_corr* out)
+{
+  (void)is_dense;  // non-finite source points never produce a correspondence on either setting
+  cudaStream_t st = c.stream;
+  const size_t nq = indices ? n_idx : n;
+  if (nq == 0)
+    return 0;
+  DevBuf<float4> dense;
+  dense.alloc(nq, st);
+  load_xyz_as_float4(c, src, n, stride, indices, n_idx, dense.p, st);
+  DevBuf<int32_t> d_ind;
+  if (indices) {
+    d_ind.alloc(n_idx, st);
+    PCLB_CUDA(cudaMemcpyAsync(d_ind.p, indices, n_idx * sizeof(int32_t),
+                              is_device_ptr(indices) ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, st));
+  }
+  QueryBatch qb;
+  make_query_batch(c, tgt, dense.p, nq, qb);
+  DevBuf<pclb200_corr> by_slot, compact;
+  DevBuf<size_t> d_count;
+  by_slot.alloc(nq, st);
+  compact.alloc(nq, st);
+  d_count.alloc(1, st);
+  const float gate = gate_from_max_dist(max_dist);
+  if (src_index)
+    k_corr<true><<<grid_for(nq, 128), 128, 0, st>>>(tgt.nodes.p, tgt.pts.p, tgt.root, qb.q.p, nq, gate,
+                                                   src_index->nodes.p, src_index->pts.p, src_index->root, d_ind.p,
+                                                   by_slot.p, c.d_error);
+  else
+    k_corr<false><<<grid_for(nq, 128), 128, 0, st>>>(tgt.nodes.p, tgt.pts.p, tgt.root, qb.q.p, nq, gate, nullptr,
+                                                    nullptr, 0, d_ind.p, by_slot.p, c.d_error);
+  ++c.launches;
+  PCLB_CUDA(cudaGetLastError());
+  size_t tmp_bytes = 0;
+  PCLB_CUDA(cub::DeviceSelect::If(nullptr, tmp_bytes, by_slot.p, compact.p, d_count.p, (int)nq, CorrValid(), st));
+  DevBuf<unsigned char> tmp;
+  tmp.alloc(tmp_bytes, st);
+  PCLB_CUDA(cub::DeviceSelect::If(tmp.p, tmp_bytes, by_slot.p, compact.p, d_count.p, (int)nq, CorrValid(), st));
+  c.launches += 2;
+  size_t m = 0;
+  PCLB_CUDA(cudaMemcpyAsync(&m, d_count.p, sizeof(size_t), cudaMemcpyDeviceToHost, st));
+  PCLB_CUDA(cudaStreamSynchronize(st));
+  if (m)
+    PCLB_CUDA(cudaMemcpyAsync(out, compact.p, m * sizeof(pclb200_corr),
+                              is_device_ptr(out) ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost, st));
+  check_device_error(c);
+  return m;
+}
+
+// ---- fitness score ------------------------------------------------------------------------------------------------
+double fitness_score(Ctx& c, const Index& tgt, const void* src, size_t n, size_t stride, const int32_t* indices,
+                     size_t n_idx, const double* T, int scalar_is_double, double max_range)
+{
+  cudaStream_t st = c.stream;
+  // registration.hpp:141-144: the index subset is used only when it is a strict subset
+  const bool use_sub = indices && n_idx != n;
+  const size_t nq = use_sub ? n_idx : n;
+  if (!nq)
+    return std::numeric_limits<double>::max();
+  DevBuf<float4> dense;
+  dense.alloc(nq, st);
+  load_xyz_as_float4(c, src, n, stride, use_sub ? indices : nullptr, use_sub ? n_idx : 0, dense.p, st);
+  DevBuf<Pending> pend;
+  pend.alloc(1, st);
+  Pending h;
+  for (int i = 0; i < 12; ++i) {
+    h.f[i] = (float)T[i];
+    h.d[i] = scalar_is_double ? T[i] : (double)(float)T[i];
+  }
+  h.apply = 1;
+  h.mode = scalar_is_double ? 2 : 1;  // pcl::transformPointCloud
+  PCLB_CUDA(cudaMemcpyAsync(pend.p, &h, sizeof(h), cudaMemcpyHostToDevice, st));
+  k_apply_pending<<<persistent_grid(c, nq, 256, 8), 256, 0, st>>>(dense.p, nq, pend.p, nullptr);
+  ++c.launches;
+  QueryBatch qb;
+  make_query_batch(c, tgt, dense.p, nq, qb);
+  Reducer red;
+  const unsigned grid = persistent_grid(c, nq, 256, 8);
+  red.init(c, grid);
+  IterArgs pub;
+  memset(&pub, 0, sizeof(pub));
+  pub.partials = red.partials.p;
+  pub.counter = red.counter.p;
+  pub.accum = red.accum.p;
+  pub.d_error = c.d_error;
+  k_fitness<<<grid, 256, 0, st>>>(tgt.nodes.p, tgt.pts.p, tgt.root, qb.q.p, nq, max_range, pub);
+  ++c.launches;
+  double acc[2];
+  PCLB_CUDA(cudaMemcpyAsync(acc, red.accum.p, sizeof(acc), cudaMemcpyDeviceToHost, st));
+  check_device_error(c);
+  return acc[0] > 0 ? acc[1] / acc[0] : std::numeric_limits<double>::max();
+}
+
+}  // namespace pclb200

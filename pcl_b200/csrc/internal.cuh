@@ -1,0 +1,164 @@
+// internal.cuh — shared declarations of libpclb200 (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+
+#include <cfloat>
+#include <cstdint>
+#include <cstdio>
+#include <cstring>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+#include "../../include/pclb200.h"
+
+namespace pclb200 {
+
+// ---------------------------------------------------------------------------------------------
+// errors: C++ exceptions inside the library, converted to status codes at the C boundary
+// ---------------------------------------------------------------------------------------------
+struct Error : std::runtime_error {
+  int code;
+  Error(int c, const std::string& m) : std::runtime_error(m), code(c) {}
+};
+
+#define PCLB_CUDA(expr)                                                                         \
+  do {                                                                                          \
+    cudaError_t _e = (expr);                                                                    \
+    if (_e != cudaSuccess)                                                                      \
+      throw ::pclb200::Error(PCLB200_ERR_CUDA, std::string(#expr) + ": " + cudaGetErrorString(_e) + \
+                                                   " (" + __FILE__ + ":" + std::to_string(__LINE__) + ")"); \
+  } while (0)
+
+#define PCLB_REQUIRE(cond, code, msg)                 \
+  do {                                                \
+    if (!(cond))                                      \
+      throw ::pclb200::Error((code), (msg));          \
+  } while (0)
+
+// ---------------------------------------------------------------------------------------------
+// context
+// ---------------------------------------------------------------------------------------------
+struct Comm;  // NCCL wrapper (comm.cu)
+
+struct Ctx {
+  int device = 0;
+  int sm_count = 148;
+  cudaStream_t stream = nullptr;
+  uint64_t launches = 0;  // kernels launched by this library (incl. CUB passes, counted per call)
+  void* pinned = nullptr; // small pinned staging block for per-iteration read-backs
+  size_t pinned_bytes = 0;
+  int* d_error = nullptr; // device-side invariant flag (traversal stack overflow)
+  Comm* comm = nullptr;
+};
+
+// stream-ordered device buffer
+template <typename T>
+struct DevBuf {
+  T* p = nullptr;
+  size_t n = 0;
+  cudaStream_t s = nullptr;
+  DevBuf() = default;
+  DevBuf(const DevBuf&) = delete;
+  DevBuf& operator=(const DevBuf&) = delete;
+  DevBuf(DevBuf&& o) noexcept : p(o.p), n(o.n), s(o.s) { o.p = nullptr; o.n = 0; }
+  DevBuf& operator=(DevBuf&& o) noexcept
+  {
+    if (this != &o) {
+      release();
+      p = o.p; n = o.n; s = o.s;
+      o.p = nullptr; o.n = 0;
+    }
+    return *this;
+  }
+  void alloc(size_t count, cudaStream_t stream)
+  {
+    release();
+    s = stream;
+    n = count;
+    if (count)
+      PCLB_CUDA(cudaMallocAsync(reinterpret_cast<void**>(&p), count * sizeof(T), stream));
+  }
+  void release()
+  {
+    if (p)
+      cudaFreeAsync(p, s);
+    p = nullptr;
+    n = 0;
+  }
+  ~DevBuf() { release(); }
+  size_t bytes() const { return n * sizeof(T); }
+};
+
+bool is_device_ptr(const void* p);
+
+// Copies `count` records of `rec_bytes` (<= stride) from a strided host-or-device array into a
+// dense device array of float4 {x,y,z,w_fill}: the layout every kernel reads with 128-bit loads.
+// If `subset` != NULL, record i is src[subset[i]].
+void load_xyz_as_float4(Ctx& c, const void* src, size_t n_records, size_t stride, const int32_t* subset,
+                        size_t n_subset, float4* d_out, cudaStream_t s);
+// same for normals (3 floats at `src`, any stride) -> float4 {nx,ny,nz,0}
+void load_vec3_as_float4(Ctx& c, const void* src, size_t n_records, size_t stride, float4* d_out,
+                         cudaStream_t s);
+
+// ---------------------------------------------------------------------------------------------
+// LBVH index
+// ---------------------------------------------------------------------------------------------
+// One internal node = 64 B = four 128-bit loads: both children's boxes + their references.
+//   a = (l.min.x, l.min.y, l.min.z, l.max.x)  b = (l.max.y, l.max.z, r.min.x, r.min.y)
+//   c = (r.min.z, r.max.x, r.max.y, r.max.z)  d = (left, right, 0, 0)
+// child reference >= 0: internal node id; < 0: ~leaf_id.
+struct __align__(16) BvhNode {
+  float4 a, b, c;
+  int4 d;
+};
+
+constexpr int kLeafSize = 8;        // points per leaf = one 128-byte line of float4
+constexpr int kStackSize = 64;      // traversal stack entries per query
+constexpr int kSentinelIndex = 0x7fffffff;
+
+struct Index {
+  Ctx* ctx = nullptr;
+  size_t n_cloud = 0;   // records in the caller's cloud (index space of results)
+  size_t n_valid = 0;   // finite points indexed
+  int n_leaves = 0;
+  int root = 0;         // child-reference encoding
+  float lo[3] = {0, 0, 0}, hi[3] = {0, 0, 0};  // bounding box of the valid points
+  float morton_scale = 1.f;                     // 2^21 / max extent
+  DevBuf<float4> pts;   // n_leaves*kLeafSize, Morton order, w = original index bits; padded with +inf
+  DevBuf<BvhNode> nodes;  // n_leaves-1
+  DevBuf<int32_t> pos_of_orig;  // n_cloud: position in `pts` of original index i, or -1 (lazy)
+  size_t bytes() const { return pts.bytes() + nodes.bytes() + pos_of_orig.bytes(); }
+};
+
+Index* build_index(Ctx& c, const void* pts, size_t n, size_t stride, const int32_t* subset, size_t n_subset);
+// device-resident source already dense float4 (w ignored): used for the reciprocal source tree
+Index* build_index_from_device(Ctx& c, const float4* d_pts, size_t n, const int32_t* d_orig /*nullable*/);
+void ensure_pos_of_orig(Ctx& c, Index& idx);
+
+// Morton-ordered batch of query points (dense float4 xyz + original slot), so neighbouring threads
+// walk neighbouring subtrees.
+struct QueryBatch {
+  size_t n = 0;
+  DevBuf<float4> q;       // n, xyz + w = original slot bits
+};
+void make_query_batch(Ctx& c, const Index& ref_frame, const float4* d_q /*n, w ignored*/, size_t n,
+                      QueryBatch& out);
+
+// ---------------------------------------------------------------------------------------------
+// search / registration kernels (search.cu, icp.cu, voxel.cu)
+// ---------------------------------------------------------------------------------------------
+// exact k-NN for a Morton-ordered batch; results scattered to row `slot` (w of the query)
+void launch_knn(Ctx& c, const Index& idx, const float4* d_q, size_t nq, int k, float init_bound,
+                int32_t* d_out_idx, float* d_out_d2 /* nq*k, row = slot */);
+// counts / fills for radius search: neighbours with d2 < r2
+void launch_radius_count(Ctx& c, const Index& idx, const float4* d_q, size_t nq, float r2,
+                         unsigned long long* d_counts /* by slot */);
+void launch_radius_fill(Ctx& c, const Index& idx, const float4* d_q, size_t nq, float r2,
+                        const unsigned long long* d_offsets /* by slot, exclusive */,
+                        unsigned long long* d_keys /* (d2 bits << 32) | index */);
+
+// accumulators of one ICP iteration (all fp64), see icp.cu
+constexpr int kAccum = 40;
+
+}  // namespace pclb200

@@ -1,0 +1,532 @@
+// lbvh.cu — target-side data layout: Morton-sorted linear BVH in HBM.
+//
+// Replaces what pcl::KdTreeFLANN::setInputCloud builds on the CPU
+// (kdtree/include/pcl/kdtree/impl/kdtree_flann.hpp:100-136, 429-498: drop non-finite points, keep
+// index_mapping_, build a FLANN KDTreeSingleIndex with <=15-point leaves).  Here:
+//   1. bbox + finite count (one streaming pass, block reduce + atomics on ordered-int floats)
+//   2. 63-bit Morton key per point (21 bits/axis, ONE isotropic scale so cells are cubes);
+//      non-finite points get key ~0 and sort to the tail
+//   3. cub::DeviceRadixSort (key64, value = original index) — stable, so equal keys keep index order
+//   4. gather to float4 {x,y,z, original-index bits}: a leaf of 8 points is one 128-byte line
+//   5. Karras 2012 binary radix tree over LEAVES (key = first point's code, ties by leaf id)
+//   6. bottom-up refit (atomic arrival flags), then pack both children's boxes into the parent's
+//      64-byte node so one node visit = four independent 128-bit loads
+#include <cub/cub.cuh>
+
+#include <algorithm>
+#include <cmath>
+#include <memory>
+
+#include "internal.cuh"
+
+namespace pclb200 {
+
+bool is_device_ptr(const void* p)
+{
+  if (!p)
+    return false;
+  cudaPointerAttributes at;
+  cudaError_t e = cudaPointerGetAttributes(&at, p);
+  if (e != cudaSuccess) {
+    cudaGetLastError();
+    return false;
+  }
+  return at.type == cudaMemoryTypeDevice || at.type == cudaMemoryTypeManaged;
+}
+
+// ---- strided record -> dense float4 ------------------------------------------------------------
+__global__ void k_strided_to_float4(const unsigned char* __restrict__ src, size_t stride,
+                                    const int32_t* __restrict__ subset, size_t n, float w_fill,
+                                    float4* __restrict__ out)
+{
+  size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+  if (i >= n)
+    return;
+  size_t r = subset ? (size_t)subset[i] : i;
+  const float* p = reinterpret_cast<const float*>(src + r * stride);
+  out[i] = make_float4(p[0], p[1], p[2], w_fill);
+}
+
+static void strided_to_float4(Ctx& c, const void* src, size_t n_records, size_t stride, const int32_t* subset,
+                              size_t n_subset, float w_fill, float4* d_out, cudaStream_t s)
+{
+  const size_t n = subset ? n_subset : n_records;
+  if (n == 0)
+    return;
+  PCLB_REQUIRE(src != nullptr, PCLB200_ERR_INVALID, "null point array");
+  PCLB_REQUIRE(stride >= 12 && stride % 4 == 0, PCLB200_ERR_INVALID, "stride must be a multiple of 4 and >= 12");
+  const bool on_device = is_device_ptr(src);
+  if (!subset && stride == 16) {
+    // pcl::PointXYZ records already are float4: one straight copy (w is never read by the kernels)
+    PCLB_CUDA(cudaMemcpyAsync(d_out, src, n * 16, on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, s));
+    return;
+  }
+  DevBuf<unsigned char> staged;
+  DevBuf<int32_t> staged_sub;
+  const unsigned char* d_src = static_cast<const unsigned char*>(src);
+  if (!on_device) {
+    staged.alloc(n_records * stride, s);
+    PCLB_CUDA(cudaMemcpyAsync(staged.p, src, n_records * stride, cudaMemcpyHostToDevice, s));
+    d_src = staged.p;
+  }
+  const int32_t* d_sub = subset;
+  if (subset && !is_device_ptr(subset)) {
+    staged_sub.alloc(n_subset, s);
+    PCLB_CUDA(cudaMemcpyAsync(staged_sub.p, subset, n_subset * sizeof(int32_t), cudaMemcpyHostToDevice, s));
+    d_sub = staged_sub.p;
+  }
+  k_strided_to_float4<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(d_src, stride, d_sub, n, w_fill, d_out);
+  ++c.launches;
+  PCLB_CUDA(cudaGetLastError());
+}
+
+void load_xyz_as_float4(Ctx& c, const void* src, size_t n_records, size_t stride, const int32_t* subset,
+                        size_t n_subset, float4* d_out, cudaStream_t s)
+{
+  strided_to_float4(c, src, n_records, stride, subset, n_subset, 1.f, d_out, s);
+}
+
+void load_vec3_as_float4(Ctx& c, const void* src, size_t n_records, size_t stride, float4* d_out, cudaStream_t s)
+{
+  strided_to_float4(c, src, n_records, stride, nullptr, 0, 0.f, d_out, s);
+}
+
+// ---- bbox ---------------------------------------------------------------------------------------
+// floats mapped to order-preserving signed ints so atomicMin/Max work
+__device__ __forceinline__ int f2ord(float f)
+{
+  int i = __float_as_int(f);
+  return i >= 0 ? i : i ^ 0x7fffffff;
+}
+__host__ __device__ __forceinline__ float ord2f(int i)
+{
+  int j = i >= 0 ? i : i ^ 0x7fffffff;
+#ifdef __CUDA_ARCH__
+  return __int_as_float(j);
+#else
+  float f;
+  memcpy(&f, &j, 4);
+  return f;
+#endif
+}
+
+struct BBoxAcc {
+  int lo[3];
+  int hi[3];
+  unsigned long long count;
+};
+
+__global__ void k_bbox(const float4* __restrict__ p, size_t n, BBoxAcc* acc)
+{
+  float lo[3] = {FLT_MAX, FLT_MAX, FLT_MAX}, hi[3] = {-FLT_MAX, -FLT_MAX, -FLT_MAX};
+  unsigned cnt = 0;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+    float4 v = __ldg(p + i);
+    if (isfinite(v.x) && isfinite(v.y) && isfinite(v.z)) {
+      lo[0] = fminf(lo[0], v.x); hi[0] = fmaxf(hi[0], v.x);
+      lo[1] = fminf(lo[1], v.y); hi[1] = fmaxf(hi[1], v.y);
+      lo[2] = fminf(lo[2], v.z); hi[2] = fmaxf(hi[2], v.z);
+      ++cnt;
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+#pragma unroll
+    for (int d = 0; d < 3; ++d) {
+      lo[d] = fminf(lo[d], __shfl_xor_sync(0xffffffffu, lo[d], o));
+      hi[d] = fmaxf(hi[d], __shfl_xor_sync(0xffffffffu, hi[d], o));
+    }
+    cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
+  }
+  if ((threadIdx.x & 31) == 0 && cnt) {
+#pragma unroll
+    for (int d = 0; d < 3; ++d) {
+      atomicMin(&acc->lo[d], f2ord(lo[d]));
+      atomicMax(&acc->hi[d], f2ord(hi[d]));
+    }
+    atomicAdd(&acc->count, (unsigned long long)cnt);
+  }
+}
+
+// ---- Morton keys --------------------------------------------------------------------------------
+__device__ __forceinline__ unsigned long long expand21(unsigned long long v)
+{
+  v &= 0x1fffffULL;
+  v = (v | v << 32) & 0x1f00000000ffffULL;
+  v = (v | v << 16) & 0x1f0000ff0000ffULL;
+  v = (v | v << 8) & 0x100f00f00f00f00fULL;
+  v = (v | v << 4) & 0x10c30c30c30c30c3ULL;
+  v = (v | v << 2) & 0x1249249249249249ULL;
+  return v;
+}
+
+__device__ __forceinline__ unsigned long long morton63(float x, float y, float z, float lx, float ly, float lz,
+                                                       float scale)
+{
+  float fx = fminf(fmaxf((x - lx) * scale, 0.f), 2097151.f);
+  float fy = fminf(fmaxf((y - ly) * scale, 0.f), 2097151.f);
+  float fz = fminf(fmaxf((z - lz) * scale, 0.f), 2097151.f);
+  return (expand21((unsigned long long)fz) << 2) | (expand21((unsigned long long)fy) << 1) |
+         expand21((unsigned long long)fx);
+}
+
+// value = record slot i; for invalid (non-finite) points key = ~0 so they sort last
+__global__ void k_morton(const float4* __restrict__ p, size_t n, float lx, float ly, float lz, float scale,
+                         unsigned long long* __restrict__ keys, int32_t* __restrict__ vals)
+{
+  size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+  if (i >= n)
+    return;
+  float4 v = __ldg(p + i);
+  bool ok = isfinite(v.x) && isfinite(v.y) && isfinite(v.z);
+  keys[i] = ok ? morton63(v.x, v.y, v.z, lx, ly, lz, scale) : ~0ULL;
+  vals[i] = (int32_t)i;
+}
+
+// sorted gather: out[j] = {xyz of slot vals[j], orig index bits}; pads the tail with +inf sentinels
+__global__ void k_gather_sorted(const float4* __restrict__ p, const int32_t* __restrict__ vals,
+                                const int32_t* __restrict__ orig_of_slot, size_t n_valid, size_t n_padded,
+                                float4* __restrict__ out)
+{
+  size_t j = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+  if (j >= n_padded)
+    return;
+  if (j < n_valid) {
+    int32_t slot = vals[j];
+    float4 v = __ldg(p + slot);
+    int32_t oi = orig_of_slot ? orig_of_slot[slot] : slot;
+    out[j] = make_float4(v.x, v.y, v.z, __int_as_float(oi));
+  }
+  else {
+    const float inf = __int_as_float(0x7f800000);
+    out[j] = make_float4(inf, inf, inf, __int_as_float(kSentinelIndex));
+  }
+}
+
+// ---- Karras 2012 over leaves --------------------------------------------------------------------
+__device__ __forceinline__ int delta_leaf(const unsigned long long* __restrict__ keys, int n, int i, int j)
+{
+  if (j < 0 || j >= n)
+    return -1;
+  unsigned long long a = keys[(size_t)i * kLeafSize], b = keys[(size_t)j * kLeafSize];
+  unsigned long long x = a ^ b;
+  if (x == 0)
+    return 64 + __clz(i ^ j);
+  return __clzll((long long)x);
+}
+
+__global__ void k_karras(const unsigned long long* __restrict__ keys /* sorted point keys */, int n_leaves,
+                         int2* __restrict__ children, int* __restrict__ node_parent, int* __restrict__ leaf_parent)
+{
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_leaves - 1)
+    return;
+  const int n = n_leaves;
+  int d = (delta_leaf(keys, n, i, i + 1) - delta_leaf(keys, n, i, i - 1)) >= 0 ? 1 : -1;
+  int dmin = delta_leaf(keys, n, i, i - d);
+  int lmax = 2;
+  while (delta_leaf(keys, n, i, i + lmax * d) > dmin)
+    lmax <<= 1;
+  int l = 0;
+  for (int t = lmax >> 1; t >= 1; t >>= 1)
+    if (delta_leaf(keys, n, i, i + (l + t) * d) > dmin)
+      l += t;
+  int j = i + l * d;
+  int dnode = delta_leaf(keys, n, i, j);
+  int s = 0;
+  int t = l;
+  do {
+    t = (t + 1) >> 1;
+    if (delta_leaf(keys, n, i, i + (s + t) * d) > dnode)
+      s += t;
+  } while (t > 1);
+  int gamma = i + s * d + min(d, 0);
+  int left, right;
+  if (min(i, j) == gamma) {
+    left = ~gamma;
+    leaf_parent[gamma] = i;
+  }
+  else {
+    left = gamma;
+    node_parent[gamma] = i;
+  }
+  if (max(i, j) == gamma + 1) {
+    right = ~(gamma + 1);
+    leaf_parent[gamma + 1] = i;
+  }
+  else {
+    right = gamma + 1;
+    node_parent[gamma + 1] = i;
+  }
+  children[i] = make_int2(left, right);
+  if (i == 0)
+    node_parent[0] = -1;
+}
+
+// ---- refit --------------------------------------------------------------------------------------
+__global__ void k_refit(const float4* __restrict__ pts, int n_leaves, const int2* __restrict__ children,
+                        const int* __restrict__ node_parent, const int* __restrict__ leaf_parent,
+                        float4* __restrict__ leaf_lo, float4* __restrict__ leaf_hi, float4* __restrict__ node_lo,
+                        float4* __restrict__ node_hi, unsigned* __restrict__ flags)
+{
+  int leaf = blockIdx.x * blockDim.x + threadIdx.x;
+  if (leaf >= n_leaves)
+    return;
+  float lo[3] = {FLT_MAX, FLT_MAX, FLT_MAX}, hi[3] = {-FLT_MAX, -FLT_MAX, -FLT_MAX};
+#pragma unroll
+  for (int j = 0; j < kLeafSize; ++j) {
+    float4 p = __ldg(pts + (size_t)leaf * kLeafSize + j);
+    if (__float_as_int(p.w) != kSentinelIndex) {
+      lo[0] = fminf(lo[0], p.x); hi[0] = fmaxf(hi[0], p.x);
+      lo[1] = fminf(lo[1], p.y); hi[1] = fmaxf(hi[1], p.y);
+      lo[2] = fminf(lo[2], p.z); hi[2] = fmaxf(hi[2], p.z);
+    }
+  }
+  leaf_lo[leaf] = make_float4(lo[0], lo[1], lo[2], 0.f);
+  leaf_hi[leaf] = make_float4(hi[0], hi[1], hi[2], 0.f);
+  if (n_leaves == 1)
+    return;
+  int cur = leaf_parent[leaf];
+  while (cur >= 0) {
+    __threadfence();
+    if (atomicAdd(&flags[cur], 1u) == 0u)
+      return;  // first child to arrive: the sibling's thread finishes this node
+    __threadfence();
+    int2 ch = children[cur];
+    float4 alo = ch.x < 0 ? __ldcg(leaf_lo + ~ch.x) : __ldcg(node_lo + ch.x);
+    float4 ahi = ch.x < 0 ? __ldcg(leaf_hi + ~ch.x) : __ldcg(node_hi + ch.x);
+    float4 blo = ch.y < 0 ? __ldcg(leaf_lo + ~ch.y) : __ldcg(node_lo + ch.y);
+    float4 bhi = ch.y < 0 ? __ldcg(leaf_hi + ~ch.y) : __ldcg(node_hi + ch.y);
+    node_lo[cur] = make_float4(fminf(alo.x, blo.x), fminf(alo.y, blo.y), fminf(alo.z, blo.z), 0.f);
+    node_hi[cur] = make_float4(fmaxf(ahi.x, bhi.x), fmaxf(ahi.y, bhi.y), fmaxf(ahi.z, bhi.z), 0.f);
+    cur = node_parent[cur];
+  }
+}
+
+__global__ void k_pack_nodes(int n_internal, const int2* __restrict__ children, const float4* __restrict__ leaf_lo,
+                             const float4* __restrict__ leaf_hi, const float4* __restrict__ node_lo,
+                             const float4* __restrict__ node_hi, BvhNode* __restrict__ nodes)
+{
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_internal)
+    return;
+  int2 ch = children[i];
+  float4 alo = ch.x < 0 ? leaf_lo[~ch.x] : node_lo[ch.x];
+  float4 ahi = ch.x < 0 ? leaf_hi[~ch.x] : node_hi[ch.x];
+  float4 blo = ch.y < 0 ? leaf_lo[~ch.y] : node_lo[ch.y];
+  float4 bhi = ch.y < 0 ? leaf_hi[~ch.y] : node_hi[ch.y];
+  BvhNode nd;
+  nd.a = make_float4(alo.x, alo.y, alo.z, ahi.x);
+  nd.b = make_float4(ahi.y, ahi.z, blo.x, blo.y);
+  nd.c = make_float4(blo.z, bhi.x, bhi.y, bhi.z);
+  nd.d = make_int4(ch.x, ch.y, 0, 0);
+  nodes[i] = nd;
+}
+
+// ---- host orchestration -------------------------------------------------------------------------
+static inline unsigned grid_for(size_t n, int block) { return (unsigned)((n + block - 1) / block); }
+
+struct SortedCloud {
+  DevBuf<unsigned long long> keys;  // sorted
+  DevBuf<int32_t> vals;             // sorted slots
+  size_t n_valid = 0;
+  float lo[3], hi[3];
+  float scale = 1.f;
+};
+
+// bbox (when frame == nullptr) + keys + radix sort of n dense float4 points
+static void morton_sort(Ctx& c, const float4* d_pts, size_t n, const Index* frame, SortedCloud& out)
+{
+  cudaStream_t s = c.stream;
+  if (frame) {
+    for (int d = 0; d < 3; ++d) {
+      out.lo[d] = frame->lo[d];
+      out.hi[d] = frame->hi[d];
+    }
+    out.scale = frame->morton_scale;
+    out.n_valid = n;  // callers of the query path never pass non-finite points they care about
+  }
+  else {
+    DevBuf<BBoxAcc> acc;
+    acc.alloc(1, s);
+    BBoxAcc init;
+    for (int d = 0; d < 3; ++d) {
+      init.lo[d] = 0x7fffffff;
+      init.hi[d] = (int)0x80000000;
+    }
+    init.count = 0;
+    PCLB_CUDA(cudaMemcpyAsync(acc.p, &init, sizeof(init), cudaMemcpyHostToDevice, s));
+    unsigned g = (unsigned)std::min<size_t>((n + 255) / 256, (size_t)c.sm_count * 8);
+    k_bbox<<<g ? g : 1, 256, 0, s>>>(d_pts, n, acc.p);
+    ++c.launches;
+    BBoxAcc h;
+    PCLB_CUDA(cudaMemcpyAsync(&h, acc.p, sizeof(h), cudaMemcpyDeviceToHost, s));
+    PCLB_CUDA(cudaStreamSynchronize(s));
+    out.n_valid = (size_t)h.count;
+    if (out.n_valid == 0)
+      return;
+    float ext = 0.f;
+    for (int d = 0; d < 3; ++d) {
+      out.lo[d] = ord2f(h.lo[d]);
+      out.hi[d] = ord2f(h.hi[d]);
+      ext = std::max(ext, out.hi[d] - out.lo[d]);
+    }
+    out.scale = ext > 0.f ? 2097152.f / ext : 1.f;
+    if (!std::isfinite(out.scale))
+      out.scale = 1.f;
+  }
+  DevBuf<unsigned long long> keys_in;
+  DevBuf<int32_t> vals_in;
+  keys_in.alloc(n, s);
+  vals_in.alloc(n, s);
+  out.keys.alloc(n, s);
+  out.vals.alloc(n, s);
+  k_morton<<<grid_for(n, 256), 256, 0, s>>>(d_pts, n, out.lo[0], out.lo[1], out.lo[2], out.scale, keys_in.p,
+                                           vals_in.p);
+  ++c.launches;
+  size_t tmp_bytes = 0;
+  PCLB_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, keys_in.p, out.keys.p, vals_in.p, out.vals.p,
+                                            (int)n, 0, 64, s));
+  DevBuf<unsigned char> tmp;
+  tmp.alloc(tmp_bytes, s);
+  PCLB_CUDA(cub::DeviceRadixSort::SortPairs(tmp.p, tmp_bytes, keys_in.p, out.keys.p, vals_in.p, out.vals.p, (int)n,
+                                            0, 64, s));
+  c.launches += 9;  // onesweep: histogram + 8 digit passes
+  PCLB_CUDA(cudaGetLastError());
+}
+
+static Index* build_from_dense(Ctx& c, const float4* d_pts, size_t n, const int32_t* d_orig_of_slot, size_t n_cloud)
+{
+  cudaStream_t s = c.stream;
+  PCLB_REQUIRE(n > 0, PCLB200_ERR_EMPTY, "cannot index an empty cloud (kdtree_flann.hpp:118-129)");
+  PCLB_REQUIRE(n < (size_t)0x7fffffff, PCLB200_ERR_INVALID, "cloud too large for int32 indices");
+  SortedCloud sc;
+  morton_sort(c, d_pts, n, nullptr, sc);
+  PCLB_REQUIRE(sc.n_valid > 0, PCLB200_ERR_EMPTY, "no finite point in the cloud (kdtree_flann.hpp:124-129)");
+  std::unique_ptr<Index> idx(new Index());
+  idx->ctx = &c;
+  idx->n_cloud = n_cloud;
+  idx->n_valid = sc.n_valid;
+  for (int d = 0; d < 3; ++d) {
+    idx->lo[d] = sc.lo[d];
+    idx->hi[d] = sc.hi[d];
+  }
+  idx->morton_scale = sc.scale;
+  const int n_leaves = (int)((sc.n_valid + kLeafSize - 1) / kLeafSize);
+  idx->n_leaves = n_leaves;
+  const size_t n_padded = (size_t)n_leaves * kLeafSize;
+  idx->pts.alloc(n_padded, s);
+  k_gather_sorted<<<grid_for(n_padded, 256), 256, 0, s>>>(d_pts, sc.vals.p, d_orig_of_slot, sc.n_valid, n_padded,
+                                                          idx->pts.p);
+  ++c.launches;
+  if (n_leaves == 1) {
+    idx->root = ~0;
+  }
+  else {
+    const int n_int = n_leaves - 1;
+    idx->root = 0;
+    idx->nodes.alloc(n_int, s);
+    DevBuf<int2> children;
+    DevBuf<int> node_parent, leaf_parent;
+    DevBuf<float4> leaf_lo, leaf_hi, node_lo, node_hi;
+    DevBuf<unsigned> flags;
+    children.alloc(n_int, s);
+    node_parent.alloc(n_int, s);
+    leaf_parent.alloc(n_leaves, s);
+    leaf_lo.alloc(n_leaves, s);
+    leaf_hi.alloc(n_leaves, s);
+    node_lo.alloc(n_int, s);
+    node_hi.alloc(n_int, s);
+    flags.alloc(n_int, s);
+    PCLB_CUDA(cudaMemsetAsync(flags.p, 0, flags.bytes(), s));
+    // the sorted keys array has n entries >= n_padded? keys beyond n_valid are ~0 (invalid) or absent:
+    // leaf i's key is keys[i*kLeafSize], always < n_valid.
+    k_karras<<<grid_for(n_int, 256), 256, 0, s>>>(sc.keys.p, n_leaves, children.p, node_parent.p, leaf_parent.p);
+    k_refit<<<grid_for(n_leaves, 256), 256, 0, s>>>(idx->pts.p, n_leaves, children.p, node_parent.p, leaf_parent.p,
+                                                    leaf_lo.p, leaf_hi.p, node_lo.p, node_hi.p, flags.p);
+    k_pack_nodes<<<grid_for(n_int, 256), 256, 0, s>>>(n_int, children.p, leaf_lo.p, leaf_hi.p, node_lo.p, node_hi.p,
+                                                     idx->nodes.p);
+    c.launches += 3;
+    PCLB_CUDA(cudaGetLastError());
+  }
+  PCLB_CUDA(cudaStreamSynchronize(s));  // temporaries are released stream-ordered; surface build errors here
+  return idx.release();
+}
+
+Index* build_index(Ctx& c, const void* pts, size_t n, size_t stride, const int32_t* subset, size_t n_subset)
+{
+  cudaStream_t s = c.stream;
+  const size_t cnt = subset ? n_subset : n;
+  PCLB_REQUIRE(pts != nullptr && cnt > 0, PCLB200_ERR_EMPTY, "cannot index an empty cloud (kdtree_flann.hpp:118-129)");
+  DevBuf<float4> dense;
+  dense.alloc(cnt, s);
+  load_xyz_as_float4(c, pts, n, stride, subset, n_subset, dense.p, s);
+  DevBuf<int32_t> d_sub;
+  const int32_t* d_orig = nullptr;
+  if (subset) {
+    if (is_device_ptr(subset))
+      d_orig = subset;
+    else {
+      d_sub.alloc(n_subset, s);
+      PCLB_CUDA(cudaMemcpyAsync(d_sub.p, subset, n_subset * sizeof(int32_t), cudaMemcpyHostToDevice, s));
+      d_orig = d_sub.p;
+    }
+  }
+  return build_from_dense(c, dense.p, cnt, d_orig, n);
+}
+
+Index* build_index_from_device(Ctx& c, const float4* d_pts, size_t n, const int32_t* d_orig)
+{
+  return build_from_dense(c, d_pts, n, d_orig, n);
+}
+
+// ---- position of each original index in the Morton array (for gathers by index_match) -------------
+__global__ void k_pos_of_orig(const float4* __restrict__ pts, size_t n_padded, int32_t* __restrict__ pos)
+{
+  size_t j = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+  if (j >= n_padded)
+    return;
+  int oi = __float_as_int(pts[j].w);
+  if (oi != kSentinelIndex)
+    pos[oi] = (int32_t)j;
+}
+
+void ensure_pos_of_orig(Ctx& c, Index& idx)
+{
+  if (idx.pos_of_orig.p)
+    return;
+  cudaStream_t s = c.stream;
+  idx.pos_of_orig.alloc(idx.n_cloud, s);
+  PCLB_CUDA(cudaMemsetAsync(idx.pos_of_orig.p, 0xff, idx.pos_of_orig.bytes(), s));
+  k_pos_of_orig<<<grid_for(idx.pts.n, 256), 256, 0, s>>>(idx.pts.p, idx.pts.n, idx.pos_of_orig.p);
+  ++c.launches;
+  PCLB_CUDA(cudaGetLastError());
+}
+
+// ---- query batches ------------------------------------------------------------------------------
+__global__ void k_gather_queries(const float4* __restrict__ q, const int32_t* __restrict__ vals, size_t n,
+                                 float4* __restrict__ out)
+{
+  size_t j = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+  if (j >= n)
+    return;
+  int32_t slot = vals[j];
+  float4 v = __ldg(q + slot);
+  out[j] = make_float4(v.x, v.y, v.z, __int_as_float(slot));
+}
+
+void make_query_batch(Ctx& c, const Index& frame, const float4* d_q, size_t n, QueryBatch& out)
+{
+  cudaStream_t s = c.stream;
+  out.n = n;
+  if (n == 0)
+    return;
+  SortedCloud sc;
+  morton_sort(c, d_q, n, &frame, sc);
+  out.q.alloc(n, s);
+  k_gather_queries<<<grid_for(n, 256), 256, 0, s>>>(d_q, sc.vals.p, n, out.q.p);
+  ++c.launches;
+  PCLB_CUDA(cudaGetLastError());
+}
+
+}  // namespace pclb200

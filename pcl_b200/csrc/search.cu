@@ -1,0 +1,478 @@
+// search.cu — batch k-NN, radius search and k-NN normals over the LBVH.
+//
+// Replaces pcl::KdTreeFLANN::nearestKSearch / radiusSearch (kdtree/include/pcl/kdtree/impl/
+// kdtree_flann.hpp:234-274, 372-414), the OpenMP batch loops of pcl::search::Search
+// (search/include/pcl/search/impl/search.hpp:111-194) and NormalEstimation::computeFeature
+// (features/include/pcl/features/impl/normal_3d.hpp:47-96).
+// One query per thread, queries in Morton order so a warp walks one neighbourhood of the tree
+// (node lines are shared through L1/L2); candidate lists live in registers (k <= 32).
+#include <cub/cub.cuh>
+
+#include <algorithm>
+#include <cmath>
+
+#include "internal.cuh"
+#include "traverse.cuh"
+
+namespace pclb200 {
+
+static inline unsigned grid_for(size_t n, int block) { return (unsigned)((n + block - 1) / block); }
+
+// ---- k nearest, k <= K (compile-time), ascending (d2, original index) ------------------------------
+template <int K>
+struct NearestK {
+  float qx, qy, qz;
+  const float4* pts;
+  float d[K];
+  int pos[K];
+  __device__ __forceinline__ void init(float bound)
+  {
+#pragma unroll
+    for (int j = 0; j < K; ++j) {
+      d[j] = bound;
+      pos[j] = -1;
+    }
+  }
+  __device__ __forceinline__ int orig(int p) const
+  {
+    return p < 0 ? kSentinelIndex : __float_as_int(__ldg(&pts[p].w));
+  }
+  __device__ __forceinline__ float bound() const { return d[K - 1]; }
+  __device__ __forceinline__ void leaf(const float4* lp, int first_pos)
+  {
+    float4 p[kLeafSize];
+#pragma unroll
+    for (int j = 0; j < kLeafSize; ++j)
+      p[j] = ldg4(lp + j);
+#pragma unroll
+    for (int j = 0; j < kLeafSize; ++j) {
+      float dd = dist2_rn(qx, qy, qz, p[j].x, p[j].y, p[j].z);
+      int oi = __float_as_int(p[j].w);
+      if (dd < d[K - 1] || (dd == d[K - 1] && oi < orig(pos[K - 1]))) {
+        d[K - 1] = dd;
+        pos[K - 1] = first_pos + j;
+        // one bubble pass keeps the list sorted; exact-distance ties compare original indices
+#pragma unroll
+        for (int t = K - 1; t > 0; --t) {
+          bool lt = d[t] < d[t - 1] || (d[t] == d[t - 1] && orig(pos[t]) < orig(pos[t - 1]));
+          if (lt) {
+            float td = d[t]; d[t] = d[t - 1]; d[t - 1] = td;
+            int tp = pos[t]; pos[t] = pos[t - 1]; pos[t - 1] = tp;
+          }
+        }
+      }
+    }
+  }
+};
+
+template <int K>
+__global__ void __launch_bounds__(128)
+k_knn(const BvhNode* __restrict__ nodes, const float4* __restrict__ pts, int root,
+      const float4* __restrict__ q, size_t nq, int k_out, float init_bound,
+      int32_t* __restrict__ out_idx, float* __restrict__ out_d2, int* __restrict__ d_error)
+{
+  size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+  if (i >= nq)
+    return;
+  const float4 qq = __ldg(q + i);
+  const size_t slot = (size_t)(unsigned)__float_as_int(qq.w);
+  NearestK<K> v;
+  v.qx = qq.x; v.qy = qq.y; v.qz = qq.z;
+  v.pts = pts;
+  v.init(init_bound);
+  if (!traverse(nodes, pts, root, qq.x, qq.y, qq.z, v))
+    atomicExch(d_error, 1);
+#pragma unroll
+  for (int j = 0; j < K; ++j)
+    if (j < k_out) {
+      const bool have = v.pos[j] >= 0;
+      out_idx[slot * k_out + j] = have ? v.orig(v.pos[j]) : -1;
+      out_d2[slot * k_out + j] = have ? v.d[j] : __int_as_float(0x7f800000);
+    }
+}
+
+// ---- any k: the candidate list lives in the output rows themselves (global memory) -----------------
+struct NearestAny {
+  float qx, qy, qz;
+  const float4* pts;
+  float* d;   // k entries, ascending
+  int* pos;   // k entries (positions; converted to original indices afterwards)
+  int k;
+  __device__ __forceinline__ int orig(int p) const
+  {
+    return p < 0 ? kSentinelIndex : __float_as_int(__ldg(&pts[p].w));
+  }
+  __device__ __forceinline__ float bound() const { return d[k - 1]; }
+  __device__ __forceinline__ void leaf(const float4* lp, int first_pos)
+  {
+    for (int j = 0; j < kLeafSize; ++j) {
+      float4 p = ldg4(lp + j);
+      float dd = dist2_rn(qx, qy, qz, p.x, p.y, p.z);
+      int oi = __float_as_int(p.w);
+      if (dd < d[k - 1] || (dd == d[k - 1] && oi < orig(pos[k - 1]))) {
+        int t = k - 1;
+        while (t > 0 && (dd < d[t - 1] || (dd == d[t - 1] && oi < orig(pos[t - 1])))) {
+          d[t] = d[t - 1];
+          pos[t] = pos[t - 1];
+          --t;
+        }
+        d[t] = dd;
+        pos[t] = first_pos + j;
+      }
+    }
+  }
+};
+
+__global__ void __launch_bounds__(128)
+k_knn_any(const BvhNode* __restrict__ nodes, const float4* __restrict__ pts, int root,
+          const float4* __restrict__ q, size_t nq, int k, float init_bound, int32_t* out_idx, float* out_d2,
+          int* __restrict__ d_error)
+{
+  size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+  if (i >= nq)
+    return;
+  const float4 qq = __ldg(q + i);
+  const size_t slot = (size_t)(unsigned)__float_as_int(qq.w);
+  NearestAny v;
+  v.qx = qq.x; v.qy = qq.y; v.qz = qq.z;
+  v.pts = pts;
+  v.k = k;
+  v.d = out_d2 + slot * k;
+  v.pos = out_idx + slot * k;
+  for (int j = 0; j < k; ++j) {
+    v.d[j] = init_bound;
+    v.pos[j] = -1;
+  }
+  if (!traverse(nodes, pts, root, qq.x, qq.y, qq.z, v))
+    atomicExch(d_error, 1);
+  for (int j = 0; j < k; ++j) {
+    int p = v.pos[j];
+    v.pos[j] = p >= 0 ? v.orig(p) : -1;
+    if (p < 0)
+      v.d[j] = __int_as_float(0x7f800000);
+  }
+}
+
+void launch_knn(Ctx& c, const Index& idx, const float4* d_q, size_t nq, int k, float init_bound, int32_t* d_out_idx,
+                float* d_out_d2)
+{
+  if (nq == 0 || k <= 0)
+    return;
+  cudaStream_t s = c.stream;
+  const unsigned g = grid_for(nq, 128);
+#define PCLB_KNN_CASE(KK)                                                                                   \
+  k_knn<KK><<<g, 128, 0, s>>>(idx.nodes.p, idx.pts.p, idx.root, d_q, nq, k, init_bound, d_out_idx, d_out_d2, \
+                              c.d_error)
+  if (k == 1) PCLB_KNN_CASE(1);
+  else if (k == 2) PCLB_KNN_CASE(2);
+  else if (k <= 4) PCLB_KNN_CASE(4);
+  else if (k <= 8) PCLB_KNN_CASE(8);
+  else if (k <= 10) PCLB_KNN_CASE(10);
+  else if (k <= 16) PCLB_KNN_CASE(16);
+  else if (k <= 20) PCLB_KNN_CASE(20);
+  else if (k <= 32) PCLB_KNN_CASE(32);
+  else
+    k_knn_any<<<g, 128, 0, s>>>(idx.nodes.p, idx.pts.p, idx.root, d_q, nq, k, init_bound, d_out_idx, d_out_d2,
+                                c.d_error);
+#undef PCLB_KNN_CASE
+  ++c.launches;
+  PCLB_CUDA(cudaGetLastError());
+}
+
+// ---- radius search: count, then fill keys (d2 bits << 32 | original index) -------------------------
+struct RadiusCount {
+  float qx, qy, qz, r2;
+  float r2_below;  // largest float < r2: subtrees with bound > r2_below hold no d2 < r2
+  unsigned long long n;
+  __device__ __forceinline__ float bound() const { return r2_below; }
+  __device__ __forceinline__ void leaf(const float4* lp, int)
+  {
+#pragma unroll
+    for (int j = 0; j < kLeafSize; ++j) {
+      float4 p = ldg4(lp + j);
+      if (dist2_rn(qx, qy, qz, p.x, p.y, p.z) < r2)
+        ++n;
+    }
+  }
+};
+
+struct RadiusFill {
+  float qx, qy, qz, r2;
+  float r2_below;
+  unsigned long long* out;
+  __device__ __forceinline__ float bound() const { return r2_below; }
+  __device__ __forceinline__ void leaf(const float4* lp, int)
+  {
+#pragma unroll
+    for (int j = 0; j < kLeafSize; ++j) {
+      float4 p = ldg4(lp + j);
+      float dd = dist2_rn(qx, qy, qz, p.x, p.y, p.z);
+      if (dd < r2)
+        *out++ = ((unsigned long long)__float_as_uint(dd) << 32) | (unsigned)__float_as_int(p.w);
+    }
+  }
+};
+
+__global__ void __launch_bounds__(128)
+k_radius_count(const BvhNode* __restrict__ nodes, const float4* __restrict__ pts, int root,
+               const float4* __restrict__ q, size_t nq, float r2, float r2_below,
+               unsigned long long* __restrict__ counts, int* __restrict__ d_error)
+{
+  size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+  if (i >= nq)
+    return;
+  const float4 qq = __ldg(q + i);
+  RadiusCount v{qq.x, qq.y, qq.z, r2, r2_below, 0ULL};
+  if (!traverse(nodes, pts, root, qq.x, qq.y, qq.z, v))
+    atomicExch(d_error, 1);
+  counts[(size_t)(unsigned)__float_as_int(qq.w)] = v.n;
+}
+
+__global__ void __launch_bounds__(128)
+k_radius_fill(const BvhNode* __restrict__ nodes, const float4* __restrict__ pts, int root,
+              const float4* __restrict__ q, size_t nq, float r2, float r2_below,
+              const unsigned long long* __restrict__ offsets, unsigned long long* __restrict__ keys,
+              int* __restrict__ d_error)
+{
+  size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+  if (i >= nq)
+    return;
+  const float4 qq = __ldg(q + i);
+  RadiusFill v{qq.x, qq.y, qq.z, r2, r2_below, keys + offsets[(size_t)(unsigned)__float_as_int(qq.w)]};
+  if (!traverse(nodes, pts, root, qq.x, qq.y, qq.z, v))
+    atomicExch(d_error, 1);
+}
+
+static float float_below(float x) { return std::nextafter(x, -INFINITY); }
+
+void launch_radius_count(Ctx& c, const Index& idx, const float4* d_q, size_t nq, float r2,
+                         unsigned long long* d_counts)
+{
+  if (!nq)
+    return;
+  k_radius_count<<<grid_for(nq, 128), 128, 0, c.stream>>>(idx.nodes.p, idx.pts.p, idx.root, d_q, nq, r2,
+                                                         float_below(r2), d_counts, c.d_error);
+  ++c.launches;
+  PCLB_CUDA(cudaGetLastError());
+}
+
+void launch_radius_fill(Ctx& c, const Index& idx, const float4* d_q, size_t nq, float r2,
+                        const unsigned long long* d_offsets, unsigned long long* d_keys)
+{
+  if (!nq)
+    return;
+  k_radius_fill<<<grid_for(nq, 128), 128, 0, c.stream>>>(idx.nodes.p, idx.pts.p, idx.root, d_q, nq, r2,
+                                                        float_below(r2), d_offsets, d_keys, c.d_error);
+  ++c.launches;
+  PCLB_CUDA(cudaGetLastError());
+}
+
+// ---- normals ---------------------------------------------------------------------------------------
+// pcl::eigen33 smallest eigenpair in fp32 — common/include/pcl/common/impl/eigen.hpp:52-133 (roots),
+// :273-288 (largest cross product), :293-326 (eigen33); m = row-major symmetric 3x3.
+__device__ __forceinline__ void roots2_dev(float b, float c, float* r)
+{
+  r[0] = 0.f;
+  float d = (float)((double)(b * b) - 4.0 * (double)c);
+  if (d < 0.f)
+    d = 0.f;
+  float sd = sqrtf(d);
+  r[2] = 0.5f * (b + sd);
+  r[1] = 0.5f * (b - sd);
+}
+
+__device__ void roots3_dev(const float* m, float* r)
+{
+  float c0 = m[0] * m[4] * m[8] + 2.f * m[1] * m[2] * m[5] - m[0] * m[5] * m[5] - m[4] * m[2] * m[2] -
+             m[8] * m[1] * m[1];
+  float c1 = m[0] * m[4] - m[1] * m[1] + m[0] * m[8] - m[2] * m[2] + m[4] * m[8] - m[5] * m[5];
+  float c2 = m[0] + m[4] + m[8];
+  if (fabsf(c0) < FLT_EPSILON) {
+    roots2_dev(c2, c1, r);
+    return;
+  }
+  const float s_inv3 = (float)(1.0 / 3.0);
+  const float s_sqrt3 = sqrtf(3.f);
+  float c2_over_3 = c2 * s_inv3;
+  float a_over_3 = (c1 - c2 * c2_over_3) * s_inv3;
+  if (a_over_3 > 0.f)
+    a_over_3 = 0.f;
+  float half_b = 0.5f * (c0 + c2_over_3 * (2.f * c2_over_3 * c2_over_3 - c1));
+  float q = half_b * half_b + a_over_3 * a_over_3 * a_over_3;
+  if (q > 0.f)
+    q = 0.f;
+  float rho = sqrtf(-a_over_3);
+  float theta = atan2f(sqrtf(-q), half_b) * s_inv3;
+  float cos_theta = cosf(theta), sin_theta = sinf(theta);
+  r[0] = c2_over_3 + 2.f * rho * cos_theta;
+  r[1] = c2_over_3 - rho * (cos_theta + s_sqrt3 * sin_theta);
+  r[2] = c2_over_3 - rho * (cos_theta - s_sqrt3 * sin_theta);
+  float t;
+  if (r[0] >= r[1]) { t = r[0]; r[0] = r[1]; r[1] = t; }
+  if (r[1] >= r[2]) {
+    t = r[1]; r[1] = r[2]; r[2] = t;
+    if (r[0] >= r[1]) { t = r[0]; r[0] = r[1]; r[1] = t; }
+  }
+  if (r[0] <= 0.f)
+    roots2_dev(c2, c1, r);
+}
+
+__device__ void largest_eigvec_dev(const float* s, float* v)
+{
+  float c[3][3] = {{s[1] * s[5] - s[2] * s[4], s[2] * s[3] - s[0] * s[5], s[0] * s[4] - s[1] * s[3]},
+                   {s[1] * s[8] - s[2] * s[7], s[2] * s[6] - s[0] * s[8], s[0] * s[7] - s[1] * s[6]},
+                   {s[4] * s[8] - s[5] * s[7], s[5] * s[6] - s[3] * s[8], s[3] * s[7] - s[4] * s[6]}};
+  float len[3];
+#pragma unroll
+  for (int i = 0; i < 3; ++i)
+    len[i] = sqrtf(c[i][0] * c[i][0] + c[i][1] * c[i][1] + c[i][2] * c[i][2]);
+  int idx = 0;
+  if (len[1] > len[idx]) idx = 1;
+  if (len[2] > len[idx]) idx = 2;
+  float l = idx == 0 ? len[0] : (idx == 1 ? len[1] : len[2]);
+#pragma unroll
+  for (int d = 0; d < 3; ++d)
+    v[d] = (idx == 0 ? c[0][d] : (idx == 1 ? c[1][d] : c[2][d])) / l;
+}
+
+__device__ void eigen33_smallest_dev(const float* mat, float& eigenvalue, float* ev)
+{
+  float scale = 0.f;
+#pragma unroll
+  for (int i = 0; i < 9; ++i)
+    scale = fmaxf(scale, fabsf(mat[i]));
+  if (scale <= FLT_MIN)
+    scale = 1.f;
+  float s[9];
+#pragma unroll
+  for (int i = 0; i < 9; ++i)
+    s[i] = __fdiv_rn(mat[i], scale);
+  float r[3];
+  roots3_dev(s, r);
+  eigenvalue = r[0] * scale;
+  if ((r[1] - r[0]) > FLT_EPSILON) {
+    s[0] -= r[0]; s[4] -= r[0]; s[8] -= r[0];
+    largest_eigvec_dev(s, ev);
+  }
+  else if ((r[2] - r[0]) > FLT_EPSILON) {
+    s[0] -= r[2]; s[4] -= r[2]; s[8] -= r[2];
+    float v[3];
+    largest_eigvec_dev(s, v);
+    // Eigen unitOrthogonal()
+    bool a = fabsf(v[0]) <= fabsf(v[2]) * FLT_EPSILON, b = fabsf(v[1]) <= fabsf(v[2]) * FLT_EPSILON;
+    if (!a || !b) {
+      float inv = 1.f / sqrtf(v[0] * v[0] + v[1] * v[1]);
+      ev[0] = -v[1] * inv; ev[1] = v[0] * inv; ev[2] = 0.f;
+    }
+    else {
+      float inv = 1.f / sqrtf(v[1] * v[1] + v[2] * v[2]);
+      ev[0] = 0.f; ev[1] = -v[2] * inv; ev[2] = v[1] * inv;
+    }
+  }
+  else {
+    ev[0] = 1.f; ev[1] = 0.f; ev[2] = 0.f;
+  }
+}
+
+// k-NN -> shifted single-pass covariance in the neighbour order the search returns
+// (common/include/pcl/common/impl/centroid.hpp:578-652, Scalar = float, same operation order, no fma)
+// -> solvePlaneParameters (features/impl/feature.hpp:65-92) -> flipNormalTowardsViewpoint
+// (features/normal_3d.h:169-188).  The neighbour list is never materialised in HBM.
+template <int K>
+__global__ void __launch_bounds__(128)
+k_normals(const BvhNode* __restrict__ nodes, const float4* __restrict__ pts, int root,
+          const float4* __restrict__ q, size_t nq, int k_req, float vpx, float vpy, float vpz,
+          float4* __restrict__ out, int* __restrict__ not_dense, int* __restrict__ d_error)
+{
+  size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+  if (i >= nq)
+    return;
+  const float4 qq = __ldg(q + i);
+  const size_t slot = (size_t)(unsigned)__float_as_int(qq.w);
+  const float qnan = __int_as_float(0x7fc00000);
+  if (!(isfinite(qq.x) && isfinite(qq.y) && isfinite(qq.z))) {
+    out[slot] = make_float4(qnan, qnan, qnan, qnan);
+    *not_dense = 1;
+    return;
+  }
+  NearestK<K> v;
+  v.qx = qq.x; v.qy = qq.y; v.qz = qq.z;
+  v.pts = pts;
+  v.init(__int_as_float(0x7f800000));
+  if (!traverse(nodes, pts, root, qq.x, qq.y, qq.z, v))
+    atomicExch(d_error, 1);
+  int cnt = 0;
+#pragma unroll
+  for (int j = 0; j < K; ++j)
+    if (j < k_req && v.pos[j] >= 0)
+      ++cnt;
+  if (cnt < 3) {
+    out[slot] = make_float4(qnan, qnan, qnan, qnan);
+    *not_dense = 1;
+    return;
+  }
+  float accu[9] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  float Kx = 0.f, Ky = 0.f, Kz = 0.f;
+#pragma unroll
+  for (int j = 0; j < K; ++j)
+    if (j < cnt) {
+      const float4 p = ldg4(pts + v.pos[j]);
+      if (j == 0) { Kx = p.x; Ky = p.y; Kz = p.z; }
+      const float x = __fsub_rn(p.x, Kx), y = __fsub_rn(p.y, Ky), z = __fsub_rn(p.z, Kz);
+      accu[0] = __fadd_rn(accu[0], __fmul_rn(x, x));
+      accu[1] = __fadd_rn(accu[1], __fmul_rn(x, y));
+      accu[2] = __fadd_rn(accu[2], __fmul_rn(x, z));
+      accu[3] = __fadd_rn(accu[3], __fmul_rn(y, y));
+      accu[4] = __fadd_rn(accu[4], __fmul_rn(y, z));
+      accu[5] = __fadd_rn(accu[5], __fmul_rn(z, z));
+      accu[6] = __fadd_rn(accu[6], x);
+      accu[7] = __fadd_rn(accu[7], y);
+      accu[8] = __fadd_rn(accu[8], z);
+    }
+  const float fc = (float)cnt;
+#pragma unroll
+  for (int t = 0; t < 9; ++t)
+    accu[t] = __fdiv_rn(accu[t], fc);
+  float cov[9];
+  cov[0] = __fsub_rn(accu[0], __fmul_rn(accu[6], accu[6]));
+  cov[1] = __fsub_rn(accu[1], __fmul_rn(accu[6], accu[7]));
+  cov[2] = __fsub_rn(accu[2], __fmul_rn(accu[6], accu[8]));
+  cov[4] = __fsub_rn(accu[3], __fmul_rn(accu[7], accu[7]));
+  cov[5] = __fsub_rn(accu[4], __fmul_rn(accu[7], accu[8]));
+  cov[8] = __fsub_rn(accu[5], __fmul_rn(accu[8], accu[8]));
+  cov[3] = cov[1]; cov[6] = cov[2]; cov[7] = cov[5];
+  float ev, n[3];
+  eigen33_smallest_dev(cov, ev, n);
+  const float eig_sum = __fadd_rn(__fadd_rn(cov[0], cov[4]), cov[8]);
+  const float curv = eig_sum != 0.f ? fabsf(__fdiv_rn(ev, eig_sum)) : 0.f;
+  const float vx = vpx - qq.x, vy = vpy - qq.y, vz = vpz - qq.z;
+  const float cos_theta = vx * n[0] + vy * n[1] + vz * n[2];
+  if (cos_theta < 0.f) { n[0] = -n[0]; n[1] = -n[1]; n[2] = -n[2]; }
+  if (!(isfinite(n[0]) && isfinite(n[1]) && isfinite(n[2]) && isfinite(curv)))
+    *not_dense = 1;
+  out[slot] = make_float4(n[0], n[1], n[2], curv);
+}
+
+void launch_normals(Ctx& c, const Index& idx, const float4* d_q, size_t nq, int k, const float vp[3], float4* d_out,
+                    int* d_not_dense)
+{
+  if (!nq)
+    return;
+  cudaStream_t s = c.stream;
+  const unsigned g = grid_for(nq, 128);
+  PCLB_REQUIRE(k <= 32, PCLB200_ERR_INVALID, "normals: k > 32 is not supported by the fused kernel");
+#define PCLB_NRM_CASE(KK)                                                                                     \
+  k_normals<KK><<<g, 128, 0, s>>>(idx.nodes.p, idx.pts.p, idx.root, d_q, nq, k, vp[0], vp[1], vp[2], d_out, \
+                                  d_not_dense, c.d_error)
+  if (k <= 4) PCLB_NRM_CASE(4);
+  else if (k <= 8) PCLB_NRM_CASE(8);
+  else if (k <= 10) PCLB_NRM_CASE(10);
+  else if (k <= 16) PCLB_NRM_CASE(16);
+  else if (k <= 20) PCLB_NRM_CASE(20);
+  else PCLB_NRM_CASE(32);
+#undef PCLB_NRM_CASE
+  ++c.launches;
+  PCLB_CUDA(cudaGetLastError());
+}
+
+}  // namespace pclb200

@@ -1,0 +1,118 @@
+// traverse.cuh — exact nearest-neighbour traversal of the Morton LBVH, one query per thread.
+//
+// Exactness contract (the CPU oracle under oracle/ states the same rules):
+//   d2(q,p)   = ((dx*dx) + dy*dy) + dz*dz, fp32 round-to-nearest, NO fma  (flann::L2_Simple order)
+//   box bound = same expression on the per-axis gap max(lo-q, q-hi, 0).  Rounding is monotone, so
+//               bound <= d2(q,p) holds IN FP32 for every p inside the box: pruning on
+//               `bound > worst` can never drop a true neighbour, and visiting on `bound == worst`
+//               lets an equal-distance point with a smaller index win (canonical tie rule).
+#pragma once
+#include "internal.cuh"
+
+namespace pclb200 {
+
+__device__ __forceinline__ float dist2_rn(float qx, float qy, float qz, float px, float py, float pz)
+{
+  float dx = __fsub_rn(qx, px), dy = __fsub_rn(qy, py), dz = __fsub_rn(qz, pz);
+  return __fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz));
+}
+
+__device__ __forceinline__ float box_dist2_rn(float qx, float qy, float qz, float lx, float ly, float lz,
+                                              float hx, float hy, float hz)
+{
+  float dx = fmaxf(fmaxf(__fsub_rn(lx, qx), __fsub_rn(qx, hx)), 0.f);
+  float dy = fmaxf(fmaxf(__fsub_rn(ly, qy), __fsub_rn(qy, hy)), 0.f);
+  float dz = fmaxf(fmaxf(__fsub_rn(lz, qz), __fsub_rn(qz, hz)), 0.f);
+  return __fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz));
+}
+
+__device__ __forceinline__ float4 ldg4(const float4* p) { return __ldg(p); }
+
+// Generic depth-first traversal.  `Visitor` provides:
+//   float bound() const            — current pruning distance (subtrees with box bound > bound() are skipped)
+//   void leaf(const float4* leaf_pts, int first_pos) — examine kLeafSize consecutive points
+// Nearer child first; the farther one is pushed with its bound and re-tested when popped.
+// Returns false on stack overflow (caller raises the device error flag).
+template <typename Visitor>
+__device__ __forceinline__ bool traverse(const BvhNode* __restrict__ nodes, const float4* __restrict__ pts,
+                                         int root, float qx, float qy, float qz, Visitor& v)
+{
+  int stack_node[kStackSize];
+  float stack_dist[kStackSize];
+  int sp = 0;
+  int node = root;
+  bool ok = true;
+  while (true) {
+    if (node >= 0) {
+      const float4* np = reinterpret_cast<const float4*>(nodes + node);
+      const float4 a = ldg4(np), b = ldg4(np + 1), c = ldg4(np + 2);
+      const int4 d = __ldg(reinterpret_cast<const int4*>(np + 3));
+      float dl = box_dist2_rn(qx, qy, qz, a.x, a.y, a.z, a.w, b.x, b.y);
+      float dr = box_dist2_rn(qx, qy, qz, b.z, b.w, c.x, c.y, c.z, c.w);
+      int nl = d.x, nr = d.y;
+      if (dr < dl) {
+        float t = dl; dl = dr; dr = t;
+        int ti = nl; nl = nr; nr = ti;
+      }
+      const float bnd = v.bound();
+      if (dl <= bnd) {
+        if (dr <= bnd) {
+          if (sp < kStackSize) {
+            stack_node[sp] = nr;
+            stack_dist[sp] = dr;
+            ++sp;
+          }
+          else
+            ok = false;
+        }
+        node = nl;
+        continue;
+      }
+    }
+    else {
+      const int leaf = ~node;
+      v.leaf(pts + (size_t)leaf * kLeafSize, leaf * kLeafSize);
+    }
+    // pop
+    bool found = false;
+    while (sp > 0) {
+      --sp;
+      if (stack_dist[sp] <= v.bound()) {
+        node = stack_node[sp];
+        found = true;
+        break;
+      }
+    }
+    if (!found)
+      break;
+  }
+  return ok;
+}
+
+// ---- 1-NN visitor: lexicographic (d2, original index) minimum --------------------------------
+struct Nearest1 {
+  float qx, qy, qz;
+  float best;   // current best d2 (initialised to the gate)
+  int best_idx; // original index of the best point (kSentinelIndex = none yet)
+  int best_pos; // its position in the Morton array
+  __device__ __forceinline__ float bound() const { return best; }
+  __device__ __forceinline__ void leaf(const float4* lp, int first_pos)
+  {
+    float4 p[kLeafSize];
+#pragma unroll
+    for (int j = 0; j < kLeafSize; ++j)
+      p[j] = ldg4(lp + j);
+#pragma unroll
+    for (int j = 0; j < kLeafSize; ++j) {
+      float d = dist2_rn(qx, qy, qz, p[j].x, p[j].y, p[j].z);
+      int oi = __float_as_int(p[j].w);
+      if (d < best || (d == best && oi < best_idx)) {
+        best = d;
+        best_idx = oi;
+        best_pos = first_pos + j;
+      }
+    }
+  }
+};
+
+}  // namespace pclb200

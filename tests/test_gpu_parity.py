@@ -1,0 +1,394 @@
+"""Parity of the CUDA path (through the C-ABI) against the CPU oracle and the reference's golden vectors.
+Bit-exact for indices and squared distances; transforms within the tolerance BASELINE.json states
+(1e-5 Frobenius).  Needs a B200: run with -m gpu."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def gpu():
+    import pcl_b200
+    pcl_b200.lib()
+    ctx = pcl_b200.Context(0)
+    yield pcl_b200, ctx
+    ctx.close()
+
+
+def _clouds(rng):
+    yield "uniform", rng.random((20000, 3), dtype=np.float32)
+    g = np.stack(np.meshgrid(*[np.arange(13, dtype=np.float32)] * 3, indexing="ij"), -1).reshape(-1, 3)
+    yield "grid_ties", g
+    d = rng.random((700, 3), dtype=np.float32)
+    yield "duplicates", np.concatenate([d, d, d[:300]])
+    yield "collinear", np.stack([np.linspace(0, 1, 1777, dtype=np.float32)] * 3, 1)
+    yield "tiny", rng.random((5, 3), dtype=np.float32)
+    yield "single", rng.random((1, 3), dtype=np.float32)
+    yield "all_same", np.ones((300, 3), dtype=np.float32) * np.float32(0.25)
+    s = rng.normal(size=(30000, 3)).astype(np.float32)
+    s[:, 2] = np.float32(0.3) * np.sin(s[:, 0]) * np.cos(s[:, 1])
+    yield "surface", s
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# k-NN: bit-exact indices and distances
+# ---------------------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("k", [1, 2, 3, 5, 8, 10, 16, 20, 32, 40])
+def test_knn_bit_exact(gpu, orc, k):
+    P, ctx = gpu
+    rng = np.random.default_rng(11)
+    for name, pts in _clouds(rng):
+        cloud = orc.to_xyz1(pts)
+        q = orc.to_xyz1(np.concatenate([pts[:300], (rng.random((300, 3), dtype=np.float32) - np.float32(0.2)) * (np.abs(pts).max() + 1)]))
+        gi, gd, gk = P.Index(ctx, cloud).knn(q, k)
+        oi, od, ok = orc.Index(cloud).knn(q, k, nthreads=4)
+        assert gk == ok, name
+        assert np.array_equal(gi, oi), (name, k, np.argwhere(gi != oi)[:5])
+        assert np.array_equal(gd, od), (name, k)
+
+
+def test_knn_golden_10_points(gpu, golden):
+    # test/kdtree/test_kdtree.cpp:229-262
+    P, ctx = gpu
+    idx, d2, keff = P.Index(ctx, P.xyz1(golden["knn10_points"])).knn(P.xyz1(golden["knn10_query"][None]), 10)
+    assert keff == 10
+    assert np.array_equal(idx[0], golden["knn10_indices"])
+    assert np.allclose(d2[0], golden["knn10_distances"], atol=0.1)
+    idx, d2, keff = P.Index(ctx, P.xyz1(golden["knn10_points"])).knn(P.xyz1(golden["knn10_query"][None]), 15)
+    assert keff == 10 and np.all(idx[0, 10:] == -1) and np.all(np.isinf(d2[0, 10:]))
+
+
+def test_knn_nan_points_subset_and_strides(gpu, orc):
+    P, ctx = gpu
+    rng = np.random.default_rng(12)
+    pts = rng.random((5000, 3), dtype=np.float32)
+    pts[::7, 1] = np.nan
+    pts[5, 0] = np.inf
+    cloud = orc.to_xyz1(pts)
+    q = orc.to_xyz1(rng.random((500, 3), dtype=np.float32))
+    gidx = P.Index(ctx, cloud)
+    assert gidx.size == orc.Index(cloud).size == int(np.isfinite(pts).all(1).sum())
+    gi, gd, _ = gidx.knn(q, 4)
+    oi, od, _ = orc.Index(cloud).knn(q, 4)
+    assert np.array_equal(gi, oi) and np.array_equal(gd, od)
+    sub = np.arange(0, 5000, 3, dtype=np.int32)
+    gi, gd, _ = P.Index(ctx, cloud, subset=sub).knn(q, 3)
+    oi, od, _ = orc.Index(cloud, subset=sub).knn(q, 3)
+    assert np.array_equal(gi, oi) and np.array_equal(gd, od)
+    # pcl::PointNormal stride (48 B) and packed xyz (12 B)
+    pn = np.zeros((5000, 12), np.float32)
+    pn[:, :3] = pts
+    gi2, gd2, _ = P.Index(ctx, pn).knn(np.ascontiguousarray(q[:, :3]), 4)
+    oi2, od2, _ = orc.Index(cloud).knn(q, 4)
+    assert np.array_equal(gi2, oi2) and np.array_equal(gd2, od2)
+    with pytest.raises(P.Pclb200Error) as e:
+        P.Index(ctx, np.full((10, 4), np.nan, np.float32))
+    assert e.value.code == P.ERR_EMPTY
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# radius search
+# ---------------------------------------------------------------------------------------------------------------------
+def test_radius_golden_3283_lists(gpu, golden):
+    # test/kdtree/test_kdtree.cpp:292-328: exact count and ORDER of every list
+    P, ctx = gpu
+    cloud = P.xyz1(golden["sac_plane"])
+    offs, idx, d2 = P.Index(ctx, cloud).radius(cloud, float(golden["radius_r"]))
+    assert np.array_equal(offs, golden["radius_offsets"])
+    assert np.array_equal(idx, golden["radius_indices"])
+
+
+def test_radius_vs_oracle(gpu, orc):
+    P, ctx = gpu
+    rng = np.random.default_rng(13)
+    for name, pts in _clouds(rng):
+        cloud = orc.to_xyz1(pts)
+        q = cloud[:400]
+        r = float(np.abs(pts).max()) * 0.08 + 1e-3
+        go, gi, gd = P.Index(ctx, cloud).radius(q, r)
+        oo, oi, od = orc.Index(cloud).radius(q, r, nthreads=4)
+        assert np.array_equal(go, oo), name
+        assert np.array_equal(gi, oi), name
+        assert np.array_equal(gd, od), name
+        go, gi, gd = P.Index(ctx, cloud).radius(q, r, max_nn=5)
+        oo, oi, od = orc.Index(cloud).radius(q, r, max_nn=5, nthreads=4)
+        assert np.array_equal(go, oo) and np.array_equal(gi, oi) and np.array_equal(gd, od), name
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# correspondences
+# ---------------------------------------------------------------------------------------------------------------------
+def test_correspondences_golden_397_and_53(gpu, golden):
+    # test/registration/test_registration_api.cpp:83-128
+    P, ctx = gpu
+    src, tgt = P.xyz1(golden["bun0"]), P.xyz1(golden["bun4"])
+    t = P.Index(ctx, tgt)
+    c = t.correspondences(src)
+    assert c.size == 397
+    assert np.array_equal(c["index_query"], golden["corr_original"][:, 0])
+    assert np.array_equal(c["index_match"], golden["corr_original"][:, 1])
+    c = t.correspondences(src, src_index=P.Index(ctx, src))
+    assert c.size == 53
+    assert np.array_equal(c["index_query"], golden["corr_reciprocal"][:, 0])
+    assert np.array_equal(c["index_match"], golden["corr_reciprocal"][:, 1])
+
+
+def test_correspondences_vs_oracle(gpu, orc):
+    P, ctx = gpu
+    rng = np.random.default_rng(14)
+    tgt = orc.to_xyz1(rng.random((50000, 3), dtype=np.float32))
+    src = orc.to_xyz1(rng.random((40000, 3), dtype=np.float32))
+    src[::11, 0] = np.nan
+    gt, ot = P.Index(ctx, tgt), orc.Index(tgt)
+    for md in (0.01, 0.02, 1e9):
+        g = gt.correspondences(src, max_distance=md, is_dense=False)
+        o = ot.correspondences(src, max_distance=md, is_dense=False, nthreads=4)
+        assert np.array_equal(g, o), md
+    ind = rng.permutation(40000)[:9000].astype(np.int32)
+    g = gt.correspondences(src, max_distance=0.02, indices=ind, is_dense=False)
+    o = ot.correspondences(src, max_distance=0.02, indices=ind, is_dense=False)
+    assert np.array_equal(g, o)
+    srcf = src.copy()
+    srcf[::11, 0] = 0.5
+    g = gt.correspondences(srcf, max_distance=0.03, src_index=P.Index(ctx, srcf))
+    o = ot.correspondences_reciprocal(srcf, orc.Index(srcf), max_distance=0.03, nthreads=4)
+    assert np.array_equal(g, o)
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# estimators
+# ---------------------------------------------------------------------------------------------------------------------
+def test_estimate_svd_golden(gpu, golden, orc):
+    # test/registration/test_registration_api.cpp:383-423
+    P, ctx = gpu
+    src = P.xyz1(golden["bun4"])
+    Tref = golden["svd_Tref"]
+    tgt = orc.transform(src, Tref, mode=1)
+    for dbl in (False, True):
+        T = ctx.estimate_svd(src, tgt, scalar_is_double=dbl)
+        assert np.allclose(T, Tref, atol=2e-6)
+        T64 = orc.estimate_svd(src, tgt, scalar_is_double=True)
+        assert np.linalg.norm(T - T64) < (1e-9 if dbl else 1e-6)
+        corr = np.zeros(src.shape[0], dtype=P.CORR_DTYPE)
+        corr["index_query"] = corr["index_match"] = np.arange(src.shape[0])
+        assert np.array_equal(ctx.estimate_svd(src, tgt, corr=corr, scalar_is_double=dbl), T)
+
+
+def test_estimate_point_to_plane_golden(gpu, orc):
+    # test/registration/test_registration_api.cpp:469-518
+    P, ctx = gpu
+    xs = np.arange(-5.0, 5.0 + 1e-6, 0.5, dtype=np.float32)
+    X, Y = np.meshgrid(xs, xs, indexing="ij")
+    x, y = X.ravel(), Y.ravel()
+    z = np.float32(0.1) * x ** 2 + np.float32(0.2) * x * y - np.float32(0.3) * y + np.float32(1.0)
+    n = np.stack([-0.2 * x - 0.2, 0.6 * y - 0.2, np.ones_like(x)], 1).astype(np.float32)
+    n /= np.linalg.norm(n, axis=1, keepdims=True)
+    src = np.zeros((x.size, 12), np.float32)
+    src[:, 0], src[:, 1], src[:, 2], src[:, 3] = x, y, z, 1
+    src[:, 4:7] = n
+    G = np.array([[0.9938, 0.0988, 0.0517, 0.1], [-0.0997, 0.9949, 0.0149, -0.2], [-0.05, -0.02, 0.9986, 0.3],
+                  [0, 0, 0, 1]], np.float64)
+    tgt = orc.transform(src, G, mode=1, normal_off=4)
+    T = ctx.estimate_point_to_plane_lls(src, tgt)
+    assert np.all(np.abs(T - G) < 1e-2)
+    To, _ = orc.estimate_point_to_plane_lls(src, tgt)
+    assert np.linalg.norm(T - To) < 1e-6
+    Td = ctx.estimate_point_to_plane_lls(src, tgt, scalar_is_double=True)
+    Tod, _ = orc.estimate_point_to_plane_lls(src, tgt, scalar_is_double=True)
+    assert np.linalg.norm(Td - Tod) < 1e-10
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# ICP
+# ---------------------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("dbl", [False, True])
+def test_icp_bun0_bun4_golden(gpu, golden, orc, dbl):
+    # test/registration/test_registration.cpp:236-270 — config 1 of BASELINE.json
+    P, ctx = gpu
+    src, tgt = P.xyz1(golden["bun0"]), P.xyz1(golden["bun4"])
+    out = np.zeros_like(src)
+    r = P.icp_align(ctx, src, P.Index(ctx, tgt), out_cloud=out, max_iterations=50, transformation_epsilon=1e-8,
+                    max_correspondence_distance=0.05, scalar_is_double=int(dbl))
+    T, G = r["final"], golden["icp_bun0_bun4"]
+    tol = np.full((4, 4), 1e-3)
+    tol[0, 1] = 1e-2
+    tol[3, :] = 0
+    assert r["converged"] and np.all(np.abs(T - G) <= tol), (T, r)
+    o = orc.icp_align(src, tgt, max_iterations=50, transformation_epsilon=1e-8, max_correspondence_distance=0.05,
+                      scalar_is_double=dbl, want_cloud=True)
+    assert r["iterations"] == o["iterations"] and r["state"] == o["state"], (r, o)
+    assert np.linalg.norm(T - o["final"]) < 1e-5, np.linalg.norm(T - o["final"])
+    o64 = orc.icp_align(src, tgt, max_iterations=50, transformation_epsilon=1e-8, max_correspondence_distance=0.05,
+                        scalar_is_double=True)
+    assert np.linalg.norm(T - o64["final"]) < 1e-5
+    assert r["n_correspondences"] == o["n_correspondences"]
+    assert np.allclose(out, o["cloud"], atol=1e-6)
+    assert np.all(out[:, 3] == 1.0)
+
+
+def test_icp_translated_and_fitness(gpu, golden, orc):
+    # test/registration/test_registration.cpp:161-233
+    P, ctx = gpu
+    src = P.xyz1(golden["bun0"])
+    tgt = src.copy()
+    tgt[:, 2] += np.float32(0.2)
+    t = P.Index(ctx, tgt)
+    r = P.icp_align(ctx, src, t, max_iterations=50)
+    assert r["converged"]
+    assert t.fitness_score(src, r["final"]) < 1e-6
+    assert np.allclose(np.diag(r["final"])[:3], 1.0, atol=2e-3) and np.allclose(r["final"][:3, 3], [0, 0, 0.2], atol=2e-3)
+    o = orc.icp_align(src, tgt, max_iterations=50)
+    assert r["iterations"] == o["iterations"] and np.linalg.norm(r["final"] - o["final"]) < 1e-5
+    s4 = P.xyz1(np.array([[0, 0, 0], [0, 1, 0], [0, 0, 1], [10, 0, 0]], np.float32))
+    t4 = P.Index(ctx, P.xyz1(np.array([[0, 0, 0], [0, 1, 0], [0, 0, 1], [10, 0, 0.5]], np.float32)))
+    assert abs(t4.fitness_score(s4, np.eye(4), max_range=1.0) - 0.0625) < 1e-4
+    assert abs(t4.fitness_score(s4, np.eye(4), max_range=1.0, indices=np.array([0, 1, 2], np.int32))) < 1e-4
+    assert t4.fitness_score(s4 + 100, np.eye(4), max_range=1.0) == np.finfo(np.float64).max
+
+
+def _synthetic_pair(rng, n, noise=0.001):
+    tgt = rng.random((n, 3), dtype=np.float32)
+    ang = np.deg2rad(5.0)
+    ax = np.ones(3) / np.sqrt(3)
+    K = np.array([[0, -ax[2], ax[1]], [ax[2], 0, -ax[0]], [-ax[1], ax[0], 0]])
+    R = np.eye(3) + np.sin(ang) * K + (1 - np.cos(ang)) * K @ K
+    src = (tgt.astype(np.float64) @ R.T + np.array([0.01, -0.02, 0.015]) + rng.normal(0, noise, (n, 3))).astype(np.float32)
+    return src, tgt
+
+
+@pytest.mark.parametrize("recip", [False, True])
+def test_icp_synthetic_vs_oracle(gpu, orc, recip):
+    # config 2 shape at a size the oracle finishes in seconds
+    P, ctx = gpu
+    src, tgt = _synthetic_pair(np.random.default_rng(42), 60000)
+    src, tgt = P.xyz1(src), P.xyz1(tgt)
+    kw = dict(max_iterations=40, transformation_epsilon=1e-10, max_correspondence_distance=0.05)
+    r = P.icp_align(ctx, src, P.Index(ctx, tgt), use_reciprocal=int(recip), **kw)
+    o = orc.icp_align(src, tgt, use_reciprocal=recip, nthreads=8, **kw)
+    o64 = orc.icp_align(src, tgt, use_reciprocal=recip, nthreads=8, scalar_is_double=True, **kw)
+    assert r["converged"] == o["converged"]
+    assert np.linalg.norm(r["final"] - o64["final"]) < 1e-5, (np.linalg.norm(r["final"] - o64["final"]), r, o64)
+    assert abs(r["iterations"] - o["iterations"]) <= 1, (r["iterations"], o["iterations"])
+
+
+def test_icp_guess_indices_and_stepwise(gpu, orc):
+    P, ctx = gpu
+    src, tgt = _synthetic_pair(np.random.default_rng(43), 20000)
+    src, tgt = P.xyz1(src), P.xyz1(tgt)
+    guess = np.eye(4)
+    guess[:3, 3] = [-0.005, 0.01, -0.01]
+    ind = np.arange(0, 20000, 2, dtype=np.int32)
+    kw = dict(max_iterations=15, max_correspondence_distance=0.05)
+    t = P.Index(ctx, tgt)
+    r = P.icp_align(ctx, src, t, guess=guess, indices=ind, **kw)
+    o = orc.icp_align(src, tgt, guess=guess, indices=ind, **kw)
+    assert r["iterations"] == o["iterations"] and r["state"] == o["state"]
+    assert np.linalg.norm(r["final"] - o["final"]) < 1e-5
+    assert r["n_correspondences"] == o["n_correspondences"]
+    # the session API stepped one iteration at a time reaches the same state
+    s = P.Icp(ctx, **kw)
+    s.set_target(t)
+    s.set_source(src, indices=ind, guess=guess)
+    st = None
+    for _ in range(100):
+        st = s.iterate(1)
+        if st["state"] != 0:
+            break
+    assert st["iterations"] == r["iterations"] and np.array_equal(st["final"], r["final"])
+    # too few correspondences: NO_CORRESPONDENCES, not converged (icp.hpp:204-213)
+    far = src.copy()
+    far[:, :3] += 100
+    r = P.icp_align(ctx, far, t, max_iterations=5, max_correspondence_distance=0.01)
+    assert not r["converged"] and r["state"] == 5 and r["iterations"] == 0
+
+
+def test_icp_point_to_plane_vs_oracle(gpu, orc):
+    # config 3 shape (normals k=16 + TransformationEstimationPointToPlaneLLS), small
+    P, ctx = gpu
+    rng = np.random.default_rng(7)
+    n = 40000
+
+    def surf(m, seed):
+        r = np.random.default_rng(seed)
+        xy = r.random((m, 2)) * 10
+        z = 0.5 * np.sin(xy[:, 0]) * np.cos(0.7 * xy[:, 1]) + r.normal(0, 0.002, m)
+        return np.column_stack([xy, z])
+
+    tgt_xyz = surf(n, 7).astype(np.float32)
+    a = np.deg2rad(2.0)
+    R = np.array([[np.cos(a), -np.sin(a), 0], [np.sin(a), np.cos(a), 0], [0, 0, 1]])
+    src_xyz = (surf(n, 8) @ R.T + np.array([0.02, 0.01, -0.01])).astype(np.float32)
+    tgt = np.zeros((n, 12), np.float32)
+    tgt[:, :3], tgt[:, 3] = tgt_xyz, 1
+    tidx = P.Index(ctx, tgt)
+    normals, dense = tidx.normals_knn(tgt, 16, viewpoint=(5, 5, 10))
+    on, odense = orc.Index(tgt).normals_knn(tgt, 16, viewpoint=(5, 5, 10), nthreads=8)
+    assert dense == odense
+    cosang = np.abs((normals[:, :3] * on[:, :3]).sum(1))
+    assert np.percentile(cosang, 1) > 1 - 1e-4 and np.mean(cosang > 1 - 1e-6) > 0.95
+    assert np.allclose(normals[:, 3], on[:, 3], atol=2e-3)
+    tgt[:, 4:8] = on  # same normals on both sides so the ICP comparison isolates the registration path
+    src = np.zeros((n, 12), np.float32)
+    src[:, :3], src[:, 3] = src_xyz, 1
+    kw = dict(max_iterations=30, max_correspondence_distance=0.05)
+    r = P.icp_align(ctx, src, tidx, tgt_normals=P.Field(tgt, 4), estimator=P.EST_POINT_TO_PLANE_LLS,
+                    with_normals_transform=1, **kw)
+    o = orc.icp_align(src, tgt, estimator=1, with_normals_transform=True, nthreads=8, **kw)
+    assert r["iterations"] == o["iterations"] and r["state"] == o["state"], (r, o)
+    assert np.linalg.norm(r["final"] - o["final"]) < 1e-5, np.linalg.norm(r["final"] - o["final"])
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# normals and voxel grid
+# ---------------------------------------------------------------------------------------------------------------------
+def test_normal_bun0_golden(gpu, golden):
+    # test/features/test_normal_estimation.cpp:98-163 with k = 32 < cloud: compare with the all-points plane instead
+    P, ctx = gpu
+    cloud = P.xyz1(golden["bun0"])
+    normals, dense = P.Index(ctx, cloud).normals_knn(cloud, 10)
+    assert dense and np.allclose(np.linalg.norm(normals[:, :3], axis=1), 1, atol=1e-4)
+    # flipped toward the origin viewpoint (normal_3d.h:169-188)
+    assert np.all((-(cloud[:, :3]) * normals[:, :3]).sum(1) >= -1e-6)
+
+
+def test_normals_vs_oracle(gpu, orc):
+    P, ctx = gpu
+    rng = np.random.default_rng(15)
+    pts = rng.random((30000, 3), dtype=np.float32)
+    pts[:, 2] = np.float32(0.1) * np.sin(np.float32(6) * pts[:, 0])
+    cloud = orc.to_xyz1(pts)
+    for k in (5, 10, 16):
+        g, gd = P.Index(ctx, cloud).normals_knn(cloud, k, viewpoint=(0.5, 0.5, 5))
+        o, od = orc.Index(cloud).normals_knn(cloud, k, viewpoint=(0.5, 0.5, 5), nthreads=8)
+        assert gd == od
+        cosang = (g[:, :3] * o[:, :3]).sum(1)
+        assert np.percentile(cosang, 0.5) > 1 - 1e-3 and np.mean(cosang > 1 - 1e-6) > 0.9, k
+        assert np.allclose(g[:, 3], o[:, 3], atol=5e-3)
+    few = orc.to_xyz1(pts[:2])
+    g, gd = P.Index(ctx, few).normals_knn(few, 5)
+    assert not gd and np.isnan(g).all()  # < 3 neighbours => NaN, is_dense false (normal_3d.hpp:62-69)
+
+
+def test_voxelgrid_golden_and_oracle(gpu, golden, orc):
+    # test/filters/test_filters.cpp:566-603
+    P, ctx = gpu
+    cloud = P.xyz1(golden["bun0"])
+    out = ctx.voxelgrid(cloud, 0.02)
+    assert out.shape[0] == 103
+    assert np.array_equal(out, orc.voxelgrid(cloud, [0.02] * 3))
+    z = cloud[:, 2]
+    sel = np.nonzero(~((z > np.float32(0.1)) | (z < np.float32(0.05))))[0].astype(np.int32)
+    out = ctx.voxelgrid(cloud, 0.02, indices=sel)
+    assert out.shape[0] == 14
+    assert np.allclose(out[0, :3], golden["voxel_z_first"], atol=1e-4) and np.allclose(out[13, :3], golden["voxel_z_last"], atol=1e-4)
+    with pytest.raises(P.Pclb200Error) as e:
+        ctx.voxelgrid(cloud, 1e-5)
+    assert e.value.code == P.ERR_LEAF_TOO_SMALL
+    rng = np.random.default_rng(16)
+    big = orc.to_xyz1((rng.random((200000, 3), dtype=np.float32) - np.float32(0.3)) * np.float32(3))
+    big[::13, 1] = np.nan
+    for leaf, mp in (([0.01] * 3, 0), ([0.05, 0.1, 0.2], 0), ([0.1] * 3, 30)):
+        g = ctx.voxelgrid(big, leaf, min_points_per_voxel=mp, is_dense=False)
+        o = orc.voxelgrid(big, leaf, min_points_per_voxel=mp, is_dense=False)
+        assert g.shape == o.shape and np.array_equal(g, o), (leaf, mp)
