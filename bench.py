@@ -1,0 +1,363 @@
+#!/usr/bin/env python3
+"""bench.py — BASELINE.json's metric on BASELINE.json's 10 M-point configuration.
+
+Workload (config.workload = "cfg3_10M_point_to_plane", BASELINE.json configs[2]):
+  target : 10 000 000 points, (x,y) ~ U[0,10)^2, z = 0.5 sin(x) cos(0.7 y) + N(0, 0.002^2), seed 7
+  source : the same surface re-sampled (seed 8 + rank), rotated 2 deg about z, t = (0.02, 0.01, -0.01)
+  target normals: NormalEstimation k = 16, viewpoint (5,5,10)  (set-up, timed separately, not part of a step)
+  ICP    : IterativeClosestPointWithNormals (non-symmetric => TransformationEstimationPointToPlaneLLS),
+           max correspondence distance 0.05, k = 1
+A STEP is one Registration::align() of ICP_ITERS = 10 iterations (PCL's default max_iterations_,
+registration.h:566) over the whole source cloud: source upload -> Morton ordering of the queries -> 10 x
+(1-NN search + gate + 6x6 accumulation + solve + transform) -> output cloud.  The target index is built once
+before the timed region, exactly as pcl::Registration keeps its tree across align() calls
+(registration.hpp:84-87).
+  value : correspondences/s with source, target index and output resident in HBM (device pointers through
+          the same C-ABI call pclb200_icp_align)
+  e2e   : the same call with HOST buffers (pinned pcl::PointNormal records, 48 B/pt): H2D of the source and
+          D2H of the aligned cloud inside the timed region
+  N > 1 : weak scaling — every rank holds a replica of the target index and its own 10 M-point source shard;
+          the 40 fp64 accumulators are all-reduced (NCCL) once per iteration.
+--impl reference times the CPU restatement of PCL's own path (oracle/, the reference cannot be compiled in this
+image: no Eigen/Boost/FLANN) on the box's host cores, on a bounded sample of the same workload.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+ICP_ITERS = 10
+MAX_CORR_DIST = 0.05
+N_DEFAULT = 10_000_000
+METRIC = "icp_correspondences_per_sec"
+UNIT = "correspondences/s"
+
+
+def surface(n, seed):
+    r = np.random.default_rng(seed)
+    xy = r.random((n, 2)) * 10.0
+    z = 0.5 * np.sin(xy[:, 0]) * np.cos(0.7 * xy[:, 1]) + r.normal(0.0, 0.002, n)
+    return xy[:, 0], xy[:, 1], z
+
+
+def make_target(n):
+    x, y, z = surface(n, 7)
+    t = np.zeros((n, 12), dtype=np.float32)  # pcl::PointNormal records
+    t[:, 0], t[:, 1], t[:, 2], t[:, 3] = x, y, z, 1.0
+    return t
+
+
+def make_source(n, rank):
+    x, y, z = surface(n, 8 + rank)
+    a = np.deg2rad(2.0)
+    c, s = np.cos(a), np.sin(a)
+    out = np.zeros((n, 12), dtype=np.float32)
+    out[:, 0] = c * x - s * y + 0.02
+    out[:, 1] = s * x + c * y + 0.01
+    out[:, 2] = z - 0.01
+    out[:, 3] = 1.0
+    return out
+
+
+def analytic_normals(t, vp=(5.0, 5.0, 10.0)):
+    """Normals of z = 0.5 sin x cos 0.7y (used by the REFERENCE arm only: it may not call our normals kernel)."""
+    x, y = t[:, 0].astype(np.float64), t[:, 1].astype(np.float64)
+    n = np.stack([-0.5 * np.cos(x) * np.cos(0.7 * y), 0.35 * np.sin(x) * np.sin(0.7 * y), np.ones_like(x)], 1)
+    n /= np.linalg.norm(n, axis=1, keepdims=True)
+    flip = ((np.asarray(vp) - t[:, :3]) * n).sum(1) < 0
+    n[flip] *= -1
+    return n.astype(np.float32)
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+
+    def __init__(self, gpu_index):
+        self.rows = []
+        self.proc = None
+        self.gpu = gpu_index
+
+    def start(self):
+        q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+             "clocks_event_reasons.sw_power_cap")
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), f"--query-gpu={q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.th = threading.Thread(target=self._read, daemon=True)
+            self.th.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            f = [v.strip() for v in r.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0]))
+                mx.append(float(f[1]))
+            except ValueError:
+                continue
+            for nm, v in zip(names, f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": float(max(mx)) if mx else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def measured_peak_gbs():
+    try:
+        return float(json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"]), "measured"
+    except Exception:
+        return 6650.0, "fallback"
+
+
+def dist_env():
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    return rank, world, local
+
+
+# -----------------------------------------------------------------------------------------------------------------
+# reference arm: the CPU restatement of PCL's path (oracle/), all host threads, bounded sample
+# -----------------------------------------------------------------------------------------------------------------
+def run_reference(args):
+    rank, world, _ = dist_env()
+    if rank != 0:
+        return
+    import oracle
+    n = args.points
+    cores = oracle.max_threads()
+    tgt = make_target(n)
+    tgt[:, 4:7] = analytic_normals(tgt)
+    src_full = make_source(n, 0)
+    t0 = time.time()
+    tree = oracle.Index(tgt)  # pcl::KdTreeFLANN::setInputCloud, kept across align() calls
+    build_s = time.time() - t0
+    kw = dict(max_iterations=ICP_ITERS, max_correspondence_distance=MAX_CORR_DIST, estimator=1,
+              with_normals_transform=True, source_has_normals=True, nthreads=cores, index=tree)
+    # calibrate the sample so that (steps + warmup) aligns end within ~150 s
+    probe = min(n, 100_000)
+    t0 = time.time()
+    r = oracle.icp_align(src_full[:probe], tgt, want_cloud=True, **kw)
+    rate = max(r["total_correspondences"], 1) / max(time.time() - t0, 1e-6)
+    budget_s = 150.0 / max(args.steps + args.warmup, 1)
+    sample = int(min(n, max(probe, rate * budget_s / ICP_ITERS)))
+    src = np.ascontiguousarray(src_full[:sample])
+    out = np.empty_like(src)
+    for _ in range(args.warmup):
+        oracle.icp_align(src, tgt, out=out, **kw)
+    total, t0 = 0, time.time()
+    for _ in range(args.steps):
+        r = oracle.icp_align(src, tgt, out=out, **kw)
+        total += r["total_correspondences"]
+    dt = time.time() - t0
+    val = total / dt
+    sample_desc = (f"{sample} of {n} source points (first rows) x {ICP_ITERS} iterations per step against the full "
+                   f"{n}-point target; kd-tree build ({build_s:.1f} s, 1 thread) outside the timed region; "
+                   "analytic target normals")
+    line = {"impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / max(args.steps, 1),
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": "cfg3_10M_point_to_plane", "points_target": n, "points_source_per_step": sample,
+                       "icp_iterations_per_step": ICP_ITERS, "max_correspondence_distance": MAX_CORR_DIST,
+                       "estimator": "point_to_plane_lls", "k": 1},
+            "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample_desc},
+            "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+# -----------------------------------------------------------------------------------------------------------------
+# our arm
+# -----------------------------------------------------------------------------------------------------------------
+def run_ours(args):
+    import torch
+    import pcl_b200 as P
+    rank, world, local = dist_env()
+    n = args.points
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=dev)
+    P.lib()
+    ctx = P.Context(local)
+    if world > 1:
+        uid = [P.comm_unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(uid, src=0)
+        ctx.comm_init(rank, world, uid[0])
+    stream = torch.cuda.ExternalStream(ctx.stream, device=dev)
+
+    # ---- set-up (outside the timed region): target index + k=16 normals, both on the GPU ----------------------
+    tgt = make_target(n)
+    src_host = torch.from_numpy(make_source(n, rank)).pin_memory()           # pcl::PointNormal records, pinned
+    out_host = torch.empty_like(src_host).pin_memory()
+    ctx.profile(True)
+    tidx = P.Index(ctx, tgt)
+    tgt_dev = torch.from_numpy(tgt).to(dev)
+    nrm_dev = torch.empty((n, 4), dtype=torch.float32, device=dev)
+    tidx.normals_knn(tgt_dev, 16, viewpoint=(5.0, 5.0, 10.0), out=nrm_dev)
+    build_ms, _ = ctx.profile_get("index_build")
+    normals_ms, _ = ctx.profile_get("normals")
+    del tgt_dev
+    src_dev = src_host.to(dev)                    # value leg: 48-byte records already resident in HBM
+    out_dev = torch.empty_like(src_dev)
+    params = P.default_params(max_iterations=ICP_ITERS, max_correspondence_distance=MAX_CORR_DIST,
+                              estimator=P.EST_POINT_TO_PLANE_LLS, with_normals_transform=1, mse_threshold_absolute=0.0)
+
+    def align(src, out):
+        return P.icp_align(ctx, src, tidx, params=params, src_normals=P.Field(src, 4), tgt_normals=nrm_dev,
+                           out_cloud=out)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(src, out, steps, warmup, sample_clocks):
+        for _ in range(warmup):
+            align(src, out)
+        ctx.profile_reset()
+        l0 = ctx.launches
+        barrier()
+        sampler = ClockSampler(local) if sample_clocks else None
+        if sampler:
+            sampler.start()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        total = 0
+        e0.record(stream)
+        for _ in range(steps):
+            total += align(src, out)["total_correspondences"]
+        e1.record(stream)
+        barrier()
+        clocks = sampler.stop() if sampler else None
+        ms = e0.elapsed_time(e1)
+        t = torch.tensor([ms, float(total)], dtype=torch.float64, device=dev)
+        if world > 1:
+            tm = t.clone()
+            dist.all_reduce(tm, op=dist.ReduceOp.MAX)
+            dist.all_reduce(t, op=dist.ReduceOp.SUM)
+            ms, total = float(tm[0]), float(t[1])
+        # NOTE: with the all-reduce inside every iteration each rank already reports the GLOBAL pair count;
+        # `total` summed over ranks would double count, so take rank 0's figure in that case.
+        return ms, total, ctx.launches - l0, clocks
+
+    # device-resident leg (value) --------------------------------------------------------------------------------
+    ms_v, tot_v, launches, clocks = timed(src_dev, out_dev, args.steps, args.warmup, True)
+    iter_ms, iter_n = ctx.profile_get("icp_iter")
+    sort_ms, _ = ctx.profile_get("query_sort")
+    solve_ms, _ = ctx.profile_get("solve")
+    out_ms, _ = ctx.profile_get("transform_out")
+    # host-buffer leg (e2e) --------------------------------------------------------------------------------------
+    ms_e, tot_e, _, _ = timed(src_host, out_host, args.steps, max(1, args.warmup // 2), False)
+    if world > 1:  # stats already carry the all-reduced (global) pair counts on every rank
+        tot_v /= world
+        tot_e /= world
+    value = tot_v / (ms_v * 1e-3)
+    e2e = tot_e / (ms_e * 1e-3)
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    # roofline of the dominant kernel (k_icp_iter), algorithmic bytes per correspondence:
+    #   16 source read + 16 source write-back + (16*N_t points + 64*N_t/8 nodes + 16*N_t normals)/N_s = 72 B at N_s = N_t
+    bytes_per_corr = 16 + 16 + (16 + 8 + 16) * 1.0
+    peak, peak_src = measured_peak_gbs()
+    avg_iter_s = (iter_ms / max(iter_n, 1)) * 1e-3
+    achieved = bytes_per_corr * n / avg_iter_s / 1e9 if avg_iter_s > 0 else 0.0
+    roofline = {"bound": "hbm", "kernel": "k_icp_iter<point_to_plane>", "achieved": achieved, "peak": peak,
+                "peak_source": peak_src, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+                "algorithmic_bytes_per_launch": bytes_per_corr * n, "avg_launch_ms": avg_iter_s * 1e3,
+                "launches_timed": iter_n,
+                "note": "BVH traversal is latency/issue bound, not HBM bound (SURVEY.md §7 hard part ii, DESIGN.md)"}
+
+    # CPU baseline (oracle port) on a bounded sample: one align() of ICP_ITERS iterations, sample sized for ~15 s
+    cpu = None
+    if world == 1 and not args.no_cpu_baseline:
+        import oracle
+        cores = oracle.max_threads()
+        tgt_n = tgt.copy()
+        tgt_n[:, 4:8] = nrm_dev.cpu().numpy()
+        t0 = time.time()
+        tree = oracle.Index(tgt_n)
+        build_s = time.time() - t0
+        kw = dict(max_iterations=ICP_ITERS, max_correspondence_distance=MAX_CORR_DIST, estimator=1,
+                  with_normals_transform=True, source_has_normals=True, nthreads=cores, index=tree)
+        src_np = src_host.numpy()
+        probe = min(n, 100_000)
+        t0 = time.time()
+        r = oracle.icp_align(src_np[:probe], tgt_n, **kw)
+        rate = max(r["total_correspondences"], 1) / max(time.time() - t0, 1e-6)
+        sample = int(min(n, max(probe, rate * 15.0 / ICP_ITERS)))
+        t0 = time.time()
+        r = oracle.icp_align(np.ascontiguousarray(src_np[:sample]), tgt_n, want_cloud=True, **kw)
+        dt = time.time() - t0
+        cpu = {"value": r["total_correspondences"] / dt, "unit": UNIT, "cores": cores, "kind": "port",
+               "sample": f"{sample} of {n} source points x {ICP_ITERS} iterations (one align) against the full "
+                         f"{n}-point target, GPU-computed normals; kd-tree build {build_s:.1f} s excluded"}
+
+    line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms_v / args.steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": "cfg3_10M_point_to_plane", "points_target": n, "points_source_per_gpu": n,
+                       "icp_iterations_per_step": ICP_ITERS, "max_correspondence_distance": MAX_CORR_DIST,
+                       "estimator": "point_to_plane_lls", "k": 1, "normals_k": 16,
+                       "l2_policy": "inputs larger than L2 (target 160 MB + nodes 80 MB + normals 160 MB + source 160 MB)",
+                       "parallelism": f"source sharded x{world}, target replicated, 40-double all-reduce/iteration"},
+            "ms_per_iter": ms_v / args.steps / ICP_ITERS,
+            "breakdown_ms_per_step": {"icp_iter_kernel": iter_ms / args.steps, "query_sort": sort_ms / args.steps,
+                                      "solve": solve_ms / args.steps, "transform_out": out_ms / args.steps},
+            "setup_ms": {"index_build": build_ms, "normals_k16": normals_ms},
+            "e2e": {"value": e2e, "unit": UNIT, "ms_per_step": ms_e / args.steps,
+                    "h2d_bytes_per_step": int(src_host.numel() * 4), "d2h_bytes_per_step": int(out_host.numel() * 4 + 512 * ICP_ITERS)},
+            "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline}
+    if cpu:
+        line["cpu_baseline"] = cpu
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--points", type=int, default=N_DEFAULT)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

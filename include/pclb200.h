@@ -75,6 +75,13 @@ PCLB200_API int pclb200_launch_count(pclb200_ctx* ctx, uint64_t* out);
 /* raw cudaStream_t of the ctx (so callers can record CUDA events on the launching stream) */
 PCLB200_API int pclb200_stream(pclb200_ctx* ctx, void** out_stream);
 PCLB200_API void pclb200_free(void* host_ptr); /* frees arrays returned by pclb200_radius */
+/* measurement hooks (bench.py's roofline leg): when enabled, the library brackets its named kernels
+ * ("icp_iter", "solve", "query_sort", "index_build", "normals", "knn", "voxelgrid", "transform_out") with
+ * CUDA events on the ctx stream; profile_get synchronises, returns the summed device time and the number of
+ * bracketed launches of that name since the last reset, and profile_reset drops the records. */
+PCLB200_API int pclb200_profile_enable(pclb200_ctx* ctx, int enable);
+PCLB200_API int pclb200_profile_get(pclb200_ctx* ctx, const char* name, double* total_ms, uint64_t* count);
+PCLB200_API int pclb200_profile_reset(pclb200_ctx* ctx);
 
 /* ---- index: replaces pcl::KdTreeFLANN<PointT>::setInputCloud(cloud, indices) ------------------
  * kdtree/include/pcl/kdtree/impl/kdtree_flann.hpp:100-136, 429-498 (reached through
@@ -175,6 +182,7 @@ typedef struct pclb200_icp_stats {
   double mse;                 /* mean squared correspondence distance of that iteration */
   double final_transformation[16];  /* row-major, rounded to Scalar */
   double last_transformation[16];   /* getLastIncrementalTransformation */
+  int64_t total_correspondences;    /* sum of accepted pairs over all iterations since set_source */
 } pclb200_icp_stats;
 
 PCLB200_API void pclb200_icp_default_params(pclb200_icp_params* p);

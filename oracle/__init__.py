@@ -42,7 +42,7 @@ class IcpParams(C.Structure):
 class IcpResult(C.Structure):
     _fields_ = [("final_transformation", C.c_double * 16), ("last_transformation", C.c_double * 16),
                 ("converged", C.c_int32), ("state", C.c_int32), ("iterations", C.c_int32),
-                ("n_correspondences", C.c_int32), ("mse", C.c_double)]
+                ("n_correspondences", C.c_int32), ("mse", C.c_double), ("total_correspondences", C.c_longlong)]
 
 
 _lib = None
@@ -70,6 +70,7 @@ def lib():
         L.orc_estimate_point_to_plane_lls.argtypes = [fp, sz, fp, fp, sz, C.POINTER(Corr), sz, C.c_int, dp]
         L.orc_transform.argtypes = [fp, sz, sz, C.c_int, dp, C.c_int, C.c_int]
         L.orc_icp_align.argtypes = [C.POINTER(IcpParams), fp, sz, sz, i32p, sz, fp, sz, sz, dp, C.POINTER(IcpResult), fp]
+        L.orc_icp_align_tree.argtypes = [C.POINTER(IcpParams), vp, fp, sz, sz, i32p, sz, fp, sz, sz, dp, C.POINTER(IcpResult), fp]
         L.orc_fitness_score.restype = C.c_double
         L.orc_fitness_score.argtypes = [vp, fp, sz, sz, i32p, sz, C.c_int, dp, C.c_int, C.c_double, C.c_int]
         L.orc_voxelgrid.restype = C.c_longlong
@@ -243,7 +244,7 @@ def icp_align(src, tgt, max_iterations=10, max_correspondence_distance=np.sqrt(n
               transformation_epsilon=0.0, transformation_rotation_epsilon=0.0,
               euclidean_fitness_epsilon=-np.finfo(np.float64).max, use_reciprocal=False, estimator=0,
               scalar_is_double=False, with_normals_transform=False, source_has_normals=False,
-              is_dense=True, guess=None, indices=None, nthreads=1, want_cloud=False):
+              is_dense=True, guess=None, indices=None, nthreads=1, want_cloud=False, index=None, out=None):
     src, tgt = as_cloud(src), as_cloud(tgt)
     P = IcpParams(max_iterations, int(use_reciprocal), estimator, int(scalar_is_double),
                   int(with_normals_transform), int(source_has_normals), int(is_dense), nthreads,
@@ -252,14 +253,20 @@ def icp_align(src, tgt, max_iterations=10, max_correspondence_distance=np.sqrt(n
     R = IcpResult()
     g = None if guess is None else np.ascontiguousarray(guess, dtype=np.float64)
     indices = None if indices is None else np.ascontiguousarray(indices, dtype=np.int32)
-    out = np.empty_like(src) if want_cloud else None
-    lib().orc_icp_align(C.byref(P), _f(src), src.shape[0], src.shape[1], _i(indices),
-                        0 if indices is None else indices.size, _f(tgt), tgt.shape[0], tgt.shape[1], _d(g),
-                        C.byref(R), None if out is None else _f(out))
+    if out is None:
+        out = np.empty_like(src) if want_cloud else None
+    if index is not None:
+        lib().orc_icp_align_tree(C.byref(P), index.h, _f(src), src.shape[0], src.shape[1], _i(indices),
+                                 0 if indices is None else indices.size, _f(tgt), tgt.shape[0], tgt.shape[1],
+                                 _d(g), C.byref(R), None if out is None else _f(out))
+    else:
+        lib().orc_icp_align(C.byref(P), _f(src), src.shape[0], src.shape[1], _i(indices),
+                            0 if indices is None else indices.size, _f(tgt), tgt.shape[0], tgt.shape[1], _d(g),
+                            C.byref(R), None if out is None else _f(out))
     res = dict(final=np.array(R.final_transformation).reshape(4, 4),
                last=np.array(R.last_transformation).reshape(4, 4), converged=bool(R.converged),
                state=int(R.state), iterations=int(R.iterations), n_correspondences=int(R.n_correspondences),
-               mse=float(R.mse))
+               mse=float(R.mse), total_correspondences=int(R.total_correspondences))
     if want_cloud:
         res["cloud"] = out
     return res

@@ -1192,18 +1192,22 @@ struct orc_icp_result {
   int32_t iterations;
   int32_t n_correspondences;         // of the last evaluated iteration
   double mse;                        // of the last evaluated iteration
+  long long total_correspondences;   // summed over the iterations (throughput accounting in bench.py)
 };
 
 template <typename S>
 static void icp_run(const orc_icp_params& P, const float* src, size_t n_s, size_t ss,
                     const int32_t* indices, size_t n_idx, const float* tgt, size_t n_t, size_t ts,
-                    const double* guess, orc_icp_result& R, float* out_cloud)
+                    const double* guess, orc_icp_result& R, float* out_cloud, void* prebuilt_tree = nullptr)
 {
   // Registration::align (registration/.../impl/registration.hpp:172-221) +
   // IterativeClosestPoint::computeTransformation (impl/icp.hpp:113-268)
   const int noff = P.source_has_normals ? 4 : -1;
   const int tmode = P.with_normals_transform ? 1 : 0;
-  KdTree* tree = static_cast<KdTree*>(orc_index_build(tgt, n_t, ts, nullptr, 0));
+  // Registration::initCompute rebuilds the target tree only when the target changed
+  // (registration.hpp:84-87): a caller that keeps the target passes the tree it already has.
+  KdTree* tree = prebuilt_tree ? static_cast<KdTree*>(prebuilt_tree)
+                               : static_cast<KdTree*>(orc_index_build(tgt, n_t, ts, nullptr, 0));
   S final_T[16], T[16], G[16];
   bool guess_is_identity = true;
   for (int i = 0; i < 16; ++i) {
@@ -1227,6 +1231,7 @@ static void icp_run(const orc_icp_params& P, const float* src, size_t n_s, size_
   bool converged = false;
   size_t nc = 0;
   double mse = 0;
+  long long total_nc = 0;
   do {
     if (P.use_reciprocal) {
       KdTree* stree = static_cast<KdTree*>(orc_index_build(cur.data(), n_s, ss, indices, indices ? n_idx : 0));
@@ -1238,6 +1243,7 @@ static void icp_run(const orc_icp_params& P, const float* src, size_t n_s, size_
     else
       nc = orc_correspondences(tree, cur.data(), n_s, ss, indices, n_idx, P.is_dense,
                                P.max_correspondence_distance, corr.data(), P.nthreads);
+    total_nc += (long long)nc;
     if (nc < 3) {  // min_number_correspondences_, registration.h:621; icp.hpp:204-213
       conv.state = NO_CORRESPONDENCES;
       converged = false;
@@ -1269,11 +1275,13 @@ static void icp_run(const orc_icp_params& P, const float* src, size_t n_s, size_
   R.iterations = iterations;
   R.n_correspondences = (int32_t)nc;
   R.mse = mse;
+  R.total_correspondences = total_nc;
   if (out_cloud) {  // output = *input_; transformCloud(*input_, output, final) — icp.hpp:265-267
     std::memcpy(out_cloud, src, n_s * ss * sizeof(float));
     transform_points<S>(out_cloud, n_s, ss, noff, final_T, tmode);
   }
-  orc_index_free(tree);
+  if (!prebuilt_tree)
+    orc_index_free(tree);
 }
 
 ORC_API void orc_icp_align(const orc_icp_params* P, const float* src, size_t n_s, size_t sstride,
@@ -1284,6 +1292,17 @@ ORC_API void orc_icp_align(const orc_icp_params* P, const float* src, size_t n_s
     icp_run<double>(*P, src, n_s, sstride, indices, n_idx, tgt, n_t, tstride, guess, *R, out_cloud);
   else
     icp_run<float>(*P, src, n_s, sstride, indices, n_idx, tgt, n_t, tstride, guess, *R, out_cloud);
+}
+
+ORC_API void orc_icp_align_tree(const orc_icp_params* P, void* h_tgt, const float* src, size_t n_s,
+                                size_t sstride, const int32_t* indices, size_t n_idx, const float* tgt,
+                                size_t n_t, size_t tstride, const double* guess, orc_icp_result* R,
+                                float* out_cloud)
+{
+  if (P->scalar_is_double)
+    icp_run<double>(*P, src, n_s, sstride, indices, n_idx, tgt, n_t, tstride, guess, *R, out_cloud, h_tgt);
+  else
+    icp_run<float>(*P, src, n_s, sstride, indices, n_idx, tgt, n_t, tstride, guess, *R, out_cloud, h_tgt);
 }
 
 // Registration::getFitnessScore — registration/.../impl/registration.hpp:134-168

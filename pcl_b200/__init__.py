@@ -40,11 +40,12 @@ class IcpParams(C.Structure):
 class IcpStats(C.Structure):
     _fields_ = [("converged", C.c_int32), ("state", C.c_int32), ("iterations", C.c_int32), ("reserved", C.c_int32),
                 ("n_correspondences", C.c_int64), ("mse", C.c_double), ("final_transformation", C.c_double * 16),
-                ("last_transformation", C.c_double * 16)]
+                ("last_transformation", C.c_double * 16), ("total_correspondences", C.c_int64)]
 
     def as_dict(self):
         return dict(converged=bool(self.converged), state=int(self.state), iterations=int(self.iterations),
                     n_correspondences=int(self.n_correspondences), mse=float(self.mse),
+                    total_correspondences=int(self.total_correspondences),
                     final=np.array(self.final_transformation).reshape(4, 4),
                     last=np.array(self.last_transformation).reshape(4, 4))
 
@@ -52,7 +53,8 @@ class IcpStats(C.Structure):
 # every symbol include/pclb200.h declares (tests/test_capi_symbols.py checks the two lists agree)
 SYMBOLS = [
     "pclb200_version", "pclb200_last_error", "pclb200_create", "pclb200_destroy", "pclb200_synchronize",
-    "pclb200_launch_count", "pclb200_stream", "pclb200_free", "pclb200_index_build", "pclb200_index_destroy",
+    "pclb200_launch_count", "pclb200_stream", "pclb200_free", "pclb200_profile_enable", "pclb200_profile_get",
+    "pclb200_profile_reset", "pclb200_index_build", "pclb200_index_destroy",
     "pclb200_index_size", "pclb200_index_stats", "pclb200_knn", "pclb200_radius", "pclb200_correspondences",
     "pclb200_estimate_svd", "pclb200_estimate_point_to_plane_lls", "pclb200_icp_default_params",
     "pclb200_icp_create", "pclb200_icp_destroy", "pclb200_icp_set_params", "pclb200_icp_set_target",
@@ -82,6 +84,9 @@ def lib():
     L.pclb200_stream.argtypes = [vp, C.POINTER(vp)]
     L.pclb200_free.argtypes = [vp]
     L.pclb200_free.restype = None
+    L.pclb200_profile_enable.argtypes = [vp, C.c_int]
+    L.pclb200_profile_get.argtypes = [vp, C.c_char_p, dp, C.POINTER(C.c_uint64)]
+    L.pclb200_profile_reset.argtypes = [vp]
     L.pclb200_index_build.argtypes = [vp, vp, sz, sz, vp, sz, C.POINTER(vp)]
     L.pclb200_index_destroy.argtypes = [vp]
     L.pclb200_index_size.argtypes = [vp, C.POINTER(sz)]
@@ -202,6 +207,17 @@ class Context:
         s = C.c_void_p()
         _check(lib().pclb200_stream(self.h, C.byref(s)))
         return s.value or 0
+
+    def profile(self, enable=True):
+        _check(lib().pclb200_profile_enable(self.h, int(enable)))
+
+    def profile_reset(self):
+        _check(lib().pclb200_profile_reset(self.h))
+
+    def profile_get(self, name):
+        ms, n = C.c_double(), C.c_uint64()
+        _check(lib().pclb200_profile_get(self.h, name.encode(), C.byref(ms), C.byref(n)))
+        return float(ms.value), int(n.value)
 
     def comm_init(self, rank, nranks, unique_id_bytes):
         buf = C.create_string_buffer(bytes(unique_id_bytes), 128)

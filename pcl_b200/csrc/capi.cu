@@ -176,6 +176,10 @@ int pclb200_destroy(pclb200_ctx* ctx)
     comm_destroy(c);
     if (c.stream)
       cudaStreamSynchronize(c.stream);
+    for (auto& e : c.prof) {
+      cudaEventDestroy(e.a);
+      cudaEventDestroy(e.b);
+    }
     if (c.pinned)
       cudaFreeHost(c.pinned);
     if (c.d_error)
@@ -212,6 +216,46 @@ int pclb200_stream(pclb200_ctx* ctx, void** out_stream)
 
 void pclb200_free(void* p) { free(p); }
 
+int pclb200_profile_enable(pclb200_ctx* ctx, int enable)
+{
+  return guarded([&] {
+    PCLB_REQUIRE(ctx, PCLB200_ERR_INVALID, "ctx == NULL");
+    ctx->c.profiling = enable != 0;
+  });
+}
+
+int pclb200_profile_reset(pclb200_ctx* ctx)
+{
+  return guarded([&] {
+    PCLB_REQUIRE(ctx, PCLB200_ERR_INVALID, "ctx == NULL");
+    PCLB_CUDA(cudaStreamSynchronize(ctx->c.stream));
+    for (auto& e : ctx->c.prof) {
+      cudaEventDestroy(e.a);
+      cudaEventDestroy(e.b);
+    }
+    ctx->c.prof.clear();
+  });
+}
+
+int pclb200_profile_get(pclb200_ctx* ctx, const char* name, double* total_ms, uint64_t* count)
+{
+  return guarded([&] {
+    PCLB_REQUIRE(ctx && name && total_ms && count, PCLB200_ERR_INVALID, "NULL argument");
+    PCLB_CUDA(cudaStreamSynchronize(ctx->c.stream));
+    double t = 0.0;
+    uint64_t n = 0;
+    for (auto& e : ctx->c.prof)
+      if (strcmp(e.name, name) == 0) {
+        float ms = 0.f;
+        PCLB_CUDA(cudaEventElapsedTime(&ms, e.a, e.b));
+        t += ms;
+        ++n;
+      }
+    *total_ms = t;
+    *count = n;
+  });
+}
+
 // ---- index -----------------------------------------------------------------------------------------------------
 int pclb200_index_build(pclb200_ctx* ctx, const void* pts, size_t n, size_t stride, const int32_t* subset,
                         size_t n_subset, pclb200_index** out)
@@ -219,7 +263,11 @@ int pclb200_index_build(pclb200_ctx* ctx, const void* pts, size_t n, size_t stri
   return guarded([&] {
     PCLB_REQUIRE(ctx && out, PCLB200_ERR_INVALID, "NULL argument");
     PCLB_CUDA(cudaSetDevice(ctx->c.device));
-    Index* idx = build_index(ctx->c, pts, n, stride, subset, n_subset);
+    Index* idx = nullptr;
+    {
+      ProfScope ps(ctx->c, "index_build");
+      idx = build_index(ctx->c, pts, n, stride, subset, n_subset);
+    }
     *out = new pclb200_index{idx};
   });
 }
@@ -289,7 +337,10 @@ int pclb200_knn(pclb200_ctx* ctx, const pclb200_index* h, const void* queries, s
       pi = d_idx.p;
       pd = d_d2.p;
     }
-    launch_knn(c, idx, qb.q.p, nq, k, std::numeric_limits<float>::infinity(), pi, pd);
+    {
+      ProfScope ps(c, "knn");
+      launch_knn(c, idx, qb.q.p, nq, k, std::numeric_limits<float>::infinity(), pi, pd);
+    }
     if (!dev_out) {
       PCLB_CUDA(cudaMemcpyAsync(out_idx, pi, nq * (size_t)k * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
       PCLB_CUDA(cudaMemcpyAsync(out_d2, pd, nq * (size_t)k * sizeof(float), cudaMemcpyDeviceToHost, st));
@@ -588,7 +639,10 @@ int pclb200_normals_knn(pclb200_ctx* ctx, const pclb200_index* h, const void* pt
       d_out.alloc(nq, st);
       po = d_out.p;
     }
-    launch_normals(c, *h->idx, qb.q.p, nq, k, viewpoint, po, d_flag.p);
+    {
+      ProfScope ps(c, "normals");
+      launch_normals(c, *h->idx, qb.q.p, nq, k, viewpoint, po, d_flag.p);
+    }
     int flag = 0;
     PCLB_CUDA(cudaMemcpyAsync(&flag, d_flag.p, sizeof(int), cudaMemcpyDeviceToHost, st));
     if (!dev_out)
@@ -606,6 +660,7 @@ int pclb200_voxelgrid(pclb200_ctx* ctx, const void* pts, size_t n, size_t stride
   return guarded([&] {
     PCLB_REQUIRE(ctx && leaf && out_xyz1 && n_out, PCLB200_ERR_INVALID, "NULL argument");
     PCLB_CUDA(cudaSetDevice(ctx->c.device));
+    ProfScope ps(ctx->c, "voxelgrid");
     *n_out = voxelgrid(ctx->c, pts, n, stride, indices, n_idx, is_dense, leaf, min_points_per_voxel, out_xyz1);
   });
 }

@@ -672,6 +672,10 @@ struct Icp {
   DevBuf<float4> cur;           // Morton order, w = slot
   DevBuf<int32_t> cur_label;    // Morton order: original source index of cur[i] (labels of the reciprocal tree)
   bool have_src_normals = false;
+  DevBuf<unsigned char> src_raw; // the caller's records verbatim (kept when stride != 16) for output = *input_
+  size_t src_stride = 0;
+  ptrdiff_t src_normal_off = -1; // byte offset of nx inside a record, when the normals live in the same records
+  int64_t total_corr = 0;
   // device state
   DevBuf<Pending> pending;
   DevBuf<SolveOut> solve_out;
@@ -791,6 +795,7 @@ void icp_reset_state(Icp& s, const double* guess)
   s.state = PCLB200_CONV_NOT_CONVERGED;
   s.converged = false;
   s.n_corr = 0;
+  s.total_corr = 0;
   s.mse = 0.0;
   s.prev_mse = std::numeric_limits<double>::max();
   s.iterations_similar = 0;
@@ -805,11 +810,31 @@ void icp_set_source(Icp& s, const void* src, size_t n, size_t stride, const void
   PCLB_REQUIRE(src != nullptr && n > 0, PCLB200_ERR_INVALID, "icp: empty source");
   s.n_all = n;
   s.src_all.alloc(n, st);
-  load_xyz_as_float4(c, src, n, stride, nullptr, 0, s.src_all.p, st);
+  s.src_stride = stride;
+  s.src_raw.release();
+  s.src_normal_off = -1;
+  if (src_normals) {
+    const ptrdiff_t off = static_cast<const unsigned char*>(src_normals) - static_cast<const unsigned char*>(src);
+    if (stride_n == stride && off > 0 && (size_t)off + 12 <= stride)
+      s.src_normal_off = off;
+  }
+  const void* src_dev = src;
+  if (stride != 16) {
+    // one contiguous H2D of the records; every field other than xyz/normals is carried through to the output
+    PCLB_REQUIRE(stride >= 12 && stride % 4 == 0, PCLB200_ERR_INVALID, "stride must be a multiple of 4 and >= 12");
+    s.src_raw.alloc(n * stride, st);
+    PCLB_CUDA(cudaMemcpyAsync(s.src_raw.p, src, n * stride,
+                              is_device_ptr(src) ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, st));
+    src_dev = s.src_raw.p;
+  }
+  load_xyz_as_float4(c, src_dev, n, stride, nullptr, 0, s.src_all.p, st);
   s.have_src_normals = src_normals != nullptr;
   if (src_normals) {
     s.src_normals.alloc(n, st);
-    load_vec3_as_float4(c, src_normals, n, stride_n, s.src_normals.p, st);
+    if (s.src_normal_off >= 0 && s.src_raw.p)
+      load_vec3_as_float4(c, s.src_raw.p + s.src_normal_off, n, stride, s.src_normals.p, st);
+    else
+      load_vec3_as_float4(c, src_normals, n, stride_n, s.src_normals.p, st);
   }
   else
     s.src_normals.release();
@@ -830,7 +855,10 @@ void icp_set_source(Icp& s, const void* src, size_t n, size_t stride, const void
     d_q = sub.p;
   }
   QueryBatch qb;
-  make_query_batch(c, *s.tgt, d_q, s.n_q, qb);
+  {
+    ProfScope ps(c, "query_sort");
+    make_query_batch(c, *s.tgt, d_q, s.n_q, qb);
+  }
   s.cur = std::move(qb.q);
   s.cur_label.alloc(s.n_q, st);
   if (s.n_q) {
@@ -930,6 +958,7 @@ static void fill_stats(const Icp& s, pclb200_icp_stats* st)
   st->iterations = s.iterations;
   st->reserved = 0;
   st->n_correspondences = s.n_corr;
+  st->total_correspondences = s.total_corr;
   st->mse = s.mse;
   for (int i = 0; i < 16; ++i) {
     st->final_transformation[i] = s.final_T[i];
@@ -988,6 +1017,8 @@ void icp_iterate(Icp& s, int max_steps, pclb200_icp_stats* stats)
       a.s_pts = src_index->pts.p;
       a.s_root = src_index->root;
     }
+    {
+    ProfScope ps(c, "icp_iter");
     if (s.P.estimator == PCLB200_EST_SVD) {
       if (s.P.use_reciprocal) launch_iter<PCLB200_EST_SVD, true>(c, a, grid);
       else launch_iter<PCLB200_EST_SVD, false>(c, a, grid);
@@ -996,10 +1027,17 @@ void icp_iterate(Icp& s, int max_steps, pclb200_icp_stats* stats)
       if (s.P.use_reciprocal) launch_iter<PCLB200_EST_POINT_TO_PLANE_LLS, true>(c, a, grid);
       else launch_iter<PCLB200_EST_POINT_TO_PLANE_LLS, false>(c, a, grid);
     }
+    }
     PCLB_CUDA(cudaGetLastError());
-    comm_allreduce_sum(c, s.red.accum.p, kAccum);
-    k_solve<<<1, 32, 0, st>>>(s.red.accum.p, s.P.estimator, s.P.scalar_is_double, transform_mode(s.P), (double)a.ox,
-                              (double)a.oy, (double)a.oz, 3, s.pending.p, s.solve_out.p);
+    {
+      ProfScope ps(c, "allreduce");
+      comm_allreduce_sum(c, s.red.accum.p, kAccum);
+    }
+    {
+      ProfScope ps(c, "solve");
+      k_solve<<<1, 32, 0, st>>>(s.red.accum.p, s.P.estimator, s.P.scalar_is_double, transform_mode(s.P), (double)a.ox,
+                                (double)a.oy, (double)a.oz, 3, s.pending.p, s.solve_out.p);
+    }
     ++c.launches;
     PCLB_CUDA(cudaMemcpyAsync(h_out, s.solve_out.p, sizeof(SolveOut), cudaMemcpyDeviceToHost, st));
     int h_err = 0;
@@ -1011,6 +1049,7 @@ void icp_iterate(Icp& s, int max_steps, pclb200_icp_stats* stats)
     }
     ++steps;
     s.n_corr = (int64_t)h_out->n;
+    s.total_corr += s.n_corr;
     s.mse = h_out->n > 0 ? h_out->sum_d / h_out->n : 0.0;
     if (!h_out->ok) {  // icp.hpp:204-213
       s.state = PCLB200_CONV_NO_CORRESPONDENCES;
@@ -1061,8 +1100,37 @@ void icp_get_cloud(Icp& s, void* out_pts, size_t stride_out, void* out_normals, 
   h.apply = 1;
   h.mode = transform_mode(s.P);
   PCLB_CUDA(cudaMemcpyAsync(pend.p, &h, sizeof(h), cudaMemcpyHostToDevice, st));
-  k_apply_pending<<<persistent_grid(c, s.n_all, 256, 8), 256, 0, st>>>(tmp.p, s.n_all, pend.p, do_n ? tmpn.p : nullptr);
+  {
+    ProfScope ps(c, "transform_out");
+    k_apply_pending<<<persistent_grid(c, s.n_all, 256, 8), 256, 0, st>>>(tmp.p, s.n_all, pend.p, do_n ? tmpn.p : nullptr);
+  }
   ++c.launches;
+  const bool normals_inside =
+      do_n && s.src_normal_off >= 0 &&
+      static_cast<unsigned char*>(out_normals) - static_cast<unsigned char*>(out_pts) == s.src_normal_off && stride_n == stride_out;
+  if (s.src_raw.p && stride_out == s.src_stride && (!do_n || normals_inside)) {
+    // output = *input_ (all fields), then xyz / normals overwritten: assembled on the device, one contiguous copy out
+    DevBuf<unsigned char> rec;
+    unsigned char* d_rec = nullptr;
+    const bool out_dev = is_device_ptr(out_pts);
+    if (out_dev)
+      d_rec = static_cast<unsigned char*>(out_pts);
+    else {
+      rec.alloc(s.n_all * stride_out, st);
+      d_rec = rec.p;
+    }
+    PCLB_CUDA(cudaMemcpyAsync(d_rec, s.src_raw.p, s.n_all * stride_out, cudaMemcpyDeviceToDevice, st));
+    k_scatter_xyz<<<grid_for(s.n_all, 256), 256, 0, st>>>(tmp.p, s.n_all, d_rec, stride_out, 0, 0.f);
+    ++c.launches;
+    if (do_n) {
+      k_scatter_xyz<<<grid_for(s.n_all, 256), 256, 0, st>>>(tmpn.p, s.n_all, d_rec + s.src_normal_off, stride_out, 0, 0.f);
+      ++c.launches;
+    }
+    if (!out_dev)
+      PCLB_CUDA(cudaMemcpyAsync(out_pts, d_rec, s.n_all * stride_out, cudaMemcpyDeviceToHost, st));
+    PCLB_CUDA(cudaStreamSynchronize(st));
+    return;
+  }
   auto write_back = [&](const DevBuf<float4>& d, void* out, size_t stride, int write_w, float w) {
     if (stride == 16 && write_w) {
       PCLB_CUDA(cudaMemcpyAsync(out, d.p, s.n_all * 16, is_device_ptr(out) ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost, st));

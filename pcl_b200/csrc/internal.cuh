@@ -41,8 +41,15 @@ struct Error : std::runtime_error {
 // ---------------------------------------------------------------------------------------------
 struct Comm;  // NCCL wrapper (comm.cu)
 
+struct ProfEvent {
+  const char* name;
+  cudaEvent_t a, b;
+};
+
 struct Ctx {
   int device = 0;
+  bool profiling = false;            // pclb200_profile_enable: CUDA-event pairs around the named kernels
+  std::vector<ProfEvent> prof;
   int sm_count = 148;
   cudaStream_t stream = nullptr;
   uint64_t launches = 0;  // kernels launched by this library (incl. CUB passes, counted per call)
@@ -50,6 +57,28 @@ struct Ctx {
   size_t pinned_bytes = 0;
   int* d_error = nullptr; // device-side invariant flag (traversal stack overflow)
   Comm* comm = nullptr;
+};
+
+// records a CUDA-event pair around a region of the ctx stream when profiling is on
+struct ProfScope {
+  Ctx& c;
+  cudaEvent_t b = nullptr;
+  ProfScope(Ctx& ctx, const char* name) : c(ctx)
+  {
+    if (!c.profiling)
+      return;
+    ProfEvent e{name, nullptr, nullptr};
+    if (cudaEventCreate(&e.a) != cudaSuccess || cudaEventCreate(&e.b) != cudaSuccess)
+      return;
+    cudaEventRecord(e.a, c.stream);
+    b = e.b;
+    c.prof.push_back(e);
+  }
+  ~ProfScope()
+  {
+    if (b)
+      cudaEventRecord(b, c.stream);
+  }
 };
 
 // stream-ordered device buffer
