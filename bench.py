@@ -269,7 +269,8 @@ def run_ours(args):
 
     # device-resident leg (value) --------------------------------------------------------------------------------
     ms_v, tot_v, launches, clocks = timed(src_dev, out_dev, args.steps, args.warmup, True)
-    iter_ms, iter_n = ctx.profile_get("icp_iter")
+    iter_ms, iter_n = ctx.profile_get("icp_search")
+    accum_ms, _ = ctx.profile_get("icp_accum")
     sort_ms, _ = ctx.profile_get("query_sort")
     solve_ms, _ = ctx.profile_get("solve")
     out_ms, _ = ctx.profile_get("transform_out")
@@ -285,13 +286,14 @@ def run_ours(args):
             dist.destroy_process_group()
         return
 
-    # roofline of the dominant kernel (k_icp_iter), algorithmic bytes per correspondence:
-    #   16 source read + 16 source write-back + (16*N_t points + 64*N_t/8 nodes + 16*N_t normals)/N_s = 72 B at N_s = N_t
-    bytes_per_corr = 16 + 16 + (16 + 8 + 16) * 1.0
+    # roofline of the dominant kernel (k_search), algorithmic bytes per correspondence:
+    #   16 source read + 16 source write-back (T_k applied in place) + 8 seed read + 8 match write
+    #   + (16*N_t points + 64*N_t/8 nodes)/N_s, each read once under Morton-coherent queries  = 72 B at N_s = N_t
+    bytes_per_corr = 16 + 16 + 8 + 8 + (16 + 8) * 1.0
     peak, peak_src = measured_peak_gbs()
     avg_iter_s = (iter_ms / max(iter_n, 1)) * 1e-3
     achieved = bytes_per_corr * n / avg_iter_s / 1e9 if avg_iter_s > 0 else 0.0
-    roofline = {"bound": "hbm", "kernel": "k_icp_iter<point_to_plane>", "achieved": achieved, "peak": peak,
+    roofline = {"bound": "hbm", "kernel": "k_search (1-NN + gate + in-place transform)", "achieved": achieved, "peak": peak,
                 "peak_source": peak_src, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
                 "algorithmic_bytes_per_launch": bytes_per_corr * n, "avg_launch_ms": avg_iter_s * 1e3,
                 "launches_timed": iter_n,
@@ -331,7 +333,7 @@ def run_ours(args):
                        "l2_policy": "inputs larger than L2 (target 160 MB + nodes 80 MB + normals 160 MB + source 160 MB)",
                        "parallelism": f"source sharded x{world}, target replicated, 40-double all-reduce/iteration"},
             "ms_per_iter": ms_v / args.steps / ICP_ITERS,
-            "breakdown_ms_per_step": {"icp_iter_kernel": iter_ms / args.steps, "query_sort": sort_ms / args.steps,
+            "breakdown_ms_per_step": {"icp_search_kernel": iter_ms / args.steps, "icp_accum_kernel": accum_ms / args.steps, "query_sort": sort_ms / args.steps,
                                       "solve": solve_ms / args.steps, "transform_out": out_ms / args.steps},
             "setup_ms": {"index_build": build_ms, "normals_k16": normals_ms},
             "e2e": {"value": e2e, "unit": UNIT, "ms_per_step": ms_e / args.steps,

@@ -161,43 +161,86 @@ __device__ __forceinline__ void block_reduce_and_publish(double* acc, const Iter
   }
 }
 
-template <int EST, bool RECIP>
+// match of one query, in Morton slot order of `cur`
+struct __align__(8) Match {
+  int pos;    // position of the matched target point in the Morton array, -1 = no correspondence
+  float d2;   // squared distance
+};
+
+// Search kernel: [apply pending T_k] -> exact 1-NN (seeded with the previous iteration's match: its leaf is
+// scanned first, which makes the pruning bound tight before the descent starts; the result is still the exact
+// lexicographic minimum because every candidate is a real point) -> gate -> optional reciprocal check.
+// Lean on registers (no accumulators live across the traversal) so the latency-bound walk runs at high occupancy.
+template <bool RECIP>
 __global__ void __launch_bounds__(256)
-k_icp_iter(const IterArgs a)
+k_search(const IterArgs a, Match* __restrict__ match)
+{
+  __shared__ Pending sP;
+  if (threadIdx.x == 0)
+    sP = *a.pending;
+  __syncthreads();
+  bool overflow = false;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < a.n; i += (size_t)gridDim.x * blockDim.x) {
+    float4 p = a.cur[i];
+    Match m;
+    m.pos = -1;
+    m.d2 = 0.f;
+    const int seed = match[i].pos;
+    if (isfinite(p.x) && isfinite(p.y) && isfinite(p.z)) {
+      // non-finite points: transformCloud leaves them untouched (icp.hpp:90-91), no correspondence (:173-174)
+      if (sP.apply) {
+        apply_pending(sP, p.x, p.y, p.z);
+        a.cur[i] = p;
+      }
+      Nearest1 v{p.x, p.y, p.z, a.gate, kSentinelIndex, -1};
+      if (seed >= 0) {
+        const int leaf = seed / kLeafSize;
+        v.leaf(a.pts + (size_t)leaf * kLeafSize, leaf * kLeafSize);
+      }
+      if (!traverse(a.nodes, a.pts, a.root, p.x, p.y, p.z, v))
+        overflow = true;
+      if (v.best_pos >= 0) {  // else distance[0] > max_dist_sqr (correspondence_estimation.hpp:176)
+        bool keep = true;
+        if (RECIP) {
+          // correspondence_estimation.hpp:259-269: 1-NN of the matched target point back into the source
+          const float4 q = ldg4(a.pts + v.best_pos);
+          Nearest1 b{q.x, q.y, q.z, a.gate, kSentinelIndex, -1};
+          if (!traverse(a.s_nodes, a.s_pts, a.s_root, q.x, q.y, q.z, b))
+            overflow = true;
+          const int slot = __float_as_int(p.w);
+          const int my_orig = a.src_orig ? a.src_orig[slot] : slot;
+          keep = b.best_pos >= 0 && b.best_idx == my_orig;
+        }
+        if (keep) {
+          m.pos = v.best_pos;
+          m.d2 = v.best;
+        }
+      }
+    }
+    match[i] = m;
+  }
+  if (overflow)
+    atomicExch(a.d_error, 1);
+}
+
+// Accumulation kernel: one streaming pass over (source point, match) pairs; fp64 sums, fixed reduction order.
+template <int EST>
+__global__ void __launch_bounds__(256)
+k_accum(const IterArgs a, const Match* __restrict__ match)
 {
   constexpr int NACC = EST == PCLB200_EST_SVD ? kAccSvd : kAccLls;
   double acc[NACC];
 #pragma unroll
   for (int t = 0; t < NACC; ++t)
     acc[t] = 0.0;
-  const Pending P = *a.pending;
-  bool overflow = false;
   for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < a.n; i += (size_t)gridDim.x * blockDim.x) {
-    float4 p = a.cur[i];
-    if (!(isfinite(p.x) && isfinite(p.y) && isfinite(p.z)))
-      continue;  // transformCloud leaves it untouched (icp.hpp:90-91); no correspondence (:173-174)
-    if (P.apply) {
-      apply_pending(P, p.x, p.y, p.z);
-      a.cur[i] = p;
-    }
-    Nearest1 v{p.x, p.y, p.z, a.gate, kSentinelIndex, -1};
-    if (!traverse(a.nodes, a.pts, a.root, p.x, p.y, p.z, v))
-      overflow = true;
-    if (v.best_pos < 0)
-      continue;  // distance[0] > max_dist_sqr (correspondence_estimation.hpp:176)
-    const float4 q = ldg4(a.pts + v.best_pos);
-    if (RECIP) {
-      // correspondence_estimation.hpp:259-269: 1-NN of the matched target point back into the source
-      Nearest1 b{q.x, q.y, q.z, a.gate, kSentinelIndex, -1};
-      if (!traverse(a.s_nodes, a.s_pts, a.s_root, q.x, q.y, q.z, b))
-        overflow = true;
-      const int slot = __float_as_int(p.w);
-      const int my_orig = a.src_orig ? a.src_orig[slot] : slot;
-      if (b.best_pos < 0 || b.best_idx != my_orig)
-        continue;
-    }
+    const Match m = match[i];
+    if (m.pos < 0)
+      continue;
+    const float4 p = a.cur[i];
+    const float4 q = ldg4(a.pts + m.pos);
     acc[0] += 1.0;
-    acc[1] += (double)v.best;
+    acc[1] += (double)m.d2;
     if (EST == PCLB200_EST_SVD) {
       const double px = (double)p.x - (double)a.ox, py = (double)p.y - (double)a.oy, pz = (double)p.z - (double)a.oz;
       const double qx = (double)q.x - (double)a.ox, qy = (double)q.y - (double)a.oy, qz = (double)q.z - (double)a.oz;
@@ -208,7 +251,7 @@ k_icp_iter(const IterArgs a)
       acc[14] += qz * px; acc[15] += qz * py; acc[16] += qz * pz;
     }
     else {
-      const float4 nn = ldg4(a.tgt_normals + v.best_pos);
+      const float4 nn = ldg4(a.tgt_normals + m.pos);
       if (!(isfinite(nn.x) && isfinite(nn.y) && isfinite(nn.z)))
         continue;  // point_to_plane_lls.hpp:182-190 (pair skipped by the estimator, still a correspondence)
       const float sx = p.x, sy = p.y, sz = p.z, dx = q.x, dy = q.y, dz = q.z, nx = nn.x, ny = nn.y, nz = nn.z;
@@ -230,8 +273,6 @@ k_icp_iter(const IterArgs a)
       acc[26] += (double)nx * D; acc[27] += (double)ny * D; acc[28] += (double)nz * D;
     }
   }
-  if (overflow)
-    atomicExch(a.d_error, 1);
   block_reduce_and_publish<NACC>(acc, a);
 }
 
@@ -670,6 +711,7 @@ struct Icp {
   DevBuf<float4> src_normals;   // original order (optional)
   DevBuf<int32_t> src_orig;     // slot -> original source index (when indices were given)
   DevBuf<float4> cur;           // Morton order, w = slot
+  DevBuf<Match> match;          // Morton order: this iteration's matches = next iteration's seeds
   DevBuf<int32_t> cur_label;    // Morton order: original source index of cur[i] (labels of the reciprocal tree)
   bool have_src_normals = false;
   DevBuf<unsigned char> src_raw; // the caller's records verbatim (kept when stride != 16) for output = *input_
@@ -860,6 +902,8 @@ void icp_set_source(Icp& s, const void* src, size_t n, size_t stride, const void
     make_query_batch(c, *s.tgt, d_q, s.n_q, qb);
   }
   s.cur = std::move(qb.q);
+  s.match.alloc(s.n_q, st);
+  PCLB_CUDA(cudaMemsetAsync(s.match.p, 0xff, s.n_q * sizeof(Match), st));  // pos = -1: no seed yet
   s.cur_label.alloc(s.n_q, st);
   if (s.n_q) {
     k_cur_labels<<<grid_for(s.n_q, 256), 256, 0, st>>>(s.cur.p, s.src_orig.p, s.n_q, s.cur_label.p);
@@ -966,13 +1010,6 @@ static void fill_stats(const Icp& s, pclb200_icp_stats* st)
   }
 }
 
-template <int EST, bool RECIP>
-static void launch_iter(Ctx& c, const IterArgs& a, unsigned grid)
-{
-  k_icp_iter<EST, RECIP><<<grid, 256, 0, c.stream>>>(a);
-  ++c.launches;
-}
-
 void icp_iterate(Icp& s, int max_steps, pclb200_icp_stats* stats)
 {
   Ctx& c = *s.ctx;
@@ -1018,15 +1055,21 @@ void icp_iterate(Icp& s, int max_steps, pclb200_icp_stats* stats)
       a.s_root = src_index->root;
     }
     {
-    ProfScope ps(c, "icp_iter");
-    if (s.P.estimator == PCLB200_EST_SVD) {
-      if (s.P.use_reciprocal) launch_iter<PCLB200_EST_SVD, true>(c, a, grid);
-      else launch_iter<PCLB200_EST_SVD, false>(c, a, grid);
+      ProfScope ps(c, "icp_search");
+      const unsigned sgrid = persistent_grid(c, s.n_q, 256, 16);
+      if (s.P.use_reciprocal)
+        k_search<true><<<sgrid, 256, 0, st>>>(a, s.match.p);
+      else
+        k_search<false><<<sgrid, 256, 0, st>>>(a, s.match.p);
+      ++c.launches;
     }
-    else {
-      if (s.P.use_reciprocal) launch_iter<PCLB200_EST_POINT_TO_PLANE_LLS, true>(c, a, grid);
-      else launch_iter<PCLB200_EST_POINT_TO_PLANE_LLS, false>(c, a, grid);
-    }
+    {
+      ProfScope ps(c, "icp_accum");
+      if (s.P.estimator == PCLB200_EST_SVD)
+        k_accum<PCLB200_EST_SVD><<<grid, 256, 0, st>>>(a, s.match.p);
+      else
+        k_accum<PCLB200_EST_POINT_TO_PLANE_LLS><<<grid, 256, 0, st>>>(a, s.match.p);
+      ++c.launches;
     }
     PCLB_CUDA(cudaGetLastError());
     {

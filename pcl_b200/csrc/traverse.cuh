@@ -28,11 +28,15 @@ __device__ __forceinline__ float box_dist2_rn(float qx, float qy, float qz, floa
 
 __device__ __forceinline__ float4 ldg4(const float4* p) { return __ldg(p); }
 
-// Generic depth-first traversal.  `Visitor` provides:
+// Generic depth-first traversal ("while-while"): the inner loop walks internal nodes only, so the lanes of a
+// warp that are still descending are not serialised against lanes scanning a leaf; leaf scans (the long,
+// fully unrolled body) run once the warp has left the inner loop.  `Visitor` provides:
 //   float bound() const            — current pruning distance (subtrees with box bound > bound() are skipped)
 //   void leaf(const float4* leaf_pts, int first_pos) — examine kLeafSize consecutive points
 // Nearer child first; the farther one is pushed with its bound and re-tested when popped.
 // Returns false on stack overflow (caller raises the device error flag).
+constexpr int kDone = 0x7fffffff;  // "no node": internal ids are >= 0 and < 2^31-1, leaves are negative
+
 template <typename Visitor>
 __device__ __forceinline__ bool traverse(const BvhNode* __restrict__ nodes, const float4* __restrict__ pts,
                                          int root, float qx, float qy, float qz, Visitor& v)
@@ -42,8 +46,8 @@ __device__ __forceinline__ bool traverse(const BvhNode* __restrict__ nodes, cons
   int sp = 0;
   int node = root;
   bool ok = true;
-  while (true) {
-    if (node >= 0) {
+  while (node != kDone) {
+    while (node >= 0 && node != kDone) {
       const float4* np = reinterpret_cast<const float4*>(nodes + node);
       const float4 a = ldg4(np), b = ldg4(np + 1), c = ldg4(np + 2);
       const int4 d = __ldg(reinterpret_cast<const int4*>(np + 3));
@@ -66,25 +70,31 @@ __device__ __forceinline__ bool traverse(const BvhNode* __restrict__ nodes, cons
             ok = false;
         }
         node = nl;
-        continue;
+      }
+      else {
+        node = kDone;
+        while (sp > 0) {
+          --sp;
+          if (stack_dist[sp] <= bnd) {
+            node = stack_node[sp];
+            break;
+          }
+        }
       }
     }
-    else {
-      const int leaf = ~node;
-      v.leaf(pts + (size_t)leaf * kLeafSize, leaf * kLeafSize);
-    }
-    // pop
-    bool found = false;
+    if (node == kDone)
+      break;
+    const int leaf = ~node;
+    v.leaf(pts + (size_t)leaf * kLeafSize, leaf * kLeafSize);
+    node = kDone;
+    const float bnd = v.bound();
     while (sp > 0) {
       --sp;
-      if (stack_dist[sp] <= v.bound()) {
+      if (stack_dist[sp] <= bnd) {
         node = stack_node[sp];
-        found = true;
         break;
       }
     }
-    if (!found)
-      break;
   }
   return ok;
 }
