@@ -78,54 +78,55 @@ def analytic_normals(t, vp=(5.0, 5.0, 10.0)):
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    """SM clock and throttle reasons sampled DURING the timed region through NVML (in-process thread; the same
+    counters `nvidia-smi --query-gpu=clocks.sm,clocks_event_reasons.*` prints, B200_PROFILING.md recipe)."""
 
-    def __init__(self, gpu_index):
-        self.rows = []
-        self.proc = None
-        self.gpu = gpu_index
+    def __init__(self, gpu_index, period_s=0.05):
+        self.gpu, self.period = gpu_index, period_s
+        self.sm, self.reasons, self.max_mhz = [], set(), None
+        self.stop_flag = threading.Event()
+        self.th = None
+        self.err = None
 
     def start(self):
-        q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
-             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
-             "clocks_event_reasons.sw_power_cap")
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), f"--query-gpu={q}",
-                                          "--format=csv,noheader,nounits", "-lms", "100"],
-                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-            self.th = threading.Thread(target=self._read, daemon=True)
+            import pynvml as nv
+            nv.nvmlInit()
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+            idx = int(vis.split(",")[self.gpu]) if vis and vis.split(",")[0].isdigit() else self.gpu
+            self.h = nv.nvmlDeviceGetHandleByIndex(idx)
+            self.nv = nv
+            self.max_mhz = float(nv.nvmlDeviceGetMaxClockInfo(self.h, nv.NVML_CLOCK_SM))
+            self.th = threading.Thread(target=self._run, daemon=True)
             self.th.start()
-        except Exception:
-            self.proc = None
+        except Exception as e:  # noqa
+            self.err = repr(e)
 
-    def _read(self):
-        for line in self.proc.stdout:
-            self.rows.append(line.strip())
+    def _run(self):
+        nv = self.nv
+        bits = {"hw_slowdown": 0x8, "sw_power_cap": 0x4, "hw_thermal_slowdown": 0x40, "sw_thermal_slowdown": 0x20,
+                "hw_power_brake_slowdown": 0x80}
+        while not self.stop_flag.is_set():
+            try:
+                self.sm.append(float(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)))
+                r = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+                for k, b in bits.items():
+                    if r & b:
+                        self.reasons.add(k)
+            except Exception as e:  # noqa
+                self.err = repr(e)
+                break
+            self.stop_flag.wait(self.period)
 
     def stop(self):
-        if not self.proc:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        self.proc.terminate()
-        try:
-            self.proc.wait(timeout=2)
-        except Exception:
-            self.proc.kill()
-        sm, mx, reasons = [], [], set()
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for r in self.rows:
-            f = [v.strip() for v in r.split(",")]
-            if len(f) < 7:
-                continue
-            try:
-                sm.append(float(f[0]))
-                mx.append(float(f[1]))
-            except ValueError:
-                continue
-            for nm, v in zip(names, f[3:7]):
-                if v.lower().startswith("active"):
-                    reasons.add(nm)
-        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": float(max(mx)) if mx else None,
-                "samples": len(sm), "reasons": sorted(reasons)}
+        self.stop_flag.set()
+        if self.th:
+            self.th.join(timeout=2)
+        out = {"sm_mhz": float(np.median(self.sm)) if self.sm else None, "sm_max_mhz": self.max_mhz,
+               "samples": len(self.sm), "reasons": sorted(self.reasons), "how": "NVML, 50 ms period, timed region only"}
+        if self.err:
+            out["error"] = self.err
+        return out
 
 
 def measured_peak_gbs():
@@ -268,7 +269,7 @@ def run_ours(args):
         return ms, total, ctx.launches - l0, clocks
 
     # device-resident leg (value) --------------------------------------------------------------------------------
-    ms_v, tot_v, launches, clocks = timed(src_dev, out_dev, args.steps, args.warmup, True)
+    ms_v, tot_v, launches, clocks = timed(src_dev, out_dev, args.steps, args.warmup, not args.no_clocks)
     iter_ms, iter_n = ctx.profile_get("icp_search")
     accum_ms, _ = ctx.profile_get("icp_accum")
     sort_ms, _ = ctx.profile_get("query_sort")
@@ -354,6 +355,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--points", type=int, default=N_DEFAULT)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-clocks", action="store_true", help="debug: do not sample clocks during the timed region")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
