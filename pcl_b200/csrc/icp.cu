@@ -223,6 +223,69 @@ k_search(const IterArgs a, Match* __restrict__ match)
     atomicExch(a.d_error, 1);
 }
 
+// Packet variant of the search kernel: the 32 Morton-adjacent queries of a warp share ONE walk of the tree
+// (traverse_packet).  Chosen by the host when the queries are about as dense as the target (ICP's normal case).
+template <bool RECIP>
+__global__ void __launch_bounds__(256)
+k_search_packet(const IterArgs a, Match* __restrict__ match)
+{
+  __shared__ Pending sP;
+  __shared__ int s_node[8][kWarpStack];
+  __shared__ float s_dist[8][kWarpStack];
+  if (threadIdx.x == 0)
+    sP = *a.pending;
+  __syncthreads();
+  const int warp = threadIdx.x >> 5;
+  bool overflow = false;
+  // warp-uniform trip count: every lane of a warp runs the same number of rounds
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  const size_t first = blockIdx.x * (size_t)blockDim.x + (threadIdx.x & ~31);
+  for (size_t base = first; base < a.n; base += stride) {
+    const size_t i = base + (threadIdx.x & 31);
+    const bool in_range = i < a.n;
+    float4 p = in_range ? a.cur[i] : make_float4(0.f, 0.f, 0.f, 0.f);
+    const int seed = in_range ? match[i].pos : -1;
+    const bool valid = in_range && isfinite(p.x) && isfinite(p.y) && isfinite(p.z);
+    if (valid && sP.apply) {
+      apply_pending(sP, p.x, p.y, p.z);
+      a.cur[i] = p;
+    }
+    Nearest1 v{p.x, p.y, p.z, valid ? a.gate : -1.f, kSentinelIndex, -1};
+    if (valid && seed >= 0) {
+      const int leaf = seed / kLeafSize;
+      v.leaf(a.pts + (size_t)leaf * kLeafSize, leaf * kLeafSize);
+    }
+    __syncwarp();
+    if (!traverse_packet(a.nodes, a.pts, a.root, p.x, p.y, p.z, v, s_node[warp], s_dist[warp]))
+      overflow = true;
+    Match m;
+    m.pos = -1;
+    m.d2 = 0.f;
+    bool keep = valid && v.best_pos >= 0;
+    if (RECIP) {
+      // correspondence_estimation.hpp:259-269: back-search of the matched target point in the source tree
+      const float4 q = keep ? ldg4(a.pts + v.best_pos) : make_float4(0.f, 0.f, 0.f, 0.f);
+      Nearest1 b{q.x, q.y, q.z, keep ? a.gate : -1.f, kSentinelIndex, -1};
+      __syncwarp();
+      if (!traverse_packet(a.s_nodes, a.s_pts, a.s_root, q.x, q.y, q.z, b, s_node[warp], s_dist[warp]))
+        overflow = true;
+      if (keep) {
+        const int slot = __float_as_int(p.w);
+        const int my_orig = a.src_orig ? a.src_orig[slot] : slot;
+        keep = b.best_pos >= 0 && b.best_idx == my_orig;
+      }
+    }
+    if (keep) {
+      m.pos = v.best_pos;
+      m.d2 = v.best;
+    }
+    if (in_range)
+      match[i] = m;
+  }
+  if (overflow)
+    atomicExch(a.d_error, 1);
+}
+
 // Accumulation kernel: one streaming pass over (source point, match) pairs; fp64 sums, fixed reduction order.
 template <int EST>
 __global__ void __launch_bounds__(256)
@@ -1057,10 +1120,24 @@ void icp_iterate(Icp& s, int max_steps, pclb200_icp_stats* stats)
     {
       ProfScope ps(c, "icp_search");
       const unsigned sgrid = persistent_grid(c, s.n_q, 256, 16);
-      if (s.P.use_reciprocal)
-        k_search<true><<<sgrid, 256, 0, st>>>(a, s.match.p);
-      else
-        k_search<false><<<sgrid, 256, 0, st>>>(a, s.match.p);
+      // packet walk when the queries are about as dense as the target (32 Morton-adjacent queries then share
+      // most of their path); per-query walk when they are much sparser.  PCLB200_SEARCH=packet|single overrides.
+      static const char* force = getenv("PCLB200_SEARCH");
+      bool packet = (double)T.n_valid <= 64.0 * (double)s.n_q;
+      if (force && force[0] == 'p') packet = true;
+      if (force && force[0] == 's') packet = false;
+      if (packet) {
+        if (s.P.use_reciprocal)
+          k_search_packet<true><<<sgrid, 256, 0, st>>>(a, s.match.p);
+        else
+          k_search_packet<false><<<sgrid, 256, 0, st>>>(a, s.match.p);
+      }
+      else {
+        if (s.P.use_reciprocal)
+          k_search<true><<<sgrid, 256, 0, st>>>(a, s.match.p);
+        else
+          k_search<false><<<sgrid, 256, 0, st>>>(a, s.match.p);
+      }
       ++c.launches;
     }
     {

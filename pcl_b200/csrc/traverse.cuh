@@ -125,4 +125,74 @@ struct Nearest1 {
   }
 };
 
+// ---- packet traversal: one walk of the tree per WARP, shared by its 32 Morton-adjacent queries ---------------
+// All lanes follow the same path (no divergence, every node / leaf line is one broadcast load, the stack is one
+// per-warp array in shared memory).  A subtree is entered when ANY lane still needs it (box bound <= that lane's
+// current best) — so every lane sees a superset of the leaves its own exact search would visit and its result is
+// still the exact lexicographic minimum.  The nearer child is the one with the smaller warp-minimum bound; the other
+// is pushed with that minimum and re-tested on pop against the warp-maximum best (conservative).
+// Lanes without a query pass best = -1 (never want anything).  Must be called by all 32 lanes.
+constexpr int kWarpStack = 64;
+
+__device__ __forceinline__ bool traverse_packet(const BvhNode* __restrict__ nodes, const float4* __restrict__ pts,
+                                                int root, float qx, float qy, float qz, Nearest1& v,
+                                                int* __restrict__ wnode, float* __restrict__ wdist)
+{
+  const unsigned full = 0xffffffffu;
+  const unsigned INF_BITS = 0x7f800000u;
+  int sp = 0;
+  int node = root;
+  bool ok = true;
+  while (node != kDone) {
+    while (node >= 0 && node != kDone) {
+      const float4* np = reinterpret_cast<const float4*>(nodes + node);
+      const float4 a = ldg4(np), b = ldg4(np + 1), c = ldg4(np + 2);
+      const int4 d = __ldg(reinterpret_cast<const int4*>(np + 3));
+      const float dl = box_dist2_rn(qx, qy, qz, a.x, a.y, a.z, a.w, b.x, b.y);
+      const float dr = box_dist2_rn(qx, qy, qz, b.z, b.w, c.x, c.y, c.z, c.w);
+      const float bnd = v.best;
+      const unsigned ml = __reduce_min_sync(full, dl <= bnd ? __float_as_uint(dl) : INF_BITS);
+      const unsigned mr = __reduce_min_sync(full, dr <= bnd ? __float_as_uint(dr) : INF_BITS);
+      if (ml == INF_BITS && mr == INF_BITS) {
+        node = kDone;
+        const unsigned wmax = __reduce_max_sync(full, __float_as_uint(fmaxf(bnd, 0.f)));
+        while (sp > 0) {
+          --sp;
+          if (__float_as_uint(wdist[sp]) <= wmax) {
+            node = wnode[sp];
+            break;
+          }
+        }
+      }
+      else if (ml != INF_BITS && mr != INF_BITS) {
+        const bool left_first = ml <= mr;
+        if (sp < kWarpStack) {
+          wnode[sp] = left_first ? d.y : d.x;
+          wdist[sp] = __uint_as_float(left_first ? mr : ml);
+          ++sp;
+        }
+        else
+          ok = false;
+        node = left_first ? d.x : d.y;
+      }
+      else
+        node = ml != INF_BITS ? d.x : d.y;
+    }
+    if (node == kDone)
+      break;
+    const int leaf = ~node;
+    v.leaf(pts + (size_t)leaf * kLeafSize, leaf * kLeafSize);
+    node = kDone;
+    const unsigned wmax = __reduce_max_sync(full, __float_as_uint(fmaxf(v.best, 0.f)));
+    while (sp > 0) {
+      --sp;
+      if (__float_as_uint(wdist[sp]) <= wmax) {
+        node = wnode[sp];
+        break;
+      }
+    }
+  }
+  return ok;
+}
+
 }  // namespace pclb200
