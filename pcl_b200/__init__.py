@@ -11,7 +11,7 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libpclb200.so")
+LIB_PATH = os.environ.get("PCLB200_LIB", os.path.join(_HERE, "libpclb200.so"))  # override = experiments only
 
 OK = 0
 ERR_CUDA, ERR_INVALID, ERR_EMPTY, ERR_LEAF_TOO_SMALL, ERR_INTERNAL, ERR_NCCL = -1, -2, -3, -4, -5, -6

@@ -29,7 +29,15 @@ def _newer(target, deps):
     return any(os.path.getmtime(d) > t for d in deps)
 
 
-def build(force=False, verbose=False):
+def build(force=False, verbose=False, leaf=None, tag=None):
+    """leaf/tag: build an experimental variant (libpclb200_<tag>.so with -DPCLB_LEAF=<leaf>) next to the default."""
+    global OBJ, SO
+    flags = list(FLAGS)
+    if tag:
+        OBJ = os.path.join(HERE, "build_" + tag)
+        SO = os.path.join(HERE, f"libpclb200_{tag}.so")
+    if leaf:
+        flags += [f"-DPCLB_LEAF={int(leaf)}"]
     os.makedirs(OBJ, exist_ok=True)
     hdrs = [os.path.normpath(os.path.join(CSRC, h)) for h in HEADERS]
     jobs = []
@@ -41,7 +49,7 @@ def build(force=False, verbose=False):
 
     def compile_one(job):
         src, obj = job
-        r = subprocess.run([NVCC] + FLAGS + ["-c", src, "-o", obj], capture_output=True, text=True)
+        r = subprocess.run([NVCC] + flags + ["-c", src, "-o", obj], capture_output=True, text=True)
         if verbose or r.returncode != 0:
             sys.stderr.write(r.stdout + r.stderr)
         else:
@@ -64,4 +72,10 @@ def build(force=False, verbose=False):
 
 
 if __name__ == "__main__":
-    print(build(force="--force" in sys.argv, verbose="--verbose" in sys.argv))
+    kw = {}
+    for a in sys.argv[1:]:
+        if a.startswith("--leaf="):
+            kw["leaf"] = int(a.split("=")[1])
+        if a.startswith("--tag="):
+            kw["tag"] = a.split("=")[1]
+    print(build(force="--force" in sys.argv, verbose="--verbose" in sys.argv, **kw))

@@ -142,7 +142,11 @@ struct __align__(16) BvhNode {
   int4 d;
 };
 
-constexpr int kLeafSize = 8;        // points per leaf = one 128-byte line of float4
+#ifndef PCLB_LEAF
+#define PCLB_LEAF 8
+#endif
+constexpr int kLeafSize = PCLB_LEAF;  // points per leaf (multiple of 8): 8 points = one 128-byte line of float4
+static_assert(kLeafSize % 8 == 0 && kLeafSize >= 8 && kLeafSize <= 64, "leaf size must be a multiple of 8");
 constexpr int kStackSize = 64;      // traversal stack entries per query
 constexpr int kSentinelIndex = 0x7fffffff;
 

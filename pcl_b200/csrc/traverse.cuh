@@ -108,18 +108,33 @@ struct Nearest1 {
   __device__ __forceinline__ float bound() const { return best; }
   __device__ __forceinline__ void leaf(const float4* lp, int first_pos)
   {
-    float4 p[kLeafSize];
+    // distances first, one min-reduction, and the (rare) index bookkeeping only when the leaf can improve the
+    // best: most visited leaves do not, so the common path is 8 flops per point plus one compare per leaf.
 #pragma unroll
-    for (int j = 0; j < kLeafSize; ++j)
-      p[j] = ldg4(lp + j);
+    for (int j0 = 0; j0 < kLeafSize; j0 += 8) {
+      float4 p[8];
+      float d[8];
+      float m = __int_as_float(0x7f800000);
 #pragma unroll
-    for (int j = 0; j < kLeafSize; ++j) {
-      float d = dist2_rn(qx, qy, qz, p[j].x, p[j].y, p[j].z);
-      int oi = __float_as_int(p[j].w);
-      if (d < best || (d == best && oi < best_idx)) {
-        best = d;
-        best_idx = oi;
-        best_pos = first_pos + j;
+      for (int j = 0; j < 8; ++j)
+        p[j] = ldg4(lp + j0 + j);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        d[j] = dist2_rn(qx, qy, qz, p[j].x, p[j].y, p[j].z);
+        m = fminf(m, d[j]);
+      }
+      if (m <= best) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          if (d[j] <= best) {
+            const int oi = __float_as_int(p[j].w);
+            if (d[j] < best || oi < best_idx) {
+              best = d[j];
+              best_idx = oi;
+              best_pos = first_pos + j0 + j;
+            }
+          }
+        }
       }
     }
   }
