@@ -28,7 +28,7 @@ size_t correspondences(Ctx& c, const Index& tgt, const Index* src_index, const v
 double fitness_score(Ctx& c, const Index& tgt, const void* src, size_t n, size_t stride, const int32_t* indices,
                      size_t n_idx, const double* T, int scalar_is_double, double max_range);
 // search.cu
-void launch_normals(Ctx& c, const Index& idx, const float4* d_q, size_t nq, int k, const float vp[3], float4* d_out,
+void launch_normals(Ctx& c, Index& idx, const float4* d_q, size_t nq, int k, const float vp[3], float4* d_out,
                     int* d_not_dense);
 // voxel.cu
 size_t voxelgrid(Ctx& c, const void* pts, size_t n, size_t stride, const int32_t* indices, size_t n_idx, int is_dense,

@@ -453,14 +453,88 @@ k_normals(const BvhNode* __restrict__ nodes, const float4* __restrict__ pts, int
   out[slot] = make_float4(n[0], n[1], n[2], curv);
 }
 
-void launch_normals(Ctx& c, const Index& idx, const float4* d_q, size_t nq, int k, const float vp[3], float4* d_out,
+// normals from materialised neighbour lists (k > 32): same arithmetic as k_normals, neighbours fetched through
+// pos_of_orig.  lists are rows of pitch k indexed by the query's slot.
+__global__ void __launch_bounds__(128)
+k_normals_from_lists(const float4* __restrict__ pts, const int32_t* __restrict__ pos_of_orig,
+                     const float4* __restrict__ q, size_t nq, int k, const int32_t* __restrict__ lists, size_t slot0,
+                     float vpx, float vpy, float vpz, float4* __restrict__ out, int* __restrict__ not_dense)
+{
+  size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+  if (i >= nq)
+    return;
+  const float4 qq = __ldg(q + i);
+  const size_t slot = (size_t)(unsigned)__float_as_int(qq.w);
+  const int32_t* nn = lists + (slot - slot0) * (size_t)k;
+  const float qnan = __int_as_float(0x7fc00000);
+  int cnt = 0;
+  for (int j = 0; j < k; ++j)
+    if (nn[j] >= 0)
+      ++cnt;
+  if (!(isfinite(qq.x) && isfinite(qq.y) && isfinite(qq.z)) || cnt < 3) {
+    out[slot] = make_float4(qnan, qnan, qnan, qnan);
+    *not_dense = 1;
+    return;
+  }
+  float accu[9] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  float Kx = 0.f, Ky = 0.f, Kz = 0.f;
+  for (int j = 0; j < cnt; ++j) {
+    const float4 p = ldg4(pts + pos_of_orig[nn[j]]);
+    if (j == 0) { Kx = p.x; Ky = p.y; Kz = p.z; }
+    const float x = __fsub_rn(p.x, Kx), y = __fsub_rn(p.y, Ky), z = __fsub_rn(p.z, Kz);
+    accu[0] = __fadd_rn(accu[0], __fmul_rn(x, x));
+    accu[1] = __fadd_rn(accu[1], __fmul_rn(x, y));
+    accu[2] = __fadd_rn(accu[2], __fmul_rn(x, z));
+    accu[3] = __fadd_rn(accu[3], __fmul_rn(y, y));
+    accu[4] = __fadd_rn(accu[4], __fmul_rn(y, z));
+    accu[5] = __fadd_rn(accu[5], __fmul_rn(z, z));
+    accu[6] = __fadd_rn(accu[6], x);
+    accu[7] = __fadd_rn(accu[7], y);
+    accu[8] = __fadd_rn(accu[8], z);
+  }
+  const float fc = (float)cnt;
+  for (int t = 0; t < 9; ++t)
+    accu[t] = __fdiv_rn(accu[t], fc);
+  float cov[9];
+  cov[0] = __fsub_rn(accu[0], __fmul_rn(accu[6], accu[6]));
+  cov[1] = __fsub_rn(accu[1], __fmul_rn(accu[6], accu[7]));
+  cov[2] = __fsub_rn(accu[2], __fmul_rn(accu[6], accu[8]));
+  cov[4] = __fsub_rn(accu[3], __fmul_rn(accu[7], accu[7]));
+  cov[5] = __fsub_rn(accu[4], __fmul_rn(accu[7], accu[8]));
+  cov[8] = __fsub_rn(accu[5], __fmul_rn(accu[8], accu[8]));
+  cov[3] = cov[1]; cov[6] = cov[2]; cov[7] = cov[5];
+  float ev, n[3];
+  eigen33_smallest_dev(cov, ev, n);
+  const float eig_sum = __fadd_rn(__fadd_rn(cov[0], cov[4]), cov[8]);
+  const float curv = eig_sum != 0.f ? fabsf(__fdiv_rn(ev, eig_sum)) : 0.f;
+  const float vx = vpx - qq.x, vy = vpy - qq.y, vz = vpz - qq.z;
+  if (vx * n[0] + vy * n[1] + vz * n[2] < 0.f) { n[0] = -n[0]; n[1] = -n[1]; n[2] = -n[2]; }
+  if (!(isfinite(n[0]) && isfinite(n[1]) && isfinite(n[2]) && isfinite(curv)))
+    *not_dense = 1;
+  out[slot] = make_float4(n[0], n[1], n[2], curv);
+}
+
+void launch_normals(Ctx& c, Index& idx, const float4* d_q, size_t nq, int k, const float vp[3], float4* d_out,
                     int* d_not_dense)
 {
   if (!nq)
     return;
   cudaStream_t s = c.stream;
   const unsigned g = grid_for(nq, 128);
-  PCLB_REQUIRE(k <= 32, PCLB200_ERR_INVALID, "normals: k > 32 is not supported by the fused kernel");
+  if (k > 32) {
+    // large neighbourhoods: materialise the exact k-NN lists (any-k kernel), then fold them
+    ensure_pos_of_orig(c, idx);
+    DevBuf<int32_t> li;
+    DevBuf<float> ld;
+    li.alloc(nq * (size_t)k, s);
+    ld.alloc(nq * (size_t)k, s);
+    launch_knn(c, idx, d_q, nq, k, __builtin_inff(), li.p, ld.p);
+    k_normals_from_lists<<<g, 128, 0, s>>>(idx.pts.p, idx.pos_of_orig.p, d_q, nq, k, li.p, 0, vp[0], vp[1], vp[2], d_out,
+                                           d_not_dense);
+    ++c.launches;
+    PCLB_CUDA(cudaGetLastError());
+    return;
+  }
 #define PCLB_NRM_CASE(KK)                                                                                     \
   k_normals<KK><<<g, 128, 0, s>>>(idx.nodes.p, idx.pts.p, idx.root, d_q, nq, k, vp[0], vp[1], vp[2], d_out, \
                                   d_not_dense, c.d_error)

@@ -1,0 +1,65 @@
+// pcl/eigen_lite.h — the few Eigen types PCL's registration API exposes (Matrix4f/Matrix4d/Vector4f), for
+// builds where Eigen is absent (this image).  With real Eigen present, include <Eigen/Core> BEFORE the facade
+// headers and define PCLB200_USE_EIGEN: the facade then uses Eigen's own types and this file is skipped.
+#pragma once
+#ifdef PCLB200_USE_EIGEN
+#include <Eigen/Core>
+#else
+#include <cmath>
+#include <cstddef>
+namespace Eigen {
+template <typename S, int R, int C>
+struct Matrix {
+  S m[R * C];  // column-major like Eigen's default
+  Matrix() { for (int i = 0; i < R * C; ++i) m[i] = S(0); }
+  static Matrix Identity()
+  {
+    Matrix r;
+    for (int i = 0; i < (R < C ? R : C); ++i) r(i, i) = S(1);
+    return r;
+  }
+  static Matrix Zero() { return Matrix(); }
+  S& operator()(int r, int c) { return m[c * R + r]; }
+  const S& operator()(int r, int c) const { return m[c * R + r]; }
+  S& operator[](int i) { return m[i]; }
+  const S& operator[](int i) const { return m[i]; }
+  S& coeffRef(int r, int c) { return (*this)(r, c); }
+  S coeff(int r, int c) const { return (*this)(r, c); }
+  static constexpr int rows() { return R; }
+  static constexpr int cols() { return C; }
+  void setIdentity() { *this = Identity(); }
+  bool operator==(const Matrix& o) const
+  {
+    for (int i = 0; i < R * C; ++i)
+      if (m[i] != o.m[i]) return false;
+    return true;
+  }
+  bool operator!=(const Matrix& o) const { return !(*this == o); }
+  template <typename T>
+  Matrix<T, R, C> cast() const
+  {
+    Matrix<T, R, C> r;
+    for (int i = 0; i < R * C; ++i) r.m[i] = static_cast<T>(m[i]);
+    return r;
+  }
+  // coefficient-based product, Eigen order ((a0*b0 + a1*b1) + a2*b2) + a3*b3
+  template <int K>
+  Matrix<S, R, K> operator*(const Matrix<S, C, K>& o) const
+  {
+    Matrix<S, R, K> r;
+    for (int i = 0; i < R; ++i)
+      for (int j = 0; j < K; ++j) {
+        S acc = (*this)(i, 0) * o(0, j);
+        for (int k = 1; k < C; ++k) acc = acc + (*this)(i, k) * o(k, j);
+        r(i, j) = acc;
+      }
+    return r;
+  }
+};
+using Matrix4f = Matrix<float, 4, 4>;
+using Matrix4d = Matrix<double, 4, 4>;
+using Matrix3f = Matrix<float, 3, 3>;
+using Vector4f = Matrix<float, 4, 1>;
+using Vector3f = Matrix<float, 3, 1>;
+}  // namespace Eigen
+#endif

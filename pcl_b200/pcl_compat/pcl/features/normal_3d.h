@@ -1,0 +1,99 @@
+// pcl/features/normal_3d.h — pcl::NormalEstimation[OMP]<PointInT, PointOutT> with setKSearch(k) on the device
+// (features/include/pcl/features/normal_3d.h:242-415, impl/normal_3d.hpp:47-96, impl/feature.hpp:95-230).
+#pragma once
+#include <cstdio>
+#include <limits>
+
+#include "../point_types.h"
+#include "../search/kdtree.h"
+
+namespace pcl {
+template <typename PointInT, typename PointOutT>
+class NormalEstimation : public PCLBase<PointInT> {
+public:
+  using PointCloudOut = pcl::PointCloud<PointOutT>;
+  using KdTreePtr = typename pcl::search::KdTree<PointInT>::Ptr;
+  using PointCloudInConstPtr = typename pcl::PointCloud<PointInT>::ConstPtr;
+
+  void setInputCloud(const PointCloudInConstPtr& cloud) override
+  {
+    this->input_ = cloud;
+    if (use_sensor_origin_ && cloud) {  // normal_3d.h:328-337
+      vp_[0] = cloud->sensor_origin_[0];
+      vp_[1] = cloud->sensor_origin_[1];
+      vp_[2] = cloud->sensor_origin_[2];
+    }
+  }
+  void setSearchSurface(const PointCloudInConstPtr& cloud) { surface_ = cloud; fake_surface_ = false; }
+  void setSearchMethod(const KdTreePtr& tree) { tree_ = tree; }
+  KdTreePtr getSearchMethod() const { return tree_; }
+  void setKSearch(int k) { k_ = k; }
+  int getKSearch() const { return k_; }
+  void setRadiusSearch(double r) { search_radius_ = r; }
+  void setViewPoint(float x, float y, float z) { vp_[0] = x; vp_[1] = y; vp_[2] = z; use_sensor_origin_ = false; }
+  void getViewPoint(float& x, float& y, float& z) { x = vp_[0]; y = vp_[1]; z = vp_[2]; }
+  void useSensorOriginAsViewPoint()
+  {
+    use_sensor_origin_ = true;
+    if (this->input_) { vp_[0] = this->input_->sensor_origin_[0]; vp_[1] = this->input_->sensor_origin_[1]; vp_[2] = this->input_->sensor_origin_[2]; }
+  }
+  void setNumberOfThreads(unsigned int) {}
+
+  // Feature::compute — impl/feature.hpp:195-230
+  void compute(PointCloudOut& output)
+  {
+    output.clear();
+    if (!this->input_ || this->input_->empty()) {
+      std::fprintf(stderr, "[pcl::NormalEstimation::compute] input cloud is empty!\n");
+      return;
+    }
+    if (search_radius_ != 0.0 && k_ != 0) {  // impl/feature.hpp:135-141
+      std::fprintf(stderr, "[pcl::NormalEstimation::compute] Both radius and K defined! Set one of them to zero first.\n");
+      return;
+    }
+    if (k_ == 0) {
+      std::fprintf(stderr, "[pcl::NormalEstimation::compute] only setKSearch(k) is on the accelerated path (radius: SURVEY.md §8f).\n");
+      return;
+    }
+    PCLBase<PointInT>::initCompute();
+    if (!surface_) { surface_ = this->input_; fake_surface_ = true; }
+    if (!tree_) tree_.reset(new pcl::search::KdTree<PointInT>());
+    if (tree_->getInputCloud() != surface_ || !tree_->deviceIndex()) tree_->setInputCloud(surface_);
+    if (!tree_->deviceIndex()) return;
+    const std::size_t n = this->indices_->size();
+    output.header = this->input_->header;
+    output.points.assign(n, PointOutT());
+    std::vector<float> buf(4 * (n ? n : 1));
+    int dense = 1;
+    int rc = pclb200_normals_knn(b200::Context::get(), tree_->deviceIndex(), this->input_->points.data(), this->input_->size(),
+                                 sizeof(PointInT), this->abiIndices(), this->abiIndexCount(), this->input_->is_dense ? 1 : 0, k_, vp_,
+                                 buf.data(), &dense);
+    if (rc != PCLB200_OK) {
+      std::fprintf(stderr, "[pcl::NormalEstimation::compute] %s\n", pclb200_last_error());
+      output.clear();
+      return;
+    }
+    for (std::size_t i = 0; i < n; ++i) {
+      output.points[i].normal_x = buf[4 * i];
+      output.points[i].normal_y = buf[4 * i + 1];
+      output.points[i].normal_z = buf[4 * i + 2];
+      output.points[i].curvature = buf[4 * i + 3];
+    }
+    if (n != this->input_->size()) { output.width = static_cast<std::uint32_t>(n); output.height = 1; }
+    else { output.width = this->input_->width; output.height = this->input_->height; }
+    output.is_dense = dense != 0;
+    if (fake_surface_) surface_.reset();
+  }
+
+protected:
+  PointCloudInConstPtr surface_;
+  bool fake_surface_ = false;
+  KdTreePtr tree_;
+  int k_ = 0;
+  double search_radius_ = 0.0;
+  float vp_[3] = {0.f, 0.f, 0.f};
+  bool use_sensor_origin_ = true;
+};
+template <typename PointInT, typename PointOutT>
+using NormalEstimationOMP = NormalEstimation<PointInT, PointOutT>;
+}  // namespace pcl

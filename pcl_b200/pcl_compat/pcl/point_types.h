@@ -1,0 +1,57 @@
+// pcl/point_types.h — the three point layouts on the ICP path, byte-identical to
+// common/include/pcl/impl/point_types.hpp:205-227 (PointXYZ, 16 B), :769-794 (Normal, 32 B),
+// :824-855 (PointNormal, 48 B); all 16-byte aligned.
+#pragma once
+#include <cmath>
+namespace pcl {
+struct alignas(16) PointXYZ {
+  union {
+    float data[4];
+    struct { float x, y, z; };
+  };
+  PointXYZ() : data{0.f, 0.f, 0.f, 1.f} {}
+  PointXYZ(float _x, float _y, float _z) : data{_x, _y, _z, 1.f} {}
+};
+struct alignas(16) Normal {
+  union {
+    float data_n[4];
+    float normal[3];
+    struct { float normal_x, normal_y, normal_z; };
+  };
+  union {
+    struct { float curvature; };
+    float data_c[4];
+  };
+  Normal() : data_n{0.f, 0.f, 0.f, 0.f}, data_c{0.f, 0.f, 0.f, 0.f} {}
+  Normal(float nx, float ny, float nz, float c = 0.f) : data_n{nx, ny, nz, 0.f}, data_c{c, 0.f, 0.f, 0.f} {}
+};
+struct alignas(16) PointNormal {
+  union {
+    float data[4];
+    struct { float x, y, z; };
+  };
+  union {
+    float data_n[4];
+    float normal[3];
+    struct { float normal_x, normal_y, normal_z; };
+  };
+  union {
+    struct { float curvature; };
+    float data_c[4];
+  };
+  PointNormal() : data{0.f, 0.f, 0.f, 1.f}, data_n{0.f, 0.f, 0.f, 0.f}, data_c{0.f, 0.f, 0.f, 0.f} {}
+  PointNormal(float _x, float _y, float _z, float nx = 0.f, float ny = 0.f, float nz = 0.f, float c = 0.f)
+  : data{_x, _y, _z, 1.f}, data_n{nx, ny, nz, 0.f}, data_c{c, 0.f, 0.f, 0.f} {}
+};
+static_assert(sizeof(PointXYZ) == 16 && sizeof(Normal) == 32 && sizeof(PointNormal) == 48, "PCL layouts");
+
+template <typename T> struct has_normal { static constexpr bool value = false; };
+template <> struct has_normal<PointNormal> { static constexpr bool value = true; };
+template <> struct has_normal<Normal> { static constexpr bool value = true; };
+
+template <typename PointT> inline bool isXYZFinite(const PointT& p)
+{
+  return std::isfinite(p.x) && std::isfinite(p.y) && std::isfinite(p.z);
+}
+template <typename PointT> inline bool isFinite(const PointT& p) { return isXYZFinite(p); }
+}  // namespace pcl

@@ -1,0 +1,125 @@
+// pcl/registration/correspondence_estimation.h — pcl::registration::CorrespondenceEstimation on the device.
+// Reference: registration/include/pcl/registration/correspondence_estimation.h:59-504 and
+// impl/correspondence_estimation.hpp:52-311.
+#pragma once
+#include <cmath>
+#include <cstdio>
+#include <limits>
+
+#include "../correspondence.h"
+#include "../search/kdtree.h"
+
+namespace pcl {
+namespace registration {
+
+template <typename PointSource, typename PointTarget, typename Scalar = float>
+class CorrespondenceEstimation : public PCLBase<PointSource> {
+public:
+  using Ptr = std::shared_ptr<CorrespondenceEstimation>;
+  using KdTree = pcl::search::KdTree<PointTarget>;
+  using KdTreePtr = typename KdTree::Ptr;
+  using KdTreeReciprocal = pcl::search::KdTree<PointSource>;
+  using KdTreeReciprocalPtr = typename KdTreeReciprocal::Ptr;
+  using PointCloudSourceConstPtr = typename pcl::PointCloud<PointSource>::ConstPtr;
+  using PointCloudTargetConstPtr = typename pcl::PointCloud<PointTarget>::ConstPtr;
+
+  CorrespondenceEstimation() : tree_(new KdTree), tree_reciprocal_(new KdTreeReciprocal) {}
+
+  void setInputSource(const PointCloudSourceConstPtr& cloud)
+  {
+    source_cloud_updated_ = true;
+    PCLBase<PointSource>::setInputCloud(cloud);
+  }
+  PointCloudSourceConstPtr const getInputSource() { return this->input_; }
+  void setInputTarget(const PointCloudTargetConstPtr& cloud)
+  {
+    if (!cloud || cloud->empty()) {
+      std::fprintf(stderr, "[pcl::registration::CorrespondenceEstimation::setInputTarget] Invalid or empty point cloud dataset given!\n");
+      return;
+    }
+    target_ = cloud;
+    target_cloud_updated_ = true;
+  }
+  PointCloudTargetConstPtr const getInputTarget() { return target_; }
+  void setIndicesSource(const IndicesPtr& indices) { this->setIndices(indices); }
+  void setIndicesTarget(const IndicesPtr& indices) { target_cloud_updated_ = true; target_indices_ = indices; }
+  void setSearchMethodTarget(const KdTreePtr& tree, bool force_no_recompute = false)
+  {
+    tree_ = tree;
+    force_no_recompute_ = force_no_recompute;
+    target_cloud_updated_ = true;
+  }
+  KdTreePtr getSearchMethodTarget() const { return tree_; }
+  void setSearchMethodSource(const KdTreeReciprocalPtr& tree, bool force_no_recompute = false)
+  {
+    tree_reciprocal_ = tree;
+    force_no_recompute_reciprocal_ = force_no_recompute;
+    source_cloud_updated_ = true;
+  }
+  void setNumberOfThreads(unsigned int) {}  // one device launch replaces the OpenMP loop (:163-165)
+
+  // impl/correspondence_estimation.hpp:145-218
+  void determineCorrespondences(pcl::Correspondences& correspondences,
+                                double max_distance = std::numeric_limits<double>::max())
+  {
+    run(correspondences, max_distance, false);
+  }
+  // impl/correspondence_estimation.hpp:220-311
+  void determineReciprocalCorrespondences(pcl::Correspondences& correspondences,
+                                          double max_distance = std::numeric_limits<double>::max())
+  {
+    run(correspondences, max_distance, true);
+  }
+
+protected:
+  bool initCompute()
+  {
+    if (!target_) {
+      std::fprintf(stderr, "[pcl::registration::CorrespondenceEstimation::compute] No input target dataset was given!\n");
+      return false;
+    }
+    if (target_cloud_updated_ && !force_no_recompute_) {  // :83-91
+      tree_->setInputCloud(target_, target_indices_);
+      target_cloud_updated_ = false;
+    }
+    return PCLBase<PointSource>::initCompute();
+  }
+  bool initComputeReciprocal()
+  {
+    if (source_cloud_updated_ && !force_no_recompute_reciprocal_) {  // :117-135
+      tree_reciprocal_->setInputCloud(this->input_, this->use_indices_ && !this->fake_indices_ ? IndicesConstPtr(this->indices_) : IndicesConstPtr());
+      source_cloud_updated_ = false;
+    }
+    return true;
+  }
+  void run(pcl::Correspondences& out, double max_distance, bool reciprocal)
+  {
+    out.clear();
+    if (!initCompute()) return;
+    if (reciprocal && !initComputeReciprocal()) return;
+    if (!tree_->deviceIndex() || (reciprocal && !tree_reciprocal_->deviceIndex())) return;
+    out.resize(this->indices_->size());
+    std::size_t n_out = 0;
+    // max_distance = DBL_MAX squares to +inf (no gate), exactly like `max_distance * max_distance` at :161
+    int rc = pclb200_correspondences(b200::Context::get(), tree_->deviceIndex(),
+                                     reciprocal ? tree_reciprocal_->deviceIndex() : nullptr, this->input_->points.data(),
+                                     this->input_->size(), sizeof(PointSource), this->abiIndices(), this->abiIndexCount(),
+                                     this->input_->is_dense ? 1 : 0, max_distance,
+                                     reinterpret_cast<pclb200_corr*>(out.data()), &n_out);
+    if (rc != PCLB200_OK) {
+      std::fprintf(stderr, "[pcl::registration::CorrespondenceEstimation] %s\n", pclb200_last_error());
+      n_out = 0;
+    }
+    out.resize(n_out);
+  }
+
+  KdTreePtr tree_;
+  KdTreeReciprocalPtr tree_reciprocal_;
+  PointCloudTargetConstPtr target_;
+  IndicesPtr target_indices_;
+  bool target_cloud_updated_ = true, source_cloud_updated_ = true;
+  bool force_no_recompute_ = false, force_no_recompute_reciprocal_ = false;
+};
+
+}  // namespace registration
+}  // namespace pcl

@@ -1,0 +1,348 @@
+// pcl/registration/registration.h + icp.h — pcl::Registration / pcl::IterativeClosestPoint[WithNormals] whose
+// computeTransformation runs the device-resident loop of libpclb200 (pclb200_icp_* session).
+// Reference: registration/include/pcl/registration/registration.h:56-700, impl/registration.hpp:45-221,
+// icp.h:97-456, impl/icp.hpp:113-318, default_convergence_criteria.h:64-326.
+#pragma once
+#include <cfloat>
+#include <cmath>
+#include <cstdio>
+#include <functional>
+#include <limits>
+#include <memory>
+#include <string>
+
+#include "../search/kdtree.h"
+#include "correspondence_estimation.h"
+#include "transformation_estimation.h"
+
+namespace pcl {
+namespace registration {
+// default_convergence_criteria.h:75-83 — the state enum and the accessor PCL users reach through getConvergeCriteria()
+template <typename Scalar = float>
+class DefaultConvergenceCriteria {
+public:
+  using Ptr = std::shared_ptr<DefaultConvergenceCriteria<Scalar>>;
+  enum ConvergenceState {
+    CONVERGENCE_CRITERIA_NOT_CONVERGED = PCLB200_CONV_NOT_CONVERGED,
+    CONVERGENCE_CRITERIA_ITERATIONS = PCLB200_CONV_ITERATIONS,
+    CONVERGENCE_CRITERIA_TRANSFORM = PCLB200_CONV_TRANSFORM,
+    CONVERGENCE_CRITERIA_ABS_MSE = PCLB200_CONV_ABS_MSE,
+    CONVERGENCE_CRITERIA_REL_MSE = PCLB200_CONV_REL_MSE,
+    CONVERGENCE_CRITERIA_NO_CORRESPONDENCES = PCLB200_CONV_NO_CORRESPONDENCES,
+    CONVERGENCE_CRITERIA_FAILURE_AFTER_MAX_ITERATIONS = PCLB200_CONV_FAILURE_AFTER_MAX_ITERATIONS
+  };
+  ConvergenceState getConvergenceState() const { return state_; }
+  void setFailureAfterMaximumIterations(bool f) { failure_after_max_iter_ = f; }
+  bool getFailureAfterMaximumIterations() const { return failure_after_max_iter_; }
+  void setMaximumIterationsSimilarTransforms(int n) { max_iterations_similar_transforms_ = n; }
+  int getMaximumIterationsSimilarTransforms() const { return max_iterations_similar_transforms_; }
+  void setAbsoluteMSE(double v) { mse_threshold_absolute_ = v; }
+  double getAbsoluteMSE() const { return mse_threshold_absolute_; }
+  // written by Registration after every run
+  ConvergenceState state_ = CONVERGENCE_CRITERIA_NOT_CONVERGED;
+  bool failure_after_max_iter_ = false;
+  int max_iterations_similar_transforms_ = 0;
+  double mse_threshold_absolute_ = 1e-12;
+};
+}  // namespace registration
+
+template <typename PointSource, typename PointTarget, typename Scalar = float>
+class Registration : public PCLBase<PointSource> {
+public:
+  using Matrix4 = Eigen::Matrix<Scalar, 4, 4>;
+  using Ptr = std::shared_ptr<Registration>;
+  using KdTree = pcl::search::KdTree<PointTarget>;
+  using KdTreePtr = typename KdTree::Ptr;
+  using KdTreeReciprocal = pcl::search::KdTree<PointSource>;
+  using KdTreeReciprocalPtr = typename KdTreeReciprocal::Ptr;
+  using PointCloudSource = pcl::PointCloud<PointSource>;
+  using PointCloudSourceConstPtr = typename PointCloudSource::ConstPtr;
+  using PointCloudTarget = pcl::PointCloud<PointTarget>;
+  using PointCloudTargetConstPtr = typename PointCloudTarget::ConstPtr;
+  using TransformationEstimation = pcl::registration::TransformationEstimation<PointSource, PointTarget, Scalar>;
+  using TransformationEstimationPtr = typename TransformationEstimation::Ptr;
+  using CorrespondenceEstimation = pcl::registration::CorrespondenceEstimation<PointSource, PointTarget, Scalar>;
+  using CorrespondenceEstimationPtr = typename CorrespondenceEstimation::Ptr;
+
+  Registration()
+  : tree_(new KdTree), tree_reciprocal_(new KdTreeReciprocal), final_transformation_(Matrix4::Identity()),
+    transformation_(Matrix4::Identity()), previous_transformation_(Matrix4::Identity()),
+    euclidean_fitness_epsilon_(-std::numeric_limits<double>::max()),
+    corr_dist_threshold_(std::sqrt(std::numeric_limits<double>::max()))
+  {
+  }
+  ~Registration() override
+  {
+    if (icp_) pclb200_icp_destroy(icp_);
+  }
+
+  void setTransformationEstimation(const TransformationEstimationPtr& te) { transformation_estimation_ = te; }
+  void setCorrespondenceEstimation(const CorrespondenceEstimationPtr& ce) { correspondence_estimation_ = ce; }
+
+  // impl/registration.hpp:47-71
+  virtual void setInputSource(const PointCloudSourceConstPtr& cloud)
+  {
+    if (!cloud || cloud->empty()) {
+      std::fprintf(stderr, "[pcl::%s::setInputSource] Invalid or empty point cloud dataset given!\n", getClassName().c_str());
+      return;
+    }
+    source_cloud_updated_ = true;
+    PCLBase<PointSource>::setInputCloud(cloud);
+  }
+  PointCloudSourceConstPtr const getInputSource() { return this->input_; }
+  virtual void setInputTarget(const PointCloudTargetConstPtr& cloud)
+  {
+    if (!cloud || cloud->empty()) {
+      std::fprintf(stderr, "[pcl::%s::setInputTarget] Invalid or empty point cloud dataset given!\n", getClassName().c_str());
+      return;
+    }
+    target_ = cloud;
+    target_cloud_updated_ = true;
+  }
+  PointCloudTargetConstPtr const getInputTarget() { return target_; }
+
+  // registration.h:214-246
+  void setSearchMethodTarget(const KdTreePtr& tree, bool force_no_recompute = false)
+  {
+    tree_ = tree;
+    force_no_recompute_ = force_no_recompute;
+    target_cloud_updated_ = true;
+  }
+  KdTreePtr getSearchMethodTarget() const { return tree_; }
+  void setSearchMethodSource(const KdTreeReciprocalPtr& tree, bool force_no_recompute = false)
+  {
+    tree_reciprocal_ = tree;
+    force_no_recompute_reciprocal_ = force_no_recompute;
+    source_cloud_updated_ = true;
+  }
+  KdTreeReciprocalPtr getSearchMethodSource() const { return tree_reciprocal_; }
+
+  Matrix4 getFinalTransformation() { return final_transformation_; }
+  Matrix4 getLastIncrementalTransformation() { return transformation_; }
+  void setMaximumIterations(int n) { max_iterations_ = n; }
+  int getMaximumIterations() { return max_iterations_; }
+  void setRANSACIterations(int n) { ransac_iterations_ = n; }
+  void setRANSACOutlierRejectionThreshold(double t) { inlier_threshold_ = t; }
+  void setMaxCorrespondenceDistance(double d) { corr_dist_threshold_ = d; }
+  double getMaxCorrespondenceDistance() { return corr_dist_threshold_; }
+  void setTransformationEpsilon(double e) { transformation_epsilon_ = e; }
+  double getTransformationEpsilon() { return transformation_epsilon_; }
+  void setTransformationRotationEpsilon(double e) { transformation_rotation_epsilon_ = e; }
+  double getTransformationRotationEpsilon() { return transformation_rotation_epsilon_; }
+  void setEuclideanFitnessEpsilon(double e) { euclidean_fitness_epsilon_ = e; }
+  double getEuclideanFitnessEpsilon() { return euclidean_fitness_epsilon_; }
+  bool hasConverged() const { return converged_; }
+  const std::string& getClassName() const { return reg_name_; }
+
+  // impl/registration.hpp:134-168
+  double getFitnessScore(double max_range = std::numeric_limits<double>::max(), bool use_indices = false)
+  {
+    if (!tree_->deviceIndex() || !this->input_) return std::numeric_limits<double>::max();
+    double T[16], score = std::numeric_limits<double>::max();
+    toRowMajor(final_transformation_, T);
+    const bool sub = use_indices && this->indices_ && this->indices_->size() != this->input_->size();
+    int rc = pclb200_fitness_score(b200::Context::get(), tree_->deviceIndex(), this->input_->points.data(), this->input_->size(),
+                                   sizeof(PointSource), sub ? this->indices_->data() : nullptr, sub ? this->indices_->size() : 0,
+                                   this->input_->is_dense ? 1 : 0, T, sizeof(Scalar) == 8, max_range, &score);
+    if (rc != PCLB200_OK) std::fprintf(stderr, "[pcl::%s::getFitnessScore] %s\n", getClassName().c_str(), pclb200_last_error());
+    return score;
+  }
+
+  // impl/registration.hpp:172-221
+  void align(PointCloudSource& output) { align(output, Matrix4::Identity()); }
+  void align(PointCloudSource& output, const Matrix4& guess)
+  {
+    if (!initCompute()) return;
+    output.resize(this->indices_->size());
+    output.header = this->input_->header;
+    if (this->indices_->size() != this->input_->size()) {
+      output.width = static_cast<std::uint32_t>(this->indices_->size());
+      output.height = 1;
+    }
+    else {
+      output.width = this->input_->width;
+      output.height = this->input_->height;
+    }
+    output.is_dense = this->input_->is_dense;
+    converged_ = false;
+    final_transformation_ = transformation_ = previous_transformation_ = Matrix4::Identity();
+    computeTransformation(output, guess);
+    this->deinitCompute();
+  }
+
+protected:
+  // impl/registration.hpp:73-101
+  bool initCompute()
+  {
+    if (!target_) {
+      std::fprintf(stderr, "[pcl::registration::%s::compute] No input target dataset was given!\n", getClassName().c_str());
+      return false;
+    }
+    if (target_cloud_updated_ && !force_no_recompute_) {
+      tree_->setInputCloud(target_);
+      target_cloud_updated_ = false;
+      target_uploaded_ = false;
+    }
+    return PCLBase<PointSource>::initCompute();
+  }
+  virtual void computeTransformation(PointCloudSource& output, const Matrix4& guess) = 0;
+
+  static void toRowMajor(const Matrix4& M, double* t)
+  {
+    for (int r = 0; r < 4; ++r)
+      for (int c = 0; c < 4; ++c) t[4 * r + c] = static_cast<double>(M(r, c));
+  }
+  static void fromRowMajor(const double* t, Matrix4& M)
+  {
+    for (int r = 0; r < 4; ++r)
+      for (int c = 0; c < 4; ++c) M(r, c) = static_cast<Scalar>(t[4 * r + c]);
+  }
+
+  std::string reg_name_ = "Registration";
+  KdTreePtr tree_;
+  KdTreeReciprocalPtr tree_reciprocal_;
+  int nr_iterations_ = 0;
+  int max_iterations_ = 10;  // registration.h:566
+  int ransac_iterations_ = 0;
+  PointCloudTargetConstPtr target_;
+  Matrix4 final_transformation_, transformation_, previous_transformation_;
+  double transformation_epsilon_ = 0.0;           // :588
+  double transformation_rotation_epsilon_ = 0.0;
+  double euclidean_fitness_epsilon_;              // :116
+  double corr_dist_threshold_;                    // :117
+  double inlier_threshold_ = 0.05;
+  bool converged_ = false;
+  CorrespondenceEstimationPtr correspondence_estimation_;
+  TransformationEstimationPtr transformation_estimation_;
+  bool target_cloud_updated_ = true, source_cloud_updated_ = true;
+  bool force_no_recompute_ = false, force_no_recompute_reciprocal_ = false;
+  bool target_uploaded_ = false;
+  pclb200_icp* icp_ = nullptr;
+};
+
+template <typename PointSource, typename PointTarget, typename Scalar = float>
+class IterativeClosestPoint : public Registration<PointSource, PointTarget, Scalar> {
+public:
+  using Base = Registration<PointSource, PointTarget, Scalar>;
+  using Matrix4 = typename Base::Matrix4;
+  using Ptr = std::shared_ptr<IterativeClosestPoint>;
+  using PointCloudSource = typename Base::PointCloudSource;
+  using ConvergenceCriteria = pcl::registration::DefaultConvergenceCriteria<Scalar>;
+
+  IterativeClosestPoint() : convergence_criteria_(new ConvergenceCriteria)
+  {
+    this->reg_name_ = "IterativeClosestPoint";
+    this->transformation_estimation_.reset(new pcl::registration::TransformationEstimationSVD<PointSource, PointTarget, Scalar>());
+    this->correspondence_estimation_.reset(new pcl::registration::CorrespondenceEstimation<PointSource, PointTarget, Scalar>());
+  }
+  typename ConvergenceCriteria::Ptr getConvergeCriteria() { return convergence_criteria_; }
+  void setUseReciprocalCorrespondences(bool v) { use_reciprocal_correspondence_ = v; }
+  bool getUseReciprocalCorrespondences() const { return use_reciprocal_correspondence_; }
+  void setNumberOfThreads(unsigned int) {}
+  int getNumberOfIterations() const { return this->nr_iterations_; }
+  std::int64_t getNumberOfCorrespondences() const { return n_correspondences_; }
+
+protected:
+  virtual bool withNormalsTransform() const { return false; }
+
+  // impl/icp.hpp:113-268 — the whole do-while runs on the device; the host only evaluates the convergence criteria
+  void computeTransformation(PointCloudSource& output, const Matrix4& guess) override
+  {
+    pclb200_ctx* ctx = b200::Context::get();
+    pclb200_icp_params P;
+    pclb200_icp_default_params(&P);
+    P.max_iterations = this->max_iterations_;
+    P.use_reciprocal = use_reciprocal_correspondence_ ? 1 : 0;
+    P.estimator = this->transformation_estimation_->abiEstimator();
+    P.scalar_is_double = sizeof(Scalar) == 8;
+    P.with_normals_transform = withNormalsTransform() ? 1 : 0;
+    P.is_dense = this->input_->is_dense ? 1 : 0;
+    P.failure_after_max_iter = convergence_criteria_->failure_after_max_iter_ ? 1 : 0;
+    P.max_iterations_similar_transforms = convergence_criteria_->max_iterations_similar_transforms_;
+    P.max_correspondence_distance = this->corr_dist_threshold_;
+    P.transformation_epsilon = this->transformation_epsilon_;
+    P.transformation_rotation_epsilon = this->transformation_rotation_epsilon_;
+    P.euclidean_fitness_epsilon = this->euclidean_fitness_epsilon_;
+    P.mse_threshold_absolute = convergence_criteria_->mse_threshold_absolute_;
+    this->nr_iterations_ = 0;
+    this->converged_ = false;
+    this->final_transformation_ = guess;
+    auto fail = [&](const char* where) {
+      std::fprintf(stderr, "[pcl::%s::computeTransformation] %s: %s\n", this->getClassName().c_str(), where, pclb200_last_error());
+    };
+    if (!this->tree_->deviceIndex()) { fail("target index"); return; }
+    if (!this->icp_) {
+      if (pclb200_icp_create(ctx, &P, &this->icp_) != PCLB200_OK) { fail("icp_create"); return; }
+      this->target_uploaded_ = false;
+    }
+    else if (pclb200_icp_set_params(this->icp_, &P) != PCLB200_OK) { fail("icp_set_params"); return; }
+    if (!this->target_uploaded_ || uploaded_index_ != this->tree_->deviceIndex()) {
+      const void* tn = nullptr;
+      if (has_normal<PointTarget>::value && !this->target_->empty())
+        tn = reinterpret_cast<const unsigned char*>(this->target_->points.data()) + 16;  // normal_x of point 0
+      if (pclb200_icp_set_target(this->icp_, this->tree_->deviceIndex(), tn, sizeof(PointTarget)) != PCLB200_OK) { fail("icp_set_target"); return; }
+      this->target_uploaded_ = true;
+      uploaded_index_ = this->tree_->deviceIndex();
+    }
+    double g[16];
+    Base::toRowMajor(guess, g);
+    const void* sn = nullptr;
+    if (has_normal<PointSource>::value)
+      sn = reinterpret_cast<const unsigned char*>(this->input_->points.data()) + 16;
+    if (pclb200_icp_set_source(this->icp_, this->input_->points.data(), this->input_->size(), sizeof(PointSource), sn, sizeof(PointSource),
+                               this->abiIndices(), this->abiIndexCount(), guess == Matrix4::Identity() ? nullptr : g) != PCLB200_OK) {
+      fail("icp_set_source");
+      return;
+    }
+    pclb200_icp_stats st;
+    if (pclb200_icp_iterate(this->icp_, std::numeric_limits<int>::max(), &st) != PCLB200_OK) { fail("icp_iterate"); return; }
+    Base::fromRowMajor(st.final_transformation, this->final_transformation_);
+    Base::fromRowMajor(st.last_transformation, this->transformation_);
+    this->previous_transformation_ = this->transformation_;
+    this->nr_iterations_ = st.iterations;
+    this->converged_ = st.converged != 0;
+    n_correspondences_ = st.n_correspondences;
+    convergence_criteria_->state_ = static_cast<typename ConvergenceCriteria::ConvergenceState>(st.state);
+    if (st.state == PCLB200_CONV_NO_CORRESPONDENCES)
+      std::fprintf(stderr, "[pcl::%s::computeTransformation] Not enough correspondences found. Relax your threshold parameters.\n",
+                   this->getClassName().c_str());
+    // output = *input_, transformed by final_transformation_ (icp.hpp:265-267)
+    output = *this->input_;
+    void* on = has_normal<PointSource>::value ? reinterpret_cast<unsigned char*>(output.points.data()) + 16 : nullptr;
+    if (pclb200_icp_get_cloud(this->icp_, output.points.data(), sizeof(PointSource), on, sizeof(PointSource)) != PCLB200_OK)
+      fail("icp_get_cloud");
+  }
+
+  typename ConvergenceCriteria::Ptr convergence_criteria_;
+  bool use_reciprocal_correspondence_ = false;
+  std::int64_t n_correspondences_ = 0;
+  pclb200_index* uploaded_index_ = nullptr;
+};
+
+// icp.h:339-456 — point-to-plane variant (non-symmetric objective)
+template <typename PointSource, typename PointTarget, typename Scalar = float>
+class IterativeClosestPointWithNormals : public IterativeClosestPoint<PointSource, PointTarget, Scalar> {
+public:
+  using Ptr = std::shared_ptr<IterativeClosestPointWithNormals>;
+  IterativeClosestPointWithNormals()
+  {
+    this->reg_name_ = "IterativeClosestPointWithNormals";
+    setUseSymmetricObjective(false);
+  }
+  void setUseSymmetricObjective(bool symmetric)
+  {
+    if (symmetric)
+      std::fprintf(stderr, "[pcl::IterativeClosestPointWithNormals] the symmetric objective is outside the accelerated path "
+                           "(SURVEY.md §8f #2); using TransformationEstimationPointToPlaneLLS\n");
+    use_symmetric_objective_ = false;
+    this->transformation_estimation_.reset(new pcl::registration::TransformationEstimationPointToPlaneLLS<PointSource, PointTarget, Scalar>());
+  }
+  bool getUseSymmetricObjective() const { return use_symmetric_objective_; }
+  void setEnforceSameDirectionNormals(bool) {}
+
+protected:
+  bool withNormalsTransform() const override { return true; }  // impl/icp.hpp:312-318
+  bool use_symmetric_objective_ = false;
+};
+
+}  // namespace pcl

@@ -1,0 +1,202 @@
+// pcl/search/kdtree.h — pcl::search::KdTree<PointT> backed by the device LBVH.
+//
+// Mirrors the public surface of search/include/pcl/search/search.h:73-437 + kdtree.h:61-168 that the ICP path
+// uses: setInputCloud, nearestKSearch / radiusSearch (per point, per index, and the batch overloads of
+// impl/search.hpp:111-194), setSortedResults, setEpsilon.  Conventions preserved: output vectors
+// are RESIZED by the callee, return value = number of neighbours (0 on error), indices refer to the ORIGINAL cloud,
+// distances are squared, k is clamped to the number of valid points.  With real PCL headers this class derives
+// from pcl::search::KdTree<PointT> through its protected (name, sorted) constructor exactly like
+// pcl::search::KdTreeNanoflann does (search/include/pcl/search/kdtree_nanoflann.h:186,310-325) — INTEGRATION.md.
+#pragma once
+#include <cstdio>
+#include <memory>
+#include <string>
+#include <vector>
+
+#include "../b200/context.h"
+#include "../point_cloud.h"
+#include "../types.h"
+
+namespace pcl {
+namespace search {
+
+template <typename PointT>
+class KdTree {
+public:
+  using PointCloud = pcl::PointCloud<PointT>;
+  using PointCloudConstPtr = typename PointCloud::ConstPtr;
+  using Ptr = std::shared_ptr<KdTree<PointT>>;
+  using ConstPtr = std::shared_ptr<const KdTree<PointT>>;
+
+  explicit KdTree(bool sorted = true) : sorted_results_(sorted) {}
+  virtual ~KdTree() = default;
+
+  virtual const std::string& getName() const { return name_; }
+  virtual void setSortedResults(bool sorted) { sorted_results_ = sorted; }
+  virtual bool getSortedResults() const { return sorted_results_; }
+  void setEpsilon(float eps) { epsilon_ = eps; }  // accepted for API parity; the search is always exact (eps = 0)
+  float getEpsilon() const { return epsilon_; }
+
+  // KdTreeFLANN::setInputCloud — kdtree_flann.hpp:100-136: rebuilds from scratch, epsilon reset to 0
+  virtual bool setInputCloud(const PointCloudConstPtr& cloud, const IndicesConstPtr& indices = IndicesConstPtr())
+  {
+    input_ = cloud;
+    indices_ = indices;
+    epsilon_ = 0.f;
+    index_.reset();
+    if (!cloud || cloud->empty()) {
+      std::fprintf(stderr, "[pcl::search::KdTree::setInputCloud] Invalid input!\n");
+      return false;
+    }
+    pclb200_index* h = nullptr;
+    int rc = pclb200_index_build(b200::Context::get(), cloud->points.data(), cloud->size(), sizeof(PointT),
+                                 indices ? indices->data() : nullptr, indices ? indices->size() : 0, &h);
+    if (rc != PCLB200_OK) {
+      std::fprintf(stderr, "[pcl::search::KdTree::setInputCloud] %s\n", pclb200_last_error());
+      return false;
+    }
+    index_.reset(new b200::IndexHandle(h));
+    return true;
+  }
+  PointCloudConstPtr getInputCloud() const { return input_; }
+  IndicesConstPtr getIndices() const { return indices_; }
+  pclb200_index* deviceIndex() const { return index_ ? index_->h : nullptr; }
+
+  // ---- k-NN ---------------------------------------------------------------------------------------------
+  virtual int nearestKSearch(const PointT& point, int k, Indices& k_indices, std::vector<float>& k_sqr_distances) const
+  {
+    return knn(&point, 1, k, &k_indices, &k_sqr_distances);
+  }
+  int nearestKSearch(const PointCloud& cloud, index_t index, int k, Indices& ki, std::vector<float>& kd) const
+  {
+    return nearestKSearch(cloud[index], k, ki, kd);
+  }
+  int nearestKSearch(index_t index, int k, Indices& ki, std::vector<float>& kd) const
+  {
+    return nearestKSearch((*input_)[indices_ ? (*indices_)[index] : index], k, ki, kd);
+  }
+  template <typename PointTDiff>
+  int nearestKSearchT(const PointTDiff& p, int k, Indices& ki, std::vector<float>& kd) const
+  {
+    PointT q;
+    q.x = p.x; q.y = p.y; q.z = p.z;
+    return nearestKSearch(q, k, ki, kd);
+  }
+  // batch overload (search.h:216-219, impl/search.hpp:111-137): ONE device launch for the whole cloud
+  virtual void nearestKSearch(const PointCloud& cloud, const Indices& indices, int k, std::vector<Indices>& k_indices,
+                              std::vector<std::vector<float>>& k_sqr_distances) const
+  {
+    std::vector<PointT> q;
+    const PointT* qp = cloud.points.data();
+    std::size_t nq = cloud.size();
+    if (!indices.empty()) {
+      q.reserve(indices.size());
+      for (index_t i : indices) q.push_back(cloud[i]);
+      qp = q.data();
+      nq = q.size();
+    }
+    k_indices.assign(nq, Indices());
+    k_sqr_distances.assign(nq, std::vector<float>());
+    if (!index_ || k <= 0 || nq == 0) return;
+    std::vector<index_t> oi(nq * static_cast<std::size_t>(k));
+    std::vector<float> od(nq * static_cast<std::size_t>(k));
+    int keff = 0;
+    if (pclb200_knn(b200::Context::get(), index_->h, qp, nq, sizeof(PointT), k, oi.data(), od.data(), &keff) != PCLB200_OK) {
+      std::fprintf(stderr, "[pcl::search::KdTree::nearestKSearch] %s\n", pclb200_last_error());
+      return;
+    }
+    for (std::size_t i = 0; i < nq; ++i) {
+      k_indices[i].assign(oi.begin() + i * k, oi.begin() + i * k + keff);
+      k_sqr_distances[i].assign(od.begin() + i * k, od.begin() + i * k + keff);
+    }
+  }
+
+  // ---- radius ---------------------------------------------------------------------------------------------
+  virtual int radiusSearch(const PointT& point, double radius, Indices& k_indices, std::vector<float>& k_sqr_distances,
+                           unsigned int max_nn = 0) const
+  {
+    k_indices.clear();
+    k_sqr_distances.clear();
+    if (!index_) return 0;
+    std::int64_t offs[2] = {0, 0};
+    index_t* pi = nullptr;
+    float* pd = nullptr;
+    if (pclb200_radius(b200::Context::get(), index_->h, &point, 1, sizeof(PointT), radius, max_nn, sorted_results_ ? 1 : 0,
+                       offs, &pi, &pd) != PCLB200_OK) {
+      std::fprintf(stderr, "[pcl::search::KdTree::radiusSearch] %s\n", pclb200_last_error());
+      return 0;
+    }
+    k_indices.assign(pi, pi + offs[1]);
+    k_sqr_distances.assign(pd, pd + offs[1]);
+    pclb200_free(pi);
+    pclb200_free(pd);
+    return static_cast<int>(offs[1]);
+  }
+  int radiusSearch(index_t index, double radius, Indices& ki, std::vector<float>& kd, unsigned int max_nn = 0) const
+  {
+    return radiusSearch((*input_)[indices_ ? (*indices_)[index] : index], radius, ki, kd, max_nn);
+  }
+  // batch overload (search.h:349-355, impl/search.hpp:157-194)
+  virtual void radiusSearch(const PointCloud& cloud, const Indices& indices, double radius, std::vector<Indices>& k_indices,
+                            std::vector<std::vector<float>>& k_sqr_distances, unsigned int max_nn = 0) const
+  {
+    std::vector<PointT> q;
+    const PointT* qp = cloud.points.data();
+    std::size_t nq = cloud.size();
+    if (!indices.empty()) {
+      q.reserve(indices.size());
+      for (index_t i : indices) q.push_back(cloud[i]);
+      qp = q.data();
+      nq = q.size();
+    }
+    k_indices.assign(nq, Indices());
+    k_sqr_distances.assign(nq, std::vector<float>());
+    if (!index_ || nq == 0) return;
+    std::vector<std::int64_t> offs(nq + 1, 0);
+    index_t* pi = nullptr;
+    float* pd = nullptr;
+    if (pclb200_radius(b200::Context::get(), index_->h, qp, nq, sizeof(PointT), radius, max_nn, sorted_results_ ? 1 : 0,
+                       offs.data(), &pi, &pd) != PCLB200_OK) {
+      std::fprintf(stderr, "[pcl::search::KdTree::radiusSearch] %s\n", pclb200_last_error());
+      return;
+    }
+    for (std::size_t i = 0; i < nq; ++i) {
+      k_indices[i].assign(pi + offs[i], pi + offs[i + 1]);
+      k_sqr_distances[i].assign(pd + offs[i], pd + offs[i + 1]);
+    }
+    pclb200_free(pi);
+    pclb200_free(pd);
+  }
+
+protected:
+  int knn(const PointT* q, std::size_t nq, int k, Indices* ki, std::vector<float>* kd) const
+  {
+    ki->clear();
+    kd->clear();
+    if (!index_ || k <= 0) return 0;
+    std::vector<index_t> oi(nq * static_cast<std::size_t>(k));
+    std::vector<float> od(nq * static_cast<std::size_t>(k));
+    int keff = 0;
+    if (pclb200_knn(b200::Context::get(), index_->h, q, nq, sizeof(PointT), k, oi.data(), od.data(), &keff) != PCLB200_OK) {
+      std::fprintf(stderr, "[pcl::search::KdTree::nearestKSearch] %s\n", pclb200_last_error());
+      return 0;
+    }
+    ki->assign(oi.begin(), oi.begin() + keff);  // resized to the clamped k (kdtree_flann.hpp:241-245)
+    kd->assign(od.begin(), od.begin() + keff);
+    return keff;
+  }
+
+  PointCloudConstPtr input_;
+  IndicesConstPtr indices_;
+  std::shared_ptr<b200::IndexHandle> index_;
+  bool sorted_results_ = true;
+  float epsilon_ = 0.f;
+  std::string name_ = "KdTree";
+};
+
+}  // namespace search
+
+// pcl::KdTreeFLANN<PointT> call sites compile unchanged against the same backend
+template <typename PointT>
+using KdTreeFLANN = search::KdTree<PointT>;
+}  // namespace pcl

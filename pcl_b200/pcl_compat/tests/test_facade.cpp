@@ -1,0 +1,299 @@
+// test_facade.cpp — the reference's own registration / kdtree / filters / features tests, re-expressed against the
+// facade (same class names, same calls, same expectations).  Each block cites the PCL test it mirrors.
+// usage: test_facade <bun0.pcd> <bun4.pcd> <golden.txt>
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <fstream>
+#include <map>
+#include <string>
+#include <vector>
+
+#include <pcl/features/normal_3d.h>
+#include <pcl/filters/voxel_grid.h>
+#include <pcl/io/pcd_io.h>
+#include <pcl/kdtree/kdtree_flann.h>
+#include <pcl/point_cloud.h>
+#include <pcl/point_types.h>
+#include <pcl/registration/correspondence_estimation.h>
+#include <pcl/registration/icp.h>
+#include <pcl/registration/transformation_estimation_point_to_plane_lls.h>
+#include <pcl/registration/transformation_estimation_svd.h>
+
+using namespace pcl;
+
+static int g_fail = 0, g_checks = 0;
+#define EXPECT_TRUE(c) do { ++g_checks; if (!(c)) { ++g_fail; std::printf("FAIL %s:%d  %s\n", __FILE__, __LINE__, #c); } } while (0)
+#define EXPECT_EQ(a, b) do { ++g_checks; if (!((a) == (b))) { ++g_fail; std::printf("FAIL %s:%d  %s == %s  (%g vs %g)\n", __FILE__, __LINE__, #a, #b, (double)(a), (double)(b)); } } while (0)
+#define EXPECT_NEAR(a, b, tol) do { ++g_checks; if (!(std::fabs((double)(a) - (double)(b)) <= (tol))) { ++g_fail; std::printf("FAIL %s:%d  |%s - %s| <= %g  (%.9g vs %.9g)\n", __FILE__, __LINE__, #a, #b, (double)(tol), (double)(a), (double)(b)); } } while (0)
+#define EXPECT_LT(a, b) do { ++g_checks; if (!((a) < (b))) { ++g_fail; std::printf("FAIL %s:%d  %s < %s  (%g vs %g)\n", __FILE__, __LINE__, #a, #b, (double)(a), (double)(b)); } } while (0)
+
+static std::map<std::string, std::vector<double>> load_golden(const char* path)
+{
+  std::map<std::string, std::vector<double>> g;
+  std::ifstream in(path);
+  std::string name;
+  std::size_t n;
+  while (in >> name >> n) {
+    std::vector<double> v(n);
+    for (auto& x : v) in >> x;
+    g[name] = v;
+  }
+  return g;
+}
+
+int main(int argc, char** argv)
+{
+  if (argc < 4) { std::fprintf(stderr, "usage: %s bun0.pcd bun4.pcd golden.txt\n", argv[0]); return 2; }
+  PointCloud<PointXYZ> cloud_source, cloud_target, cloud_reg;
+  if (io::loadPCDFile(argv[1], cloud_source) || io::loadPCDFile(argv[2], cloud_target)) return 2;
+  auto G = load_golden(argv[3]);
+  EXPECT_EQ(cloud_source.size(), 397u);
+  EXPECT_EQ(cloud_target.size(), 361u);
+
+  {  // TEST (PCL, CorrespondenceEstimation) + Reciprocal — test/registration/test_registration_api.cpp:83-128
+    CorrespondencesPtr corr(new Correspondences);
+    registration::CorrespondenceEstimation<PointXYZ, PointXYZ> corr_est;
+    corr_est.setInputSource(cloud_source.makeShared());
+    corr_est.setInputTarget(cloud_target.makeShared());
+    corr_est.determineCorrespondences(*corr);
+    const auto& g = G["corr_original"];
+    EXPECT_EQ(corr->size(), g.size() / 2);
+    for (std::size_t i = 0; i < corr->size() && 2 * i + 1 < g.size(); ++i) {
+      EXPECT_EQ((*corr)[i].index_query, (int)i);
+      EXPECT_EQ((*corr)[i].index_match, (int)g[2 * i + 1]);
+    }
+    corr_est.determineReciprocalCorrespondences(*corr);
+    const auto& r = G["corr_reciprocal"];
+    EXPECT_EQ(corr->size(), r.size() / 2);
+    for (std::size_t i = 0; i < corr->size() && 2 * i + 1 < r.size(); ++i) {
+      EXPECT_EQ((*corr)[i].index_query, (int)r[2 * i]);
+      EXPECT_EQ((*corr)[i].index_match, (int)r[2 * i + 1]);
+    }
+  }
+
+  {  // TEST (PCL, KdTreeFLANN_setPointRepresentation), default representation — test/kdtree/test_kdtree.cpp:226-262
+    PointCloud<PointXYZ>::Ptr c(new PointCloud<PointXYZ>);
+    const float pts[10][3] = {{86.6f, 42.1f, 92.4f}, {63.1f, 18.4f, 22.3f}, {35.5f, 72.5f, 37.3f}, {99.7f, 37.0f, 8.7f},
+                              {22.4f, 84.1f, 64.0f}, {65.2f, 73.4f, 18.0f}, {60.4f, 57.1f, 4.5f},  {38.7f, 17.6f, 72.3f},
+                              {14.2f, 95.7f, 34.7f}, {2.5f, 26.5f, 66.0f}};
+    for (auto& p : pts) c->emplace_back(p[0], p[1], p[2]);
+    KdTreeFLANN<PointXYZ> kdtree;
+    kdtree.setInputCloud(c);
+    Indices ki(10);
+    std::vector<float> kd(10);
+    EXPECT_EQ(kdtree.nearestKSearch(PointXYZ(50.f, 50.f, 50.f), 10, ki, kd), 10);
+    const int gt_i[10] = {2, 7, 5, 1, 4, 6, 9, 0, 8, 3};
+    const float gt_d[10] = {877.8f, 1674.7f, 1802.6f, 1937.5f, 2120.6f, 2228.8f, 3064.5f, 3199.7f, 3604.2f, 4344.8f};
+    for (int i = 0; i < 10; ++i) { EXPECT_EQ(ki[i], gt_i[i]); EXPECT_NEAR(kd[i], gt_d[i], 0.1); }
+    EXPECT_EQ(kdtree.nearestKSearch(PointXYZ(50.f, 50.f, 50.f), 25, ki, kd), 10);  // k clamped (kdtree_flann.hpp:241-245)
+    EXPECT_EQ(ki.size(), 10u);
+    // radius search: brute-force ball, sorted (test/kdtree/test_kdtree.cpp:92-123 shape)
+    Indices ri;
+    std::vector<float> rd;
+    int nfound = kdtree.radiusSearch(PointXYZ(50.f, 50.f, 50.f), 45.0, ri, rd);
+    int expect = 0;
+    for (int i = 0; i < 10; ++i) expect += gt_d[i] < 45.0f * 45.0f ? 1 : 0;
+    EXPECT_EQ(nfound, expect);
+    for (int i = 0; i < nfound; ++i) EXPECT_EQ(ri[i], gt_i[i]);
+  }
+
+  Eigen::Matrix4f T_ref;
+  {
+    const auto& t = G["svd_Tref"];
+    for (int r = 0; r < 4; ++r) for (int c = 0; c < 4; ++c) T_ref(r, c) = (float)t[4 * r + c];
+  }
+  {  // TEST (PCL, TransformationEstimationSVD) — test_registration_api.cpp:383-423
+    PointCloud<PointXYZ> source = cloud_target, target = cloud_target;
+    for (auto& p : target) {  // pcl::transformPointCloud (SSE order, transforms.hpp:119-133)
+      float x = p.x, y = p.y, z = p.z;
+      p.x = T_ref(0, 0) * x + (T_ref(0, 1) * y + (T_ref(0, 2) * z + T_ref(0, 3)));
+      p.y = T_ref(1, 0) * x + (T_ref(1, 1) * y + (T_ref(1, 2) * z + T_ref(1, 3)));
+      p.z = T_ref(2, 0) * x + (T_ref(2, 1) * y + (T_ref(2, 2) * z + T_ref(2, 3)));
+    }
+    Eigen::Matrix4f T1, T2;
+    const registration::TransformationEstimationSVD<PointXYZ, PointXYZ> est;
+    est.estimateRigidTransformation(source, target, T1);
+    for (int r = 0; r < 3; ++r) for (int c = 0; c < 4; ++c) EXPECT_NEAR(T1(r, c), T_ref(r, c), 2e-6);
+    Correspondences corr;
+    for (std::size_t i = 0; i < source.size(); ++i) corr.emplace_back((index_t)i, (index_t)i, 0.f);
+    est.estimateRigidTransformation(source, target, corr, T2);
+    for (int r = 0; r < 4; ++r) for (int c = 0; c < 4; ++c) EXPECT_EQ(T1(r, c), T2(r, c));
+  }
+
+  {  // TEST (PCL, TransformationEstimationPointToPlaneLLS) — test_registration_api.cpp:469-518
+    registration::TransformationEstimationPointToPlaneLLS<PointNormal, PointNormal> est;
+    PointCloud<PointNormal>::Ptr src(new PointCloud<PointNormal>), tgt(new PointCloud<PointNormal>);
+    for (float x = -5.0f; x <= 5.0f; x += 0.5f)
+      for (float y = -5.0f; y <= 5.0f; y += 0.5f) {
+        PointNormal p;
+        p.x = x; p.y = y;
+        p.z = 0.1f * powf(x, 2.0f) + 0.2f * p.x * p.y - 0.3f * y + 1.0f;
+        float nx = -0.2f * p.x - 0.2f, ny = 0.6f * p.y - 0.2f, nz = 1.0f;
+        float m = std::sqrt(nx * nx + ny * ny + nz * nz);
+        p.normal_x = nx / m; p.normal_y = ny / m; p.normal_z = nz / m;
+        src->push_back(p);
+      }
+    Eigen::Matrix4f gt = Eigen::Matrix4f::Identity();
+    const float rows[3][4] = {{0.9938f, 0.0988f, 0.0517f, 0.1f}, {-0.0997f, 0.9949f, 0.0149f, -0.2f}, {-0.05f, -0.02f, 0.9986f, 0.3f}};
+    for (int r = 0; r < 3; ++r) for (int c = 0; c < 4; ++c) gt(r, c) = rows[r][c];
+    *tgt = *src;
+    for (auto& p : *tgt) {  // pcl::transformPointCloudWithNormals
+      float x = p.x, y = p.y, z = p.z, a = p.normal_x, b = p.normal_y, c = p.normal_z;
+      p.x = gt(0, 0) * x + (gt(0, 1) * y + (gt(0, 2) * z + gt(0, 3)));
+      p.y = gt(1, 0) * x + (gt(1, 1) * y + (gt(1, 2) * z + gt(1, 3)));
+      p.z = gt(2, 0) * x + (gt(2, 1) * y + (gt(2, 2) * z + gt(2, 3)));
+      p.normal_x = gt(0, 0) * a + (gt(0, 1) * b + gt(0, 2) * c);
+      p.normal_y = gt(1, 0) * a + (gt(1, 1) * b + gt(1, 2) * c);
+      p.normal_z = gt(2, 0) * a + (gt(2, 1) * b + gt(2, 2) * c);
+    }
+    Eigen::Matrix4f est_T;
+    est.estimateRigidTransformation(*src, *tgt, est_T);
+    for (int i = 0; i < 4; ++i) for (int j = 0; j < 4; ++j) EXPECT_NEAR(est_T(i, j), gt(i, j), 1e-2);
+  }
+
+  {  // TEST (PCL, IterativeClosestPoint) — test/registration/test_registration.cpp:236-270
+    IterativeClosestPoint<PointXYZ, PointXYZ> reg;
+    reg.setInputSource(cloud_source.makeShared());
+    reg.setInputTarget(cloud_target.makeShared());
+    reg.setMaximumIterations(50);
+    reg.setTransformationEpsilon(1e-8);
+    reg.setMaxCorrespondenceDistance(0.05);
+    reg.align(cloud_reg);
+    EXPECT_EQ(cloud_reg.size(), cloud_source.size());
+    Eigen::Matrix4f T = reg.getFinalTransformation();
+    const auto& g = G["icp_bun0_bun4"];
+    for (int r = 0; r < 3; ++r) for (int c = 0; c < 4; ++c) EXPECT_NEAR(T(r, c), g[4 * r + c], (r == 0 && c == 1) ? 1e-2 : 1e-3);
+    EXPECT_EQ(T(3, 0), 0); EXPECT_EQ(T(3, 1), 0); EXPECT_EQ(T(3, 2), 0); EXPECT_EQ(T(3, 3), 1);
+    EXPECT_TRUE(reg.hasConverged());
+    // the aligned cloud is the source under the final transform
+    const PointXYZ& s = cloud_source[7];
+    EXPECT_NEAR(cloud_reg[7].x, T(0, 0) * s.x + T(0, 1) * s.y + T(0, 2) * s.z + T(0, 3), 1e-6);
+  }
+
+  {  // TEST(PCL, ICP_translated) — test_registration.cpp:161-195
+    PointCloud<PointXYZ>::Ptr in(new PointCloud<PointXYZ>(cloud_source)), out(new PointCloud<PointXYZ>(cloud_source));
+    for (auto& p : *out) p.z += 0.2f;
+    IterativeClosestPoint<PointXYZ, PointXYZ> icp;
+    icp.setInputSource(in);
+    icp.setInputTarget(out);
+    icp.setMaximumIterations(50);
+    PointCloud<PointXYZ> Final;
+    icp.align(Final);
+    EXPECT_TRUE(icp.hasConverged());
+    EXPECT_LT(icp.getFitnessScore(), 1e-6);
+    EXPECT_NEAR(icp.getFinalTransformation()(0, 0), 1.0, 2e-3);
+    EXPECT_NEAR(icp.getFinalTransformation()(1, 1), 1.0, 2e-3);
+    EXPECT_NEAR(icp.getFinalTransformation()(2, 2), 1.0, 2e-3);
+    EXPECT_NEAR(icp.getFinalTransformation()(0, 3), 0.0, 2e-3);
+    EXPECT_NEAR(icp.getFinalTransformation()(1, 3), 0.0, 2e-3);
+    EXPECT_NEAR(icp.getFinalTransformation()(2, 3), 0.2, 2e-3);
+  }
+
+  {  // TEST(PCL, Registration_getFitnessScore_Indices) — test_registration.cpp:198-233
+    PointCloud<PointXYZ>::Ptr in(new PointCloud<PointXYZ>), out(new PointCloud<PointXYZ>);
+    in->push_back(PointXYZ(0, 0, 0)); in->push_back(PointXYZ(0, 1, 0)); in->push_back(PointXYZ(0, 0, 1)); in->push_back(PointXYZ(10, 0, 0));
+    out->push_back(PointXYZ(0, 0, 0)); out->push_back(PointXYZ(0, 1, 0)); out->push_back(PointXYZ(0, 0, 1)); out->push_back(PointXYZ(10, 0, 0.5));
+    IterativeClosestPoint<PointXYZ, PointXYZ> reg;
+    reg.setInputSource(in);
+    reg.setInputTarget(out);
+    IndicesPtr ind(new Indices{0, 1, 2});
+    reg.setIndices(ind);
+    PointCloud<PointXYZ> fin;
+    reg.align(fin);
+    EXPECT_NEAR(reg.getFitnessScore(1.0, false), 0.0625, 1e-4);
+    EXPECT_NEAR(reg.getFitnessScore(1.0, true), 0.0, 1e-4);
+  }
+
+  {  // TEST (PCL, IterativeClosestPointWithNormals) float and double — test_registration.cpp:272-323
+    PointCloud<PointNormal>::Ptr src(new PointCloud<PointNormal>), tgt(new PointCloud<PointNormal>);
+    NormalEstimation<PointXYZ, Normal> ne;
+    ne.setKSearch(10);
+    PointCloud<Normal> ns, nt;
+    ne.setInputCloud(cloud_source.makeShared());
+    ne.compute(ns);
+    ne.setInputCloud(cloud_target.makeShared());
+    ne.compute(nt);
+    EXPECT_EQ(ns.size(), cloud_source.size());
+    for (std::size_t i = 0; i < cloud_source.size(); ++i)
+      src->push_back(PointNormal(cloud_source[i].x, cloud_source[i].y, cloud_source[i].z, ns[i].normal_x, ns[i].normal_y, ns[i].normal_z, ns[i].curvature));
+    for (std::size_t i = 0; i < cloud_target.size(); ++i)
+      tgt->push_back(PointNormal(cloud_target[i].x, cloud_target[i].y, cloud_target[i].z, nt[i].normal_x, nt[i].normal_y, nt[i].normal_z, nt[i].curvature));
+    IterativeClosestPointWithNormals<PointNormal, PointNormal, float> regf;
+    regf.setInputSource(src);
+    regf.setInputTarget(tgt);
+    regf.setMaximumIterations(50);
+    regf.setTransformationEpsilon(1e-8);
+    regf.setMaxCorrespondenceDistance(0.05);
+    PointCloud<PointNormal> outf;
+    regf.align(outf);
+    EXPECT_EQ(outf.size(), src->size());
+    EXPECT_TRUE(regf.hasConverged());
+    EXPECT_LT(regf.getFitnessScore(), 0.001);
+    EXPECT_NEAR(outf[0].curvature, (*src)[0].curvature, 0.0);  // fields other than xyz/normal are carried through
+    IterativeClosestPointWithNormals<PointNormal, PointNormal, double> regd;
+    regd.setInputSource(src);
+    regd.setInputTarget(tgt);
+    regd.setMaximumIterations(50);
+    regd.setTransformationEpsilon(1e-8);
+    regd.setMaxCorrespondenceDistance(0.05);
+    PointCloud<PointNormal> outd;
+    regd.align(outd);
+    EXPECT_TRUE(regd.hasConverged());
+    EXPECT_LT(regd.getFitnessScore(), 0.001);
+    Eigen::Matrix4d Td = regd.getFinalTransformation();
+    Eigen::Matrix4f Tf = regf.getFinalTransformation();
+    for (int r = 0; r < 3; ++r) for (int c = 0; c < 4; ++c) EXPECT_NEAR(Td(r, c), Tf(r, c), 5e-3);
+    // cached target tree: setSearchMethodTarget(tree, force_no_recompute) — test_registration.cpp:513-600 shape
+    search::KdTree<PointNormal>::Ptr tree(new search::KdTree<PointNormal>);
+    tree->setInputCloud(tgt);
+    IterativeClosestPointWithNormals<PointNormal, PointNormal, float> regc;
+    regc.setInputSource(src);
+    regc.setInputTarget(tgt);
+    regc.setSearchMethodTarget(tree, true);
+    regc.setMaximumIterations(50);
+    regc.setTransformationEpsilon(1e-8);
+    regc.setMaxCorrespondenceDistance(0.05);
+    PointCloud<PointNormal> outc;
+    regc.align(outc);
+    EXPECT_LT(regc.getFitnessScore(), 0.005);
+    for (int r = 0; r < 3; ++r) for (int c = 0; c < 4; ++c) EXPECT_EQ(regc.getFinalTransformation()(r, c), Tf(r, c));
+  }
+
+  {  // TEST (VoxelGrid, Filters) — test/filters/test_filters.cpp:566-580
+    PointCloud<PointXYZ> output;
+    VoxelGrid<PointXYZ> grid;
+    grid.setLeafSize(0.02f, 0.02f, 0.02f);
+    grid.setInputCloud(cloud_source.makeShared());
+    grid.filter(output);
+    EXPECT_EQ(output.size(), 103u);
+    EXPECT_EQ(output.width, 103u);
+    EXPECT_EQ(output.height, 1u);
+    EXPECT_TRUE(output.is_dense);
+    grid.setLeafSize(1e-5f, 1e-5f, 1e-5f);  // overflow guard: input returned unfiltered (voxel_grid.hpp:620-629)
+    grid.filter(output);
+    EXPECT_EQ(output.size(), cloud_source.size());
+  }
+
+  {  // TEST (PCL, NormalEstimation) — test/features/test_normal_estimation.cpp:128-163: k = all points
+    NormalEstimation<PointXYZ, Normal> n;
+    PointCloud<Normal> normals;
+    search::KdTree<PointXYZ>::Ptr tree(new search::KdTree<PointXYZ>);
+    auto cptr = cloud_source.makeShared();
+    n.setInputCloud(cptr);
+    n.setSearchMethod(tree);
+    n.setKSearch(static_cast<int>(cloud_source.size()));
+    n.compute(normals);
+    EXPECT_EQ(normals.size(), cloud_source.size());
+    const auto& g = G["normal_bun0"];
+    for (const auto& p : normals.points) {
+      EXPECT_NEAR(p.normal_x, -g[0], 1e-4);
+      EXPECT_NEAR(p.normal_y, -g[1], 1e-4);
+      EXPECT_NEAR(p.normal_z, -g[2], 1e-4);
+      EXPECT_NEAR(p.curvature, g[4], 1e-4);
+    }
+  }
+
+  std::printf("%s: %d checks, %d failures\n", g_fail ? "FAILED" : "PASSED", g_checks, g_fail);
+  return g_fail ? 1 : 0;
+}
