@@ -37,6 +37,7 @@ sys.path.insert(0, ROOT)
 ICP_ITERS = 10
 MAX_CORR_DIST = 0.05
 N_DEFAULT = 10_000_000
+_JSON_OUT = sys.stdout
 METRIC = "icp_correspondences_per_sec"
 UNIT = "correspondences/s"
 
@@ -190,7 +191,8 @@ def run_reference(args):
             "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample_desc},
             "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
-    print(json.dumps(line), flush=True)
+    _JSON_OUT.write(json.dumps(line) + "\n")
+    _JSON_OUT.flush()
 
 
 # -----------------------------------------------------------------------------------------------------------------
@@ -342,12 +344,23 @@ def run_ours(args):
             "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline}
     if cpu:
         line["cpu_baseline"] = cpu
-    print(json.dumps(line), flush=True)
+    _JSON_OUT.write(json.dumps(line) + "\n")
+    _JSON_OUT.flush()
     if world > 1:
         dist.destroy_process_group()
 
 
+def _protect_stdout():
+    """Keep stdout for the ONE JSON line: libraries (NCCL prints its version banner) get stderr instead."""
+    sys.stdout.flush()
+    saved = os.dup(1)
+    os.dup2(2, 1)
+    return os.fdopen(saved, "w")
+
+
 def main():
+    global _JSON_OUT
+    _JSON_OUT = _protect_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=5)
