@@ -262,6 +262,7 @@ int pclb200_index_build(pclb200_ctx* ctx, const void* pts, size_t n, size_t stri
 {
   return guarded([&] {
     PCLB_REQUIRE(ctx && out, PCLB200_ERR_INVALID, "NULL argument");
+    std::lock_guard<std::recursive_mutex> lk(ctx->c.mu);
     PCLB_CUDA(cudaSetDevice(ctx->c.device));
     Index* idx = nullptr;
     {
@@ -312,6 +313,7 @@ int pclb200_knn(pclb200_ctx* ctx, const pclb200_index* h, const void* queries, s
     PCLB_REQUIRE(ctx && h && h->idx, PCLB200_ERR_INVALID, "NULL argument");
     PCLB_REQUIRE(k >= 0, PCLB200_ERR_INVALID, "k < 0");
     Ctx& c = ctx->c;
+    std::lock_guard<std::recursive_mutex> lk(c.mu);
     PCLB_CUDA(cudaSetDevice(c.device));
     const Index& idx = *h->idx;
     const int keff = (int)std::min<size_t>((size_t)k, idx.n_valid);  // kdtree_flann.hpp:241-242
@@ -357,6 +359,7 @@ int pclb200_radius(pclb200_ctx* ctx, const pclb200_index* h, const void* queries
   return guarded([&] {
     PCLB_REQUIRE(ctx && h && h->idx && out_offsets && out_idx && out_d2, PCLB200_ERR_INVALID, "NULL argument");
     Ctx& c = ctx->c;
+    std::lock_guard<std::recursive_mutex> lk(c.mu);
     PCLB_CUDA(cudaSetDevice(c.device));
     const Index& idx = *h->idx;
     *out_idx = nullptr;
@@ -455,6 +458,7 @@ int pclb200_correspondences(pclb200_ctx* ctx, const pclb200_index* idx_tgt, cons
 {
   return guarded([&] {
     PCLB_REQUIRE(ctx && idx_tgt && idx_tgt->idx && n_out, PCLB200_ERR_INVALID, "NULL argument");
+    std::lock_guard<std::recursive_mutex> lk(ctx->c.mu);
     PCLB_CUDA(cudaSetDevice(ctx->c.device));
     *n_out = correspondences(ctx->c, *idx_tgt->idx, idx_src ? idx_src->idx : nullptr, src, n, stride, src_indices, n_idx,
                              is_dense, max_dist, out);
@@ -467,6 +471,7 @@ int pclb200_estimate_svd(pclb200_ctx* ctx, const void* src, size_t stride_s, con
 {
   return guarded([&] {
     PCLB_REQUIRE(ctx && T_out, PCLB200_ERR_INVALID, "NULL argument");
+    std::lock_guard<std::recursive_mutex> lk(ctx->c.mu);
     PCLB_CUDA(cudaSetDevice(ctx->c.device));
     estimate_pairs(ctx->c, PCLB200_EST_SVD, src, stride_s, tgt, nullptr, stride_t, corr, n, scalar_is_double, T_out);
   });
@@ -478,6 +483,7 @@ int pclb200_estimate_point_to_plane_lls(pclb200_ctx* ctx, const void* src, size_
 {
   return guarded([&] {
     PCLB_REQUIRE(ctx && T_out, PCLB200_ERR_INVALID, "NULL argument");
+    std::lock_guard<std::recursive_mutex> lk(ctx->c.mu);
     PCLB_CUDA(cudaSetDevice(ctx->c.device));
     estimate_pairs(ctx->c, PCLB200_EST_POINT_TO_PLANE_LLS, src, stride_s, tgt, tgt_normals, stride_t, corr, n,
                    scalar_is_double, T_out);
@@ -504,6 +510,7 @@ int pclb200_icp_create(pclb200_ctx* ctx, const pclb200_icp_params* params, pclb2
 {
   return guarded([&] {
     PCLB_REQUIRE(ctx && out, PCLB200_ERR_INVALID, "NULL argument");
+    std::lock_guard<std::recursive_mutex> lk(ctx->c.mu);
     PCLB_CUDA(cudaSetDevice(ctx->c.device));
     pclb200_icp_params P;
     if (params)
@@ -537,6 +544,7 @@ int pclb200_icp_set_target(pclb200_icp* icp, const pclb200_index* idx_tgt, const
 {
   return guarded([&] {
     PCLB_REQUIRE(icp && idx_tgt && idx_tgt->idx, PCLB200_ERR_INVALID, "NULL argument");
+    std::lock_guard<std::recursive_mutex> lk(icp->ctx->c.mu);
     PCLB_CUDA(cudaSetDevice(icp->ctx->c.device));
     icp_set_target(*icp->s, idx_tgt->idx, tgt_normals, stride_n);
   });
@@ -547,6 +555,7 @@ int pclb200_icp_set_source(pclb200_icp* icp, const void* src, size_t n, size_t s
 {
   return guarded([&] {
     PCLB_REQUIRE(icp, PCLB200_ERR_INVALID, "NULL argument");
+    std::lock_guard<std::recursive_mutex> lk(icp->ctx->c.mu);
     PCLB_CUDA(cudaSetDevice(icp->ctx->c.device));
     icp_set_source(*icp->s, src, n, stride, src_normals, stride_n, src_indices, n_idx, guess);
   });
@@ -556,6 +565,7 @@ int pclb200_icp_iterate(pclb200_icp* icp, int max_steps, pclb200_icp_stats* stat
 {
   return guarded([&] {
     PCLB_REQUIRE(icp, PCLB200_ERR_INVALID, "NULL argument");
+    std::lock_guard<std::recursive_mutex> lk(icp->ctx->c.mu);
     PCLB_CUDA(cudaSetDevice(icp->ctx->c.device));
     icp_iterate(*icp->s, max_steps, stats);
   });
@@ -565,6 +575,7 @@ int pclb200_icp_get_cloud(pclb200_icp* icp, void* out_pts, size_t stride_out, vo
 {
   return guarded([&] {
     PCLB_REQUIRE(icp && out_pts, PCLB200_ERR_INVALID, "NULL argument");
+    std::lock_guard<std::recursive_mutex> lk(icp->ctx->c.mu);
     PCLB_CUDA(cudaSetDevice(icp->ctx->c.device));
     icp_get_cloud(*icp->s, out_pts, stride_out, out_normals, stride_n);
   });
@@ -577,6 +588,7 @@ int pclb200_icp_align(pclb200_ctx* ctx, const pclb200_icp_params* params, const 
 {
   return guarded([&] {
     PCLB_REQUIRE(ctx && params && idx_tgt && idx_tgt->idx, PCLB200_ERR_INVALID, "NULL argument");
+    std::lock_guard<std::recursive_mutex> lk(ctx->c.mu);
     PCLB_CUDA(cudaSetDevice(ctx->c.device));
     struct Guard {
       Icp* s;
@@ -602,6 +614,7 @@ int pclb200_fitness_score(pclb200_ctx* ctx, const pclb200_index* idx_tgt, const 
   (void)is_dense;
   return guarded([&] {
     PCLB_REQUIRE(ctx && idx_tgt && idx_tgt->idx && T && score, PCLB200_ERR_INVALID, "NULL argument");
+    std::lock_guard<std::recursive_mutex> lk(ctx->c.mu);
     PCLB_CUDA(cudaSetDevice(ctx->c.device));
     *score = fitness_score(ctx->c, *idx_tgt->idx, src, n, stride, src_indices, n_idx, T, scalar_is_double, max_range);
   });
@@ -617,6 +630,7 @@ int pclb200_normals_knn(pclb200_ctx* ctx, const pclb200_index* h, const void* pt
     PCLB_REQUIRE(ctx && h && h->idx && out && viewpoint, PCLB200_ERR_INVALID, "NULL argument");
     PCLB_REQUIRE(k > 0, PCLB200_ERR_INVALID, "k must be positive (feature.hpp:135-176)");
     Ctx& c = ctx->c;
+    std::lock_guard<std::recursive_mutex> lk(c.mu);
     PCLB_CUDA(cudaSetDevice(c.device));
     cudaStream_t st = c.stream;
     const size_t nq = indices ? n_idx : n;
@@ -659,6 +673,7 @@ int pclb200_voxelgrid(pclb200_ctx* ctx, const void* pts, size_t n, size_t stride
 {
   return guarded([&] {
     PCLB_REQUIRE(ctx && leaf && out_xyz1 && n_out, PCLB200_ERR_INVALID, "NULL argument");
+    std::lock_guard<std::recursive_mutex> lk(ctx->c.mu);
     PCLB_CUDA(cudaSetDevice(ctx->c.device));
     ProfScope ps(ctx->c, "voxelgrid");
     *n_out = voxelgrid(ctx->c, pts, n, stride, indices, n_idx, is_dense, leaf, min_points_per_voxel, out_xyz1);

@@ -6,6 +6,7 @@
 #include <cstdint>
 #include <cstdio>
 #include <cstring>
+#include <mutex>
 #include <stdexcept>
 #include <string>
 #include <vector>
@@ -47,6 +48,8 @@ struct ProfEvent {
 };
 
 struct Ctx {
+  std::recursive_mutex mu;           // every C-ABI entry point holds it: calls on one ctx serialise (PCL's query
+                                     // methods are const and may be called from several OpenMP threads)
   int device = 0;
   bool profiling = false;            // pclb200_profile_enable: CUDA-event pairs around the named kernels
   std::vector<ProfEvent> prof;
