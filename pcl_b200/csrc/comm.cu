@@ -7,6 +7,9 @@
 // has no link-time dependency and single-GPU users never touch it.
 #include <dlfcn.h>
 
+#include <cstdlib>
+#include <vector>
+
 #include "internal.cuh"
 
 namespace pclb200 {
@@ -23,6 +26,7 @@ struct NcclApi {
   int (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int) = nullptr;
   int (*CommDestroy)(ncclComm_t) = nullptr;
   int (*AllReduce)(const void*, void*, size_t, int, int, ncclComm_t, cudaStream_t) = nullptr;
+  int (*AllGather)(const void*, void*, size_t, int, ncclComm_t, cudaStream_t) = nullptr;
   const char* (*GetErrorString)(int) = nullptr;
 };
 
@@ -38,6 +42,7 @@ static NcclApi& nccl()
     api.CommInitRank = reinterpret_cast<decltype(api.CommInitRank)>(dlsym(api.h, "ncclCommInitRank"));
     api.CommDestroy = reinterpret_cast<decltype(api.CommDestroy)>(dlsym(api.h, "ncclCommDestroy"));
     api.AllReduce = reinterpret_cast<decltype(api.AllReduce)>(dlsym(api.h, "ncclAllReduce"));
+    api.AllGather = reinterpret_cast<decltype(api.AllGather)>(dlsym(api.h, "ncclAllGather"));
     api.GetErrorString = reinterpret_cast<decltype(api.GetErrorString)>(dlsym(api.h, "ncclGetErrorString"));
     PCLB_REQUIRE(api.GetUniqueId && api.CommInitRank && api.AllReduce, PCLB200_ERR_NCCL, "libnccl lacks expected symbols");
   }
@@ -52,10 +57,99 @@ static NcclApi& nccl()
                                         (nccl().GetErrorString ? nccl().GetErrorString(_r) : "nccl error")); \
   } while (0)
 
+enum { ncclUint8 = 1 };
+
 struct Comm {
   ncclComm_t comm = nullptr;
   int rank = 0, nranks = 1;
+  // fused peer-memory reduce (NVLink): one IPC-shared block per rank
+  unsigned char* local_block = nullptr;
+  void* peer_block[kMaxRanks] = {};
+  PeerView view;
+  bool peer_ok = false;
+  unsigned long long seq = 0;
 };
+
+static size_t peer_block_bytes() { return kMaxRanks * sizeof(unsigned long long) + 2ull * kMaxRanks * kAccum * sizeof(double); }
+
+// Maps every rank's exchange block into this process (CUDA IPC over NVLink / NVSwitch).  Any failure leaves
+// peer_ok = false and the per-iteration reduce falls back to ncclAllReduce.
+static void setup_peer_reduce(Ctx& c, Comm& cm)
+{
+  const char* mode = getenv("PCLB200_REDUCE");  // "nccl" forces the library collective (A/B measurements)
+  if (mode && mode[0] == 'n')
+    return;
+  if (cm.nranks > kMaxRanks || !nccl().AllGather)
+    return;
+  cudaStream_t st = c.stream;
+  if (cudaMalloc(reinterpret_cast<void**>(&cm.local_block), peer_block_bytes()) != cudaSuccess) {
+    cudaGetLastError();
+    return;
+  }
+  cudaMemsetAsync(cm.local_block, 0, peer_block_bytes(), st);
+  cudaIpcMemHandle_t mine;
+  bool ok = cudaIpcGetMemHandle(&mine, cm.local_block) == cudaSuccess;
+  // exchange handles (+ an "ok" byte) through the communicator we already have
+  struct Rec { cudaIpcMemHandle_t h; unsigned char ok; unsigned char pad[63]; };
+  static_assert(sizeof(Rec) == 128, "record size");
+  Rec r;
+  memset(&r, 0, sizeof(r));
+  r.h = mine;
+  r.ok = ok ? 1 : 0;
+  DevBuf<unsigned char> d_send, d_recv;
+  d_send.alloc(sizeof(Rec), st);
+  d_recv.alloc(sizeof(Rec) * cm.nranks, st);
+  PCLB_CUDA(cudaMemcpyAsync(d_send.p, &r, sizeof(Rec), cudaMemcpyHostToDevice, st));
+  PCLB_NCCL(nccl().AllGather(d_send.p, d_recv.p, sizeof(Rec), ncclUint8, cm.comm, st));
+  std::vector<Rec> all(cm.nranks);
+  PCLB_CUDA(cudaMemcpyAsync(all.data(), d_recv.p, sizeof(Rec) * cm.nranks, cudaMemcpyDeviceToHost, st));
+  PCLB_CUDA(cudaStreamSynchronize(st));
+  bool all_ok = true;
+  for (int p = 0; p < cm.nranks; ++p)
+    all_ok = all_ok && all[p].ok;
+  if (all_ok) {
+    for (int p = 0; p < cm.nranks && all_ok; ++p) {
+      if (p == cm.rank) {
+        cm.peer_block[p] = cm.local_block;
+        continue;
+      }
+      if (cudaIpcOpenMemHandle(&cm.peer_block[p], all[p].h, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) {
+        cudaGetLastError();
+        cm.peer_block[p] = nullptr;
+        all_ok = false;
+      }
+    }
+  }
+  // every rank must take the same decision: agree through one more tiny all-reduce
+  DevBuf<double> d_flag;
+  d_flag.alloc(1, st);
+  double hv = all_ok ? 0.0 : 1.0;
+  PCLB_CUDA(cudaMemcpyAsync(d_flag.p, &hv, sizeof(double), cudaMemcpyHostToDevice, st));
+  PCLB_NCCL(nccl().AllReduce(d_flag.p, d_flag.p, 1, ncclFloat64, ncclSum, cm.comm, st));
+  PCLB_CUDA(cudaMemcpyAsync(&hv, d_flag.p, sizeof(double), cudaMemcpyDeviceToHost, st));
+  PCLB_CUDA(cudaStreamSynchronize(st));
+  if (hv != 0.0)
+    return;
+  cm.view.rank = cm.rank;
+  cm.view.nranks = cm.nranks;
+  for (int p = 0; p < cm.nranks; ++p) {
+    unsigned char* b = static_cast<unsigned char*>(cm.peer_block[p]);
+    cm.view.flags[p] = reinterpret_cast<unsigned long long*>(b);
+    cm.view.slots[p] = reinterpret_cast<double*>(b + kMaxRanks * sizeof(unsigned long long));
+  }
+  cm.peer_ok = true;
+}
+
+static void teardown_peer_reduce(Comm& cm)
+{
+  for (int p = 0; p < cm.nranks && p < kMaxRanks; ++p)
+    if (p != cm.rank && cm.peer_block[p])
+      cudaIpcCloseMemHandle(cm.peer_block[p]);
+  if (cm.local_block)
+    cudaFree(cm.local_block);
+  cm.local_block = nullptr;
+  cm.peer_ok = false;
+}
 
 void comm_unique_id(void* out128)
 {
@@ -68,6 +162,7 @@ void comm_init(Ctx& c, int rank, int nranks, const void* unique_id)
 {
   PCLB_REQUIRE(nranks >= 1 && rank >= 0 && rank < nranks, PCLB200_ERR_INVALID, "bad rank / nranks");
   if (c.comm) {
+    teardown_peer_reduce(*c.comm);
     if (c.comm->comm)
       nccl().CommDestroy(c.comm->comm);
     delete c.comm;
@@ -87,11 +182,18 @@ void comm_init(Ctx& c, int rank, int nranks, const void* unique_id)
     throw Error(PCLB200_ERR_NCCL, "ncclCommInitRank failed");
   }
   c.comm = cm;
+  try {
+    setup_peer_reduce(c, *cm);
+  }
+  catch (const Error&) {
+    cm->peer_ok = false;  // keep the NCCL path
+  }
 }
 
 void comm_destroy(Ctx& c)
 {
   if (c.comm) {
+    teardown_peer_reduce(*c.comm);
     if (c.comm->comm)
       nccl().CommDestroy(c.comm->comm);
     delete c.comm;
@@ -100,6 +202,16 @@ void comm_destroy(Ctx& c)
 }
 
 bool comm_active(const Ctx& c) { return c.comm && c.comm->nranks > 1; }
+
+// view + next sequence number for a fused in-kernel exchange; returns false when the NCCL path must be used
+bool comm_peer_view(Ctx& c, PeerView* view, unsigned long long* seq)
+{
+  if (!comm_active(c) || !c.comm->peer_ok)
+    return false;
+  *view = c.comm->view;
+  *seq = ++c.comm->seq;
+  return true;
+}
 
 void comm_allreduce_sum(Ctx& c, double* d_buf, int count)
 {

@@ -28,6 +28,7 @@ namespace pclb200 {
 
 void comm_allreduce_sum(Ctx& c, double* d_buf, int count);  // comm.cu (no-op without a communicator)
 bool comm_active(const Ctx& c);
+bool comm_peer_view(Ctx& c, PeerView* view, unsigned long long* seq);
 
 static inline unsigned grid_for(size_t n, int block) { return (unsigned)((n + block - 1) / block); }
 
@@ -115,6 +116,9 @@ struct IterArgs {
   const float4* s_pts;
   int s_root;
   const int32_t* src_orig;    // slot -> original source index (nullable = identity)
+  // fused cross-GPU reduce (optional): peer-mapped exchange buffers + this iteration's sequence number
+  PeerView peer;
+  unsigned long long seq;
 };
 
 template <int NACC>
@@ -158,6 +162,53 @@ __device__ __forceinline__ void block_reduce_and_publish(double* acc, const Iter
       a.accum[threadIdx.x] = 0.0;
     if (threadIdx.x == 0)
       *a.counter = 0;
+    if (a.peer.nranks > 1) {
+      // ---- fused all-reduce over NVLink peer memory (replaces a separate ncclAllReduce launch) ----
+      // 1. store this rank's totals into EVERY rank's slots[seq&1][rank][.]   (remote stores)
+      // 2. fence, then publish the sequence number into every rank's flags[rank]
+      // 3. wait until all peers have published >= seq in OUR flags, then fold the slots in rank order:
+      //    every rank adds the same numbers in the same order => bitwise identical sums everywhere.
+      // Two slot sets alternate by sequence parity: a peer can be at most one iteration ahead (it needs
+      // our flag for seq+1 before it can finish seq+1), so it never overwrites what we are still reading.
+      __syncthreads();
+      const int buf = (int)(a.seq & 1ull);
+      if (threadIdx.x < kAccum) {
+        const double v = a.accum[threadIdx.x];
+        for (int p = 0; p < a.peer.nranks; ++p)
+          a.peer.slots[p][((size_t)buf * kMaxRanks + a.peer.rank) * kAccum + threadIdx.x] = v;
+      }
+      __threadfence_system();
+      __syncthreads();
+      if (threadIdx.x < a.peer.nranks)
+        *reinterpret_cast<volatile unsigned long long*>(&a.peer.flags[threadIdx.x][a.peer.rank]) = a.seq;
+      __shared__ int timed_out;
+      if (threadIdx.x == 0)
+        timed_out = 0;
+      __syncthreads();
+      if (threadIdx.x < a.peer.nranks) {
+        const volatile unsigned long long* f = a.peer.flags[a.peer.rank] + threadIdx.x;
+        const long long t0 = clock64();
+        while (*f < a.seq) {
+          if (clock64() - t0 > 20000000000LL) {  // ~10 s: a peer died — fail loudly instead of hanging the GPU
+            timed_out = 1;
+            break;
+          }
+        }
+      }
+      __threadfence_system();
+      __syncthreads();
+      if (timed_out) {
+        if (threadIdx.x == 0)
+          atomicExch(a.d_error, 2);
+      }
+      else if (threadIdx.x < kAccum) {
+        double v = 0.0;
+        const volatile double* mine = a.peer.slots[a.peer.rank] + (size_t)buf * kMaxRanks * kAccum;
+        for (int r = 0; r < a.peer.nranks; ++r)
+          v += mine[(size_t)r * kAccum + threadIdx.x];
+        a.accum[threadIdx.x] = v;
+      }
+    }
   }
 }
 
@@ -1104,6 +1155,9 @@ void icp_iterate(Icp& s, int max_steps, pclb200_icp_stats* stats)
     a.accum = s.red.accum.p;
     a.d_error = c.d_error;
     a.src_orig = s.src_orig.p;
+    a.peer.nranks = 0;
+    a.seq = 0;
+    const bool fused_reduce = comm_peer_view(c, &a.peer, &a.seq);
     const unsigned grid = persistent_grid(c, s.n_q, 256, 8);
     std::unique_ptr<Index> src_index;
     if (s.P.use_reciprocal) {
@@ -1149,7 +1203,7 @@ void icp_iterate(Icp& s, int max_steps, pclb200_icp_stats* stats)
       ++c.launches;
     }
     PCLB_CUDA(cudaGetLastError());
-    {
+    if (!fused_reduce) {
       ProfScope ps(c, "allreduce");
       comm_allreduce_sum(c, s.red.accum.p, kAccum);
     }
@@ -1165,6 +1219,8 @@ void icp_iterate(Icp& s, int max_steps, pclb200_icp_stats* stats)
     PCLB_CUDA(cudaStreamSynchronize(st));
     if (h_err) {
       PCLB_CUDA(cudaMemsetAsync(c.d_error, 0, sizeof(int), st));
+      if (h_err == 2)
+        throw Error(PCLB200_ERR_NCCL, "fused cross-GPU reduce timed out waiting for a peer rank");
       throw Error(PCLB200_ERR_INTERNAL, "LBVH traversal stack overflow (tree deeper than the per-query stack)");
     }
     ++steps;

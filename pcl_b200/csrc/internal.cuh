@@ -197,4 +197,16 @@ void launch_radius_fill(Ctx& c, const Index& idx, const float4* d_q, size_t nq, 
 // accumulators of one ICP iteration (all fp64), see icp.cu
 constexpr int kAccum = 40;
 
+// Cross-GPU exchange buffers of the fused reduce (comm.cu): every rank owns one block
+//   flags[kMaxRanks] (u64, latest sequence number published by each peer) | slots[2][kMaxRanks][kAccum] (fp64)
+// mapped into every peer through CUDA IPC, so a kernel on rank r can store its partial sums straight into
+// rank p's slots[.][r][.] over NVLink.
+constexpr int kMaxRanks = 8;
+struct PeerView {
+  int rank = 0;
+  int nranks = 0;                       // 0 / 1 = no exchange
+  unsigned long long* flags[kMaxRanks]; // flags[p] = base of rank p's flag array (peer-mapped, [rank] = self)
+  double* slots[kMaxRanks];             // slots[p] = base of rank p's slot array
+};
+
 }  // namespace pclb200

@@ -15,6 +15,7 @@
 
 #include <algorithm>
 #include <cmath>
+#include <cstdlib>
 #include <memory>
 
 #include "internal.cuh"
@@ -170,7 +171,42 @@ __device__ __forceinline__ unsigned long long morton63(float x, float y, float z
          expand21((unsigned long long)fx);
 }
 
+// 63-bit Hilbert index of the same 21-bit cell coordinates (Skilling's transpose algorithm).  Used to ORDER QUERIES
+// only: a run of 32 consecutive points along the Hilbert curve is always a compact cluster (the Z-order curve jumps),
+// so the packet walk of a warp touches fewer nodes.  The tree itself needs Morton prefixes and stays Morton-ordered.
+__device__ __forceinline__ unsigned long long hilbert63(float x, float y, float z, float lx, float ly, float lz,
+                                                        float scale)
+{
+  unsigned X[3];
+  X[0] = (unsigned)fminf(fmaxf((x - lx) * scale, 0.f), 2097151.f);
+  X[1] = (unsigned)fminf(fmaxf((y - ly) * scale, 0.f), 2097151.f);
+  X[2] = (unsigned)fminf(fmaxf((z - lz) * scale, 0.f), 2097151.f);
+  const unsigned M = 1u << 20;
+  for (unsigned Q = M; Q > 1; Q >>= 1) {
+    const unsigned P = Q - 1;
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+      if (X[i] & Q)
+        X[0] ^= P;
+      else {
+        const unsigned t = (X[0] ^ X[i]) & P;
+        X[0] ^= t;
+        X[i] ^= t;
+      }
+    }
+  }
+  X[1] ^= X[0];
+  X[2] ^= X[1];
+  unsigned t = 0;
+  for (unsigned Q = M; Q > 1; Q >>= 1)
+    if (X[2] & Q)
+      t ^= Q - 1;
+  X[0] ^= t; X[1] ^= t; X[2] ^= t;
+  return (expand21(X[0]) << 2) | (expand21(X[1]) << 1) | expand21(X[2]);
+}
+
 // value = record slot i; for invalid (non-finite) points key = ~0 so they sort last
+template <bool HILBERT>
 __global__ void k_morton(const float4* __restrict__ p, size_t n, float lx, float ly, float lz, float scale,
                          unsigned long long* __restrict__ keys, int32_t* __restrict__ vals)
 {
@@ -179,7 +215,8 @@ __global__ void k_morton(const float4* __restrict__ p, size_t n, float lx, float
     return;
   float4 v = __ldg(p + i);
   bool ok = isfinite(v.x) && isfinite(v.y) && isfinite(v.z);
-  keys[i] = ok ? morton63(v.x, v.y, v.z, lx, ly, lz, scale) : ~0ULL;
+  keys[i] = !ok ? ~0ULL
+                : (HILBERT ? hilbert63(v.x, v.y, v.z, lx, ly, lz, scale) : morton63(v.x, v.y, v.z, lx, ly, lz, scale));
   vals[i] = (int32_t)i;
 }
 
@@ -381,8 +418,14 @@ static void morton_sort(Ctx& c, const float4* d_pts, size_t n, const Index* fram
   vals_in.alloc(n, s);
   out.keys.alloc(n, s);
   out.vals.alloc(n, s);
-  k_morton<<<grid_for(n, 256), 256, 0, s>>>(d_pts, n, out.lo[0], out.lo[1], out.lo[2], out.scale, keys_in.p,
-                                           vals_in.p);
+  static const char* order_env = getenv("PCLB200_QUERY_ORDER");  // experiments: "morton" restores Z-order queries
+  const bool hilbert = frame != nullptr && !(order_env && order_env[0] == 'm');
+  if (hilbert)
+    k_morton<true><<<grid_for(n, 256), 256, 0, s>>>(d_pts, n, out.lo[0], out.lo[1], out.lo[2], out.scale, keys_in.p,
+                                                   vals_in.p);
+  else
+    k_morton<false><<<grid_for(n, 256), 256, 0, s>>>(d_pts, n, out.lo[0], out.lo[1], out.lo[2], out.scale, keys_in.p,
+                                                    vals_in.p);
   ++c.launches;
   size_t tmp_bytes = 0;
   PCLB_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, keys_in.p, out.keys.p, vals_in.p, out.vals.p,
