@@ -274,6 +274,7 @@ def run_ours(args):
     ms_v, tot_v, launches, clocks = timed(src_dev, out_dev, args.steps, args.warmup, not args.no_clocks)
     iter_ms, iter_n = ctx.profile_get("icp_search")
     accum_ms, _ = ctx.profile_get("icp_accum")
+    allreduce_ms, _ = ctx.profile_get("allreduce")
     sort_ms, _ = ctx.profile_get("query_sort")
     solve_ms, _ = ctx.profile_get("solve")
     out_ms, _ = ctx.profile_get("transform_out")
@@ -336,7 +337,7 @@ def run_ours(args):
                        "l2_policy": "inputs larger than L2 (target 160 MB + nodes 80 MB + normals 160 MB + source 160 MB)",
                        "parallelism": f"source sharded x{world}, target replicated, 40-double all-reduce/iteration"},
             "ms_per_iter": ms_v / args.steps / ICP_ITERS,
-            "breakdown_ms_per_step": {"icp_search_kernel": iter_ms / args.steps, "icp_accum_kernel": accum_ms / args.steps, "query_sort": sort_ms / args.steps,
+            "breakdown_ms_per_step": {"icp_search_kernel": iter_ms / args.steps, "icp_accum_kernel": accum_ms / args.steps, "nccl_allreduce": allreduce_ms / args.steps, "query_sort": sort_ms / args.steps,
                                       "solve": solve_ms / args.steps, "transform_out": out_ms / args.steps},
             "setup_ms": {"index_build": build_ms, "normals_k16": normals_ms},
             "e2e": {"value": e2e, "unit": UNIT, "ms_per_step": ms_e / args.steps,

@@ -127,6 +127,7 @@ struct pclb200_index {
 struct pclb200_icp {
   Icp* s;
   pclb200_ctx* ctx;
+  int device;
 };
 
 extern "C" {
@@ -153,10 +154,6 @@ int pclb200_create(int device, pclb200_ctx** out)
     PCLB_CUDA(cudaGetDeviceProperties(&prop, device));
     c.sm_count = prop.multiProcessorCount;
     PCLB_CUDA(cudaStreamCreateWithFlags(&c.stream, cudaStreamNonBlocking));
-    cudaMemPool_t pool;
-    PCLB_CUDA(cudaDeviceGetDefaultMemPool(&pool, device));
-    uint64_t thr = UINT64_MAX;  // keep freed blocks cached: the ICP loop reuses the same sizes every call
-    PCLB_CUDA(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr));
     c.pinned_bytes = 4096;
     PCLB_CUDA(cudaMallocHost(&c.pinned, c.pinned_bytes));
     PCLB_CUDA(cudaMalloc(reinterpret_cast<void**>(&c.d_error), sizeof(int)));
@@ -184,8 +181,10 @@ int pclb200_destroy(pclb200_ctx* ctx)
       cudaFreeHost(c.pinned);
     if (c.d_error)
       cudaFree(c.d_error);
-    if (c.stream)
+    if (c.stream) {
+      cached_release_all(c.stream);  // every DevBuf of this ctx is gone or orphaned by now
       cudaStreamDestroy(c.stream);
+    }
     delete ctx;
   });
 }
@@ -279,7 +278,7 @@ int pclb200_index_destroy(pclb200_index* h)
     if (!h)
       return;
     if (h->idx) {
-      cudaSetDevice(h->idx->ctx->device);
+      cudaSetDevice(h->idx->device);
       delete h->idx;
     }
     delete h;
@@ -517,7 +516,7 @@ int pclb200_icp_create(pclb200_ctx* ctx, const pclb200_icp_params* params, pclb2
       P = *params;
     else
       pclb200_icp_default_params(&P);
-    *out = new pclb200_icp{icp_create(ctx->c, P), ctx};
+    *out = new pclb200_icp{icp_create(ctx->c, P), ctx, ctx->c.device};
   });
 }
 
@@ -526,7 +525,7 @@ int pclb200_icp_destroy(pclb200_icp* icp)
   return guarded([&] {
     if (!icp)
       return;
-    cudaSetDevice(icp->ctx->c.device);
+    cudaSetDevice(icp->device);
     icp_destroy(icp->s);
     delete icp;
   });

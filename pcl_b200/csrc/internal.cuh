@@ -84,6 +84,15 @@ struct ProfScope {
   }
 };
 
+// Device memory comes from a small per-stream block cache (alloc.cu): after the first align() every request is
+// served from blocks the previous call returned, so the steady-state loop never enters the driver's allocator
+// (cudaMallocAsync pool growth showed up as multi-millisecond host stalls between launches on shared boxes).
+// Re-use is safe without events because a ctx issues all its work on ONE stream: a block handed out again is
+// only touched by work enqueued after the work that used it before.
+void* cached_alloc(cudaStream_t s, size_t bytes);
+void cached_free(cudaStream_t s, void* p);
+void cached_release_all(cudaStream_t s);
+
 // stream-ordered device buffer
 template <typename T>
 struct DevBuf {
@@ -109,12 +118,12 @@ struct DevBuf {
     s = stream;
     n = count;
     if (count)
-      PCLB_CUDA(cudaMallocAsync(reinterpret_cast<void**>(&p), count * sizeof(T), stream));
+      p = static_cast<T*>(cached_alloc(stream, count * sizeof(T)));
   }
   void release()
   {
     if (p)
-      cudaFreeAsync(p, s);
+      cached_free(s, p);
     p = nullptr;
     n = 0;
   }
@@ -155,6 +164,7 @@ constexpr int kSentinelIndex = 0x7fffffff;
 
 struct Index {
   Ctx* ctx = nullptr;
+  int device = 0;
   size_t n_cloud = 0;   // records in the caller's cloud (index space of results)
   size_t n_valid = 0;   // finite points indexed
   int n_leaves = 0;

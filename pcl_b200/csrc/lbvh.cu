@@ -448,6 +448,7 @@ static Index* build_from_dense(Ctx& c, const float4* d_pts, size_t n, const int3
   PCLB_REQUIRE(sc.n_valid > 0, PCLB200_ERR_EMPTY, "no finite point in the cloud (kdtree_flann.hpp:124-129)");
   std::unique_ptr<Index> idx(new Index());
   idx->ctx = &c;
+  idx->device = c.device;
   idx->n_cloud = n_cloud;
   idx->n_valid = sc.n_valid;
   for (int d = 0; d < 3; ++d) {
