@@ -1,0 +1,173 @@
+"""BASELINE.json's other configurations as parity cases (configs[1], [3], [4] scaled so the oracle finishes in
+seconds) and full-size (10 M-point) size-independent properties.  Needs a B200: run with -m gpu."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def gpu():
+    import pcl_b200
+    pcl_b200.lib()
+    ctx = pcl_b200.Context(0)
+    yield pcl_b200, ctx
+    ctx.close()
+
+
+def _rot(axis, deg):
+    a = np.deg2rad(deg)
+    ax = np.asarray(axis, np.float64) / np.linalg.norm(axis)
+    K = np.array([[0, -ax[2], ax[1]], [ax[2], 0, -ax[0]], [-ax[1], ax[0], 0]])
+    return np.eye(3) + np.sin(a) * K + (1 - np.cos(a)) * K @ K
+
+
+def test_config2_voxelgrid_then_icp(gpu, orc):
+    """configs[1]: uniform cube + 5 deg rotation about (1,1,1), VoxelGrid leaf 0.01 on both clouds, ICP SVD k=1
+    (SURVEY.md §8d row 2), at 300 k points so the CPU oracle stays in seconds."""
+    P, ctx = gpu
+    n = 300_000
+    tgt = np.random.default_rng(42).random((n, 3), dtype=np.float32)
+    R = _rot([1, 1, 1], 5.0)
+    src = (tgt.astype(np.float64) @ R.T + [0.01, -0.02, 0.015] +
+           np.random.default_rng(43).normal(0, 0.001, (n, 3))).astype(np.float32)
+    leaf = 0.01
+    vt, vs = ctx.voxelgrid(P.xyz1(tgt), leaf), ctx.voxelgrid(P.xyz1(src), leaf)
+    ot, os_ = orc.voxelgrid(orc.to_xyz1(tgt), [leaf] * 3), orc.voxelgrid(orc.to_xyz1(src), [leaf] * 3)
+    assert np.array_equal(vt, ot) and np.array_equal(vs, os_)           # downsample front-end: bit-exact
+    cells = 101 ** 3                                                      # occupied cells of a Poisson cloud
+    assert abs(vt.shape[0] - cells * (1 - np.exp(-n / cells))) < 0.02 * n  # (~63 % of n survive at n = 1 M)
+    kw = dict(max_iterations=50, transformation_epsilon=1e-8, max_correspondence_distance=0.05)
+    r = P.icp_align(ctx, vs, P.Index(ctx, vt), **kw)
+    o64 = orc.icp_align(os_, ot, scalar_is_double=True, nthreads=8, **kw)
+    assert r["converged"] and o64["converged"]
+    assert np.linalg.norm(r["final"] - o64["final"]) < 1e-5, np.linalg.norm(r["final"] - o64["final"])
+    # and it is the inverse of the motion that was applied (source = R*target + t  =>  final ~ [R^T | -R^T t])
+    assert np.allclose(r["final"][:3, :3], R.T, atol=2e-3)
+
+
+def test_config4_radius_gate_and_maxnn(gpu, orc):
+    """configs[3]: 'radiusSearch r = 0.05 correspondence estimation' == 1-NN with the 0.05 gate, plus a true
+    radiusSearch(r = 0.05, max_nn = 32), on a scaled-down planes-and-noise scene."""
+    P, ctx = gpu
+    rng = np.random.default_rng(11)
+    n = 200_000
+    planes = []
+    for _ in range(10):
+        o, u, v = rng.random(3) * 20, rng.normal(size=3), rng.normal(size=3)
+        u /= np.linalg.norm(u)
+        v -= u * (u @ v)
+        v /= np.linalg.norm(v)
+        ab = rng.random((n // 10, 2)) * 6
+        planes.append(o + ab[:, :1] * u + ab[:, 1:] * v)
+    tgt = (np.concatenate(planes) + rng.normal(0, 0.005, (n, 3))).astype(np.float32)
+    R = _rot(rng.normal(size=3), 1.0)
+    src = (tgt.astype(np.float64) @ R.T + 0.02 * np.array([0.6, 0.0, 0.8])).astype(np.float32)
+    T, S = P.xyz1(tgt), P.xyz1(src)
+    gi, oi = P.Index(ctx, T), orc.Index(T)
+    g = gi.correspondences(S, max_distance=0.05)
+    o = oi.correspondences(S, max_distance=0.05, nthreads=8)
+    assert np.array_equal(g, o) and 0 < g.size < n
+    q = S[::50]
+    go, gidx, gd = gi.radius(q, 0.05, max_nn=32)
+    oo, oidx, od = oi.radius(q, 0.05, max_nn=32, nthreads=8)
+    assert np.array_equal(go, oo) and np.array_equal(gidx, oidx) and np.array_equal(gd, od)
+    assert np.diff(go).max() <= 32
+
+
+def test_config5_exactly_30_iterations(gpu, orc):
+    """configs[4] shape: VoxelGrid then ICP with eps = 0 runs EXACTLY max_iterations (only the cap stops it),
+    scaled to 100 k points of a ground-plane-plus-boxes sweep."""
+    P, ctx = gpu
+    rng = np.random.default_rng(21)
+    n = 100_000
+    xy = (rng.random((n, 2)) - 0.5) * 200
+    z = np.where(rng.random(n) < 0.2, rng.random(n) * 5, 0.0) + rng.normal(0, 0.02, n)
+    tgt = np.column_stack([xy, z]).astype(np.float32)
+    R = _rot([0, 0, 1], 1.5)
+    src = (tgt.astype(np.float64) @ R.T + [0.5, 0.1, 0.0]).astype(np.float32)
+    vt, vs = ctx.voxelgrid(P.xyz1(tgt), 0.5), ctx.voxelgrid(P.xyz1(src), 0.5)
+    kw = dict(max_iterations=30, max_correspondence_distance=2.0)
+    r = P.icp_align(ctx, vs, P.Index(ctx, vt), mse_threshold_absolute=0.0, **kw)
+    assert r["iterations"] == 30 and r["state"] == 1 and r["converged"]  # CONVERGENCE_CRITERIA_ITERATIONS
+    assert r["total_correspondences"] >= 30 * 3
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# full-size properties (10 M points): no oracle run, the domain's own invariants
+# ---------------------------------------------------------------------------------------------------------------------
+@pytest.fixture(scope="module")
+def big(gpu):
+    import bench
+    P, ctx = gpu
+    n = 10_000_000
+    tgt = bench.make_target(n)
+    return tgt, P.Index(ctx, tgt)
+
+
+def test_fullsize_self_query_is_identity(gpu, big):
+    """k-NN of the cloud's own points returns each point itself at distance 0 first, ascending distances, valid
+    unique indices (the invariants test/search/test_search.cpp:293-362 checks)."""
+    P, ctx = gpu
+    tgt, idx = big
+    q = np.ascontiguousarray(tgt[::37])
+    ki, kd, keff = idx.knn(q, 8)
+    assert keff == 8
+    assert np.all(kd[:, 0] == 0)
+    same = (tgt[ki[:, 0], :3] == q[:, :3]).all(1)     # an exact duplicate with a smaller index may legitimately win
+    assert same.all()
+    assert np.all(np.diff(kd, axis=1) >= 0)
+    assert ki.min() >= 0 and ki.max() < tgt.shape[0]
+    srt = np.sort(ki, axis=1)
+    assert np.all(srt[:, 1:] != srt[:, :-1])
+    d = ((tgt[ki[:, 7], :3] - q[:, :3]) ** 2)
+    assert np.array_equal((d[:, 0] + d[:, 1]) + d[:, 2], kd[:, 7])   # reported d2 is the canonical fp32 expression
+
+
+def test_fullsize_icp_recovers_motion_and_fixed_point(gpu, big):
+    """At BASELINE's 10 M size: ICP undoes a known rigid motion of the target itself; re-aligning the aligned cloud
+    is a fixed point (identity increment); correspondences == source size when nothing is gated."""
+    P, ctx = gpu
+    tgt, idx = big
+    n = tgt.shape[0]
+    # a motion smaller than half the point spacing (~0.003): nearly every source point's nearest neighbour is its
+    # own pre-image, so point-to-point ICP must recover the inverse motion essentially exactly
+    R = _rot([0.2, -0.1, 1.0], 0.004)
+    t = np.array([0.0004, -0.0003, 0.0002])
+    src = np.ones((n, 4), np.float32)
+    src[:, :3] = (tgt[:, :3].astype(np.float64) @ R.T + t).astype(np.float32)
+    out = np.empty_like(src)
+    r = P.icp_align(ctx, src, idx, out_cloud=out, max_iterations=40, transformation_epsilon=1e-12,
+                    max_correspondence_distance=0.05)
+    Tinv = np.eye(4)
+    Tinv[:3, :3], Tinv[:3, 3] = R.T, -R.T @ t
+    assert r["converged"] and r["n_correspondences"] == n
+    assert np.linalg.norm(r["final"] - Tinv) < 1e-5, np.linalg.norm(r["final"] - Tinv)
+    assert np.abs(out[:, :3] - tgt[:, :3]).max() < 5e-5
+    r2 = P.icp_align(ctx, out, idx, max_iterations=3, max_correspondence_distance=0.05)
+    assert np.linalg.norm(r2["final"] - np.eye(4)) < 1e-5
+
+
+def test_fullsize_voxelgrid_mass_conservation(gpu, big):
+    """VoxelGrid at 10 M points: sum(count_i * centroid_i) == sum(points) (mass conservation to fp32 accumulation
+    error), one output per occupied cell, output ordered by cell index (voxel_grid.hpp:737-748)."""
+    P, ctx = gpu
+    tgt, _ = big
+    leaf = 0.05
+    pts = np.ascontiguousarray(tgt[:, :4])
+    out = ctx.voxelgrid(pts, leaf)
+    mn = pts[:, :3].min(0)
+    inv = np.float32(1.0) / np.float32(leaf)
+    min_b = np.floor(mn * inv).astype(np.int64)
+    max_b = np.floor(pts[:, :3].max(0) * inv).astype(np.int64)
+    div = max_b - min_b + 1
+    cell = (np.floor(pts[:, :3] * inv) - min_b.astype(np.float32)).astype(np.int64)
+    key = cell[:, 0] + cell[:, 1] * div[0] + cell[:, 2] * div[0] * div[1]
+    uk, cnt = np.unique(key, return_counts=True)
+    assert out.shape[0] == uk.size
+    ocell = (np.floor(out[:, :3] * inv) - min_b.astype(np.float32)).astype(np.int64)
+    okey = ocell[:, 0] + ocell[:, 1] * div[0] + ocell[:, 2] * div[0] * div[1]
+    # a centroid lies in its own cell except when it rounds onto the boundary; order must follow the cell index
+    assert (okey == uk).mean() > 0.999
+    total = (out[:, :3].astype(np.float64) * cnt[:, None]).sum(0)
+    assert np.allclose(total, pts[:, :3].astype(np.float64).sum(0), rtol=1e-5)
