@@ -183,6 +183,7 @@ typedef struct pclb200_icp_stats {
   double final_transformation[16];  /* row-major, rounded to Scalar */
   double last_transformation[16];   /* getLastIncrementalTransformation */
   int64_t total_correspondences;    /* sum of accepted pairs over all iterations since set_source */
+  int64_t total_skipped_walks;      /* queries (this rank) whose tree walk was skipped by the temporal-coherence test */
 } pclb200_icp_stats;
 
 PCLB200_API void pclb200_icp_default_params(pclb200_icp_params* p);
@@ -210,6 +211,9 @@ PCLB200_API int pclb200_icp_set_source(pclb200_icp* icp, const void* src, size_t
 PCLB200_API int pclb200_icp_iterate(pclb200_icp* icp, int max_steps, pclb200_icp_stats* stats);
 PCLB200_API int pclb200_icp_get_cloud(pclb200_icp* icp, void* out_pts, size_t stride_out,
                                       void* out_normals, size_t stride_n);
+/* correspondences of the last evaluated iteration (Registration::correspondences_, what icp.hpp:228-236 hands to
+ * the visualisation callback): capacity = number of indexed source points, ordered like the source index list. */
+PCLB200_API int pclb200_icp_get_correspondences(pclb200_icp* icp, pclb200_corr* out, size_t* n_out);
 
 /* one-call form: Registration::align(output, guess) (registration.hpp:172-221) */
 PCLB200_API int pclb200_icp_align(pclb200_ctx* ctx, const pclb200_icp_params* params,

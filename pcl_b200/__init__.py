@@ -40,12 +40,13 @@ class IcpParams(C.Structure):
 class IcpStats(C.Structure):
     _fields_ = [("converged", C.c_int32), ("state", C.c_int32), ("iterations", C.c_int32), ("reserved", C.c_int32),
                 ("n_correspondences", C.c_int64), ("mse", C.c_double), ("final_transformation", C.c_double * 16),
-                ("last_transformation", C.c_double * 16), ("total_correspondences", C.c_int64)]
+                ("last_transformation", C.c_double * 16), ("total_correspondences", C.c_int64), ("total_skipped_walks", C.c_int64)]
 
     def as_dict(self):
         return dict(converged=bool(self.converged), state=int(self.state), iterations=int(self.iterations),
                     n_correspondences=int(self.n_correspondences), mse=float(self.mse),
                     total_correspondences=int(self.total_correspondences),
+                    total_skipped_walks=int(self.total_skipped_walks),
                     final=np.array(self.final_transformation).reshape(4, 4),
                     last=np.array(self.last_transformation).reshape(4, 4))
 
@@ -58,7 +59,8 @@ SYMBOLS = [
     "pclb200_index_size", "pclb200_index_stats", "pclb200_knn", "pclb200_radius", "pclb200_correspondences",
     "pclb200_estimate_svd", "pclb200_estimate_point_to_plane_lls", "pclb200_icp_default_params",
     "pclb200_icp_create", "pclb200_icp_destroy", "pclb200_icp_set_params", "pclb200_icp_set_target",
-    "pclb200_icp_set_source", "pclb200_icp_iterate", "pclb200_icp_get_cloud", "pclb200_icp_align",
+    "pclb200_icp_set_source", "pclb200_icp_iterate", "pclb200_icp_get_cloud", "pclb200_icp_get_correspondences",
+    "pclb200_icp_align",
     "pclb200_fitness_score", "pclb200_normals_knn", "pclb200_voxelgrid", "pclb200_comm_unique_id",
     "pclb200_comm_init",
 ]
@@ -106,6 +108,7 @@ def lib():
     L.pclb200_icp_set_source.argtypes = [vp, vp, sz, sz, vp, sz, vp, sz, dp]
     L.pclb200_icp_iterate.argtypes = [vp, C.c_int, C.POINTER(IcpStats)]
     L.pclb200_icp_get_cloud.argtypes = [vp, vp, sz, vp, sz]
+    L.pclb200_icp_get_correspondences.argtypes = [vp, vp, C.POINTER(sz)]
     L.pclb200_icp_align.argtypes = [vp, C.POINTER(IcpParams), vp, sz, sz, vp, sz, vp, sz, vp, vp, sz, dp, vp, sz,
                                     C.POINTER(IcpStats)]
     L.pclb200_fitness_score.argtypes = [vp, vp, vp, sz, sz, vp, sz, C.c_int, dp, C.c_int, C.c_double, dp]
@@ -388,11 +391,18 @@ class Icp:
         _check(lib().pclb200_icp_set_source(self.h, b.ptr, b.rows, b.stride, nb.ptr, nb.stride, ib.ptr, ib.rows,
                                             None if g is None else g.ctypes.data_as(C.POINTER(C.c_double))))
         self.n_src = b.rows
+        self.n_queries = ib.rows if indices is not None else b.rows
 
     def iterate(self, max_steps=2 ** 31 - 1):
         st = IcpStats()
         _check(lib().pclb200_icp_iterate(self.h, int(max_steps), C.byref(st)))
         return st.as_dict()
+
+    def get_correspondences(self):
+        out = np.empty(max(self.n_queries, 1), dtype=CORR_DTYPE)
+        m = C.c_size_t()
+        _check(lib().pclb200_icp_get_correspondences(self.h, C.c_void_p(out.ctypes.data), C.byref(m)))
+        return out[:m.value]
 
     def get_cloud(self, out=None, stride_floats=4):
         if out is None:

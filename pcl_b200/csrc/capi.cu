@@ -21,6 +21,7 @@ void icp_set_source(Icp& s, const void* src, size_t n, size_t stride, const void
                     const int32_t* indices, size_t n_idx, const double* guess);
 void icp_iterate(Icp& s, int max_steps, pclb200_icp_stats* stats);
 void icp_get_cloud(Icp& s, void* out_pts, size_t stride_out, void* out_normals, size_t stride_n);
+size_t icp_get_correspondences(Icp& s, pclb200_corr* out);
 void estimate_pairs(Ctx& c, int est, const void* src, size_t stride_s, const void* tgt, const void* tgt_normals,
                     size_t stride_t, const pclb200_corr* corr, size_t n, int scalar_is_double, double* T_out);
 size_t correspondences(Ctx& c, const Index& tgt, const Index* src_index, const void* src, size_t n, size_t stride,
@@ -577,6 +578,16 @@ int pclb200_icp_get_cloud(pclb200_icp* icp, void* out_pts, size_t stride_out, vo
     std::lock_guard<std::recursive_mutex> lk(icp->ctx->c.mu);
     PCLB_CUDA(cudaSetDevice(icp->ctx->c.device));
     icp_get_cloud(*icp->s, out_pts, stride_out, out_normals, stride_n);
+  });
+}
+
+int pclb200_icp_get_correspondences(pclb200_icp* icp, pclb200_corr* out, size_t* n_out)
+{
+  return guarded([&] {
+    PCLB_REQUIRE(icp && out && n_out, PCLB200_ERR_INVALID, "NULL argument");
+    std::lock_guard<std::recursive_mutex> lk(icp->ctx->c.mu);
+    PCLB_CUDA(cudaSetDevice(icp->device));
+    *n_out = icp_get_correspondences(*icp->s, out);
   });
 }
 

@@ -116,6 +116,7 @@ struct IterArgs {
   const float4* s_pts;
   int s_root;
   const int32_t* src_orig;    // slot -> original source index (nullable = identity)
+  unsigned long long* skip_count;  // queries answered by the temporal-coherence test (statistics)
   // fused cross-GPU reduce (optional): peer-mapped exchange buffers + this iteration's sequence number
   PeerView peer;
   unsigned long long seq;
@@ -213,16 +214,35 @@ __device__ __forceinline__ void block_reduce_and_publish(double* acc, const Iter
 }
 
 // match of one query, in Morton slot order of `cur`
-struct __align__(8) Match {
-  int pos;    // position of the matched target point in the Morton array, -1 = no correspondence
-  float d2;   // squared distance
+struct __align__(16) Match {
+  int pos;       // position of the nearest target point in the Morton array (-1 = unknown / none inside the gate)
+  float d2;      // squared distance to it
+  float lb;      // lower bound on the DISTANCE (not squared) from the query to every OTHER target point; 0 = unknown
+  int accepted;  // 1 = this iteration's correspondence (inside the gate, reciprocal test passed)
 };
 
-// Search kernel: [apply pending T_k] -> exact 1-NN (seeded with the previous iteration's match: its leaf is
-// scanned first, which makes the pruning bound tight before the descent starts; the result is still the exact
-// lexicographic minimum because every candidate is a real point) -> gate -> optional reciprocal check.
-// Lean on registers (no accumulators live across the traversal) so the latency-bound walk runs at high occupancy.
-template <bool RECIP>
+constexpr float kRelMargin = 1e-5f;  // >> fp32 rounding of the distances involved (~2e-7): keeps the skip test exact
+
+// Temporal-coherence test.  Let m be the previous match at distance D1 from the old query position, L a lower
+// bound on the distance from the old position to every other point, and delta the distance the query moved.
+// Triangle inequality: the new distance to m is <= D1 + delta, the new distance to any other x is >= L - delta.
+// If D1 + delta < L - delta (with a relative safety margin far above fp32 round-off) m is still the UNIQUE nearest
+// neighbour, so the exact search result is (m, dist2(p_new, m)) and the tree walk can be skipped.
+__device__ __forceinline__ bool still_nearest(const Match& prev, float delta, float* new_lb)
+{
+  if (prev.pos < 0 || !(prev.lb > 0.f))
+    return false;
+  const float D1 = sqrtf(prev.d2);
+  const float lhs = (D1 + 2.f * delta) * (1.f + kRelMargin);
+  const float rhs = prev.lb * (1.f - kRelMargin);
+  *new_lb = (prev.lb - delta * (1.f + kRelMargin)) * (1.f - kRelMargin);
+  return lhs < rhs && *new_lb > 0.f;
+}
+
+// Search kernel, one query per thread: [apply pending T_k] -> (skip test) -> exact 1-NN seeded with the previous
+// match (its leaf is scanned first, so the pruning bound is tight before the descent starts) -> gate -> optional
+// reciprocal back-search.  Lean on registers so the latency-bound walk runs at high occupancy.
+template <bool RECIP, bool TRACK>
 __global__ void __launch_bounds__(256)
 k_search(const IterArgs a, Match* __restrict__ match)
 {
@@ -233,38 +253,54 @@ k_search(const IterArgs a, Match* __restrict__ match)
   bool overflow = false;
   for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < a.n; i += (size_t)gridDim.x * blockDim.x) {
     float4 p = a.cur[i];
+    const Match prev = match[i];
     Match m;
     m.pos = -1;
     m.d2 = 0.f;
-    const int seed = match[i].pos;
+    m.lb = 0.f;
+    m.accepted = 0;
     if (isfinite(p.x) && isfinite(p.y) && isfinite(p.z)) {
       // non-finite points: transformCloud leaves them untouched (icp.hpp:90-91), no correspondence (:173-174)
+      float delta = 0.f;
       if (sP.apply) {
+        const float ox = p.x, oy = p.y, oz = p.z;
         apply_pending(sP, p.x, p.y, p.z);
         a.cur[i] = p;
+        delta = sqrtf(dist2_rn(p.x, p.y, p.z, ox, oy, oz));
       }
-      Nearest1 v{p.x, p.y, p.z, a.gate, kSentinelIndex, -1};
-      if (seed >= 0) {
-        const int leaf = seed / kLeafSize;
-        v.leaf(a.pts + (size_t)leaf * kLeafSize, leaf * kLeafSize);
+      float nlb;
+      if (TRACK && !RECIP && still_nearest(prev, delta, &nlb)) {
+        const float4 q = ldg4(a.pts + prev.pos);
+        m.pos = prev.pos;
+        m.d2 = dist2_rn(p.x, p.y, p.z, q.x, q.y, q.z);
+        m.lb = nlb;
+        m.accepted = m.d2 <= a.gate ? 1 : 0;  // distance[0] > max_dist_sqr drops it (correspondence_estimation.hpp:176)
+        atomicAdd(a.skip_count, 1ULL);
       }
-      if (!traverse(a.nodes, a.pts, a.root, p.x, p.y, p.z, v))
-        overflow = true;
-      if (v.best_pos >= 0) {  // else distance[0] > max_dist_sqr (correspondence_estimation.hpp:176)
-        bool keep = true;
-        if (RECIP) {
-          // correspondence_estimation.hpp:259-269: 1-NN of the matched target point back into the source
-          const float4 q = ldg4(a.pts + v.best_pos);
-          Nearest1 b{q.x, q.y, q.z, a.gate, kSentinelIndex, -1};
-          if (!traverse(a.s_nodes, a.s_pts, a.s_root, q.x, q.y, q.z, b))
-            overflow = true;
-          const int slot = __float_as_int(p.w);
-          const int my_orig = a.src_orig ? a.src_orig[slot] : slot;
-          keep = b.best_pos >= 0 && b.best_idx == my_orig;
+      else {
+        Nearest1T<TRACK> v{p.x, p.y, p.z, a.gate, kSentinelIndex, -1, __int_as_float(0x7f800000),
+                           __int_as_float(0x7f800000), __int_as_float(0x7f800000)};
+        if (prev.pos >= 0) {
+          const int leaf = prev.pos / kLeafSize;
+          v.template scan<false>(a.pts + (size_t)leaf * kLeafSize, leaf * kLeafSize);
         }
-        if (keep) {
+        if (!traverse(a.nodes, a.pts, a.root, p.x, p.y, p.z, v))
+          overflow = true;
+        if (v.best_pos >= 0) {
           m.pos = v.best_pos;
           m.d2 = v.best;
+          m.lb = TRACK ? sqrtf(v.lower_bound2()) : 0.f;
+          m.accepted = 1;
+          if (RECIP) {
+            // correspondence_estimation.hpp:259-269: 1-NN of the matched target point back into the source
+            const float4 q = ldg4(a.pts + v.best_pos);
+            Nearest1 b{q.x, q.y, q.z, a.gate, kSentinelIndex, -1};
+            if (!traverse(a.s_nodes, a.s_pts, a.s_root, q.x, q.y, q.z, b))
+              overflow = true;
+            const int slot = __float_as_int(p.w);
+            const int my_orig = a.src_orig ? a.src_orig[slot] : slot;
+            m.accepted = (b.best_pos >= 0 && b.best_idx == my_orig) ? 1 : 0;
+          }
         }
       }
     }
@@ -274,9 +310,11 @@ k_search(const IterArgs a, Match* __restrict__ match)
     atomicExch(a.d_error, 1);
 }
 
-// Packet variant of the search kernel: the 32 Morton-adjacent queries of a warp share ONE walk of the tree
-// (traverse_packet).  Chosen by the host when the queries are about as dense as the target (ICP's normal case).
-template <bool RECIP>
+// Packet variant: the 32 Morton/Hilbert-adjacent queries of a warp share ONE walk of the tree (traverse_packet).
+// Lanes whose previous match is provably still nearest (still_nearest) sit the walk out; a warp whose 32 lanes all
+// pass the test does not touch the tree at all.  Chosen by the host when the queries are about as dense as the
+// target (ICP's normal case).
+template <bool RECIP, bool TRACK>
 __global__ void __launch_bounds__(256)
 k_search_packet(const IterArgs a, Match* __restrict__ match)
 {
@@ -291,44 +329,72 @@ k_search_packet(const IterArgs a, Match* __restrict__ match)
   // warp-uniform trip count: every lane of a warp runs the same number of rounds
   const size_t stride = (size_t)gridDim.x * blockDim.x;
   const size_t first = blockIdx.x * (size_t)blockDim.x + (threadIdx.x & ~31);
+  const float inf = __int_as_float(0x7f800000);
   for (size_t base = first; base < a.n; base += stride) {
     const size_t i = base + (threadIdx.x & 31);
     const bool in_range = i < a.n;
     float4 p = in_range ? a.cur[i] : make_float4(0.f, 0.f, 0.f, 0.f);
-    const int seed = in_range ? match[i].pos : -1;
+    Match prev;
+    if (in_range)
+      prev = match[i];
+    else {
+      prev.pos = -1; prev.d2 = 0.f; prev.lb = 0.f; prev.accepted = 0;
+    }
     const bool valid = in_range && isfinite(p.x) && isfinite(p.y) && isfinite(p.z);
+    float delta = 0.f;
     if (valid && sP.apply) {
+      const float ox = p.x, oy = p.y, oz = p.z;
       apply_pending(sP, p.x, p.y, p.z);
       a.cur[i] = p;
+      delta = sqrtf(dist2_rn(p.x, p.y, p.z, ox, oy, oz));
     }
-    Nearest1 v{p.x, p.y, p.z, valid ? a.gate : -1.f, kSentinelIndex, -1};
-    if (valid && seed >= 0) {
-      const int leaf = seed / kLeafSize;
-      v.leaf(a.pts + (size_t)leaf * kLeafSize, leaf * kLeafSize);
-    }
-    __syncwarp();
-    if (!traverse_packet(a.nodes, a.pts, a.root, p.x, p.y, p.z, v, s_node[warp], s_dist[warp]))
-      overflow = true;
     Match m;
-    m.pos = -1;
-    m.d2 = 0.f;
-    bool keep = valid && v.best_pos >= 0;
-    if (RECIP) {
-      // correspondence_estimation.hpp:259-269: back-search of the matched target point in the source tree
-      const float4 q = keep ? ldg4(a.pts + v.best_pos) : make_float4(0.f, 0.f, 0.f, 0.f);
-      Nearest1 b{q.x, q.y, q.z, keep ? a.gate : -1.f, kSentinelIndex, -1};
-      __syncwarp();
-      if (!traverse_packet(a.s_nodes, a.s_pts, a.s_root, q.x, q.y, q.z, b, s_node[warp], s_dist[warp]))
-        overflow = true;
-      if (keep) {
-        const int slot = __float_as_int(p.w);
-        const int my_orig = a.src_orig ? a.src_orig[slot] : slot;
-        keep = b.best_pos >= 0 && b.best_idx == my_orig;
-      }
+    m.pos = -1; m.d2 = 0.f; m.lb = 0.f; m.accepted = 0;
+    float nlb = 0.f;
+    const bool skip = TRACK && !RECIP && valid && still_nearest(prev, delta, &nlb);
+    if (skip) {
+      const float4 q = ldg4(a.pts + prev.pos);
+      m.pos = prev.pos;
+      m.d2 = dist2_rn(p.x, p.y, p.z, q.x, q.y, q.z);
+      m.lb = nlb;
+      m.accepted = m.d2 <= a.gate ? 1 : 0;
     }
-    if (keep) {
-      m.pos = v.best_pos;
-      m.d2 = v.best;
+    const bool walk = valid && !skip;
+    {
+      const unsigned sk = __ballot_sync(0xffffffffu, skip);
+      if (sk && (threadIdx.x & 31) == 0)
+        atomicAdd(a.skip_count, (unsigned long long)__popc(sk));
+    }
+    if (__any_sync(0xffffffffu, walk)) {
+      Nearest1T<TRACK> v{p.x, p.y, p.z, walk ? a.gate : -1.f, kSentinelIndex, -1, inf, inf, inf};
+      if (walk && prev.pos >= 0) {
+        const int leaf = prev.pos / kLeafSize;
+        v.template scan<false>(a.pts + (size_t)leaf * kLeafSize, leaf * kLeafSize);
+      }
+      __syncwarp();
+      if (!traverse_packet(a.nodes, a.pts, a.root, p.x, p.y, p.z, v, s_node[warp], s_dist[warp]))
+        overflow = true;
+      bool keep = walk && v.best_pos >= 0;
+      if (keep) {
+        m.pos = v.best_pos;
+        m.d2 = v.best;
+        m.lb = TRACK ? sqrtf(v.lower_bound2()) : 0.f;
+      }
+      if (RECIP) {
+        // correspondence_estimation.hpp:259-269: back-search of the matched target point in the source tree
+        const float4 q = keep ? ldg4(a.pts + v.best_pos) : make_float4(0.f, 0.f, 0.f, 0.f);
+        Nearest1 b{q.x, q.y, q.z, keep ? a.gate : -1.f, kSentinelIndex, -1};
+        __syncwarp();
+        if (!traverse_packet(a.s_nodes, a.s_pts, a.s_root, q.x, q.y, q.z, b, s_node[warp], s_dist[warp]))
+          overflow = true;
+        if (keep) {
+          const int slot = __float_as_int(p.w);
+          const int my_orig = a.src_orig ? a.src_orig[slot] : slot;
+          keep = b.best_pos >= 0 && b.best_idx == my_orig;
+        }
+      }
+      if (walk)
+        m.accepted = keep ? 1 : 0;
     }
     if (in_range)
       match[i] = m;
@@ -349,7 +415,7 @@ k_accum(const IterArgs a, const Match* __restrict__ match)
     acc[t] = 0.0;
   for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < a.n; i += (size_t)gridDim.x * blockDim.x) {
     const Match m = match[i];
-    if (m.pos < 0)
+    if (!m.accepted)
       continue;
     const float4 p = a.cur[i];
     const float4 q = ldg4(a.pts + m.pos);
@@ -735,9 +801,6 @@ k_corr(const BvhNode* __restrict__ nodes, const float4* __restrict__ pts, int ro
   out[slot] = r;
 }
 
-struct CorrValid {
-  __host__ __device__ bool operator()(const pclb200_corr& c) const { return c.index_match >= 0; }
-};
 
 // fitness: sum of d2 <= max_range and count (registration.hpp:146-163)
 __global__ void __launch_bounds__(256)
@@ -835,6 +898,9 @@ struct Icp {
   // device state
   DevBuf<Pending> pending;
   DevBuf<SolveOut> solve_out;
+  DevBuf<unsigned long long> skip_count;
+  int64_t total_skipped = 0;
+  bool track_next = false;      // run the next search with lower-bound tracking / skip test (set per iteration)
   Reducer red;
   // host state (Scalar-typed values are kept in double; float mode rounds after every operation)
   double final_T[16], last_T[16];
@@ -881,6 +947,8 @@ Icp* icp_create(Ctx& c, const pclb200_icp_params& P)
   s->P = P;
   s->pending.alloc(1, c.stream);
   s->solve_out.alloc(1, c.stream);
+  s->skip_count.alloc(1, c.stream);
+  PCLB_CUDA(cudaMemsetAsync(s->skip_count.p, 0, sizeof(unsigned long long), c.stream));
   s->red.init(c, (unsigned)c.sm_count * 8);
   set_identity(s->final_T);
   set_identity(s->last_T);
@@ -951,6 +1019,9 @@ void icp_reset_state(Icp& s, const double* guess)
   s.state = PCLB200_CONV_NOT_CONVERGED;
   s.converged = false;
   s.n_corr = 0;
+  s.track_next = false;
+  s.total_skipped = 0;
+  PCLB_CUDA(cudaMemsetAsync(s.skip_count.p, 0, sizeof(unsigned long long), s.ctx->stream));
   s.total_corr = 0;
   s.mse = 0.0;
   s.prev_mse = std::numeric_limits<double>::max();
@@ -1117,6 +1188,7 @@ static void fill_stats(const Icp& s, pclb200_icp_stats* st)
   st->reserved = 0;
   st->n_correspondences = s.n_corr;
   st->total_correspondences = s.total_corr;
+  st->total_skipped_walks = s.total_skipped;
   st->mse = s.mse;
   for (int i = 0; i < 16; ++i) {
     st->final_transformation[i] = s.final_T[i];
@@ -1155,6 +1227,7 @@ void icp_iterate(Icp& s, int max_steps, pclb200_icp_stats* stats)
     a.accum = s.red.accum.p;
     a.d_error = c.d_error;
     a.src_orig = s.src_orig.p;
+    a.skip_count = s.skip_count.p;
     a.peer.nranks = 0;
     a.seq = 0;
     const bool fused_reduce = comm_peer_view(c, &a.peer, &a.seq);
@@ -1176,21 +1249,32 @@ void icp_iterate(Icp& s, int max_steps, pclb200_icp_stats* stats)
       const unsigned sgrid = persistent_grid(c, s.n_q, 256, 16);
       // packet walk when the queries are about as dense as the target (32 Morton-adjacent queries then share
       // most of their path); per-query walk when they are much sparser.  PCLB200_SEARCH=packet|single overrides.
-      static const char* force = getenv("PCLB200_SEARCH");
+      const char* force = getenv("PCLB200_SEARCH");  // read per call so tests can exercise both kernels
       bool packet = (double)T.n_valid <= 64.0 * (double)s.n_q;
       if (force && force[0] == 'p') packet = true;
       if (force && force[0] == 's') packet = false;
+      // Temporal coherence (still_nearest) pays once the cloud has almost stopped moving: tracking the lower
+      // bounds costs ~6 % of a walk, so it is switched on when the last increment displaced no point by more than
+      // half the RMS correspondence distance, and the skip test then fires from the following iteration on.
+      const char* tc = getenv("PCLB200_TRACK");  // "1" / "0" force it (tests, A/B measurements)
+      bool track = s.track_next && !s.P.use_reciprocal;
+      if (tc && tc[0] == '1') track = !s.P.use_reciprocal;
+      if (tc && tc[0] == '0') track = false;
       if (packet) {
         if (s.P.use_reciprocal)
-          k_search_packet<true><<<sgrid, 256, 0, st>>>(a, s.match.p);
+          k_search_packet<true, false><<<sgrid, 256, 0, st>>>(a, s.match.p);
+        else if (track)
+          k_search_packet<false, true><<<sgrid, 256, 0, st>>>(a, s.match.p);
         else
-          k_search_packet<false><<<sgrid, 256, 0, st>>>(a, s.match.p);
+          k_search_packet<false, false><<<sgrid, 256, 0, st>>>(a, s.match.p);
       }
       else {
         if (s.P.use_reciprocal)
-          k_search<true><<<sgrid, 256, 0, st>>>(a, s.match.p);
+          k_search<true, false><<<sgrid, 256, 0, st>>>(a, s.match.p);
+        else if (track)
+          k_search<false, true><<<sgrid, 256, 0, st>>>(a, s.match.p);
         else
-          k_search<false><<<sgrid, 256, 0, st>>>(a, s.match.p);
+          k_search<false, false><<<sgrid, 256, 0, st>>>(a, s.match.p);
       }
       ++c.launches;
     }
@@ -1248,8 +1332,81 @@ void icp_iterate(Icp& s, int max_steps, pclb200_icp_stats* stats)
     }
     ++s.iterations;
     s.converged = s.P.scalar_is_double ? has_converged<double>(s, s.last_T) : has_converged<float>(s, s.last_T);
+    {
+      // upper bound of the displacement T_k causes anywhere near the target: |R - I|_F * r_max + |t|
+      double rf = 0.0, tn = 0.0, rmax = 0.0;
+      for (int r = 0; r < 3; ++r) {
+        for (int cc = 0; cc < 3; ++cc) {
+          const double d = s.last_T[4 * r + cc] - (r == cc ? 1.0 : 0.0);
+          rf += d * d;
+        }
+        tn += s.last_T[4 * r + 3] * s.last_T[4 * r + 3];
+        const double m = std::max(std::fabs((double)T.lo[r]), std::fabs((double)T.hi[r]));
+        rmax += m * m;
+      }
+      const double disp = std::sqrt(rf) * std::sqrt(rmax) + std::sqrt(tn);
+      s.track_next = disp < 0.5 * std::sqrt(std::max(s.mse, 0.0));
+    }
+  }
+  if (stats) {
+    unsigned long long h = 0;
+    PCLB_CUDA(cudaMemcpyAsync(&h, s.skip_count.p, sizeof(h), cudaMemcpyDeviceToHost, st));
+    PCLB_CUDA(cudaStreamSynchronize(st));
+    s.total_skipped = (int64_t)h;
   }
   fill_stats(s, stats);
+}
+
+struct CorrValid {
+  __host__ __device__ bool operator()(const pclb200_corr& c) const { return c.index_match >= 0; }
+};
+
+// correspondences of the last evaluated iteration (Registration::correspondences_, what PCL hands to the
+// visualisation callback at icp.hpp:228-236), ordered by position in the source index list
+__global__ void k_matches_to_corr(const float4* __restrict__ cur, const Match* __restrict__ match, size_t n,
+                                  const float4* __restrict__ tgt_pts, const int32_t* __restrict__ src_orig,
+                                  pclb200_corr* __restrict__ by_slot)
+{
+  size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+  if (i >= n)
+    return;
+  const int slot = __float_as_int(cur[i].w);
+  const Match m = match[i];
+  pclb200_corr r;
+  r.index_query = src_orig ? src_orig[slot] : slot;
+  r.index_match = m.accepted ? __float_as_int(tgt_pts[m.pos].w) : -1;
+  r.distance = m.accepted ? m.d2 : 0.f;
+  by_slot[slot] = r;
+}
+
+size_t icp_get_correspondences(Icp& s, pclb200_corr* out)
+{
+  Ctx& c = *s.ctx;
+  cudaStream_t st = c.stream;
+  PCLB_REQUIRE(s.tgt && s.cur.p && s.match.p, PCLB200_ERR_INVALID, "icp: no iteration has run");
+  if (!s.n_q || s.iterations == 0)
+    return 0;
+  DevBuf<pclb200_corr> by_slot, compact;
+  DevBuf<size_t> d_count;
+  by_slot.alloc(s.n_q, st);
+  compact.alloc(s.n_q, st);
+  d_count.alloc(1, st);
+  k_matches_to_corr<<<grid_for(s.n_q, 256), 256, 0, st>>>(s.cur.p, s.match.p, s.n_q, s.tgt->pts.p, s.src_orig.p, by_slot.p);
+  ++c.launches;
+  size_t tmp_bytes = 0;
+  PCLB_CUDA(cub::DeviceSelect::If(nullptr, tmp_bytes, by_slot.p, compact.p, d_count.p, (int)s.n_q, CorrValid(), st));
+  DevBuf<unsigned char> tmp;
+  tmp.alloc(tmp_bytes, st);
+  PCLB_CUDA(cub::DeviceSelect::If(tmp.p, tmp_bytes, by_slot.p, compact.p, d_count.p, (int)s.n_q, CorrValid(), st));
+  c.launches += 2;
+  size_t m = 0;
+  PCLB_CUDA(cudaMemcpyAsync(&m, d_count.p, sizeof(size_t), cudaMemcpyDeviceToHost, st));
+  PCLB_CUDA(cudaStreamSynchronize(st));
+  if (m)
+    PCLB_CUDA(cudaMemcpyAsync(out, compact.p, m * sizeof(pclb200_corr),
+                              is_device_ptr(out) ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost, st));
+  PCLB_CUDA(cudaStreamSynchronize(st));
+  return m;
 }
 
 // output = *input_ ; transformCloud(*input_, output, final_transformation_) — icp.hpp:265-267

@@ -38,6 +38,7 @@ struct NearestK {
     return p < 0 ? kSentinelIndex : __float_as_int(__ldg(&pts[p].w));
   }
   __device__ __forceinline__ float bound() const { return d[K - 1]; }
+  __device__ __forceinline__ void prune(float) {}
   __device__ __forceinline__ void leaf(const float4* lp, int first_pos)
   {
     float4 p[kLeafSize];
@@ -103,6 +104,7 @@ struct NearestAny {
     return p < 0 ? kSentinelIndex : __float_as_int(__ldg(&pts[p].w));
   }
   __device__ __forceinline__ float bound() const { return d[k - 1]; }
+  __device__ __forceinline__ void prune(float) {}
   __device__ __forceinline__ void leaf(const float4* lp, int first_pos)
   {
     for (int j = 0; j < kLeafSize; ++j) {
@@ -185,6 +187,7 @@ struct RadiusCount {
   float r2_below;  // largest float < r2: subtrees with bound > r2_below hold no d2 < r2
   unsigned long long n;
   __device__ __forceinline__ float bound() const { return r2_below; }
+  __device__ __forceinline__ void prune(float) {}
   __device__ __forceinline__ void leaf(const float4* lp, int)
   {
 #pragma unroll
@@ -201,6 +204,7 @@ struct RadiusFill {
   float r2_below;
   unsigned long long* out;
   __device__ __forceinline__ float bound() const { return r2_below; }
+  __device__ __forceinline__ void prune(float) {}
   __device__ __forceinline__ void leaf(const float4* lp, int)
   {
 #pragma unroll

@@ -69,9 +69,12 @@ __device__ __forceinline__ bool traverse(const BvhNode* __restrict__ nodes, cons
           else
             ok = false;
         }
+        else
+          v.prune(dr);
         node = nl;
       }
       else {
+        v.prune(dl);  // dl <= dr: both subtrees are at least this far
         node = kDone;
         while (sp > 0) {
           --sp;
@@ -79,6 +82,7 @@ __device__ __forceinline__ bool traverse(const BvhNode* __restrict__ nodes, cons
             node = stack_node[sp];
             break;
           }
+          v.prune(stack_dist[sp]);
         }
       }
     }
@@ -94,19 +98,35 @@ __device__ __forceinline__ bool traverse(const BvhNode* __restrict__ nodes, cons
         node = stack_node[sp];
         break;
       }
+      v.prune(stack_dist[sp]);
     }
   }
   return ok;
 }
 
 // ---- 1-NN visitor: lexicographic (d2, original index) minimum --------------------------------
-struct Nearest1 {
+// TRACK = true additionally maintains a LOWER BOUND on the distance to every point other than the best one:
+//   m2     = second smallest d2 among the points actually evaluated during the walk
+//   pruned = smallest box bound of any subtree the walk skipped (every point in it is at least that far)
+// lower_bound2() = min(m2, pruned) is what lets the next ICP iteration prove, by the triangle inequality, that the
+// previous match is still the nearest neighbour without walking the tree again (icp.cu, k_search*).
+template <bool TRACK>
+struct Nearest1T {
   float qx, qy, qz;
   float best;   // current best d2 (initialised to the gate)
   int best_idx; // original index of the best point (kSentinelIndex = none yet)
   int best_pos; // its position in the Morton array
+  float m1, m2, pruned_min;  // TRACK only (initialise to +inf)
   __device__ __forceinline__ float bound() const { return best; }
-  __device__ __forceinline__ void leaf(const float4* lp, int first_pos)
+  __device__ __forceinline__ void prune(float d)
+  {
+    if (TRACK)
+      pruned_min = fminf(pruned_min, d);
+  }
+  __device__ __forceinline__ float lower_bound2() const { return fminf(m2, pruned_min); }
+  // scan that only improves (best, best_idx, best_pos): used for the seed leaf, which the walk visits again
+  template <bool COUNT>
+  __device__ __forceinline__ void scan(const float4* lp, int first_pos)
   {
     // distances first, one min-reduction, and the (rare) index bookkeeping only when the leaf can improve the
     // best: most visited leaves do not, so the common path is 8 flops per point plus one compare per leaf.
@@ -122,6 +142,10 @@ struct Nearest1 {
       for (int j = 0; j < 8; ++j) {
         d[j] = dist2_rn(qx, qy, qz, p[j].x, p[j].y, p[j].z);
         m = fminf(m, d[j]);
+        if (TRACK && COUNT) {
+          m2 = fminf(m2, fmaxf(m1, d[j]));
+          m1 = fminf(m1, d[j]);
+        }
       }
       if (m <= best) {
 #pragma unroll
@@ -138,7 +162,9 @@ struct Nearest1 {
       }
     }
   }
+  __device__ __forceinline__ void leaf(const float4* lp, int first_pos) { scan<true>(lp, first_pos); }
 };
+using Nearest1 = Nearest1T<false>;
 
 // ---- packet traversal: one walk of the tree per WARP, shared by its 32 Morton-adjacent queries ---------------
 // All lanes follow the same path (no divergence, every node / leaf line is one broadcast load, the stack is one
@@ -149,8 +175,9 @@ struct Nearest1 {
 // Lanes without a query pass best = -1 (never want anything).  Must be called by all 32 lanes.
 constexpr int kWarpStack = 64;
 
+template <typename V>
 __device__ __forceinline__ bool traverse_packet(const BvhNode* __restrict__ nodes, const float4* __restrict__ pts,
-                                                int root, float qx, float qy, float qz, Nearest1& v,
+                                                int root, float qx, float qy, float qz, V& v,
                                                 int* __restrict__ wnode, float* __restrict__ wdist)
 {
   const unsigned full = 0xffffffffu;
@@ -168,6 +195,11 @@ __device__ __forceinline__ bool traverse_packet(const BvhNode* __restrict__ node
       const float bnd = v.best;
       const unsigned ml = __reduce_min_sync(full, dl <= bnd ? __float_as_uint(dl) : INF_BITS);
       const unsigned mr = __reduce_min_sync(full, dr <= bnd ? __float_as_uint(dr) : INF_BITS);
+      // a child no lane wants is skipped for good: each lane notes ITS OWN bound to that box
+      if (ml == INF_BITS)
+        v.prune(dl);
+      if (mr == INF_BITS)
+        v.prune(dr);
       if (ml == INF_BITS && mr == INF_BITS) {
         node = kDone;
         const unsigned wmax = __reduce_max_sync(full, __float_as_uint(fmaxf(bnd, 0.f)));
@@ -177,6 +209,7 @@ __device__ __forceinline__ bool traverse_packet(const BvhNode* __restrict__ node
             node = wnode[sp];
             break;
           }
+          v.prune(wdist[sp]);  // warp-minimum bound of a discarded entry: valid (weaker) bound for every lane
         }
       }
       else if (ml != INF_BITS && mr != INF_BITS) {
@@ -205,6 +238,7 @@ __device__ __forceinline__ bool traverse_packet(const BvhNode* __restrict__ node
         node = wnode[sp];
         break;
       }
+      v.prune(wdist[sp]);
     }
   }
   return ok;

@@ -395,3 +395,42 @@ def test_voxelgrid_golden_and_oracle(gpu, golden, orc):
         g = ctx.voxelgrid(big, leaf, min_points_per_voxel=mp, is_dense=False)
         o = orc.voxelgrid(big, leaf, min_points_per_voxel=mp, is_dense=False)
         assert g.shape == o.shape and np.array_equal(g, o), (leaf, mp)
+
+
+def test_icp_per_iteration_correspondences_exact(gpu, orc):
+    """The search kernels skip the tree walk for queries whose previous match is provably still nearest (temporal
+    coherence).  That must never change a result: every iteration's correspondence list is compared, bit for bit,
+    with a fresh exact search of the oracle on the same (re-transformed) cloud."""
+    P, ctx = gpu
+    rng = np.random.default_rng(77)
+    n = 50000
+    xy = rng.random((n, 2)) * 4
+    tgt = np.column_stack([xy, 0.3 * np.sin(xy[:, 0]) * np.cos(xy[:, 1]) + rng.normal(0, 0.002, n)]).astype(np.float32)
+    a = np.deg2rad(1.0)
+    R = np.array([[np.cos(a), -np.sin(a), 0], [np.sin(a), np.cos(a), 0], [0, 0, 1]])
+    src = (tgt.astype(np.float64)[::2] @ R.T + [0.01, 0.005, -0.004]).astype(np.float32)
+    src[5, 0] = np.nan
+    T, S = P.xyz1(tgt), P.xyz1(src)
+    oidx = orc.Index(T)
+    import os
+    os.environ["PCLB200_TRACK"] = "1"   # force the skip test on from the first iteration
+    for search in ("packet", "single"):
+        os.environ["PCLB200_SEARCH"] = search
+        s = P.Icp(ctx, max_iterations=25, max_correspondence_distance=0.05, is_dense=0, mse_threshold_absolute=0.0)
+        s.set_target(P.Index(ctx, T))
+        s.set_source(S)
+        cloud = S.copy()
+        skipped_any = False
+        for it in range(25):
+            st = s.iterate(1)
+            g = s.get_correspondences()
+            o = oidx.correspondences(cloud, max_distance=0.05, is_dense=False, nthreads=4)
+            assert np.array_equal(g, o), (search, it, g.size, o.size)
+            assert st["n_correspondences"] == o.size
+            cloud = orc.transform(cloud, st["last"], mode=0)   # IterativeClosestPoint::transformCloud, fp32
+            if st["state"] != 0:
+                break
+        assert st["iterations"] >= 5
+        assert st["total_skipped_walks"] > 0, "the temporal-coherence path was never exercised"
+    os.environ.pop("PCLB200_SEARCH", None)
+    os.environ.pop("PCLB200_TRACK", None)
