@@ -233,9 +233,17 @@ def run_ours(args):
     params = P.default_params(max_iterations=ICP_ITERS, max_correspondence_distance=MAX_CORR_DIST,
                               estimator=P.EST_POINT_TO_PLANE_LLS, with_normals_transform=1, mse_threshold_absolute=0.0)
 
+    # One registration object for the whole run, like a pcl::IterativeClosestPointWithNormals instance whose target
+    # was set once (Registration::setInputTarget): the target index and its normals stay on the device across
+    # align() calls (registration.hpp:84-87); every step is setInputSource + align(output).
+    icp = P.Icp(ctx, params=params)
+    icp.set_target(tidx, normals=nrm_dev)
+
     def align(src, out):
-        return P.icp_align(ctx, src, tidx, params=params, src_normals=P.Field(src, 4), tgt_normals=nrm_dev,
-                           out_cloud=out)
+        icp.set_source(src, normals=P.Field(src, 4))
+        st = icp.iterate()
+        icp.get_cloud(out, normals=P.Field(out, 4))
+        return st
 
     def barrier():
         if world > 1:

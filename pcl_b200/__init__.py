@@ -404,11 +404,11 @@ class Icp:
         _check(lib().pclb200_icp_get_correspondences(self.h, C.c_void_p(out.ctypes.data), C.byref(m)))
         return out[:m.value]
 
-    def get_cloud(self, out=None, stride_floats=4):
+    def get_cloud(self, out=None, stride_floats=4, normals=None):
         if out is None:
             out = np.zeros((self.n_src, stride_floats), dtype=np.float32)
-        ob = _Buf(out)
-        _check(lib().pclb200_icp_get_cloud(self.h, ob.ptr, ob.stride, None, 0))
+        ob, nb = _Buf(out), _Buf(normals)
+        _check(lib().pclb200_icp_get_cloud(self.h, ob.ptr, ob.stride, nb.ptr, nb.stride))
         return out
 
 

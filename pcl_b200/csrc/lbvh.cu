@@ -360,6 +360,158 @@ __global__ void k_pack_nodes(int n_internal, const int2* __restrict__ children, 
   nodes[i] = nd;
 }
 
+// ---- cell-aligned leaves --------------------------------------------------------------------------------------
+// A leaf is a whole radix-tree cell holding <= kLeafSize points (the subtree of the Karras tree over POINTS whose
+// parent holds more), stored padded to kLeafSize slots with +inf sentinels.  Compared with "kLeafSize consecutive
+// Morton points" the leaf boxes never straddle a cell boundary: measured with tools/lbvh_emul.cpp on the bench
+// surface the average leaf diagonal drops 2.5x, a seeded 1-NN walk needs 1.9 instead of 5.8 leaf scans and 25
+// instead of 45 node visits, a 32-query packet 59 instead of 79 nodes.
+
+// Karras 2012 over the sorted point keys (ties by index); also records each node's key range [lo, hi].
+__device__ __forceinline__ int delta_pt(const unsigned long long* __restrict__ keys, int n, int i, int j)
+{
+  if (j < 0 || j >= n)
+    return -1;
+  const unsigned long long x = keys[i] ^ keys[j];
+  if (x == 0)
+    return 64 + __clz(i ^ j);
+  return __clzll((long long)x);
+}
+
+__global__ void k_karras_points(const unsigned long long* __restrict__ keys, int n, int2* __restrict__ children,
+                                int* __restrict__ node_parent, int* __restrict__ point_parent, int2* __restrict__ range)
+{
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n - 1)
+    return;
+  int d = (delta_pt(keys, n, i, i + 1) - delta_pt(keys, n, i, i - 1)) >= 0 ? 1 : -1;
+  int dmin = delta_pt(keys, n, i, i - d);
+  int lmax = 2;
+  while (delta_pt(keys, n, i, i + lmax * d) > dmin)
+    lmax <<= 1;
+  int l = 0;
+  for (int t = lmax >> 1; t >= 1; t >>= 1)
+    if (delta_pt(keys, n, i, i + (l + t) * d) > dmin)
+      l += t;
+  int j = i + l * d;
+  int dnode = delta_pt(keys, n, i, j);
+  int s = 0;
+  int t = l;
+  do {
+    t = (t + 1) >> 1;
+    if (delta_pt(keys, n, i, i + (s + t) * d) > dnode)
+      s += t;
+  } while (t > 1);
+  int gamma = i + s * d + min(d, 0);
+  int left, right;
+  if (min(i, j) == gamma) {
+    left = ~gamma;
+    point_parent[gamma] = i;
+  }
+  else {
+    left = gamma;
+    node_parent[gamma] = i;
+  }
+  if (max(i, j) == gamma + 1) {
+    right = ~(gamma + 1);
+    point_parent[gamma + 1] = i;
+  }
+  else {
+    right = gamma + 1;
+    node_parent[gamma + 1] = i;
+  }
+  children[i] = make_int2(left, right);
+  range[i] = make_int2(min(i, j), max(i, j));
+  if (i == 0)
+    node_parent[0] = -1;
+}
+
+// keep[i] = node i stays an internal node of the final tree (holds more than kLeafSize points);
+// leaf_flag[pos] = 1 at the first sorted position of every leaf cell
+__global__ void k_mark_cells(int n, const int2* __restrict__ range, const int* __restrict__ node_parent,
+                             const int* __restrict__ point_parent, int* __restrict__ keep, int* __restrict__ leaf_flag)
+{
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n - 1) {
+    const int2 r = range[i];
+    const int cnt = r.y - r.x + 1;
+    const int par = node_parent[i];
+    const int pcnt = par < 0 ? 0x7fffffff : (range[par].y - range[par].x + 1);
+    keep[i] = cnt > kLeafSize ? 1 : 0;
+    if (cnt <= kLeafSize && pcnt > kLeafSize)
+      leaf_flag[r.x] = 1;
+  }
+  if (i < n) {
+    const int par = point_parent[i];
+    if (range[par].y - range[par].x + 1 > kLeafSize)
+      leaf_flag[i] = 1;  // a single point whose sibling subtree is large
+  }
+}
+
+__global__ void k_leaf_starts(int n, const int* __restrict__ leaf_flag, const int* __restrict__ leaf_incl,
+                              int* __restrict__ leaf_start)
+{
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n && leaf_flag[i])
+    leaf_start[leaf_incl[i] - 1] = i;
+}
+
+__global__ void k_fill_sentinels(float4* __restrict__ out, size_t n)
+{
+  size_t j = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+  if (j < n) {
+    const float inf = __int_as_float(0x7f800000);
+    out[j] = make_float4(inf, inf, inf, __int_as_float(kSentinelIndex));
+  }
+}
+
+// sorted position -> padded leaf slot
+__global__ void k_scatter_cells(const float4* __restrict__ p, const int32_t* __restrict__ vals,
+                                const int32_t* __restrict__ orig_of_slot, int n, const int* __restrict__ leaf_incl,
+                                const int* __restrict__ leaf_start, float4* __restrict__ out)
+{
+  int pos = blockIdx.x * blockDim.x + threadIdx.x;
+  if (pos >= n)
+    return;
+  const int leaf = leaf_incl[pos] - 1;
+  const int32_t slot = vals[pos];
+  const float4 v = __ldg(p + slot);
+  const int32_t oi = orig_of_slot ? orig_of_slot[slot] : slot;
+  out[(size_t)leaf * kLeafSize + (pos - leaf_start[leaf])] = make_float4(v.x, v.y, v.z, __int_as_float(oi));
+}
+
+// children / parents of the final tree (kept nodes renumbered by new_id; everything below becomes a leaf)
+__global__ void k_link_cells(int n, const int2* __restrict__ children, const int2* __restrict__ range,
+                             const int* __restrict__ keep, const int* __restrict__ new_id,
+                             const int* __restrict__ leaf_incl, int2* __restrict__ out_children,
+                             int* __restrict__ out_node_parent, int* __restrict__ out_leaf_parent)
+{
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n - 1 || !keep[i])
+    return;
+  const int nid = new_id[i];
+  const int2 ch = children[i];
+  int ref[2];
+  const int c2[2] = {ch.x, ch.y};
+#pragma unroll
+  for (int k = 0; k < 2; ++k) {
+    const int cc = c2[k];
+    if (cc >= 0 && keep[cc]) {
+      ref[k] = new_id[cc];
+      out_node_parent[new_id[cc]] = nid;
+    }
+    else {
+      const int first = cc >= 0 ? range[cc].x : ~cc;
+      const int leaf = leaf_incl[first] - 1;
+      ref[k] = ~leaf;
+      out_leaf_parent[leaf] = nid;
+    }
+  }
+  out_children[nid] = make_int2(ref[0], ref[1]);
+  if (i == 0)
+    out_node_parent[nid] = -1;
+}
+
 // ---- host orchestration -------------------------------------------------------------------------
 static inline unsigned grid_for(size_t n, int block) { return (unsigned)((n + block - 1) / block); }
 
@@ -456,41 +608,78 @@ static Index* build_from_dense(Ctx& c, const float4* d_pts, size_t n, const int3
     idx->hi[d] = sc.hi[d];
   }
   idx->morton_scale = sc.scale;
-  const int n_leaves = (int)((sc.n_valid + kLeafSize - 1) / kLeafSize);
-  idx->n_leaves = n_leaves;
-  const size_t n_padded = (size_t)n_leaves * kLeafSize;
-  idx->pts.alloc(n_padded, s);
-  k_gather_sorted<<<grid_for(n_padded, 256), 256, 0, s>>>(d_pts, sc.vals.p, d_orig_of_slot, sc.n_valid, n_padded,
-                                                          idx->pts.p);
-  ++c.launches;
-  if (n_leaves == 1) {
+  const int nv = (int)sc.n_valid;
+  if (nv <= kLeafSize) {
+    // the whole cloud is one leaf
+    idx->n_leaves = 1;
     idx->root = ~0;
+    idx->pts.alloc(kLeafSize, s);
+    k_gather_sorted<<<1, 256, 0, s>>>(d_pts, sc.vals.p, d_orig_of_slot, sc.n_valid, kLeafSize, idx->pts.p);
+    ++c.launches;
   }
   else {
-    const int n_int = n_leaves - 1;
+    // 1. radix tree over the points, 2. cut it where a cell holds <= kLeafSize points, 3. renumber, 4. refit + pack
+    const int ni = nv - 1;
+    DevBuf<int2> kchildren, krange;
+    DevBuf<int> knode_parent, kpoint_parent, keep, new_id, leaf_flag, leaf_incl;
+    kchildren.alloc(ni, s);
+    krange.alloc(ni, s);
+    knode_parent.alloc(ni, s);
+    kpoint_parent.alloc(nv, s);
+    keep.alloc(ni, s);
+    new_id.alloc(ni, s);
+    leaf_flag.alloc(nv, s);
+    leaf_incl.alloc(nv, s);
+    PCLB_CUDA(cudaMemsetAsync(leaf_flag.p, 0, leaf_flag.bytes(), s));
+    k_karras_points<<<grid_for(ni, 256), 256, 0, s>>>(sc.keys.p, nv, kchildren.p, knode_parent.p, kpoint_parent.p,
+                                                      krange.p);
+    k_mark_cells<<<grid_for(nv, 256), 256, 0, s>>>(nv, krange.p, knode_parent.p, kpoint_parent.p, keep.p, leaf_flag.p);
+    size_t tb = 0, tb2 = 0;
+    PCLB_CUDA(cub::DeviceScan::InclusiveSum(nullptr, tb, leaf_flag.p, leaf_incl.p, nv, s));
+    PCLB_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, tb2, keep.p, new_id.p, ni, s));
+    DevBuf<unsigned char> tmp;
+    tmp.alloc(std::max(tb, tb2), s);
+    PCLB_CUDA(cub::DeviceScan::InclusiveSum(tmp.p, tb, leaf_flag.p, leaf_incl.p, nv, s));
+    PCLB_CUDA(cub::DeviceScan::ExclusiveSum(tmp.p, tb2, keep.p, new_id.p, ni, s));
+    c.launches += 4;
+    int h_leaves = 0, h_last_id = 0, h_last_keep = 0;
+    PCLB_CUDA(cudaMemcpyAsync(&h_leaves, leaf_incl.p + (nv - 1), sizeof(int), cudaMemcpyDeviceToHost, s));
+    PCLB_CUDA(cudaMemcpyAsync(&h_last_id, new_id.p + (ni - 1), sizeof(int), cudaMemcpyDeviceToHost, s));
+    PCLB_CUDA(cudaMemcpyAsync(&h_last_keep, keep.p + (ni - 1), sizeof(int), cudaMemcpyDeviceToHost, s));
+    PCLB_CUDA(cudaStreamSynchronize(s));
+    const int n_leaves = h_leaves;
+    const int n_int = h_last_id + h_last_keep;
+    PCLB_REQUIRE(n_leaves >= 2 && n_int == n_leaves - 1, PCLB200_ERR_INTERNAL, "LBVH build: inconsistent cell cut");
+    idx->n_leaves = n_leaves;
     idx->root = 0;
+    const size_t n_padded = (size_t)n_leaves * kLeafSize;
+    idx->pts.alloc(n_padded, s);
     idx->nodes.alloc(n_int, s);
+    DevBuf<int> leaf_start, node_parent, leaf_parent;
     DevBuf<int2> children;
-    DevBuf<int> node_parent, leaf_parent;
     DevBuf<float4> leaf_lo, leaf_hi, node_lo, node_hi;
     DevBuf<unsigned> flags;
-    children.alloc(n_int, s);
+    leaf_start.alloc(n_leaves, s);
     node_parent.alloc(n_int, s);
     leaf_parent.alloc(n_leaves, s);
+    children.alloc(n_int, s);
     leaf_lo.alloc(n_leaves, s);
     leaf_hi.alloc(n_leaves, s);
     node_lo.alloc(n_int, s);
     node_hi.alloc(n_int, s);
     flags.alloc(n_int, s);
     PCLB_CUDA(cudaMemsetAsync(flags.p, 0, flags.bytes(), s));
-    // the sorted keys array has n entries >= n_padded? keys beyond n_valid are ~0 (invalid) or absent:
-    // leaf i's key is keys[i*kLeafSize], always < n_valid.
-    k_karras<<<grid_for(n_int, 256), 256, 0, s>>>(sc.keys.p, n_leaves, children.p, node_parent.p, leaf_parent.p);
+    k_leaf_starts<<<grid_for(nv, 256), 256, 0, s>>>(nv, leaf_flag.p, leaf_incl.p, leaf_start.p);
+    k_fill_sentinels<<<grid_for(n_padded, 256), 256, 0, s>>>(idx->pts.p, n_padded);
+    k_scatter_cells<<<grid_for(nv, 256), 256, 0, s>>>(d_pts, sc.vals.p, d_orig_of_slot, nv, leaf_incl.p, leaf_start.p,
+                                                      idx->pts.p);
+    k_link_cells<<<grid_for(ni, 256), 256, 0, s>>>(nv, kchildren.p, krange.p, keep.p, new_id.p, leaf_incl.p, children.p,
+                                                   node_parent.p, leaf_parent.p);
     k_refit<<<grid_for(n_leaves, 256), 256, 0, s>>>(idx->pts.p, n_leaves, children.p, node_parent.p, leaf_parent.p,
                                                     leaf_lo.p, leaf_hi.p, node_lo.p, node_hi.p, flags.p);
     k_pack_nodes<<<grid_for(n_int, 256), 256, 0, s>>>(n_int, children.p, leaf_lo.p, leaf_hi.p, node_lo.p, node_hi.p,
                                                      idx->nodes.p);
-    c.launches += 3;
+    c.launches += 8;
     PCLB_CUDA(cudaGetLastError());
   }
   PCLB_CUDA(cudaStreamSynchronize(s));  // temporaries are released stream-ordered; surface build errors here

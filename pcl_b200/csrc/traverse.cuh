@@ -195,10 +195,13 @@ __device__ __forceinline__ bool traverse_packet(const BvhNode* __restrict__ node
       const float bnd = v.best;
       const unsigned ml = __reduce_min_sync(full, dl <= bnd ? __float_as_uint(dl) : INF_BITS);
       const unsigned mr = __reduce_min_sync(full, dr <= bnd ? __float_as_uint(dr) : INF_BITS);
-      // a child no lane wants is skipped for good: each lane notes ITS OWN bound to that box
-      if (ml == INF_BITS)
+      // Lower-bound bookkeeping (TRACK visitors): a lane that does not need a child notes ITS OWN bound to that
+      // box, whether or not the warp enters the subtree for other lanes.  (The warp-minimum stored with a pushed
+      // entry is a minimum over the lanes that WANTED it, so it bounds only those lanes when the entry is later
+      // discarded; the others are covered here.)
+      if (!(dl <= bnd))
         v.prune(dl);
-      if (mr == INF_BITS)
+      if (!(dr <= bnd))
         v.prune(dr);
       if (ml == INF_BITS && mr == INF_BITS) {
         node = kDone;

@@ -397,11 +397,7 @@ def test_voxelgrid_golden_and_oracle(gpu, golden, orc):
         assert g.shape == o.shape and np.array_equal(g, o), (leaf, mp)
 
 
-def test_icp_per_iteration_correspondences_exact(gpu, orc):
-    """The search kernels skip the tree walk for queries whose previous match is provably still nearest (temporal
-    coherence).  That must never change a result: every iteration's correspondence list is compared, bit for bit,
-    with a fresh exact search of the oracle on the same (re-transformed) cloud."""
-    P, ctx = gpu
+def _coherence_scenes():
     rng = np.random.default_rng(77)
     n = 50000
     xy = rng.random((n, 2)) * 4
@@ -410,27 +406,48 @@ def test_icp_per_iteration_correspondences_exact(gpu, orc):
     R = np.array([[np.cos(a), -np.sin(a), 0], [np.sin(a), np.cos(a), 0], [0, 0, 1]])
     src = (tgt.astype(np.float64)[::2] @ R.T + [0.01, 0.005, -0.004]).astype(np.float32)
     src[5, 0] = np.nan
-    T, S = P.xyz1(tgt), P.xyz1(src)
-    oidx = orc.Index(T)
+    yield "surface_subsample", tgt, src, 0.05
+    # a different sample of the same surface (no exact mates), tiny motion: the regime where most walks are skipped
+    xy2 = rng.random((30000, 2)) * 4
+    src2 = np.column_stack([xy2 + 0.0005, 0.3 * np.sin(xy2[:, 0]) * np.cos(xy2[:, 1]) + rng.normal(0, 0.002, 30000)]).astype(np.float32)
+    yield "surface_resample", tgt, src2, 0.05
+    cube = rng.random((40000, 3), dtype=np.float32)
+    yield "cube_gated", cube, (cube[:20000].astype(np.float64) * 1.0005 + 0.002).astype(np.float32), 0.02
+    g = np.stack(np.meshgrid(*[np.arange(24, dtype=np.float32)] * 3, indexing="ij"), -1).reshape(-1, 3)
+    yield "lattice_ties", g, (g[::3] + np.float32(0.26)).astype(np.float32), 1e9
+
+
+def test_icp_per_iteration_correspondences_exact(gpu, orc):
+    """The search kernels skip the tree walk for queries whose previous match is provably still nearest (temporal
+    coherence).  That must never change a result: every iteration's correspondence list is compared, bit for bit,
+    with a fresh exact search of the oracle on the same (re-transformed) cloud — for both search kernels, with the
+    lower-bound tracking forced on from the first iteration, on scenes with duplicates, exact ties, a gate and NaNs."""
     import os
-    os.environ["PCLB200_TRACK"] = "1"   # force the skip test on from the first iteration
-    for search in ("packet", "single"):
-        os.environ["PCLB200_SEARCH"] = search
-        s = P.Icp(ctx, max_iterations=25, max_correspondence_distance=0.05, is_dense=0, mse_threshold_absolute=0.0)
-        s.set_target(P.Index(ctx, T))
-        s.set_source(S)
-        cloud = S.copy()
-        skipped_any = False
-        for it in range(25):
-            st = s.iterate(1)
-            g = s.get_correspondences()
-            o = oidx.correspondences(cloud, max_distance=0.05, is_dense=False, nthreads=4)
-            assert np.array_equal(g, o), (search, it, g.size, o.size)
-            assert st["n_correspondences"] == o.size
-            cloud = orc.transform(cloud, st["last"], mode=0)   # IterativeClosestPoint::transformCloud, fp32
-            if st["state"] != 0:
-                break
-        assert st["iterations"] >= 5
-        assert st["total_skipped_walks"] > 0, "the temporal-coherence path was never exercised"
-    os.environ.pop("PCLB200_SEARCH", None)
-    os.environ.pop("PCLB200_TRACK", None)
+    P, ctx = gpu
+    os.environ["PCLB200_TRACK"] = "1"
+    total_skipped = 0
+    try:
+        for name, tgt, src, gate in _coherence_scenes():
+            T, S = P.xyz1(tgt), P.xyz1(src)
+            oidx = orc.Index(T)
+            for search in ("packet", "single"):
+                os.environ["PCLB200_SEARCH"] = search
+                s = P.Icp(ctx, max_iterations=30, max_correspondence_distance=gate, is_dense=0, mse_threshold_absolute=0.0)
+                s.set_target(P.Index(ctx, T))
+                s.set_source(S)
+                cloud = S.copy()
+                st = None
+                for it in range(30):
+                    st = s.iterate(1)
+                    g = s.get_correspondences()
+                    o = oidx.correspondences(cloud, max_distance=gate, is_dense=False, nthreads=4)
+                    assert np.array_equal(g, o), (name, search, it, g.size, o.size)
+                    assert st["n_correspondences"] == o.size
+                    cloud = orc.transform(cloud, st["last"], mode=0)   # IterativeClosestPoint::transformCloud, fp32
+                    if st["state"] != 0:
+                        break
+                total_skipped += st["total_skipped_walks"]
+        assert total_skipped > 0, "the temporal-coherence path was never exercised"
+    finally:
+        os.environ.pop("PCLB200_SEARCH", None)
+        os.environ.pop("PCLB200_TRACK", None)
