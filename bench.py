@@ -13,7 +13,7 @@ registration.h:566) over the whole source cloud: source upload -> Morton orderin
 before the timed region, exactly as pcl::Registration keeps its tree across align() calls
 (registration.hpp:84-87).
   value : correspondences/s with source, target index and output resident in HBM (device pointers through
-          the same C-ABI call pclb200_icp_align)
+          the same C-ABI calls pclb200_icp_set_source / _iterate / _get_cloud the C++ facade's align() makes)
   e2e   : the same call with HOST buffers (pinned pcl::PointNormal records, 48 B/pt): H2D of the source and
           D2H of the aligned cloud inside the timed region
   N > 1 : weak scaling — every rank holds a replica of the target index and its own 10 M-point source shard;
@@ -298,17 +298,22 @@ def run_ours(args):
             dist.destroy_process_group()
         return
 
-    # roofline of the dominant kernel (k_search), algorithmic bytes per correspondence:
-    #   16 source read + 16 source write-back (T_k applied in place) + 8 seed read + 8 match write
-    #   + (16*N_t points + 64*N_t/8 nodes)/N_s, each read once under Morton-coherent queries  = 72 B at N_s = N_t
-    bytes_per_corr = 16 + 16 + 8 + 8 + (16 + 8) * 1.0
+    # roofline of the dominant kernel (k_search_packet), algorithmic bytes per correspondence:
+    #   16 source read + 16 source write-back (T_k applied in place) + 16 previous match read + 16 match write
+    #   + (target leaf slots + nodes, each read once under Hilbert-coherent query packets) / N_s
+    st_idx = tidx.stats
+    bytes_per_corr = 16 + 16 + 16 + 16 + st_idx["bytes"] / float(n)
     peak, peak_src = measured_peak_gbs()
     avg_iter_s = (iter_ms / max(iter_n, 1)) * 1e-3
     achieved = bytes_per_corr * n / avg_iter_s / 1e9 if avg_iter_s > 0 else 0.0
-    roofline = {"bound": "hbm", "kernel": "k_search (1-NN + gate + in-place transform)", "achieved": achieved, "peak": peak,
-                "peak_source": peak_src, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+    roofline = {"bound": "hbm", "kernel": "k_search_packet (in-place transform + exact 1-NN + gate)", "achieved": achieved, "peak": peak,
+                "peak_source": peak_src, "unit": "GB/s", "frac": achieved / peak,
+                # dram__bytes_read.sum + dram__bytes_write.sum of one `ncu --set full` capture of this kernel on this
+                # workload (profiles/r1e_k_search_packet_ncu.txt: 657.6 MB + 288.0 MB); only valid for the 10 M default
+                "traffic": 945.6e6 if n == N_DEFAULT else None,
                 "algorithmic_bytes_per_launch": bytes_per_corr * n, "avg_launch_ms": avg_iter_s * 1e3,
-                "launches_timed": iter_n,
+                "launches_timed": iter_n, "algorithmic_bytes_per_correspondence": bytes_per_corr,
+                "index": st_idx,
                 "note": "BVH traversal is latency/issue bound, not HBM bound (SURVEY.md §7 hard part ii, DESIGN.md)"}
 
     # CPU baseline (oracle port) on a bounded sample: one align() of ICP_ITERS iterations, sample sized for ~15 s
