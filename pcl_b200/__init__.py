@@ -301,8 +301,8 @@ class Index:
     def knn(self, q, k, out_idx=None, out_d2=None):
         b = _Buf(q)
         if out_idx is None:
-            out_idx = np.empty((b.rows, k), dtype=np.int32)
-            out_d2 = np.empty((b.rows, k), dtype=np.float32)
+            out_idx = np.empty((b.rows, max(k, 0)), dtype=np.int32)
+            out_d2 = np.empty((b.rows, max(k, 0)), dtype=np.float32)
         oi, od = _Buf(out_idx, np.int32), _Buf(out_d2)
         keff = C.c_int()
         _check(lib().pclb200_knn(self.ctx.h, self.h, b.ptr, b.rows, b.stride, k, oi.ptr, od.ptr, C.byref(keff)))
