@@ -205,7 +205,8 @@ int main(int argc, char** argv)
   const int npk = std::min(n / 32, 20000);
   const int stride = (n / 32) / npk;
   double tot_nodes = 0, tot_leaves = 0, tot_pts = 0, tot_single_nodes = 0, tot_single_leaves = 0;
-#pragma omp parallel for reduction(+ : tot_nodes, tot_leaves, tot_pts, tot_single_nodes, tot_single_leaves) schedule(dynamic, 64)
+  double w_nodes = 0, w_boxes = 0, w_leaves = 0;
+#pragma omp parallel for reduction(+ : tot_nodes, tot_leaves, tot_pts, tot_single_nodes, tot_single_leaves, w_nodes, w_boxes, w_leaves) schedule(dynamic, 64)
   for (int pk = 0; pk < npk; ++pk) {
     const P3* q = &src[(size_t)pk * stride * 32];
     float best[32];
@@ -234,6 +235,43 @@ int main(int argc, char** argv)
         float d0 = bdist(q[l], t.nodes[nd].b[0]), d1 = bdist(q[l], t.nodes[nd].b[1]);
         if (d1 <= b) s2.push_back({t.nodes[nd].child[1], d1});
         if (d0 <= b) s2.push_back({t.nodes[nd].child[0], d0});
+      }
+    }
+    // 4-wide packet walk: a wide node = a binary node with its internal children expanded one level
+    {
+      float b4[32];
+      for (int l = 0; l < 32; ++l) b4[l] = best[l];
+      std::vector<std::pair<int, float>> s4{{t.root, 0.f}};
+      while (!s4.empty()) {
+        auto e = s4.back(); s4.pop_back();
+        float wmax = 0;
+        for (int l = 0; l < 32; ++l) wmax = std::max(wmax, b4[l]);
+        if (e.second > wmax) continue;
+        if (e.first < 0) {
+          const Leaf& lf = t.leaves[~e.first];
+          w_leaves += 1;
+          for (int l = 0; l < 32; ++l)
+            for (int i = 0; i < lf.count; ++i) b4[l] = std::min(b4[l], pdist(q[l], t.pts[lf.first + i]));
+          continue;
+        }
+        w_nodes += 1;
+        // gather up to 4 children
+        int ch[4]; Box bx[4]; int nc = 0;
+        const Node& nd = t.nodes[e.first];
+        for (int k = 0; k < 2; ++k) {
+          int c = nd.child[k];
+          if (c >= 0) { for (int k2 = 0; k2 < 2; ++k2) { ch[nc] = t.nodes[c].child[k2]; bx[nc] = t.nodes[c].b[k2]; ++nc; } }
+          else { ch[nc] = c; bx[nc] = nd.b[k]; ++nc; }
+        }
+        w_boxes += nc;
+        std::pair<float, int> want[4]; int nw = 0;
+        for (int k = 0; k < nc; ++k) {
+          float m = 1e30f;
+          for (int l = 0; l < 32; ++l) { float d = bdist(q[l], bx[k]); if (d <= b4[l]) m = std::min(m, d); }
+          if (m != 1e30f) want[nw++] = {m, ch[k]};
+        }
+        std::sort(want, want + nw, [](auto& a, auto& b) { return a.first > b.first; });
+        for (int k = 0; k < nw; ++k) s4.push_back({want[k].second, want[k].first});
       }
     }
     // packet walk
@@ -279,5 +317,7 @@ int main(int argc, char** argv)
   }
   std::printf("packet walk: %.1f nodes, %.1f leaves, %.1f points per packet | single walk: %.1f nodes, %.1f leaves per query\n", tot_nodes / npk,
               tot_leaves / npk, tot_pts / npk, tot_single_nodes / npk / 32, tot_single_leaves / npk / 32);
+  std::printf("4-wide packet walk: %.1f wide nodes, %.1f box tests, %.1f leaves per packet (binary: %.1f box tests)\n", w_nodes / npk, w_boxes / npk,
+              w_leaves / npk, 2 * tot_nodes / npk);
   return 0;
 }
