@@ -127,6 +127,29 @@ PCLB200_API int pclb200_correspondences(pclb200_ctx* ctx, const pclb200_index* i
                                         int is_dense, double max_dist, pclb200_corr* out,
                                         size_t* n_out);
 
+/* ---- correspondence rejectors: the stage between estimation and solve, icp.hpp:187-201 -------
+ * DISTANCE   CorrespondenceRejectorDistance        registration/src/correspondence_rejection_distance.cpp:44-68
+ *            p = maximum distance (NOT squared, as setMaximumDistance takes it); keeps distance < p*p
+ * MEDIAN     CorrespondenceRejectorMedianDistance  .../correspondence_rejection_median_distance.cpp:44-70
+ *            p = median factor; keeps distance <= median * p; *median_out = the median (squared) distance
+ * ONE_TO_ONE CorrespondenceRejectorOneToOne        .../correspondence_rejection_one_to_one.cpp:44-71
+ *            the closest query of every index_match; output ordered by index_match
+ * TRIMMED    CorrespondenceRejectorTrimmed         .../correspondence_rejection_trimmed.cpp:44-63
+ *            p = overlap ratio; keeps max(floor(p * n), min_correspondences) smallest distances (sorted output)
+ * Exact-distance ties (std::sort in the reference is unstable) resolve to the entry that comes first in the input. */
+#define PCLB200_REJ_DISTANCE 0
+#define PCLB200_REJ_MEDIAN 1
+#define PCLB200_REJ_ONE_TO_ONE 2
+#define PCLB200_REJ_TRIMMED 3
+typedef struct pclb200_rejector {
+  int32_t kind;
+  int32_t min_correspondences; /* TRIMMED only (nr_min_correspondences_) */
+  double p;
+} pclb200_rejector;
+/* getRemainingCorrespondences: in/out may be host or device arrays; out capacity n */
+PCLB200_API int pclb200_reject(pclb200_ctx* ctx, const pclb200_rejector* rejector, const pclb200_corr* in, size_t n,
+                               pclb200_corr* out, size_t* n_out, double* median_out);
+
 /* ---- transformation estimation: replaces TransformationEstimationSVD::estimateRigidTransformation
  * (impl/transformation_estimation_svd.hpp:50-181, Umeyama path, common/impl/eigen.hpp:675-734) and
  * TransformationEstimationPointToPlaneLLS (impl/transformation_estimation_point_to_plane_lls.hpp
@@ -202,6 +225,10 @@ PCLB200_API int pclb200_icp_create(pclb200_ctx* ctx, const pclb200_icp_params* p
                                    pclb200_icp** out);
 PCLB200_API int pclb200_icp_destroy(pclb200_icp* icp);
 PCLB200_API int pclb200_icp_set_params(pclb200_icp* icp, const pclb200_icp_params* params);
+/* Registration::addCorrespondenceRejector / clearCorrespondenceRejectors (registration.h:373-416): the chain is
+ * applied on the device, in order, to every iteration's correspondences (n == 0 clears it).  Not available together
+ * with a multi-GPU communicator (median / trimmed are global statistics of the whole correspondence set). */
+PCLB200_API int pclb200_icp_set_rejectors(pclb200_icp* icp, const pclb200_rejector* list, int n);
 PCLB200_API int pclb200_icp_set_target(pclb200_icp* icp, const pclb200_index* idx_tgt,
                                        const void* tgt_normals, size_t stride_n);
 PCLB200_API int pclb200_icp_set_source(pclb200_icp* icp, const void* src, size_t n, size_t stride,

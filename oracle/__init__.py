@@ -45,6 +45,12 @@ class IcpResult(C.Structure):
                 ("n_correspondences", C.c_int32), ("mse", C.c_double), ("total_correspondences", C.c_longlong)]
 
 
+class Rejector(C.Structure):
+    _fields_ = [("kind", C.c_int32), ("min_correspondences", C.c_int32), ("p", C.c_double)]
+
+
+REJ_DISTANCE, REJ_MEDIAN, REJ_ONE_TO_ONE, REJ_TRIMMED = 0, 1, 2, 3
+
 _lib = None
 
 
@@ -71,6 +77,9 @@ def lib():
         L.orc_transform.argtypes = [fp, sz, sz, C.c_int, dp, C.c_int, C.c_int]
         L.orc_icp_align.argtypes = [C.POINTER(IcpParams), fp, sz, sz, i32p, sz, fp, sz, sz, dp, C.POINTER(IcpResult), fp]
         L.orc_icp_align_tree.argtypes = [C.POINTER(IcpParams), vp, fp, sz, sz, i32p, sz, fp, sz, sz, dp, C.POINTER(IcpResult), fp]
+        L.orc_reject.restype = sz
+        L.orc_reject.argtypes = [C.POINTER(Rejector), C.POINTER(Corr), sz, C.POINTER(Corr), dp]
+        L.orc_icp_align_rej.argtypes = [C.POINTER(IcpParams), C.POINTER(Rejector), C.c_int, fp, sz, sz, fp, sz, sz, C.POINTER(IcpResult)]
         L.orc_fitness_score.restype = C.c_double
         L.orc_fitness_score.argtypes = [vp, fp, sz, sz, i32p, sz, C.c_int, dp, C.c_int, C.c_double, C.c_int]
         L.orc_voxelgrid.restype = C.c_longlong
@@ -270,6 +279,31 @@ def icp_align(src, tgt, max_iterations=10, max_correspondence_distance=np.sqrt(n
     if want_cloud:
         res["cloud"] = out
     return res
+
+
+def reject(corr, kind, p=0.0, min_correspondences=0):
+    """Applies one correspondence rejector; returns (remaining, median) (median only meaningful for REJ_MEDIAN)."""
+    corr = np.ascontiguousarray(corr, dtype=CORR_DTYPE)
+    out = np.empty(max(corr.size, 1), dtype=CORR_DTYPE)
+    r = Rejector(kind, min_correspondences, float(p))
+    med = C.c_double(0.0)
+    m = lib().orc_reject(C.byref(r), corr.ctypes.data_as(C.POINTER(Corr)), corr.size, out.ctypes.data_as(C.POINTER(Corr)),
+                         C.byref(med))
+    return out[:m].copy(), float(med.value)
+
+
+def icp_align_rejectors(src, tgt, rejectors, **kw):
+    """ICP with a chain of rejectors [(kind, p, min_correspondences), ...] (icp.hpp:187-201)."""
+    src, tgt = as_cloud(src), as_cloud(tgt)
+    P = IcpParams(kw.get("max_iterations", 10), 0, 0, int(kw.get("scalar_is_double", False)), 0, 0, 1,
+                  kw.get("nthreads", 1), float(kw.get("max_correspondence_distance", np.sqrt(np.finfo(np.float64).max))),
+                  float(kw.get("transformation_epsilon", 0.0)), 0.0, float(kw.get("euclidean_fitness_epsilon", -np.finfo(np.float64).max)))
+    arr = (Rejector * len(rejectors))(*[Rejector(k, m, float(p)) for (k, p, m) in rejectors])
+    R = IcpResult()
+    lib().orc_icp_align_rej(C.byref(P), arr, len(rejectors), _f(src), src.shape[0], src.shape[1], _f(tgt), tgt.shape[0],
+                            tgt.shape[1], C.byref(R))
+    return dict(final=np.array(R.final_transformation).reshape(4, 4), converged=bool(R.converged), state=int(R.state),
+                iterations=int(R.iterations), n_correspondences=int(R.n_correspondences), mse=float(R.mse))
 
 
 def voxelgrid(cloud, leaf, min_points_per_voxel=0, indices=None, is_dense=True):

@@ -1168,6 +1168,82 @@ ORC_API void orc_transform(float* pts, size_t n, size_t stride, int normal_off, 
   }
 }
 
+// ---- correspondence rejectors ----------------------------------------------------------
+// registration/src/correspondence_rejection_distance.cpp:44-68            keep distance <  max_dist^2 (float), order kept
+// registration/src/correspondence_rejection_median_distance.cpp:44-70     keep distance <= median * factor (double), order kept
+// registration/src/correspondence_rejection_one_to_one.cpp:44-71          sort by (index_match, distance), first per match
+// registration/src/correspondence_rejection_trimmed.cpp:44-63             floor(overlap * n) (>= min) smallest distances
+// std::sort in the last two is unstable; canonical tie rule here and on the device: smaller index_query first.
+enum { REJ_DISTANCE = 0, REJ_MEDIAN = 1, REJ_ONE_TO_ONE = 2, REJ_TRIMMED = 3 };
+
+struct orc_rejector {
+  int32_t kind;
+  int32_t min_correspondences;  // trimmed: nr_min_correspondences_
+  double p;                     // distance: max distance (not squared); median: factor; trimmed: overlap ratio
+};
+
+static void apply_rejector(const orc_rejector& r, std::vector<orc_corr>& c, double* median_out)
+{
+  std::vector<orc_corr> out;
+  out.reserve(c.size());
+  if (r.kind == REJ_DISTANCE) {
+    const float md = static_cast<float>(r.p) * static_cast<float>(r.p);  // setMaximumDistance: max_distance_ = d*d (float)
+    for (const auto& x : c)
+      if (x.distance < md)
+        out.push_back(x);
+  }
+  else if (r.kind == REJ_MEDIAN) {
+    if (c.empty())
+      return;
+    std::vector<double> d(c.size());
+    for (size_t i = 0; i < c.size(); ++i)
+      d[i] = c[i].distance;
+    std::vector<double> nth(d);
+    std::nth_element(nth.begin(), nth.begin() + (nth.size() / 2), nth.end());
+    const double med = nth[nth.size() / 2];
+    if (median_out)
+      *median_out = med;
+    for (size_t i = 0; i < c.size(); ++i)
+      if (d[i] <= med * r.p)
+        out.push_back(c[i]);
+  }
+  else if (r.kind == REJ_ONE_TO_ONE) {
+    std::vector<orc_corr> in(c);
+    std::stable_sort(in.begin(), in.end(), [](const orc_corr& a, const orc_corr& b) {
+      return a.index_match < b.index_match || (a.index_match == b.index_match && a.distance < b.distance);
+    });
+    int32_t last = -1;
+    for (const auto& x : in) {
+      if (x.index_match < 0)
+        continue;
+      if (x.index_match != last) {
+        out.push_back(x);
+        last = x.index_match;
+      }
+    }
+  }
+  else {  // trimmed
+    unsigned keep = static_cast<unsigned>(std::floor(static_cast<float>(r.p) * static_cast<float>(c.size())));
+    keep = std::max(keep, static_cast<unsigned>(r.min_correspondences));
+    if (keep < c.size()) {
+      out = c;
+      std::stable_sort(out.begin(), out.end(), [](const orc_corr& a, const orc_corr& b) { return a.distance < b.distance; });
+      out.resize(keep);
+    }
+    else
+      return;
+  }
+  c.swap(out);
+}
+
+ORC_API size_t orc_reject(const orc_rejector* r, const orc_corr* in, size_t n, orc_corr* out, double* median_out)
+{
+  std::vector<orc_corr> c(in, in + n);
+  apply_rejector(*r, c, median_out);
+  std::copy(c.begin(), c.end(), out);
+  return c.size();
+}
+
 // ---- ICP --------------------------------------------------------------------------------
 struct orc_icp_params {
   int32_t max_iterations;            // registration.h:566 default 10
@@ -1198,7 +1274,8 @@ struct orc_icp_result {
 template <typename S>
 static void icp_run(const orc_icp_params& P, const float* src, size_t n_s, size_t ss,
                     const int32_t* indices, size_t n_idx, const float* tgt, size_t n_t, size_t ts,
-                    const double* guess, orc_icp_result& R, float* out_cloud, void* prebuilt_tree = nullptr)
+                    const double* guess, orc_icp_result& R, float* out_cloud, void* prebuilt_tree = nullptr,
+                    const orc_rejector* rejectors = nullptr, int n_rejectors = 0)
 {
   // Registration::align (registration/.../impl/registration.hpp:172-221) +
   // IterativeClosestPoint::computeTransformation (impl/icp.hpp:113-268)
@@ -1243,6 +1320,13 @@ static void icp_run(const orc_icp_params& P, const float* src, size_t n_s, size_
     else
       nc = orc_correspondences(tree, cur.data(), n_s, ss, indices, n_idx, P.is_dense,
                                P.max_correspondence_distance, corr.data(), P.nthreads);
+    if (n_rejectors > 0) {  // icp.hpp:187-201: each rejector filters the previous one's output
+      std::vector<orc_corr> cc(corr.begin(), corr.begin() + nc);
+      for (int ri = 0; ri < n_rejectors; ++ri)
+        apply_rejector(rejectors[ri], cc, nullptr);
+      nc = cc.size();
+      std::copy(cc.begin(), cc.end(), corr.begin());
+    }
     total_nc += (long long)nc;
     if (nc < 3) {  // min_number_correspondences_, registration.h:621; icp.hpp:204-213
       conv.state = NO_CORRESPONDENCES;
@@ -1303,6 +1387,16 @@ ORC_API void orc_icp_align_tree(const orc_icp_params* P, void* h_tgt, const floa
     icp_run<double>(*P, src, n_s, sstride, indices, n_idx, tgt, n_t, tstride, guess, *R, out_cloud, h_tgt);
   else
     icp_run<float>(*P, src, n_s, sstride, indices, n_idx, tgt, n_t, tstride, guess, *R, out_cloud, h_tgt);
+}
+
+ORC_API void orc_icp_align_rej(const orc_icp_params* P, const orc_rejector* rej, int n_rej, const float* src,
+                               size_t n_s, size_t sstride, const float* tgt, size_t n_t, size_t tstride,
+                               orc_icp_result* R)
+{
+  if (P->scalar_is_double)
+    icp_run<double>(*P, src, n_s, sstride, nullptr, 0, tgt, n_t, tstride, nullptr, *R, nullptr, nullptr, rej, n_rej);
+  else
+    icp_run<float>(*P, src, n_s, sstride, nullptr, 0, tgt, n_t, tstride, nullptr, *R, nullptr, nullptr, rej, n_rej);
 }
 
 // Registration::getFitnessScore — registration/.../impl/registration.hpp:134-168

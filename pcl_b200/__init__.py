@@ -51,6 +51,13 @@ class IcpStats(C.Structure):
                     last=np.array(self.last_transformation).reshape(4, 4))
 
 
+class Rejector(C.Structure):
+    _fields_ = [("kind", C.c_int32), ("min_correspondences", C.c_int32), ("p", C.c_double)]
+
+
+REJ_DISTANCE, REJ_MEDIAN, REJ_ONE_TO_ONE, REJ_TRIMMED = 0, 1, 2, 3
+
+
 # every symbol include/pclb200.h declares (tests/test_capi_symbols.py checks the two lists agree)
 SYMBOLS = [
     "pclb200_version", "pclb200_last_error", "pclb200_create", "pclb200_destroy", "pclb200_synchronize",
@@ -61,7 +68,7 @@ SYMBOLS = [
     "pclb200_icp_create", "pclb200_icp_destroy", "pclb200_icp_set_params", "pclb200_icp_set_target",
     "pclb200_icp_set_source", "pclb200_icp_iterate", "pclb200_icp_get_cloud", "pclb200_icp_get_correspondences",
     "pclb200_icp_align",
-    "pclb200_fitness_score", "pclb200_normals_knn", "pclb200_voxelgrid", "pclb200_comm_unique_id",
+    "pclb200_fitness_score", "pclb200_reject", "pclb200_icp_set_rejectors", "pclb200_normals_knn", "pclb200_voxelgrid", "pclb200_comm_unique_id",
     "pclb200_comm_init",
 ]
 
@@ -111,6 +118,8 @@ def lib():
     L.pclb200_icp_get_correspondences.argtypes = [vp, vp, C.POINTER(sz)]
     L.pclb200_icp_align.argtypes = [vp, C.POINTER(IcpParams), vp, sz, sz, vp, sz, vp, sz, vp, vp, sz, dp, vp, sz,
                                     C.POINTER(IcpStats)]
+    L.pclb200_reject.argtypes = [vp, C.POINTER(Rejector), vp, sz, vp, C.POINTER(sz), dp]
+    L.pclb200_icp_set_rejectors.argtypes = [vp, C.POINTER(Rejector), C.c_int]
     L.pclb200_fitness_score.argtypes = [vp, vp, vp, sz, sz, vp, sz, C.c_int, dp, C.c_int, C.c_double, dp]
     L.pclb200_normals_knn.argtypes = [vp, vp, vp, sz, sz, vp, sz, C.c_int, C.c_int, fp, vp, C.POINTER(C.c_int)]
     L.pclb200_voxelgrid.argtypes = [vp, vp, sz, sz, vp, sz, C.c_int, fp, C.c_uint, vp, C.POINTER(sz)]
@@ -240,6 +249,16 @@ class Context:
         _check(lib().pclb200_voxelgrid(self.h, b.ptr, b.rows, b.stride, ib.ptr, ib.rows, int(is_dense), leaf,
                                        int(min_points_per_voxel), ob.ptr, C.byref(m)))
         return out[:m.value].copy() if host_out else out[:m.value]
+
+    def reject(self, corr, kind, p=0.0, min_correspondences=0):
+        """One correspondence rejector (getRemainingCorrespondences); returns (remaining, median)."""
+        corr = np.ascontiguousarray(corr, dtype=CORR_DTYPE)
+        out = np.empty(max(corr.size, 1), dtype=CORR_DTYPE)
+        r = Rejector(kind, min_correspondences, float(p))
+        m, med = C.c_size_t(), C.c_double()
+        _check(lib().pclb200_reject(self.h, C.byref(r), C.c_void_p(corr.ctypes.data), corr.size,
+                                    C.c_void_p(out.ctypes.data), C.byref(m), C.byref(med)))
+        return out[:m.value].copy(), float(med.value)
 
     def estimate_svd(self, src, tgt, corr=None, scalar_is_double=False):
         s, t = _Buf(src), _Buf(tgt)
@@ -379,6 +398,11 @@ class Icp:
             self.close()
         except Exception:
             pass
+
+    def set_rejectors(self, rejectors):
+        """rejectors: [(kind, p, min_correspondences), ...] applied in order every iteration; [] clears."""
+        arr = (Rejector * max(len(rejectors), 1))(*[Rejector(k, m, float(p)) for (k, p, m) in rejectors])
+        _check(lib().pclb200_icp_set_rejectors(self.h, arr, len(rejectors)))
 
     def set_target(self, index, normals=None):
         nb = _Buf(normals)

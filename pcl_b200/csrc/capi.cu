@@ -16,6 +16,9 @@ struct Icp;
 Icp* icp_create(Ctx& c, const pclb200_icp_params& P);
 void icp_destroy(Icp* s);
 void icp_set_params(Icp& s, const pclb200_icp_params& P);
+void icp_set_rejectors(Icp& s, const pclb200_rejector* list, int n);
+size_t reject_standalone(Ctx& c, const pclb200_rejector& r, const pclb200_corr* in, size_t n, pclb200_corr* out,
+                         double* median_out);
 void icp_set_target(Icp& s, const Index* idx, const void* tgt_normals, size_t stride_n);
 void icp_set_source(Icp& s, const void* src, size_t n, size_t stride, const void* src_normals, size_t stride_n,
                     const int32_t* indices, size_t n_idx, const double* guess);
@@ -537,6 +540,27 @@ int pclb200_icp_set_params(pclb200_icp* icp, const pclb200_icp_params* params)
   return guarded([&] {
     PCLB_REQUIRE(icp && params, PCLB200_ERR_INVALID, "NULL argument");
     icp_set_params(*icp->s, *params);
+  });
+}
+
+int pclb200_icp_set_rejectors(pclb200_icp* icp, const pclb200_rejector* list, int n)
+{
+  return guarded([&] {
+    PCLB_REQUIRE(icp && (n <= 0 || list), PCLB200_ERR_INVALID, "NULL argument");
+    icp_set_rejectors(*icp->s, list, n);
+  });
+}
+
+int pclb200_reject(pclb200_ctx* ctx, const pclb200_rejector* rejector, const pclb200_corr* in, size_t n,
+                   pclb200_corr* out, size_t* n_out, double* median_out)
+{
+  return guarded([&] {
+    PCLB_REQUIRE(ctx && rejector && n_out && (n == 0 || (in && out)), PCLB200_ERR_INVALID, "NULL argument");
+    PCLB_REQUIRE(rejector->kind >= PCLB200_REJ_DISTANCE && rejector->kind <= PCLB200_REJ_TRIMMED, PCLB200_ERR_INVALID,
+                 "unknown rejector kind");
+    std::lock_guard<std::recursive_mutex> lk(ctx->c.mu);
+    PCLB_CUDA(cudaSetDevice(ctx->c.device));
+    *n_out = reject_standalone(ctx->c, *rejector, in, n, out, median_out);
   });
 }
 

@@ -900,6 +900,7 @@ struct Icp {
   DevBuf<SolveOut> solve_out;
   DevBuf<unsigned long long> skip_count;
   int64_t total_skipped = 0;
+  std::vector<pclb200_rejector> rejectors;  // applied in order after every search (icp.hpp:187-201)
   bool track_next = false;      // run the next search with lower-bound tracking / skip test (set per iteration)
   Reducer red;
   // host state (Scalar-typed values are kept in double; float mode rounds after every operation)
@@ -959,6 +960,62 @@ Icp* icp_create(Ctx& c, const pclb200_icp_params& P)
 void icp_destroy(Icp* s) { delete s; }
 
 void icp_set_params(Icp& s, const pclb200_icp_params& P) { s.P = P; }
+
+void icp_set_rejectors(Icp& s, const pclb200_rejector* list, int n)
+{
+  s.rejectors.assign(list, list + (n > 0 ? n : 0));
+  for (const auto& r : s.rejectors)
+    PCLB_REQUIRE(r.kind >= PCLB200_REJ_DISTANCE && r.kind <= PCLB200_REJ_TRIMMED, PCLB200_ERR_INVALID, "unknown rejector kind");
+}
+
+// Match array <-> flat rejector arrays (tie-break = slot = position in the source index list = the order of the
+// reference's correspondences_ vector; target identity = position in the Morton array)
+__global__ void k_match_to_arrays(const float4* __restrict__ cur, const Match* __restrict__ match, size_t n,
+                                  float* __restrict__ d2, int* __restrict__ mt, unsigned* __restrict__ tie, int* __restrict__ acc)
+{
+  size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+  if (i >= n)
+    return;
+  const Match m = match[i];
+  d2[i] = m.d2;
+  mt[i] = m.pos;
+  tie[i] = (unsigned)__float_as_int(cur[i].w);
+  acc[i] = m.accepted;
+}
+
+__global__ void k_arrays_to_match(const int* __restrict__ acc, size_t n, Match* __restrict__ match)
+{
+  size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+  if (i < n)
+    match[i].accepted = acc[i];
+}
+
+static void run_rejectors(Icp& s)
+{
+  Ctx& c = *s.ctx;
+  cudaStream_t st = c.stream;
+  const size_t n = s.n_q;
+  DevBuf<float> d2;
+  DevBuf<int> mt, acc;
+  DevBuf<unsigned> tie;
+  d2.alloc(n, st);
+  mt.alloc(n, st);
+  acc.alloc(n, st);
+  tie.alloc(n, st);
+  k_match_to_arrays<<<grid_for(n, 256), 256, 0, st>>>(s.cur.p, s.match.p, n, d2.p, mt.p, tie.p, acc.p);
+  ++c.launches;
+  RejectArrays a;
+  a.n = n;
+  a.d2 = d2.p;
+  a.match = mt.p;
+  a.tie = tie.p;
+  a.acc = acc.p;
+  for (const auto& r : s.rejectors)
+    apply_rejector(c, r, a, nullptr, nullptr, nullptr, nullptr);
+  k_arrays_to_match<<<grid_for(n, 256), 256, 0, st>>>(acc.p, n, s.match.p);
+  ++c.launches;
+  PCLB_CUDA(cudaGetLastError());
+}
 
 __global__ void k_permute_normals(const float4* __restrict__ nrm_orig, const float4* __restrict__ pts, size_t n_padded,
                                   float4* __restrict__ out)
@@ -1277,6 +1334,12 @@ void icp_iterate(Icp& s, int max_steps, pclb200_icp_stats* stats)
           k_search<false, false><<<sgrid, 256, 0, st>>>(a, s.match.p);
       }
       ++c.launches;
+    }
+    if (!s.rejectors.empty()) {
+      PCLB_REQUIRE(!comm_active(c), PCLB200_ERR_INVALID,
+                   "correspondence rejectors need the whole correspondence set: not available with a sharded source");
+      ProfScope ps(c, "icp_reject");
+      run_rejectors(s);
     }
     {
       ProfScope ps(c, "icp_accum");

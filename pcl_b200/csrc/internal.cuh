@@ -204,6 +204,17 @@ void launch_radius_fill(Ctx& c, const Index& idx, const float4* d_q, size_t nq, 
                         const unsigned long long* d_offsets /* by slot, exclusive */,
                         unsigned long long* d_keys /* (d2 bits << 32) | index */);
 
+// flat per-correspondence arrays the rejectors work on (reject.cu)
+struct RejectArrays {
+  size_t n = 0;
+  const float* d2 = nullptr;      // squared distance
+  const int* match = nullptr;     // index_match (any non-negative id that identifies the target point)
+  const unsigned* tie = nullptr;  // position in the input list (tie-break)
+  int* acc = nullptr;             // in/out: 1 = still a correspondence
+};
+void apply_rejector(Ctx& c, const pclb200_rejector& r, const RejectArrays& a, int* perm, int* keep_sorted, double* d_info,
+                    int* trimmed_flag);
+
 // accumulators of one ICP iteration (all fp64), see icp.cu
 constexpr int kAccum = 40;
 

@@ -12,7 +12,11 @@
 #include <string>
 
 #include "../search/kdtree.h"
+#include <algorithm>
+#include <vector>
+
 #include "correspondence_estimation.h"
+#include "correspondence_rejection.h"
 #include "transformation_estimation.h"
 
 namespace pcl {
@@ -75,6 +79,18 @@ public:
   {
     if (icp_) pclb200_icp_destroy(icp_);
   }
+
+  using CorrespondenceRejectorPtr = pcl::registration::CorrespondenceRejector::Ptr;
+  // registration.h:373-416
+  void addCorrespondenceRejector(const CorrespondenceRejectorPtr& rejector) { correspondence_rejectors_.push_back(rejector); }
+  std::vector<CorrespondenceRejectorPtr> getCorrespondenceRejectors() { return correspondence_rejectors_; }
+  bool removeCorrespondenceRejector(unsigned int i)
+  {
+    if (i >= correspondence_rejectors_.size()) return false;
+    correspondence_rejectors_.erase(correspondence_rejectors_.begin() + i);
+    return true;
+  }
+  void clearCorrespondenceRejectors() { correspondence_rejectors_.clear(); }
 
   void setTransformationEstimation(const TransformationEstimationPtr& te) { transformation_estimation_ = te; }
   void setCorrespondenceEstimation(const CorrespondenceEstimationPtr& ce) { correspondence_estimation_ = ce; }
@@ -214,6 +230,7 @@ protected:
   bool converged_ = false;
   CorrespondenceEstimationPtr correspondence_estimation_;
   TransformationEstimationPtr transformation_estimation_;
+  std::vector<CorrespondenceRejectorPtr> correspondence_rejectors_;
   bool target_cloud_updated_ = true, source_cloud_updated_ = true;
   bool force_no_recompute_ = false, force_no_recompute_reciprocal_ = false;
   bool target_uploaded_ = false;
@@ -283,6 +300,11 @@ protected:
       if (pclb200_icp_set_target(this->icp_, this->tree_->deviceIndex(), tn, sizeof(PointTarget)) != PCLB200_OK) { fail("icp_set_target"); return; }
       this->target_uploaded_ = true;
       uploaded_index_ = this->tree_->deviceIndex();
+    }
+    {
+      std::vector<pclb200_rejector> chain;
+      for (const auto& r : this->correspondence_rejectors_) chain.push_back(r->abiRejector());
+      if (pclb200_icp_set_rejectors(this->icp_, chain.data(), static_cast<int>(chain.size())) != PCLB200_OK) { fail("icp_set_rejectors"); return; }
     }
     double g[16];
     Base::toRowMajor(guess, g);

@@ -16,6 +16,10 @@
 #include <pcl/point_cloud.h>
 #include <pcl/point_types.h>
 #include <pcl/registration/correspondence_estimation.h>
+#include <pcl/registration/correspondence_rejection_distance.h>
+#include <pcl/registration/correspondence_rejection_median_distance.h>
+#include <pcl/registration/correspondence_rejection_one_to_one.h>
+#include <pcl/registration/correspondence_rejection_trimmed.h>
 #include <pcl/registration/icp.h>
 #include <pcl/registration/transformation_estimation_point_to_plane_lls.h>
 #include <pcl/registration/transformation_estimation_svd.h>
@@ -70,6 +74,54 @@ int main(int argc, char** argv)
       EXPECT_EQ((*corr)[i].index_query, (int)r[2 * i]);
       EXPECT_EQ((*corr)[i].index_match, (int)r[2 * i + 1]);
     }
+  }
+
+  {  // TEST (PCL, CorrespondenceRejector{Distance,MedianDistance,OneToOne,Trimmed}) — test_registration_api.cpp:131-380
+    CorrespondencesPtr corr(new Correspondences);
+    registration::CorrespondenceEstimation<PointXYZ, PointXYZ> corr_est;
+    corr_est.setInputSource(cloud_source.makeShared());
+    corr_est.setInputTarget(cloud_target.makeShared());
+    corr_est.determineCorrespondences(*corr);
+    auto check = [&](registration::CorrespondenceRejector& rej, const char* key) {
+      Correspondences out;
+      rej.setInputCorrespondences(corr);
+      rej.getCorrespondences(out);
+      const auto& g = G[key];
+      EXPECT_EQ(out.size(), g.size() / 2);
+      for (std::size_t i = 0; i < out.size() && 2 * i + 1 < g.size(); ++i) {
+        EXPECT_EQ(out[i].index_query, (int)g[2 * i]);
+        EXPECT_EQ(out[i].index_match, (int)g[2 * i + 1]);
+      }
+    };
+    registration::CorrespondenceRejectorDistance rd;
+    rd.setMaximumDistance(0.01f);
+    check(rd, "corr_rej_dist");
+    registration::CorrespondenceRejectorMedianDistance rm;
+    rm.setMedianFactor(0.5);
+    check(rm, "corr_rej_median");
+    EXPECT_NEAR(rm.getMedianDistance(), 0.000465391, 1e-4);
+    registration::CorrespondenceRejectorOneToOne ro;
+    check(ro, "corr_rej_one_to_one");
+    registration::CorrespondenceRejectorTrimmed rt;
+    rt.setOverlapRatio(0.5f);
+    check(rt, "corr_rej_trimmed");
+    // ICP with a rejector chain (test_registration.cpp:336-382 shape): converges to the same neighbourhood
+    IterativeClosestPoint<PointXYZ, PointXYZ> reg;
+    reg.setInputSource(cloud_source.makeShared());
+    reg.setInputTarget(cloud_target.makeShared());
+    reg.setMaximumIterations(50);
+    reg.setTransformationEpsilon(1e-8);
+    reg.setMaxCorrespondenceDistance(0.15);
+    registration::CorrespondenceRejectorMedianDistance::Ptr rmp(new registration::CorrespondenceRejectorMedianDistance);
+    rmp->setMedianFactor(4.0);
+    reg.addCorrespondenceRejector(rmp);
+    registration::CorrespondenceRejectorOneToOne::Ptr rop(new registration::CorrespondenceRejectorOneToOne);
+    reg.addCorrespondenceRejector(rop);
+    PointCloud<PointXYZ> aligned;
+    reg.align(aligned);
+    EXPECT_TRUE(reg.hasConverged());
+    EXPECT_EQ(reg.getCorrespondenceRejectors().size(), 2u);
+    EXPECT_LT(reg.getFitnessScore(), 1e-3);
   }
 
   {  // TEST (PCL, KdTreeFLANN_setPointRepresentation), default representation — test/kdtree/test_kdtree.cpp:226-262

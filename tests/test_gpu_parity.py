@@ -451,3 +451,70 @@ def test_icp_per_iteration_correspondences_exact(gpu, orc):
     finally:
         os.environ.pop("PCLB200_SEARCH", None)
         os.environ.pop("PCLB200_TRACK", None)
+
+
+def test_rejectors_golden_and_oracle(gpu, golden, orc):
+    """The four correspondence rejectors: PCL's golden pair lists
+    (test/registration/test_registration_api.cpp:131-380) and bit-exact agreement with the oracle on random input."""
+    P, ctx = gpu
+    c = P.Index(ctx, P.xyz1(golden["bun4"])).correspondences(P.xyz1(golden["bun0"]))
+    for kind, p, key in ((P.REJ_DISTANCE, 0.01, "corr_rej_dist"), (P.REJ_MEDIAN, 0.5, "corr_rej_median"),
+                         (P.REJ_ONE_TO_ONE, 0.0, "corr_rej_one_to_one"), (P.REJ_TRIMMED, 0.5, "corr_rej_trimmed")):
+        r, med = ctx.reject(c, kind, p=p)
+        assert np.array_equal(np.stack([r["index_query"], r["index_match"]], 1), golden[key]), key
+        if kind == P.REJ_MEDIAN:
+            assert abs(med - 0.000465391) < 1e-4
+    rng = np.random.default_rng(31)
+    n = 200000
+    big = np.zeros(n, dtype=P.CORR_DTYPE)
+    big["index_query"] = np.arange(n)
+    big["index_match"] = rng.integers(0, n // 3, n)
+    big["distance"] = (rng.random(n, dtype=np.float32) ** 2).astype(np.float32)
+    big["distance"][::97] = big["distance"][5]           # exact ties
+    for kind, p, m in ((P.REJ_DISTANCE, 0.5, 0), (P.REJ_MEDIAN, 1.7, 0), (P.REJ_ONE_TO_ONE, 0.0, 0),
+                       (P.REJ_TRIMMED, 0.37, 0), (P.REJ_TRIMMED, 0.01, 5000), (P.REJ_TRIMMED, 1.0, 0)):
+        g, gm = ctx.reject(big, kind, p=p, min_correspondences=m)
+        o, om = orc.reject(big, kind, p=p, min_correspondences=m)
+        assert np.array_equal(g, o), (kind, p, m, g.size, o.size)
+        assert gm == om
+    e, _ = ctx.reject(big[:0], P.REJ_MEDIAN, p=1.0)
+    assert e.size == 0
+
+
+def test_icp_with_rejector_chain_vs_oracle(gpu, orc):
+    """Rejectors inside the device loop (icp.hpp:187-201): per-iteration correspondence counts and the final
+    transform agree with the oracle's loop (counts to 0.1 %: the float and double solves move borderline pairs)."""
+    P, ctx = gpu
+    rng = np.random.default_rng(32)
+    n = 40000
+    tgt = rng.random((n, 3), dtype=np.float32)
+    a = np.deg2rad(3.0)
+    R = np.array([[np.cos(a), -np.sin(a), 0], [np.sin(a), np.cos(a), 0], [0, 0, 1]])
+    src = (tgt.astype(np.float64)[: n // 2] @ R.T + [0.01, -0.01, 0.02] + rng.normal(0, 0.002, (n // 2, 3))).astype(np.float32)
+    src[:500] += np.float32(0.3)                          # gross outliers for the rejectors to remove
+    S, T = P.xyz1(src), P.xyz1(tgt)
+    chains = [[(P.REJ_MEDIAN, 3.0, 0)], [(P.REJ_ONE_TO_ONE, 0.0, 0)], [(P.REJ_TRIMMED, 0.9, 100)], [(P.REJ_DISTANCE, 0.2, 0)],
+              [(P.REJ_MEDIAN, 3.0, 0), (P.REJ_ONE_TO_ONE, 0.0, 0), (P.REJ_TRIMMED, 0.9, 100), (P.REJ_DISTANCE, 0.2, 0)]]
+    tidx = P.Index(ctx, T)
+    for chain in chains:
+        s = P.Icp(ctx, max_iterations=30, transformation_epsilon=1e-9)
+        s.set_rejectors(chain)
+        s.set_target(tidx)
+        s.set_source(S)
+        for k in range(1, 7):
+            g = s.iterate(1)
+            o = orc.icp_align_rejectors(S, T, chain, nthreads=4, max_iterations=k, transformation_epsilon=1e-9)
+            assert abs(g["n_correspondences"] - o["n_correspondences"]) <= max(3, 0.001 * o["n_correspondences"]), (chain, k)
+            # mid-trajectory: a handful of borderline pairs flip between the fp32 (oracle) and fp64 (device) solves
+            assert np.linalg.norm(g["final"] - o["final"]) < 1e-4, (chain, k)
+        if len(chain) == 4:
+            assert g["n_correspondences"] < 0.8 * S.shape[0]
+        g = s.iterate()                                      # run to convergence
+        o64 = orc.icp_align_rejectors(S, T, chain, nthreads=4, max_iterations=30, transformation_epsilon=1e-9,
+                                      scalar_is_double=True)
+        assert g["converged"] and o64["converged"]
+        assert np.linalg.norm(g["final"] - o64["final"]) < 5e-5, (chain, np.linalg.norm(g["final"] - o64["final"]))
+    s = P.Icp(ctx, max_iterations=30, transformation_epsilon=1e-9)
+    s.set_target(tidx)
+    s.set_source(S)
+    assert s.iterate(1)["n_correspondences"] == S.shape[0]   # no rejectors, no gate: every source point pairs up

@@ -158,3 +158,17 @@ def test_normal_bun0(golden, orc):
     assert dense
     assert np.allclose(normals[:, :3], -g[:3], atol=1e-4)
     assert np.allclose(normals[:, 3], g[4], atol=1e-4)
+
+
+def test_rejectors_golden(golden, orc):
+    # test/registration/test_registration_api.cpp:131-380 + test_registration_api_data.h:461-1119
+    c = orc.Index(orc.to_xyz1(golden["bun4"])).correspondences(orc.to_xyz1(golden["bun0"]))
+    r, _ = orc.reject(c, orc.REJ_DISTANCE, p=0.01)                       # rej_dist_max_dist = 0.01f
+    assert np.array_equal(np.stack([r["index_query"], r["index_match"]], 1), golden["corr_rej_dist"])
+    r, med = orc.reject(c, orc.REJ_MEDIAN, p=0.5)                        # rej_median_factor = 0.5
+    assert np.array_equal(np.stack([r["index_query"], r["index_match"]], 1), golden["corr_rej_median"])
+    assert abs(med - 0.000465391) < 1e-4
+    r, _ = orc.reject(c, orc.REJ_ONE_TO_ONE)
+    assert np.array_equal(np.stack([r["index_query"], r["index_match"]], 1), golden["corr_rej_one_to_one"])
+    r, _ = orc.reject(c, orc.REJ_TRIMMED, p=0.5)                         # rej_trimmed_overlap = 0.5
+    assert np.array_equal(np.stack([r["index_query"], r["index_match"]], 1), golden["corr_rej_trimmed"])

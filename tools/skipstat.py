@@ -1,5 +1,5 @@
 import sys, numpy as np, torch
-sys.path.insert(0, '/root/repo')
+sys.path.insert(0, __import__('os').path.dirname(__import__('os').path.dirname(__import__('os').path.abspath(__file__))))
 import bench, pcl_b200 as P
 n = 10_000_000
 ctx = P.Context(0)
