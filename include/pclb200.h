@@ -164,11 +164,20 @@ PCLB200_API int pclb200_estimate_point_to_plane_lls(pclb200_ctx* ctx, const void
                                                     const pclb200_corr* corr, size_t n,
                                                     int scalar_is_double, double T_out[16]);
 
+PCLB200_API int pclb200_estimate_symmetric_point_to_plane_lls(pclb200_ctx* ctx, const void* src,
+                                                              const void* src_normals, size_t stride_s,
+                                                              const void* tgt, const void* tgt_normals,
+                                                              size_t stride_t, const pclb200_corr* corr, size_t n,
+                                                              int enforce_same_direction_normals,
+                                                              int scalar_is_double, double T_out[16]);
+
 /* ---- ICP: replaces pcl::IterativeClosestPoint[WithNormals]::computeTransformation and the
  * pcl::Registration state around it (impl/icp.hpp:113-268; impl/registration.hpp:45-221;
  * default_convergence_criteria.h:64-326). */
 #define PCLB200_EST_SVD 0            /* TransformationEstimationSVD (default of IterativeClosestPoint) */
 #define PCLB200_EST_POINT_TO_PLANE_LLS 1 /* IterativeClosestPointWithNormals, non-symmetric */
+#define PCLB200_EST_SYMMETRIC_POINT_TO_PLANE_LLS 2 /* setUseSymmetricObjective(true): needs source AND target normals
+    (impl/transformation_estimation_symmetric_point_to_plane_lls.hpp:128-200) */
 
 /* DefaultConvergenceCriteria::ConvergenceState — default_convergence_criteria.h:75-83 */
 #define PCLB200_CONV_NOT_CONVERGED 0
@@ -189,6 +198,8 @@ typedef struct pclb200_icp_params {
   int32_t is_dense;               /* input_->is_dense: 0 => skip non-finite source points */
   int32_t failure_after_max_iter; /* default_convergence_criteria.h:148-152 */
   int32_t max_iterations_similar_transforms; /* :310, default 0 */
+  int32_t enforce_same_direction_normals;    /* symmetric estimator: n = n1 - n2 when n1.n2 < 0 (icp.h:402-418), default 1 */
+  int32_t reserved0;
   double max_correspondence_distance;     /* registration.h:117, default sqrt(DBL_MAX) */
   double transformation_epsilon;          /* registration.h:588, default 0 */
   double transformation_rotation_epsilon; /* default 0 = keep criteria default 0.99999 */

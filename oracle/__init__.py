@@ -74,6 +74,7 @@ def lib():
         L.orc_correspondences_reciprocal.argtypes = [vp, vp, fp, sz, sz, fp, sz, i32p, sz, C.c_int, C.c_double, C.POINTER(Corr), C.c_int]
         L.orc_estimate_svd.argtypes = [fp, sz, fp, sz, C.POINTER(Corr), sz, C.c_int, dp]
         L.orc_estimate_point_to_plane_lls.argtypes = [fp, sz, fp, fp, sz, C.POINTER(Corr), sz, C.c_int, dp]
+        L.orc_estimate_symmetric_lls.argtypes = [fp, fp, sz, fp, fp, sz, C.POINTER(Corr), sz, C.c_int, C.c_int, dp]
         L.orc_transform.argtypes = [fp, sz, sz, C.c_int, dp, C.c_int, C.c_int]
         L.orc_icp_align.argtypes = [C.POINTER(IcpParams), fp, sz, sz, i32p, sz, fp, sz, sz, dp, C.POINTER(IcpResult), fp]
         L.orc_icp_align_tree.argtypes = [C.POINTER(IcpParams), vp, fp, sz, sz, i32p, sz, fp, sz, sz, dp, C.POINTER(IcpResult), fp]
@@ -239,6 +240,19 @@ def estimate_point_to_plane_lls(src, tgt_point_normal, corr=None, scalar_is_doub
         _f(src), src.shape[1], _f(tgt), tn.ctypes.data_as(C.POINTER(C.c_float)), tgt.shape[1],
         None if corr is None else corr.ctypes.data_as(C.POINTER(Corr)),
         n if corr is not None else src.shape[0], int(scalar_is_double), _d(T))
+    return T.reshape(4, 4), rc
+
+
+def estimate_symmetric_lls(src_point_normal, tgt_point_normal, corr=None, enforce_same_direction=True, scalar_is_double=False):
+    """Both clouds as pcl::PointNormal rows (normals at float offset 4)."""
+    src, tgt = as_cloud(src_point_normal), as_cloud(tgt_point_normal)
+    corr, n = _corr_ptr(corr)
+    T = np.zeros(16, dtype=np.float64)
+    rc = lib().orc_estimate_symmetric_lls(
+        _f(src), src[:, 4:].ctypes.data_as(C.POINTER(C.c_float)), src.shape[1], _f(tgt),
+        tgt[:, 4:].ctypes.data_as(C.POINTER(C.c_float)), tgt.shape[1],
+        None if corr is None else corr.ctypes.data_as(C.POINTER(Corr)), n if corr is not None else src.shape[0],
+        int(enforce_same_direction), int(scalar_is_double), _d(T))
     return T.reshape(4, 4), rc
 
 

@@ -496,6 +496,67 @@ static bool p2plane_lls(const float* src, size_t ss, const float* tgt, const flo
 }
 
 // ------------------------------------------------------------------------------------------
+// TransformationEstimationSymmetricPointToPlaneLLS —
+// registration/include/pcl/registration/impl/transformation_estimation_symmetric_point_to_plane_lls.hpp
+// :150-200 (v = [(p+q) x n, n], n = n1 +/- n2, rank-1 updates and v*((q-p).n) accumulated in Scalar, LDLT solve)
+// and :128-147 (T = Rz Ry Rx * translation * Rz Ry Rx).  sn / tn = first nx of source / target normals.
+// ------------------------------------------------------------------------------------------
+template <typename S>
+static bool sym_p2plane_lls(const float* src, const float* sn, size_t ss, const float* tgt, const float* tn, size_t ts,
+                            const int32_t* qi, const int32_t* mi, size_t n, bool enforce_same_direction, S T[16])
+{
+  S ATA[36], ATb[6];
+  for (int i = 0; i < 36; ++i) ATA[i] = S(0);
+  for (int i = 0; i < 6; ++i) ATb[i] = S(0);
+  for (size_t i = 0; i < n; ++i) {
+    size_t si = (size_t)(qi ? qi[i] : (int32_t)i), ti = (size_t)(mi ? mi[i] : (int32_t)i);
+    const float* pf = src + ss * si;
+    const float* qf = tgt + ts * ti;
+    const float* n1f = sn + ss * si;
+    const float* n2f = tn + ts * ti;
+    S p[3], q[3], n1[3], n2[3], nn[3];
+    for (int d = 0; d < 3; ++d) { p[d] = pf[d]; q[d] = qf[d]; n1[d] = n1f[d]; n2[d] = n2f[d]; }
+    const bool same = !enforce_same_direction || (n1[0] * n2[0] + n1[1] * n2[1] + n1[2] * n2[2]) >= S(0);
+    for (int d = 0; d < 3; ++d) nn[d] = same ? n1[d] + n2[d] : n1[d] - n2[d];
+    if (!std::isfinite(p[0] + p[1] + p[2]) || !std::isfinite(q[0] + q[1] + q[2]) || !std::isfinite(nn[0] + nn[1] + nn[2]))
+      continue;
+    const S s3[3] = {p[0] + q[0], p[1] + q[1], p[2] + q[2]};
+    S v[6] = {s3[1] * nn[2] - s3[2] * nn[1], s3[2] * nn[0] - s3[0] * nn[2], s3[0] * nn[1] - s3[1] * nn[0], nn[0], nn[1], nn[2]};
+    for (int r = 0; r < 6; ++r)
+      for (int c = r; c < 6; ++c)
+        ATA[6 * r + c] += v[r] * v[c];
+    const S b = (q[0] - p[0]) * nn[0] + (q[1] - p[1]) * nn[1] + (q[2] - p[2]) * nn[2];
+    for (int r = 0; r < 6; ++r)
+      ATb[r] += v[r] * b;
+  }
+  double A[36], B[6], x[6];
+  for (int r = 0; r < 6; ++r)
+    for (int c = 0; c < 6; ++c)
+      A[6 * r + c] = static_cast<double>(c >= r ? ATA[6 * r + c] : ATA[6 * c + r]);
+  for (int r = 0; r < 6; ++r)
+    B[r] = static_cast<double>(ATb[r]);
+  bool ok = solve6(A, B, x);
+  if (!ok)
+    for (int i = 0; i < 6; ++i) x[i] = std::numeric_limits<double>::quiet_NaN();
+  const S al = static_cast<S>(x[0]), be = static_cast<S>(x[1]), ga = static_cast<S>(x[2]);
+  const S ca = std::cos(al), sa = std::sin(al), cb = std::cos(be), sb = std::sin(be), cg = std::cos(ga), sg = std::sin(ga);
+  // R = Rz(ga) Ry(be) Rx(al)
+  const S Rm[9] = {cg * cb, cg * sb * sa - sg * ca, cg * sb * ca + sg * sa,
+                   sg * cb, sg * sb * sa + cg * ca, sg * sb * ca - cg * sa,
+                   -sb,     cb * sa,                cb * ca};
+  const S tr[3] = {static_cast<S>(x[3]), static_cast<S>(x[4]), static_cast<S>(x[5])};
+  // T = [R | 0] * [I | t] * [R | 0] = [R R | R t]
+  for (int i = 0; i < 16; ++i) T[i] = S(0);
+  for (int r = 0; r < 3; ++r) {
+    for (int c = 0; c < 3; ++c)
+      T[4 * r + c] = Rm[3 * r] * Rm[c] + Rm[3 * r + 1] * Rm[3 + c] + Rm[3 * r + 2] * Rm[6 + c];
+    T[4 * r + 3] = Rm[3 * r] * tr[0] + Rm[3 * r + 1] * tr[1] + Rm[3 * r + 2] * tr[2];
+  }
+  T[15] = S(1);
+  return ok;
+}
+
+// ------------------------------------------------------------------------------------------
 // point transforms
 //   mode 0: IterativeClosestPoint::transformCloud (registration/.../impl/icp.hpp:49-111):
 //           tr = transform.cast<float>(); pt_t = tr * (x,y,z,1)  -> ((c0*x + c1*y) + c2*z) + c3
@@ -1154,6 +1215,35 @@ ORC_API int orc_estimate_point_to_plane_lls(const float* src, size_t sstride, co
   return ok ? 0 : -1;
 }
 
+ORC_API int orc_estimate_symmetric_lls(const float* src, const float* src_normals, size_t sstride, const float* tgt,
+                                       const float* tgt_normals, size_t tstride, const orc_corr* corr, size_t n,
+                                       int enforce_same_direction, int scalar_is_double, double* T_out)
+{
+  std::vector<int32_t> qi, mi;
+  if (corr) {
+    qi.resize(n);
+    mi.resize(n);
+    for (size_t i = 0; i < n; ++i) {
+      qi[i] = corr[i].index_query;
+      mi[i] = corr[i].index_match;
+    }
+  }
+  bool ok;
+  if (scalar_is_double) {
+    double T[16];
+    ok = sym_p2plane_lls<double>(src, src_normals, sstride, tgt, tgt_normals, tstride, corr ? qi.data() : nullptr,
+                                 corr ? mi.data() : nullptr, n, enforce_same_direction != 0, T);
+    for (int i = 0; i < 16; ++i) T_out[i] = T[i];
+  }
+  else {
+    float T[16];
+    ok = sym_p2plane_lls<float>(src, src_normals, sstride, tgt, tgt_normals, tstride, corr ? qi.data() : nullptr,
+                                corr ? mi.data() : nullptr, n, enforce_same_direction != 0, T);
+    for (int i = 0; i < 16; ++i) T_out[i] = T[i];
+  }
+  return ok ? 0 : -1;
+}
+
 // in-place transform; T row-major 16 doubles (narrowed to float first when !scalar_is_double)
 ORC_API void orc_transform(float* pts, size_t n, size_t stride, int normal_off, const double* T,
                            int scalar_is_double, int mode)
@@ -1343,8 +1433,10 @@ static void icp_run(const orc_icp_params& P, const float* src, size_t n_s, size_
     mse /= static_cast<double>(nc);
     if (P.estimator == 0)
       umeyama<S>(cur.data(), ss, tgt, ts, qi.data(), mi.data(), nc, T);
-    else
+    else if (P.estimator == 1)
       p2plane_lls<S>(cur.data(), ss, tgt, tgt + 4, ts, qi.data(), mi.data(), nc, T);
+    else  // symmetric objective; setEnforceSameDirectionNormals(true) is the class default (icp.h:366-371)
+      sym_p2plane_lls<S>(cur.data(), cur.data() + 4, ss, tgt, tgt + 4, ts, qi.data(), mi.data(), nc, true, T);
     transform_points<S>(cur.data(), n_s, ss, noff, T, tmode);
     mat4_mul<S>(T, final_T, final_T);
     ++iterations;

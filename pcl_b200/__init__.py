@@ -15,7 +15,7 @@ LIB_PATH = os.environ.get("PCLB200_LIB", os.path.join(_HERE, "libpclb200.so"))  
 
 OK = 0
 ERR_CUDA, ERR_INVALID, ERR_EMPTY, ERR_LEAF_TOO_SMALL, ERR_INTERNAL, ERR_NCCL = -1, -2, -3, -4, -5, -6
-EST_SVD, EST_POINT_TO_PLANE_LLS = 0, 1
+EST_SVD, EST_POINT_TO_PLANE_LLS, EST_SYMMETRIC_POINT_TO_PLANE_LLS = 0, 1, 2
 CONV_NAMES = ["NOT_CONVERGED", "ITERATIONS", "TRANSFORM", "ABS_MSE", "REL_MSE", "NO_CORRESPONDENCES",
               "FAILURE_AFTER_MAX_ITERATIONS"]
 
@@ -32,6 +32,7 @@ class IcpParams(C.Structure):
     _fields_ = [("max_iterations", C.c_int32), ("use_reciprocal", C.c_int32), ("estimator", C.c_int32),
                 ("scalar_is_double", C.c_int32), ("with_normals_transform", C.c_int32), ("is_dense", C.c_int32),
                 ("failure_after_max_iter", C.c_int32), ("max_iterations_similar_transforms", C.c_int32),
+                ("enforce_same_direction_normals", C.c_int32), ("reserved0", C.c_int32),
                 ("max_correspondence_distance", C.c_double), ("transformation_epsilon", C.c_double),
                 ("transformation_rotation_epsilon", C.c_double), ("euclidean_fitness_epsilon", C.c_double),
                 ("mse_threshold_absolute", C.c_double)]
@@ -64,7 +65,7 @@ SYMBOLS = [
     "pclb200_launch_count", "pclb200_stream", "pclb200_free", "pclb200_profile_enable", "pclb200_profile_get",
     "pclb200_profile_reset", "pclb200_index_build", "pclb200_index_destroy",
     "pclb200_index_size", "pclb200_index_stats", "pclb200_knn", "pclb200_radius", "pclb200_correspondences",
-    "pclb200_estimate_svd", "pclb200_estimate_point_to_plane_lls", "pclb200_icp_default_params",
+    "pclb200_estimate_svd", "pclb200_estimate_point_to_plane_lls", "pclb200_estimate_symmetric_point_to_plane_lls", "pclb200_icp_default_params",
     "pclb200_icp_create", "pclb200_icp_destroy", "pclb200_icp_set_params", "pclb200_icp_set_target",
     "pclb200_icp_set_source", "pclb200_icp_iterate", "pclb200_icp_get_cloud", "pclb200_icp_get_correspondences",
     "pclb200_icp_align",
@@ -106,6 +107,7 @@ def lib():
     L.pclb200_correspondences.argtypes = [vp, vp, vp, vp, sz, sz, vp, sz, C.c_int, C.c_double, vp, C.POINTER(sz)]
     L.pclb200_estimate_svd.argtypes = [vp, vp, sz, vp, sz, vp, sz, C.c_int, dp]
     L.pclb200_estimate_point_to_plane_lls.argtypes = [vp, vp, sz, vp, vp, sz, vp, sz, C.c_int, dp]
+    L.pclb200_estimate_symmetric_point_to_plane_lls.argtypes = [vp, vp, vp, sz, vp, vp, sz, vp, sz, C.c_int, C.c_int, dp]
     L.pclb200_icp_default_params.argtypes = [C.POINTER(IcpParams)]
     L.pclb200_icp_default_params.restype = None
     L.pclb200_icp_create.argtypes = [vp, C.POINTER(IcpParams), C.POINTER(vp)]
@@ -268,6 +270,20 @@ class Context:
         _check(lib().pclb200_estimate_svd(self.h, s.ptr, s.stride, t.ptr, t.stride,
                                           None if cb is None else C.c_void_p(cb.ctypes.data), n, int(scalar_is_double),
                                           T.ctypes.data_as(C.POINTER(C.c_double))))
+        return T.reshape(4, 4)
+
+    def estimate_symmetric_lls(self, src_point_normal, tgt_point_normal, corr=None, enforce_same_direction=True,
+                               scalar_is_double=False):
+        src = np.ascontiguousarray(src_point_normal, dtype=np.float32)
+        tgt = np.ascontiguousarray(tgt_point_normal, dtype=np.float32)
+        cb = None if corr is None else np.ascontiguousarray(corr, dtype=CORR_DTYPE)
+        n = src.shape[0] if cb is None else cb.size
+        T = np.zeros(16)
+        _check(lib().pclb200_estimate_symmetric_point_to_plane_lls(
+            self.h, C.c_void_p(src.ctypes.data), C.c_void_p(src.ctypes.data + 16), src.strides[0],
+            C.c_void_p(tgt.ctypes.data), C.c_void_p(tgt.ctypes.data + 16), tgt.strides[0],
+            None if cb is None else C.c_void_p(cb.ctypes.data), n, int(enforce_same_direction), int(scalar_is_double),
+            T.ctypes.data_as(C.POINTER(C.c_double))))
         return T.reshape(4, 4)
 
     def estimate_point_to_plane_lls(self, src, tgt_point_normal, corr=None, scalar_is_double=False):

@@ -26,7 +26,8 @@ void icp_iterate(Icp& s, int max_steps, pclb200_icp_stats* stats);
 void icp_get_cloud(Icp& s, void* out_pts, size_t stride_out, void* out_normals, size_t stride_n);
 size_t icp_get_correspondences(Icp& s, pclb200_corr* out);
 void estimate_pairs(Ctx& c, int est, const void* src, size_t stride_s, const void* tgt, const void* tgt_normals,
-                    size_t stride_t, const pclb200_corr* corr, size_t n, int scalar_is_double, double* T_out);
+                    size_t stride_t, const pclb200_corr* corr, size_t n, int scalar_is_double, double* T_out,
+                    const void* src_normals = nullptr, int enforce_same_dir = 1);
 size_t correspondences(Ctx& c, const Index& tgt, const Index* src_index, const void* src, size_t n, size_t stride,
                        const int32_t* indices, size_t n_idx, int is_dense, double max_dist, pclb200_corr* out);
 double fitness_score(Ctx& c, const Index& tgt, const void* src, size_t n, size_t stride, const int32_t* indices,
@@ -493,6 +494,21 @@ int pclb200_estimate_point_to_plane_lls(pclb200_ctx* ctx, const void* src, size_
   });
 }
 
+int pclb200_estimate_symmetric_point_to_plane_lls(pclb200_ctx* ctx, const void* src, const void* src_normals,
+                                                  size_t stride_s, const void* tgt, const void* tgt_normals,
+                                                  size_t stride_t, const pclb200_corr* corr, size_t n,
+                                                  int enforce_same_direction_normals, int scalar_is_double,
+                                                  double T_out[16])
+{
+  return guarded([&] {
+    PCLB_REQUIRE(ctx && T_out, PCLB200_ERR_INVALID, "NULL argument");
+    std::lock_guard<std::recursive_mutex> lk(ctx->c.mu);
+    PCLB_CUDA(cudaSetDevice(ctx->c.device));
+    estimate_pairs(ctx->c, PCLB200_EST_SYMMETRIC_POINT_TO_PLANE_LLS, src, stride_s, tgt, tgt_normals, stride_t, corr, n,
+                   scalar_is_double, T_out, src_normals, enforce_same_direction_normals);
+  });
+}
+
 // ---- ICP ------------------------------------------------------------------------------------------------------------------
 void pclb200_icp_default_params(pclb200_icp_params* p)
 {
@@ -502,6 +518,7 @@ void pclb200_icp_default_params(pclb200_icp_params* p)
   p->max_iterations = 10;
   p->estimator = PCLB200_EST_SVD;
   p->is_dense = 1;
+  p->enforce_same_direction_normals = 1;
   p->max_correspondence_distance = std::sqrt(std::numeric_limits<double>::max());
   p->transformation_epsilon = 0.0;
   p->transformation_rotation_epsilon = 0.0;

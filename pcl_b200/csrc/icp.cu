@@ -117,6 +117,8 @@ struct IterArgs {
   int s_root;
   const int32_t* src_orig;    // slot -> original source index (nullable = identity)
   unsigned long long* skip_count;  // queries answered by the temporal-coherence test (statistics)
+  float4* cur_normals;             // source normals, same order as cur (symmetric objective), rotated with T_k
+  int enforce_same_dir;
   // fused cross-GPU reduce (optional): peer-mapped exchange buffers + this iteration's sequence number
   PeerView peer;
   unsigned long long seq;
@@ -267,6 +269,11 @@ k_search(const IterArgs a, Match* __restrict__ match)
         apply_pending(sP, p.x, p.y, p.z);
         a.cur[i] = p;
         delta = sqrtf(dist2_rn(p.x, p.y, p.z, ox, oy, oz));
+        if (a.cur_normals) {
+          float4 nn = a.cur_normals[i];
+          apply_pending_normal(sP, nn.x, nn.y, nn.z);
+          a.cur_normals[i] = nn;
+        }
       }
       float nlb;
       if (TRACK && !RECIP && still_nearest(prev, delta, &nlb)) {
@@ -347,6 +354,11 @@ k_search_packet(const IterArgs a, Match* __restrict__ match)
       apply_pending(sP, p.x, p.y, p.z);
       a.cur[i] = p;
       delta = sqrtf(dist2_rn(p.x, p.y, p.z, ox, oy, oz));
+      if (a.cur_normals) {
+        float4 nn = a.cur_normals[i];
+        apply_pending_normal(sP, nn.x, nn.y, nn.z);
+        a.cur_normals[i] = nn;
+      }
     }
     Match m;
     m.pos = -1; m.d2 = 0.f; m.lb = 0.f; m.accepted = 0;
@@ -430,6 +442,28 @@ k_accum(const IterArgs a, const Match* __restrict__ match)
       acc[11] += qy * px; acc[12] += qy * py; acc[13] += qy * pz;
       acc[14] += qz * px; acc[15] += qz * py; acc[16] += qz * pz;
     }
+    else if (EST == PCLB200_EST_SYMMETRIC_POINT_TO_PLANE_LLS) {
+      // symmetric_point_to_plane_lls.hpp:166-193: n = n1 +/- n2, v = [(p+q) x n, n], A^T A += v v^T, A^T b += v ((q-p).n)
+      const float4 n2 = ldg4(a.tgt_normals + m.pos);
+      const float4 n1 = a.cur_normals[i];
+      const double d12 = (double)n1.x * n2.x + (double)n1.y * n2.y + (double)n1.z * n2.z;
+      const double sg = (!a.enforce_same_dir || d12 >= 0.0) ? 1.0 : -1.0;
+      const double nx = (double)n1.x + sg * n2.x, ny = (double)n1.y + sg * n2.y, nz = (double)n1.z + sg * n2.z;
+      if (!(isfinite(nx) && isfinite(ny) && isfinite(nz)))
+        continue;
+      const double sx = (double)p.x + q.x, sy = (double)p.y + q.y, sz = (double)p.z + q.z;
+      const double v[6] = {sy * nz - sz * ny, sz * nx - sx * nz, sx * ny - sy * nx, nx, ny, nz};
+      const double b = ((double)q.x - p.x) * nx + ((double)q.y - p.y) * ny + ((double)q.z - p.z) * nz;
+      int t = 2;
+#pragma unroll
+      for (int r = 0; r < 6; ++r)
+#pragma unroll
+        for (int cc = r; cc < 6; ++cc)
+          acc[t++] += v[r] * v[cc];
+#pragma unroll
+      for (int r = 0; r < 6; ++r)
+        acc[23 + r] += v[r] * b;
+    }
     else {
       const float4 nn = ldg4(a.tgt_normals + m.pos);
       if (!(isfinite(nn.x) && isfinite(nn.y) && isfinite(nn.z)))
@@ -461,6 +495,8 @@ struct PairArgs {
   const float4* src;          // dense, original order
   const float4* tgt;          // dense, original order
   const float4* tgt_normals;  // dense, original order (LLS)
+  const float4* src_normals;  // dense, original order (symmetric LLS)
+  int enforce_same_dir;
   const pclb200_corr* corr;   // nullable: pair i <-> i
   size_t n;
   float ox, oy, oz;
@@ -491,6 +527,28 @@ k_accum_pairs(const PairArgs a)
       acc[8] += qx * px; acc[9] += qx * py; acc[10] += qx * pz;
       acc[11] += qy * px; acc[12] += qy * py; acc[13] += qy * pz;
       acc[14] += qz * px; acc[15] += qz * py; acc[16] += qz * pz;
+    }
+    else if (EST == PCLB200_EST_SYMMETRIC_POINT_TO_PLANE_LLS) {
+      const float4 n2 = ldg4(a.tgt_normals + mi);
+      const float4 n1 = ldg4(a.src_normals + qi);
+      const double d12 = (double)n1.x * n2.x + (double)n1.y * n2.y + (double)n1.z * n2.z;
+      const double sg = (!a.enforce_same_dir || d12 >= 0.0) ? 1.0 : -1.0;
+      const double nx = (double)n1.x + sg * n2.x, ny = (double)n1.y + sg * n2.y, nz = (double)n1.z + sg * n2.z;
+      if (!(isfinite(p.x) && isfinite(p.y) && isfinite(p.z) && isfinite(q.x) && isfinite(q.y) && isfinite(q.z) &&
+            isfinite(nx) && isfinite(ny) && isfinite(nz)))
+        continue;
+      const double sx = (double)p.x + q.x, sy = (double)p.y + q.y, sz = (double)p.z + q.z;
+      const double v[6] = {sy * nz - sz * ny, sz * nx - sx * nz, sx * ny - sy * nx, nx, ny, nz};
+      const double b = ((double)q.x - p.x) * nx + ((double)q.y - p.y) * ny + ((double)q.z - p.z) * nz;
+      int t = 2;
+#pragma unroll
+      for (int r = 0; r < 6; ++r)
+#pragma unroll
+        for (int cc = r; cc < 6; ++cc)
+          acc[t++] += v[r] * v[cc];
+#pragma unroll
+      for (int r = 0; r < 6; ++r)
+        acc[23 + r] += v[r] * b;
     }
     else {
       const float4 nn = ldg4(a.tgt_normals + mi);
@@ -693,6 +751,20 @@ __global__ void k_solve(const double* __restrict__ accum, int est, int scalar_is
     const double al = x[0], be = x[1], ga = x[2];
     for (int i = 0; i < 16; ++i)
       T[i] = 0.0;
+    if (est == PCLB200_EST_SYMMETRIC_POINT_TO_PLANE_LLS) {
+      // T = Rz Ry Rx * translation * Rz Ry Rx = [R R | R t]  (symmetric_point_to_plane_lls.hpp:128-147)
+      const double ca = cos(al), sa = sin(al), cb = cos(be), sb = sin(be), cg = cos(ga), sg = sin(ga);
+      const double Rm[9] = {cg * cb, cg * sb * sa - sg * ca, cg * sb * ca + sg * sa,
+                            sg * cb, sg * sb * sa + cg * ca, sg * sb * ca - cg * sa,
+                            -sb,     cb * sa,                cb * ca};
+      for (int r = 0; r < 3; ++r) {
+        for (int cc = 0; cc < 3; ++cc)
+          T[4 * r + cc] = Rm[3 * r] * Rm[cc] + Rm[3 * r + 1] * Rm[3 + cc] + Rm[3 * r + 2] * Rm[6 + cc];
+        T[4 * r + 3] = Rm[3 * r] * x[3] + Rm[3 * r + 1] * x[4] + Rm[3 * r + 2] * x[5];
+      }
+      T[15] = 1.0;
+    }
+    else {
     T[0] = cos(ga) * cos(be);
     T[1] = -sin(ga) * cos(al) + cos(ga) * sin(be) * sin(al);
     T[2] = sin(ga) * sin(al) + cos(ga) * sin(be) * cos(al);
@@ -706,6 +778,7 @@ __global__ void k_solve(const double* __restrict__ accum, int est, int scalar_is
     T[7] = x[4];
     T[11] = x[5];
     T[15] = 1.0;
+    }
   }
   if (!scalar_is_double)
     for (int i = 0; i < 16; ++i)
@@ -888,6 +961,7 @@ struct Icp {
   DevBuf<float4> src_normals;   // original order (optional)
   DevBuf<int32_t> src_orig;     // slot -> original source index (when indices were given)
   DevBuf<float4> cur;           // Morton order, w = slot
+  DevBuf<float4> cur_normals;   // source normals in the order of `cur` (symmetric objective only)
   DevBuf<Match> match;          // Morton order: this iteration's matches = next iteration's seeds
   DevBuf<int32_t> cur_label;    // Morton order: original source index of cur[i] (labels of the reciprocal tree)
   bool have_src_normals = false;
@@ -1055,6 +1129,16 @@ __global__ void k_cur_labels(const float4* __restrict__ cur, const int32_t* __re
   label[i] = src_orig ? src_orig[slot] : slot;
 }
 
+__global__ void k_gather_cur_normals(const float4* __restrict__ cur, const float4* __restrict__ nrm_all,
+                                     const int32_t* __restrict__ src_orig, size_t n, float4* __restrict__ out)
+{
+  size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+  if (i >= n)
+    return;
+  const int slot = __float_as_int(cur[i].w);
+  out[i] = nrm_all[src_orig ? src_orig[slot] : slot];
+}
+
 __global__ void k_gather_subset(const float4* __restrict__ all, const int32_t* __restrict__ sub, size_t n,
                                 float4* __restrict__ out)
 {
@@ -1144,6 +1228,16 @@ void icp_set_source(Icp& s, const void* src, size_t n, size_t stride, const void
     make_query_batch(c, *s.tgt, d_q, s.n_q, qb);
   }
   s.cur = std::move(qb.q);
+  s.cur_normals.release();
+  if (s.P.estimator == PCLB200_EST_SYMMETRIC_POINT_TO_PLANE_LLS) {
+    PCLB_REQUIRE(s.have_src_normals, PCLB200_ERR_INVALID, "icp: the symmetric objective needs source normals");
+    s.cur_normals.alloc(s.n_q, st);
+    if (s.n_q) {
+      k_gather_cur_normals<<<grid_for(s.n_q, 256), 256, 0, st>>>(s.cur.p, s.src_normals.p, s.src_orig.p, s.n_q,
+                                                                 s.cur_normals.p);
+      ++c.launches;
+    }
+  }
   s.match.alloc(s.n_q, st);
   PCLB_CUDA(cudaMemsetAsync(s.match.p, 0xff, s.n_q * sizeof(Match), st));  // pos = -1: no seed yet
   s.cur_label.alloc(s.n_q, st);
@@ -1160,7 +1254,7 @@ void icp_set_source(Icp& s, const void* src, size_t n, size_t stride, const void
         guess_identity = false;
   if (!guess_identity) {
     upload_pending(s, s.final_T, 1);
-    k_apply_pending<<<persistent_grid(c, s.n_q, 256, 8), 256, 0, st>>>(s.cur.p, s.n_q, s.pending.p, nullptr);
+    k_apply_pending<<<persistent_grid(c, s.n_q, 256, 8), 256, 0, st>>>(s.cur.p, s.n_q, s.pending.p, s.cur_normals.p);
     ++c.launches;
   }
   upload_pending(s, s.last_T, 0);
@@ -1285,6 +1379,8 @@ void icp_iterate(Icp& s, int max_steps, pclb200_icp_stats* stats)
     a.d_error = c.d_error;
     a.src_orig = s.src_orig.p;
     a.skip_count = s.skip_count.p;
+    a.cur_normals = s.cur_normals.p;
+    a.enforce_same_dir = s.P.enforce_same_direction_normals;
     a.peer.nranks = 0;
     a.seq = 0;
     const bool fused_reduce = comm_peer_view(c, &a.peer, &a.seq);
@@ -1293,7 +1389,7 @@ void icp_iterate(Icp& s, int max_steps, pclb200_icp_stats* stats)
     if (s.P.use_reciprocal) {
       // tree_reciprocal_ is rebuilt over the transformed source every iteration
       // (correspondence_estimation.hpp:117-135 via setInputSource at icp.hpp:175)
-      k_apply_pending<<<grid, 256, 0, st>>>(s.cur.p, s.n_q, s.pending.p, nullptr);
+      k_apply_pending<<<grid, 256, 0, st>>>(s.cur.p, s.n_q, s.pending.p, s.cur_normals.p);
       k_clear_apply<<<1, 1, 0, st>>>(s.pending.p);
       c.launches += 2;
       src_index.reset(build_index_from_device(c, s.cur.p, s.n_q, s.cur_label.p));
@@ -1345,8 +1441,10 @@ void icp_iterate(Icp& s, int max_steps, pclb200_icp_stats* stats)
       ProfScope ps(c, "icp_accum");
       if (s.P.estimator == PCLB200_EST_SVD)
         k_accum<PCLB200_EST_SVD><<<grid, 256, 0, st>>>(a, s.match.p);
-      else
+      else if (s.P.estimator == PCLB200_EST_POINT_TO_PLANE_LLS)
         k_accum<PCLB200_EST_POINT_TO_PLANE_LLS><<<grid, 256, 0, st>>>(a, s.match.p);
+      else
+        k_accum<PCLB200_EST_SYMMETRIC_POINT_TO_PLANE_LLS><<<grid, 256, 0, st>>>(a, s.match.p);
       ++c.launches;
     }
     PCLB_CUDA(cudaGetLastError());
@@ -1559,7 +1657,8 @@ void icp_get_cloud(Icp& s, void* out_pts, size_t stride_out, void* out_normals, 
 
 // ---- stand-alone estimators ----------------------------------------------------------------------------------
 void estimate_pairs(Ctx& c, int est, const void* src, size_t stride_s, const void* tgt, const void* tgt_normals,
-                    size_t stride_t, const pclb200_corr* corr, size_t n, int scalar_is_double, double* T_out)
+                    size_t stride_t, const pclb200_corr* corr, size_t n, int scalar_is_double, double* T_out,
+                    const void* src_normals, int enforce_same_dir)
 {
   cudaStream_t st = c.stream;
   PCLB_REQUIRE(src && tgt && n > 0, PCLB200_ERR_INVALID, "estimate: empty input");
@@ -1591,10 +1690,16 @@ void estimate_pairs(Ctx& c, int est, const void* src, size_t stride_s, const voi
   dt.alloc(n_tgt, st);
   load_xyz_as_float4(c, src, n_src, stride_s, nullptr, 0, ds.p, st);
   load_xyz_as_float4(c, tgt, n_tgt, stride_t, nullptr, 0, dt.p, st);
-  if (est == PCLB200_EST_POINT_TO_PLANE_LLS) {
+  DevBuf<float4> dsn;
+  if (est != PCLB200_EST_SVD) {
     PCLB_REQUIRE(tgt_normals, PCLB200_ERR_INVALID, "point-to-plane needs target normals");
     dn.alloc(n_tgt, st);
     load_vec3_as_float4(c, tgt_normals, n_tgt, stride_t, dn.p, st);
+  }
+  if (est == PCLB200_EST_SYMMETRIC_POINT_TO_PLANE_LLS) {
+    PCLB_REQUIRE(src_normals, PCLB200_ERR_INVALID, "the symmetric objective needs source normals");
+    dsn.alloc(n_src, st);
+    load_vec3_as_float4(c, src_normals, n_src, stride_s, dsn.p, st);
   }
   Reducer red;
   const unsigned grid = persistent_grid(c, n, 256, 4);
@@ -1606,6 +1711,8 @@ void estimate_pairs(Ctx& c, int est, const void* src, size_t stride_s, const voi
   a.src = ds.p;
   a.tgt = dt.p;
   a.tgt_normals = dn.p;
+  a.src_normals = dsn.p;
+  a.enforce_same_dir = enforce_same_dir;
   a.corr = d_corr.p;
   a.n = n;
   a.ox = a.oy = a.oz = 0.f;
@@ -1622,8 +1729,10 @@ void estimate_pairs(Ctx& c, int est, const void* src, size_t stride_s, const voi
     }
     k_accum_pairs<PCLB200_EST_SVD><<<grid, 256, 0, st>>>(a);
   }
-  else
+  else if (est == PCLB200_EST_POINT_TO_PLANE_LLS)
     k_accum_pairs<PCLB200_EST_POINT_TO_PLANE_LLS><<<grid, 256, 0, st>>>(a);
+  else
+    k_accum_pairs<PCLB200_EST_SYMMETRIC_POINT_TO_PLANE_LLS><<<grid, 256, 0, st>>>(a);
   k_solve<<<1, 32, 0, st>>>(red.accum.p, est, scalar_is_double, 0, (double)a.ox, (double)a.oy, (double)a.oz, 1, nullptr,
                             so.p);
   c.launches += 2;

@@ -7,6 +7,7 @@
 #include <cmath>
 #include <cstdio>
 #include <functional>
+#include <type_traits>
 #include <limits>
 #include <memory>
 #include <string>
@@ -261,6 +262,7 @@ public:
 
 protected:
   virtual bool withNormalsTransform() const { return false; }
+  virtual bool enforceSameDirectionNormals() const { return true; }
 
   // impl/icp.hpp:113-268 — the whole do-while runs on the device; the host only evaluates the convergence criteria
   void computeTransformation(PointCloudSource& output, const Matrix4& guess) override
@@ -274,6 +276,7 @@ protected:
     P.scalar_is_double = sizeof(Scalar) == 8;
     P.with_normals_transform = withNormalsTransform() ? 1 : 0;
     P.is_dense = this->input_->is_dense ? 1 : 0;
+    P.enforce_same_direction_normals = enforceSameDirectionNormals() ? 1 : 0;
     P.failure_after_max_iter = convergence_criteria_->failure_after_max_iter_ ? 1 : 0;
     P.max_iterations_similar_transforms = convergence_criteria_->max_iterations_similar_transforms_;
     P.max_correspondence_distance = this->corr_dist_threshold_;
@@ -349,22 +352,39 @@ public:
   IterativeClosestPointWithNormals()
   {
     this->reg_name_ = "IterativeClosestPointWithNormals";
-    setUseSymmetricObjective(false);
+    setUseSymmetricObjective(false);          // icp.h:366-371
+    setEnforceSameDirectionNormals(true);
   }
-  void setUseSymmetricObjective(bool symmetric)
-  {
-    if (symmetric)
-      std::fprintf(stderr, "[pcl::IterativeClosestPointWithNormals] the symmetric objective is outside the accelerated path "
-                           "(SURVEY.md §8f #2); using TransformationEstimationPointToPlaneLLS\n");
-    use_symmetric_objective_ = false;
-    this->transformation_estimation_.reset(new pcl::registration::TransformationEstimationPointToPlaneLLS<PointSource, PointTarget, Scalar>());
-  }
+  // icp.h:381-418
+  void setUseSymmetricObjective(bool symmetric) { use_symmetric_objective_ = symmetric; resetEstimator(); }
   bool getUseSymmetricObjective() const { return use_symmetric_objective_; }
-  void setEnforceSameDirectionNormals(bool) {}
+  void setEnforceSameDirectionNormals(bool v) { enforce_same_direction_normals_ = v; resetEstimator(); }
+  bool getEnforceSameDirectionNormals() const { return enforce_same_direction_normals_; }
 
 protected:
   bool withNormalsTransform() const override { return true; }  // impl/icp.hpp:312-318
+  bool enforceSameDirectionNormals() const override { return enforce_same_direction_normals_; }
+  template <typename PS = PointSource>
+  typename std::enable_if<has_normal<PS>::value>::type makeSymmetric()
+  {
+    auto est = std::make_shared<pcl::registration::TransformationEstimationSymmetricPointToPlaneLLS<PointSource, PointTarget, Scalar>>();
+    est->setEnforceSameDirectionNormals(enforce_same_direction_normals_);
+    this->transformation_estimation_ = est;
+  }
+  template <typename PS = PointSource>
+  typename std::enable_if<!has_normal<PS>::value>::type makeSymmetric()
+  {
+    std::fprintf(stderr, "[pcl::IterativeClosestPointWithNormals] the symmetric objective needs source normals\n");
+  }
+  void resetEstimator()
+  {
+    if (use_symmetric_objective_)
+      makeSymmetric();
+    else
+      this->transformation_estimation_.reset(new pcl::registration::TransformationEstimationPointToPlaneLLS<PointSource, PointTarget, Scalar>());
+  }
   bool use_symmetric_objective_ = false;
+  bool enforce_same_direction_normals_ = true;
 };
 
 }  // namespace pcl

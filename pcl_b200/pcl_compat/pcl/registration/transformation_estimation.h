@@ -154,5 +154,61 @@ protected:
   }
 };
 
+// impl/transformation_estimation_symmetric_point_to_plane_lls.hpp:50-215
+template <typename PointSource, typename PointTarget, typename Scalar = float>
+class TransformationEstimationSymmetricPointToPlaneLLS : public TransformationEstimation<PointSource, PointTarget, Scalar> {
+public:
+  using Base = TransformationEstimation<PointSource, PointTarget, Scalar>;
+  using Matrix4 = typename Base::Matrix4;
+  using Ptr = std::shared_ptr<TransformationEstimationSymmetricPointToPlaneLLS>;
+  static_assert(has_normal<PointSource>::value && has_normal<PointTarget>::value,
+                "TransformationEstimationSymmetricPointToPlaneLLS needs source and target normals");
+  int abiEstimator() const override { return PCLB200_EST_SYMMETRIC_POINT_TO_PLANE_LLS; }
+  void setEnforceSameDirectionNormals(bool v) { enforce_same_direction_normals_ = v; }
+  bool getEnforceSameDirectionNormals() const { return enforce_same_direction_normals_; }
+
+  void estimateRigidTransformation(const pcl::PointCloud<PointSource>& s, const pcl::PointCloud<PointTarget>& t, Matrix4& T) const override
+  {
+    if (s.size() != t.size()) {
+      std::fprintf(stderr, "[pcl::TransformationEstimationSymmetricPointToPlaneLLS::estimateRigidTransformation] Number or points in source (%zu) differs than target (%zu)!\n", s.size(), t.size());
+      return;
+    }
+    solve(s, t, nullptr, s.size(), T);
+  }
+  void estimateRigidTransformation(const pcl::PointCloud<PointSource>& s, const pcl::Indices& is, const pcl::PointCloud<PointTarget>& t, Matrix4& T) const override
+  {
+    if (is.size() != t.size()) return;
+    pcl::Indices it(t.size());
+    for (std::size_t i = 0; i < it.size(); ++i) it[i] = static_cast<index_t>(i);
+    auto c = Base::pairs(is, it);
+    solve(s, t, c.data(), c.size(), T);
+  }
+  void estimateRigidTransformation(const pcl::PointCloud<PointSource>& s, const pcl::Indices& is, const pcl::PointCloud<PointTarget>& t, const pcl::Indices& it, Matrix4& T) const override
+  {
+    if (is.size() != it.size()) return;
+    auto c = Base::pairs(is, it);
+    solve(s, t, c.data(), c.size(), T);
+  }
+  void estimateRigidTransformation(const pcl::PointCloud<PointSource>& s, const pcl::PointCloud<PointTarget>& t, const pcl::Correspondences& corr, Matrix4& T) const override
+  {
+    solve(s, t, reinterpret_cast<const pclb200_corr*>(corr.data()), corr.size(), T);
+  }
+
+protected:
+  void solve(const pcl::PointCloud<PointSource>& s, const pcl::PointCloud<PointTarget>& t, const pclb200_corr* c, std::size_t n, Matrix4& T) const
+  {
+    double out[16];
+    if (n == 0 || s.empty() || t.empty() ||
+        pclb200_estimate_symmetric_point_to_plane_lls(b200::Context::get(), s.points.data(), &s.points[0].normal_x, sizeof(PointSource),
+                                                      t.points.data(), &t.points[0].normal_x, sizeof(PointTarget), c, n,
+                                                      enforce_same_direction_normals_ ? 1 : 0, sizeof(Scalar) == 8, out) != PCLB200_OK) {
+      std::fprintf(stderr, "[pcl::TransformationEstimationSymmetricPointToPlaneLLS] %s\n", n ? pclb200_last_error() : "no point pairs");
+      return;
+    }
+    Base::fromRowMajor(out, T);
+  }
+  bool enforce_same_direction_normals_ = true;
+};
+
 }  // namespace registration
 }  // namespace pcl

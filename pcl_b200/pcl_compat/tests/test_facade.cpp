@@ -23,6 +23,7 @@
 #include <pcl/registration/icp.h>
 #include <pcl/registration/transformation_estimation_point_to_plane_lls.h>
 #include <pcl/registration/transformation_estimation_svd.h>
+#include <pcl/registration/transformation_estimation_symmetric_point_to_plane_lls.h>
 
 using namespace pcl;
 
@@ -202,6 +203,11 @@ int main(int argc, char** argv)
     Eigen::Matrix4f est_T;
     est.estimateRigidTransformation(*src, *tgt, est_T);
     for (int i = 0; i < 4; ++i) for (int j = 0; j < 4; ++j) EXPECT_NEAR(est_T(i, j), gt(i, j), 1e-2);
+    // TEST (PCL, TransformationEstimationSymmetricPointToPlaneLLS) — test_registration_api.cpp:663-713
+    registration::TransformationEstimationSymmetricPointToPlaneLLS<PointNormal, PointNormal> sym;
+    Eigen::Matrix4f sym_T;
+    sym.estimateRigidTransformation(*src, *tgt, sym_T);
+    for (int i = 0; i < 4; ++i) for (int j = 0; j < 4; ++j) EXPECT_NEAR(sym_T(i, j), gt(i, j), 1e-2);
   }
 
   {  // TEST (PCL, IterativeClosestPoint) — test/registration/test_registration.cpp:236-270
@@ -296,6 +302,20 @@ int main(int argc, char** argv)
     Eigen::Matrix4d Td = regd.getFinalTransformation();
     Eigen::Matrix4f Tf = regf.getFinalTransformation();
     for (int r = 0; r < 3; ++r) for (int c = 0; c < 4; ++c) EXPECT_NEAR(Td(r, c), Tf(r, c), 5e-3);
+    // symmetric objective (icp.h:381-393): same neighbourhood of the solution
+    IterativeClosestPointWithNormals<PointNormal, PointNormal, float> regs;
+    regs.setUseSymmetricObjective(true);
+    regs.setInputSource(src);
+    regs.setInputTarget(tgt);
+    regs.setMaximumIterations(50);
+    regs.setTransformationEpsilon(1e-8);
+    regs.setMaxCorrespondenceDistance(0.05);
+    PointCloud<PointNormal> outs;
+    regs.align(outs);
+    EXPECT_TRUE(regs.hasConverged());
+    EXPECT_TRUE(regs.getUseSymmetricObjective());
+    EXPECT_LT(regs.getFitnessScore(), 0.001);
+    for (int r = 0; r < 3; ++r) for (int c = 0; c < 4; ++c) EXPECT_NEAR(regs.getFinalTransformation()(r, c), Tf(r, c), 2e-2);
     // cached target tree: setSearchMethodTarget(tree, force_no_recompute) — test_registration.cpp:513-600 shape
     search::KdTree<PointNormal>::Ptr tree(new search::KdTree<PointNormal>);
     tree->setInputCloud(tgt);

@@ -518,3 +518,61 @@ def test_icp_with_rejector_chain_vs_oracle(gpu, orc):
     s.set_target(tidx)
     s.set_source(S)
     assert s.iterate(1)["n_correspondences"] == S.shape[0]   # no rejectors, no gate: every source point pairs up
+
+
+def test_symmetric_point_to_plane(gpu, orc):
+    """TransformationEstimationSymmetricPointToPlaneLLS: the reference's paraboloid test
+    (test_registration_api.cpp:663-713), oracle parity, and ICP with setUseSymmetricObjective(true)."""
+    P, ctx = gpu
+    xs = np.arange(-5.0, 5.0 + 1e-6, 0.5, dtype=np.float32)
+    X, Y = np.meshgrid(xs, xs, indexing="ij")
+    x, y = X.ravel(), Y.ravel()
+    z = np.float32(0.1) * x ** 2 + np.float32(0.2) * x * y - np.float32(0.3) * y + np.float32(1.0)
+    nrm = np.stack([-0.2 * x - 0.2, 0.6 * y - 0.2, np.ones_like(x)], 1).astype(np.float32)
+    nrm /= np.linalg.norm(nrm, axis=1, keepdims=True)
+    src = np.zeros((x.size, 12), np.float32)
+    src[:, 0], src[:, 1], src[:, 2], src[:, 3] = x, y, z, 1
+    src[:, 4:7] = nrm
+    G = np.array([[0.9938, 0.0988, 0.0517, 0.1], [-0.0997, 0.9949, 0.0149, -0.2], [-0.05, -0.02, 0.9986, 0.3],
+                  [0, 0, 0, 1]], np.float64)
+    tgt = orc.transform(src, G, mode=1, normal_off=4)
+    for enforce in (True, False):
+        T = ctx.estimate_symmetric_lls(src, tgt, enforce_same_direction=enforce, scalar_is_double=True)
+        assert np.all(np.abs(T - G) < 1e-2)
+        To, _ = orc.estimate_symmetric_lls(src, tgt, enforce_same_direction=enforce, scalar_is_double=True)
+        assert np.linalg.norm(T - To) < 1e-9, np.linalg.norm(T - To)
+        Tf = ctx.estimate_symmetric_lls(src, tgt, enforce_same_direction=enforce)
+        Tof, _ = orc.estimate_symmetric_lls(src, tgt, enforce_same_direction=enforce)
+        assert np.linalg.norm(Tf - Tof) < 2e-5          # the oracle (like PCL) accumulates in float here
+    # ICP on a noisy surface, both clouds with normals
+    rng = np.random.default_rng(41)
+    n = 30000
+
+    def surf(m):
+        xy = rng.random((m, 2)) * 4
+        zz = 0.3 * np.sin(xy[:, 0]) * np.cos(xy[:, 1])
+        nn = np.stack([-0.3 * np.cos(xy[:, 0]) * np.cos(xy[:, 1]), 0.3 * np.sin(xy[:, 0]) * np.sin(xy[:, 1]), np.ones(m)], 1)
+        nn /= np.linalg.norm(nn, axis=1, keepdims=True)
+        c = np.zeros((m, 12), np.float32)
+        c[:, :3] = np.column_stack([xy, zz + rng.normal(0, 0.001, m)])
+        c[:, 3] = 1
+        c[:, 4:7] = nn
+        return c
+
+    T0 = np.eye(4)
+    a = np.deg2rad(1.5)
+    T0[:3, :3] = [[np.cos(a), -np.sin(a), 0], [np.sin(a), np.cos(a), 0], [0, 0, 1]]
+    T0[:3, 3] = [0.01, -0.005, 0.004]
+    tgt_c = surf(n)
+    src_c = orc.transform(surf(n), T0, mode=1, normal_off=4)
+    kw = dict(max_iterations=30, max_correspondence_distance=0.05, transformation_epsilon=1e-10)
+    r = P.icp_align(ctx, src_c, P.Index(ctx, tgt_c), src_normals=P.Field(src_c, 4), tgt_normals=P.Field(tgt_c, 4),
+                    estimator=P.EST_SYMMETRIC_POINT_TO_PLANE_LLS, with_normals_transform=1, **kw)
+    o64 = orc.icp_align(src_c, tgt_c, estimator=2, with_normals_transform=True, source_has_normals=True,
+                        scalar_is_double=True, nthreads=8, **kw)
+    assert r["converged"] and o64["converged"]
+    assert np.linalg.norm(r["final"] - o64["final"]) < 5e-5, np.linalg.norm(r["final"] - o64["final"])
+    assert np.linalg.norm(r["final"] @ T0 - np.eye(4)) < 5e-3     # undoes the applied motion
+    with pytest.raises(P.Pclb200Error):                            # symmetric objective without source normals
+        P.icp_align(ctx, src_c, P.Index(ctx, tgt_c), tgt_normals=P.Field(tgt_c, 4),
+                    estimator=P.EST_SYMMETRIC_POINT_TO_PLANE_LLS, **kw)

@@ -172,3 +172,26 @@ def test_rejectors_golden(golden, orc):
     assert np.array_equal(np.stack([r["index_query"], r["index_match"]], 1), golden["corr_rej_one_to_one"])
     r, _ = orc.reject(c, orc.REJ_TRIMMED, p=0.5)                         # rej_trimmed_overlap = 0.5
     assert np.array_equal(np.stack([r["index_query"], r["index_match"]], 1), golden["corr_rej_trimmed"])
+
+
+def _paraboloid(orc):
+    xs = np.arange(-5.0, 5.0 + 1e-6, 0.5, dtype=np.float32)
+    X, Y = np.meshgrid(xs, xs, indexing="ij")
+    x, y = X.ravel(), Y.ravel()
+    z = np.float32(0.1) * x ** 2 + np.float32(0.2) * x * y - np.float32(0.3) * y + np.float32(1.0)
+    n = np.stack([-0.2 * x - 0.2, 0.6 * y - 0.2, np.ones_like(x)], 1).astype(np.float32)
+    n /= np.linalg.norm(n, axis=1, keepdims=True)
+    src = np.zeros((x.size, 12), np.float32)
+    src[:, 0], src[:, 1], src[:, 2], src[:, 3] = x, y, z, 1
+    src[:, 4:7] = n
+    G = np.array([[0.9938, 0.0988, 0.0517, 0.1], [-0.0997, 0.9949, 0.0149, -0.2],
+                  [-0.05, -0.02, 0.9986, 0.3], [0, 0, 0, 1]], np.float64)
+    return src, orc.transform(src, G, mode=1, normal_off=4), G
+
+
+def test_symmetric_point_to_plane_lls_paraboloid(orc):
+    # test/registration/test_registration_api.cpp:663-713
+    src, tgt, G = _paraboloid(orc)
+    for dbl in (False, True):
+        T, rc = orc.estimate_symmetric_lls(src, tgt, scalar_is_double=dbl)
+        assert rc == 0 and np.all(np.abs(T - G) < 1e-2), T
