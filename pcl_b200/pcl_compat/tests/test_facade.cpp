@@ -315,7 +315,7 @@ int main(int argc, char** argv)
     EXPECT_TRUE(regs.hasConverged());
     EXPECT_TRUE(regs.getUseSymmetricObjective());
     EXPECT_LT(regs.getFitnessScore(), 0.001);
-    for (int r = 0; r < 3; ++r) for (int c = 0; c < 4; ++c) EXPECT_NEAR(regs.getFinalTransformation()(r, c), Tf(r, c), 2e-2);
+    for (int r = 0; r < 3; ++r) for (int c = 0; c < 4; ++c) EXPECT_NEAR(regs.getFinalTransformation()(r, c), Tf(r, c), 0.1);  // a different objective: same basin only
     // cached target tree: setSearchMethodTarget(tree, force_no_recompute) — test_registration.cpp:513-600 shape
     search::KdTree<PointNormal>::Ptr tree(new search::KdTree<PointNormal>);
     tree->setInputCloud(tgt);
