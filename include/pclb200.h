@@ -103,6 +103,14 @@ PCLB200_API int pclb200_knn(pclb200_ctx* ctx, const pclb200_index* idx, const vo
                             size_t nq, size_t stride, int k, int32_t* out_idx, float* out_d2,
                             int* k_eff);
 
+/* ---- k-NN statistics: the per-point quantities pcl::StatisticalOutlierRemoval and pcl::RadiusOutlierRemoval derive
+ * from nearestKSearch (filters/include/pcl/filters/impl/statistical_outlier_removal.hpp:72-97,
+ * radius_outlier_removal.hpp:74-118), computed on the device so only 4-8 bytes per point come back.
+ * out_mean (nullable): mean distance to neighbours 1..k'-1 (neighbour 0 = the query itself), k' = min(k, indexed points);
+ *   0 for non-finite queries.  out_kth (nullable): squared distance of neighbour k-1, +inf if fewer than k points. */
+PCLB200_API int pclb200_knn_stats(pclb200_ctx* ctx, const pclb200_index* idx, const void* pts, size_t n, size_t stride,
+                                  const int32_t* indices, size_t n_idx, int k, float* out_mean, float* out_kth);
+
 /* ---- radius: replaces pcl::KdTreeFLANN::radiusSearch (kdtree_flann.hpp:372-414) and the batch
  * overload search.hpp:157-194.  Neighbours with d2 < float(radius*radius) (strict, FLANN
  * RadiusResultSet); max_nn == 0 or > N => unlimited, else the max_nn nearest; always returned

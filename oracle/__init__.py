@@ -87,6 +87,12 @@ def lib():
         L.orc_voxelgrid.argtypes = [fp, sz, sz, i32p, sz, C.c_int, fp, C.c_uint, fp]
         L.orc_point_normal.argtypes = [fp, sz, C.c_int, i32p, sz, fp]
         L.orc_normals_knn.argtypes = [vp, fp, sz, sz, i32p, sz, C.c_int, C.c_int, fp, fp, C.c_int]
+        u8p = C.POINTER(C.c_uint8)
+        L.orc_knn_stats.argtypes = [vp, fp, sz, sz, i32p, sz, C.c_int, fp, fp, C.c_int]
+        L.orc_sor.restype = sz
+        L.orc_sor.argtypes = [vp, fp, sz, sz, i32p, sz, C.c_int, C.c_double, C.c_int, u8p, C.c_int]
+        L.orc_ror.restype = sz
+        L.orc_ror.argtypes = [vp, fp, sz, sz, i32p, sz, C.c_int, C.c_double, C.c_int, C.c_int, u8p, C.c_int]
         L.orc_max_threads.restype = C.c_int
         _lib = L
     return _lib
@@ -190,6 +196,27 @@ class Index:
         return float(lib().orc_fitness_score(self.h, _f(src), src.shape[0], src.shape[1], _i(indices),
                                              0 if indices is None else indices.size, int(is_dense), _d(T),
                                              int(scalar_is_double), float(max_range), 1))
+
+    def knn_stats(self, cloud, k, nthreads=1):
+        cloud = as_cloud(cloud)
+        mean = np.empty(cloud.shape[0], np.float32)
+        kth = np.empty(cloud.shape[0], np.float32)
+        lib().orc_knn_stats(self.h, _f(cloud), cloud.shape[0], cloud.shape[1], None, 0, k, _f(mean), _f(kth), nthreads)
+        return mean, kth
+
+    def statistical_outlier_removal(self, cloud, mean_k, std_mul, negative=False, nthreads=1):
+        cloud = as_cloud(cloud)
+        keep = np.empty(cloud.shape[0], np.uint8)
+        lib().orc_sor(self.h, _f(cloud), cloud.shape[0], cloud.shape[1], None, 0, mean_k, float(std_mul), int(negative),
+                      keep.ctypes.data_as(C.POINTER(C.c_uint8)), nthreads)
+        return np.nonzero(keep)[0].astype(np.int32)
+
+    def radius_outlier_removal(self, cloud, radius, min_pts, negative=False, is_dense=True, nthreads=1):
+        cloud = as_cloud(cloud)
+        keep = np.empty(cloud.shape[0], np.uint8)
+        lib().orc_ror(self.h, _f(cloud), cloud.shape[0], cloud.shape[1], None, 0, int(is_dense), float(radius), min_pts,
+                      int(negative), keep.ctypes.data_as(C.POINTER(C.c_uint8)), nthreads)
+        return np.nonzero(keep)[0].astype(np.int32)
 
     def normals_knn(self, cloud, k, viewpoint=(0, 0, 0), indices=None, is_dense=True, nthreads=1):
         cloud = as_cloud(cloud)

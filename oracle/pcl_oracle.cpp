@@ -1651,6 +1651,106 @@ ORC_API int orc_normals_knn(void* h, const float* cloud, size_t n, size_t stride
   return dense_out;
 }
 
+// ---- k-NN statistics + the two outlier filters built on them ---------------------------
+// out_mean[i] = float( sum_{j=1..k'-1} sqrt(double(d2_j)) / (k'-1) ), k' = min(k, #indexed points), j = 0 is the query
+//               itself (filters/include/pcl/filters/impl/statistical_outlier_removal.hpp:88-97); 0 for non-finite queries
+// out_kth[i]  = d2 of the k-th neighbour (index k-1), +inf when fewer than k points are indexed
+ORC_API void orc_knn_stats(void* h, const float* cloud, size_t n, size_t stride, const int32_t* indices, size_t n_idx,
+                           int k, float* out_mean, float* out_kth, int nthreads)
+{
+  const KdTree& t = *static_cast<KdTree*>(h);
+  size_t cnt = indices ? n_idx : n;
+  int keff = (int)std::min<size_t>((size_t)std::max(k, 0), t.n);
+#pragma omp parallel num_threads(nthreads > 0 ? nthreads : 1)
+  {
+    std::vector<Cand> buf((size_t)std::max(keff, 1));
+#pragma omp for schedule(dynamic, 512)
+    for (long long i = 0; i < (long long)cnt; ++i) {
+      const float* p = cloud + stride * (size_t)(indices ? indices[i] : (int32_t)i);
+      float mean = 0.0f, kth = std::numeric_limits<float>::infinity();
+      if (finite3(p) && keff > 0) {
+        KnnSet rs{buf.data(), keff, 0};
+        kd_knn_rec(t, 0, p, rs);
+        double sum = 0.0;
+        for (int j = 1; j < rs.n; ++j)
+          sum += std::sqrt(static_cast<double>(rs.c[j].d));
+        if (rs.n > 1)
+          mean = static_cast<float>(sum / (rs.n - 1));
+        if (rs.n == k)
+          kth = rs.c[k - 1].d;
+      }
+      if (out_mean) out_mean[i] = mean;
+      if (out_kth) out_kth[i] = kth;
+    }
+  }
+}
+
+// StatisticalOutlierRemoval::applyFilterIndices — statistical_outlier_removal.hpp:47-135.  keep[i] in {0,1}.
+ORC_API size_t orc_sor(void* h, const float* cloud, size_t n, size_t stride, const int32_t* indices, size_t n_idx,
+                       int mean_k, double std_mul, int negative, uint8_t* keep, int nthreads)
+{
+  size_t cnt = indices ? n_idx : n;
+  std::vector<float> dist(cnt);
+  orc_knn_stats(h, cloud, n, stride, indices, n_idx, mean_k + 1, dist.data(), nullptr, nthreads);
+  long long valid = 0;
+  for (size_t i = 0; i < cnt; ++i)
+    if (finite3(cloud + stride * (size_t)(indices ? indices[i] : (int32_t)i)))
+      ++valid;
+  double sum = 0, sq_sum = 0;
+  for (float d : dist) {
+    sum += d;
+    sq_sum += d * d;
+  }
+  double mean = sum / static_cast<double>(valid);
+  double variance = (sq_sum - sum * sum / static_cast<double>(valid)) / (static_cast<double>(valid) - 1);
+  double thr = mean + std_mul * std::sqrt(variance);
+  size_t kept = 0;
+  for (size_t i = 0; i < cnt; ++i) {
+    bool removed = (!negative && dist[i] > thr) || (negative && dist[i] <= thr);
+    keep[i] = removed ? 0 : 1;
+    kept += keep[i];
+  }
+  return kept;
+}
+
+// RadiusOutlierRemoval::applyFilterIndices — radius_outlier_removal.hpp:49-179 (dense: k-NN rule with <=; non-dense:
+// radius rule with the strict FLANN comparison).
+ORC_API size_t orc_ror(void* h, const float* cloud, size_t n, size_t stride, const int32_t* indices, size_t n_idx,
+                       int is_dense, double radius, int min_pts, int negative, uint8_t* keep, int nthreads)
+{
+  size_t cnt = indices ? n_idx : n;
+  const int mean_k = min_pts + 1;
+  std::vector<float> kth(cnt);
+  orc_knn_stats(h, cloud, n, stride, indices, n_idx, mean_k, nullptr, kth.data(), nthreads);
+  const double nn_dists_max = radius * radius;
+  const float r2f = static_cast<float>(radius * radius);
+  size_t kept = 0;
+  for (size_t i = 0; i < cnt; ++i) {
+    const float* p = cloud + stride * (size_t)(indices ? indices[i] : (int32_t)i);
+    bool k = true;
+    if (is_dense) {
+      if (std::isfinite(kth[i])) {  // k == mean_k neighbours found
+        if ((!negative && nn_dists_max < kth[i]) || (negative && nn_dists_max >= kth[i]))
+          k = false;
+      }
+      else if (!negative)
+        k = false;
+    }
+    else {
+      if (!finite3(p))
+        k = false;
+      else {
+        const bool enough = kth[i] < r2f;  // radiusSearch found min_pts + 1 neighbours (strict d2 < r2)
+        if ((!negative && !enough) || (negative && enough))
+          k = false;
+      }
+    }
+    keep[i] = k ? 1 : 0;
+    kept += keep[i];
+  }
+  return kept;
+}
+
 ORC_API int orc_max_threads()
 {
 #ifdef _OPENMP

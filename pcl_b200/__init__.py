@@ -64,7 +64,7 @@ SYMBOLS = [
     "pclb200_version", "pclb200_last_error", "pclb200_create", "pclb200_destroy", "pclb200_synchronize",
     "pclb200_launch_count", "pclb200_stream", "pclb200_free", "pclb200_profile_enable", "pclb200_profile_get",
     "pclb200_profile_reset", "pclb200_index_build", "pclb200_index_destroy",
-    "pclb200_index_size", "pclb200_index_stats", "pclb200_knn", "pclb200_radius", "pclb200_correspondences",
+    "pclb200_index_size", "pclb200_index_stats", "pclb200_knn", "pclb200_knn_stats", "pclb200_radius", "pclb200_correspondences",
     "pclb200_estimate_svd", "pclb200_estimate_point_to_plane_lls", "pclb200_estimate_symmetric_point_to_plane_lls", "pclb200_icp_default_params",
     "pclb200_icp_create", "pclb200_icp_destroy", "pclb200_icp_set_params", "pclb200_icp_set_target",
     "pclb200_icp_set_source", "pclb200_icp_iterate", "pclb200_icp_get_cloud", "pclb200_icp_get_correspondences",
@@ -102,6 +102,7 @@ def lib():
     L.pclb200_index_size.argtypes = [vp, C.POINTER(sz)]
     L.pclb200_index_stats.argtypes = [vp, C.POINTER(C.c_uint64)]
     L.pclb200_knn.argtypes = [vp, vp, vp, sz, sz, C.c_int, vp, vp, C.POINTER(C.c_int)]
+    L.pclb200_knn_stats.argtypes = [vp, vp, vp, sz, sz, vp, sz, C.c_int, vp, vp]
     L.pclb200_radius.argtypes = [vp, vp, vp, sz, sz, C.c_double, C.c_uint, C.c_int, C.POINTER(C.c_int64),
                                  C.POINTER(i32p), C.POINTER(fp)]
     L.pclb200_correspondences.argtypes = [vp, vp, vp, vp, sz, sz, vp, sz, C.c_int, C.c_double, vp, C.POINTER(sz)]
@@ -342,6 +343,15 @@ class Index:
         keff = C.c_int()
         _check(lib().pclb200_knn(self.ctx.h, self.h, b.ptr, b.rows, b.stride, k, oi.ptr, od.ptr, C.byref(keff)))
         return out_idx, out_d2, int(keff.value)
+
+    def knn_stats(self, cloud, k, indices=None):
+        """(mean distance to the k-1 nearest other points, squared distance of neighbour k-1) per point."""
+        b, ib = _Buf(cloud), _Buf(indices, np.int32)
+        n = ib.rows if indices is not None else b.rows
+        mean, kth = np.empty(n, np.float32), np.empty(n, np.float32)
+        _check(lib().pclb200_knn_stats(self.ctx.h, self.h, b.ptr, b.rows, b.stride, ib.ptr, ib.rows, k,
+                                       C.c_void_p(mean.ctypes.data), C.c_void_p(kth.ctypes.data)))
+        return mean, kth
 
     def radius(self, q, r, max_nn=0, sorted_results=True):
         b = _Buf(q)

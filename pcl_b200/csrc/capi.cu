@@ -35,6 +35,7 @@ double fitness_score(Ctx& c, const Index& tgt, const void* src, size_t n, size_t
 // search.cu
 void launch_normals(Ctx& c, Index& idx, const float4* d_q, size_t nq, int k, const float vp[3], float4* d_out,
                     int* d_not_dense);
+void launch_knn_stats(Ctx& c, const Index& idx, const float4* d_q, size_t nq, int k, float* d_mean, float* d_kth);
 // voxel.cu
 size_t voxelgrid(Ctx& c, const void* pts, size_t n, size_t stride, const int32_t* indices, size_t n_idx, int is_dense,
                  const float leaf[3], unsigned min_pts, float* out_xyz1);
@@ -351,6 +352,48 @@ int pclb200_knn(pclb200_ctx* ctx, const pclb200_index* h, const void* queries, s
       PCLB_CUDA(cudaMemcpyAsync(out_idx, pi, nq * (size_t)k * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
       PCLB_CUDA(cudaMemcpyAsync(out_d2, pd, nq * (size_t)k * sizeof(float), cudaMemcpyDeviceToHost, st));
     }
+    raise_if_device_error(c);
+  });
+}
+
+int pclb200_knn_stats(pclb200_ctx* ctx, const pclb200_index* h, const void* pts, size_t n, size_t stride,
+                      const int32_t* indices, size_t n_idx, int k, float* out_mean, float* out_kth)
+{
+  return guarded([&] {
+    PCLB_REQUIRE(ctx && h && h->idx && (out_mean || out_kth), PCLB200_ERR_INVALID, "NULL argument");
+    PCLB_REQUIRE(k > 0, PCLB200_ERR_INVALID, "k must be positive");
+    Ctx& c = ctx->c;
+    std::lock_guard<std::recursive_mutex> lk(c.mu);
+    PCLB_CUDA(cudaSetDevice(c.device));
+    cudaStream_t st = c.stream;
+    const size_t nq = indices ? n_idx : n;
+    if (!nq)
+      return;
+    DevBuf<float4> dense;
+    dense.alloc(nq, st);
+    load_xyz_as_float4(c, pts, n, stride, indices, n_idx, dense.p, st);
+    QueryBatch qb;
+    make_query_batch(c, *h->idx, dense.p, nq, qb);
+    DevBuf<float> dm, dk;
+    float* pm = out_mean;
+    float* pk = out_kth;
+    const bool m_dev = out_mean && is_device_ptr(out_mean), k_dev = out_kth && is_device_ptr(out_kth);
+    if (out_mean && !m_dev) {
+      dm.alloc(nq, st);
+      pm = dm.p;
+    }
+    if (out_kth && !k_dev) {
+      dk.alloc(nq, st);
+      pk = dk.p;
+    }
+    {
+      ProfScope ps(c, "knn_stats");
+      launch_knn_stats(c, *h->idx, qb.q.p, nq, k, pm, pk);
+    }
+    if (out_mean && !m_dev)
+      PCLB_CUDA(cudaMemcpyAsync(out_mean, pm, nq * sizeof(float), cudaMemcpyDeviceToHost, st));
+    if (out_kth && !k_dev)
+      PCLB_CUDA(cudaMemcpyAsync(out_kth, pk, nq * sizeof(float), cudaMemcpyDeviceToHost, st));
     raise_if_device_error(c);
   });
 }

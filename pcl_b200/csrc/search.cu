@@ -181,6 +181,111 @@ void launch_knn(Ctx& c, const Index& idx, const float4* d_q, size_t nq, int k, f
   PCLB_CUDA(cudaGetLastError());
 }
 
+// ---- per-query statistics of the k nearest neighbours (outlier filters) -------------------------------------------
+// mean[slot] = float( sum_{j=1..k'-1} sqrt(double(d2_j)) / (k'-1) )   (statistical_outlier_removal.hpp:88-97; j = 0 is
+//              the query itself when it belongs to the cloud), 0 for non-finite queries
+// kth[slot]  = d2 of neighbour k-1, +inf when fewer than k points are indexed (radius_outlier_removal.hpp:86-118)
+template <int K>
+__global__ void __launch_bounds__(128)
+k_knn_stats(const BvhNode* __restrict__ nodes, const float4* __restrict__ pts, int root, const float4* __restrict__ q,
+            size_t nq, int k, float* __restrict__ out_mean, float* __restrict__ out_kth, int* __restrict__ d_error)
+{
+  size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+  if (i >= nq)
+    return;
+  const float4 qq = __ldg(q + i);
+  const size_t slot = (size_t)(unsigned)__float_as_int(qq.w);
+  float mean = 0.f, kth = __int_as_float(0x7f800000);
+  if (isfinite(qq.x) && isfinite(qq.y) && isfinite(qq.z)) {
+    NearestK<K> v;
+    v.qx = qq.x; v.qy = qq.y; v.qz = qq.z;
+    v.pts = pts;
+    v.init(__int_as_float(0x7f800000));
+    if (!traverse(nodes, pts, root, qq.x, qq.y, qq.z, v))
+      atomicExch(d_error, 1);
+    double sum = 0.0;
+    int cnt = 0;
+#pragma unroll
+    for (int j = 0; j < K; ++j)
+      if (j < k && v.pos[j] >= 0) {
+        if (j >= 1)
+          sum += sqrt((double)v.d[j]);
+        ++cnt;
+        if (j == k - 1)
+          kth = v.d[j];
+      }
+    if (cnt > 1)
+      mean = (float)(sum / (double)(cnt - 1));
+  }
+  if (out_mean)
+    out_mean[slot] = mean;
+  if (out_kth)
+    out_kth[slot] = kth;
+}
+
+// same from materialised lists (k > 32): rows of pitch k by slot
+__global__ void k_stats_from_lists(const float4* __restrict__ q, size_t nq, int k, const int32_t* __restrict__ li,
+                                   const float* __restrict__ ld, float* __restrict__ out_mean, float* __restrict__ out_kth)
+{
+  size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+  if (i >= nq)
+    return;
+  const float4 qq = __ldg(q + i);
+  const size_t slot = (size_t)(unsigned)__float_as_int(qq.w);
+  float mean = 0.f, kth = __int_as_float(0x7f800000);
+  if (isfinite(qq.x) && isfinite(qq.y) && isfinite(qq.z)) {
+    double sum = 0.0;
+    int cnt = 0;
+    for (int j = 0; j < k; ++j)
+      if (li[slot * k + j] >= 0) {
+        if (j >= 1)
+          sum += sqrt((double)ld[slot * k + j]);
+        ++cnt;
+        if (j == k - 1)
+          kth = ld[slot * k + j];
+      }
+    if (cnt > 1)
+      mean = (float)(sum / (double)(cnt - 1));
+  }
+  if (out_mean)
+    out_mean[slot] = mean;
+  if (out_kth)
+    out_kth[slot] = kth;
+}
+
+void launch_knn_stats(Ctx& c, const Index& idx, const float4* d_q, size_t nq, int k, float* d_mean, float* d_kth)
+{
+  if (!nq || k <= 0)
+    return;
+  cudaStream_t s = c.stream;
+  const unsigned g = grid_for(nq, 128);
+  if (k > 32) {
+    // large neighbourhoods (StatisticalOutlierRemoval's usual mean_k = 50): exact lists first, folded afterwards.
+    // NaN queries get empty rows from the walk (no box is ever within a NaN bound) and are zeroed by the fold.
+    DevBuf<int32_t> li;
+    DevBuf<float> ld;
+    li.alloc(nq * (size_t)k, s);
+    ld.alloc(nq * (size_t)k, s);
+    launch_knn(c, idx, d_q, nq, k, __builtin_inff(), li.p, ld.p);
+    k_stats_from_lists<<<grid_for(nq, 256), 256, 0, s>>>(d_q, nq, k, li.p, ld.p, d_mean, d_kth);
+    ++c.launches;
+    PCLB_CUDA(cudaGetLastError());
+    return;
+  }
+#define PCLB_STAT_CASE(KK) \
+  k_knn_stats<KK><<<g, 128, 0, s>>>(idx.nodes.p, idx.pts.p, idx.root, d_q, nq, k, d_mean, d_kth, c.d_error)
+  if (k <= 2) PCLB_STAT_CASE(2);
+  else if (k <= 4) PCLB_STAT_CASE(4);
+  else if (k <= 8) PCLB_STAT_CASE(8);
+  else if (k <= 10) PCLB_STAT_CASE(10);
+  else if (k <= 16) PCLB_STAT_CASE(16);
+  else if (k <= 20) PCLB_STAT_CASE(20);
+  else PCLB_STAT_CASE(32);
+#undef PCLB_STAT_CASE
+  ++c.launches;
+  PCLB_CUDA(cudaGetLastError());
+}
+
 // ---- radius search: count, then fill keys (d2 bits << 32 | original index) -------------------------
 struct RadiusCount {
   float qx, qy, qz, r2;

@@ -10,6 +10,8 @@
 #include <vector>
 
 #include <pcl/features/normal_3d.h>
+#include <pcl/filters/radius_outlier_removal.h>
+#include <pcl/filters/statistical_outlier_removal.h>
 #include <pcl/filters/voxel_grid.h>
 #include <pcl/io/pcd_io.h>
 #include <pcl/kdtree/kdtree_flann.h>
@@ -345,6 +347,42 @@ int main(int argc, char** argv)
     grid.setLeafSize(1e-5f, 1e-5f, 1e-5f);  // overflow guard: input returned unfiltered (voxel_grid.hpp:620-629)
     grid.filter(output);
     EXPECT_EQ(output.size(), cloud_source.size());
+  }
+
+  {  // TEST (RadiusOutlierRemoval, Filters) — test/filters/test_filters.cpp:1494-1515
+    PointCloud<PointXYZ> out, out_neg;
+    RadiusOutlierRemoval<PointXYZ> outrem;
+    outrem.setInputCloud(cloud_source.makeShared());
+    outrem.setRadiusSearch(0.02);
+    outrem.setMinNeighborsInRadius(14);
+    outrem.filter(out);
+    EXPECT_EQ(out.size(), 307u);
+    EXPECT_EQ(out.width, 307u);
+    EXPECT_TRUE(out.is_dense);
+    outrem.setNegative(true);
+    outrem.filter(out_neg);
+    EXPECT_EQ(out_neg.size(), 90u);
+  }
+  {  // TEST (StatisticalOutlierRemoval, Filters) — test/filters/test_filters.cpp:1587-1613
+    PointCloud<PointXYZ> output;
+    StatisticalOutlierRemoval<PointXYZ> outrem(true);
+    outrem.setInputCloud(cloud_source.makeShared());
+    outrem.setMeanK(50);
+    outrem.setStddevMulThresh(1.0);
+    outrem.filter(output);
+    EXPECT_EQ(output.size(), 352u);
+    EXPECT_EQ(output.width, 352u);
+    EXPECT_TRUE(output.is_dense);
+    EXPECT_NEAR(output[output.size() - 1].x, -0.034667, 1e-4);
+    EXPECT_NEAR(output[output.size() - 1].y, 0.15131, 1e-4);
+    EXPECT_NEAR(output[output.size() - 1].z, -0.00071029, 1e-4);
+    EXPECT_EQ(outrem.getRemovedIndices()->size(), cloud_source.size() - 352);
+    outrem.setNegative(true);
+    outrem.filter(output);
+    EXPECT_EQ(output.size(), cloud_source.size() - 352);
+    EXPECT_NEAR(output[output.size() - 1].x, -0.07793, 1e-4);
+    EXPECT_NEAR(output[output.size() - 1].y, 0.17516, 1e-4);
+    EXPECT_NEAR(output[output.size() - 1].z, -0.0444, 1e-4);
   }
 
   {  // TEST (PCL, NormalEstimation) — test/features/test_normal_estimation.cpp:128-163: k = all points

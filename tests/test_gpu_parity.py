@@ -576,3 +576,33 @@ def test_symmetric_point_to_plane(gpu, orc):
     with pytest.raises(P.Pclb200Error):                            # symmetric objective without source normals
         P.icp_align(ctx, src_c, P.Index(ctx, tgt_c), tgt_normals=P.Field(tgt_c, 4),
                     estimator=P.EST_SYMMETRIC_POINT_TO_PLANE_LLS, **kw)
+
+
+def test_knn_stats_and_outlier_filters(gpu, golden, orc):
+    """pclb200_knn_stats (what StatisticalOutlierRemoval / RadiusOutlierRemoval derive from nearestKSearch): bit-exact
+    against the oracle for register (k <= 32) and list (k > 32) kernels, with NaN points and subsets; and the two
+    filters' golden counts on bun0 (test/filters/test_filters.cpp:1494-1515, 1587-1613)."""
+    P, ctx = gpu
+    rng = np.random.default_rng(51)
+    pts = rng.random((20000, 3), dtype=np.float32)
+    pts[::53, 2] = np.nan
+    cloud = orc.to_xyz1(pts)
+    gi, oi = P.Index(ctx, cloud), orc.Index(cloud)
+    for k in (2, 9, 15, 32, 51):
+        gm, gk = gi.knn_stats(cloud, k)
+        om, ok = oi.knn_stats(cloud, k, nthreads=4)
+        assert np.array_equal(gm, om), k
+        assert np.array_equal(gk, ok), k
+    sub = np.arange(0, 20000, 7, dtype=np.int32)
+    gm, gk = gi.knn_stats(cloud, 6, indices=sub)
+    om, ok = oi.knn_stats(cloud, 6, nthreads=4)
+    assert np.array_equal(gm, om[sub]) and np.array_equal(gk, ok[sub])
+    bun = P.xyz1(golden["bun0"])
+    bi = P.Index(ctx, bun)
+    _, kth = bi.knn_stats(bun, 15)
+    assert int((kth <= 0.02 * 0.02).sum()) == 307                       # RadiusOutlierRemoval(0.02, 14): dense rule
+    mean, _ = bi.knn_stats(bun, 51)
+    s = mean.astype(np.float64)
+    mu = s.sum() / 397
+    var = ((mean * mean).astype(np.float64).sum() - s.sum() ** 2 / 397) / 396
+    assert int((mean <= mu + 1.0 * np.sqrt(var)).sum()) == 352          # StatisticalOutlierRemoval(50, 1.0)

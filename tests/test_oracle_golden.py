@@ -195,3 +195,18 @@ def test_symmetric_point_to_plane_lls_paraboloid(orc):
     for dbl in (False, True):
         T, rc = orc.estimate_symmetric_lls(src, tgt, scalar_is_double=dbl)
         assert rc == 0 and np.all(np.abs(T - G) < 1e-2), T
+
+
+def test_outlier_filters_bun0(golden, orc):
+    # test/filters/test_filters.cpp:1494-1515 (RadiusOutlierRemoval) and :1587-1613 (StatisticalOutlierRemoval)
+    cloud = orc.to_xyz1(golden["bun0"])
+    idx = orc.Index(cloud)
+    assert idx.radius_outlier_removal(cloud, 0.02, 14).size == 307
+    assert idx.radius_outlier_removal(cloud, 0.02, 14, negative=True).size == 90
+    assert idx.radius_outlier_removal(cloud, 0.02, 14, is_dense=False).size == 307
+    k = idx.statistical_outlier_removal(cloud, 50, 1.0)
+    assert k.size == 352
+    assert np.allclose(cloud[k[-1], :3], [-0.034667, 0.15131, -0.00071029], atol=1e-4)
+    kn = idx.statistical_outlier_removal(cloud, 50, 1.0, negative=True)
+    assert kn.size == 397 - 352
+    assert np.allclose(cloud[kn[-1], :3], [-0.07793, 0.17516, -0.0444], atol=1e-4)
