@@ -415,6 +415,135 @@ k_search_packet(const IterArgs a, Match* __restrict__ match)
     atomicExch(a.d_error, 1);
 }
 
+// Compacting variant of the packet kernel for the converged regime (lower-bound tracking on): a block takes a tile
+// of kTile Hilbert-consecutive queries, first runs the streaming part for all of them (apply T_k, temporal-coherence
+// test, results of the queries that pass it), appends the queries that still need a walk to a shared-memory list
+// IN ORDER, and then walks the tree with full 32-query packets drawn from that list.  With 90 % of the queries
+// skipping, the plain packet kernel still walks nearly every warp for its few remaining lanes; here the walks shrink
+// with the number of queries that need them.
+constexpr int kTile = 1024;
+
+__global__ void __launch_bounds__(256)
+k_search_packet_compact(const IterArgs a, Match* __restrict__ match)
+{
+  __shared__ Pending sP;
+  __shared__ int s_node[8][kWarpStack];
+  __shared__ float s_dist[8][kWarpStack];
+  __shared__ int s_list[kTile];
+  __shared__ int s_wcnt[8];
+  __shared__ int s_count;
+  if (threadIdx.x == 0)
+    sP = *a.pending;
+  __syncthreads();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const float inf = __int_as_float(0x7f800000);
+  bool overflow = false;
+  unsigned long long skipped = 0;
+  for (size_t tile = (size_t)blockIdx.x * kTile; tile < a.n; tile += (size_t)gridDim.x * kTile) {
+    if (threadIdx.x == 0)
+      s_count = 0;
+    __syncthreads();
+    // ---- phase 1: streaming part, order-preserving compaction of the queries that must walk
+#pragma unroll 1
+    for (int r = 0; r < kTile / 256; ++r) {
+      const size_t i = tile + (size_t)r * 256 + threadIdx.x;
+      const bool in_range = i < a.n;
+      bool walk = false;
+      if (in_range) {
+        float4 p = a.cur[i];
+        const Match prev = match[i];
+        if (isfinite(p.x) && isfinite(p.y) && isfinite(p.z)) {
+          float delta = 0.f;
+          if (sP.apply) {
+            const float ox = p.x, oy = p.y, oz = p.z;
+            apply_pending(sP, p.x, p.y, p.z);
+            a.cur[i] = p;
+            delta = sqrtf(dist2_rn(p.x, p.y, p.z, ox, oy, oz));
+            if (a.cur_normals) {
+              float4 nn = a.cur_normals[i];
+              apply_pending_normal(sP, nn.x, nn.y, nn.z);
+              a.cur_normals[i] = nn;
+            }
+          }
+          float nlb;
+          if (still_nearest(prev, delta, &nlb)) {
+            const float4 q = ldg4(a.pts + prev.pos);
+            Match m;
+            m.pos = prev.pos;
+            m.d2 = dist2_rn(p.x, p.y, p.z, q.x, q.y, q.z);
+            m.lb = nlb;
+            m.accepted = m.d2 <= a.gate ? 1 : 0;
+            match[i] = m;
+            ++skipped;
+          }
+          else
+            walk = true;  // match[i] still holds the previous iteration's entry: phase 2 seeds from it
+        }
+        else {
+          Match m;
+          m.pos = -1; m.d2 = 0.f; m.lb = 0.f; m.accepted = 0;
+          match[i] = m;
+        }
+      }
+      const unsigned bal = __ballot_sync(0xffffffffu, walk);
+      if (lane == 0)
+        s_wcnt[warp] = __popc(bal);
+      __syncthreads();
+      int base = s_count;
+      for (int w = 0; w < warp; ++w)
+        base += s_wcnt[w];
+      if (walk)
+        s_list[base + __popc(bal & ((1u << lane) - 1u))] = (int)(i - tile);
+      __syncthreads();
+      if (threadIdx.x == 0) {
+        int t = 0;
+        for (int w = 0; w < 8; ++w)
+          t += s_wcnt[w];
+        s_count += t;
+      }
+      __syncthreads();
+    }
+    // ---- phase 2: full packets from the compacted list
+    const int total = s_count;
+    for (int k0 = warp * 32; k0 < total; k0 += 8 * 32) {
+      const int j = k0 + lane;
+      const bool active = j < total;
+      const size_t i = tile + (size_t)(active ? s_list[j] : 0);
+      const float4 p = active ? a.cur[i] : make_float4(0.f, 0.f, 0.f, 0.f);
+      Match prev;
+      prev.pos = -1;
+      if (active)
+        prev = match[i];
+      Nearest1T<true> v{p.x, p.y, p.z, active ? a.gate : -1.f, kSentinelIndex, -1, inf, inf, inf};
+      if (active && prev.pos >= 0) {
+        const int leaf = prev.pos / kLeafSize;
+        v.template scan<false>(a.pts + (size_t)leaf * kLeafSize, leaf * kLeafSize);
+      }
+      __syncwarp();
+      if (!traverse_packet(a.nodes, a.pts, a.root, p.x, p.y, p.z, v, s_node[warp], s_dist[warp]))
+        overflow = true;
+      if (active) {
+        Match m;
+        m.pos = -1; m.d2 = 0.f; m.lb = 0.f; m.accepted = 0;
+        if (v.best_pos >= 0) {
+          m.pos = v.best_pos;
+          m.d2 = v.best;
+          m.lb = sqrtf(v.lower_bound2());
+          m.accepted = 1;
+        }
+        match[i] = m;
+      }
+    }
+    __syncthreads();  // s_list / s_count are reused by the next tile
+  }
+  for (int o = 16; o > 0; o >>= 1)
+    skipped += __shfl_xor_sync(0xffffffffu, skipped, o);
+  if (lane == 0 && skipped)
+    atomicAdd(a.skip_count, skipped);
+  if (overflow)
+    atomicExch(a.d_error, 1);
+}
+
 // Accumulation kernel: one streaming pass over (source point, match) pairs; fp64 sums, fixed reduction order.
 template <int EST>
 __global__ void __launch_bounds__(256)
@@ -1416,8 +1545,14 @@ void icp_iterate(Icp& s, int max_steps, pclb200_icp_stats* stats)
       if (packet) {
         if (s.P.use_reciprocal)
           k_search_packet<true, false><<<sgrid, 256, 0, st>>>(a, s.match.p);
-        else if (track)
-          k_search_packet<false, true><<<sgrid, 256, 0, st>>>(a, s.match.p);
+        else if (track) {
+          const unsigned cgrid = persistent_grid(c, (s.n_q + kTile - 1) / kTile * 256, 256, 4);
+          const char* cm = getenv("PCLB200_COMPACT");  // "0": plain packet kernel with tracking (A/B measurements)
+          if (cm && cm[0] == '0')
+            k_search_packet<false, true><<<sgrid, 256, 0, st>>>(a, s.match.p);
+          else
+            k_search_packet_compact<<<cgrid, 256, 0, st>>>(a, s.match.p);
+        }
         else
           k_search_packet<false, false><<<sgrid, 256, 0, st>>>(a, s.match.p);
       }

@@ -159,7 +159,9 @@ struct __align__(16) BvhNode {
 #endif
 constexpr int kLeafSize = PCLB_LEAF;  // points per leaf (multiple of 8): 8 points = one 128-byte line of float4
 static_assert(kLeafSize % 8 == 0 && kLeafSize >= 8 && kLeafSize <= 64, "leaf size must be a multiple of 8");
-constexpr int kStackSize = 64;      // traversal stack entries per query
+// A walk pushes at most one entry per level.  The radix tree is at most 63 (key bits) + 31 (index tie-break bits)
+// = 94 levels deep, so 96 entries can never overflow (the overflow check stays as a guard, not as an expected path).
+constexpr int kStackSize = 96;      // traversal stack entries per query
 constexpr int kSentinelIndex = 0x7fffffff;
 
 struct Index {

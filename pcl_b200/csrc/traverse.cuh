@@ -173,7 +173,7 @@ using Nearest1 = Nearest1T<false>;
 // still the exact lexicographic minimum.  The nearer child is the one with the smaller warp-minimum bound; the other
 // is pushed with that minimum and re-tested on pop against the warp-maximum best (conservative).
 // Lanes without a query pass best = -1 (never want anything).  Must be called by all 32 lanes.
-constexpr int kWarpStack = 64;
+constexpr int kWarpStack = kStackSize;
 
 template <typename V>
 __device__ __forceinline__ bool traverse_packet(const BvhNode* __restrict__ nodes, const float4* __restrict__ pts,
