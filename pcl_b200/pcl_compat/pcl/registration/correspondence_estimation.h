@@ -57,6 +57,9 @@ public:
     source_cloud_updated_ = true;
   }
   void setNumberOfThreads(unsigned int) {}  // one device launch replaces the OpenMP loop (:163-165)
+  Ptr clone() const { return Ptr(new CorrespondenceEstimation(*this)); }  // correspondence_estimation.h:493-498
+  bool requiresSourceNormals() const { return false; }
+  bool requiresTargetNormals() const { return false; }
 
   // impl/correspondence_estimation.hpp:145-218
   void determineCorrespondences(pcl::Correspondences& correspondences,

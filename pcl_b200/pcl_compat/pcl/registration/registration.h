@@ -165,6 +165,23 @@ public:
     return score;
   }
 
+  // getFitnessScore(distances_a, distances_b) — impl/registration.hpp:105-130
+  double getFitnessScore(const std::vector<float>& distances_a, const std::vector<float>& distances_b)
+  {
+    const unsigned int nr = static_cast<unsigned int>(std::min(distances_a.size(), distances_b.size()));
+    double sum = 0.0;
+    for (unsigned int i = 0; i < nr; ++i) sum += static_cast<double>(distances_a[i]) - static_cast<double>(distances_b[i]);
+    return nr ? std::abs(sum / nr) : 0.0;
+  }
+  // registration.h:431-442: called after every iteration with the transformed source and the correspondences
+  using UpdateVisualizerCallbackSignature = void(const pcl::PointCloud<PointSource>&, const pcl::Indices&,
+                                                 const pcl::PointCloud<PointTarget>&, const pcl::Indices&);
+  bool registerVisualizationCallback(std::function<UpdateVisualizerCallbackSignature>& cb)
+  {
+    if (cb) { update_visualizer_ = cb; return true; }
+    return false;
+  }
+
   // impl/registration.hpp:172-221
   void align(PointCloudSource& output) { align(output, Matrix4::Identity()); }
   void align(PointCloudSource& output, const Matrix4& guess)
@@ -236,6 +253,7 @@ protected:
   bool force_no_recompute_ = false, force_no_recompute_reciprocal_ = false;
   bool target_uploaded_ = false;
   pclb200_icp* icp_ = nullptr;
+  std::function<UpdateVisualizerCallbackSignature> update_visualizer_;
 };
 
 template <typename PointSource, typename PointTarget, typename Scalar = float>
@@ -320,7 +338,28 @@ protected:
       return;
     }
     pclb200_icp_stats st;
-    if (pclb200_icp_iterate(this->icp_, std::numeric_limits<int>::max(), &st) != PCLB200_OK) { fail("icp_iterate"); return; }
+    if (!this->update_visualizer_) {
+      if (pclb200_icp_iterate(this->icp_, std::numeric_limits<int>::max(), &st) != PCLB200_OK) { fail("icp_iterate"); return; }
+    }
+    else {
+      // icp.hpp:228-236: one iteration at a time so the callback sees every intermediate state
+      pcl::Correspondences corr;
+      PointCloudSource moved;
+      do {
+        if (pclb200_icp_iterate(this->icp_, 1, &st) != PCLB200_OK) { fail("icp_iterate"); return; }
+        if (st.state == PCLB200_CONV_NO_CORRESPONDENCES) break;
+        corr.resize(this->indices_->size());
+        std::size_t nc = 0;
+        if (pclb200_icp_get_correspondences(this->icp_, reinterpret_cast<pclb200_corr*>(corr.data()), &nc) != PCLB200_OK) { fail("icp_get_correspondences"); return; }
+        corr.resize(nc);
+        moved = *this->input_;
+        void* mn = has_normal<PointSource>::value ? reinterpret_cast<unsigned char*>(moved.points.data()) + 16 : nullptr;
+        if (pclb200_icp_get_cloud(this->icp_, moved.points.data(), sizeof(PointSource), mn, sizeof(PointSource)) != PCLB200_OK) { fail("icp_get_cloud"); return; }
+        pcl::Indices si, ti;
+        for (const auto& c : corr) { si.push_back(c.index_query); ti.push_back(c.index_match); }
+        this->update_visualizer_(moved, si, *this->target_, ti);
+      } while (st.state == PCLB200_CONV_NOT_CONVERGED);
+    }
     Base::fromRowMajor(st.final_transformation, this->final_transformation_);
     Base::fromRowMajor(st.last_transformation, this->transformation_);
     this->previous_transformation_ = this->transformation_;

@@ -36,6 +36,8 @@ public:
   virtual bool getSortedResults() const { return sorted_results_; }
   void setEpsilon(float eps) { epsilon_ = eps; }  // accepted for API parity; the search is always exact (eps = 0)
   float getEpsilon() const { return epsilon_; }
+  void setMinPts(int min_pts) { min_pts_ = min_pts; }  // kdtree.h:322-333 (stored, never consulted — as in KdTreeFLANN)
+  int getMinPts() const { return min_pts_; }
 
   // KdTreeFLANN::setInputCloud — kdtree_flann.hpp:100-136: rebuilds from scratch, epsilon reset to 0
   virtual bool setInputCloud(const PointCloudConstPtr& cloud, const IndicesConstPtr& indices = IndicesConstPtr())
@@ -191,6 +193,7 @@ protected:
   std::shared_ptr<b200::IndexHandle> index_;
   bool sorted_results_ = true;
   float epsilon_ = 0.f;
+  int min_pts_ = 1;
   std::string name_ = "KdTree";
 };
 

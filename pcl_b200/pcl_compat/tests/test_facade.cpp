@@ -226,6 +226,28 @@ int main(int argc, char** argv)
     for (int r = 0; r < 3; ++r) for (int c = 0; c < 4; ++c) EXPECT_NEAR(T(r, c), g[4 * r + c], (r == 0 && c == 1) ? 1e-2 : 1e-3);
     EXPECT_EQ(T(3, 0), 0); EXPECT_EQ(T(3, 1), 0); EXPECT_EQ(T(3, 2), 0); EXPECT_EQ(T(3, 3), 1);
     EXPECT_TRUE(reg.hasConverged());
+    {  // visualisation callback (registration.h:431-442): same result, one call per iteration with valid indices
+      IterativeClosestPoint<PointXYZ, PointXYZ> regv;
+      regv.setInputSource(cloud_source.makeShared());
+      regv.setInputTarget(cloud_target.makeShared());
+      regv.setMaximumIterations(50);
+      regv.setTransformationEpsilon(1e-8);
+      regv.setMaxCorrespondenceDistance(0.05);
+      int calls = 0;
+      bool ok_idx = true;
+      std::function<void(const PointCloud<PointXYZ>&, const Indices&, const PointCloud<PointXYZ>&, const Indices&)> cb =
+          [&](const PointCloud<PointXYZ>& s, const Indices& si, const PointCloud<PointXYZ>& t, const Indices& ti) {
+            ++calls;
+            ok_idx = ok_idx && si.size() == ti.size() && s.size() == cloud_source.size();
+            for (std::size_t i = 0; i < si.size(); ++i) ok_idx = ok_idx && si[i] >= 0 && ti[i] >= 0 && (std::size_t)ti[i] < t.size();
+          };
+      regv.registerVisualizationCallback(cb);
+      PointCloud<PointXYZ> outv;
+      regv.align(outv);
+      EXPECT_EQ(calls, regv.getNumberOfIterations());
+      EXPECT_TRUE(ok_idx);
+      for (int r = 0; r < 4; ++r) for (int c = 0; c < 4; ++c) EXPECT_EQ(regv.getFinalTransformation()(r, c), T(r, c));
+    }
     // the aligned cloud is the source under the final transform
     const PointXYZ& s = cloud_source[7];
     EXPECT_NEAR(cloud_reg[7].x, T(0, 0) * s.x + T(0, 1) * s.y + T(0, 2) * s.z + T(0, 3), 1e-6);
@@ -344,6 +366,21 @@ int main(int argc, char** argv)
     EXPECT_EQ(output.width, 103u);
     EXPECT_EQ(output.height, 1u);
     EXPECT_TRUE(output.is_dense);
+    grid.setFilterFieldName("z");           // test_filters.cpp:582-603
+    grid.setFilterLimits(0.05, 0.1);
+    grid.filter(output);
+    EXPECT_EQ(output.size(), 14u);
+    EXPECT_EQ(output.width, 14u);
+    EXPECT_NEAR(output[0].x, -0.026125, 1e-4);
+    EXPECT_NEAR(output[0].y, 0.039788, 1e-4);
+    EXPECT_NEAR(output[0].z, 0.052827, 1e-4);
+    EXPECT_NEAR(output[13].x, -0.073202, 1e-4);
+    EXPECT_NEAR(output[13].y, 0.1296, 1e-4);
+    EXPECT_NEAR(output[13].z, 0.051333, 1e-4);
+    grid.setFilterLimitsNegative(true);
+    grid.filter(output);
+    EXPECT_EQ(output.size(), 100u);
+    grid.setFilterFieldName("");
     grid.setLeafSize(1e-5f, 1e-5f, 1e-5f);  // overflow guard: input returned unfiltered (voxel_grid.hpp:620-629)
     grid.filter(output);
     EXPECT_EQ(output.size(), cloud_source.size());
