@@ -135,6 +135,26 @@ PCLB200_API int pclb200_correspondences(pclb200_ctx* ctx, const pclb200_index* i
                                         int is_dense, double max_dist, pclb200_corr* out,
                                         size_t* n_out);
 
+/* ---- correspondences from the k nearest + normals: replaces
+ * CorrespondenceEstimationNormalShooting::determineCorrespondences
+ *   (registration/include/pcl/registration/impl/correspondence_estimation_normal_shooting.hpp:66-131): among the k
+ *   nearest target points, the one closest to the line through the source point along its normal (|N x V|^2 in
+ *   double); that squared line distance is gated against max_dist itself (:121, as in the reference); the stored
+ *   distance is the squared point distance (:126) — kind = PCLB200_CORR_NORMAL_SHOOTING, tgt_normals unused;
+ * CorrespondenceEstimationBackProjection::determineCorrespondences
+ *   (impl/correspondence_estimation_backprojection.hpp:66-118): minimises d2 * (2 - cos^2(n_src, n_tgt)) in float —
+ *   kind = PCLB200_CORR_BACK_PROJECTION.
+ * src_normals: n records (same indexing as src); tgt_normals: one record per point of the cloud idx_tgt was built
+ * from.  Non-finite source points produce no pair.  out: capacity n_idx (or n), ordered by index_query. */
+#define PCLB200_CORR_NEAREST 0
+#define PCLB200_CORR_NORMAL_SHOOTING 1
+#define PCLB200_CORR_BACK_PROJECTION 2
+PCLB200_API int pclb200_correspondences_normals(pclb200_ctx* ctx, const pclb200_index* idx_tgt, int kind,
+                                                const void* src, size_t n, size_t stride, const void* src_normals,
+                                                size_t stride_sn, const void* tgt_normals, size_t stride_tn,
+                                                const int32_t* src_indices, size_t n_idx, int k, double max_dist,
+                                                pclb200_corr* out, size_t* n_out);
+
 /* ---- correspondence rejectors: the stage between estimation and solve, icp.hpp:187-201 -------
  * DISTANCE   CorrespondenceRejectorDistance        registration/src/correspondence_rejection_distance.cpp:44-68
  *            p = maximum distance (NOT squared, as setMaximumDistance takes it); keeps distance < p*p
@@ -149,6 +169,11 @@ PCLB200_API int pclb200_correspondences(pclb200_ctx* ctx, const pclb200_index* i
 #define PCLB200_REJ_MEDIAN 1
 #define PCLB200_REJ_ONE_TO_ONE 2
 #define PCLB200_REJ_TRIMMED 3
+/* SURFACE_NORMAL CorrespondenceRejectorSurfaceNormal .../correspondence_rejection_surface_normal.cpp:43-66
+ *            p = threshold; keeps pairs whose normals' float dot product, as double, is > p (correspondence_rejection.h
+ *            :378-389).  Inside an ICP session it sees the rotated source normals and the target normals given to
+ *            set_source / set_target; stand-alone use goes through pclb200_reject_surface_normal (it needs the normals). */
+#define PCLB200_REJ_SURFACE_NORMAL 4
 typedef struct pclb200_rejector {
   int32_t kind;
   int32_t min_correspondences; /* TRIMMED only (nr_min_correspondences_) */
@@ -157,6 +182,11 @@ typedef struct pclb200_rejector {
 /* getRemainingCorrespondences: in/out may be host or device arrays; out capacity n */
 PCLB200_API int pclb200_reject(pclb200_ctx* ctx, const pclb200_rejector* rejector, const pclb200_corr* in, size_t n,
                                pclb200_corr* out, size_t* n_out, double* median_out);
+
+PCLB200_API int pclb200_reject_surface_normal(pclb200_ctx* ctx, const pclb200_corr* in, size_t n,
+                                              const void* src_normals, size_t n_src, size_t stride_sn,
+                                              const void* tgt_normals, size_t n_tgt, size_t stride_tn, double threshold,
+                                              pclb200_corr* out, size_t* n_out);
 
 /* ---- transformation estimation: replaces TransformationEstimationSVD::estimateRigidTransformation
  * (impl/transformation_estimation_svd.hpp:50-181, Umeyama path, common/impl/eigen.hpp:675-734) and
@@ -207,12 +237,14 @@ typedef struct pclb200_icp_params {
   int32_t failure_after_max_iter; /* default_convergence_criteria.h:148-152 */
   int32_t max_iterations_similar_transforms; /* :310, default 0 */
   int32_t enforce_same_direction_normals;    /* symmetric estimator: n = n1 - n2 when n1.n2 < 0 (icp.h:402-418), default 1 */
-  int32_t reserved0;
+  int32_t correspondence_kind;    /* PCLB200_CORR_*: which CorrespondenceEstimation runs inside the loop, default NEAREST */
   double max_correspondence_distance;     /* registration.h:117, default sqrt(DBL_MAX) */
   double transformation_epsilon;          /* registration.h:588, default 0 */
   double transformation_rotation_epsilon; /* default 0 = keep criteria default 0.99999 */
   double euclidean_fitness_epsilon;       /* registration.h:116, default -DBL_MAX */
   double mse_threshold_absolute;          /* default_convergence_criteria.h:307, default 1e-12 */
+  int32_t correspondence_k;       /* k_ of the normal-shooting / back-projection estimators (setKSearch, default 10) */
+  int32_t reserved1;
 } pclb200_icp_params;
 
 typedef struct pclb200_icp_stats {
@@ -287,6 +319,13 @@ PCLB200_API int pclb200_normals_knn(pclb200_ctx* ctx, const pclb200_index* idx, 
                                     size_t n, size_t stride, const int32_t* indices, size_t n_idx,
                                     int is_dense, int k, const float viewpoint[3], float* out,
                                     int* is_dense_out);
+/* setRadiusSearch(radius) variant: the neighbourhood is radiusSearch(point, radius) with max_nn = 0
+ * (features/include/pcl/features/impl/feature.hpp:149-166), i.e. every indexed point with d2 < float(radius^2) in
+ * ascending (d2, index) order; everything after the search is the k-NN path's arithmetic. */
+PCLB200_API int pclb200_normals_radius(pclb200_ctx* ctx, const pclb200_index* idx, const void* pts,
+                                       size_t n, size_t stride, const int32_t* indices, size_t n_idx,
+                                       int is_dense, double radius, const float viewpoint[3], float* out,
+                                       int* is_dense_out);
 
 /* ---- VoxelGrid: replaces pcl::VoxelGrid<PointT>::applyFilter (no filter field)
  * (filters/include/pcl/filters/impl/voxel_grid.hpp:596-814).  out_xyz1: capacity n records

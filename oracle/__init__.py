@@ -36,7 +36,8 @@ class IcpParams(C.Structure):
                 ("max_correspondence_distance", C.c_double),
                 ("transformation_epsilon", C.c_double),
                 ("transformation_rotation_epsilon", C.c_double),
-                ("euclidean_fitness_epsilon", C.c_double)]
+                ("euclidean_fitness_epsilon", C.c_double),
+                ("correspondence_kind", C.c_int32), ("correspondence_k", C.c_int32)]
 
 
 class IcpResult(C.Structure):
@@ -49,7 +50,8 @@ class Rejector(C.Structure):
     _fields_ = [("kind", C.c_int32), ("min_correspondences", C.c_int32), ("p", C.c_double)]
 
 
-REJ_DISTANCE, REJ_MEDIAN, REJ_ONE_TO_ONE, REJ_TRIMMED = 0, 1, 2, 3
+REJ_DISTANCE, REJ_MEDIAN, REJ_ONE_TO_ONE, REJ_TRIMMED, REJ_SURFACE_NORMAL = 0, 1, 2, 3, 4
+CORR_NEAREST, CORR_NORMAL_SHOOTING, CORR_BACK_PROJECTION = 0, 1, 2
 
 _lib = None
 
@@ -93,6 +95,12 @@ def lib():
         L.orc_sor.argtypes = [vp, fp, sz, sz, i32p, sz, C.c_int, C.c_double, C.c_int, u8p, C.c_int]
         L.orc_ror.restype = sz
         L.orc_ror.argtypes = [vp, fp, sz, sz, i32p, sz, C.c_int, C.c_double, C.c_int, C.c_int, u8p, C.c_int]
+        L.orc_correspondences_normals.restype = sz
+        L.orc_correspondences_normals.argtypes = [vp, C.c_int, fp, sz, sz, fp, sz, fp, sz, fp, sz, i32p, sz, C.c_int,
+                                                  C.c_double, C.POINTER(Corr), C.c_int]
+        L.orc_reject_surface_normal.restype = sz
+        L.orc_reject_surface_normal.argtypes = [C.POINTER(Corr), sz, fp, sz, fp, sz, C.c_double, C.POINTER(Corr)]
+        L.orc_normals_radius.argtypes = [vp, fp, sz, sz, i32p, sz, C.c_int, C.c_double, fp, fp, C.c_int]
         L.orc_max_threads.restype = C.c_int
         _lib = L
     return _lib
@@ -230,6 +238,45 @@ class Index:
         return out, bool(dense)
 
 
+    def normals_radius(self, cloud, radius, viewpoint=(0, 0, 0), indices=None, is_dense=True, nthreads=1):
+        """NormalEstimation with setRadiusSearch(radius)."""
+        cloud = as_cloud(cloud)
+        indices = None if indices is None else np.ascontiguousarray(indices, dtype=np.int32)
+        n = cloud.shape[0] if indices is None else indices.size
+        out = np.empty((n, 4), dtype=np.float32)
+        vp = np.asarray(viewpoint, dtype=np.float32)
+        dense = lib().orc_normals_radius(self.h, _f(cloud), cloud.shape[0], cloud.shape[1], _i(indices),
+                                         0 if indices is None else indices.size, int(is_dense), float(radius), _f(vp),
+                                         _f(out), nthreads)
+        return out, bool(dense)
+
+    def correspondences_normals(self, kind, src_point_normal, tgt_point_normal, k=10,
+                                max_distance=np.sqrt(np.finfo(np.float64).max), indices=None, nthreads=1):
+        """CorrespondenceEstimationNormalShooting (kind 1) / ...BackProjection (kind 2); both clouds as rows with
+        the normal at float offset 4 (pcl::PointNormal); the index must have been built over tgt_point_normal."""
+        src, tgt = as_cloud(src_point_normal), as_cloud(tgt_point_normal)
+        indices = None if indices is None else np.ascontiguousarray(indices, dtype=np.int32)
+        n = src.shape[0] if indices is None else indices.size
+        out = np.empty(max(n, 1), dtype=CORR_DTYPE)
+        fpt = C.POINTER(C.c_float)
+        m = lib().orc_correspondences_normals(
+            self.h, int(kind), _f(src), src.shape[0], src.shape[1], src[:, 4:].ctypes.data_as(fpt), src.shape[1],
+            _f(tgt), tgt.shape[1], tgt[:, 4:].ctypes.data_as(fpt), tgt.shape[1], _i(indices),
+            0 if indices is None else indices.size, int(k), float(max_distance), out.ctypes.data_as(C.POINTER(Corr)),
+            nthreads)
+        return out[:m].copy()
+
+
+def reject_surface_normal(corr, src_normals, tgt_normals, threshold):
+    """CorrespondenceRejectorSurfaceNormal; normals as (n,>=3) float rows indexed by index_query / index_match."""
+    corr = np.ascontiguousarray(corr, dtype=CORR_DTYPE)
+    sn, tn = as_cloud(src_normals), as_cloud(tgt_normals)
+    out = np.empty(max(corr.size, 1), dtype=CORR_DTYPE)
+    m = lib().orc_reject_surface_normal(corr.ctypes.data_as(C.POINTER(Corr)), corr.size, _f(sn), sn.shape[1], _f(tn),
+                                        tn.shape[1], float(threshold), out.ctypes.data_as(C.POINTER(Corr)))
+    return out[:m].copy()
+
+
 def knn_bruteforce(cloud, q, k):
     cloud, q = as_cloud(cloud), as_cloud(q)
     idx = np.empty((q.shape[0], k), dtype=np.int32)
@@ -294,12 +341,14 @@ def icp_align(src, tgt, max_iterations=10, max_correspondence_distance=np.sqrt(n
               transformation_epsilon=0.0, transformation_rotation_epsilon=0.0,
               euclidean_fitness_epsilon=-np.finfo(np.float64).max, use_reciprocal=False, estimator=0,
               scalar_is_double=False, with_normals_transform=False, source_has_normals=False,
-              is_dense=True, guess=None, indices=None, nthreads=1, want_cloud=False, index=None, out=None):
+              is_dense=True, guess=None, indices=None, nthreads=1, want_cloud=False, index=None, out=None,
+              correspondence_kind=0, correspondence_k=10):
     src, tgt = as_cloud(src), as_cloud(tgt)
     P = IcpParams(max_iterations, int(use_reciprocal), estimator, int(scalar_is_double),
                   int(with_normals_transform), int(source_has_normals), int(is_dense), nthreads,
                   float(max_correspondence_distance), float(transformation_epsilon),
-                  float(transformation_rotation_epsilon), float(euclidean_fitness_epsilon))
+                  float(transformation_rotation_epsilon), float(euclidean_fitness_epsilon),
+                  int(correspondence_kind), int(correspondence_k))
     R = IcpResult()
     g = None if guess is None else np.ascontiguousarray(guess, dtype=np.float64)
     indices = None if indices is None else np.ascontiguousarray(indices, dtype=np.int32)
@@ -336,9 +385,12 @@ def reject(corr, kind, p=0.0, min_correspondences=0):
 def icp_align_rejectors(src, tgt, rejectors, **kw):
     """ICP with a chain of rejectors [(kind, p, min_correspondences), ...] (icp.hpp:187-201)."""
     src, tgt = as_cloud(src), as_cloud(tgt)
-    P = IcpParams(kw.get("max_iterations", 10), 0, 0, int(kw.get("scalar_is_double", False)), 0, 0, 1,
+    has_n = int(kw.get("source_has_normals", False))
+    P = IcpParams(kw.get("max_iterations", 10), 0, int(kw.get("estimator", 0)), int(kw.get("scalar_is_double", False)),
+                  has_n, has_n, 1,
                   kw.get("nthreads", 1), float(kw.get("max_correspondence_distance", np.sqrt(np.finfo(np.float64).max))),
-                  float(kw.get("transformation_epsilon", 0.0)), 0.0, float(kw.get("euclidean_fitness_epsilon", -np.finfo(np.float64).max)))
+                  float(kw.get("transformation_epsilon", 0.0)), 0.0, float(kw.get("euclidean_fitness_epsilon", -np.finfo(np.float64).max)),
+                  int(kw.get("correspondence_kind", 0)), int(kw.get("correspondence_k", 10)))
     arr = (Rejector * len(rejectors))(*[Rejector(k, m, float(p)) for (k, p, m) in rejectors])
     R = IcpResult()
     lib().orc_icp_align_rej(C.byref(P), arr, len(rejectors), _f(src), src.shape[0], src.shape[1], _f(tgt), tgt.shape[0],

@@ -1264,7 +1264,7 @@ ORC_API void orc_transform(float* pts, size_t n, size_t stride, int normal_off, 
 // registration/src/correspondence_rejection_one_to_one.cpp:44-71          sort by (index_match, distance), first per match
 // registration/src/correspondence_rejection_trimmed.cpp:44-63             floor(overlap * n) (>= min) smallest distances
 // std::sort in the last two is unstable; canonical tie rule here and on the device: smaller index_query first.
-enum { REJ_DISTANCE = 0, REJ_MEDIAN = 1, REJ_ONE_TO_ONE = 2, REJ_TRIMMED = 3 };
+enum { REJ_DISTANCE = 0, REJ_MEDIAN = 1, REJ_ONE_TO_ONE = 2, REJ_TRIMMED = 3, REJ_SURFACE_NORMAL = 4 };
 
 struct orc_rejector {
   int32_t kind;
@@ -1334,6 +1334,115 @@ ORC_API size_t orc_reject(const orc_rejector* r, const orc_corr* in, size_t n, o
   return c.size();
 }
 
+// ---- correspondence estimators that use normals ------------------------
+// kind 1: CorrespondenceEstimationNormalShooting::determineCorrespondences —
+//   registration/include/pcl/registration/impl/correspondence_estimation_normal_shooting.hpp:66-131: among the k
+//   nearest target points pick the one closest to the line through the source point along its normal
+//   (|N x V|^2 in double, V = float differences); the gate compares that SQUARED line distance with max_distance
+//   itself (:121, kept as in the reference); the stored distance is the squared point distance (:126).
+// kind 2: CorrespondenceEstimationBackProjection::determineCorrespondences —
+//   impl/correspondence_estimation_backprojection.hpp:66-118: minimise d2 * (2 - cos^2) in float.
+// Not covered by the reference (no check there, the query would be UB in FLANN): non-finite source points give no
+// correspondence; when every candidate score is NaN the first neighbour is taken (the reference would reuse the
+// previous point's min_index).
+enum { CORR_NEAREST = 0, CORR_NORMAL_SHOOTING = 1, CORR_BACK_PROJECTION = 2 };
+
+static size_t corr_knn_select(const KdTree& t, int kind, const float* src, size_t n_src, size_t sstride,
+                              const float* sn, size_t snstride, const float* tgt, size_t tstride, const float* tn,
+                              size_t tnstride, const int32_t* indices, size_t n_idx, int k, double max_distance,
+                              orc_corr* out, int nthreads)
+{
+  size_t cnt = indices ? n_idx : n_src;
+  const int keff = (int)std::min<size_t>((size_t)std::max(k, 0), t.n);
+  if (keff == 0)
+    return 0;
+  std::vector<orc_corr> tmp(cnt);
+  std::vector<uint8_t> keep(cnt, 0);
+#pragma omp parallel num_threads(nthreads > 0 ? nthreads : 1)
+  {
+    std::vector<Cand> buf((size_t)keff);
+#pragma omp for schedule(dynamic, 512)
+    for (long long i = 0; i < (long long)cnt; ++i) {
+      const int32_t idx = indices ? indices[i] : (int32_t)i;
+      const float* p = src + sstride * (size_t)idx;
+      if (!finite3(p))
+        continue;
+      KnnSet rs{buf.data(), keff, 0};
+      kd_knn_rec(t, 0, p, rs);
+      const float* n = sn + snstride * (size_t)idx;
+      int min_j = 0;
+      if (kind == CORR_NORMAL_SHOOTING) {
+        double min_dist = std::numeric_limits<double>::max();
+        const double Nx = n[0], Ny = n[1], Nz = n[2];
+        for (int j = 0; j < rs.n; ++j) {
+          const float* q = tgt + tstride * (size_t)rs.c[j].i;
+          const float vx = q[0] - p[0], vy = q[1] - p[1], vz = q[2] - p[2];
+          const double Vx = vx, Vy = vy, Vz = vz;
+          const double Cx = Ny * Vz - Nz * Vy, Cy = Nz * Vx - Nx * Vz, Cz = Nx * Vy - Ny * Vx;
+          const double dist = (Cx * Cx + Cy * Cy) + Cz * Cz;
+          if (dist < min_dist) {
+            min_dist = dist;
+            min_j = j;
+          }
+        }
+        if (min_dist > max_distance)
+          continue;
+      }
+      else {
+        float min_dist = std::numeric_limits<float>::max();
+        for (int j = 0; j < rs.n; ++j) {
+          const float* m = tn + tnstride * (size_t)rs.c[j].i;
+          const float cos_angle = n[0] * m[0] + n[1] * m[1] + n[2] * m[2];
+          const float dist = rs.c[j].d * (2.0f - cos_angle * cos_angle);
+          if (dist < min_dist) {
+            min_dist = dist;
+            min_j = j;
+          }
+        }
+        if (min_dist > max_distance)
+          continue;
+      }
+      tmp[i] = orc_corr{idx, rs.c[min_j].i, rs.c[min_j].d};
+      keep[i] = 1;
+    }
+  }
+  size_t m = 0;
+  for (size_t i = 0; i < cnt; ++i)
+    if (keep[i])
+      out[m++] = tmp[i];
+  return m;
+}
+
+ORC_API size_t orc_correspondences_normals(void* h_tgt, int kind, const float* src, size_t n_src, size_t sstride,
+                                           const float* sn, size_t snstride, const float* tgt, size_t tstride,
+                                           const float* tn, size_t tnstride, const int32_t* indices, size_t n_idx,
+                                           int k, double max_distance, orc_corr* out, int nthreads)
+{
+  return corr_knn_select(*static_cast<KdTree*>(h_tgt), kind, src, n_src, sstride, sn, snstride, tgt, tstride, tn,
+                         tnstride, indices, n_idx, k, max_distance, out, nthreads);
+}
+
+// CorrespondenceRejectorSurfaceNormal::getRemainingCorrespondences —
+// registration/src/correspondence_rejection_surface_normal.cpp:43-66 with the score of
+// DataContainer::getCorrespondenceScoreFromNormals (registration/correspondence_rejection.h:378-389): the float dot
+// product of the two normals, kept when (double)dot > threshold.
+static inline bool surface_normal_keeps(const float* a, const float* b, double threshold)
+{
+  const float dot = (a[0] * b[0]) + (a[1] * b[1]) + (a[2] * b[2]);
+  return static_cast<double>(dot) > threshold;
+}
+
+ORC_API size_t orc_reject_surface_normal(const orc_corr* in, size_t n, const float* sn, size_t snstride,
+                                         const float* tn, size_t tnstride, double threshold, orc_corr* out)
+{
+  size_t m = 0;
+  for (size_t i = 0; i < n; ++i)
+    if (surface_normal_keeps(sn + snstride * (size_t)in[i].index_query, tn + tnstride * (size_t)in[i].index_match,
+                             threshold))
+      out[m++] = in[i];
+  return m;
+}
+
 // ---- ICP --------------------------------------------------------------------------------
 struct orc_icp_params {
   int32_t max_iterations;            // registration.h:566 default 10
@@ -1348,6 +1457,8 @@ struct orc_icp_params {
   double transformation_epsilon;             // registration.h:588 default 0
   double transformation_rotation_epsilon;    // default 0 (= unused)
   double euclidean_fitness_epsilon;          // registration.h:116 default -DBL_MAX
+  int32_t correspondence_kind;               // 0 nearest, 1 normal shooting, 2 back projection (need source normals)
+  int32_t correspondence_k;                  // k_ of the two normal-based estimators (default 10)
 };
 
 struct orc_icp_result {
@@ -1407,13 +1518,25 @@ static void icp_run(const orc_icp_params& P, const float* src, size_t n_s, size_
                                           P.nthreads);
       orc_index_free(stree);
     }
+    else if (P.correspondence_kind != CORR_NEAREST)
+      // icp.hpp:166-180: the estimator sees the transformed source and its rotated normals
+      nc = corr_knn_select(*tree, P.correspondence_kind, cur.data(), n_s, ss, cur.data() + 4, ss, tgt, ts, tgt + 4, ts,
+                           indices, n_idx, P.correspondence_k, P.max_correspondence_distance, corr.data(), P.nthreads);
     else
       nc = orc_correspondences(tree, cur.data(), n_s, ss, indices, n_idx, P.is_dense,
                                P.max_correspondence_distance, corr.data(), P.nthreads);
     if (n_rejectors > 0) {  // icp.hpp:187-201: each rejector filters the previous one's output
       std::vector<orc_corr> cc(corr.begin(), corr.begin() + nc);
-      for (int ri = 0; ri < n_rejectors; ++ri)
+      for (int ri = 0; ri < n_rejectors; ++ri) {
+        if (rejectors[ri].kind == REJ_SURFACE_NORMAL) {  // normals of the transformed source vs the target's
+          std::vector<orc_corr> kept(cc.size());
+          kept.resize(orc_reject_surface_normal(cc.data(), cc.size(), cur.data() + 4, ss, tgt + 4, ts,
+                                                rejectors[ri].p, kept.data()));
+          cc.swap(kept);
+          continue;
+        }
         apply_rejector(rejectors[ri], cc, nullptr);
+      }
       nc = cc.size();
       std::copy(cc.begin(), cc.end(), corr.begin());
     }
@@ -1638,6 +1761,47 @@ ORC_API int orc_normals_knn(void* h, const float* cloud, size_t n, size_t stride
         for (int j = 0; j < rs.n; ++j)
           nn[j] = rs.c[j].i;
         ok = point_normal(cloud, stride, is_dense != 0, nn.data(), (size_t)rs.n, o);
+      }
+      if (!ok) {
+        o[0] = o[1] = o[2] = o[3] = qnan;
+#pragma omp atomic write
+        dense_out = 0;
+        continue;
+      }
+      flip_to_viewpoint(p, vp, o);
+    }
+  }
+  return dense_out;
+}
+
+// NormalEstimation with setRadiusSearch — Feature::initCompute picks radiusSearch(point, radius) with max_nn = 0
+// (features/include/pcl/features/impl/feature.hpp:149-166), so the neighbourhood is every point with d2 < r2 in
+// ascending (d2, index) order; the rest is identical to the k-NN path (normal_3d.hpp:47-96).
+ORC_API int orc_normals_radius(void* h, const float* cloud, size_t n, size_t stride, const int32_t* indices,
+                               size_t n_idx, int is_dense, double radius, const float vp[3], float* out, int nthreads)
+{
+  const KdTree& t = *static_cast<KdTree*>(h);
+  size_t cnt = indices ? n_idx : n;
+  const float r2 = static_cast<float>(radius * radius);
+  int dense_out = 1;
+  const float qnan = std::numeric_limits<float>::quiet_NaN();
+#pragma omp parallel num_threads(nthreads > 0 ? nthreads : 1)
+  {
+    std::vector<Cand> found;
+    std::vector<int32_t> nn;
+#pragma omp for schedule(dynamic, 512)
+    for (long long i = 0; i < (long long)cnt; ++i) {
+      const float* p = cloud + stride * (size_t)(indices ? indices[i] : (int32_t)i);
+      float* o = out + 4 * (size_t)i;
+      bool ok = t.n > 0 && (is_dense || finite3(p));
+      if (ok) {
+        found.clear();
+        kd_radius_rec(t, 0, p, r2, found);
+        std::sort(found.begin(), found.end(), cand_less);
+        nn.resize(found.size());
+        for (size_t j = 0; j < found.size(); ++j)
+          nn[j] = found[j].i;
+        ok = point_normal(cloud, stride, is_dense != 0, nn.data(), nn.size(), o);
       }
       if (!ok) {
         o[0] = o[1] = o[2] = o[3] = qnan;

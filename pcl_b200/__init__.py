@@ -32,10 +32,10 @@ class IcpParams(C.Structure):
     _fields_ = [("max_iterations", C.c_int32), ("use_reciprocal", C.c_int32), ("estimator", C.c_int32),
                 ("scalar_is_double", C.c_int32), ("with_normals_transform", C.c_int32), ("is_dense", C.c_int32),
                 ("failure_after_max_iter", C.c_int32), ("max_iterations_similar_transforms", C.c_int32),
-                ("enforce_same_direction_normals", C.c_int32), ("reserved0", C.c_int32),
+                ("enforce_same_direction_normals", C.c_int32), ("correspondence_kind", C.c_int32),
                 ("max_correspondence_distance", C.c_double), ("transformation_epsilon", C.c_double),
                 ("transformation_rotation_epsilon", C.c_double), ("euclidean_fitness_epsilon", C.c_double),
-                ("mse_threshold_absolute", C.c_double)]
+                ("mse_threshold_absolute", C.c_double), ("correspondence_k", C.c_int32), ("reserved1", C.c_int32)]
 
 
 class IcpStats(C.Structure):
@@ -56,7 +56,8 @@ class Rejector(C.Structure):
     _fields_ = [("kind", C.c_int32), ("min_correspondences", C.c_int32), ("p", C.c_double)]
 
 
-REJ_DISTANCE, REJ_MEDIAN, REJ_ONE_TO_ONE, REJ_TRIMMED = 0, 1, 2, 3
+REJ_DISTANCE, REJ_MEDIAN, REJ_ONE_TO_ONE, REJ_TRIMMED, REJ_SURFACE_NORMAL = 0, 1, 2, 3, 4
+CORR_NEAREST, CORR_NORMAL_SHOOTING, CORR_BACK_PROJECTION = 0, 1, 2
 
 
 # every symbol include/pclb200.h declares (tests/test_capi_symbols.py checks the two lists agree)
@@ -69,7 +70,8 @@ SYMBOLS = [
     "pclb200_icp_create", "pclb200_icp_destroy", "pclb200_icp_set_params", "pclb200_icp_set_target",
     "pclb200_icp_set_source", "pclb200_icp_iterate", "pclb200_icp_get_cloud", "pclb200_icp_get_correspondences",
     "pclb200_icp_align",
-    "pclb200_fitness_score", "pclb200_reject", "pclb200_icp_set_rejectors", "pclb200_normals_knn", "pclb200_voxelgrid", "pclb200_comm_unique_id",
+    "pclb200_fitness_score", "pclb200_reject", "pclb200_icp_set_rejectors", "pclb200_normals_knn", "pclb200_normals_radius",
+    "pclb200_correspondences_normals", "pclb200_reject_surface_normal", "pclb200_voxelgrid", "pclb200_comm_unique_id",
     "pclb200_comm_init",
 ]
 
@@ -125,6 +127,10 @@ def lib():
     L.pclb200_icp_set_rejectors.argtypes = [vp, C.POINTER(Rejector), C.c_int]
     L.pclb200_fitness_score.argtypes = [vp, vp, vp, sz, sz, vp, sz, C.c_int, dp, C.c_int, C.c_double, dp]
     L.pclb200_normals_knn.argtypes = [vp, vp, vp, sz, sz, vp, sz, C.c_int, C.c_int, fp, vp, C.POINTER(C.c_int)]
+    L.pclb200_normals_radius.argtypes = [vp, vp, vp, sz, sz, vp, sz, C.c_int, C.c_double, fp, vp, C.POINTER(C.c_int)]
+    L.pclb200_correspondences_normals.argtypes = [vp, vp, C.c_int, vp, sz, sz, vp, sz, vp, sz, vp, sz, C.c_int, C.c_double,
+                                                  vp, C.POINTER(sz)]
+    L.pclb200_reject_surface_normal.argtypes = [vp, vp, sz, vp, sz, sz, vp, sz, sz, C.c_double, vp, C.POINTER(sz)]
     L.pclb200_voxelgrid.argtypes = [vp, vp, sz, sz, vp, sz, C.c_int, fp, C.c_uint, vp, C.POINTER(sz)]
     L.pclb200_comm_unique_id.argtypes = [vp]
     L.pclb200_comm_init.argtypes = [vp, C.c_int, C.c_int, vp]
@@ -263,6 +269,17 @@ class Context:
                                     C.c_void_p(out.ctypes.data), C.byref(m), C.byref(med)))
         return out[:m.value].copy(), float(med.value)
 
+    def reject_surface_normal(self, corr, src_normals, tgt_normals, threshold):
+        """CorrespondenceRejectorSurfaceNormal; normals are arrays (or Fields) indexed by index_query / index_match."""
+        corr = np.ascontiguousarray(corr, dtype=CORR_DTYPE)
+        out = np.empty(max(corr.size, 1), dtype=CORR_DTYPE)
+        sn, tn = _Buf(src_normals), _Buf(tgt_normals)
+        m = C.c_size_t()
+        _check(lib().pclb200_reject_surface_normal(self.h, C.c_void_p(corr.ctypes.data), corr.size, sn.ptr, sn.rows,
+                                                   sn.stride, tn.ptr, tn.rows, tn.stride, float(threshold),
+                                                   C.c_void_p(out.ctypes.data), C.byref(m)))
+        return out[:m.value].copy()
+
     def estimate_svd(self, src, tgt, corr=None, scalar_is_double=False):
         s, t = _Buf(src), _Buf(tgt)
         cb = None if corr is None else np.ascontiguousarray(corr, dtype=CORR_DTYPE)
@@ -379,6 +396,19 @@ class Index:
                                              C.c_void_p(out.ctypes.data), C.byref(m)))
         return out[:m.value]
 
+    def correspondences_normals(self, kind, src, src_normals, tgt_normals=None, k=10,
+                                max_distance=np.sqrt(np.finfo(np.float64).max), indices=None):
+        """CorrespondenceEstimationNormalShooting (kind 1) / ...BackProjection (kind 2)."""
+        b, sn, tn = _Buf(src), _Buf(src_normals), _Buf(tgt_normals)
+        ib = _Buf(indices, np.int32)
+        n = ib.rows if indices is not None else b.rows
+        out = np.empty(max(n, 1), dtype=CORR_DTYPE)
+        m = C.c_size_t()
+        _check(lib().pclb200_correspondences_normals(self.ctx.h, self.h, int(kind), b.ptr, b.rows, b.stride, sn.ptr,
+                                                     sn.stride, tn.ptr, tn.stride, ib.ptr, ib.rows, int(k),
+                                                     float(max_distance), C.c_void_p(out.ctypes.data), C.byref(m)))
+        return out[:m.value]
+
     def fitness_score(self, src, T, max_range=np.finfo(np.float64).max, scalar_is_double=False, indices=None,
                       is_dense=True):
         b = _Buf(src)
@@ -401,6 +431,21 @@ class Index:
         dense = C.c_int()
         _check(lib().pclb200_normals_knn(self.ctx.h, self.h, b.ptr, b.rows, b.stride, ib.ptr, ib.rows, int(is_dense), k,
                                          vp, ob.ptr, C.byref(dense)))
+        return out, bool(dense.value)
+
+
+    def normals_radius(self, cloud, radius, viewpoint=(0, 0, 0), indices=None, is_dense=True, out=None):
+        """NormalEstimation with setRadiusSearch(radius)."""
+        b = _Buf(cloud)
+        ib = _Buf(indices, np.int32)
+        n = ib.rows if indices is not None else b.rows
+        if out is None:
+            out = np.empty((n, 4), dtype=np.float32)
+        ob = _Buf(out)
+        vp = (C.c_float * 3)(*[float(v) for v in viewpoint])
+        dense = C.c_int()
+        _check(lib().pclb200_normals_radius(self.ctx.h, self.h, b.ptr, b.rows, b.stride, ib.ptr, ib.rows, int(is_dense),
+                                            float(radius), vp, ob.ptr, C.byref(dense)))
         return out, bool(dense.value)
 
 

@@ -112,6 +112,37 @@ __global__ void k_truncate_segments(const unsigned long long* __restrict__ keys,
     out[bo + j] = keys[b + j];
 }
 
+// max_nn <= 32 radius search = "the max_nn nearest inside the ball": k-NN rows (-1 padded) -> CSR
+__global__ void k_count_row_entries(const int32_t* __restrict__ rows, size_t nq, int k, unsigned long long* __restrict__ counts)
+{
+  size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+  if (i >= nq)
+    return;
+  unsigned long long c = 0;
+  for (int j = 0; j < k; ++j)
+    if (rows[i * (size_t)k + j] >= 0)
+      ++c;
+  counts[i] = c;
+}
+
+__global__ void k_pack_rows(const int32_t* __restrict__ rows, const float* __restrict__ rows_d2, size_t nq, int k,
+                            const unsigned long long* __restrict__ offsets, int32_t* __restrict__ idx,
+                            float* __restrict__ d2)
+{
+  size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+  if (i >= nq)
+    return;
+  unsigned long long o = offsets[i];
+  for (int j = 0; j < k; ++j) {
+    const int32_t v = rows[i * (size_t)k + j];
+    if (v < 0)
+      break;  // rows are filled from the front
+    idx[o] = v;
+    d2[o] = rows_d2[i * (size_t)k + j];
+    ++o;
+  }
+}
+
 __global__ void k_clamp_counts(const unsigned long long* __restrict__ in, size_t n, unsigned long long cap,
                                unsigned long long* __restrict__ out)
 {
@@ -423,47 +454,74 @@ int pclb200_radius(pclb200_ctx* ctx, const pclb200_index* h, const void* queries
     load_xyz_as_float4(c, queries, nq, stride, nullptr, 0, dense.p, st);
     QueryBatch qb;
     make_query_batch(c, idx, dense.p, nq, qb);
-    DevBuf<unsigned long long> counts, offsets;
-    counts.alloc(nq + 1, st);
-    offsets.alloc(nq + 1, st);
-    PCLB_CUDA(cudaMemsetAsync(counts.p, 0, (nq + 1) * sizeof(unsigned long long), st));
-    launch_radius_count(c, idx, qb.q.p, nq, r2, counts.p);
-    size_t tb = 0;
-    PCLB_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, tb, counts.p, offsets.p, (int)(nq + 1), st));
-    DevBuf<unsigned char> tmp;
-    tmp.alloc(tb, st);
-    PCLB_CUDA(cub::DeviceScan::ExclusiveSum(tmp.p, tb, counts.p, offsets.p, (int)(nq + 1), st));
-    ++c.launches;
+    if ((size_t)max_nn < idx.n_valid && max_nn <= 32) {
+      // KNNRadiusResultSet semantics (kdtree_flann.hpp:382-391): the max_nn nearest among those with d2 < r2.  That is
+      // the register k-NN kernel started with the pruning bound just below r2 (every d2 < r2 is <= that bound; a
+      // candidate AT the bound still enters through the index tie rule) — no count / fill / sort passes.
+      const int k = (int)max_nn;
+      DevBuf<int32_t> rows;
+      DevBuf<float> rows_d2;
+      rows.alloc(nq * (size_t)k, st);
+      rows_d2.alloc(nq * (size_t)k, st);
+      {
+        ProfScope ps(c, "radius_knn");
+        launch_knn(c, idx, qb.q.p, nq, k, std::nextafter(r2, -std::numeric_limits<float>::infinity()), rows.p, rows_d2.p);
+      }
+      DevBuf<unsigned long long> cnt, off;
+      cnt.alloc(nq + 1, st);
+      off.alloc(nq + 1, st);
+      PCLB_CUDA(cudaMemsetAsync(cnt.p, 0, (nq + 1) * sizeof(unsigned long long), st));
+      k_count_row_entries<<<grid_for(nq, 256), 256, 0, st>>>(rows.p, nq, k, cnt.p);
+      size_t tb = 0;
+      PCLB_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, tb, cnt.p, off.p, (int)(nq + 1), st));
+      DevBuf<unsigned char> tmp;
+      tmp.alloc(tb, st);
+      PCLB_CUDA(cub::DeviceScan::ExclusiveSum(tmp.p, tb, cnt.p, off.p, (int)(nq + 1), st));
+      c.launches += 2;
+      std::vector<unsigned long long> h_off(nq + 1, 0);
+      PCLB_CUDA(cudaMemcpyAsync(h_off.data(), off.p, (nq + 1) * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
+      PCLB_CUDA(cudaStreamSynchronize(st));
+      const unsigned long long total = h_off[nq];
+      for (size_t i = 0; i <= nq; ++i)
+        out_offsets[i] = (int64_t)h_off[i];
+      int32_t* hi = static_cast<int32_t*>(malloc(std::max<size_t>(total, 1) * sizeof(int32_t)));
+      float* hd = static_cast<float*>(malloc(std::max<size_t>(total, 1) * sizeof(float)));
+      PCLB_REQUIRE(hi && hd, PCLB200_ERR_INTERNAL, "host allocation failed");
+      *out_idx = hi;  // owned by the caller from here on (pclb200_free), also on the error paths below
+      *out_d2 = hd;
+      if (total > 0) {
+        DevBuf<int32_t> di;
+        DevBuf<float> dd;
+        di.alloc(total, st);
+        dd.alloc(total, st);
+        k_pack_rows<<<grid_for(nq, 256), 256, 0, st>>>(rows.p, rows_d2.p, nq, k, off.p, di.p, dd.p);
+        ++c.launches;
+        PCLB_CUDA(cudaMemcpyAsync(hi, di.p, total * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+        PCLB_CUDA(cudaMemcpyAsync(hd, dd.p, total * sizeof(float), cudaMemcpyDeviceToHost, st));
+        PCLB_CUDA(cudaStreamSynchronize(st));
+      }
+      raise_if_device_error(c);
+      return;
+    }
+    DevBuf<unsigned long long> counts, offsets, keys_sorted;
     unsigned long long total = 0;
-    PCLB_CUDA(cudaMemcpyAsync(&total, offsets.p + nq, sizeof(total), cudaMemcpyDeviceToHost, st));
-    PCLB_CUDA(cudaStreamSynchronize(st));
+    radius_csr(c, idx, qb.q.p, nq, r2, counts, offsets, keys_sorted, total);
     std::vector<unsigned long long> h_off(nq + 1, 0);
-    DevBuf<unsigned long long> keys, keys_sorted;
     const unsigned long long* d_final_keys = nullptr;
     const unsigned long long* d_final_off = offsets.p;
     unsigned long long final_total = total;
     DevBuf<unsigned long long> counts2, offsets2, keys_trunc;
     if (total > 0) {
-      PCLB_REQUIRE(total < (unsigned long long)std::numeric_limits<int>::max(), PCLB200_ERR_INVALID,
-                   "radius search result exceeds 2^31 neighbours; lower the radius or set max_nn");
-      keys.alloc(total, st);
-      keys_sorted.alloc(total, st);
-      launch_radius_fill(c, idx, qb.q.p, nq, r2, offsets.p, keys.p);
-      // ascending (d2, index) inside every query's segment
-      size_t tb2 = 0;
-      PCLB_CUDA(cub::DeviceSegmentedSort::SortKeys(nullptr, tb2, keys.p, keys_sorted.p, (int)total, (int)nq, offsets.p,
-                                                   offsets.p + 1, st));
-      DevBuf<unsigned char> tmp2;
-      tmp2.alloc(tb2, st);
-      PCLB_CUDA(cub::DeviceSegmentedSort::SortKeys(tmp2.p, tb2, keys.p, keys_sorted.p, (int)total, (int)nq, offsets.p,
-                                                   offsets.p + 1, st));
-      c.launches += 3;
       d_final_keys = keys_sorted.p;
       if ((size_t)max_nn < idx.n_valid) {  // KNNRadius semantics: the max_nn nearest inside the ball
         counts2.alloc(nq + 1, st);
         offsets2.alloc(nq + 1, st);
         PCLB_CUDA(cudaMemsetAsync(counts2.p, 0, (nq + 1) * sizeof(unsigned long long), st));
         k_clamp_counts<<<grid_for(nq, 256), 256, 0, st>>>(counts.p, nq, (unsigned long long)max_nn, counts2.p);
+        size_t tb = 0;
+        PCLB_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, tb, counts2.p, offsets2.p, (int)(nq + 1), st));
+        DevBuf<unsigned char> tmp;
+        tmp.alloc(tb, st);
         PCLB_CUDA(cub::DeviceScan::ExclusiveSum(tmp.p, tb, counts2.p, offsets2.p, (int)(nq + 1), st));
         PCLB_CUDA(cudaMemcpyAsync(&final_total, offsets2.p + nq, sizeof(final_total), cudaMemcpyDeviceToHost, st));
         PCLB_CUDA(cudaStreamSynchronize(st));
@@ -509,6 +567,51 @@ int pclb200_correspondences(pclb200_ctx* ctx, const pclb200_index* idx_tgt, cons
     PCLB_CUDA(cudaSetDevice(ctx->c.device));
     *n_out = correspondences(ctx->c, *idx_tgt->idx, idx_src ? idx_src->idx : nullptr, src, n, stride, src_indices, n_idx,
                              is_dense, max_dist, out);
+  });
+}
+
+int pclb200_correspondences_normals(pclb200_ctx* ctx, const pclb200_index* idx_tgt, int kind, const void* src, size_t n,
+                                    size_t stride, const void* src_normals, size_t stride_sn, const void* tgt_normals,
+                                    size_t stride_tn, const int32_t* src_indices, size_t n_idx, int k, double max_dist,
+                                    pclb200_corr* out, size_t* n_out)
+{
+  return guarded([&] {
+    PCLB_REQUIRE(ctx && idx_tgt && idx_tgt->idx && n_out, PCLB200_ERR_INVALID, "NULL argument");
+    PCLB_REQUIRE(kind == PCLB200_CORR_NORMAL_SHOOTING || kind == PCLB200_CORR_BACK_PROJECTION, PCLB200_ERR_INVALID,
+                 "kind must be PCLB200_CORR_NORMAL_SHOOTING or PCLB200_CORR_BACK_PROJECTION");
+    PCLB_REQUIRE(k >= 0, PCLB200_ERR_INVALID, "k < 0");
+    *n_out = 0;
+    const size_t nq = src_indices ? n_idx : n;
+    if (nq == 0 || k == 0)
+      return;
+    PCLB_REQUIRE(src && out, PCLB200_ERR_INVALID, "NULL argument");
+    // correspondence_estimation_normal_shooting.hpp:51-57 / backprojection.hpp:51-57: normals are mandatory
+    PCLB_REQUIRE(src_normals, PCLB200_ERR_INVALID, "source normals are required");
+    PCLB_REQUIRE(kind != PCLB200_CORR_BACK_PROJECTION || tgt_normals, PCLB200_ERR_INVALID,
+                 "back projection needs target normals");
+    std::lock_guard<std::recursive_mutex> lk(ctx->c.mu);
+    PCLB_CUDA(cudaSetDevice(ctx->c.device));
+    *n_out = correspondences_by_normals(ctx->c, *idx_tgt->idx, kind, src, n, stride, src_normals, stride_sn, tgt_normals,
+                                        stride_tn, src_indices, n_idx, k, max_dist, out);
+    raise_if_device_error(ctx->c);
+  });
+}
+
+int pclb200_reject_surface_normal(pclb200_ctx* ctx, const pclb200_corr* in, size_t n, const void* src_normals, size_t n_src,
+                                  size_t stride_sn, const void* tgt_normals, size_t n_tgt, size_t stride_tn,
+                                  double threshold, pclb200_corr* out, size_t* n_out)
+{
+  return guarded([&] {
+    PCLB_REQUIRE(ctx && n_out, PCLB200_ERR_INVALID, "NULL argument");
+    *n_out = 0;
+    if (n == 0)
+      return;
+    PCLB_REQUIRE(in && out && src_normals && tgt_normals && n_src && n_tgt, PCLB200_ERR_INVALID,
+                 "NULL argument (correspondence_rejection_surface_normal.cpp:49-54: the normals must be set)");
+    std::lock_guard<std::recursive_mutex> lk(ctx->c.mu);
+    PCLB_CUDA(cudaSetDevice(ctx->c.device));
+    *n_out = reject_surface_normal(ctx->c, in, n, src_normals, n_src, stride_sn, tgt_normals, n_tgt, stride_tn, threshold,
+                                   out);
   });
 }
 
@@ -562,6 +665,8 @@ void pclb200_icp_default_params(pclb200_icp_params* p)
   p->estimator = PCLB200_EST_SVD;
   p->is_dense = 1;
   p->enforce_same_direction_normals = 1;
+  p->correspondence_kind = PCLB200_CORR_NEAREST;
+  p->correspondence_k = 10;  // k_{10}: correspondence_estimation_normal_shooting.h:251, ..._backprojection.h:251
   p->max_correspondence_distance = std::sqrt(std::numeric_limits<double>::max());
   p->transformation_epsilon = 0.0;
   p->transformation_rotation_epsilon = 0.0;
@@ -750,6 +855,52 @@ int pclb200_normals_knn(pclb200_ctx* ctx, const pclb200_index* h, const void* pt
     {
       ProfScope ps(c, "normals");
       launch_normals(c, *h->idx, qb.q.p, nq, k, viewpoint, po, d_flag.p);
+    }
+    int flag = 0;
+    PCLB_CUDA(cudaMemcpyAsync(&flag, d_flag.p, sizeof(int), cudaMemcpyDeviceToHost, st));
+    if (!dev_out)
+      PCLB_CUDA(cudaMemcpyAsync(out, po, nq * sizeof(float4), cudaMemcpyDeviceToHost, st));
+    raise_if_device_error(c);
+    if (is_dense_out)
+      *is_dense_out = flag ? 0 : 1;
+  });
+}
+
+int pclb200_normals_radius(pclb200_ctx* ctx, const pclb200_index* h, const void* pts, size_t n, size_t stride,
+                           const int32_t* indices, size_t n_idx, int is_dense, double radius, const float viewpoint[3],
+                           float* out, int* is_dense_out)
+{
+  (void)is_dense;
+  return guarded([&] {
+    PCLB_REQUIRE(ctx && h && h->idx && out && viewpoint, PCLB200_ERR_INVALID, "NULL argument");
+    PCLB_REQUIRE(radius > 0.0, PCLB200_ERR_INVALID, "radius must be positive (feature.hpp:135-176)");
+    Ctx& c = ctx->c;
+    std::lock_guard<std::recursive_mutex> lk(c.mu);
+    PCLB_CUDA(cudaSetDevice(c.device));
+    cudaStream_t st = c.stream;
+    const size_t nq = indices ? n_idx : n;
+    if (is_dense_out)
+      *is_dense_out = 1;
+    if (!nq)
+      return;
+    DevBuf<float4> dense;
+    dense.alloc(nq, st);
+    load_xyz_as_float4(c, pts, n, stride, indices, n_idx, dense.p, st);
+    QueryBatch qb;
+    make_query_batch(c, *h->idx, dense.p, nq, qb);
+    DevBuf<float4> d_out;
+    DevBuf<int> d_flag;
+    d_flag.alloc(1, st);
+    PCLB_CUDA(cudaMemsetAsync(d_flag.p, 0, sizeof(int), st));
+    const bool dev_out = is_device_ptr(out);
+    float4* po = reinterpret_cast<float4*>(out);
+    if (!dev_out) {
+      d_out.alloc(nq, st);
+      po = d_out.p;
+    }
+    {
+      ProfScope ps(c, "normals");
+      launch_normals_radius(c, *h->idx, qb.q.p, nq, (float)(radius * radius), viewpoint, po, d_flag.p);
     }
     int flag = 0;
     PCLB_CUDA(cudaMemcpyAsync(&flag, d_flag.p, sizeof(int), cudaMemcpyDeviceToHost, st));

@@ -22,6 +22,7 @@
 #include <memory>
 
 #include "internal.cuh"
+#include "corr_select.cuh"
 #include "traverse.cuh"
 
 namespace pclb200 {
@@ -1168,7 +1169,8 @@ void icp_set_rejectors(Icp& s, const pclb200_rejector* list, int n)
 {
   s.rejectors.assign(list, list + (n > 0 ? n : 0));
   for (const auto& r : s.rejectors)
-    PCLB_REQUIRE(r.kind >= PCLB200_REJ_DISTANCE && r.kind <= PCLB200_REJ_TRIMMED, PCLB200_ERR_INVALID, "unknown rejector kind");
+    PCLB_REQUIRE(r.kind >= PCLB200_REJ_DISTANCE && r.kind <= PCLB200_REJ_SURFACE_NORMAL, PCLB200_ERR_INVALID,
+                 "unknown rejector kind");
 }
 
 // Match array <-> flat rejector arrays (tie-break = slot = position in the source index list = the order of the
@@ -1193,6 +1195,66 @@ __global__ void k_arrays_to_match(const int* __restrict__ acc, size_t n, Match* 
     match[i].accepted = acc[i];
 }
 
+// CorrespondenceEstimationNormalShooting / ...BackProjection inside the loop: the candidate rows come from the
+// exact k-NN kernel (rows addressed by slot), the choice is corr_select.cuh's; the result is a Match like the 1-NN
+// search kernels produce, so the rejectors / accumulation / solve downstream are unchanged.
+__global__ void __launch_bounds__(128)
+k_select_match(const float4* __restrict__ cur, const float4* __restrict__ cur_normals, size_t n, int kind, int k,
+               const int32_t* __restrict__ nn_idx, const float* __restrict__ nn_d2, const float4* __restrict__ tgt_pts,
+               const int32_t* __restrict__ pos_of_orig, const float4* __restrict__ tgt_nrm_by_pos, double max_dist,
+               Match* __restrict__ match)
+{
+  const size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+  if (i >= n)
+    return;
+  const float4 p = cur[i];
+  Match m;
+  m.pos = -1;
+  m.d2 = 0.f;
+  m.lb = 0.f;
+  m.accepted = 0;
+  if (isfinite(p.x) && isfinite(p.y) && isfinite(p.z)) {
+    const size_t slot = (size_t)(unsigned)__float_as_int(p.w);
+    const float4 nn = cur_normals[i];
+    const int32_t* row_idx = nn_idx + slot * (size_t)k;
+    const float* row_d2 = nn_d2 + slot * (size_t)k;
+    const int j = select_by_normals<true>(kind, k, row_idx, row_d2, p.x, p.y, p.z, nn.x, nn.y, nn.z, tgt_pts,
+                                          pos_of_orig, tgt_nrm_by_pos, max_dist);
+    if (j >= 0 && row_idx[j] >= 0) {
+      m.pos = pos_of_orig[row_idx[j]];
+      m.d2 = row_d2[j];
+      m.accepted = 1;
+    }
+  }
+  match[i] = m;
+}
+
+// CorrespondenceRejectorSurfaceNormal inside the loop: rotated source normal vs the matched target's normal
+__global__ void k_reject_surface_normal(const float4* __restrict__ cur_normals, const float4* __restrict__ tgt_nrm_by_pos,
+                                        const int* __restrict__ mt, size_t n, double threshold, int* __restrict__ acc)
+{
+  const size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+  if (i >= n || !acc[i])
+    return;
+  if (!surface_normal_keeps(cur_normals[i], tgt_nrm_by_pos[mt[i]], threshold))
+    acc[i] = 0;
+}
+
+static bool has_surface_normal_rejector(const Icp& s)
+{
+  for (const auto& r : s.rejectors)
+    if (r.kind == PCLB200_REJ_SURFACE_NORMAL)
+      return true;
+  return false;
+}
+
+// the session keeps a rotated copy of the source normals only for the components that read them every iteration
+static bool needs_cur_normals(const Icp& s)
+{
+  return s.P.estimator == PCLB200_EST_SYMMETRIC_POINT_TO_PLANE_LLS || s.P.correspondence_kind != PCLB200_CORR_NEAREST ||
+         has_surface_normal_rejector(s);
+}
+
 static void run_rejectors(Icp& s)
 {
   Ctx& c = *s.ctx;
@@ -1213,8 +1275,16 @@ static void run_rejectors(Icp& s)
   a.match = mt.p;
   a.tie = tie.p;
   a.acc = acc.p;
-  for (const auto& r : s.rejectors)
+  for (const auto& r : s.rejectors) {
+    if (r.kind == PCLB200_REJ_SURFACE_NORMAL) {
+      PCLB_REQUIRE(s.cur_normals.p && s.tgt_normals.p, PCLB200_ERR_INVALID,
+                   "icp: the surface-normal rejector needs source and target normals (set the rejectors before the source)");
+      k_reject_surface_normal<<<grid_for(n, 256), 256, 0, st>>>(s.cur_normals.p, s.tgt_normals.p, mt.p, n, r.p, acc.p);
+      ++c.launches;
+      continue;
+    }
     apply_rejector(c, r, a, nullptr, nullptr, nullptr, nullptr);
+  }
   k_arrays_to_match<<<grid_for(n, 256), 256, 0, st>>>(acc.p, n, s.match.p);
   ++c.launches;
   PCLB_CUDA(cudaGetLastError());
@@ -1358,8 +1428,10 @@ void icp_set_source(Icp& s, const void* src, size_t n, size_t stride, const void
   }
   s.cur = std::move(qb.q);
   s.cur_normals.release();
-  if (s.P.estimator == PCLB200_EST_SYMMETRIC_POINT_TO_PLANE_LLS) {
-    PCLB_REQUIRE(s.have_src_normals, PCLB200_ERR_INVALID, "icp: the symmetric objective needs source normals");
+  if (needs_cur_normals(s)) {
+    PCLB_REQUIRE(s.have_src_normals, PCLB200_ERR_INVALID,
+                 "icp: the symmetric objective, the normal-based correspondence estimators and the surface-normal "
+                 "rejector need source normals");
     s.cur_normals.alloc(s.n_q, st);
     if (s.n_q) {
       k_gather_cur_normals<<<grid_for(s.n_q, 256), 256, 0, st>>>(s.cur.p, s.src_normals.p, s.src_orig.p, s.n_q,
@@ -1526,7 +1598,35 @@ void icp_iterate(Icp& s, int max_steps, pclb200_icp_stats* stats)
       a.s_pts = src_index->pts.p;
       a.s_root = src_index->root;
     }
-    {
+    if (s.P.correspondence_kind != PCLB200_CORR_NEAREST) {
+      // setCorrespondenceEstimation(NormalShooting / BackProjection): k-NN candidates, then the normal-based choice
+      ProfScope ps(c, "icp_search");
+      const int kind = s.P.correspondence_kind;
+      PCLB_REQUIRE(kind == PCLB200_CORR_NORMAL_SHOOTING || kind == PCLB200_CORR_BACK_PROJECTION, PCLB200_ERR_INVALID,
+                   "icp: unknown correspondence_kind");
+      PCLB_REQUIRE(!s.P.use_reciprocal, PCLB200_ERR_INVALID,
+                   "icp: reciprocal correspondences are only built for the nearest-neighbour estimator");
+      PCLB_REQUIRE(s.cur_normals.p, PCLB200_ERR_INVALID, "icp: the normal-based estimators need source normals");
+      PCLB_REQUIRE(kind != PCLB200_CORR_BACK_PROJECTION || s.tgt_normals.p, PCLB200_ERR_INVALID,
+                   "icp: back projection needs target normals");
+      const int keff = (int)std::min<size_t>((size_t)std::max(s.P.correspondence_k, 0), T.n_valid);
+      PCLB_REQUIRE(keff > 0, PCLB200_ERR_INVALID, "icp: correspondence_k must be positive");
+      k_apply_pending<<<grid, 256, 0, st>>>(s.cur.p, s.n_q, s.pending.p, s.cur_normals.p);
+      k_clear_apply<<<1, 1, 0, st>>>(s.pending.p);
+      c.launches += 2;
+      DevBuf<int32_t> nn_idx;
+      DevBuf<float> nn_d2;
+      nn_idx.alloc(s.n_q * (size_t)keff, st);
+      nn_d2.alloc(s.n_q * (size_t)keff, st);
+      launch_knn(c, T, s.cur.p, s.n_q, keff, std::numeric_limits<float>::infinity(), nn_idx.p, nn_d2.p);
+      ensure_pos_of_orig(c, const_cast<Index&>(T));
+      k_select_match<<<grid_for(s.n_q, 128), 128, 0, st>>>(s.cur.p, s.cur_normals.p, s.n_q, kind, keff, nn_idx.p, nn_d2.p,
+                                                          T.pts.p, T.pos_of_orig.p, s.tgt_normals.p,
+                                                          s.P.max_correspondence_distance, s.match.p);
+      ++c.launches;
+      PCLB_CUDA(cudaGetLastError());
+    }
+    else {
       ProfScope ps(c, "icp_search");
       const unsigned sgrid = persistent_grid(c, s.n_q, 256, 16);
       // packet walk when the queries are about as dense as the target (32 Morton-adjacent queries then share

@@ -206,6 +206,19 @@ void launch_radius_fill(Ctx& c, const Index& idx, const float4* d_q, size_t nq, 
                         const unsigned long long* d_offsets /* by slot, exclusive */,
                         unsigned long long* d_keys /* (d2 bits << 32) | index */);
 
+// sorted radius neighbourhoods as CSR rows of packed keys ((d2 bits << 32) | original index), addressed by query slot
+void radius_csr(Ctx& c, const Index& idx, const float4* d_q, size_t nq, float r2, DevBuf<unsigned long long>& counts,
+                DevBuf<unsigned long long>& offsets, DevBuf<unsigned long long>& keys_sorted, unsigned long long& total);
+void launch_normals_radius(Ctx& c, Index& idx, const float4* d_q, size_t nq, float r2, const float vp[3], float4* d_out,
+                           int* d_not_dense);
+// correspondences chosen among the k nearest with the help of normals; surface-normal rejector (normals_corr.cu)
+size_t correspondences_by_normals(Ctx& c, Index& tgt, int kind, const void* src, size_t n, size_t stride,
+                                  const void* src_normals, size_t stride_sn, const void* tgt_normals, size_t stride_tn,
+                                  const int32_t* indices, size_t n_idx, int k, double max_dist, pclb200_corr* out);
+size_t reject_surface_normal(Ctx& c, const pclb200_corr* in, size_t n, const void* src_normals, size_t n_src,
+                             size_t stride_sn, const void* tgt_normals, size_t n_tgt, size_t stride_tn,
+                             double threshold, pclb200_corr* out);
+
 // flat per-correspondence arrays the rejectors work on (reject.cu)
 struct RejectArrays {
   size_t n = 0;

@@ -66,8 +66,11 @@ static void strided_to_float4(Ctx& c, const void* src, size_t n_records, size_t 
   DevBuf<int32_t> staged_sub;
   const unsigned char* d_src = static_cast<const unsigned char*>(src);
   if (!on_device) {
-    staged.alloc(n_records * stride, s);
-    PCLB_CUDA(cudaMemcpyAsync(staged.p, src, n_records * stride, cudaMemcpyHostToDevice, s));
+    // only up to the last byte a record's xyz can occupy: `src` may point INSIDE the caller's records (normals at
+    // offset 16 of a PointNormal), so n_records * stride bytes would run past the end of the caller's array
+    const size_t bytes = (n_records - 1) * stride + 12;
+    staged.alloc(bytes, s);
+    PCLB_CUDA(cudaMemcpyAsync(staged.p, src, bytes, cudaMemcpyHostToDevice, s));
     d_src = staged.p;
   }
   const int32_t* d_sub = subset;

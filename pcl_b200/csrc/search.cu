@@ -81,7 +81,9 @@ k_knn(const BvhNode* __restrict__ nodes, const float4* __restrict__ pts, int roo
   v.qx = qq.x; v.qy = qq.y; v.qz = qq.z;
   v.pts = pts;
   v.init(init_bound);
-  if (!traverse(nodes, pts, root, qq.x, qq.y, qq.z, v))
+  // a non-finite query has no neighbours (every comparison with NaN fails; rows stay (-1, +inf)) — without the guard
+  // it would walk the whole tree, because a NaN box bound never prunes
+  if (isfinite(qq.x) && isfinite(qq.y) && isfinite(qq.z) && !traverse(nodes, pts, root, qq.x, qq.y, qq.z, v))
     atomicExch(d_error, 1);
 #pragma unroll
   for (int j = 0; j < K; ++j)
@@ -145,7 +147,7 @@ k_knn_any(const BvhNode* __restrict__ nodes, const float4* __restrict__ pts, int
     v.d[j] = init_bound;
     v.pos[j] = -1;
   }
-  if (!traverse(nodes, pts, root, qq.x, qq.y, qq.z, v))
+  if (isfinite(qq.x) && isfinite(qq.y) && isfinite(qq.z) && !traverse(nodes, pts, root, qq.x, qq.y, qq.z, v))
     atomicExch(d_error, 1);
   for (int j = 0; j < k; ++j) {
     int p = v.pos[j];
@@ -332,7 +334,8 @@ k_radius_count(const BvhNode* __restrict__ nodes, const float4* __restrict__ pts
     return;
   const float4 qq = __ldg(q + i);
   RadiusCount v{qq.x, qq.y, qq.z, r2, r2_below, 0ULL};
-  if (!traverse(nodes, pts, root, qq.x, qq.y, qq.z, v))
+  // a non-finite query has no neighbour (every comparison with NaN fails) — and would otherwise walk the whole tree
+  if (isfinite(qq.x) && isfinite(qq.y) && isfinite(qq.z) && !traverse(nodes, pts, root, qq.x, qq.y, qq.z, v))
     atomicExch(d_error, 1);
   counts[(size_t)(unsigned)__float_as_int(qq.w)] = v.n;
 }
@@ -348,7 +351,7 @@ k_radius_fill(const BvhNode* __restrict__ nodes, const float4* __restrict__ pts,
     return;
   const float4 qq = __ldg(q + i);
   RadiusFill v{qq.x, qq.y, qq.z, r2, r2_below, keys + offsets[(size_t)(unsigned)__float_as_int(qq.w)]};
-  if (!traverse(nodes, pts, root, qq.x, qq.y, qq.z, v))
+  if (isfinite(qq.x) && isfinite(qq.y) && isfinite(qq.z) && !traverse(nodes, pts, root, qq.x, qq.y, qq.z, v))
     atomicExch(d_error, 1);
 }
 
@@ -374,6 +377,44 @@ void launch_radius_fill(Ctx& c, const Index& idx, const float4* d_q, size_t nq, 
                                                         float_below(r2), d_offsets, d_keys, c.d_error);
   ++c.launches;
   PCLB_CUDA(cudaGetLastError());
+}
+
+// Sorted radius neighbourhoods of a query batch as CSR rows addressed by the query's slot:
+// keys = (d2 bits << 32) | original index, ascending inside every row (= ascending (d2, index)).
+// counts / offsets have nq + 1 entries (offsets[nq] = total).  Synchronises once to learn the total.
+void radius_csr(Ctx& c, const Index& idx, const float4* d_q, size_t nq, float r2, DevBuf<unsigned long long>& counts,
+                DevBuf<unsigned long long>& offsets, DevBuf<unsigned long long>& keys_sorted, unsigned long long& total)
+{
+  cudaStream_t st = c.stream;
+  counts.alloc(nq + 1, st);
+  offsets.alloc(nq + 1, st);
+  PCLB_CUDA(cudaMemsetAsync(counts.p, 0, (nq + 1) * sizeof(unsigned long long), st));
+  launch_radius_count(c, idx, d_q, nq, r2, counts.p);
+  size_t tb = 0;
+  PCLB_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, tb, counts.p, offsets.p, (int)(nq + 1), st));
+  DevBuf<unsigned char> tmp;
+  tmp.alloc(tb, st);
+  PCLB_CUDA(cub::DeviceScan::ExclusiveSum(tmp.p, tb, counts.p, offsets.p, (int)(nq + 1), st));
+  ++c.launches;
+  total = 0;
+  PCLB_CUDA(cudaMemcpyAsync(&total, offsets.p + nq, sizeof(total), cudaMemcpyDeviceToHost, st));
+  PCLB_CUDA(cudaStreamSynchronize(st));
+  if (total == 0)
+    return;
+  PCLB_REQUIRE(total < (unsigned long long)std::numeric_limits<int>::max(), PCLB200_ERR_INVALID,
+               "radius search result exceeds 2^31 neighbours; lower the radius or set max_nn");
+  DevBuf<unsigned long long> keys;
+  keys.alloc(total, st);
+  keys_sorted.alloc(total, st);
+  launch_radius_fill(c, idx, d_q, nq, r2, offsets.p, keys.p);
+  size_t tb2 = 0;
+  PCLB_CUDA(cub::DeviceSegmentedSort::SortKeys(nullptr, tb2, keys.p, keys_sorted.p, (int)total, (int)nq, offsets.p,
+                                               offsets.p + 1, st));
+  DevBuf<unsigned char> tmp2;
+  tmp2.alloc(tb2, st);
+  PCLB_CUDA(cub::DeviceSegmentedSort::SortKeys(tmp2.p, tb2, keys.p, keys_sorted.p, (int)total, (int)nq, offsets.p,
+                                               offsets.p + 1, st));
+  c.launches += 3;
 }
 
 // ---- normals ---------------------------------------------------------------------------------------
@@ -483,6 +524,50 @@ __device__ void eigen33_smallest_dev(const float* mat, float& eigenvalue, float*
   }
 }
 
+// shifted single-pass moments (centroid.hpp:605-640): one neighbour, K = the first neighbour of the list
+__device__ __forceinline__ void moments_add(float (&accu)[9], float Kx, float Ky, float Kz, const float4 p)
+{
+  const float x = __fsub_rn(p.x, Kx), y = __fsub_rn(p.y, Ky), z = __fsub_rn(p.z, Kz);
+  accu[0] = __fadd_rn(accu[0], __fmul_rn(x, x));
+  accu[1] = __fadd_rn(accu[1], __fmul_rn(x, y));
+  accu[2] = __fadd_rn(accu[2], __fmul_rn(x, z));
+  accu[3] = __fadd_rn(accu[3], __fmul_rn(y, y));
+  accu[4] = __fadd_rn(accu[4], __fmul_rn(y, z));
+  accu[5] = __fadd_rn(accu[5], __fmul_rn(z, z));
+  accu[6] = __fadd_rn(accu[6], x);
+  accu[7] = __fadd_rn(accu[7], y);
+  accu[8] = __fadd_rn(accu[8], z);
+}
+
+// moments -> covariance (centroid.hpp:641-651) -> solvePlaneParameters (feature.hpp:65-92) ->
+// flipNormalTowardsViewpoint (normal_3d.h:169-188); returns {nx, ny, nz, curvature}
+__device__ __forceinline__ float4 normal_from_moments(float (&accu)[9], int cnt, const float4 qq, float vpx, float vpy,
+                                                      float vpz, int* __restrict__ not_dense)
+{
+  const float fc = (float)cnt;
+#pragma unroll
+  for (int t = 0; t < 9; ++t)
+    accu[t] = __fdiv_rn(accu[t], fc);
+  float cov[9];
+  cov[0] = __fsub_rn(accu[0], __fmul_rn(accu[6], accu[6]));
+  cov[1] = __fsub_rn(accu[1], __fmul_rn(accu[6], accu[7]));
+  cov[2] = __fsub_rn(accu[2], __fmul_rn(accu[6], accu[8]));
+  cov[4] = __fsub_rn(accu[3], __fmul_rn(accu[7], accu[7]));
+  cov[5] = __fsub_rn(accu[4], __fmul_rn(accu[7], accu[8]));
+  cov[8] = __fsub_rn(accu[5], __fmul_rn(accu[8], accu[8]));
+  cov[3] = cov[1]; cov[6] = cov[2]; cov[7] = cov[5];
+  float ev, n[3];
+  eigen33_smallest_dev(cov, ev, n);
+  const float eig_sum = __fadd_rn(__fadd_rn(cov[0], cov[4]), cov[8]);
+  const float curv = eig_sum != 0.f ? fabsf(__fdiv_rn(ev, eig_sum)) : 0.f;
+  const float vx = vpx - qq.x, vy = vpy - qq.y, vz = vpz - qq.z;
+  const float cos_theta = vx * n[0] + vy * n[1] + vz * n[2];
+  if (cos_theta < 0.f) { n[0] = -n[0]; n[1] = -n[1]; n[2] = -n[2]; }
+  if (!(isfinite(n[0]) && isfinite(n[1]) && isfinite(n[2]) && isfinite(curv)))
+    *not_dense = 1;
+  return make_float4(n[0], n[1], n[2], curv);
+}
+
 // k-NN -> shifted single-pass covariance in the neighbour order the search returns
 // (common/include/pcl/common/impl/centroid.hpp:578-652, Scalar = float, same operation order, no fma)
 // -> solvePlaneParameters (features/impl/feature.hpp:65-92) -> flipNormalTowardsViewpoint
@@ -527,39 +612,9 @@ k_normals(const BvhNode* __restrict__ nodes, const float4* __restrict__ pts, int
     if (j < cnt) {
       const float4 p = ldg4(pts + v.pos[j]);
       if (j == 0) { Kx = p.x; Ky = p.y; Kz = p.z; }
-      const float x = __fsub_rn(p.x, Kx), y = __fsub_rn(p.y, Ky), z = __fsub_rn(p.z, Kz);
-      accu[0] = __fadd_rn(accu[0], __fmul_rn(x, x));
-      accu[1] = __fadd_rn(accu[1], __fmul_rn(x, y));
-      accu[2] = __fadd_rn(accu[2], __fmul_rn(x, z));
-      accu[3] = __fadd_rn(accu[3], __fmul_rn(y, y));
-      accu[4] = __fadd_rn(accu[4], __fmul_rn(y, z));
-      accu[5] = __fadd_rn(accu[5], __fmul_rn(z, z));
-      accu[6] = __fadd_rn(accu[6], x);
-      accu[7] = __fadd_rn(accu[7], y);
-      accu[8] = __fadd_rn(accu[8], z);
+      moments_add(accu, Kx, Ky, Kz, p);
     }
-  const float fc = (float)cnt;
-#pragma unroll
-  for (int t = 0; t < 9; ++t)
-    accu[t] = __fdiv_rn(accu[t], fc);
-  float cov[9];
-  cov[0] = __fsub_rn(accu[0], __fmul_rn(accu[6], accu[6]));
-  cov[1] = __fsub_rn(accu[1], __fmul_rn(accu[6], accu[7]));
-  cov[2] = __fsub_rn(accu[2], __fmul_rn(accu[6], accu[8]));
-  cov[4] = __fsub_rn(accu[3], __fmul_rn(accu[7], accu[7]));
-  cov[5] = __fsub_rn(accu[4], __fmul_rn(accu[7], accu[8]));
-  cov[8] = __fsub_rn(accu[5], __fmul_rn(accu[8], accu[8]));
-  cov[3] = cov[1]; cov[6] = cov[2]; cov[7] = cov[5];
-  float ev, n[3];
-  eigen33_smallest_dev(cov, ev, n);
-  const float eig_sum = __fadd_rn(__fadd_rn(cov[0], cov[4]), cov[8]);
-  const float curv = eig_sum != 0.f ? fabsf(__fdiv_rn(ev, eig_sum)) : 0.f;
-  const float vx = vpx - qq.x, vy = vpy - qq.y, vz = vpz - qq.z;
-  const float cos_theta = vx * n[0] + vy * n[1] + vz * n[2];
-  if (cos_theta < 0.f) { n[0] = -n[0]; n[1] = -n[1]; n[2] = -n[2]; }
-  if (!(isfinite(n[0]) && isfinite(n[1]) && isfinite(n[2]) && isfinite(curv)))
-    *not_dense = 1;
-  out[slot] = make_float4(n[0], n[1], n[2], curv);
+  out[slot] = normal_from_moments(accu, cnt, qq, vpx, vpy, vpz, not_dense);
 }
 
 // normals from materialised neighbour lists (k > 32): same arithmetic as k_normals, neighbours fetched through
@@ -590,37 +645,56 @@ k_normals_from_lists(const float4* __restrict__ pts, const int32_t* __restrict__
   for (int j = 0; j < cnt; ++j) {
     const float4 p = ldg4(pts + pos_of_orig[nn[j]]);
     if (j == 0) { Kx = p.x; Ky = p.y; Kz = p.z; }
-    const float x = __fsub_rn(p.x, Kx), y = __fsub_rn(p.y, Ky), z = __fsub_rn(p.z, Kz);
-    accu[0] = __fadd_rn(accu[0], __fmul_rn(x, x));
-    accu[1] = __fadd_rn(accu[1], __fmul_rn(x, y));
-    accu[2] = __fadd_rn(accu[2], __fmul_rn(x, z));
-    accu[3] = __fadd_rn(accu[3], __fmul_rn(y, y));
-    accu[4] = __fadd_rn(accu[4], __fmul_rn(y, z));
-    accu[5] = __fadd_rn(accu[5], __fmul_rn(z, z));
-    accu[6] = __fadd_rn(accu[6], x);
-    accu[7] = __fadd_rn(accu[7], y);
-    accu[8] = __fadd_rn(accu[8], z);
+    moments_add(accu, Kx, Ky, Kz, p);
   }
-  const float fc = (float)cnt;
-  for (int t = 0; t < 9; ++t)
-    accu[t] = __fdiv_rn(accu[t], fc);
-  float cov[9];
-  cov[0] = __fsub_rn(accu[0], __fmul_rn(accu[6], accu[6]));
-  cov[1] = __fsub_rn(accu[1], __fmul_rn(accu[6], accu[7]));
-  cov[2] = __fsub_rn(accu[2], __fmul_rn(accu[6], accu[8]));
-  cov[4] = __fsub_rn(accu[3], __fmul_rn(accu[7], accu[7]));
-  cov[5] = __fsub_rn(accu[4], __fmul_rn(accu[7], accu[8]));
-  cov[8] = __fsub_rn(accu[5], __fmul_rn(accu[8], accu[8]));
-  cov[3] = cov[1]; cov[6] = cov[2]; cov[7] = cov[5];
-  float ev, n[3];
-  eigen33_smallest_dev(cov, ev, n);
-  const float eig_sum = __fadd_rn(__fadd_rn(cov[0], cov[4]), cov[8]);
-  const float curv = eig_sum != 0.f ? fabsf(__fdiv_rn(ev, eig_sum)) : 0.f;
-  const float vx = vpx - qq.x, vy = vpy - qq.y, vz = vpz - qq.z;
-  if (vx * n[0] + vy * n[1] + vz * n[2] < 0.f) { n[0] = -n[0]; n[1] = -n[1]; n[2] = -n[2]; }
-  if (!(isfinite(n[0]) && isfinite(n[1]) && isfinite(n[2]) && isfinite(curv)))
+  out[slot] = normal_from_moments(accu, cnt, qq, vpx, vpy, vpz, not_dense);
+}
+
+// normals from radius neighbourhoods (setRadiusSearch): rows of a CSR of packed keys (radius_csr), addressed by the
+// query's slot; same arithmetic as k_normals over a variable-length, (d2, index)-ascending neighbour list.
+__global__ void __launch_bounds__(128)
+k_normals_from_csr(const float4* __restrict__ pts, const int32_t* __restrict__ pos_of_orig,
+                   const float4* __restrict__ q, size_t nq, const unsigned long long* __restrict__ offsets,
+                   const unsigned long long* __restrict__ keys, float vpx, float vpy, float vpz,
+                   float4* __restrict__ out, int* __restrict__ not_dense)
+{
+  size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+  if (i >= nq)
+    return;
+  const float4 qq = __ldg(q + i);
+  const size_t slot = (size_t)(unsigned)__float_as_int(qq.w);
+  const unsigned long long b = offsets[slot], e = offsets[slot + 1];
+  const float qnan = __int_as_float(0x7fc00000);
+  if (!(isfinite(qq.x) && isfinite(qq.y) && isfinite(qq.z)) || e - b < 3ULL) {  // normal_3d.h:308-312
+    out[slot] = make_float4(qnan, qnan, qnan, qnan);
     *not_dense = 1;
-  out[slot] = make_float4(n[0], n[1], n[2], curv);
+    return;
+  }
+  float accu[9] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  float Kx = 0.f, Ky = 0.f, Kz = 0.f;
+  for (unsigned long long j = b; j < e; ++j) {
+    const int oi = (int)(unsigned)(keys[j] & 0xffffffffULL);
+    const float4 p = ldg4(pts + pos_of_orig[oi]);
+    if (j == b) { Kx = p.x; Ky = p.y; Kz = p.z; }
+    moments_add(accu, Kx, Ky, Kz, p);
+  }
+  out[slot] = normal_from_moments(accu, (int)(e - b), qq, vpx, vpy, vpz, not_dense);
+}
+
+void launch_normals_radius(Ctx& c, Index& idx, const float4* d_q, size_t nq, float r2, const float vp[3], float4* d_out,
+                           int* d_not_dense)
+{
+  if (!nq)
+    return;
+  cudaStream_t s = c.stream;
+  DevBuf<unsigned long long> counts, offsets, keys;
+  unsigned long long total = 0;
+  radius_csr(c, idx, d_q, nq, r2, counts, offsets, keys, total);
+  ensure_pos_of_orig(c, idx);
+  k_normals_from_csr<<<grid_for(nq, 128), 128, 0, s>>>(idx.pts.p, idx.pos_of_orig.p, d_q, nq, offsets.p, keys.p, vp[0],
+                                                      vp[1], vp[2], d_out, d_not_dense);
+  ++c.launches;
+  PCLB_CUDA(cudaGetLastError());
 }
 
 void launch_normals(Ctx& c, Index& idx, const float4* d_q, size_t nq, int k, const float vp[3], float4* d_out,

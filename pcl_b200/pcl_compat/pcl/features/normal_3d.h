@@ -1,4 +1,4 @@
-// pcl/features/normal_3d.h — pcl::NormalEstimation[OMP]<PointInT, PointOutT> with setKSearch(k) on the device
+// pcl/features/normal_3d.h — pcl::NormalEstimation[OMP]<PointInT, PointOutT> (setKSearch or setRadiusSearch) on the device
 // (features/include/pcl/features/normal_3d.h:242-415, impl/normal_3d.hpp:47-96, impl/feature.hpp:95-230).
 #pragma once
 #include <cstdio>
@@ -30,6 +30,7 @@ public:
   void setKSearch(int k) { k_ = k; }
   int getKSearch() const { return k_; }
   void setRadiusSearch(double r) { search_radius_ = r; }
+  double getRadiusSearch() const { return search_radius_; }
   void setViewPoint(float x, float y, float z) { vp_[0] = x; vp_[1] = y; vp_[2] = z; use_sensor_origin_ = false; }
   void getViewPoint(float& x, float& y, float& z) { x = vp_[0]; y = vp_[1]; z = vp_[2]; }
   void useSensorOriginAsViewPoint()
@@ -51,8 +52,8 @@ public:
       std::fprintf(stderr, "[pcl::NormalEstimation::compute] Both radius and K defined! Set one of them to zero first.\n");
       return;
     }
-    if (k_ == 0) {
-      std::fprintf(stderr, "[pcl::NormalEstimation::compute] only setKSearch(k) is on the accelerated path (radius: SURVEY.md §8f).\n");
+    if (k_ == 0 && search_radius_ == 0.0) {  // impl/feature.hpp:168-173
+      std::fprintf(stderr, "[pcl::NormalEstimation::compute] Neither radius nor K defined! Set one of them to a positive number first.\n");
       return;
     }
     PCLBase<PointInT>::initCompute();
@@ -65,9 +66,13 @@ public:
     output.points.assign(n, PointOutT());
     std::vector<float> buf(4 * (n ? n : 1));
     int dense = 1;
-    int rc = pclb200_normals_knn(b200::Context::get(), tree_->deviceIndex(), this->input_->points.data(), this->input_->size(),
-                                 sizeof(PointInT), this->abiIndices(), this->abiIndexCount(), this->input_->is_dense ? 1 : 0, k_, vp_,
-                                 buf.data(), &dense);
+    int rc = search_radius_ != 0.0
+                 ? pclb200_normals_radius(b200::Context::get(), tree_->deviceIndex(), this->input_->points.data(),
+                                          this->input_->size(), sizeof(PointInT), this->abiIndices(), this->abiIndexCount(),
+                                          this->input_->is_dense ? 1 : 0, search_radius_, vp_, buf.data(), &dense)
+                 : pclb200_normals_knn(b200::Context::get(), tree_->deviceIndex(), this->input_->points.data(),
+                                       this->input_->size(), sizeof(PointInT), this->abiIndices(), this->abiIndexCount(),
+                                       this->input_->is_dense ? 1 : 0, k_, vp_, buf.data(), &dense);
     if (rc != PCLB200_OK) {
       std::fprintf(stderr, "[pcl::NormalEstimation::compute] %s\n", pclb200_last_error());
       output.clear();

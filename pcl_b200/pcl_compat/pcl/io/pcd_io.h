@@ -1,10 +1,21 @@
-// pcl/io/pcd_io.h — minimal PCD reader/writer (ASCII and binary, float fields) so the reference's own fixtures
-// and tutorials (doc/tutorials/content/sources/iterative_closest_point) run end to end.  io/src/pcd_io.cpp proper
-// (compressed PCD, PCLPointCloud2 blobs) is outside the accelerated path.
+// pcl/io/pcd_io.h — PCD reader / writer for the point types of the ICP path: DATA ascii, binary and
+// binary_compressed (LZF, structure-of-arrays), every numeric field type, COUNT > 1 and "_" padding fields, the
+// VIEWPOINT line, organised (WIDTH x HEIGHT) clouds.
+// Reference behaviour: io/src/pcd_io.cpp:120-395 (header), :443-576 (ASCII body), :580-668 (binary and
+// binary_compressed bodies, is_dense), io/include/pcl/io/pcd_io.h:633-800 (load/save free functions),
+// io/include/pcl/io/impl/pcd_io.hpp:66-130 (header text), :232-428 (writeBinaryCompressed), :430-560 (writeASCII).
+// The LZF coder below is written from the published stream format (a control byte < 32 starts a literal run of
+// ctrl + 1 bytes; otherwise a back reference of length (ctrl >> 5) + 2 — 7 means "add the next byte" — at distance
+// ((ctrl & 31) << 8 | next byte) + 1); any valid stream decodes with the reference's lzfDecompress and vice versa.
+// PCLPointCloud2 blobs are not built: clouds are read straight into pcl::PointCloud<PointT>, fields matched by name.
 #pragma once
+#include <cmath>
+#include <cstdint>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <fstream>
+#include <limits>
 #include <sstream>
 #include <string>
 #include <vector>
@@ -15,101 +26,513 @@
 namespace pcl {
 namespace io {
 namespace detail {
-template <typename P> inline void setField(P&, const std::string&, float) {}
-inline void setXYZ(float* x, float* y, float* z, const std::string& f, float v)
+
+// ---- LZF ----------------------------------------------------------------------------------------------------------
+// returns the number of bytes written, 0 when `out` is too small
+inline std::size_t lzfCompress(const unsigned char* in, std::size_t n, unsigned char* out, std::size_t cap)
 {
-  if (f == "x") *x = v; else if (f == "y") *y = v; else if (f == "z") *z = v;
+  constexpr std::size_t kMaxOff = 1u << 13, kMaxLen = 264, kHashBits = 16;
+  std::vector<std::int64_t> table(std::size_t(1) << kHashBits, -1);
+  std::size_t op = 0, lit = 0;
+  auto flush = [&](std::size_t end) -> bool {  // literal runs of at most 32 bytes
+    while (lit < end) {
+      const std::size_t run = std::min<std::size_t>(32, end - lit);
+      if (op + 1 + run > cap) return false;
+      out[op++] = static_cast<unsigned char>(run - 1);
+      std::memcpy(out + op, in + lit, run);
+      op += run;
+      lit += run;
+    }
+    return true;
+  };
+  auto slot = [&](std::size_t i) -> std::int64_t& {  // hash of the three bytes at i
+    const std::uint32_t v = (std::uint32_t(in[i]) << 16) | (std::uint32_t(in[i + 1]) << 8) | in[i + 2];
+    return table[((v * 2654435761u) >> (32 - kHashBits)) & ((1u << kHashBits) - 1)];
+  };
+  std::size_t ip = 0;
+  while (ip + 2 < n) {
+    std::int64_t& entry = slot(ip);
+    const std::int64_t ref = entry;
+    entry = static_cast<std::int64_t>(ip);
+    if (ref >= 0 && ip - static_cast<std::size_t>(ref) <= kMaxOff && in[ref] == in[ip] && in[ref + 1] == in[ip + 1] &&
+        in[ref + 2] == in[ip + 2]) {
+      if (!flush(ip)) return 0;
+      std::size_t len = 3;
+      const std::size_t max_len = std::min<std::size_t>(kMaxLen, n - ip);
+      while (len < max_len && in[ref + len] == in[ip + len]) ++len;
+      const std::size_t off = ip - static_cast<std::size_t>(ref) - 1, l = len - 2;
+      if (op + 3 > cap) return 0;
+      if (l < 7)
+        out[op++] = static_cast<unsigned char>((l << 5) | (off >> 8));
+      else {
+        out[op++] = static_cast<unsigned char>((7u << 5) | (off >> 8));
+        out[op++] = static_cast<unsigned char>(l - 7);
+      }
+      out[op++] = static_cast<unsigned char>(off & 0xff);
+      for (std::size_t j = ip + 1; j < ip + len && j + 2 < n; ++j) slot(j) = static_cast<std::int64_t>(j);  // keep the table fresh
+      ip += len;
+      lit = ip;
+    }
+    else
+      ++ip;
+  }
+  if (!flush(n)) return 0;
+  return op;
 }
-inline void setField(PointXYZ& p, const std::string& f, float v) { setXYZ(&p.x, &p.y, &p.z, f, v); }
-inline void setField(PointNormal& p, const std::string& f, float v)
+
+// returns the number of bytes produced, 0 on a corrupt stream or when `out` is too small
+inline std::size_t lzfDecompress(const unsigned char* in, std::size_t n, unsigned char* out, std::size_t cap)
 {
-  setXYZ(&p.x, &p.y, &p.z, f, v);
-  if (f == "normal_x") p.normal_x = v; else if (f == "normal_y") p.normal_y = v; else if (f == "normal_z") p.normal_z = v;
-  else if (f == "curvature") p.curvature = v;
+  std::size_t ip = 0, op = 0;
+  while (ip < n) {
+    const unsigned ctrl = in[ip++];
+    if (ctrl < 32) {
+      const std::size_t run = ctrl + 1;
+      if (ip + run > n || op + run > cap) return 0;
+      std::memcpy(out + op, in + ip, run);
+      ip += run;
+      op += run;
+    }
+    else {
+      std::size_t len = ctrl >> 5;
+      if (len == 7) {
+        if (ip >= n) return 0;
+        len += in[ip++];
+      }
+      if (ip >= n) return 0;
+      const std::size_t dist = ((std::size_t(ctrl & 0x1f) << 8) | in[ip++]) + 1;
+      len += 2;
+      if (dist > op || op + len > cap) return 0;
+      for (std::size_t i = 0; i < len; ++i, ++op) out[op] = out[op - dist];  // may overlap: byte by byte
+    }
+  }
+  return op;
 }
-inline void setField(Normal& p, const std::string& f, float v)
+
+// ---- fields of the supported point types (all FLOAT32, COUNT 1; pcl::getFields<PointT>) ---------------------------
+struct FieldDesc {
+  const char* name;
+  std::size_t offset;
+};
+template <typename P> struct point_fields;
+template <> struct point_fields<PointXYZ> {
+  static std::vector<FieldDesc> get() { return {{"x", 0}, {"y", 4}, {"z", 8}}; }
+};
+template <> struct point_fields<Normal> {
+  static std::vector<FieldDesc> get() { return {{"normal_x", 0}, {"normal_y", 4}, {"normal_z", 8}, {"curvature", 16}}; }
+};
+template <> struct point_fields<PointNormal> {
+  static std::vector<FieldDesc> get()
+  {
+    return {{"x", 0}, {"y", 4}, {"z", 8}, {"normal_x", 16}, {"normal_y", 20}, {"normal_z", 24}, {"curvature", 32}};
+  }
+};
+
+struct FileField {
+  std::string name;
+  int size = 4;
+  char type = 'F';
+  int count = 1;
+  std::size_t offset = 0;  // inside one binary record
+};
+
+struct Header {
+  std::vector<FileField> fields;
+  std::size_t width = 0, height = 1, points = 0, point_step = 0;
+  bool width_read = false, height_read = false;
+  float viewpoint[7] = {0, 0, 0, 1, 0, 0, 0};
+  int data_type = -1;  // 0 ascii, 1 binary, 2 binary_compressed
+  std::size_t data_offset = 0;
+};
+
+inline double readValue(const unsigned char* p, char type, int size, bool* finite)
 {
-  if (f == "normal_x") p.normal_x = v; else if (f == "normal_y") p.normal_y = v; else if (f == "normal_z") p.normal_z = v;
-  else if (f == "curvature") p.curvature = v;
+  *finite = true;
+  switch (type) {
+    case 'F':
+      if (size == 4) { float v; std::memcpy(&v, p, 4); *finite = std::isfinite(v); return v; }
+      if (size == 8) { double v; std::memcpy(&v, p, 8); *finite = std::isfinite(v); return v; }
+      break;
+    case 'I':
+      if (size == 1) { std::int8_t v; std::memcpy(&v, p, 1); return v; }
+      if (size == 2) { std::int16_t v; std::memcpy(&v, p, 2); return v; }
+      if (size == 4) { std::int32_t v; std::memcpy(&v, p, 4); return v; }
+      if (size == 8) { std::int64_t v; std::memcpy(&v, p, 8); return static_cast<double>(v); }
+      break;
+    case 'U':
+      if (size == 1) { std::uint8_t v; std::memcpy(&v, p, 1); return v; }
+      if (size == 2) { std::uint16_t v; std::memcpy(&v, p, 2); return v; }
+      if (size == 4) { std::uint32_t v; std::memcpy(&v, p, 4); return v; }
+      if (size == 8) { std::uint64_t v; std::memcpy(&v, p, 8); return static_cast<double>(v); }
+      break;
+    default: break;
+  }
+  return 0.0;
+}
+
+// io/src/pcd_io.cpp:120-395
+inline int readHeader(std::istream& fs, Header& h)
+{
+  std::string line;
+  bool sizes_read = false, types_read = false;
+  auto fail = [](const char* msg) {
+    std::fprintf(stderr, "[pcl::PCDReader::readHeader] %s\n", msg);
+    return -1;
+  };
+  auto finish_offsets = [&]() {
+    std::size_t off = 0;
+    for (auto& f : h.fields) {
+      f.offset = off;
+      off += static_cast<std::size_t>(f.size) * static_cast<std::size_t>(std::max(f.count, 0));
+    }
+    h.point_step = off;
+  };
+  bool points_read = false;
+  while (std::getline(fs, line)) {
+    if (!line.empty() && line.back() == '\r') line.pop_back();
+    if (line.empty()) continue;
+    std::istringstream ss(line);
+    std::string key;
+    ss >> key;
+    if (key.empty() || key[0] == '#') continue;
+    std::vector<std::string> tok;
+    for (std::string t; ss >> t;) tok.push_back(t);
+    if (key.compare(0, 7, "VERSION") == 0) continue;
+    if (key.compare(0, 6, "FIELDS") == 0 || key.compare(0, 7, "COLUMNS") == 0) {
+      h.fields.assign(tok.size(), FileField());
+      for (std::size_t i = 0; i < tok.size(); ++i) h.fields[i].name = tok[i];
+      finish_offsets();  // float32 / count 1 until SIZE, TYPE, COUNT say otherwise (:176-185)
+      continue;
+    }
+    if (key.compare(0, 4, "SIZE") == 0) {
+      if (tok.size() != h.fields.size()) return fail("The number of elements in <SIZE> differs than the number of elements in <FIELDS>!");
+      for (std::size_t i = 0; i < tok.size(); ++i) h.fields[i].size = std::atoi(tok[i].c_str());
+      sizes_read = true;
+      finish_offsets();
+      continue;
+    }
+    if (key.compare(0, 4, "TYPE") == 0) {
+      if (!sizes_read) return fail("TYPE of FIELDS specified before SIZE in header!");
+      if (tok.size() != h.fields.size()) return fail("The number of elements in <TYPE> differs than the number of elements in <FIELDS>!");
+      for (std::size_t i = 0; i < tok.size(); ++i) h.fields[i].type = tok[i][0];
+      types_read = true;
+      continue;
+    }
+    if (key.compare(0, 5, "COUNT") == 0) {
+      if (!sizes_read || !types_read) return fail("COUNT of FIELDS specified before SIZE or TYPE in header!");
+      if (tok.size() != h.fields.size()) return fail("The number of elements in <COUNT> differs than the number of elements in <FIELDS>!");
+      for (std::size_t i = 0; i < tok.size(); ++i) h.fields[i].count = std::atoi(tok[i].c_str());
+      finish_offsets();
+      continue;
+    }
+    if (key.compare(0, 5, "WIDTH") == 0) {
+      if (tok.empty()) return fail("Invalid WIDTH value specified.");
+      h.width = std::strtoull(tok[0].c_str(), nullptr, 10);
+      h.width_read = true;
+      continue;
+    }
+    if (key.compare(0, 6, "HEIGHT") == 0) {
+      if (tok.empty()) return fail("Invalid HEIGHT value specified.");
+      h.height = std::strtoull(tok[0].c_str(), nullptr, 10);
+      h.height_read = true;
+      continue;
+    }
+    if (key.compare(0, 9, "VIEWPOINT") == 0) {
+      if (tok.size() < 7) return fail("Not enough number of elements in <VIEWPOINT>! Need 7 values (tx ty tz qw qx qy qz).");
+      for (int i = 0; i < 7; ++i) h.viewpoint[i] = std::strtof(tok[i].c_str(), nullptr);
+      continue;
+    }
+    if (key.compare(0, 6, "POINTS") == 0) {
+      if (!h.point_step) return fail("Number of POINTS specified before COUNT in header!");
+      if (tok.empty()) return fail("Invalid POINTS value specified.");
+      h.points = std::strtoull(tok[0].c_str(), nullptr, 10);
+      points_read = true;
+      continue;
+    }
+    if (key.compare(0, 4, "DATA") == 0) {
+      if (tok.empty()) return fail("Unknown DATA format");
+      if (tok[0].compare(0, 17, "binary_compressed") == 0) h.data_type = 2;
+      else if (tok[0].compare(0, 6, "binary") == 0) h.data_type = 1;
+      else if (tok[0].compare(0, 5, "ascii") == 0) h.data_type = 0;
+      else return fail("Unknown DATA format");
+      h.data_offset = static_cast<std::size_t>(fs.tellg());
+      break;  // DATA is the last header entry
+    }
+  }
+  if (h.data_type < 0) return fail("no DATA line");
+  (void)points_read;
+  // compatibility with older files (:351-383)
+  if (!h.width_read && !h.height_read) { h.width = h.points; h.height = 1; }
+  if (!h.height_read) { h.height = 1; if (h.width == 0) h.width = h.points; }
+  else if (h.width == 0 && h.points != 0) return fail("HEIGHT given but no WIDTH!");
+  if (h.points == 0) h.points = h.width * h.height;
+  if (h.width * h.height != h.points) return fail("HEIGHT x WIDTH != number of points");
+  return 0;
+}
+
+// header text of the writers — io/include/pcl/io/impl/pcd_io.hpp:66-130
+inline std::string headerText(const std::vector<FieldDesc>& fields, std::size_t width, std::size_t height, std::size_t n,
+                              const float vp[7], const char* data)
+{
+  std::ostringstream os;
+  os << "# .PCD v0.7 - Point Cloud Data file format\nVERSION 0.7\nFIELDS";
+  for (const auto& f : fields) os << ' ' << f.name;
+  os << "\nSIZE";
+  for (std::size_t i = 0; i < fields.size(); ++i) os << " 4";
+  os << "\nTYPE";
+  for (std::size_t i = 0; i < fields.size(); ++i) os << " F";
+  os << "\nCOUNT";
+  for (std::size_t i = 0; i < fields.size(); ++i) os << " 1";
+  os << "\nWIDTH " << width << "\nHEIGHT " << height << "\nVIEWPOINT " << vp[0] << ' ' << vp[1] << ' ' << vp[2] << ' ' << vp[3]
+     << ' ' << vp[4] << ' ' << vp[5] << ' ' << vp[6] << "\nPOINTS " << n << "\nDATA " << data << "\n";
+  return os.str();
+}
+
+template <typename PointT> inline void writerGeometry(const pcl::PointCloud<PointT>& cloud, std::size_t& w, std::size_t& h, float vp[7])
+{
+  const std::size_t n = cloud.size();
+  w = cloud.width;
+  h = cloud.height;
+  if (w * h != n) { w = n; h = 1; }  // pcd_io.hpp:76-84: an inconsistent cloud is written as unorganised
+  vp[0] = cloud.sensor_origin_[0]; vp[1] = cloud.sensor_origin_[1]; vp[2] = cloud.sensor_origin_[2];
+  vp[3] = 1.f; vp[4] = vp[5] = vp[6] = 0.f;
 }
 }  // namespace detail
 
+// pcl::io::loadPCDFile<PointT> — io/include/pcl/io/pcd_io.h:662-667 (PCDReader::read + fromPCLPointCloud2)
 template <typename PointT>
 int loadPCDFile(const std::string& file, pcl::PointCloud<PointT>& cloud)
 {
   std::ifstream in(file, std::ios::binary);
   if (!in) { std::fprintf(stderr, "[pcl::PCDReader::read] Could not find file '%s'.\n", file.c_str()); return -1; }
-  std::vector<std::string> fields;
-  std::vector<int> sizes, counts;
-  std::vector<char> types;
-  std::size_t npts = 0, width = 0, height = 1;
-  std::string line, mode;
-  while (std::getline(in, line)) {
-    if (line.empty() || line[0] == '#') continue;
-    std::istringstream ss(line);
-    std::string key;
-    ss >> key;
-    if (key == "FIELDS" || key == "COLUMNS") { std::string f; while (ss >> f) fields.push_back(f); }
-    else if (key == "SIZE") { int v; while (ss >> v) sizes.push_back(v); }
-    else if (key == "TYPE") { char v; while (ss >> v) types.push_back(v); }
-    else if (key == "COUNT") { int v; while (ss >> v) counts.push_back(v); }
-    else if (key == "WIDTH") ss >> width;
-    else if (key == "HEIGHT") ss >> height;
-    else if (key == "POINTS") ss >> npts;
-    else if (key == "DATA") { ss >> mode; break; }
-  }
-  if (npts == 0) npts = width * height;
-  if (sizes.empty()) sizes.assign(fields.size(), 4);
-  if (types.empty()) types.assign(fields.size(), 'F');
-  if (counts.empty()) counts.assign(fields.size(), 1);
+  detail::Header h;
+  if (detail::readHeader(in, h) != 0) return -1;
+  const std::size_t npts = h.points;
   cloud.points.assign(npts, PointT());
-  cloud.width = static_cast<std::uint32_t>(width ? width : npts);
-  cloud.height = static_cast<std::uint32_t>(height);
+  cloud.width = static_cast<std::uint32_t>(h.width);
+  cloud.height = static_cast<std::uint32_t>(h.height);
   cloud.is_dense = true;
-  if (mode == "ascii") {
-    for (std::size_t i = 0; i < npts; ++i)
-      for (std::size_t f = 0; f < fields.size(); ++f)
-        for (int c = 0; c < counts[f]; ++c) {
-          std::string tok;
-          in >> tok;
-          float v = std::strtof(tok.c_str(), nullptr);
-          if (c == 0) detail::setField(cloud.points[i], fields[f], v);
-        }
-  }
-  else if (mode == "binary") {
-    std::size_t rec = 0;
-    for (std::size_t f = 0; f < fields.size(); ++f) rec += static_cast<std::size_t>(sizes[f]) * counts[f];
-    std::vector<char> buf(rec);
-    for (std::size_t i = 0; i < npts; ++i) {
-      in.read(buf.data(), static_cast<std::streamsize>(rec));
-      std::size_t off = 0;
-      for (std::size_t f = 0; f < fields.size(); ++f) {
-        if (types[f] == 'F' && sizes[f] == 4) {
-          float v;
-          std::memcpy(&v, buf.data() + off, 4);
-          detail::setField(cloud.points[i], fields[f], v);
-        }
-        off += static_cast<std::size_t>(sizes[f]) * counts[f];
+  cloud.sensor_origin_[0] = h.viewpoint[0];
+  cloud.sensor_origin_[1] = h.viewpoint[1];
+  cloud.sensor_origin_[2] = h.viewpoint[2];
+  cloud.sensor_origin_[3] = 0.f;
+  // file field -> byte offset inside PointT (or -1: not part of this point type, skipped like fromPCLPointCloud2 does)
+  const auto want = detail::point_fields<PointT>::get();
+  std::vector<std::ptrdiff_t> dst(h.fields.size(), -1);
+  std::size_t matched = 0;
+  for (std::size_t f = 0; f < h.fields.size(); ++f)
+    for (const auto& w : want)
+      if (h.fields[f].name == w.name && h.fields[f].count >= 1) { dst[f] = static_cast<std::ptrdiff_t>(w.offset); ++matched; }
+  if (matched < want.size())
+    std::fprintf(stderr, "[pcl::PCDReader::read] Failed to find match for some fields of the point type in '%s'.\n", file.c_str());
+  auto store = [&](std::size_t i, std::size_t f, double v) {
+    const float fv = static_cast<float>(v);
+    std::memcpy(reinterpret_cast<unsigned char*>(&cloud.points[i]) + dst[f], &fv, 4);
+  };
+  if (h.data_type == 0) {  // io/src/pcd_io.cpp:443-576
+    std::size_t per_line = 0;
+    for (const auto& f : h.fields) per_line += static_cast<std::size_t>(std::max(f.count, 0));
+    std::string line;
+    std::size_t i = 0;
+    std::vector<std::string> tok;
+    while (i < npts && std::getline(in, line)) {
+      tok.clear();
+      std::istringstream ss(line);
+      for (std::string t; ss >> t;) tok.push_back(t);
+      if (tok.empty()) continue;
+      if (tok.size() != per_line) {  // :487-493: malformed line, the point keeps its defaults
+        std::fprintf(stderr, "[pcl::PCDReader::readBodyASCII] Possibly malformed PCD file: point number %zu has %zu elements, but should have %zu\n",
+                     i + 1, tok.size(), per_line);
+        ++i;
+        continue;
       }
+      std::size_t t = 0;
+      for (std::size_t f = 0; f < h.fields.size(); ++f) {
+        const int cnt = std::max(h.fields[f].count, 0);
+        if (h.fields[f].name != "_" && cnt > 0) {
+          for (int c = 0; c < cnt; ++c) {
+            const double v = std::strtod(tok[t + c].c_str(), nullptr);
+            if (!std::isfinite(v)) cloud.is_dense = false;
+            if (c == 0 && dst[f] >= 0) store(i, f, v);
+          }
+        }
+        t += static_cast<std::size_t>(cnt);
+      }
+      ++i;
     }
+    if (i != npts) {
+      std::fprintf(stderr, "[pcl::PCDReader::read] Number of points read (%zu) is different than expected (%zu)\n", i, npts);
+      return -1;
+    }
+    return 0;
   }
-  else {
-    std::fprintf(stderr, "[pcl::PCDReader::read] unsupported DATA mode '%s'\n", mode.c_str());
+  // binary bodies — io/src/pcd_io.cpp:580-668
+  in.seekg(0, std::ios::end);
+  const std::size_t file_size = static_cast<std::size_t>(in.tellg());
+  in.seekg(static_cast<std::streamoff>(h.data_offset));
+  if (h.data_type == 1) {
+    const std::size_t bytes = npts * h.point_step;
+    if (h.data_offset + bytes > file_size) {
+      std::fprintf(stderr, "[pcl::PCDReader::read] Corrupted PCD file. The file is smaller than expected!\n");
+      return -1;
+    }
+    std::vector<unsigned char> buf(bytes ? bytes : 1);
+    in.read(reinterpret_cast<char*>(buf.data()), static_cast<std::streamsize>(bytes));
+    for (std::size_t i = 0; i < npts; ++i)
+      for (std::size_t f = 0; f < h.fields.size(); ++f) {
+        const auto& ff = h.fields[f];
+        for (int c = 0; c < ff.count; ++c) {
+          bool fin;
+          const double v = detail::readValue(buf.data() + i * h.point_step + ff.offset + static_cast<std::size_t>(c) * ff.size, ff.type, ff.size, &fin);
+          if (!fin) cloud.is_dense = false;
+          if (c == 0 && dst[f] >= 0) store(i, f, v);
+        }
+      }
+    return 0;
+  }
+  // binary_compressed: u32 compressed size, u32 uncompressed size, LZF stream of the fields as planes (all x, all y, …),
+  // "_" padding fields not stored (:587-631)
+  if (h.data_offset + 8 > file_size) { std::fprintf(stderr, "[pcl::PCDReader::read] Corrupted PCD file.\n"); return -1; }
+  std::uint32_t csize = 0, usize = 0;
+  in.read(reinterpret_cast<char*>(&csize), 4);
+  in.read(reinterpret_cast<char*>(&usize), 4);
+  if (h.data_offset + 8 + csize > file_size) {
+    std::fprintf(stderr, "[pcl::PCDReader::read] Corrupted PCD file. The file is smaller than expected!\n");
     return -1;
   }
-  for (const auto& p : cloud.points)
-    if (!std::isfinite(p.data[0] + p.data[1] + p.data[2])) { cloud.is_dense = false; break; }
+  std::size_t plane_bytes = 0;
+  for (const auto& f : h.fields)
+    if (f.name != "_") plane_bytes += static_cast<std::size_t>(f.size) * static_cast<std::size_t>(std::max(f.count, 0));
+  if (static_cast<std::size_t>(usize) != plane_bytes * npts)
+    std::fprintf(stderr, "[pcl::PCDReader::read] The estimated cloud.data size (%zu) is different than the saved uncompressed value (%u)! Data corruption?\n",
+                 plane_bytes * npts, usize);
+  if (usize == 0) return 0;
+  std::vector<unsigned char> cbuf(csize ? csize : 1), buf(usize);
+  in.read(reinterpret_cast<char*>(cbuf.data()), static_cast<std::streamsize>(csize));
+  const std::size_t got = detail::lzfDecompress(cbuf.data(), csize, buf.data(), usize);
+  if (got != usize) {
+    std::fprintf(stderr, "[pcl::PCDReader::read] Size of decompressed lzf data (%zu) does not match value stored in PCD header (%u).\n", got, usize);
+    return -1;
+  }
+  if (plane_bytes * npts > usize) return -1;
+  std::size_t plane = 0;
+  for (std::size_t f = 0; f < h.fields.size(); ++f) {
+    const auto& ff = h.fields[f];
+    if (ff.name == "_" || ff.count < 1) continue;
+    const std::size_t fs = static_cast<std::size_t>(ff.size) * static_cast<std::size_t>(ff.count);
+    for (std::size_t i = 0; i < npts; ++i)
+      for (int c = 0; c < ff.count; ++c) {
+        bool fin;
+        const double v = detail::readValue(buf.data() + plane + i * fs + static_cast<std::size_t>(c) * ff.size, ff.type, ff.size, &fin);
+        if (!fin) cloud.is_dense = false;
+        if (c == 0 && dst[f] >= 0) store(i, f, v);
+      }
+    plane += fs * npts;
+  }
   return 0;
 }
 
-inline int savePCDFileBinary(const std::string& file, const pcl::PointCloud<PointXYZ>& cloud)
+// PCDWriter::writeASCII — io/include/pcl/io/impl/pcd_io.hpp:430-560 (precision 8, NaN written as "nan")
+template <typename PointT>
+int savePCDFileASCII(const std::string& file, const pcl::PointCloud<PointT>& cloud, int precision = 8)
 {
+  if (cloud.empty()) std::fprintf(stderr, "[pcl::PCDWriter::writeASCII] Input point cloud has no data!\n");
   std::ofstream out(file, std::ios::binary);
-  if (!out) return -1;
-  out << "# .PCD v0.7 - Point Cloud Data file format\nVERSION 0.7\nFIELDS x y z\nSIZE 4 4 4\nTYPE F F F\nCOUNT 1 1 1\nWIDTH "
-      << cloud.size() << "\nHEIGHT 1\nVIEWPOINT 0 0 0 1 0 0 0\nPOINTS " << cloud.size() << "\nDATA binary\n";
-  for (const auto& p : cloud.points) out.write(reinterpret_cast<const char*>(&p.x), 12);
+  if (!out) { std::fprintf(stderr, "[pcl::PCDWriter::writeASCII] Could not open file for writing!\n"); return -1; }
+  const auto fields = detail::point_fields<PointT>::get();
+  std::size_t w, h;
+  float vp[7];
+  detail::writerGeometry(cloud, w, h, vp);
+  out << detail::headerText(fields, w, h, cloud.size(), vp, "ascii");
+  out.precision(precision);
+  for (const auto& p : cloud.points) {
+    for (std::size_t f = 0; f < fields.size(); ++f) {
+      float v;
+      std::memcpy(&v, reinterpret_cast<const unsigned char*>(&p) + fields[f].offset, 4);
+      if (f) out << ' ';
+      if (std::isnan(v)) out << "nan";
+      else out << v;
+    }
+    out << '\n';
+  }
   return out ? 0 : -1;
 }
+
+// PCDWriter::writeBinary — io/include/pcl/io/impl/pcd_io.hpp:132-230: records of the point type's fields, no padding
+template <typename PointT>
+int savePCDFileBinary(const std::string& file, const pcl::PointCloud<PointT>& cloud)
+{
+  if (cloud.empty()) std::fprintf(stderr, "[pcl::PCDWriter::writeBinary] Input point cloud has no data!\n");
+  std::ofstream out(file, std::ios::binary);
+  if (!out) { std::fprintf(stderr, "[pcl::PCDWriter::writeBinary] Could not open file for writing!\n"); return -1; }
+  const auto fields = detail::point_fields<PointT>::get();
+  std::size_t w, h;
+  float vp[7];
+  detail::writerGeometry(cloud, w, h, vp);
+  out << detail::headerText(fields, w, h, cloud.size(), vp, "binary");
+  std::vector<unsigned char> buf(cloud.size() * fields.size() * 4 + 1);
+  std::size_t o = 0;
+  for (const auto& p : cloud.points)
+    for (const auto& f : fields) {
+      std::memcpy(buf.data() + o, reinterpret_cast<const unsigned char*>(&p) + f.offset, 4);
+      o += 4;
+    }
+  out.write(reinterpret_cast<const char*>(buf.data()), static_cast<std::streamsize>(o));
+  return out ? 0 : -1;
+}
+
+// PCDWriter::writeBinaryCompressed — io/include/pcl/io/impl/pcd_io.hpp:232-428: planes per field, LZF, two u32 sizes
+template <typename PointT>
+int savePCDFileBinaryCompressed(const std::string& file, const pcl::PointCloud<PointT>& cloud)
+{
+  if (cloud.empty()) std::fprintf(stderr, "[pcl::PCDWriter::writeBinaryCompressed] Input point cloud has no data!\n");
+  const auto fields = detail::point_fields<PointT>::get();
+  const std::size_t n = cloud.size(), data_size = n * fields.size() * 4;
+  if (data_size * 3 / 2 > std::numeric_limits<std::uint32_t>::max()) {  // :296-300
+    std::fprintf(stderr, "[pcl::PCDWriter::writeBinaryCompressed] The input data exceeds the maximum size for compressed version 0.7 pcds.\n");
+    return -2;
+  }
+  std::ofstream out(file, std::ios::binary);
+  if (!out) { std::fprintf(stderr, "[pcl::PCDWriter::writeBinaryCompressed] Could not open file for writing!\n"); return -1; }
+  std::size_t w, h;
+  float vp[7];
+  detail::writerGeometry(cloud, w, h, vp);
+  out << detail::headerText(fields, w, h, n, vp, "binary_compressed");
+  std::vector<unsigned char> planes(data_size ? data_size : 1);
+  for (std::size_t f = 0; f < fields.size(); ++f)
+    for (std::size_t i = 0; i < n; ++i)
+      std::memcpy(planes.data() + (f * n + i) * 4, reinterpret_cast<const unsigned char*>(&cloud.points[i]) + fields[f].offset, 4);
+  std::vector<unsigned char> comp(data_size + data_size / 16 + 64);
+  std::uint32_t csize = 0;
+  const std::uint32_t usize = static_cast<std::uint32_t>(data_size);
+  if (data_size) {
+    csize = static_cast<std::uint32_t>(detail::lzfCompress(planes.data(), data_size, comp.data(), comp.size()));
+    if (csize == 0) { std::fprintf(stderr, "[pcl::PCDWriter::writeBinaryCompressed] Error during compression!\n"); return -1; }
+  }
+  out.write(reinterpret_cast<const char*>(&csize), 4);
+  out.write(reinterpret_cast<const char*>(&usize), 4);
+  out.write(reinterpret_cast<const char*>(comp.data()), csize);
+  return out ? 0 : -1;
+}
+
+// io/include/pcl/io/pcd_io.h:708-713
+template <typename PointT>
+int savePCDFile(const std::string& file, const pcl::PointCloud<PointT>& cloud, bool binary_mode = false)
+{
+  return binary_mode ? savePCDFileBinary(file, cloud) : savePCDFileASCII(file, cloud);
+}
 }  // namespace io
+
+// io/include/pcl/io/pcd_io.h:71-600 — the class forms of the same calls
+class PCDReader {
+public:
+  template <typename PointT> int read(const std::string& file, pcl::PointCloud<PointT>& cloud, const int = 0) { return io::loadPCDFile(file, cloud); }
+};
+class PCDWriter {
+public:
+  template <typename PointT> int write(const std::string& file, const pcl::PointCloud<PointT>& cloud, bool binary = false) { return io::savePCDFile(file, cloud, binary); }
+  template <typename PointT> int writeASCII(const std::string& file, const pcl::PointCloud<PointT>& cloud, int precision = 8) { return io::savePCDFileASCII(file, cloud, precision); }
+  template <typename PointT> int writeBinary(const std::string& file, const pcl::PointCloud<PointT>& cloud) { return io::savePCDFileBinary(file, cloud); }
+  template <typename PointT> int writeBinaryCompressed(const std::string& file, const pcl::PointCloud<PointT>& cloud) { return io::savePCDFileBinaryCompressed(file, cloud); }
+};
 }  // namespace pcl

@@ -2,6 +2,7 @@
 // common/include/pcl/impl/point_types.hpp:205-227 (PointXYZ, 16 B), :769-794 (Normal, 32 B),
 // :824-855 (PointNormal, 48 B); all 16-byte aligned.
 #pragma once
+#include <cstddef>
 #include <cmath>
 namespace pcl {
 struct alignas(16) PointXYZ {
@@ -48,6 +49,9 @@ static_assert(sizeof(PointXYZ) == 16 && sizeof(Normal) == 32 && sizeof(PointNorm
 template <typename T> struct has_normal { static constexpr bool value = false; };
 template <> struct has_normal<PointNormal> { static constexpr bool value = true; };
 template <> struct has_normal<Normal> { static constexpr bool value = true; };
+// byte offset of normal_x inside a record (pcl::Normal: 0, pcl::PointNormal: 16 — impl/point_types.hpp:769-855)
+template <typename T> struct normal_offset { static constexpr std::size_t value = 16; };
+template <> struct normal_offset<Normal> { static constexpr std::size_t value = 0; };
 
 template <typename PointT> inline bool isXYZFinite(const PointT& p)
 {

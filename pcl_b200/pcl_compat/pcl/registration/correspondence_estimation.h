@@ -12,10 +12,13 @@
 namespace pcl {
 namespace registration {
 
+// correspondence_estimation.h:59-384 — state and setters every estimator shares; the two determine* methods are the
+// virtual interface Registration calls (and what a drop-in subclass overrides).
 template <typename PointSource, typename PointTarget, typename Scalar = float>
-class CorrespondenceEstimation : public PCLBase<PointSource> {
+class CorrespondenceEstimationBase : public PCLBase<PointSource> {
 public:
-  using Ptr = std::shared_ptr<CorrespondenceEstimation>;
+  using Ptr = std::shared_ptr<CorrespondenceEstimationBase>;
+  using ConstPtr = std::shared_ptr<const CorrespondenceEstimationBase>;
   using KdTree = pcl::search::KdTree<PointTarget>;
   using KdTreePtr = typename KdTree::Ptr;
   using KdTreeReciprocal = pcl::search::KdTree<PointSource>;
@@ -23,7 +26,7 @@ public:
   using PointCloudSourceConstPtr = typename pcl::PointCloud<PointSource>::ConstPtr;
   using PointCloudTargetConstPtr = typename pcl::PointCloud<PointTarget>::ConstPtr;
 
-  CorrespondenceEstimation() : tree_(new KdTree), tree_reciprocal_(new KdTreeReciprocal) {}
+  CorrespondenceEstimationBase() : tree_(new KdTree), tree_reciprocal_(new KdTreeReciprocal) {}
 
   void setInputSource(const PointCloudSourceConstPtr& cloud)
   {
@@ -56,23 +59,18 @@ public:
     force_no_recompute_reciprocal_ = force_no_recompute;
     source_cloud_updated_ = true;
   }
+  KdTreeReciprocalPtr getSearchMethodSource() const { return tree_reciprocal_; }
   void setNumberOfThreads(unsigned int) {}  // one device launch replaces the OpenMP loop (:163-165)
-  Ptr clone() const { return Ptr(new CorrespondenceEstimation(*this)); }  // correspondence_estimation.h:493-498
-  bool requiresSourceNormals() const { return false; }
-  bool requiresTargetNormals() const { return false; }
-
-  // impl/correspondence_estimation.hpp:145-218
-  void determineCorrespondences(pcl::Correspondences& correspondences,
-                                double max_distance = std::numeric_limits<double>::max())
-  {
-    run(correspondences, max_distance, false);
-  }
-  // impl/correspondence_estimation.hpp:220-311
-  void determineReciprocalCorrespondences(pcl::Correspondences& correspondences,
-                                          double max_distance = std::numeric_limits<double>::max())
-  {
-    run(correspondences, max_distance, true);
-  }
+  virtual Ptr clone() const = 0;            // correspondence_estimation.h:315
+  virtual bool requiresSourceNormals() const { return false; }
+  virtual bool requiresTargetNormals() const { return false; }
+  virtual void determineCorrespondences(pcl::Correspondences& correspondences,
+                                        double max_distance = std::numeric_limits<double>::max()) = 0;
+  virtual void determineReciprocalCorrespondences(pcl::Correspondences& correspondences,
+                                                  double max_distance = std::numeric_limits<double>::max()) = 0;
+  // which estimator IterativeClosestPoint's fused device loop runs for this object (PCLB200_CORR_*) and its k
+  virtual int abiKind() const { return PCLB200_CORR_NEAREST; }
+  virtual int abiK() const { return 1; }
 
 protected:
   bool initCompute()
@@ -95,17 +93,47 @@ protected:
     }
     return true;
   }
+  KdTreePtr tree_;
+  KdTreeReciprocalPtr tree_reciprocal_;
+  PointCloudTargetConstPtr target_;
+  IndicesPtr target_indices_;
+  bool target_cloud_updated_ = true, source_cloud_updated_ = true;
+  bool force_no_recompute_ = false, force_no_recompute_reciprocal_ = false;
+};
+
+// correspondence_estimation.h:407-504 — nearest neighbour (+ reciprocal) estimator
+template <typename PointSource, typename PointTarget, typename Scalar = float>
+class CorrespondenceEstimation : public CorrespondenceEstimationBase<PointSource, PointTarget, Scalar> {
+public:
+  using Base = CorrespondenceEstimationBase<PointSource, PointTarget, Scalar>;
+  using Ptr = std::shared_ptr<CorrespondenceEstimation>;
+  using ConstPtr = std::shared_ptr<const CorrespondenceEstimation>;
+  typename Base::Ptr clone() const override { return typename Base::Ptr(new CorrespondenceEstimation(*this)); }  // :493-498
+  // impl/correspondence_estimation.hpp:145-218
+  void determineCorrespondences(pcl::Correspondences& correspondences,
+                                double max_distance = std::numeric_limits<double>::max()) override
+  {
+    run(correspondences, max_distance, false);
+  }
+  // impl/correspondence_estimation.hpp:220-311
+  void determineReciprocalCorrespondences(pcl::Correspondences& correspondences,
+                                          double max_distance = std::numeric_limits<double>::max()) override
+  {
+    run(correspondences, max_distance, true);
+  }
+
+protected:
   void run(pcl::Correspondences& out, double max_distance, bool reciprocal)
   {
     out.clear();
-    if (!initCompute()) return;
-    if (reciprocal && !initComputeReciprocal()) return;
-    if (!tree_->deviceIndex() || (reciprocal && !tree_reciprocal_->deviceIndex())) return;
+    if (!this->initCompute()) return;
+    if (reciprocal && !this->initComputeReciprocal()) return;
+    if (!this->tree_->deviceIndex() || (reciprocal && !this->tree_reciprocal_->deviceIndex())) return;
     out.resize(this->indices_->size());
     std::size_t n_out = 0;
     // max_distance = DBL_MAX squares to +inf (no gate), exactly like `max_distance * max_distance` at :161
-    int rc = pclb200_correspondences(b200::Context::get(), tree_->deviceIndex(),
-                                     reciprocal ? tree_reciprocal_->deviceIndex() : nullptr, this->input_->points.data(),
+    int rc = pclb200_correspondences(b200::Context::get(), this->tree_->deviceIndex(),
+                                     reciprocal ? this->tree_reciprocal_->deviceIndex() : nullptr, this->input_->points.data(),
                                      this->input_->size(), sizeof(PointSource), this->abiIndices(), this->abiIndexCount(),
                                      this->input_->is_dense ? 1 : 0, max_distance,
                                      reinterpret_cast<pclb200_corr*>(out.data()), &n_out);
@@ -116,12 +144,6 @@ protected:
     out.resize(n_out);
   }
 
-  KdTreePtr tree_;
-  KdTreeReciprocalPtr tree_reciprocal_;
-  PointCloudTargetConstPtr target_;
-  IndicesPtr target_indices_;
-  bool target_cloud_updated_ = true, source_cloud_updated_ = true;
-  bool force_no_recompute_ = false, force_no_recompute_reciprocal_ = false;
 };
 
 }  // namespace registration

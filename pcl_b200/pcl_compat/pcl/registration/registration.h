@@ -66,8 +66,8 @@ public:
   using PointCloudTargetConstPtr = typename PointCloudTarget::ConstPtr;
   using TransformationEstimation = pcl::registration::TransformationEstimation<PointSource, PointTarget, Scalar>;
   using TransformationEstimationPtr = typename TransformationEstimation::Ptr;
-  using CorrespondenceEstimation = pcl::registration::CorrespondenceEstimation<PointSource, PointTarget, Scalar>;
-  using CorrespondenceEstimationPtr = typename CorrespondenceEstimation::Ptr;
+  using CorrespondenceEstimation = pcl::registration::CorrespondenceEstimationBase<PointSource, PointTarget, Scalar>;
+  using CorrespondenceEstimationPtr = typename CorrespondenceEstimation::Ptr;  // registration.h:99-101
 
   Registration()
   : tree_(new KdTree), tree_reciprocal_(new KdTreeReciprocal), final_transformation_(Matrix4::Identity()),
@@ -302,6 +302,10 @@ protected:
     P.transformation_rotation_epsilon = this->transformation_rotation_epsilon_;
     P.euclidean_fitness_epsilon = this->euclidean_fitness_epsilon_;
     P.mse_threshold_absolute = convergence_criteria_->mse_threshold_absolute_;
+    // setCorrespondenceEstimation(NormalShooting / BackProjection): the fused loop runs that estimator, on the normal
+    // fields of the two clouds (what icp.hpp:166-180 hands over as blobs)
+    P.correspondence_kind = this->correspondence_estimation_->abiKind();
+    P.correspondence_k = this->correspondence_estimation_->abiK();
     this->nr_iterations_ = 0;
     this->converged_ = false;
     this->final_transformation_ = guess;

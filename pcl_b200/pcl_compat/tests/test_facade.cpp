@@ -18,6 +18,9 @@
 #include <pcl/point_cloud.h>
 #include <pcl/point_types.h>
 #include <pcl/registration/correspondence_estimation.h>
+#include <pcl/registration/correspondence_estimation_backprojection.h>
+#include <pcl/registration/correspondence_estimation_normal_shooting.h>
+#include <pcl/registration/correspondence_rejection_surface_normal.h>
 #include <pcl/registration/correspondence_rejection_distance.h>
 #include <pcl/registration/correspondence_rejection_median_distance.h>
 #include <pcl/registration/correspondence_rejection_one_to_one.h>
@@ -439,6 +442,158 @@ int main(int argc, char** argv)
       EXPECT_NEAR(p.normal_z, -g[2], 1e-4);
       EXPECT_NEAR(p.curvature, g[4], 1e-4);
     }
+  }
+
+
+  {  // radius-search normals: a radius that holds the whole cloud is the k = all-points case above
+    NormalEstimation<PointXYZ, Normal> n;
+    PointCloud<Normal> normals;
+    n.setInputCloud(cloud_source.makeShared());
+    n.setRadiusSearch(10.0);
+    n.compute(normals);
+    EXPECT_EQ(normals.size(), cloud_source.size());
+    EXPECT_TRUE(normals.is_dense);
+    const auto& g = G["normal_bun0"];
+    for (const auto& p : normals.points) {
+      EXPECT_NEAR(p.normal_x, -g[0], 1e-4);
+      EXPECT_NEAR(p.normal_y, -g[1], 1e-4);
+      EXPECT_NEAR(p.normal_z, -g[2], 1e-4);
+      EXPECT_NEAR(p.curvature, g[4], 1e-4);
+    }
+    n.setRadiusSearch(1e-4);  // nobody has 3 neighbours: NaN normals, is_dense = false (normal_3d.hpp:62-69)
+    n.compute(normals);
+    EXPECT_EQ(normals.size(), cloud_source.size());
+    EXPECT_TRUE(!normals.is_dense);
+    EXPECT_TRUE(std::isnan(normals[0].normal_x) && std::isnan(normals[0].curvature));
+    n.setKSearch(5);  // both set: error, empty output (feature.hpp:135-141)
+    n.compute(normals);
+    EXPECT_EQ(normals.size(), 0u);
+  }
+
+  {  // TYPED_TEST (CorrespondenceEstimationTestSuite, CorrespondenceEstimationNormalShooting) —
+     // test/registration/test_correspondence_estimation.cpp:95-137
+    auto cloud1 = std::make_shared<PointCloud<PointXYZ>>();
+    auto cloud2 = std::make_shared<PointCloud<PointXYZ>>();
+    for (std::size_t i = 0; i < 50; ++i)
+      for (std::size_t j = 0; j < 25; ++j) {
+        cloud1->push_back(PointXYZ(i * 0.2f, 0.f, j * 0.2f));
+        cloud2->push_back(PointXYZ(i * 0.2f, 2.f, j * 0.2f));
+      }
+    NormalEstimation<PointXYZ, Normal> ne;
+    ne.setInputCloud(cloud1);
+    ne.setSearchMethod(std::make_shared<search::KdTree<PointXYZ>>());
+    auto cloud1_normals = std::make_shared<PointCloud<Normal>>();
+    ne.setKSearch(5);
+    ne.compute(*cloud1_normals);
+    auto corr = std::make_shared<Correspondences>();
+    registration::CorrespondenceEstimationNormalShooting<PointXYZ, PointXYZ, Normal> ce;
+    ce.setInputSource(cloud1);
+    ce.setKSearch(10);
+    ce.setSourceNormals(cloud1_normals);
+    ce.setInputTarget(cloud2);
+    ce.determineCorrespondences(*corr);
+    EXPECT_EQ(corr->size(), cloud1->size());
+    for (std::size_t i = 0; i < corr->size(); i++) EXPECT_EQ((*corr)[i].index_query, (*corr)[i].index_match);
+    registration::CorrespondenceEstimationBackProjection<PointXYZ, PointXYZ, Normal> cb;
+    cb.setInputSource(cloud1);
+    cb.setSourceNormals(cloud1_normals);
+    cb.setTargetNormals(cloud1_normals);
+    cb.setInputTarget(cloud2);
+    corr->clear();
+    cb.determineCorrespondences(*corr);
+    EXPECT_EQ(corr->size(), cloud1->size());
+    for (std::size_t i = 0; i < corr->size(); i++) EXPECT_EQ((*corr)[i].index_query, (*corr)[i].index_match);
+    auto cl = ce.clone();
+    EXPECT_TRUE(cl->requiresSourceNormals() && !cl->requiresTargetNormals() && cb.requiresTargetNormals());
+  }
+
+  {  // TEST (PCL, CorrespondenceRejectorSurfaceNormal) — test_registration_api.cpp:266-317, and
+     // TEST (PCL, IterativeClosestPoint_PointToPlane)'s estimator / rejector combination — test_registration.cpp:511-560
+    auto src = std::make_shared<PointCloud<PointNormal>>();
+    auto tgt = std::make_shared<PointCloud<PointNormal>>();
+    for (const auto& p : cloud_source.points) src->push_back(PointNormal(p.x, p.y, p.z));
+    for (const auto& p : cloud_target.points) tgt->push_back(PointNormal(p.x, p.y, p.z));
+    for (auto* c : {&src, &tgt}) {
+      NormalEstimation<PointNormal, PointNormal> norm_est;
+      norm_est.setSearchMethod(std::make_shared<search::KdTree<PointNormal>>());
+      norm_est.setKSearch(10);
+      norm_est.setInputCloud(*c);
+      PointCloud<PointNormal> nrm;
+      norm_est.compute(nrm);
+      EXPECT_EQ(nrm.size(), (*c)->size());
+      for (std::size_t i = 0; i < nrm.size(); ++i) {
+        (**c)[i].normal_x = nrm[i].normal_x;
+        (**c)[i].normal_y = nrm[i].normal_y;
+        (**c)[i].normal_z = nrm[i].normal_z;
+        (**c)[i].curvature = nrm[i].curvature;
+      }
+    }
+    auto correspondences = std::make_shared<Correspondences>();
+    registration::CorrespondenceEstimation<PointNormal, PointNormal> corr_est;
+    corr_est.setInputSource(src);
+    corr_est.setInputTarget(tgt);
+    corr_est.determineCorrespondences(*correspondences);
+    EXPECT_EQ(correspondences->size(), 397u);
+    registration::CorrespondenceRejectorSurfaceNormal rej;
+    rej.initializeDataContainer<PointNormal, PointNormal>();
+    rej.setInputSource<PointNormal>(src);
+    rej.setInputTarget<PointNormal>(tgt);
+    rej.setInputNormals<PointNormal, PointNormal>(src);
+    rej.setTargetNormals<PointNormal, PointNormal>(tgt);
+    rej.setInputCorrespondences(correspondences);
+    rej.setThreshold(0.5);
+    Correspondences kept;
+    rej.getCorrespondences(kept);
+    EXPECT_TRUE(kept.size() > 0 && kept.size() < correspondences->size());
+    std::size_t expect = 0;  // the same float dot product on the host
+    for (const auto& c : *correspondences) {
+      const auto& a = (*src)[c.index_query];
+      const auto& b = (*tgt)[c.index_match];
+      const float dot = (a.normal_x * b.normal_x) + (a.normal_y * b.normal_y) + (a.normal_z * b.normal_z);
+      if (static_cast<double>(dot) > 0.5) {
+        if (expect < kept.size()) {
+          EXPECT_EQ(kept[expect].index_query, c.index_query);
+          EXPECT_EQ(kept[expect].index_match, c.index_match);
+        }
+        ++expect;
+      }
+    }
+    EXPECT_EQ(kept.size(), expect);
+
+    IterativeClosestPoint<PointNormal, PointNormal> reg;
+    reg.setTransformationEstimation(std::make_shared<registration::TransformationEstimationPointToPlaneLLS<PointNormal, PointNormal>>());
+    reg.setInputSource(src);
+    reg.setInputTarget(tgt);
+    reg.setMaximumIterations(50);
+    reg.setTransformationEpsilon(1e-8);
+    auto ce = std::make_shared<registration::CorrespondenceEstimationNormalShooting<PointNormal, PointNormal, PointNormal>>();
+    reg.setCorrespondenceEstimation(ce);
+    auto rej2 = std::make_shared<registration::CorrespondenceRejectorSurfaceNormal>();
+    rej2->setThreshold(0);
+    reg.addCorrespondenceRejector(rej2);
+    PointCloud<PointNormal> output;
+    reg.align(output);
+    EXPECT_EQ(output.size(), cloud_source.size());
+    EXPECT_TRUE(reg.hasConverged());
+    EXPECT_LT(reg.getFitnessScore(), 0.005);
+    for (int iter = 0; iter < 4; iter++) {  // "Check again, for all possible caching schemes" (:543-559)
+      const bool force_cache = static_cast<bool>(iter / 2);
+      const bool force_cache_reciprocal = static_cast<bool>(iter % 2);
+      auto tree = std::make_shared<search::KdTree<PointNormal>>();
+      if (force_cache) tree->setInputCloud(tgt);
+      reg.setSearchMethodTarget(tree, force_cache);
+      auto tree_recip = std::make_shared<search::KdTree<PointNormal>>();
+      if (force_cache_reciprocal) tree_recip->setInputCloud(src);
+      reg.setSearchMethodSource(tree_recip, force_cache_reciprocal);
+      reg.align(output);
+      EXPECT_EQ(output.size(), cloud_source.size());
+      EXPECT_LT(reg.getFitnessScore(), 0.005);
+    }
+    auto cbp = std::make_shared<registration::CorrespondenceEstimationBackProjection<PointNormal, PointNormal, PointNormal>>();
+    reg.setCorrespondenceEstimation(cbp);
+    reg.align(output);
+    EXPECT_TRUE(reg.hasConverged());
+    EXPECT_LT(reg.getFitnessScore(), 0.005);
   }
 
   std::printf("%s: %d checks, %d failures\n", g_fail ? "FAILED" : "PASSED", g_checks, g_fail);

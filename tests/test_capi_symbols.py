@@ -58,3 +58,17 @@ def test_product_never_imports_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".h", ".hpp", ".cpp")):
                 txt = open(os.path.join(dirpath, f), errors="ignore").read()
                 assert "import oracle" not in txt and "from oracle" not in txt and "pcl_oracle" not in txt, f
+
+
+def test_default_params_layout(built):
+    """pclb200_icp_default_params is pure host code: its values, read back through the ctypes mirror of the struct,
+    prove that the Python layout of pclb200_icp_params matches the header (field order, padding, trailing fields)."""
+    import numpy as np
+    import pcl_b200 as P
+    p = P.default_params()
+    assert p.max_iterations == 10 and p.estimator == P.EST_SVD and p.is_dense == 1
+    assert p.enforce_same_direction_normals == 1 and p.correspondence_kind == P.CORR_NEAREST
+    assert p.max_correspondence_distance == np.sqrt(np.finfo(np.float64).max)
+    assert p.euclidean_fitness_epsilon == -np.finfo(np.float64).max
+    assert p.mse_threshold_absolute == 1e-12
+    assert p.correspondence_k == 10 and p.reserved1 == 0
