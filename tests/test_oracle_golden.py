@@ -210,3 +210,81 @@ def test_outlier_filters_bun0(golden, orc):
     kn = idx.statistical_outlier_removal(cloud, 50, 1.0, negative=True)
     assert kn.size == 397 - 352
     assert np.allclose(cloud[kn[-1], :3], [-0.07793, 0.17516, -0.0444], atol=1e-4)
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# normal-based correspondence estimators, surface-normal rejector, radius-search normals
+# ---------------------------------------------------------------------------------------------------------------------
+def _point_normal_rows(xyz, normals=None):
+    out = np.zeros((xyz.shape[0], 12), np.float32)
+    out[:, :3] = xyz[:, :3]
+    out[:, 3] = 1
+    if normals is not None:
+        out[:, 4:4 + normals.shape[1]] = normals
+    return out
+
+
+def test_normal_shooting_reference_planes(orc):
+    """test/registration/test_correspondence_estimation.cpp:95-137: two parallel planes, normals from k = 5,
+    CorrespondenceEstimationNormalShooting with k = 10 must pair every point with its counterpart."""
+    ii, jj = np.meshgrid(np.arange(50), np.arange(25), indexing="ij")
+    x = ii.ravel().astype(np.float32) * np.float32(0.2)
+    z = jj.ravel().astype(np.float32) * np.float32(0.2)
+    c1 = _point_normal_rows(np.stack([x, np.zeros_like(x), z], 1))
+    c2 = _point_normal_rows(np.stack([x, np.full_like(x, 2), z], 1))
+    nrm, dense = orc.Index(c1).normals_knn(c1, 5)
+    assert dense and np.allclose(np.abs(nrm[:, :3]), [0, 1, 0], atol=1e-6)  # "All normals are perpendicular to the plane"
+    c1[:, 4:8] = nrm
+    c2[:, 4:8] = nrm
+    it = orc.Index(c2)
+    for kind in (orc.CORR_NORMAL_SHOOTING, orc.CORR_BACK_PROJECTION):
+        c = it.correspondences_normals(kind, c1, c2, k=10)
+        assert len(c) == 1250 and np.array_equal(c["index_query"], c["index_match"])
+        assert np.all(c["distance"] == np.float32(4.0))  # the stored distance is the squared POINT distance (:126)
+    # the gate compares the squared line distance with max_distance itself (:121): 0 passes any gate, a tilted normal fails
+    c1[:, 4:7] = np.float32([0.6, 0.8, 0.0])
+    assert len(it.correspondences_normals(orc.CORR_NORMAL_SHOOTING, c1, c2, k=10, max_distance=1e-3)) == 0
+
+
+def test_surface_normal_rejector_and_icp_with_normal_shooting(golden, orc):
+    """test_registration_api.cpp:266-317 (rejector) and test_registration.cpp:511-560 (ICP whose correspondences come from
+    normal shooting, filtered by the surface-normal rejector with threshold 0; accepted when the fitness score < 0.005)."""
+    b0, b4 = _point_normal_rows(golden["bun0"]), _point_normal_rows(golden["bun4"])
+    i0, i4 = orc.Index(b0), orc.Index(b4)
+    b0[:, 4:8] = i0.normals_knn(b0, 10)[0]
+    b4[:, 4:8] = i4.normals_knn(b4, 10)[0]
+    corr = i4.correspondences(b0)
+    kept = orc.reject_surface_normal(corr, b0[:, 4:], b4[:, 4:], 0.5)
+    dots = (b0[corr["index_query"], 4:7] * b4[corr["index_match"], 4:7]).sum(1)
+    assert 0 < len(kept) < len(corr) and abs(len(kept) - int((dots > 0.5).sum())) <= 1  # fp32 vs numpy summation order
+    assert np.array_equal(orc.reject_surface_normal(corr, b0[:, 4:], b4[:, 4:], -2.0), corr)
+    assert len(orc.reject_surface_normal(corr, b0[:, 4:], b4[:, 4:], 1.5)) == 0
+    for kind in (orc.CORR_NORMAL_SHOOTING, orc.CORR_BACK_PROJECTION):
+        for dbl in (False, True):
+            r = orc.icp_align_rejectors(b0, b4, [(orc.REJ_SURFACE_NORMAL, 0.0, 0)], estimator=1, source_has_normals=True,
+                                        scalar_is_double=dbl, correspondence_kind=kind, correspondence_k=10,
+                                        max_iterations=50, transformation_epsilon=1e-8)
+            assert r["converged"] and r["iterations"] < 50
+            assert i4.fitness_score(b0, r["final"], scalar_is_double=dbl) < 0.005
+
+
+def test_radius_normals(golden, orc):
+    """A radius that holds the whole cloud is NormalEstimation with k = all points, whose result the reference pins
+    (test/features/test_normal_estimation.cpp:128-163); a radius with < 3 neighbours gives NaN and is_dense = false."""
+    b0 = orc.to_xyz1(golden["bun0"])
+    idx = orc.Index(b0)
+    n, dense = idx.normals_radius(b0, 10.0)
+    g = golden["normal_bun0"]
+    assert dense
+    assert np.allclose(n[:, :3], -g[:3], atol=1e-4) and np.allclose(n[:, 3], g[4], atol=1e-4)
+    nk, _ = idx.normals_knn(b0, 397)
+    assert np.array_equal(n, nk)  # same neighbour lists in the same (d2, index) order -> identical arithmetic
+    n, dense = idx.normals_radius(b0, 1e-4)
+    assert not dense and np.isnan(n).all()
+    # radius lists and radius normals agree: recompute one normal from its radius list
+    offs, ids, _ = idx.radius(b0[:5], 0.02)
+    nr, _ = idx.normals_radius(b0[:5], 0.02)
+    for i in range(5):
+        lst = ids[offs[i]:offs[i + 1]]
+        pn, ok = orc.point_normal(b0, lst)
+        assert ok and np.allclose(np.abs(pn), np.abs(nr[i]), atol=0)

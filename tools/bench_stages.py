@@ -5,7 +5,11 @@ writes one JSON object per stage to stdout.  Inputs are torch CUDA tensors (resi
 returns host arrays (radius), in which case the D2H of the result is part of the time and said so."""
 import argparse
 import json
+import os
+import sys
 import time
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 
 import numpy as np
 import torch
