@@ -327,6 +327,18 @@ PCLB200_API int pclb200_normals_radius(pclb200_ctx* ctx, const pclb200_index* id
                                        int is_dense, double radius, const float viewpoint[3], float* out,
                                        int* is_dense_out);
 
+/* ---- Euclidean clustering: replaces the flood fill of pcl::extractEuclideanClusters /
+ * EuclideanClusterExtraction<PointT>::extract (segmentation/include/pcl/segmentation/impl/extract_clusters.hpp:45-257),
+ * one radiusSearch per point on one thread, by the connected components of the graph "d2 < float(tolerance)^2" over
+ * the points of idx (the cloud, or cloud + indices, the tree would be built from) — the same sets, because the fp32
+ * squared distance is symmetric and the radius test is the searcher's own.
+ * out_labels: one entry per point of the cloud idx was built from (n_labels must equal that count; host or device):
+ * the SMALLEST ORIGINAL INDEX of the point's component, -1 for points idx does not hold (non-finite / outside the subset;
+ * the reference never clusters those either, since the tree cannot return them).  Grouping by label, the size window
+ * [min, max] and the final ordering by size (extract_clusters.hpp:249) stay with the caller: they touch 4 bytes/point. */
+PCLB200_API int pclb200_cluster_labels(pclb200_ctx* ctx, const pclb200_index* idx, double tolerance,
+                                       int32_t* out_labels, size_t n_labels);
+
 /* ---- VoxelGrid: replaces pcl::VoxelGrid<PointT>::applyFilter (no filter field)
  * (filters/include/pcl/filters/impl/voxel_grid.hpp:596-814).  out_xyz1: capacity n records
  * {x,y,z,1}; ordered by voxel linear index.  PCLB200_ERR_LEAF_TOO_SMALL mirrors :620-629 (the

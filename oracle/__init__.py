@@ -101,6 +101,8 @@ def lib():
         L.orc_reject_surface_normal.restype = sz
         L.orc_reject_surface_normal.argtypes = [C.POINTER(Corr), sz, fp, sz, fp, sz, C.c_double, C.POINTER(Corr)]
         L.orc_normals_radius.argtypes = [vp, fp, sz, sz, i32p, sz, C.c_int, C.c_double, fp, fp, C.c_int]
+        L.orc_cluster_labels.argtypes = [vp, sz, C.c_double, i32p]
+        L.orc_cluster_labels.restype = None
         L.orc_max_threads.restype = C.c_int
         _lib = L
     return _lib
@@ -237,6 +239,12 @@ class Index:
                                       _f(out), nthreads)
         return out, bool(dense)
 
+
+    def cluster_labels(self, tolerance):
+        """extractEuclideanClusters over the indexed points: label = smallest index of the point's cluster, -1 = not held."""
+        out = np.empty(self.cloud.shape[0], dtype=np.int32)
+        lib().orc_cluster_labels(self.h, self.cloud.shape[0], float(tolerance), _i(out))
+        return out
 
     def normals_radius(self, cloud, radius, viewpoint=(0, 0, 0), indices=None, is_dense=True, nthreads=1):
         """NormalEstimation with setRadiusSearch(radius)."""

@@ -1815,6 +1815,42 @@ ORC_API int orc_normals_radius(void* h, const float* cloud, size_t n, size_t str
   return dense_out;
 }
 
+// ---- Euclidean clustering ---------------------------------------------------------------------
+// pcl::extractEuclideanClusters, indices form — segmentation/include/pcl/segmentation/impl/extract_clusters.hpp
+// :124-223: breadth-first flood fill, one radiusSearch(point, tolerance) per queue entry, over the points the tree
+// holds; the tolerance reaches it as float (:246).  out_labels[i] = smallest index of point i's cluster (the seed, since
+// seeds are taken in ascending order and a cluster's indices are sorted at :208), -1 for points the tree does not hold.
+// Size window and ordering by size (:196, :249) are applied by the caller on the labels.
+ORC_API void orc_cluster_labels(void* h, size_t n_cloud, double tolerance, int32_t* out_labels)
+{
+  const KdTree& t = *static_cast<KdTree*>(h);
+  std::fill(out_labels, out_labels + n_cloud, -1);
+  const double tol = static_cast<double>(static_cast<float>(tolerance));
+  const float r2 = static_cast<float>(tol * tol);
+  // tree slot of every original index it holds, so a queue entry's coordinates can be looked up
+  std::vector<int32_t> slot_of(n_cloud, -1);
+  for (size_t i = 0; i < t.n; ++i)
+    slot_of[(size_t)t.orig[i]] = (int32_t)i;
+  std::vector<Cand> found;
+  std::vector<int32_t> queue;
+  for (size_t seed = 0; seed < n_cloud; ++seed) {
+    if (slot_of[seed] < 0 || out_labels[seed] >= 0)
+      continue;
+    queue.clear();
+    queue.push_back((int32_t)seed);
+    out_labels[seed] = (int32_t)seed;
+    for (size_t qi = 0; qi < queue.size(); ++qi) {
+      found.clear();
+      kd_radius_rec(t, 0, &t.pts[3 * (size_t)slot_of[(size_t)queue[qi]]], r2, found);
+      for (const Cand& c : found)
+        if (out_labels[(size_t)c.i] < 0) {
+          out_labels[(size_t)c.i] = (int32_t)seed;
+          queue.push_back(c.i);
+        }
+    }
+  }
+}
+
 // ---- k-NN statistics + the two outlier filters built on them ---------------------------
 // out_mean[i] = float( sum_{j=1..k'-1} sqrt(double(d2_j)) / (k'-1) ), k' = min(k, #indexed points), j = 0 is the query
 //               itself (filters/include/pcl/filters/impl/statistical_outlier_removal.hpp:88-97); 0 for non-finite queries

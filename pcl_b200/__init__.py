@@ -71,7 +71,7 @@ SYMBOLS = [
     "pclb200_icp_set_source", "pclb200_icp_iterate", "pclb200_icp_get_cloud", "pclb200_icp_get_correspondences",
     "pclb200_icp_align",
     "pclb200_fitness_score", "pclb200_reject", "pclb200_icp_set_rejectors", "pclb200_normals_knn", "pclb200_normals_radius",
-    "pclb200_correspondences_normals", "pclb200_reject_surface_normal", "pclb200_voxelgrid", "pclb200_comm_unique_id",
+    "pclb200_correspondences_normals", "pclb200_reject_surface_normal", "pclb200_cluster_labels", "pclb200_voxelgrid", "pclb200_comm_unique_id",
     "pclb200_comm_init",
 ]
 
@@ -131,6 +131,7 @@ def lib():
     L.pclb200_correspondences_normals.argtypes = [vp, vp, C.c_int, vp, sz, sz, vp, sz, vp, sz, vp, sz, C.c_int, C.c_double,
                                                   vp, C.POINTER(sz)]
     L.pclb200_reject_surface_normal.argtypes = [vp, vp, sz, vp, sz, sz, vp, sz, sz, C.c_double, vp, C.POINTER(sz)]
+    L.pclb200_cluster_labels.argtypes = [vp, vp, C.c_double, vp, sz]
     L.pclb200_voxelgrid.argtypes = [vp, vp, sz, sz, vp, sz, C.c_int, fp, C.c_uint, vp, C.POINTER(sz)]
     L.pclb200_comm_unique_id.argtypes = [vp]
     L.pclb200_comm_init.argtypes = [vp, C.c_int, C.c_int, vp]
@@ -434,6 +435,20 @@ class Index:
         return out, bool(dense.value)
 
 
+    def cluster_labels(self, tolerance, out=None):
+        """Connected components of d2 < tolerance^2 over the indexed points: label = smallest original index of the
+        component, -1 for points the index does not hold."""
+        if out is None:
+            out = np.empty(self.n_cloud, dtype=np.int32)
+        ob = _Buf(out, np.int32)
+        _check(lib().pclb200_cluster_labels(self.ctx.h, self.h, float(tolerance), ob.ptr, self.n_cloud))
+        return out
+
+    def euclidean_clusters(self, tolerance, min_size=1, max_size=2 ** 32 - 1):
+        """EuclideanClusterExtraction::extract: list of index arrays (ascending inside a cluster), largest first,
+        equal sizes ordered by their smallest index."""
+        return clusters_from_labels(self.cluster_labels(tolerance), min_size, max_size)
+
     def normals_radius(self, cloud, radius, viewpoint=(0, 0, 0), indices=None, is_dense=True, out=None):
         """NormalEstimation with setRadiusSearch(radius)."""
         b = _Buf(cloud)
@@ -447,6 +462,20 @@ class Index:
         _check(lib().pclb200_normals_radius(self.ctx.h, self.h, b.ptr, b.rows, b.stride, ib.ptr, ib.rows, int(is_dense),
                                             float(radius), vp, ob.ptr, C.byref(dense)))
         return out, bool(dense.value)
+
+
+def clusters_from_labels(labels, min_size=1, max_size=2 ** 32 - 1):
+    """Groups component labels into clusters the way EuclideanClusterExtraction::extract returns them
+    (extract_clusters.hpp:98-113, 249): indices ascending inside a cluster, clusters by size descending."""
+    labels = np.asarray(labels)
+    valid = np.nonzero(labels >= 0)[0]
+    order = valid[np.argsort(labels[valid], kind="stable")]
+    lab_sorted = labels[order]
+    starts = np.nonzero(np.r_[True, lab_sorted[1:] != lab_sorted[:-1]])[0] if order.size else np.zeros(0, np.int64)
+    ends = np.r_[starts[1:], order.size] if order.size else starts
+    out = [order[b:e].astype(np.int32) for b, e in zip(starts, ends) if min_size <= e - b <= max_size]
+    out.sort(key=lambda a: (-a.size, int(a[0])))
+    return out
 
 
 class Icp:

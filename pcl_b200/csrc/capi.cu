@@ -505,7 +505,10 @@ int pclb200_radius(pclb200_ctx* ctx, const pclb200_index* h, const void* queries
     }
     DevBuf<unsigned long long> counts, offsets, keys_sorted;
     unsigned long long total = 0;
-    radius_csr(c, idx, qb.q.p, nq, r2, counts, offsets, keys_sorted, total);
+    {
+      ProfScope ps(c, "radius");
+      radius_csr(c, idx, qb.q.p, nq, r2, counts, offsets, keys_sorted, total);
+    }
     std::vector<unsigned long long> h_off(nq + 1, 0);
     const unsigned long long* d_final_keys = nullptr;
     const unsigned long long* d_final_off = offsets.p;
@@ -909,6 +912,33 @@ int pclb200_normals_radius(pclb200_ctx* ctx, const pclb200_index* h, const void*
     raise_if_device_error(c);
     if (is_dense_out)
       *is_dense_out = flag ? 0 : 1;
+  });
+}
+
+// ---- Euclidean clustering --------------------------------------------------------------------------------------------------
+int pclb200_cluster_labels(pclb200_ctx* ctx, const pclb200_index* h, double tolerance, int32_t* out_labels, size_t n_labels)
+{
+  return guarded([&] {
+    PCLB_REQUIRE(ctx && h && h->idx && out_labels, PCLB200_ERR_INVALID, "NULL argument");
+    PCLB_REQUIRE(tolerance >= 0.0, PCLB200_ERR_INVALID, "negative cluster tolerance");
+    Ctx& c = ctx->c;
+    std::lock_guard<std::recursive_mutex> lk(c.mu);
+    PCLB_CUDA(cudaSetDevice(c.device));
+    const Index& idx = *h->idx;
+    PCLB_REQUIRE(n_labels == idx.n_cloud, PCLB200_ERR_INVALID,
+                 "out_labels must hold one entry per point of the cloud the index was built from");
+    cudaStream_t st = c.stream;
+    DevBuf<int32_t> d;
+    int32_t* pl = out_labels;
+    const bool dev_out = is_device_ptr(out_labels);
+    if (!dev_out) {
+      d.alloc(n_labels, st);
+      pl = d.p;
+    }
+    cluster_labels(c, idx, tolerance, pl);
+    if (!dev_out)
+      PCLB_CUDA(cudaMemcpyAsync(out_labels, pl, n_labels * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+    raise_if_device_error(c);
   });
 }
 

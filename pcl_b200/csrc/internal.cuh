@@ -219,6 +219,9 @@ size_t reject_surface_normal(Ctx& c, const pclb200_corr* in, size_t n, const voi
                              size_t stride_sn, const void* tgt_normals, size_t n_tgt, size_t stride_tn,
                              double threshold, pclb200_corr* out);
 
+// connected components of the d2 < tolerance^2 graph over the indexed points (cluster.cu)
+void cluster_labels(Ctx& c, const Index& idx, double tolerance, int32_t* d_labels /* idx.n_cloud */);
+
 // flat per-correspondence arrays the rejectors work on (reject.cu)
 struct RejectArrays {
   size_t n = 0;

@@ -26,6 +26,7 @@
 #include <pcl/registration/correspondence_rejection_one_to_one.h>
 #include <pcl/registration/correspondence_rejection_trimmed.h>
 #include <pcl/registration/icp.h>
+#include <pcl/segmentation/extract_clusters.h>
 #include <pcl/registration/transformation_estimation_point_to_plane_lls.h>
 #include <pcl/registration/transformation_estimation_svd.h>
 #include <pcl/registration/transformation_estimation_symmetric_point_to_plane_lls.h>
@@ -594,6 +595,50 @@ int main(int argc, char** argv)
     reg.align(output);
     EXPECT_TRUE(reg.hasConverged());
     EXPECT_LT(reg.getFitnessScore(), 0.005);
+  }
+
+
+  {  // EuclideanClusterExtraction (segmentation/impl/extract_clusters.hpp:225-252): three well separated blobs + stragglers
+    auto cloud = std::make_shared<PointCloud<PointXYZ>>();
+    unsigned s = 12345;
+    auto rnd = [&]() { s = s * 1664525u + 1013904223u; return (s >> 8) * (1.f / 16777216.f); };
+    const float centres[3][3] = {{0, 0, 0}, {5, 0, 0}, {0, 5, 0}};
+    const int sizes[3] = {300, 200, 100};
+    for (int b = 0; b < 3; ++b)
+      for (int i = 0; i < sizes[b]; ++i)
+        cloud->push_back(PointXYZ(centres[b][0] + 0.3f * rnd(), centres[b][1] + 0.3f * rnd(), centres[b][2] + 0.3f * rnd()));
+    for (int i = 0; i < 7; ++i) cloud->push_back(PointXYZ(20.f + 3.f * i, 20.f, 20.f));  // isolated points
+    EuclideanClusterExtraction<PointXYZ> ec;
+    ec.setClusterTolerance(0.2);
+    ec.setMinClusterSize(50);
+    ec.setMaxClusterSize(25000);
+    ec.setSearchMethod(std::make_shared<search::KdTree<PointXYZ>>());
+    ec.setInputCloud(cloud);
+    std::vector<PointIndices> clusters;
+    ec.extract(clusters);
+    EXPECT_EQ(clusters.size(), 3u);
+    if (clusters.size() == 3) {
+      EXPECT_EQ(clusters[0].indices.size(), 300u);  // largest first
+      EXPECT_EQ(clusters[1].indices.size(), 200u);
+      EXPECT_EQ(clusters[2].indices.size(), 100u);
+      EXPECT_EQ(clusters[0].indices.front(), 0);
+      EXPECT_EQ(clusters[0].indices.back(), 299);   // indices ascending inside a cluster
+      EXPECT_EQ(clusters[1].indices.front(), 300);
+      EXPECT_EQ(clusters[2].indices.back(), 599);
+    }
+    ec.setMinClusterSize(1);
+    ec.extract(clusters);
+    EXPECT_EQ(clusters.size(), 10u);  // + the 7 singletons
+    auto idx = std::make_shared<Indices>();
+    for (int i = 0; i < 300; i += 2) idx->push_back(i);  // every other point of the first blob only
+    ec.setIndices(idx);
+    ec.setClusterTolerance(0.3);
+    ec.extract(clusters);
+    EXPECT_EQ(clusters.size(), 1u);
+    if (!clusters.empty()) {
+      EXPECT_EQ(clusters[0].indices.size(), 150u);
+      EXPECT_EQ(clusters[0].indices[1], 2);
+    }
   }
 
   std::printf("%s: %d checks, %d failures\n", g_fail ? "FAILED" : "PASSED", g_checks, g_fail);

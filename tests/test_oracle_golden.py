@@ -288,3 +288,34 @@ def test_radius_normals(golden, orc):
         lst = ids[offs[i]:offs[i + 1]]
         pn, ok = orc.point_normal(b0, lst)
         assert ok and np.allclose(np.abs(pn), np.abs(nr[i]), atol=0)
+
+
+def test_cluster_labels_are_connected_components(orc):
+    """extractEuclideanClusters (extract_clusters.hpp:124-223) restated as a flood fill; an independent
+    scipy connected-components labelling of the same d2 < r2 graph must give the same partition."""
+    from scipy.sparse import coo_matrix
+    from scipy.sparse.csgraph import connected_components
+    from scipy.spatial import cKDTree
+    import pcl_b200 as P  # only the host-side grouping helper (no device call)
+    rng = np.random.default_rng(3)
+    c = orc.to_xyz1(rng.random((20000, 3), dtype=np.float32))
+    c[::97, 0] = np.nan
+    ok = np.isfinite(c[:, 0])
+    idx = np.nonzero(ok)[0]
+    tree = cKDTree(c[ok, :3].astype(np.float64))
+    for tol, n_expected in ((0.0, idx.size), (0.035, None), (0.05, None)):
+        lab = orc.Index(c).cluster_labels(tol)
+        assert np.array_equal(lab >= 0, ok)
+        assert np.all(lab[idx] <= idx)  # the label is the smallest index of the cluster
+        pairs = tree.query_pairs(float(np.float32(tol)) * 1.000001 + 1e-12, output_type="ndarray")
+        d = c[idx[pairs[:, 0]], :3] - c[idx[pairs[:, 1]], :3]
+        d2 = ((d[:, 0] * d[:, 0]) + d[:, 1] * d[:, 1]) + d[:, 2] * d[:, 2]
+        keep = d2 < np.float32(np.float64(np.float32(tol)) ** 2)
+        g = coo_matrix((np.ones(int(keep.sum())), (pairs[keep, 0], pairs[keep, 1])), shape=(idx.size, idx.size))
+        nc, l = connected_components(g, directed=False)
+        first = {}
+        assert all(first.setdefault(a, b) == b for a, b in zip(l, lab[idx])) and len(set(first.values())) == nc
+        if n_expected is not None:
+            assert nc == n_expected
+        cl = P.clusters_from_labels(lab, 3, 100)
+        assert all(3 <= a.size <= 100 for a in cl) and [a.size for a in cl] == sorted((a.size for a in cl), reverse=True)

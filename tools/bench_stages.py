@@ -68,11 +68,19 @@ def main():
     nq = min(n, 2_000_000)
     qv = vol[:nq].contiguous()
     res = {}
-    t = timed(ctx, lambda: res.__setitem__("r", vi.radius(qv, r)), reps=2)
-    emit("radius_unlimited_volume", t, nq, "queries", radius=r, neighbours=int(res["r"][0][-1]), includes="D2H of the lists")
-    t = timed(ctx, lambda: res.__setitem__("r", vi.radius(qv, r, max_nn=32)), reps=2)
-    emit("radius_maxnn32_volume", t, nq, "queries", radius=r, neighbours=int(res["r"][0][-1]), includes="D2H of the lists")
+    ctx.profile(True)
+    for name, scope, kw in (("radius_unlimited_volume", "radius", {}), ("radius_maxnn32_volume", "radius_knn", dict(max_nn=32))):
+        t = timed(ctx, lambda: res.__setitem__("r", vi.radius(qv, r, **kw)), reps=2)
+        ctx.profile_reset()
+        vi.radius(qv, r, **kw)
+        dev_ms, _ = ctx.profile_get(scope)  # the search itself (count + fill + sort, or the bounded k-NN) on the device
+        emit(name, t, nq, "queries", radius=r, neighbours=int(res["r"][0][-1]), includes="D2H of the lists into malloc'd host arrays",
+             device_search_ms=round(dev_ms, 3), device_rate=nq / (dev_ms * 1e-3) if dev_ms > 0 else None)
+    ctx.profile(False)
     emit("normals_radius_volume", timed(ctx, lambda: vi.normals_radius(qv, r, out=nrm[:nq]), reps=2), nq, "points", radius=r)
+    lab = torch.empty(n, dtype=torch.int32, device="cuda")
+    emit("cluster_labels_volume", timed(ctx, lambda: vi.cluster_labels(r * 0.6, out=lab), reps=2), n, "points", tolerance=r * 0.6)
+    emit("cluster_labels_surface", timed(ctx, lambda: si.cluster_labels(0.004, out=lab), reps=2), n, "points", tolerance=0.004)
     vg = torch.empty((n, 4), device="cuda")
     emit("voxelgrid_leaf0.05_volume", timed(ctx, lambda: ctx.voxelgrid(vol, 0.05, out=vg)), n, "points")
     emit("voxelgrid_leaf0.01_surface", timed(ctx, lambda: ctx.voxelgrid(surf, 0.01, out=vg)), n, "points")
