@@ -454,10 +454,18 @@ int pclb200_radius(pclb200_ctx* ctx, const pclb200_index* h, const void* queries
     load_xyz_as_float4(c, queries, nq, stride, nullptr, 0, dense.p, st);
     QueryBatch qb;
     make_query_batch(c, idx, dense.p, nq, qb);
-    if ((size_t)max_nn < idx.n_valid && max_nn <= 32) {
-      // KNNRadiusResultSet semantics (kdtree_flann.hpp:382-391): the max_nn nearest among those with d2 < r2.  That is
-      // the register k-NN kernel started with the pruning bound just below r2 (every d2 < r2 is <= that bound; a
-      // candidate AT the bound still enters through the index tie rule) — no count / fill / sort passes.
+    DevBuf<unsigned long long> counts, offsets, keys_sorted;
+    unsigned long long total = 0;
+    {
+      ProfScope ps(c, "radius_count");
+      radius_count(c, idx, qb.q.p, nq, r2, counts, offsets, total);
+    }
+    // KNNRadiusResultSet semantics (kdtree_flann.hpp:382-391): the max_nn nearest among those with d2 < r2.  Normally
+    // the whole ball is materialised, sorted and cut (the passes below: ~3 ms per million queries at ~30 neighbours).
+    // When the balls hold far more than max_nn points that would move (or overflow on) data that is thrown away, so
+    // for max_nn <= 32 the register k-NN kernel runs instead, started with the pruning bound just below r2 (every
+    // d2 < r2 is <= that bound; a candidate AT the bound still enters through the index tie rule).
+    if ((size_t)max_nn < idx.n_valid && max_nn <= 32 && total > 16ULL * (unsigned long long)nq * max_nn) {
       const int k = (int)max_nn;
       DevBuf<int32_t> rows;
       DevBuf<float> rows_d2;
@@ -481,33 +489,31 @@ int pclb200_radius(pclb200_ctx* ctx, const pclb200_index* h, const void* queries
       std::vector<unsigned long long> h_off(nq + 1, 0);
       PCLB_CUDA(cudaMemcpyAsync(h_off.data(), off.p, (nq + 1) * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
       PCLB_CUDA(cudaStreamSynchronize(st));
-      const unsigned long long total = h_off[nq];
+      const unsigned long long kept = h_off[nq];
       for (size_t i = 0; i <= nq; ++i)
         out_offsets[i] = (int64_t)h_off[i];
-      int32_t* hi = static_cast<int32_t*>(malloc(std::max<size_t>(total, 1) * sizeof(int32_t)));
-      float* hd = static_cast<float*>(malloc(std::max<size_t>(total, 1) * sizeof(float)));
+      int32_t* hi = static_cast<int32_t*>(malloc(std::max<size_t>(kept, 1) * sizeof(int32_t)));
+      float* hd = static_cast<float*>(malloc(std::max<size_t>(kept, 1) * sizeof(float)));
       PCLB_REQUIRE(hi && hd, PCLB200_ERR_INTERNAL, "host allocation failed");
       *out_idx = hi;  // owned by the caller from here on (pclb200_free), also on the error paths below
       *out_d2 = hd;
-      if (total > 0) {
+      if (kept > 0) {
         DevBuf<int32_t> di;
         DevBuf<float> dd;
-        di.alloc(total, st);
-        dd.alloc(total, st);
+        di.alloc(kept, st);
+        dd.alloc(kept, st);
         k_pack_rows<<<grid_for(nq, 256), 256, 0, st>>>(rows.p, rows_d2.p, nq, k, off.p, di.p, dd.p);
         ++c.launches;
-        PCLB_CUDA(cudaMemcpyAsync(hi, di.p, total * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
-        PCLB_CUDA(cudaMemcpyAsync(hd, dd.p, total * sizeof(float), cudaMemcpyDeviceToHost, st));
+        PCLB_CUDA(cudaMemcpyAsync(hi, di.p, kept * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+        PCLB_CUDA(cudaMemcpyAsync(hd, dd.p, kept * sizeof(float), cudaMemcpyDeviceToHost, st));
         PCLB_CUDA(cudaStreamSynchronize(st));
       }
       raise_if_device_error(c);
       return;
     }
-    DevBuf<unsigned long long> counts, offsets, keys_sorted;
-    unsigned long long total = 0;
     {
       ProfScope ps(c, "radius");
-      radius_csr(c, idx, qb.q.p, nq, r2, counts, offsets, keys_sorted, total);
+      radius_fill_sorted(c, idx, qb.q.p, nq, r2, offsets, total, keys_sorted);
     }
     std::vector<unsigned long long> h_off(nq + 1, 0);
     const unsigned long long* d_final_keys = nullptr;

@@ -207,6 +207,11 @@ void launch_radius_fill(Ctx& c, const Index& idx, const float4* d_q, size_t nq, 
                         unsigned long long* d_keys /* (d2 bits << 32) | index */);
 
 // sorted radius neighbourhoods as CSR rows of packed keys ((d2 bits << 32) | original index), addressed by query slot
+void radius_count(Ctx& c, const Index& idx, const float4* d_q, size_t nq, float r2, DevBuf<unsigned long long>& counts,
+                  DevBuf<unsigned long long>& offsets, unsigned long long& total);
+void radius_fill_sorted(Ctx& c, const Index& idx, const float4* d_q, size_t nq, float r2,
+                        const DevBuf<unsigned long long>& offsets, unsigned long long total,
+                        DevBuf<unsigned long long>& keys_sorted);
 void radius_csr(Ctx& c, const Index& idx, const float4* d_q, size_t nq, float r2, DevBuf<unsigned long long>& counts,
                 DevBuf<unsigned long long>& offsets, DevBuf<unsigned long long>& keys_sorted, unsigned long long& total);
 void launch_normals_radius(Ctx& c, Index& idx, const float4* d_q, size_t nq, float r2, const float vp[3], float4* d_out,

@@ -379,11 +379,12 @@ void launch_radius_fill(Ctx& c, const Index& idx, const float4* d_q, size_t nq, 
   PCLB_CUDA(cudaGetLastError());
 }
 
-// Sorted radius neighbourhoods of a query batch as CSR rows addressed by the query's slot:
-// keys = (d2 bits << 32) | original index, ascending inside every row (= ascending (d2, index)).
-// counts / offsets have nq + 1 entries (offsets[nq] = total).  Synchronises once to learn the total.
-void radius_csr(Ctx& c, const Index& idx, const float4* d_q, size_t nq, float r2, DevBuf<unsigned long long>& counts,
-                DevBuf<unsigned long long>& offsets, DevBuf<unsigned long long>& keys_sorted, unsigned long long& total)
+// Radius neighbourhoods of a query batch as CSR rows addressed by the query's slot, in two steps so the caller can look
+// at the total before materialising anything:
+//   radius_count       counts / offsets (nq + 1 entries, offsets[nq] = total); synchronises once to read the total
+//   radius_fill_sorted keys = (d2 bits << 32) | original index, ascending inside every row (= ascending (d2, index))
+void radius_count(Ctx& c, const Index& idx, const float4* d_q, size_t nq, float r2, DevBuf<unsigned long long>& counts,
+                  DevBuf<unsigned long long>& offsets, unsigned long long& total)
 {
   cudaStream_t st = c.stream;
   counts.alloc(nq + 1, st);
@@ -399,10 +400,18 @@ void radius_csr(Ctx& c, const Index& idx, const float4* d_q, size_t nq, float r2
   total = 0;
   PCLB_CUDA(cudaMemcpyAsync(&total, offsets.p + nq, sizeof(total), cudaMemcpyDeviceToHost, st));
   PCLB_CUDA(cudaStreamSynchronize(st));
+}
+
+void radius_fill_sorted(Ctx& c, const Index& idx, const float4* d_q, size_t nq, float r2,
+                        const DevBuf<unsigned long long>& offsets, unsigned long long total,
+                        DevBuf<unsigned long long>& keys_sorted)
+{
   if (total == 0)
     return;
+  cudaStream_t st = c.stream;
   PCLB_REQUIRE(total < (unsigned long long)std::numeric_limits<int>::max(), PCLB200_ERR_INVALID,
-               "radius search result exceeds 2^31 neighbours; lower the radius or set max_nn");
+               "radius search result exceeds 2^31 neighbours; lower the radius or set max_nn (<= 32 is searched without "
+               "materialising the whole ball)");
   DevBuf<unsigned long long> keys;
   keys.alloc(total, st);
   keys_sorted.alloc(total, st);
@@ -415,6 +424,13 @@ void radius_csr(Ctx& c, const Index& idx, const float4* d_q, size_t nq, float r2
   PCLB_CUDA(cub::DeviceSegmentedSort::SortKeys(tmp2.p, tb2, keys.p, keys_sorted.p, (int)total, (int)nq, offsets.p,
                                                offsets.p + 1, st));
   c.launches += 3;
+}
+
+void radius_csr(Ctx& c, const Index& idx, const float4* d_q, size_t nq, float r2, DevBuf<unsigned long long>& counts,
+                DevBuf<unsigned long long>& offsets, DevBuf<unsigned long long>& keys_sorted, unsigned long long& total)
+{
+  radius_count(c, idx, d_q, nq, r2, counts, offsets, total);
+  radius_fill_sorted(c, idx, d_q, nq, r2, offsets, total, keys_sorted);
 }
 
 // ---- normals ---------------------------------------------------------------------------------------

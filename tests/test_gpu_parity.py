@@ -116,6 +116,23 @@ def test_radius_vs_oracle(gpu, orc):
         assert np.array_equal(go, oo) and np.array_equal(gi, oi) and np.array_equal(gd, od), name
 
 
+def test_radius_maxnn_dense_balls(gpu, orc):
+    """Balls that hold far more than max_nn points are searched by the bounded k-NN kernel instead of being
+    materialised (capi.cu: pclb200_radius); both strategies must return FLANN's KNNRadius answer."""
+    P, ctx = gpu
+    rng = np.random.default_rng(14)
+    pts = rng.random((40000, 3), dtype=np.float32)
+    pts[::9] = pts[1::9][: pts[::9].shape[0]]  # exact duplicates: distance ties inside the kept prefix
+    cloud = orc.to_xyz1(pts)
+    q = orc.to_xyz1(np.concatenate([pts[:500], rng.random((300, 3), dtype=np.float32) * 1.4 - 0.2]))
+    gi, oi = P.Index(ctx, cloud), orc.Index(cloud)
+    for r, max_nn in ((0.2, 4), (0.2, 32), (0.12, 10), (0.05, 3), (0.02, 32)):  # ~1300 / ~290 / ~20 / ~1.3 points per ball
+        go, gidx, gd = gi.radius(q, r, max_nn=max_nn)
+        oo, oidx, od = oi.radius(q, r, max_nn=max_nn, nthreads=8)
+        assert np.array_equal(go, oo) and np.array_equal(gidx, oidx) and np.array_equal(gd, od), (r, max_nn)
+        assert np.diff(go).max() <= max_nn
+
+
 # ---------------------------------------------------------------------------------------------------------------------
 # correspondences
 # ---------------------------------------------------------------------------------------------------------------------
