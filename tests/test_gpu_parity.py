@@ -59,6 +59,35 @@ def test_knn_golden_10_points(gpu, golden):
     assert keff == 10 and np.all(idx[0, 10:] == -1) and np.all(np.isinf(d2[0, 10:]))
 
 
+@pytest.mark.parametrize("walk", ["single", "packet"])
+def test_knn_and_normals_both_walks(gpu, orc, walk, monkeypatch):
+    """The per-query and the per-warp (packet) k-NN walks return the same exact lists; normals built on them agree."""
+    P, ctx = gpu
+    monkeypatch.setenv("PCLB200_KNN", walk)  # read by the library at every call
+    rng = np.random.default_rng(12)
+    for name, pts in _clouds(rng):
+        cloud = orc.to_xyz1(pts)
+        q = orc.to_xyz1(np.concatenate([pts[:257], (rng.random((100, 3), dtype=np.float32) - np.float32(0.2)) * (np.abs(pts).max() + 1)]))
+        q[3::50, 2] = np.nan  # non-finite queries: empty rows
+        for k in (1, 4, 10, 16, 20, 32):
+            gi, gd, gk = P.Index(ctx, cloud).knn(q, k)
+            oi, od, ok = orc.Index(cloud).knn(q, k, nthreads=4)
+            fin = np.isfinite(q[:, 2])
+            assert gk == ok and np.array_equal(gi[fin], oi[fin]) and np.array_equal(gd[fin], od[fin]), (name, k, walk)
+            assert np.all(gi[~fin] == -1) and np.all(np.isinf(gd[~fin]))
+    pts = rng.random((30000, 3), dtype=np.float32)
+    pts[:, 2] = np.float32(0.1) * np.sin(np.float32(6) * pts[:, 0])
+    cloud = orc.to_xyz1(pts)
+    cloud[::301, 1] = np.nan
+    for k in (5, 16, 32):
+        g, gd = P.Index(ctx, cloud).normals_knn(cloud, k, viewpoint=(0.5, 0.5, 5), is_dense=False)
+        o, od = orc.Index(cloud).normals_knn(cloud, k, viewpoint=(0.5, 0.5, 5), is_dense=False, nthreads=8)
+        assert gd == od and np.array_equal(np.isnan(g[:, 0]), np.isnan(o[:, 0]))
+        ok = ~np.isnan(o[:, 0])
+        cosang = (g[ok, :3] * o[ok, :3]).sum(1)
+        assert np.percentile(cosang, 0.5) > 1 - 1e-3 and np.mean(cosang > 1 - 1e-6) > 0.9, (k, walk)
+
+
 def test_knn_nan_points_subset_and_strides(gpu, orc):
     P, ctx = gpu
     rng = np.random.default_rng(12)

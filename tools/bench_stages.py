@@ -57,12 +57,18 @@ def main():
     emit("index_build_volume", timed(ctx, lambda: holder.__setitem__("v", P.Index(ctx, vol))), n, "points")
     si, vi = holder["s"], holder["v"]
     q = surf[torch.randperm(n, generator=g, device="cuda")].contiguous()
-    for k in (1, 10, 16):
-        oi = torch.empty((n, k), dtype=torch.int32, device="cuda")
-        od = torch.empty((n, k), dtype=torch.float32, device="cuda")
-        emit(f"knn_k{k}_self_surface", timed(ctx, lambda: si.knn(q, k, oi, od)), n, "queries", k=k)
     nrm = torch.empty((n, 4), device="cuda")
-    emit("normals_knn16_surface", timed(ctx, lambda: si.normals_knn(surf, 16, (5, 5, 10), out=nrm)), n, "points")
+    for walk in ("single", "packet"):  # per-query walk vs one walk per warp (search.cu: use_packet_knn)
+        os.environ["PCLB200_KNN"] = walk
+        for k in (1, 10, 16, 32):
+            oi = torch.empty((n, k), dtype=torch.int32, device="cuda")
+            od = torch.empty((n, k), dtype=torch.float32, device="cuda")
+            emit(f"knn_k{k}_self_surface_{walk}", timed(ctx, lambda: si.knn(q, k, oi, od)), n, "queries", k=k, walk=walk)
+            del oi, od
+        emit(f"normals_knn16_surface_{walk}", timed(ctx, lambda: si.normals_knn(surf, 16, (5, 5, 10), out=nrm)), n, "points", walk=walk)
+        emit(f"knn_k10_volume_{walk}", timed(ctx, lambda: vi.knn(vol[:2_000_000], 10), reps=2), 2_000_000, "queries", k=10, walk=walk,
+             includes="D2H of the rows")
+    del os.environ["PCLB200_KNN"]
     # radius search: density n/8000 per unit volume; r so that a ball holds ~30 points
     r = float((30.0 / (n / 8000.0) * 3 / (4 * np.pi)) ** (1 / 3))
     nq = min(n, 2_000_000)
