@@ -95,7 +95,7 @@ k_knn(const BvhNode* __restrict__ nodes, const float4* __restrict__ pts, int roo
     }
 }
 
-// ---- packet variant: the 32 Hilbert-adjacent queries of a warp share ONE walk (traverse_packet) --------------------
+// ---- packet variant (opt-in): the 32 Hilbert-adjacent queries of a warp share ONE walk (traverse_packet) ----------
 // Every node and leaf line is a broadcast load instead of 32 scattered ones and the stack lives once per warp in shared
 // memory; a subtree is entered when ANY lane's k-th distance still reaches it, so each lane sees a superset of the
 // leaves its own exact walk would visit and its list is still the exact lexicographic k smallest.
@@ -144,14 +144,15 @@ k_knn_packet(const BvhNode* __restrict__ nodes, const float4* __restrict__ pts, 
     }
 }
 
-// Packet walk when the queries are about as dense as the indexed cloud (then the 32 queries of a warp share most of
-// their neighbourhoods); per-query walk for sparse query sets.  PCLB200_KNN=packet|single overrides (A/B, tests).
-static bool use_packet_knn(const Index& idx, size_t nq)
+// Which walk launch_knn / launch_normals use.  Measured on B200 (profiles/r1i_stage_throughput.jsonl, 10 M self-queries
+// on the 10 M-point sheet): the per-query walk wins for every k (k = 1: 2.6 vs 3.3 ms, k = 16: 40 vs 74 ms) — unlike
+// the seeded 1-NN of the ICP loop, an unseeded k-NN packet visits the UNION of its 32 lanes' leaf sets, while the
+// while-while per-query walk lets the lanes scan 32 DIFFERENT leaves at the same time.  So the packet kernels stay an
+// opt-in (PCLB200_KNN=packet; tests run both).
+static bool use_packet_knn(const Index&, size_t)
 {
   const char* force = getenv("PCLB200_KNN");
-  if (force && force[0] == 'p') return true;
-  if (force && force[0] == 's') return false;
-  return (double)idx.n_valid <= 64.0 * (double)nq;
+  return force && force[0] == 'p';
 }
 
 // ---- any k: the candidate list lives in the output rows themselves (global memory) -----------------
