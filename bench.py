@@ -306,7 +306,7 @@ def run_ours(args):
     peak, peak_src = measured_peak_gbs()
     avg_iter_s = (iter_ms / max(iter_n, 1)) * 1e-3
     achieved = bytes_per_corr * n / avg_iter_s / 1e9 if avg_iter_s > 0 else 0.0
-    roofline = {"bound": "hbm", "kernel": "k_search_packet (in-place transform + exact 1-NN + gate)", "achieved": achieved, "peak": peak,
+    roofline = {"bound": "hbm", "kernel": "k_search (in-place transform + exact seeded 1-NN + gate; first search of a step: k_search_packet)", "achieved": achieved, "peak": peak,
                 "peak_source": peak_src, "unit": "GB/s", "frac": achieved / peak,
                 # dram__bytes_read.sum + dram__bytes_write.sum of one `ncu --set full` capture of this kernel on this
                 # workload (profiles/r1e_k_search_packet_ncu.txt: 657.6 MB + 288.0 MB); only valid for the 10 M default

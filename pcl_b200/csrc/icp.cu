@@ -1104,6 +1104,7 @@ struct Icp {
   DevBuf<SolveOut> solve_out;
   DevBuf<unsigned long long> skip_count;
   int64_t total_skipped = 0;
+  int searches = 0;             // search launches since set_source (the first one has no seeds)
   std::vector<pclb200_rejector> rejectors;  // applied in order after every search (icp.hpp:187-201)
   bool track_next = false;      // run the next search with lower-bound tracking / skip test (set per iteration)
   Reducer red;
@@ -1361,6 +1362,7 @@ void icp_reset_state(Icp& s, const double* guess)
   s.n_corr = 0;
   s.track_next = false;
   s.total_skipped = 0;
+  s.searches = 0;
   PCLB_CUDA(cudaMemsetAsync(s.skip_count.p, 0, sizeof(unsigned long long), s.ctx->stream));
   s.total_corr = 0;
   s.mse = 0.0;
@@ -1629,12 +1631,17 @@ void icp_iterate(Icp& s, int max_steps, pclb200_icp_stats* stats)
     else {
       ProfScope ps(c, "icp_search");
       const unsigned sgrid = persistent_grid(c, s.n_q, 256, 16);
-      // packet walk when the queries are about as dense as the target (32 Morton-adjacent queries then share
-      // most of their path); per-query walk when they are much sparser.  PCLB200_SEARCH=packet|single overrides.
+      // Which walk.  The per-query kernel seeds every walk with the previous iteration's match, so its lanes start with
+      // a tight bound and the while-while walk lets them scan 32 DIFFERENT leaves at the same time; the packet kernel
+      // makes the warp scan the UNION of its lanes' leaves but shares every node fetch.  Measured on the bench surface
+      // (profiles/r1j_*): seeded iterations 1.65 ms per-query vs 2.45 ms packet; the first, unseeded search 2.6 vs
+      // 2.2 ms.  So: packet only for the first search after set_source (no seeds yet) when the queries are about as
+      // dense as the target, per-query from then on.  PCLB200_SEARCH=packet|single overrides (tests run both).
       const char* force = getenv("PCLB200_SEARCH");  // read per call so tests can exercise both kernels
-      bool packet = (double)T.n_valid <= 64.0 * (double)s.n_q;
+      bool packet = s.searches == 0 && (double)T.n_valid <= 64.0 * (double)s.n_q;
       if (force && force[0] == 'p') packet = true;
       if (force && force[0] == 's') packet = false;
+      ++s.searches;
       // Temporal coherence (still_nearest) pays once the cloud has almost stopped moving: tracking the lower
       // bounds costs ~6 % of a walk, so it is switched on when the last increment displaced no point by more than
       // half the RMS correspondence distance, and the skip test then fires from the following iteration on.
