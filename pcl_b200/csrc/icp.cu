@@ -120,6 +120,8 @@ struct IterArgs {
   unsigned long long* skip_count;  // queries answered by the temporal-coherence test (statistics)
   float4* cur_normals;             // source normals, same order as cur (symmetric objective), rotated with T_k
   int enforce_same_dir;
+  const int* node_parent;          // parent arrays of the target index (nullptr = seeded walks start at the root)
+  const int* leaf_parent;
   // fused cross-GPU reduce (optional): peer-mapped exchange buffers + this iteration's sequence number
   PeerView peer;
   unsigned long long seq;
@@ -224,6 +226,7 @@ struct __align__(16) Match {
   int accepted;  // 1 = this iteration's correspondence (inside the gate, reciprocal test passed)
 };
 
+constexpr bool kClimbDefault = false;  // see PCLB200_CLIMB in icp_iterate
 constexpr float kRelMargin = 1e-5f;  // >> fp32 rounding of the distances involved (~2e-7): keeps the skip test exact
 
 // Temporal-coherence test.  Let m be the previous match at distance D1 from the old query position, L a lower
@@ -288,11 +291,18 @@ k_search(const IterArgs a, Match* __restrict__ match)
       else {
         Nearest1T<TRACK> v{p.x, p.y, p.z, a.gate, kSentinelIndex, -1, __int_as_float(0x7f800000),
                            __int_as_float(0x7f800000), __int_as_float(0x7f800000)};
+        int start = a.root;
         if (prev.pos >= 0) {
           const int leaf = prev.pos / kLeafSize;
           v.template scan<false>(a.pts + (size_t)leaf * kLeafSize, leaf * kLeafSize);
+          // the candidate ball now has radius sqrt(v.best): start at the smallest spatial cell that contains it
+          // (TRACK: a ball three times as wide, so the exit distance leaves room for the skip test's lower bound)
+          float exit2;
+          start = climb_start(a.nodes, a.node_parent, a.leaf_parent, a.root, leaf, p.x, p.y, p.z, v.best,
+                              TRACK ? 3.f : 1.00001f, &exit2);
+          v.prune(exit2);  // every point outside the start cell is at least that far (no-op for the root / non-TRACK)
         }
-        if (!traverse(a.nodes, a.pts, a.root, p.x, p.y, p.z, v))
+        if (!traverse(a.nodes, a.pts, start, p.x, p.y, p.z, v))
           overflow = true;
         if (v.best_pos >= 0) {
           m.pos = v.best_pos;
@@ -1584,6 +1594,14 @@ void icp_iterate(Icp& s, int max_steps, pclb200_icp_stats* stats)
     a.skip_count = s.skip_count.p;
     a.cur_normals = s.cur_normals.p;
     a.enforce_same_dir = s.P.enforce_same_direction_normals;
+    {
+      // seeded walks start at the smallest cell that holds their candidate ball (traverse.cuh: climb_start);
+      // PCLB200_CLIMB=0|1 overrides the default (A/B measurements, tests run both)
+      const char* cl = getenv("PCLB200_CLIMB");
+      const bool climb = cl ? cl[0] == '1' : kClimbDefault;
+      a.node_parent = climb ? T.node_parent.p : nullptr;
+      a.leaf_parent = climb ? T.leaf_parent.p : nullptr;
+    }
     a.peer.nranks = 0;
     a.seq = 0;
     const bool fused_reduce = comm_peer_view(c, &a.peer, &a.seq);

@@ -345,7 +345,8 @@ __global__ void k_refit(const float4* __restrict__ pts, int n_leaves, const int2
 
 __global__ void k_pack_nodes(int n_internal, const int2* __restrict__ children, const float4* __restrict__ leaf_lo,
                              const float4* __restrict__ leaf_hi, const float4* __restrict__ node_lo,
-                             const float4* __restrict__ node_hi, BvhNode* __restrict__ nodes)
+                             const float4* __restrict__ node_hi, const unsigned char* __restrict__ child_flags,
+                             BvhNode* __restrict__ nodes)
 {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n_internal)
@@ -359,7 +360,7 @@ __global__ void k_pack_nodes(int n_internal, const int2* __restrict__ children, 
   nd.a = make_float4(alo.x, alo.y, alo.z, ahi.x);
   nd.b = make_float4(ahi.y, ahi.z, blo.x, blo.y);
   nd.c = make_float4(blo.z, bhi.x, bhi.y, bhi.z);
-  nd.d = make_int4(ch.x, ch.y, 0, 0);
+  nd.d = make_int4(ch.x, ch.y, child_flags ? (int)child_flags[i] : 0, 0);
   nodes[i] = nd;
 }
 
@@ -486,8 +487,9 @@ __global__ void k_scatter_cells(const float4* __restrict__ p, const int32_t* __r
 // children / parents of the final tree (kept nodes renumbered by new_id; everything below becomes a leaf)
 __global__ void k_link_cells(int n, const int2* __restrict__ children, const int2* __restrict__ range,
                              const int* __restrict__ keep, const int* __restrict__ new_id,
-                             const int* __restrict__ leaf_incl, int2* __restrict__ out_children,
-                             int* __restrict__ out_node_parent, int* __restrict__ out_leaf_parent)
+                             const int* __restrict__ leaf_incl, const unsigned long long* __restrict__ keys,
+                             int2* __restrict__ out_children, int* __restrict__ out_node_parent,
+                             int* __restrict__ out_leaf_parent, unsigned char* __restrict__ out_child_flags)
 {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n - 1 || !keep[i])
@@ -496,9 +498,14 @@ __global__ void k_link_cells(int n, const int2* __restrict__ children, const int
   const int2 ch = children[i];
   int ref[2];
   const int c2[2] = {ch.x, ch.y};
+  unsigned flags = 0;
 #pragma unroll
   for (int k = 0; k < 2; ++k) {
     const int cc = c2[k];
+    // a radix-tree node whose first and last Morton codes differ has a purely spatial prefix: it holds EVERY indexed
+    // point of its prefix cell.  Cells cut inside a run of equal codes (and single points) are not marked.
+    if (cc >= 0 && keys[range[cc].x] != keys[range[cc].y])
+      flags |= 1u << k;
     if (cc >= 0 && keep[cc]) {
       ref[k] = new_id[cc];
       out_node_parent[new_id[cc]] = nid;
@@ -511,6 +518,7 @@ __global__ void k_link_cells(int n, const int2* __restrict__ children, const int
     }
   }
   out_children[nid] = make_int2(ref[0], ref[1]);
+  out_child_flags[nid] = (unsigned char)flags;
   if (i == 0)
     out_node_parent[nid] = -1;
 }
@@ -658,7 +666,10 @@ static Index* build_from_dense(Ctx& c, const float4* d_pts, size_t n, const int3
     const size_t n_padded = (size_t)n_leaves * kLeafSize;
     idx->pts.alloc(n_padded, s);
     idx->nodes.alloc(n_int, s);
-    DevBuf<int> leaf_start, node_parent, leaf_parent;
+    DevBuf<int> leaf_start;
+    DevBuf<int>& node_parent = idx->node_parent;  // kept: seeded walks climb from the previous match's leaf
+    DevBuf<int>& leaf_parent = idx->leaf_parent;
+    DevBuf<unsigned char> child_flags;
     DevBuf<int2> children;
     DevBuf<float4> leaf_lo, leaf_hi, node_lo, node_hi;
     DevBuf<unsigned> flags;
@@ -666,6 +677,7 @@ static Index* build_from_dense(Ctx& c, const float4* d_pts, size_t n, const int3
     node_parent.alloc(n_int, s);
     leaf_parent.alloc(n_leaves, s);
     children.alloc(n_int, s);
+    child_flags.alloc(n_int, s);
     leaf_lo.alloc(n_leaves, s);
     leaf_hi.alloc(n_leaves, s);
     node_lo.alloc(n_int, s);
@@ -676,12 +688,12 @@ static Index* build_from_dense(Ctx& c, const float4* d_pts, size_t n, const int3
     k_fill_sentinels<<<grid_for(n_padded, 256), 256, 0, s>>>(idx->pts.p, n_padded);
     k_scatter_cells<<<grid_for(nv, 256), 256, 0, s>>>(d_pts, sc.vals.p, d_orig_of_slot, nv, leaf_incl.p, leaf_start.p,
                                                       idx->pts.p);
-    k_link_cells<<<grid_for(ni, 256), 256, 0, s>>>(nv, kchildren.p, krange.p, keep.p, new_id.p, leaf_incl.p, children.p,
-                                                   node_parent.p, leaf_parent.p);
+    k_link_cells<<<grid_for(ni, 256), 256, 0, s>>>(nv, kchildren.p, krange.p, keep.p, new_id.p, leaf_incl.p, sc.keys.p,
+                                                   children.p, node_parent.p, leaf_parent.p, child_flags.p);
     k_refit<<<grid_for(n_leaves, 256), 256, 0, s>>>(idx->pts.p, n_leaves, children.p, node_parent.p, leaf_parent.p,
                                                     leaf_lo.p, leaf_hi.p, node_lo.p, node_hi.p, flags.p);
     k_pack_nodes<<<grid_for(n_int, 256), 256, 0, s>>>(n_int, children.p, leaf_lo.p, leaf_hi.p, node_lo.p, node_hi.p,
-                                                     idx->nodes.p);
+                                                     child_flags.p, idx->nodes.p);
     c.launches += 8;
     PCLB_CUDA(cudaGetLastError());
   }

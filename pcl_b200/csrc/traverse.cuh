@@ -104,6 +104,52 @@ __device__ __forceinline__ bool traverse(const BvhNode* __restrict__ nodes, cons
   return ok;
 }
 
+// ---- start node of a SEEDED walk ---------------------------------------------------------------------------------
+// A walk that already holds a candidate at squared distance `best` (the previous iteration's match, re-measured) only
+// has to look at points inside the closed ball B(q, sqrt(best)).  The tree is a radix tree over Morton codes, so a
+// SPATIAL cell X (BvhNode::d.z) holds every indexed point whose code starts with X's prefix, i.e. every indexed point
+// of an axis-aligned region that contains box(X).  Hence, if the ball lies inside box(X), every point of the ball
+// belongs to X's subtree and the walk can start at X instead of the root: the 20-odd levels above X are never touched.
+// climb_start walks up from the seed's leaf (parent arrays of the index) until such an X is found, at most kClimbLevels
+// levels; otherwise it returns the root.  `factor` (> 1) inflates the radius: 1.00001 covers the fp32 rounding of the
+// distances that are compared later (relative error ~3e-7), larger values buy a larger exit distance for the
+// temporal-coherence bound.  *exit2 = squared distance from q to the outside of box(X) (rounded down; +inf for the
+// root): a lower bound on the squared distance to every point the restricted walk does not see.
+constexpr int kClimbLevels = 12;
+
+__device__ __forceinline__ int climb_start(const BvhNode* __restrict__ nodes, const int* __restrict__ node_parent,
+                                           const int* __restrict__ leaf_parent, int root, int seed_leaf, float qx,
+                                           float qy, float qz, float best, float factor, float* __restrict__ exit2)
+{
+  *exit2 = __int_as_float(0x7f800000);
+  if (node_parent == nullptr || !(best < __int_as_float(0x7f800000)))
+    return root;
+  const float r = __fmul_ru(__fsqrt_ru(best), factor);
+  int child = ~seed_leaf;
+  int cur = __ldg(leaf_parent + seed_leaf);
+#pragma unroll 1
+  for (int lvl = 0; lvl < kClimbLevels && cur >= 0; ++lvl) {
+    const float4* np = reinterpret_cast<const float4*>(nodes + cur);
+    const int4 d = __ldg(reinterpret_cast<const int4*>(np + 3));
+    const bool is_left = d.x == child;
+    if ((d.z >> (is_left ? 0 : 1)) & 1) {
+      const float4 a = ldg4(np), b = ldg4(np + 1), c = ldg4(np + 2);
+      const float lox = is_left ? a.x : b.z, loy = is_left ? a.y : b.w, loz = is_left ? a.z : c.x;
+      const float hix = is_left ? a.w : c.y, hiy = is_left ? b.x : c.z, hiz = is_left ? b.y : c.w;
+      // distance from q to the nearest face, rounded down; negative when q is outside the box
+      const float e = fminf(fminf(fminf(__fsub_rd(qx, lox), __fsub_rd(hix, qx)), fminf(__fsub_rd(qy, loy), __fsub_rd(hiy, qy))),
+                            fminf(__fsub_rd(qz, loz), __fsub_rd(hiz, qz)));
+      if (e >= r) {
+        *exit2 = __fmul_rd(e, e);
+        return child;
+      }
+    }
+    child = cur;
+    cur = __ldg(node_parent + cur);
+  }
+  return root;
+}
+
 // ---- 1-NN visitor: lexicographic (d2, original index) minimum --------------------------------
 // TRACK = true additionally maintains a LOWER BOUND on the distance to every point other than the best one:
 //   m2     = second smallest d2 among the points actually evaluated during the walk

@@ -461,6 +461,12 @@ def _coherence_scenes():
     yield "cube_gated", cube, (cube[:20000].astype(np.float64) * 1.0005 + 0.002).astype(np.float32), 0.02
     g = np.stack(np.meshgrid(*[np.arange(24, dtype=np.float32)] * 3, indexing="ij"), -1).reshape(-1, 3)
     yield "lattice_ties", g, (g[::3] + np.float32(0.26)).astype(np.float32), 1e9
+    # every target point 12 times (more copies than a leaf holds: the tree has to cut INSIDE runs of equal Morton codes,
+    # the cells a seeded walk must not start from) plus clusters far tighter than the quantisation step
+    base = rng.random((1500, 3), dtype=np.float32)
+    dup = np.concatenate([np.repeat(base, 12, axis=0), base[:200] + np.float32(1e-7) * rng.standard_normal((200, 3)).astype(np.float32)])
+    dup = dup[rng.permutation(dup.shape[0])]
+    yield "duplicates_x12", dup, (base[:900].astype(np.float64) * 1.001 + 0.0007).astype(np.float32), 1e9
 
 
 def test_icp_per_iteration_correspondences_exact(gpu, orc):
@@ -470,14 +476,17 @@ def test_icp_per_iteration_correspondences_exact(gpu, orc):
     lower-bound tracking forced on from the first iteration, on scenes with duplicates, exact ties, a gate and NaNs."""
     import os
     P, ctx = gpu
-    os.environ["PCLB200_TRACK"] = "1"
     total_skipped = 0
     try:
         for name, tgt, src, gate in _coherence_scenes():
             T, S = P.xyz1(tgt), P.xyz1(src)
             oidx = orc.Index(T)
-            for search in ("packet", "single"):
+            # (search kernel, lower-bound tracking, seeded walks start at the smallest cell holding their candidate ball)
+            for search, track, climb in (("packet", "1", "0"), ("single", "1", "0"), ("single", "1", "1"), ("single", "0", "1"),
+                                         ("single", "0", "0")):
                 os.environ["PCLB200_SEARCH"] = search
+                os.environ["PCLB200_TRACK"] = track
+                os.environ["PCLB200_CLIMB"] = climb
                 s = P.Icp(ctx, max_iterations=30, max_correspondence_distance=gate, is_dense=0, mse_threshold_absolute=0.0)
                 s.set_target(P.Index(ctx, T))
                 s.set_source(S)
@@ -487,7 +496,7 @@ def test_icp_per_iteration_correspondences_exact(gpu, orc):
                     st = s.iterate(1)
                     g = s.get_correspondences()
                     o = oidx.correspondences(cloud, max_distance=gate, is_dense=False, nthreads=4)
-                    assert np.array_equal(g, o), (name, search, it, g.size, o.size)
+                    assert np.array_equal(g, o), (name, search, track, climb, it, g.size, o.size)
                     assert st["n_correspondences"] == o.size
                     cloud = orc.transform(cloud, st["last"], mode=0)   # IterativeClosestPoint::transformCloud, fp32
                     if st["state"] != 0:
@@ -497,6 +506,7 @@ def test_icp_per_iteration_correspondences_exact(gpu, orc):
     finally:
         os.environ.pop("PCLB200_SEARCH", None)
         os.environ.pop("PCLB200_TRACK", None)
+        os.environ.pop("PCLB200_CLIMB", None)
 
 
 def test_rejectors_golden_and_oracle(gpu, golden, orc):
