@@ -7,10 +7,11 @@
 //   2. 63-bit Morton key per point (21 bits/axis, ONE isotropic scale so cells are cubes);
 //      non-finite points get key ~0 and sort to the tail
 //   3. cub::DeviceRadixSort (key64, value = original index) — stable, so equal keys keep index order
-//   4. gather to float4 {x,y,z, original-index bits}: a leaf of 8 points is one 128-byte line
-//   5. Karras 2012 binary radix tree over LEAVES (key = first point's code, ties by leaf id)
-//   6. bottom-up refit (atomic arrival flags), then pack both children's boxes into the parent's
-//      64-byte node so one node visit = four independent 128-bit loads
+//   4. Karras 2012 binary radix tree over the POINTS (ties by index), cut where a cell holds <= 8 points: every leaf is a
+//      whole radix-tree cell, stored as one 128-byte line of float4 {x,y,z, original-index bits} padded with +inf
+//   5. bottom-up refit (atomic arrival flags), then both children's boxes are packed into the parent's 64-byte node so
+//      one node visit = four independent 128-bit loads; parent arrays and "spatial cell" flags are kept for walks
+//      that start below the root (traverse.cuh: climb_start)
 #include <cub/cub.cuh>
 
 #include <algorithm>
@@ -241,66 +242,6 @@ __global__ void k_gather_sorted(const float4* __restrict__ p, const int32_t* __r
     const float inf = __int_as_float(0x7f800000);
     out[j] = make_float4(inf, inf, inf, __int_as_float(kSentinelIndex));
   }
-}
-
-// ---- Karras 2012 over leaves --------------------------------------------------------------------
-__device__ __forceinline__ int delta_leaf(const unsigned long long* __restrict__ keys, int n, int i, int j)
-{
-  if (j < 0 || j >= n)
-    return -1;
-  unsigned long long a = keys[(size_t)i * kLeafSize], b = keys[(size_t)j * kLeafSize];
-  unsigned long long x = a ^ b;
-  if (x == 0)
-    return 64 + __clz(i ^ j);
-  return __clzll((long long)x);
-}
-
-__global__ void k_karras(const unsigned long long* __restrict__ keys /* sorted point keys */, int n_leaves,
-                         int2* __restrict__ children, int* __restrict__ node_parent, int* __restrict__ leaf_parent)
-{
-  int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n_leaves - 1)
-    return;
-  const int n = n_leaves;
-  int d = (delta_leaf(keys, n, i, i + 1) - delta_leaf(keys, n, i, i - 1)) >= 0 ? 1 : -1;
-  int dmin = delta_leaf(keys, n, i, i - d);
-  int lmax = 2;
-  while (delta_leaf(keys, n, i, i + lmax * d) > dmin)
-    lmax <<= 1;
-  int l = 0;
-  for (int t = lmax >> 1; t >= 1; t >>= 1)
-    if (delta_leaf(keys, n, i, i + (l + t) * d) > dmin)
-      l += t;
-  int j = i + l * d;
-  int dnode = delta_leaf(keys, n, i, j);
-  int s = 0;
-  int t = l;
-  do {
-    t = (t + 1) >> 1;
-    if (delta_leaf(keys, n, i, i + (s + t) * d) > dnode)
-      s += t;
-  } while (t > 1);
-  int gamma = i + s * d + min(d, 0);
-  int left, right;
-  if (min(i, j) == gamma) {
-    left = ~gamma;
-    leaf_parent[gamma] = i;
-  }
-  else {
-    left = gamma;
-    node_parent[gamma] = i;
-  }
-  if (max(i, j) == gamma + 1) {
-    right = ~(gamma + 1);
-    leaf_parent[gamma + 1] = i;
-  }
-  else {
-    right = gamma + 1;
-    node_parent[gamma + 1] = i;
-  }
-  children[i] = make_int2(left, right);
-  if (i == 0)
-    node_parent[0] = -1;
 }
 
 // ---- refit --------------------------------------------------------------------------------------
