@@ -328,6 +328,183 @@ k_search(const IterArgs a, Match* __restrict__ match)
     atomicExch(a.d_error, 1);
 }
 
+// Per-query walk with DYNAMIC FETCH (persistent warps).  In k_search the lanes of a warp start 32 walks together and
+// the warp lasts as long as its longest walk: ncu shows 13 of 32 lanes doing useful work per instruction.  Here a lane
+// whose walk has ended takes the next query of its block's contiguous range (one shared counter per block, so the
+// eight warps of a block keep consuming one spatially coherent stream) while its neighbours keep walking; lanes are
+// refilled whenever fewer than kRefillBelow of them are busy.  The walk itself is traverse()'s while-while loop unrolled
+// into rounds (descend while the node is internal -> scan a leaf -> pop), so the per-query result is identical.
+constexpr int kRefillBelow = 24;
+
+template <bool TRACK>
+__global__ void __launch_bounds__(256)
+k_search_dyn(const IterArgs a, Match* __restrict__ match)
+{
+  __shared__ Pending sP;
+  __shared__ unsigned long long s_next;
+  const unsigned full = 0xffffffffu;
+  const int lane = threadIdx.x & 31;
+  // this block's contiguous range of queries (multiple of 32 so refills stay aligned)
+  const size_t per_block = (((a.n + gridDim.x - 1) / gridDim.x) + 31) / 32 * 32;
+  const size_t blk_begin = (size_t)blockIdx.x * per_block;
+  const size_t blk_end = blk_begin + per_block < a.n ? blk_begin + per_block : a.n;
+  if (threadIdx.x == 0) {
+    sP = *a.pending;
+    s_next = blk_begin;
+  }
+  __syncthreads();
+  bool overflow = false;
+  // per-lane walk state
+  bool busy = false;
+  size_t qi = 0;
+  float px = 0.f, py = 0.f, pz = 0.f;
+  int node = kDone, sp = 0;
+  int stack_node[kStackSize];
+  float stack_dist[kStackSize];
+  Nearest1T<TRACK> v{0.f, 0.f, 0.f, 0.f, kSentinelIndex, -1, 0.f, 0.f, 0.f};
+  bool exhausted = blk_begin >= blk_end;  // warp-uniform: the block's range has been handed out completely
+  for (;;) {
+    const unsigned busy_mask = __ballot_sync(full, busy);
+    if (__popc(busy_mask) < kRefillBelow && !exhausted) {
+      // ---- refill: idle lanes take consecutive queries --------------------------------------------------------
+      const unsigned idle = ~busy_mask;
+      const int want = __popc(idle);
+      unsigned long long base = 0;
+      if (lane == 0)
+        base = atomicAdd(&s_next, (unsigned long long)want);
+      base = __shfl_sync(full, base, 0);
+      if (base + (unsigned long long)want >= (unsigned long long)blk_end)
+        exhausted = true;
+      const size_t i = (size_t)base + (size_t)__popc(idle & ((1u << lane) - 1u));
+      if (!busy && i < blk_end) {
+        float4 p = a.cur[i];
+        const Match prev = match[i];
+        Match m;
+        m.pos = -1;
+        m.d2 = 0.f;
+        m.lb = 0.f;
+        m.accepted = 0;
+        bool walk = false;
+        if (isfinite(p.x) && isfinite(p.y) && isfinite(p.z)) {
+          float delta = 0.f;
+          if (sP.apply) {
+            const float ox = p.x, oy = p.y, oz = p.z;
+            apply_pending(sP, p.x, p.y, p.z);
+            a.cur[i] = p;
+            delta = sqrtf(dist2_rn(p.x, p.y, p.z, ox, oy, oz));
+            if (a.cur_normals) {
+              float4 nn = a.cur_normals[i];
+              apply_pending_normal(sP, nn.x, nn.y, nn.z);
+              a.cur_normals[i] = nn;
+            }
+          }
+          float nlb;
+          if (TRACK && still_nearest(prev, delta, &nlb)) {
+            const float4 q = ldg4(a.pts + prev.pos);
+            m.pos = prev.pos;
+            m.d2 = dist2_rn(p.x, p.y, p.z, q.x, q.y, q.z);
+            m.lb = nlb;
+            m.accepted = m.d2 <= a.gate ? 1 : 0;
+            atomicAdd(a.skip_count, 1ULL);
+          }
+          else {
+            v = Nearest1T<TRACK>{p.x, p.y, p.z, a.gate, kSentinelIndex, -1, __int_as_float(0x7f800000),
+                                 __int_as_float(0x7f800000), __int_as_float(0x7f800000)};
+            if (prev.pos >= 0) {
+              const int leaf = prev.pos / kLeafSize;
+              v.template scan<false>(a.pts + (size_t)leaf * kLeafSize, leaf * kLeafSize);
+            }
+            walk = true;
+          }
+        }
+        if (walk) {
+          busy = true;
+          qi = i;
+          px = p.x; py = p.y; pz = p.z;
+          node = a.root;
+          sp = 0;
+        }
+        else
+          match[i] = m;
+      }
+      continue;
+    }
+    if (busy_mask == 0)
+      break;  // nothing in flight and nothing left to fetch
+    // ---- one round of the while-while walk ------------------------------------------------------------------------
+    while (busy && node >= 0 && node != kDone) {
+      const float4* np = reinterpret_cast<const float4*>(a.nodes + node);
+      const float4 na = ldg4(np), nb = ldg4(np + 1), nc = ldg4(np + 2);
+      const int4 nd = __ldg(reinterpret_cast<const int4*>(np + 3));
+      float dl = box_dist2_rn(px, py, pz, na.x, na.y, na.z, na.w, nb.x, nb.y);
+      float dr = box_dist2_rn(px, py, pz, nb.z, nb.w, nc.x, nc.y, nc.z, nc.w);
+      int nl = nd.x, nr = nd.y;
+      if (dr < dl) {
+        float t = dl; dl = dr; dr = t;
+        int ti = nl; nl = nr; nr = ti;
+      }
+      const float bnd = v.bound();
+      if (dl <= bnd) {
+        if (dr <= bnd) {
+          if (sp < kStackSize) {
+            stack_node[sp] = nr;
+            stack_dist[sp] = dr;
+            ++sp;
+          }
+          else
+            overflow = true;
+        }
+        else
+          v.prune(dr);
+        node = nl;
+      }
+      else {
+        v.prune(dl);
+        node = kDone;
+        while (sp > 0) {
+          --sp;
+          if (stack_dist[sp] <= bnd) {
+            node = stack_node[sp];
+            break;
+          }
+          v.prune(stack_dist[sp]);
+        }
+      }
+    }
+    if (busy && node != kDone) {  // node < 0: a leaf
+      const int leaf = ~node;
+      v.leaf(a.pts + (size_t)leaf * kLeafSize, leaf * kLeafSize);
+      node = kDone;
+      const float bnd = v.bound();
+      while (sp > 0) {
+        --sp;
+        if (stack_dist[sp] <= bnd) {
+          node = stack_node[sp];
+          break;
+        }
+        v.prune(stack_dist[sp]);
+      }
+    }
+    if (busy && node == kDone) {  // walk finished: publish and become idle
+      Match m;
+      m.pos = -1;
+      m.d2 = 0.f;
+      m.lb = 0.f;
+      m.accepted = 0;
+      if (v.best_pos >= 0) {
+        m.pos = v.best_pos;
+        m.d2 = v.best;
+        m.lb = TRACK ? sqrtf(v.lower_bound2()) : 0.f;
+        m.accepted = 1;
+      }
+      match[qi] = m;
+      busy = false;
+    }
+  }
+  if (overflow)
+    atomicExch(a.d_error, 1);
+}
+
 // Packet variant: the 32 Morton/Hilbert-adjacent queries of a warp share ONE walk of the tree (traverse_packet).
 // Lanes whose previous match is provably still nearest (still_nearest) sit the walk out; a warp whose 32 lanes all
 // pass the test does not touch the tree at all.  Chosen by the host when the queries are about as dense as the
@@ -1682,7 +1859,14 @@ void icp_iterate(Icp& s, int max_steps, pclb200_icp_stats* stats)
           k_search_packet<false, false><<<sgrid, 256, 0, st>>>(a, s.match.p);
       }
       else {
-        if (s.P.use_reciprocal)
+        // PCLB200_SEARCH=dynamic: persistent warps with dynamic fetch (k_search_dyn) instead of one walk per thread
+        const bool dyn = force && force[0] == 'd' && !s.P.use_reciprocal;
+        const unsigned dgrid = persistent_grid(c, s.n_q, 256, 4);
+        if (dyn && track)
+          k_search_dyn<true><<<dgrid, 256, 0, st>>>(a, s.match.p);
+        else if (dyn)
+          k_search_dyn<false><<<dgrid, 256, 0, st>>>(a, s.match.p);
+        else if (s.P.use_reciprocal)
           k_search<true, false><<<sgrid, 256, 0, st>>>(a, s.match.p);
         else if (track)
           k_search<false, true><<<sgrid, 256, 0, st>>>(a, s.match.p);

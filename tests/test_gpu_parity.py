@@ -481,9 +481,10 @@ def test_icp_per_iteration_correspondences_exact(gpu, orc):
         for name, tgt, src, gate in _coherence_scenes():
             T, S = P.xyz1(tgt), P.xyz1(src)
             oidx = orc.Index(T)
-            # (search kernel, lower-bound tracking, seeded walks start at the smallest cell holding their candidate ball)
+            # (search kernel [dynamic = persistent warps with dynamic fetch], lower-bound tracking, seeded walks start at
+            # the smallest cell holding their candidate ball)
             for search, track, climb in (("packet", "1", "0"), ("single", "1", "0"), ("single", "1", "1"), ("single", "0", "1"),
-                                         ("single", "0", "0")):
+                                         ("single", "0", "0"), ("dynamic", "1", "0"), ("dynamic", "0", "0")):
                 os.environ["PCLB200_SEARCH"] = search
                 os.environ["PCLB200_TRACK"] = track
                 os.environ["PCLB200_CLIMB"] = climb
