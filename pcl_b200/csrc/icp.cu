@@ -122,6 +122,8 @@ struct IterArgs {
   int enforce_same_dir;
   const int* node_parent;          // parent arrays of the target index (nullptr = seeded walks start at the root)
   const int* leaf_parent;
+  TopTables top;                   // prefix tables of the target index (all nullptr = not used)
+  int top_on;
   // fused cross-GPU reduce (optional): peer-mapped exchange buffers + this iteration's sequence number
   PeerView peer;
   unsigned long long seq;
@@ -301,6 +303,14 @@ k_search(const IterArgs a, Match* __restrict__ match)
           start = climb_start(a.nodes, a.node_parent, a.leaf_parent, a.root, leaf, p.x, p.y, p.z, v.best,
                               TRACK ? 3.f : 1.00001f, &exit2);
           v.prune(exit2);  // every point outside the start cell is at least that far (no-op for the root / non-TRACK)
+          if (a.top_on && v.best < __int_as_float(0x7f800000)) {
+            // prefix tables: one coherent load instead of the descent (traverse.cuh: top_start).  The radius is inflated
+            // like climb_start's; every indexed point outside the start subtree lies outside [q - r, q + r]^3.
+            const float r = __fmul_ru(__fsqrt_ru(v.best), TRACK ? 3.f : 1.00001f);
+            start = top_start(a.top, a.root, p.x, p.y, p.z, r);
+            if (start != a.root)
+              v.prune(__fmul_rd(r, r));
+          }
         }
         if (!traverse(a.nodes, a.pts, start, p.x, p.y, p.z, v))
           overflow = true;
@@ -1778,6 +1788,17 @@ void icp_iterate(Icp& s, int max_steps, pclb200_icp_stats* stats)
       const bool climb = cl ? cl[0] == '1' : kClimbDefault;
       a.node_parent = climb ? T.node_parent.p : nullptr;
       a.leaf_parent = climb ? T.leaf_parent.p : nullptr;
+      // prefix tables (built only when PCLB200_TOP=1 was set at index-build time)
+      a.top_on = 0;
+      for (int b = 0; b < kTopLevels; ++b) {
+        a.top.table[b] = T.top[b].p;
+        if (T.top[b].p)
+          a.top_on = 1;
+      }
+      a.top.lo[0] = T.lo[0];
+      a.top.lo[1] = T.lo[1];
+      a.top.lo[2] = T.lo[2];
+      a.top.scale = T.morton_scale;
     }
     a.peer.nranks = 0;
     a.seq = 0;

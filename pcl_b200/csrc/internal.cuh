@@ -182,9 +182,13 @@ struct Index {
   DevBuf<int32_t> pos_of_orig;  // n_cloud: position in `pts` of original index i, or -1 (lazy)
   DevBuf<int> node_parent;      // n_leaves-1: parent of internal node i (-1 for the root); seeded walks climb with it
   DevBuf<int> leaf_parent;      // n_leaves: internal node that holds leaf l as a child
+  DevBuf<int> top[5];           // prefix tables, 3b-bit Morton prefix -> deepest node holding all its points, b = 4..8
+                                // (traverse.cuh: top_start; levels above ~4 entries per point are not built)
   size_t bytes() const
   {
-    return pts.bytes() + nodes.bytes() + pos_of_orig.bytes() + node_parent.bytes() + leaf_parent.bytes();
+    size_t t = 0;
+    for (const auto& b : top) t += b.bytes();
+    return pts.bytes() + nodes.bytes() + pos_of_orig.bytes() + node_parent.bytes() + leaf_parent.bytes() + t;
   }
 };
 

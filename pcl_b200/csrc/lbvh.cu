@@ -20,6 +20,7 @@
 #include <memory>
 
 #include "internal.cuh"
+#include "traverse.cuh"
 
 namespace pclb200 {
 
@@ -154,25 +155,11 @@ __global__ void k_bbox(const float4* __restrict__ p, size_t n, BBoxAcc* acc)
 }
 
 // ---- Morton keys --------------------------------------------------------------------------------
-__device__ __forceinline__ unsigned long long expand21(unsigned long long v)
-{
-  v &= 0x1fffffULL;
-  v = (v | v << 32) & 0x1f00000000ffffULL;
-  v = (v | v << 16) & 0x1f0000ff0000ffULL;
-  v = (v | v << 8) & 0x100f00f00f00f00fULL;
-  v = (v | v << 4) & 0x10c30c30c30c30c3ULL;
-  v = (v | v << 2) & 0x1249249249249249ULL;
-  return v;
-}
-
 __device__ __forceinline__ unsigned long long morton63(float x, float y, float z, float lx, float ly, float lz,
                                                        float scale)
 {
-  float fx = fminf(fmaxf((x - lx) * scale, 0.f), 2097151.f);
-  float fy = fminf(fmaxf((y - ly) * scale, 0.f), 2097151.f);
-  float fz = fminf(fmaxf((z - lz) * scale, 0.f), 2097151.f);
-  return (expand21((unsigned long long)fz) << 2) | (expand21((unsigned long long)fy) << 1) |
-         expand21((unsigned long long)fx);
+  return (expand21(morton_cell(z, lz, scale)) << 2) | (expand21(morton_cell(y, ly, scale)) << 1) |
+         expand21(morton_cell(x, lx, scale));
 }
 
 // 63-bit Hilbert index of the same 21-bit cell coordinates (Skilling's transpose algorithm).  Used to ORDER QUERIES
@@ -182,9 +169,9 @@ __device__ __forceinline__ unsigned long long hilbert63(float x, float y, float 
                                                         float scale)
 {
   unsigned X[3];
-  X[0] = (unsigned)fminf(fmaxf((x - lx) * scale, 0.f), 2097151.f);
-  X[1] = (unsigned)fminf(fmaxf((y - ly) * scale, 0.f), 2097151.f);
-  X[2] = (unsigned)fminf(fmaxf((z - lz) * scale, 0.f), 2097151.f);
+  X[0] = morton_cell(x, lx, scale);
+  X[1] = morton_cell(y, ly, scale);
+  X[2] = morton_cell(z, lz, scale);
   const unsigned M = 1u << 20;
   for (unsigned Q = M; Q > 1; Q >>= 1) {
     const unsigned P = Q - 1;
@@ -425,12 +412,31 @@ __global__ void k_scatter_cells(const float4* __restrict__ p, const int32_t* __r
   out[(size_t)leaf * kLeafSize + (pos - leaf_start[leaf])] = make_float4(v.x, v.y, v.z, __int_as_float(oi));
 }
 
+struct TopTablesW {
+  int* table[kTopLevels];
+};
+
+// number of leading bits two 63-bit Morton codes share (63 when they are equal)
+__device__ __forceinline__ int prefix_len63(unsigned long long a, unsigned long long b)
+{
+  const unsigned long long x = a ^ b;
+  return x == 0 ? 63 : __clzll((long long)x) - 1;
+}
+
+__global__ void k_fill_int(int* __restrict__ p, size_t n, int v)
+{
+  size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+  if (i < n)
+    p[i] = v;
+}
+
 // children / parents of the final tree (kept nodes renumbered by new_id; everything below becomes a leaf)
 __global__ void k_link_cells(int n, const int2* __restrict__ children, const int2* __restrict__ range,
                              const int* __restrict__ keep, const int* __restrict__ new_id,
                              const int* __restrict__ leaf_incl, const unsigned long long* __restrict__ keys,
                              int2* __restrict__ out_children, int* __restrict__ out_node_parent,
-                             int* __restrict__ out_leaf_parent, unsigned char* __restrict__ out_child_flags)
+                             int* __restrict__ out_leaf_parent, unsigned char* __restrict__ out_child_flags,
+                             TopTablesW top)
 {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n - 1 || !keep[i])
@@ -460,6 +466,29 @@ __global__ void k_link_cells(int n, const int2* __restrict__ children, const int
   }
   out_children[nid] = make_int2(ref[0], ref[1]);
   out_child_flags[nid] = (unsigned char)flags;
+  // prefix tables (traverse.cuh: top_start): child C is the deepest node that holds every indexed point of a 3b-bit
+  // prefix cell exactly when  prefix_len(this node) < 3b <= prefix_len(C)
+  const int l_self = prefix_len63(keys[range[i].x], keys[range[i].y]);
+#pragma unroll
+  for (int k = 0; k < 2; ++k) {
+    const int cc = c2[k];
+    const int first = cc >= 0 ? range[cc].x : ~cc;
+    const int l_child = cc >= 0 ? prefix_len63(keys[range[cc].x], keys[range[cc].y]) : 63;
+    const bool is_leaf = !(cc >= 0 && keep[cc]);
+    const int last = cc >= 0 ? range[cc].y : ~cc;
+#pragma unroll
+    for (int b = kTopMinBits; b <= kTopMaxBits; ++b) {
+      int* tb = top.table[b - kTopMinBits];
+      if (tb == nullptr || !(l_self < 3 * b))
+        continue;
+      if (3 * b <= l_child)
+        tb[(size_t)(keys[first] >> (63 - 3 * b))] = ref[k];
+      else if (is_leaf)
+        // a leaf that spans several 3b-cells still holds every indexed point of each of them
+        for (int j = first; j <= last; ++j)
+          tb[(size_t)(keys[j] >> (63 - 3 * b))] = ref[k];
+    }
+  }
   if (i == 0)
     out_node_parent[nid] = -1;
 }
@@ -542,7 +571,8 @@ static void morton_sort(Ctx& c, const float4* d_pts, size_t n, const Index* fram
   PCLB_CUDA(cudaGetLastError());
 }
 
-static Index* build_from_dense(Ctx& c, const float4* d_pts, size_t n, const int32_t* d_orig_of_slot, size_t n_cloud)
+static Index* build_from_dense(Ctx& c, const float4* d_pts, size_t n, const int32_t* d_orig_of_slot, size_t n_cloud,
+                                bool build_top_tables)
 {
   cudaStream_t s = c.stream;
   PCLB_REQUIRE(n > 0, PCLB200_ERR_EMPTY, "cannot index an empty cloud (kdtree_flann.hpp:118-129)");
@@ -629,8 +659,24 @@ static Index* build_from_dense(Ctx& c, const float4* d_pts, size_t n, const int3
     k_fill_sentinels<<<grid_for(n_padded, 256), 256, 0, s>>>(idx->pts.p, n_padded);
     k_scatter_cells<<<grid_for(nv, 256), 256, 0, s>>>(d_pts, sc.vals.p, d_orig_of_slot, nv, leaf_incl.p, leaf_start.p,
                                                       idx->pts.p);
+    // prefix tables for walks that start below the root: level b (2^(3b) entries) is built while it stays within
+    // ~4 entries per indexed point; every entry starts as "root"
+    // (opt-in while the feature is being measured: PCLB200_TOP=1 at index-build time)
+    const char* top_env = getenv("PCLB200_TOP");
+    const bool want_top = build_top_tables && top_env && top_env[0] == '1';
+    TopTablesW topw;
+    for (int b = kTopMinBits; b <= kTopMaxBits; ++b) {
+      const size_t entries = (size_t)1 << (3 * b);
+      topw.table[b - kTopMinBits] = nullptr;
+      if (want_top && entries <= 4 * (size_t)nv) {
+        idx->top[b - kTopMinBits].alloc(entries, s);
+        k_fill_int<<<grid_for(entries, 256), 256, 0, s>>>(idx->top[b - kTopMinBits].p, entries, idx->root);
+        ++c.launches;
+        topw.table[b - kTopMinBits] = idx->top[b - kTopMinBits].p;
+      }
+    }
     k_link_cells<<<grid_for(ni, 256), 256, 0, s>>>(nv, kchildren.p, krange.p, keep.p, new_id.p, leaf_incl.p, sc.keys.p,
-                                                   children.p, node_parent.p, leaf_parent.p, child_flags.p);
+                                                   children.p, node_parent.p, leaf_parent.p, child_flags.p, topw);
     k_refit<<<grid_for(n_leaves, 256), 256, 0, s>>>(idx->pts.p, n_leaves, children.p, node_parent.p, leaf_parent.p,
                                                     leaf_lo.p, leaf_hi.p, node_lo.p, node_hi.p, flags.p);
     k_pack_nodes<<<grid_for(n_int, 256), 256, 0, s>>>(n_int, children.p, leaf_lo.p, leaf_hi.p, node_lo.p, node_hi.p,
@@ -661,12 +707,12 @@ Index* build_index(Ctx& c, const void* pts, size_t n, size_t stride, const int32
       d_orig = d_sub.p;
     }
   }
-  return build_from_dense(c, dense.p, cnt, d_orig, n);
+  return build_from_dense(c, dense.p, cnt, d_orig, n, true);
 }
 
 Index* build_index_from_device(Ctx& c, const float4* d_pts, size_t n, const int32_t* d_orig)
 {
-  return build_from_dense(c, d_pts, n, d_orig, n);
+  return build_from_dense(c, d_pts, n, d_orig, n, false);  // rebuilt every reciprocal iteration: no tables
 }
 
 // ---- position of each original index in the Morton array (for gathers by index_match) -------------

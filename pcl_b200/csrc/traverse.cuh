@@ -104,6 +104,57 @@ __device__ __forceinline__ bool traverse(const BvhNode* __restrict__ nodes, cons
   return ok;
 }
 
+// ---- Morton cell coordinates (shared by the build, lbvh.cu, and by walks that start below the root) --------------
+// 21-bit cell coordinate of x along one axis: the build's quantiser, monotone non-decreasing in x.
+__device__ __forceinline__ unsigned morton_cell(float x, float lo, float scale)
+{
+  return (unsigned)fminf(fmaxf(__fmul_rn(__fsub_rn(x, lo), scale), 0.f), 2097151.f);
+}
+
+__device__ __forceinline__ unsigned long long expand21(unsigned long long v)
+{
+  v &= 0x1fffffULL;
+  v = (v | v << 32) & 0x1f00000000ffffULL;
+  v = (v | v << 16) & 0x1f0000ff0000ffULL;
+  v = (v | v << 8) & 0x100f00f00f00f00fULL;
+  v = (v | v << 4) & 0x10c30c30c30c30c3ULL;
+  v = (v | v << 2) & 0x1249249249249249ULL;
+  return v;
+}
+
+// ---- start node from the prefix tables -------------------------------------------------------------------------------
+// Index::top[b - kTopMinBits][P] = the deepest node that holds EVERY indexed point whose 63-bit Morton code starts with
+// the 3b-bit prefix P (root where no such point exists).  A walk that only needs the points of the closed box
+// [q - r, q + r]^3 may start there if the box lies inside ONE 3b-cell: the quantiser is monotone, so every indexed point
+// of the box has a cell coordinate between those of the two corners, i.e. the same prefix — an integer test.  The finest
+// table whose cell holds the box is used; if even the coarsest does not, the walk starts at the root.
+constexpr int kTopMinBits = 4, kTopMaxBits = 8, kTopLevels = kTopMaxBits - kTopMinBits + 1;
+
+struct TopTables {
+  const int* table[kTopLevels];  // nullptr = level not built
+  float lo[3];
+  float scale;
+};
+
+__device__ __forceinline__ int top_start(const TopTables& T, int root, float qx, float qy, float qz, float r)
+{
+  const unsigned ax = morton_cell(__fsub_rd(qx, r), T.lo[0], T.scale), bx = morton_cell(__fadd_ru(qx, r), T.lo[0], T.scale);
+  const unsigned ay = morton_cell(__fsub_rd(qy, r), T.lo[1], T.scale), by = morton_cell(__fadd_ru(qy, r), T.lo[1], T.scale);
+  const unsigned az = morton_cell(__fsub_rd(qz, r), T.lo[2], T.scale), bz = morton_cell(__fadd_ru(qz, r), T.lo[2], T.scale);
+  const unsigned diff = (ax ^ bx) | (ay ^ by) | (az ^ bz);  // bit k set: some axis' corners differ in cell bit k
+  // the corners share their top b bits on every axis  <=>  diff < 2^(21 - b)
+  const int common = diff == 0 ? 21 : __clz(diff) - 11;  // number of shared leading bits (of 21)
+#pragma unroll
+  for (int b = kTopMaxBits; b >= kTopMinBits; --b) {
+    const int* tb = T.table[b - kTopMinBits];
+    if (tb != nullptr && common >= b) {
+      const unsigned long long key = (expand21(az) << 2) | (expand21(ay) << 1) | expand21(ax);
+      return __ldg(tb + (size_t)(key >> (63 - 3 * b)));
+    }
+  }
+  return root;
+}
+
 // ---- start node of a SEEDED walk ---------------------------------------------------------------------------------
 // A walk that already holds a candidate at squared distance `best` (the previous iteration's match, re-measured) only
 // has to look at points inside the closed ball B(q, sqrt(best)).  The tree is a radix tree over Morton codes, so a

@@ -483,11 +483,13 @@ def test_icp_per_iteration_correspondences_exact(gpu, orc):
             oidx = orc.Index(T)
             # (search kernel [dynamic = persistent warps with dynamic fetch], lower-bound tracking, seeded walks start at
             # the smallest cell holding their candidate ball)
-            for search, track, climb in (("packet", "1", "0"), ("single", "1", "0"), ("single", "1", "1"), ("single", "0", "1"),
-                                         ("single", "0", "0"), ("dynamic", "1", "0"), ("dynamic", "0", "0")):
+            for search, track, climb, top in (("packet", "1", "0", "0"), ("single", "1", "0", "0"), ("single", "1", "1", "0"),
+                                              ("single", "0", "1", "0"), ("single", "0", "0", "0"), ("dynamic", "1", "0", "0"),
+                                              ("dynamic", "0", "0", "0"), ("single", "1", "0", "1"), ("single", "0", "0", "1")):
                 os.environ["PCLB200_SEARCH"] = search
                 os.environ["PCLB200_TRACK"] = track
                 os.environ["PCLB200_CLIMB"] = climb
+                os.environ["PCLB200_TOP"] = top  # read when the index is built: prefix tables for walks below the root
                 s = P.Icp(ctx, max_iterations=30, max_correspondence_distance=gate, is_dense=0, mse_threshold_absolute=0.0)
                 s.set_target(P.Index(ctx, T))
                 s.set_source(S)
@@ -497,7 +499,7 @@ def test_icp_per_iteration_correspondences_exact(gpu, orc):
                     st = s.iterate(1)
                     g = s.get_correspondences()
                     o = oidx.correspondences(cloud, max_distance=gate, is_dense=False, nthreads=4)
-                    assert np.array_equal(g, o), (name, search, track, climb, it, g.size, o.size)
+                    assert np.array_equal(g, o), (name, search, track, climb, top, it, g.size, o.size)
                     assert st["n_correspondences"] == o.size
                     cloud = orc.transform(cloud, st["last"], mode=0)   # IterativeClosestPoint::transformCloud, fp32
                     if st["state"] != 0:
@@ -508,6 +510,7 @@ def test_icp_per_iteration_correspondences_exact(gpu, orc):
         os.environ.pop("PCLB200_SEARCH", None)
         os.environ.pop("PCLB200_TRACK", None)
         os.environ.pop("PCLB200_CLIMB", None)
+        os.environ.pop("PCLB200_TOP", None)
 
 
 def test_rejectors_golden_and_oracle(gpu, golden, orc):
