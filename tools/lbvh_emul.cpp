@@ -206,10 +206,12 @@ int main(int argc, char** argv)
   const int stride = (n / 32) / npk;
   double tot_nodes = 0, tot_leaves = 0, tot_pts = 0, tot_single_nodes = 0, tot_single_leaves = 0;
   double w_nodes = 0, w_boxes = 0, w_leaves = 0;
-#pragma omp parallel for reduction(+ : tot_nodes, tot_leaves, tot_pts, tot_single_nodes, tot_single_leaves, w_nodes, w_boxes, w_leaves) schedule(dynamic, 64)
+  double ls_max_nodes = 0, ls_max_leaves = 0, ls_depth = 0;  // lock-step view of the 32 single walks of a warp
+#pragma omp parallel for reduction(+ : tot_nodes, tot_leaves, tot_pts, tot_single_nodes, tot_single_leaves, w_nodes, w_boxes, w_leaves, ls_max_nodes, ls_max_leaves, ls_depth) schedule(dynamic, 64)
   for (int pk = 0; pk < npk; ++pk) {
     const P3* q = &src[(size_t)pk * stride * 32];
     float best[32];
+    int lane_nodes[32], lane_leaves[32];
     // seed = exact NN distance (what the previous iteration's match provides once ICP has nearly converged):
     // obtained here by a plain single-query traversal
     for (int l = 0; l < 32; ++l) {
@@ -227,15 +229,26 @@ int main(int argc, char** argv)
       best[l] = b;
       // single-query seeded walk cost
       std::vector<std::pair<int, float>> s2{{t.root, 0.f}};
+      lane_nodes[l] = lane_leaves[l] = 0;
       while (!s2.empty()) {
         auto [nd, dd] = s2.back(); s2.pop_back();
         if (dd > b) continue;
-        if (nd < 0) { tot_single_leaves += 1; continue; }
+        if (nd < 0) { tot_single_leaves += 1; lane_leaves[l] += 1; continue; }
         tot_single_nodes += 1;
+        lane_nodes[l] += 1;
         float d0 = bdist(q[l], t.nodes[nd].b[0]), d1 = bdist(q[l], t.nodes[nd].b[1]);
         if (d1 <= b) s2.push_back({t.nodes[nd].child[1], d1});
         if (d0 <= b) s2.push_back({t.nodes[nd].child[0], d0});
       }
+    }
+    {
+      int mn = 0, ml = 0;
+      for (int l = 0; l < 32; ++l) { mn = std::max(mn, lane_nodes[l]); ml = std::max(ml, lane_leaves[l]); }
+      ls_max_nodes += mn; ls_max_leaves += ml;
+      // depth of the query's own leaf = nodes on the direct path (lane 0)
+      int d = 0, nd = t.root;
+      while (nd >= 0) { ++d; float d0 = bdist(q[0], t.nodes[nd].b[0]), d1 = bdist(q[0], t.nodes[nd].b[1]); nd = d0 <= d1 ? t.nodes[nd].child[0] : t.nodes[nd].child[1]; }
+      ls_depth += d;
     }
     // 4-wide packet walk: a wide node = a binary node with its internal children expanded one level
     {
@@ -317,6 +330,11 @@ int main(int argc, char** argv)
   }
   std::printf("packet walk: %.1f nodes, %.1f leaves, %.1f points per packet | single walk: %.1f nodes, %.1f leaves per query\n", tot_nodes / npk,
               tot_leaves / npk, tot_pts / npk, tot_single_nodes / npk / 32, tot_single_leaves / npk / 32);
+  std::printf("lock-step view of 32 seeded single walks: slowest lane %.1f nodes / %.1f leaves vs mean %.1f / %.1f (lane utilisation if\n"
+              "  all lanes ran to the slowest lane's count: nodes %.0f %%, leaves %.0f %%); depth of the direct path %.1f\n",
+              ls_max_nodes / npk, ls_max_leaves / npk, tot_single_nodes / npk / 32, tot_single_leaves / npk / 32,
+              100.0 * (tot_single_nodes / npk / 32) / (ls_max_nodes / npk), 100.0 * (tot_single_leaves / npk / 32) / (ls_max_leaves / npk),
+              ls_depth / npk);
   std::printf("4-wide packet walk: %.1f wide nodes, %.1f box tests, %.1f leaves per packet (binary: %.1f box tests)\n", w_nodes / npk, w_boxes / npk,
               w_leaves / npk, 2 * tot_nodes / npk);
   return 0;
