@@ -298,9 +298,10 @@ def run_ours(args):
             dist.destroy_process_group()
         return
 
-    # roofline of the dominant kernel (k_search_packet), algorithmic bytes per correspondence:
+    # roofline of the dominant kernel (k_search; the first search of a step is k_search_packet), algorithmic bytes per
+    # correspondence:
     #   16 source read + 16 source write-back (T_k applied in place) + 16 previous match read + 16 match write
-    #   + (target leaf slots + nodes, each read once under Hilbert-coherent query packets) / N_s
+    #   + (target leaf slots + nodes, each read about once under Hilbert-ordered queries) / N_s
     st_idx = tidx.stats
     bytes_per_corr = 16 + 16 + 16 + 16 + st_idx["bytes"] / float(n)
     peak, peak_src = measured_peak_gbs()
@@ -309,8 +310,8 @@ def run_ours(args):
     roofline = {"bound": "hbm", "kernel": "k_search (in-place transform + exact seeded 1-NN + gate; first search of a step: k_search_packet)", "achieved": achieved, "peak": peak,
                 "peak_source": peak_src, "unit": "GB/s", "frac": achieved / peak,
                 # dram__bytes_read.sum + dram__bytes_write.sum of one `ncu --set full` capture of this kernel on this
-                # workload (profiles/r1e_k_search_packet_ncu.txt: 657.6 MB + 288.0 MB); only valid for the 10 M default
-                "traffic": 945.6e6 if n == N_DEFAULT else None,
+                # workload (profiles/r1k_k_search_ncu.txt: k_search<0,0>, 698.3 MB + 313.6 MB); only valid for the 10 M default
+                "traffic": 1011.9e6 if n == N_DEFAULT else None,
                 "algorithmic_bytes_per_launch": bytes_per_corr * n, "avg_launch_ms": avg_iter_s * 1e3,
                 "launches_timed": iter_n, "algorithmic_bytes_per_correspondence": bytes_per_corr,
                 "index": st_idx,
