@@ -312,6 +312,7 @@ def run_ours(args):
     achieved = bytes_per_corr * n / avg_iter_s / 1e9 if avg_iter_s > 0 else 0.0
     roofline = {"bound": "hbm", "kernel": "k_search (in-place transform + exact seeded 1-NN + gate; first search of a step: k_search_packet)", "achieved": achieved, "peak": peak,
                 "peak_source": peak_src, "unit": "GB/s", "frac": achieved / peak,
+                "frac_of_nominal_8000_GBs": achieved / 8000.0,  # report both denominators
                 # dram__bytes_read.sum + dram__bytes_write.sum of one `ncu --set full` capture of this kernel on this
                 # workload (profiles/r1k_k_search_ncu.txt: k_search<0,0>, 698.3 MB + 313.6 MB); only valid for the 10 M default
                 "traffic": 1011.9e6 if n == N_DEFAULT else None,
