@@ -226,6 +226,13 @@ PCLB200_API int pclb200_estimate_symmetric_point_to_plane_lls(pclb200_ctx* ctx, 
 #define PCLB200_CONV_NO_CORRESPONDENCES 5
 #define PCLB200_CONV_FAILURE_AFTER_MAX_ITERATIONS 6
 
+/* Temporal coherence of the per-iteration 1-NN search: a query whose previous match is PROVABLY still its unique nearest
+ * neighbour (triangle inequality on a tracked lower bound) skips the tree walk.  Results are identical in every mode;
+ * AUTO (default) switches the tracking on once an iteration moves the cloud by less than half the RMS residual. */
+#define PCLB200_TRACK_AUTO 0
+#define PCLB200_TRACK_ON 1
+#define PCLB200_TRACK_OFF 2
+
 typedef struct pclb200_icp_params {
   int32_t max_iterations;         /* registration.h:566, default 10 */
   int32_t use_reciprocal;         /* icp.h:265-280 setUseReciprocalCorrespondences */
@@ -244,7 +251,7 @@ typedef struct pclb200_icp_params {
   double euclidean_fitness_epsilon;       /* registration.h:116, default -DBL_MAX */
   double mse_threshold_absolute;          /* default_convergence_criteria.h:307, default 1e-12 */
   int32_t correspondence_k;       /* k_ of the normal-shooting / back-projection estimators (setKSearch, default 10) */
-  int32_t reserved1;
+  int32_t track_mode;             /* PCLB200_TRACK_*: temporal-coherence skip test of the 1-NN search (exact either way) */
 } pclb200_icp_params;
 
 typedef struct pclb200_icp_stats {

@@ -16,6 +16,7 @@ LIB_PATH = os.environ.get("PCLB200_LIB", os.path.join(_HERE, "libpclb200.so"))  
 OK = 0
 ERR_CUDA, ERR_INVALID, ERR_EMPTY, ERR_LEAF_TOO_SMALL, ERR_INTERNAL, ERR_NCCL = -1, -2, -3, -4, -5, -6
 EST_SVD, EST_POINT_TO_PLANE_LLS, EST_SYMMETRIC_POINT_TO_PLANE_LLS = 0, 1, 2
+TRACK_AUTO, TRACK_ON, TRACK_OFF = 0, 1, 2
 CONV_NAMES = ["NOT_CONVERGED", "ITERATIONS", "TRANSFORM", "ABS_MSE", "REL_MSE", "NO_CORRESPONDENCES",
               "FAILURE_AFTER_MAX_ITERATIONS"]
 
@@ -35,7 +36,7 @@ class IcpParams(C.Structure):
                 ("enforce_same_direction_normals", C.c_int32), ("correspondence_kind", C.c_int32),
                 ("max_correspondence_distance", C.c_double), ("transformation_epsilon", C.c_double),
                 ("transformation_rotation_epsilon", C.c_double), ("euclidean_fitness_epsilon", C.c_double),
-                ("mse_threshold_absolute", C.c_double), ("correspondence_k", C.c_int32), ("reserved1", C.c_int32)]
+                ("mse_threshold_absolute", C.c_double), ("correspondence_k", C.c_int32), ("track_mode", C.c_int32)]
 
 
 class IcpStats(C.Structure):

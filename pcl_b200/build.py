@@ -29,7 +29,7 @@ def _newer(target, deps):
     return any(os.path.getmtime(d) > t for d in deps)
 
 
-def build(force=False, verbose=False, leaf=None, tag=None):
+def build(force=False, verbose=False, leaf=None, tag=None, defines=()):
     """leaf/tag: build an experimental variant (libpclb200_<tag>.so with -DPCLB_LEAF=<leaf>) next to the default."""
     global OBJ, SO
     flags = list(FLAGS)
@@ -38,6 +38,7 @@ def build(force=False, verbose=False, leaf=None, tag=None):
         SO = os.path.join(HERE, f"libpclb200_{tag}.so")
     if leaf:
         flags += [f"-DPCLB_LEAF={int(leaf)}"]
+    flags += [f"-D{d}" for d in defines]
     os.makedirs(OBJ, exist_ok=True)
     hdrs = [os.path.normpath(os.path.join(CSRC, h)) for h in HEADERS]
     jobs = []
@@ -78,4 +79,6 @@ if __name__ == "__main__":
             kw["leaf"] = int(a.split("=")[1])
         if a.startswith("--tag="):
             kw["tag"] = a.split("=")[1]
+        if a.startswith("--define="):
+            kw.setdefault("defines", []).append(a.split("=", 1)[1])
     print(build(force="--force" in sys.argv, verbose="--verbose" in sys.argv, **kw))

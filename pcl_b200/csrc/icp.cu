@@ -109,6 +109,7 @@ struct IterArgs {
   float gate;
   float ox, oy, oz;           // accumulation origin (target bbox centre)
   double* partials;           // gridDim.x * kAccum
+  double* partials2;          // gridDim.x * 128 (two 8x8 fp64 tiles per block: k_icp_wq)
   unsigned* counter;
   double* accum;              // kAccum
   int* d_error;
@@ -120,14 +121,63 @@ struct IterArgs {
   unsigned long long* skip_count;  // queries answered by the temporal-coherence test (statistics)
   float4* cur_normals;             // source normals, same order as cur (symmetric objective), rotated with T_k
   int enforce_same_dir;
-  const int* node_parent;          // parent arrays of the target index (nullptr = seeded walks start at the root)
-  const int* leaf_parent;
-  TopTables top;                   // prefix tables of the target index (all nullptr = not used)
-  int top_on;
+  CellTable cells;                 // cell table of the target index (walks start at the candidate ball)
   // fused cross-GPU reduce (optional): peer-mapped exchange buffers + this iteration's sequence number
   PeerView peer;
   unsigned long long seq;
 };
+
+// Fused all-reduce over NVLink peer memory (replaces a separate ncclAllReduce launch); called by every thread of the
+// LAST block of an accumulating kernel once a.accum[0..kAccum) holds this rank's totals.
+//   1. store this rank's totals into EVERY rank's slots[seq&1][rank][.]   (remote stores)
+//   2. fence, then publish the sequence number into every rank's flags[rank]
+//   3. wait until all peers have published >= seq in OUR flags, then fold the slots in rank order:
+//      every rank adds the same numbers in the same order => bitwise identical sums everywhere.
+// Two slot sets alternate by sequence parity: a peer can be at most one iteration ahead (it needs our flag for
+// seq+1 before it can finish seq+1), so it never overwrites what we are still reading.
+__device__ __forceinline__ void peer_exchange(const IterArgs& a)
+{
+  if (a.peer.nranks <= 1)
+    return;
+  __syncthreads();
+  const int buf = (int)(a.seq & 1ull);
+  if (threadIdx.x < kAccum) {
+    const double v = a.accum[threadIdx.x];
+    for (int p = 0; p < a.peer.nranks; ++p)
+      a.peer.slots[p][((size_t)buf * kMaxRanks + a.peer.rank) * kAccum + threadIdx.x] = v;
+  }
+  __threadfence_system();
+  __syncthreads();
+  if (threadIdx.x < a.peer.nranks)
+    *reinterpret_cast<volatile unsigned long long*>(&a.peer.flags[threadIdx.x][a.peer.rank]) = a.seq;
+  __shared__ int timed_out;
+  if (threadIdx.x == 0)
+    timed_out = 0;
+  __syncthreads();
+  if (threadIdx.x < a.peer.nranks) {
+    const volatile unsigned long long* f = a.peer.flags[a.peer.rank] + threadIdx.x;
+    const long long t0 = clock64();
+    while (*f < a.seq) {
+      if (clock64() - t0 > 20000000000LL) {  // ~10 s: a peer died — fail loudly instead of hanging the GPU
+        timed_out = 1;
+        break;
+      }
+    }
+  }
+  __threadfence_system();
+  __syncthreads();
+  if (timed_out) {
+    if (threadIdx.x == 0)
+      atomicExch(a.d_error, 2);
+  }
+  else if (threadIdx.x < kAccum) {
+    double v = 0.0;
+    const volatile double* mine = a.peer.slots[a.peer.rank] + (size_t)buf * kMaxRanks * kAccum;
+    for (int r = 0; r < a.peer.nranks; ++r)
+      v += mine[(size_t)r * kAccum + threadIdx.x];
+    a.accum[threadIdx.x] = v;
+  }
+}
 
 template <int NACC>
 __device__ __forceinline__ void block_reduce_and_publish(double* acc, const IterArgs& a)
@@ -170,103 +220,70 @@ __device__ __forceinline__ void block_reduce_and_publish(double* acc, const Iter
       a.accum[threadIdx.x] = 0.0;
     if (threadIdx.x == 0)
       *a.counter = 0;
-    if (a.peer.nranks > 1) {
-      // ---- fused all-reduce over NVLink peer memory (replaces a separate ncclAllReduce launch) ----
-      // 1. store this rank's totals into EVERY rank's slots[seq&1][rank][.]   (remote stores)
-      // 2. fence, then publish the sequence number into every rank's flags[rank]
-      // 3. wait until all peers have published >= seq in OUR flags, then fold the slots in rank order:
-      //    every rank adds the same numbers in the same order => bitwise identical sums everywhere.
-      // Two slot sets alternate by sequence parity: a peer can be at most one iteration ahead (it needs
-      // our flag for seq+1 before it can finish seq+1), so it never overwrites what we are still reading.
-      __syncthreads();
-      const int buf = (int)(a.seq & 1ull);
-      if (threadIdx.x < kAccum) {
-        const double v = a.accum[threadIdx.x];
-        for (int p = 0; p < a.peer.nranks; ++p)
-          a.peer.slots[p][((size_t)buf * kMaxRanks + a.peer.rank) * kAccum + threadIdx.x] = v;
-      }
-      __threadfence_system();
-      __syncthreads();
-      if (threadIdx.x < a.peer.nranks)
-        *reinterpret_cast<volatile unsigned long long*>(&a.peer.flags[threadIdx.x][a.peer.rank]) = a.seq;
-      __shared__ int timed_out;
-      if (threadIdx.x == 0)
-        timed_out = 0;
-      __syncthreads();
-      if (threadIdx.x < a.peer.nranks) {
-        const volatile unsigned long long* f = a.peer.flags[a.peer.rank] + threadIdx.x;
-        const long long t0 = clock64();
-        while (*f < a.seq) {
-          if (clock64() - t0 > 20000000000LL) {  // ~10 s: a peer died — fail loudly instead of hanging the GPU
-            timed_out = 1;
-            break;
-          }
-        }
-      }
-      __threadfence_system();
-      __syncthreads();
-      if (timed_out) {
-        if (threadIdx.x == 0)
-          atomicExch(a.d_error, 2);
-      }
-      else if (threadIdx.x < kAccum) {
-        double v = 0.0;
-        const volatile double* mine = a.peer.slots[a.peer.rank] + (size_t)buf * kMaxRanks * kAccum;
-        for (int r = 0; r < a.peer.nranks; ++r)
-          v += mine[(size_t)r * kAccum + threadIdx.x];
-        a.accum[threadIdx.x] = v;
-      }
-    }
+    peer_exchange(a);
   }
 }
 
-// match of one query, in Morton slot order of `cur`
-struct __align__(16) Match {
-  int pos;       // position of the nearest target point in the Morton array (-1 = unknown / none inside the gate)
-  float d2;      // squared distance to it
-  float lb;      // lower bound on the DISTANCE (not squared) from the query to every OTHER target point; 0 = unknown
-  int accepted;  // 1 = this iteration's correspondence (inside the gate, reciprocal test passed)
+// match of one query, in the (Hilbert) slot order of `cur`: this iteration's result and the next iteration's seed
+struct __align__(8) Match {
+  int pos;   // position of the nearest target point in the Morton array; -1 = none inside the gate;
+             // kNotAccepted set = found, but not a correspondence of this iteration (gate on a carried-over match,
+             // reciprocal test failed, dropped by a rejector) — still the seed of the next search
+  float d2;  // squared distance to it
 };
+constexpr int kNotAccepted = 1 << 30;
+constexpr int kPosMask = kNotAccepted - 1;
+__host__ __device__ __forceinline__ bool match_accepted(const Match& m) { return m.pos >= 0 && !(m.pos & kNotAccepted); }
+__host__ __device__ __forceinline__ int match_pos(const Match& m) { return m.pos & kPosMask; }  // only if m.pos >= 0
 
-constexpr bool kClimbDefault = false;  // see PCLB200_CLIMB in icp_iterate
+#ifdef PCLB_STATS
+__device__ unsigned long long g_walk_stats[8];
+#endif
+
 constexpr float kRelMargin = 1e-5f;  // >> fp32 rounding of the distances involved (~2e-7): keeps the skip test exact
+// TRACK walks look at a ball kTrackInflate times wider than the candidate distance: every point they do not see is
+// then at least that much farther than the match, which is the head-room the next iteration's skip test lives on
+constexpr float kTrackInflate = 2.5f;
 
 // Temporal-coherence test.  Let m be the previous match at distance D1 from the old query position, L a lower
 // bound on the distance from the old position to every other point, and delta the distance the query moved.
 // Triangle inequality: the new distance to m is <= D1 + delta, the new distance to any other x is >= L - delta.
 // If D1 + delta < L - delta (with a relative safety margin far above fp32 round-off) m is still the UNIQUE nearest
 // neighbour, so the exact search result is (m, dist2(p_new, m)) and the tree walk can be skipped.
-__device__ __forceinline__ bool still_nearest(const Match& prev, float delta, float* new_lb)
+__device__ __forceinline__ bool still_nearest(float prev_d2, float prev_lb, float delta, float* new_lb)
 {
-  if (prev.pos < 0 || !(prev.lb > 0.f))
+  if (!(prev_lb > 0.f))
     return false;
-  const float D1 = sqrtf(prev.d2);
+  const float D1 = sqrtf(prev_d2);
   const float lhs = (D1 + 2.f * delta) * (1.f + kRelMargin);
-  const float rhs = prev.lb * (1.f - kRelMargin);
-  *new_lb = (prev.lb - delta * (1.f + kRelMargin)) * (1.f - kRelMargin);
+  const float rhs = prev_lb * (1.f - kRelMargin);
+  *new_lb = (prev_lb - delta * (1.f + kRelMargin)) * (1.f - kRelMargin);
   return lhs < rhs && *new_lb > 0.f;
 }
 
-// Search kernel, one query per thread: [apply pending T_k] -> (skip test) -> exact 1-NN seeded with the previous
-// match (its leaf is scanned first, so the pruning bound is tight before the descent starts) -> gate -> optional
-// reciprocal back-search.  Lean on registers so the latency-bound walk runs at high occupancy.
+// Search kernel, one query per thread: apply the pending T_k in place (reference fp32 operation order, icp.hpp:49-111)
+// -> [TRACK: skip test] -> exact 1-NN started at the candidate ball (traverse.cuh: nearest1 — seed = previous match,
+// cell-table start, ordinary exact walk below) -> gate -> optional reciprocal back-search.
+// lbs (TRACK only): per query, a lower bound on the DISTANCE to every target point other than the match; 0 = unknown.
 template <bool RECIP, bool TRACK>
 __global__ void __launch_bounds__(256)
-k_search(const IterArgs a, Match* __restrict__ match)
+k_search(const IterArgs a, Match* __restrict__ match, float* __restrict__ lbs)
 {
   __shared__ Pending sP;
   if (threadIdx.x == 0)
     sP = *a.pending;
   __syncthreads();
+  const TreeView T{a.nodes, a.pts, a.root, a.cells};
   bool overflow = false;
+  unsigned skipped = 0;
+  WalkStats ws{};
   for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < a.n; i += (size_t)gridDim.x * blockDim.x) {
     float4 p = a.cur[i];
     const Match prev = match[i];
     Match m;
     m.pos = -1;
     m.d2 = 0.f;
-    m.lb = 0.f;
-    m.accepted = 0;
+    float lb_out = 0.f;
     if (isfinite(p.x) && isfinite(p.y) && isfinite(p.z)) {
       // non-finite points: transformCloud leaves them untouched (icp.hpp:90-91), no correspondence (:173-174)
       float delta = 0.f;
@@ -281,44 +298,25 @@ k_search(const IterArgs a, Match* __restrict__ match)
           a.cur_normals[i] = nn;
         }
       }
-      float nlb;
-      if (TRACK && !RECIP && still_nearest(prev, delta, &nlb)) {
-        const float4 q = ldg4(a.pts + prev.pos);
-        m.pos = prev.pos;
+      const int seed = prev.pos >= 0 ? match_pos(prev) : -1;
+      float nlb = 0.f;
+      if (TRACK && !RECIP && seed >= 0 && still_nearest(prev.d2, lbs[i], delta, &nlb)) {
+        const float4 q = ldg4(a.pts + seed);
         m.d2 = dist2_rn(p.x, p.y, p.z, q.x, q.y, q.z);
-        m.lb = nlb;
-        m.accepted = m.d2 <= a.gate ? 1 : 0;  // distance[0] > max_dist_sqr drops it (correspondence_estimation.hpp:176)
-        atomicAdd(a.skip_count, 1ULL);
+        // distance[0] > max_dist_sqr drops the pair (correspondence_estimation.hpp:176); the match stays the seed
+        m.pos = m.d2 <= a.gate ? seed : (seed | kNotAccepted);
+        lb_out = nlb;
+        ++skipped;
       }
       else {
-        Nearest1T<TRACK> v{p.x, p.y, p.z, a.gate, kSentinelIndex, -1, __int_as_float(0x7f800000),
-                           __int_as_float(0x7f800000), __int_as_float(0x7f800000)};
-        int start = a.root;
-        if (prev.pos >= 0) {
-          const int leaf = prev.pos / kLeafSize;
-          v.template scan<false>(a.pts + (size_t)leaf * kLeafSize, leaf * kLeafSize);
-          // the candidate ball now has radius sqrt(v.best): start at the smallest spatial cell that contains it
-          // (TRACK: a ball three times as wide, so the exit distance leaves room for the skip test's lower bound)
-          float exit2;
-          start = climb_start(a.nodes, a.node_parent, a.leaf_parent, a.root, leaf, p.x, p.y, p.z, v.best,
-                              TRACK ? 3.f : 1.00001f, &exit2);
-          v.prune(exit2);  // every point outside the start cell is at least that far (no-op for the root / non-TRACK)
-          if (a.top_on && v.best < __int_as_float(0x7f800000)) {
-            // prefix tables: one coherent load instead of the descent (traverse.cuh: top_start).  The radius is inflated
-            // like climb_start's; every indexed point outside the start subtree lies outside [q - r, q + r]^3.
-            const float r = __fmul_ru(__fsqrt_ru(v.best), TRACK ? 3.f : 1.00001f);
-            start = top_start(a.top, a.root, p.x, p.y, p.z, r);
-            if (start != a.root)
-              v.prune(__fmul_rd(r, r));
-          }
-        }
-        if (!traverse(a.nodes, a.pts, start, p.x, p.y, p.z, v))
+        const float inf = __int_as_float(0x7f800000);
+        Nearest1T<TRACK> v{p.x, p.y, p.z, a.gate, kSentinelIndex, -1, inf, inf, inf};
+        if (!nearest1<TRACK>(T, p.x, p.y, p.z, v, seed, TRACK ? kTrackInflate : 1.00001f, ws))
           overflow = true;
         if (v.best_pos >= 0) {
           m.pos = v.best_pos;
           m.d2 = v.best;
-          m.lb = TRACK ? sqrtf(v.lower_bound2()) : 0.f;
-          m.accepted = 1;
+          lb_out = TRACK ? sqrtf(v.lower_bound2()) : 0.f;
           if (RECIP) {
             // correspondence_estimation.hpp:259-269: 1-NN of the matched target point back into the source
             const float4 q = ldg4(a.pts + v.best_pos);
@@ -327,224 +325,222 @@ k_search(const IterArgs a, Match* __restrict__ match)
               overflow = true;
             const int slot = __float_as_int(p.w);
             const int my_orig = a.src_orig ? a.src_orig[slot] : slot;
-            m.accepted = (b.best_pos >= 0 && b.best_idx == my_orig) ? 1 : 0;
+            if (!(b.best_pos >= 0 && b.best_idx == my_orig))
+              m.pos |= kNotAccepted;
           }
         }
       }
     }
     match[i] = m;
+    if (TRACK)
+      lbs[i] = lb_out;
+  }
+#ifdef PCLB_STATS
+  for (int k = 0; k < 8; ++k)
+    atomicAdd(&g_walk_stats[k], (unsigned long long)ws.n[k]);
+#endif
+  if (TRACK) {
+    for (int o = 16; o > 0; o >>= 1)
+      skipped += __shfl_xor_sync(0xffffffffu, skipped, o);
+    if ((threadIdx.x & 31) == 0 && skipped)
+      atomicAdd(a.skip_count, (unsigned long long)skipped);
   }
   if (overflow)
     atomicExch(a.d_error, 1);
 }
 
-// Per-query walk with DYNAMIC FETCH (persistent warps).  In k_search the lanes of a warp start 32 walks together and
-// the warp lasts as long as its longest walk: ncu shows 13 of 32 lanes doing useful work per instruction.  Here a lane
-// whose walk has ended takes the next query of its block's contiguous range (one shared counter per block, so the
-// eight warps of a block keep consuming one spatially coherent stream) while its neighbours keep walking; lanes are
-// refilled whenever fewer than kRefillBelow of them are busy.  The walk itself is traverse()'s while-while loop unrolled
-// into rounds (descend while the node is internal -> scan a leaf -> pop), so the per-query result is identical.
-constexpr int kRefillBelow = 24;
+// =============================================================================================================
+// Warp work-queue search with fused tensor-core accumulation
+// =============================================================================================================
+// One query per thread wastes most of a warp: the lanes' walks differ in length (1..8 cells, 1..40 nodes), the warp
+// lasts as long as its longest lane, and ncu measured 11 of 32 lanes active per instruction.  Here a warp owns a batch
+// of 32 Hilbert-consecutive queries and a set of WORK QUEUES in shared memory; every unit of work — look one cell up,
+// visit one node, scan one leaf — is an item {reference, lower bound, owner query}, and each round all 32 lanes take
+// one item each OF THE SAME KIND, whoever the owner is.  A query with eight cells and a query with one keep the same
+// number of lanes busy.  The per-query state the items share (coordinates, current best) lives in shared memory; the
+// best is a 64-bit word (d2 bits << 32 | Morton position) updated by compare-and-swap under the reference's order
+// (smaller d2, then smaller ORIGINAL index), so the result does not depend on which lane scans which leaf.  Items are
+// popped LIFO (nearer child pushed last), i.e. depth first: bounds tighten early and the frontier stays short.
+// Exactness is the per-thread walk's (traverse.cuh): an item is only dropped when its bound exceeds the owner's best.
+//
+// Epilogue (EST >= 0): the 3x3 / 6x6 normal equations are sums of outer products, i.e. V^T V with V = one row of <= 8
+// components per correspondence — a dense fp64 contraction.  The warp stages its 32 rows in shared memory and issues
+// mma.sync.m8n8k4.f64 (fp64 tensor cores): the whole accumulator tile lives in TWO registers per lane instead of 29
+// fp64 registers per thread, which is what makes fusing the accumulation into the search kernel affordable.  The
+// Match array is still written (next iteration's seeds, getCorrespondences) but never read back by an accumulate pass.
+constexpr int kWqCells = 192, kWqLeaf = 128, kWqNode = 192;
+constexpr int kWqWarps = 4;
+constexpr int kEstNone = -1;
+constexpr unsigned kWqNoPos = 0x7fffffffu;
 
-template <bool TRACK>
-__global__ void __launch_bounds__(256)
-k_search_dyn(const IterArgs a, Match* __restrict__ match)
+struct __align__(16) WarpWork {
+  uint2 q[kWqCells + kWqLeaf + kWqNode];  // cell | leaf | node queues {reference, bound bits (low 5 bits = owner)};
+                                          // reused as two 32 x 8 fp64 staging tiles by the accumulate epilogue
+  unsigned long long best[32];            // per query: d2 bits << 32 | Morton position (kWqNoPos = none yet)
+  float qx[32], qy[32], qz[32];
+  int skipa[32], skipb[32];               // leaves already scanned by the owner (seed leaves)
+  unsigned m2[32], pruned[32];            // TRACK: second-smallest evaluated d2 / smallest bound of anything skipped
+};
+static_assert(sizeof(uint2) * (kWqCells + kWqLeaf + kWqNode) >= 2 * 32 * 8 * sizeof(double), "staging tiles must fit");
+
+__device__ __forceinline__ unsigned wq_pack(float bound, int owner) { return (__float_as_uint(bound) & ~31u) | (unsigned)owner; }
+__device__ __forceinline__ float wq_bound(unsigned bo) { return __uint_as_float(bo & ~31u); }  // rounded DOWN: still a lower bound
+__device__ __forceinline__ float wq_best_d2(const unsigned long long* slot)
 {
-  __shared__ Pending sP;
-  __shared__ unsigned long long s_next;
-  const unsigned full = 0xffffffffu;
-  const int lane = threadIdx.x & 31;
-  // this block's contiguous range of queries (multiple of 32 so refills stay aligned)
-  const size_t per_block = (((a.n + gridDim.x - 1) / gridDim.x) + 31) / 32 * 32;
-  const size_t blk_begin = (size_t)blockIdx.x * per_block;
-  const size_t blk_end = blk_begin + per_block < a.n ? blk_begin + per_block : a.n;
-  if (threadIdx.x == 0) {
-    sP = *a.pending;
-    s_next = blk_begin;
-  }
-  __syncthreads();
-  bool overflow = false;
-  // per-lane walk state
-  bool busy = false;
-  size_t qi = 0;
-  float px = 0.f, py = 0.f, pz = 0.f;
-  int node = kDone, sp = 0;
-  int stack_node[kStackSize];
-  float stack_dist[kStackSize];
-  Nearest1T<TRACK> v{0.f, 0.f, 0.f, 0.f, kSentinelIndex, -1, 0.f, 0.f, 0.f};
-  bool exhausted = blk_begin >= blk_end;  // warp-uniform: the block's range has been handed out completely
+  return __uint_as_float((unsigned)(*reinterpret_cast<const volatile unsigned long long*>(slot) >> 32));
+}
+
+// lexicographic-min update of a query's best with the point (d, pos, orig); returns the d2 bits that LOST (the displaced
+// previous best, or d itself when it did not win; 0xffffffff when nothing real lost) — TRACK folds those into m2
+__device__ __forceinline__ unsigned wq_update(unsigned long long* slot, float d, int pos, int orig,
+                                              const float4* __restrict__ pts)
+{
+  const unsigned md = __float_as_uint(d);
+  const unsigned long long mine = ((unsigned long long)md << 32) | (unsigned)pos;
+  unsigned long long cur = *reinterpret_cast<volatile unsigned long long*>(slot);
   for (;;) {
-    const unsigned busy_mask = __ballot_sync(full, busy);
-    if (__popc(busy_mask) < kRefillBelow && !exhausted) {
-      // ---- refill: idle lanes take consecutive queries --------------------------------------------------------
-      const unsigned idle = ~busy_mask;
-      const int want = __popc(idle);
-      unsigned long long base = 0;
-      if (lane == 0)
-        base = atomicAdd(&s_next, (unsigned long long)want);
-      base = __shfl_sync(full, base, 0);
-      if (base + (unsigned long long)want >= (unsigned long long)blk_end)
-        exhausted = true;
-      const size_t i = (size_t)base + (size_t)__popc(idle & ((1u << lane) - 1u));
-      if (!busy && i < blk_end) {
-        float4 p = a.cur[i];
-        const Match prev = match[i];
-        Match m;
-        m.pos = -1;
-        m.d2 = 0.f;
-        m.lb = 0.f;
-        m.accepted = 0;
-        bool walk = false;
-        if (isfinite(p.x) && isfinite(p.y) && isfinite(p.z)) {
-          float delta = 0.f;
-          if (sP.apply) {
-            const float ox = p.x, oy = p.y, oz = p.z;
-            apply_pending(sP, p.x, p.y, p.z);
-            a.cur[i] = p;
-            delta = sqrtf(dist2_rn(p.x, p.y, p.z, ox, oy, oz));
-            if (a.cur_normals) {
-              float4 nn = a.cur_normals[i];
-              apply_pending_normal(sP, nn.x, nn.y, nn.z);
-              a.cur_normals[i] = nn;
-            }
-          }
-          float nlb;
-          if (TRACK && still_nearest(prev, delta, &nlb)) {
-            const float4 q = ldg4(a.pts + prev.pos);
-            m.pos = prev.pos;
-            m.d2 = dist2_rn(p.x, p.y, p.z, q.x, q.y, q.z);
-            m.lb = nlb;
-            m.accepted = m.d2 <= a.gate ? 1 : 0;
-            atomicAdd(a.skip_count, 1ULL);
-          }
-          else {
-            v = Nearest1T<TRACK>{p.x, p.y, p.z, a.gate, kSentinelIndex, -1, __int_as_float(0x7f800000),
-                                 __int_as_float(0x7f800000), __int_as_float(0x7f800000)};
-            if (prev.pos >= 0) {
-              const int leaf = prev.pos / kLeafSize;
-              v.template scan<false>(a.pts + (size_t)leaf * kLeafSize, leaf * kLeafSize);
-            }
-            walk = true;
-          }
-        }
-        if (walk) {
-          busy = true;
-          qi = i;
-          px = p.x; py = p.y; pz = p.z;
-          node = a.root;
-          sp = 0;
-        }
-        else
-          match[i] = m;
-      }
-      continue;
+    const unsigned cd = (unsigned)(cur >> 32), cpos = (unsigned)cur;
+    bool better = md < cd;
+    if (md == cd) {
+      if (cpos == (unsigned)pos)
+        return md;  // the same point, scanned twice
+      const int corig = cpos == kWqNoPos ? kSentinelIndex : __float_as_int(__ldg(&pts[cpos].w));
+      better = orig < corig;
     }
-    if (busy_mask == 0)
-      break;  // nothing in flight and nothing left to fetch
-    // ---- one round of the while-while walk ------------------------------------------------------------------------
-    while (busy && node >= 0 && node != kDone) {
-      const float4* np = reinterpret_cast<const float4*>(a.nodes + node);
-      const float4 na = ldg4(np), nb = ldg4(np + 1), nc = ldg4(np + 2);
-      const int4 nd = __ldg(reinterpret_cast<const int4*>(np + 3));
-      float dl = box_dist2_rn(px, py, pz, na.x, na.y, na.z, na.w, nb.x, nb.y);
-      float dr = box_dist2_rn(px, py, pz, nb.z, nb.w, nc.x, nc.y, nc.z, nc.w);
-      int nl = nd.x, nr = nd.y;
-      if (dr < dl) {
-        float t = dl; dl = dr; dr = t;
-        int ti = nl; nl = nr; nr = ti;
-      }
-      const float bnd = v.bound();
-      if (dl <= bnd) {
-        if (dr <= bnd) {
-          if (sp < kStackSize) {
-            stack_node[sp] = nr;
-            stack_dist[sp] = dr;
-            ++sp;
-          }
-          else
-            overflow = true;
-        }
-        else
-          v.prune(dr);
-        node = nl;
-      }
-      else {
-        v.prune(dl);
-        node = kDone;
-        while (sp > 0) {
-          --sp;
-          if (stack_dist[sp] <= bnd) {
-            node = stack_node[sp];
-            break;
-          }
-          v.prune(stack_dist[sp]);
-        }
-      }
-    }
-    if (busy && node != kDone) {  // node < 0: a leaf
-      const int leaf = ~node;
-      v.leaf(a.pts + (size_t)leaf * kLeafSize, leaf * kLeafSize);
-      node = kDone;
-      const float bnd = v.bound();
-      while (sp > 0) {
-        --sp;
-        if (stack_dist[sp] <= bnd) {
-          node = stack_node[sp];
-          break;
-        }
-        v.prune(stack_dist[sp]);
-      }
-    }
-    if (busy && node == kDone) {  // walk finished: publish and become idle
-      Match m;
-      m.pos = -1;
-      m.d2 = 0.f;
-      m.lb = 0.f;
-      m.accepted = 0;
-      if (v.best_pos >= 0) {
-        m.pos = v.best_pos;
-        m.d2 = v.best;
-        m.lb = TRACK ? sqrtf(v.lower_bound2()) : 0.f;
-        m.accepted = 1;
-      }
-      match[qi] = m;
-      busy = false;
-    }
+    if (!better)
+      return md;
+    const unsigned long long old = atomicCAS(slot, cur, mine);
+    if (old == cur)
+      return cpos == kWqNoPos ? 0xffffffffu : cd;
+    cur = old;
   }
-  if (overflow)
-    atomicExch(a.d_error, 1);
 }
 
-// Packet variant: the 32 Morton/Hilbert-adjacent queries of a warp share ONE walk of the tree (traverse_packet).
-// Lanes whose previous match is provably still nearest (still_nearest) sit the walk out; a warp whose 32 lanes all
-// pass the test does not touch the tree at all.  Chosen by the host when the queries are about as dense as the
-// target (ICP's normal case).
-template <bool RECIP, bool TRACK>
-__global__ void __launch_bounds__(256)
-k_search_packet(const IterArgs a, Match* __restrict__ match)
+// scan one leaf for query `o` of the warp's batch
+template <bool TRACK>
+__device__ __forceinline__ void wq_scan_leaf(WarpWork& W, int o, const float4* __restrict__ pts, int leaf)
+{
+  const float qx = W.qx[o], qy = W.qy[o], qz = W.qz[o];
+  const float4* lp = pts + (size_t)leaf * kLeafSize;
+  float4 p[8];
+  float d[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j)
+    p[j] = ldg4(lp + j);
+  float m = __int_as_float(0x7f800000), m2nd = __int_as_float(0x7f800000);
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    d[j] = dist2_rn(qx, qy, qz, p[j].x, p[j].y, p[j].z);
+    if (TRACK)
+      m2nd = fminf(m2nd, fmaxf(m, d[j]));
+    m = fminf(m, d[j]);
+  }
+  unsigned lost = 0xffffffffu;
+  if (m <= wq_best_d2(&W.best[o])) {
+    int jm = 0, im = kSentinelIndex;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int oi = __float_as_int(p[j].w);
+      if (d[j] == m && oi < im) {
+        im = oi;
+        jm = j;
+      }
+    }
+    lost = wq_update(&W.best[o], m, leaf * kLeafSize + jm, im, pts);
+  }
+  else
+    lost = __float_as_uint(m);
+  if (TRACK) {
+    atomicMin(&W.m2[o], __float_as_uint(m2nd));
+    if (lost != 0xffffffffu)
+      atomicMin(&W.m2[o], lost);
+  }
+}
+
+// visitor over the shared per-query state, for the private walks of a drain round (node queue full)
+template <bool TRACK>
+struct WqShared {
+  WarpWork& W;
+  int o;
+  const float4* pts;
+  __device__ __forceinline__ float bound() const { return wq_best_d2(&W.best[o]); }
+  __device__ __forceinline__ void prune(float d)
+  {
+    if (TRACK)
+      atomicMin(&W.pruned[o], __float_as_uint(d));
+  }
+  __device__ __forceinline__ void leaf(const float4*, int first_pos) { wq_scan_leaf<TRACK>(W, o, pts, first_pos / kLeafSize); }
+};
+
+__device__ __forceinline__ void dmma884(double& c0, double& c1, double a, double b)
+{
+  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+               : "+d"(c0), "+d"(c1)
+               : "d"(a), "d"(b));
+}
+
+// where accumulator slot k of the kAccum layout (top of this file) sits in the two 8x8 tiles: tile * 64 + row * 8 + col
+__device__ __forceinline__ int wq_accum_source(int est, int k)
+{
+  if (est == PCLB200_EST_SVD) {
+    // tile 0 = sum w u^T, w = (q - o, 1, d2), u = (p - o, 1)
+    if (k == 0) return 3 * 8 + 3;
+    if (k == 1) return 4 * 8 + 3;
+    if (k < 5) return 3 * 8 + (k - 2);
+    if (k < 8) return (k - 5) * 8 + 3;
+    if (k < 17) return ((k - 8) / 3) * 8 + (k - 8) % 3;
+    return -1;
+  }
+  // tile 0 = sum v v^T, v = (A, B, C, nx, ny, nz, D, 0); tile 1 column 0 = sum w, w = (nxnx .. nznz as FLOAT products, d2, 1)
+  if (k == 0) return 64 + 7 * 8;
+  if (k == 1) return 64 + 6 * 8;
+  if (k < 23) {
+    int t = k - 2, r = 0;
+    while (t >= 6 - r) {
+      t -= 6 - r;
+      ++r;
+    }
+    const int c = r + t;
+    if (r >= 3)
+      return 64 + ((r == 3 ? c - 3 : (r == 4 ? 3 + (c - 4) : 5))) * 8;
+    return r * 8 + c;
+  }
+  if (k < 29) return (k - 23) * 8 + 6;
+  return -1;
+}
+
+template <int EST, bool RECIP, bool TRACK>
+__global__ void __launch_bounds__(kWqWarps * 32)
+k_icp_wq(const IterArgs a, Match* __restrict__ match, float* __restrict__ lbs)
 {
   __shared__ Pending sP;
-  __shared__ int s_node[8][kWarpStack];
-  __shared__ float s_dist[8][kWarpStack];
+  __shared__ WarpWork sW[kWqWarps];
   if (threadIdx.x == 0)
     sP = *a.pending;
   __syncthreads();
-  const int warp = threadIdx.x >> 5;
-  bool overflow = false;
-  // warp-uniform trip count: every lane of a warp runs the same number of rounds
-  const size_t stride = (size_t)gridDim.x * blockDim.x;
-  const size_t first = blockIdx.x * (size_t)blockDim.x + (threadIdx.x & ~31);
+  const unsigned full = 0xffffffffu;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const unsigned lt = (1u << lane) - 1u;
+  WarpWork& W = sW[warp];
+  uint2* const cellq = W.q;
+  uint2* const leafq = W.q + kWqCells;
+  uint2* const nodeq = W.q + kWqCells + kWqLeaf;
+  const CellTable& C = a.cells;
   const float inf = __int_as_float(0x7f800000);
-  for (size_t base = first; base < a.n; base += stride) {
-    const size_t i = base + (threadIdx.x & 31);
+  double c1a = 0.0, c1b = 0.0, c2a = 0.0, c2b = 0.0;  // fragments of the two accumulator tiles (EST >= 0)
+  unsigned skipped = 0;
+  bool overflow = false;
+  const size_t nwarps = (size_t)gridDim.x * kWqWarps;
+  for (size_t base = ((size_t)blockIdx.x * kWqWarps + warp) * 32; base < a.n; base += nwarps * 32) {
+    // ================= phase A: own query — transform, skip test, seed leaves ====================================
+    const size_t i = base + lane;
     const bool in_range = i < a.n;
     float4 p = in_range ? a.cur[i] : make_float4(0.f, 0.f, 0.f, 0.f);
     Match prev;
+    prev.pos = -1;
+    prev.d2 = 0.f;
     if (in_range)
       prev = match[i];
-    else {
-      prev.pos = -1; prev.d2 = 0.f; prev.lb = 0.f; prev.accepted = 0;
-    }
     const bool valid = in_range && isfinite(p.x) && isfinite(p.y) && isfinite(p.z);
     float delta = 0.f;
     if (valid && sP.apply) {
@@ -559,187 +555,412 @@ k_search_packet(const IterArgs a, Match* __restrict__ match)
       }
     }
     Match m;
-    m.pos = -1; m.d2 = 0.f; m.lb = 0.f; m.accepted = 0;
-    float nlb = 0.f;
-    const bool skip = TRACK && !RECIP && valid && still_nearest(prev, delta, &nlb);
-    if (skip) {
-      const float4 q = ldg4(a.pts + prev.pos);
-      m.pos = prev.pos;
-      m.d2 = dist2_rn(p.x, p.y, p.z, q.x, q.y, q.z);
-      m.lb = nlb;
-      m.accepted = m.d2 <= a.gate ? 1 : 0;
-    }
-    const bool walk = valid && !skip;
-    {
-      const unsigned sk = __ballot_sync(0xffffffffu, skip);
-      if (sk && (threadIdx.x & 31) == 0)
-        atomicAdd(a.skip_count, (unsigned long long)__popc(sk));
-    }
-    if (__any_sync(0xffffffffu, walk)) {
-      Nearest1T<TRACK> v{p.x, p.y, p.z, walk ? a.gate : -1.f, kSentinelIndex, -1, inf, inf, inf};
-      if (walk && prev.pos >= 0) {
-        const int leaf = prev.pos / kLeafSize;
-        v.template scan<false>(a.pts + (size_t)leaf * kLeafSize, leaf * kLeafSize);
+    m.pos = -1;
+    m.d2 = 0.f;
+    float lb_out = 0.f;
+    const int seed = (valid && prev.pos >= 0) ? match_pos(prev) : -1;
+    bool walkq = valid;
+    if (TRACK && !RECIP && seed >= 0) {
+      float nlb = 0.f;
+      if (still_nearest(prev.d2, lbs[i], delta, &nlb)) {
+        const float4 q = ldg4(a.pts + seed);
+        m.d2 = dist2_rn(p.x, p.y, p.z, q.x, q.y, q.z);
+        m.pos = m.d2 <= a.gate ? seed : (seed | kNotAccepted);
+        lb_out = nlb;
+        ++skipped;
+        walkq = false;
       }
-      __syncwarp();
-      if (!traverse_packet(a.nodes, a.pts, a.root, p.x, p.y, p.z, v, s_node[warp], s_dist[warp]))
-        overflow = true;
-      bool keep = walk && v.best_pos >= 0;
-      if (keep) {
-        m.pos = v.best_pos;
-        m.d2 = v.best;
-        m.lb = TRACK ? sqrtf(v.lower_bound2()) : 0.f;
-      }
-      if (RECIP) {
-        // correspondence_estimation.hpp:259-269: back-search of the matched target point in the source tree
-        const float4 q = keep ? ldg4(a.pts + v.best_pos) : make_float4(0.f, 0.f, 0.f, 0.f);
-        Nearest1 b{q.x, q.y, q.z, keep ? a.gate : -1.f, kSentinelIndex, -1};
-        __syncwarp();
-        if (!traverse_packet(a.s_nodes, a.s_pts, a.s_root, q.x, q.y, q.z, b, s_node[warp], s_dist[warp]))
-          overflow = true;
-        if (keep) {
-          const int slot = __float_as_int(p.w);
-          const int my_orig = a.src_orig ? a.src_orig[slot] : slot;
-          keep = b.best_pos >= 0 && b.best_idx == my_orig;
-        }
-      }
-      if (walk)
-        m.accepted = keep ? 1 : 0;
     }
-    if (in_range)
-      match[i] = m;
-  }
-  if (overflow)
-    atomicExch(a.d_error, 1);
-}
-
-// Compacting variant of the packet kernel for the converged regime (lower-bound tracking on): a block takes a tile
-// of kTile Hilbert-consecutive queries, first runs the streaming part for all of them (apply T_k, temporal-coherence
-// test, results of the queries that pass it), appends the queries that still need a walk to a shared-memory list
-// IN ORDER, and then walks the tree with full 32-query packets drawn from that list.  With 90 % of the queries
-// skipping, the plain packet kernel still walks nearly every warp for its few remaining lanes; here the walks shrink
-// with the number of queries that need them.
-constexpr int kTile = 1024;
-
-__global__ void __launch_bounds__(256)
-k_search_packet_compact(const IterArgs a, Match* __restrict__ match)
-{
-  __shared__ Pending sP;
-  __shared__ int s_node[8][kWarpStack];
-  __shared__ float s_dist[8][kWarpStack];
-  __shared__ int s_list[kTile];
-  __shared__ int s_wcnt[8];
-  __shared__ int s_count;
-  if (threadIdx.x == 0)
-    sP = *a.pending;
-  __syncthreads();
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const float inf = __int_as_float(0x7f800000);
-  bool overflow = false;
-  unsigned long long skipped = 0;
-  for (size_t tile = (size_t)blockIdx.x * kTile; tile < a.n; tile += (size_t)gridDim.x * kTile) {
-    if (threadIdx.x == 0)
-      s_count = 0;
-    __syncthreads();
-    // ---- phase 1: streaming part, order-preserving compaction of the queries that must walk
-#pragma unroll 1
-    for (int r = 0; r < kTile / 256; ++r) {
-      const size_t i = tile + (size_t)r * 256 + threadIdx.x;
-      const bool in_range = i < a.n;
-      bool walk = false;
-      if (in_range) {
-        float4 p = a.cur[i];
-        const Match prev = match[i];
-        if (isfinite(p.x) && isfinite(p.y) && isfinite(p.z)) {
-          float delta = 0.f;
-          if (sP.apply) {
-            const float ox = p.x, oy = p.y, oz = p.z;
-            apply_pending(sP, p.x, p.y, p.z);
-            a.cur[i] = p;
-            delta = sqrtf(dist2_rn(p.x, p.y, p.z, ox, oy, oz));
-            if (a.cur_normals) {
-              float4 nn = a.cur_normals[i];
-              apply_pending_normal(sP, nn.x, nn.y, nn.z);
-              a.cur_normals[i] = nn;
+    Nearest1T<TRACK> v{p.x, p.y, p.z, a.gate, kSentinelIndex, -1, inf, inf, inf};
+    int skip_a = kDone, skip_b = kDone;
+    bool rooted = true;
+    unsigned E = 0, hx = 0, hy = 0, hz = 0, ox = 0, oy = 0, oz = 0;
+    float gx2 = 0.f, gy2 = 0.f, gz2 = 0.f;
+    int lvl = 0;
+    if (walkq) {
+      if (seed >= 0) {
+        const int leaf = seed / kLeafSize;
+        v.template scan<true>(a.pts + (size_t)leaf * kLeafSize, leaf * kLeafSize);
+        skip_a = ~leaf;
+      }
+      if (C.slots != nullptr) {
+        const unsigned cqx = morton_cell(p.x, C.lo[0], C.scale), cqy = morton_cell(p.y, C.lo[1], C.scale),
+                       cqz = morton_cell(p.z, C.lo[2], C.scale);
+        const int smin = 21 - C.bmax;
+        unsigned ax, ay, az, bx, by, bz;
+        float r;
+        int s;
+        auto ball_level = [&]() {
+          r = __fmul_ru(__fsqrt_ru(v.best), TRACK ? kTrackInflate : 1.00001f);
+          ax = morton_cell(__fsub_rd(p.x, r), C.lo[0], C.scale); bx = morton_cell(__fadd_ru(p.x, r), C.lo[0], C.scale);
+          ay = morton_cell(__fsub_rd(p.y, r), C.lo[1], C.scale); by = morton_cell(__fadd_ru(p.y, r), C.lo[1], C.scale);
+          az = morton_cell(__fsub_rd(p.z, r), C.lo[2], C.scale); bz = morton_cell(__fadd_ru(p.z, r), C.lo[2], C.scale);
+          const unsigned d = max(max(bx - ax, by - ay), bz - az);
+          s = (d <= 1u ? 0 : 32 - __clz((int)(d - 1u))) + kCellLevelBias;
+        };
+        ball_level();
+        if (v.best_pos < 0 || s > smin + 2) {
+          // home seed (traverse.cuh: nearest1, step 2)
+          int ref = kDone;
+          int lo_b = 0, hi_b = C.bmax;
+          while (lo_b < hi_b) {
+            const int b = (lo_b + hi_b + 1) >> 1;
+            const int sh = 21 - b;
+            const int rr = cell_lookup(C, cell_key(b, cqx >> sh, cqy >> sh, cqz >> sh));
+            if (rr != kDone) {
+              lo_b = b;
+              ref = rr;
+            }
+            else
+              hi_b = b - 1;
+          }
+          if (ref != kDone) {
+            while (ref >= 0) {
+              const float4* np = reinterpret_cast<const float4*>(a.nodes + ref);
+              const float4 na = ldg4(np), nb = ldg4(np + 1), nc4 = ldg4(np + 2);
+              const int4 nd = __ldg(reinterpret_cast<const int4*>(np + 3));
+              const float dl = box_dist2_rn(p.x, p.y, p.z, na.x, na.y, na.z, na.w, nb.x, nb.y);
+              const float dr = box_dist2_rn(p.x, p.y, p.z, nb.z, nb.w, nc4.x, nc4.y, nc4.z, nc4.w);
+              ref = dr < dl ? nd.y : nd.x;
+            }
+            if (ref != skip_a) {
+              const int leaf = ~ref;
+              v.template scan<true>(a.pts + (size_t)leaf * kLeafSize, leaf * kLeafSize);
+              skip_b = ref;
+              ball_level();
             }
           }
-          float nlb;
-          if (still_nearest(prev, delta, &nlb)) {
-            const float4 q = ldg4(a.pts + prev.pos);
-            Match m;
-            m.pos = prev.pos;
-            m.d2 = dist2_rn(p.x, p.y, p.z, q.x, q.y, q.z);
-            m.lb = nlb;
-            m.accepted = m.d2 <= a.gate ? 1 : 0;
-            match[i] = m;
-            ++skipped;
-          }
-          else
-            walk = true;  // match[i] still holds the previous iteration's entry: phase 2 seeds from it
         }
-        else {
-          Match m;
-          m.pos = -1; m.d2 = 0.f; m.lb = 0.f; m.accepted = 0;
-          match[i] = m;
+        if (s < smin)
+          s = smin;
+        if (s <= 20) {
+          rooted = false;
+          lvl = 21 - s;
+          hx = cqx >> s; hy = cqy >> s; hz = cqz >> s;
+          ox = (ax >> s) + (bx >> s) - hx; oy = (ay >> s) + (by >> s) - hy; oz = (az >> s) + (bz >> s) - hz;
+          E = (ox != hx ? 1u : 0u) | (oy != hy ? 2u : 0u) | (oz != hz ? 4u : 0u);
+          gx2 = (E & 1u) ? cell_gap2(C, 0, p.x, hx, ox, s) : 0.f;
+          gy2 = (E & 2u) ? cell_gap2(C, 1, p.y, hy, oy, s) : 0.f;
+          gz2 = (E & 4u) ? cell_gap2(C, 2, p.z, hz, oz, s) : 0.f;
+          v.prune(__fmul_rd(r, r));  // every indexed point outside the cells lies outside [q - r, q + r]^3
         }
       }
-      const unsigned bal = __ballot_sync(0xffffffffu, walk);
-      if (lane == 0)
-        s_wcnt[warp] = __popc(bal);
-      __syncthreads();
-      int base = s_count;
-      for (int w = 0; w < warp; ++w)
-        base += s_wcnt[w];
-      if (walk)
-        s_list[base + __popc(bal & ((1u << lane) - 1u))] = (int)(i - tile);
-      __syncthreads();
-      if (threadIdx.x == 0) {
-        int t = 0;
-        for (int w = 0; w < 8; ++w)
-          t += s_wcnt[w];
-        s_count += t;
-      }
-      __syncthreads();
     }
-    // ---- phase 2: full packets from the compacted list
-    const int total = s_count;
-    for (int k0 = warp * 32; k0 < total; k0 += 8 * 32) {
-      const int j = k0 + lane;
-      const bool active = j < total;
-      const size_t i = tile + (size_t)(active ? s_list[j] : 0);
-      const float4 p = active ? a.cur[i] : make_float4(0.f, 0.f, 0.f, 0.f);
-      Match prev;
-      prev.pos = -1;
-      if (active)
-        prev = match[i];
-      Nearest1T<true> v{p.x, p.y, p.z, active ? a.gate : -1.f, kSentinelIndex, -1, inf, inf, inf};
-      if (active && prev.pos >= 0) {
-        const int leaf = prev.pos / kLeafSize;
-        v.template scan<false>(a.pts + (size_t)leaf * kLeafSize, leaf * kLeafSize);
+    // publish the per-query state the items share
+    W.qx[lane] = p.x;
+    W.qy[lane] = p.y;
+    W.qz[lane] = p.z;
+    W.best[lane] = walkq ? (((unsigned long long)__float_as_uint(v.best) << 32) | (v.best_pos >= 0 ? (unsigned)v.best_pos : kWqNoPos))
+                         : 0ULL;  // a query that does not walk never wants anything (bound 0, and it owns no items)
+    W.skipa[lane] = skip_a;
+    W.skipb[lane] = skip_b;
+    if (TRACK) {
+      W.m2[lane] = __float_as_uint(v.m2);
+      W.pruned[lane] = __float_as_uint(v.pruned_min);
+    }
+    __syncwarp();
+    // ================= phase B/C: items ============================================================================
+    int nc = 0, nl = 0, nn = 0;  // queue sizes (warp-uniform)
+    {
+      // walks without a cell start: one item, the root
+      const bool wr = walkq && rooted;
+      const unsigned mr = __ballot_sync(full, wr);
+      if (mr) {
+        uint2* rq = a.root < 0 ? leafq : nodeq;
+        if (wr)
+          rq[__popc(mr & lt)] = make_uint2(a.root < 0 ? (unsigned)~a.root : (unsigned)a.root, wq_pack(0.f, lane));
+        if (a.root < 0)
+          nl = __popc(mr);
+        else
+          nn = __popc(mr);
+      }
+    }
+    bool pend = walkq && !rooted;
+    do {
+      {
+        // enqueue the cells of as many pending queries as fit (all of them, unless the batch has > kWqCells cells)
+        const int want = pend ? (1 << __popc(E)) : 0;
+        int x = want;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+          const int y = __shfl_up_sync(full, x, o);
+          if (lane >= o)
+            x += y;
+        }
+        const bool fits = pend && x <= kWqCells;  // a prefix of the pending lanes
+        if (fits) {
+          int j = x - want;
+          for (unsigned sm = E;; sm = (sm - 1u) & E) {
+            const float bound = __fadd_rd(__fadd_rd((sm & 1u) ? gx2 : 0.f, (sm & 2u) ? gy2 : 0.f), (sm & 4u) ? gz2 : 0.f);
+            cellq[j++] = make_uint2(cell_key(lvl, (sm & 1u) ? ox : hx, (sm & 2u) ? oy : hy, (sm & 4u) ? oz : hz),
+                                    wq_pack(bound, lane));
+            if (sm == 0u)
+              break;
+          }
+        }
+        const unsigned mf = __ballot_sync(full, fits);
+        nc = mf ? __shfl_sync(full, x, 31 - __clz((int)mf)) : 0;
+        pend = pend && !fits;
       }
       __syncwarp();
-      if (!traverse_packet(a.nodes, a.pts, a.root, p.x, p.y, p.z, v, s_node[warp], s_dist[warp]))
-        overflow = true;
-      if (active) {
-        Match m;
-        m.pos = -1; m.d2 = 0.f; m.lb = 0.f; m.accepted = 0;
-        if (v.best_pos >= 0) {
-          m.pos = v.best_pos;
-          m.d2 = v.best;
-          m.lb = sqrtf(v.lower_bound2());
-          m.accepted = 1;
+      for (;;) {
+        const int ntake = min(min(32, nn), kWqNode - nn);
+        if (nc > 0 && nl <= kWqLeaf - 32 && nn <= kWqNode - 32) {
+          // ---- cell round: one hash lookup per lane --------------------------------------------------------------
+          const int take = min(32, nc);
+          const bool act = lane < take;
+          int ref = kDone;
+          unsigned bo = 0;
+          int o = 0;
+          if (act) {
+            const uint2 it = cellq[nc - 1 - lane];
+            bo = it.y;
+            o = (int)(bo & 31u);
+            if (wq_bound(bo) <= wq_best_d2(&W.best[o])) {
+              ref = cell_lookup(C, it.x);
+              if (ref == W.skipa[o] || ref == W.skipb[o])
+                ref = kDone;
+            }
+            else if (TRACK)
+              atomicMin(&W.pruned[o], bo & ~31u);
+          }
+          nc -= take;
+          // a leaf that spans several cells is returned for each of them: keep one item per (owner, reference)
+          const unsigned long long tag = ref != kDone ? (((unsigned long long)o << 32) | (unsigned)ref)
+                                                      : (0xffffffff00000000ULL | (unsigned)lane);
+          const unsigned grp = __match_any_sync(full, tag);
+          if ((grp & lt) != 0u)
+            ref = kDone;
+          const unsigned ml = __ballot_sync(full, ref != kDone && ref < 0);
+          const unsigned mn = __ballot_sync(full, ref != kDone && ref >= 0);
+          if (ref != kDone) {
+            if (ref < 0)
+              leafq[nl + __popc(ml & lt)] = make_uint2((unsigned)~ref, bo);
+            else
+              nodeq[nn + __popc(mn & lt)] = make_uint2((unsigned)ref, bo);
+          }
+          nl += __popc(ml);
+          nn += __popc(mn);
         }
-        match[i] = m;
+        else if (nl >= 32 || (nl > 0 && !(nn > 0 && ntake > 0 && nl + 2 * ntake <= kWqLeaf))) {
+          // ---- leaf round: one leaf (8 points) per lane -----------------------------------------------------------
+          const int take = min(32, nl);
+          if (lane < take) {
+            const uint2 it = leafq[nl - 1 - lane];
+            const int o = (int)(it.y & 31u);
+            if (wq_bound(it.y) <= wq_best_d2(&W.best[o]))
+              wq_scan_leaf<TRACK>(W, o, a.pts, (int)it.x);
+            else if (TRACK)
+              atomicMin(&W.pruned[o], it.y & ~31u);
+          }
+          nl -= take;
+        }
+        else if (nn > 0 && ntake > 0) {
+          // ---- node round: one node (two child boxes) per lane ----------------------------------------------------
+          const bool act = lane < ntake;
+          int rn = kDone, rf = kDone;  // nearer / farther child, kDone = not wanted
+          unsigned bn = 0, bf = 0;
+          if (act) {
+            const uint2 it = nodeq[nn - 1 - lane];
+            const int o = (int)(it.y & 31u);
+            const float bestd = wq_best_d2(&W.best[o]);
+            if (wq_bound(it.y) <= bestd) {
+              const float4* np = reinterpret_cast<const float4*>(a.nodes + it.x);
+              const float4 na = ldg4(np), nb = ldg4(np + 1), nc4 = ldg4(np + 2);
+              const int4 nd = __ldg(reinterpret_cast<const int4*>(np + 3));
+              const float qx = W.qx[o], qy = W.qy[o], qz = W.qz[o];
+              float dl = box_dist2_rn(qx, qy, qz, na.x, na.y, na.z, na.w, nb.x, nb.y);
+              float dr = box_dist2_rn(qx, qy, qz, nb.z, nb.w, nc4.x, nc4.y, nc4.z, nc4.w);
+              int cl = nd.x, cr = nd.y;
+              if (dr < dl) {
+                const float t = dl; dl = dr; dr = t;
+                const int ti = cl; cl = cr; cr = ti;
+              }
+              if (dl <= bestd) {
+                rn = cl;
+                bn = wq_pack(dl, o);
+              }
+              else if (TRACK)
+                atomicMin(&W.pruned[o], __float_as_uint(dl));
+              if (dr <= bestd) {
+                rf = cr;
+                bf = wq_pack(dr, o);
+              }
+              else if (TRACK)
+                atomicMin(&W.pruned[o], __float_as_uint(dr));
+            }
+            else if (TRACK)
+              atomicMin(&W.pruned[o], it.y & ~31u);
+          }
+          nn -= ntake;
+          // farther children first, nearer ones on top (popped first: depth first)
+#pragma unroll
+          for (int pass = 0; pass < 2; ++pass) {
+            const int ref = pass == 0 ? rf : rn;
+            const unsigned bo = pass == 0 ? bf : bn;
+            const unsigned ml = __ballot_sync(full, ref != kDone && ref < 0);
+            const unsigned mn = __ballot_sync(full, ref != kDone && ref >= 0);
+            if (ref != kDone) {
+              if (ref < 0)
+                leafq[nl + __popc(ml & lt)] = make_uint2((unsigned)~ref, bo);
+              else
+                nodeq[nn + __popc(mn & lt)] = make_uint2((unsigned)ref, bo);
+            }
+            nl += __popc(ml);
+            nn += __popc(mn);
+          }
+        }
+        else if (nn > 0) {
+          // ---- drain round (node queue full): every lane walks one queued subtree with a private stack ------------
+          const int take = min(32, nn);
+          if (lane < take) {
+            const uint2 it = nodeq[nn - 1 - lane];
+            const int o = (int)(it.y & 31u);
+            if (wq_bound(it.y) <= wq_best_d2(&W.best[o])) {
+              WqShared<TRACK> sv{W, o, a.pts};
+              if (!traverse(a.nodes, a.pts, (int)it.x, W.qx[o], W.qy[o], W.qz[o], sv))
+                overflow = true;
+            }
+            else if (TRACK)
+              atomicMin(&W.pruned[o], it.y & ~31u);
+          }
+          nn -= take;
+        }
+        else
+          break;
+        __syncwarp();
+      }
+    } while (__any_sync(full, pend));
+    // ================= phase D: results ============================================================================
+    if (walkq) {
+      const unsigned long long fin = W.best[lane];
+      const unsigned fpos = (unsigned)fin;
+      if (fpos != kWqNoPos) {
+        m.pos = (int)fpos;
+        m.d2 = __uint_as_float((unsigned)(fin >> 32));
+        if (TRACK)
+          lb_out = sqrtf(fminf(__uint_as_float(W.m2[lane]), __uint_as_float(W.pruned[lane])));
+        if (RECIP) {
+          // correspondence_estimation.hpp:259-269: 1-NN of the matched target point back into the source
+          const float4 q = ldg4(a.pts + fpos);
+          Nearest1 b{q.x, q.y, q.z, a.gate, kSentinelIndex, -1};
+          if (!traverse(a.s_nodes, a.s_pts, a.s_root, q.x, q.y, q.z, b))
+            overflow = true;
+          const int slot = __float_as_int(p.w);
+          const int my_orig = a.src_orig ? a.src_orig[slot] : slot;
+          if (!(b.best_pos >= 0 && b.best_idx == my_orig))
+            m.pos |= kNotAccepted;
+        }
       }
     }
-    __syncthreads();  // s_list / s_count are reused by the next tile
+    if (in_range) {
+      match[i] = m;
+      if (TRACK)
+        lbs[i] = lb_out;
+    }
+    // ================= epilogue: normal equations on the fp64 tensor cores ========================================
+    if (EST != kEstNone) {
+      __syncwarp();  // the queues are dead: their memory becomes the staging tiles
+      double* tA = reinterpret_cast<double*>(W.q);
+      double* tB = tA + 32 * 8;
+      double ra[8] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0}, rb[8] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
+      if (match_accepted(m)) {
+        const float4 q = ldg4(a.pts + m.pos);
+        if (EST == PCLB200_EST_SVD) {
+          // w = (q - o, 1, d2), u = (p - o, 1): sum w u^T holds sum q p^T, sum q, sum p, n and sum d2
+          ra[0] = (double)q.x - (double)a.ox; ra[1] = (double)q.y - (double)a.oy; ra[2] = (double)q.z - (double)a.oz;
+          ra[3] = 1.0;
+          ra[4] = (double)m.d2;
+          rb[0] = (double)p.x - (double)a.ox; rb[1] = (double)p.y - (double)a.oy; rb[2] = (double)p.z - (double)a.oz;
+          rb[3] = 1.0;
+        }
+        else {
+          rb[6] = (double)m.d2;
+          rb[7] = 1.0;
+          const float4 nn = ldg4(a.tgt_normals + m.pos);
+          if (isfinite(nn.x) && isfinite(nn.y) && isfinite(nn.z)) {  // point_to_plane_lls.hpp:182-190
+            const float sx = p.x, sy = p.y, sz = p.z, dx = q.x, dy = q.y, dz = q.z, nx = nn.x, ny = nn.y, nz = nn.z;
+            // float expressions widened to double, exactly as :202-204 and :235 (no fma: -fmad=false)
+            ra[0] = (double)(nz * sy - ny * sz);
+            ra[1] = (double)(nx * sz - nz * sx);
+            ra[2] = (double)(ny * sx - nx * sy);
+            ra[3] = (double)nx; ra[4] = (double)ny; ra[5] = (double)nz;
+            ra[6] = (double)(nx * dx + ny * dy + nz * dz - nx * sx - ny * sy - nz * sz);
+            rb[0] = (double)(nx * nx); rb[1] = (double)(nx * ny); rb[2] = (double)(nx * nz);  // FLOAT products (:228-233)
+            rb[3] = (double)(ny * ny); rb[4] = (double)(ny * nz); rb[5] = (double)(nz * nz);
+          }
+        }
+      }
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        tA[lane * 8 + k] = ra[k];
+        tB[lane * 8 + k] = rb[k];
+      }
+      __syncwarp();
+      const int g = lane >> 2, t = lane & 3;
+      const double e0 = g == 0 ? 1.0 : 0.0;
+#pragma unroll
+      for (int st = 0; st < 8; ++st) {
+        const double va = tA[(4 * st + t) * 8 + g];
+        const double vb = tB[(4 * st + t) * 8 + g];
+        if (EST == PCLB200_EST_SVD)
+          dmma884(c1a, c1b, va, vb);     // C1[i][j] += w_i u_j
+        else {
+          dmma884(c1a, c1b, va, va);     // C1[i][j] += v_i v_j
+          dmma884(c2a, c2b, vb, e0);     // C2[i][0] += w_i
+        }
+      }
+      __syncwarp();
+    }
   }
-  for (int o = 16; o > 0; o >>= 1)
-    skipped += __shfl_xor_sync(0xffffffffu, skipped, o);
-  if (lane == 0 && skipped)
-    atomicAdd(a.skip_count, skipped);
+  if (TRACK) {
+    for (int o = 16; o > 0; o >>= 1)
+      skipped += __shfl_xor_sync(full, skipped, o);
+    if (lane == 0 && skipped)
+      atomicAdd(a.skip_count, (unsigned long long)skipped);
+  }
   if (overflow)
     atomicExch(a.d_error, 1);
+  if (EST != kEstNone) {
+    // warp tiles -> block (fixed order) -> grid (fixed order, last block) -> the kAccum layout k_solve reads
+    __shared__ double s_tiles[kWqWarps][128];
+    __shared__ double s_fin[128];
+    __shared__ bool is_last;
+    const int g = lane >> 2, t = lane & 3;
+    s_tiles[warp][g * 8 + 2 * t] = c1a;
+    s_tiles[warp][g * 8 + 2 * t + 1] = c1b;
+    s_tiles[warp][64 + g * 8 + 2 * t] = c2a;
+    s_tiles[warp][64 + g * 8 + 2 * t + 1] = c2b;
+    __syncthreads();
+    {
+      double vsum = 0.0;
+      for (int w = 0; w < kWqWarps; ++w)
+        vsum += s_tiles[w][threadIdx.x];
+      a.partials2[(size_t)blockIdx.x * 128 + threadIdx.x] = vsum;
+    }
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      const unsigned tk = atomicAdd(a.counter, 1u);
+      is_last = (tk == gridDim.x - 1);
+    }
+    __syncthreads();
+    if (is_last) {
+      __threadfence();
+      double vsum = 0.0;
+      for (unsigned b = 0; b < gridDim.x; ++b)  // fixed order => bitwise reproducible
+        vsum += __ldcg(&a.partials2[(size_t)b * 128 + threadIdx.x]);
+      s_fin[threadIdx.x] = vsum;
+      __syncthreads();
+      if (threadIdx.x < kAccum) {
+        const int src = wq_accum_source(EST, threadIdx.x);
+        a.accum[threadIdx.x] = src >= 0 ? s_fin[src] : 0.0;
+      }
+      if (threadIdx.x == 0)
+        *a.counter = 0;
+      peer_exchange(a);
+    }
+  }
 }
 
 // Accumulation kernel: one streaming pass over (source point, match) pairs; fp64 sums, fixed reduction order.
@@ -754,7 +975,7 @@ k_accum(const IterArgs a, const Match* __restrict__ match)
     acc[t] = 0.0;
   for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < a.n; i += (size_t)gridDim.x * blockDim.x) {
     const Match m = match[i];
-    if (!m.accepted)
+    if (!match_accepted(m))
       continue;
     const float4 p = a.cur[i];
     const float4 q = ldg4(a.pts + m.pos);
@@ -1165,7 +1386,7 @@ __global__ void k_scatter_xyz(const float4* __restrict__ src, size_t n, unsigned
 // correspondences by slot: match = original target index or -1
 template <bool RECIP>
 __global__ void __launch_bounds__(128)
-k_corr(const BvhNode* __restrict__ nodes, const float4* __restrict__ pts, int root, const float4* __restrict__ q,
+k_corr(const TreeView T, const float4* __restrict__ q,
        size_t nq, float gate, const BvhNode* __restrict__ s_nodes, const float4* __restrict__ s_pts, int s_root,
        const int32_t* __restrict__ src_orig, pclb200_corr* __restrict__ out, int* __restrict__ d_error)
 {
@@ -1181,12 +1402,13 @@ k_corr(const BvhNode* __restrict__ nodes, const float4* __restrict__ pts, int ro
   r.distance = 0.f;
   if (isfinite(p.x) && isfinite(p.y) && isfinite(p.z)) {
     Nearest1 v{p.x, p.y, p.z, gate, kSentinelIndex, -1};
-    if (!traverse(nodes, pts, root, p.x, p.y, p.z, v))
+    WalkStats ws{};
+    if (!nearest1<false>(T, p.x, p.y, p.z, v, -1, 1.00001f, ws))
       atomicExch(d_error, 1);
     if (v.best_pos >= 0) {
       bool keep = true;
       if (RECIP) {
-        const float4 t = ldg4(pts + v.best_pos);
+        const float4 t = ldg4(T.pts + v.best_pos);
         Nearest1 b{t.x, t.y, t.z, gate, kSentinelIndex, -1};
         if (!traverse(s_nodes, s_pts, s_root, t.x, t.y, t.z, b))
           atomicExch(d_error, 1);
@@ -1204,8 +1426,7 @@ k_corr(const BvhNode* __restrict__ nodes, const float4* __restrict__ pts, int ro
 
 // fitness: sum of d2 <= max_range and count (registration.hpp:146-163)
 __global__ void __launch_bounds__(256)
-k_fitness(const BvhNode* __restrict__ nodes, const float4* __restrict__ pts, int root, const float4* __restrict__ q,
-          size_t nq, double max_range, IterArgs pub)
+k_fitness(const TreeView T, const float4* __restrict__ q, size_t nq, double max_range, IterArgs pub)
 {
   double acc[2] = {0.0, 0.0};
   bool overflow = false;
@@ -1214,7 +1435,8 @@ k_fitness(const BvhNode* __restrict__ nodes, const float4* __restrict__ pts, int
     if (!(isfinite(p.x) && isfinite(p.y) && isfinite(p.z)))
       continue;
     Nearest1 v{p.x, p.y, p.z, __int_as_float(0x7f800000), kSentinelIndex, -1};
-    if (!traverse(nodes, pts, root, p.x, p.y, p.z, v))
+    WalkStats ws{};
+    if (!nearest1<false>(T, p.x, p.y, p.z, v, -1, 1.00001f, ws))
       overflow = true;
     if (v.best_pos >= 0 && (double)v.best <= max_range) {
       acc[0] += 1.0;
@@ -1229,6 +1451,19 @@ k_fitness(const BvhNode* __restrict__ nodes, const float4* __restrict__ pts, int
 // =============================================================================================================
 // host side
 // =============================================================================================================
+#ifdef PCLB_STATS
+extern "C" __attribute__((visibility("default"))) int pclb200_debug_walk_stats(unsigned long long out[8], int reset)
+{
+  cudaDeviceSynchronize();
+  cudaMemcpyFromSymbol(out, g_walk_stats, 8 * sizeof(unsigned long long));
+  if (reset) {
+    unsigned long long z[8] = {0};
+    cudaMemcpyToSymbol(g_walk_stats, z, sizeof(z));
+  }
+  return 0;
+}
+#endif
+
 float gate_from_max_dist(double max_dist)
 {
   // d2 (float) is kept iff (double)d2 <= max_dist^2  <=>  d2 <= largest float <= max_dist^2
@@ -1255,6 +1490,7 @@ static void mat4_mul(const S* A, const S* B, S* C)
 
 struct Reducer {  // scratch for block_reduce_and_publish
   DevBuf<double> partials;
+  DevBuf<double> partials2;  // max_blocks * 128 (k_icp_wq)
   DevBuf<unsigned> counter;
   DevBuf<double> accum;
   unsigned max_blocks = 0;
@@ -1262,6 +1498,7 @@ struct Reducer {  // scratch for block_reduce_and_publish
   {
     max_blocks = blocks;
     partials.alloc((size_t)blocks * kAccum, c.stream);
+    partials2.alloc((size_t)blocks * 128, c.stream);
     counter.alloc(1, c.stream);
     accum.alloc(kAccum, c.stream);
     PCLB_CUDA(cudaMemsetAsync(counter.p, 0, sizeof(unsigned), c.stream));
@@ -1290,6 +1527,8 @@ struct Icp {
   DevBuf<float4> cur;           // Morton order, w = slot
   DevBuf<float4> cur_normals;   // source normals in the order of `cur` (symmetric objective only)
   DevBuf<Match> match;          // Morton order: this iteration's matches = next iteration's seeds
+  DevBuf<float> lb;             // per query: lower bound on the distance to every OTHER target point (TRACK searches)
+  bool lb_valid = false;        // lb was written by the previous search
   DevBuf<int32_t> cur_label;    // Morton order: original source index of cur[i] (labels of the reciprocal tree)
   bool have_src_normals = false;
   DevBuf<unsigned char> src_raw; // the caller's records verbatim (kept when stride != 16) for output = *input_
@@ -1381,16 +1620,19 @@ __global__ void k_match_to_arrays(const float4* __restrict__ cur, const Match* _
     return;
   const Match m = match[i];
   d2[i] = m.d2;
-  mt[i] = m.pos;
+  mt[i] = m.pos >= 0 ? match_pos(m) : -1;
   tie[i] = (unsigned)__float_as_int(cur[i].w);
-  acc[i] = m.accepted;
+  acc[i] = match_accepted(m) ? 1 : 0;
 }
 
 __global__ void k_arrays_to_match(const int* __restrict__ acc, size_t n, Match* __restrict__ match)
 {
   size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
-  if (i < n)
-    match[i].accepted = acc[i];
+  if (i < n) {
+    const int pos = match[i].pos;
+    if (pos >= 0)
+      match[i].pos = acc[i] ? (pos & kPosMask) : (pos | kNotAccepted);
+  }
 }
 
 // CorrespondenceEstimationNormalShooting / ...BackProjection inside the loop: the candidate rows come from the
@@ -1409,8 +1651,6 @@ k_select_match(const float4* __restrict__ cur, const float4* __restrict__ cur_no
   Match m;
   m.pos = -1;
   m.d2 = 0.f;
-  m.lb = 0.f;
-  m.accepted = 0;
   if (isfinite(p.x) && isfinite(p.y) && isfinite(p.z)) {
     const size_t slot = (size_t)(unsigned)__float_as_int(p.w);
     const float4 nn = cur_normals[i];
@@ -1421,7 +1661,6 @@ k_select_match(const float4* __restrict__ cur, const float4* __restrict__ cur_no
     if (j >= 0 && row_idx[j] >= 0) {
       m.pos = pos_of_orig[row_idx[j]];
       m.d2 = row_d2[j];
-      m.accepted = 1;
     }
   }
   match[i] = m;
@@ -1558,6 +1797,7 @@ void icp_reset_state(Icp& s, const double* guess)
   s.converged = false;
   s.n_corr = 0;
   s.track_next = false;
+  s.lb_valid = false;
   s.total_skipped = 0;
   s.searches = 0;
   PCLB_CUDA(cudaMemsetAsync(s.skip_count.p, 0, sizeof(unsigned long long), s.ctx->stream));
@@ -1640,6 +1880,8 @@ void icp_set_source(Icp& s, const void* src, size_t n, size_t stride, const void
   }
   s.match.alloc(s.n_q, st);
   PCLB_CUDA(cudaMemsetAsync(s.match.p, 0xff, s.n_q * sizeof(Match), st));  // pos = -1: no seed yet
+  s.lb.alloc(s.n_q, st);
+  s.lb_valid = false;
   s.cur_label.alloc(s.n_q, st);
   if (s.n_q) {
     k_cur_labels<<<grid_for(s.n_q, 256), 256, 0, st>>>(s.cur.p, s.src_orig.p, s.n_q, s.cur_label.p);
@@ -1754,6 +1996,11 @@ void icp_iterate(Icp& s, int max_steps, pclb200_icp_stats* stats)
   PCLB_REQUIRE(s.tgt && s.cur.p, PCLB200_ERR_INVALID, "icp: set_target and set_source must precede iterate");
   PCLB_REQUIRE(s.P.estimator == PCLB200_EST_SVD || s.tgt_normals.p, PCLB200_ERR_INVALID,
                "icp: point-to-plane needs target normals");
+  PCLB_REQUIRE(s.P.estimator != PCLB200_EST_SYMMETRIC_POINT_TO_PLANE_LLS || s.cur_normals.p, PCLB200_ERR_INVALID,
+               "icp: the symmetric objective needs source normals (choose the estimator before set_source)");
+  // a sharded source sees only its own shard in the reciprocal tree: a different answer, not a smaller one
+  PCLB_REQUIRE(!(comm_active(c) && s.P.use_reciprocal), PCLB200_ERR_INVALID,
+               "icp: reciprocal correspondences are not available with a sharded source (multi-GPU communicator)");
   const Index& T = *s.tgt;
   SolveOut* h_out = reinterpret_cast<SolveOut*>(c.pinned);
   int steps = 0;
@@ -1774,6 +2021,7 @@ void icp_iterate(Icp& s, int max_steps, pclb200_icp_stats* stats)
     a.oy = 0.5f * (T.lo[1] + T.hi[1]);
     a.oz = 0.5f * (T.lo[2] + T.hi[2]);
     a.partials = s.red.partials.p;
+    a.partials2 = s.red.partials2.p;
     a.counter = s.red.counter.p;
     a.accum = s.red.accum.p;
     a.d_error = c.d_error;
@@ -1781,28 +2029,11 @@ void icp_iterate(Icp& s, int max_steps, pclb200_icp_stats* stats)
     a.skip_count = s.skip_count.p;
     a.cur_normals = s.cur_normals.p;
     a.enforce_same_dir = s.P.enforce_same_direction_normals;
-    {
-      // seeded walks start at the smallest cell that holds their candidate ball (traverse.cuh: climb_start);
-      // PCLB200_CLIMB=0|1 overrides the default (A/B measurements, tests run both)
-      const char* cl = getenv("PCLB200_CLIMB");
-      const bool climb = cl ? cl[0] == '1' : kClimbDefault;
-      a.node_parent = climb ? T.node_parent.p : nullptr;
-      a.leaf_parent = climb ? T.leaf_parent.p : nullptr;
-      // prefix tables (built only when PCLB200_TOP=1 was set at index-build time)
-      a.top_on = 0;
-      for (int b = 0; b < kTopLevels; ++b) {
-        a.top.table[b] = T.top[b].p;
-        if (T.top[b].p)
-          a.top_on = 1;
-      }
-      a.top.lo[0] = T.lo[0];
-      a.top.lo[1] = T.lo[1];
-      a.top.lo[2] = T.lo[2];
-      a.top.scale = T.morton_scale;
-    }
+    a.cells = tree_view(T).cells;
     a.peer.nranks = 0;
     a.seq = 0;
     const bool fused_reduce = comm_peer_view(c, &a.peer, &a.seq);
+    bool fused_accum = false;  // the search kernel also accumulated the normal equations
     const unsigned grid = persistent_grid(c, s.n_q, 256, 8);
     std::unique_ptr<Index> src_index;
     if (s.P.use_reciprocal) {
@@ -1846,53 +2077,42 @@ void icp_iterate(Icp& s, int max_steps, pclb200_icp_stats* stats)
     }
     else {
       ProfScope ps(c, "icp_search");
-      const unsigned sgrid = persistent_grid(c, s.n_q, 256, 16);
-      // Which walk.  The per-query kernel seeds every walk with the previous iteration's match, so its lanes start with
-      // a tight bound and the while-while walk lets them scan 32 DIFFERENT leaves at the same time; the packet kernel
-      // makes the warp scan the UNION of its lanes' leaves but shares every node fetch.  Measured on the bench surface
-      // (profiles/r1j_*): seeded iterations 1.65 ms per-query vs 2.45 ms packet; the first, unseeded search 2.6 vs
-      // 2.2 ms.  So: packet only for the first search after set_source (no seeds yet) when the queries are about as
-      // dense as the target, per-query from then on.  PCLB200_SEARCH=packet|single overrides (tests run both).
-      const char* force = getenv("PCLB200_SEARCH");  // read per call so tests can exercise both kernels
-      bool packet = s.searches == 0 && (double)T.n_valid <= 64.0 * (double)s.n_q;
-      if (force && force[0] == 'p') packet = true;
-      if (force && force[0] == 's') packet = false;
       ++s.searches;
-      // Temporal coherence (still_nearest) pays once the cloud has almost stopped moving: tracking the lower
-      // bounds costs ~6 % of a walk, so it is switched on when the last increment displaced no point by more than
-      // half the RMS correspondence distance, and the skip test then fires from the following iteration on.
-      const char* tc = getenv("PCLB200_TRACK");  // "1" / "0" force it (tests, A/B measurements)
-      bool track = s.track_next && !s.P.use_reciprocal;
-      if (tc && tc[0] == '1') track = !s.P.use_reciprocal;
-      if (tc && tc[0] == '0') track = false;
-      if (packet) {
-        if (s.P.use_reciprocal)
-          k_search_packet<true, false><<<sgrid, 256, 0, st>>>(a, s.match.p);
-        else if (track) {
-          const unsigned cgrid = persistent_grid(c, (s.n_q + kTile - 1) / kTile * 256, 256, 4);
-          const char* cm = getenv("PCLB200_COMPACT");  // "0": plain packet kernel with tracking (A/B measurements)
-          if (cm && cm[0] == '0')
-            k_search_packet<false, true><<<sgrid, 256, 0, st>>>(a, s.match.p);
-          else
-            k_search_packet_compact<<<cgrid, 256, 0, st>>>(a, s.match.p);
-        }
+      // Temporal coherence (still_nearest) pays once the cloud has almost stopped moving: tracking the lower bounds makes
+      // a walk look at a wider ball, so it is switched on when the last increment displaced no point by more than half
+      // the RMS correspondence distance (or always / never: pclb200_icp_params::track_mode), and the skip test then
+      // fires from the following iteration on.
+      bool track = s.P.track_mode == PCLB200_TRACK_ON || (s.P.track_mode == PCLB200_TRACK_AUTO && s.track_next);
+      if (s.P.use_reciprocal)
+        track = false;
+      if (track && !s.lb_valid)  // bounds left by an earlier TRACK phase say nothing about the current matches
+        PCLB_CUDA(cudaMemsetAsync(s.lb.p, 0, s.n_q * sizeof(float), st));
+      s.lb_valid = track;
+      // the accumulation rides in the search kernel's epilogue unless something sits between the two
+      // (rejectors) or the estimator needs what the epilogue does not carry (source normals)
+      fused_accum = !s.P.use_reciprocal && s.rejectors.empty() &&
+                    (s.P.estimator == PCLB200_EST_SVD || s.P.estimator == PCLB200_EST_POINT_TO_PLANE_LLS);
+      const unsigned wgrid = persistent_grid(c, s.n_q, kWqWarps * 32, 8);
+      const int blk = kWqWarps * 32;
+      if (s.P.use_reciprocal)
+        k_icp_wq<kEstNone, true, false><<<wgrid, blk, 0, st>>>(a, s.match.p, s.lb.p);
+      else if (!fused_accum) {
+        if (track)
+          k_icp_wq<kEstNone, false, true><<<wgrid, blk, 0, st>>>(a, s.match.p, s.lb.p);
         else
-          k_search_packet<false, false><<<sgrid, 256, 0, st>>>(a, s.match.p);
+          k_icp_wq<kEstNone, false, false><<<wgrid, blk, 0, st>>>(a, s.match.p, s.lb.p);
+      }
+      else if (s.P.estimator == PCLB200_EST_SVD) {
+        if (track)
+          k_icp_wq<PCLB200_EST_SVD, false, true><<<wgrid, blk, 0, st>>>(a, s.match.p, s.lb.p);
+        else
+          k_icp_wq<PCLB200_EST_SVD, false, false><<<wgrid, blk, 0, st>>>(a, s.match.p, s.lb.p);
       }
       else {
-        // PCLB200_SEARCH=dynamic: persistent warps with dynamic fetch (k_search_dyn) instead of one walk per thread
-        const bool dyn = force && force[0] == 'd' && !s.P.use_reciprocal;
-        const unsigned dgrid = persistent_grid(c, s.n_q, 256, 4);
-        if (dyn && track)
-          k_search_dyn<true><<<dgrid, 256, 0, st>>>(a, s.match.p);
-        else if (dyn)
-          k_search_dyn<false><<<dgrid, 256, 0, st>>>(a, s.match.p);
-        else if (s.P.use_reciprocal)
-          k_search<true, false><<<sgrid, 256, 0, st>>>(a, s.match.p);
-        else if (track)
-          k_search<false, true><<<sgrid, 256, 0, st>>>(a, s.match.p);
+        if (track)
+          k_icp_wq<PCLB200_EST_POINT_TO_PLANE_LLS, false, true><<<wgrid, blk, 0, st>>>(a, s.match.p, s.lb.p);
         else
-          k_search<false, false><<<sgrid, 256, 0, st>>>(a, s.match.p);
+          k_icp_wq<PCLB200_EST_POINT_TO_PLANE_LLS, false, false><<<wgrid, blk, 0, st>>>(a, s.match.p, s.lb.p);
       }
       ++c.launches;
     }
@@ -1902,7 +2122,7 @@ void icp_iterate(Icp& s, int max_steps, pclb200_icp_stats* stats)
       ProfScope ps(c, "icp_reject");
       run_rejectors(s);
     }
-    {
+    if (!fused_accum) {
       ProfScope ps(c, "icp_accum");
       if (s.P.estimator == PCLB200_EST_SVD)
         k_accum<PCLB200_EST_SVD><<<grid, 256, 0, st>>>(a, s.match.p);
@@ -2000,8 +2220,9 @@ __global__ void k_matches_to_corr(const float4* __restrict__ cur, const Match* _
   const Match m = match[i];
   pclb200_corr r;
   r.index_query = src_orig ? src_orig[slot] : slot;
-  r.index_match = m.accepted ? __float_as_int(tgt_pts[m.pos].w) : -1;
-  r.distance = m.accepted ? m.d2 : 0.f;
+  const bool acc = match_accepted(m);
+  r.index_match = acc ? __float_as_int(tgt_pts[m.pos].w) : -1;
+  r.distance = acc ? m.d2 : 0.f;
   by_slot[slot] = r;
 }
 
@@ -2235,11 +2456,11 @@ size_t correspondences(Ctx& c, const Index& tgt, const Index* src_index, const v
   d_count.alloc(1, st);
   const float gate = gate_from_max_dist(max_dist);
   if (src_index)
-    k_corr<true><<<grid_for(nq, 128), 128, 0, st>>>(tgt.nodes.p, tgt.pts.p, tgt.root, qb.q.p, nq, gate,
+    k_corr<true><<<grid_for(nq, 128), 128, 0, st>>>(tree_view(tgt), qb.q.p, nq, gate,
                                                    src_index->nodes.p, src_index->pts.p, src_index->root, d_ind.p,
                                                    by_slot.p, c.d_error);
   else
-    k_corr<false><<<grid_for(nq, 128), 128, 0, st>>>(tgt.nodes.p, tgt.pts.p, tgt.root, qb.q.p, nq, gate, nullptr,
+    k_corr<false><<<grid_for(nq, 128), 128, 0, st>>>(tree_view(tgt), qb.q.p, nq, gate, nullptr,
                                                     nullptr, 0, d_ind.p, by_slot.p, c.d_error);
   ++c.launches;
   PCLB_CUDA(cudaGetLastError());
@@ -2295,7 +2516,7 @@ double fitness_score(Ctx& c, const Index& tgt, const void* src, size_t n, size_t
   pub.counter = red.counter.p;
   pub.accum = red.accum.p;
   pub.d_error = c.d_error;
-  k_fitness<<<grid, 256, 0, st>>>(tgt.nodes.p, tgt.pts.p, tgt.root, qb.q.p, nq, max_range, pub);
+  k_fitness<<<grid, 256, 0, st>>>(tree_view(tgt), qb.q.p, nq, max_range, pub);
   ++c.launches;
   double acc[2];
   PCLB_CUDA(cudaMemcpyAsync(acc, red.accum.p, sizeof(acc), cudaMemcpyDeviceToHost, st));

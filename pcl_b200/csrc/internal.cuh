@@ -149,10 +149,6 @@ void load_vec3_as_float4(Ctx& c, const void* src, size_t n_records, size_t strid
 //   a = (l.min.x, l.min.y, l.min.z, l.max.x)  b = (l.max.y, l.max.z, r.min.x, r.min.y)
 //   c = (r.min.z, r.max.x, r.max.y, r.max.z)  d = (left, right, 0, 0)
 // child reference >= 0: internal node id; < 0: ~leaf_id.
-// d.z: bit 0 / bit 1 = the left / right child is a SPATIAL cell: its points are exactly the indexed points whose Morton
-//      code starts with the child's prefix (false for cells cut between points that share one Morton code, where the
-//      split is by index and says nothing about space).  A seeded walk may start at such a child instead of the root
-//      when the query's candidate ball lies inside the child's box (traverse.cuh: climb_start).
 struct __align__(16) BvhNode {
   float4 a, b, c;
   int4 d;
@@ -168,6 +164,14 @@ static_assert(kLeafSize % 8 == 0 && kLeafSize >= 8 && kLeafSize <= 64, "leaf siz
 constexpr int kStackSize = 96;      // traversal stack entries per query
 constexpr int kSentinelIndex = 0x7fffffff;
 
+// host-side description of the index's cell table (lbvh.cu builds it, traverse.cuh: CellTable reads it)
+struct CellTableHost {
+  unsigned log2_slots = 0;  // 0 = no table
+  int bmax = 0;             // finest level present (cells of 2^-bmax of the frame per axis)
+  uint64_t entries = 0;
+  float margin = 0.f;
+};
+
 struct Index {
   Ctx* ctx = nullptr;
   int device = 0;
@@ -180,16 +184,9 @@ struct Index {
   DevBuf<float4> pts;   // n_leaves*kLeafSize, Morton order, w = original index bits; padded with +inf
   DevBuf<BvhNode> nodes;  // n_leaves-1
   DevBuf<int32_t> pos_of_orig;  // n_cloud: position in `pts` of original index i, or -1 (lazy)
-  DevBuf<int> node_parent;      // n_leaves-1: parent of internal node i (-1 for the root); seeded walks climb with it
-  DevBuf<int> leaf_parent;      // n_leaves: internal node that holds leaf l as a child
-  DevBuf<int> top[5];           // prefix tables, 3b-bit Morton prefix -> deepest node holding all its points, b = 4..8
-                                // (traverse.cuh: top_start; levels above ~4 entries per point are not built)
-  size_t bytes() const
-  {
-    size_t t = 0;
-    for (const auto& b : top) t += b.bytes();
-    return pts.bytes() + nodes.bytes() + pos_of_orig.bytes() + node_parent.bytes() + leaf_parent.bytes() + t;
-  }
+  DevBuf<uint2> cell_slots;     // hash table (level, cell) -> deepest node / leaf holding every point of the cell
+  CellTableHost cells;          // its description (traverse.cuh: CellTable is the device-side view)
+  size_t bytes() const { return pts.bytes() + nodes.bytes() + pos_of_orig.bytes() + cell_slots.bytes(); }
 };
 
 Index* build_index(Ctx& c, const void* pts, size_t n, size_t stride, const int32_t* subset, size_t n_subset);

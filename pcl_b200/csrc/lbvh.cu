@@ -10,8 +10,10 @@
 //   4. Karras 2012 binary radix tree over the POINTS (ties by index), cut where a cell holds <= 8 points: every leaf is a
 //      whole radix-tree cell, stored as one 128-byte line of float4 {x,y,z, original-index bits} padded with +inf
 //   5. bottom-up refit (atomic arrival flags), then both children's boxes are packed into the parent's 64-byte node so
-//      one node visit = four independent 128-bit loads; parent arrays and "spatial cell" flags are kept for walks
-//      that start below the root (traverse.cuh: climb_start)
+//      one node visit = four independent 128-bit loads
+//   6. cell table: every occupied cell of the levels 1..bmax of the Morton grid -> the deepest node / leaf that holds all
+//      its points (open-addressing hash, 8 B per slot), so that walks start at the candidate ball instead of the root
+//      (traverse.cuh: CellTable, nearest1)
 #include <cub/cub.cuh>
 
 #include <algorithm>
@@ -273,8 +275,7 @@ __global__ void k_refit(const float4* __restrict__ pts, int n_leaves, const int2
 
 __global__ void k_pack_nodes(int n_internal, const int2* __restrict__ children, const float4* __restrict__ leaf_lo,
                              const float4* __restrict__ leaf_hi, const float4* __restrict__ node_lo,
-                             const float4* __restrict__ node_hi, const unsigned char* __restrict__ child_flags,
-                             BvhNode* __restrict__ nodes)
+                             const float4* __restrict__ node_hi, BvhNode* __restrict__ nodes)
 {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n_internal)
@@ -288,7 +289,7 @@ __global__ void k_pack_nodes(int n_internal, const int2* __restrict__ children, 
   nd.a = make_float4(alo.x, alo.y, alo.z, ahi.x);
   nd.b = make_float4(ahi.y, ahi.z, blo.x, blo.y);
   nd.c = make_float4(blo.z, bhi.x, bhi.y, bhi.z);
-  nd.d = make_int4(ch.x, ch.y, child_flags ? (int)child_flags[i] : 0, 0);
+  nd.d = make_int4(ch.x, ch.y, 0, 0);
   nodes[i] = nd;
 }
 
@@ -412,8 +413,11 @@ __global__ void k_scatter_cells(const float4* __restrict__ p, const int32_t* __r
   out[(size_t)leaf * kLeafSize + (pos - leaf_start[leaf])] = make_float4(v.x, v.y, v.z, __int_as_float(oi));
 }
 
-struct TopTablesW {
-  int* table[kTopLevels];
+// ---- cell table -------------------------------------------------------------------------------------------------------
+struct CellTableW {
+  unsigned long long* slots;  // packed {key (low 32), reference (high 32)}; nullptr = not built
+  unsigned shift, mask;
+  int bmax;
 };
 
 // number of leading bits two 63-bit Morton codes share (63 when they are equal)
@@ -423,11 +427,47 @@ __device__ __forceinline__ int prefix_len63(unsigned long long a, unsigned long 
   return x == 0 ? 63 : __clzll((long long)x) - 1;
 }
 
-__global__ void k_fill_int(int* __restrict__ p, size_t n, int v)
+// hist[l] = number of adjacent sorted pairs that share exactly l leading bits: the number of occupied cells of level b is
+// 1 + sum_{l < 3b} hist[l], which sizes the table before it is filled
+__global__ void k_prefix_hist(const unsigned long long* __restrict__ keys, int n, unsigned* __restrict__ hist)
 {
-  size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
-  if (i < n)
-    p[i] = v;
+  __shared__ unsigned sh[64];
+  if (threadIdx.x < 64)
+    sh[threadIdx.x] = 0;
+  __syncthreads();
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x + 1; i < n; i += gridDim.x * blockDim.x)
+    atomicAdd(&sh[prefix_len63(keys[i - 1], keys[i])], 1u);
+  __syncthreads();
+  if (threadIdx.x < 64 && sh[threadIdx.x])
+    atomicAdd(&hist[threadIdx.x], sh[threadIdx.x]);
+}
+
+// every third bit of v, packed (inverse of expand21)
+__device__ __forceinline__ unsigned compact21(unsigned long long v)
+{
+  v &= 0x1249249249249249ULL;
+  v = (v | v >> 2) & 0x10c30c30c30c30c3ULL;
+  v = (v | v >> 4) & 0x100f00f00f00f00fULL;
+  v = (v | v >> 8) & 0x1f0000ff0000ffULL;
+  v = (v | v >> 16) & 0x1f00000000ffffULL;
+  v = (v | v >> 32) & 0x1fffffULL;
+  return (unsigned)v;
+}
+
+// (level b, cell of Morton code `code`) -> ref.  Several threads may insert the same pair (a leaf that spans several
+// cells is inserted once per point): the first wins, the others see their own key and stop.
+__device__ __forceinline__ void cell_insert(const CellTableW& T, int b, unsigned long long code, int ref)
+{
+  const unsigned long long P = code >> (63 - 3 * b);
+  const unsigned key = cell_key(b, compact21(P), compact21(P >> 1), compact21(P >> 2));
+  const unsigned long long packed = ((unsigned long long)(unsigned)ref << 32) | key;
+  unsigned h = (key * 0x9E3779B1u) >> T.shift;
+  for (;;) {
+    const unsigned long long old = atomicCAS(T.slots + h, 0ULL, packed);
+    if (old == 0ULL || (unsigned)old == key)
+      return;
+    h = (h + 1u) & T.mask;
+  }
 }
 
 // children / parents of the final tree (kept nodes renumbered by new_id; everything below becomes a leaf)
@@ -435,8 +475,7 @@ __global__ void k_link_cells(int n, const int2* __restrict__ children, const int
                              const int* __restrict__ keep, const int* __restrict__ new_id,
                              const int* __restrict__ leaf_incl, const unsigned long long* __restrict__ keys,
                              int2* __restrict__ out_children, int* __restrict__ out_node_parent,
-                             int* __restrict__ out_leaf_parent, unsigned char* __restrict__ out_child_flags,
-                             TopTablesW top)
+                             int* __restrict__ out_leaf_parent, CellTableW cells)
 {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n - 1 || !keep[i])
@@ -445,14 +484,9 @@ __global__ void k_link_cells(int n, const int2* __restrict__ children, const int
   const int2 ch = children[i];
   int ref[2];
   const int c2[2] = {ch.x, ch.y};
-  unsigned flags = 0;
 #pragma unroll
   for (int k = 0; k < 2; ++k) {
     const int cc = c2[k];
-    // a radix-tree node whose first and last Morton codes differ has a purely spatial prefix: it holds EVERY indexed
-    // point of its prefix cell.  Cells cut inside a run of equal codes (and single points) are not marked.
-    if (cc >= 0 && keys[range[cc].x] != keys[range[cc].y])
-      flags |= 1u << k;
     if (cc >= 0 && keep[cc]) {
       ref[k] = new_id[cc];
       out_node_parent[new_id[cc]] = nid;
@@ -465,32 +499,36 @@ __global__ void k_link_cells(int n, const int2* __restrict__ children, const int
     }
   }
   out_children[nid] = make_int2(ref[0], ref[1]);
-  out_child_flags[nid] = (unsigned char)flags;
-  // prefix tables (traverse.cuh: top_start): child C is the deepest node that holds every indexed point of a 3b-bit
-  // prefix cell exactly when  prefix_len(this node) < 3b <= prefix_len(C)
+  if (i == 0)
+    out_node_parent[nid] = -1;
+  if (cells.slots == nullptr)
+    return;
+  // cell table: child C is the deepest node that holds every indexed point of a 3b-bit prefix cell exactly when
+  //   prefix_len(this node) < 3b <= prefix_len(C).
+  // (Nodes cut INSIDE a run of equal codes have prefix length 63 like their parent and never qualify: only purely
+  // spatial cells enter the table.)
   const int l_self = prefix_len63(keys[range[i].x], keys[range[i].y]);
+  if (i == 0)  // the root holds every point of the cells its own prefix spans (degenerate frames only)
+    for (int b = 1; b <= cells.bmax && 3 * b <= l_self; ++b)
+      cell_insert(cells, b, keys[0], nid);
 #pragma unroll
   for (int k = 0; k < 2; ++k) {
     const int cc = c2[k];
     const int first = cc >= 0 ? range[cc].x : ~cc;
-    const int l_child = cc >= 0 ? prefix_len63(keys[range[cc].x], keys[range[cc].y]) : 63;
-    const bool is_leaf = !(cc >= 0 && keep[cc]);
     const int last = cc >= 0 ? range[cc].y : ~cc;
-#pragma unroll
-    for (int b = kTopMinBits; b <= kTopMaxBits; ++b) {
-      int* tb = top.table[b - kTopMinBits];
-      if (tb == nullptr || !(l_self < 3 * b))
-        continue;
+    const int l_child = cc >= 0 ? prefix_len63(keys[first], keys[last]) : 63;
+    const bool is_leaf = !(cc >= 0 && keep[cc]);
+    for (int b = l_self / 3 + 1; b <= cells.bmax; ++b) {  // 3b > l_self
       if (3 * b <= l_child)
-        tb[(size_t)(keys[first] >> (63 - 3 * b))] = ref[k];
+        cell_insert(cells, b, keys[first], ref[k]);
       else if (is_leaf)
-        // a leaf that spans several 3b-cells still holds every indexed point of each of them
+        // a leaf that spans several level-b cells still holds every indexed point of each of them
         for (int j = first; j <= last; ++j)
-          tb[(size_t)(keys[j] >> (63 - 3 * b))] = ref[k];
+          cell_insert(cells, b, keys[j], ref[k]);
+      else
+        break;  // a kept child with a shorter prefix: its own thread inserts the finer levels
     }
   }
-  if (i == 0)
-    out_node_parent[nid] = -1;
 }
 
 // ---- host orchestration -------------------------------------------------------------------------
@@ -551,8 +589,7 @@ static void morton_sort(Ctx& c, const float4* d_pts, size_t n, const Index* fram
   vals_in.alloc(n, s);
   out.keys.alloc(n, s);
   out.vals.alloc(n, s);
-  static const char* order_env = getenv("PCLB200_QUERY_ORDER");  // experiments: "morton" restores Z-order queries
-  const bool hilbert = frame != nullptr && !(order_env && order_env[0] == 'm');
+  const bool hilbert = frame != nullptr;  // queries: Hilbert order (compact runs of 32); the tree itself: Morton
   if (hilbert)
     k_morton<true><<<grid_for(n, 256), 256, 0, s>>>(d_pts, n, out.lo[0], out.lo[1], out.lo[2], out.scale, keys_in.p,
                                                    vals_in.p);
@@ -572,7 +609,7 @@ static void morton_sort(Ctx& c, const float4* d_pts, size_t n, const Index* fram
 }
 
 static Index* build_from_dense(Ctx& c, const float4* d_pts, size_t n, const int32_t* d_orig_of_slot, size_t n_cloud,
-                                bool build_top_tables)
+                                bool build_cell_table)
 {
   cudaStream_t s = c.stream;
   PCLB_REQUIRE(n > 0, PCLB200_ERR_EMPTY, "cannot index an empty cloud (kdtree_flann.hpp:118-129)");
@@ -624,6 +661,16 @@ static Index* build_from_dense(Ctx& c, const float4* d_pts, size_t n, const int3
     PCLB_CUDA(cub::DeviceScan::InclusiveSum(tmp.p, tb, leaf_flag.p, leaf_incl.p, nv, s));
     PCLB_CUDA(cub::DeviceScan::ExclusiveSum(tmp.p, tb2, keep.p, new_id.p, ni, s));
     c.launches += 4;
+    DevBuf<unsigned> hist;
+    unsigned h_hist[64] = {0};
+    const bool want_cells = build_cell_table && nv >= 256;
+    if (want_cells) {
+      hist.alloc(64, s);
+      PCLB_CUDA(cudaMemsetAsync(hist.p, 0, 64 * sizeof(unsigned), s));
+      k_prefix_hist<<<std::min<unsigned>(grid_for(nv, 256), (unsigned)c.sm_count * 8), 256, 0, s>>>(sc.keys.p, nv, hist.p);
+      ++c.launches;
+      PCLB_CUDA(cudaMemcpyAsync(h_hist, hist.p, sizeof(h_hist), cudaMemcpyDeviceToHost, s));
+    }
     int h_leaves = 0, h_last_id = 0, h_last_keep = 0;
     PCLB_CUDA(cudaMemcpyAsync(&h_leaves, leaf_incl.p + (nv - 1), sizeof(int), cudaMemcpyDeviceToHost, s));
     PCLB_CUDA(cudaMemcpyAsync(&h_last_id, new_id.p + (ni - 1), sizeof(int), cudaMemcpyDeviceToHost, s));
@@ -638,9 +685,7 @@ static Index* build_from_dense(Ctx& c, const float4* d_pts, size_t n, const int3
     idx->pts.alloc(n_padded, s);
     idx->nodes.alloc(n_int, s);
     DevBuf<int> leaf_start;
-    DevBuf<int>& node_parent = idx->node_parent;  // kept: seeded walks climb from the previous match's leaf
-    DevBuf<int>& leaf_parent = idx->leaf_parent;
-    DevBuf<unsigned char> child_flags;
+    DevBuf<int> node_parent, leaf_parent;  // build-time only (bottom-up refit)
     DevBuf<int2> children;
     DevBuf<float4> leaf_lo, leaf_hi, node_lo, node_hi;
     DevBuf<unsigned> flags;
@@ -648,7 +693,6 @@ static Index* build_from_dense(Ctx& c, const float4* d_pts, size_t n, const int3
     node_parent.alloc(n_int, s);
     leaf_parent.alloc(n_leaves, s);
     children.alloc(n_int, s);
-    child_flags.alloc(n_int, s);
     leaf_lo.alloc(n_leaves, s);
     leaf_hi.alloc(n_leaves, s);
     node_lo.alloc(n_int, s);
@@ -659,28 +703,47 @@ static Index* build_from_dense(Ctx& c, const float4* d_pts, size_t n, const int3
     k_fill_sentinels<<<grid_for(n_padded, 256), 256, 0, s>>>(idx->pts.p, n_padded);
     k_scatter_cells<<<grid_for(nv, 256), 256, 0, s>>>(d_pts, sc.vals.p, d_orig_of_slot, nv, leaf_incl.p, leaf_start.p,
                                                       idx->pts.p);
-    // prefix tables for walks that start below the root: level b (2^(3b) entries) is built while it stays within
-    // ~4 entries per indexed point; every entry starts as "root"
-    // (opt-in while the feature is being measured: PCLB200_TOP=1 at index-build time)
-    const char* top_env = getenv("PCLB200_TOP");
-    const bool want_top = build_top_tables && top_env && top_env[0] == '1';
-    TopTablesW topw;
-    for (int b = kTopMinBits; b <= kTopMaxBits; ++b) {
-      const size_t entries = (size_t)1 << (3 * b);
-      topw.table[b - kTopMinBits] = nullptr;
-      if (want_top && entries <= 4 * (size_t)nv) {
-        idx->top[b - kTopMinBits].alloc(entries, s);
-        k_fill_int<<<grid_for(entries, 256), 256, 0, s>>>(idx->top[b - kTopMinBits].p, entries, idx->root);
-        ++c.launches;
-        topw.table[b - kTopMinBits] = idx->top[b - kTopMinBits].p;
+    // cell table (traverse.cuh: CellTable): levels 1..bmax, bmax = the finest level (<= kCellMaxBits) whose occupied
+    // cells still hold >= 4 indexed points on average — finer levels would mostly map single points.  The number of
+    // entries is known exactly from the prefix-length histogram; the table gets >= 2 slots per entry.
+    CellTableW cellw{nullptr, 0, 0, 0};
+    if (want_cells) {
+      uint64_t cum = 1, entries = 0;
+      int l = 0, bmax = 0;
+      for (int b = 1; b <= kCellMaxBits; ++b) {
+        for (; l < 3 * b; ++l)
+          cum += h_hist[l];
+        if (cum > (uint64_t)nv / 4)
+          break;
+        bmax = b;
+        entries += cum;
+      }
+      if (bmax >= 1) {
+        unsigned lg = 6;
+        while (((uint64_t)1 << lg) < 2 * entries)
+          ++lg;
+        idx->cell_slots.alloc((size_t)1 << lg, s);
+        PCLB_CUDA(cudaMemsetAsync(idx->cell_slots.p, 0, idx->cell_slots.bytes(), s));
+        idx->cells.log2_slots = lg;
+        idx->cells.bmax = bmax;
+        idx->cells.entries = entries;
+        float m = 0.f;
+        for (int d = 0; d < 3; ++d)
+          m = std::max(m, std::max(std::fabs(idx->lo[d]), std::fabs(idx->hi[d])));
+        m = std::max(m, 2097152.f / idx->morton_scale);
+        idx->cells.margin = 2e-6f * m;
+        cellw.slots = reinterpret_cast<unsigned long long*>(idx->cell_slots.p);
+        cellw.shift = 32 - lg;
+        cellw.mask = (1u << lg) - 1u;
+        cellw.bmax = bmax;
       }
     }
     k_link_cells<<<grid_for(ni, 256), 256, 0, s>>>(nv, kchildren.p, krange.p, keep.p, new_id.p, leaf_incl.p, sc.keys.p,
-                                                   children.p, node_parent.p, leaf_parent.p, child_flags.p, topw);
+                                                   children.p, node_parent.p, leaf_parent.p, cellw);
     k_refit<<<grid_for(n_leaves, 256), 256, 0, s>>>(idx->pts.p, n_leaves, children.p, node_parent.p, leaf_parent.p,
                                                     leaf_lo.p, leaf_hi.p, node_lo.p, node_hi.p, flags.p);
     k_pack_nodes<<<grid_for(n_int, 256), 256, 0, s>>>(n_int, children.p, leaf_lo.p, leaf_hi.p, node_lo.p, node_hi.p,
-                                                     child_flags.p, idx->nodes.p);
+                                                     idx->nodes.p);
     c.launches += 8;
     PCLB_CUDA(cudaGetLastError());
   }
@@ -712,7 +775,7 @@ Index* build_index(Ctx& c, const void* pts, size_t n, size_t stride, const int32
 
 Index* build_index_from_device(Ctx& c, const float4* d_pts, size_t n, const int32_t* d_orig)
 {
-  return build_from_dense(c, d_pts, n, d_orig, n, false);  // rebuilt every reciprocal iteration: no tables
+  return build_from_dense(c, d_pts, n, d_orig, n, false);  // rebuilt every reciprocal iteration: no cell table
 }
 
 // ---- position of each original index in the Morton array (for gathers by index_match) -------------

@@ -95,66 +95,6 @@ k_knn(const BvhNode* __restrict__ nodes, const float4* __restrict__ pts, int roo
     }
 }
 
-// ---- packet variant (opt-in): the 32 Hilbert-adjacent queries of a warp share ONE walk (traverse_packet) ----------
-// Every node and leaf line is a broadcast load instead of 32 scattered ones and the stack lives once per warp in shared
-// memory; a subtree is entered when ANY lane's k-th distance still reaches it, so each lane sees a superset of the
-// leaves its own exact walk would visit and its list is still the exact lexicographic k smallest.
-template <int K>
-struct NearestKP : NearestK<K> {
-  float best;   // traverse_packet's per-lane pruning bound: the current k-th distance, -1 = this lane wants nothing
-  bool active;
-  __device__ __forceinline__ void leaf(const float4* lp, int first_pos)
-  {
-    if (!active)
-      return;
-    NearestK<K>::leaf(lp, first_pos);
-    best = this->d[K - 1];
-  }
-};
-
-template <int K>
-__global__ void __launch_bounds__(128)
-k_knn_packet(const BvhNode* __restrict__ nodes, const float4* __restrict__ pts, int root,
-             const float4* __restrict__ q, size_t nq, int k_out, float init_bound,
-             int32_t* __restrict__ out_idx, float* __restrict__ out_d2, int* __restrict__ d_error)
-{
-  __shared__ int s_node[4][kWarpStack];
-  __shared__ float s_dist[4][kWarpStack];
-  const int warp = threadIdx.x >> 5;
-  const size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
-  const bool have = i < nq;  // no early return: all 32 lanes take part in the warp votes
-  const float4 qq = have ? __ldg(q + i) : make_float4(0.f, 0.f, 0.f, 0.f);
-  NearestKP<K> v;
-  v.qx = qq.x; v.qy = qq.y; v.qz = qq.z;
-  v.pts = pts;
-  v.init(init_bound);
-  v.active = have && isfinite(qq.x) && isfinite(qq.y) && isfinite(qq.z);
-  v.best = v.active ? init_bound : -1.f;
-  if (!traverse_packet(nodes, pts, root, qq.x, qq.y, qq.z, v, s_node[warp], s_dist[warp]))
-    atomicExch(d_error, 1);
-  if (!have)
-    return;
-  const size_t slot = (size_t)(unsigned)__float_as_int(qq.w);
-#pragma unroll
-  for (int j = 0; j < K; ++j)
-    if (j < k_out) {
-      const bool got = v.pos[j] >= 0;
-      out_idx[slot * k_out + j] = got ? v.orig(v.pos[j]) : -1;
-      out_d2[slot * k_out + j] = got ? v.d[j] : __int_as_float(0x7f800000);
-    }
-}
-
-// Which walk launch_knn / launch_normals use.  Measured on B200 (profiles/r1i_stage_throughput.jsonl, 10 M self-queries
-// on the 10 M-point sheet): the per-query walk wins for every k (k = 1: 2.6 vs 3.3 ms, k = 16: 40 vs 74 ms) — unlike
-// the seeded 1-NN of the ICP loop, an unseeded k-NN packet visits the UNION of its 32 lanes' leaf sets, while the
-// while-while per-query walk lets the lanes scan 32 DIFFERENT leaves at the same time.  So the packet kernels stay an
-// opt-in (PCLB200_KNN=packet; tests run both).
-static bool use_packet_knn(const Index&, size_t)
-{
-  const char* force = getenv("PCLB200_KNN");
-  return force && force[0] == 'p';
-}
-
 // ---- any k: the candidate list lives in the output rows themselves (global memory) -----------------
 struct NearestAny {
   float qx, qy, qz;
@@ -225,16 +165,8 @@ void launch_knn(Ctx& c, const Index& idx, const float4* d_q, size_t nq, int k, f
     return;
   cudaStream_t s = c.stream;
   const unsigned g = grid_for(nq, 128);
-  const bool packet = use_packet_knn(idx, nq);
 #define PCLB_KNN_CASE(KK)                                                                                            \
-  do {                                                                                                               \
-    if (packet)                                                                                                      \
-      k_knn_packet<KK><<<g, 128, 0, s>>>(idx.nodes.p, idx.pts.p, idx.root, d_q, nq, k, init_bound, d_out_idx,        \
-                                         d_out_d2, c.d_error);                                                       \
-    else                                                                                                             \
-      k_knn<KK><<<g, 128, 0, s>>>(idx.nodes.p, idx.pts.p, idx.root, d_q, nq, k, init_bound, d_out_idx, d_out_d2,     \
-                                  c.d_error);                                                                        \
-  } while (0)
+  k_knn<KK><<<g, 128, 0, s>>>(idx.nodes.p, idx.pts.p, idx.root, d_q, nq, k, init_bound, d_out_idx, d_out_d2, c.d_error)
   if (k == 1) PCLB_KNN_CASE(1);
   else if (k == 2) PCLB_KNN_CASE(2);
   else if (k <= 4) PCLB_KNN_CASE(4);
@@ -656,46 +588,28 @@ __device__ __forceinline__ float4 normal_from_moments(float (&accu)[9], int cnt,
 // (common/include/pcl/common/impl/centroid.hpp:578-652, Scalar = float, same operation order, no fma)
 // -> solvePlaneParameters (features/impl/feature.hpp:65-92) -> flipNormalTowardsViewpoint
 // (features/normal_3d.h:169-188).  The neighbour list is never materialised in HBM.
-template <int K, bool PACKET>
+template <int K>
 __global__ void __launch_bounds__(128)
 k_normals(const BvhNode* __restrict__ nodes, const float4* __restrict__ pts, int root,
           const float4* __restrict__ q, size_t nq, int k_req, float vpx, float vpy, float vpz,
           float4* __restrict__ out, int* __restrict__ not_dense, int* __restrict__ d_error)
 {
-  __shared__ int s_node[PACKET ? 4 : 1][PACKET ? kWarpStack : 1];
-  __shared__ float s_dist[PACKET ? 4 : 1][PACKET ? kWarpStack : 1];
   const size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
-  const bool have = i < nq;
-  if (!PACKET && !have)
+  if (i >= nq)
     return;
-  const float4 qq = have ? __ldg(q + i) : make_float4(0.f, 0.f, 0.f, 0.f);
+  const float4 qq = __ldg(q + i);
   const size_t slot = (size_t)(unsigned)__float_as_int(qq.w);
   const float qnan = __int_as_float(0x7fc00000);
-  const bool finite_q = have && isfinite(qq.x) && isfinite(qq.y) && isfinite(qq.z);
-  if (!PACKET && !finite_q) {
+  if (!(isfinite(qq.x) && isfinite(qq.y) && isfinite(qq.z))) {
     out[slot] = make_float4(qnan, qnan, qnan, qnan);
     *not_dense = 1;
     return;
   }
-  NearestKP<K> v;
+  NearestK<K> v;
   v.qx = qq.x; v.qy = qq.y; v.qz = qq.z;
   v.pts = pts;
   v.init(__int_as_float(0x7f800000));
-  v.active = finite_q;
-  v.best = finite_q ? __int_as_float(0x7f800000) : -1.f;
-  if (PACKET) {  // all 32 lanes take part in the warp votes; lanes without a (finite) query want nothing
-    const int warp = threadIdx.x >> 5;
-    if (!traverse_packet(nodes, pts, root, qq.x, qq.y, qq.z, v, s_node[warp], s_dist[warp]))
-      atomicExch(d_error, 1);
-    if (!have)
-      return;
-    if (!finite_q) {
-      out[slot] = make_float4(qnan, qnan, qnan, qnan);
-      *not_dense = 1;
-      return;
-    }
-  }
-  else if (!traverse(nodes, pts, root, qq.x, qq.y, qq.z, static_cast<NearestK<K>&>(v)))
+  if (!traverse(nodes, pts, root, qq.x, qq.y, qq.z, v))
     atomicExch(d_error, 1);
   int cnt = 0;
 #pragma unroll
@@ -820,16 +734,9 @@ void launch_normals(Ctx& c, Index& idx, const float4* d_q, size_t nq, int k, con
     PCLB_CUDA(cudaGetLastError());
     return;
   }
-  const bool packet = use_packet_knn(idx, nq);
 #define PCLB_NRM_CASE(KK)                                                                                              \
-  do {                                                                                                                 \
-    if (packet)                                                                                                        \
-      k_normals<KK, true><<<g, 128, 0, s>>>(idx.nodes.p, idx.pts.p, idx.root, d_q, nq, k, vp[0], vp[1], vp[2], d_out,  \
-                                            d_not_dense, c.d_error);                                                   \
-    else                                                                                                               \
-      k_normals<KK, false><<<g, 128, 0, s>>>(idx.nodes.p, idx.pts.p, idx.root, d_q, nq, k, vp[0], vp[1], vp[2], d_out, \
-                                             d_not_dense, c.d_error);                                                  \
-  } while (0)
+  k_normals<KK><<<g, 128, 0, s>>>(idx.nodes.p, idx.pts.p, idx.root, d_q, nq, k, vp[0], vp[1], vp[2], d_out, d_not_dense, \
+                                  c.d_error)
   if (k <= 4) PCLB_NRM_CASE(4);
   else if (k <= 8) PCLB_NRM_CASE(8);
   else if (k <= 10) PCLB_NRM_CASE(10);

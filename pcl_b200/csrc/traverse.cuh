@@ -11,6 +11,15 @@
 
 namespace pclb200 {
 
+// -DPCLB_STATS (experimental builds only, tools/): per-walk event counts, accumulated per thread and flushed once
+#ifdef PCLB_STATS
+struct WalkStats { unsigned n[8]; };  // 0 lookups 1 node visits 2 leaf scans 3 pushes 4 home seeds 5 rooted walks 6 cells pushed 7 queries
+#define PCLB_STAT(st, k) (++(st).n[k])
+#else
+struct WalkStats {};
+#define PCLB_STAT(st, k) ((void)0)
+#endif
+
 __device__ __forceinline__ float dist2_rn(float qx, float qy, float qz, float px, float py, float pz)
 {
   float dx = __fsub_rn(qx, px), dy = __fsub_rn(qy, py), dz = __fsub_rn(qz, pz);
@@ -32,25 +41,39 @@ __device__ __forceinline__ float4 ldg4(const float4* p) { return __ldg(p); }
 // warp that are still descending are not serialised against lanes scanning a leaf; leaf scans (the long,
 // fully unrolled body) run once the warp has left the inner loop.  `Visitor` provides:
 //   float bound() const            — current pruning distance (subtrees with box bound > bound() are skipped)
+//   void prune(float d2)           — a subtree / cell whose every point is at least d2 away was skipped
 //   void leaf(const float4* leaf_pts, int first_pos) — examine kLeafSize consecutive points
 // Nearer child first; the farther one is pushed with its bound and re-tested when popped.
+// The stack is the caller's: walks that start from several subtrees at once (cell-table starts, below) pre-fill it
+// with (subtree, lower bound) pairs and pass node = kDone; a plain walk passes sp = 0 and node = root.
+// skip_a / skip_b: leaf references (~leaf) the caller has already scanned (seed leaves) — not scanned again.
 // Returns false on stack overflow (caller raises the device error flag).
 constexpr int kDone = 0x7fffffff;  // "no node": internal ids are >= 0 and < 2^31-1, leaves are negative
 
 template <typename Visitor>
-__device__ __forceinline__ bool traverse(const BvhNode* __restrict__ nodes, const float4* __restrict__ pts,
-                                         int root, float qx, float qy, float qz, Visitor& v)
+__device__ __forceinline__ bool walk(const BvhNode* __restrict__ nodes, const float4* __restrict__ pts,
+                                     int* __restrict__ stack_node, float* __restrict__ stack_dist, int sp, int node,
+                                     float qx, float qy, float qz, Visitor& v, int skip_a, int skip_b,
+                                     WalkStats& ws)
 {
-  int stack_node[kStackSize];
-  float stack_dist[kStackSize];
-  int sp = 0;
-  int node = root;
   bool ok = true;
+  if (node == kDone) {
+    const float bnd = v.bound();
+    while (sp > 0) {
+      --sp;
+      if (stack_dist[sp] <= bnd) {
+        node = stack_node[sp];
+        break;
+      }
+      v.prune(stack_dist[sp]);
+    }
+  }
   while (node != kDone) {
     while (node >= 0 && node != kDone) {
       const float4* np = reinterpret_cast<const float4*>(nodes + node);
       const float4 a = ldg4(np), b = ldg4(np + 1), c = ldg4(np + 2);
       const int4 d = __ldg(reinterpret_cast<const int4*>(np + 3));
+      PCLB_STAT(ws, 1);
       float dl = box_dist2_rn(qx, qy, qz, a.x, a.y, a.z, a.w, b.x, b.y);
       float dr = box_dist2_rn(qx, qy, qz, b.z, b.w, c.x, c.y, c.z, c.w);
       int nl = d.x, nr = d.y;
@@ -65,6 +88,7 @@ __device__ __forceinline__ bool traverse(const BvhNode* __restrict__ nodes, cons
             stack_node[sp] = nr;
             stack_dist[sp] = dr;
             ++sp;
+            PCLB_STAT(ws, 3);
           }
           else
             ok = false;
@@ -88,8 +112,11 @@ __device__ __forceinline__ bool traverse(const BvhNode* __restrict__ nodes, cons
     }
     if (node == kDone)
       break;
-    const int leaf = ~node;
-    v.leaf(pts + (size_t)leaf * kLeafSize, leaf * kLeafSize);
+    if (node != skip_a && node != skip_b) {
+      const int leaf = ~node;
+      v.leaf(pts + (size_t)leaf * kLeafSize, leaf * kLeafSize);
+      PCLB_STAT(ws, 2);
+    }
     node = kDone;
     const float bnd = v.bound();
     while (sp > 0) {
@@ -102,6 +129,17 @@ __device__ __forceinline__ bool traverse(const BvhNode* __restrict__ nodes, cons
     }
   }
   return ok;
+}
+
+// plain walk from `root` with a private stack
+template <typename Visitor>
+__device__ __forceinline__ bool traverse(const BvhNode* __restrict__ nodes, const float4* __restrict__ pts,
+                                         int root, float qx, float qy, float qz, Visitor& v)
+{
+  int stack_node[kStackSize];
+  float stack_dist[kStackSize];
+  WalkStats ws;
+  return walk(nodes, pts, stack_node, stack_dist, 0, root, qx, qy, qz, v, kDone, kDone, ws);
 }
 
 // ---- Morton cell coordinates (shared by the build, lbvh.cu, and by walks that start below the root) --------------
@@ -122,83 +160,95 @@ __device__ __forceinline__ unsigned long long expand21(unsigned long long v)
   return v;
 }
 
-// ---- start node from the prefix tables -------------------------------------------------------------------------------
-// Index::top[b - kTopMinBits][P] = the deepest node that holds EVERY indexed point whose 63-bit Morton code starts with
-// the 3b-bit prefix P (root where no such point exists).  A walk that only needs the points of the closed box
-// [q - r, q + r]^3 may start there if the box lies inside ONE 3b-cell: the quantiser is monotone, so every indexed point
-// of the box has a cell coordinate between those of the two corners, i.e. the same prefix — an integer test.  The finest
-// table whose cell holds the box is used; if even the coarsest does not, the walk starts at the root.
-constexpr int kTopMinBits = 4, kTopMaxBits = 8, kTopLevels = kTopMaxBits - kTopMinBits + 1;
+// ---- cell table: walks that start at the candidate ball instead of the root ------------------------------------
+// The tree is a radix tree over Morton codes, so for every level b (cells of 2^-b of the index's frame per axis) and every
+// OCCUPIED cell there is one deepest node — or leaf — that holds EVERY indexed point of that cell (lbvh.cu inserts exactly
+// these (level, cell) -> reference pairs into one open-addressing hash table, levels 1..bmax).  A 1-NN walk that already
+// holds a candidate at squared distance `best` only has to look at indexed points inside the closed ball B(q, r),
+// r = sqrt(best): all of them lie in the box [q - r, q + r]^3, the build's quantiser is monotone, so their cell
+// coordinates lie between those of the box's two corners; at the level where the box is at most one cell wide that is
+// at most 2 x 2 x 2 cells.  The walk therefore looks those cells up, pushes their subtrees (with an arithmetic lower
+// bound on the distance to the cell) and runs the ordinary exact traversal from there: the ~20 levels between the root
+// and the neighbourhood of the query are never touched, and the cost follows the number of points near the ball, not
+// the size of the cloud.  Exactness needs nothing beyond the monotone quantiser (an integer argument) — the float
+// bounds only ever prune a cell when every point of it is provably farther than the current best.
+#ifndef PCLB_LEVEL_BIAS
+#define PCLB_LEVEL_BIAS 0
+#endif
+constexpr int kCellLevelBias = PCLB_LEVEL_BIAS;  // walk cells 2^bias times wider than the minimum (fewer cells, deeper subtrees)
+constexpr int kCellMaxBits = 10;  // finest level: 3 * 10 bits of cell coordinates + a level marker fit one 32-bit key
 
-struct TopTables {
-  const int* table[kTopLevels];  // nullptr = level not built
-  float lo[3];
-  float scale;
+struct CellTable {
+  const uint2* slots = nullptr;  // {key, reference}; key 0 = empty.  nullptr: the index has no table (walks start at the root)
+  unsigned shift = 0;            // 32 - log2(#slots)
+  unsigned mask = 0;             // #slots - 1
+  int bmax = 0;                  // finest level present
+  float lo[3] = {0.f, 0.f, 0.f}; // frame of the index (same numbers the Morton keys were built with)
+  float scale = 1.f;
+  float inv_scale = 1.f;
+  float margin = 0.f;            // absolute slack of a cell boundary computed in fp32 (see cell_gap2)
 };
 
-__device__ __forceinline__ int top_start(const TopTables& T, int root, float qx, float qy, float qz, float r)
+struct TreeView {
+  const BvhNode* nodes;
+  const float4* pts;
+  int root;
+  CellTable cells;
+};
+
+// device-side view of an index (host helper)
+inline TreeView tree_view(const Index& idx)
 {
-  const unsigned ax = morton_cell(__fsub_rd(qx, r), T.lo[0], T.scale), bx = morton_cell(__fadd_ru(qx, r), T.lo[0], T.scale);
-  const unsigned ay = morton_cell(__fsub_rd(qy, r), T.lo[1], T.scale), by = morton_cell(__fadd_ru(qy, r), T.lo[1], T.scale);
-  const unsigned az = morton_cell(__fsub_rd(qz, r), T.lo[2], T.scale), bz = morton_cell(__fadd_ru(qz, r), T.lo[2], T.scale);
-  const unsigned diff = (ax ^ bx) | (ay ^ by) | (az ^ bz);  // bit k set: some axis' corners differ in cell bit k
-  // the corners share their top b bits on every axis  <=>  diff < 2^(21 - b)
-  const int common = diff == 0 ? 21 : __clz(diff) - 11;  // number of shared leading bits (of 21)
-#pragma unroll
-  for (int b = kTopMaxBits; b >= kTopMinBits; --b) {
-    const int* tb = T.table[b - kTopMinBits];
-    if (tb != nullptr && common >= b) {
-      const unsigned long long key = (expand21(az) << 2) | (expand21(ay) << 1) | expand21(ax);
-      return __ldg(tb + (size_t)(key >> (63 - 3 * b)));
-    }
+  TreeView t;
+  t.nodes = idx.nodes.p;
+  t.pts = idx.pts.p;
+  t.root = idx.root;
+  if (idx.cell_slots.p && idx.cells.log2_slots) {
+    t.cells.slots = idx.cell_slots.p;
+    t.cells.shift = 32u - idx.cells.log2_slots;
+    t.cells.mask = (1u << idx.cells.log2_slots) - 1u;
+    t.cells.bmax = idx.cells.bmax;
+    for (int d = 0; d < 3; ++d)
+      t.cells.lo[d] = idx.lo[d];
+    t.cells.scale = idx.morton_scale;
+    t.cells.inv_scale = 1.f / idx.morton_scale;
+    t.cells.margin = idx.cells.margin;
   }
-  return root;
+  return t;
 }
 
-// ---- start node of a SEEDED walk ---------------------------------------------------------------------------------
-// A walk that already holds a candidate at squared distance `best` (the previous iteration's match, re-measured) only
-// has to look at points inside the closed ball B(q, sqrt(best)).  The tree is a radix tree over Morton codes, so a
-// SPATIAL cell X (BvhNode::d.z) holds every indexed point whose code starts with X's prefix, i.e. every indexed point
-// of an axis-aligned region that contains box(X).  Hence, if the ball lies inside box(X), every point of the ball
-// belongs to X's subtree and the walk can start at X instead of the root: the 20-odd levels above X are never touched.
-// climb_start walks up from the seed's leaf (parent arrays of the index) until such an X is found, at most kClimbLevels
-// levels; otherwise it returns the root.  `factor` (> 1) inflates the radius: 1.00001 covers the fp32 rounding of the
-// distances that are compared later (relative error ~3e-7), larger values buy a larger exit distance for the
-// temporal-coherence bound.  *exit2 = squared distance from q to the outside of box(X) (rounded down; +inf for the
-// root): a lower bound on the squared distance to every point the restricted walk does not see.
-constexpr int kClimbLevels = 12;
-
-__device__ __forceinline__ int climb_start(const BvhNode* __restrict__ nodes, const int* __restrict__ node_parent,
-                                           const int* __restrict__ leaf_parent, int root, int seed_leaf, float qx,
-                                           float qy, float qz, float best, float factor, float* __restrict__ exit2)
+__host__ __device__ __forceinline__ unsigned cell_key(int b, unsigned cx, unsigned cy, unsigned cz)
 {
-  *exit2 = __int_as_float(0x7f800000);
-  if (node_parent == nullptr || !(best < __int_as_float(0x7f800000)))
-    return root;
-  const float r = __fmul_ru(__fsqrt_ru(best), factor);
-  int child = ~seed_leaf;
-  int cur = __ldg(leaf_parent + seed_leaf);
-#pragma unroll 1
-  for (int lvl = 0; lvl < kClimbLevels && cur >= 0; ++lvl) {
-    const float4* np = reinterpret_cast<const float4*>(nodes + cur);
-    const int4 d = __ldg(reinterpret_cast<const int4*>(np + 3));
-    const bool is_left = d.x == child;
-    if ((d.z >> (is_left ? 0 : 1)) & 1) {
-      const float4 a = ldg4(np), b = ldg4(np + 1), c = ldg4(np + 2);
-      const float lox = is_left ? a.x : b.z, loy = is_left ? a.y : b.w, loz = is_left ? a.z : c.x;
-      const float hix = is_left ? a.w : c.y, hiy = is_left ? b.x : c.z, hiz = is_left ? b.y : c.w;
-      // distance from q to the nearest face, rounded down; negative when q is outside the box
-      const float e = fminf(fminf(fminf(__fsub_rd(qx, lox), __fsub_rd(hix, qx)), fminf(__fsub_rd(qy, loy), __fsub_rd(hiy, qy))),
-                            fminf(__fsub_rd(qz, loz), __fsub_rd(hiz, qz)));
-      if (e >= r) {
-        *exit2 = __fmul_rd(e, e);
-        return child;
-      }
-    }
-    child = cur;
-    cur = __ldg(node_parent + cur);
+  return (1u << (3 * b)) | (cz << (2 * b)) | (cy << b) | cx;
+}
+
+__device__ __forceinline__ int cell_lookup(const CellTable& C, unsigned key)
+{
+  unsigned h = (key * 0x9E3779B1u) >> C.shift;
+  for (;;) {
+    const uint2 s = __ldg(C.slots + h);
+    if (s.x == key)
+      return (int)s.y;
+    if (s.x == 0u)
+      return kDone;
+    h = (h + 1u) & C.mask;
   }
-  return root;
+}
+
+// Lower bound (squared, rounded down) on the per-axis distance from coordinate q to every point whose level-(21-s) cell
+// along this axis is `other`, given that q's own cell is `home` != other.  Points of a cell `other` > home have
+// morton_cell(x) >= K = other << s, points of a cell < home have morton_cell(x) < K = home << s.  morton_cell is
+// floor(fl(fl(x - lo) * scale)) clamped, so its switch-over point differs from lo + K / scale by at most a few ulps of
+// the frame (|lo|, extent); `margin` = 2e-6 * max(|lo|, |hi|, extent) covers that with a wide berth, and the factor
+// (1 - 2e-6) covers the rounding of the subtraction and of the squared distances compared against it (~3e-7 relative).
+__device__ __forceinline__ float cell_gap2(const CellTable& C, int axis, float q, unsigned home, unsigned other, int s)
+{
+  const unsigned K = (other > home ? other : home) << s;
+  const float xk = __fadd_rn(C.lo[axis], __fmul_rn((float)K, C.inv_scale));
+  float g = other > home ? __fsub_rn(xk, q) : __fsub_rn(q, xk);
+  g = __fsub_rd(__fmul_rd(g, 0.999998f), C.margin);
+  g = fmaxf(g, 0.f);
+  return __fmul_rd(g, g);
 }
 
 // ---- 1-NN visitor: lexicographic (d2, original index) minimum --------------------------------
@@ -263,85 +313,125 @@ struct Nearest1T {
 };
 using Nearest1 = Nearest1T<false>;
 
-// ---- packet traversal: one walk of the tree per WARP, shared by its 32 Morton-adjacent queries ---------------
-// All lanes follow the same path (no divergence, every node / leaf line is one broadcast load, the stack is one
-// per-warp array in shared memory).  A subtree is entered when ANY lane still needs it (box bound <= that lane's
-// current best) — so every lane sees a superset of the leaves its own exact search would visit and its result is
-// still the exact lexicographic minimum.  The nearer child is the one with the smaller warp-minimum bound; the other
-// is pushed with that minimum and re-tested on pop against the warp-maximum best (conservative).
-// Lanes without a query pass best = -1 (never want anything).  Must be called by all 32 lanes.
-constexpr int kWarpStack = kStackSize;
 
-template <typename V>
-__device__ __forceinline__ bool traverse_packet(const BvhNode* __restrict__ nodes, const float4* __restrict__ pts,
-                                                int root, float qx, float qy, float qz, V& v,
-                                                int* __restrict__ wnode, float* __restrict__ wdist)
+// ---- exact 1-NN with cell-table starts ----------------------------------------------------------------------------
+//   1. seed: the previous iteration's match (its leaf is scanned first), if any;
+//   2. home seed: when there is no candidate yet, or the candidate ball is much wider than the finest cells (the query
+//      moved far since the seed was found), the leaf reached by a greedy descent from the finest occupied cell that
+//      contains q is scanned as well — a candidate at about the local point spacing, whatever the motion was;
+//   3. the <= 8 cells the candidate ball reaches are looked up and walked (see CellTable).  Without a table, or when the
+//      ball is wider than half the frame, the walk starts at the root.
+// INFLATE > 1 widens the ball (TRACK visitors: every point outside the visited cells is farther than the inflated
+// radius, which is what bounds Nearest1T::lower_bound2 from above).
+template <bool TRACK>
+__device__ __forceinline__ bool nearest1(const TreeView& T, float qx, float qy, float qz, Nearest1T<TRACK>& v,
+                                         int seed_pos, float inflate, WalkStats& ws)
 {
-  const unsigned full = 0xffffffffu;
-  const unsigned INF_BITS = 0x7f800000u;
+  int stack_node[kStackSize];
+  float stack_dist[kStackSize];
   int sp = 0;
-  int node = root;
-  bool ok = true;
-  while (node != kDone) {
-    while (node >= 0 && node != kDone) {
-      const float4* np = reinterpret_cast<const float4*>(nodes + node);
-      const float4 a = ldg4(np), b = ldg4(np + 1), c = ldg4(np + 2);
-      const int4 d = __ldg(reinterpret_cast<const int4*>(np + 3));
-      const float dl = box_dist2_rn(qx, qy, qz, a.x, a.y, a.z, a.w, b.x, b.y);
-      const float dr = box_dist2_rn(qx, qy, qz, b.z, b.w, c.x, c.y, c.z, c.w);
-      const float bnd = v.best;
-      const unsigned ml = __reduce_min_sync(full, dl <= bnd ? __float_as_uint(dl) : INF_BITS);
-      const unsigned mr = __reduce_min_sync(full, dr <= bnd ? __float_as_uint(dr) : INF_BITS);
-      // Lower-bound bookkeeping (TRACK visitors): a lane that does not need a child notes ITS OWN bound to that
-      // box, whether or not the warp enters the subtree for other lanes.  (The warp-minimum stored with a pushed
-      // entry is a minimum over the lanes that WANTED it, so it bounds only those lanes when the entry is later
-      // discarded; the others are covered here.)
-      if (!(dl <= bnd))
-        v.prune(dl);
-      if (!(dr <= bnd))
-        v.prune(dr);
-      if (ml == INF_BITS && mr == INF_BITS) {
-        node = kDone;
-        const unsigned wmax = __reduce_max_sync(full, __float_as_uint(fmaxf(bnd, 0.f)));
-        while (sp > 0) {
-          --sp;
-          if (__float_as_uint(wdist[sp]) <= wmax) {
-            node = wnode[sp];
-            break;
-          }
-          v.prune(wdist[sp]);  // warp-minimum bound of a discarded entry: valid (weaker) bound for every lane
-        }
-      }
-      else if (ml != INF_BITS && mr != INF_BITS) {
-        const bool left_first = ml <= mr;
-        if (sp < kWarpStack) {
-          wnode[sp] = left_first ? d.y : d.x;
-          wdist[sp] = __uint_as_float(left_first ? mr : ml);
-          ++sp;
+  int skip_a = kDone, skip_b = kDone;
+  const CellTable& C = T.cells;
+  if (seed_pos >= 0) {
+    const int leaf = seed_pos / kLeafSize;
+    v.template scan<true>(T.pts + (size_t)leaf * kLeafSize, leaf * kLeafSize);
+    PCLB_STAT(ws, 2);
+    skip_a = ~leaf;
+  }
+  bool rooted = true;
+  if (C.slots != nullptr) {
+    const unsigned cqx = morton_cell(qx, C.lo[0], C.scale), cqy = morton_cell(qy, C.lo[1], C.scale),
+                   cqz = morton_cell(qz, C.lo[2], C.scale);
+    const int smin = 21 - C.bmax;
+    unsigned ax, ay, az, bx, by, bz;
+    float r;
+    int s;
+    // level at which the candidate ball's box is at most one cell wide on every axis: d <= 2^s
+    auto ball_level = [&]() {
+      r = __fmul_ru(__fsqrt_ru(v.best), inflate);
+      ax = morton_cell(__fsub_rd(qx, r), C.lo[0], C.scale); bx = morton_cell(__fadd_ru(qx, r), C.lo[0], C.scale);
+      ay = morton_cell(__fsub_rd(qy, r), C.lo[1], C.scale); by = morton_cell(__fadd_ru(qy, r), C.lo[1], C.scale);
+      az = morton_cell(__fsub_rd(qz, r), C.lo[2], C.scale); bz = morton_cell(__fadd_ru(qz, r), C.lo[2], C.scale);
+      const unsigned d = max(max(bx - ax, by - ay), bz - az);
+      s = (d <= 1u ? 0 : 32 - __clz((int)(d - 1u))) + kCellLevelBias;
+    };
+    ball_level();
+    if (v.best_pos < 0 || s > smin + 2) {
+      // finest occupied cell that contains q: occupancy is monotone in the level (a coarser cell contains the finer
+      // one), so a binary search over the levels needs ~log2(bmax) lookups
+      int ref = kDone;
+      int lo_b = 0, hi_b = C.bmax;  // invariant: level lo_b is occupied (level 0 = the root), levels > hi_b are not
+      while (lo_b < hi_b) {
+        const int b = (lo_b + hi_b + 1) >> 1;
+        const int sh = 21 - b;
+        const int rr = cell_lookup(C, cell_key(b, cqx >> sh, cqy >> sh, cqz >> sh));
+        PCLB_STAT(ws, 0);
+        if (rr != kDone) {
+          lo_b = b;
+          ref = rr;
         }
         else
-          ok = false;
-        node = left_first ? d.x : d.y;
+          hi_b = b - 1;
       }
-      else
-        node = ml != INF_BITS ? d.x : d.y;
+      if (ref != kDone) {
+        while (ref >= 0) {  // greedy descent: nearer child, no stack
+          const float4* np = reinterpret_cast<const float4*>(T.nodes + ref);
+          const float4 a = ldg4(np), b = ldg4(np + 1), c = ldg4(np + 2);
+          const int4 d = __ldg(reinterpret_cast<const int4*>(np + 3));
+          const float dl = box_dist2_rn(qx, qy, qz, a.x, a.y, a.z, a.w, b.x, b.y);
+          const float dr = box_dist2_rn(qx, qy, qz, b.z, b.w, c.x, c.y, c.z, c.w);
+          ref = dr < dl ? d.y : d.x;
+          PCLB_STAT(ws, 1);
+        }
+        if (ref != skip_a) {
+          const int leaf = ~ref;
+          v.template scan<true>(T.pts + (size_t)leaf * kLeafSize, leaf * kLeafSize);
+          PCLB_STAT(ws, 2);
+          PCLB_STAT(ws, 4);
+          skip_b = ref;
+          ball_level();
+        }
+      }
     }
-    if (node == kDone)
-      break;
-    const int leaf = ~node;
-    v.leaf(pts + (size_t)leaf * kLeafSize, leaf * kLeafSize);
-    node = kDone;
-    const unsigned wmax = __reduce_max_sync(full, __float_as_uint(fmaxf(v.best, 0.f)));
-    while (sp > 0) {
-      --sp;
-      if (__float_as_uint(wdist[sp]) <= wmax) {
-        node = wnode[sp];
-        break;
+    if (s < smin)
+      s = smin;
+    if (s <= 20) {
+      rooted = false;
+      const int b = 21 - s;
+      const unsigned hx = cqx >> s, hy = cqy >> s, hz = cqz >> s;
+      const unsigned ox = (ax >> s) + (bx >> s) - hx, oy = (ay >> s) + (by >> s) - hy, oz = (az >> s) + (bz >> s) - hz;
+      const unsigned E = (ox != hx ? 1u : 0u) | (oy != hy ? 2u : 0u) | (oz != hz ? 4u : 0u);
+      const float gx2 = (E & 1u) ? cell_gap2(C, 0, qx, hx, ox, s) : 0.f;
+      const float gy2 = (E & 2u) ? cell_gap2(C, 1, qy, hy, oy, s) : 0.f;
+      const float gz2 = (E & 4u) ? cell_gap2(C, 2, qz, hz, oz, s) : 0.f;
+      for (unsigned m = E;; m = (m - 1u) & E) {  // submasks of E, the home cell (m = 0) last = popped first
+        const float bound = __fadd_rd(__fadd_rd((m & 1u) ? gx2 : 0.f, (m & 2u) ? gy2 : 0.f), (m & 4u) ? gz2 : 0.f);
+        if (bound <= v.bound()) {
+          const int ref = cell_lookup(C, cell_key(b, (m & 1u) ? ox : hx, (m & 2u) ? oy : hy, (m & 4u) ? oz : hz));
+          PCLB_STAT(ws, 0);
+          if (ref != kDone && ref != skip_a && ref != skip_b) {
+            stack_node[sp] = ref;
+            stack_dist[sp] = bound;
+            ++sp;
+            PCLB_STAT(ws, 6);
+          }
+        }
+        else
+          v.prune(bound);
+        if (m == 0u)
+          break;
       }
-      v.prune(wdist[sp]);
+      v.prune(__fmul_rd(r, r));  // every indexed point outside the cells lies outside [q - r, q + r]^3
     }
   }
-  return ok;
+  if (rooted) {
+    PCLB_STAT(ws, 5);
+    stack_node[0] = T.root;
+    stack_dist[0] = 0.f;
+    sp = 1;
+  }
+  PCLB_STAT(ws, 7);
+  return walk(T.nodes, T.pts, stack_node, stack_dist, sp, kDone, qx, qy, qz, v, skip_a, skip_b, ws);
 }
 
 }  // namespace pclb200

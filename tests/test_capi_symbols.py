@@ -71,4 +71,4 @@ def test_default_params_layout(built):
     assert p.max_correspondence_distance == np.sqrt(np.finfo(np.float64).max)
     assert p.euclidean_fitness_epsilon == -np.finfo(np.float64).max
     assert p.mse_threshold_absolute == 1e-12
-    assert p.correspondence_k == 10 and p.reserved1 == 0
+    assert p.correspondence_k == 10 and p.track_mode == 0

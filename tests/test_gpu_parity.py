@@ -59,11 +59,10 @@ def test_knn_golden_10_points(gpu, golden):
     assert keff == 10 and np.all(idx[0, 10:] == -1) and np.all(np.isinf(d2[0, 10:]))
 
 
-@pytest.mark.parametrize("walk", ["single", "packet"])
-def test_knn_and_normals_both_walks(gpu, orc, walk, monkeypatch):
-    """The per-query and the per-warp (packet) k-NN walks return the same exact lists; normals built on them agree."""
+def test_knn_and_normals_many_k(gpu, orc):
+    """Exact k-NN lists for every compiled list size (and NaN queries); normals built on them agree with the oracle."""
     P, ctx = gpu
-    monkeypatch.setenv("PCLB200_KNN", walk)  # read by the library at every call
+    walk = "default"
     rng = np.random.default_rng(12)
     for name, pts in _clouds(rng):
         cloud = orc.to_xyz1(pts)
@@ -470,47 +469,36 @@ def _coherence_scenes():
 
 
 def test_icp_per_iteration_correspondences_exact(gpu, orc):
-    """The search kernels skip the tree walk for queries whose previous match is provably still nearest (temporal
-    coherence).  That must never change a result: every iteration's correspondence list is compared, bit for bit,
-    with a fresh exact search of the oracle on the same (re-transformed) cloud — for both search kernels, with the
-    lower-bound tracking forced on from the first iteration, on scenes with duplicates, exact ties, a gate and NaNs."""
-    import os
+    """The search kernel starts every walk at the candidate ball (cell table) and skips the walk altogether for queries
+    whose previous match is provably still nearest (temporal coherence).  Neither may ever change a result: every
+    iteration's correspondence list is compared, bit for bit, with a fresh exact search of the oracle on the same
+    (re-transformed) cloud — with the lower-bound tracking forced on from the first iteration, forced off, and in the
+    default automatic mode, on scenes with duplicates, exact ties, a gate and NaNs."""
     P, ctx = gpu
     total_skipped = 0
-    try:
-        for name, tgt, src, gate in _coherence_scenes():
-            T, S = P.xyz1(tgt), P.xyz1(src)
-            oidx = orc.Index(T)
-            # (search kernel [dynamic = persistent warps with dynamic fetch], lower-bound tracking, seeded walks start at
-            # the smallest cell holding their candidate ball)
-            for search, track, climb, top in (("packet", "1", "0", "0"), ("single", "1", "0", "0"), ("single", "1", "1", "0"),
-                                              ("single", "0", "1", "0"), ("single", "0", "0", "0"), ("dynamic", "1", "0", "0"),
-                                              ("dynamic", "0", "0", "0"), ("single", "1", "0", "1"), ("single", "0", "0", "1")):
-                os.environ["PCLB200_SEARCH"] = search
-                os.environ["PCLB200_TRACK"] = track
-                os.environ["PCLB200_CLIMB"] = climb
-                os.environ["PCLB200_TOP"] = top  # read when the index is built: prefix tables for walks below the root
-                s = P.Icp(ctx, max_iterations=30, max_correspondence_distance=gate, is_dense=0, mse_threshold_absolute=0.0)
-                s.set_target(P.Index(ctx, T))
-                s.set_source(S)
-                cloud = S.copy()
-                st = None
-                for it in range(30):
-                    st = s.iterate(1)
-                    g = s.get_correspondences()
-                    o = oidx.correspondences(cloud, max_distance=gate, is_dense=False, nthreads=4)
-                    assert np.array_equal(g, o), (name, search, track, climb, top, it, g.size, o.size)
-                    assert st["n_correspondences"] == o.size
-                    cloud = orc.transform(cloud, st["last"], mode=0)   # IterativeClosestPoint::transformCloud, fp32
-                    if st["state"] != 0:
-                        break
+    for name, tgt, src, gate in _coherence_scenes():
+        T, S = P.xyz1(tgt), P.xyz1(src)
+        oidx = orc.Index(T)
+        tidx = P.Index(ctx, T)
+        for track in (P.TRACK_ON, P.TRACK_OFF, P.TRACK_AUTO):
+            s = P.Icp(ctx, max_iterations=30, max_correspondence_distance=gate, is_dense=0, mse_threshold_absolute=0.0,
+                      track_mode=track)
+            s.set_target(tidx)
+            s.set_source(S)
+            cloud = S.copy()
+            st = None
+            for it in range(30):
+                st = s.iterate(1)
+                g = s.get_correspondences()
+                o = oidx.correspondences(cloud, max_distance=gate, is_dense=False, nthreads=4)
+                assert np.array_equal(g, o), (name, track, it, g.size, o.size)
+                assert st["n_correspondences"] == o.size
+                cloud = orc.transform(cloud, st["last"], mode=0)   # IterativeClosestPoint::transformCloud, fp32
+                if st["state"] != 0:
+                    break
+            if track == P.TRACK_ON:
                 total_skipped += st["total_skipped_walks"]
-        assert total_skipped > 0, "the temporal-coherence path was never exercised"
-    finally:
-        os.environ.pop("PCLB200_SEARCH", None)
-        os.environ.pop("PCLB200_TRACK", None)
-        os.environ.pop("PCLB200_CLIMB", None)
-        os.environ.pop("PCLB200_TOP", None)
+    assert total_skipped > 0, "the temporal-coherence path was never exercised"
 
 
 def test_rejectors_golden_and_oracle(gpu, golden, orc):

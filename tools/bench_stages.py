@@ -58,8 +58,7 @@ def main():
     si, vi = holder["s"], holder["v"]
     q = surf[torch.randperm(n, generator=g, device="cuda")].contiguous()
     nrm = torch.empty((n, 4), device="cuda")
-    for walk in ("single", "packet"):  # per-query walk vs one walk per warp (search.cu: use_packet_knn)
-        os.environ["PCLB200_KNN"] = walk
+    for walk in ("default",):
         for k in (1, 10, 16, 32):
             oi = torch.empty((n, k), dtype=torch.int32, device="cuda")
             od = torch.empty((n, k), dtype=torch.float32, device="cuda")
@@ -68,7 +67,6 @@ def main():
         emit(f"normals_knn16_surface_{walk}", timed(ctx, lambda: si.normals_knn(surf, 16, (5, 5, 10), out=nrm)), n, "points", walk=walk)
         emit(f"knn_k10_volume_{walk}", timed(ctx, lambda: vi.knn(vol[:2_000_000], 10), reps=2), 2_000_000, "queries", k=10, walk=walk,
              includes="D2H of the rows")
-    del os.environ["PCLB200_KNN"]
     # radius search: density n/8000 per unit volume; r so that a ball holds ~30 points
     r = float((30.0 / (n / 8000.0) * 3 / (4 * np.pi)) ** (1 / 3))
     nq = min(n, 2_000_000)
