@@ -1,30 +1,39 @@
 #!/usr/bin/env python3
-"""bench.py — BASELINE.json's metric on BASELINE.json's 10 M-point configuration.
+"""bench.py — BASELINE.json's metric (ICP correspondences/s, ms/iteration, HBM GB/s of the search against the roofline).
 
-Workload (config.workload = "cfg3_10M_point_to_plane", BASELINE.json configs[2]):
+Default workload (config.workload = "cfg3_10M_point_to_plane", BASELINE.json configs[2], SURVEY.md §8d — the 10 M-point
+configuration the metric is quoted on):
   target : 10 000 000 points, (x,y) ~ U[0,10)^2, z = 0.5 sin(x) cos(0.7 y) + N(0, 0.002^2), seed 7
   source : the same surface re-sampled (seed 8 + rank), rotated 2 deg about z, t = (0.02, 0.01, -0.01)
   target normals: NormalEstimation k = 16, viewpoint (5,5,10)  (set-up, timed separately, not part of a step)
   ICP    : IterativeClosestPointWithNormals (non-symmetric => TransformationEstimationPointToPlaneLLS),
            max correspondence distance 0.05, k = 1
-A STEP is one Registration::align() of ICP_ITERS = 10 iterations (PCL's default max_iterations_,
-registration.h:566) over the whole source cloud: source upload -> Morton ordering of the queries -> 10 x
-(1-NN search + gate + 6x6 accumulation + solve + transform) -> output cloud.  The target index is built once
-before the timed region, exactly as pcl::Registration keeps its tree across align() calls
-(registration.hpp:84-87).
-  value : correspondences/s with source, target index and output resident in HBM (device pointers through
-          the same C-ABI calls pclb200_icp_set_source / _iterate / _get_cloud the C++ facade's align() makes)
-  e2e   : the same call with HOST buffers (pinned pcl::PointNormal records, 48 B/pt): H2D of the source and
-          D2H of the aligned cloud inside the timed region
-  N > 1 : weak scaling — every rank holds a replica of the target index and its own 10 M-point source shard;
-          the 40 fp64 accumulators are all-reduced (NCCL) once per iteration.
---impl reference times the CPU restatement of PCL's own path (oracle/, the reference cannot be compiled in this
+A STEP is one Registration::align() of ICP_ITERS iterations (10 = PCL's default max_iterations_, registration.h:566)
+over the whole source cloud: source upload -> Hilbert ordering of the queries -> ICP_ITERS x (transform + exact 1-NN +
+gate + normal-equation accumulation + solve) -> output cloud.  The target index is built once before the timed region,
+exactly as pcl::Registration keeps its tree across align() calls (registration.hpp:84-87).
+  value : correspondences/s with source, target index and output resident in HBM (device pointers through the same
+          C-ABI calls pclb200_icp_set_source / _iterate / _get_cloud the C++ facade's align() makes)
+  e2e   : the same calls with HOST buffers (pinned records): H2D of the source and D2H of the aligned cloud inside the
+          timed region
+Other workloads (--workload; the driver's default run is cfg3):
+  cfg4 : 50 M-point scene of 40 planar patches in [0,20)^3 + N(0,0.005^2); source re-sampled, rotated 1 deg about a
+         random axis, |t| = 0.02; point-to-point (TransformationEstimationSVD), gate 0.05; intended for 4 GPUs
+  cfg5 : 200 M-ray spinning-LiDAR sweep (64 beams) of a 200 m x 30 m street canyon (ground, two facades, end walls),
+         range noise N(0,0.02^2); second sweep after ego-motion (yaw 1.5 deg, t = (0.5,0.1,0)); both clouds through
+         VoxelGrid leaf 0.1 (the finest leaf below the INT32 guard, voxel_grid.hpp:620-629), then ICP SVD with exactly 30
+         iterations (all epsilons 0); intended for 8 GPUs
+Scaling (--scaling):
+  weak   : every rank holds a replica of the target index and its OWN source cloud of the full size (default)
+  strong : ONE source; rank r gets the r-th contiguous range of its Morton order (a spatial tile), so per-GPU work
+           shrinks with N.  The 40 fp64 accumulators are exchanged once per iteration over NVLink (fused into the
+           search kernel's last block; NCCL bootstraps the peer mappings).
+--impl reference times the CPU restatement of PCL's own path (oracle/; the reference itself cannot be compiled in this
 image: no Eigen/Boost/FLANN) on the box's host cores, on a bounded sample of the same workload.
 """
 import argparse
 import json
 import os
-import subprocess
 import sys
 import threading
 import time
@@ -42,6 +51,9 @@ METRIC = "icp_correspondences_per_sec"
 UNIT = "correspondences/s"
 
 
+# -----------------------------------------------------------------------------------------------------------------
+# cfg3: Gaussian surface (records = pcl::PointNormal, 12 floats)
+# -----------------------------------------------------------------------------------------------------------------
 def surface(n, seed):
     r = np.random.default_rng(seed)
     xy = r.random((n, 2)) * 10.0
@@ -76,6 +88,148 @@ def analytic_normals(t, vp=(5.0, 5.0, 10.0)):
     flip = ((np.asarray(vp) - t[:, :3]) * n).sum(1) < 0
     n[flip] *= -1
     return n.astype(np.float32)
+
+
+# -----------------------------------------------------------------------------------------------------------------
+# cfg4: scene of planar patches (records = pcl::PointXYZ, 4 floats)
+# -----------------------------------------------------------------------------------------------------------------
+def _scene_patches():
+    r = np.random.default_rng(11)
+    patches = []
+    for _ in range(40):
+        c = r.uniform(3.0, 17.0, 3)
+        u = r.normal(size=3)
+        u /= np.linalg.norm(u)
+        w = r.normal(size=3)
+        v = np.cross(u, w)
+        v /= np.linalg.norm(v)
+        patches.append((c, u * r.uniform(2.0, 6.0), v * r.uniform(2.0, 6.0)))
+    return patches
+
+
+def scene_points(n, seed):
+    patches = _scene_patches()
+    r = np.random.default_rng(seed)
+    area = np.array([np.linalg.norm(np.cross(u, v)) for (_, u, v) in patches])
+    counts = np.floor(n * area / area.sum()).astype(np.int64)
+    counts[0] += n - counts.sum()
+    out = np.empty((n, 4), dtype=np.float32)
+    k = 0
+    for (c, u, v), m in zip(patches, counts):
+        ab = r.uniform(-0.5, 0.5, (m, 2)).astype(np.float32)
+        p = c.astype(np.float32) + ab[:, :1] * u.astype(np.float32) + ab[:, 1:] * v.astype(np.float32)
+        p += r.normal(0.0, 0.005, (m, 3)).astype(np.float32)
+        out[k:k + m, :3] = np.clip(p, 0.0, np.float32(19.999))
+        k += m
+    out[:, 3] = 1.0
+    return out
+
+
+def scene_source(n, seed):
+    p = scene_points(n, seed)
+    r = np.random.default_rng(12)
+    ax = r.normal(size=3)
+    ax /= np.linalg.norm(ax)
+    a = np.deg2rad(1.0)
+    K = np.array([[0, -ax[2], ax[1]], [ax[2], 0, -ax[0]], [-ax[1], ax[0], 0]])
+    R = np.eye(3) + np.sin(a) * K + (1 - np.cos(a)) * (K @ K)
+    t = r.normal(size=3)
+    t *= 0.02 / np.linalg.norm(t)
+    c = np.array([10.0, 10.0, 10.0])
+    q = (p[:, :3].astype(np.float64) - c) @ R.T + c + t
+    p[:, :3] = q.astype(np.float32)
+    return p
+
+
+# -----------------------------------------------------------------------------------------------------------------
+# cfg5: spinning-LiDAR sweep of a street canyon (records = pcl::PointXYZ)
+# -----------------------------------------------------------------------------------------------------------------
+def lidar_sweep(n_rays, seed, yaw_deg=0.0, tx=0.0, ty=0.0, chunk=25_000_000, device=None):
+    """n_rays rays of a 64-beam spinning sensor at world (tx, ty, 2) with heading yaw; returns the hits in the SENSOR
+    frame (x forward) as an (m, 4) float32 numpy array.  Scene: ground z = 0, facades y = +-15 (20 m high), end walls
+    x = +-100; max range 120 m.  Generated with torch (on `device` when given: 200 M rays take seconds on the GPU and
+    minutes in numpy); the stream depends on the device type, the distribution does not."""
+    import torch
+    dev = torch.device(device if device is not None else "cpu")
+    g = torch.Generator(device=dev)
+    g.manual_seed(int(seed))
+    elev = torch.deg2rad(torch.linspace(-25.0, 15.0, 64, device=dev))
+    yaw = float(np.deg2rad(yaw_deg))
+    c, sn = float(np.cos(yaw)), float(np.sin(yaw))
+    inf = float("inf")
+    out = []
+    for s in range(0, n_rays, chunk):
+        m = min(chunk, n_rays - s)
+        az = torch.rand(m, generator=g, device=dev) * (2 * np.pi) + yaw
+        el = elev[torch.randint(0, 64, (m,), generator=g, device=dev)]
+        ce = torch.cos(el)
+        dx, dy, dz = ce * torch.cos(az), ce * torch.sin(az), torch.sin(el)  # world direction
+        del az, el, ce
+        t = torch.where(dz < 0, -2.0 / dz, torch.full_like(dz, inf))
+        for d_ax, o_ax, planes in ((dy, ty, (-15.0, 15.0)), (dx, tx, (-100.0, 100.0))):
+            for pl in planes:
+                tt = (pl - o_ax) / d_ax
+                z = 2.0 + tt * dz
+                ok = (tt > 0) & (z >= 0) & (z <= 20.0)
+                t = torch.minimum(t, torch.where(ok, tt, torch.full_like(tt, inf)))
+        ok = torch.isfinite(t) & (t < 120.0)
+        t = t[ok]
+        t = t + torch.randn(t.shape[0], generator=g, device=dev) * 0.02
+        hx, hy, hz = t * dx[ok], t * dy[ok], 2.0 + t * dz[ok]   # hit relative to the sensor's ground position
+        p = torch.ones((t.shape[0], 4), dtype=torch.float32, device=dev)
+        p[:, 0] = c * hx + sn * hy   # world -> sensor frame
+        p[:, 1] = -sn * hx + c * hy
+        p[:, 2] = hz
+        out.append(p.cpu())
+        del dx, dy, dz, t, ok, hx, hy, hz, p
+    return torch.cat(out, 0).numpy()
+
+
+WORKLOADS = {
+    "cfg3": dict(name="cfg3_10M_point_to_plane", n=N_DEFAULT, iters=ICP_ITERS, gate=MAX_CORR_DIST, width=12,
+                 estimator="point_to_plane_lls", normals_k=16, voxel_leaf=None),
+    "cfg4": dict(name="cfg4_50M_scene_gate_0.05", n=50_000_000, iters=ICP_ITERS, gate=0.05, width=4,
+                 estimator="svd", normals_k=0, voxel_leaf=None),
+    "cfg5": dict(name="cfg5_200M_lidar_voxelgrid_30iters", n=200_000_000, iters=30, gate=1.0, width=4,
+                 estimator="svd", normals_k=0, voxel_leaf=0.1),
+}
+
+
+def gen_clouds(wl, n, rank, strong, device=None):
+    """(target records, full source records) as numpy arrays; under strong scaling every rank generates the same source."""
+    src_rank = 0 if strong else rank
+    if wl == "cfg3":
+        return make_target(n), make_source(n, src_rank)
+    if wl == "cfg4":
+        return scene_points(n, 11), scene_source(n, 13 + src_rank)
+    return lidar_sweep(n, 21, device=device), lidar_sweep(n, 22 + src_rank, yaw_deg=1.5, tx=0.5, ty=0.1, device=device)
+
+
+def morton_order(xyz):
+    """argsort by a 30-bit Morton code of the cloud's own bounding box (host side, set-up only)."""
+    lo = xyz.min(0)
+    ext = float((xyz.max(0) - lo).max()) or 1.0
+    q = np.minimum(((xyz - lo) * (1023.999 / ext)).astype(np.uint32), 1023)
+
+    def spread(v):
+        v = v.astype(np.uint64)
+        v = (v | (v << 16)) & np.uint64(0x030000FF)
+        v = (v | (v << 8)) & np.uint64(0x0300F00F)
+        v = (v | (v << 4)) & np.uint64(0x030C30C3)
+        v = (v | (v << 2)) & np.uint64(0x09249249)
+        return v
+    key = spread(q[:, 0]) | (spread(q[:, 1]) << np.uint64(1)) | (spread(q[:, 2]) << np.uint64(2))
+    return np.argsort(key, kind="stable")
+
+
+def shard_strong(src, rank, world):
+    """rank r's spatial tile: the r-th contiguous range of the Morton order of the ONE source cloud."""
+    if world == 1:
+        return src
+    order = morton_order(src[:, :3])
+    n = src.shape[0]
+    lo, hi = (n * rank) // world, (n * (rank + 1)) // world
+    return np.ascontiguousarray(src[np.sort(order[lo:hi])])
 
 
 class ClockSampler:
@@ -137,6 +291,19 @@ def measured_peak_gbs():
         return 6650.0, "fallback"
 
 
+def ncu_traffic(kernel_key, n):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel, from the committed ncu capture
+    (profiles/ncu_traffic.json, written from a `ncu --set full` run of this workload); None when no capture matches."""
+    try:
+        t = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json")))
+        e = t.get(kernel_key)
+        if e and int(e.get("points", -1)) == int(n):
+            return float(e["dram_bytes_per_launch"])
+    except Exception:
+        pass
+    return None
+
+
 def dist_env():
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -144,31 +311,46 @@ def dist_env():
     return rank, world, local
 
 
+def host_cores():
+    return int(os.cpu_count() or 1)
+
+
 # -----------------------------------------------------------------------------------------------------------------
 # reference arm: the CPU restatement of PCL's path (oracle/), all host threads, bounded sample
 # -----------------------------------------------------------------------------------------------------------------
+def oracle_kw(W, cores, tree):
+    return dict(max_iterations=W["iters"], max_correspondence_distance=W["gate"],
+                estimator=1 if W["estimator"] == "point_to_plane_lls" else 0,
+                with_normals_transform=W["estimator"] == "point_to_plane_lls",
+                source_has_normals=W["estimator"] == "point_to_plane_lls", nthreads=cores, index=tree)
+
+
 def run_reference(args):
     rank, world, _ = dist_env()
     if rank != 0:
         return
     import oracle
-    n = args.points
-    cores = oracle.max_threads()
-    tgt = make_target(n)
-    tgt[:, 4:7] = analytic_normals(tgt)
-    src_full = make_source(n, 0)
+    W = WORKLOADS[args.workload]
+    n = args.points or W["n"]
+    cores = host_cores()
+    tgt, src_full = gen_clouds(args.workload, n, 0, False)
+    if args.workload == "cfg3":
+        tgt[:, 4:7] = analytic_normals(tgt)
+    if W["voxel_leaf"]:
+        # the reference pipeline's front-end (VoxelGrid on both clouds), untimed here like the kd-tree build
+        tgt = oracle.voxelgrid(tgt, [W["voxel_leaf"]] * 3)
+        src_full = oracle.voxelgrid(src_full, [W["voxel_leaf"]] * 3)
     t0 = time.time()
     tree = oracle.Index(tgt)  # pcl::KdTreeFLANN::setInputCloud, kept across align() calls
     build_s = time.time() - t0
-    kw = dict(max_iterations=ICP_ITERS, max_correspondence_distance=MAX_CORR_DIST, estimator=1,
-              with_normals_transform=True, source_has_normals=True, nthreads=cores, index=tree)
+    kw = oracle_kw(W, cores, tree)
     # calibrate the sample so that (steps + warmup) aligns end within ~150 s
-    probe = min(n, 100_000)
+    probe = min(src_full.shape[0], 100_000)
     t0 = time.time()
     r = oracle.icp_align(src_full[:probe], tgt, want_cloud=True, **kw)
     rate = max(r["total_correspondences"], 1) / max(time.time() - t0, 1e-6)
     budget_s = 150.0 / max(args.steps + args.warmup, 1)
-    sample = int(min(n, max(probe, rate * budget_s / ICP_ITERS)))
+    sample = int(min(src_full.shape[0], max(probe, rate * budget_s / W["iters"])))
     src = np.ascontiguousarray(src_full[:sample])
     out = np.empty_like(src)
     for _ in range(args.warmup):
@@ -179,15 +361,15 @@ def run_reference(args):
         total += r["total_correspondences"]
     dt = time.time() - t0
     val = total / dt
-    sample_desc = (f"{sample} of {n} source points (first rows) x {ICP_ITERS} iterations per step against the full "
-                   f"{n}-point target; kd-tree build ({build_s:.1f} s, 1 thread) outside the timed region; "
-                   "analytic target normals")
+    sample_desc = (f"{sample} of {src_full.shape[0]} source points (first rows) x {W['iters']} iterations per step against "
+                   f"the full {tgt.shape[0]}-point target; kd-tree build ({build_s:.1f} s, 1 thread) outside the timed "
+                   "region" + ("; analytic target normals" if args.workload == "cfg3" else ""))
     line = {"impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / max(args.steps, 1),
-            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": "cfg3_10M_point_to_plane", "points_target": n, "points_source_per_step": sample,
-                       "icp_iterations_per_step": ICP_ITERS, "max_correspondence_distance": MAX_CORR_DIST,
-                       "estimator": "point_to_plane_lls", "k": 1},
+            "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": W["name"], "points_target": int(tgt.shape[0]), "points_source_per_step": sample,
+                       "icp_iterations_per_step": W["iters"], "max_correspondence_distance": W["gate"],
+                       "estimator": W["estimator"], "k": 1},
             "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample_desc},
             "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
@@ -202,7 +384,10 @@ def run_ours(args):
     import torch
     import pcl_b200 as P
     rank, world, local = dist_env()
-    n = args.points
+    W = WORKLOADS[args.workload]
+    n = args.points or W["n"]
+    strong = args.scaling == "strong"
+    p2plane = W["estimator"] == "point_to_plane_lls"
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
@@ -216,33 +401,66 @@ def run_ours(args):
         ctx.comm_init(rank, world, uid[0])
     stream = torch.cuda.ExternalStream(ctx.stream, device=dev)
 
-    # ---- set-up (outside the timed region): target index + k=16 normals, both on the GPU ----------------------
-    tgt = make_target(n)
-    src_host = torch.from_numpy(make_source(n, rank)).pin_memory()           # pcl::PointNormal records, pinned
-    out_host = torch.empty_like(src_host).pin_memory()
+    # ---- set-up (outside the timed region): clouds, VoxelGrid front-end, target index, normals ------------------------
+    tgt, src_full = gen_clouds(args.workload, n, rank, strong, device=dev)
+    setup_ms = {}
     ctx.profile(True)
+    if W["voxel_leaf"]:
+        # cfg5: both clouds through VoxelGrid on the GPU (the reference's downsample front-end); the filtered source
+        # is what gets sharded, so every N aligns exactly the same clouds
+        for nm in ("target", "source"):
+            a = torch.from_numpy(tgt if nm == "target" else src_full).to(dev)
+            o = torch.empty_like(a)
+            ctx.profile_reset()
+            f = ctx.voxelgrid(a, [W["voxel_leaf"]] * 3, out=o)
+            setup_ms[f"voxelgrid_{nm}"] = ctx.profile_get("voxelgrid")[0]
+            setup_ms[f"voxelgrid_{nm}_points_in"] = int(a.shape[0])
+            res = f.cpu().numpy().copy()
+            if nm == "target":
+                tgt = res
+            else:
+                src_full = res
+            del a, o, f
+        torch.cuda.empty_cache()
+    n_tgt = int(tgt.shape[0])
+    src_np = shard_strong(src_full, rank, world) if strong else src_full
+    n_src_total = int(src_full.shape[0]) * (1 if strong else world)
+    del src_full
+    src_host = torch.from_numpy(src_np).pin_memory()
+    out_host = torch.empty_like(src_host).pin_memory()
+    ctx.profile_reset()
     tidx = P.Index(ctx, tgt)
-    tgt_dev = torch.from_numpy(tgt).to(dev)
-    nrm_dev = torch.empty((n, 4), dtype=torch.float32, device=dev)
-    tidx.normals_knn(tgt_dev, 16, viewpoint=(5.0, 5.0, 10.0), out=nrm_dev)
-    build_ms, _ = ctx.profile_get("index_build")
-    normals_ms, _ = ctx.profile_get("normals")
-    del tgt_dev
-    src_dev = src_host.to(dev)                    # value leg: 48-byte records already resident in HBM
+    setup_ms["index_build"] = ctx.profile_get("index_build")[0]
+    nrm_dev = None
+    if p2plane:
+        tgt_dev = torch.from_numpy(tgt).to(dev)
+        nrm_dev = torch.empty((n_tgt, 4), dtype=torch.float32, device=dev)
+        tidx.normals_knn(tgt_dev, W["normals_k"], viewpoint=(5.0, 5.0, 10.0), out=nrm_dev)
+        setup_ms[f"normals_k{W['normals_k']}"] = ctx.profile_get("normals")[0]
+        del tgt_dev
+    src_dev = src_host.to(dev)                    # value leg: records already resident in HBM
     out_dev = torch.empty_like(src_dev)
-    params = P.default_params(max_iterations=ICP_ITERS, max_correspondence_distance=MAX_CORR_DIST,
-                              estimator=P.EST_POINT_TO_PLANE_LLS, with_normals_transform=1, mse_threshold_absolute=0.0)
+    params = P.default_params(max_iterations=W["iters"], max_correspondence_distance=W["gate"],
+                              estimator=P.EST_POINT_TO_PLANE_LLS if p2plane else P.EST_SVD,
+                              with_normals_transform=1 if p2plane else 0, mse_threshold_absolute=0.0,
+                              transformation_epsilon=0.0)
 
-    # One registration object for the whole run, like a pcl::IterativeClosestPointWithNormals instance whose target
+    # One registration object for the whole run, like a pcl::IterativeClosestPoint[WithNormals] instance whose target
     # was set once (Registration::setInputTarget): the target index and its normals stay on the device across
     # align() calls (registration.hpp:84-87); every step is setInputSource + align(output).
     icp = P.Icp(ctx, params=params)
     icp.set_target(tidx, normals=nrm_dev)
 
     def align(src, out):
-        icp.set_source(src, normals=P.Field(src, 4))
+        if p2plane:
+            icp.set_source(src, normals=P.Field(src, 4))
+        else:
+            icp.set_source(src)
         st = icp.iterate()
-        icp.get_cloud(out, normals=P.Field(out, 4))
+        if p2plane:
+            icp.get_cloud(out, normals=P.Field(out, 4))
+        else:
+            icp.get_cloud(out)
         return st
 
     def barrier():
@@ -260,37 +478,28 @@ def run_ours(args):
         if sampler:
             sampler.start()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        total = 0
+        total, iters = 0, 0
         e0.record(stream)
         for _ in range(steps):
-            total += align(src, out)["total_correspondences"]
+            st = align(src, out)
+            total += st["total_correspondences"]
+            iters += st["iterations"]
         e1.record(stream)
         barrier()
         clocks = sampler.stop() if sampler else None
         ms = e0.elapsed_time(e1)
-        t = torch.tensor([ms, float(total)], dtype=torch.float64, device=dev)
         if world > 1:
-            tm = t.clone()
+            tm = torch.tensor([ms], dtype=torch.float64, device=dev)
             dist.all_reduce(tm, op=dist.ReduceOp.MAX)
-            dist.all_reduce(t, op=dist.ReduceOp.SUM)
-            ms, total = float(tm[0]), float(t[1])
-        # NOTE: with the all-reduce inside every iteration each rank already reports the GLOBAL pair count;
-        # `total` summed over ranks would double count, so take rank 0's figure in that case.
-        return ms, total, ctx.launches - l0, clocks
+            ms = float(tm[0])
+        # with the exchange inside every iteration each rank's stats already carry the GLOBAL pair counts
+        return ms, float(total), ctx.launches - l0, clocks, iters
 
     # device-resident leg (value) --------------------------------------------------------------------------------
-    ms_v, tot_v, launches, clocks = timed(src_dev, out_dev, args.steps, args.warmup, not args.no_clocks)
-    iter_ms, iter_n = ctx.profile_get("icp_search")
-    accum_ms, _ = ctx.profile_get("icp_accum")
-    allreduce_ms, _ = ctx.profile_get("allreduce")
-    sort_ms, _ = ctx.profile_get("query_sort")
-    solve_ms, _ = ctx.profile_get("solve")
-    out_ms, _ = ctx.profile_get("transform_out")
+    ms_v, tot_v, launches, clocks, iters_v = timed(src_dev, out_dev, args.steps, args.warmup, not args.no_clocks)
+    prof = {k: ctx.profile_get(k) for k in ("icp_search", "icp_accum", "allreduce", "query_sort", "solve", "transform_out")}
     # host-buffer leg (e2e) --------------------------------------------------------------------------------------
-    ms_e, tot_e, _, _ = timed(src_host, out_host, args.steps, max(1, args.warmup // 2), False)
-    if world > 1:  # stats already carry the all-reduced (global) pair counts on every rank
-        tot_v /= world
-        tot_e /= world
+    ms_e, tot_e, _, _, _ = timed(src_host, out_host, args.steps, max(1, args.warmup // 2), False)
     value = tot_v / (ms_v * 1e-3)
     e2e = tot_e / (ms_e * 1e-3)
     if rank != 0:
@@ -298,68 +507,82 @@ def run_ours(args):
             dist.destroy_process_group()
         return
 
-    # roofline of the dominant kernel (k_search; the first search of a step is k_search_packet), algorithmic bytes per
-    # correspondence:
-    #   16 source read + 16 source write-back (T_k applied in place) + 16 previous match read + 16 match write
-    #   + (target leaf slots + nodes, each read about once under Hilbert-ordered queries) / N_s
+    # ---- roofline of the dominant kernel ----------------------------------------------------------
+    # k_icp_wq = transform + exact 1-NN + gate + normal-equation accumulation of one ICP iteration, fused.
+    # ALGORITHMIC bytes per correspondence (§8d): 16 (query read) + 24 * N_t / N_s (every target point, 16 B, and its
+    # share of a 32-B node per 8-point leaf, read once under coherent queries) = 40 B at N_s = N_t, + 16 * N_t / N_s for
+    # the target normals of the point-to-plane objective = 56 B.  The implementation moves more than that (the in-place
+    # fp32 re-transform of the source that reproduces icp.hpp:220 bit for bit, the 8-B match = next iteration's seed,
+    # leaf padding, 64-B nodes, the cell table); that figure is `implementation_bytes_per_correspondence`, and the measured
+    # DRAM bytes of an ncu capture are `traffic`.
     st_idx = tidx.stats
-    # what a search reads of the index: the padded leaf lines (16 B per slot) and the 64-byte nodes — not the auxiliary
-    # arrays the index also owns (parent pointers, lazily built position maps), which the default walk never touches
-    tree_bytes = st_idx["leaves"] * st_idx["leaf_size"] * 16 + st_idx["nodes"] * 64
-    bytes_per_corr = 16 + 16 + 16 + 16 + tree_bytes / float(n)
+    n_local = int(src_np.shape[0])
+    ratio = n_tgt / float(n_local)
+    alg_bytes = 16.0 + 24.0 * ratio + (16.0 * ratio if p2plane else 0.0)
+    impl_bytes = (16 + 16 + 8 + 8 + (16 * ratio if p2plane else 0.0) +
+                  (st_idx["leaves"] * st_idx["leaf_size"] * 16 + st_idx["nodes"] * 64) / float(n_local))
     peak, peak_src = measured_peak_gbs()
+    iter_ms, iter_n = prof["icp_search"]
     avg_iter_s = (iter_ms / max(iter_n, 1)) * 1e-3
-    achieved = bytes_per_corr * n / avg_iter_s / 1e9 if avg_iter_s > 0 else 0.0
-    roofline = {"bound": "hbm", "kernel": "k_search (in-place transform + exact seeded 1-NN + gate; first search of a step: k_search_packet)", "achieved": achieved, "peak": peak,
-                "peak_source": peak_src, "unit": "GB/s", "frac": achieved / peak,
+    achieved = alg_bytes * n_local / avg_iter_s / 1e9 if avg_iter_s > 0 else 0.0
+    roofline = {"bound": "hbm",
+                "kernel": "k_icp_wq (one ICP iteration fused: in-place transform + exact seeded 1-NN + gate + "
+                          "fp64 tensor-core accumulation of the normal equations)",
+                "achieved": achieved, "peak": peak, "peak_source": peak_src, "unit": "GB/s", "frac": achieved / peak,
                 "frac_of_nominal_8000_GBs": achieved / 8000.0,  # report both denominators
-                # dram__bytes_read.sum + dram__bytes_write.sum of one `ncu --set full` capture of this kernel on this
-                # workload (profiles/r1k_k_search_ncu.txt: k_search<0,0>, 698.3 MB + 313.6 MB); only valid for the 10 M default
-                "traffic": 1011.9e6 if n == N_DEFAULT else None,
-                "algorithmic_bytes_per_launch": bytes_per_corr * n, "avg_launch_ms": avg_iter_s * 1e3,
-                "launches_timed": iter_n, "algorithmic_bytes_per_correspondence": bytes_per_corr,
-                "index": st_idx,
-                "note": "BVH traversal is latency/issue bound, not HBM bound (SURVEY.md §7 hard part ii, DESIGN.md)"}
+                "traffic": ncu_traffic("k_icp_wq_" + args.workload, n),
+                "algorithmic_bytes_per_launch": alg_bytes * n_local, "avg_launch_ms": avg_iter_s * 1e3,
+                "launches_timed": iter_n, "algorithmic_bytes_per_correspondence": alg_bytes,
+                "implementation_bytes_per_correspondence": impl_bytes, "index": st_idx,
+                "note": "the walk is latency/issue bound, not HBM bound (SURVEY.md §7 hard part ii, DESIGN.md §3); frac "
+                        "is the §8(d) algorithmic figure over the measured copy peak"}
 
-    # CPU baseline (oracle port) on a bounded sample: one align() of ICP_ITERS iterations, sample sized for ~15 s
+    # CPU baseline (oracle port) on a bounded sample: one align(), sample sized for ~15 s, all host threads
     cpu = None
     if world == 1 and not args.no_cpu_baseline:
         import oracle
-        cores = oracle.max_threads()
+        cores = host_cores()
         tgt_n = tgt.copy()
-        tgt_n[:, 4:8] = nrm_dev.cpu().numpy()
+        if p2plane:
+            tgt_n[:, 4:8] = nrm_dev.cpu().numpy()
         t0 = time.time()
         tree = oracle.Index(tgt_n)
         build_s = time.time() - t0
-        kw = dict(max_iterations=ICP_ITERS, max_correspondence_distance=MAX_CORR_DIST, estimator=1,
-                  with_normals_transform=True, source_has_normals=True, nthreads=cores, index=tree)
-        src_np = src_host.numpy()
-        probe = min(n, 100_000)
+        kw = oracle_kw(W, cores, tree)
+        probe = min(n_local, 100_000)
         t0 = time.time()
         r = oracle.icp_align(src_np[:probe], tgt_n, **kw)
         rate = max(r["total_correspondences"], 1) / max(time.time() - t0, 1e-6)
-        sample = int(min(n, max(probe, rate * 15.0 / ICP_ITERS)))
+        sample = int(min(n_local, max(probe, rate * 15.0 / W["iters"])))
         t0 = time.time()
         r = oracle.icp_align(np.ascontiguousarray(src_np[:sample]), tgt_n, want_cloud=True, **kw)
         dt = time.time() - t0
         cpu = {"value": r["total_correspondences"] / dt, "unit": UNIT, "cores": cores, "kind": "port",
-               "sample": f"{sample} of {n} source points x {ICP_ITERS} iterations (one align) against the full "
-                         f"{n}-point target, GPU-computed normals; kd-tree build {build_s:.1f} s excluded"}
+               "sample": f"{sample} of {n_local} source points x {W['iters']} iterations (one align) against the full "
+                         f"{n_tgt}-point target" + (", GPU-computed normals" if p2plane else "") +
+                         f"; kd-tree build {build_s:.1f} s excluded"}
 
+    rec_bytes = int(src_host.numel() * 4)
+    steps = max(args.steps, 1)
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": ms_v / args.steps, "higher_is_better": True, "scaling": "weak",
+            "warmup": args.warmup, "ms_per_step": ms_v / steps, "higher_is_better": True, "scaling": args.scaling,
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": "cfg3_10M_point_to_plane", "points_target": n, "points_source_per_gpu": n,
-                       "icp_iterations_per_step": ICP_ITERS, "max_correspondence_distance": MAX_CORR_DIST,
-                       "estimator": "point_to_plane_lls", "k": 1, "normals_k": 16,
-                       "l2_policy": "inputs larger than L2 (target 160 MB + nodes 80 MB + normals 160 MB + source 160 MB)",
-                       "parallelism": f"source sharded x{world}, target replicated, 40-double all-reduce/iteration"},
-            "ms_per_iter": ms_v / args.steps / ICP_ITERS,
-            "breakdown_ms_per_step": {"icp_search_kernel": iter_ms / args.steps, "icp_accum_kernel": accum_ms / args.steps, "nccl_allreduce": allreduce_ms / args.steps, "query_sort": sort_ms / args.steps,
-                                      "solve": solve_ms / args.steps, "transform_out": out_ms / args.steps},
-            "setup_ms": {"index_build": build_ms, "normals_k16": normals_ms},
-            "e2e": {"value": e2e, "unit": UNIT, "ms_per_step": ms_e / args.steps,
-                    "h2d_bytes_per_step": int(src_host.numel() * 4), "d2h_bytes_per_step": int(out_host.numel() * 4 + 512 * ICP_ITERS)},
+            "config": {"workload": W["name"], "points_target": n_tgt, "points_source_total": n_src_total,
+                       "points_source_per_gpu": n_local, "icp_iterations_per_step": W["iters"],
+                       "max_correspondence_distance": W["gate"], "estimator": W["estimator"], "k": 1,
+                       "normals_k": W["normals_k"], "voxel_leaf": W["voxel_leaf"],
+                       "l2_policy": "inputs larger than L2 (target points + nodes + normals + source >> 126 MB)",
+                       "parallelism": (f"source sharded x{world} ({'Morton-range tiles of one cloud' if strong else 'one cloud per rank'}), "
+                                       "target replicated, 40-double exchange per iteration fused into the search kernel")},
+            "ms_per_iter": ms_v / max(iters_v, 1),
+            "breakdown_ms_per_step": {"icp_iteration_kernel": prof["icp_search"][0] / steps,
+                                      "icp_accum_kernel": prof["icp_accum"][0] / steps,
+                                      "nccl_allreduce": prof["allreduce"][0] / steps,
+                                      "query_sort": prof["query_sort"][0] / steps, "solve": prof["solve"][0] / steps,
+                                      "transform_out": prof["transform_out"][0] / steps},
+            "setup_ms": setup_ms,
+            "e2e": {"value": e2e, "unit": UNIT, "ms_per_step": ms_e / steps, "h2d_bytes_per_step": rec_bytes,
+                    "d2h_bytes_per_step": rec_bytes + 512 * W["iters"]},
             "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline}
     if cpu:
         line["cpu_baseline"] = cpu
@@ -385,7 +608,9 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--points", type=int, default=N_DEFAULT)
+    ap.add_argument("--workload", default="cfg3", choices=sorted(WORKLOADS))
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"])
+    ap.add_argument("--points", type=int, default=0, help="override the workload's point count (debug / smaller boxes)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-clocks", action="store_true", help="debug: do not sample clocks during the timed region")
     args = ap.parse_args()

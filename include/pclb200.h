@@ -120,6 +120,13 @@ PCLB200_API int pclb200_knn_stats(pclb200_ctx* ctx, const pclb200_index* idx, co
 PCLB200_API int pclb200_radius(pclb200_ctx* ctx, const pclb200_index* idx, const void* queries,
                                size_t nq, size_t stride, double radius, unsigned max_nn, int sorted,
                                int64_t* out_offsets, int32_t** out_idx, float** out_d2);
+/* The same search into CALLER buffers (host — preferably pinned — or device): no allocation, no pageable staging.
+ * out_offsets: nq + 1 entries; out_idx / out_d2: `capacity` entries each; *total = number of neighbours found.  If
+ * *total > capacity nothing is written to out_idx / out_d2 (offsets and *total are valid): call again with larger
+ * buffers, or first with capacity = 0 to size them.  With device buffers the lists never leave HBM. */
+PCLB200_API int pclb200_radius_into(pclb200_ctx* ctx, const pclb200_index* idx, const void* queries, size_t nq,
+                                    size_t stride, double radius, unsigned max_nn, int64_t* out_offsets,
+                                    int32_t* out_idx, float* out_d2, size_t capacity, size_t* total);
 
 /* ---- correspondences: replaces CorrespondenceEstimation::determineCorrespondences and
  * ::determineReciprocalCorrespondences (registration/include/pcl/registration/impl/
@@ -316,6 +323,21 @@ PCLB200_API int pclb200_fitness_score(pclb200_ctx* ctx, const pclb200_index* idx
                                       const double T[16], int scalar_is_double, double max_range,
                                       double* score);
 
+/* TransformationValidationEuclidean::validateTransformation — registration/include/pcl/registration/impl/
+ * transformation_validation_euclidean.hpp:50-109: the source transformed by T (products and sums in Scalar, left to right,
+ * cast to float: :62-75), 1-NN into the target, mean of the squared distances that are <= max_range (the reference compares
+ * the squared distance with max_range_ as given); DBL_MAX when none is. */
+PCLB200_API int pclb200_validate_transformation(pclb200_ctx* ctx, const pclb200_index* idx_tgt, const void* src, size_t n,
+                                                size_t stride, const double T[16], int scalar_is_double,
+                                                double max_range, double* score);
+
+/* SampleConsensusPrerejective::getFitness — impl/sample_consensus_prerejective.hpp:308-347: the source transformed by T
+ * (pcl::transformPointCloud, float), 1-NN into the target, inliers = points whose squared distance is STRICTLY below
+ * inlier_threshold^2 (float).  out (capacity n): one pclb200_corr per inlier {source index, nearest target index, d2},
+ * ascending source index — the caller sums `distance` in that order (float) to reproduce the reference's fitness. */
+PCLB200_API int pclb200_inliers(pclb200_ctx* ctx, const pclb200_index* idx_tgt, const void* src, size_t n, size_t stride,
+                                const double T[16], float inlier_threshold, pclb200_corr* out, size_t* n_out);
+
 /* ---- normals: replaces NormalEstimation[OMP]::computeFeature with setKSearch(k)
  * (features/include/pcl/features/impl/normal_3d.hpp:47-96; normal_3d.h:169-188,308-322;
  * common/impl/centroid.hpp:578-652; features/impl/feature.hpp:65-92; common/impl/eigen.hpp:68-326).
@@ -355,12 +377,35 @@ PCLB200_API int pclb200_voxelgrid(pclb200_ctx* ctx, const void* pts, size_t n, s
                                   const float leaf[3], unsigned min_points_per_voxel,
                                   float* out_xyz1, size_t* n_out);
 
+/* The same filter for records that carry a normal and a curvature (pcl::PointNormal, pcl::Normal), with the
+ * reference's default downsample_all_data_ = true (voxel_grid.hpp:796-806, CentroidPoint): per voxel the normals are
+ * summed as 4-vectors and normalised (accumulators.hpp:86-116), the curvature is averaged (:118-133).
+ * normals: pointer to the first normal_x (PointNormal: base + 16); the 5 floats {nx, ny, nz, n4, curvature} are read at
+ * stride_n.  out_normal_curv: capacity n records of 8 floats {nx, ny, nz, n4, curvature, 0, 0, 0} — bytes 16..47 of a
+ * pcl::PointNormal. */
+PCLB200_API int pclb200_voxelgrid_normals(pclb200_ctx* ctx, const void* pts, size_t n, size_t stride, const void* normals,
+                                          size_t stride_n, const int32_t* indices, size_t n_idx, int is_dense,
+                                          const float leaf[3], unsigned min_points_per_voxel, float* out_xyz1,
+                                          float* out_normal_curv, size_t* n_out);
+
 /* ---- multi-GPU: one process per GPU; every rank holds a replica of the target index and a
  * shard of the source.  After comm_init, pclb200_icp_iterate all-reduces the 32 fp64 accumulators
  * of each iteration across ranks, so every rank computes the identical transform.
  * unique_id: 128 bytes from pclb200_comm_unique_id on rank 0, broadcast by the caller. */
 PCLB200_API int pclb200_comm_unique_id(void* out_128_bytes);
 PCLB200_API int pclb200_comm_init(pclb200_ctx* ctx, int rank, int nranks, const void* unique_id);
+/* The per-iteration exchange: FUSED (default) = the last block of the iteration kernel stores its 40 sums into every
+ * peer's memory over NVLink and folds all ranks' sums in rank order (no collective launch, bitwise identical on all
+ * ranks); NCCL = a separate ncclAllReduce after the kernel (kept for comparison and as the fallback when peer mappings
+ * cannot be made). */
+#define PCLB200_REDUCE_FUSED 0
+#define PCLB200_REDUCE_NCCL 1
+PCLB200_API int pclb200_comm_set_mode(pclb200_ctx* ctx, int mode);
+/* NCCL-free bootstrap of the FUSED exchange, for launchers that can all-gather 64 bytes per rank themselves (MPI, gloo,
+ * a shared file) and for ranks that share one GPU: comm_export returns this rank's 64-byte cudaIpcMemHandle_t;
+ * comm_import takes the nranks handles in rank order. */
+PCLB200_API int pclb200_comm_export(pclb200_ctx* ctx, void* out_handle_64_bytes);
+PCLB200_API int pclb200_comm_import(pclb200_ctx* ctx, int rank, int nranks, const void* handles);
 
 #ifdef __cplusplus
 }

@@ -87,6 +87,8 @@ def lib():
         L.orc_fitness_score.argtypes = [vp, fp, sz, sz, i32p, sz, C.c_int, dp, C.c_int, C.c_double, C.c_int]
         L.orc_voxelgrid.restype = C.c_longlong
         L.orc_voxelgrid.argtypes = [fp, sz, sz, i32p, sz, C.c_int, fp, C.c_uint, fp]
+        L.orc_voxelgrid_normals.restype = C.c_longlong
+        L.orc_voxelgrid_normals.argtypes = [fp, sz, sz, i32p, sz, C.c_int, fp, C.c_uint, fp, C.c_long, fp]
         L.orc_point_normal.argtypes = [fp, sz, C.c_int, i32p, sz, fp]
         L.orc_normals_knn.argtypes = [vp, fp, sz, sz, i32p, sz, C.c_int, C.c_int, fp, fp, C.c_int]
         u8p = C.POINTER(C.c_uint8)
@@ -418,6 +420,21 @@ def voxelgrid(cloud, leaf, min_points_per_voxel=0, indices=None, is_dense=True):
     if m < 0:
         return None  # overflow guard: reference returns the input unfiltered
     return out[:m].copy()
+
+
+def voxelgrid_normals(cloud, leaf, min_points_per_voxel=0, indices=None, is_dense=True, normal_offset=4):
+    """VoxelGrid<PointNormal> with downsample_all_data_: (xyz1 rows, {nx,ny,nz,n4,curvature,0,0,0} rows)."""
+    cloud = as_cloud(cloud)
+    leaf = np.asarray(leaf, dtype=np.float32).reshape(3)
+    indices = None if indices is None else np.ascontiguousarray(indices, dtype=np.int32)
+    out = np.empty((max(cloud.shape[0], 1), 4), dtype=np.float32)
+    nc = np.empty((max(cloud.shape[0], 1), 8), dtype=np.float32)
+    m = lib().orc_voxelgrid_normals(_f(cloud), cloud.shape[0], cloud.shape[1], _i(indices),
+                                    0 if indices is None else indices.size, int(is_dense), _f(leaf),
+                                    min_points_per_voxel, _f(out), normal_offset, _f(nc))
+    if m < 0:
+        return None
+    return out[:m].copy(), nc[:m].copy()
 
 
 def point_normal(cloud, indices, is_dense=True):

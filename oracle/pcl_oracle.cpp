@@ -1654,9 +1654,12 @@ ORC_API double orc_fitness_score(void* h_tgt, const float* src, size_t n_s, size
 // AccumulatorXYZ (common/include/pcl/common/impl/accumulators.hpp:68-85): float sums, / n.
 // out: capacity n*4 floats (x,y,z,1).  Returns the number of output points, or -1 when the
 // INT32 overflow guard trips (reference then copies the input unfiltered, :620-629).
-ORC_API long long orc_voxelgrid(const float* pts, size_t n, size_t stride, const int32_t* indices,
-                                size_t n_idx, int is_dense, const float leaf[3], unsigned min_pts,
-                                float* out)
+// normal_off >= 0 (float offset of normal_x inside a record) additionally averages the normal and the curvature like
+// CentroidPoint does under downsample_all_data_ (voxel_grid.hpp:796-806; AccumulatorNormal / AccumulatorCurvature,
+// accumulators.hpp:86-133): out_nc gets 8 floats per voxel {normalised 4-vector sum, mean curvature, 0, 0, 0}.
+static long long voxelgrid_impl(const float* pts, size_t n, size_t stride, const int32_t* indices, size_t n_idx,
+                                int is_dense, const float leaf[3], unsigned min_pts, float* out, long normal_off,
+                                float* out_nc)
 {
   size_t cnt = indices ? n_idx : n;
   float inv[3] = {1.0f / leaf[0], 1.0f / leaf[1], 1.0f / leaf[2]};
@@ -1718,11 +1721,41 @@ ORC_API long long orc_voxelgrid(const float* pts, size_t n, size_t stride, const
       out[4 * total + 1] = c[1] / fn;
       out[4 * total + 2] = c[2] / fn;
       out[4 * total + 3] = 1.0f;
+      if (normal_off >= 0 && out_nc) {
+        float nv[4] = {0, 0, 0, 0}, cv = 0;
+        for (size_t li = index; li < i; ++li) {
+          const float* p = pts + stride * (size_t)iv[li].second + normal_off;
+          nv[0] += p[0]; nv[1] += p[1]; nv[2] += p[2]; nv[3] += p[3];
+          cv += p[4];
+        }
+        const float sq = (nv[0] * nv[0] + nv[1] * nv[1]) + (nv[2] * nv[2] + nv[3] * nv[3]);
+        if (sq > 0.f) {
+          const float nrm = std::sqrt(sq);
+          for (int d = 0; d < 4; ++d) nv[d] /= nrm;
+        }
+        float* o = out_nc + 8 * total;
+        o[0] = nv[0]; o[1] = nv[1]; o[2] = nv[2]; o[3] = nv[3];
+        o[4] = cv / fn; o[5] = o[6] = o[7] = 0.f;
+      }
       ++total;
     }
     index = i;
   }
   return total;
+}
+
+ORC_API long long orc_voxelgrid(const float* pts, size_t n, size_t stride, const int32_t* indices,
+                                size_t n_idx, int is_dense, const float leaf[3], unsigned min_pts,
+                                float* out)
+{
+  return voxelgrid_impl(pts, n, stride, indices, n_idx, is_dense, leaf, min_pts, out, -1, nullptr);
+}
+
+ORC_API long long orc_voxelgrid_normals(const float* pts, size_t n, size_t stride, const int32_t* indices,
+                                        size_t n_idx, int is_dense, const float leaf[3], unsigned min_pts,
+                                        float* out, long normal_off, float* out_nc)
+{
+  return voxelgrid_impl(pts, n, stride, indices, n_idx, is_dense, leaf, min_pts, out, normal_off, out_nc);
 }
 
 // ---- normals ----------------------------------------------------------------------------

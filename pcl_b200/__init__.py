@@ -17,6 +17,7 @@ OK = 0
 ERR_CUDA, ERR_INVALID, ERR_EMPTY, ERR_LEAF_TOO_SMALL, ERR_INTERNAL, ERR_NCCL = -1, -2, -3, -4, -5, -6
 EST_SVD, EST_POINT_TO_PLANE_LLS, EST_SYMMETRIC_POINT_TO_PLANE_LLS = 0, 1, 2
 TRACK_AUTO, TRACK_ON, TRACK_OFF = 0, 1, 2
+REDUCE_FUSED, REDUCE_NCCL = 0, 1
 CONV_NAMES = ["NOT_CONVERGED", "ITERATIONS", "TRANSFORM", "ABS_MSE", "REL_MSE", "NO_CORRESPONDENCES",
               "FAILURE_AFTER_MAX_ITERATIONS"]
 
@@ -72,7 +73,7 @@ SYMBOLS = [
     "pclb200_icp_set_source", "pclb200_icp_iterate", "pclb200_icp_get_cloud", "pclb200_icp_get_correspondences",
     "pclb200_icp_align",
     "pclb200_fitness_score", "pclb200_reject", "pclb200_icp_set_rejectors", "pclb200_normals_knn", "pclb200_normals_radius",
-    "pclb200_correspondences_normals", "pclb200_reject_surface_normal", "pclb200_cluster_labels", "pclb200_voxelgrid", "pclb200_comm_unique_id",
+    "pclb200_correspondences_normals", "pclb200_reject_surface_normal", "pclb200_cluster_labels", "pclb200_voxelgrid", "pclb200_voxelgrid_normals", "pclb200_validate_transformation", "pclb200_inliers", "pclb200_radius_into", "pclb200_comm_unique_id", "pclb200_comm_set_mode", "pclb200_comm_export", "pclb200_comm_import",
     "pclb200_comm_init",
 ]
 
@@ -134,7 +135,14 @@ def lib():
     L.pclb200_reject_surface_normal.argtypes = [vp, vp, sz, vp, sz, sz, vp, sz, sz, C.c_double, vp, C.POINTER(sz)]
     L.pclb200_cluster_labels.argtypes = [vp, vp, C.c_double, vp, sz]
     L.pclb200_voxelgrid.argtypes = [vp, vp, sz, sz, vp, sz, C.c_int, fp, C.c_uint, vp, C.POINTER(sz)]
+    L.pclb200_voxelgrid_normals.argtypes = [vp, vp, sz, sz, vp, sz, vp, sz, C.c_int, fp, C.c_uint, vp, vp, C.POINTER(sz)]
+    L.pclb200_validate_transformation.argtypes = [vp, vp, vp, sz, sz, dp, C.c_int, C.c_double, dp]
+    L.pclb200_inliers.argtypes = [vp, vp, vp, sz, sz, dp, C.c_float, vp, C.POINTER(sz)]
+    L.pclb200_radius_into.argtypes = [vp, vp, vp, sz, sz, C.c_double, C.c_uint, vp, vp, vp, sz, C.POINTER(sz)]
     L.pclb200_comm_unique_id.argtypes = [vp]
+    L.pclb200_comm_set_mode.argtypes = [vp, C.c_int]
+    L.pclb200_comm_export.argtypes = [vp, vp]
+    L.pclb200_comm_import.argtypes = [vp, C.c_int, C.c_int, vp]
     L.pclb200_comm_init.argtypes = [vp, C.c_int, C.c_int, vp]
     for s in SYMBOLS:
         getattr(L, s)  # AttributeError here == header and library disagree
@@ -246,6 +254,21 @@ class Context:
         buf = C.create_string_buffer(bytes(unique_id_bytes), 128)
         _check(lib().pclb200_comm_init(self.h, rank, nranks, buf))
 
+    def comm_set_mode(self, mode):
+        _check(lib().pclb200_comm_set_mode(self.h, int(mode)))
+
+    def comm_export(self):
+        buf = C.create_string_buffer(64)
+        _check(lib().pclb200_comm_export(self.h, buf))
+        return buf.raw
+
+    def comm_import(self, rank, nranks, handles):
+        """handles: the nranks 64-byte blobs of comm_export, in rank order."""
+        blob = b"".join(bytes(h) for h in handles)
+        assert len(blob) == 64 * nranks
+        buf = C.create_string_buffer(blob, len(blob))
+        _check(lib().pclb200_comm_import(self.h, rank, nranks, buf))
+
     # ---- stand-alone operators -----------------------------------------------------------------
     def voxelgrid(self, cloud, leaf, min_points_per_voxel=0, indices=None, is_dense=True, out=None):
         b = _Buf(cloud)
@@ -260,6 +283,21 @@ class Context:
         _check(lib().pclb200_voxelgrid(self.h, b.ptr, b.rows, b.stride, ib.ptr, ib.rows, int(is_dense), leaf,
                                        int(min_points_per_voxel), ob.ptr, C.byref(m)))
         return out[:m.value].copy() if host_out else out[:m.value]
+
+    def voxelgrid_normals(self, cloud, leaf, min_points_per_voxel=0, indices=None, is_dense=True, normal_offset=4):
+        """VoxelGrid<PointNormal> with downsample_all_data_ = true: (xyz1 rows, {nx,ny,nz,n4,curvature,0,0,0} rows)."""
+        b = _Buf(cloud)
+        nb = _Buf(Field(cloud, normal_offset))
+        ib = _Buf(indices, np.int32)
+        n = ib.rows if indices is not None else b.rows
+        leaf = (C.c_float * 3)(*[float(x) for x in np.broadcast_to(np.asarray(leaf, dtype=np.float32), (3,))])
+        out = np.empty((max(n, 1), 4), dtype=np.float32)
+        nc = np.empty((max(n, 1), 8), dtype=np.float32)
+        m = C.c_size_t()
+        _check(lib().pclb200_voxelgrid_normals(self.h, b.ptr, b.rows, b.stride, nb.ptr, nb.stride, ib.ptr, ib.rows,
+                                               int(is_dense), leaf, int(min_points_per_voxel),
+                                               C.c_void_p(out.ctypes.data), C.c_void_p(nc.ctypes.data), C.byref(m)))
+        return out[:m.value].copy(), nc[:m.value].copy()
 
     def reject(self, corr, kind, p=0.0, min_correspondences=0):
         """One correspondence rejector (getRemainingCorrespondences); returns (remaining, median)."""
@@ -386,6 +424,16 @@ class Index:
         lib().pclb200_free(pd)
         return offs, idx, d2
 
+    def radius_into(self, q, r, offsets, idx, d2, max_nn=0):
+        """radiusSearch into caller buffers (numpy or torch, host or cuda); returns the total number of neighbours —
+        when it exceeds the capacity of idx / d2 only `offsets` was written."""
+        b = _Buf(q)
+        ob, ib, db = _Buf(offsets, np.int64), _Buf(idx, np.int32), _Buf(d2)
+        total = C.c_size_t()
+        _check(lib().pclb200_radius_into(self.ctx.h, self.h, b.ptr, b.rows, b.stride, float(r), int(max_nn), ob.ptr,
+                                         ib.ptr, db.ptr, min(ib.rows, db.rows), C.byref(total)))
+        return int(total.value)
+
     def correspondences(self, src, max_distance=np.sqrt(np.finfo(np.float64).max), indices=None, is_dense=True,
                         src_index=None):
         b = _Buf(src)
@@ -421,6 +469,31 @@ class Index:
                                            T.ctypes.data_as(C.POINTER(C.c_double)), int(scalar_is_double),
                                            float(max_range), C.byref(out)))
         return float(out.value)
+
+    def validate_transformation(self, src, T, max_range=np.finfo(np.float64).max, scalar_is_double=False):
+        """TransformationValidationEuclidean::validateTransformation."""
+        b = _Buf(src)
+        T = np.ascontiguousarray(T, dtype=np.float64)
+        out = C.c_double()
+        _check(lib().pclb200_validate_transformation(self.ctx.h, self.h, b.ptr, b.rows, b.stride,
+                                                     T.ctypes.data_as(C.POINTER(C.c_double)), int(scalar_is_double),
+                                                     float(max_range), C.byref(out)))
+        return float(out.value)
+
+    def inliers(self, src, T, inlier_threshold):
+        """SampleConsensusPrerejective::getFitness: (inlier indices, fitness = float mean of their squared distances)."""
+        b = _Buf(src)
+        T = np.ascontiguousarray(T, dtype=np.float64)
+        out = np.empty(max(b.rows, 1), dtype=CORR_DTYPE)
+        m = C.c_size_t()
+        _check(lib().pclb200_inliers(self.ctx.h, self.h, b.ptr, b.rows, b.stride, T.ctypes.data_as(C.POINTER(C.c_double)),
+                                     float(inlier_threshold), C.c_void_p(out.ctypes.data), C.byref(m)))
+        c = out[:m.value]
+        fit = np.float32(0.0)
+        for d in c["distance"]:   # sequential float sum, like the reference's loop
+            fit = np.float32(fit + d)
+        fit = np.float32(fit / np.float32(m.value)) if m.value else np.finfo(np.float32).max
+        return c["index_query"].copy(), float(fit)
 
     def normals_knn(self, cloud, k, viewpoint=(0, 0, 0), indices=None, is_dense=True, out=None):
         b = _Buf(cloud)

@@ -29,18 +29,23 @@ void estimate_pairs(Ctx& c, int est, const void* src, size_t stride_s, const voi
                     size_t stride_t, const pclb200_corr* corr, size_t n, int scalar_is_double, double* T_out,
                     const void* src_normals = nullptr, int enforce_same_dir = 1);
 size_t correspondences(Ctx& c, const Index& tgt, const Index* src_index, const void* src, size_t n, size_t stride,
-                       const int32_t* indices, size_t n_idx, int is_dense, double max_dist, pclb200_corr* out);
+                       const int32_t* indices, size_t n_idx, int is_dense, double max_dist, pclb200_corr* out,
+                       const double* pre_T = nullptr, int pre_mode = 0, const float* gate_override = nullptr);
 double fitness_score(Ctx& c, const Index& tgt, const void* src, size_t n, size_t stride, const int32_t* indices,
-                     size_t n_idx, const double* T, int scalar_is_double, double max_range);
+                     size_t n_idx, const double* T, int scalar_is_double, double max_range, int mode_override = -1);
 // search.cu
 void launch_normals(Ctx& c, Index& idx, const float4* d_q, size_t nq, int k, const float vp[3], float4* d_out,
                     int* d_not_dense);
 void launch_knn_stats(Ctx& c, const Index& idx, const float4* d_q, size_t nq, int k, float* d_mean, float* d_kth);
 // voxel.cu
 size_t voxelgrid(Ctx& c, const void* pts, size_t n, size_t stride, const int32_t* indices, size_t n_idx, int is_dense,
-                 const float leaf[3], unsigned min_pts, float* out_xyz1);
+                 const float leaf[3], unsigned min_pts, float* out_xyz1, const void* normals, size_t stride_n,
+                 float* out_normal_curv);
 // comm.cu
 void comm_unique_id(void* out128);
+void comm_export(Ctx& c, void* out64);
+void comm_import(Ctx& c, int rank, int nranks, const void* handles);
+void comm_set_mode(Ctx& c, int mode);
 void comm_init(Ctx& c, int rank, int nranks, const void* unique_id);
 void comm_destroy(Ctx& c);
 
@@ -166,6 +171,154 @@ struct pclb200_icp {
   pclb200_ctx* ctx;
   int device;
 };
+
+// Shared body of pclb200_radius / pclb200_radius_into.  `sink(total)` returns where the packed lists go (host or device
+// pointers; {nullptr, nullptr} = do not deliver, e.g. the caller's buffers are too small); offsets are written to
+// out_offsets (host or device, nq + 1 entries).
+struct RadiusSinkBuffers {
+  int32_t* idx;
+  float* d2;
+};
+
+__global__ void k_offsets_to_i64(const unsigned long long* __restrict__ in, size_t n, int64_t* __restrict__ out)
+{
+  size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+  if (i < n)
+    out[i] = (int64_t)in[i];
+}
+
+template <typename Sink>
+static void radius_impl(Ctx& c, const Index& idx, const void* queries, size_t nq, size_t stride, double radius,
+                        unsigned max_nn, int64_t* out_offsets, Sink&& sink)
+{
+    cudaStream_t st = c.stream;
+    auto write_offsets = [&](const unsigned long long* d_off) {
+      if (is_device_ptr(out_offsets)) {
+        k_offsets_to_i64<<<grid_for(nq + 1, 256), 256, 0, st>>>(d_off, nq + 1, out_offsets);
+        ++c.launches;
+      }
+      else {
+        static_assert(sizeof(unsigned long long) == sizeof(int64_t), "offset width");
+        PCLB_CUDA(cudaMemcpyAsync(out_offsets, d_off, (nq + 1) * sizeof(int64_t), cudaMemcpyDeviceToHost, st));
+      }
+    };
+    auto deliver = [&](const RadiusSinkBuffers& o, const int32_t* di, const float* dd, unsigned long long n) {
+      if (!o.idx || !o.d2 || n == 0)
+        return;
+      PCLB_CUDA(cudaMemcpyAsync(o.idx, di, n * sizeof(int32_t),
+                                is_device_ptr(o.idx) ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost, st));
+      PCLB_CUDA(cudaMemcpyAsync(o.d2, dd, n * sizeof(float),
+                                is_device_ptr(o.d2) ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost, st));
+    };
+    const float r2 = (float)(radius * radius);  // kdtree_flann.hpp:398
+    if (max_nn == 0 || (size_t)max_nn > idx.n_valid)
+      max_nn = (unsigned)idx.n_valid;            // :382-383
+    DevBuf<float4> dense;
+    dense.alloc(nq, st);
+    load_xyz_as_float4(c, queries, nq, stride, nullptr, 0, dense.p, st);
+    QueryBatch qb;
+    make_query_batch(c, idx, dense.p, nq, qb);
+    DevBuf<unsigned long long> counts, offsets, keys_sorted;
+    unsigned long long total = 0;
+    {
+      ProfScope ps(c, "radius_count");
+      radius_count(c, idx, qb.q.p, nq, r2, counts, offsets, total);
+    }
+    // KNNRadiusResultSet semantics (kdtree_flann.hpp:382-391): the max_nn nearest among those with d2 < r2.  Normally
+    // the whole ball is materialised, sorted and cut (the passes below: ~3 ms per million queries at ~30 neighbours).
+    // When the balls hold far more than max_nn points that would move (or overflow on) data that is thrown away, so
+    // for max_nn <= 32 the register k-NN kernel runs instead, started with the pruning bound just below r2 (every
+    // d2 < r2 is <= that bound; a candidate AT the bound still enters through the index tie rule).
+    if ((size_t)max_nn < idx.n_valid && max_nn <= 32 && total > 16ULL * (unsigned long long)nq * max_nn) {
+      const int k = (int)max_nn;
+      DevBuf<int32_t> rows;
+      DevBuf<float> rows_d2;
+      rows.alloc(nq * (size_t)k, st);
+      rows_d2.alloc(nq * (size_t)k, st);
+      {
+        ProfScope ps(c, "radius_knn");
+        launch_knn(c, idx, qb.q.p, nq, k, std::nextafter(r2, -std::numeric_limits<float>::infinity()), rows.p, rows_d2.p);
+      }
+      DevBuf<unsigned long long> cnt, off;
+      cnt.alloc(nq + 1, st);
+      off.alloc(nq + 1, st);
+      PCLB_CUDA(cudaMemsetAsync(cnt.p, 0, (nq + 1) * sizeof(unsigned long long), st));
+      k_count_row_entries<<<grid_for(nq, 256), 256, 0, st>>>(rows.p, nq, k, cnt.p);
+      size_t tb = 0;
+      PCLB_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, tb, cnt.p, off.p, (int)(nq + 1), st));
+      DevBuf<unsigned char> tmp;
+      tmp.alloc(tb, st);
+      PCLB_CUDA(cub::DeviceScan::ExclusiveSum(tmp.p, tb, cnt.p, off.p, (int)(nq + 1), st));
+      c.launches += 2;
+      unsigned long long kept = 0;
+      PCLB_CUDA(cudaMemcpyAsync(&kept, off.p + nq, sizeof(kept), cudaMemcpyDeviceToHost, st));
+      write_offsets(off.p);
+      PCLB_CUDA(cudaStreamSynchronize(st));
+      const RadiusSinkBuffers o = sink(kept);
+      if (kept > 0 && o.idx && o.d2) {
+        DevBuf<int32_t> di;
+        DevBuf<float> dd;
+        di.alloc(kept, st);
+        dd.alloc(kept, st);
+        k_pack_rows<<<grid_for(nq, 256), 256, 0, st>>>(rows.p, rows_d2.p, nq, k, off.p, di.p, dd.p);
+        ++c.launches;
+        deliver(o, di.p, dd.p, kept);
+        PCLB_CUDA(cudaStreamSynchronize(st));
+      }
+      raise_if_device_error(c);
+      return;
+    }
+    {
+      ProfScope ps(c, "radius");
+      radius_fill_sorted(c, idx, qb.q.p, nq, r2, offsets, total, keys_sorted);
+    }
+    const unsigned long long* d_final_keys = nullptr;
+    const unsigned long long* d_final_off = offsets.p;
+    unsigned long long final_total = total;
+    DevBuf<unsigned long long> counts2, offsets2, keys_trunc;
+    if (total > 0) {
+      d_final_keys = keys_sorted.p;
+      if ((size_t)max_nn < idx.n_valid) {  // KNNRadius semantics: the max_nn nearest inside the ball
+        counts2.alloc(nq + 1, st);
+        offsets2.alloc(nq + 1, st);
+        PCLB_CUDA(cudaMemsetAsync(counts2.p, 0, (nq + 1) * sizeof(unsigned long long), st));
+        k_clamp_counts<<<grid_for(nq, 256), 256, 0, st>>>(counts.p, nq, (unsigned long long)max_nn, counts2.p);
+        size_t tb = 0;
+        PCLB_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, tb, counts2.p, offsets2.p, (int)(nq + 1), st));
+        DevBuf<unsigned char> tmp;
+        tmp.alloc(tb, st);
+        PCLB_CUDA(cub::DeviceScan::ExclusiveSum(tmp.p, tb, counts2.p, offsets2.p, (int)(nq + 1), st));
+        PCLB_CUDA(cudaMemcpyAsync(&final_total, offsets2.p + nq, sizeof(final_total), cudaMemcpyDeviceToHost, st));
+        PCLB_CUDA(cudaStreamSynchronize(st));
+        keys_trunc.alloc(std::max<unsigned long long>(final_total, 1), st);
+        k_truncate_segments<<<(unsigned)nq, 64, 0, st>>>(keys_sorted.p, offsets.p, offsets2.p, nq, keys_trunc.p);
+        c.launches += 3;
+        d_final_keys = keys_trunc.p;
+        d_final_off = offsets2.p;
+      }
+    }
+    write_offsets(d_final_off);
+    PCLB_CUDA(cudaStreamSynchronize(st));
+    const RadiusSinkBuffers o = sink(final_total);
+    if (final_total > 0 && o.idx && o.d2) {
+      if (is_device_ptr(o.idx) && is_device_ptr(o.d2)) {  // device-resident result: the unpack kernel writes it in place
+        k_unpack_keys<<<grid_for(final_total, 256), 256, 0, st>>>(d_final_keys, final_total, o.idx, o.d2);
+        ++c.launches;
+      }
+      else {
+        DevBuf<int32_t> di;
+        DevBuf<float> dd;
+        di.alloc(final_total, st);
+        dd.alloc(final_total, st);
+        k_unpack_keys<<<grid_for(final_total, 256), 256, 0, st>>>(d_final_keys, final_total, di.p, dd.p);
+        ++c.launches;
+        deliver(o, di.p, dd.p, final_total);
+      }
+      PCLB_CUDA(cudaStreamSynchronize(st));
+    }
+    raise_if_device_error(c);
+}
+
 
 extern "C" {
 
@@ -436,132 +589,48 @@ int pclb200_radius(pclb200_ctx* ctx, const pclb200_index* h, const void* queries
   (void)sorted;
   return guarded([&] {
     PCLB_REQUIRE(ctx && h && h->idx && out_offsets && out_idx && out_d2, PCLB200_ERR_INVALID, "NULL argument");
+    PCLB_REQUIRE(!is_device_ptr(out_offsets), PCLB200_ERR_INVALID, "pclb200_radius returns host arrays: out_offsets must be host memory");
     Ctx& c = ctx->c;
     std::lock_guard<std::recursive_mutex> lk(c.mu);
     PCLB_CUDA(cudaSetDevice(c.device));
-    const Index& idx = *h->idx;
     *out_idx = nullptr;
     *out_d2 = nullptr;
     out_offsets[0] = 0;
     if (nq == 0)
       return;
-    cudaStream_t st = c.stream;
-    const float r2 = (float)(radius * radius);  // kdtree_flann.hpp:398
-    if (max_nn == 0 || (size_t)max_nn > idx.n_valid)
-      max_nn = (unsigned)idx.n_valid;            // :382-383
-    DevBuf<float4> dense;
-    dense.alloc(nq, st);
-    load_xyz_as_float4(c, queries, nq, stride, nullptr, 0, dense.p, st);
-    QueryBatch qb;
-    make_query_batch(c, idx, dense.p, nq, qb);
-    DevBuf<unsigned long long> counts, offsets, keys_sorted;
-    unsigned long long total = 0;
-    {
-      ProfScope ps(c, "radius_count");
-      radius_count(c, idx, qb.q.p, nq, r2, counts, offsets, total);
-    }
-    // KNNRadiusResultSet semantics (kdtree_flann.hpp:382-391): the max_nn nearest among those with d2 < r2.  Normally
-    // the whole ball is materialised, sorted and cut (the passes below: ~3 ms per million queries at ~30 neighbours).
-    // When the balls hold far more than max_nn points that would move (or overflow on) data that is thrown away, so
-    // for max_nn <= 32 the register k-NN kernel runs instead, started with the pruning bound just below r2 (every
-    // d2 < r2 is <= that bound; a candidate AT the bound still enters through the index tie rule).
-    if ((size_t)max_nn < idx.n_valid && max_nn <= 32 && total > 16ULL * (unsigned long long)nq * max_nn) {
-      const int k = (int)max_nn;
-      DevBuf<int32_t> rows;
-      DevBuf<float> rows_d2;
-      rows.alloc(nq * (size_t)k, st);
-      rows_d2.alloc(nq * (size_t)k, st);
-      {
-        ProfScope ps(c, "radius_knn");
-        launch_knn(c, idx, qb.q.p, nq, k, std::nextafter(r2, -std::numeric_limits<float>::infinity()), rows.p, rows_d2.p);
-      }
-      DevBuf<unsigned long long> cnt, off;
-      cnt.alloc(nq + 1, st);
-      off.alloc(nq + 1, st);
-      PCLB_CUDA(cudaMemsetAsync(cnt.p, 0, (nq + 1) * sizeof(unsigned long long), st));
-      k_count_row_entries<<<grid_for(nq, 256), 256, 0, st>>>(rows.p, nq, k, cnt.p);
-      size_t tb = 0;
-      PCLB_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, tb, cnt.p, off.p, (int)(nq + 1), st));
-      DevBuf<unsigned char> tmp;
-      tmp.alloc(tb, st);
-      PCLB_CUDA(cub::DeviceScan::ExclusiveSum(tmp.p, tb, cnt.p, off.p, (int)(nq + 1), st));
-      c.launches += 2;
-      std::vector<unsigned long long> h_off(nq + 1, 0);
-      PCLB_CUDA(cudaMemcpyAsync(h_off.data(), off.p, (nq + 1) * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
-      PCLB_CUDA(cudaStreamSynchronize(st));
-      const unsigned long long kept = h_off[nq];
-      for (size_t i = 0; i <= nq; ++i)
-        out_offsets[i] = (int64_t)h_off[i];
-      int32_t* hi = static_cast<int32_t*>(malloc(std::max<size_t>(kept, 1) * sizeof(int32_t)));
-      float* hd = static_cast<float*>(malloc(std::max<size_t>(kept, 1) * sizeof(float)));
-      PCLB_REQUIRE(hi && hd, PCLB200_ERR_INTERNAL, "host allocation failed");
-      *out_idx = hi;  // owned by the caller from here on (pclb200_free), also on the error paths below
+    radius_impl(c, *h->idx, queries, nq, stride, radius, max_nn, out_offsets, [&](unsigned long long total) {
+      int32_t* hi = static_cast<int32_t*>(malloc(std::max<size_t>(total, 1) * sizeof(int32_t)));
+      float* hd = static_cast<float*>(malloc(std::max<size_t>(total, 1) * sizeof(float)));
+      *out_idx = hi;  // owned by the caller from here on (pclb200_free), also on the error paths
       *out_d2 = hd;
-      if (kept > 0) {
-        DevBuf<int32_t> di;
-        DevBuf<float> dd;
-        di.alloc(kept, st);
-        dd.alloc(kept, st);
-        k_pack_rows<<<grid_for(nq, 256), 256, 0, st>>>(rows.p, rows_d2.p, nq, k, off.p, di.p, dd.p);
-        ++c.launches;
-        PCLB_CUDA(cudaMemcpyAsync(hi, di.p, kept * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
-        PCLB_CUDA(cudaMemcpyAsync(hd, dd.p, kept * sizeof(float), cudaMemcpyDeviceToHost, st));
-        PCLB_CUDA(cudaStreamSynchronize(st));
-      }
-      raise_if_device_error(c);
+      PCLB_REQUIRE(hi && hd, PCLB200_ERR_INTERNAL, "host allocation failed");
+      return RadiusSinkBuffers{hi, hd};
+    });
+  });
+}
+
+int pclb200_radius_into(pclb200_ctx* ctx, const pclb200_index* h, const void* queries, size_t nq, size_t stride,
+                        double radius, unsigned max_nn, int64_t* out_offsets, int32_t* out_idx, float* out_d2,
+                        size_t capacity, size_t* total)
+{
+  return guarded([&] {
+    PCLB_REQUIRE(ctx && h && h->idx && out_offsets && total, PCLB200_ERR_INVALID, "NULL argument");
+    PCLB_REQUIRE(capacity == 0 || (out_idx && out_d2), PCLB200_ERR_INVALID, "NULL output buffers with a non-zero capacity");
+    Ctx& c = ctx->c;
+    std::lock_guard<std::recursive_mutex> lk(c.mu);
+    PCLB_CUDA(cudaSetDevice(c.device));
+    *total = 0;
+    if (nq == 0) {
+      const int64_t zero = 0;
+      PCLB_CUDA(cudaMemcpy(out_offsets, &zero, sizeof(zero), cudaMemcpyDefault));
       return;
     }
-    {
-      ProfScope ps(c, "radius");
-      radius_fill_sorted(c, idx, qb.q.p, nq, r2, offsets, total, keys_sorted);
-    }
-    std::vector<unsigned long long> h_off(nq + 1, 0);
-    const unsigned long long* d_final_keys = nullptr;
-    const unsigned long long* d_final_off = offsets.p;
-    unsigned long long final_total = total;
-    DevBuf<unsigned long long> counts2, offsets2, keys_trunc;
-    if (total > 0) {
-      d_final_keys = keys_sorted.p;
-      if ((size_t)max_nn < idx.n_valid) {  // KNNRadius semantics: the max_nn nearest inside the ball
-        counts2.alloc(nq + 1, st);
-        offsets2.alloc(nq + 1, st);
-        PCLB_CUDA(cudaMemsetAsync(counts2.p, 0, (nq + 1) * sizeof(unsigned long long), st));
-        k_clamp_counts<<<grid_for(nq, 256), 256, 0, st>>>(counts.p, nq, (unsigned long long)max_nn, counts2.p);
-        size_t tb = 0;
-        PCLB_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, tb, counts2.p, offsets2.p, (int)(nq + 1), st));
-        DevBuf<unsigned char> tmp;
-        tmp.alloc(tb, st);
-        PCLB_CUDA(cub::DeviceScan::ExclusiveSum(tmp.p, tb, counts2.p, offsets2.p, (int)(nq + 1), st));
-        PCLB_CUDA(cudaMemcpyAsync(&final_total, offsets2.p + nq, sizeof(final_total), cudaMemcpyDeviceToHost, st));
-        PCLB_CUDA(cudaStreamSynchronize(st));
-        keys_trunc.alloc(std::max<unsigned long long>(final_total, 1), st);
-        k_truncate_segments<<<(unsigned)nq, 64, 0, st>>>(keys_sorted.p, offsets.p, offsets2.p, nq, keys_trunc.p);
-        c.launches += 3;
-        d_final_keys = keys_trunc.p;
-        d_final_off = offsets2.p;
-      }
-    }
-    PCLB_CUDA(cudaMemcpyAsync(h_off.data(), d_final_off, (nq + 1) * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
-    PCLB_CUDA(cudaStreamSynchronize(st));
-    for (size_t i = 0; i <= nq; ++i)
-      out_offsets[i] = (int64_t)h_off[i];
-    int32_t* hi = static_cast<int32_t*>(malloc(std::max<size_t>(final_total, 1) * sizeof(int32_t)));
-    float* hd = static_cast<float*>(malloc(std::max<size_t>(final_total, 1) * sizeof(float)));
-    PCLB_REQUIRE(hi && hd, PCLB200_ERR_INTERNAL, "host allocation failed");
-    if (final_total > 0) {
-      DevBuf<int32_t> di;
-      DevBuf<float> dd;
-      di.alloc(final_total, st);
-      dd.alloc(final_total, st);
-      k_unpack_keys<<<grid_for(final_total, 256), 256, 0, st>>>(d_final_keys, final_total, di.p, dd.p);
-      ++c.launches;
-      PCLB_CUDA(cudaMemcpyAsync(hi, di.p, final_total * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
-      PCLB_CUDA(cudaMemcpyAsync(hd, dd.p, final_total * sizeof(float), cudaMemcpyDeviceToHost, st));
-      PCLB_CUDA(cudaStreamSynchronize(st));
-    }
-    *out_idx = hi;
-    *out_d2 = hd;
-    raise_if_device_error(c);
+    radius_impl(c, *h->idx, queries, nq, stride, radius, max_nn, out_offsets, [&](unsigned long long n) {
+      *total = (size_t)n;
+      if ((size_t)n > capacity)
+        return RadiusSinkBuffers{nullptr, nullptr};  // offsets and *total are valid; call again with larger buffers
+      return RadiusSinkBuffers{out_idx, out_d2};
+    });
   });
 }
 
@@ -828,6 +897,38 @@ int pclb200_fitness_score(pclb200_ctx* ctx, const pclb200_index* idx_tgt, const 
   });
 }
 
+int pclb200_validate_transformation(pclb200_ctx* ctx, const pclb200_index* idx_tgt, const void* src, size_t n,
+                                    size_t stride, const double T[16], int scalar_is_double, double max_range,
+                                    double* score)
+{
+  return guarded([&] {
+    PCLB_REQUIRE(ctx && idx_tgt && idx_tgt->idx && T && score, PCLB200_ERR_INVALID, "NULL argument");
+    std::lock_guard<std::recursive_mutex> lk(ctx->c.mu);
+    PCLB_CUDA(cudaSetDevice(ctx->c.device));
+    // transformation_validation_euclidean.hpp:62-75: T(0,0)*x + T(0,1)*y + T(0,2)*z + T(0,3) in Scalar, cast to float
+    *score = fitness_score(ctx->c, *idx_tgt->idx, src, n, stride, nullptr, 0, T, scalar_is_double, max_range,
+                           scalar_is_double ? 3 : 0);
+  });
+}
+
+int pclb200_inliers(pclb200_ctx* ctx, const pclb200_index* idx_tgt, const void* src, size_t n, size_t stride,
+                    const double T[16], float inlier_threshold, pclb200_corr* out, size_t* n_out)
+{
+  return guarded([&] {
+    PCLB_REQUIRE(ctx && idx_tgt && idx_tgt->idx && T && out && n_out, PCLB200_ERR_INVALID, "NULL argument");
+    std::lock_guard<std::recursive_mutex> lk(ctx->c.mu);
+    PCLB_CUDA(cudaSetDevice(ctx->c.device));
+    // sample_consensus_prerejective.hpp:318-338: transformPointCloud (float), then nn_dists[0] < max_range (STRICT, float)
+    const float max_range = inlier_threshold * inlier_threshold;
+    const float gate = std::nextafter(max_range, -std::numeric_limits<float>::infinity());  // d2 <= gate  <=>  d2 < max_range
+    double Tf[16];
+    for (int i = 0; i < 16; ++i)
+      Tf[i] = (double)(float)T[i];
+    *n_out = max_range > 0.f ? correspondences(ctx->c, *idx_tgt->idx, nullptr, src, n, stride, nullptr, 0, 1, 0.0, out, Tf, 1, &gate)
+                             : 0;
+  });
+}
+
 // ---- normals ----------------------------------------------------------------------------------------------------------------
 int pclb200_normals_knn(pclb200_ctx* ctx, const pclb200_index* h, const void* pts, size_t n, size_t stride,
                         const int32_t* indices, size_t n_idx, int is_dense, int k, const float viewpoint[3], float* out,
@@ -957,7 +1058,22 @@ int pclb200_voxelgrid(pclb200_ctx* ctx, const void* pts, size_t n, size_t stride
     std::lock_guard<std::recursive_mutex> lk(ctx->c.mu);
     PCLB_CUDA(cudaSetDevice(ctx->c.device));
     ProfScope ps(ctx->c, "voxelgrid");
-    *n_out = voxelgrid(ctx->c, pts, n, stride, indices, n_idx, is_dense, leaf, min_points_per_voxel, out_xyz1);
+    *n_out = voxelgrid(ctx->c, pts, n, stride, indices, n_idx, is_dense, leaf, min_points_per_voxel, out_xyz1, nullptr, 0,
+                       nullptr);
+  });
+}
+
+int pclb200_voxelgrid_normals(pclb200_ctx* ctx, const void* pts, size_t n, size_t stride, const void* normals,
+                              size_t stride_n, const int32_t* indices, size_t n_idx, int is_dense, const float leaf[3],
+                              unsigned min_points_per_voxel, float* out_xyz1, float* out_normal_curv, size_t* n_out)
+{
+  return guarded([&] {
+    PCLB_REQUIRE(ctx && leaf && out_xyz1 && n_out && normals && out_normal_curv, PCLB200_ERR_INVALID, "NULL argument");
+    std::lock_guard<std::recursive_mutex> lk(ctx->c.mu);
+    PCLB_CUDA(cudaSetDevice(ctx->c.device));
+    ProfScope ps(ctx->c, "voxelgrid");
+    *n_out = voxelgrid(ctx->c, pts, n, stride, indices, n_idx, is_dense, leaf, min_points_per_voxel, out_xyz1, normals,
+                       stride_n, out_normal_curv);
   });
 }
 
@@ -975,6 +1091,34 @@ int pclb200_comm_init(pclb200_ctx* ctx, int rank, int nranks, const void* unique
   return guarded([&] {
     PCLB_REQUIRE(ctx && (nranks == 1 || unique_id), PCLB200_ERR_INVALID, "NULL argument");
     comm_init(ctx->c, rank, nranks, unique_id);
+  });
+}
+
+int pclb200_comm_set_mode(pclb200_ctx* ctx, int mode)
+{
+  return guarded([&] {
+    PCLB_REQUIRE(ctx, PCLB200_ERR_INVALID, "NULL argument");
+    std::lock_guard<std::recursive_mutex> lk(ctx->c.mu);
+    comm_set_mode(ctx->c, mode);
+  });
+}
+
+int pclb200_comm_export(pclb200_ctx* ctx, void* out_handle_64_bytes)
+{
+  return guarded([&] {
+    PCLB_REQUIRE(ctx && out_handle_64_bytes, PCLB200_ERR_INVALID, "NULL argument");
+    std::lock_guard<std::recursive_mutex> lk(ctx->c.mu);
+    comm_export(ctx->c, out_handle_64_bytes);
+  });
+}
+
+int pclb200_comm_import(pclb200_ctx* ctx, int rank, int nranks, const void* handles)
+{
+  return guarded([&] {
+    PCLB_REQUIRE(ctx && handles, PCLB200_ERR_INVALID, "NULL argument");
+    std::lock_guard<std::recursive_mutex> lk(ctx->c.mu);
+    PCLB_CUDA(cudaSetDevice(ctx->c.device));
+    comm_import(ctx->c, rank, nranks, handles);
   });
 }
 

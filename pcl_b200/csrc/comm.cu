@@ -60,8 +60,9 @@ static NcclApi& nccl()
 enum { ncclUint8 = 1 };
 
 struct Comm {
-  ncclComm_t comm = nullptr;
+  ncclComm_t comm = nullptr;  // nullptr: peer-memory exchange bootstrapped by the caller (comm_import), no NCCL at all
   int rank = 0, nranks = 1;
+  int mode = PCLB200_REDUCE_FUSED;
   // fused peer-memory reduce (NVLink): one IPC-shared block per rank
   unsigned char* local_block = nullptr;
   void* peer_block[kMaxRanks] = {};
@@ -70,15 +71,14 @@ struct Comm {
   unsigned long long seq = 0;
 };
 
+void comm_destroy(Ctx& c);
+
 static size_t peer_block_bytes() { return kMaxRanks * sizeof(unsigned long long) + 2ull * kMaxRanks * kAccum * sizeof(double); }
 
 // Maps every rank's exchange block into this process (CUDA IPC over NVLink / NVSwitch).  Any failure leaves
 // peer_ok = false and the per-iteration reduce falls back to ncclAllReduce.
 static void setup_peer_reduce(Ctx& c, Comm& cm)
 {
-  const char* mode = getenv("PCLB200_REDUCE");  // "nccl" forces the library collective (A/B measurements)
-  if (mode && mode[0] == 'n')
-    return;
   if (cm.nranks > kMaxRanks || !nccl().AllGather)
     return;
   cudaStream_t st = c.stream;
@@ -201,12 +201,71 @@ void comm_destroy(Ctx& c)
   }
 }
 
+// ---- caller-bootstrapped peer exchange (no NCCL): export the local block's IPC handle, import everybody's ----------------
+// For deployments whose launcher already has a way to all-gather 64 bytes per rank (MPI, gloo, a file), and for
+// ranks that share one GPU (NCCL refuses duplicate devices; CUDA IPC does not).
+static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+
+void comm_export(Ctx& c, void* out64)
+{
+  comm_destroy(c);
+  Comm* cm = new Comm();
+  c.comm = cm;
+  PCLB_CUDA(cudaSetDevice(c.device));
+  PCLB_CUDA(cudaMalloc(reinterpret_cast<void**>(&cm->local_block), peer_block_bytes()));
+  PCLB_CUDA(cudaMemsetAsync(cm->local_block, 0, peer_block_bytes(), c.stream));
+  PCLB_CUDA(cudaStreamSynchronize(c.stream));
+  cudaIpcMemHandle_t h;
+  PCLB_CUDA(cudaIpcGetMemHandle(&h, cm->local_block));
+  memcpy(out64, &h, sizeof(h));
+}
+
+void comm_import(Ctx& c, int rank, int nranks, const void* handles)
+{
+  PCLB_REQUIRE(c.comm && c.comm->local_block && !c.comm->comm, PCLB200_ERR_INVALID, "comm_import: call comm_export first");
+  PCLB_REQUIRE(nranks >= 2 && nranks <= kMaxRanks && rank >= 0 && rank < nranks, PCLB200_ERR_INVALID, "bad rank / nranks");
+  Comm& cm = *c.comm;
+  cm.rank = rank;
+  cm.nranks = nranks;
+  const cudaIpcMemHandle_t* all = static_cast<const cudaIpcMemHandle_t*>(handles);
+  for (int p = 0; p < nranks; ++p) {
+    if (p == rank) {
+      cm.peer_block[p] = cm.local_block;
+      continue;
+    }
+    cudaError_t e = cudaIpcOpenMemHandle(&cm.peer_block[p], all[p], cudaIpcMemLazyEnablePeerAccess);
+    if (e != cudaSuccess) {
+      cudaGetLastError();
+      cm.peer_block[p] = nullptr;
+      throw Error(PCLB200_ERR_CUDA, std::string("comm_import: cudaIpcOpenMemHandle failed for rank ") + std::to_string(p) +
+                                        ": " + cudaGetErrorString(e));
+    }
+  }
+  cm.view.rank = rank;
+  cm.view.nranks = nranks;
+  for (int p = 0; p < nranks; ++p) {
+    unsigned char* b = static_cast<unsigned char*>(cm.peer_block[p]);
+    cm.view.flags[p] = reinterpret_cast<unsigned long long*>(b);
+    cm.view.slots[p] = reinterpret_cast<double*>(b + kMaxRanks * sizeof(unsigned long long));
+  }
+  cm.peer_ok = true;
+}
+
+void comm_set_mode(Ctx& c, int mode)
+{
+  PCLB_REQUIRE(mode == PCLB200_REDUCE_FUSED || mode == PCLB200_REDUCE_NCCL, PCLB200_ERR_INVALID, "unknown reduce mode");
+  PCLB_REQUIRE(c.comm != nullptr, PCLB200_ERR_INVALID, "no communicator");
+  PCLB_REQUIRE(mode == PCLB200_REDUCE_FUSED || c.comm->comm != nullptr, PCLB200_ERR_INVALID,
+               "the NCCL reduce needs a communicator made by pclb200_comm_init");
+  c.comm->mode = mode;
+}
+
 bool comm_active(const Ctx& c) { return c.comm && c.comm->nranks > 1; }
 
 // view + next sequence number for a fused in-kernel exchange; returns false when the NCCL path must be used
 bool comm_peer_view(Ctx& c, PeerView* view, unsigned long long* seq)
 {
-  if (!comm_active(c) || !c.comm->peer_ok)
+  if (!comm_active(c) || !c.comm->peer_ok || c.comm->mode != PCLB200_REDUCE_FUSED)
     return false;
   *view = c.comm->view;
   *seq = ++c.comm->seq;
@@ -217,6 +276,7 @@ void comm_allreduce_sum(Ctx& c, double* d_buf, int count)
 {
   if (!comm_active(c))
     return;
+  PCLB_REQUIRE(c.comm->comm != nullptr, PCLB200_ERR_NCCL, "no NCCL communicator for the library all-reduce");
   PCLB_NCCL(nccl().AllReduce(d_buf, d_buf, (size_t)count, ncclFloat64, ncclSum, c.comm->comm, c.stream));
   ++c.launches;
 }

@@ -45,7 +45,8 @@ struct Pending {
   float f[12];   // rows 0..2 of T_k, already rounded like the reference (cast<float>)
   double d[12];  // same rows in double (Transformer<double> path)
   int apply;     // 0 = identity / nothing to apply
-  int mode;      // 0: icp.hpp:49-111 order, 1: transforms.hpp SSE float order, 2: transforms.hpp double order
+  int mode;      // 0: icp.hpp:49-111 order, 1: transforms.hpp SSE float order, 2: transforms.hpp double order,
+                 // 3: transformation_validation_euclidean.hpp:62-75 with a double matrix (left-to-right, cast at the end)
 };
 
 struct SolveOut {
@@ -68,6 +69,12 @@ __device__ __forceinline__ void apply_pending(const Pending& P, float& x, float&
     x = P.f[0] * px + (P.f[1] * py + (P.f[2] * pz + P.f[3]));
     y = P.f[4] * px + (P.f[5] * py + (P.f[6] * pz + P.f[7]));
     z = P.f[8] * px + (P.f[9] * py + (P.f[10] * pz + P.f[11]));
+  }
+  else if (P.mode == 3) {
+    const double dx = px, dy = py, dz = pz;
+    x = (float)(((P.d[0] * dx + P.d[1] * dy) + P.d[2] * dz) + P.d[3]);
+    y = (float)(((P.d[4] * dx + P.d[5] * dy) + P.d[6] * dz) + P.d[7]);
+    z = (float)(((P.d[8] * dx + P.d[9] * dy) + P.d[10] * dz) + P.d[11]);
   }
   else {
     const double dx = px, dy = py, dz = pz;
@@ -261,30 +268,202 @@ __device__ __forceinline__ bool still_nearest(float prev_d2, float prev_lb, floa
   return lhs < rhs && *new_lb > 0.f;
 }
 
+// ---- normal equations on the fp64 tensor cores ------------------------------------------------------------------------
+// The 3x3 / 6x6 normal equations of one ICP iteration are sums of outer products over the correspondences, i.e. V^T V
+// with one row of <= 8 components per pair — a dense fp64 contraction.  A warp stages the rows of its 32 pairs in shared
+// memory (two 32 x 8 float tiles: every component is a float, or a float minus the fp64 accumulation origin) and issues
+// mma.sync.m8n8k4.f64: lane (g = lane / 4, t = lane % 4) feeds component g of pair 4 * step + t as both the A (row g,
+// column t) and the B (row t, column g) fragment, and holds C[g][2t], C[g][2t + 1].  The whole accumulator tile lives
+// in TWO fp64 registers per lane instead of 29 per thread, so the accumulation can ride in the search kernel.
+//   SVD  : tile 0 = sum w u^T, w = (q - o, 1, d2), u = (p - o, 1)   -> sum q p^T, sum q, sum p, n, sum d2
+//   LLS  : tile 0 = sum v v^T, v = (A, B, C, nx, ny, nz, D)         -> A^T A without its normal-normal block, A^T b
+//          tile 1 column 0 = sum w, w = (nx nx, nx ny, nx nz, ny ny, ny nz, nz nz as FLOAT products — the reference
+//          adds float products there, point_to_plane_lls.hpp:228-233 —, d2, 1)
+// Products are exact fp64 products of the widened floats (the reference multiplies the same widened values), sums are
+// fp64 in a fixed order: bitwise reproducible, and within fp64 round-off of the oracle's sequential sums.
+__device__ __forceinline__ void dmma884(double& c0, double& c1, double a, double b)
+{
+  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+               : "+d"(c0), "+d"(c1)
+               : "d"(a), "d"(b));
+}
+
+constexpr int kEstNone = -1;
+
+// tiles: 2 x 32 x 8 floats of this warp's shared memory.  Must be called by all 32 lanes (converged).
+template <int EST>
+__device__ __forceinline__ void accumulate_pairs_dmma(const IterArgs& a, float* __restrict__ tiles, int lane, const Match& m,
+                                                      const float4& p, double& c1a, double& c1b, double& c2a, double& c2b)
+{
+  float* tA = tiles;
+  float* tB = tiles + 32 * 8;
+  float ra[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f}, rb[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  if (match_accepted(m)) {
+    const float4 q = ldg4(a.pts + m.pos);
+    if (EST == PCLB200_EST_SVD) {
+      ra[0] = q.x; ra[1] = q.y; ra[2] = q.z; ra[3] = 1.f; ra[4] = m.d2;
+      rb[0] = p.x; rb[1] = p.y; rb[2] = p.z; rb[3] = 1.f;
+    }
+    else {
+      rb[6] = m.d2;
+      rb[7] = 1.f;
+      const float4 nn = ldg4(a.tgt_normals + m.pos);
+      if (isfinite(nn.x) && isfinite(nn.y) && isfinite(nn.z)) {  // point_to_plane_lls.hpp:182-190
+        const float sx = p.x, sy = p.y, sz = p.z, dx = q.x, dy = q.y, dz = q.z, nx = nn.x, ny = nn.y, nz = nn.z;
+        // float expressions, widened to double when they enter the products, exactly as :202-204 and :235
+        // (no fma: -fmad=false)
+        ra[0] = nz * sy - ny * sz;
+        ra[1] = nx * sz - nz * sx;
+        ra[2] = ny * sx - nx * sy;
+        ra[3] = nx; ra[4] = ny; ra[5] = nz;
+        ra[6] = nx * dx + ny * dy + nz * dz - nx * sx - ny * sy - nz * sz;
+        rb[0] = nx * nx; rb[1] = nx * ny; rb[2] = nx * nz;
+        rb[3] = ny * ny; rb[4] = ny * nz; rb[5] = nz * nz;
+      }
+    }
+  }
+  *reinterpret_cast<float4*>(tA + lane * 8) = make_float4(ra[0], ra[1], ra[2], ra[3]);
+  *reinterpret_cast<float4*>(tA + lane * 8 + 4) = make_float4(ra[4], ra[5], ra[6], ra[7]);
+  *reinterpret_cast<float4*>(tB + lane * 8) = make_float4(rb[0], rb[1], rb[2], rb[3]);
+  *reinterpret_cast<float4*>(tB + lane * 8 + 4) = make_float4(rb[4], rb[5], rb[6], rb[7]);
+  __syncwarp();
+  const int g = lane >> 2, t = lane & 3;
+  const double og = g == 0 ? (double)a.ox : (g == 1 ? (double)a.oy : (double)a.oz);
+  const double e0 = g == 0 ? 1.0 : 0.0;
+#pragma unroll
+  for (int st = 0; st < 8; ++st) {
+    const int row = (4 * st + t) * 8;
+    double va = (double)tA[row + g];
+    double vb = (double)tB[row + g];
+    if (EST == PCLB200_EST_SVD) {
+      if (g < 3) {  // coordinates enter shifted by the accumulation origin, in fp64; pairs that are not accepted stay zero
+        const bool on = tA[row + 3] != 0.f;
+        va = on ? va - og : 0.0;
+        vb = on ? vb - og : 0.0;
+      }
+      dmma884(c1a, c1b, va, vb);     // C1[i][j] += w_i u_j
+    }
+    else {
+      dmma884(c1a, c1b, va, va);     // C1[i][j] += v_i v_j
+      dmma884(c2a, c2b, vb, e0);     // C2[i][0] += w_i
+    }
+  }
+  __syncwarp();
+}
+
+// where accumulator slot k of the kAccum layout (top of this file) sits in the two 8x8 tiles: tile * 64 + row * 8 + col
+__device__ __forceinline__ int dmma_accum_source(int est, int k)
+{
+  if (est == PCLB200_EST_SVD) {
+    if (k == 0) return 3 * 8 + 3;
+    if (k == 1) return 4 * 8 + 3;
+    if (k < 5) return 3 * 8 + (k - 2);
+    if (k < 8) return (k - 5) * 8 + 3;
+    if (k < 17) return ((k - 8) / 3) * 8 + (k - 8) % 3;
+    return -1;
+  }
+  if (k == 0) return 64 + 7 * 8;
+  if (k == 1) return 64 + 6 * 8;
+  if (k < 23) {
+    int t = k - 2, r = 0;
+    while (t >= 6 - r) {
+      t -= 6 - r;
+      ++r;
+    }
+    const int c = r + t;
+    if (r >= 3)
+      return 64 + ((r == 3 ? c - 3 : (r == 4 ? 3 + (c - 4) : 5))) * 8;
+    return r * 8 + c;
+  }
+  if (k < 29) return (k - 23) * 8 + 6;
+  return -1;
+}
+
+// warp tiles -> block (fixed order) -> grid (fixed order, last block) -> the kAccum layout k_solve reads -> peers.
+// Must be called by every thread of every block; blockDim.x = NWARPS * 32 >= 128.
+template <int EST, int NWARPS>
+__device__ __forceinline__ void fold_tiles_and_publish(const IterArgs& a, double c1a, double c1b, double c2a, double c2b)
+{
+  __shared__ double s_tiles[NWARPS][128];
+  __shared__ double s_fin[128];
+  __shared__ bool is_last;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int g = lane >> 2, t = lane & 3;
+  s_tiles[warp][g * 8 + 2 * t] = c1a;
+  s_tiles[warp][g * 8 + 2 * t + 1] = c1b;
+  s_tiles[warp][64 + g * 8 + 2 * t] = c2a;
+  s_tiles[warp][64 + g * 8 + 2 * t + 1] = c2b;
+  __syncthreads();
+  if (threadIdx.x < 128) {
+    double vsum = 0.0;
+    for (int w = 0; w < NWARPS; ++w)
+      vsum += s_tiles[w][threadIdx.x];
+    a.partials2[(size_t)blockIdx.x * 128 + threadIdx.x] = vsum;
+  }
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const unsigned tk = atomicAdd(a.counter, 1u);
+    is_last = (tk == gridDim.x - 1);
+  }
+  __syncthreads();
+  if (is_last) {
+    __threadfence();
+    if (threadIdx.x < 128) {
+      double vsum = 0.0;
+      for (unsigned b = 0; b < gridDim.x; ++b)  // fixed order => bitwise reproducible
+        vsum += __ldcg(&a.partials2[(size_t)b * 128 + threadIdx.x]);
+      s_fin[threadIdx.x] = vsum;
+    }
+    __syncthreads();
+    if (threadIdx.x < kAccum) {
+      const int src = dmma_accum_source(EST, threadIdx.x);
+      a.accum[threadIdx.x] = src >= 0 ? s_fin[src] : 0.0;
+    }
+    if (threadIdx.x == 0)
+      *a.counter = 0;
+    peer_exchange(a);
+  }
+}
+
 // Search kernel, one query per thread: apply the pending T_k in place (reference fp32 operation order, icp.hpp:49-111)
 // -> [TRACK: skip test] -> exact 1-NN started at the candidate ball (traverse.cuh: nearest1 — seed = previous match,
 // cell-table start, ordinary exact walk below) -> gate -> optional reciprocal back-search.
 // lbs (TRACK only): per query, a lower bound on the DISTANCE to every target point other than the match; 0 = unknown.
-template <bool RECIP, bool TRACK>
-__global__ void __launch_bounds__(256)
+#ifndef PCLB_SEARCH_MINBLOCKS
+#define PCLB_SEARCH_MINBLOCKS 1
+#endif
+template <int EST, bool RECIP, bool TRACK>
+__global__ void __launch_bounds__(256, PCLB_SEARCH_MINBLOCKS)
 k_search(const IterArgs a, Match* __restrict__ match, float* __restrict__ lbs)
 {
   __shared__ Pending sP;
+  __shared__ __align__(16) float s_stage[EST != kEstNone ? 8 : 1][EST != kEstNone ? 2 * 32 * 8 : 4];  // DMMA staging tiles
   if (threadIdx.x == 0)
     sP = *a.pending;
   __syncthreads();
   const TreeView T{a.nodes, a.pts, a.root, a.cells};
+  const int lane = threadIdx.x & 31;
   bool overflow = false;
   unsigned skipped = 0;
   WalkStats ws{};
-  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < a.n; i += (size_t)gridDim.x * blockDim.x) {
-    float4 p = a.cur[i];
-    const Match prev = match[i];
+  double c1a = 0.0, c1b = 0.0, c2a = 0.0, c2b = 0.0;  // fragments of the two accumulator tiles (EST >= 0)
+  // warp-uniform trip count (the epilogue is warp-synchronous): a warp takes 32 consecutive queries per round
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  for (size_t base = blockIdx.x * (size_t)blockDim.x + (threadIdx.x & ~31); base < a.n; base += stride) {
+    const size_t i = base + lane;
+    const bool in_range = i < a.n;
+    float4 p = in_range ? a.cur[i] : make_float4(0.f, 0.f, 0.f, 0.f);
+    Match prev;
+    prev.pos = -1;
+    prev.d2 = 0.f;
+    if (in_range)
+      prev = match[i];
     Match m;
     m.pos = -1;
     m.d2 = 0.f;
     float lb_out = 0.f;
-    if (isfinite(p.x) && isfinite(p.y) && isfinite(p.z)) {
+    if (in_range && isfinite(p.x) && isfinite(p.y) && isfinite(p.z)) {
       // non-finite points: transformCloud leaves them untouched (icp.hpp:90-91), no correspondence (:173-174)
       float delta = 0.f;
       if (sP.apply) {
@@ -331,9 +510,15 @@ k_search(const IterArgs a, Match* __restrict__ match, float* __restrict__ lbs)
         }
       }
     }
-    match[i] = m;
-    if (TRACK)
-      lbs[i] = lb_out;
+    if (in_range) {
+      match[i] = m;
+      if (TRACK)
+        lbs[i] = lb_out;
+    }
+    if (EST != kEstNone) {
+      __syncwarp();
+      accumulate_pairs_dmma<EST>(a, s_stage[threadIdx.x >> 5], lane, m, p, c1a, c1b, c2a, c2b);
+    }
   }
 #ifdef PCLB_STATS
   for (int k = 0; k < 8; ++k)
@@ -342,11 +527,13 @@ k_search(const IterArgs a, Match* __restrict__ match, float* __restrict__ lbs)
   if (TRACK) {
     for (int o = 16; o > 0; o >>= 1)
       skipped += __shfl_xor_sync(0xffffffffu, skipped, o);
-    if ((threadIdx.x & 31) == 0 && skipped)
+    if (lane == 0 && skipped)
       atomicAdd(a.skip_count, (unsigned long long)skipped);
   }
   if (overflow)
     atomicExch(a.d_error, 1);
+  if (EST != kEstNone)
+    fold_tiles_and_publish<EST, 8>(a, c1a, c1b, c2a, c2b);
 }
 
 // =============================================================================================================
@@ -370,7 +557,6 @@ k_search(const IterArgs a, Match* __restrict__ match, float* __restrict__ lbs)
 // Match array is still written (next iteration's seeds, getCorrespondences) but never read back by an accumulate pass.
 constexpr int kWqCells = 192, kWqLeaf = 128, kWqNode = 192;
 constexpr int kWqWarps = 4;
-constexpr int kEstNone = -1;
 constexpr unsigned kWqNoPos = 0x7fffffffu;
 
 struct __align__(16) WarpWork {
@@ -381,7 +567,7 @@ struct __align__(16) WarpWork {
   int skipa[32], skipb[32];               // leaves already scanned by the owner (seed leaves)
   unsigned m2[32], pruned[32];            // TRACK: second-smallest evaluated d2 / smallest bound of anything skipped
 };
-static_assert(sizeof(uint2) * (kWqCells + kWqLeaf + kWqNode) >= 2 * 32 * 8 * sizeof(double), "staging tiles must fit");
+static_assert(sizeof(uint2) * (kWqCells + kWqLeaf + kWqNode) >= 2 * 32 * 8 * sizeof(float), "staging tiles must fit");
 
 __device__ __forceinline__ unsigned wq_pack(float bound, int owner) { return (__float_as_uint(bound) & ~31u) | (unsigned)owner; }
 __device__ __forceinline__ float wq_bound(unsigned bo) { return __uint_as_float(bo & ~31u); }  // rounded DOWN: still a lower bound
@@ -471,43 +657,6 @@ struct WqShared {
   }
   __device__ __forceinline__ void leaf(const float4*, int first_pos) { wq_scan_leaf<TRACK>(W, o, pts, first_pos / kLeafSize); }
 };
-
-__device__ __forceinline__ void dmma884(double& c0, double& c1, double a, double b)
-{
-  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
-               : "+d"(c0), "+d"(c1)
-               : "d"(a), "d"(b));
-}
-
-// where accumulator slot k of the kAccum layout (top of this file) sits in the two 8x8 tiles: tile * 64 + row * 8 + col
-__device__ __forceinline__ int wq_accum_source(int est, int k)
-{
-  if (est == PCLB200_EST_SVD) {
-    // tile 0 = sum w u^T, w = (q - o, 1, d2), u = (p - o, 1)
-    if (k == 0) return 3 * 8 + 3;
-    if (k == 1) return 4 * 8 + 3;
-    if (k < 5) return 3 * 8 + (k - 2);
-    if (k < 8) return (k - 5) * 8 + 3;
-    if (k < 17) return ((k - 8) / 3) * 8 + (k - 8) % 3;
-    return -1;
-  }
-  // tile 0 = sum v v^T, v = (A, B, C, nx, ny, nz, D, 0); tile 1 column 0 = sum w, w = (nxnx .. nznz as FLOAT products, d2, 1)
-  if (k == 0) return 64 + 7 * 8;
-  if (k == 1) return 64 + 6 * 8;
-  if (k < 23) {
-    int t = k - 2, r = 0;
-    while (t >= 6 - r) {
-      t -= 6 - r;
-      ++r;
-    }
-    const int c = r + t;
-    if (r >= 3)
-      return 64 + ((r == 3 ? c - 3 : (r == 4 ? 3 + (c - 4) : 5))) * 8;
-    return r * 8 + c;
-  }
-  if (k < 29) return (k - 23) * 8 + 6;
-  return -1;
-}
 
 template <int EST, bool RECIP, bool TRACK>
 __global__ void __launch_bounds__(kWqWarps * 32)
@@ -861,56 +1010,7 @@ k_icp_wq(const IterArgs a, Match* __restrict__ match, float* __restrict__ lbs)
     // ================= epilogue: normal equations on the fp64 tensor cores ========================================
     if (EST != kEstNone) {
       __syncwarp();  // the queues are dead: their memory becomes the staging tiles
-      double* tA = reinterpret_cast<double*>(W.q);
-      double* tB = tA + 32 * 8;
-      double ra[8] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0}, rb[8] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
-      if (match_accepted(m)) {
-        const float4 q = ldg4(a.pts + m.pos);
-        if (EST == PCLB200_EST_SVD) {
-          // w = (q - o, 1, d2), u = (p - o, 1): sum w u^T holds sum q p^T, sum q, sum p, n and sum d2
-          ra[0] = (double)q.x - (double)a.ox; ra[1] = (double)q.y - (double)a.oy; ra[2] = (double)q.z - (double)a.oz;
-          ra[3] = 1.0;
-          ra[4] = (double)m.d2;
-          rb[0] = (double)p.x - (double)a.ox; rb[1] = (double)p.y - (double)a.oy; rb[2] = (double)p.z - (double)a.oz;
-          rb[3] = 1.0;
-        }
-        else {
-          rb[6] = (double)m.d2;
-          rb[7] = 1.0;
-          const float4 nn = ldg4(a.tgt_normals + m.pos);
-          if (isfinite(nn.x) && isfinite(nn.y) && isfinite(nn.z)) {  // point_to_plane_lls.hpp:182-190
-            const float sx = p.x, sy = p.y, sz = p.z, dx = q.x, dy = q.y, dz = q.z, nx = nn.x, ny = nn.y, nz = nn.z;
-            // float expressions widened to double, exactly as :202-204 and :235 (no fma: -fmad=false)
-            ra[0] = (double)(nz * sy - ny * sz);
-            ra[1] = (double)(nx * sz - nz * sx);
-            ra[2] = (double)(ny * sx - nx * sy);
-            ra[3] = (double)nx; ra[4] = (double)ny; ra[5] = (double)nz;
-            ra[6] = (double)(nx * dx + ny * dy + nz * dz - nx * sx - ny * sy - nz * sz);
-            rb[0] = (double)(nx * nx); rb[1] = (double)(nx * ny); rb[2] = (double)(nx * nz);  // FLOAT products (:228-233)
-            rb[3] = (double)(ny * ny); rb[4] = (double)(ny * nz); rb[5] = (double)(nz * nz);
-          }
-        }
-      }
-#pragma unroll
-      for (int k = 0; k < 8; ++k) {
-        tA[lane * 8 + k] = ra[k];
-        tB[lane * 8 + k] = rb[k];
-      }
-      __syncwarp();
-      const int g = lane >> 2, t = lane & 3;
-      const double e0 = g == 0 ? 1.0 : 0.0;
-#pragma unroll
-      for (int st = 0; st < 8; ++st) {
-        const double va = tA[(4 * st + t) * 8 + g];
-        const double vb = tB[(4 * st + t) * 8 + g];
-        if (EST == PCLB200_EST_SVD)
-          dmma884(c1a, c1b, va, vb);     // C1[i][j] += w_i u_j
-        else {
-          dmma884(c1a, c1b, va, va);     // C1[i][j] += v_i v_j
-          dmma884(c2a, c2b, vb, e0);     // C2[i][0] += w_i
-        }
-      }
-      __syncwarp();
+      accumulate_pairs_dmma<EST>(a, reinterpret_cast<float*>(W.q), lane, m, p, c1a, c1b, c2a, c2b);
     }
   }
   if (TRACK) {
@@ -921,46 +1021,8 @@ k_icp_wq(const IterArgs a, Match* __restrict__ match, float* __restrict__ lbs)
   }
   if (overflow)
     atomicExch(a.d_error, 1);
-  if (EST != kEstNone) {
-    // warp tiles -> block (fixed order) -> grid (fixed order, last block) -> the kAccum layout k_solve reads
-    __shared__ double s_tiles[kWqWarps][128];
-    __shared__ double s_fin[128];
-    __shared__ bool is_last;
-    const int g = lane >> 2, t = lane & 3;
-    s_tiles[warp][g * 8 + 2 * t] = c1a;
-    s_tiles[warp][g * 8 + 2 * t + 1] = c1b;
-    s_tiles[warp][64 + g * 8 + 2 * t] = c2a;
-    s_tiles[warp][64 + g * 8 + 2 * t + 1] = c2b;
-    __syncthreads();
-    {
-      double vsum = 0.0;
-      for (int w = 0; w < kWqWarps; ++w)
-        vsum += s_tiles[w][threadIdx.x];
-      a.partials2[(size_t)blockIdx.x * 128 + threadIdx.x] = vsum;
-    }
-    __threadfence();
-    __syncthreads();
-    if (threadIdx.x == 0) {
-      const unsigned tk = atomicAdd(a.counter, 1u);
-      is_last = (tk == gridDim.x - 1);
-    }
-    __syncthreads();
-    if (is_last) {
-      __threadfence();
-      double vsum = 0.0;
-      for (unsigned b = 0; b < gridDim.x; ++b)  // fixed order => bitwise reproducible
-        vsum += __ldcg(&a.partials2[(size_t)b * 128 + threadIdx.x]);
-      s_fin[threadIdx.x] = vsum;
-      __syncthreads();
-      if (threadIdx.x < kAccum) {
-        const int src = wq_accum_source(EST, threadIdx.x);
-        a.accum[threadIdx.x] = src >= 0 ? s_fin[src] : 0.0;
-      }
-      if (threadIdx.x == 0)
-        *a.counter = 0;
-      peer_exchange(a);
-    }
-  }
+  if (EST != kEstNone)
+    fold_tiles_and_publish<EST, kWqWarps>(a, c1a, c1b, c2a, c2b);
 }
 
 // Accumulation kernel: one streaming pass over (source point, match) pairs; fp64 sums, fixed reduction order.
@@ -1591,7 +1653,7 @@ Icp* icp_create(Ctx& c, const pclb200_icp_params& P)
   s->solve_out.alloc(1, c.stream);
   s->skip_count.alloc(1, c.stream);
   PCLB_CUDA(cudaMemsetAsync(s->skip_count.p, 0, sizeof(unsigned long long), c.stream));
-  s->red.init(c, (unsigned)c.sm_count * 8);
+  s->red.init(c, (unsigned)c.sm_count * 16);
   set_identity(s->final_T);
   set_identity(s->last_T);
   upload_pending(*s, s->final_T, 0);
@@ -2092,28 +2154,36 @@ void icp_iterate(Icp& s, int max_steps, pclb200_icp_stats* stats)
       // (rejectors) or the estimator needs what the epilogue does not carry (source normals)
       fused_accum = !s.P.use_reciprocal && s.rejectors.empty() &&
                     (s.P.estimator == PCLB200_EST_SVD || s.P.estimator == PCLB200_EST_POINT_TO_PLANE_LLS);
-      const unsigned wgrid = persistent_grid(c, s.n_q, kWqWarps * 32, 8);
+#ifdef PCLB_SEARCH_WQ
+      const unsigned wgrid = std::min(persistent_grid(c, s.n_q, kWqWarps * 32, 8), s.red.max_blocks);
       const int blk = kWqWarps * 32;
+#define PCLB_SEARCH_KERNEL k_icp_wq
+#else
+      const unsigned wgrid = std::min(persistent_grid(c, s.n_q, 256, 16), s.red.max_blocks);
+      const int blk = 256;
+#define PCLB_SEARCH_KERNEL k_search
+#endif
       if (s.P.use_reciprocal)
-        k_icp_wq<kEstNone, true, false><<<wgrid, blk, 0, st>>>(a, s.match.p, s.lb.p);
+        PCLB_SEARCH_KERNEL<kEstNone, true, false><<<wgrid, blk, 0, st>>>(a, s.match.p, s.lb.p);
       else if (!fused_accum) {
         if (track)
-          k_icp_wq<kEstNone, false, true><<<wgrid, blk, 0, st>>>(a, s.match.p, s.lb.p);
+          PCLB_SEARCH_KERNEL<kEstNone, false, true><<<wgrid, blk, 0, st>>>(a, s.match.p, s.lb.p);
         else
-          k_icp_wq<kEstNone, false, false><<<wgrid, blk, 0, st>>>(a, s.match.p, s.lb.p);
+          PCLB_SEARCH_KERNEL<kEstNone, false, false><<<wgrid, blk, 0, st>>>(a, s.match.p, s.lb.p);
       }
       else if (s.P.estimator == PCLB200_EST_SVD) {
         if (track)
-          k_icp_wq<PCLB200_EST_SVD, false, true><<<wgrid, blk, 0, st>>>(a, s.match.p, s.lb.p);
+          PCLB_SEARCH_KERNEL<PCLB200_EST_SVD, false, true><<<wgrid, blk, 0, st>>>(a, s.match.p, s.lb.p);
         else
-          k_icp_wq<PCLB200_EST_SVD, false, false><<<wgrid, blk, 0, st>>>(a, s.match.p, s.lb.p);
+          PCLB_SEARCH_KERNEL<PCLB200_EST_SVD, false, false><<<wgrid, blk, 0, st>>>(a, s.match.p, s.lb.p);
       }
       else {
         if (track)
-          k_icp_wq<PCLB200_EST_POINT_TO_PLANE_LLS, false, true><<<wgrid, blk, 0, st>>>(a, s.match.p, s.lb.p);
+          PCLB_SEARCH_KERNEL<PCLB200_EST_POINT_TO_PLANE_LLS, false, true><<<wgrid, blk, 0, st>>>(a, s.match.p, s.lb.p);
         else
-          k_icp_wq<PCLB200_EST_POINT_TO_PLANE_LLS, false, false><<<wgrid, blk, 0, st>>>(a, s.match.p, s.lb.p);
+          PCLB_SEARCH_KERNEL<PCLB200_EST_POINT_TO_PLANE_LLS, false, false><<<wgrid, blk, 0, st>>>(a, s.match.p, s.lb.p);
       }
+#undef PCLB_SEARCH_KERNEL
       ++c.launches;
     }
     if (!s.rejectors.empty()) {
@@ -2431,7 +2501,8 @@ void estimate_pairs(Ctx& c, int est, const void* src, size_t stride_s, const voi
 
 // ---- correspondences (materialised) -----------------------------------------------------------------------------
 size_t correspondences(Ctx& c, const Index& tgt, const Index* src_index, const void* src, size_t n, size_t stride,
-                       const int32_t* indices, size_t n_idx, int is_dense, double max_dist, pclb200_corr* out)
+                       const int32_t* indices, size_t n_idx, int is_dense, double max_dist, pclb200_corr* out,
+                       const double* pre_T, int pre_mode, const float* gate_override)
 {
   (void)is_dense;  // non-finite source points never produce a correspondence on either setting
   cudaStream_t st = c.stream;
@@ -2441,6 +2512,21 @@ size_t correspondences(Ctx& c, const Index& tgt, const Index* src_index, const v
   DevBuf<float4> dense;
   dense.alloc(nq, st);
   load_xyz_as_float4(c, src, n, stride, indices, n_idx, dense.p, st);
+  DevBuf<Pending> pend;
+  if (pre_T) {  // the caller's cloud is searched after a rigid transform (consumers that validate a pose)
+    pend.alloc(1, st);
+    Pending h;
+    for (int i = 0; i < 12; ++i) {
+      h.f[i] = (float)pre_T[i];
+      h.d[i] = pre_T[i];
+    }
+    h.apply = 1;
+    h.mode = pre_mode;
+    PCLB_CUDA(cudaMemcpyAsync(pend.p, &h, sizeof(h), cudaMemcpyHostToDevice, st));
+    PCLB_CUDA(cudaStreamSynchronize(st));  // h is a stack object
+    k_apply_pending<<<persistent_grid(c, nq, 256, 8), 256, 0, st>>>(dense.p, nq, pend.p, nullptr);
+    ++c.launches;
+  }
   DevBuf<int32_t> d_ind;
   if (indices) {
     d_ind.alloc(n_idx, st);
@@ -2454,7 +2540,7 @@ size_t correspondences(Ctx& c, const Index& tgt, const Index* src_index, const v
   by_slot.alloc(nq, st);
   compact.alloc(nq, st);
   d_count.alloc(1, st);
-  const float gate = gate_from_max_dist(max_dist);
+  const float gate = gate_override ? *gate_override : gate_from_max_dist(max_dist);
   if (src_index)
     k_corr<true><<<grid_for(nq, 128), 128, 0, st>>>(tree_view(tgt), qb.q.p, nq, gate,
                                                    src_index->nodes.p, src_index->pts.p, src_index->root, d_ind.p,
@@ -2482,7 +2568,7 @@ size_t correspondences(Ctx& c, const Index& tgt, const Index* src_index, const v
 
 // ---- fitness score ------------------------------------------------------------------------------------------------
 double fitness_score(Ctx& c, const Index& tgt, const void* src, size_t n, size_t stride, const int32_t* indices,
-                     size_t n_idx, const double* T, int scalar_is_double, double max_range)
+                     size_t n_idx, const double* T, int scalar_is_double, double max_range, int mode_override)
 {
   cudaStream_t st = c.stream;
   // registration.hpp:141-144: the index subset is used only when it is a strict subset
@@ -2501,7 +2587,7 @@ double fitness_score(Ctx& c, const Index& tgt, const void* src, size_t n, size_t
     h.d[i] = scalar_is_double ? T[i] : (double)(float)T[i];
   }
   h.apply = 1;
-  h.mode = scalar_is_double ? 2 : 1;  // pcl::transformPointCloud
+  h.mode = mode_override >= 0 ? mode_override : (scalar_is_double ? 2 : 1);  // default: pcl::transformPointCloud
   PCLB_CUDA(cudaMemcpyAsync(pend.p, &h, sizeof(h), cudaMemcpyHostToDevice, st));
   k_apply_pending<<<persistent_grid(c, nq, 256, 8), 256, 0, st>>>(dense.p, nq, pend.p, nullptr);
   ++c.launches;

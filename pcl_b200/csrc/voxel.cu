@@ -144,12 +144,51 @@ __global__ void k_vg_centroids(const float4* __restrict__ p, const int32_t* __re
   out[m] = make_float4(__fdiv_rn(cx, fn), __fdiv_rn(cy, fn), __fdiv_rn(cz, fn), 1.0f);
 }
 
+// downsample_all_data_ (voxel_grid.hpp:796-806, CentroidPoint): normals are summed as 4-vectors and normalised
+// (AccumulatorNormal, accumulators.hpp:86-116), the curvature is averaged (AccumulatorCurvature, :118-133).
+// nc: two float4 per selected point {nx,ny,nz,n4} {curvature,-,-,-}; out: two float4 per voxel, same layout
+__global__ void k_vg_load_nc(const unsigned char* __restrict__ src, size_t stride, const int32_t* __restrict__ subset,
+                             size_t n, float4* __restrict__ out)
+{
+  size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+  if (i >= n)
+    return;
+  const size_t r = subset ? (size_t)subset[i] : i;
+  const float* f = reinterpret_cast<const float*>(src + r * stride);
+  out[2 * i] = make_float4(f[0], f[1], f[2], f[3]);
+  out[2 * i + 1] = make_float4(f[4], 0.f, 0.f, 0.f);
+}
+
+__global__ void k_vg_normals(const float4* __restrict__ nc, const int32_t* __restrict__ vals, const RunRef* __restrict__ runs,
+                             size_t n_runs, float4* __restrict__ out)
+{
+  size_t m = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+  if (m >= n_runs)
+    return;
+  const RunRef r = runs[m];
+  float nx = 0.f, ny = 0.f, nz = 0.f, nw = 0.f, cv = 0.f;
+  for (unsigned j = r.begin; j < r.end; ++j) {
+    const float4 a = __ldg(nc + 2 * (size_t)vals[j]);
+    const float4 b = __ldg(nc + 2 * (size_t)vals[j] + 1);
+    nx = __fadd_rn(nx, a.x); ny = __fadd_rn(ny, a.y); nz = __fadd_rn(nz, a.z); nw = __fadd_rn(nw, a.w);
+    cv = __fadd_rn(cv, b.x);
+  }
+  const float sq = __fadd_rn(__fadd_rn(__fmul_rn(nx, nx), __fmul_rn(ny, ny)), __fadd_rn(__fmul_rn(nz, nz), __fmul_rn(nw, nw)));
+  if (sq > 0.f) {  // Eigen's normalized(): the zero vector stays zero
+    const float nrm = __fsqrt_rn(sq);
+    nx = __fdiv_rn(nx, nrm); ny = __fdiv_rn(ny, nrm); nz = __fdiv_rn(nz, nrm); nw = __fdiv_rn(nw, nrm);
+  }
+  out[2 * m] = make_float4(nx, ny, nz, nw);
+  out[2 * m + 1] = make_float4(__fdiv_rn(cv, (float)(r.end - r.begin)), 0.f, 0.f, 0.f);
+}
+
 struct IsSet {
   __host__ __device__ bool operator()(unsigned char v) const { return v != 0; }
 };
 
 size_t voxelgrid(Ctx& c, const void* pts, size_t n, size_t stride, const int32_t* indices, size_t n_idx, int is_dense,
-                 const float leaf[3], unsigned min_pts, float* out_xyz1)
+                 const float leaf[3], unsigned min_pts, float* out_xyz1, const void* normals, size_t stride_n,
+                 float* out_normal_curv)
 {
   (void)is_dense;  // non-finite points are skipped on either setting (a dense cloud has none)
   cudaStream_t st = c.stream;
@@ -276,6 +315,41 @@ size_t voxelgrid(Ctx& c, const void* pts, size_t n, size_t stride, const int32_t
   PCLB_CUDA(cudaGetLastError());
   if (!out_on_device)
     PCLB_CUDA(cudaMemcpyAsync(out_xyz1, out.p, n_out * sizeof(float4), cudaMemcpyDeviceToHost, st));
+  if (normals && out_normal_curv) {
+    // the remaining fields of a PointNormal / Normal record, averaged over the same runs in the same order
+    PCLB_REQUIRE(stride_n >= 20 && stride_n % 4 == 0, PCLB200_ERR_INVALID, "normal stride must be a multiple of 4 and >= 20");
+    DevBuf<unsigned char> staged;
+    DevBuf<int32_t> staged_sub;
+    const unsigned char* d_src = static_cast<const unsigned char*>(normals);
+    if (!is_device_ptr(normals)) {
+      const size_t bytes = (n - 1) * stride_n + 20;
+      staged.alloc(bytes, st);
+      PCLB_CUDA(cudaMemcpyAsync(staged.p, normals, bytes, cudaMemcpyHostToDevice, st));
+      d_src = staged.p;
+    }
+    const int32_t* d_sub = indices;
+    if (indices && !is_device_ptr(indices)) {
+      staged_sub.alloc(n_idx, st);
+      PCLB_CUDA(cudaMemcpyAsync(staged_sub.p, indices, n_idx * sizeof(int32_t), cudaMemcpyHostToDevice, st));
+      d_sub = staged_sub.p;
+    }
+    DevBuf<float4> nc, nout;
+    nc.alloc(2 * cnt, st);
+    k_vg_load_nc<<<grid_for(cnt, 256), 256, 0, st>>>(d_src, stride_n, d_sub, cnt, nc.p);
+    const bool nc_on_device = is_device_ptr(out_normal_curv);
+    float4* d_nout = reinterpret_cast<float4*>(out_normal_curv);
+    if (!nc_on_device) {
+      nout.alloc(2 * n_out, st);
+      d_nout = nout.p;
+    }
+    k_vg_normals<<<grid_for(n_out, 128), 128, 0, st>>>(nc.p, vals.p, d_runs, n_out, d_nout);
+    c.launches += 2;
+    PCLB_CUDA(cudaGetLastError());
+    if (!nc_on_device)
+      PCLB_CUDA(cudaMemcpyAsync(out_normal_curv, nout.p, 2 * n_out * sizeof(float4), cudaMemcpyDeviceToHost, st));
+    PCLB_CUDA(cudaStreamSynchronize(st));
+    return n_out;
+  }
   PCLB_CUDA(cudaStreamSynchronize(st));
   return n_out;
 }

@@ -36,11 +36,11 @@ public:
     if (!this->input_ || this->input_->empty()) return;
     PCLBase<PointT>::initCompute();
     if (!searcher_) searcher_.reset(new pcl::search::KdTree<PointT>());
-    if (searcher_->getInputCloud() != this->input_ || !searcher_->deviceIndex()) {
-      if (!searcher_->setInputCloud(this->input_)) {
-        std::fprintf(stderr, "[pcl::%s::applyFilter] Error when initializing search method!\n", name_);
-        return;
-      }
+    // like the reference (statistical_outlier_removal.hpp:63, radius_outlier_removal.hpp:66): the searcher is handed the
+    // input on EVERY call — a cloud mutated in place, or a tree that was rebuilt elsewhere, must not meet a stale index
+    if (!searcher_->setInputCloud(this->input_)) {
+      std::fprintf(stderr, "[pcl::%s::applyFilter] Error when initializing search method!\n", name_);
+      return;
     }
     std::vector<std::uint8_t> keep;
     if (!classify(keep)) return;

@@ -1,9 +1,12 @@
 // pcl/filters/voxel_grid.h — pcl::VoxelGrid<PointT> (filters/include/pcl/filters/voxel_grid.h:220-530,
 // impl/voxel_grid.hpp:596-814) on the device.  Supported: setLeafSize, setMinimumPointsNumberPerVoxel, indices,
-// filter().  downsample_all_data only matters for fields beyond xyz: the centroid of xyz is produced, other fields
-// of the output are default-initialised.
+// filter().  downsample_all_data_ (default true, voxel_grid.hpp:796-806): for point types that carry a normal and a
+// curvature (PointNormal) those fields are averaged on the device too, like CentroidPoint does (normal = normalised
+// 4-vector sum, curvature = mean); with setDownsampleAllData(false) only xyz is produced and the other fields are
+// default-initialised (voxel_grid.hpp:784-794 copies just the 4-float centroid).
 #pragma once
 #include <cstdio>
+#include <cstring>
 #include <limits>
 #include <string>
 #include <vector>
@@ -68,10 +71,21 @@ public:
     }
     const std::size_t n = abi_idx ? abi_cnt : this->indices_->size();
     std::vector<float> xyz1(4 * (n ? n : 1));
+    std::vector<float> ncurv;
     std::size_t m = 0;
-    int rc = pclb200_voxelgrid(b200::Context::get(), this->input_->points.data(), this->input_->size(), sizeof(PointT),
-                               abi_idx, abi_cnt, this->input_->is_dense ? 1 : 0, leaf_, min_points_per_voxel_,
-                               xyz1.data(), &m);
+    int rc;
+    constexpr bool has_normal = pcl::has_normal<PointT>::value && sizeof(PointT) == 48;  // pcl::PointNormal: {xyz1 | normal4 | curvature, pad}
+    if (has_normal && downsample_all_data_) {
+      ncurv.resize(8 * (n ? n : 1));
+      const unsigned char* base = reinterpret_cast<const unsigned char*>(this->input_->points.data());
+      rc = pclb200_voxelgrid_normals(b200::Context::get(), base, this->input_->size(), sizeof(PointT), base + 16,
+                                     sizeof(PointT), abi_idx, abi_cnt, this->input_->is_dense ? 1 : 0, leaf_,
+                                     min_points_per_voxel_, xyz1.data(), ncurv.data(), &m);
+    }
+    else
+      rc = pclb200_voxelgrid(b200::Context::get(), this->input_->points.data(), this->input_->size(), sizeof(PointT),
+                             abi_idx, abi_cnt, this->input_->is_dense ? 1 : 0, leaf_, min_points_per_voxel_,
+                             xyz1.data(), &m);
     if (rc == PCLB200_ERR_LEAF_TOO_SMALL) {  // voxel_grid.hpp:620-629: warn and return the input unfiltered
       std::fprintf(stderr, "[pcl::VoxelGrid::applyFilter] Leaf size is too small for the input dataset. Integer indices would overflow.\n");
       output = *this->input_;
@@ -87,6 +101,8 @@ public:
       output.points[i].x = xyz1[4 * i];
       output.points[i].y = xyz1[4 * i + 1];
       output.points[i].z = xyz1[4 * i + 2];
+      if (!ncurv.empty())  // bytes 16..47 of a PointNormal: normal4 | curvature
+        std::memcpy(reinterpret_cast<unsigned char*>(&output.points[i]) + 16, &ncurv[8 * i], 32);
     }
     output.width = static_cast<std::uint32_t>(m);
     output.height = 1;       // downsampling breaks the organized structure (:609)

@@ -261,6 +261,19 @@ inline int readHeader(std::istream& fs, Header& h)
   }
   if (h.data_type < 0) return fail("no DATA line");
   (void)points_read;
+  // An untrusted header must not be able to wrap an offset or request an absurd allocation: sizes are the four PCD
+  // allows, counts are positive, the type fits its size (io/src/pcd_io.cpp:200-260 rejects the same things), and every
+  // product below is checked for overflow.
+  if (h.fields.empty()) return fail("no FIELDS");
+  for (const auto& f : h.fields) {
+    if (!(f.size == 1 || f.size == 2 || f.size == 4 || f.size == 8)) return fail("invalid SIZE (must be 1, 2, 4 or 8)");
+    if (f.count < 1 || f.count > (1 << 20)) return fail("invalid COUNT (must be >= 1)");
+    if (!(f.type == 'F' || f.type == 'I' || f.type == 'U')) return fail("invalid TYPE (must be F, I or U)");
+    if (f.type == 'F' && f.size < 4) return fail("TYPE F needs SIZE 4 or 8");
+  }
+  if (h.point_step == 0 || h.point_step > (std::size_t(1) << 30)) return fail("invalid point step");
+  if (h.width != 0 && h.height > std::numeric_limits<std::size_t>::max() / h.width) return fail("WIDTH x HEIGHT overflows");
+  if (h.points > std::numeric_limits<std::size_t>::max() / h.point_step) return fail("POINTS x point step overflows");
   // compatibility with older files (:351-383)
   if (!h.width_read && !h.height_read) { h.width = h.points; h.height = 1; }
   if (!h.height_read) { h.height = 1; if (h.width == 0) h.width = h.points; }
@@ -308,6 +321,22 @@ int loadPCDFile(const std::string& file, pcl::PointCloud<PointT>& cloud)
   detail::Header h;
   if (detail::readHeader(in, h) != 0) return -1;
   const std::size_t npts = h.points;
+  {
+    // a point needs at least one byte of file per field in every encoding (ascii: a digit; binary: >= 1 byte;
+    // compressed: checked against the declared uncompressed size below) — refuse before allocating
+    const std::streampos here = in.tellg();
+    in.seekg(0, std::ios::end);
+    const std::size_t fsz = static_cast<std::size_t>(in.tellg());
+    in.seekg(here);
+    const std::size_t body = fsz > h.data_offset ? fsz - h.data_offset : 0;
+    const bool too_many = h.data_type == 1 ? npts * h.point_step > body
+                          : h.data_type == 0 ? npts > body
+                                             : npts > (std::size_t(1) << 32);  // usize is a u32
+    if (too_many) {
+      std::fprintf(stderr, "[pcl::PCDReader::read] Corrupted PCD file: %zu points do not fit %zu bytes of data.\n", npts, body);
+      return -1;
+    }
+  }
   cloud.points.assign(npts, PointT());
   cloud.width = static_cast<std::uint32_t>(h.width);
   cloud.height = static_cast<std::uint32_t>(h.height);
@@ -407,6 +436,11 @@ int loadPCDFile(const std::string& file, pcl::PointCloud<PointT>& cloud)
     std::fprintf(stderr, "[pcl::PCDReader::read] The estimated cloud.data size (%zu) is different than the saved uncompressed value (%u)! Data corruption?\n",
                  plane_bytes * npts, usize);
   if (usize == 0) return 0;
+  // an LZF back-reference of 2-3 bytes yields at most 264: a stream cannot expand by more than ~132x
+  if (static_cast<std::uint64_t>(usize) > static_cast<std::uint64_t>(csize) * 256u + 64u) {
+    std::fprintf(stderr, "[pcl::PCDReader::read] Corrupted PCD file: %u compressed bytes cannot hold %u uncompressed.\n", csize, usize);
+    return -1;
+  }
   std::vector<unsigned char> cbuf(csize ? csize : 1), buf(usize);
   in.read(reinterpret_cast<char*>(cbuf.data()), static_cast<std::streamsize>(csize));
   const std::size_t got = detail::lzfDecompress(cbuf.data(), csize, buf.data(), usize);

@@ -144,3 +144,36 @@ def test_concurrent_callers_and_session_reuse(gpu, orc):
         a = sess.iterate()
         b = P.icp_align(ctx, Sx, idx, max_iterations=12, max_correspondence_distance=0.1)
         assert np.array_equal(a["final"], b["final"]) and a["iterations"] == b["iterations"]
+
+
+def test_radius_into_caller_buffers(gpu):
+    """pclb200_radius_into: the same lists as pclb200_radius, written into caller buffers — host arrays, pinned host
+    tensors and device tensors — without library-side allocation; a too-small capacity only reports the total."""
+    import torch
+    P, ctx = gpu
+    rng = np.random.default_rng(8)
+    cloud = P.xyz1(rng.random((50000, 3), dtype=np.float32))
+    q = P.xyz1(rng.random((3000, 3), dtype=np.float32))
+    idx = P.Index(ctx, cloud)
+    for max_nn in (0, 7):
+        offs, ii, dd = idx.radius(q, 0.05, max_nn=max_nn)
+        total = int(offs[-1])
+        o2 = np.zeros(q.shape[0] + 1, np.int64)
+        assert idx.radius_into(q, 0.05, o2, np.empty(0, np.int32), np.empty(0, np.float32), max_nn=max_nn) == total
+        assert np.array_equal(o2, offs)                     # sizing call: offsets + total, nothing else written
+        i2, d2 = np.full(total + 5, -7, np.int32), np.full(total + 5, -7, np.float32)
+        assert idx.radius_into(q, 0.05, o2, i2, d2, max_nn=max_nn) == total
+        assert np.array_equal(i2[:total], ii) and np.array_equal(d2[:total], dd) and np.all(i2[total:] == -7)
+        # device-resident result (queries, offsets and lists all in HBM)
+        dq = torch.from_numpy(q).cuda()
+        do = torch.zeros(q.shape[0] + 1, dtype=torch.int64, device="cuda")
+        di = torch.empty(total, dtype=torch.int32, device="cuda")
+        ddv = torch.empty(total, dtype=torch.float32, device="cuda")
+        assert idx.radius_into(dq, 0.05, do, di, ddv, max_nn=max_nn) == total
+        assert np.array_equal(do.cpu().numpy(), offs) and np.array_equal(di.cpu().numpy(), ii)
+        assert np.array_equal(ddv.cpu().numpy(), dd)
+        # pinned host buffers
+        pi, pd = torch.empty(total, dtype=torch.int32).pin_memory(), torch.empty(total, dtype=torch.float32).pin_memory()
+        po = torch.zeros(q.shape[0] + 1, dtype=torch.int64).pin_memory()
+        assert idx.radius_into(q, 0.05, po, pi, pd, max_nn=max_nn) == total
+        assert np.array_equal(pi.numpy(), ii) and np.array_equal(pd.numpy(), dd) and np.array_equal(po.numpy(), offs)

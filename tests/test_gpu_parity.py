@@ -654,3 +654,27 @@ def test_knn_stats_and_outlier_filters(gpu, golden, orc):
     mu = s.sum() / 397
     var = ((mean * mean).astype(np.float64).sum() - s.sum() ** 2 / 397) / 396
     assert int((mean <= mu + 1.0 * np.sqrt(var)).sum()) == 352          # StatisticalOutlierRemoval(50, 1.0)
+
+
+def test_voxelgrid_point_normal_all_fields(gpu, orc):
+    """VoxelGrid<PointNormal> with the reference's default downsample_all_data_ = true averages the normal (normalised
+    4-vector sum) and the curvature per voxel as well (voxel_grid.hpp:796-806, accumulators.hpp:86-133); xyz stays
+    bit-exact, the normalised sums agree to rounding of the square root / division."""
+    P, ctx = gpu
+    rng = np.random.default_rng(5)
+    n = 60000
+    rec = np.zeros((n, 12), dtype=np.float32)
+    rec[:, :3] = rng.random((n, 3), dtype=np.float32) * np.float32(2.0)
+    rec[:, 3] = 1.0
+    nrm = rng.normal(size=(n, 3)).astype(np.float32)
+    nrm /= np.linalg.norm(nrm, axis=1, keepdims=True)
+    rec[:, 4:7] = nrm
+    rec[:, 8] = rng.random(n, dtype=np.float32)
+    rec[::97, 1] = np.nan
+    idx = rng.permutation(n)[: n // 2].astype(np.int32)
+    for leaf, mp, ind in (([0.05] * 3, 0, None), ([0.1, 0.2, 0.05], 3, idx)):
+        gx, gn = ctx.voxelgrid_normals(rec, leaf, min_points_per_voxel=mp, indices=ind, is_dense=False)
+        ox, on = orc.voxelgrid_normals(rec, leaf, min_points_per_voxel=mp, indices=ind, is_dense=False)
+        assert gx.shape == ox.shape and np.array_equal(gx, ox)
+        assert np.allclose(gn, on, rtol=0, atol=2e-7), float(np.abs(gn - on).max())
+        assert np.allclose(np.linalg.norm(gn[:, :4], axis=1), 1.0, atol=1e-5)

@@ -108,7 +108,7 @@ def test_sharded_accumulators_match_whole_cloud(orc):
 def test_two_gpu_icp_matches_single_gpu():
     """Needs 2 GPUs: the sharded ICP (NCCL all-reduce per iteration) reaches the single-GPU transform."""
     if torch.cuda.device_count() < 2:
-        pytest.skip("needs 2 GPUs")
+        pytest.skip("needs 2 GPUs (VISIBLE SKIP: the same product path runs on one GPU in test_two_ranks_share_one_gpu)")
     import subprocess
     import sys
     script = os.path.join(ROOT, "tests", "_two_gpu_icp.py")
@@ -117,3 +117,18 @@ def test_two_gpu_icp_matches_single_gpu():
                        capture_output=True, text=True, timeout=600)
     print(r.stdout[-2000:], r.stderr[-2000:])
     assert r.returncode == 0 and "TWO_GPU_OK" in r.stdout
+
+
+@pytest.mark.gpu
+def test_two_ranks_share_one_gpu():
+    """The N > 1 product path on ANY box with one GPU: two processes on cuda:0, the peer exchange bootstrapped over gloo
+    (pclb200_comm_export / _import), 40 accumulators per iteration crossing between the processes inside the iteration
+    kernel.  Sharded == whole-cloud result; reciprocal + communicator is refused (tests/_two_rank_one_gpu.py)."""
+    import subprocess
+    import sys
+    script = os.path.join(ROOT, "tests", "_two_rank_one_gpu.py")
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2",
+                        "--master-addr", "127.0.0.1", "--master-port", str(_free_port()), script],
+                       capture_output=True, text=True, timeout=600)
+    print(r.stdout[-3000:], r.stderr[-3000:])
+    assert r.returncode == 0 and "TWO_RANK_ONE_GPU_OK" in r.stdout

@@ -147,3 +147,25 @@ def test_ascii_fixtures_match_golden(exe, tmp_path, golden):
         assert h == 1 and w == got.shape[0]
         assert dense == (name != "sac_plane_test.pcd")  # that file carries NaN normals: every field counts (pcd_io.cpp:636-665)
         assert np.array_equal(got, golden[key][:, :3].astype(np.float32))
+
+
+@pytest.mark.parametrize("header,body", [
+    # negative SIZE: used to wrap a field offset to 2^64-4 and read outside the buffer
+    ("FIELDS a x y\nSIZE -4 4 4\nTYPE F F F\nCOUNT 1 1 1\nWIDTH 2\nHEIGHT 1\nPOINTS 2\nDATA binary\n", b"\0" * 32),
+    ("FIELDS x y z\nSIZE 4 4 3\nTYPE F F F\nCOUNT 1 1 1\nWIDTH 1\nHEIGHT 1\nPOINTS 1\nDATA binary\n", b"\0" * 16),
+    ("FIELDS x y z\nSIZE 4 4 4\nTYPE F F F\nCOUNT 1 0 1\nWIDTH 1\nHEIGHT 1\nPOINTS 1\nDATA binary\n", b"\0" * 16),
+    ("FIELDS x y z\nSIZE 4 4 4\nTYPE F F Q\nCOUNT 1 1 1\nWIDTH 1\nHEIGHT 1\nPOINTS 1\nDATA binary\n", b"\0" * 16),
+    # a tiny file that asks for a huge allocation
+    ("FIELDS x y z\nSIZE 4 4 4\nTYPE F F F\nCOUNT 1 1 1\nWIDTH 4000000000\nHEIGHT 1\nPOINTS 4000000000\nDATA binary\n", b"\0" * 12),
+    ("FIELDS x y z\nSIZE 4 4 4\nTYPE F F F\nCOUNT 1 1 1\nWIDTH 4000000000\nHEIGHT 1\nPOINTS 4000000000\nDATA ascii\n", b"1 2 3\n"),
+    ("FIELDS x y z\nSIZE 4 4 4\nTYPE F F F\nCOUNT 1 1 1\nWIDTH 100\nHEIGHT 1\nPOINTS 100\nDATA binary_compressed\n",
+     struct.pack("<II", 4, 4000000000) + b"\0" * 4),
+    ("FIELDS x y z\nSIZE 4 4 4\nTYPE F F F\nCOUNT 1 1 1\nWIDTH 18446744073709551615\nHEIGHT 3\nPOINTS 5\nDATA ascii\n", b""),
+])
+def test_malformed_headers_are_rejected(exe, tmp_path, header, body):
+    """Untrusted files: bad SIZE / COUNT / TYPE and point counts the file cannot hold are refused (exit code 2 of the
+    dump tool = loadPCDFile returned -1) instead of wrapping offsets, reading out of bounds or allocating gigabytes."""
+    f = tmp_path / "bad.pcd"
+    f.write_bytes(("# .PCD v0.7\nVERSION 0.7\n" + header).encode() + body)
+    r = subprocess.run([exe, "dump", str(f), str(tmp_path / "o.bin")], capture_output=True, timeout=20)
+    assert r.returncode == 2, (r.returncode, r.stderr[-300:])
