@@ -323,6 +323,14 @@ PCLB200_API int pclb200_fitness_score(pclb200_ctx* ctx, const pclb200_index* idx
                                       const double T[16], int scalar_is_double, double max_range,
                                       double* score);
 
+/* GeneralizedIterativeClosestPoint::computeCovariances — registration/include/pcl/registration/impl/gicp.hpp:69-147
+ * (SURVEY.md §8f #2): for every point of `pts` (the cloud idx was built over, so neighbours and queries are the same
+ * cloud) the covariance of its k nearest neighbours relative to the point, mean removed, singular values replaced by
+ * (1, 1, gicp_epsilon) (:136-147).  out_cov: n x 9 doubles, row-major 3x3 (host or device); zeros for non-finite points.
+ * k = k_correspondences_ (default 20), gicp_epsilon default 0.001 (gicp.h:127-129). */
+PCLB200_API int pclb200_gicp_covariances(pclb200_ctx* ctx, const pclb200_index* idx, const void* pts, size_t n,
+                                         size_t stride, int k, double gicp_epsilon, double* out_cov);
+
 /* TransformationValidationEuclidean::validateTransformation — registration/include/pcl/registration/impl/
  * transformation_validation_euclidean.hpp:50-109: the source transformed by T (products and sums in Scalar, left to right,
  * cast to float: :62-75), 1-NN into the target, mean of the squared distances that are <= max_range (the reference compares

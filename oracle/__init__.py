@@ -87,6 +87,8 @@ def lib():
         L.orc_fitness_score.argtypes = [vp, fp, sz, sz, i32p, sz, C.c_int, dp, C.c_int, C.c_double, C.c_int]
         L.orc_voxelgrid.restype = C.c_longlong
         L.orc_voxelgrid.argtypes = [fp, sz, sz, i32p, sz, C.c_int, fp, C.c_uint, fp]
+        L.orc_gicp_covariances.restype = None
+        L.orc_gicp_covariances.argtypes = [vp, fp, sz, sz, C.c_int, C.c_double, dp, C.c_int]
         L.orc_voxelgrid_normals.restype = C.c_longlong
         L.orc_voxelgrid_normals.argtypes = [fp, sz, sz, i32p, sz, C.c_int, fp, C.c_uint, fp, C.c_long, fp]
         L.orc_point_normal.argtypes = [fp, sz, C.c_int, i32p, sz, fp]
@@ -208,6 +210,13 @@ class Index:
         return float(lib().orc_fitness_score(self.h, _f(src), src.shape[0], src.shape[1], _i(indices),
                                              0 if indices is None else indices.size, int(is_dense), _d(T),
                                              int(scalar_is_double), float(max_range), 1))
+
+    def gicp_covariances(self, k=20, gicp_epsilon=0.001, nthreads=1):
+        """GeneralizedIterativeClosestPoint::computeCovariances over the indexed cloud: (n, 3, 3) float64."""
+        out = np.zeros((self.cloud.shape[0], 9), dtype=np.float64)
+        lib().orc_gicp_covariances(self.h, _f(self.cloud), self.cloud.shape[0], self.cloud.shape[1], int(k),
+                                   float(gicp_epsilon), _d(out), nthreads)
+        return out.reshape(-1, 3, 3)
 
     def knn_stats(self, cloud, k, nthreads=1):
         cloud = as_cloud(cloud)

@@ -1008,6 +1008,59 @@ ORC_API int orc_knn(void* h, const float* q, size_t nq, size_t qstride, int k, i
   return keff;
 }
 
+// GeneralizedIterativeClosestPoint::computeCovariances — registration/include/pcl/registration/impl/gicp.hpp:69-147.
+// For every point of `cloud` (the cloud the tree h was built over): k nearest neighbours, covariance of the neighbourhood
+// relative to the query (float differences widened to double, :108-111), mean removed (:127-134), SVD, singular values
+// replaced by (1, 1, gicp_epsilon) and the matrix reassembled from the columns of U (:136-147).  out: n x 9 doubles,
+// row-major.
+ORC_API void orc_gicp_covariances(void* h, const float* cloud, size_t n, size_t stride, int k, double gicp_epsilon,
+                                  double* out, int nthreads)
+{
+  const KdTree& t = *static_cast<KdTree*>(h);
+  const int keff = (int)std::min<size_t>((size_t)std::max(k, 0), t.n);
+#pragma omp parallel num_threads(nthreads > 0 ? nthreads : 1)
+  {
+    std::vector<Cand> buf((size_t)std::max(keff, 1));
+#pragma omp for schedule(dynamic, 256)
+    for (long long i = 0; i < (long long)n; ++i) {
+      const float* q = cloud + stride * (size_t)i;
+      double* o = out + 9 * (size_t)i;
+      for (int e = 0; e < 9; ++e)
+        o[e] = 0.0;
+      if (!finite3(q) || keff <= 0)
+        continue;
+      KnnSet rs{buf.data(), keff, 0};
+      kd_knn_rec(t, 0, q, rs);
+      double mean[3] = {0, 0, 0}, cov[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+      for (int j = 0; j < rs.n; ++j) {
+        const float* p = cloud + stride * (size_t)rs.c[j].i;
+        const double ptx = p[0] - q[0], pty = p[1] - q[1], ptz = p[2] - q[2];
+        mean[0] += ptx; mean[1] += pty; mean[2] += ptz;
+        cov[0] += ptx * ptx;
+        cov[3] += pty * ptx; cov[4] += pty * pty;
+        cov[6] += ptz * ptx; cov[7] += ptz * pty; cov[8] += ptz * ptz;
+      }
+      const double kk = static_cast<double>(k);
+      for (int d = 0; d < 3; ++d)
+        mean[d] /= kk;
+      for (int r = 0; r < 3; ++r)
+        for (int c = 0; c <= r; ++c) {
+          cov[3 * r + c] /= kk;
+          cov[3 * r + c] -= mean[r] * mean[c];
+          cov[3 * c + r] = cov[3 * r + c];
+        }
+      double U[9], sv[3], V[9];
+      svd3<double>(cov, U, sv, V);
+      for (int kcol = 0; kcol < 3; ++kcol) {
+        const double v = kcol == 2 ? gicp_epsilon : 1.0;
+        for (int r = 0; r < 3; ++r)
+          for (int c = 0; c < 3; ++c)
+            o[3 * r + c] += v * U[3 * r + kcol] * U[3 * c + kcol];
+      }
+    }
+  }
+}
+
 // brute-force k-NN over the raw cloud (ground truth for the tree itself; same conventions)
 ORC_API int orc_knn_bruteforce(const float* pts, size_t n, size_t stride, const float* q, size_t nq,
                                size_t qstride, int k, int32_t* out_idx, float* out_d2)

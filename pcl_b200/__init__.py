@@ -73,7 +73,7 @@ SYMBOLS = [
     "pclb200_icp_set_source", "pclb200_icp_iterate", "pclb200_icp_get_cloud", "pclb200_icp_get_correspondences",
     "pclb200_icp_align",
     "pclb200_fitness_score", "pclb200_reject", "pclb200_icp_set_rejectors", "pclb200_normals_knn", "pclb200_normals_radius",
-    "pclb200_correspondences_normals", "pclb200_reject_surface_normal", "pclb200_cluster_labels", "pclb200_voxelgrid", "pclb200_voxelgrid_normals", "pclb200_validate_transformation", "pclb200_inliers", "pclb200_radius_into", "pclb200_comm_unique_id", "pclb200_comm_set_mode", "pclb200_comm_export", "pclb200_comm_import",
+    "pclb200_correspondences_normals", "pclb200_reject_surface_normal", "pclb200_cluster_labels", "pclb200_voxelgrid", "pclb200_voxelgrid_normals", "pclb200_validate_transformation", "pclb200_inliers", "pclb200_radius_into", "pclb200_gicp_covariances", "pclb200_comm_unique_id", "pclb200_comm_set_mode", "pclb200_comm_export", "pclb200_comm_import",
     "pclb200_comm_init",
 ]
 
@@ -138,6 +138,7 @@ def lib():
     L.pclb200_voxelgrid_normals.argtypes = [vp, vp, sz, sz, vp, sz, vp, sz, C.c_int, fp, C.c_uint, vp, vp, C.POINTER(sz)]
     L.pclb200_validate_transformation.argtypes = [vp, vp, vp, sz, sz, dp, C.c_int, C.c_double, dp]
     L.pclb200_inliers.argtypes = [vp, vp, vp, sz, sz, dp, C.c_float, vp, C.POINTER(sz)]
+    L.pclb200_gicp_covariances.argtypes = [vp, vp, vp, sz, sz, C.c_int, C.c_double, vp]
     L.pclb200_radius_into.argtypes = [vp, vp, vp, sz, sz, C.c_double, C.c_uint, vp, vp, vp, sz, C.POINTER(sz)]
     L.pclb200_comm_unique_id.argtypes = [vp]
     L.pclb200_comm_set_mode.argtypes = [vp, C.c_int]
@@ -469,6 +470,14 @@ class Index:
                                            T.ctypes.data_as(C.POINTER(C.c_double)), int(scalar_is_double),
                                            float(max_range), C.byref(out)))
         return float(out.value)
+
+    def gicp_covariances(self, cloud, k=20, gicp_epsilon=0.001):
+        """GeneralizedIterativeClosestPoint::computeCovariances: (n, 3, 3) float64 for the indexed cloud."""
+        b = _Buf(cloud)
+        out = np.zeros((b.rows, 9), dtype=np.float64)
+        _check(lib().pclb200_gicp_covariances(self.ctx.h, self.h, b.ptr, b.rows, b.stride, int(k), float(gicp_epsilon),
+                                              C.c_void_p(out.ctypes.data)))
+        return out.reshape(-1, 3, 3)
 
     def validate_transformation(self, src, T, max_range=np.finfo(np.float64).max, scalar_is_double=False):
         """TransformationValidationEuclidean::validateTransformation."""

@@ -33,6 +33,8 @@ size_t correspondences(Ctx& c, const Index& tgt, const Index* src_index, const v
                        const double* pre_T = nullptr, int pre_mode = 0, const float* gate_override = nullptr);
 double fitness_score(Ctx& c, const Index& tgt, const void* src, size_t n, size_t stride, const int32_t* indices,
                      size_t n_idx, const double* T, int scalar_is_double, double max_range, int mode_override = -1);
+void gicp_covariances(Ctx& c, Index& idx, const void* pts, size_t n, size_t stride, int k, double gicp_epsilon,
+                      double* out);
 // search.cu
 void launch_normals(Ctx& c, Index& idx, const float4* d_q, size_t nq, int k, const float vp[3], float4* d_out,
                     int* d_not_dense);
@@ -894,6 +896,18 @@ int pclb200_fitness_score(pclb200_ctx* ctx, const pclb200_index* idx_tgt, const 
     std::lock_guard<std::recursive_mutex> lk(ctx->c.mu);
     PCLB_CUDA(cudaSetDevice(ctx->c.device));
     *score = fitness_score(ctx->c, *idx_tgt->idx, src, n, stride, src_indices, n_idx, T, scalar_is_double, max_range);
+  });
+}
+
+int pclb200_gicp_covariances(pclb200_ctx* ctx, const pclb200_index* idx, const void* pts, size_t n, size_t stride, int k,
+                             double gicp_epsilon, double* out_cov)
+{
+  return guarded([&] {
+    PCLB_REQUIRE(ctx && idx && idx->idx && pts && out_cov, PCLB200_ERR_INVALID, "NULL argument");
+    std::lock_guard<std::recursive_mutex> lk(ctx->c.mu);
+    PCLB_CUDA(cudaSetDevice(ctx->c.device));
+    ProfScope ps(ctx->c, "gicp_covariances");
+    gicp_covariances(ctx->c, *idx->idx, pts, n, stride, k, gicp_epsilon, out_cov);
   });
 }
 

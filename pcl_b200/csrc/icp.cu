@@ -116,7 +116,7 @@ struct IterArgs {
   float gate;
   float ox, oy, oz;           // accumulation origin (target bbox centre)
   double* partials;           // gridDim.x * kAccum
-  double* partials2;          // gridDim.x * 128 (two 8x8 fp64 tiles per block: k_icp_wq)
+  double* partials2;          // gridDim.x * 128 (two 8x8 fp64 tiles per block: k_accum_dmma)
   unsigned* counter;
   double* accum;              // kAccum
   int* d_error;
@@ -430,15 +430,13 @@ __device__ __forceinline__ void fold_tiles_and_publish(const IterArgs& a, double
 // -> [TRACK: skip test] -> exact 1-NN started at the candidate ball (traverse.cuh: nearest1 — seed = previous match,
 // cell-table start, ordinary exact walk below) -> gate -> optional reciprocal back-search.
 // lbs (TRACK only): per query, a lower bound on the DISTANCE to every target point other than the match; 0 = unknown.
-#ifndef PCLB_SEARCH_MINBLOCKS
-#define PCLB_SEARCH_MINBLOCKS 1
-#endif
-template <int EST, bool RECIP, bool TRACK>
-__global__ void __launch_bounds__(256, PCLB_SEARCH_MINBLOCKS)
+// 6 blocks of 256 threads per SM (<= 40 registers): the walk is a chain of dependent loads, occupancy is what hides them
+// (measured: 4 -> 6 resident blocks = -3 % per step; fusing the accumulation into this kernel = +20 %, profiles/r2h)
+template <bool RECIP, bool TRACK>
+__global__ void __launch_bounds__(256, 6)
 k_search(const IterArgs a, Match* __restrict__ match, float* __restrict__ lbs)
 {
   __shared__ Pending sP;
-  __shared__ __align__(16) float s_stage[EST != kEstNone ? 8 : 1][EST != kEstNone ? 2 * 32 * 8 : 4];  // DMMA staging tiles
   if (threadIdx.x == 0)
     sP = *a.pending;
   __syncthreads();
@@ -447,8 +445,6 @@ k_search(const IterArgs a, Match* __restrict__ match, float* __restrict__ lbs)
   bool overflow = false;
   unsigned skipped = 0;
   WalkStats ws{};
-  double c1a = 0.0, c1b = 0.0, c2a = 0.0, c2b = 0.0;  // fragments of the two accumulator tiles (EST >= 0)
-  // warp-uniform trip count (the epilogue is warp-synchronous): a warp takes 32 consecutive queries per round
   const size_t stride = (size_t)gridDim.x * blockDim.x;
   for (size_t base = blockIdx.x * (size_t)blockDim.x + (threadIdx.x & ~31); base < a.n; base += stride) {
     const size_t i = base + lane;
@@ -515,10 +511,6 @@ k_search(const IterArgs a, Match* __restrict__ match, float* __restrict__ lbs)
       if (TRACK)
         lbs[i] = lb_out;
     }
-    if (EST != kEstNone) {
-      __syncwarp();
-      accumulate_pairs_dmma<EST>(a, s_stage[threadIdx.x >> 5], lane, m, p, c1a, c1b, c2a, c2b);
-    }
   }
 #ifdef PCLB_STATS
   for (int k = 0; k < 8; ++k)
@@ -532,497 +524,33 @@ k_search(const IterArgs a, Match* __restrict__ match, float* __restrict__ lbs)
   }
   if (overflow)
     atomicExch(a.d_error, 1);
-  if (EST != kEstNone)
-    fold_tiles_and_publish<EST, 8>(a, c1a, c1b, c2a, c2b);
 }
 
-// =============================================================================================================
-// Warp work-queue search with fused tensor-core accumulation
-// =============================================================================================================
-// One query per thread wastes most of a warp: the lanes' walks differ in length (1..8 cells, 1..40 nodes), the warp
-// lasts as long as its longest lane, and ncu measured 11 of 32 lanes active per instruction.  Here a warp owns a batch
-// of 32 Hilbert-consecutive queries and a set of WORK QUEUES in shared memory; every unit of work — look one cell up,
-// visit one node, scan one leaf — is an item {reference, lower bound, owner query}, and each round all 32 lanes take
-// one item each OF THE SAME KIND, whoever the owner is.  A query with eight cells and a query with one keep the same
-// number of lanes busy.  The per-query state the items share (coordinates, current best) lives in shared memory; the
-// best is a 64-bit word (d2 bits << 32 | Morton position) updated by compare-and-swap under the reference's order
-// (smaller d2, then smaller ORIGINAL index), so the result does not depend on which lane scans which leaf.  Items are
-// popped LIFO (nearer child pushed last), i.e. depth first: bounds tighten early and the frontier stays short.
-// Exactness is the per-thread walk's (traverse.cuh): an item is only dropped when its bound exceeds the owner's best.
-//
-// Epilogue (EST >= 0): the 3x3 / 6x6 normal equations are sums of outer products, i.e. V^T V with V = one row of <= 8
-// components per correspondence — a dense fp64 contraction.  The warp stages its 32 rows in shared memory and issues
-// mma.sync.m8n8k4.f64 (fp64 tensor cores): the whole accumulator tile lives in TWO registers per lane instead of 29
-// fp64 registers per thread, which is what makes fusing the accumulation into the search kernel affordable.  The
-// Match array is still written (next iteration's seeds, getCorrespondences) but never read back by an accumulate pass.
-constexpr int kWqCells = 192, kWqLeaf = 128, kWqNode = 192;
-constexpr int kWqWarps = 4;
-constexpr unsigned kWqNoPos = 0x7fffffffu;
-
-struct __align__(16) WarpWork {
-  uint2 q[kWqCells + kWqLeaf + kWqNode];  // cell | leaf | node queues {reference, bound bits (low 5 bits = owner)};
-                                          // reused as two 32 x 8 fp64 staging tiles by the accumulate epilogue
-  unsigned long long best[32];            // per query: d2 bits << 32 | Morton position (kWqNoPos = none yet)
-  float qx[32], qy[32], qz[32];
-  int skipa[32], skipb[32];               // leaves already scanned by the owner (seed leaves)
-  unsigned m2[32], pruned[32];            // TRACK: second-smallest evaluated d2 / smallest bound of anything skipped
-};
-static_assert(sizeof(uint2) * (kWqCells + kWqLeaf + kWqNode) >= 2 * 32 * 8 * sizeof(float), "staging tiles must fit");
-
-__device__ __forceinline__ unsigned wq_pack(float bound, int owner) { return (__float_as_uint(bound) & ~31u) | (unsigned)owner; }
-__device__ __forceinline__ float wq_bound(unsigned bo) { return __uint_as_float(bo & ~31u); }  // rounded DOWN: still a lower bound
-__device__ __forceinline__ float wq_best_d2(const unsigned long long* slot)
+// Streaming accumulation on the fp64 tensor cores: one pass over (source point, match) pairs, the normal equations
+// built by accumulate_pairs_dmma.  Four fp64 registers of accumulators per lane (instead of 29 per thread) leave room
+// for full occupancy, which is what a gather-bound streaming kernel needs.
+template <int EST>
+__global__ void __launch_bounds__(256)
+k_accum_dmma(const IterArgs a, const Match* __restrict__ match)
 {
-  return __uint_as_float((unsigned)(*reinterpret_cast<const volatile unsigned long long*>(slot) >> 32));
-}
-
-// lexicographic-min update of a query's best with the point (d, pos, orig); returns the d2 bits that LOST (the displaced
-// previous best, or d itself when it did not win; 0xffffffff when nothing real lost) — TRACK folds those into m2
-__device__ __forceinline__ unsigned wq_update(unsigned long long* slot, float d, int pos, int orig,
-                                              const float4* __restrict__ pts)
-{
-  const unsigned md = __float_as_uint(d);
-  const unsigned long long mine = ((unsigned long long)md << 32) | (unsigned)pos;
-  unsigned long long cur = *reinterpret_cast<volatile unsigned long long*>(slot);
-  for (;;) {
-    const unsigned cd = (unsigned)(cur >> 32), cpos = (unsigned)cur;
-    bool better = md < cd;
-    if (md == cd) {
-      if (cpos == (unsigned)pos)
-        return md;  // the same point, scanned twice
-      const int corig = cpos == kWqNoPos ? kSentinelIndex : __float_as_int(__ldg(&pts[cpos].w));
-      better = orig < corig;
-    }
-    if (!better)
-      return md;
-    const unsigned long long old = atomicCAS(slot, cur, mine);
-    if (old == cur)
-      return cpos == kWqNoPos ? 0xffffffffu : cd;
-    cur = old;
-  }
-}
-
-// scan one leaf for query `o` of the warp's batch
-template <bool TRACK>
-__device__ __forceinline__ void wq_scan_leaf(WarpWork& W, int o, const float4* __restrict__ pts, int leaf)
-{
-  const float qx = W.qx[o], qy = W.qy[o], qz = W.qz[o];
-  const float4* lp = pts + (size_t)leaf * kLeafSize;
-  float4 p[8];
-  float d[8];
-#pragma unroll
-  for (int j = 0; j < 8; ++j)
-    p[j] = ldg4(lp + j);
-  float m = __int_as_float(0x7f800000), m2nd = __int_as_float(0x7f800000);
-#pragma unroll
-  for (int j = 0; j < 8; ++j) {
-    d[j] = dist2_rn(qx, qy, qz, p[j].x, p[j].y, p[j].z);
-    if (TRACK)
-      m2nd = fminf(m2nd, fmaxf(m, d[j]));
-    m = fminf(m, d[j]);
-  }
-  unsigned lost = 0xffffffffu;
-  if (m <= wq_best_d2(&W.best[o])) {
-    int jm = 0, im = kSentinelIndex;
-#pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      const int oi = __float_as_int(p[j].w);
-      if (d[j] == m && oi < im) {
-        im = oi;
-        jm = j;
-      }
-    }
-    lost = wq_update(&W.best[o], m, leaf * kLeafSize + jm, im, pts);
-  }
-  else
-    lost = __float_as_uint(m);
-  if (TRACK) {
-    atomicMin(&W.m2[o], __float_as_uint(m2nd));
-    if (lost != 0xffffffffu)
-      atomicMin(&W.m2[o], lost);
-  }
-}
-
-// visitor over the shared per-query state, for the private walks of a drain round (node queue full)
-template <bool TRACK>
-struct WqShared {
-  WarpWork& W;
-  int o;
-  const float4* pts;
-  __device__ __forceinline__ float bound() const { return wq_best_d2(&W.best[o]); }
-  __device__ __forceinline__ void prune(float d)
-  {
-    if (TRACK)
-      atomicMin(&W.pruned[o], __float_as_uint(d));
-  }
-  __device__ __forceinline__ void leaf(const float4*, int first_pos) { wq_scan_leaf<TRACK>(W, o, pts, first_pos / kLeafSize); }
-};
-
-template <int EST, bool RECIP, bool TRACK>
-__global__ void __launch_bounds__(kWqWarps * 32)
-k_icp_wq(const IterArgs a, Match* __restrict__ match, float* __restrict__ lbs)
-{
-  __shared__ Pending sP;
-  __shared__ WarpWork sW[kWqWarps];
-  if (threadIdx.x == 0)
-    sP = *a.pending;
-  __syncthreads();
-  const unsigned full = 0xffffffffu;
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const unsigned lt = (1u << lane) - 1u;
-  WarpWork& W = sW[warp];
-  uint2* const cellq = W.q;
-  uint2* const leafq = W.q + kWqCells;
-  uint2* const nodeq = W.q + kWqCells + kWqLeaf;
-  const CellTable& C = a.cells;
-  const float inf = __int_as_float(0x7f800000);
-  double c1a = 0.0, c1b = 0.0, c2a = 0.0, c2b = 0.0;  // fragments of the two accumulator tiles (EST >= 0)
-  unsigned skipped = 0;
-  bool overflow = false;
-  const size_t nwarps = (size_t)gridDim.x * kWqWarps;
-  for (size_t base = ((size_t)blockIdx.x * kWqWarps + warp) * 32; base < a.n; base += nwarps * 32) {
-    // ================= phase A: own query — transform, skip test, seed leaves ====================================
+  __shared__ __align__(16) float s_stage[8][2 * 32 * 8];
+  const int lane = threadIdx.x & 31;
+  double c1a = 0.0, c1b = 0.0, c2a = 0.0, c2b = 0.0;
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  for (size_t base = blockIdx.x * (size_t)blockDim.x + (threadIdx.x & ~31); base < a.n; base += stride) {
     const size_t i = base + lane;
-    const bool in_range = i < a.n;
-    float4 p = in_range ? a.cur[i] : make_float4(0.f, 0.f, 0.f, 0.f);
-    Match prev;
-    prev.pos = -1;
-    prev.d2 = 0.f;
-    if (in_range)
-      prev = match[i];
-    const bool valid = in_range && isfinite(p.x) && isfinite(p.y) && isfinite(p.z);
-    float delta = 0.f;
-    if (valid && sP.apply) {
-      const float ox = p.x, oy = p.y, oz = p.z;
-      apply_pending(sP, p.x, p.y, p.z);
-      a.cur[i] = p;
-      delta = sqrtf(dist2_rn(p.x, p.y, p.z, ox, oy, oz));
-      if (a.cur_normals) {
-        float4 nn = a.cur_normals[i];
-        apply_pending_normal(sP, nn.x, nn.y, nn.z);
-        a.cur_normals[i] = nn;
-      }
-    }
     Match m;
     m.pos = -1;
     m.d2 = 0.f;
-    float lb_out = 0.f;
-    const int seed = (valid && prev.pos >= 0) ? match_pos(prev) : -1;
-    bool walkq = valid;
-    if (TRACK && !RECIP && seed >= 0) {
-      float nlb = 0.f;
-      if (still_nearest(prev.d2, lbs[i], delta, &nlb)) {
-        const float4 q = ldg4(a.pts + seed);
-        m.d2 = dist2_rn(p.x, p.y, p.z, q.x, q.y, q.z);
-        m.pos = m.d2 <= a.gate ? seed : (seed | kNotAccepted);
-        lb_out = nlb;
-        ++skipped;
-        walkq = false;
-      }
+    float4 p = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (i < a.n) {
+      m = match[i];
+      if (match_accepted(m))
+        p = a.cur[i];
     }
-    Nearest1T<TRACK> v{p.x, p.y, p.z, a.gate, kSentinelIndex, -1, inf, inf, inf};
-    int skip_a = kDone, skip_b = kDone;
-    bool rooted = true;
-    unsigned E = 0, hx = 0, hy = 0, hz = 0, ox = 0, oy = 0, oz = 0;
-    float gx2 = 0.f, gy2 = 0.f, gz2 = 0.f;
-    int lvl = 0;
-    if (walkq) {
-      if (seed >= 0) {
-        const int leaf = seed / kLeafSize;
-        v.template scan<true>(a.pts + (size_t)leaf * kLeafSize, leaf * kLeafSize);
-        skip_a = ~leaf;
-      }
-      if (C.slots != nullptr) {
-        const unsigned cqx = morton_cell(p.x, C.lo[0], C.scale), cqy = morton_cell(p.y, C.lo[1], C.scale),
-                       cqz = morton_cell(p.z, C.lo[2], C.scale);
-        const int smin = 21 - C.bmax;
-        unsigned ax, ay, az, bx, by, bz;
-        float r;
-        int s;
-        auto ball_level = [&]() {
-          r = __fmul_ru(__fsqrt_ru(v.best), TRACK ? kTrackInflate : 1.00001f);
-          ax = morton_cell(__fsub_rd(p.x, r), C.lo[0], C.scale); bx = morton_cell(__fadd_ru(p.x, r), C.lo[0], C.scale);
-          ay = morton_cell(__fsub_rd(p.y, r), C.lo[1], C.scale); by = morton_cell(__fadd_ru(p.y, r), C.lo[1], C.scale);
-          az = morton_cell(__fsub_rd(p.z, r), C.lo[2], C.scale); bz = morton_cell(__fadd_ru(p.z, r), C.lo[2], C.scale);
-          const unsigned d = max(max(bx - ax, by - ay), bz - az);
-          s = (d <= 1u ? 0 : 32 - __clz((int)(d - 1u))) + kCellLevelBias;
-        };
-        ball_level();
-        if (v.best_pos < 0 || s > smin + 2) {
-          // home seed (traverse.cuh: nearest1, step 2)
-          int ref = kDone;
-          int lo_b = 0, hi_b = C.bmax;
-          while (lo_b < hi_b) {
-            const int b = (lo_b + hi_b + 1) >> 1;
-            const int sh = 21 - b;
-            const int rr = cell_lookup(C, cell_key(b, cqx >> sh, cqy >> sh, cqz >> sh));
-            if (rr != kDone) {
-              lo_b = b;
-              ref = rr;
-            }
-            else
-              hi_b = b - 1;
-          }
-          if (ref != kDone) {
-            while (ref >= 0) {
-              const float4* np = reinterpret_cast<const float4*>(a.nodes + ref);
-              const float4 na = ldg4(np), nb = ldg4(np + 1), nc4 = ldg4(np + 2);
-              const int4 nd = __ldg(reinterpret_cast<const int4*>(np + 3));
-              const float dl = box_dist2_rn(p.x, p.y, p.z, na.x, na.y, na.z, na.w, nb.x, nb.y);
-              const float dr = box_dist2_rn(p.x, p.y, p.z, nb.z, nb.w, nc4.x, nc4.y, nc4.z, nc4.w);
-              ref = dr < dl ? nd.y : nd.x;
-            }
-            if (ref != skip_a) {
-              const int leaf = ~ref;
-              v.template scan<true>(a.pts + (size_t)leaf * kLeafSize, leaf * kLeafSize);
-              skip_b = ref;
-              ball_level();
-            }
-          }
-        }
-        if (s < smin)
-          s = smin;
-        if (s <= 20) {
-          rooted = false;
-          lvl = 21 - s;
-          hx = cqx >> s; hy = cqy >> s; hz = cqz >> s;
-          ox = (ax >> s) + (bx >> s) - hx; oy = (ay >> s) + (by >> s) - hy; oz = (az >> s) + (bz >> s) - hz;
-          E = (ox != hx ? 1u : 0u) | (oy != hy ? 2u : 0u) | (oz != hz ? 4u : 0u);
-          gx2 = (E & 1u) ? cell_gap2(C, 0, p.x, hx, ox, s) : 0.f;
-          gy2 = (E & 2u) ? cell_gap2(C, 1, p.y, hy, oy, s) : 0.f;
-          gz2 = (E & 4u) ? cell_gap2(C, 2, p.z, hz, oz, s) : 0.f;
-          v.prune(__fmul_rd(r, r));  // every indexed point outside the cells lies outside [q - r, q + r]^3
-        }
-      }
-    }
-    // publish the per-query state the items share
-    W.qx[lane] = p.x;
-    W.qy[lane] = p.y;
-    W.qz[lane] = p.z;
-    W.best[lane] = walkq ? (((unsigned long long)__float_as_uint(v.best) << 32) | (v.best_pos >= 0 ? (unsigned)v.best_pos : kWqNoPos))
-                         : 0ULL;  // a query that does not walk never wants anything (bound 0, and it owns no items)
-    W.skipa[lane] = skip_a;
-    W.skipb[lane] = skip_b;
-    if (TRACK) {
-      W.m2[lane] = __float_as_uint(v.m2);
-      W.pruned[lane] = __float_as_uint(v.pruned_min);
-    }
-    __syncwarp();
-    // ================= phase B/C: items ============================================================================
-    int nc = 0, nl = 0, nn = 0;  // queue sizes (warp-uniform)
-    {
-      // walks without a cell start: one item, the root
-      const bool wr = walkq && rooted;
-      const unsigned mr = __ballot_sync(full, wr);
-      if (mr) {
-        uint2* rq = a.root < 0 ? leafq : nodeq;
-        if (wr)
-          rq[__popc(mr & lt)] = make_uint2(a.root < 0 ? (unsigned)~a.root : (unsigned)a.root, wq_pack(0.f, lane));
-        if (a.root < 0)
-          nl = __popc(mr);
-        else
-          nn = __popc(mr);
-      }
-    }
-    bool pend = walkq && !rooted;
-    do {
-      {
-        // enqueue the cells of as many pending queries as fit (all of them, unless the batch has > kWqCells cells)
-        const int want = pend ? (1 << __popc(E)) : 0;
-        int x = want;
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-          const int y = __shfl_up_sync(full, x, o);
-          if (lane >= o)
-            x += y;
-        }
-        const bool fits = pend && x <= kWqCells;  // a prefix of the pending lanes
-        if (fits) {
-          int j = x - want;
-          for (unsigned sm = E;; sm = (sm - 1u) & E) {
-            const float bound = __fadd_rd(__fadd_rd((sm & 1u) ? gx2 : 0.f, (sm & 2u) ? gy2 : 0.f), (sm & 4u) ? gz2 : 0.f);
-            cellq[j++] = make_uint2(cell_key(lvl, (sm & 1u) ? ox : hx, (sm & 2u) ? oy : hy, (sm & 4u) ? oz : hz),
-                                    wq_pack(bound, lane));
-            if (sm == 0u)
-              break;
-          }
-        }
-        const unsigned mf = __ballot_sync(full, fits);
-        nc = mf ? __shfl_sync(full, x, 31 - __clz((int)mf)) : 0;
-        pend = pend && !fits;
-      }
-      __syncwarp();
-      for (;;) {
-        const int ntake = min(min(32, nn), kWqNode - nn);
-        if (nc > 0 && nl <= kWqLeaf - 32 && nn <= kWqNode - 32) {
-          // ---- cell round: one hash lookup per lane --------------------------------------------------------------
-          const int take = min(32, nc);
-          const bool act = lane < take;
-          int ref = kDone;
-          unsigned bo = 0;
-          int o = 0;
-          if (act) {
-            const uint2 it = cellq[nc - 1 - lane];
-            bo = it.y;
-            o = (int)(bo & 31u);
-            if (wq_bound(bo) <= wq_best_d2(&W.best[o])) {
-              ref = cell_lookup(C, it.x);
-              if (ref == W.skipa[o] || ref == W.skipb[o])
-                ref = kDone;
-            }
-            else if (TRACK)
-              atomicMin(&W.pruned[o], bo & ~31u);
-          }
-          nc -= take;
-          // a leaf that spans several cells is returned for each of them: keep one item per (owner, reference)
-          const unsigned long long tag = ref != kDone ? (((unsigned long long)o << 32) | (unsigned)ref)
-                                                      : (0xffffffff00000000ULL | (unsigned)lane);
-          const unsigned grp = __match_any_sync(full, tag);
-          if ((grp & lt) != 0u)
-            ref = kDone;
-          const unsigned ml = __ballot_sync(full, ref != kDone && ref < 0);
-          const unsigned mn = __ballot_sync(full, ref != kDone && ref >= 0);
-          if (ref != kDone) {
-            if (ref < 0)
-              leafq[nl + __popc(ml & lt)] = make_uint2((unsigned)~ref, bo);
-            else
-              nodeq[nn + __popc(mn & lt)] = make_uint2((unsigned)ref, bo);
-          }
-          nl += __popc(ml);
-          nn += __popc(mn);
-        }
-        else if (nl >= 32 || (nl > 0 && !(nn > 0 && ntake > 0 && nl + 2 * ntake <= kWqLeaf))) {
-          // ---- leaf round: one leaf (8 points) per lane -----------------------------------------------------------
-          const int take = min(32, nl);
-          if (lane < take) {
-            const uint2 it = leafq[nl - 1 - lane];
-            const int o = (int)(it.y & 31u);
-            if (wq_bound(it.y) <= wq_best_d2(&W.best[o]))
-              wq_scan_leaf<TRACK>(W, o, a.pts, (int)it.x);
-            else if (TRACK)
-              atomicMin(&W.pruned[o], it.y & ~31u);
-          }
-          nl -= take;
-        }
-        else if (nn > 0 && ntake > 0) {
-          // ---- node round: one node (two child boxes) per lane ----------------------------------------------------
-          const bool act = lane < ntake;
-          int rn = kDone, rf = kDone;  // nearer / farther child, kDone = not wanted
-          unsigned bn = 0, bf = 0;
-          if (act) {
-            const uint2 it = nodeq[nn - 1 - lane];
-            const int o = (int)(it.y & 31u);
-            const float bestd = wq_best_d2(&W.best[o]);
-            if (wq_bound(it.y) <= bestd) {
-              const float4* np = reinterpret_cast<const float4*>(a.nodes + it.x);
-              const float4 na = ldg4(np), nb = ldg4(np + 1), nc4 = ldg4(np + 2);
-              const int4 nd = __ldg(reinterpret_cast<const int4*>(np + 3));
-              const float qx = W.qx[o], qy = W.qy[o], qz = W.qz[o];
-              float dl = box_dist2_rn(qx, qy, qz, na.x, na.y, na.z, na.w, nb.x, nb.y);
-              float dr = box_dist2_rn(qx, qy, qz, nb.z, nb.w, nc4.x, nc4.y, nc4.z, nc4.w);
-              int cl = nd.x, cr = nd.y;
-              if (dr < dl) {
-                const float t = dl; dl = dr; dr = t;
-                const int ti = cl; cl = cr; cr = ti;
-              }
-              if (dl <= bestd) {
-                rn = cl;
-                bn = wq_pack(dl, o);
-              }
-              else if (TRACK)
-                atomicMin(&W.pruned[o], __float_as_uint(dl));
-              if (dr <= bestd) {
-                rf = cr;
-                bf = wq_pack(dr, o);
-              }
-              else if (TRACK)
-                atomicMin(&W.pruned[o], __float_as_uint(dr));
-            }
-            else if (TRACK)
-              atomicMin(&W.pruned[o], it.y & ~31u);
-          }
-          nn -= ntake;
-          // farther children first, nearer ones on top (popped first: depth first)
-#pragma unroll
-          for (int pass = 0; pass < 2; ++pass) {
-            const int ref = pass == 0 ? rf : rn;
-            const unsigned bo = pass == 0 ? bf : bn;
-            const unsigned ml = __ballot_sync(full, ref != kDone && ref < 0);
-            const unsigned mn = __ballot_sync(full, ref != kDone && ref >= 0);
-            if (ref != kDone) {
-              if (ref < 0)
-                leafq[nl + __popc(ml & lt)] = make_uint2((unsigned)~ref, bo);
-              else
-                nodeq[nn + __popc(mn & lt)] = make_uint2((unsigned)ref, bo);
-            }
-            nl += __popc(ml);
-            nn += __popc(mn);
-          }
-        }
-        else if (nn > 0) {
-          // ---- drain round (node queue full): every lane walks one queued subtree with a private stack ------------
-          const int take = min(32, nn);
-          if (lane < take) {
-            const uint2 it = nodeq[nn - 1 - lane];
-            const int o = (int)(it.y & 31u);
-            if (wq_bound(it.y) <= wq_best_d2(&W.best[o])) {
-              WqShared<TRACK> sv{W, o, a.pts};
-              if (!traverse(a.nodes, a.pts, (int)it.x, W.qx[o], W.qy[o], W.qz[o], sv))
-                overflow = true;
-            }
-            else if (TRACK)
-              atomicMin(&W.pruned[o], it.y & ~31u);
-          }
-          nn -= take;
-        }
-        else
-          break;
-        __syncwarp();
-      }
-    } while (__any_sync(full, pend));
-    // ================= phase D: results ============================================================================
-    if (walkq) {
-      const unsigned long long fin = W.best[lane];
-      const unsigned fpos = (unsigned)fin;
-      if (fpos != kWqNoPos) {
-        m.pos = (int)fpos;
-        m.d2 = __uint_as_float((unsigned)(fin >> 32));
-        if (TRACK)
-          lb_out = sqrtf(fminf(__uint_as_float(W.m2[lane]), __uint_as_float(W.pruned[lane])));
-        if (RECIP) {
-          // correspondence_estimation.hpp:259-269: 1-NN of the matched target point back into the source
-          const float4 q = ldg4(a.pts + fpos);
-          Nearest1 b{q.x, q.y, q.z, a.gate, kSentinelIndex, -1};
-          if (!traverse(a.s_nodes, a.s_pts, a.s_root, q.x, q.y, q.z, b))
-            overflow = true;
-          const int slot = __float_as_int(p.w);
-          const int my_orig = a.src_orig ? a.src_orig[slot] : slot;
-          if (!(b.best_pos >= 0 && b.best_idx == my_orig))
-            m.pos |= kNotAccepted;
-        }
-      }
-    }
-    if (in_range) {
-      match[i] = m;
-      if (TRACK)
-        lbs[i] = lb_out;
-    }
-    // ================= epilogue: normal equations on the fp64 tensor cores ========================================
-    if (EST != kEstNone) {
-      __syncwarp();  // the queues are dead: their memory becomes the staging tiles
-      accumulate_pairs_dmma<EST>(a, reinterpret_cast<float*>(W.q), lane, m, p, c1a, c1b, c2a, c2b);
-    }
+    accumulate_pairs_dmma<EST>(a, s_stage[threadIdx.x >> 5], lane, m, p, c1a, c1b, c2a, c2b);
   }
-  if (TRACK) {
-    for (int o = 16; o > 0; o >>= 1)
-      skipped += __shfl_xor_sync(full, skipped, o);
-    if (lane == 0 && skipped)
-      atomicAdd(a.skip_count, (unsigned long long)skipped);
-  }
-  if (overflow)
-    atomicExch(a.d_error, 1);
-  if (EST != kEstNone)
-    fold_tiles_and_publish<EST, kWqWarps>(a, c1a, c1b, c2a, c2b);
+  fold_tiles_and_publish<EST, 8>(a, c1a, c1b, c2a, c2b);
 }
 
 // Accumulation kernel: one streaming pass over (source point, match) pairs; fp64 sums, fixed reduction order.
@@ -1513,6 +1041,93 @@ k_fitness(const TreeView T, const float4* __restrict__ q, size_t nq, double max_
 // =============================================================================================================
 // host side
 // =============================================================================================================
+static void check_device_error(Ctx& c);
+
+// ---- GICP covariances -----------------------------------------------------------------------------------------------
+// GeneralizedIterativeClosestPoint::computeCovariances (registration/impl/gicp.hpp:69-147): per point, the covariance
+// of its k nearest neighbours relative to the point (float differences widened to double), mean removed, SVD, singular
+// values replaced by (1, 1, gicp_epsilon), reassembled from the columns of U.  One thread per point over the exact k-NN
+// rows of launch_knn; the 3x3 Jacobi SVD is k_solve's.
+__global__ void __launch_bounds__(128)
+k_gicp_cov(const float4* __restrict__ q, size_t n, const int32_t* __restrict__ rows, int k_rows, int k_div,
+           const float4* __restrict__ pts, const int32_t* __restrict__ pos_of_orig, double gicp_epsilon,
+           double* __restrict__ out)
+{
+  const size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+  if (i >= n)
+    return;
+  const float4 qq = q[i];
+  double o[9] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
+  if (isfinite(qq.x) && isfinite(qq.y) && isfinite(qq.z)) {
+    double mean[3] = {0.0, 0.0, 0.0}, cov[9] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
+    const int32_t* row = rows + i * (size_t)k_rows;
+    for (int j = 0; j < k_rows; ++j) {
+      const int32_t oi = row[j];
+      if (oi < 0)
+        break;
+      const float4 p = ldg4(pts + pos_of_orig[oi]);
+      const double ptx = (double)__fsub_rn(p.x, qq.x), pty = (double)__fsub_rn(p.y, qq.y), ptz = (double)__fsub_rn(p.z, qq.z);
+      mean[0] += ptx; mean[1] += pty; mean[2] += ptz;
+      cov[0] += ptx * ptx;
+      cov[3] += pty * ptx; cov[4] += pty * pty;
+      cov[6] += ptz * ptx; cov[7] += ptz * pty; cov[8] += ptz * ptz;
+    }
+    const double kk = (double)k_div;
+    for (int d = 0; d < 3; ++d)
+      mean[d] /= kk;
+    for (int r = 0; r < 3; ++r)
+      for (int c = 0; c <= r; ++c) {
+        cov[3 * r + c] /= kk;
+        cov[3 * r + c] -= mean[r] * mean[c];
+        cov[3 * c + r] = cov[3 * r + c];
+      }
+    double U[9], sv[3], V[9];
+    svd3_dev(cov, U, sv, V);
+    for (int kc = 0; kc < 3; ++kc) {
+      const double v = kc == 2 ? gicp_epsilon : 1.0;
+      for (int r = 0; r < 3; ++r)
+        for (int c = 0; c < 3; ++c)
+          o[3 * r + c] += v * U[3 * r + kc] * U[3 * c + kc];
+    }
+  }
+  for (int e = 0; e < 9; ++e)
+    out[9 * i + e] = o[e];
+}
+
+void gicp_covariances(Ctx& c, Index& idx, const void* pts, size_t n, size_t stride, int k, double gicp_epsilon,
+                      double* out)
+{
+  cudaStream_t st = c.stream;
+  if (n == 0)
+    return;
+  PCLB_REQUIRE(k >= 1, PCLB200_ERR_INVALID, "k must be positive");
+  const int keff = (int)std::min<size_t>((size_t)k, idx.n_valid);
+  DevBuf<float4> dense;
+  dense.alloc(n, st);
+  load_xyz_as_float4(c, pts, n, stride, nullptr, 0, dense.p, st);
+  QueryBatch qb;
+  make_query_batch(c, idx, dense.p, n, qb);
+  DevBuf<int32_t> rows;
+  DevBuf<float> rows_d2;
+  rows.alloc(n * (size_t)keff, st);
+  rows_d2.alloc(n * (size_t)keff, st);
+  launch_knn(c, idx, qb.q.p, n, keff, std::numeric_limits<float>::infinity(), rows.p, rows_d2.p);
+  ensure_pos_of_orig(c, idx);
+  DevBuf<double> d_out;
+  const bool on_dev = is_device_ptr(out);
+  double* d_o = out;
+  if (!on_dev) {
+    d_out.alloc(n * 9, st);
+    d_o = d_out.p;
+  }
+  k_gicp_cov<<<grid_for(n, 128), 128, 0, st>>>(dense.p, n, rows.p, keff, k, idx.pts.p, idx.pos_of_orig.p, gicp_epsilon, d_o);
+  ++c.launches;
+  PCLB_CUDA(cudaGetLastError());
+  if (!on_dev)
+    PCLB_CUDA(cudaMemcpyAsync(out, d_out.p, n * 9 * sizeof(double), cudaMemcpyDeviceToHost, st));
+  check_device_error(c);
+}
+
 #ifdef PCLB_STATS
 extern "C" __attribute__((visibility("default"))) int pclb200_debug_walk_stats(unsigned long long out[8], int reset)
 {
@@ -1552,7 +1167,7 @@ static void mat4_mul(const S* A, const S* B, S* C)
 
 struct Reducer {  // scratch for block_reduce_and_publish
   DevBuf<double> partials;
-  DevBuf<double> partials2;  // max_blocks * 128 (k_icp_wq)
+  DevBuf<double> partials2;  // max_blocks * 128 (k_accum_dmma)
   DevBuf<unsigned> counter;
   DevBuf<double> accum;
   unsigned max_blocks = 0;
@@ -2095,7 +1710,6 @@ void icp_iterate(Icp& s, int max_steps, pclb200_icp_stats* stats)
     a.peer.nranks = 0;
     a.seq = 0;
     const bool fused_reduce = comm_peer_view(c, &a.peer, &a.seq);
-    bool fused_accum = false;  // the search kernel also accumulated the normal equations
     const unsigned grid = persistent_grid(c, s.n_q, 256, 8);
     std::unique_ptr<Index> src_index;
     if (s.P.use_reciprocal) {
@@ -2150,40 +1764,13 @@ void icp_iterate(Icp& s, int max_steps, pclb200_icp_stats* stats)
       if (track && !s.lb_valid)  // bounds left by an earlier TRACK phase say nothing about the current matches
         PCLB_CUDA(cudaMemsetAsync(s.lb.p, 0, s.n_q * sizeof(float), st));
       s.lb_valid = track;
-      // the accumulation rides in the search kernel's epilogue unless something sits between the two
-      // (rejectors) or the estimator needs what the epilogue does not carry (source normals)
-      fused_accum = !s.P.use_reciprocal && s.rejectors.empty() &&
-                    (s.P.estimator == PCLB200_EST_SVD || s.P.estimator == PCLB200_EST_POINT_TO_PLANE_LLS);
-#ifdef PCLB_SEARCH_WQ
-      const unsigned wgrid = std::min(persistent_grid(c, s.n_q, kWqWarps * 32, 8), s.red.max_blocks);
-      const int blk = kWqWarps * 32;
-#define PCLB_SEARCH_KERNEL k_icp_wq
-#else
-      const unsigned wgrid = std::min(persistent_grid(c, s.n_q, 256, 16), s.red.max_blocks);
-      const int blk = 256;
-#define PCLB_SEARCH_KERNEL k_search
-#endif
+      const unsigned wgrid = persistent_grid(c, s.n_q, 256, 18);
       if (s.P.use_reciprocal)
-        PCLB_SEARCH_KERNEL<kEstNone, true, false><<<wgrid, blk, 0, st>>>(a, s.match.p, s.lb.p);
-      else if (!fused_accum) {
-        if (track)
-          PCLB_SEARCH_KERNEL<kEstNone, false, true><<<wgrid, blk, 0, st>>>(a, s.match.p, s.lb.p);
-        else
-          PCLB_SEARCH_KERNEL<kEstNone, false, false><<<wgrid, blk, 0, st>>>(a, s.match.p, s.lb.p);
-      }
-      else if (s.P.estimator == PCLB200_EST_SVD) {
-        if (track)
-          PCLB_SEARCH_KERNEL<PCLB200_EST_SVD, false, true><<<wgrid, blk, 0, st>>>(a, s.match.p, s.lb.p);
-        else
-          PCLB_SEARCH_KERNEL<PCLB200_EST_SVD, false, false><<<wgrid, blk, 0, st>>>(a, s.match.p, s.lb.p);
-      }
-      else {
-        if (track)
-          PCLB_SEARCH_KERNEL<PCLB200_EST_POINT_TO_PLANE_LLS, false, true><<<wgrid, blk, 0, st>>>(a, s.match.p, s.lb.p);
-        else
-          PCLB_SEARCH_KERNEL<PCLB200_EST_POINT_TO_PLANE_LLS, false, false><<<wgrid, blk, 0, st>>>(a, s.match.p, s.lb.p);
-      }
-#undef PCLB_SEARCH_KERNEL
+        k_search<true, false><<<wgrid, 256, 0, st>>>(a, s.match.p, s.lb.p);
+      else if (track)
+        k_search<false, true><<<wgrid, 256, 0, st>>>(a, s.match.p, s.lb.p);
+      else
+        k_search<false, false><<<wgrid, 256, 0, st>>>(a, s.match.p, s.lb.p);
       ++c.launches;
     }
     if (!s.rejectors.empty()) {
@@ -2192,12 +1779,13 @@ void icp_iterate(Icp& s, int max_steps, pclb200_icp_stats* stats)
       ProfScope ps(c, "icp_reject");
       run_rejectors(s);
     }
-    if (!fused_accum) {
+    {
       ProfScope ps(c, "icp_accum");
+      const unsigned agrid = std::min(persistent_grid(c, s.n_q, 256, 8), s.red.max_blocks);
       if (s.P.estimator == PCLB200_EST_SVD)
-        k_accum<PCLB200_EST_SVD><<<grid, 256, 0, st>>>(a, s.match.p);
+        k_accum_dmma<PCLB200_EST_SVD><<<agrid, 256, 0, st>>>(a, s.match.p);
       else if (s.P.estimator == PCLB200_EST_POINT_TO_PLANE_LLS)
-        k_accum<PCLB200_EST_POINT_TO_PLANE_LLS><<<grid, 256, 0, st>>>(a, s.match.p);
+        k_accum_dmma<PCLB200_EST_POINT_TO_PLANE_LLS><<<agrid, 256, 0, st>>>(a, s.match.p);
       else
         k_accum<PCLB200_EST_SYMMETRIC_POINT_TO_PLANE_LLS><<<grid, 256, 0, st>>>(a, s.match.p);
       ++c.launches;

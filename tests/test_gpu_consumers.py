@@ -80,3 +80,22 @@ def test_sample_consensus_prerejective_inliers(gpu, orc):
         inl, got_fit = idx.inliers(S, T, thr)
         assert np.array_equal(inl, want), thr
         assert got_fit == want_fit, thr
+
+
+def test_gicp_covariances(gpu, orc):
+    """registration/impl/gicp.hpp:69-147: k = 20 neighbourhood covariance, regularised to singular values (1, 1, eps)."""
+    P, ctx = gpu
+    rng = np.random.default_rng(2)
+    n = 30000
+    pts = rng.random((n, 3), dtype=np.float32) * np.float32(3)
+    pts[:, 2] = np.float32(0.2) * np.sin(np.float32(4) * pts[:, 0]) + np.float32(0.003) * rng.standard_normal(n).astype(np.float32)
+    cloud = P.xyz1(pts)
+    cloud[11, 1] = np.nan
+    g = P.Index(ctx, cloud).gicp_covariances(cloud, k=20, gicp_epsilon=0.001)
+    o = orc.Index(cloud).gicp_covariances(k=20, gicp_epsilon=0.001, nthreads=8)
+    assert np.all(g[11] == 0) and np.all(o[11] == 0)
+    ok = np.isfinite(cloud[:, 1])
+    # the regularised matrix is I - (1 - eps) n n^T: well conditioned wherever the smallest singular value is isolated
+    assert np.abs(g[ok] - o[ok]).max() < 1e-9, float(np.abs(g[ok] - o[ok]).max())
+    w = np.linalg.eigvalsh(g[ok])
+    assert np.allclose(w[:, 0], 0.001, atol=1e-9) and np.allclose(w[:, 1:], 1.0, atol=1e-9)
