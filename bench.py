@@ -27,7 +27,7 @@ Scaling (--scaling):
   weak   : every rank holds a replica of the target index and its OWN source cloud of the full size (default)
   strong : ONE source; rank r gets the r-th contiguous range of its Morton order (a spatial tile), so per-GPU work
            shrinks with N.  The 40 fp64 accumulators are exchanged once per iteration over NVLink (fused into the
-           search kernel's last block; NCCL bootstraps the peer mappings).
+           accumulate kernel's last block; NCCL bootstraps the peer mappings).
 --impl reference times the CPU restatement of PCL's own path (oracle/; the reference itself cannot be compiled in this
 image: no Eigen/Boost/FLANN) on the box's host cores, on a bounded sample of the same workload.
 """
@@ -401,33 +401,47 @@ def run_ours(args):
         ctx.comm_init(rank, world, uid[0])
     stream = torch.cuda.ExternalStream(ctx.stream, device=dev)
 
-    # ---- set-up (outside the timed region): clouds, VoxelGrid front-end, target index, normals ------------------------
+    # ---- set-up (outside the timed region): clouds, target-side VoxelGrid, target index, normals -------------------------
     tgt, src_full = gen_clouds(args.workload, n, rank, strong, device=dev)
     setup_ms = {}
     ctx.profile(True)
-    if W["voxel_leaf"]:
-        # cfg5: both clouds through VoxelGrid on the GPU (the reference's downsample front-end); the filtered source
-        # is what gets sharded, so every N aligns exactly the same clouds
-        for nm in ("target", "source"):
-            a = torch.from_numpy(tgt if nm == "target" else src_full).to(dev)
-            o = torch.empty_like(a)
-            ctx.profile_reset()
-            f = ctx.voxelgrid(a, [W["voxel_leaf"]] * 3, out=o)
-            setup_ms[f"voxelgrid_{nm}"] = ctx.profile_get("voxelgrid")[0]
-            setup_ms[f"voxelgrid_{nm}_points_in"] = int(a.shape[0])
-            res = f.cpu().numpy().copy()
-            if nm == "target":
-                tgt = res
-            else:
-                src_full = res
-            del a, o, f
+    leaf = W["voxel_leaf"]
+    grid_bounds = None
+    if leaf:
+        # cfg5.  Target: one VoxelGrid over the whole sweep (set-up, like the index build).  Source: the RAW sweep is cut
+        # into spatial tiles along voxel columns of the WHOLE sweep's grid; every step each rank filters its tile on that
+        # grid (pclb200_voxelgrid_tile: the tiles' voxels are exactly the voxels of one VoxelGrid over the whole sweep)
+        # and aligns the result — the downsample front-end is part of the step and shards with the source.
+        a = torch.from_numpy(tgt).to(dev)
+        o = torch.empty_like(a)
+        ctx.profile_reset()
+        f = ctx.voxelgrid(a, [leaf] * 3, out=o)
+        setup_ms["voxelgrid_target"] = ctx.profile_get("voxelgrid")[0]
+        setup_ms["voxelgrid_target_points_in"] = int(a.shape[0])
+        tgt = f.cpu().numpy().copy()
+        del a, o, f
         torch.cuda.empty_cache()
+        lo, hi = src_full[:, :3].min(0), src_full[:, :3].max(0)
+        grid_bounds = np.concatenate([lo, hi]).astype(np.float32)
+        if strong and world > 1:
+            inv = np.float32(1.0) / np.float32(leaf)
+            col = (np.floor(src_full[:, 0] * inv) - np.floor(lo[0] * inv)).astype(np.int64)
+            cum = np.cumsum(np.bincount(col))
+            cuts = [0] + [int(np.searchsorted(cum, cum[-1] * r / world)) + 1 for r in range(1, world)] + [int(col.max()) + 1]
+            src_full = np.ascontiguousarray(src_full[(col >= cuts[rank]) & (col < cuts[rank + 1])])
+            del col
     n_tgt = int(tgt.shape[0])
-    src_np = shard_strong(src_full, rank, world) if strong else src_full
-    n_src_total = int(src_full.shape[0]) * (1 if strong else world)
+    n_src_total = int(src_full.shape[0]) * (1 if (strong and not leaf) else world)
+    if leaf:
+        src_np = src_full                                  # this rank's raw tile (strong) / own sweep (weak)
+        if strong and world > 1:
+            t = torch.tensor([float(src_np.shape[0])], dtype=torch.float64, device=dev)
+            dist.all_reduce(t)
+            n_src_total = int(t[0])
+    else:
+        src_np = shard_strong(src_full, rank, world) if strong else src_full
     del src_full
     src_host = torch.from_numpy(src_np).pin_memory()
-    out_host = torch.empty_like(src_host).pin_memory()
     ctx.profile_reset()
     tidx = P.Index(ctx, tgt)
     setup_ms["index_build"] = ctx.profile_get("index_build")[0]
@@ -439,7 +453,16 @@ def run_ours(args):
         setup_ms[f"normals_k{W['normals_k']}"] = ctx.profile_get("normals")[0]
         del tgt_dev
     src_dev = src_host.to(dev)                    # value leg: records already resident in HBM
-    out_dev = torch.empty_like(src_dev)
+    vg_buf = None
+    n_filtered = int(src_np.shape[0])
+    if leaf:
+        vg_buf = torch.empty_like(src_dev)
+        n_filtered = int(ctx.voxelgrid_tile(src_dev, [leaf] * 3, grid_bounds, out=vg_buf).shape[0])
+        out_host = torch.empty((n_filtered, src_host.shape[1]), dtype=torch.float32).pin_memory()
+        out_dev = torch.empty((n_filtered, src_host.shape[1]), dtype=torch.float32, device=dev)
+    else:
+        out_host = torch.empty_like(src_host).pin_memory()
+        out_dev = torch.empty_like(src_dev)
     params = P.default_params(max_iterations=W["iters"], max_correspondence_distance=W["gate"],
                               estimator=P.EST_POINT_TO_PLANE_LLS if p2plane else P.EST_SVD,
                               with_normals_transform=1 if p2plane else 0, mse_threshold_absolute=0.0,
@@ -452,6 +475,8 @@ def run_ours(args):
     icp.set_target(tidx, normals=nrm_dev)
 
     def align(src, out):
+        if leaf:
+            src = ctx.voxelgrid_tile(src, [leaf] * 3, grid_bounds, out=vg_buf)   # the step's downsample front-end
         if p2plane:
             icp.set_source(src, normals=P.Field(src, 4))
         else:
@@ -497,7 +522,8 @@ def run_ours(args):
 
     # device-resident leg (value) --------------------------------------------------------------------------------
     ms_v, tot_v, launches, clocks, iters_v = timed(src_dev, out_dev, args.steps, args.warmup, not args.no_clocks)
-    prof = {k: ctx.profile_get(k) for k in ("icp_search", "icp_accum", "allreduce", "query_sort", "solve", "transform_out")}
+    prof = {k: ctx.profile_get(k) for k in ("icp_search", "icp_accum", "allreduce", "query_sort", "solve", "transform_out",
+                                            "voxelgrid")}
     # host-buffer leg (e2e) --------------------------------------------------------------------------------------
     ms_e, tot_e, _, _, _ = timed(src_host, out_host, args.steps, max(1, args.warmup // 2), False)
     value = tot_v / (ms_v * 1e-3)
@@ -508,32 +534,40 @@ def run_ours(args):
         return
 
     # ---- roofline of the dominant kernel ----------------------------------------------------------
-    # k_icp_wq = transform + exact 1-NN + gate + normal-equation accumulation of one ICP iteration, fused.
+    # k_search = in-place transform + exact seeded 1-NN + gate of one ICP iteration (>= 85 % of a step).
     # ALGORITHMIC bytes per correspondence (§8d): 16 (query read) + 24 * N_t / N_s (every target point, 16 B, and its
-    # share of a 32-B node per 8-point leaf, read once under coherent queries) = 40 B at N_s = N_t, + 16 * N_t / N_s for
-    # the target normals of the point-to-plane objective = 56 B.  The implementation moves more than that (the in-place
-    # fp32 re-transform of the source that reproduces icp.hpp:220 bit for bit, the 8-B match = next iteration's seed,
-    # leaf padding, 64-B nodes, the cell table); that figure is `implementation_bytes_per_correspondence`, and the measured
-    # DRAM bytes of an ncu capture are `traffic`.
+    # share of a 32-B node per 8-point leaf, read once under coherent queries) = 40 B at N_s = N_t.  The whole iteration
+    # (k_search + k_accum_dmma) adds 16 * N_t / N_s for the target normals of the point-to-plane objective = 56 B; it is
+    # reported as `iteration`.  The implementation moves more than that (the in-place fp32 re-transform of the source
+    # that reproduces icp.hpp:220 bit for bit, the 8-B match = next iteration's seed, leaf padding, 64-B nodes, the cell
+    # table): `implementation_bytes_per_correspondence`; the DRAM bytes ncu measured per launch are `traffic`.
     st_idx = tidx.stats
-    n_local = int(src_np.shape[0])
+    n_local = n_filtered
     ratio = n_tgt / float(n_local)
-    alg_bytes = 16.0 + 24.0 * ratio + (16.0 * ratio if p2plane else 0.0)
-    impl_bytes = (16 + 16 + 8 + 8 + (16 * ratio if p2plane else 0.0) +
-                  (st_idx["leaves"] * st_idx["leaf_size"] * 16 + st_idx["nodes"] * 64) / float(n_local))
+    alg_search = 16.0 + 24.0 * ratio
+    alg_iter = alg_search + (16.0 * ratio if p2plane else 0.0)
+    impl_bytes = (16 + 16 + 8 + 8 + (st_idx["leaves"] * st_idx["leaf_size"] * 16 + st_idx["nodes"] * 64) / float(n_local))
     peak, peak_src = measured_peak_gbs()
     iter_ms, iter_n = prof["icp_search"]
-    avg_iter_s = (iter_ms / max(iter_n, 1)) * 1e-3
-    achieved = alg_bytes * n_local / avg_iter_s / 1e9 if avg_iter_s > 0 else 0.0
+    acc_ms, acc_n = prof["icp_accum"]
+    avg_search_s = (iter_ms / max(iter_n, 1)) * 1e-3
+    avg_iter_s = avg_search_s + (acc_ms / max(acc_n, 1)) * 1e-3
+    achieved = alg_search * n_local / avg_search_s / 1e9 if avg_search_s > 0 else 0.0
+    ach_iter = alg_iter * n_local / avg_iter_s / 1e9 if avg_iter_s > 0 else 0.0
     roofline = {"bound": "hbm",
-                "kernel": "k_icp_wq (one ICP iteration fused: in-place transform + exact seeded 1-NN + gate + "
-                          "fp64 tensor-core accumulation of the normal equations)",
+                "kernel": "k_search (in-place transform + exact seeded 1-NN started at the candidate ball + gate)",
                 "achieved": achieved, "peak": peak, "peak_source": peak_src, "unit": "GB/s", "frac": achieved / peak,
                 "frac_of_nominal_8000_GBs": achieved / 8000.0,  # report both denominators
-                "traffic": ncu_traffic("k_icp_wq_" + args.workload, n),
-                "algorithmic_bytes_per_launch": alg_bytes * n_local, "avg_launch_ms": avg_iter_s * 1e3,
-                "launches_timed": iter_n, "algorithmic_bytes_per_correspondence": alg_bytes,
-                "implementation_bytes_per_correspondence": impl_bytes, "index": st_idx,
+                "traffic": ncu_traffic("k_search_" + args.workload, n),
+                "algorithmic_bytes_per_launch": alg_search * n_local, "avg_launch_ms": avg_search_s * 1e3,
+                "launches_timed": iter_n, "algorithmic_bytes_per_correspondence": alg_search,
+                "implementation_bytes_per_correspondence": impl_bytes,
+                "iteration": {"kernels": "k_search + k_accum_dmma", "algorithmic_bytes_per_correspondence": alg_iter,
+                              "avg_ms": avg_iter_s * 1e3, "achieved": ach_iter, "frac": ach_iter / peak,
+                              "accum_kernel_ms": acc_ms / max(acc_n, 1),
+                              "accum_kernel_GBs_of_its_56B": ((8 + 16 + 16 + (16 if p2plane else 0)) * n_local /
+                                                             max(acc_ms / max(acc_n, 1) * 1e-3, 1e-12) / 1e9)},
+                "index": st_idx,
                 "note": "the walk is latency/issue bound, not HBM bound (SURVEY.md §7 hard part ii, DESIGN.md §3); frac "
                         "is the §8(d) algorithmic figure over the measured copy peak"}
 
@@ -549,6 +583,8 @@ def run_ours(args):
         tree = oracle.Index(tgt_n)
         build_s = time.time() - t0
         kw = oracle_kw(W, cores, tree)
+        if leaf:   # the CPU arm aligns the filtered cloud too (its own VoxelGrid outside the sample timing)
+            src_np = oracle.voxelgrid(src_np, [leaf] * 3)
         probe = min(n_local, 100_000)
         t0 = time.time()
         r = oracle.icp_align(src_np[:probe], tgt_n, **kw)
@@ -563,26 +599,29 @@ def run_ours(args):
                          f"; kd-tree build {build_s:.1f} s excluded"}
 
     rec_bytes = int(src_host.numel() * 4)
+    out_bytes = int(out_host.numel() * 4)
     steps = max(args.steps, 1)
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_v / steps, "higher_is_better": True, "scaling": args.scaling,
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": W["name"], "points_target": n_tgt, "points_source_total": n_src_total,
-                       "points_source_per_gpu": n_local, "icp_iterations_per_step": W["iters"],
+                       "points_source_per_gpu": int(src_np.shape[0]), "points_aligned_per_gpu": n_local,
+                       "icp_iterations_per_step": W["iters"],
                        "max_correspondence_distance": W["gate"], "estimator": W["estimator"], "k": 1,
                        "normals_k": W["normals_k"], "voxel_leaf": W["voxel_leaf"],
                        "l2_policy": "inputs larger than L2 (target points + nodes + normals + source >> 126 MB)",
                        "parallelism": (f"source sharded x{world} ({'Morton-range tiles of one cloud' if strong else 'one cloud per rank'}), "
-                                       "target replicated, 40-double exchange per iteration fused into the search kernel")},
+                                       "target replicated, 40-double exchange per iteration fused into the accumulate kernel")},
             "ms_per_iter": ms_v / max(iters_v, 1),
             "breakdown_ms_per_step": {"icp_iteration_kernel": prof["icp_search"][0] / steps,
                                       "icp_accum_kernel": prof["icp_accum"][0] / steps,
                                       "nccl_allreduce": prof["allreduce"][0] / steps,
+                                      "voxelgrid_source_tile": prof["voxelgrid"][0] / steps,
                                       "query_sort": prof["query_sort"][0] / steps, "solve": prof["solve"][0] / steps,
                                       "transform_out": prof["transform_out"][0] / steps},
             "setup_ms": setup_ms,
             "e2e": {"value": e2e, "unit": UNIT, "ms_per_step": ms_e / steps, "h2d_bytes_per_step": rec_bytes,
-                    "d2h_bytes_per_step": rec_bytes + 512 * W["iters"]},
+                    "d2h_bytes_per_step": out_bytes + 512 * W["iters"]},
             "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline}
     if cpu:
         line["cpu_baseline"] = cpu

@@ -203,6 +203,12 @@ PCLB200_API int pclb200_reject_surface_normal(pclb200_ctx* ctx, const pclb200_co
 PCLB200_API int pclb200_estimate_svd(pclb200_ctx* ctx, const void* src, size_t stride_s,
                                      const void* tgt, size_t stride_t, const pclb200_corr* corr,
                                      size_t n, int scalar_is_double, double T_out[16]);
+/* TransformationEstimationSVD(use_umeyama = false): compute3DCentroid + demeanPointCloud + getTransformationFromCorrelation
+ * (impl/transformation_estimation_svd.hpp:156-225; common/impl/centroid.hpp:55-85, 933-964): H = sum (p - cp)(q - cq)^T,
+ * SVD, R = V U^T (last column of V negated when det(U) det(V) < 0), t = cq - R cp. */
+PCLB200_API int pclb200_estimate_svd_correlation(pclb200_ctx* ctx, const void* src, size_t stride_s,
+                                                 const void* tgt, size_t stride_t, const pclb200_corr* corr,
+                                                 size_t n, int scalar_is_double, double T_out[16]);
 PCLB200_API int pclb200_estimate_point_to_plane_lls(pclb200_ctx* ctx, const void* src,
                                                     size_t stride_s, const void* tgt,
                                                     const void* tgt_normals, size_t stride_t,
@@ -259,6 +265,9 @@ typedef struct pclb200_icp_params {
   double mse_threshold_absolute;          /* default_convergence_criteria.h:307, default 1e-12 */
   int32_t correspondence_k;       /* k_ of the normal-shooting / back-projection estimators (setKSearch, default 10) */
   int32_t track_mode;             /* PCLB200_TRACK_*: temporal-coherence skip test of the 1-NN search (exact either way) */
+  int32_t svd_no_umeyama;         /* TransformationEstimationSVD(use_umeyama = false): getTransformationFromCorrelation
+                                     (transformation_estimation_svd.hpp:156-225) instead of Eigen::umeyama; default 0 */
+  int32_t reserved2;
 } pclb200_icp_params;
 
 typedef struct pclb200_icp_stats {
@@ -384,6 +393,14 @@ PCLB200_API int pclb200_voxelgrid(pclb200_ctx* ctx, const void* pts, size_t n, s
                                   const int32_t* indices, size_t n_idx, int is_dense,
                                   const float leaf[3], unsigned min_points_per_voxel,
                                   float* out_xyz1, size_t* n_out);
+
+/* One SPATIAL TILE of a VoxelGrid over a larger cloud (multi-GPU front-end): grid_bounds = {min x,y,z,
+ * max x,y,z} of the WHOLE cloud fix the grid (min_b, div_b: voxel_grid.hpp:632-644), so a tile cut along voxel boundaries
+ * yields exactly the centroids a single VoxelGrid over the whole cloud yields for those voxels; the tiles' outputs,
+ * concatenated, are the whole output as a set.  The INT32 guard (:620-629) applies to the whole grid. */
+PCLB200_API int pclb200_voxelgrid_tile(pclb200_ctx* ctx, const void* pts, size_t n, size_t stride,
+                                       const float grid_bounds[6], const float leaf[3], unsigned min_points_per_voxel,
+                                       float* out_xyz1, size_t* n_out);
 
 /* The same filter for records that carry a normal and a curvature (pcl::PointNormal, pcl::Normal), with the
  * reference's default downsample_all_data_ = true (voxel_grid.hpp:796-806, CentroidPoint): per voxel the normals are

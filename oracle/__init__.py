@@ -75,6 +75,7 @@ def lib():
         L.orc_correspondences_reciprocal.restype = sz
         L.orc_correspondences_reciprocal.argtypes = [vp, vp, fp, sz, sz, fp, sz, i32p, sz, C.c_int, C.c_double, C.POINTER(Corr), C.c_int]
         L.orc_estimate_svd.argtypes = [fp, sz, fp, sz, C.POINTER(Corr), sz, C.c_int, dp]
+        L.orc_estimate_svd_correlation.argtypes = [fp, sz, fp, sz, C.POINTER(Corr), sz, C.c_int, dp]
         L.orc_estimate_point_to_plane_lls.argtypes = [fp, sz, fp, fp, sz, C.POINTER(Corr), sz, C.c_int, dp]
         L.orc_estimate_symmetric_lls.argtypes = [fp, fp, sz, fp, fp, sz, C.POINTER(Corr), sz, C.c_int, C.c_int, dp]
         L.orc_transform.argtypes = [fp, sz, sz, C.c_int, dp, C.c_int, C.c_int]
@@ -312,11 +313,12 @@ def _corr_ptr(corr):
     return corr, corr.size
 
 
-def estimate_svd(src, tgt, corr=None, scalar_is_double=False):
+def estimate_svd(src, tgt, corr=None, scalar_is_double=False, use_umeyama=True):
     src, tgt = as_cloud(src), as_cloud(tgt)
     corr, n = _corr_ptr(corr)
     T = np.zeros(16, dtype=np.float64)
-    lib().orc_estimate_svd(_f(src), src.shape[1], _f(tgt), tgt.shape[1],
+    fn = lib().orc_estimate_svd if use_umeyama else lib().orc_estimate_svd_correlation
+    fn(_f(src), src.shape[1], _f(tgt), tgt.shape[1],
                            None if corr is None else corr.ctypes.data_as(C.POINTER(Corr)),
                            n if corr is not None else src.shape[0], int(scalar_is_double), _d(T))
     return T.reshape(4, 4)

@@ -1236,6 +1236,85 @@ ORC_API void orc_estimate_svd(const float* src, size_t sstride, const float* tgt
   }
 }
 
+// TransformationEstimationSVD with use_umeyama_ = false — impl/transformation_estimation_svd.hpp:156-225:
+// compute3DCentroid (common/impl/centroid.hpp:55-85: sums in Scalar, / n), demeanPointCloud (:933-964),
+// getTransformationFromCorrelation: H = src_demean * tgt_demean^T, JacobiSVD, R = V U^T (last column of V negated when
+// det(U) det(V) < 0), t = c_tgt - R c_src.
+template <typename S>
+static void correlation_svd(const float* src, size_t sstride, const float* tgt, size_t tstride, const int32_t* qi,
+                            const int32_t* mi, size_t n, S T[16])
+{
+  S cs[3] = {0, 0, 0}, ct[3] = {0, 0, 0};
+  for (size_t i = 0; i < n; ++i) {
+    const float* p = src + sstride * (size_t)(qi ? qi[i] : (int32_t)i);
+    const float* q = tgt + tstride * (size_t)(mi ? mi[i] : (int32_t)i);
+    for (int d = 0; d < 3; ++d) {
+      cs[d] += p[d];
+      ct[d] += q[d];
+    }
+  }
+  for (int d = 0; d < 3; ++d) {
+    cs[d] /= static_cast<S>(n);
+    ct[d] /= static_cast<S>(n);
+  }
+  S H[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+  for (size_t i = 0; i < n; ++i) {
+    const float* p = src + sstride * (size_t)(qi ? qi[i] : (int32_t)i);
+    const float* q = tgt + tstride * (size_t)(mi ? mi[i] : (int32_t)i);
+    const S a[3] = {p[0] - cs[0], p[1] - cs[1], p[2] - cs[2]};
+    const S b[3] = {q[0] - ct[0], q[1] - ct[1], q[2] - ct[2]};
+    for (int r = 0; r < 3; ++r)
+      for (int c = 0; c < 3; ++c)
+        H[3 * r + c] += a[r] * b[c];
+  }
+  S U[9], sv[3], V[9];
+  svd3<S>(H, U, sv, V);
+  if (det3<S>(U) * det3<S>(V) < 0)
+    for (int x = 0; x < 3; ++x)
+      V[3 * x + 2] = -V[3 * x + 2];
+  S R[9];
+  for (int r = 0; r < 3; ++r)
+    for (int c = 0; c < 3; ++c) {
+      S acc = 0;
+      for (int k = 0; k < 3; ++k)
+        acc += V[3 * r + k] * U[3 * c + k];
+      R[3 * r + c] = acc;
+    }
+  for (int i = 0; i < 16; ++i)
+    T[i] = (i % 5 == 0) ? S(1) : S(0);
+  for (int r = 0; r < 3; ++r) {
+    for (int c = 0; c < 3; ++c)
+      T[4 * r + c] = R[3 * r + c];
+    T[4 * r + 3] = ct[r] - (R[3 * r] * cs[0] + R[3 * r + 1] * cs[1] + R[3 * r + 2] * cs[2]);
+  }
+}
+
+ORC_API void orc_estimate_svd_correlation(const float* src, size_t sstride, const float* tgt, size_t tstride,
+                                          const orc_corr* corr, size_t n, int scalar_is_double, double* T_out)
+{
+  std::vector<int32_t> qi, mi;
+  if (corr) {
+    qi.resize(n);
+    mi.resize(n);
+    for (size_t i = 0; i < n; ++i) {
+      qi[i] = corr[i].index_query;
+      mi[i] = corr[i].index_match;
+    }
+  }
+  if (scalar_is_double) {
+    double T[16];
+    correlation_svd<double>(src, sstride, tgt, tstride, corr ? qi.data() : nullptr, corr ? mi.data() : nullptr, n, T);
+    for (int i = 0; i < 16; ++i)
+      T_out[i] = T[i];
+  }
+  else {
+    float T[16];
+    correlation_svd<float>(src, sstride, tgt, tstride, corr ? qi.data() : nullptr, corr ? mi.data() : nullptr, n, T);
+    for (int i = 0; i < 16; ++i)
+      T_out[i] = T[i];
+  }
+}
+
 ORC_API int orc_estimate_point_to_plane_lls(const float* src, size_t sstride, const float* tgt,
                                             const float* tgt_normals, size_t tstride,
                                             const orc_corr* corr, size_t n, int scalar_is_double,

@@ -37,7 +37,7 @@ class IcpParams(C.Structure):
                 ("enforce_same_direction_normals", C.c_int32), ("correspondence_kind", C.c_int32),
                 ("max_correspondence_distance", C.c_double), ("transformation_epsilon", C.c_double),
                 ("transformation_rotation_epsilon", C.c_double), ("euclidean_fitness_epsilon", C.c_double),
-                ("mse_threshold_absolute", C.c_double), ("correspondence_k", C.c_int32), ("track_mode", C.c_int32)]
+                ("mse_threshold_absolute", C.c_double), ("correspondence_k", C.c_int32), ("track_mode", C.c_int32), ("svd_no_umeyama", C.c_int32), ("reserved2", C.c_int32)]
 
 
 class IcpStats(C.Structure):
@@ -68,12 +68,12 @@ SYMBOLS = [
     "pclb200_launch_count", "pclb200_stream", "pclb200_free", "pclb200_profile_enable", "pclb200_profile_get",
     "pclb200_profile_reset", "pclb200_index_build", "pclb200_index_destroy",
     "pclb200_index_size", "pclb200_index_stats", "pclb200_knn", "pclb200_knn_stats", "pclb200_radius", "pclb200_correspondences",
-    "pclb200_estimate_svd", "pclb200_estimate_point_to_plane_lls", "pclb200_estimate_symmetric_point_to_plane_lls", "pclb200_icp_default_params",
+    "pclb200_estimate_svd", "pclb200_estimate_svd_correlation", "pclb200_estimate_point_to_plane_lls", "pclb200_estimate_symmetric_point_to_plane_lls", "pclb200_icp_default_params",
     "pclb200_icp_create", "pclb200_icp_destroy", "pclb200_icp_set_params", "pclb200_icp_set_target",
     "pclb200_icp_set_source", "pclb200_icp_iterate", "pclb200_icp_get_cloud", "pclb200_icp_get_correspondences",
     "pclb200_icp_align",
     "pclb200_fitness_score", "pclb200_reject", "pclb200_icp_set_rejectors", "pclb200_normals_knn", "pclb200_normals_radius",
-    "pclb200_correspondences_normals", "pclb200_reject_surface_normal", "pclb200_cluster_labels", "pclb200_voxelgrid", "pclb200_voxelgrid_normals", "pclb200_validate_transformation", "pclb200_inliers", "pclb200_radius_into", "pclb200_gicp_covariances", "pclb200_comm_unique_id", "pclb200_comm_set_mode", "pclb200_comm_export", "pclb200_comm_import",
+    "pclb200_correspondences_normals", "pclb200_reject_surface_normal", "pclb200_cluster_labels", "pclb200_voxelgrid", "pclb200_voxelgrid_normals", "pclb200_voxelgrid_tile", "pclb200_validate_transformation", "pclb200_inliers", "pclb200_radius_into", "pclb200_gicp_covariances", "pclb200_comm_unique_id", "pclb200_comm_set_mode", "pclb200_comm_export", "pclb200_comm_import",
     "pclb200_comm_init",
 ]
 
@@ -111,6 +111,7 @@ def lib():
                                  C.POINTER(i32p), C.POINTER(fp)]
     L.pclb200_correspondences.argtypes = [vp, vp, vp, vp, sz, sz, vp, sz, C.c_int, C.c_double, vp, C.POINTER(sz)]
     L.pclb200_estimate_svd.argtypes = [vp, vp, sz, vp, sz, vp, sz, C.c_int, dp]
+    L.pclb200_estimate_svd_correlation.argtypes = [vp, vp, sz, vp, sz, vp, sz, C.c_int, dp]
     L.pclb200_estimate_point_to_plane_lls.argtypes = [vp, vp, sz, vp, vp, sz, vp, sz, C.c_int, dp]
     L.pclb200_estimate_symmetric_point_to_plane_lls.argtypes = [vp, vp, vp, sz, vp, vp, sz, vp, sz, C.c_int, C.c_int, dp]
     L.pclb200_icp_default_params.argtypes = [C.POINTER(IcpParams)]
@@ -135,6 +136,7 @@ def lib():
     L.pclb200_reject_surface_normal.argtypes = [vp, vp, sz, vp, sz, sz, vp, sz, sz, C.c_double, vp, C.POINTER(sz)]
     L.pclb200_cluster_labels.argtypes = [vp, vp, C.c_double, vp, sz]
     L.pclb200_voxelgrid.argtypes = [vp, vp, sz, sz, vp, sz, C.c_int, fp, C.c_uint, vp, C.POINTER(sz)]
+    L.pclb200_voxelgrid_tile.argtypes = [vp, vp, sz, sz, fp, fp, C.c_uint, vp, C.POINTER(sz)]
     L.pclb200_voxelgrid_normals.argtypes = [vp, vp, sz, sz, vp, sz, vp, sz, C.c_int, fp, C.c_uint, vp, vp, C.POINTER(sz)]
     L.pclb200_validate_transformation.argtypes = [vp, vp, vp, sz, sz, dp, C.c_int, C.c_double, dp]
     L.pclb200_inliers.argtypes = [vp, vp, vp, sz, sz, dp, C.c_float, vp, C.POINTER(sz)]
@@ -285,6 +287,20 @@ class Context:
                                        int(min_points_per_voxel), ob.ptr, C.byref(m)))
         return out[:m.value].copy() if host_out else out[:m.value]
 
+    def voxelgrid_tile(self, cloud, leaf, grid_bounds, min_points_per_voxel=0, out=None):
+        """VoxelGrid of one spatial tile on the grid of the whole cloud (grid_bounds = its min xyz + max xyz)."""
+        b = _Buf(cloud)
+        leaf = (C.c_float * 3)(*[float(x) for x in np.broadcast_to(np.asarray(leaf, dtype=np.float32), (3,))])
+        gb = (C.c_float * 6)(*[float(x) for x in np.asarray(grid_bounds, dtype=np.float32).reshape(6)])
+        host_out = out is None
+        if host_out:
+            out = np.empty((max(b.rows, 1), 4), dtype=np.float32)
+        ob = _Buf(out)
+        m = C.c_size_t()
+        _check(lib().pclb200_voxelgrid_tile(self.h, b.ptr, b.rows, b.stride, gb, leaf, int(min_points_per_voxel), ob.ptr,
+                                            C.byref(m)))
+        return out[:m.value].copy() if host_out else out[:m.value]
+
     def voxelgrid_normals(self, cloud, leaf, min_points_per_voxel=0, indices=None, is_dense=True, normal_offset=4):
         """VoxelGrid<PointNormal> with downsample_all_data_ = true: (xyz1 rows, {nx,ny,nz,n4,curvature,0,0,0} rows)."""
         b = _Buf(cloud)
@@ -321,12 +337,13 @@ class Context:
                                                    C.c_void_p(out.ctypes.data), C.byref(m)))
         return out[:m.value].copy()
 
-    def estimate_svd(self, src, tgt, corr=None, scalar_is_double=False):
+    def estimate_svd(self, src, tgt, corr=None, scalar_is_double=False, use_umeyama=True):
         s, t = _Buf(src), _Buf(tgt)
         cb = None if corr is None else np.ascontiguousarray(corr, dtype=CORR_DTYPE)
         n = s.rows if cb is None else cb.size
         T = np.zeros(16)
-        _check(lib().pclb200_estimate_svd(self.h, s.ptr, s.stride, t.ptr, t.stride,
+        fn = lib().pclb200_estimate_svd if use_umeyama else lib().pclb200_estimate_svd_correlation
+        _check(fn(self.h, s.ptr, s.stride, t.ptr, t.stride,
                                           None if cb is None else C.c_void_p(cb.ctypes.data), n, int(scalar_is_double),
                                           T.ctypes.data_as(C.POINTER(C.c_double))))
         return T.reshape(4, 4)

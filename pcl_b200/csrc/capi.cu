@@ -27,7 +27,7 @@ void icp_get_cloud(Icp& s, void* out_pts, size_t stride_out, void* out_normals, 
 size_t icp_get_correspondences(Icp& s, pclb200_corr* out);
 void estimate_pairs(Ctx& c, int est, const void* src, size_t stride_s, const void* tgt, const void* tgt_normals,
                     size_t stride_t, const pclb200_corr* corr, size_t n, int scalar_is_double, double* T_out,
-                    const void* src_normals = nullptr, int enforce_same_dir = 1);
+                    const void* src_normals = nullptr, int enforce_same_dir = 1, int svd_correlation = 0);
 size_t correspondences(Ctx& c, const Index& tgt, const Index* src_index, const void* src, size_t n, size_t stride,
                        const int32_t* indices, size_t n_idx, int is_dense, double max_dist, pclb200_corr* out,
                        const double* pre_T = nullptr, int pre_mode = 0, const float* gate_override = nullptr);
@@ -42,7 +42,7 @@ void launch_knn_stats(Ctx& c, const Index& idx, const float4* d_q, size_t nq, in
 // voxel.cu
 size_t voxelgrid(Ctx& c, const void* pts, size_t n, size_t stride, const int32_t* indices, size_t n_idx, int is_dense,
                  const float leaf[3], unsigned min_pts, float* out_xyz1, const void* normals, size_t stride_n,
-                 float* out_normal_curv);
+                 float* out_normal_curv, const float* grid_bounds = nullptr);
 // comm.cu
 void comm_unique_id(void* out128);
 void comm_export(Ctx& c, void* out64);
@@ -707,6 +707,18 @@ int pclb200_estimate_svd(pclb200_ctx* ctx, const void* src, size_t stride_s, con
   });
 }
 
+int pclb200_estimate_svd_correlation(pclb200_ctx* ctx, const void* src, size_t stride_s, const void* tgt, size_t stride_t,
+                                     const pclb200_corr* corr, size_t n, int scalar_is_double, double T_out[16])
+{
+  return guarded([&] {
+    PCLB_REQUIRE(ctx && T_out, PCLB200_ERR_INVALID, "NULL argument");
+    std::lock_guard<std::recursive_mutex> lk(ctx->c.mu);
+    PCLB_CUDA(cudaSetDevice(ctx->c.device));
+    estimate_pairs(ctx->c, PCLB200_EST_SVD, src, stride_s, tgt, nullptr, stride_t, corr, n, scalar_is_double, T_out, nullptr,
+                   1, 1);
+  });
+}
+
 int pclb200_estimate_point_to_plane_lls(pclb200_ctx* ctx, const void* src, size_t stride_s, const void* tgt,
                                         const void* tgt_normals, size_t stride_t, const pclb200_corr* corr, size_t n,
                                         int scalar_is_double, double T_out[16])
@@ -1074,6 +1086,19 @@ int pclb200_voxelgrid(pclb200_ctx* ctx, const void* pts, size_t n, size_t stride
     ProfScope ps(ctx->c, "voxelgrid");
     *n_out = voxelgrid(ctx->c, pts, n, stride, indices, n_idx, is_dense, leaf, min_points_per_voxel, out_xyz1, nullptr, 0,
                        nullptr);
+  });
+}
+
+int pclb200_voxelgrid_tile(pclb200_ctx* ctx, const void* pts, size_t n, size_t stride, const float grid_bounds[6],
+                           const float leaf[3], unsigned min_points_per_voxel, float* out_xyz1, size_t* n_out)
+{
+  return guarded([&] {
+    PCLB_REQUIRE(ctx && leaf && out_xyz1 && n_out && grid_bounds, PCLB200_ERR_INVALID, "NULL argument");
+    std::lock_guard<std::recursive_mutex> lk(ctx->c.mu);
+    PCLB_CUDA(cudaSetDevice(ctx->c.device));
+    ProfScope ps(ctx->c, "voxelgrid");
+    *n_out = voxelgrid(ctx->c, pts, n, stride, nullptr, 0, 0, leaf, min_points_per_voxel, out_xyz1, nullptr, 0, nullptr,
+                       grid_bounds);
   });
 }
 

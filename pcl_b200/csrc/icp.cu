@@ -293,7 +293,7 @@ constexpr int kEstNone = -1;
 // tiles: 2 x 32 x 8 floats of this warp's shared memory.  Must be called by all 32 lanes (converged).
 template <int EST>
 __device__ __forceinline__ void accumulate_pairs_dmma(const IterArgs& a, float* __restrict__ tiles, int lane, const Match& m,
-                                                      const float4& p, double& c1a, double& c1b, double& c2a, double& c2b)
+                                                      const float4& p, double& c1a, double& c1b, double (&wsum)[8])
 {
   float* tA = tiles;
   float* tB = tiles + 32 * 8;
@@ -324,18 +324,26 @@ __device__ __forceinline__ void accumulate_pairs_dmma(const IterArgs& a, float* 
   }
   *reinterpret_cast<float4*>(tA + lane * 8) = make_float4(ra[0], ra[1], ra[2], ra[3]);
   *reinterpret_cast<float4*>(tA + lane * 8 + 4) = make_float4(ra[4], ra[5], ra[6], ra[7]);
-  *reinterpret_cast<float4*>(tB + lane * 8) = make_float4(rb[0], rb[1], rb[2], rb[3]);
-  *reinterpret_cast<float4*>(tB + lane * 8 + 4) = make_float4(rb[4], rb[5], rb[6], rb[7]);
+  if (EST == PCLB200_EST_SVD) {
+    *reinterpret_cast<float4*>(tB + lane * 8) = make_float4(rb[0], rb[1], rb[2], rb[3]);
+    *reinterpret_cast<float4*>(tB + lane * 8 + 4) = make_float4(rb[4], rb[5], rb[6], rb[7]);
+  }
+  else {
+    // the eight plain sums (float products of the normal, d2, count) stay per thread: an MMA would spend a whole 8x8x4
+    // tile on them, and the fp64 tensor pipe is this kernel's second limiter (ncu: 45 % active with two MMAs per step)
+#pragma unroll
+    for (int k = 0; k < 8; ++k)
+      wsum[k] += (double)rb[k];
+  }
   __syncwarp();
   const int g = lane >> 2, t = lane & 3;
   const double og = g == 0 ? (double)a.ox : (g == 1 ? (double)a.oy : (double)a.oz);
-  const double e0 = g == 0 ? 1.0 : 0.0;
 #pragma unroll
   for (int st = 0; st < 8; ++st) {
     const int row = (4 * st + t) * 8;
     double va = (double)tA[row + g];
-    double vb = (double)tB[row + g];
     if (EST == PCLB200_EST_SVD) {
+      double vb = (double)tB[row + g];
       if (g < 3) {  // coordinates enter shifted by the accumulation origin, in fp64; pairs that are not accepted stay zero
         const bool on = tA[row + 3] != 0.f;
         va = on ? va - og : 0.0;
@@ -343,10 +351,8 @@ __device__ __forceinline__ void accumulate_pairs_dmma(const IterArgs& a, float* 
       }
       dmma884(c1a, c1b, va, vb);     // C1[i][j] += w_i u_j
     }
-    else {
+    else
       dmma884(c1a, c1b, va, va);     // C1[i][j] += v_i v_j
-      dmma884(c2a, c2b, vb, e0);     // C2[i][0] += w_i
-    }
   }
   __syncwarp();
 }
@@ -382,7 +388,7 @@ __device__ __forceinline__ int dmma_accum_source(int est, int k)
 // warp tiles -> block (fixed order) -> grid (fixed order, last block) -> the kAccum layout k_solve reads -> peers.
 // Must be called by every thread of every block; blockDim.x = NWARPS * 32 >= 128.
 template <int EST, int NWARPS>
-__device__ __forceinline__ void fold_tiles_and_publish(const IterArgs& a, double c1a, double c1b, double c2a, double c2b)
+__device__ __forceinline__ void fold_tiles_and_publish(const IterArgs& a, double c1a, double c1b, double (&wsum)[8])
 {
   __shared__ double s_tiles[NWARPS][128];
   __shared__ double s_fin[128];
@@ -391,8 +397,18 @@ __device__ __forceinline__ void fold_tiles_and_publish(const IterArgs& a, double
   const int g = lane >> 2, t = lane & 3;
   s_tiles[warp][g * 8 + 2 * t] = c1a;
   s_tiles[warp][g * 8 + 2 * t + 1] = c1b;
-  s_tiles[warp][64 + g * 8 + 2 * t] = c2a;
-  s_tiles[warp][64 + g * 8 + 2 * t + 1] = c2b;
+  s_tiles[warp][64 + lane] = 0.0;       // tile 1: only column 0 is used (the eight per-thread sums, folded over the warp)
+  s_tiles[warp][96 + lane] = 0.0;
+  __syncwarp();
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+    double v = wsum[k];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1)
+      v += __shfl_down_sync(0xffffffffu, v, o);
+    if (lane == 0)
+      s_tiles[warp][64 + k * 8] = v;
+  }
   __syncthreads();
   if (threadIdx.x < 128) {
     double vsum = 0.0;
@@ -535,7 +551,8 @@ k_accum_dmma(const IterArgs a, const Match* __restrict__ match)
 {
   __shared__ __align__(16) float s_stage[8][2 * 32 * 8];
   const int lane = threadIdx.x & 31;
-  double c1a = 0.0, c1b = 0.0, c2a = 0.0, c2b = 0.0;
+  double c1a = 0.0, c1b = 0.0;
+  double wsum[8] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
   const size_t stride = (size_t)gridDim.x * blockDim.x;
   for (size_t base = blockIdx.x * (size_t)blockDim.x + (threadIdx.x & ~31); base < a.n; base += stride) {
     const size_t i = base + lane;
@@ -548,9 +565,9 @@ k_accum_dmma(const IterArgs a, const Match* __restrict__ match)
       if (match_accepted(m))
         p = a.cur[i];
     }
-    accumulate_pairs_dmma<EST>(a, s_stage[threadIdx.x >> 5], lane, m, p, c1a, c1b, c2a, c2b);
+    accumulate_pairs_dmma<EST>(a, s_stage[threadIdx.x >> 5], lane, m, p, c1a, c1b, wsum);
   }
-  fold_tiles_and_publish<EST, 8>(a, c1a, c1b, c2a, c2b);
+  fold_tiles_and_publish<EST, 8>(a, c1a, c1b, wsum);
 }
 
 // Accumulation kernel: one streaming pass over (source point, match) pairs; fp64 sums, fixed reduction order.
@@ -830,8 +847,12 @@ __device__ bool solve6_dev(double (*A)[7], double* x)
   return true;
 }
 
+// svd_correlation != 0: TransformationEstimationSVD with use_umeyama_ = false — getTransformationFromCorrelation
+// (transformation_estimation_svd.hpp:183-225): H = sum (p - cp)(q - cq)^T = U S V^T, R = V U^T with the last column of V
+// negated when det(U) det(V) < 0, t = cq - R cp.  The same least-squares rotation as Umeyama's, by the reference's other
+// formula (the sums are the same accumulators: H is n times the transpose of Umeyama's covariance).
 __global__ void k_solve(const double* __restrict__ accum, int est, int scalar_is_double, int mode, double ox,
-                        double oy, double oz, int min_corr, Pending* pending, SolveOut* out)
+                        double oy, double oz, int min_corr, Pending* pending, SolveOut* out, int svd_correlation)
 {
   if (threadIdx.x != 0 || blockIdx.x != 0)
     return;
@@ -851,18 +872,37 @@ __global__ void k_solve(const double* __restrict__ accum, int est, int scalar_is
       for (int c = 0; c < 3; ++c)
         sig[3 * r + c] = accum[8 + 3 * r + c] * inv_n - mq[r] * mp[c];
     double U[9], sv[3], V[9];
-    svd3_dev(sig, U, sv, V);
-    double S[3] = {1.0, 1.0, 1.0};
-    if (det3_dev(U) * det3_dev(V) < 0.0)
-      S[2] = -1.0;
     double R[9];
-    for (int r = 0; r < 3; ++r)
-      for (int c = 0; c < 3; ++c) {
-        double a = 0.0;
-        for (int k = 0; k < 3; ++k)
-          a += U[3 * r + k] * S[k] * V[3 * c + k];
-        R[3 * r + c] = a;
-      }
+    if (svd_correlation) {
+      double H[9];
+      for (int r = 0; r < 3; ++r)
+        for (int c = 0; c < 3; ++c)
+          H[3 * r + c] = sig[3 * c + r] * n;
+      svd3_dev(H, U, sv, V);
+      if (det3_dev(U) * det3_dev(V) < 0.0)
+        for (int x = 0; x < 3; ++x)
+          V[3 * x + 2] = -V[3 * x + 2];
+      for (int r = 0; r < 3; ++r)
+        for (int c = 0; c < 3; ++c) {
+          double a = 0.0;
+          for (int k = 0; k < 3; ++k)
+            a += V[3 * r + k] * U[3 * c + k];
+          R[3 * r + c] = a;
+        }
+    }
+    else {
+      svd3_dev(sig, U, sv, V);
+      double S[3] = {1.0, 1.0, 1.0};
+      if (det3_dev(U) * det3_dev(V) < 0.0)
+        S[2] = -1.0;
+      for (int r = 0; r < 3; ++r)
+        for (int c = 0; c < 3; ++c) {
+          double a = 0.0;
+          for (int k = 0; k < 3; ++k)
+            a += U[3 * r + k] * S[k] * V[3 * c + k];
+          R[3 * r + c] = a;
+        }
+    }
     const double o[3] = {ox, oy, oz};
     for (int r = 0; r < 3; ++r) {
       for (int c = 0; c < 3; ++c)
@@ -1798,7 +1838,7 @@ void icp_iterate(Icp& s, int max_steps, pclb200_icp_stats* stats)
     {
       ProfScope ps(c, "solve");
       k_solve<<<1, 32, 0, st>>>(s.red.accum.p, s.P.estimator, s.P.scalar_is_double, transform_mode(s.P), (double)a.ox,
-                                (double)a.oy, (double)a.oz, 3, s.pending.p, s.solve_out.p);
+                                (double)a.oy, (double)a.oz, 3, s.pending.p, s.solve_out.p, s.P.svd_no_umeyama);
     }
     ++c.launches;
     PCLB_CUDA(cudaMemcpyAsync(h_out, s.solve_out.p, sizeof(SolveOut), cudaMemcpyDeviceToHost, st));
@@ -2002,7 +2042,7 @@ void icp_get_cloud(Icp& s, void* out_pts, size_t stride_out, void* out_normals, 
 // ---- stand-alone estimators ----------------------------------------------------------------------------------
 void estimate_pairs(Ctx& c, int est, const void* src, size_t stride_s, const void* tgt, const void* tgt_normals,
                     size_t stride_t, const pclb200_corr* corr, size_t n, int scalar_is_double, double* T_out,
-                    const void* src_normals, int enforce_same_dir)
+                    const void* src_normals, int enforce_same_dir, int svd_correlation)
 {
   cudaStream_t st = c.stream;
   PCLB_REQUIRE(src && tgt && n > 0, PCLB200_ERR_INVALID, "estimate: empty input");
@@ -2078,7 +2118,7 @@ void estimate_pairs(Ctx& c, int est, const void* src, size_t stride_s, const voi
   else
     k_accum_pairs<PCLB200_EST_SYMMETRIC_POINT_TO_PLANE_LLS><<<grid, 256, 0, st>>>(a);
   k_solve<<<1, 32, 0, st>>>(red.accum.p, est, scalar_is_double, 0, (double)a.ox, (double)a.oy, (double)a.oz, 1, nullptr,
-                            so.p);
+                            so.p, svd_correlation);
   c.launches += 2;
   SolveOut h;
   PCLB_CUDA(cudaMemcpyAsync(&h, so.p, sizeof(h), cudaMemcpyDeviceToHost, st));

@@ -170,6 +170,7 @@ struct CellTableHost {
   int bmax = 0;             // finest level present (cells of 2^-bmax of the frame per axis)
   uint64_t entries = 0;
   float margin = 0.f;
+  uint64_t occupied[16] = {0};  // occupied cells per level (index = level), from the prefix-length histogram
 };
 
 struct Index {
@@ -184,9 +185,10 @@ struct Index {
   DevBuf<float4> pts;   // n_leaves*kLeafSize, Morton order, w = original index bits; padded with +inf
   DevBuf<BvhNode> nodes;  // n_leaves-1
   DevBuf<int32_t> pos_of_orig;  // n_cloud: position in `pts` of original index i, or -1 (lazy)
+  DevBuf<int2> node_leaves;     // per internal node: {first leaf, number of leaves} — a subtree's leaves are consecutive
   DevBuf<uint2> cell_slots;     // hash table (level, cell) -> deepest node / leaf holding every point of the cell
   CellTableHost cells;          // its description (traverse.cuh: CellTable is the device-side view)
-  size_t bytes() const { return pts.bytes() + nodes.bytes() + pos_of_orig.bytes() + cell_slots.bytes(); }
+  size_t bytes() const { return pts.bytes() + nodes.bytes() + pos_of_orig.bytes() + cell_slots.bytes() + node_leaves.bytes(); }
 };
 
 Index* build_index(Ctx& c, const void* pts, size_t n, size_t stride, const int32_t* subset, size_t n_subset);

@@ -475,7 +475,7 @@ __global__ void k_link_cells(int n, const int2* __restrict__ children, const int
                              const int* __restrict__ keep, const int* __restrict__ new_id,
                              const int* __restrict__ leaf_incl, const unsigned long long* __restrict__ keys,
                              int2* __restrict__ out_children, int* __restrict__ out_node_parent,
-                             int* __restrict__ out_leaf_parent, CellTableW cells)
+                             int* __restrict__ out_leaf_parent, int2* __restrict__ out_node_leaves, CellTableW cells)
 {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n - 1 || !keep[i])
@@ -499,6 +499,11 @@ __global__ void k_link_cells(int n, const int2* __restrict__ children, const int
     }
   }
   out_children[nid] = make_int2(ref[0], ref[1]);
+  {
+    // a subtree's leaves are consecutive in Morton order: the warp-cooperative k-NN gathers whole cells as one range
+    const int fl = leaf_incl[range[i].x] - 1, ll = leaf_incl[range[i].y] - 1;
+    out_node_leaves[nid] = make_int2(fl, ll - fl + 1);
+  }
   if (i == 0)
     out_node_parent[nid] = -1;
   if (cells.slots == nullptr)
@@ -693,6 +698,7 @@ static Index* build_from_dense(Ctx& c, const float4* d_pts, size_t n, const int3
     node_parent.alloc(n_int, s);
     leaf_parent.alloc(n_leaves, s);
     children.alloc(n_int, s);
+    idx->node_leaves.alloc(n_int, s);
     leaf_lo.alloc(n_leaves, s);
     leaf_hi.alloc(n_leaves, s);
     node_lo.alloc(n_int, s);
@@ -717,6 +723,7 @@ static Index* build_from_dense(Ctx& c, const float4* d_pts, size_t n, const int3
           break;
         bmax = b;
         entries += cum;
+        idx->cells.occupied[b] = cum;
       }
       if (bmax >= 1) {
         unsigned lg = 6;
@@ -739,7 +746,7 @@ static Index* build_from_dense(Ctx& c, const float4* d_pts, size_t n, const int3
       }
     }
     k_link_cells<<<grid_for(ni, 256), 256, 0, s>>>(nv, kchildren.p, krange.p, keep.p, new_id.p, leaf_incl.p, sc.keys.p,
-                                                   children.p, node_parent.p, leaf_parent.p, cellw);
+                                                   children.p, node_parent.p, leaf_parent.p, idx->node_leaves.p, cellw);
     k_refit<<<grid_for(n_leaves, 256), 256, 0, s>>>(idx->pts.p, n_leaves, children.p, node_parent.p, leaf_parent.p,
                                                     leaf_lo.p, leaf_hi.p, node_lo.p, node_hi.p, flags.p);
     k_pack_nodes<<<grid_for(n_int, 256), 256, 0, s>>>(n_int, children.p, leaf_lo.p, leaf_hi.p, node_lo.p, node_hi.p,

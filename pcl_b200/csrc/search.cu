@@ -11,6 +11,7 @@
 #include <algorithm>
 #include <cmath>
 #include <cstdlib>
+#include <limits>
 
 #include "internal.cuh"
 #include "traverse.cuh"
@@ -71,10 +72,11 @@ template <int K>
 __global__ void __launch_bounds__(128)
 k_knn(const BvhNode* __restrict__ nodes, const float4* __restrict__ pts, int root,
       const float4* __restrict__ q, size_t nq, int k_out, float init_bound,
-      int32_t* __restrict__ out_idx, float* __restrict__ out_d2, int* __restrict__ d_error)
+      int32_t* __restrict__ out_idx, float* __restrict__ out_d2, int* __restrict__ d_error,
+      const unsigned char* __restrict__ only = nullptr)
 {
   size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
-  if (i >= nq)
+  if (i >= nq || (only && !only[i]))  // fix-up pass: only the queries the warp kernel handed back
     return;
   const float4 qq = __ldg(q + i);
   const size_t slot = (size_t)(unsigned)__float_as_int(qq.w);
@@ -158,6 +160,11 @@ k_knn_any(const BvhNode* __restrict__ nodes, const float4* __restrict__ pts, int
   }
 }
 
+// warp-cooperative path (defined below): returns the per-query "redo" flags of the queries it handed back, or an empty
+// buffer when it does not apply (no cell table, k outside 8..32)
+static bool warp_knn_lists(Ctx& c, const Index& idx, const float4* d_q, size_t nq, int k, int32_t* d_out_idx,
+                           float* d_out_d2, DevBuf<unsigned char>& redo);
+
 void launch_knn(Ctx& c, const Index& idx, const float4* d_q, size_t nq, int k, float init_bound, int32_t* d_out_idx,
                 float* d_out_d2)
 {
@@ -165,8 +172,12 @@ void launch_knn(Ctx& c, const Index& idx, const float4* d_q, size_t nq, int k, f
     return;
   cudaStream_t s = c.stream;
   const unsigned g = grid_for(nq, 128);
+  DevBuf<unsigned char> redo;
+  const unsigned char* only = nullptr;
+  if (init_bound == std::numeric_limits<float>::infinity() && warp_knn_lists(c, idx, d_q, nq, k, d_out_idx, d_out_d2, redo))
+    only = redo.p;  // the per-thread kernel below only redoes what the warp kernel handed back
 #define PCLB_KNN_CASE(KK)                                                                                            \
-  k_knn<KK><<<g, 128, 0, s>>>(idx.nodes.p, idx.pts.p, idx.root, d_q, nq, k, init_bound, d_out_idx, d_out_d2, c.d_error)
+  k_knn<KK><<<g, 128, 0, s>>>(idx.nodes.p, idx.pts.p, idx.root, d_q, nq, k, init_bound, d_out_idx, d_out_d2, c.d_error, only)
   if (k == 1) PCLB_KNN_CASE(1);
   else if (k == 2) PCLB_KNN_CASE(2);
   else if (k <= 4) PCLB_KNN_CASE(4);
@@ -592,10 +603,11 @@ template <int K>
 __global__ void __launch_bounds__(128)
 k_normals(const BvhNode* __restrict__ nodes, const float4* __restrict__ pts, int root,
           const float4* __restrict__ q, size_t nq, int k_req, float vpx, float vpy, float vpz,
-          float4* __restrict__ out, int* __restrict__ not_dense, int* __restrict__ d_error)
+          float4* __restrict__ out, int* __restrict__ not_dense, int* __restrict__ d_error,
+          const unsigned char* __restrict__ only = nullptr)
 {
   const size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
-  if (i >= nq)
+  if (i >= nq || (only && !only[i]))
     return;
   const float4 qq = __ldg(q + i);
   const size_t slot = (size_t)(unsigned)__float_as_int(qq.w);
@@ -697,6 +709,325 @@ k_normals_from_csr(const float4* __restrict__ pts, const int32_t* __restrict__ p
   out[slot] = normal_from_moments(accu, (int)(e - b), qq, vpx, vpy, vpz, not_dense);
 }
 
+
+// =============================================================================================================
+// Warp-cooperative k-NN (k <= 32): one WARP per query, brute force over the cells that hold the answer
+// =============================================================================================================
+// The per-thread kernels above keep a k-deep sorted list in registers: at k = 16 every accepted candidate costs a
+// ~100-instruction dependent bubble pass executed under divergence (ncu, profiles/r2i: 914 warp-instructions per query,
+// 10 of 32 lanes active, 19 % issue utilisation, 42 ms for 10 M normals).  Here the list is ONE ENTRY PER LANE, sorted
+// across the warp, and candidates arrive 32 at a time from CONTIGUOUS memory:
+//   * the cell table (traverse.cuh) maps a cell of level b to the subtree holding exactly its points; a subtree's leaves
+//     are consecutive in the Morton array, so "all points of a cell" is one coalesced range;
+//   * a ball of radius R = half a level-b cell reaches at most 2 x 2 x 2 cells.  The warp gathers those cells, keeps the k
+//     smallest (d2, index) — a bitonic sort / merge by shuffles when many candidates beat the current k-th, a ranked
+//     insertion (ballot + shuffle-up) when few do — and the result is EXACT iff the k-th distance is below R: every
+//     point outside the gathered cells lies outside [q - R, q + R]^3.  Otherwise the next coarser level (R doubles).
+//   * the start level comes from the index's density (cells that hold ~2k points on average), so one attempt is the norm.
+// Queries the scheme does not fit (far outside the cloud, > kWarpKnnMaxLeaves leaves in reach, no level certifies) are
+// flagged and redone by the per-thread kernel — same results, the exact walk is the fallback, never an approximation.
+constexpr int kWarpKnnMaxLeaves = 1024;
+
+__device__ __forceinline__ bool lex_less(float da, int ia, float db, int ib) { return da < db || (da == db && ia < ib); }
+
+// ascending bitonic sort of one (d, i, p) triple per lane
+__device__ __forceinline__ void warp_sort32(float& d, int& i, int& p, int lane)
+{
+  const unsigned full = 0xffffffffu;
+#pragma unroll
+  for (int k2 = 2; k2 <= 32; k2 <<= 1)
+#pragma unroll
+    for (int j = k2 >> 1; j > 0; j >>= 1) {
+      const float pd = __shfl_xor_sync(full, d, j);
+      const int pi = __shfl_xor_sync(full, i, j);
+      const int pp = __shfl_xor_sync(full, p, j);
+      const bool asc = (lane & k2) == 0, lower = (lane & j) == 0;
+      const bool mine_first = lex_less(d, i, pd, pi);
+      const bool keep = (lower == asc) ? mine_first : !mine_first;
+      if (!keep) {
+        d = pd; i = pi; p = pp;
+      }
+    }
+}
+
+// list (sorted ascending across lanes) <- the 32 smallest of list U cand (cand sorted ascending across lanes)
+__device__ __forceinline__ void warp_merge32(float& ld, int& li, int& lp, float cd, int ci, int cp, int lane)
+{
+  const unsigned full = 0xffffffffu;
+  const float rd = __shfl_sync(full, cd, 31 - lane);
+  const int ri = __shfl_sync(full, ci, 31 - lane);
+  const int rp = __shfl_sync(full, cp, 31 - lane);
+  if (lex_less(rd, ri, ld, li)) {  // elementwise min of an ascending and a descending sequence: bitonic, the 32 smallest
+    ld = rd; li = ri; lp = rp;
+  }
+#pragma unroll
+  for (int j = 16; j > 0; j >>= 1) {
+    const float pd = __shfl_xor_sync(full, ld, j);
+    const int pi = __shfl_xor_sync(full, li, j);
+    const int pp = __shfl_xor_sync(full, lp, j);
+    const bool lower = (lane & j) == 0;
+    const bool mine_first = lex_less(ld, li, pd, pi);
+    if (lower != mine_first) {
+      ld = pd; li = pi; lp = pp;
+    }
+  }
+}
+
+template <bool NORMALS>
+__global__ void __launch_bounds__(256)
+k_knn_warp(const TreeView T, const int2* __restrict__ node_leaves, int b_start, const float4* __restrict__ q, size_t nq,
+           int k, int32_t* __restrict__ out_idx, float* __restrict__ out_d2, float vpx, float vpy, float vpz,
+           float4* __restrict__ out_n, int* __restrict__ not_dense, unsigned char* __restrict__ redo)
+{
+  __shared__ int s_pos[NORMALS ? 8 : 1][NORMALS ? 32 : 1][NORMALS ? 33 : 1];  // per warp: 32 queries x k neighbour positions (+1: no bank conflicts)
+  __shared__ float s_cd[8][64];  // per warp: buffered candidates (d2, original index, Morton position)
+  __shared__ int s_ci[8][64];
+  __shared__ int s_cp[8][64];
+  const unsigned full = 0xffffffffu;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const unsigned lt = (1u << lane) - 1u;
+  const CellTable& C = T.cells;
+  const float inf = __int_as_float(0x7f800000);
+  const float qnan = __int_as_float(0x7fc00000);
+  const size_t n_warps = (size_t)gridDim.x * (blockDim.x >> 5);
+  const size_t n_batches = (nq + 31) / 32;
+  for (size_t batch = (size_t)blockIdx.x * (blockDim.x >> 5) + warp; batch < n_batches; batch += n_warps) {
+    int my_state = 0;  // epilogue (NORMALS): state of query batch*32 + lane: 0 = none, 1 = list ready, 2 = NaN row, 3 = redo
+    for (int t = 0; t < 32; ++t) {
+      const size_t qi = batch * 32 + t;
+      if (qi >= nq)
+        break;
+      const float4 qq = __ldg(q + qi);
+      const size_t slot = (size_t)(unsigned)__float_as_int(qq.w);
+      if (!(isfinite(qq.x) && isfinite(qq.y) && isfinite(qq.z))) {
+        if (NORMALS) {
+          if (lane == t)
+            my_state = 2;
+        }
+        else if (lane < k) {
+          out_idx[slot * k + lane] = -1;
+          out_d2[slot * k + lane] = inf;
+        }
+        continue;
+      }
+      const unsigned cqx = morton_cell(qq.x, C.lo[0], C.scale), cqy = morton_cell(qq.y, C.lo[1], C.scale),
+                     cqz = morton_cell(qq.z, C.lo[2], C.scale);
+      float ld = inf;
+      int li = kSentinelIndex, lp = -1;
+      bool done = false;
+      for (int b = b_start; b >= 1 && !done; --b) {
+        const int s = 21 - b;
+        const float R = __fmul_rd(__fmul_rd(0.5f * (float)(1u << s), C.inv_scale), 0.999f);
+        const unsigned ax = morton_cell(__fsub_rd(qq.x, R), C.lo[0], C.scale), bx = morton_cell(__fadd_ru(qq.x, R), C.lo[0], C.scale);
+        const unsigned ay = morton_cell(__fsub_rd(qq.y, R), C.lo[1], C.scale), by = morton_cell(__fadd_ru(qq.y, R), C.lo[1], C.scale);
+        const unsigned az = morton_cell(__fsub_rd(qq.z, R), C.lo[2], C.scale), bz = morton_cell(__fadd_ru(qq.z, R), C.lo[2], C.scale);
+        if ((bx >> s) - (ax >> s) > 1u || (by >> s) - (ay >> s) > 1u || (bz >> s) - (az >> s) > 1u)
+          continue;  // (rounding at a cell edge) the box needs the next coarser level
+        const unsigned hx = cqx >> s, hy = cqy >> s, hz = cqz >> s;
+        const unsigned ox = (ax >> s) + (bx >> s) - hx, oy = (ay >> s) + (by >> s) - hy, oz = (az >> s) + (bz >> s) - hz;
+        const unsigned E = (ox != hx ? 1u : 0u) | (oy != hy ? 2u : 0u) | (oz != hz ? 4u : 0u);
+        // lanes 0..7 look one cell up each; a leaf that spans several cells comes back several times: keep one
+        int ref = kDone;
+        if (lane < 8 && ((unsigned)lane & ~E) == 0u)
+          ref = cell_lookup(C, cell_key(b, (lane & 1) ? ox : hx, (lane & 2) ? oy : hy, (lane & 4) ? oz : hz));
+        const unsigned grp = __match_any_sync(full, ref != kDone ? ref : (int)(0x40000000 | lane));
+        if (ref != kDone && (grp & lt) != 0u)
+          ref = kDone;
+        int first = 0, cnt = 0;
+        if (ref != kDone) {
+          if (ref < 0) {
+            first = ~ref;
+            cnt = 1;
+          }
+          else {
+            const int2 r = __ldg(node_leaves + ref);
+            first = r.x;
+            cnt = r.y;
+          }
+        }
+        int tot = cnt;
+#pragma unroll
+        for (int o = 4; o > 0; o >>= 1)
+          tot += __shfl_xor_sync(full, tot, o);
+        tot = __shfl_sync(full, tot, 0);
+        if (tot > kWarpKnnMaxLeaves)
+          break;  // a dense knot (duplicates): the exact walk prunes it, a brute-force gather would not
+        ld = inf;
+        li = kSentinelIndex;
+        lp = -1;
+        // Candidates that beat the current k-th are only APPENDED to a per-warp buffer; the list is updated (sort + merge,
+        // or a few ranked insertions) when 32 have collected and at the end of the home cell, so the expensive network
+        // runs once per ~32 survivors instead of once per round.  A stale threshold only admits extra candidates.
+        float Tk = inf;
+        int Ti = kSentinelIndex;
+        int nbuf = 0;
+        auto flush = [&](int take) {  // fold the first `take` (<= 32) buffered candidates into the list
+          float cd = inf;
+          int ci = kSentinelIndex, cp = -1;
+          if (lane < take) {
+            cd = s_cd[warp][lane];
+            ci = s_ci[warp][lane];
+            cp = s_cp[warp][lane];
+          }
+          if (take > 6) {
+            warp_sort32(cd, ci, cp, lane);
+            warp_merge32(ld, li, lp, cd, ci, cp, lane);
+          }
+          else {
+            for (int src = 0; src < take; ++src) {
+              const float xd = __shfl_sync(full, cd, src);
+              const int xi = __shfl_sync(full, ci, src), xp = __shfl_sync(full, cp, src);
+              const int rank = __popc(__ballot_sync(full, lex_less(ld, li, xd, xi)));  // entries that stay in front
+              const float ud = __shfl_up_sync(full, ld, 1);
+              const int ui = __shfl_up_sync(full, li, 1), up = __shfl_up_sync(full, lp, 1);
+              if (lane > rank) {
+                ld = ud; li = ui; lp = up;
+              }
+              else if (lane == rank) {
+                ld = xd; li = xi; lp = xp;
+              }
+            }
+          }
+          __syncwarp();
+          // keep what is left of the buffer (at most 31 entries) at its front
+          const int rest = nbuf - take;
+          float md = 0.f;
+          int mi = 0, mp = 0;
+          if (lane < rest) {
+            md = s_cd[warp][take + lane];
+            mi = s_ci[warp][take + lane];
+            mp = s_cp[warp][take + lane];
+          }
+          __syncwarp();
+          if (lane < rest) {
+            s_cd[warp][lane] = md;
+            s_ci[warp][lane] = mi;
+            s_cp[warp][lane] = mp;
+          }
+          nbuf = rest;
+          Tk = __shfl_sync(full, ld, k - 1);
+          Ti = __shfl_sync(full, li, k - 1);
+          __syncwarp();
+        };
+        const float gx2 = (E & 1u) ? cell_gap2(C, 0, qq.x, hx, ox, s) : 0.f;
+        const float gy2 = (E & 2u) ? cell_gap2(C, 1, qq.y, hy, oy, s) : 0.f;
+        const float gz2 = (E & 4u) ? cell_gap2(C, 2, qq.z, hz, oz, s) : 0.f;
+        for (int c = 0; c < 8; ++c) {
+          const int f = __shfl_sync(full, first, c), n = __shfl_sync(full, cnt, c);
+          if (n == 0)
+            continue;
+          // every point of cell c is at least this far (traverse.cuh: cell_gap2): a cell the k-th already beats is skipped
+          const float bound = __fadd_rd(__fadd_rd((c & 1) ? gx2 : 0.f, (c & 2) ? gy2 : 0.f), (c & 4) ? gz2 : 0.f);
+          if (!(bound <= Tk))
+            continue;
+          const int end = (f + n) * kLeafSize;
+          const float4 pad = make_float4(inf, inf, inf, __int_as_float(kSentinelIndex));
+          float4 pnext = f * kLeafSize + lane < end ? ldg4(T.pts + f * kLeafSize + lane) : pad;
+          for (int base = f * kLeafSize; base < end; base += 32) {
+            const int sidx = base + lane;
+            const float4 p = pnext;
+            if (base + 32 < end)  // the next round's line is in flight while this one is folded
+              pnext = sidx + 32 < end ? ldg4(T.pts + sidx + 32) : pad;
+            const float d = dist2_rn(qq.x, qq.y, qq.z, p.x, p.y, p.z);  // +inf for padding slots
+            const int oi = __float_as_int(p.w);
+            const bool pass = d < inf && lex_less(d, oi, Tk, Ti);
+            const unsigned pm = __ballot_sync(full, pass);
+            if (!pm)
+              continue;
+            if (pass) {
+              const int at = nbuf + __popc(pm & lt);
+              s_cd[warp][at] = d;
+              s_ci[warp][at] = oi;
+              s_cp[warp][at] = sidx;
+            }
+            nbuf += __popc(pm);
+            __syncwarp();
+            if (nbuf >= 32)
+              flush(32);
+          }
+          if (c == 0 && nbuf > 0)
+            flush(nbuf);  // the home cell's points set a tight threshold before any neighbour cell is considered
+        }
+        if (nbuf > 0)
+          flush(nbuf);
+        // exact iff the k-th neighbour lies strictly inside the gathered box (margin >> fp32 rounding of d2)
+        const float dk = __shfl_sync(full, ld, k - 1);
+        done = dk < __fmul_rd(__fmul_rd(R, R), 0.999998f);
+      }
+      if (!done) {
+        redo[qi] = 1;  // (all lanes store the same byte)
+        if (NORMALS && lane == t)
+          my_state = 3;
+        continue;
+      }
+      if (NORMALS) {
+        if (lane < k)
+          s_pos[warp][t][lane] = lp;
+        if (lane == t)
+          my_state = 1;
+      }
+      else if (lane < k) {
+        out_idx[slot * k + lane] = li;
+        out_d2[slot * k + lane] = ld;
+      }
+    }
+    if (NORMALS) {
+      // epilogue: lane t folds query t's neighbours sequentially, in list order — the arithmetic of k_normals
+      __syncwarp();
+      const size_t qi = batch * 32 + lane;
+      if (qi < nq && my_state != 0 && my_state != 3) {
+        const float4 qq = __ldg(q + qi);
+        const size_t slot = (size_t)(unsigned)__float_as_int(qq.w);
+        if (my_state == 2) {
+          out_n[slot] = make_float4(qnan, qnan, qnan, qnan);
+          *not_dense = 1;
+        }
+        else {
+          float accu[9] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+          float Kx = 0.f, Ky = 0.f, Kz = 0.f;
+          for (int j = 0; j < k; ++j) {
+            const float4 p = ldg4(T.pts + s_pos[warp][lane][j]);
+            if (j == 0) { Kx = p.x; Ky = p.y; Kz = p.z; }
+            moments_add(accu, Kx, Ky, Kz, p);
+          }
+          out_n[slot] = normal_from_moments(accu, k, qq, vpx, vpy, vpz, not_dense);
+        }
+      }
+      __syncwarp();
+    }
+  }
+}
+
+// level whose occupied cells hold ~2k indexed points on average: a ball of half that cell holds >= k points in a cloud
+// of locally uniform density (2-D: 0.79 of a cell's points, 3-D: 0.52), so the first attempt usually certifies
+static int warp_knn_start_level(const Index& idx, int k)
+{
+  int b = 0;
+  for (int l = 1; l <= idx.cells.bmax; ++l)
+    if (idx.cells.occupied[l] > 0 && (double)idx.n_valid / (double)idx.cells.occupied[l] >= 2.0 * k)
+      b = l;
+  return b;  // 0: no level is coarse enough (tiny cloud) -> per-thread kernels
+}
+
+static bool warp_knn_lists(Ctx& c, const Index& idx, const float4* d_q, size_t nq, int k, int32_t* d_out_idx,
+                           float* d_out_d2, DevBuf<unsigned char>& redo)
+{
+  if (!(idx.cell_slots.p && idx.node_leaves.p) || k < 12 || k > 32 || (size_t)k > idx.n_valid)
+    return false;
+  const int b0 = warp_knn_start_level(idx, k);
+  if (b0 < 1)
+    return false;
+  cudaStream_t s = c.stream;
+  redo.alloc(nq, s);
+  PCLB_CUDA(cudaMemsetAsync(redo.p, 0, nq, s));
+  const unsigned wg = (unsigned)std::min<size_t>((nq + 255) / 256, (size_t)c.sm_count * 8);
+  k_knn_warp<false><<<wg, 256, 0, s>>>(tree_view(idx), idx.node_leaves.p, b0, d_q, nq, k, d_out_idx, d_out_d2, 0.f, 0.f, 0.f,
+                                      nullptr, nullptr, redo.p);
+  ++c.launches;
+  PCLB_CUDA(cudaGetLastError());
+  return true;
+}
+
 void launch_normals_radius(Ctx& c, Index& idx, const float4* d_q, size_t nq, float r2, const float vp[3], float4* d_out,
                            int* d_not_dense)
 {
@@ -734,9 +1065,23 @@ void launch_normals(Ctx& c, Index& idx, const float4* d_q, size_t nq, int k, con
     PCLB_CUDA(cudaGetLastError());
     return;
   }
+  DevBuf<unsigned char> redo;
+  const unsigned char* only = nullptr;
+  {
+    const int b0 = (idx.cell_slots.p && idx.node_leaves.p && k >= 12) ? warp_knn_start_level(idx, k) : 0;
+    if (b0 >= 1 && (size_t)k <= idx.n_valid) {
+      redo.alloc(nq, s);
+      PCLB_CUDA(cudaMemsetAsync(redo.p, 0, nq, s));
+      const unsigned wg = (unsigned)std::min<size_t>((nq + 255) / 256, (size_t)c.sm_count * 8);
+      k_knn_warp<true><<<wg, 256, 0, s>>>(tree_view(idx), idx.node_leaves.p, b0, d_q, nq, k, nullptr, nullptr, vp[0], vp[1],
+                                         vp[2], d_out, d_not_dense, redo.p);
+      ++c.launches;
+      only = redo.p;
+    }
+  }
 #define PCLB_NRM_CASE(KK)                                                                                              \
   k_normals<KK><<<g, 128, 0, s>>>(idx.nodes.p, idx.pts.p, idx.root, d_q, nq, k, vp[0], vp[1], vp[2], d_out, d_not_dense, \
-                                  c.d_error)
+                                  c.d_error, only)
   if (k <= 4) PCLB_NRM_CASE(4);
   else if (k <= 8) PCLB_NRM_CASE(8);
   else if (k <= 10) PCLB_NRM_CASE(10);

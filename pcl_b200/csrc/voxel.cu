@@ -188,7 +188,7 @@ struct IsSet {
 
 size_t voxelgrid(Ctx& c, const void* pts, size_t n, size_t stride, const int32_t* indices, size_t n_idx, int is_dense,
                  const float leaf[3], unsigned min_pts, float* out_xyz1, const void* normals, size_t stride_n,
-                 float* out_normal_curv)
+                 float* out_normal_curv, const float* grid_bounds)
 {
   (void)is_dense;  // non-finite points are skipped on either setting (a dense cloud has none)
   cudaStream_t st = c.stream;
@@ -223,6 +223,16 @@ size_t voxelgrid(Ctx& c, const void* pts, size_t n, size_t stride, const int32_t
     mn[d] = vord2f(h.lo[d]);
     mx[d] = vord2f(h.hi[d]);
     inv[d] = 1.0f / leaf[d];  // inverse_leaf_size_ = 1 / leaf_size_ (voxel_grid.h:266,282)
+  }
+  if (grid_bounds) {
+    // a spatial tile of a larger cloud: the grid (min_b, div_b) is the WHOLE cloud's, so that the tiles' voxels are the
+    // voxels a single VoxelGrid over the whole cloud would form (the caller cuts tiles along voxel boundaries)
+    for (int d = 0; d < 3; ++d) {
+      PCLB_REQUIRE(grid_bounds[d] <= mn[d] && grid_bounds[3 + d] >= mx[d], PCLB200_ERR_INVALID,
+                   "voxelgrid: the given grid bounds do not contain the points");
+      mn[d] = grid_bounds[d];
+      mx[d] = grid_bounds[3 + d];
+    }
   }
   // guard, in the reference's float arithmetic (voxel_grid.hpp:620-629)
   volatile float e0 = (mx[0] - mn[0]) * inv[0], e1 = (mx[1] - mn[1]) * inv[1], e2 = (mx[2] - mn[2]) * inv[2];

@@ -291,6 +291,9 @@ protected:
     P.max_iterations = this->max_iterations_;
     P.use_reciprocal = use_reciprocal_correspondence_ ? 1 : 0;
     P.estimator = this->transformation_estimation_->abiEstimator();
+    if (auto* svd = dynamic_cast<const registration::TransformationEstimationSVD<PointSource, PointTarget, Scalar>*>(
+            this->transformation_estimation_.get()))
+      P.svd_no_umeyama = svd->usesUmeyama() ? 0 : 1;  // TransformationEstimationSVD(false): the correlation formula
     P.scalar_is_double = sizeof(Scalar) == 8;
     P.with_normals_transform = withNormalsTransform() ? 1 : 0;
     P.is_dense = this->input_->is_dense ? 1 : 0;

@@ -56,6 +56,7 @@ public:
   using Ptr = std::shared_ptr<TransformationEstimationSVD>;
   explicit TransformationEstimationSVD(bool use_umeyama = true) : use_umeyama_(use_umeyama) {}
   int abiEstimator() const override { return PCLB200_EST_SVD; }
+  bool usesUmeyama() const { return use_umeyama_; }
 
   void estimateRigidTransformation(const pcl::PointCloud<PointSource>& s, const pcl::PointCloud<PointTarget>& t, Matrix4& T) const override
   {
@@ -94,8 +95,10 @@ protected:
   void solve(const pcl::PointCloud<PointSource>& s, const pcl::PointCloud<PointTarget>& t, const pclb200_corr* c, std::size_t n, Matrix4& T) const
   {
     double out[16];
-    if (n == 0 || pclb200_estimate_svd(b200::Context::get(), s.points.data(), sizeof(PointSource), t.points.data(), sizeof(PointTarget), c, n,
-                                       sizeof(Scalar) == 8, out) != PCLB200_OK) {
+    // use_umeyama_ = false selects getTransformationFromCorrelation (impl/transformation_estimation_svd.hpp:156-225)
+    auto fn = use_umeyama_ ? pclb200_estimate_svd : pclb200_estimate_svd_correlation;
+    if (n == 0 || fn(b200::Context::get(), s.points.data(), sizeof(PointSource), t.points.data(), sizeof(PointTarget), c, n,
+                     sizeof(Scalar) == 8, out) != PCLB200_OK) {
       std::fprintf(stderr, "[pcl::TransformationEstimationSVD] %s\n", n ? pclb200_last_error() : "no point pairs");
       return;
     }

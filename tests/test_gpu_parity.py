@@ -678,3 +678,58 @@ def test_voxelgrid_point_normal_all_fields(gpu, orc):
         assert gx.shape == ox.shape and np.array_equal(gx, ox)
         assert np.allclose(gn, on, rtol=0, atol=2e-7), float(np.abs(gn - on).max())
         assert np.allclose(np.linalg.norm(gn[:, :4], axis=1), 1.0, atol=1e-5)
+
+
+def test_voxelgrid_tiles_equal_whole(gpu, orc):
+    """Spatial tiles cut along voxel boundaries and filtered on the WHOLE cloud's grid (pclb200_voxelgrid_tile) give,
+    concatenated, exactly the centroids of one VoxelGrid over the whole cloud (the multi-GPU front-end of config 5)."""
+    P, ctx = gpu
+    rng = np.random.default_rng(17)
+    n = 200000
+    pts = P.xyz1((rng.random((n, 3), dtype=np.float32) * np.array([40, 10, 3], np.float32)) - np.float32(7))
+    leaf = np.float32(0.25)
+    whole = ctx.voxelgrid(pts, leaf)
+    lo, hi = pts[:, :3].min(0), pts[:, :3].max(0)
+    inv = np.float32(1.0) / leaf
+    i = (np.floor(pts[:, 0] * inv) - np.floor(lo[0] * inv)).astype(np.int64)   # voxel column of every point
+    cuts = [0, int(i.max()) // 3, 2 * int(i.max()) // 3, int(i.max()) + 1]
+    tiles = []
+    for a, b in zip(cuts[:-1], cuts[1:]):
+        sel = pts[(i >= a) & (i < b)]
+        tiles.append(ctx.voxelgrid_tile(sel, leaf, np.concatenate([lo, hi])))
+    got = np.concatenate(tiles)
+    assert got.shape == whole.shape
+
+    def canon(a):
+        return a[np.lexsort((a[:, 2], a[:, 1], a[:, 0]))]
+    assert np.array_equal(canon(got), canon(whole))
+
+
+def test_estimate_svd_correlation_path(gpu, orc):
+    """TransformationEstimationSVD(use_umeyama = false): getTransformationFromCorrelation
+    (transformation_estimation_svd.hpp:156-225) — stand-alone and inside the ICP loop (svd_no_umeyama)."""
+    P, ctx = gpu
+    rng = np.random.default_rng(3)
+    n = 20000
+    src = rng.random((n, 3), dtype=np.float32) * 3
+    a = np.deg2rad(7.0)
+    R = np.array([[np.cos(a), 0, np.sin(a)], [0, 1, 0], [-np.sin(a), 0, np.cos(a)]])
+    tgt = (src.astype(np.float64) @ R.T + [0.3, -0.2, 0.1] + rng.normal(0, 1e-3, (n, 3))).astype(np.float32)
+    S, T = P.xyz1(src), P.xyz1(tgt)
+    corr = np.zeros(n // 2, dtype=P.CORR_DTYPE)
+    corr["index_query"] = rng.permutation(n)[: n // 2]
+    corr["index_match"] = corr["index_query"]
+    for c in (None, corr):
+        g = ctx.estimate_svd(S, T, c, scalar_is_double=True, use_umeyama=False)
+        o = orc.estimate_svd(S, T, c, scalar_is_double=True, use_umeyama=False)
+        u = ctx.estimate_svd(S, T, c, scalar_is_double=True, use_umeyama=True)
+        assert np.linalg.norm(g - o) < 1e-9 and np.linalg.norm(g - u) < 1e-9   # same least-squares solution
+        gf = ctx.estimate_svd(S, T, c, use_umeyama=False)
+        of = orc.estimate_svd(S, T, c, use_umeyama=False)
+        assert np.linalg.norm(gf - of) < 2e-5     # float Scalar: the reference sums in float, the device in fp64
+    # inside the loop
+    kw = dict(max_iterations=25, max_correspondence_distance=0.5, transformation_epsilon=1e-10)
+    idx = P.Index(ctx, T)
+    r0 = P.icp_align(ctx, S, idx, **kw)
+    r1 = P.icp_align(ctx, S, idx, svd_no_umeyama=1, **kw)
+    assert r0["converged"] and r1["converged"] and np.linalg.norm(r0["final"] - r1["final"]) < 1e-5
