@@ -93,6 +93,14 @@ public:
   }
   void clearCorrespondenceRejectors() { correspondence_rejectors_.clear(); }
 
+  // registration.h:419-425: the representation the TARGET searcher indexes with (dimensions / rescale values)
+  using PointRepresentationConstPtr = typename KdTree::PointRepresentationConstPtr;
+  void setPointRepresentation(const PointRepresentationConstPtr& point_representation)
+  {
+    point_representation_ = point_representation;
+    target_cloud_updated_ = true;
+  }
+
   void setTransformationEstimation(const TransformationEstimationPtr& te) { transformation_estimation_ = te; }
   void setCorrespondenceEstimation(const CorrespondenceEstimationPtr& ce) { correspondence_estimation_ = ce; }
 
@@ -213,6 +221,8 @@ protected:
       return false;
     }
     if (target_cloud_updated_ && !force_no_recompute_) {
+      if (point_representation_)  // impl/registration.hpp:84-91
+        tree_->setPointRepresentation(point_representation_);
       tree_->setInputCloud(target_);
       target_cloud_updated_ = false;
       target_uploaded_ = false;
@@ -252,6 +262,7 @@ protected:
   bool target_cloud_updated_ = true, source_cloud_updated_ = true;
   bool force_no_recompute_ = false, force_no_recompute_reciprocal_ = false;
   bool target_uploaded_ = false;
+  PointRepresentationConstPtr point_representation_;
   pclb200_icp* icp_ = nullptr;
   std::function<UpdateVisualizerCallbackSignature> update_visualizer_;
 };
@@ -282,9 +293,123 @@ protected:
   virtual bool withNormalsTransform() const { return false; }
   virtual bool enforceSameDirectionNormals() const { return true; }
 
+  // ---- the reference's loop, stage by stage, for searchers that index representation vectors --------------------------
+  // With a non-trivial PointRepresentation (dimensions dropped, per-dimension rescale) the correspondence search runs in
+  // the representation's space while the transform is estimated on the real coordinates (impl/icp.hpp:164-241).  The
+  // fused device loop searches raw xyz, so this case runs the reference's own structure: batch 1-NN through the
+  // searcher (one device launch), gate, rejector chain, estimator (device), transformCloud, convergence criteria.
+  static void transformCloudHost(const PointCloudSource& in, PointCloudSource& out, const Matrix4& T)
+  {
+    float tr[12];
+    for (int r = 0; r < 3; ++r)
+      for (int c = 0; c < 4; ++c) tr[4 * r + c] = static_cast<float>(T(r, c));
+    if (&in != &out) out = in;
+    for (auto& p : out.points) {  // impl/icp.hpp:49-111 (fp32, left to right; non-finite points untouched)
+      if (!isXYZFinite(p)) continue;
+      const float x = p.x, y = p.y, z = p.z;
+      p.x = ((tr[0] * x + tr[1] * y) + tr[2] * z) + tr[3];
+      p.y = ((tr[4] * x + tr[5] * y) + tr[6] * z) + tr[7];
+      p.z = ((tr[8] * x + tr[9] * y) + tr[10] * z) + tr[11];
+    }
+  }
+  void computeTransformationStaged(PointCloudSource& output, const Matrix4& guess)
+  {
+    using State = typename ConvergenceCriteria::ConvergenceState;
+    PointCloudSource moved = *this->input_;
+    this->nr_iterations_ = 0;
+    this->converged_ = false;
+    this->final_transformation_ = guess;
+    if (!(guess == Matrix4::Identity())) transformCloudHost(*this->input_, moved, guess);  // impl/icp.hpp:125-134
+    this->transformation_ = Matrix4::Identity();
+    State state = ConvergenceCriteria::CONVERGENCE_CRITERIA_NOT_CONVERGED;
+    double prev_mse = std::numeric_limits<double>::max();
+    int iterations_similar = 0;
+    const double max_d2 = this->corr_dist_threshold_ * this->corr_dist_threshold_;
+    pcl::Correspondences corr, tmp;
+    do {
+      this->previous_transformation_ = this->transformation_;
+      // correspondences (impl/correspondence_estimation.hpp:145-218): one batch 1-NN for all source indices
+      std::vector<Indices> ki;
+      std::vector<std::vector<float>> kd;
+      {
+        pcl::PointCloud<PointTarget> q;
+        q.points.reserve(this->indices_->size());
+        for (index_t i : *this->indices_) {
+          PointTarget t;
+          t.x = moved[i].x; t.y = moved[i].y; t.z = moved[i].z;
+          q.points.push_back(t);
+        }
+        this->tree_->nearestKSearch(q, Indices(), 1, ki, kd);
+      }
+      corr.clear();
+      for (std::size_t j = 0; j < this->indices_->size(); ++j) {
+        const index_t i = (*this->indices_)[j];
+        if (!this->input_->is_dense && !isXYZFinite(moved[i])) continue;
+        if (ki[j].empty() || static_cast<double>(kd[j][0]) > max_d2) continue;
+        corr.emplace_back(i, ki[j][0], kd[j][0]);
+      }
+      for (const auto& rej : this->correspondence_rejectors_) {  // impl/icp.hpp:187-201
+        rej->getRemainingCorrespondences(corr, tmp);
+        corr.swap(tmp);
+      }
+      if (corr.size() < 3) {  // impl/icp.hpp:204-213
+        std::fprintf(stderr, "[pcl::%s::computeTransformation] Not enough correspondences found. Relax your threshold parameters.\n",
+                     this->getClassName().c_str());
+        state = ConvergenceCriteria::CONVERGENCE_CRITERIA_NO_CORRESPONDENCES;
+        this->converged_ = false;
+        break;
+      }
+      this->transformation_estimation_->estimateRigidTransformation(moved, *this->target_, corr, this->transformation_);
+      transformCloudHost(moved, moved, this->transformation_);
+      this->final_transformation_ = this->transformation_ * this->final_transformation_;
+      ++this->nr_iterations_;
+      n_correspondences_ = static_cast<std::int64_t>(corr.size());
+      // DefaultConvergenceCriteria::hasConverged — impl/default_convergence_criteria.hpp:49-140
+      {
+        if (state != ConvergenceCriteria::CONVERGENCE_CRITERIA_NOT_CONVERGED) {
+          iterations_similar = 0;
+          state = ConvergenceCriteria::CONVERGENCE_CRITERIA_NOT_CONVERGED;
+        }
+        bool conv = false, similar = false;
+        const auto& cc = *convergence_criteria_;
+        if (this->nr_iterations_ >= this->max_iterations_) {
+          if (!cc.failure_after_max_iter_) { state = ConvergenceCriteria::CONVERGENCE_CRITERIA_ITERATIONS; conv = true; }
+          else state = ConvergenceCriteria::CONVERGENCE_CRITERIA_FAILURE_AFTER_MAX_ITERATIONS;
+        }
+        if (!conv) {
+          const Matrix4& T = this->transformation_;
+          const double cos_angle = 0.5 * (T(0, 0) + T(1, 1) + T(2, 2) - 1);
+          const double t2 = T(0, 3) * T(0, 3) + T(1, 3) * T(1, 3) + T(2, 3) * T(2, 3);
+          const double rot_thr = this->transformation_rotation_epsilon_ > 0 ? this->transformation_rotation_epsilon_ : 0.99999;
+          double mse = 0.0;
+          for (const auto& c : corr) mse += c.distance;
+          mse /= static_cast<double>(corr.size());
+          auto hit = [&](State s2) {
+            if (iterations_similar >= cc.max_iterations_similar_transforms_) { state = s2; conv = true; }
+            else similar = true;
+          };
+          if (cos_angle >= rot_thr && t2 <= this->transformation_epsilon_) hit(ConvergenceCriteria::CONVERGENCE_CRITERIA_TRANSFORM);
+          if (!conv && std::abs(mse - prev_mse) < cc.mse_threshold_absolute_) hit(ConvergenceCriteria::CONVERGENCE_CRITERIA_ABS_MSE);
+          if (!conv && std::abs(mse - prev_mse) / prev_mse < this->euclidean_fitness_epsilon_) hit(ConvergenceCriteria::CONVERGENCE_CRITERIA_REL_MSE);
+          if (!conv) {
+            iterations_similar = similar ? iterations_similar + 1 : 0;
+            prev_mse = mse;
+          }
+        }
+        this->converged_ = conv;
+      }
+    } while (!this->converged_ && state != ConvergenceCriteria::CONVERGENCE_CRITERIA_FAILURE_AFTER_MAX_ITERATIONS);
+    convergence_criteria_->state_ = state;
+    transformCloudHost(*this->input_, output, this->final_transformation_);  // impl/icp.hpp:265-267
+  }
+
   // impl/icp.hpp:113-268 — the whole do-while runs on the device; the host only evaluates the convergence criteria
   void computeTransformation(PointCloudSource& output, const Matrix4& guess) override
   {
+    if (this->tree_->usesRepresentationVectors()) {
+      computeTransformationStaged(output, guess);
+      return;
+    }
     pclb200_ctx* ctx = b200::Context::get();
     pclb200_icp_params P;
     pclb200_icp_default_params(&P);

@@ -9,12 +9,14 @@
 // pcl::search::KdTreeNanoflann does (search/include/pcl/search/kdtree_nanoflann.h:186,310-325) — INTEGRATION.md.
 #pragma once
 #include <cstdio>
+#include <limits>
 #include <memory>
 #include <string>
 #include <vector>
 
 #include "../b200/context.h"
 #include "../point_cloud.h"
+#include "../point_representation.h"
 #include "../types.h"
 
 namespace pcl {
@@ -27,8 +29,19 @@ public:
   using PointCloudConstPtr = typename PointCloud::ConstPtr;
   using Ptr = std::shared_ptr<KdTree<PointT>>;
   using ConstPtr = std::shared_ptr<const KdTree<PointT>>;
+  using PointRepresentationConstPtr = typename pcl::PointRepresentation<PointT>::ConstPtr;
 
   explicit KdTree(bool sorted = true) : sorted_results_(sorted) {}
+
+  // kdtree.h:104-119 / search/kdtree.h:106-119: the representation decides which float vector of a point is indexed.
+  // A cloud that is already set is re-indexed at once, like the reference does.  Up to three dimensions.
+  void setPointRepresentation(const PointRepresentationConstPtr& rep)
+  {
+    point_representation_ = rep;
+    if (input_)  // KdTreeFLANN::setPointRepresentation re-indexes a cloud that is already set (kdtree_flann.hpp)
+      setInputCloud(input_, indices_);
+  }
+  PointRepresentationConstPtr getPointRepresentation() const { return point_representation_; }
   virtual ~KdTree() = default;
 
   virtual const std::string& getName() const { return name_; }
@@ -51,8 +64,29 @@ public:
       return false;
     }
     pclb200_index* h = nullptr;
-    int rc = pclb200_index_build(b200::Context::get(), cloud->points.data(), cloud->size(), sizeof(PointT),
-                                 indices ? indices->data() : nullptr, indices ? indices->size() : 0, &h);
+    int rc;
+    vectorized_ = point_representation_ && !point_representation_->isTrivial();
+    if (vectorized_) {
+      // KdTreeFLANN::convertCloudToArray (kdtree_flann.hpp:429-498): valid points only, through vectorize(); an invalid
+      // point becomes a NaN row, which the index drops while keeping the original numbering (index_mapping_)
+      const int dim = point_representation_->getNumberOfDimensions();
+      if (dim < 1 || dim > 3) {
+        std::fprintf(stderr, "[pcl::search::KdTree::setInputCloud] the device index is 3-D: a %d-dimensional point representation is not supported\n", dim);
+        return false;
+      }
+      std::vector<float> v(3 * cloud->size(), 0.f);
+      for (std::size_t i = 0; i < cloud->size(); ++i) {
+        if (point_representation_->isValid((*cloud)[i]))
+          point_representation_->vectorize((*cloud)[i], &v[3 * i]);
+        else
+          v[3 * i] = std::numeric_limits<float>::quiet_NaN();
+      }
+      rc = pclb200_index_build(b200::Context::get(), v.data(), cloud->size(), 12, indices ? indices->data() : nullptr,
+                               indices ? indices->size() : 0, &h);
+    }
+    else
+      rc = pclb200_index_build(b200::Context::get(), cloud->points.data(), cloud->size(), sizeof(PointT),
+                               indices ? indices->data() : nullptr, indices ? indices->size() : 0, &h);
     if (rc != PCLB200_OK) {
       std::fprintf(stderr, "[pcl::search::KdTree::setInputCloud] %s\n", pclb200_last_error());
       return false;
@@ -63,6 +97,7 @@ public:
   PointCloudConstPtr getInputCloud() const { return input_; }
   IndicesConstPtr getIndices() const { return indices_; }
   pclb200_index* deviceIndex() const { return index_ ? index_->h : nullptr; }
+  bool usesRepresentationVectors() const { return vectorized_; }
 
   // ---- k-NN ---------------------------------------------------------------------------------------------
   virtual int nearestKSearch(const PointT& point, int k, Indices& k_indices, std::vector<float>& k_sqr_distances) const
@@ -103,7 +138,8 @@ public:
     std::vector<index_t> oi(nq * static_cast<std::size_t>(k));
     std::vector<float> od(nq * static_cast<std::size_t>(k));
     int keff = 0;
-    if (pclb200_knn(b200::Context::get(), index_->h, qp, nq, sizeof(PointT), k, oi.data(), od.data(), &keff) != PCLB200_OK) {
+    const Queries qs = queries(qp, nq);
+    if (pclb200_knn(b200::Context::get(), index_->h, qs.ptr, nq, qs.stride, k, oi.data(), od.data(), &keff) != PCLB200_OK) {
       std::fprintf(stderr, "[pcl::search::KdTree::nearestKSearch] %s\n", pclb200_last_error());
       return;
     }
@@ -123,7 +159,8 @@ public:
     std::int64_t offs[2] = {0, 0};
     index_t* pi = nullptr;
     float* pd = nullptr;
-    if (pclb200_radius(b200::Context::get(), index_->h, &point, 1, sizeof(PointT), radius, max_nn, sorted_results_ ? 1 : 0,
+    const Queries qs = queries(&point, 1);
+    if (pclb200_radius(b200::Context::get(), index_->h, qs.ptr, 1, qs.stride, radius, max_nn, sorted_results_ ? 1 : 0,
                        offs, &pi, &pd) != PCLB200_OK) {
       std::fprintf(stderr, "[pcl::search::KdTree::radiusSearch] %s\n", pclb200_last_error());
       return 0;
@@ -157,7 +194,8 @@ public:
     std::vector<std::int64_t> offs(nq + 1, 0);
     index_t* pi = nullptr;
     float* pd = nullptr;
-    if (pclb200_radius(b200::Context::get(), index_->h, qp, nq, sizeof(PointT), radius, max_nn, sorted_results_ ? 1 : 0,
+    const Queries qs = queries(qp, nq);
+    if (pclb200_radius(b200::Context::get(), index_->h, qs.ptr, nq, qs.stride, radius, max_nn, sorted_results_ ? 1 : 0,
                        offs.data(), &pi, &pd) != PCLB200_OK) {
       std::fprintf(stderr, "[pcl::search::KdTree::radiusSearch] %s\n", pclb200_last_error());
       return;
@@ -171,15 +209,34 @@ public:
   }
 
 protected:
+  // queries go through the same representation as the indexed points
+  struct Queries {
+    const void* ptr;
+    std::size_t stride;
+    std::vector<float> store;
+  };
+  Queries queries(const PointT* q, std::size_t nq) const
+  {
+    Queries r{q, sizeof(PointT), {}};
+    if (vectorized_) {
+      r.store.assign(3 * nq, 0.f);
+      for (std::size_t i = 0; i < nq; ++i) point_representation_->vectorize(q[i], &r.store[3 * i]);
+      r.ptr = r.store.data();
+      r.stride = 12;
+    }
+    return r;
+  }
+
   int knn(const PointT* q, std::size_t nq, int k, Indices* ki, std::vector<float>* kd) const
   {
     ki->clear();
     kd->clear();
     if (!index_ || k <= 0) return 0;
+    const Queries qs = queries(q, nq);
     std::vector<index_t> oi(nq * static_cast<std::size_t>(k));
     std::vector<float> od(nq * static_cast<std::size_t>(k));
     int keff = 0;
-    if (pclb200_knn(b200::Context::get(), index_->h, q, nq, sizeof(PointT), k, oi.data(), od.data(), &keff) != PCLB200_OK) {
+    if (pclb200_knn(b200::Context::get(), index_->h, qs.ptr, nq, qs.stride, k, oi.data(), od.data(), &keff) != PCLB200_OK) {
       std::fprintf(stderr, "[pcl::search::KdTree::nearestKSearch] %s\n", pclb200_last_error());
       return 0;
     }
@@ -190,6 +247,8 @@ protected:
 
   PointCloudConstPtr input_;
   IndicesConstPtr indices_;
+  PointRepresentationConstPtr point_representation_;
+  bool vectorized_ = false;  // the index holds representation vectors, not raw xyz
   std::shared_ptr<b200::IndexHandle> index_;
   bool sorted_results_ = true;
   float epsilon_ = 0.f;

@@ -5,6 +5,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <fstream>
+#include <limits>
 #include <map>
 #include <string>
 #include <vector>
@@ -16,6 +17,8 @@
 #include <pcl/io/pcd_io.h>
 #include <pcl/kdtree/kdtree_flann.h>
 #include <pcl/point_cloud.h>
+#include <pcl/point_representation.h>
+#include <pcl/registration/transformation_validation_euclidean.h>
 #include <pcl/point_types.h>
 #include <pcl/registration/correspondence_estimation.h>
 #include <pcl/registration/correspondence_estimation_backprojection.h>
@@ -155,6 +158,82 @@ int main(int argc, char** argv)
     for (int i = 0; i < 10; ++i) expect += gt_d[i] < 45.0f * 45.0f ? 1 : 0;
     EXPECT_EQ(nfound, expect);
     for (int i = 0; i < nfound; ++i) EXPECT_EQ(ri[i], gt_i[i]);
+    // the same test's second and third parts (test/kdtree/test_kdtree.cpp:255-289): a 2-D (x, y) representation, then the
+    // default one with rescale values {1, 2, 3} — the reference's own ground truth
+    {
+      CustomPointRepresentation<PointXYZ>::Ptr xy(new CustomPointRepresentation<PointXYZ>(2, 0));
+      kdtree.setPointRepresentation(xy);
+      EXPECT_EQ(kdtree.nearestKSearch(PointXYZ(50.f, 50.f, 50.f), 10, ki, kd), 10);
+      const int g2[10] = {6, 2, 5, 1, 7, 0, 4, 3, 9, 8};
+      const float d2[10] = {158.6f, 716.5f, 778.6f, 1170.2f, 1177.5f, 1402.0f, 1924.6f, 2639.1f, 2808.5f, 3370.1f};
+      for (int i = 0; i < 10; ++i) { EXPECT_EQ(ki[i], g2[i]); EXPECT_NEAR(kd[i], d2[i], 0.1); }
+      DefaultPointRepresentation<PointXYZ> point_rep;
+      const float alpha[3] = {1.0f, 2.0f, 3.0f};
+      point_rep.setRescaleValues(alpha);
+      kdtree.setPointRepresentation(point_rep.makeShared());
+      EXPECT_EQ(kdtree.nearestKSearch(PointXYZ(50.f, 50.f, 50.f), 10, ki, kd), 10);
+      const int g3[10] = {2, 9, 4, 7, 1, 5, 8, 0, 3, 6};
+      const float d3[10] = {3686.9f, 6769.2f, 7177.0f, 8802.3f, 11071.5f, 11637.3f, 11742.4f, 17769.0f, 18497.3f, 18942.0f};
+      for (int i = 0; i < 10; ++i) { EXPECT_EQ(ki[i], g3[i]); EXPECT_NEAR(kd[i], d3[i], 0.5); }
+    }
+  }
+
+  {  // Registration::setPointRepresentation (registration.h:419-425): the searcher indexes rescaled coordinates, the
+     // transform is estimated on the real ones.  A uniform rescale leaves every nearest neighbour where it was, so the
+     // staged loop must land on the fused loop's transform; an anisotropic one still has to register the scans.
+    PointCloud<PointXYZ>::Ptr src(new PointCloud<PointXYZ>(cloud_source)), tgt(new PointCloud<PointXYZ>(cloud_target));
+    IterativeClosestPoint<PointXYZ, PointXYZ> plain, uniform, aniso;
+    PointCloud<PointXYZ> out;
+    for (auto* reg : {&plain, &uniform, &aniso}) {
+      reg->setInputSource(src);
+      reg->setInputTarget(tgt);
+      reg->setMaximumIterations(50);
+      reg->setTransformationEpsilon(1e-8);
+    }
+    plain.setMaxCorrespondenceDistance(0.05);
+    plain.align(out);
+    DefaultPointRepresentation<PointXYZ> rep2, rep3;
+    const float a2[3] = {2.f, 2.f, 2.f}, a3[3] = {1.f, 1.5f, 0.75f};
+    rep2.setRescaleValues(a2);
+    rep3.setRescaleValues(a3);
+    uniform.setPointRepresentation(rep2.makeShared());
+    uniform.setMaxCorrespondenceDistance(0.1);  // distances are measured in the representation's space: 2 x 0.05
+    uniform.align(out);
+    EXPECT_TRUE(plain.hasConverged() && uniform.hasConverged());
+    EXPECT_EQ(plain.getNumberOfIterations(), uniform.getNumberOfIterations());
+    for (int r = 0; r < 4; ++r)
+      for (int c = 0; c < 4; ++c) EXPECT_NEAR(plain.getFinalTransformation()(r, c), uniform.getFinalTransformation()(r, c), 2e-5);
+    aniso.setPointRepresentation(rep3.makeShared());
+    aniso.setMaxCorrespondenceDistance(0.05);
+    aniso.align(out);
+    EXPECT_TRUE(aniso.hasConverged());
+    for (int r = 0; r < 3; ++r)
+      for (int c = 0; c < 4; ++c) EXPECT_NEAR(plain.getFinalTransformation()(r, c), aniso.getFinalTransformation()(r, c), 2e-2);
+  }
+
+  {  // TransformationValidationEuclidean (transformation_validation_euclidean.h:77-263): identity on a cloud against itself
+     // scores 0; the ICP result scores far below the identity on the bunny pair; isValid needs a threshold
+    PointCloud<PointXYZ>::Ptr src(new PointCloud<PointXYZ>(cloud_source)), tgt(new PointCloud<PointXYZ>(cloud_target));
+    registration::TransformationValidationEuclidean<PointXYZ, PointXYZ> tve;
+    EXPECT_NEAR(tve.validateTransformation(tgt, tgt, Eigen::Matrix4f::Identity()), 0.0, 1e-12);
+    IterativeClosestPoint<PointXYZ, PointXYZ> reg;
+    PointCloud<PointXYZ> out;
+    reg.setInputSource(src);
+    reg.setInputTarget(tgt);
+    reg.setMaximumIterations(50);
+    reg.setTransformationEpsilon(1e-8);
+    reg.setMaxCorrespondenceDistance(0.05);
+    reg.align(out);
+    const double s_id = tve.validateTransformation(src, tgt, Eigen::Matrix4f::Identity());
+    const double s_icp = tve.validateTransformation(src, tgt, reg.getFinalTransformation());
+    EXPECT_LT(s_icp, 0.25 * s_id);
+    EXPECT_NEAR(s_icp, reg.getFitnessScore(), 1e-7);   // the same quantity by Registration::getFitnessScore
+    EXPECT_TRUE(!tve.isValid(src, tgt, reg.getFinalTransformation()));  // threshold not set (:176-181)
+    tve.setThreshold(2.0 * s_icp);
+    EXPECT_TRUE(tve.isValid(src, tgt, reg.getFinalTransformation()));
+    EXPECT_TRUE(!tve.isValid(src, tgt, Eigen::Matrix4f::Identity()));
+    tve.setMaxRange(1e-12);
+    EXPECT_EQ(tve.validateTransformation(src, tgt, reg.getFinalTransformation()), std::numeric_limits<double>::max());
   }
 
   Eigen::Matrix4f T_ref;
