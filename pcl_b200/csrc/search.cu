@@ -858,9 +858,13 @@ k_knn_warp(const TreeView T, const int2* __restrict__ node_leaves, int b_start, 
         // Candidates that beat the current k-th are only APPENDED to a per-warp buffer; the list is updated (sort + merge,
         // or a few ranked insertions) when 32 have collected and at the end of the home cell, so the expensive network
         // runs once per ~32 survivors instead of once per round.  A stale threshold only admits extra candidates.
-        float Tk = inf;
+        // the running threshold starts at the certification radius: a candidate beyond it cannot be part of a certified
+        // answer, so only the points inside the ball (~k..2k of the few hundred gathered) ever reach the sorting network
+        const float R2cert = __fmul_rd(__fmul_rd(R, R), 0.999998f);
+        float Tk = R2cert;
         int Ti = kSentinelIndex;
         int nbuf = 0;
+        bool have_list = false;
         auto flush = [&](int take) {  // fold the first `take` (<= 32) buffered candidates into the list
           float cd = inf;
           int ci = kSentinelIndex, cp = -1;
@@ -869,9 +873,14 @@ k_knn_warp(const TreeView T, const int2* __restrict__ node_leaves, int b_start, 
             ci = s_ci[warp][lane];
             cp = s_cp[warp][lane];
           }
-          if (take > 6) {
+          if (!have_list || take > 12) {
             warp_sort32(cd, ci, cp, lane);
-            warp_merge32(ld, li, lp, cd, ci, cp, lane);
+            if (have_list)
+              warp_merge32(ld, li, lp, cd, ci, cp, lane);
+            else {  // nothing to merge with yet: the sorted candidates are the list
+              ld = cd; li = ci; lp = cp;
+              have_list = true;
+            }
           }
           else {
             for (int src = 0; src < take; ++src) {
@@ -905,8 +914,14 @@ k_knn_warp(const TreeView T, const int2* __restrict__ node_leaves, int b_start, 
             s_cp[warp][lane] = mp;
           }
           nbuf = rest;
-          Tk = __shfl_sync(full, ld, k - 1);
-          Ti = __shfl_sync(full, li, k - 1);
+          {
+            const float nk = __shfl_sync(full, ld, k - 1);
+            const int ni = __shfl_sync(full, li, k - 1);
+            if (lex_less(nk, ni, Tk, Ti)) {  // never looser than the certification radius
+              Tk = nk;
+              Ti = ni;
+            }
+          }
           __syncwarp();
         };
         const float gx2 = (E & 1u) ? cell_gap2(C, 0, qq.x, hx, ox, s) : 0.f;
@@ -952,7 +967,7 @@ k_knn_warp(const TreeView T, const int2* __restrict__ node_leaves, int b_start, 
           flush(nbuf);
         // exact iff the k-th neighbour lies strictly inside the gathered box (margin >> fp32 rounding of d2)
         const float dk = __shfl_sync(full, ld, k - 1);
-        done = dk < __fmul_rd(__fmul_rd(R, R), 0.999998f);
+        done = dk < R2cert;
       }
       if (!done) {
         redo[qi] = 1;  // (all lanes store the same byte)

@@ -72,3 +72,12 @@ def test_default_params_layout(built):
     assert p.euclidean_fitness_epsilon == -np.finfo(np.float64).max
     assert p.mse_threshold_absolute == 1e-12
     assert p.correspondence_k == 10 and p.track_mode == 0
+
+
+def test_library_sources_read_no_environment_variable():
+    """A drop-in library must not change behaviour on environment variables: every switch is a params field or an explicit
+    call.  (The .so still imports getenv — the statically linked CUDA runtime reads its own CUDA_* variables.)"""
+    import glob
+    root = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "pcl_b200", "csrc")
+    offenders = [f for f in glob.glob(os.path.join(root, "*.cu*")) if "getenv" in open(f).read()]
+    assert not offenders, offenders
