@@ -356,6 +356,16 @@ __device__ __forceinline__ bool nearest1(const TreeView& T, float qx, float qy, 
     };
     ball_level();
     if (v.best_pos < 0 || s > smin + 2) {
+#ifdef PCLB_HOME_NEAR
+      // only the two finest levels: a query whose own fine cells are empty is far from the cloud, and a seed reached by
+      // a long greedy descent costs as much as the walk it is meant to shorten
+      int ref = kDone;
+      for (int b = C.bmax; b >= C.bmax - 1 && b >= 1 && ref == kDone; --b) {
+        const int sh = 21 - b;
+        ref = cell_lookup(C, cell_key(b, cqx >> sh, cqy >> sh, cqz >> sh));
+        PCLB_STAT(ws, 0);
+      }
+#else
       // finest occupied cell that contains q: occupancy is monotone in the level (a coarser cell contains the finer
       // one), so a binary search over the levels needs ~log2(bmax) lookups
       int ref = kDone;
@@ -372,6 +382,7 @@ __device__ __forceinline__ bool nearest1(const TreeView& T, float qx, float qy, 
         else
           hi_b = b - 1;
       }
+#endif
       if (ref != kDone) {
         while (ref >= 0) {  // greedy descent: nearer child, no stack
           const float4* np = reinterpret_cast<const float4*>(T.nodes + ref);

@@ -7,7 +7,8 @@
 // The LZF coder below is written from the published stream format (a control byte < 32 starts a literal run of
 // ctrl + 1 bytes; otherwise a back reference of length (ctrl >> 5) + 2 — 7 means "add the next byte" — at distance
 // ((ctrl & 31) << 8 | next byte) + 1); any valid stream decodes with the reference's lzfDecompress and vice versa.
-// PCLPointCloud2 blobs are not built: clouds are read straight into pcl::PointCloud<PointT>, fields matched by name.
+// Clouds are read straight into pcl::PointCloud<PointT>, fields matched by name (what PCDReader::read + fromPCLPointCloud2
+// amount to); the blob type itself lives in pcl/PCLPointCloud2.h.
 #pragma once
 #include <cmath>
 #include <cstdint>

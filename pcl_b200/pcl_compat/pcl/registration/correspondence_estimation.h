@@ -2,6 +2,7 @@
 // Reference: registration/include/pcl/registration/correspondence_estimation.h:59-504 and
 // impl/correspondence_estimation.hpp:52-311.
 #pragma once
+#include "../PCLPointCloud2.h"
 #include <cmath>
 #include <cstdio>
 #include <limits>
@@ -64,6 +65,10 @@ public:
   virtual Ptr clone() const = 0;            // correspondence_estimation.h:315
   virtual bool requiresSourceNormals() const { return false; }
   virtual bool requiresTargetNormals() const { return false; }
+  // correspondence_estimation.h:277-322: the type-erased route by which IterativeClosestPoint hands an estimator the
+  // normals it requires (impl/icp.hpp:142,169); estimators that need none ignore the blob
+  virtual void setSourceNormals(pcl::PCLPointCloud2::ConstPtr /*cloud2*/) {}
+  virtual void setTargetNormals(pcl::PCLPointCloud2::ConstPtr /*cloud2*/) {}
   virtual void determineCorrespondences(pcl::Correspondences& correspondences,
                                         double max_distance = std::numeric_limits<double>::max()) = 0;
   virtual void determineReciprocalCorrespondences(pcl::Correspondences& correspondences,

@@ -19,6 +19,21 @@ public:
 
   void setSourceNormals(const NormalsConstPtr& normals) { source_normals_ = normals; }
   NormalsConstPtr getSourceNormals() const { return source_normals_; }
+  // blob form (impl/correspondence_estimation_normal_shooting.hpp / …backprojection.hpp: fromPCLPointCloud2 + the typed setter)
+  void setSourceNormals(pcl::PCLPointCloud2::ConstPtr cloud2) override
+  {
+    NormalsPtr cloud(new pcl::PointCloud<NormalT>);
+    fromPCLPointCloud2(*cloud2, *cloud);
+    setSourceNormals(NormalsConstPtr(cloud));
+  }
+  void setTargetNormals(pcl::PCLPointCloud2::ConstPtr cloud2) override
+  {
+    if (Kind != PCLB200_CORR_BACK_PROJECTION)
+      return;
+    NormalsPtr cloud(new pcl::PointCloud<NormalT>);
+    fromPCLPointCloud2(*cloud2, *cloud);
+    target_normals_ = cloud;
+  }
   void setKSearch(unsigned int k) { k_ = k; }
   unsigned int getKSearch() const { return k_; }
   bool requiresSourceNormals() const override { return true; }
@@ -89,6 +104,7 @@ public:
   using Ptr = std::shared_ptr<CorrespondenceEstimationBackProjection>;
   using ConstPtr = std::shared_ptr<const CorrespondenceEstimationBackProjection>;
   using NormalsConstPtr = typename pcl::PointCloud<NormalT>::ConstPtr;
+  using detail::CorrespondenceEstimationByNormals<PointSource, PointTarget, NormalT, Scalar, PCLB200_CORR_BACK_PROJECTION>::setTargetNormals;
   void setTargetNormals(const NormalsConstPtr& normals) { this->target_normals_ = normals; }
   NormalsConstPtr getTargetNormals() const { return this->target_normals_; }
   bool requiresTargetNormals() const override { return true; }

@@ -17,6 +17,7 @@
 #include <pcl/io/pcd_io.h>
 #include <pcl/kdtree/kdtree_flann.h>
 #include <pcl/point_cloud.h>
+#include <pcl/conversions.h>
 #include <pcl/point_representation.h>
 #include <pcl/registration/transformation_validation_euclidean.h>
 #include <pcl/point_types.h>
@@ -209,6 +210,33 @@ int main(int argc, char** argv)
     EXPECT_TRUE(aniso.hasConverged());
     for (int r = 0; r < 3; ++r)
       for (int c = 0; c < 4; ++c) EXPECT_NEAR(plain.getFinalTransformation()(r, c), aniso.getFinalTransformation()(r, c), 2e-2);
+  }
+
+  {  // PCLPointCloud2 blobs (conversions.h:166-330): round trip by field NAME, and the blob form of setSourceNormals
+    PointCloud<PointNormal> pn;
+    for (int i = 0; i < 50; ++i) pn.emplace_back(0.1f * i, 1.f - 0.02f * i, 0.5f * i, 0.f, 0.6f, 0.8f, 0.01f * i);
+    PCLPointCloud2 blob;
+    toPCLPointCloud2(pn, blob);
+    EXPECT_EQ(blob.point_step, 48u);
+    EXPECT_EQ(blob.fields.size(), 7u);
+    EXPECT_EQ(blob.width * blob.height, 50u);
+    PointCloud<PointNormal> back;
+    fromPCLPointCloud2(blob, back);
+    EXPECT_EQ(back.size(), 50u);
+    PointCloud<Normal> only_normals;   // a different point type picks its fields out of the same blob
+    fromPCLPointCloud2(blob, only_normals);
+    PointCloud<PointXYZ> only_xyz;
+    fromPCLPointCloud2(blob, only_xyz);
+    for (int i = 0; i < 50; i += 7) {
+      EXPECT_EQ(back[i].x, pn[i].x); EXPECT_EQ(back[i].normal_z, pn[i].normal_z); EXPECT_EQ(back[i].curvature, pn[i].curvature);
+      EXPECT_EQ(only_normals[i].normal_y, pn[i].normal_y); EXPECT_EQ(only_normals[i].curvature, pn[i].curvature);
+      EXPECT_EQ(only_xyz[i].z, pn[i].z);
+    }
+    registration::CorrespondenceEstimationNormalShooting<PointXYZ, PointXYZ, Normal> ns;
+    PCLPointCloud2::Ptr nb(new PCLPointCloud2(blob));
+    ns.setSourceNormals(PCLPointCloud2::ConstPtr(nb));
+    EXPECT_TRUE(ns.getSourceNormals() && ns.getSourceNormals()->size() == 50u);
+    if (ns.getSourceNormals()) EXPECT_EQ((*ns.getSourceNormals())[10].normal_z, 0.8f);
   }
 
   {  // TransformationValidationEuclidean (transformation_validation_euclidean.h:77-263): identity on a cloud against itself
