@@ -25,8 +25,8 @@ Other workloads (--workload; the driver's default run is c
          iterations (all epsilons 0); intended for 8 GPUs
 Scaling (--scaling):
   weak   : every rank holds a replica of the target index and its OWN source cloud of the full size (default)
-  strong : ONE source; rank r gets the r-th contiguous range of its Morton order (a spatial tile), so per-GPU work
-           shrinks with N.  The 40 fp64 accumulators are exchanged once per iteration over NVLink (fused into the
+  strong : ONE source, cut into spatial tiles (chunks of 65 536 Morton-consecutive points dealt round-robin to the ranks;
+           --shard contiguous = one Morton range per rank), so per-GPU work shrinks with N.  The 40 fp64 accumulators are exchanged once per iteration over NVLink (fused into the
            accumulate kernel's last block; NCCL bootstraps the peer mappings).
 --impl reference times the CPU restatement of PCL's own path (oracle/; the reference itself cannot be compiled in this
 image: no Eigen/Boost/FLANN) on the box's host cores, on a bounded sample of the same workload.
@@ -222,14 +222,27 @@ def morton_order(xyz):
     return np.argsort(key, kind="stable")
 
 
-def shard_strong(src, rank, world):
-    """rank r's spatial tile: the r-th contiguous range of the Morton order of the ONE source cloud."""
+SHARD_CHUNK = 65536
+
+
+def shard_strong(src, rank, world, mode="cyclic"):
+    """rank r's share of the ONE source cloud, as spatial tiles: the cloud in Morton order is cut into chunks of
+    SHARD_CHUNK consecutive points (compact patches) that are dealt round-robin to the ranks ("cyclic", default), or into
+    `world` contiguous ranges ("contiguous").  Equal point counts either way; the cyclic deal also equalises the WORK —
+    a rigid motion displaces one end of the cloud more than the other, walks there are longer, and with one contiguous
+    range per rank the fastest rank waits in the per-iteration exchange (measured at N = 2: 17.5 ms per step, 6.3 ms
+    of it spent waiting in the accumulate kernel, profiles/r2n_cfg3_strong_2gpu_contiguous.json)."""
     if world == 1:
         return src
     order = morton_order(src[:, :3])
     n = src.shape[0]
-    lo, hi = (n * rank) // world, (n * (rank + 1)) // world
-    return np.ascontiguousarray(src[np.sort(order[lo:hi])])
+    if mode == "contiguous":
+        lo, hi = (n * rank) // world, (n * (rank + 1)) // world
+        mine = order[lo:hi]
+    else:
+        chunk = np.arange(n) // SHARD_CHUNK
+        mine = order[(chunk % world) == rank]
+    return np.ascontiguousarray(src[np.sort(mine)])
 
 
 class ClockSampler:
@@ -439,7 +452,7 @@ def run_ours(args):
             dist.all_reduce(t)
             n_src_total = int(t[0])
     else:
-        src_np = shard_strong(src_full, rank, world) if strong else src_full
+        src_np = shard_strong(src_full, rank, world, args.shard) if strong else src_full
     del src_full
     src_host = torch.from_numpy(src_np).pin_memory()
     ctx.profile_reset()
@@ -610,7 +623,7 @@ def run_ours(args):
                        "max_correspondence_distance": W["gate"], "estimator": W["estimator"], "k": 1,
                        "normals_k": W["normals_k"], "voxel_leaf": W["voxel_leaf"],
                        "l2_policy": "inputs larger than L2 (target points + nodes + normals + source >> 126 MB)",
-                       "parallelism": (f"source sharded x{world} ({'Morton-range tiles of one cloud' if strong else 'one cloud per rank'}), "
+                       "parallelism": (f"source sharded x{world} ({'Morton tiles of one cloud, ' + args.shard if strong else 'one cloud per rank'}), "
                                        "target replicated, 40-double exchange per iteration fused into the accumulate kernel")},
             "ms_per_iter": ms_v / max(iters_v, 1),
             "breakdown_ms_per_step": {"icp_iteration_kernel": prof["icp_search"][0] / steps,
@@ -649,6 +662,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="cfg3", choices=sorted(WORKLOADS))
     ap.add_argument("--scaling", default="weak", choices=["weak", "strong"])
+    ap.add_argument("--shard", default="cyclic", choices=["cyclic", "contiguous"],
+                    help="strong scaling: Morton chunks dealt round-robin (balanced work) or one contiguous Morton range per rank")
     ap.add_argument("--points", type=int, default=0, help="override the workload's point count (debug / smaller boxes)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-clocks", action="store_true", help="debug: do not sample clocks during the timed region")

@@ -262,6 +262,8 @@ void comm_set_mode(Ctx& c, int mode)
 
 bool comm_active(const Ctx& c) { return c.comm && c.comm->nranks > 1; }
 
+bool comm_peer_fused(const Ctx& c) { return comm_active(c) && c.comm->peer_ok && c.comm->mode == PCLB200_REDUCE_FUSED; }
+
 // view + next sequence number for a fused in-kernel exchange; returns false when the NCCL path must be used
 bool comm_peer_view(Ctx& c, PeerView* view, unsigned long long* seq)
 {

@@ -30,6 +30,7 @@ namespace pclb200 {
 void comm_allreduce_sum(Ctx& c, double* d_buf, int count);  // comm.cu (no-op without a communicator)
 bool comm_active(const Ctx& c);
 bool comm_peer_view(Ctx& c, PeerView* view, unsigned long long* seq);
+bool comm_peer_fused(const Ctx& c);  // the per-iteration exchange happens inside the accumulate kernel
 
 static inline unsigned grid_for(size_t n, int block) { return (unsigned)((n + block - 1) / block); }
 
@@ -55,6 +56,29 @@ struct SolveOut {
   double sum_d;
   int ok;
   int pad;
+};
+
+// Loop state that lives on the device so that a whole align() can be enqueued without a host round trip per iteration:
+// k_solve composes final = T_k * final, counts the iteration and evaluates DefaultConvergenceCriteria itself; once a
+// criterion fires (or there are too few correspondences) `done` turns the remaining enqueued kernels into no-ops.
+struct LoopCtrl {
+  int done;                // remaining enqueued iterations must not run
+  int iterations;          // nr_iterations_
+  int state;               // PCLB200_CONV_*
+  int converged;
+  int iterations_similar;  // DefaultConvergenceCriteria::iterations_similar_transforms_
+  int track_next;          // the next search keeps / uses the temporal-coherence bounds
+  int lb_valid;            // the previous search wrote them
+  int n_run;               // iterations executed since the host last reset it
+  double prev_mse, mse, n_corr;
+  long long total_corr;
+  double final_T[16], last_T[16];
+};
+
+struct CritParams {  // what DefaultConvergenceCriteria and the tracking heuristic need (pclb200_icp_params subset)
+  int max_iterations, failure_after_max_iter, max_iterations_similar, scalar_is_double, track_mode;
+  double rot_eps, trans_eps, rel_mse, abs_mse;
+  double rmax;  // sqrt(sum_axis max(|lo|, |hi|)^2) of the target frame: bounds the displacement a rotation causes
 };
 
 __device__ __forceinline__ void apply_pending(const Pending& P, float& x, float& y, float& z)
@@ -129,6 +153,8 @@ struct IterArgs {
   float4* cur_normals;             // source normals, same order as cur (symmetric objective), rotated with T_k
   int enforce_same_dir;
   CellTable cells;                 // cell table of the target index (walks start at the candidate ball)
+  LoopCtrl* ctrl;                  // device-side loop state (nullptr: the host decides everything, one iteration per sync)
+  int track_sel;                   // 1: the search kernel runs only if ctrl->track_next matches its TRACK flavour
   // fused cross-GPU reduce (optional): peer-mapped exchange buffers + this iteration's sequence number
   PeerView peer;
   unsigned long long seq;
@@ -245,6 +271,8 @@ __host__ __device__ __forceinline__ int match_pos(const Match& m) { return m.pos
 
 #ifdef PCLB_STATS
 __device__ unsigned long long g_walk_stats[8];
+__device__ unsigned long long g_walk_imbalance[2];
+__device__ unsigned long long g_walk_hist[64];
 #endif
 
 constexpr float kRelMargin = 1e-5f;  // >> fp32 rounding of the distances involved (~2e-7): keeps the skip test exact
@@ -452,6 +480,11 @@ template <bool RECIP, bool TRACK>
 __global__ void __launch_bounds__(256, 6)
 k_search(const IterArgs a, Match* __restrict__ match, float* __restrict__ lbs)
 {
+  if (a.ctrl) {  // enqueued ahead of the host: a finished loop, or the other TRACK flavour, leaves nothing to do
+    if (a.ctrl->done || (a.track_sel && (a.ctrl->track_next != 0) != TRACK))
+      return;
+  }
+  const bool lb_ok = a.ctrl ? a.ctrl->lb_valid != 0 : true;  // bounds of an earlier TRACK phase say nothing now
   __shared__ Pending sP;
   if (threadIdx.x == 0)
     sP = *a.pending;
@@ -461,6 +494,9 @@ k_search(const IterArgs a, Match* __restrict__ match, float* __restrict__ lbs)
   bool overflow = false;
   unsigned skipped = 0;
   WalkStats ws{};
+#ifdef PCLB_STATS
+  unsigned my_nodes = 0;
+#endif
   const size_t stride = (size_t)gridDim.x * blockDim.x;
   for (size_t base = blockIdx.x * (size_t)blockDim.x + (threadIdx.x & ~31); base < a.n; base += stride) {
     const size_t i = base + lane;
@@ -491,7 +527,7 @@ k_search(const IterArgs a, Match* __restrict__ match, float* __restrict__ lbs)
       }
       const int seed = prev.pos >= 0 ? match_pos(prev) : -1;
       float nlb = 0.f;
-      if (TRACK && !RECIP && seed >= 0 && still_nearest(prev.d2, lbs[i], delta, &nlb)) {
+      if (TRACK && !RECIP && seed >= 0 && lb_ok && still_nearest(prev.d2, lbs[i], delta, &nlb)) {
         const float4 q = ldg4(a.pts + seed);
         m.d2 = dist2_rn(p.x, p.y, p.z, q.x, q.y, q.z);
         // distance[0] > max_dist_sqr drops the pair (correspondence_estimation.hpp:176); the match stays the seed
@@ -502,8 +538,14 @@ k_search(const IterArgs a, Match* __restrict__ match, float* __restrict__ lbs)
       else {
         const float inf = __int_as_float(0x7f800000);
         Nearest1T<TRACK> v{p.x, p.y, p.z, a.gate, kSentinelIndex, -1, inf, inf, inf};
+#ifdef PCLB_STATS
+        const unsigned nodes_before = ws.n[1];
+#endif
         if (!nearest1<TRACK>(T, p.x, p.y, p.z, v, seed, TRACK ? kTrackInflate : 1.00001f, ws))
           overflow = true;
+#ifdef PCLB_STATS
+        my_nodes = ws.n[1] - nodes_before;
+#endif
         if (v.best_pos >= 0) {
           m.pos = v.best_pos;
           m.d2 = v.best;
@@ -527,6 +569,22 @@ k_search(const IterArgs a, Match* __restrict__ match, float* __restrict__ lbs)
       if (TRACK)
         lbs[i] = lb_out;
     }
+#ifdef PCLB_STATS
+    {
+      // per-warp imbalance of the node visits: sum over lanes and 32 x max over lanes (their ratio = lane utilisation bound)
+      unsigned sm = my_nodes, mx = my_nodes;
+      for (int o = 16; o > 0; o >>= 1) {
+        sm += __shfl_xor_sync(0xffffffffu, sm, o);
+        mx = max(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+      }
+      if (lane == 0) {
+        atomicAdd(&g_walk_imbalance[0], (unsigned long long)sm);
+        atomicAdd(&g_walk_imbalance[1], (unsigned long long)mx * 32ull);
+      }
+      atomicAdd(&g_walk_hist[min(my_nodes, 63u)], 1ull);
+      my_nodes = 0;
+    }
+#endif
   }
 #ifdef PCLB_STATS
   for (int k = 0; k < 8; ++k)
@@ -549,6 +607,8 @@ template <int EST>
 __global__ void __launch_bounds__(256)
 k_accum_dmma(const IterArgs a, const Match* __restrict__ match)
 {
+  if (a.ctrl && a.ctrl->done)
+    return;
   __shared__ __align__(16) float s_stage[8][2 * 32 * 8];
   const int lane = threadIdx.x & 31;
   double c1a = 0.0, c1b = 0.0;
@@ -575,6 +635,8 @@ template <int EST>
 __global__ void __launch_bounds__(256)
 k_accum(const IterArgs a, const Match* __restrict__ match)
 {
+  if (a.ctrl && a.ctrl->done)
+    return;
   constexpr int NACC = EST == PCLB200_EST_SVD ? kAccSvd : kAccLls;
   double acc[NACC];
 #pragma unroll
@@ -851,10 +913,78 @@ __device__ bool solve6_dev(double (*A)[7], double* x)
 // (transformation_estimation_svd.hpp:183-225): H = sum (p - cp)(q - cq)^T = U S V^T, R = V U^T with the last column of V
 // negated when det(U) det(V) < 0, t = cq - R cp.  The same least-squares rotation as Umeyama's, by the reference's other
 // formula (the sums are the same accumulators: H is n times the transpose of Umeyama's covariance).
+// C = A * B, row-major, Eigen's coefficient order, in Scalar S (final = T_k * final, icp.hpp:223)
+template <typename S>
+__device__ void mat4_mul_dev(const double* A, const double* B, double* C)
+{
+  S R[16];
+  for (int r = 0; r < 4; ++r)
+    for (int c = 0; c < 4; ++c)
+      R[4 * r + c] = (((S)A[4 * r] * (S)B[c] + (S)A[4 * r + 1] * (S)B[4 + c]) + (S)A[4 * r + 2] * (S)B[8 + c]) +
+                     (S)A[4 * r + 3] * (S)B[12 + c];
+  for (int i = 0; i < 16; ++i)
+    C[i] = (double)R[i];
+}
+
+// DefaultConvergenceCriteria::hasConverged (impl/default_convergence_criteria.hpp:49-140) on the loop state L; T = T_k
+template <typename S>
+__device__ bool has_converged_dev(LoopCtrl& L, const CritParams& P, const double* Td)
+{
+  if (L.state != PCLB200_CONV_NOT_CONVERGED) {
+    L.iterations_similar = 0;
+    L.state = PCLB200_CONV_NOT_CONVERGED;
+  }
+  bool is_similar = false;
+  if (L.iterations >= P.max_iterations) {
+    if (!P.failure_after_max_iter) {
+      L.state = PCLB200_CONV_ITERATIONS;
+      return true;
+    }
+    L.state = PCLB200_CONV_FAILURE_AFTER_MAX_ITERATIONS;
+  }
+  S T[16];
+  for (int i = 0; i < 16; ++i)
+    T[i] = (S)Td[i];
+  const double rotation_threshold = P.rot_eps > 0 ? P.rot_eps : 0.99999;
+  const double cos_angle = 0.5 * (T[0] + T[5] + T[10] - 1);
+  const double translation_sqr = T[3] * T[3] + T[7] * T[7] + T[11] * T[11];
+  if (cos_angle >= rotation_threshold && translation_sqr <= P.trans_eps) {
+    if (L.iterations_similar >= P.max_iterations_similar) {
+      L.state = PCLB200_CONV_TRANSFORM;
+      return true;
+    }
+    is_similar = true;
+  }
+  const double cur_mse = L.mse;
+  if (fabs(cur_mse - L.prev_mse) < P.abs_mse) {
+    if (L.iterations_similar >= P.max_iterations_similar) {
+      L.state = PCLB200_CONV_ABS_MSE;
+      return true;
+    }
+    is_similar = true;
+  }
+  if (fabs(cur_mse - L.prev_mse) / L.prev_mse < P.rel_mse) {
+    if (L.iterations_similar >= P.max_iterations_similar) {
+      L.state = PCLB200_CONV_REL_MSE;
+      return true;
+    }
+    is_similar = true;
+  }
+  if (is_similar)
+    ++L.iterations_similar;
+  else
+    L.iterations_similar = 0;
+  L.prev_mse = cur_mse;
+  return false;
+}
+
 __global__ void k_solve(const double* __restrict__ accum, int est, int scalar_is_double, int mode, double ox,
-                        double oy, double oz, int min_corr, Pending* pending, SolveOut* out, int svd_correlation)
+                        double oy, double oz, int min_corr, Pending* pending, SolveOut* out, int svd_correlation,
+                        LoopCtrl* ctrl, CritParams crit)
 {
   if (threadIdx.x != 0 || blockIdx.x != 0)
+    return;
+  if (ctrl && ctrl->done)
     return;
   const double n = accum[0];
   out->n = n;
@@ -971,6 +1101,46 @@ __global__ void k_solve(const double* __restrict__ accum, int est, int scalar_is
     }
     pending->apply = ok ? 1 : 0;
     pending->mode = mode;
+  }
+  if (ctrl) {
+    // the tail of one pass of the do-while at icp.hpp:164-241, in the caller's Scalar
+    LoopCtrl& L = *ctrl;
+    ++L.n_run;
+    L.n_corr = n;
+    L.total_corr += (long long)n;
+    L.mse = n > 0 ? accum[1] / n : 0.0;
+    const int tracked = L.track_next;
+    if (!ok) {  // icp.hpp:204-213
+      L.state = PCLB200_CONV_NO_CORRESPONDENCES;
+      L.converged = 0;
+      L.done = 1;
+    }
+    else {
+      for (int i = 0; i < 16; ++i)
+        L.last_T[i] = T[i];
+      if (scalar_is_double)
+        mat4_mul_dev<double>(L.last_T, L.final_T, L.final_T);
+      else
+        mat4_mul_dev<float>(L.last_T, L.final_T, L.final_T);
+      ++L.iterations;
+      L.converged = (scalar_is_double ? has_converged_dev<double>(L, crit, L.last_T) : has_converged_dev<float>(L, crit, L.last_T)) ? 1 : 0;
+      if (L.state != PCLB200_CONV_NOT_CONVERGED)
+        L.done = 1;
+      // tracking pays once the cloud has almost stopped moving: upper bound of the displacement T_k causes anywhere
+      // near the target, |R - I|_F * r_max + |t|, against half the RMS correspondence distance
+      double rf = 0.0, tn = 0.0;
+      for (int r = 0; r < 3; ++r) {
+        for (int cc = 0; cc < 3; ++cc) {
+          const double d = T[4 * r + cc] - (r == cc ? 1.0 : 0.0);
+          rf += d * d;
+        }
+        tn += T[4 * r + 3] * T[4 * r + 3];
+      }
+      const double disp = sqrt(rf) * crit.rmax + sqrt(tn);
+      L.track_next = crit.track_mode == PCLB200_TRACK_ON ? 1
+                     : crit.track_mode == PCLB200_TRACK_OFF ? 0 : (disp < 0.5 * sqrt(fmax(L.mse, 0.0)) ? 1 : 0);
+    }
+    L.lb_valid = tracked;  // the search of THIS iteration wrote the bounds iff it was a TRACK search
   }
 }
 
@@ -1179,6 +1349,18 @@ extern "C" __attribute__((visibility("default"))) int pclb200_debug_walk_stats(u
   }
   return 0;
 }
+extern "C" __attribute__((visibility("default"))) int pclb200_debug_walk_hist(unsigned long long out[66], int reset)
+{
+  cudaDeviceSynchronize();
+  cudaMemcpyFromSymbol(out, g_walk_imbalance, 2 * sizeof(unsigned long long));
+  cudaMemcpyFromSymbol(out + 2, g_walk_hist, 64 * sizeof(unsigned long long));
+  if (reset) {
+    unsigned long long z[64] = {0};
+    cudaMemcpyToSymbol(g_walk_imbalance, z, 2 * sizeof(unsigned long long));
+    cudaMemcpyToSymbol(g_walk_hist, z, sizeof(z));
+  }
+  return 0;
+}
 #endif
 
 float gate_from_max_dist(double max_dist)
@@ -1244,6 +1426,7 @@ struct Icp {
   DevBuf<float4> cur;           // Morton order, w = slot
   DevBuf<float4> cur_normals;   // source normals in the order of `cur` (symmetric objective only)
   DevBuf<Match> match;          // Morton order: this iteration's matches = next iteration's seeds
+  DevBuf<LoopCtrl> ctrl;        // device-side loop state of the enqueue-ahead path (icp_iterate)
   DevBuf<float> lb;             // per query: lower bound on the distance to every OTHER target point (TRACK searches)
   bool lb_valid = false;        // lb was written by the previous search
   DevBuf<int32_t> cur_label;    // Morton order: original source index of cur[i] (labels of the reciprocal tree)
@@ -1306,6 +1489,7 @@ Icp* icp_create(Ctx& c, const pclb200_icp_params& P)
   s->P = P;
   s->pending.alloc(1, c.stream);
   s->solve_out.alloc(1, c.stream);
+  s->ctrl.alloc(1, c.stream);
   s->skip_count.alloc(1, c.stream);
   PCLB_CUDA(cudaMemsetAsync(s->skip_count.p, 0, sizeof(unsigned long long), c.stream));
   s->red.init(c, (unsigned)c.sm_count * 16);
@@ -1721,9 +1905,7 @@ void icp_iterate(Icp& s, int max_steps, pclb200_icp_stats* stats)
   const Index& T = *s.tgt;
   SolveOut* h_out = reinterpret_cast<SolveOut*>(c.pinned);
   int steps = 0;
-  // the reference's do-while runs at least once per align(); a caller stepping one iteration at a time
-  // resumes a NOT_CONVERGED session, and a fresh session (iterations == 0) always enters.
-  while (steps < max_steps && (s.state == PCLB200_CONV_NOT_CONVERGED)) {
+  auto base_args = [&]() {
     IterArgs a;
     memset(&a, 0, sizeof(a));
     a.nodes = T.nodes.p;
@@ -1749,6 +1931,129 @@ void icp_iterate(Icp& s, int max_steps, pclb200_icp_stats* stats)
     a.cells = tree_view(T).cells;
     a.peer.nranks = 0;
     a.seq = 0;
+    return a;
+  };
+  auto raise_device_error = [&](int h_err) {
+    if (!h_err)
+      return;
+    PCLB_CUDA(cudaMemsetAsync(c.d_error, 0, sizeof(int), st));
+    if (h_err == 2)
+      throw Error(PCLB200_ERR_NCCL, "fused cross-GPU reduce timed out waiting for a peer rank");
+    throw Error(PCLB200_ERR_INTERNAL, "LBVH traversal stack overflow (tree deeper than the per-query stack)");
+  };
+  // ---- enqueue-ahead path ------------------------------------------------------------------------------------------
+  // The plain loop (nearest-neighbour correspondences, no rejector chain, no reciprocal tree) needs the host for nothing
+  // between iterations: k_solve leaves T_k in device memory for the next search, composes the final transform, counts
+  // the iteration and evaluates the convergence criteria (LoopCtrl).  So every iteration this call may run is enqueued
+  // at once and the stream is synchronised ONCE; when a criterion fires early the kernels still queued find `done` set
+  // and return.  With AUTO tracking both flavours of the search kernel are queued and the device picks one.
+  const bool needs_host_between = s.P.correspondence_kind != PCLB200_CORR_NEAREST || !s.rejectors.empty() ||
+                                  s.P.use_reciprocal || s.P.estimator == PCLB200_EST_SYMMETRIC_POINT_TO_PLANE_LLS ||
+                                  (comm_active(c) && !comm_peer_fused(c));
+  if (!needs_host_between && s.state == PCLB200_CONV_NOT_CONVERGED && max_steps > 0) {
+    const int left = std::max(1, s.P.max_iterations - s.iterations);  // the do-while always runs once
+    const int n_enq = std::min(max_steps, left);
+    LoopCtrl* h_ctrl = reinterpret_cast<LoopCtrl*>(static_cast<unsigned char*>(c.pinned) + 1024);
+    int* h_err = reinterpret_cast<int*>(static_cast<unsigned char*>(c.pinned) + 1024 + sizeof(LoopCtrl));
+    memset(h_ctrl, 0, sizeof(LoopCtrl));
+    h_ctrl->iterations = s.iterations;
+    h_ctrl->state = s.state;
+    h_ctrl->iterations_similar = s.iterations_similar;
+    h_ctrl->track_next = s.P.track_mode == PCLB200_TRACK_ON ? 1 : (s.P.track_mode == PCLB200_TRACK_OFF ? 0 : (s.track_next ? 1 : 0));
+    h_ctrl->lb_valid = s.lb_valid ? 1 : 0;
+    h_ctrl->prev_mse = s.prev_mse;
+    h_ctrl->total_corr = s.total_corr;
+    for (int i = 0; i < 16; ++i) {
+      h_ctrl->final_T[i] = s.final_T[i];
+      h_ctrl->last_T[i] = s.last_T[i];
+    }
+    PCLB_CUDA(cudaMemcpyAsync(s.ctrl.p, h_ctrl, sizeof(LoopCtrl), cudaMemcpyHostToDevice, st));
+    CritParams crit;
+    crit.max_iterations = s.P.max_iterations;
+    crit.failure_after_max_iter = s.P.failure_after_max_iter;
+    crit.max_iterations_similar = s.P.max_iterations_similar_transforms;
+    crit.scalar_is_double = s.P.scalar_is_double;
+    crit.track_mode = s.P.track_mode;
+    crit.rot_eps = s.P.transformation_rotation_epsilon;
+    crit.trans_eps = s.P.transformation_epsilon;
+    crit.rel_mse = s.P.euclidean_fitness_epsilon;
+    crit.abs_mse = s.P.mse_threshold_absolute;
+    {
+      double rmax = 0.0;
+      for (int r = 0; r < 3; ++r) {
+        const double m = std::max(std::fabs((double)T.lo[r]), std::fabs((double)T.hi[r]));
+        rmax += m * m;
+      }
+      crit.rmax = std::sqrt(rmax);
+    }
+    const unsigned wgrid = persistent_grid(c, s.n_q, 256, 18);
+    const unsigned agrid = std::min(persistent_grid(c, s.n_q, 256, 8), s.red.max_blocks);
+    for (int k = 0; k < n_enq; ++k) {
+      IterArgs a = base_args();
+      a.ctrl = s.ctrl.p;
+      comm_peer_view(c, &a.peer, &a.seq);
+      {
+        ProfScope ps(c, "icp_search");
+        if (s.P.track_mode == PCLB200_TRACK_AUTO) {
+          a.track_sel = 1;
+          k_search<false, false><<<wgrid, 256, 0, st>>>(a, s.match.p, s.lb.p);
+          k_search<false, true><<<wgrid, 256, 0, st>>>(a, s.match.p, s.lb.p);
+          c.launches += 2;
+        }
+        else {
+          if (s.P.track_mode == PCLB200_TRACK_ON)
+            k_search<false, true><<<wgrid, 256, 0, st>>>(a, s.match.p, s.lb.p);
+          else
+            k_search<false, false><<<wgrid, 256, 0, st>>>(a, s.match.p, s.lb.p);
+          ++c.launches;
+        }
+      }
+      {
+        ProfScope ps(c, "icp_accum");
+        if (s.P.estimator == PCLB200_EST_SVD)
+          k_accum_dmma<PCLB200_EST_SVD><<<agrid, 256, 0, st>>>(a, s.match.p);
+        else
+          k_accum_dmma<PCLB200_EST_POINT_TO_PLANE_LLS><<<agrid, 256, 0, st>>>(a, s.match.p);
+        ++c.launches;
+      }
+      {
+        ProfScope ps(c, "solve");
+        k_solve<<<1, 32, 0, st>>>(s.red.accum.p, s.P.estimator, s.P.scalar_is_double, transform_mode(s.P), (double)a.ox,
+                                  (double)a.oy, (double)a.oz, 3, s.pending.p, s.solve_out.p, s.P.svd_no_umeyama, s.ctrl.p,
+                                  crit);
+        ++c.launches;
+      }
+    }
+    PCLB_CUDA(cudaGetLastError());
+    PCLB_CUDA(cudaMemcpyAsync(h_ctrl, s.ctrl.p, sizeof(LoopCtrl), cudaMemcpyDeviceToHost, st));
+    PCLB_CUDA(cudaMemcpyAsync(h_err, c.d_error, sizeof(int), cudaMemcpyDeviceToHost, st));
+    PCLB_CUDA(cudaStreamSynchronize(st));
+    raise_device_error(*h_err);
+    steps = h_ctrl->n_run;
+    s.iterations = h_ctrl->iterations;
+    s.state = h_ctrl->state;
+    s.converged = h_ctrl->converged != 0;
+    s.iterations_similar = h_ctrl->iterations_similar;
+    s.prev_mse = h_ctrl->prev_mse;
+    s.track_next = h_ctrl->track_next != 0;
+    s.lb_valid = h_ctrl->lb_valid != 0;
+    if (steps > 0) {
+      s.n_corr = (int64_t)h_ctrl->n_corr;
+      s.mse = h_ctrl->mse;
+    }
+    s.total_corr = h_ctrl->total_corr;
+    for (int i = 0; i < 16; ++i) {
+      s.final_T[i] = h_ctrl->final_T[i];
+      s.last_T[i] = h_ctrl->last_T[i];
+    }
+    s.searches += steps;
+  }
+  // ---- stage-by-stage path: something between search and solve needs the host (rejector chain with its sorts, the
+  // reciprocal tree rebuilt every iteration, the normal-based estimators' k-NN rows, a collective launched by NCCL) ----
+  // the reference's do-while runs at least once per align(); a caller stepping one iteration at a time
+  // resumes a NOT_CONVERGED session, and a fresh session (iterations == 0) always enters.
+  while (needs_host_between && steps < max_steps && (s.state == PCLB200_CONV_NOT_CONVERGED)) {
+    IterArgs a = base_args();
     const bool fused_reduce = comm_peer_view(c, &a.peer, &a.seq);
     const unsigned grid = persistent_grid(c, s.n_q, 256, 8);
     std::unique_ptr<Index> src_index;
@@ -1838,19 +2143,15 @@ void icp_iterate(Icp& s, int max_steps, pclb200_icp_stats* stats)
     {
       ProfScope ps(c, "solve");
       k_solve<<<1, 32, 0, st>>>(s.red.accum.p, s.P.estimator, s.P.scalar_is_double, transform_mode(s.P), (double)a.ox,
-                                (double)a.oy, (double)a.oz, 3, s.pending.p, s.solve_out.p, s.P.svd_no_umeyama);
+                                (double)a.oy, (double)a.oz, 3, s.pending.p, s.solve_out.p, s.P.svd_no_umeyama, nullptr,
+                                CritParams{});
     }
     ++c.launches;
     PCLB_CUDA(cudaMemcpyAsync(h_out, s.solve_out.p, sizeof(SolveOut), cudaMemcpyDeviceToHost, st));
     int h_err = 0;
     PCLB_CUDA(cudaMemcpyAsync(&h_err, c.d_error, sizeof(int), cudaMemcpyDeviceToHost, st));
     PCLB_CUDA(cudaStreamSynchronize(st));
-    if (h_err) {
-      PCLB_CUDA(cudaMemsetAsync(c.d_error, 0, sizeof(int), st));
-      if (h_err == 2)
-        throw Error(PCLB200_ERR_NCCL, "fused cross-GPU reduce timed out waiting for a peer rank");
-      throw Error(PCLB200_ERR_INTERNAL, "LBVH traversal stack overflow (tree deeper than the per-query stack)");
-    }
+    raise_device_error(h_err);
     ++steps;
     s.n_corr = (int64_t)h_out->n;
     s.total_corr += s.n_corr;
@@ -2118,7 +2419,7 @@ void estimate_pairs(Ctx& c, int est, const void* src, size_t stride_s, const voi
   else
     k_accum_pairs<PCLB200_EST_SYMMETRIC_POINT_TO_PLANE_LLS><<<grid, 256, 0, st>>>(a);
   k_solve<<<1, 32, 0, st>>>(red.accum.p, est, scalar_is_double, 0, (double)a.ox, (double)a.oy, (double)a.oz, 1, nullptr,
-                            so.p, svd_correlation);
+                            so.p, svd_correlation, nullptr, CritParams{});
   c.launches += 2;
   SolveOut h;
   PCLB_CUDA(cudaMemcpyAsync(&h, so.p, sizeof(h), cudaMemcpyDeviceToHost, st));

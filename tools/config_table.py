@@ -1,0 +1,84 @@
+#!/usr/bin/env python3
+"""Rows 1 and 2 of BASELINE.md §4 (configs[0], configs[1]) on one B200: align() time, correspondences/s, parity vs the oracle."""
+import json
+import os
+import sys
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import oracle  # noqa: E402
+import pcl_b200 as P  # noqa: E402
+
+
+def timed_align(ctx, src, idx, reps=5, **kw):
+    r = P.icp_align(ctx, src, idx, **kw)
+    ctx.synchronize()
+    best = 1e30
+    for _ in range(reps):
+        t0 = time.perf_counter()
+        r = P.icp_align(ctx, src, idx, **kw)
+        ctx.synchronize()
+        best = min(best, time.perf_counter() - t0)
+    return r, best
+
+
+def main():
+    ctx = P.Context(0)
+    cores = os.cpu_count() or 1
+    g = dict(np.load(os.path.join(ROOT, "tests", "golden", "pcl_golden.npz")))
+    # config 1: bun0 -> bun4
+    src, tgt = P.xyz1(g["bun0"]), P.xyz1(g["bun4"])
+    kw = dict(max_iterations=50, transformation_epsilon=1e-8, max_correspondence_distance=0.05)
+    t0 = time.perf_counter()
+    idx = P.Index(ctx, tgt)
+    ctx.synchronize()
+    build = time.perf_counter() - t0
+    r, dt = timed_align(ctx, src, idx, **kw)
+    t0 = time.perf_counter()
+    o = oracle.icp_align(src, tgt, nthreads=1, **kw)
+    cpu1 = time.perf_counter() - t0
+    c = idx.correspondences(src)
+    print(json.dumps({"cfg": 1, "align_ms": dt * 1e3, "iterations": r["iterations"], "ms_per_iter": dt * 1e3 / r["iterations"],
+                      "corr_per_s": r["total_correspondences"] / dt, "build_ms": build * 1e3,
+                      "cpu_1T_corr_per_s": o["total_correspondences"] / cpu1,
+                      "dT_F": float(np.linalg.norm(r["final"] - o["final"])),
+                      "idx_mismatches": int((c["index_match"] != g["corr_original"][:, 1]).sum())}))
+    # config 2: 1 M uniform cube, 5 deg, VoxelGrid 0.01, ICP SVD
+    n = 1_000_000
+    tgt = np.random.default_rng(42).random((n, 3), dtype=np.float32)
+    a = np.deg2rad(5.0)
+    ax = np.ones(3) / np.sqrt(3)
+    K = np.array([[0, -ax[2], ax[1]], [ax[2], 0, -ax[0]], [-ax[1], ax[0], 0]])
+    R = np.eye(3) + np.sin(a) * K + (1 - np.cos(a)) * K @ K
+    src = (tgt.astype(np.float64) @ R.T + [0.01, -0.02, 0.015] + np.random.default_rng(43).normal(0, 0.001, (n, 3))).astype(np.float32)
+    t0 = time.perf_counter()
+    vt, vs = ctx.voxelgrid(P.xyz1(tgt), 0.01), ctx.voxelgrid(P.xyz1(src), 0.01)
+    vg = time.perf_counter() - t0
+    t0 = time.perf_counter()
+    idx = P.Index(ctx, vt)
+    ctx.synchronize()
+    build = time.perf_counter() - t0
+    r, dt = timed_align(ctx, vs, idx, reps=3, **kw)
+    ot, os_ = oracle.voxelgrid(oracle.to_xyz1(tgt), [0.01] * 3), oracle.voxelgrid(oracle.to_xyz1(src), [0.01] * 3)
+    tree = oracle.Index(ot)
+    t0 = time.perf_counter()
+    o1 = oracle.icp_align(os_, ot, nthreads=1, max_iterations=3, max_correspondence_distance=0.05, index=tree)
+    cpu1 = time.perf_counter() - t0
+    t0 = time.perf_counter()
+    o = oracle.icp_align(os_, ot, nthreads=cores, index=tree, **kw)
+    cpun = time.perf_counter() - t0
+    print(json.dumps({"cfg": 2, "points_after_voxelgrid": [int(vs.shape[0]), int(vt.shape[0])], "voxelgrid_both_ms_incl_copies": vg * 1e3,
+                      "align_ms": dt * 1e3, "iterations": r["iterations"], "ms_per_iter": dt * 1e3 / r["iterations"],
+                      "corr_per_s": r["total_correspondences"] / dt, "build_ms": build * 1e3,
+                      "cpu_1T_corr_per_s": o1["total_correspondences"] / cpu1, "cpu_nproc_corr_per_s": o["total_correspondences"] / cpun,
+                      "cores": cores, "dT_F": float(np.linalg.norm(r["final"] - o["final"])),
+                      "voxel_mismatches": int(vt.shape[0] != ot.shape[0] or not np.array_equal(vt, ot)),
+                      "same_iterations": bool(r["iterations"] == o["iterations"]),
+                      "same_n_corr": bool(r["n_correspondences"] == o["n_correspondences"])}))
+
+
+if __name__ == "__main__":
+    main()

@@ -21,6 +21,7 @@ def main():
     track = int(sys.argv[3]) if len(sys.argv) > 3 else P.TRACK_AUTO
     L = P.lib()
     stats_fn = getattr(L, "pclb200_debug_walk_stats", None) if hasattr(L, "pclb200_debug_walk_stats") else None
+    hist_fn = getattr(L, "pclb200_debug_walk_hist", None) if hasattr(L, "pclb200_debug_walk_hist") else None
     ctx = P.Context(0)
     dev = torch.device("cuda", 0)
     tgt = bench.make_target(n)
@@ -42,6 +43,9 @@ def main():
         if stats_fn:
             buf = (C.c_ulonglong * 8)()
             stats_fn(buf, 1)
+        if hist_fn:
+            hb = (C.c_ulonglong * 66)()
+            hist_fn(hb, 1)
         for it in range(iters):
             ctx.profile_reset()
             st = icp.iterate(1)
@@ -53,6 +57,12 @@ def main():
                 w = max(buf[7], 1)
                 row.update({k: round(buf[i] / w, 3) for i, k in enumerate(names[:7])})
                 row["walks"] = buf[7]
+            if hist_fn:
+                hist_fn(hb, 1)
+                row["node_lane_utilisation"] = round(hb[0] / max(hb[1], 1), 3)
+                h = np.array(hb[2:], dtype=np.float64)
+                c = np.cumsum(h) / max(h.sum(), 1)
+                row["node_visits_p50_p90_p99"] = [int(np.searchsorted(c, q)) for q in (0.5, 0.9, 0.99)]
             if rep == 1:
                 print(json.dumps(row))
             if st["state"] != 0:
