@@ -463,6 +463,9 @@ def run_ours(args):
         tgt_dev = torch.from_numpy(tgt).to(dev)
         nrm_dev = torch.empty((n_tgt, 4), dtype=torch.float32, device=dev)
         tidx.normals_knn(tgt_dev, W["normals_k"], viewpoint=(5.0, 5.0, 10.0), out=nrm_dev)
+        setup_ms[f"normals_k{W['normals_k']}_first_call"] = ctx.profile_get("normals")[0]   # incl. first-use allocations
+        ctx.profile_reset()
+        tidx.normals_knn(tgt_dev, W["normals_k"], viewpoint=(5.0, 5.0, 10.0), out=nrm_dev)
         setup_ms[f"normals_k{W['normals_k']}"] = ctx.profile_get("normals")[0]
         del tgt_dev
     src_dev = src_host.to(dev)                    # value leg: records already resident in HBM

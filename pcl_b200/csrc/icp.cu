@@ -311,21 +311,26 @@ __device__ __forceinline__ bool still_nearest(float prev_d2, float prev_lb, floa
 // fp64 in a fixed order: bitwise reproducible, and within fp64 round-off of the oracle's sequential sums.
 __device__ __forceinline__ void dmma884(double& c0, double& c1, double a, double b)
 {
-  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+  asm("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
                : "+d"(c0), "+d"(c1)
                : "d"(a), "d"(b));
 }
 
 constexpr int kEstNone = -1;
+#ifndef PCLB_ACCUM_BLOCKS
+#define PCLB_ACCUM_BLOCKS 5
+#endif
+constexpr int kAccumBlocksPerSM = PCLB_ACCUM_BLOCKS;
 
-// tiles: 2 x 32 x 8 floats of this warp's shared memory.  Must be called by all 32 lanes (converged).
+// One pair's row of the contraction: ra = the MMA operand (w for SVD, v for LLS), rb = u (SVD) / the eight plain sums'
+// terms (LLS).  The two gathers (matched target point, its normal) are issued here; rows of pairs that are not accepted
+// stay zero.
 template <int EST>
-__device__ __forceinline__ void accumulate_pairs_dmma(const IterArgs& a, float* __restrict__ tiles, int lane, const Match& m,
-                                                      const float4& p, double& c1a, double& c1b, double (&wsum)[8])
+__device__ __forceinline__ void pair_rows(const IterArgs& a, const Match& m, const float4& p, float (&ra)[8], float (&rb)[8])
 {
-  float* tA = tiles;
-  float* tB = tiles + 32 * 8;
-  float ra[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f}, rb[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+  for (int k = 0; k < 8; ++k)
+    ra[k] = rb[k] = 0.f;
   if (match_accepted(m)) {
     const float4 q = ldg4(a.pts + m.pos);
     if (EST == PCLB200_EST_SVD) {
@@ -350,19 +355,22 @@ __device__ __forceinline__ void accumulate_pairs_dmma(const IterArgs& a, float* 
       }
     }
   }
+}
+
+// tiles: 2 x 32 x 8 floats of this warp's shared memory.  Must be called by all 32 lanes (converged).  Even steps
+// accumulate into (ca, cb), odd steps into (da, db): two independent MMA chains.  LLS: w collects component g of the
+// plain sums (float products of the normal, d2, count) over this lane's pairs — an MMA would spend a whole 8x8x4 tile on
+// them, and one fp64 register per lane is cheaper than eight per thread.
+template <int EST>
+__device__ __forceinline__ void mma_rows(const IterArgs& a, float* __restrict__ tiles, int lane, const float (&ra)[8],
+                                         const float (&rb)[8], double& ca, double& cb, double& da, double& db, double& w)
+{
+  float* tA = tiles;
+  float* tB = tiles + 32 * 8;
   *reinterpret_cast<float4*>(tA + lane * 8) = make_float4(ra[0], ra[1], ra[2], ra[3]);
   *reinterpret_cast<float4*>(tA + lane * 8 + 4) = make_float4(ra[4], ra[5], ra[6], ra[7]);
-  if (EST == PCLB200_EST_SVD) {
-    *reinterpret_cast<float4*>(tB + lane * 8) = make_float4(rb[0], rb[1], rb[2], rb[3]);
-    *reinterpret_cast<float4*>(tB + lane * 8 + 4) = make_float4(rb[4], rb[5], rb[6], rb[7]);
-  }
-  else {
-    // the eight plain sums (float products of the normal, d2, count) stay per thread: an MMA would spend a whole 8x8x4
-    // tile on them, and the fp64 tensor pipe is this kernel's second limiter (ncu: 45 % active with two MMAs per step)
-#pragma unroll
-    for (int k = 0; k < 8; ++k)
-      wsum[k] += (double)rb[k];
-  }
+  *reinterpret_cast<float4*>(tB + lane * 8) = make_float4(rb[0], rb[1], rb[2], rb[3]);
+  *reinterpret_cast<float4*>(tB + lane * 8 + 4) = make_float4(rb[4], rb[5], rb[6], rb[7]);
   __syncwarp();
   const int g = lane >> 2, t = lane & 3;
   const double og = g == 0 ? (double)a.ox : (g == 1 ? (double)a.oy : (double)a.oz);
@@ -377,10 +385,18 @@ __device__ __forceinline__ void accumulate_pairs_dmma(const IterArgs& a, float* 
         va = on ? va - og : 0.0;
         vb = on ? vb - og : 0.0;
       }
-      dmma884(c1a, c1b, va, vb);     // C1[i][j] += w_i u_j
+      if (st & 1)
+        dmma884(da, db, va, vb);     // C1[i][j] += w_i u_j
+      else
+        dmma884(ca, cb, va, vb);
     }
-    else
-      dmma884(c1a, c1b, va, va);     // C1[i][j] += v_i v_j
+    else {
+      if (st & 1)
+        dmma884(da, db, va, va);     // C1[i][j] += v_i v_j
+      else
+        dmma884(ca, cb, va, va);
+      w += (double)tB[row + g];
+    }
   }
   __syncwarp();
 }
@@ -416,7 +432,7 @@ __device__ __forceinline__ int dmma_accum_source(int est, int k)
 // warp tiles -> block (fixed order) -> grid (fixed order, last block) -> the kAccum layout k_solve reads -> peers.
 // Must be called by every thread of every block; blockDim.x = NWARPS * 32 >= 128.
 template <int EST, int NWARPS>
-__device__ __forceinline__ void fold_tiles_and_publish(const IterArgs& a, double c1a, double c1b, double (&wsum)[8])
+__device__ __forceinline__ void fold_tiles_and_publish(const IterArgs& a, double c1a, double c1b, double w)
 {
   __shared__ double s_tiles[NWARPS][128];
   __shared__ double s_fin[128];
@@ -425,17 +441,15 @@ __device__ __forceinline__ void fold_tiles_and_publish(const IterArgs& a, double
   const int g = lane >> 2, t = lane & 3;
   s_tiles[warp][g * 8 + 2 * t] = c1a;
   s_tiles[warp][g * 8 + 2 * t + 1] = c1b;
-  s_tiles[warp][64 + lane] = 0.0;       // tile 1: only column 0 is used (the eight per-thread sums, folded over the warp)
+  s_tiles[warp][64 + lane] = 0.0;       // tile 1: only column 0 is used (the eight plain sums)
   s_tiles[warp][96 + lane] = 0.0;
   __syncwarp();
-#pragma unroll
-  for (int k = 0; k < 8; ++k) {
-    double v = wsum[k];
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1)
-      v += __shfl_down_sync(0xffffffffu, v, o);
-    if (lane == 0)
-      s_tiles[warp][64 + k * 8] = v;
+  {
+    double v = w;  // lane (g, t) holds plain sum g over its pairs: fold the four t lanes
+    v += __shfl_xor_sync(0xffffffffu, v, 1);
+    v += __shfl_xor_sync(0xffffffffu, v, 2);
+    if (t == 0)
+      s_tiles[warp][64 + g * 8] = v;
   }
   __syncthreads();
   if (threadIdx.x < 128) {
@@ -601,33 +615,36 @@ k_search(const IterArgs a, Match* __restrict__ match, float* __restrict__ lbs)
 }
 
 // Streaming accumulation on the fp64 tensor cores: one pass over (source point, match) pairs, the normal equations
-// built by accumulate_pairs_dmma.  Four fp64 registers of accumulators per lane (instead of 29 per thread) leave room
-// for full occupancy, which is what a gather-bound streaming kernel needs.
+// built by pair_rows + mma_rows.  The kernel is bound by the latency of match -> gather (ncu: long-scoreboard 22 per
+// issue at 50 % occupancy): resident warps are what hides it (two pairs in flight per thread at half the occupancy was
+// measured slower, profiles/r2u), so the state is kept to ten fp64 registers of accumulators per lane instead of 29 per
+// thread.
 template <int EST>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, kAccumBlocksPerSM)
 k_accum_dmma(const IterArgs a, const Match* __restrict__ match)
 {
   if (a.ctrl && a.ctrl->done)
     return;
   __shared__ __align__(16) float s_stage[8][2 * 32 * 8];
   const int lane = threadIdx.x & 31;
-  double c1a = 0.0, c1b = 0.0;
-  double wsum[8] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
+  double ca = 0.0, cb = 0.0, da = 0.0, db = 0.0, w = 0.0;
   const size_t stride = (size_t)gridDim.x * blockDim.x;
+  float* tiles = s_stage[threadIdx.x >> 5];
   for (size_t base = blockIdx.x * (size_t)blockDim.x + (threadIdx.x & ~31); base < a.n; base += stride) {
     const size_t i = base + lane;
     Match m;
     m.pos = -1;
     m.d2 = 0.f;
-    float4 p = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (i < a.n) {
+    if (i < a.n)
       m = match[i];
-      if (match_accepted(m))
-        p = a.cur[i];
-    }
-    accumulate_pairs_dmma<EST>(a, s_stage[threadIdx.x >> 5], lane, m, p, c1a, c1b, wsum);
+    float4 p = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (match_accepted(m))
+      p = a.cur[i];
+    float ra[8], rb[8];
+    pair_rows<EST>(a, m, p, ra, rb);
+    mma_rows<EST>(a, tiles, lane, ra, rb, ca, cb, da, db, w);
   }
-  fold_tiles_and_publish<EST, 8>(a, c1a, c1b, wsum);
+  fold_tiles_and_publish<EST, 8>(a, ca + da, cb + db, w);
 }
 
 // Accumulation kernel: one streaming pass over (source point, match) pairs; fp64 sums, fixed reduction order.
@@ -1987,7 +2004,7 @@ void icp_iterate(Icp& s, int max_steps, pclb200_icp_stats* stats)
       crit.rmax = std::sqrt(rmax);
     }
     const unsigned wgrid = persistent_grid(c, s.n_q, 256, 18);
-    const unsigned agrid = std::min(persistent_grid(c, s.n_q, 256, 8), s.red.max_blocks);
+    const unsigned agrid = std::min(persistent_grid(c, s.n_q, 256, kAccumBlocksPerSM), s.red.max_blocks);
     for (int k = 0; k < n_enq; ++k) {
       IterArgs a = base_args();
       a.ctrl = s.ctrl.p;
@@ -2126,7 +2143,7 @@ void icp_iterate(Icp& s, int max_steps, pclb200_icp_stats* stats)
     }
     {
       ProfScope ps(c, "icp_accum");
-      const unsigned agrid = std::min(persistent_grid(c, s.n_q, 256, 8), s.red.max_blocks);
+      const unsigned agrid = std::min(persistent_grid(c, s.n_q, 256, kAccumBlocksPerSM), s.red.max_blocks);
       if (s.P.estimator == PCLB200_EST_SVD)
         k_accum_dmma<PCLB200_EST_SVD><<<agrid, 256, 0, st>>>(a, s.match.p);
       else if (s.P.estimator == PCLB200_EST_POINT_TO_PLANE_LLS)

@@ -131,95 +131,6 @@ __device__ __forceinline__ bool walk(const BvhNode* __restrict__ nodes, const fl
   return ok;
 }
 
-// Variant with POSTPONED leaf scans: a lane that reaches a leaf parks it (two slots) and keeps visiting nodes from its
-// stack; the warp turns to the leaf-scan code only when its lanes have leaves parked or have run dry.  In the plain
-// while-while walk a lane that has found its leaf idles until every other lane of the warp has found one too.
-template <typename Visitor>
-__device__ __forceinline__ bool walk_defer(const BvhNode* __restrict__ nodes, const float4* __restrict__ pts,
-                                           int* __restrict__ stack_node, float* __restrict__ stack_dist, int sp, int node,
-                                           float qx, float qy, float qz, Visitor& v, int skip_a, int skip_b,
-                                           WalkStats& ws)
-{
-  bool ok = true;
-  int lq0 = kDone, lq1 = kDone;
-  auto pop = [&]() {
-    const float bnd = v.bound();
-    while (sp > 0) {
-      --sp;
-      if (stack_dist[sp] <= bnd)
-        return stack_node[sp];
-      v.prune(stack_dist[sp]);
-    }
-    return (int)kDone;
-  };
-  if (node == kDone)
-    node = pop();
-  for (;;) {
-    while (node != kDone) {
-      if (node < 0) {  // a leaf: park it and go on with the stack
-        if (node != skip_a && node != skip_b) {
-          if (lq0 == kDone)
-            lq0 = node;
-          else if (lq1 == kDone)
-            lq1 = node;
-          else
-            break;  // both slots taken: scan first (node keeps the third leaf)
-        }
-        node = pop();
-        continue;
-      }
-      const float4* np = reinterpret_cast<const float4*>(nodes + node);
-      const float4 a = ldg4(np), b = ldg4(np + 1), c = ldg4(np + 2);
-      const int4 d = __ldg(reinterpret_cast<const int4*>(np + 3));
-      PCLB_STAT(ws, 1);
-      float dl = box_dist2_rn(qx, qy, qz, a.x, a.y, a.z, a.w, b.x, b.y);
-      float dr = box_dist2_rn(qx, qy, qz, b.z, b.w, c.x, c.y, c.z, c.w);
-      int nl = d.x, nr = d.y;
-      if (dr < dl) {
-        float t = dl; dl = dr; dr = t;
-        int ti = nl; nl = nr; nr = ti;
-      }
-      const float bnd = v.bound();
-      if (dl <= bnd) {
-        if (dr <= bnd) {
-          if (sp < kStackSize) {
-            stack_node[sp] = nr;
-            stack_dist[sp] = dr;
-            ++sp;
-            PCLB_STAT(ws, 3);
-          }
-          else
-            ok = false;
-        }
-        else
-          v.prune(dr);
-        node = nl;
-      }
-      else {
-        v.prune(dl);
-        node = pop();
-      }
-    }
-    if (lq0 == kDone && node == kDone)
-      break;
-    if (lq0 != kDone) {
-      const int leaf = ~lq0;
-      v.leaf(pts + (size_t)leaf * kLeafSize, leaf * kLeafSize);
-      PCLB_STAT(ws, 2);
-      lq0 = kDone;
-    }
-    if (lq1 != kDone) {
-      const int leaf = ~lq1;
-      v.leaf(pts + (size_t)leaf * kLeafSize, leaf * kLeafSize);
-      PCLB_STAT(ws, 2);
-      lq1 = kDone;
-    }
-    if (node == kDone)
-      node = pop();
-  }
-  return ok;
-}
-
 // plain walk from `root` with a private stack
 template <typename Visitor>
 __device__ __forceinline__ bool traverse(const BvhNode* __restrict__ nodes, const float4* __restrict__ pts,
@@ -519,11 +430,7 @@ __device__ __forceinline__ bool nearest1(const TreeView& T, float qx, float qy, 
     sp = 1;
   }
   PCLB_STAT(ws, 7);
-#ifdef PCLB_WALK_DEFER
-  return walk_defer(T.nodes, T.pts, stack_node, stack_dist, sp, kDone, qx, qy, qz, v, skip_a, skip_b, ws);
-#else
   return walk(T.nodes, T.pts, stack_node, stack_dist, sp, kDone, qx, qy, qz, v, skip_a, skip_b, ws);
-#endif
 }
 
 }  // namespace pclb200

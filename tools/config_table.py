@@ -70,11 +70,18 @@ def main():
     t0 = time.perf_counter()
     o = oracle.icp_align(os_, ot, nthreads=cores, index=tree, **kw)
     cpun = time.perf_counter() - t0
+    # the reference's Scalar = float estimate is limited by its own float sums at this size (tests/test_gpu_configs.py):
+    # the parity figures are taken against the double instantiation as well
+    o64 = oracle.icp_align(os_, ot, nthreads=cores, index=tree, scalar_is_double=True, **kw)
+    r64 = P.icp_align(ctx, vs, idx, scalar_is_double=1, **kw)
     print(json.dumps({"cfg": 2, "points_after_voxelgrid": [int(vs.shape[0]), int(vt.shape[0])], "voxelgrid_both_ms_incl_copies": vg * 1e3,
                       "align_ms": dt * 1e3, "iterations": r["iterations"], "ms_per_iter": dt * 1e3 / r["iterations"],
                       "corr_per_s": r["total_correspondences"] / dt, "build_ms": build * 1e3,
                       "cpu_1T_corr_per_s": o1["total_correspondences"] / cpu1, "cpu_nproc_corr_per_s": o["total_correspondences"] / cpun,
-                      "cores": cores, "dT_F": float(np.linalg.norm(r["final"] - o["final"])),
+                      "cores": cores, "dT_F_double_scalar": float(np.linalg.norm(r64["final"] - o64["final"])),
+                      "dT_F_float_scalar_vs_double_oracle": float(np.linalg.norm(r["final"] - o64["final"])),
+                      "dT_F_float_scalar_vs_float_oracle": float(np.linalg.norm(r["final"] - o["final"])),
+                      "float_oracle_vs_double_oracle": float(np.linalg.norm(o["final"] - o64["final"])),
                       "voxel_mismatches": int(vt.shape[0] != ot.shape[0] or not np.array_equal(vt, ot)),
                       "same_iterations": bool(r["iterations"] == o["iterations"]),
                       "same_n_corr": bool(r["n_correspondences"] == o["n_correspondences"])}))
