@@ -727,6 +727,12 @@ k_normals_from_csr(const float4* __restrict__ pts, const int32_t* __restrict__ p
 // Queries the scheme does not fit (far outside the cloud, > kWarpKnnMaxLeaves leaves in reach, no level certifies) are
 // flagged and redone by the per-thread kernel — same results, the exact walk is the fallback, never an approximation.
 constexpr int kWarpKnnMaxLeaves = 1024;
+#ifndef PCLB_KNN_TARGET_X10
+#define PCLB_KNN_TARGET_X10 12
+#endif
+#ifndef PCLB_KNN_LEVEL_X10
+#define PCLB_KNN_LEVEL_X10 10
+#endif
 
 __device__ __forceinline__ bool lex_less(float da, int ia, float db, int ib) { return da < db || (da == db && ia < ib); }
 
@@ -775,7 +781,7 @@ __device__ __forceinline__ void warp_merge32(float& ld, int& li, int& lp, float 
 
 template <bool NORMALS>
 __global__ void __launch_bounds__(256)
-k_knn_warp(const TreeView T, const int2* __restrict__ node_leaves, int b_start, const float4* __restrict__ q, size_t nq,
+k_knn_warp(const TreeView T, const int2* __restrict__ node_leaves, int b_start, float r_first, const float4* __restrict__ q, size_t nq,
            int k, int32_t* __restrict__ out_idx, float* __restrict__ out_d2, float vpx, float vpy, float vpz,
            float4* __restrict__ out_n, int* __restrict__ not_dense, unsigned char* __restrict__ redo)
 {
@@ -815,9 +821,15 @@ k_knn_warp(const TreeView T, const int2* __restrict__ node_leaves, int b_start, 
       float ld = inf;
       int li = kSentinelIndex, lp = -1;
       bool done = false;
-      for (int b = b_start; b >= 1 && !done; --b) {
+      // attempts: [a ball sized for ~1.4 k points of this cloud's density, when that is well inside half a cell of the
+      // start level,] then half a cell of the start level, then of every coarser level
+      for (int attempt = 0; !done; ++attempt) {
+        const bool sized = r_first > 0.f && attempt == 0;
+        const int b = b_start - (r_first > 0.f ? max(attempt - 1, 0) : attempt);
+        if (b < 1)
+          break;
         const int s = 21 - b;
-        const float R = __fmul_rd(__fmul_rd(0.5f * (float)(1u << s), C.inv_scale), 0.999f);
+        const float R = sized ? r_first : __fmul_rd(__fmul_rd(0.5f * (float)(1u << s), C.inv_scale), 0.999f);
         const unsigned ax = morton_cell(__fsub_rd(qq.x, R), C.lo[0], C.scale), bx = morton_cell(__fadd_ru(qq.x, R), C.lo[0], C.scale);
         const unsigned ay = morton_cell(__fsub_rd(qq.y, R), C.lo[1], C.scale), by = morton_cell(__fadd_ru(qq.y, R), C.lo[1], C.scale);
         const unsigned az = morton_cell(__fsub_rd(qq.z, R), C.lo[2], C.scale), bz = morton_cell(__fadd_ru(qq.z, R), C.lo[2], C.scale);
@@ -831,6 +843,9 @@ k_knn_warp(const TreeView T, const int2* __restrict__ node_leaves, int b_start, 
         if (lane < 8 && ((unsigned)lane & ~E) == 0u)
           ref = cell_lookup(C, cell_key(b, (lane & 1) ? ox : hx, (lane & 2) ? oy : hy, (lane & 4) ? oz : hz));
         const unsigned grp = __match_any_sync(full, ref != kDone ? ref : (int)(0x40000000 | lane));
+        // a leaf shared by several cells is kept once, by the lowest lane, whose cell need not be the nearest of them
+        // (cells 3 and 5 share a leaf, cell 1 is empty): such an entry is never pruned by a cell bound
+        const bool shared = ref != kDone && (grp & (grp - 1u)) != 0u;
         if (ref != kDone && (grp & lt) != 0u)
           ref = kDone;
         int first = 0, cnt = 0;
@@ -932,7 +947,9 @@ k_knn_warp(const TreeView T, const int2* __restrict__ node_leaves, int b_start, 
           if (n == 0)
             continue;
           // every point of cell c is at least this far (traverse.cuh: cell_gap2): a cell the k-th already beats is skipped
-          const float bound = __fadd_rd(__fadd_rd((c & 1) ? gx2 : 0.f, (c & 2) ? gy2 : 0.f), (c & 4) ? gz2 : 0.f);
+          const float bound = __shfl_sync(full, shared ? 1 : 0, c)
+                                  ? 0.f
+                                  : __fadd_rd(__fadd_rd((c & 1) ? gx2 : 0.f, (c & 2) ? gy2 : 0.f), (c & 4) ? gz2 : 0.f);
           if (!(bound <= Tk))
             continue;
           const int end = (f + n) * kLeafSize;
@@ -960,8 +977,6 @@ k_knn_warp(const TreeView T, const int2* __restrict__ node_leaves, int b_start, 
             if (nbuf >= 32)
               flush(32);
           }
-          if (c == 0 && nbuf > 0)
-            flush(nbuf);  // the home cell's points set a tight threshold before any neighbour cell is considered
         }
         if (nbuf > 0)
           flush(nbuf);
@@ -1013,15 +1028,47 @@ k_knn_warp(const TreeView T, const int2* __restrict__ node_leaves, int b_start, 
   }
 }
 
-// level whose occupied cells hold ~2k indexed points on average: a ball of half that cell holds >= k points in a cloud
-// of locally uniform density (2-D: 0.79 of a cell's points, 3-D: 0.52), so the first attempt usually certifies
-static int warp_knn_start_level(const Index& idx, int k)
+// Where the warp kernel starts.  The ball it certifies should hold a little more than k points: from the occupancy of
+// the cell levels, n / occupied(l) points per cell and the ratio of two levels give the cloud's local density and
+// intrinsic dimension (4 per level = a surface, 8 = a volume), hence the radius of a ball of ~1.2 k + 4 points.  The
+// start level is the finest whose half cell holds ~k points by that estimate (the ball's box must span <= 2 cells per axis); the
+// first attempt uses the sized ball when it is well inside half a cell, later attempts half a cell of ever coarser
+// levels.  Only speed depends on this estimate: an attempt counts only if the k-th distance certifies it.
+struct WarpKnnStart {
+  int level = 0;      // 0: no level fits (tiny cloud) -> per-thread kernels
+  float r_first = 0;  // 0: start with half a cell
+};
+static WarpKnnStart warp_knn_start(const Index& idx, int k)
 {
-  int b = 0;
-  for (int l = 1; l <= idx.cells.bmax; ++l)
-    if (idx.cells.occupied[l] > 0 && (double)idx.n_valid / (double)idx.cells.occupied[l] >= 2.0 * k)
-      b = l;
-  return b;  // 0: no level is coarse enough (tiny cloud) -> per-thread kernels
+  WarpKnnStart w;
+  const CellTableHost& c = idx.cells;
+  auto avg = [&](int l) { return (double)idx.n_valid / (double)std::max<unsigned long long>(1, c.occupied[l]); };
+  int ref = 0;
+  for (int l = 2; l <= c.bmax; ++l)
+    if (c.occupied[l] > 0 && c.occupied[l - 1] > 0 && avg(l) >= 8.0)
+      ref = l;
+  if (ref < 2)
+    return w;
+  const double dim = std::min(3.0, std::max(1.0, std::log2(avg(ref - 1) / avg(ref))));
+  const double unit_ball = std::pow(M_PI, 0.5 * dim) / std::tgamma(0.5 * dim + 1.0);
+  const double width = (double)(1u << (21 - ref)) / (double)idx.morton_scale;
+  auto ball_of = [&](double points) { return width * std::pow(points / (avg(ref) * unit_ball), 1.0 / dim); };
+  const double radius = ball_of(PCLB_KNN_TARGET_X10 * 0.1 * k + 4.0);
+  // the level: the finest whose half cell still holds ~k points by the estimate, which runs ~15 % large on tilted
+  // surfaces (a level finer gathers 2-3 times fewer candidates,
+  // measured 16 vs 20 ms at k = 16, and its half-cell ball certifies most queries)
+  const double need = ball_of(PCLB_KNN_LEVEL_X10 * 0.1 * k);
+  for (int l = 1; l <= c.bmax; ++l) {
+    const double half = 0.5 * 0.999 * (double)(1u << (21 - l)) / (double)idx.morton_scale;
+    if (c.occupied[l] > 0 && half >= need)
+      w.level = l;
+  }
+  if (w.level >= 1) {
+    const double half = 0.5 * 0.999 * (double)(1u << (21 - w.level)) / (double)idx.morton_scale;
+    if (radius < 0.85 * half)
+      w.r_first = (float)radius;
+  }
+  return w;
 }
 
 static bool warp_knn_lists(Ctx& c, const Index& idx, const float4* d_q, size_t nq, int k, int32_t* d_out_idx,
@@ -1029,14 +1076,14 @@ static bool warp_knn_lists(Ctx& c, const Index& idx, const float4* d_q, size_t n
 {
   if (!(idx.cell_slots.p && idx.node_leaves.p) || k < 12 || k > 32 || (size_t)k > idx.n_valid)
     return false;
-  const int b0 = warp_knn_start_level(idx, k);
-  if (b0 < 1)
+  const WarpKnnStart w0 = warp_knn_start(idx, k);
+  if (w0.level < 1)
     return false;
   cudaStream_t s = c.stream;
   redo.alloc(nq, s);
   PCLB_CUDA(cudaMemsetAsync(redo.p, 0, nq, s));
   const unsigned wg = (unsigned)std::min<size_t>((nq + 255) / 256, (size_t)c.sm_count * 8);
-  k_knn_warp<false><<<wg, 256, 0, s>>>(tree_view(idx), idx.node_leaves.p, b0, d_q, nq, k, d_out_idx, d_out_d2, 0.f, 0.f, 0.f,
+  k_knn_warp<false><<<wg, 256, 0, s>>>(tree_view(idx), idx.node_leaves.p, w0.level, w0.r_first, d_q, nq, k, d_out_idx, d_out_d2, 0.f, 0.f, 0.f,
                                       nullptr, nullptr, redo.p);
   ++c.launches;
   PCLB_CUDA(cudaGetLastError());
@@ -1083,12 +1130,12 @@ void launch_normals(Ctx& c, Index& idx, const float4* d_q, size_t nq, int k, con
   DevBuf<unsigned char> redo;
   const unsigned char* only = nullptr;
   {
-    const int b0 = (idx.cell_slots.p && idx.node_leaves.p && k >= 12) ? warp_knn_start_level(idx, k) : 0;
-    if (b0 >= 1 && (size_t)k <= idx.n_valid) {
+    const WarpKnnStart w0 = (idx.cell_slots.p && idx.node_leaves.p && k >= 12) ? warp_knn_start(idx, k) : WarpKnnStart{};
+    if (w0.level >= 1 && (size_t)k <= idx.n_valid) {
       redo.alloc(nq, s);
       PCLB_CUDA(cudaMemsetAsync(redo.p, 0, nq, s));
       const unsigned wg = (unsigned)std::min<size_t>((nq + 255) / 256, (size_t)c.sm_count * 8);
-      k_knn_warp<true><<<wg, 256, 0, s>>>(tree_view(idx), idx.node_leaves.p, b0, d_q, nq, k, nullptr, nullptr, vp[0], vp[1],
+      k_knn_warp<true><<<wg, 256, 0, s>>>(tree_view(idx), idx.node_leaves.p, w0.level, w0.r_first, d_q, nq, k, nullptr, nullptr, vp[0], vp[1],
                                          vp[2], d_out, d_not_dense, redo.p);
       ++c.launches;
       only = redo.p;

@@ -87,6 +87,33 @@ def test_knn_and_normals_many_k(gpu, orc):
         assert np.percentile(cosang, 0.5) > 1 - 1e-3 and np.mean(cosang > 1 - 1e-6) > 0.9, (k, walk)
 
 
+def test_knn_warp_kernel_mixed_density_every_query(gpu, orc):
+    """The warp-per-query kernel (12 <= k <= 32) on a cloud whose density changes by orders of magnitude — a dense sheet
+    inside a sparse volume, so 8-point leaves span several of the cells a query gathers (a leaf shared by cells whose
+    common nearer cell is empty must not be pruned by the bound of the wrong cell) — every point as a query plus
+    queries off the cloud (empty home cell), all rows bit-exact against the oracle."""
+    import os
+    P, ctx = gpu
+    rng = np.random.default_rng(77)
+    n_sheet, n_vol = 340_000, 60_000
+    sheet = rng.random((n_sheet, 3), dtype=np.float32) * np.float32(2.0)
+    sheet[:, 2] = np.float32(0.3) * np.sin(np.float32(3) * sheet[:, 0]) * np.cos(np.float32(2) * sheet[:, 1]) + \
+        np.float32(0.001) * rng.standard_normal(n_sheet).astype(np.float32)
+    vol = (rng.random((n_vol, 3), dtype=np.float32) * np.float32(2.0))
+    vol[:, 2] = vol[:, 2] - np.float32(1.0)
+    pts = np.concatenate([sheet, vol])[rng.permutation(n_sheet + n_vol)]
+    cloud = orc.to_xyz1(pts)
+    off = orc.to_xyz1((rng.random((50_000, 3), dtype=np.float32) * np.float32(2.4) - np.float32(0.2)))
+    q = np.concatenate([cloud, off])
+    gidx, oidx = P.Index(ctx, cloud), orc.Index(cloud)
+    nt = os.cpu_count() or 8
+    for k in (12, 16, 24, 32):
+        gi, gd, gk = gidx.knn(q, k)
+        oi, od, ok = oidx.knn(q, k, nthreads=nt)
+        bad = np.nonzero((gi != oi).any(axis=1) | (gd != od).any(axis=1))[0]
+        assert gk == ok and bad.size == 0, (k, bad.size, bad[:5].tolist())
+
+
 def test_knn_nan_points_subset_and_strides(gpu, orc):
     P, ctx = gpu
     rng = np.random.default_rng(12)
