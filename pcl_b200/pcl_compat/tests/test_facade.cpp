@@ -17,6 +17,8 @@
 #include <pcl/io/pcd_io.h>
 #include <pcl/kdtree/kdtree_flann.h>
 #include <pcl/point_cloud.h>
+#include <thread>
+
 #include <pcl/conversions.h>
 #include <pcl/point_representation.h>
 #include <pcl/registration/transformation_validation_euclidean.h>
@@ -337,6 +339,36 @@ int main(int argc, char** argv)
     for (int r = 0; r < 3; ++r) for (int c = 0; c < 4; ++c) EXPECT_NEAR(T(r, c), g[4 * r + c], (r == 0 && c == 1) ? 1e-2 : 1e-3);
     EXPECT_EQ(T(3, 0), 0); EXPECT_EQ(T(3, 1), 0); EXPECT_EQ(T(3, 2), 0); EXPECT_EQ(T(3, 3), 1);
     EXPECT_TRUE(reg.hasConverged());
+    {  // two threads, each inside a b200::Context::ThreadScope (own stream): concurrent aligns that share the target
+       // tree of the process-wide context give the single-threaded matrix bit for bit
+      pcl::search::KdTree<PointXYZ>::Ptr shared_tree(new pcl::search::KdTree<PointXYZ>);
+      shared_tree->setInputCloud(cloud_target.makeShared());
+      Eigen::Matrix4f Tt[2];
+      bool conv[2] = {false, false};
+      auto work = [&](int k) {
+        b200::Context::ThreadScope scope;
+        for (int rep = 0; rep < 3; ++rep) {
+          IterativeClosestPoint<PointXYZ, PointXYZ> r2;
+          r2.setInputSource(cloud_source.makeShared());
+          r2.setInputTarget(cloud_target.makeShared());
+          r2.setSearchMethodTarget(shared_tree, true);
+          r2.setMaximumIterations(50);
+          r2.setTransformationEpsilon(1e-8);
+          r2.setMaxCorrespondenceDistance(0.05);
+          PointCloud<PointXYZ> out2;
+          r2.align(out2);
+          Tt[k] = r2.getFinalTransformation();
+          conv[k] = r2.hasConverged() && out2.size() == cloud_source.size();
+        }
+      };
+      std::thread ta(work, 0), tb(work, 1);
+      ta.join();
+      tb.join();
+      for (int k = 0; k < 2; ++k) {
+        EXPECT_TRUE(conv[k]);
+        for (int r = 0; r < 4; ++r) for (int c = 0; c < 4; ++c) EXPECT_EQ(Tt[k](r, c), T(r, c));
+      }
+    }
     {  // visualisation callback (registration.h:431-442): same result, one call per iteration with valid indices
       IterativeClosestPoint<PointXYZ, PointXYZ> regv;
       regv.setInputSource(cloud_source.makeShared());
