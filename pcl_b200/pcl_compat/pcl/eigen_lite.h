@@ -61,5 +61,21 @@ using Matrix4d = Matrix<double, 4, 4>;
 using Matrix3f = Matrix<float, 3, 3>;
 using Vector4f = Matrix<float, 4, 1>;
 using Vector3f = Matrix<float, 3, 1>;
+// the sensor pose of pcl::PointCloud (point_cloud.h:405-407) is carried, never computed with
+struct Quaternionf {
+  float qw = 1.f, qx = 0.f, qy = 0.f, qz = 0.f;
+  Quaternionf() = default;
+  Quaternionf(float w_, float x_, float y_, float z_) : qw(w_), qx(x_), qy(y_), qz(z_) {}
+  static Quaternionf Identity() { return Quaternionf(); }
+  float w() const { return qw; }
+  float x() const { return qx; }
+  float y() const { return qy; }
+  float z() const { return qz; }
+  float& w() { return qw; }
+  float& x() { return qx; }
+  float& y() { return qy; }
+  float& z() { return qz; }
+  bool operator==(const Quaternionf& o) const { return qw == o.qw && qx == o.qx && qy == o.qy && qz == o.qz; }
+};
 }  // namespace Eigen
 #endif

@@ -43,11 +43,27 @@ public:
   int getMaximumIterationsSimilarTransforms() const { return max_iterations_similar_transforms_; }
   void setAbsoluteMSE(double v) { mse_threshold_absolute_ = v; }
   double getAbsoluteMSE() const { return mse_threshold_absolute_; }
+  // default_convergence_criteria.h:130-205.  As in the reference, align() overwrites the maximum iterations, the
+  // relative MSE and the translation threshold with Registration's own setters' values (icp.hpp:157-161), and the
+  // rotation threshold only when setTransformationRotationEpsilon(> 0) was called: a threshold set HERE is what an
+  // align() without that call uses.
+  void setMaximumIterations(int n) { max_iterations_ = n; }
+  int getMaximumIterations() const { return max_iterations_; }
+  void setRotationThreshold(double cos_angle) { rotation_threshold_ = cos_angle; }
+  double getRotationThreshold() const { return rotation_threshold_; }
+  void setTranslationThreshold(double squared) { translation_threshold_ = squared; }
+  double getTranslationThreshold() const { return translation_threshold_; }
+  void setRelativeMSE(double v) { mse_threshold_relative_ = v; }
+  double getRelativeMSE() const { return mse_threshold_relative_; }
   // written by Registration after every run
   ConvergenceState state_ = CONVERGENCE_CRITERIA_NOT_CONVERGED;
   bool failure_after_max_iter_ = false;
   int max_iterations_similar_transforms_ = 0;
   double mse_threshold_absolute_ = 1e-12;
+  int max_iterations_ = 100;                // default_convergence_criteria.h:104-113
+  double rotation_threshold_ = 0.99999;
+  double translation_threshold_ = 3e-4 * 3e-4;
+  double mse_threshold_relative_ = 0.00001;
 };
 }  // namespace registration
 
@@ -148,6 +164,8 @@ public:
   int getMaximumIterations() { return max_iterations_; }
   void setRANSACIterations(int n) { ransac_iterations_ = n; }
   void setRANSACOutlierRejectionThreshold(double t) { inlier_threshold_ = t; }
+  int getRANSACIterations() { return ransac_iterations_; }                       // registration.h:299-304
+  double getRANSACOutlierRejectionThreshold() { return inlier_threshold_; }      // registration.h:322-327
   void setMaxCorrespondenceDistance(double d) { corr_dist_threshold_ = d; }
   double getMaxCorrespondenceDistance() { return corr_dist_threshold_; }
   void setTransformationEpsilon(double e) { transformation_epsilon_ = e; }
@@ -312,9 +330,20 @@ protected:
       p.z = ((tr[8] * x + tr[9] * y) + tr[10] * z) + tr[11];
     }
   }
+  // icp.hpp:157-161: the criteria object takes Registration's thresholds; the rotation threshold only when one was set
+  void syncConvergenceCriteria()
+  {
+    auto& cc = *convergence_criteria_;
+    cc.max_iterations_ = this->max_iterations_;
+    cc.mse_threshold_relative_ = this->euclidean_fitness_epsilon_;
+    cc.translation_threshold_ = this->transformation_epsilon_;
+    if (this->transformation_rotation_epsilon_ > 0) cc.rotation_threshold_ = this->transformation_rotation_epsilon_;
+  }
+
   void computeTransformationStaged(PointCloudSource& output, const Matrix4& guess)
   {
     using State = typename ConvergenceCriteria::ConvergenceState;
+    syncConvergenceCriteria();
     PointCloudSource moved = *this->input_;
     this->nr_iterations_ = 0;
     this->converged_ = false;
@@ -380,7 +409,7 @@ protected:
           const Matrix4& T = this->transformation_;
           const double cos_angle = 0.5 * (T(0, 0) + T(1, 1) + T(2, 2) - 1);
           const double t2 = T(0, 3) * T(0, 3) + T(1, 3) * T(1, 3) + T(2, 3) * T(2, 3);
-          const double rot_thr = this->transformation_rotation_epsilon_ > 0 ? this->transformation_rotation_epsilon_ : 0.99999;
+          const double rot_thr = cc.rotation_threshold_;
           double mse = 0.0;
           for (const auto& c : corr) mse += c.distance;
           mse /= static_cast<double>(corr.size());
@@ -410,6 +439,7 @@ protected:
       computeTransformationStaged(output, guess);
       return;
     }
+    syncConvergenceCriteria();
     pclb200_ctx* ctx = b200::Context::get();
     pclb200_icp_params P;
     pclb200_icp_default_params(&P);
@@ -427,7 +457,10 @@ protected:
     P.max_iterations_similar_transforms = convergence_criteria_->max_iterations_similar_transforms_;
     P.max_correspondence_distance = this->corr_dist_threshold_;
     P.transformation_epsilon = this->transformation_epsilon_;
-    P.transformation_rotation_epsilon = this->transformation_rotation_epsilon_;
+    // a threshold set on the criteria object is honoured: the library takes any value > 0 as the cos-angle threshold
+    P.transformation_rotation_epsilon = convergence_criteria_->rotation_threshold_ > 0
+                                            ? convergence_criteria_->rotation_threshold_
+                                            : this->transformation_rotation_epsilon_;
     P.euclidean_fitness_epsilon = this->euclidean_fitness_epsilon_;
     P.mse_threshold_absolute = convergence_criteria_->mse_threshold_absolute_;
     // setCorrespondenceEstimation(NormalShooting / BackProjection): the fused loop runs that estimator, on the normal

@@ -149,6 +149,19 @@ public:
     }
   }
 
+  // search.h:229-260: queries of another point type — x, y, z are copied into PointT, then the batch overload
+  template <typename PointTDiff>
+  void nearestKSearchT(const pcl::PointCloud<PointTDiff>& cloud, const Indices& indices, int k,
+                       std::vector<Indices>& k_indices, std::vector<std::vector<float>>& k_sqr_distances) const
+  {
+    PointCloud pc;
+    copyXYZ(cloud, indices, pc);
+    nearestKSearch(pc, Indices(), k, k_indices, k_sqr_distances);
+  }
+  // search.h:401-411: the host-side thread count of the batch overloads; a batch is ONE device launch here
+  void setNumberOfThreads(unsigned int nr_threads) { num_threads_ = nr_threads; }
+  unsigned int getNumberOfThreads() const { return num_threads_; }
+
   // ---- radius ---------------------------------------------------------------------------------------------
   virtual int radiusSearch(const PointT& point, double radius, Indices& k_indices, std::vector<float>& k_sqr_distances,
                            unsigned int max_nn = 0) const
@@ -174,6 +187,29 @@ public:
   int radiusSearch(index_t index, double radius, Indices& ki, std::vector<float>& kd, unsigned int max_nn = 0) const
   {
     return radiusSearch((*input_)[indices_ ? (*indices_)[index] : index], radius, ki, kd, max_nn);
+  }
+  // search.h:311-315
+  int radiusSearch(const PointCloud& cloud, index_t index, double radius, Indices& ki, std::vector<float>& kd,
+                   unsigned int max_nn = 0) const
+  {
+    return radiusSearch(cloud[index], radius, ki, kd, max_nn);
+  }
+  // search.h:285-292, 368-397
+  template <typename PointTDiff>
+  int radiusSearchT(const PointTDiff& p, double radius, Indices& ki, std::vector<float>& kd, unsigned int max_nn = 0) const
+  {
+    PointT q;
+    q.x = p.x; q.y = p.y; q.z = p.z;
+    return radiusSearch(q, radius, ki, kd, max_nn);
+  }
+  template <typename PointTDiff>
+  void radiusSearchT(const pcl::PointCloud<PointTDiff>& cloud, const Indices& indices, double radius,
+                     std::vector<Indices>& k_indices, std::vector<std::vector<float>>& k_sqr_distances,
+                     unsigned int max_nn = 0) const
+  {
+    PointCloud pc;
+    copyXYZ(cloud, indices, pc);
+    radiusSearch(pc, Indices(), radius, k_indices, k_sqr_distances, max_nn);
   }
   // batch overload (search.h:349-355, impl/search.hpp:157-194)
   virtual void radiusSearch(const PointCloud& cloud, const Indices& indices, double radius, std::vector<Indices>& k_indices,
@@ -209,6 +245,22 @@ public:
   }
 
 protected:
+  template <typename PointTDiff>
+  static void copyXYZ(const pcl::PointCloud<PointTDiff>& cloud, const Indices& indices, PointCloud& pc)
+  {
+    const std::size_t n = indices.empty() ? cloud.size() : indices.size();
+    pc.points.resize(n);
+    for (std::size_t i = 0; i < n; ++i) {
+      const PointTDiff& p = cloud[indices.empty() ? i : static_cast<std::size_t>(indices[i])];
+      PointT q;
+      q.x = p.x; q.y = p.y; q.z = p.z;
+      pc.points[i] = q;
+    }
+    pc.width = static_cast<std::uint32_t>(n);
+    pc.height = 1;
+  }
+  unsigned int num_threads_ = 1;
+
   // queries go through the same representation as the indexed points
   struct Queries {
     const void* ptr;

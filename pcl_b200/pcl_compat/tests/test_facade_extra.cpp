@@ -1,0 +1,144 @@
+// Second facade test program (runs on the device): API surface added after the main program's last run on hardware —
+// the remaining pcl::search::Search overloads, CorrespondenceEstimation::setPointRepresentation[Reciprocal] and the
+// DefaultConvergenceCriteria thresholds reached through getConvergeCriteria().  Kept apart (and run last by
+// tests/test_zz_facade_extra_gpu.py) so the main program stays exactly what was verified.
+#include <cmath>
+#include <cstdio>
+#include <limits>
+#include <vector>
+
+#include <pcl/io/pcd_io.h>
+#include <pcl/kdtree/kdtree_flann.h>
+#include <pcl/point_representation.h>
+#include <pcl/point_types.h>
+#include <pcl/registration/correspondence_estimation.h>
+#include <pcl/registration/icp.h>
+
+using namespace pcl;
+
+static int g_fail = 0, g_checks = 0;
+#define EXPECT_TRUE(c) do { ++g_checks; if (!(c)) { ++g_fail; std::printf("FAIL %s:%d  %s\n", __FILE__, __LINE__, #c); } } while (0)
+#define EXPECT_EQ(a, b) do { ++g_checks; if (!((a) == (b))) { ++g_fail; std::printf("FAIL %s:%d  %s == %s  (%g vs %g)\n", __FILE__, __LINE__, #a, #b, (double)(a), (double)(b)); } } while (0)
+#define EXPECT_NEAR(a, b, tol) do { ++g_checks; if (!(std::fabs((double)(a) - (double)(b)) <= (tol))) { ++g_fail; std::printf("FAIL %s:%d  |%s - %s| <= %g  (%.9g vs %.9g)\n", __FILE__, __LINE__, #a, #b, (double)(tol), (double)(a), (double)(b)); } } while (0)
+
+int main(int argc, char** argv)
+{
+  if (argc < 3) { std::fprintf(stderr, "usage: %s bun0.pcd bun4.pcd\n", argv[0]); return 2; }
+  PointCloud<PointXYZ> cloud_source, cloud_target;
+  if (io::loadPCDFile(argv[1], cloud_source) || io::loadPCDFile(argv[2], cloud_target)) return 2;
+
+  {  // the remaining Search<PointT> overloads (search.h:158-165, 229-260, 285-292, 311-315, 368-397): same lists as the
+     // per-point forms
+    PointCloud<PointXYZ>::Ptr c(new PointCloud<PointXYZ>(cloud_target));
+    KdTreeFLANN<PointXYZ> kdtree;
+    kdtree.setInputCloud(c);
+    Indices ri, ri2;
+    std::vector<float> rd, rd2;
+    const int n_point = kdtree.radiusSearch((*c)[3], 0.02, ri, rd);
+    EXPECT_TRUE(n_point > 1);
+    EXPECT_EQ(kdtree.radiusSearch(*c, 3, 0.02, ri2, rd2), n_point);
+    EXPECT_TRUE(ri2 == ri && rd2 == rd);
+    PointNormal pn;
+    pn.x = (*c)[3].x; pn.y = (*c)[3].y; pn.z = (*c)[3].z;
+    EXPECT_EQ(kdtree.radiusSearchT(pn, 0.02, ri2, rd2), n_point);
+    EXPECT_TRUE(ri2 == ri && rd2 == rd);
+    Indices ki, ki2;
+    std::vector<float> kd, kd2;
+    EXPECT_EQ(kdtree.nearestKSearch((*c)[3], 10, ki, kd), 10);
+    EXPECT_EQ(kdtree.nearestKSearchT(pn, 10, ki2, kd2), 10);
+    EXPECT_TRUE(ki2 == ki && kd2 == kd);
+    PointCloud<PointNormal> other;
+    other.push_back(pn);
+    std::vector<Indices> bi;
+    std::vector<std::vector<float>> bd;
+    kdtree.nearestKSearchT(other, Indices(), 10, bi, bd);
+    EXPECT_EQ(bi.size(), 1u);
+    if (bi.size() == 1) EXPECT_TRUE(bi[0] == ki && bd[0] == kd);
+    kdtree.radiusSearchT(other, Indices(), 0.02, bi, bd);
+    EXPECT_EQ(bi.size(), 1u);
+    if (bi.size() == 1) EXPECT_TRUE(bi[0] == ri && bd[0] == rd);
+    kdtree.setNumberOfThreads(4);
+    EXPECT_EQ(kdtree.getNumberOfThreads(), 4u);
+  }
+
+  {  // CorrespondenceEstimation::setPointRepresentation[Reciprocal] (correspondence_estimation.h:296-318): under a uniform
+     // rescale by 2 the pairs are those of the plain estimator and the squared distances four times larger; the gate is
+     // applied in the representation's space
+    registration::CorrespondenceEstimation<PointXYZ, PointXYZ> plain, scaled;
+    Correspondences cp, cs, rp, rs, gated;
+    plain.setInputSource(cloud_source.makeShared());
+    plain.setInputTarget(cloud_target.makeShared());
+    plain.determineCorrespondences(cp);
+    plain.determineReciprocalCorrespondences(rp);
+    DefaultPointRepresentation<PointXYZ> rep;
+    const float alpha[3] = {2.f, 2.f, 2.f};
+    rep.setRescaleValues(alpha);
+    scaled.setInputSource(cloud_source.makeShared());
+    scaled.setInputTarget(cloud_target.makeShared());
+    scaled.setPointRepresentation(rep.makeShared());
+    scaled.setPointRepresentationReciprocal(rep.makeShared());
+    scaled.determineCorrespondences(cs);
+    EXPECT_EQ(cs.size(), cp.size());
+    EXPECT_EQ(cp.size(), cloud_source.size());
+    int idx_diff = 0;
+    double worst = 0;
+    for (std::size_t i = 0; i < cs.size() && i < cp.size(); ++i) {
+      idx_diff += (cs[i].index_query != cp[i].index_query) || (cs[i].index_match != cp[i].index_match);
+      worst = std::max(worst, std::fabs((double)cs[i].distance - 4.0 * (double)cp[i].distance));
+    }
+    EXPECT_EQ(idx_diff, 0);
+    EXPECT_TRUE(worst < 1e-7);
+    scaled.determineReciprocalCorrespondences(rs);
+    EXPECT_EQ(rs.size(), rp.size());
+    idx_diff = 0;
+    for (std::size_t i = 0; i < rs.size() && i < rp.size(); ++i)
+      idx_diff += (rs[i].index_query != rp[i].index_query) || (rs[i].index_match != rp[i].index_match);
+    EXPECT_EQ(idx_diff, 0);
+    // a gate of 0.02 in the rescaled space is a gate of 0.01 in the original one (97 of the 397 pairs, by the oracle)
+    Correspondences gp;
+    plain.determineCorrespondences(gp, 0.01);
+    scaled.determineCorrespondences(gated, 0.02);
+    EXPECT_EQ(gated.size(), gp.size());
+    EXPECT_TRUE(gp.size() > 0 && gp.size() < cp.size());
+    EXPECT_TRUE(scaled.getIndicesTarget() == nullptr);
+    EXPECT_TRUE(scaled.getIndicesSource() != nullptr);
+  }
+
+  {  // DefaultConvergenceCriteria through getConvergeCriteria() (default_convergence_criteria.h:130-205): align() copies
+     // Registration's thresholds into it (icp.hpp:157-161); a rotation threshold set on the object is what an align()
+     // without setTransformationRotationEpsilon uses — an unreachable one (cos > 1) switches the TRANSFORM test off
+    using Criteria = registration::DefaultConvergenceCriteria<float>;
+    auto run = [&](double rot_thr, int& iters, Criteria::ConvergenceState& state, Criteria& seen) {
+      IterativeClosestPoint<PointXYZ, PointXYZ> reg;
+      reg.setInputSource(cloud_source.makeShared());
+      reg.setInputTarget(cloud_target.makeShared());
+      reg.setMaximumIterations(50);
+      reg.setTransformationEpsilon(1e-8);
+      reg.setMaxCorrespondenceDistance(0.05);
+      if (rot_thr > 0) reg.getConvergeCriteria()->setRotationThreshold(rot_thr);
+      PointCloud<PointXYZ> out;
+      reg.align(out);
+      iters = reg.getNumberOfIterations();
+      state = reg.getConvergeCriteria()->getConvergenceState();
+      seen = *reg.getConvergeCriteria();
+      EXPECT_EQ(reg.getRANSACIterations(), 0);
+      EXPECT_TRUE(reg.hasConverged());
+    };
+    int it_default = 0, it_off = 0;
+    Criteria::ConvergenceState st_default, st_off;
+    Criteria c_default, c_off;
+    run(0.0, it_default, st_default, c_default);
+    EXPECT_EQ(st_default, Criteria::CONVERGENCE_CRITERIA_TRANSFORM);
+    EXPECT_EQ(c_default.getMaximumIterations(), 50);
+    EXPECT_NEAR(c_default.getTranslationThreshold(), 1e-8, 1e-20);
+    EXPECT_NEAR(c_default.getRotationThreshold(), 0.99999, 1e-12);
+    EXPECT_TRUE(c_default.getRelativeMSE() < 0);
+    run(1.5, it_off, st_off, c_off);
+    EXPECT_TRUE(st_off != Criteria::CONVERGENCE_CRITERIA_TRANSFORM);
+    EXPECT_TRUE(it_off >= it_default);
+    EXPECT_NEAR(c_off.getRotationThreshold(), 1.5, 1e-12);
+  }
+
+  std::printf("%d checks, %d failures\n%s\n", g_checks, g_fail, g_fail ? "FAILED" : "PASSED");
+  return g_fail ? 1 : 0;
+}

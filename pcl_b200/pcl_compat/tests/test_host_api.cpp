@@ -1,0 +1,163 @@
+// Host-only behaviour of the facade (no device library needed): the pcl::PointCloud container's width / height
+// bookkeeping — the scenarios of the reference's test/common/test_pointcloud.cpp:24-395 — and the small host classes
+// added beside it.  Exit code 0 and "PASSED" on success.
+#include <cstdio>
+#include <vector>
+
+#include <pcl/point_cloud.h>
+#include <pcl/point_types.h>
+
+using namespace pcl;
+
+static int g_fail = 0, g_checks = 0;
+#define CHECK(c) do { ++g_checks; if (!(c)) { ++g_fail; std::printf("FAIL %s:%d  %s\n", __FILE__, __LINE__, #c); } } while (0)
+
+static PointCloud<PointXYZ> grid() { PointCloud<PointXYZ> c; c.resize(640, 480, PointXYZ(1, 1, 1)); return c; }
+
+int main()
+{
+  {  // organised or not is decided by height alone
+    PointCloud<PointXYZ> c;
+    c.width = 640; c.height = 480;
+    CHECK(c.isOrganized());
+    c.height = 1;
+    CHECK(!c.isOrganized());
+  }
+  {  // clear, insert (one / n), erase, emplace, emplace_back: an unorganised cloud of the new size
+    PointCloud<PointXYZ> c;
+    c.insert(c.end(), PointXYZ(1, 1, 1));
+    CHECK(c.size() == 1 && c.width == 1 && !c.isOrganized());
+    c.clear();
+    CHECK(c.width == 0 && c.height == 0 && c.empty());
+    c.insert(c.end(), 5, PointXYZ(1, 1, 1));
+    CHECK(c.width == 5 && c.height == 1);
+    c.erase(c.end() - 1);
+    CHECK(c.width == 4 && c.height == 1);
+    c.erase(c.begin(), c.end());
+    CHECK(c.width == 0 && c.height == 1 && c.empty());
+    c.emplace(c.end(), 1.f, 2.f, 3.f);
+    CHECK(c.width == 1 && c.front().y == 2.f);
+    PointXYZ& nb = c.emplace_back(4.f, 5.f, 6.f);
+    CHECK(c.width == 2 && &nb == &c.back() && c.back().z == 6.f);
+    std::vector<PointXYZ> more(3, PointXYZ(9, 9, 9));
+    c.insert(c.end(), more.begin(), more.end());
+    CHECK(c.width == 5 && c.height == 1);
+  }
+  {  // resize: count keeps a matching grid, (w, h) sets it, fills use the value
+    PointCloud<PointXYZ> c;
+    c.resize(640 * 360);
+    CHECK(!c.isOrganized() && c.width == 640 * 360);
+    c.resize(640, 480);
+    CHECK(c.isOrganized() && c.width == 640 && c.size() == 640u * 480u);
+    c.resize(640 * 480);  // same number of points: the grid stays
+    CHECK(c.isOrganized() && c.width == 640);
+    PointCloud<PointXYZ> d;
+    d.resize(640 * 360, PointXYZ(1, 1, 1));
+    CHECK(!d.isOrganized() && d.width == 640 * 360 && d.back().x == 1.f);
+    d.resize(640, 480, PointXYZ(2, 2, 2));
+    CHECK(d.isOrganized() && d.width == 640 && d.back().x == 2.f && d.front().x == 1.f);
+  }
+  {  // assign in all its forms; a width that does not divide the size gives one row
+    PointCloud<PointXYZ> c;
+    c.assign(640 * 360, PointXYZ(1, 1, 1));
+    CHECK(!c.isOrganized() && c.width == 640 * 360);
+    c.assign(640, 480, PointXYZ(1, 1, 1));
+    CHECK(c.isOrganized() && c.width == 640);
+    std::vector<PointXYZ> v(640 * 360, PointXYZ(2, 3, 4));
+    c.assign(v.begin(), v.end());
+    CHECK(!c.isOrganized() && c.width == 640 * 360);
+    c.assign(v.begin(), v.end(), 640);
+    CHECK(c.isOrganized() && c.width == 640 && c.height == 360);
+    std::vector<PointXYZ> w(640 * 480, PointXYZ(7, 7, 7));
+    c.assign(w.begin(), w.end(), 460);
+    CHECK(!c.isOrganized() && c.width == 640 * 480);
+    c.assign(w.begin(), w.end(), 0);
+    CHECK(!c.isOrganized() && c.width == 640 * 480);
+    c.assign({PointXYZ(3, 4, 5), PointXYZ(3, 4, 5), PointXYZ(3, 4, 5)});
+    CHECK(!c.isOrganized() && c.width == 3);
+    c.assign({PointXYZ(3, 4, 5), PointXYZ(3, 4, 5), PointXYZ(3, 4, 5), PointXYZ(3, 4, 5)}, 2);
+    CHECK(c.isOrganized() && c.width == 2 && c.height == 2);
+    c.assign({PointXYZ(3, 4, 5), PointXYZ(3, 4, 5), PointXYZ(3, 4, 5)}, 6);
+    CHECK(!c.isOrganized() && c.width == 3);
+  }
+  {  // push_back drops the grid, the transient_ members leave width / height alone
+    PointCloud<PointXYZ> c;
+    c.push_back(PointXYZ(3, 4, 5));
+    CHECK(!c.isOrganized() && c.width == 1);
+    c.resize(80, 80, PointXYZ(1, 1, 1));
+    CHECK(c.isOrganized());
+    c.push_back(PointXYZ(3, 4, 5));
+    CHECK(c.width == 80 * 80 + 1 && c.height == 1);
+    PointCloud<PointXYZ> g = grid();
+    g.transient_push_back(PointXYZ(2, 2, 2));
+    CHECK(g.isOrganized() && g.width == 640 && g.size() == 640u * 480u + 1);
+    g = grid();
+    PointXYZ& e = g.transient_emplace_back(3.f, 3.f, 3.f);
+    CHECK(g.isOrganized() && g.width == 640 && &e == &g.back());
+    g = grid();
+    g.transient_insert(g.end(), PointXYZ(1, 1, 1));
+    CHECK(g.isOrganized() && g.size() == 640u * 480u + 1);
+    g = grid();
+    g.transient_insert(g.end(), 10, PointXYZ(1, 1, 1));
+    CHECK(g.isOrganized() && g.size() == 640u * 480u + 10);
+    g = grid();
+    g.transient_emplace(g.end(), 4.f, 4.f, 4.f);
+    CHECK(g.isOrganized() && g.size() == 640u * 480u + 1 && g.back().x == 4.f);
+    g = grid();
+    g.transient_erase(g.end() - 1);
+    CHECK(g.isOrganized() && g.width == 640 && g.size() == 640u * 480u - 1);
+    g = grid();
+    g.transient_erase(g.begin(), g.end());
+    CHECK(g.isOrganized() && g.width == 640 && g.size() == 0);
+  }
+  {  // concatenation: unorganised result, newest stamp, dense only if both are; 2-D access
+    PointCloud<PointXYZ> g = grid(), u;
+    g.header.stamp = 7;
+    u.header.stamp = 3;
+    PointCloud<PointXYZ>::concatenate(u, g);
+    CHECK(!u.isOrganized() && u.width == 640 * 480 && u.header.stamp == 7);
+    PointCloud<PointXYZ> out;
+    PointCloud<PointXYZ>::concatenate(u, g, out);
+    CHECK(!out.isOrganized() && out.width == 640 * 480 * 2);
+    PointCloud<PointXYZ> sum = g + u;
+    CHECK(!sum.isOrganized() && sum.width == 640 * 480 * 2);
+    PointCloud<PointXYZ> both = g + g;
+    CHECK(!both.isOrganized() && both.size() == 614400u && both.width == 614400u);
+    PointCloud<PointXYZ> nd;
+    nd.is_dense = false;
+    u += nd;
+    CHECK(!u.is_dense);
+    bool threw = false;
+    try {
+      out.at(5, 5);
+    }
+    catch (const UnorganizedPointCloudException&) {
+      threw = true;
+    }
+    CHECK(threw);
+    const PointXYZ& last = g.at(static_cast<int>(g.width - 1), static_cast<int>(g.height - 1));
+    CHECK(&last == &g.back());
+    g(3, 2).x = 42.f;
+    CHECK(g[2 * 640 + 3].x == 42.f);
+  }
+  {  // subset copy constructor and swap
+    PointCloud<PointXYZ> c;
+    for (int i = 0; i < 10; ++i) c.emplace_back(float(i), 0.f, 0.f);
+    c.is_dense = false;
+    c.sensor_origin_[0] = 1.5f;
+    Indices idx = {7, 2, 9};
+    PointCloud<PointXYZ> s(c, idx);
+    CHECK(s.size() == 3 && s.width == 3 && s.height == 1 && !s.is_dense && s[0].x == 7.f && s[2].x == 9.f);
+    CHECK(s.sensor_origin_[0] == 1.5f && s.sensor_orientation_ == Eigen::Quaternionf::Identity());
+    PointCloud<PointXYZ> t = grid();
+    t.swap(s);
+    CHECK(t.size() == 3 && !t.is_dense && s.isOrganized() && s.width == 640 && s.is_dense);
+    PointCloud<PointXYZ> z(4, 3, PointXYZ(5, 5, 5));
+    CHECK(z.isOrganized() && z.size() == 12 && z.back().x == 5.f);
+    std::size_t cnt = 0;
+    for (auto it = z.crbegin(); it != z.crend(); ++it) ++cnt;
+    CHECK(cnt == 12 && z.max_size() > 0);
+  }
+  std::printf("%d checks, %d failures\n%s\n", g_checks, g_fail, g_fail ? "FAILED" : "PASSED");
+  return g_fail ? 1 : 0;
+}
