@@ -7,6 +7,7 @@
 #else
 #include <cmath>
 #include <cstddef>
+#include <vector>
 namespace Eigen {
 template <typename S, int R, int C>
 struct Matrix {
@@ -61,6 +62,27 @@ using Matrix4d = Matrix<double, 4, 4>;
 using Matrix3f = Matrix<float, 3, 3>;
 using Vector4f = Matrix<float, 4, 1>;
 using Vector3f = Matrix<float, 3, 1>;
+using Vector3i = Matrix<int, 3, 1>;
+using Vector4i = Matrix<int, 4, 1>;
+// run-time sized integer matrix, column-major: the lists of relative cell coordinates of pcl::VoxelGrid's neighbour
+// queries (voxel_grid.h:52-100, 356-380)
+struct MatrixXi {
+  int r = 0, c = 0;
+  std::vector<int> v;
+  MatrixXi() = default;
+  MatrixXi(int rows_, int cols_) : r(rows_), c(cols_), v(static_cast<std::size_t>(rows_) * cols_, 0) {}
+  int rows() const { return r; }
+  int cols() const { return c; }
+  int& operator()(int i, int j) { return v[static_cast<std::size_t>(j) * r + i]; }
+  int operator()(int i, int j) const { return v[static_cast<std::size_t>(j) * r + i]; }
+  void conservativeResize(int rows_, int cols_)
+  {
+    MatrixXi n(rows_, cols_);
+    for (int j = 0; j < (cols_ < c ? cols_ : c); ++j)
+      for (int i = 0; i < (rows_ < r ? rows_ : r); ++i) n(i, j) = (*this)(i, j);
+    *this = n;
+  }
+};
 // the sensor pose of pcl::PointCloud (point_cloud.h:405-407) is carried, never computed with
 struct Quaternionf {
   float qw = 1.f, qx = 0.f, qy = 0.f, qz = 0.f;

@@ -5,6 +5,8 @@
 // 4-vector sum, curvature = mean); with setDownsampleAllData(false) only xyz is produced and the other fields are
 // default-initialised (voxel_grid.hpp:784-794 copies just the 4-float centroid).
 #pragma once
+#include <algorithm>
+#include <cmath>
 #include <cstdio>
 #include <cstring>
 #include <limits>
@@ -13,12 +15,152 @@
 
 #include "../b200/context.h"
 #include "../point_cloud.h"
+#include "../point_types.h"
 
 namespace pcl {
+// voxel_grid.h:52-100: the 13 cells of the "upper half" of a cell's 26-neighbourhood, and all 26 + the cell itself
+inline Eigen::MatrixXi getHalfNeighborCellIndices()
+{
+  Eigen::MatrixXi rel(3, 13);
+  int idx = 0;
+  for (int i = -1; i < 2; ++i)      // 0 - 8
+    for (int j = -1; j < 2; ++j) {
+      rel(0, idx) = i; rel(1, idx) = j; rel(2, idx) = -1;
+      ++idx;
+    }
+  for (int i = -1; i < 2; ++i) {    // 9 - 11
+    rel(0, idx) = i; rel(1, idx) = -1; rel(2, idx) = 0;
+    ++idx;
+  }
+  rel(0, idx) = -1; rel(1, idx) = 0; rel(2, idx) = 0;  // 12
+  return rel;
+}
+inline Eigen::MatrixXi getAllNeighborCellIndices()
+{
+  const Eigen::MatrixXi half = getHalfNeighborCellIndices();
+  Eigen::MatrixXi all(3, 27);   // the 13, the cell itself (zeros), the 13 mirrored
+  for (int j = 0; j < 13; ++j)
+    for (int i = 0; i < 3; ++i) {
+      all(i, j) = half(i, j);
+      all(i, 14 + j) = -half(i, j);
+    }
+  return all;
+}
+
+namespace b200 {
+// Host-side bookkeeping of one VoxelGrid::applyFilter call (impl/voxel_grid.hpp:612-650, 700-780): the integer box of
+// the used points, the divisions, the linear-index multipliers and — on request — the leaf layout (cell -> position of
+// its centroid in the output, -1 for empty cells and cells with fewer than min_points points).  The arithmetic is the
+// reference's: float products, floor, the minimum subtracted as a float.
+struct VoxelLayout {
+  Eigen::Vector4i min_b, max_b, div_b, divb_mul;
+  std::vector<int> leaf_layout;
+  std::size_t cells_kept = 0;
+};
+template <typename PointT>
+inline bool voxel_layout(const std::vector<PointT>& pts, const index_t* idx, std::size_t n, bool is_dense, const float inv_leaf[3],
+                         unsigned int min_points, bool want_layout, VoxelLayout& L)
+{
+  float mn[3] = {std::numeric_limits<float>::max(), std::numeric_limits<float>::max(), std::numeric_limits<float>::max()};
+  float mx[3] = {-std::numeric_limits<float>::max(), -std::numeric_limits<float>::max(), -std::numeric_limits<float>::max()};
+  auto point = [&](std::size_t j) -> const PointT& { return pts[idx ? static_cast<std::size_t>(idx[j]) : j]; };
+  auto finite = [](const PointT& p) { return std::isfinite(p.x) && std::isfinite(p.y) && std::isfinite(p.z); };
+  bool any = false;
+  for (std::size_t j = 0; j < n; ++j) {
+    const PointT& p = point(j);
+    if (!is_dense && !finite(p)) continue;
+    any = true;
+    mn[0] = std::min(mn[0], p.x); mn[1] = std::min(mn[1], p.y); mn[2] = std::min(mn[2], p.z);
+    mx[0] = std::max(mx[0], p.x); mx[1] = std::max(mx[1], p.y); mx[2] = std::max(mx[2], p.z);
+  }
+  if (!any) return false;
+  for (int a = 0; a < 3; ++a) {
+    L.min_b[a] = static_cast<int>(std::floor(mn[a] * inv_leaf[a]));
+    L.max_b[a] = static_cast<int>(std::floor(mx[a] * inv_leaf[a]));
+    L.div_b[a] = L.max_b[a] - L.min_b[a] + 1;
+  }
+  L.min_b[3] = L.max_b[3] = L.div_b[3] = 0;
+  L.divb_mul[0] = 1; L.divb_mul[1] = L.div_b[0]; L.divb_mul[2] = L.div_b[0] * L.div_b[1]; L.divb_mul[3] = 0;
+  L.leaf_layout.clear();
+  L.cells_kept = 0;
+  // an oversize grid makes the filter return its input unfiltered (voxel_grid.hpp:620-629): no layout then
+  const long long cells = static_cast<long long>(L.div_b[0]) * L.div_b[1] * L.div_b[2];
+  if (!want_layout || cells > static_cast<long long>(std::numeric_limits<std::int32_t>::max())) return true;
+  std::vector<int> keys;
+  keys.reserve(n);
+  for (std::size_t j = 0; j < n; ++j) {
+    const PointT& p = point(j);
+    if (!is_dense && !finite(p)) continue;
+    const int i0 = static_cast<int>(std::floor(p.x * inv_leaf[0]) - static_cast<float>(L.min_b[0]));
+    const int i1 = static_cast<int>(std::floor(p.y * inv_leaf[1]) - static_cast<float>(L.min_b[1]));
+    const int i2 = static_cast<int>(std::floor(p.z * inv_leaf[2]) - static_cast<float>(L.min_b[2]));
+    keys.push_back(i0 * L.divb_mul[0] + i1 * L.divb_mul[1] + i2 * L.divb_mul[2]);
+  }
+  std::sort(keys.begin(), keys.end());
+  L.leaf_layout.assign(static_cast<std::size_t>(L.div_b[0]) * L.div_b[1] * L.div_b[2], -1);
+  int out = 0;
+  for (std::size_t a = 0; a < keys.size();) {
+    std::size_t b = a + 1;
+    while (b < keys.size() && keys[b] == keys[a]) ++b;
+    if (b - a >= min_points) L.leaf_layout[static_cast<std::size_t>(keys[a])] = out++;
+    a = b;
+  }
+  L.cells_kept = static_cast<std::size_t>(out);
+  return true;
+}
+}  // namespace b200
+
 template <typename PointT>
 class VoxelGrid : public PCLBase<PointT> {
 public:
   using PointCloud = pcl::PointCloud<PointT>;
+  // voxel_grid.h:296-425: grid geometry of the last filter() call and, with setSaveLeafLayout(true), the leaf layout
+  bool getDownsampleAllData() const { return downsample_all_data_; }
+  void setSaveLeafLayout(bool save_leaf_layout) { save_leaf_layout_ = save_leaf_layout; }
+  bool getSaveLeafLayout() const { return save_leaf_layout_; }
+  Eigen::Vector3i getMinBoxCoordinates() const { return head3(grid_.min_b); }
+  Eigen::Vector3i getMaxBoxCoordinates() const { return head3(grid_.max_b); }
+  Eigen::Vector3i getNrDivisions() const { return head3(grid_.div_b); }
+  Eigen::Vector3i getDivisionMultiplier() const { return head3(grid_.divb_mul); }
+  std::vector<int> getLeafLayout() const { return grid_.leaf_layout; }
+  Eigen::Vector3i getGridCoordinates(float x, float y, float z) const
+  {
+    Eigen::Vector3i g;
+    g[0] = static_cast<int>(std::floor(x * invLeaf(0)));
+    g[1] = static_cast<int>(std::floor(y * invLeaf(1)));
+    g[2] = static_cast<int>(std::floor(z * invLeaf(2)));
+    return g;
+  }
+  int getCentroidIndexAt(const Eigen::Vector3i& ijk) const
+  {
+    const long long idx = linearIndex(ijk[0], ijk[1], ijk[2]);
+    if (idx < 0 || idx >= static_cast<long long>(grid_.leaf_layout.size())) return -1;
+    return grid_.leaf_layout[static_cast<std::size_t>(idx)];
+  }
+  // index of the centroid of the cell that holds p; like the reference (std::vector::at) it throws for a cell outside
+  // the grid or when no layout was saved
+  int getCentroidIndex(const PointT& p) const
+  {
+    const Eigen::Vector3i g = getGridCoordinates(p.x, p.y, p.z);
+    return grid_.leaf_layout.at(static_cast<std::size_t>(linearIndex(g[0], g[1], g[2])));
+  }
+  std::vector<int> getNeighborCentroidIndices(const PointT& reference_point, const Eigen::MatrixXi& relative_coordinates) const
+  {
+    const Eigen::Vector3i g = getGridCoordinates(reference_point.x, reference_point.y, reference_point.z);
+    std::vector<int> neighbors(static_cast<std::size_t>(relative_coordinates.cols()), -1);
+    for (int ni = 0; ni < relative_coordinates.cols(); ++ni) {
+      bool inside = true;
+      int c[3];
+      for (int a = 0; a < 3; ++a) {
+        c[a] = g[a] + relative_coordinates(a, ni);
+        inside = inside && c[a] >= grid_.min_b[a] && c[a] <= grid_.max_b[a];
+      }
+      if (inside && !grid_.leaf_layout.empty())
+        neighbors[static_cast<std::size_t>(ni)] = grid_.leaf_layout[static_cast<std::size_t>(linearIndex(c[0], c[1], c[2]))];
+    }
+    return neighbors;
+  }
+  bool getFilterLimitsNegative() const { return filter_limit_negative_; }
   void setLeafSize(float lx, float ly, float lz) { leaf_[0] = lx; leaf_[1] = ly; leaf_[2] = lz; }
   void setMinimumPointsNumberPerVoxel(unsigned int n) { min_points_per_voxel_ = n; }
   unsigned int getMinimumPointsNumberPerVoxel() const { return min_points_per_voxel_; }
@@ -70,6 +212,13 @@ public:
       abi_cnt = selected.size();
     }
     const std::size_t n = abi_idx ? abi_cnt : this->indices_->size();
+    {  // grid geometry (always) and leaf layout (on request) of this call, like impl/voxel_grid.hpp:612-650, 757-776
+      const float inv[3] = {invLeaf(0), invLeaf(1), invLeaf(2)};
+      const index_t* used = abi_idx ? abi_idx : this->indices_->data();
+      if (!b200::voxel_layout(this->input_->points, used, n, this->input_->is_dense, inv, min_points_per_voxel_,
+                              save_leaf_layout_, grid_))
+        grid_ = b200::VoxelLayout();
+    }
     std::vector<float> xyz1(4 * (n ? n : 1));
     std::vector<float> ncurv;
     std::size_t m = 0;
@@ -96,6 +245,9 @@ public:
       output.clear();
       return;
     }
+    if (save_leaf_layout_ && grid_.cells_kept != m)  // cannot happen: both sides run the same float arithmetic
+      std::fprintf(stderr, "[pcl::VoxelGrid::applyFilter] leaf layout holds %zu cells, the filter produced %zu\n",
+                   grid_.cells_kept, m);
     output.points.assign(m, PointT());
     for (std::size_t i = 0; i < m; ++i) {
       output.points[i].x = xyz1[4 * i];
@@ -110,6 +262,20 @@ public:
   }
 
 protected:
+  static Eigen::Vector3i head3(const Eigen::Vector4i& v)
+  {
+    Eigen::Vector3i r;
+    r[0] = v[0]; r[1] = v[1]; r[2] = v[2];
+    return r;
+  }
+  float invLeaf(int a) const { return 1.0f / leaf_[a]; }  // inverse_leaf_size_ = 1 / leaf_size_ in float (voxel_grid.h:266-283)
+  long long linearIndex(int i, int j, int k) const
+  {
+    return static_cast<long long>(i - grid_.min_b[0]) * grid_.divb_mul[0] + static_cast<long long>(j - grid_.min_b[1]) * grid_.divb_mul[1] +
+           static_cast<long long>(k - grid_.min_b[2]) * grid_.divb_mul[2];
+  }
+  b200::VoxelLayout grid_;
+  bool save_leaf_layout_ = false;
   float leaf_[3] = {0.f, 0.f, 0.f};
   unsigned int min_points_per_voxel_ = 0;
   bool downsample_all_data_ = true;

@@ -7,6 +7,7 @@
 #include <limits>
 #include <vector>
 
+#include <pcl/filters/voxel_grid.h>
 #include <pcl/io/pcd_io.h>
 #include <pcl/kdtree/kdtree_flann.h>
 #include <pcl/point_representation.h>
@@ -137,6 +138,41 @@ int main(int argc, char** argv)
     EXPECT_TRUE(st_off != Criteria::CONVERGENCE_CRITERIA_TRANSFORM);
     EXPECT_TRUE(it_off >= it_default);
     EXPECT_NEAR(c_off.getRotationThreshold(), 1.5, 1e-12);
+  }
+
+  {  // VoxelGrid::setSaveLeafLayout and the grid accessors (voxel_grid.h:296-425): every input point's cell maps to the
+     // output centroid of that cell
+    VoxelGrid<PointXYZ> vg;
+    vg.setInputCloud(cloud_source.makeShared());
+    vg.setLeafSize(0.01f, 0.01f, 0.01f);
+    vg.setSaveLeafLayout(true);
+    PointCloud<PointXYZ> out;
+    vg.filter(out);
+    EXPECT_TRUE(out.size() > 10 && out.size() < cloud_source.size());
+    const Eigen::Vector3i div = vg.getNrDivisions(), mul = vg.getDivisionMultiplier();
+    EXPECT_TRUE((std::size_t)div[0] * div[1] * div[2] >= out.size());
+    EXPECT_EQ(mul[0], 1);
+    EXPECT_EQ(mul[1], div[0]);
+    EXPECT_EQ(mul[2], div[0] * div[1]);
+    EXPECT_EQ(vg.getLeafLayout().size(), (std::size_t)div[0] * div[1] * div[2]);
+    int filled = 0;
+    for (int v : vg.getLeafLayout()) filled += v >= 0;
+    EXPECT_EQ((std::size_t)filled, out.size());
+    int bad = 0;
+    const Eigen::MatrixXi all = getAllNeighborCellIndices();
+    for (const auto& p : cloud_source.points) {
+      const int c = vg.getCentroidIndex(p);
+      if (c < 0 || c >= (int)out.size()) { ++bad; continue; }
+      const float dx = out[c].x - p.x, dy = out[c].y - p.y, dz = out[c].z - p.z;
+      if (std::sqrt(dx * dx + dy * dy + dz * dz) > 0.01f * 1.7321f) ++bad;   // a centroid lies inside its cell
+      if (vg.getCentroidIndexAt(vg.getGridCoordinates(p.x, p.y, p.z)) != c) ++bad;
+      if (vg.getNeighborCentroidIndices(p, all)[13] != c) ++bad;
+    }
+    EXPECT_EQ(bad, 0);
+    Eigen::Vector3i far;
+    far[0] = vg.getMinBoxCoordinates()[0]; far[1] = vg.getMinBoxCoordinates()[1]; far[2] = vg.getMaxBoxCoordinates()[2] + 5;  // past the last slab
+    EXPECT_EQ(vg.getCentroidIndexAt(far), -1);
+    EXPECT_TRUE(vg.getSaveLeafLayout() && vg.getDownsampleAllData() && !vg.getFilterLimitsNegative());
   }
 
   std::printf("%d checks, %d failures\n%s\n", g_checks, g_fail, g_fail ? "FAILED" : "PASSED");

@@ -1,9 +1,14 @@
 // Host-only behaviour of the facade (no device library needed): the pcl::PointCloud container's width / height
 // bookkeeping — the scenarios of the reference's test/common/test_pointcloud.cpp:24-395 — and the small host classes
 // added beside it.  Exit code 0 and "PASSED" on success.
+#include <cmath>
 #include <cstdio>
+#include <limits>
+#include <map>
+#include <set>
 #include <vector>
 
+#include <pcl/filters/voxel_grid.h>
 #include <pcl/point_cloud.h>
 #include <pcl/point_types.h>
 
@@ -157,6 +162,59 @@ int main()
     std::size_t cnt = 0;
     for (auto it = z.crbegin(); it != z.crend(); ++it) ++cnt;
     CHECK(cnt == 12 && z.max_size() > 0);
+  }
+  {  // VoxelGrid's host-side grid geometry and leaf layout (b200::voxel_layout; impl/voxel_grid.hpp:612-650, 757-776)
+    std::vector<PointXYZ> pts;
+    unsigned s = 12345u;
+    auto rnd = [&]() { s = s * 1664525u + 1013904223u; return (s >> 8) * (1.0f / 16777216.0f); };
+    for (int i = 0; i < 5000; ++i) pts.emplace_back(rnd() * 2.f - 0.7f, rnd() * 1.5f - 1.1f, rnd() * 0.9f + 0.3f);
+    pts[17].x = std::numeric_limits<float>::quiet_NaN();
+    const float leaf = 0.1f, inv[3] = {1.0f / leaf, 1.0f / leaf, 1.0f / leaf};
+    b200::VoxelLayout L;
+    CHECK(b200::voxel_layout(pts, nullptr, pts.size(), false, inv, 0u, true, L));
+    // brute force: cell of every finite point, distinct cells in ascending linear order
+    std::map<int, int> count;
+    for (std::size_t i = 0; i < pts.size(); ++i) {
+      if (i == 17) continue;
+      const int c0 = (int)std::floor(pts[i].x * inv[0]) - L.min_b[0], c1 = (int)std::floor(pts[i].y * inv[1]) - L.min_b[1],
+                c2 = (int)std::floor(pts[i].z * inv[2]) - L.min_b[2];
+      CHECK(c0 >= 0 && c0 < L.div_b[0] && c1 >= 0 && c1 < L.div_b[1] && c2 >= 0 && c2 < L.div_b[2]);
+      ++count[c0 + c1 * L.div_b[0] + c2 * L.div_b[0] * L.div_b[1]];
+    }
+    CHECK(L.cells_kept == count.size());
+    CHECK(L.leaf_layout.size() == (std::size_t)L.div_b[0] * L.div_b[1] * L.div_b[2]);
+    CHECK(L.divb_mul[0] == 1 && L.divb_mul[1] == L.div_b[0] && L.divb_mul[2] == L.div_b[0] * L.div_b[1]);
+    int rank = 0, bad = 0, filled = 0;
+    for (const auto& kv : count) bad += L.leaf_layout[kv.first] != rank++;
+    for (int v : L.leaf_layout) filled += v >= 0;
+    CHECK(bad == 0 && filled == (int)count.size());
+    // cells with fewer than min_points points are dropped and the survivors renumbered
+    b200::VoxelLayout M;
+    CHECK(b200::voxel_layout(pts, nullptr, pts.size(), false, inv, 3u, true, M));
+    rank = 0; bad = 0;
+    for (const auto& kv : count) {
+      if (kv.second >= 3) bad += M.leaf_layout[kv.first] != rank++;
+      else bad += M.leaf_layout[kv.first] != -1;
+    }
+    CHECK(bad == 0 && M.cells_kept == (std::size_t)rank && M.cells_kept < L.cells_kept);
+    // an index subset; geometry only
+    Indices sub;
+    for (int i = 100; i < 900; i += 3) sub.push_back(i);
+    b200::VoxelLayout S;
+    CHECK(b200::voxel_layout(pts, sub.data(), sub.size(), true, inv, 0u, false, S));
+    CHECK(S.leaf_layout.empty() && S.div_b[0] >= 1 && S.div_b[0] <= L.div_b[0] && S.min_b[0] >= L.min_b[0] && S.max_b[2] <= L.max_b[2]);
+    // nothing finite -> no grid
+    std::vector<PointXYZ> nan1(3);
+    for (auto& p : nan1) p.x = std::numeric_limits<float>::infinity();
+    CHECK(!b200::voxel_layout(nan1, nullptr, nan1.size(), false, inv, 0u, true, S));
+    // the neighbour offset tables of voxel_grid.h:52-100
+    const Eigen::MatrixXi half = getHalfNeighborCellIndices(), all = getAllNeighborCellIndices();
+    CHECK(half.rows() == 3 && half.cols() == 13 && all.cols() == 27);
+    CHECK(all(0, 13) == 0 && all(1, 13) == 0 && all(2, 13) == 0);
+    std::set<int> seen;
+    for (int j = 0; j < 27; ++j) seen.insert((all(0, j) + 1) + 3 * (all(1, j) + 1) + 9 * (all(2, j) + 1));
+    CHECK(seen.size() == 27);
+    for (int j = 0; j < 13; ++j) CHECK(all(0, 14 + j) == -half(0, j) && all(2, 14 + j) == -half(2, j));
   }
   std::printf("%d checks, %d failures\n%s\n", g_checks, g_fail, g_fail ? "FAILED" : "PASSED");
   return g_fail ? 1 : 0;
