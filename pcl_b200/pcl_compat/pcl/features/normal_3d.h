@@ -4,10 +4,74 @@
 #include <cstdio>
 #include <limits>
 
+#include "../common/centroid.h"
 #include "../point_types.h"
 #include "../search/kdtree.h"
+#include "feature.h"
 
 namespace pcl {
+// normal_3d.h:60-111: plane (Hessian form) and curvature of a set of points, on the host.  Fewer than three points or no
+// finite one: NaNs and false.
+template <typename PointT>
+inline bool computePointNormal(const pcl::PointCloud<PointT>& cloud, Eigen::Vector4f& plane_parameters, float& curvature)
+{
+  Eigen::Matrix3f covariance_matrix;
+  Eigen::Vector4f xyz_centroid;
+  if (cloud.size() < 3 || computeMeanAndCovarianceMatrix(cloud, covariance_matrix, xyz_centroid) == 0) {
+    for (int d = 0; d < 4; ++d) plane_parameters[d] = std::numeric_limits<float>::quiet_NaN();
+    curvature = std::numeric_limits<float>::quiet_NaN();
+    return false;
+  }
+  solvePlaneParameters(covariance_matrix, xyz_centroid, plane_parameters, curvature);
+  return true;
+}
+template <typename PointT>
+inline bool computePointNormal(const pcl::PointCloud<PointT>& cloud, const Indices& indices, Eigen::Vector4f& plane_parameters,
+                               float& curvature)
+{
+  Eigen::Matrix3f covariance_matrix;
+  Eigen::Vector4f xyz_centroid;
+  if (indices.size() < 3 || computeMeanAndCovarianceMatrix(cloud, indices, covariance_matrix, xyz_centroid) == 0) {
+    for (int d = 0; d < 4; ++d) plane_parameters[d] = std::numeric_limits<float>::quiet_NaN();
+    curvature = std::numeric_limits<float>::quiet_NaN();
+    return false;
+  }
+  solvePlaneParameters(covariance_matrix, xyz_centroid, plane_parameters, curvature);
+  return true;
+}
+// normal_3d.h:113-188: turn a normal towards the viewpoint; the 4-vector form also re-derives d through the point
+template <typename PointT, typename Scalar>
+inline void flipNormalTowardsViewpoint(const PointT& point, float vp_x, float vp_y, float vp_z, Eigen::Matrix<Scalar, 4, 1>& normal)
+{
+  const Scalar vx = vp_x - point.x, vy = vp_y - point.y, vz = vp_z - point.z;
+  const float cos_theta = static_cast<float>(vx * normal[0] + vy * normal[1] + vz * normal[2] + Scalar(0) * normal[3]);
+  if (cos_theta < 0) {
+    for (int d = 0; d < 4; ++d) normal[d] *= -1;
+    normal[3] = 0.0f;
+    normal[3] = -1 * (normal[0] * point.x + normal[1] * point.y + normal[2] * point.z + normal[3] * Scalar(1));
+  }
+}
+template <typename PointT, typename Scalar>
+inline void flipNormalTowardsViewpoint(const PointT& point, float vp_x, float vp_y, float vp_z, Eigen::Matrix<Scalar, 3, 1>& normal)
+{
+  const Scalar vx = vp_x - point.x, vy = vp_y - point.y, vz = vp_z - point.z;
+  if (vx * normal[0] + vy * normal[1] + vz * normal[2] < 0)
+    for (int d = 0; d < 3; ++d) normal[d] *= -1;
+}
+template <typename PointT>
+inline void flipNormalTowardsViewpoint(const PointT& point, float vp_x, float vp_y, float vp_z, float& nx, float& ny, float& nz)
+{
+  vp_x -= point.x;
+  vp_y -= point.y;
+  vp_z -= point.z;
+  const float cos_theta = (vp_x * nx + vp_y * ny + vp_z * nz);
+  if (cos_theta < 0) {
+    nx *= -1;
+    ny *= -1;
+    nz *= -1;
+  }
+}
+
 template <typename PointInT, typename PointOutT>
 class NormalEstimation : public PCLBase<PointInT> {
 public:
@@ -25,6 +89,26 @@ public:
     }
   }
   void setSearchSurface(const PointCloudInConstPtr& cloud) { surface_ = cloud; fake_surface_ = false; }
+  PointCloudInConstPtr getSearchSurface() const { return surface_; }   // feature.h:146-150
+  double getSearchParameter() const { return search_radius_ != 0.0 ? search_radius_ : static_cast<double>(k_); }  // feature.h:170-174 (after compute)
+  // normal_3d.h:279-322: one neighbourhood on the host (the batch form is compute())
+  bool computePointNormal(const pcl::PointCloud<PointInT>& cloud, const Indices& indices, Eigen::Vector4f& plane_parameters,
+                          float& curvature)
+  {
+    return pcl::computePointNormal(cloud, indices, plane_parameters, curvature);
+  }
+  bool computePointNormal(const pcl::PointCloud<PointInT>& cloud, const Indices& indices, float& nx, float& ny, float& nz,
+                          float& curvature)
+  {
+    Eigen::Matrix3f covariance_matrix;
+    Eigen::Vector4f xyz_centroid;
+    if (indices.size() < 3 || computeMeanAndCovarianceMatrix(cloud, indices, covariance_matrix, xyz_centroid) == 0) {
+      nx = ny = nz = curvature = std::numeric_limits<float>::quiet_NaN();
+      return false;
+    }
+    solvePlaneParameters(covariance_matrix, nx, ny, nz, curvature);
+    return true;
+  }
   void setSearchMethod(const KdTreePtr& tree) { tree_ = tree; }
   KdTreePtr getSearchMethod() const { return tree_; }
   void setKSearch(int k) { k_ = k; }

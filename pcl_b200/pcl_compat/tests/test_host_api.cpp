@@ -8,7 +8,12 @@
 #include <set>
 #include <vector>
 
+#include <string>
+
+#include <pcl/common/centroid.h>
+#include <pcl/features/normal_3d.h>
 #include <pcl/filters/voxel_grid.h>
+#include <pcl/io/pcd_io.h>
 #include <pcl/point_cloud.h>
 #include <pcl/point_types.h>
 
@@ -19,8 +24,55 @@ static int g_fail = 0, g_checks = 0;
 
 static PointCloud<PointXYZ> grid() { PointCloud<PointXYZ> c; c.resize(640, 480, PointXYZ(1, 1, 1)); return c; }
 
-int main()
+// "normals <cloud.pcd> <out.bin>": plane parameters and curvature of deterministic index subsets of the cloud, written
+// as raw floats (5 per subset: nx ny nz d curvature) for tests/test_facade_host.py to compare with the oracle bit for bit;
+// subset s holds the indices (s * 37 + j * (s % 5 + 1)) % n, j < 3 + s % 40
+static int dump_normals(const char* pcd, const char* out_path)
 {
+  PointCloud<PointXYZ> cloud;
+  if (io::loadPCDFile(pcd, cloud)) return 2;
+  std::vector<float> out;
+  const int n = static_cast<int>(cloud.size());
+  for (int s = 0; s < 200; ++s) {
+    Indices idx;
+    for (int j = 0; j < 3 + s % 40; ++j) idx.push_back((s * 37 + j * (s % 5 + 1)) % n);
+    Eigen::Vector4f plane;
+    float curvature = 0.f;
+    computePointNormal(cloud, idx, plane, curvature);
+    for (int d = 0; d < 4; ++d) out.push_back(plane[d]);
+    out.push_back(curvature);
+  }
+  {  // the whole cloud, both overloads, then flipped towards the origin as in test_normal_estimation.cpp:103-138
+    Indices all(cloud.size());
+    for (int i = 0; i < n; ++i) all[i] = i;
+    Eigen::Vector4f plane, plane2;
+    float c1 = 0.f, c2 = 0.f;
+    computePointNormal(cloud, all, plane, c1);
+    computePointNormal(cloud, plane2, c2);
+    for (int d = 0; d < 4; ++d) out.push_back(plane[d]);
+    out.push_back(c1);
+    for (int d = 0; d < 4; ++d) out.push_back(plane2[d]);
+    out.push_back(c2);
+    flipNormalTowardsViewpoint(cloud[0], 0, 0, 0, plane);
+    for (int d = 0; d < 4; ++d) out.push_back(plane[d]);
+    float nx = plane2[0], ny = plane2[1], nz = plane2[2];
+    flipNormalTowardsViewpoint(cloud[0], 0, 0, 0, nx, ny, nz);
+    out.push_back(nx);
+    NormalEstimation<PointXYZ, Normal> ne;
+    float mx, my, mz, mc;
+    ne.computePointNormal(cloud, all, mx, my, mz, mc);
+    out.push_back(mx); out.push_back(my); out.push_back(mz); out.push_back(mc);
+  }
+  FILE* f = std::fopen(out_path, "wb");
+  if (!f) return 2;
+  std::fwrite(out.data(), sizeof(float), out.size(), f);
+  std::fclose(f);
+  return 0;
+}
+
+int main(int argc, char** argv)
+{
+  if (argc == 4 && std::string(argv[1]) == "normals") return dump_normals(argv[2], argv[3]);
   {  // organised or not is decided by height alone
     PointCloud<PointXYZ> c;
     c.width = 640; c.height = 480;
@@ -215,6 +267,51 @@ int main()
     for (int j = 0; j < 27; ++j) seen.insert((all(0, j) + 1) + 3 * (all(1, j) + 1) + 9 * (all(2, j) + 1));
     CHECK(seen.size() == 27);
     for (int j = 0; j < 13; ++j) CHECK(all(0, 14 + j) == -half(0, j) && all(2, 14 + j) == -half(2, j));
+  }
+  {  // moments (common/centroid.h): centroid, one-pass covariance, demeaning; non-finite points of a non-dense cloud skipped
+    PointCloud<PointXYZ> c;
+    c.emplace_back(1.f, 2.f, 3.f);
+    c.emplace_back(3.f, 2.f, 1.f);
+    c.emplace_back(2.f, 5.f, 2.f);
+    c.emplace_back(2.f, -1.f, 6.f);
+    Eigen::Vector4f cen;
+    CHECK(compute3DCentroid(c, cen) == 4 && cen[0] == 2.f && cen[1] == 2.f && cen[2] == 3.f && cen[3] == 1.f);
+    Eigen::Matrix3f cov;
+    Eigen::Vector4f cen2;
+    CHECK(computeMeanAndCovarianceMatrix(c, cov, cen2) == 4);
+    CHECK(std::fabs(cen2[0] - 2.f) < 1e-6f && std::fabs(cen2[1] - 2.f) < 1e-6f && std::fabs(cen2[2] - 3.f) < 1e-6f);
+    // population covariance by hand: x: {-1,1,0,0} -> 0.5 ; y: {0,0,3,-3} -> 4.5 ; z: {0,-2,-1,3} -> 3.5 ; xz: (0-2+0+0)/4 = -0.5
+    CHECK(std::fabs(cov(0, 0) - 0.5f) < 1e-6f && std::fabs(cov(1, 1) - 4.5f) < 1e-6f && std::fabs(cov(2, 2) - 3.5f) < 1e-6f);
+    CHECK(std::fabs(cov(0, 2) + 0.5f) < 1e-6f && cov(2, 0) == cov(0, 2) && std::fabs(cov(1, 2) + 3.f) < 1e-6f && std::fabs(cov(0, 1)) < 1e-6f);
+    PointCloud<PointXYZ> nd = c;
+    nd.is_dense = false;
+    nd.emplace_back(std::numeric_limits<float>::quiet_NaN(), 0.f, 0.f);
+    Eigen::Vector4f cen3;
+    CHECK(compute3DCentroid(nd, cen3) == 4 && cen3[1] == 2.f);
+    Indices sub = {0, 1};
+    Eigen::Matrix<double, 4, 1> cd;
+    CHECK(compute3DCentroid(c, sub, cd) == 2 && cd[0] == 2.0 && cd[2] == 2.0);
+    PointCloud<PointXYZ> dm;
+    demeanPointCloud(c, cen, dm);
+    CHECK(dm.size() == 4 && dm[0].x == -1.f && dm[3].z == 3.f);
+    demeanPointCloud(c, sub, cen, dm);
+    CHECK(dm.size() == 2 && dm.width == 2 && dm[1].x == 1.f && dm[1].z == -2.f);
+    // a plane z = 0.25: normal +-(0,0,1), curvature 0, d = -+0.25; fewer than three points -> NaN
+    PointCloud<PointXYZ> pl;
+    for (int i = 0; i < 5; ++i)
+      for (int j = 0; j < 5; ++j) pl.emplace_back(0.1f * i, 0.2f * j, 0.25f);
+    Eigen::Vector4f plane;
+    float curv = 1.f;
+    CHECK(computePointNormal(pl, plane, curv));
+    CHECK(std::fabs(std::fabs(plane[2]) - 1.f) < 1e-6f && std::fabs(plane[0]) < 1e-6f && curv < 1e-6f && std::fabs(std::fabs(plane[3]) - 0.25f) < 1e-6f);
+    flipNormalTowardsViewpoint(pl[0], 0.f, 0.f, 10.f, plane);
+    CHECK(plane[2] > 0.99f && std::fabs(plane[3] + 0.25f) < 1e-6f);
+    Eigen::Vector3f n3;
+    n3[0] = 0.f; n3[1] = 0.f; n3[2] = 1.f;
+    flipNormalTowardsViewpoint(pl[0], 0.f, 0.f, -10.f, n3);
+    CHECK(n3[2] == -1.f);
+    Indices two = {0, 1};
+    CHECK(!computePointNormal(pl, two, plane, curv) && std::isnan(plane[0]) && std::isnan(curv));
   }
   std::printf("%d checks, %d failures\n%s\n", g_checks, g_fail, g_fail ? "FAILED" : "PASSED");
   return g_fail ? 1 : 0;
