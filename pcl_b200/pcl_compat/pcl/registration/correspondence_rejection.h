@@ -8,6 +8,7 @@
 #include <memory>
 #include <string>
 
+#include "../PCLPointCloud2.h"
 #include "../b200/context.h"
 #include "../correspondence.h"
 
@@ -40,14 +41,34 @@ public:
     out.resize(n);
     last_median_ = med;
   }
+  // correspondence_rejection.h:103-121: which query points the step dropped, relative to the INPUT correspondences
+  void getRejectedQueryIndices(const pcl::Correspondences& correspondences, pcl::Indices& indices)
+  {
+    if (!input_correspondences_ || input_correspondences_->empty()) {
+      std::fprintf(stderr, "[pcl::registration::%s::getRejectedQueryIndices] Input correspondences not set (lookup of rejected "
+                           "correspondences _not_ possible).\n", getClassName().c_str());
+      return;
+    }
+    pcl::getRejectedQueryIndices(*input_correspondences_, correspondences, indices);
+  }
   const std::string& getClassName() const { return rejection_name_; }
+  // correspondence_rejection.h:130-196: the type-erased route by which IterativeClosestPoint hands a rejector the clouds
+  // or normals it asks for (impl/icp.hpp:142-155); a rejector that needs none says so
   virtual bool requiresSourcePoints() const { return false; }
+  virtual void setSourcePoints(pcl::PCLPointCloud2::ConstPtr /*cloud2*/) { notRequired("setSourcePoints", "an input source cloud"); }
   virtual bool requiresSourceNormals() const { return false; }
+  virtual void setSourceNormals(pcl::PCLPointCloud2::ConstPtr /*cloud2*/) { notRequired("setSourceNormals", "input source normals"); }
   virtual bool requiresTargetPoints() const { return false; }
+  virtual void setTargetPoints(pcl::PCLPointCloud2::ConstPtr /*cloud2*/) { notRequired("setTargetPoints", "an input target cloud"); }
   virtual bool requiresTargetNormals() const { return false; }
+  virtual void setTargetNormals(pcl::PCLPointCloud2::ConstPtr /*cloud2*/) { notRequired("setTargetNormals", "input target normals"); }
   virtual pclb200_rejector abiRejector() const = 0;  // lets ICP run the chain inside the device loop
 
 protected:
+  void notRequired(const char* method, const char* what) const
+  {
+    std::fprintf(stderr, "[pcl::registration::%s::%s] This class does not require %s\n", getClassName().c_str(), method, what);
+  }
   std::string rejection_name_;
   CorrespondencesConstPtr input_correspondences_;
   double last_median_ = 0.0;

@@ -6,6 +6,7 @@
 #pragma once
 #include <vector>
 
+#include "../PCLPointCloud2.h"
 #include "../point_cloud.h"
 #include "../point_types.h"
 #include "correspondence_rejection.h"
@@ -37,6 +38,26 @@ public:
   }
   bool requiresSourceNormals() const override { return true; }
   bool requiresTargetNormals() const override { return true; }
+  // correspondence_rejection_surface_normal.h:236-276: the blob route IterativeClosestPoint uses (impl/icp.hpp:142-155) —
+  // the normal fields are looked up by name, the data container is set up on first use
+  void setSourceNormals(pcl::PCLPointCloud2::ConstPtr cloud2) override
+  {
+    pcl::PointCloud<pcl::Normal> cloud;
+    fromPCLPointCloud2(*cloud2, cloud);
+    copyNormals<pcl::Normal>(cloud, source_normals_);
+    initialized_ = true;
+  }
+  void setTargetNormals(pcl::PCLPointCloud2::ConstPtr cloud2) override
+  {
+    pcl::PointCloud<pcl::Normal> cloud;
+    fromPCLPointCloud2(*cloud2, cloud);
+    copyNormals<pcl::Normal>(cloud, target_normals_);
+    initialized_ = true;
+  }
+  bool requiresSourcePoints() const override { return true; }   // :204-234: the container also takes the clouds
+  bool requiresTargetPoints() const override { return true; }
+  void setSourcePoints(pcl::PCLPointCloud2::ConstPtr /*cloud2*/) override {}   // only the normals are ever read
+  void setTargetPoints(pcl::PCLPointCloud2::ConstPtr /*cloud2*/) override {}
 
   void getRemainingCorrespondences(const pcl::Correspondences& in, pcl::Correspondences& out) override
   {

@@ -6,11 +6,13 @@
 #include <limits>
 #include <map>
 #include <set>
+#include <sstream>
 #include <vector>
 
 #include <string>
 
 #include <pcl/common/centroid.h>
+#include <pcl/correspondence.h>
 #include <pcl/features/normal_3d.h>
 #include <pcl/filters/voxel_grid.h>
 #include <pcl/io/pcd_io.h>
@@ -312,6 +314,22 @@ int main(int argc, char** argv)
     CHECK(n3[2] == -1.f);
     Indices two = {0, 1};
     CHECK(!computePointNormal(pl, two, plane, curv) && std::isnan(plane[0]) && std::isnan(curv));
+  }
+  {  // pcl::getRejectedQueryIndices / isBetterCorrespondence / operator<< (common/src/correspondence.cpp:46-94)
+    Correspondences before, after;
+    for (int q : {9, 2, 7, 4, 0}) before.emplace_back(q, q + 100, 0.5f * q);
+    for (int q : {7, 0}) after.emplace_back(q, q + 100, 0.5f * q);
+    Indices rej;
+    getRejectedQueryIndices(before, after, rej);
+    CHECK((rej == Indices{2, 4, 9}));
+    getRejectedQueryIndices(before, Correspondences(), rej);
+    CHECK((rej == Indices{9, 2, 7, 4, 0}));          // nothing survived: the query indices in their original order
+    getRejectedQueryIndices(Correspondences(), after, rej);
+    CHECK(rej.empty());
+    CHECK(isBetterCorrespondence(before[0], before[1]) && !isBetterCorrespondence(before[4], before[1]));
+    std::ostringstream os;
+    os << before[1];
+    CHECK(os.str() == "2 102 1");
   }
   std::printf("%d checks, %d failures\n%s\n", g_checks, g_fail, g_fail ? "FAILED" : "PASSED");
   return g_fail ? 1 : 0;
