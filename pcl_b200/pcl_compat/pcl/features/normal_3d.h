@@ -110,6 +110,11 @@ public:
     return true;
   }
   void setSearchMethod(const KdTreePtr& tree) { tree_ = tree; }
+  // feature.h:114,164-168: the reference's parameter type is pcl::search::Search<PointInT>::Ptr
+  void setSearchMethod(const typename pcl::search::Search<PointInT>::Ptr& tree)
+  {
+    tree_ = pcl::search::deviceSearcher<PointInT>(tree, "pcl::NormalEstimation");
+  }
   KdTreePtr getSearchMethod() const { return tree_; }
   void setKSearch(int k) { k_ = k; }
   int getKSearch() const { return k_; }

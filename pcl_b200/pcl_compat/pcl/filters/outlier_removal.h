@@ -28,6 +28,11 @@ public:
   void setNumberOfThreads(unsigned int) {}
   IndicesConstPtr getRemovedIndices() const { return removed_indices_; }
   void setSearchMethod(const typename pcl::search::KdTree<PointT>::Ptr& tree) { searcher_ = tree; }
+  // statistical_outlier_removal.h:88,150 / radius_outlier_removal.h:79,146: SearcherPtr = pcl::search::Search<PointT>::Ptr
+  void setSearchMethod(const typename pcl::search::Search<PointT>::Ptr& searcher)
+  {
+    searcher_ = pcl::search::deviceSearcher<PointT>(searcher, "pcl::OutlierRemoval");
+  }
 
   void filter(Indices& indices)
   {

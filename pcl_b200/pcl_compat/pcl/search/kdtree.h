@@ -18,12 +18,13 @@
 #include "../point_cloud.h"
 #include "../point_representation.h"
 #include "../types.h"
+#include "search.h"
 
 namespace pcl {
 namespace search {
 
 template <typename PointT>
-class KdTree {
+class KdTree : public Search<PointT> {
 public:
   using PointCloud = pcl::PointCloud<PointT>;
   using PointCloudConstPtr = typename PointCloud::ConstPtr;
@@ -31,7 +32,7 @@ public:
   using ConstPtr = std::shared_ptr<const KdTree<PointT>>;
   using PointRepresentationConstPtr = typename pcl::PointRepresentation<PointT>::ConstPtr;
 
-  explicit KdTree(bool sorted = true) : sorted_results_(sorted) {}
+  explicit KdTree(bool sorted = true) : Search<PointT>("KdTree", sorted), sorted_results_(sorted) {}
 
   // kdtree.h:104-119 / search/kdtree.h:106-119: the representation decides which float vector of a point is indexed.
   // A cloud that is already set is re-indexed at once, like the reference does.  Up to three dimensions.
@@ -44,16 +45,16 @@ public:
   PointRepresentationConstPtr getPointRepresentation() const { return point_representation_; }
   virtual ~KdTree() = default;
 
-  virtual const std::string& getName() const { return name_; }
-  virtual void setSortedResults(bool sorted) { sorted_results_ = sorted; }
-  virtual bool getSortedResults() const { return sorted_results_; }
+  const std::string& getName() const override { return name_; }
+  void setSortedResults(bool sorted) override { sorted_results_ = sorted; }
+  bool getSortedResults() const override { return sorted_results_; }
   void setEpsilon(float eps) { epsilon_ = eps; }  // accepted for API parity; the search is always exact (eps = 0)
   float getEpsilon() const { return epsilon_; }
   void setMinPts(int min_pts) { min_pts_ = min_pts; }  // kdtree.h:322-333 (stored, never consulted — as in KdTreeFLANN)
   int getMinPts() const { return min_pts_; }
 
   // KdTreeFLANN::setInputCloud — kdtree_flann.hpp:100-136: rebuilds from scratch, epsilon reset to 0
-  virtual bool setInputCloud(const PointCloudConstPtr& cloud, const IndicesConstPtr& indices = IndicesConstPtr())
+  bool setInputCloud(const PointCloudConstPtr& cloud, const IndicesConstPtr& indices = IndicesConstPtr()) override
   {
     input_ = cloud;
     indices_ = indices;
@@ -94,21 +95,21 @@ public:
     index_.reset(new b200::IndexHandle(h));
     return true;
   }
-  PointCloudConstPtr getInputCloud() const { return input_; }
-  IndicesConstPtr getIndices() const { return indices_; }
+  PointCloudConstPtr getInputCloud() const override { return input_; }
+  IndicesConstPtr getIndices() const override { return indices_; }
   pclb200_index* deviceIndex() const { return index_ ? index_->h : nullptr; }
   bool usesRepresentationVectors() const { return vectorized_; }
 
   // ---- k-NN ---------------------------------------------------------------------------------------------
-  virtual int nearestKSearch(const PointT& point, int k, Indices& k_indices, std::vector<float>& k_sqr_distances) const
+  int nearestKSearch(const PointT& point, int k, Indices& k_indices, std::vector<float>& k_sqr_distances) const override
   {
     return knn(&point, 1, k, &k_indices, &k_sqr_distances);
   }
-  int nearestKSearch(const PointCloud& cloud, index_t index, int k, Indices& ki, std::vector<float>& kd) const
+  int nearestKSearch(const PointCloud& cloud, index_t index, int k, Indices& ki, std::vector<float>& kd) const override
   {
     return nearestKSearch(cloud[index], k, ki, kd);
   }
-  int nearestKSearch(index_t index, int k, Indices& ki, std::vector<float>& kd) const
+  int nearestKSearch(index_t index, int k, Indices& ki, std::vector<float>& kd) const override
   {
     return nearestKSearch((*input_)[indices_ ? (*indices_)[index] : index], k, ki, kd);
   }
@@ -120,8 +121,8 @@ public:
     return nearestKSearch(q, k, ki, kd);
   }
   // batch overload (search.h:216-219, impl/search.hpp:111-137): ONE device launch for the whole cloud
-  virtual void nearestKSearch(const PointCloud& cloud, const Indices& indices, int k, std::vector<Indices>& k_indices,
-                              std::vector<std::vector<float>>& k_sqr_distances) const
+  void nearestKSearch(const PointCloud& cloud, const Indices& indices, int k, std::vector<Indices>& k_indices,
+                      std::vector<std::vector<float>>& k_sqr_distances) const override
   {
     std::vector<PointT> q;
     const PointT* qp = cloud.points.data();
@@ -158,13 +159,10 @@ public:
     copyXYZ(cloud, indices, pc);
     nearestKSearch(pc, Indices(), k, k_indices, k_sqr_distances);
   }
-  // search.h:401-411: the host-side thread count of the batch overloads; a batch is ONE device launch here
-  void setNumberOfThreads(unsigned int nr_threads) { num_threads_ = nr_threads; }
-  unsigned int getNumberOfThreads() const { return num_threads_; }
 
   // ---- radius ---------------------------------------------------------------------------------------------
-  virtual int radiusSearch(const PointT& point, double radius, Indices& k_indices, std::vector<float>& k_sqr_distances,
-                           unsigned int max_nn = 0) const
+  int radiusSearch(const PointT& point, double radius, Indices& k_indices, std::vector<float>& k_sqr_distances,
+                   unsigned int max_nn = 0) const override
   {
     k_indices.clear();
     k_sqr_distances.clear();
@@ -184,13 +182,13 @@ public:
     pclb200_free(pd);
     return static_cast<int>(offs[1]);
   }
-  int radiusSearch(index_t index, double radius, Indices& ki, std::vector<float>& kd, unsigned int max_nn = 0) const
+  int radiusSearch(index_t index, double radius, Indices& ki, std::vector<float>& kd, unsigned int max_nn = 0) const override
   {
     return radiusSearch((*input_)[indices_ ? (*indices_)[index] : index], radius, ki, kd, max_nn);
   }
   // search.h:311-315
   int radiusSearch(const PointCloud& cloud, index_t index, double radius, Indices& ki, std::vector<float>& kd,
-                   unsigned int max_nn = 0) const
+                   unsigned int max_nn = 0) const override
   {
     return radiusSearch(cloud[index], radius, ki, kd, max_nn);
   }
@@ -212,8 +210,8 @@ public:
     radiusSearch(pc, Indices(), radius, k_indices, k_sqr_distances, max_nn);
   }
   // batch overload (search.h:349-355, impl/search.hpp:157-194)
-  virtual void radiusSearch(const PointCloud& cloud, const Indices& indices, double radius, std::vector<Indices>& k_indices,
-                            std::vector<std::vector<float>>& k_sqr_distances, unsigned int max_nn = 0) const
+  void radiusSearch(const PointCloud& cloud, const Indices& indices, double radius, std::vector<Indices>& k_indices,
+                    std::vector<std::vector<float>>& k_sqr_distances, unsigned int max_nn = 0) const override
   {
     std::vector<PointT> q;
     const PointT* qp = cloud.points.data();
@@ -259,8 +257,6 @@ protected:
     pc.width = static_cast<std::uint32_t>(n);
     pc.height = 1;
   }
-  unsigned int num_threads_ = 1;
-
   // queries go through the same representation as the indexed points
   struct Queries {
     const void* ptr;
@@ -307,6 +303,20 @@ protected:
   int min_pts_ = 1;
   std::string name_ = "KdTree";
 };
+
+// The consumers (NormalEstimation, the outlier filters, EuclideanClusterExtraction) take a pcl::search::Search<PointT>::Ptr
+// in the reference.  Here they run on the device index of a pcl::search::KdTree; another Search subclass has no device
+// side, and there is no CPU path to fall back to: it is refused with a message (nullptr).
+template <typename PointT>
+inline typename KdTree<PointT>::Ptr deviceSearcher(const typename Search<PointT>::Ptr& searcher, const char* who)
+{
+  if (!searcher) return typename KdTree<PointT>::Ptr();
+  typename KdTree<PointT>::Ptr tree = std::dynamic_pointer_cast<KdTree<PointT>>(searcher);
+  if (!tree)
+    std::fprintf(stderr, "[%s::setSearchMethod] '%s' is not a pcl::search::KdTree: only the device searcher is supported\n", who,
+                 searcher->getName().c_str());
+  return tree;
+}
 
 }  // namespace search
 

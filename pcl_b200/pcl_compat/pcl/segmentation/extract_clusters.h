@@ -76,6 +76,11 @@ public:
   using KdTree = pcl::search::KdTree<PointT>;
   using KdTreePtr = typename KdTree::Ptr;
   void setSearchMethod(const KdTreePtr& tree) { tree_ = tree; }
+  // extract_clusters.h:336-353: the reference's parameter type is pcl::search::Search<PointT>::Ptr
+  void setSearchMethod(const typename pcl::search::Search<PointT>::Ptr& tree)
+  {
+    tree_ = pcl::search::deviceSearcher<PointT>(tree, "pcl::EuclideanClusterExtraction");
+  }
   KdTreePtr getSearchMethod() const { return tree_; }
   void setClusterTolerance(double tolerance) { cluster_tolerance_ = tolerance; }
   double getClusterTolerance() const { return cluster_tolerance_; }

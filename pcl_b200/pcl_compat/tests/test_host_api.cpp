@@ -1,6 +1,7 @@
 // Host-only behaviour of the facade (no device library needed): the pcl::PointCloud container's width / height
 // bookkeeping — the scenarios of the reference's test/common/test_pointcloud.cpp:24-395 — and the small host classes
 // added beside it.  Exit code 0 and "PASSED" on success.
+#include <algorithm>
 #include <cmath>
 #include <cstdio>
 #include <limits>
@@ -18,11 +19,51 @@
 #include <pcl/io/pcd_io.h>
 #include <pcl/point_cloud.h>
 #include <pcl/point_types.h>
+#include <pcl/search/kdtree.h>
+#include <pcl/search/search.h>
 
 using namespace pcl;
 
 static int g_fail = 0, g_checks = 0;
 #define CHECK(c) do { ++g_checks; if (!(c)) { ++g_fail; std::printf("FAIL %s:%d  %s\n", __FILE__, __LINE__, #c); } } while (0)
+
+// a brute-force searcher that implements only the two pure virtuals of pcl::search::Search: every other form must work
+// through them (search.h:144-146, 271-273)
+struct BruteForce : search::Search<PointXYZ> {
+  BruteForce() : search::Search<PointXYZ>("BruteForce", true) {}
+  std::vector<std::pair<float, index_t>> all(const PointXYZ& q) const
+  {
+    std::vector<std::pair<float, index_t>> v;
+    const auto in = getInputCloud();
+    const auto idx = getIndices();
+    const std::size_t n = idx ? idx->size() : in->size();
+    for (std::size_t j = 0; j < n; ++j) {
+      const index_t i = idx ? (*idx)[j] : static_cast<index_t>(j);
+      const PointXYZ& p = (*in)[i];
+      v.emplace_back((p.x - q.x) * (p.x - q.x) + (p.y - q.y) * (p.y - q.y) + (p.z - q.z) * (p.z - q.z), i);
+    }
+    std::sort(v.begin(), v.end());
+    return v;
+  }
+  int nearestKSearch(const PointXYZ& q, int k, Indices& ki, std::vector<float>& kd) const override
+  {
+    auto v = all(q);
+    if ((int)v.size() > k) v.resize(k);
+    ki.clear(); kd.clear();
+    for (auto& e : v) { ki.push_back(e.second); kd.push_back(e.first); }
+    return (int)v.size();
+  }
+  int radiusSearch(const PointXYZ& q, double r, Indices& ki, std::vector<float>& kd, unsigned int max_nn = 0) const override
+  {
+    ki.clear(); kd.clear();
+    for (auto& e : all(q))
+      if (e.first < r * r && (max_nn == 0 || ki.size() < max_nn)) { ki.push_back(e.second); kd.push_back(e.first); }
+    return (int)ki.size();
+  }
+  using search::Search<PointXYZ>::nearestKSearch;
+  using search::Search<PointXYZ>::radiusSearch;
+  using search::Search<PointXYZ>::sortResults;
+};
 
 static PointCloud<PointXYZ> grid() { PointCloud<PointXYZ> c; c.resize(640, 480, PointXYZ(1, 1, 1)); return c; }
 
@@ -314,6 +355,48 @@ int main(int argc, char** argv)
     CHECK(n3[2] == -1.f);
     Indices two = {0, 1};
     CHECK(!computePointNormal(pl, two, plane, curv) && std::isnan(plane[0]) && std::isnan(curv));
+  }
+  {  // pcl::search::Search: the index / cloud+index / batch / other-point-type forms through the two pure virtuals
+    PointCloud<PointXYZ>::Ptr c(new PointCloud<PointXYZ>);
+    for (int i = 0; i < 50; ++i) c->emplace_back(float(i), float(i % 7), float(i % 3));
+    BruteForce bf;
+    search::Search<PointXYZ>& sr = bf;
+    CHECK(sr.getName() == "BruteForce" && sr.getSortedResults());
+    sr.setInputCloud(c);
+    Indices ki, ki2;
+    std::vector<float> kd, kd2;
+    CHECK(sr.nearestKSearch((*c)[10], 4, ki, kd) == 4 && ki[0] == 10 && kd[0] == 0.f);
+    CHECK(sr.nearestKSearch(*c, 10, 4, ki2, kd2) == 4 && ki2 == ki);
+    CHECK(sr.nearestKSearch(10, 4, ki2, kd2) == 4 && ki2 == ki);
+    PointNormal pn;
+    pn.x = 10.f; pn.y = 3.f; pn.z = 1.f;
+    CHECK(sr.nearestKSearchT(pn, 4, ki2, kd2) == 4 && ki2 == ki && kd2 == kd);
+    std::vector<Indices> bi;
+    std::vector<std::vector<float>> bd;
+    sr.nearestKSearch(*c, Indices{10, 20}, 4, bi, bd);
+    CHECK(bi.size() == 2 && bi[0] == ki && bi[1][0] == 20);
+    sr.nearestKSearch(*c, Indices(), 1, bi, bd);
+    CHECK(bi.size() == 50 && bi[49][0] == 49);
+    CHECK(sr.radiusSearch((*c)[10], 2.5, ki, kd) >= 1 && ki[0] == 10);
+    CHECK(sr.radiusSearch(*c, 10, 2.5, ki2, kd2) == (int)ki.size() && ki2 == ki);
+    CHECK(sr.radiusSearch(10, 2.5, ki2, kd2, 1) == 1 && ki2[0] == 10);
+    CHECK(sr.radiusSearchT(pn, 2.5, ki2, kd2) == (int)ki.size() && ki2 == ki);
+    sr.radiusSearch(*c, Indices{10}, 2.5, bi, bd);
+    CHECK(bi.size() == 1 && bi[0] == ki);
+    // with an index list the plain index form addresses the list (impl/search.hpp:93-108)
+    IndicesPtr sub(new Indices{40, 41, 42, 43});
+    sr.setInputCloud(c, sub);
+    CHECK(sr.nearestKSearch(1, 1, ki, kd) == 1 && ki[0] == 41);
+    Indices ui = {5, 6, 7};
+    std::vector<float> ud = {3.f, 1.f, 2.f};
+    BruteForce::sortResults(ui, ud);
+    CHECK((ui == Indices{6, 7, 5}) && ud[0] == 1.f && ud[2] == 3.f);
+    sr.setNumberOfThreads(0);
+    CHECK(sr.getNumberOfThreads() == 1);
+    // a consumer handed a searcher without a device side refuses it (no CPU fallback); a null pointer stays null
+    search::Search<PointXYZ>::Ptr foreign(new BruteForce);
+    CHECK(!search::deviceSearcher<PointXYZ>(foreign, "test"));
+    CHECK(!search::deviceSearcher<PointXYZ>(search::Search<PointXYZ>::Ptr(), "test"));
   }
   {  // pcl::getRejectedQueryIndices / isBetterCorrespondence / operator<< (common/src/correspondence.cpp:46-94)
     Correspondences before, after;
