@@ -10,6 +10,7 @@
 // Clouds are read straight into pcl::PointCloud<PointT>, fields matched by name (what PCDReader::read + fromPCLPointCloud2
 // amount to); the blob type itself lives in pcl/PCLPointCloud2.h.
 #pragma once
+#include <algorithm>
 #include <cmath>
 #include <cstdint>
 #include <cstdio>
@@ -21,6 +22,8 @@
 #include <string>
 #include <vector>
 
+#include "../PCLPointCloud2.h"
+#include "../common/io.h"
 #include "../point_cloud.h"
 #include "../point_types.h"
 
@@ -556,12 +559,332 @@ int savePCDFile(const std::string& file, const pcl::PointCloud<PointT>& cloud, b
 {
   return binary_mode ? savePCDFileBinary(file, cloud) : savePCDFileASCII(file, cloud);
 }
+// ---- the type-erased route (PCDReader::read / PCDWriter::write* on pcl::PCLPointCloud2, io/src/pcd_io.cpp) -------------
+// The blob keeps the file's own record layout: every named field with its datatype, count and byte offset, "_" padding
+// skipped in the field list but kept in point_step; origin / orientation come from the VIEWPOINT line.
+namespace detail {
+inline bool blobFieldFinite(const unsigned char* p, std::uint8_t datatype)
+{
+  if (datatype == PCLPointField::FLOAT32) { float v; std::memcpy(&v, p, 4); return std::isfinite(v); }
+  if (datatype == PCLPointField::FLOAT64) { double v; std::memcpy(&v, p, 8); return std::isfinite(v); }
+  return true;
+}
+inline void storeAscii(const std::string& tok, std::uint8_t datatype, unsigned char* dst, bool* finite)
+{
+  *finite = true;
+  switch (datatype) {
+    case PCLPointField::FLOAT32: { const float v = std::strtof(tok.c_str(), nullptr); *finite = std::isfinite(v); std::memcpy(dst, &v, 4); break; }
+    case PCLPointField::FLOAT64: { const double v = std::strtod(tok.c_str(), nullptr); *finite = std::isfinite(v); std::memcpy(dst, &v, 8); break; }
+    case PCLPointField::INT8: { const std::int8_t v = static_cast<std::int8_t>(std::strtol(tok.c_str(), nullptr, 10)); std::memcpy(dst, &v, 1); break; }
+    case PCLPointField::UINT8: { const std::uint8_t v = static_cast<std::uint8_t>(std::strtoul(tok.c_str(), nullptr, 10)); std::memcpy(dst, &v, 1); break; }
+    case PCLPointField::INT16: { const std::int16_t v = static_cast<std::int16_t>(std::strtol(tok.c_str(), nullptr, 10)); std::memcpy(dst, &v, 2); break; }
+    case PCLPointField::UINT16: { const std::uint16_t v = static_cast<std::uint16_t>(std::strtoul(tok.c_str(), nullptr, 10)); std::memcpy(dst, &v, 2); break; }
+    case PCLPointField::INT32: { const std::int32_t v = static_cast<std::int32_t>(std::strtol(tok.c_str(), nullptr, 10)); std::memcpy(dst, &v, 4); break; }
+    case PCLPointField::UINT32: { const std::uint32_t v = static_cast<std::uint32_t>(std::strtoul(tok.c_str(), nullptr, 10)); std::memcpy(dst, &v, 4); break; }
+    default: break;
+  }
+}
+inline void printAscii(std::ostream& os, const unsigned char* p, std::uint8_t datatype)
+{
+  switch (datatype) {
+    case PCLPointField::FLOAT32: { float v; std::memcpy(&v, p, 4); if (std::isnan(v)) os << "nan"; else os << v; break; }
+    case PCLPointField::FLOAT64: { double v; std::memcpy(&v, p, 8); if (std::isnan(v)) os << "nan"; else os << v; break; }
+    case PCLPointField::INT8: { std::int8_t v; std::memcpy(&v, p, 1); os << static_cast<int>(v); break; }
+    case PCLPointField::UINT8: { std::uint8_t v; std::memcpy(&v, p, 1); os << static_cast<unsigned>(v); break; }
+    case PCLPointField::INT16: { std::int16_t v; std::memcpy(&v, p, 2); os << v; break; }
+    case PCLPointField::UINT16: { std::uint16_t v; std::memcpy(&v, p, 2); os << v; break; }
+    case PCLPointField::INT32: { std::int32_t v; std::memcpy(&v, p, 4); os << v; break; }
+    case PCLPointField::UINT32: { std::uint32_t v; std::memcpy(&v, p, 4); os << v; break; }
+    default: break;
+  }
+}
+// named fields in record order
+inline std::vector<PCLPointField> fieldsByOffset(const pcl::PCLPointCloud2& cloud)
+{
+  std::vector<PCLPointField> f;
+  for (const auto& x : cloud.fields)
+    if (x.name != "_") f.push_back(x);
+  std::stable_sort(f.begin(), f.end(), [](const PCLPointField& a, const PCLPointField& b) { return a.offset < b.offset; });
+  return f;
+}
+inline std::uint32_t fieldCount(const PCLPointField& f) { return f.count ? f.count : 1u; }  // 0 counts of old converters mean 1
+// header of a blob; with_padding: "_" byte fields fill the gaps so that the records can be written verbatim (binary)
+inline std::string blobHeader(const pcl::PCLPointCloud2& cloud, const Eigen::Vector4f& origin, const Eigen::Quaternionf& orientation,
+                              bool with_padding, const char* data)
+{
+  std::ostringstream names, sizes, types, counts, os;
+  std::uint32_t at = 0;
+  for (const auto& f : fieldsByOffset(cloud)) {
+    if (with_padding && f.offset > at) {
+      names << " _"; sizes << " 1"; types << " U"; counts << ' ' << (f.offset - at);
+      at = f.offset;
+    }
+    names << ' ' << f.name;
+    sizes << ' ' << getFieldSize(f.datatype);
+    types << ' ' << getFieldType(static_cast<int>(f.datatype));
+    counts << ' ' << fieldCount(f);
+    at += fieldCount(f) * static_cast<std::uint32_t>(getFieldSize(f.datatype));
+  }
+  if (with_padding && at < cloud.point_step) {
+    names << " _"; sizes << " 1"; types << " U"; counts << ' ' << (cloud.point_step - at);
+  }
+  os << "# .PCD v0.7 - Point Cloud Data file format\nVERSION 0.7\nFIELDS" << names.str() << "\nSIZE" << sizes.str() << "\nTYPE"
+     << types.str() << "\nCOUNT" << counts.str() << "\nWIDTH " << cloud.width << "\nHEIGHT " << cloud.height << "\nVIEWPOINT "
+     << origin[0] << ' ' << origin[1] << ' ' << origin[2] << ' ' << orientation.w() << ' ' << orientation.x() << ' '
+     << orientation.y() << ' ' << orientation.z() << "\nPOINTS " << static_cast<std::size_t>(cloud.width) * cloud.height << "\nDATA "
+     << data << "\n";
+  return os.str();
+}
+inline bool blobWritable(const pcl::PCLPointCloud2& cloud, const char* who)
+{
+  if (cloud.fields.empty()) {
+    std::fprintf(stderr, "[pcl::PCDWriter::%s] Input point cloud has no field data!\n", who);
+    return false;
+  }
+  const std::size_t npts = static_cast<std::size_t>(cloud.width) * cloud.height;
+  if (cloud.data.size() < npts * cloud.point_step) {
+    std::fprintf(stderr, "[pcl::PCDWriter::%s] The blob holds fewer bytes than width x height x point_step!\n", who);
+    return false;
+  }
+  for (const auto& f : cloud.fields)
+    if (f.name != "_" && (getFieldSize(f.datatype) == 0 ||
+                          f.offset + fieldCount(f) * static_cast<std::uint32_t>(getFieldSize(f.datatype)) > cloud.point_step)) {
+      std::fprintf(stderr, "[pcl::PCDWriter::%s] Field '%s' does not fit the point step!\n", who, f.name.c_str());
+      return false;
+    }
+  return true;
+}
+}  // namespace detail
+
+// PCDReader::read (file, blob, origin, orientation) — io/src/pcd_io.cpp:120-395, 443-700
+inline int loadPCDFile(const std::string& file, pcl::PCLPointCloud2& cloud, Eigen::Vector4f& origin, Eigen::Quaternionf& orientation)
+{
+  std::ifstream in(file, std::ios::binary);
+  if (!in) { std::fprintf(stderr, "[pcl::PCDReader::read] Could not find file '%s'.\n", file.c_str()); return -1; }
+  detail::Header h;
+  if (detail::readHeader(in, h) != 0) return -1;
+  origin[0] = h.viewpoint[0]; origin[1] = h.viewpoint[1]; origin[2] = h.viewpoint[2]; origin[3] = 0.f;
+  orientation = Eigen::Quaternionf(h.viewpoint[3], h.viewpoint[4], h.viewpoint[5], h.viewpoint[6]);
+  cloud = pcl::PCLPointCloud2();
+  for (const auto& f : h.fields) {
+    if (f.name == "_") continue;
+    const int dt = getFieldType(f.size, f.type);
+    if (dt < 0) {
+      std::fprintf(stderr, "[pcl::PCDReader::read] Field '%s' has a SIZE / TYPE combination (%d, %c) a PCLPointField cannot hold.\n",
+                   f.name.c_str(), f.size, f.type);
+      return -1;
+    }
+    PCLPointField pf;
+    pf.name = f.name;
+    pf.offset = static_cast<std::uint32_t>(f.offset);
+    pf.datatype = static_cast<std::uint8_t>(dt);
+    pf.count = static_cast<std::uint32_t>(f.count);
+    cloud.fields.push_back(pf);
+  }
+  const std::size_t npts = h.points;
+  in.seekg(0, std::ios::end);
+  const std::size_t file_size = static_cast<std::size_t>(in.tellg());
+  in.seekg(static_cast<std::streamoff>(h.data_offset));
+  const std::size_t body = file_size > h.data_offset ? file_size - h.data_offset : 0;
+  if ((h.data_type == 1 && npts * h.point_step > body) || (h.data_type == 0 && npts > body) ||
+      (h.data_type == 2 && npts > (std::size_t(1) << 32))) {
+    std::fprintf(stderr, "[pcl::PCDReader::read] Corrupted PCD file: %zu points do not fit %zu bytes of data.\n", npts, body);
+    return -1;
+  }
+  cloud.width = static_cast<std::uint32_t>(h.width);
+  cloud.height = static_cast<std::uint32_t>(h.height);
+  cloud.point_step = static_cast<std::uint32_t>(h.point_step);
+  cloud.row_step = cloud.point_step * cloud.width;
+  cloud.is_bigendian = 0;
+  cloud.is_dense = 1;
+  cloud.data.assign(npts * h.point_step, 0);
+  if (h.data_type == 0) {
+    std::size_t per_line = 0;
+    for (const auto& f : h.fields) per_line += static_cast<std::size_t>(f.count);
+    std::string line;
+    std::vector<std::string> tok;
+    std::size_t i = 0;
+    while (i < npts && std::getline(in, line)) {
+      tok.clear();
+      std::istringstream ss(line);
+      for (std::string t; ss >> t;) tok.push_back(t);
+      if (tok.empty()) continue;
+      if (tok.size() != per_line) {
+        std::fprintf(stderr, "[pcl::PCDReader::readBodyASCII] Possibly malformed PCD file: point number %zu has %zu elements, but should have %zu\n",
+                     i + 1, tok.size(), per_line);
+        ++i;
+        continue;
+      }
+      std::size_t t = 0;
+      for (const auto& f : h.fields) {
+        if (f.name != "_") {
+          const int dt = getFieldType(f.size, f.type);
+          for (int c = 0; c < f.count; ++c) {
+            bool fin;
+            detail::storeAscii(tok[t + c], static_cast<std::uint8_t>(dt), cloud.data.data() + i * h.point_step + f.offset + static_cast<std::size_t>(c) * f.size, &fin);
+            if (!fin) cloud.is_dense = 0;
+          }
+        }
+        t += static_cast<std::size_t>(f.count);
+      }
+      ++i;
+    }
+    if (i != npts) {
+      std::fprintf(stderr, "[pcl::PCDReader::read] Number of points read (%zu) is different than expected (%zu)\n", i, npts);
+      return -1;
+    }
+    return 0;
+  }
+  if (h.data_type == 1) {
+    in.read(reinterpret_cast<char*>(cloud.data.data()), static_cast<std::streamsize>(cloud.data.size()));
+    if (!in && !cloud.data.empty()) { std::fprintf(stderr, "[pcl::PCDReader::read] Corrupted PCD file. The file is smaller than expected!\n"); return -1; }
+  }
+  else {
+    if (h.data_offset + 8 > file_size) { std::fprintf(stderr, "[pcl::PCDReader::read] Corrupted PCD file.\n"); return -1; }
+    std::uint32_t csize = 0, usize = 0;
+    in.read(reinterpret_cast<char*>(&csize), 4);
+    in.read(reinterpret_cast<char*>(&usize), 4);
+    if (h.data_offset + 8 + csize > file_size) {
+      std::fprintf(stderr, "[pcl::PCDReader::read] Corrupted PCD file. The file is smaller than expected!\n");
+      return -1;
+    }
+    std::size_t plane_bytes = 0;
+    for (const auto& f : h.fields)
+      if (f.name != "_") plane_bytes += static_cast<std::size_t>(f.size) * static_cast<std::size_t>(f.count);
+    if (static_cast<std::size_t>(usize) != plane_bytes * npts) {
+      std::fprintf(stderr, "[pcl::PCDReader::read] The estimated cloud.data size (%zu) is different than the saved uncompressed value (%u)! Data corruption?\n",
+                   plane_bytes * npts, usize);
+      return -1;
+    }
+    if (usize) {
+      if (static_cast<std::uint64_t>(usize) > static_cast<std::uint64_t>(csize) * 256u + 64u) {
+        std::fprintf(stderr, "[pcl::PCDReader::read] Corrupted PCD file: %u compressed bytes cannot hold %u uncompressed.\n", csize, usize);
+        return -1;
+      }
+      std::vector<unsigned char> cbuf(csize ? csize : 1), buf(usize);
+      in.read(reinterpret_cast<char*>(cbuf.data()), static_cast<std::streamsize>(csize));
+      if (detail::lzfDecompress(cbuf.data(), csize, buf.data(), usize) != usize) {
+        std::fprintf(stderr, "[pcl::PCDReader::read] Size of decompressed lzf data does not match value stored in PCD header (%u).\n", usize);
+        return -1;
+      }
+      std::size_t plane = 0;   // planes (all values of field 0, then of field 1, ...) -> records
+      for (const auto& f : h.fields) {
+        if (f.name == "_") continue;
+        const std::size_t fs = static_cast<std::size_t>(f.size) * static_cast<std::size_t>(f.count);
+        for (std::size_t i = 0; i < npts; ++i)
+          std::memcpy(cloud.data.data() + i * h.point_step + f.offset, buf.data() + plane + i * fs, fs);
+        plane += fs * npts;
+      }
+    }
+  }
+  for (std::size_t i = 0; i < npts && cloud.is_dense; ++i)      // io/src/pcd_io.cpp:668-700: a non-finite float clears is_dense
+    for (const auto& f : cloud.fields)
+      for (std::uint32_t c = 0; c < f.count; ++c)
+        if (!detail::blobFieldFinite(cloud.data.data() + i * h.point_step + f.offset + c * static_cast<std::uint32_t>(getFieldSize(f.datatype)), f.datatype))
+          cloud.is_dense = 0;
+  return 0;
+}
+inline int loadPCDFile(const std::string& file, pcl::PCLPointCloud2& cloud)
+{
+  Eigen::Vector4f origin;
+  Eigen::Quaternionf orientation;
+  return loadPCDFile(file, cloud, origin, orientation);
+}
+
+// PCDWriter::writeASCII (blob) — io/src/pcd_io.cpp:1099-1215
+inline int savePCDFileASCII(const std::string& file, const pcl::PCLPointCloud2& cloud, const Eigen::Vector4f& origin = Eigen::Vector4f::Zero(),
+                            const Eigen::Quaternionf& orientation = Eigen::Quaternionf::Identity(), int precision = 8)
+{
+  if (cloud.data.empty()) std::fprintf(stderr, "[pcl::PCDWriter::writeASCII] Input point cloud has no data!\n");
+  if (!detail::blobWritable(cloud, "writeASCII")) return -1;
+  std::ofstream out(file, std::ios::binary);
+  if (!out) { std::fprintf(stderr, "[pcl::PCDWriter::writeASCII] Could not open file for writing!\n"); return -1; }
+  out << detail::blobHeader(cloud, origin, orientation, false, "ascii");
+  out.precision(precision);
+  const auto fields = detail::fieldsByOffset(cloud);
+  const std::size_t npts = static_cast<std::size_t>(cloud.width) * cloud.height;
+  for (std::size_t i = 0; i < npts; ++i) {
+    bool first = true;
+    for (const auto& f : fields)
+      for (std::uint32_t c = 0; c < detail::fieldCount(f); ++c) {
+        if (!first) out << ' ';
+        first = false;
+        detail::printAscii(out, cloud.data.data() + i * cloud.point_step + f.offset + c * static_cast<std::uint32_t>(getFieldSize(f.datatype)), f.datatype);
+      }
+    out << '\n';
+  }
+  return out ? 0 : -1;
+}
+// PCDWriter::writeBinary (blob) — io/src/pcd_io.cpp:958-1041, 1241-1330: the records verbatim, gaps declared as "_" fields
+inline int savePCDFileBinary(const std::string& file, const pcl::PCLPointCloud2& cloud, const Eigen::Vector4f& origin = Eigen::Vector4f::Zero(),
+                             const Eigen::Quaternionf& orientation = Eigen::Quaternionf::Identity())
+{
+  if (cloud.data.empty()) std::fprintf(stderr, "[pcl::PCDWriter::writeBinary] Input point cloud has no data!\n");
+  if (!detail::blobWritable(cloud, "writeBinary")) return -1;
+  std::ofstream out(file, std::ios::binary);
+  if (!out) { std::fprintf(stderr, "[pcl::PCDWriter::writeBinary] Could not open file for writing!\n"); return -1; }
+  out << detail::blobHeader(cloud, origin, orientation, true, "binary");
+  out.write(reinterpret_cast<const char*>(cloud.data.data()),
+            static_cast<std::streamsize>(static_cast<std::size_t>(cloud.width) * cloud.height * cloud.point_step));
+  return out ? 0 : -1;
+}
+// PCDWriter::writeBinaryCompressed (blob) — io/src/pcd_io.cpp:1045-1098, 1332-1480: one plane per named field, LZF
+inline int savePCDFileBinaryCompressed(const std::string& file, const pcl::PCLPointCloud2& cloud,
+                                       const Eigen::Vector4f& origin = Eigen::Vector4f::Zero(),
+                                       const Eigen::Quaternionf& orientation = Eigen::Quaternionf::Identity())
+{
+  if (cloud.data.empty()) std::fprintf(stderr, "[pcl::PCDWriter::writeBinaryCompressed] Input point cloud has no data!\n");
+  if (!detail::blobWritable(cloud, "writeBinaryCompressed")) return -1;
+  const auto fields = detail::fieldsByOffset(cloud);
+  const std::size_t npts = static_cast<std::size_t>(cloud.width) * cloud.height;
+  std::size_t rec = 0;
+  for (const auto& f : fields) rec += detail::fieldCount(f) * static_cast<std::size_t>(getFieldSize(f.datatype));
+  const std::size_t data_size = rec * npts;
+  if (data_size * 3 / 2 > std::numeric_limits<std::uint32_t>::max()) {
+    std::fprintf(stderr, "[pcl::PCDWriter::writeBinaryCompressed] The input data exceeds the maximum size for compressed version 0.7 pcds.\n");
+    return -2;
+  }
+  std::ofstream out(file, std::ios::binary);
+  if (!out) { std::fprintf(stderr, "[pcl::PCDWriter::writeBinaryCompressed] Could not open file for writing!\n"); return -1; }
+  out << detail::blobHeader(cloud, origin, orientation, false, "binary_compressed");
+  std::vector<unsigned char> planes(data_size ? data_size : 1);
+  std::size_t plane = 0;
+  for (const auto& f : fields) {
+    const std::size_t fs = detail::fieldCount(f) * static_cast<std::size_t>(getFieldSize(f.datatype));
+    for (std::size_t i = 0; i < npts; ++i) std::memcpy(planes.data() + plane + i * fs, cloud.data.data() + i * cloud.point_step + f.offset, fs);
+    plane += fs * npts;
+  }
+  std::vector<unsigned char> comp(data_size + data_size / 16 + 64);
+  std::uint32_t csize = 0;
+  const std::uint32_t usize = static_cast<std::uint32_t>(data_size);
+  if (data_size) {
+    csize = static_cast<std::uint32_t>(detail::lzfCompress(planes.data(), data_size, comp.data(), comp.size()));
+    if (csize == 0) { std::fprintf(stderr, "[pcl::PCDWriter::writeBinaryCompressed] Error during compression!\n"); return -1; }
+  }
+  out.write(reinterpret_cast<const char*>(&csize), 4);
+  out.write(reinterpret_cast<const char*>(&usize), 4);
+  out.write(reinterpret_cast<const char*>(comp.data()), csize);
+  return out ? 0 : -1;
+}
+// io/include/pcl/io/pcd_io.h:687-697
+inline int savePCDFile(const std::string& file, const pcl::PCLPointCloud2& cloud, const Eigen::Vector4f& origin = Eigen::Vector4f::Zero(),
+                       const Eigen::Quaternionf& orientation = Eigen::Quaternionf::Identity(), const bool binary_mode = false)
+{
+  return binary_mode ? savePCDFileBinary(file, cloud, origin, orientation) : savePCDFileASCII(file, cloud, origin, orientation);
+}
 }  // namespace io
 
 // io/include/pcl/io/pcd_io.h:71-600 — the class forms of the same calls
 class PCDReader {
 public:
   template <typename PointT> int read(const std::string& file, pcl::PointCloud<PointT>& cloud, const int = 0) { return io::loadPCDFile(file, cloud); }
+  int read(const std::string& file, pcl::PCLPointCloud2& cloud, Eigen::Vector4f& origin, Eigen::Quaternionf& orientation, int& pcd_version,
+           const int = 0)
+  {
+    pcd_version = 7;   // PCD_V7: the only version with a VIEWPOINT line (io/include/pcl/io/pcd_io.h:84-110)
+    return io::loadPCDFile(file, cloud, origin, orientation);
+  }
+  int read(const std::string& file, pcl::PCLPointCloud2& cloud, const int = 0) { return io::loadPCDFile(file, cloud); }
 };
 class PCDWriter {
 public:
@@ -569,5 +892,25 @@ public:
   template <typename PointT> int writeASCII(const std::string& file, const pcl::PointCloud<PointT>& cloud, int precision = 8) { return io::savePCDFileASCII(file, cloud, precision); }
   template <typename PointT> int writeBinary(const std::string& file, const pcl::PointCloud<PointT>& cloud) { return io::savePCDFileBinary(file, cloud); }
   template <typename PointT> int writeBinaryCompressed(const std::string& file, const pcl::PointCloud<PointT>& cloud) { return io::savePCDFileBinaryCompressed(file, cloud); }
+  int write(const std::string& file, const pcl::PCLPointCloud2& cloud, const Eigen::Vector4f& origin = Eigen::Vector4f::Zero(),
+            const Eigen::Quaternionf& orientation = Eigen::Quaternionf::Identity(), const bool binary = false)
+  {
+    return io::savePCDFile(file, cloud, origin, orientation, binary);
+  }
+  int writeASCII(const std::string& file, const pcl::PCLPointCloud2& cloud, const Eigen::Vector4f& origin = Eigen::Vector4f::Zero(),
+                 const Eigen::Quaternionf& orientation = Eigen::Quaternionf::Identity(), const int precision = 8)
+  {
+    return io::savePCDFileASCII(file, cloud, origin, orientation, precision);
+  }
+  int writeBinary(const std::string& file, const pcl::PCLPointCloud2& cloud, const Eigen::Vector4f& origin = Eigen::Vector4f::Zero(),
+                  const Eigen::Quaternionf& orientation = Eigen::Quaternionf::Identity())
+  {
+    return io::savePCDFileBinary(file, cloud, origin, orientation);
+  }
+  int writeBinaryCompressed(const std::string& file, const pcl::PCLPointCloud2& cloud, const Eigen::Vector4f& origin = Eigen::Vector4f::Zero(),
+                            const Eigen::Quaternionf& orientation = Eigen::Quaternionf::Identity())
+  {
+    return io::savePCDFileBinaryCompressed(file, cloud, origin, orientation);
+  }
 };
 }  // namespace pcl

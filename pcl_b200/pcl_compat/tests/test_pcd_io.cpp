@@ -6,6 +6,7 @@
 #include <cstdio>
 #include <cstring>
 #include <fstream>
+#include <limits>
 #include <random>
 #include <string>
 #include <vector>
@@ -156,12 +157,146 @@ static int selftest(const std::string& dir)
     EXPECT_EQ(io::loadPCDFile(dir + "/trunc.pcd", c), -1);
     EXPECT_EQ(io::loadPCDFile(dir + "/does_not_exist.pcd", c), -1);
   }
+  {  // the type-erased route: a blob with mixed field types, a COUNT > 1 field and padding survives all three encodings;
+     // typed and blob readers agree; concatenateFields / getFieldsList / getFieldIndex (common/src/io.cpp)
+    PCLPointCloud2 b;
+    auto add = [&](const char* name, std::uint32_t off, std::uint8_t dt, std::uint32_t cnt) {
+      PCLPointField f;
+      f.name = name; f.offset = off; f.datatype = dt; f.count = cnt;
+      b.fields.push_back(f);
+    };
+    add("x", 0, PCLPointField::FLOAT32, 1);
+    add("y", 4, PCLPointField::FLOAT32, 1);
+    add("z", 8, PCLPointField::FLOAT32, 1);
+    add("ring", 16, PCLPointField::UINT16, 1);          // bytes 12..15 and 18..19 are padding
+    add("label", 20, PCLPointField::INT32, 1);
+    add("hist", 24, PCLPointField::UINT8, 3);
+    add("t", 32, PCLPointField::FLOAT64, 1);            // bytes 27..31 padding
+    add("tag", 40, PCLPointField::INT8, 1);
+    b.point_step = 48;
+    b.width = 7;
+    b.height = 3;
+    b.row_step = b.point_step * b.width;
+    b.is_dense = 1;
+    const std::size_t n = 21;
+    b.data.assign(n * b.point_step, 0xAB);              // padding bytes are arbitrary
+    for (std::size_t i = 0; i < n; ++i) {
+      unsigned char* r = b.data.data() + i * b.point_step;
+      const float x = 0.5f * i - 3.f, y = 1.f / (i + 1.f), z = (i == 4) ? std::numeric_limits<float>::quiet_NaN() : -7.25f * i;
+      const std::uint16_t ring = static_cast<std::uint16_t>(60000 + i);
+      const std::int32_t label = -100000 * static_cast<std::int32_t>(i) + 7;
+      const std::uint8_t hist[3] = {static_cast<std::uint8_t>(i), static_cast<std::uint8_t>(255 - i), 128};
+      const double t = 1e-3 * i + 1234567.125;
+      const std::int8_t tag = static_cast<std::int8_t>(i - 10);
+      std::memcpy(r, &x, 4); std::memcpy(r + 4, &y, 4); std::memcpy(r + 8, &z, 4); std::memcpy(r + 16, &ring, 2);
+      std::memcpy(r + 20, &label, 4); std::memcpy(r + 24, hist, 3); std::memcpy(r + 32, &t, 8); std::memcpy(r + 40, &tag, 1);
+    }
+    EXPECT_TRUE(getFieldsList(b) == "x y z ring label hist t tag");
+    EXPECT_EQ(getFieldIndex(b, "label"), 4);
+    EXPECT_EQ(getFieldIndex(b, "nope"), -1);
+    Eigen::Vector4f org;
+    org[0] = 1.5f; org[1] = -2.f; org[2] = 0.25f;
+    const Eigen::Quaternionf ori(0.5f, 0.5f, -0.5f, 0.5f);
+    auto same_fields = [&](const PCLPointCloud2& a, bool offsets_too) {
+      bool ok = a.fields.size() == b.fields.size();
+      for (std::size_t f = 0; ok && f < a.fields.size(); ++f)
+        ok = a.fields[f].name == b.fields[f].name && a.fields[f].datatype == b.fields[f].datatype && a.fields[f].count == b.fields[f].count &&
+             (!offsets_too || a.fields[f].offset == b.fields[f].offset);
+      return ok;
+    };
+    auto same_values = [&](const PCLPointCloud2& a) {
+      bool ok = a.width == b.width && a.height == b.height && a.data.size() == std::size_t(a.point_step) * n;
+      for (std::size_t i = 0; ok && i < n; ++i)
+        for (std::size_t f = 0; ok && f < b.fields.size(); ++f) {
+          const std::size_t bytes = b.fields[f].count * getFieldSize(b.fields[f].datatype);
+          const unsigned char *pa = a.data.data() + i * a.point_step + a.fields[f].offset, *pb = b.data.data() + i * b.point_step + b.fields[f].offset;
+          if (b.fields[f].name == "z" && i == 4) { float v; std::memcpy(&v, pa, 4); ok = std::isnan(v); }
+          else ok = std::memcmp(pa, pb, bytes) == 0;
+        }
+      return ok;
+    };
+    for (int mode = 0; mode < 3; ++mode) {
+      const std::string f = dir + "/blob" + std::to_string(mode) + ".pcd";
+      const int rc = mode == 0 ? io::savePCDFileASCII(f, b, org, ori, 17) : mode == 1 ? io::savePCDFileBinary(f, b, org, ori) : io::savePCDFileBinaryCompressed(f, b, org, ori);
+      EXPECT_EQ(rc, 0);
+      PCLPointCloud2 r;
+      Eigen::Vector4f o2;
+      Eigen::Quaternionf q2;
+      EXPECT_EQ(io::loadPCDFile(f, r, o2, q2), 0);
+      EXPECT_TRUE(same_fields(r, mode == 1));          // only the binary form keeps the padded layout
+      EXPECT_EQ(r.point_step, mode == 1 ? 48u : 4u + 4 + 4 + 2 + 4 + 3 + 8 + 1);
+      EXPECT_TRUE(same_values(r));
+      EXPECT_EQ(r.is_dense, 0);                        // the NaN
+      EXPECT_TRUE(o2[0] == 1.5f && o2[1] == -2.f && o2[2] == 0.25f && q2 == ori);
+      PointCloud<PointXYZ> typed;                      // the typed reader sees the same coordinates
+      EXPECT_EQ(io::loadPCDFile(f, typed), 0);
+      EXPECT_TRUE(typed.size() == n && typed.width == 7 && typed.height == 3 && typed[3].x == -1.5f && std::isnan(typed[4].z));
+      PointCloud<PointXYZ> conv;
+      fromPCLPointCloud2(r, conv);
+      EXPECT_TRUE(conv.size() == n && same_bits(conv[20].y, typed[20].y) && same_bits(conv[7].z, typed[7].z));
+    }
+    // PCDReader / PCDWriter class forms
+    PCDWriter w;
+    PCDReader rd;
+    PCLPointCloud2 r2;
+    int ver = 0;
+    Eigen::Vector4f o3;
+    Eigen::Quaternionf q3;
+    EXPECT_EQ(w.writeBinaryCompressed(dir + "/blobw.pcd", b, org, ori), 0);
+    EXPECT_EQ(rd.read(dir + "/blobw.pcd", r2, o3, q3, ver), 0);
+    EXPECT_TRUE(ver == 7 && same_values(r2));
+    EXPECT_EQ(w.write(dir + "/blobw2.pcd", b), 0);     // ascii, default pose
+    EXPECT_EQ(rd.read(dir + "/blobw2.pcd", r2), 0);
+    EXPECT_TRUE(r2.fields.size() == 8 && r2.width == 7);
+    // concatenateFields: the aligned coordinates (cloud2) take the place of x y z, the rest of cloud1 follows
+    PointCloud<PointXYZ> moved;
+    moved.resize(7, 3, PointXYZ(9.f, 8.f, 7.f));
+    PCLPointCloud2 mb, cat;
+    toPCLPointCloud2(moved, mb);
+    EXPECT_TRUE(concatenateFields(b, mb, cat));
+    EXPECT_TRUE(getFieldsList(cat) == "x y z ring label hist t tag");
+    EXPECT_EQ(cat.point_step, 16u + (4 + 4 + 8 + 8 + 8));   // PointXYZ record + each carried field with its room in cloud1
+    EXPECT_TRUE(cat.width == 7 && cat.height == 3 && cat.data.size() == n * cat.point_step);
+    {
+      float x;
+      std::uint16_t ring;
+      double t;
+      const unsigned char* r = cat.data.data() + 5 * cat.point_step;
+      std::memcpy(&x, r + cat.fields[0].offset, 4);
+      std::memcpy(&ring, r + cat.fields[getFieldIndex(cat, "ring")].offset, 2);
+      std::memcpy(&t, r + cat.fields[getFieldIndex(cat, "t")].offset, 8);
+      EXPECT_TRUE(x == 9.f && ring == 60005 && t == 1e-3 * 5 + 1234567.125);
+    }
+    PCLPointCloud2 other = mb;
+    other.width = 3; other.height = 1;
+    EXPECT_TRUE(!concatenateFields(b, other, cat));
+    // a field type the blob cannot describe is refused
+    std::ofstream odd(dir + "/i8.pcd");
+    odd << "FIELDS x big\nSIZE 4 8\nTYPE F I\nCOUNT 1 1\nWIDTH 1\nHEIGHT 1\nPOINTS 1\nDATA ascii\n1 2\n";
+    odd.close();
+    EXPECT_EQ(io::loadPCDFile(dir + "/i8.pcd", r2), -1);
+  }
   std::printf("%s: %d checks, %d failures\n", g_fail ? "FAILED" : "PASSED", g_checks, g_fail);
   return g_fail ? 1 : 0;
 }
 
 int main(int argc, char** argv)
 {
+  if (argc >= 4 && std::string(argv[1]) == "dumpblob") {  // <in.pcd> <out.bin>: like dump, through the blob reader + fromPCLPointCloud2
+    PCLPointCloud2 b;
+    if (io::loadPCDFile(argv[2], b) != 0) return 2;
+    PointCloud<PointXYZ> c;
+    fromPCLPointCloud2(b, c);
+    std::ofstream out(argv[3], std::ios::binary);
+    const std::uint64_t n = c.size();
+    const std::uint32_t w = c.width, h = c.height, d = b.is_dense ? 1 : 0;
+    out.write(reinterpret_cast<const char*>(&n), 8);
+    out.write(reinterpret_cast<const char*>(&w), 4);
+    out.write(reinterpret_cast<const char*>(&h), 4);
+    out.write(reinterpret_cast<const char*>(&d), 4);
+    for (const auto& p : c.points) out.write(reinterpret_cast<const char*>(&p.x), 12);
+    return 0;
+  }
   if (argc >= 3 && std::string(argv[1]) == "selftest") return selftest(argv[2]);
   if (argc >= 4 && std::string(argv[1]) == "dump") {  // <in.pcd> <out.bin>: u64 n, u32 w, u32 h, u32 dense, n * xyz floats
     PointCloud<PointXYZ> c;

@@ -141,6 +141,39 @@ def test_reference_fixtures_decode_identically(exe, tmp_path, name):
 
 
 @pytest.mark.skipif(not os.path.isdir(REF), reason="reference fixtures are not on this machine")
+@pytest.mark.parametrize("name", ["milk.pcd", "cturtle.pcd", "car6.pcd", "noisy_slice_displaced.pcd", "colored_cloud.pcd",
+                                  "office1_keypoints.pcd", "bun0.pcd", "sac_plane_test.pcd"])
+def test_reference_fixtures_through_the_blob_reader(exe, tmp_path, name):
+    """PCDReader::read into a pcl::PCLPointCloud2 + fromPCLPointCloud2 (the route tools/iterative_closest_point.cpp takes):
+    the same coordinates as the independent Python decoder, bit for bit."""
+    path = os.path.join(REF, name)
+    want, w, h = _read_pcd_python(path)
+    out = os.path.join(str(tmp_path), "blob.bin")
+    subprocess.check_call([exe, "dumpblob", path, out])
+    raw = open(out, "rb").read()
+    n, gw, gh, dense = struct.unpack("<QIII", raw[:20])
+    got = np.frombuffer(raw[20:], dtype=np.float32).reshape(n, 3)
+    assert (gw, gh) == (w, h) and got.shape == want.shape
+    assert np.array_equal(got.view(np.uint32), want.view(np.uint32))
+    assert not dense or bool(np.isfinite(want).all())
+
+
+@pytest.mark.parametrize("header,body", [
+    ("FIELDS a x y\nSIZE -4 4 4\nTYPE F F F\nCOUNT 1 1 1\nWIDTH 2\nHEIGHT 1\nPOINTS 2\nDATA binary\n", b"\0" * 32),
+    ("FIELDS x y z\nSIZE 4 4 4\nTYPE F F F\nCOUNT 1 1 1\nWIDTH 4000000000\nHEIGHT 1\nPOINTS 4000000000\nDATA binary\n", b"\0" * 12),
+    ("FIELDS x y z\nSIZE 4 4 4\nTYPE F F F\nCOUNT 1 1 1\nWIDTH 100\nHEIGHT 1\nPOINTS 100\nDATA binary_compressed\n",
+     struct.pack("<II", 4, 4000000000) + b"\0" * 4),
+    ("FIELDS x y z\nSIZE 4 4 4\nTYPE F F F\nCOUNT 1 1 1\nWIDTH 100\nHEIGHT 1\nPOINTS 100\nDATA binary_compressed\n",
+     struct.pack("<II", 4, 1200) + b"\0" * 4),
+])
+def test_malformed_files_are_rejected_by_the_blob_reader(exe, tmp_path, header, body):
+    f = tmp_path / "bad.pcd"
+    f.write_bytes(header.encode() + body)
+    r = subprocess.run([exe, "dumpblob", str(f), str(tmp_path / "o.bin")], capture_output=True, text=True)
+    assert r.returncode == 2, (r.returncode, r.stderr)
+
+
+@pytest.mark.skipif(not os.path.isdir(REF), reason="reference fixtures are not on this machine")
 def test_ascii_fixtures_match_golden(exe, tmp_path, golden):
     for name, key in (("bun0.pcd", "bun0"), ("bun4.pcd", "bun4"), ("sac_plane_test.pcd", "sac_plane")):
         got, w, h, dense = _dump(exe, os.path.join(REF, name), str(tmp_path))
