@@ -316,7 +316,6 @@ __device__ __forceinline__ void dmma884(double& c0, double& c1, double a, double
                : "d"(a), "d"(b));
 }
 
-constexpr int kEstNone = -1;
 #ifndef PCLB_ACCUM_BLOCKS
 #define PCLB_ACCUM_BLOCKS 5
 #endif
