@@ -333,9 +333,11 @@ int loadPCDFile(const std::string& file, pcl::PointCloud<PointT>& cloud)
     const std::size_t fsz = static_cast<std::size_t>(in.tellg());
     in.seekg(here);
     const std::size_t body = fsz > h.data_offset ? fsz - h.data_offset : 0;
+    // compressed: the body is u32 csize, u32 usize, csize bytes; usize must be the planes' size and an LZF stream cannot
+    // expand more than ~132x, so the point count is bounded by the FILE size before anything is allocated
     const bool too_many = h.data_type == 1 ? npts * h.point_step > body
                           : h.data_type == 0 ? npts > body
-                                             : npts > (std::size_t(1) << 32);  // usize is a u32
+                                             : (body < 8 || npts > (body - 8) * 256 + 64);
     if (too_many) {
       std::fprintf(stderr, "[pcl::PCDReader::read] Corrupted PCD file: %zu points do not fit %zu bytes of data.\n", npts, body);
       return -1;
@@ -687,7 +689,7 @@ inline int loadPCDFile(const std::string& file, pcl::PCLPointCloud2& cloud, Eige
   in.seekg(static_cast<std::streamoff>(h.data_offset));
   const std::size_t body = file_size > h.data_offset ? file_size - h.data_offset : 0;
   if ((h.data_type == 1 && npts * h.point_step > body) || (h.data_type == 0 && npts > body) ||
-      (h.data_type == 2 && npts > (std::size_t(1) << 32))) {
+      (h.data_type == 2 && (body < 8 || npts > (body - 8) * 256 + 64))) {   // an LZF stream expands < 256x: bounded by the file
     std::fprintf(stderr, "[pcl::PCDReader::read] Corrupted PCD file: %zu points do not fit %zu bytes of data.\n", npts, body);
     return -1;
   }

@@ -165,6 +165,8 @@ def test_reference_fixtures_through_the_blob_reader(exe, tmp_path, name):
      struct.pack("<II", 4, 4000000000) + b"\0" * 4),
     ("FIELDS x y z\nSIZE 4 4 4\nTYPE F F F\nCOUNT 1 1 1\nWIDTH 100\nHEIGHT 1\nPOINTS 100\nDATA binary_compressed\n",
      struct.pack("<II", 4, 1200) + b"\0" * 4),
+    ("FIELDS x y z\nSIZE 4 4 4\nTYPE F F F\nCOUNT 1 1 1\nWIDTH 4000000000\nHEIGHT 1\nPOINTS 4000000000\nDATA binary_compressed\n",
+     struct.pack("<II", 4, 4000000000) + b"\0" * 4),
 ])
 def test_malformed_files_are_rejected_by_the_blob_reader(exe, tmp_path, header, body):
     f = tmp_path / "bad.pcd"
@@ -194,6 +196,9 @@ def test_ascii_fixtures_match_golden(exe, tmp_path, golden):
     ("FIELDS x y z\nSIZE 4 4 4\nTYPE F F F\nCOUNT 1 1 1\nWIDTH 100\nHEIGHT 1\nPOINTS 100\nDATA binary_compressed\n",
      struct.pack("<II", 4, 4000000000) + b"\0" * 4),
     ("FIELDS x y z\nSIZE 4 4 4\nTYPE F F F\nCOUNT 1 1 1\nWIDTH 18446744073709551615\nHEIGHT 3\nPOINTS 5\nDATA ascii\n", b""),
+    # compressed body of 12 bytes that claims four billion points: refused before any allocation
+    ("FIELDS x y z\nSIZE 4 4 4\nTYPE F F F\nCOUNT 1 1 1\nWIDTH 4000000000\nHEIGHT 1\nPOINTS 4000000000\nDATA binary_compressed\n",
+     struct.pack("<II", 4, 4000000000) + b"\0" * 4),
 ])
 def test_malformed_headers_are_rejected(exe, tmp_path, header, body):
     """Untrusted files: bad SIZE / COUNT / TYPE and point counts the file cannot hold are refused (exit code 2 of the
