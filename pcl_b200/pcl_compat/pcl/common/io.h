@@ -11,6 +11,8 @@
 #include <vector>
 
 #include "../PCLPointCloud2.h"
+#include "../point_cloud.h"
+#include "../types.h"
 
 namespace pcl {
 inline int getFieldIndex(const pcl::PCLPointCloud2& cloud, const std::string& field_name)
@@ -50,6 +52,48 @@ inline char getFieldType(const int datatype)          // datatype -> the PCD TYP
     case PCLPointField::UINT8: case PCLPointField::UINT16: case PCLPointField::UINT32: return 'U';
     case PCLPointField::FLOAT32: case PCLPointField::FLOAT64: return 'F';
     default: return '?';
+  }
+}
+
+// copyPointCloud (common/include/pcl/common/impl/io.hpp:112-260): same point type — all fields; an index list gives an
+// unorganised cloud of the selected points; between point types the coordinates are what both sides share here
+template <typename PointT>
+inline void copyPointCloud(const pcl::PointCloud<PointT>& cloud_in, pcl::PointCloud<PointT>& cloud_out)
+{
+  cloud_out = cloud_in;
+}
+template <typename PointT>
+inline void copyPointCloud(const pcl::PointCloud<PointT>& cloud_in, const Indices& indices, pcl::PointCloud<PointT>& cloud_out)
+{
+  if (indices.size() == cloud_in.size()) {   // io.hpp:141-146: a full-length list is taken for the identity
+    cloud_out = cloud_in;
+    return;
+  }
+  pcl::PointCloud<PointT> out;
+  out.points.resize(indices.size());
+  out.header = cloud_in.header;
+  out.width = static_cast<std::uint32_t>(indices.size());
+  out.height = 1;
+  out.is_dense = cloud_in.is_dense;
+  out.sensor_orientation_ = cloud_in.sensor_orientation_;
+  out.sensor_origin_ = cloud_in.sensor_origin_;
+  for (std::size_t i = 0; i < indices.size(); ++i) out.points[i] = cloud_in[static_cast<std::size_t>(indices[i])];
+  cloud_out = std::move(out);
+}
+template <typename PointInT, typename PointOutT>
+inline void copyPointCloud(const pcl::PointCloud<PointInT>& cloud_in, pcl::PointCloud<PointOutT>& cloud_out)
+{
+  cloud_out.header = cloud_in.header;
+  cloud_out.width = cloud_in.width;
+  cloud_out.height = cloud_in.height;
+  cloud_out.is_dense = cloud_in.is_dense;
+  cloud_out.sensor_orientation_ = cloud_in.sensor_orientation_;
+  cloud_out.sensor_origin_ = cloud_in.sensor_origin_;
+  cloud_out.points.assign(cloud_in.size(), PointOutT());
+  for (std::size_t i = 0; i < cloud_in.size(); ++i) {
+    cloud_out.points[i].x = cloud_in[i].x;
+    cloud_out.points[i].y = cloud_in[i].y;
+    cloud_out.points[i].z = cloud_in[i].z;
   }
 }
 

@@ -13,6 +13,10 @@
 #include <string>
 
 #include <pcl/common/centroid.h>
+#include <pcl/common/common.h>
+#include <pcl/common/io.h>
+#include <pcl/common/transforms.h>
+#include <pcl/filters/filter.h>
 #include <pcl/correspondence.h>
 #include <pcl/features/normal_3d.h>
 #include <pcl/filters/voxel_grid.h>
@@ -355,6 +359,72 @@ int main(int argc, char** argv)
     CHECK(n3[2] == -1.f);
     Indices two = {0, 1};
     CHECK(!computePointNormal(pl, two, plane, curv) && std::isnan(plane[0]) && std::isnan(curv));
+  }
+  {  // transformPointCloud[WithNormals] / transformPoint, getMinMax3D, removeNaNFromPointCloud, copyPointCloud
+    Eigen::Matrix4f T = Eigen::Matrix4f::Identity();
+    const float a = 0.3f;
+    T(0, 0) = std::cos(a); T(0, 1) = -std::sin(a); T(1, 0) = std::sin(a); T(1, 1) = std::cos(a);
+    T(0, 3) = 1.5f; T(1, 3) = -2.f; T(2, 3) = 0.25f;
+    PointCloud<PointNormal> c;
+    for (int i = 0; i < 12; ++i) c.emplace_back(0.1f * i, 1.f - 0.2f * i, 0.05f * i * i, 0.f, 0.6f, 0.8f, 0.01f * i);
+    c.resize(4, 3);
+    c.is_dense = false;
+    c[5].x = std::numeric_limits<float>::quiet_NaN();
+    c.header.frame_id = "lidar";
+    PointCloud<PointNormal> t, tn;
+    transformPointCloud(c, t, T);
+    transformPointCloudWithNormals(c, tn, T);
+    CHECK(t.width == 4 && t.height == 3 && !t.is_dense && t.header.frame_id == "lidar" && t.size() == 12);
+    double worst = 0;
+    for (int i = 0; i < 12; ++i) {
+      if (i == 5) continue;
+      const double x = c[i].x, y = c[i].y, z = c[i].z;
+      worst = std::max(worst, std::fabs(t[i].x - (std::cos((double)a) * x - std::sin((double)a) * y + 1.5)));
+      worst = std::max(worst, std::fabs(t[i].y - (std::sin((double)a) * x + std::cos((double)a) * y - 2.0)));
+      worst = std::max(worst, std::fabs(t[i].z - (z + 0.25)));
+      CHECK(t[i].normal_y == 0.6f && t[i].curvature == c[i].curvature);      // other fields copied, not rotated
+      CHECK(std::fabs(tn[i].normal_x - (-std::sin(a) * 0.6f)) < 1e-6f && std::fabs(tn[i].normal_y - std::cos(a) * 0.6f) < 1e-6f && tn[i].normal_z == 0.8f);
+      CHECK(tn[i].x == t[i].x && t[i].data[3] == 1.f && tn[i].data_n[3] == 0.f);
+    }
+    CHECK(worst < 1e-6);
+    CHECK(std::isnan(t[5].x) && t[5].y == c[5].y);                            // a non-finite point is left as it was
+    const PointNormal one = transformPoint(c[3], T);
+    CHECK(one.x == t[3].x && one.z == t[3].z && one.normal_y == 0.6f);
+    CHECK(transformPointWithNormal(c[3], T).normal_x == tn[3].normal_x);
+    Eigen::Matrix4d Td = T.cast<double>();
+    PointCloud<PointNormal> td;
+    transformPointCloud(c, td, Td, false);
+    CHECK(std::fabs(td[7].x - t[7].x) < 1e-6f && td[7].normal_y == 0.f);      // copy_all_fields = false: only the coordinates
+    transformPointCloud(c, c, T);                                             // in place
+    CHECK(c[3].x == t[3].x && c[11].z == t[11].z && c[3].normal_y == 0.6f);
+    PointCloud<PointNormal> sub;
+    transformPointCloud(t, Indices{2, 9}, sub, Eigen::Matrix4f::Identity());
+    CHECK(sub.size() == 2 && sub.width == 2 && sub.height == 1 && sub[1].x == t[9].x && sub[1].curvature == t[9].curvature);
+    Eigen::Vector4f mn, mx;
+    getMinMax3D(t, mn, mx);
+    float lo = 1e9f, hi = -1e9f;
+    for (int i = 0; i < 12; ++i)
+      if (i != 5) { lo = std::min(lo, t[i].y); hi = std::max(hi, t[i].y); }
+    CHECK(mn[1] == lo && mx[1] == hi && mn[0] <= mx[0]);
+    getMinMax3D(t, Indices{0, 1}, mn, mx);
+    CHECK(mn[2] == std::min(t[0].z, t[1].z) && mx[2] == std::max(t[0].z, t[1].z));
+    PointNormal pmn, pmx;
+    getMinMax3D(t, pmn, pmx);
+    CHECK(pmn.y == lo && pmx.y == hi);
+    PointCloud<PointNormal> clean;
+    Indices kept;
+    removeNaNFromPointCloud(t, clean, kept);
+    CHECK(clean.size() == 11 && clean.is_dense && clean.height == 1 && clean.width == 11 && kept.size() == 11 && kept[5] == 6 && clean[5].x == t[6].x);
+    removeNaNFromPointCloud(clean, clean, kept);                             // dense: identity
+    CHECK(clean.size() == 11 && kept[10] == 10);
+    removeNaNFromPointCloud(t, t, kept);                                     // in place
+    CHECK(t.size() == 11 && t.is_dense);
+    PointCloud<PointXYZ> xyz;
+    copyPointCloud(clean, xyz);
+    CHECK(xyz.size() == 11 && xyz[4].y == clean[4].y && xyz.width == 11);
+    PointCloud<PointNormal> picked;
+    copyPointCloud(clean, Indices{10, 0}, picked);
+    CHECK(picked.size() == 2 && picked[0].curvature == clean[10].curvature && picked.height == 1);
   }
   {  // pcl::search::Search: the index / cloud+index / batch / other-point-type forms through the two pure virtuals
     PointCloud<PointXYZ>::Ptr c(new PointCloud<PointXYZ>);
