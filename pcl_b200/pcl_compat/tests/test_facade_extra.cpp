@@ -7,6 +7,7 @@
 #include <limits>
 #include <vector>
 
+#include <pcl/common/io.h>
 #include <pcl/filters/voxel_grid.h>
 #include <pcl/io/pcd_io.h>
 #include <pcl/kdtree/kdtree_flann.h>
@@ -60,6 +61,35 @@ int main(int argc, char** argv)
     if (bi.size() == 1) EXPECT_TRUE(bi[0] == ri && bd[0] == rd);
     kdtree.setNumberOfThreads(4);
     EXPECT_EQ(kdtree.getNumberOfThreads(), 4u);
+  }
+
+  {  // TEST (PCL, KdTree_differentPointT) and (PCL, KdTree_multipointKnnSearch) — test/search/test_kdtree.cpp:127-204, with
+     // PointNormal as the foreign point type: the batch forms return what the per-point forms return
+    const unsigned int no_of_neighbors = 20;
+    pcl::search::KdTree<PointXYZ> kdtree;
+    kdtree.setInputCloud(cloud_target.makeShared());
+    PointCloud<PointNormal> cloud_other;
+    copyPointCloud(cloud_target, cloud_other);
+    std::vector<std::vector<float>> dists, dists_same;
+    std::vector<Indices> indices, indices_same;
+    kdtree.nearestKSearchT(cloud_other, Indices(), no_of_neighbors, indices, dists);
+    kdtree.nearestKSearch(cloud_target, Indices(), no_of_neighbors, indices_same, dists_same);
+    EXPECT_EQ(indices.size(), cloud_target.size());
+    EXPECT_EQ(indices_same.size(), cloud_target.size());
+    int bad = 0;
+    Indices k_indices, k_indices_t;
+    std::vector<float> k_distances, k_distances_t;
+    for (std::size_t i = 0; i < cloud_other.size() && i < indices.size() && i < indices_same.size(); i += 7) {
+      kdtree.nearestKSearchT(cloud_other[i], no_of_neighbors, k_indices_t, k_distances_t);
+      kdtree.nearestKSearch(cloud_target[i], no_of_neighbors, k_indices, k_distances);
+      if (k_indices.size() != indices[i].size() || k_distances.size() != dists[i].size() || k_indices.size() != no_of_neighbors) { ++bad; continue; }
+      for (std::size_t j = 0; j < no_of_neighbors; ++j) {
+        if (!(k_indices[j] == indices[i][j] || k_distances[j] == dists[i][j])) ++bad;
+        if (k_indices[j] != k_indices_t[j] || k_distances[j] != k_distances_t[j]) ++bad;
+        if (indices_same[i][j] != indices[i][j] || dists_same[i][j] != dists[i][j]) ++bad;
+      }
+    }
+    EXPECT_EQ(bad, 0);
   }
 
   {  // CorrespondenceEstimation::setPointRepresentation[Reciprocal] (correspondence_estimation.h:296-318): under a uniform
