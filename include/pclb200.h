@@ -75,6 +75,13 @@ PCLB200_API int pclb200_launch_count(pclb200_ctx* ctx, uint64_t* out);
 /* raw cudaStream_t of the ctx (so callers can record CUDA events on the launching stream) */
 PCLB200_API int pclb200_stream(pclb200_ctx* ctx, void** out_stream);
 PCLB200_API void pclb200_free(void* host_ptr); /* frees arrays returned by pclb200_radius */
+/* Page-lock a host buffer the caller owns (a std::vector's storage, an mmap'ed PCD body) so that every later call that
+ * takes it as an input or output moves it by DMA at PCIe rate instead of through the driver's pageable staging path —
+ * the "pinned reader" of SURVEY.md §8f #3: read the file into the buffer, register it once, hand it to
+ * pclb200_index_build / pclb200_icp_set_source.  Unregister before the buffer is freed or reallocated.  Registering a
+ * buffer twice, or a device pointer, is PCLB200_ERR_INVALID. */
+PCLB200_API int pclb200_host_register(pclb200_ctx* ctx, void* host_ptr, size_t bytes);
+PCLB200_API int pclb200_host_unregister(pclb200_ctx* ctx, void* host_ptr);
 /* measurement hooks (bench.py's roofline leg): when enabled, the library brackets its named kernels
  * ("icp_iter", "solve", "query_sort", "index_build", "normals", "knn", "voxelgrid", "transform_out") with
  * CUDA events on the ctx stream; profile_get synchronises, returns the summed device time and the number of

@@ -65,7 +65,8 @@ CORR_NEAREST, CORR_NORMAL_SHOOTING, CORR_BACK_PROJECTION = 0, 1, 2
 # every symbol include/pclb200.h declares (tests/test_capi_symbols.py checks the two lists agree)
 SYMBOLS = [
     "pclb200_version", "pclb200_last_error", "pclb200_create", "pclb200_destroy", "pclb200_synchronize",
-    "pclb200_launch_count", "pclb200_stream", "pclb200_free", "pclb200_profile_enable", "pclb200_profile_get",
+    "pclb200_launch_count", "pclb200_stream", "pclb200_free", "pclb200_host_register", "pclb200_host_unregister",
+    "pclb200_profile_enable", "pclb200_profile_get",
     "pclb200_profile_reset", "pclb200_index_build", "pclb200_index_destroy",
     "pclb200_index_size", "pclb200_index_stats", "pclb200_knn", "pclb200_knn_stats", "pclb200_radius", "pclb200_correspondences",
     "pclb200_estimate_svd", "pclb200_estimate_svd_correlation", "pclb200_estimate_point_to_plane_lls", "pclb200_estimate_symmetric_point_to_plane_lls", "pclb200_icp_default_params",
@@ -98,6 +99,8 @@ def lib():
     L.pclb200_stream.argtypes = [vp, C.POINTER(vp)]
     L.pclb200_free.argtypes = [vp]
     L.pclb200_free.restype = None
+    L.pclb200_host_register.argtypes = [vp, vp, C.c_size_t]
+    L.pclb200_host_unregister.argtypes = [vp, vp]
     L.pclb200_profile_enable.argtypes = [vp, C.c_int]
     L.pclb200_profile_get.argtypes = [vp, C.c_char_p, dp, C.POINTER(C.c_uint64)]
     L.pclb200_profile_reset.argtypes = [vp]
@@ -229,6 +232,15 @@ class Context:
 
     def synchronize(self):
         _check(lib().pclb200_synchronize(self.h))
+
+    def host_register(self, array):
+        """Page-lock a host numpy array in place (cudaHostRegister): later calls move it by DMA.  Undo with
+        host_unregister before the array is freed."""
+        b = _Buf(array)
+        _check(lib().pclb200_host_register(self.h, b.ptr, int(np.asarray(array).nbytes)))
+
+    def host_unregister(self, array):
+        _check(lib().pclb200_host_unregister(self.h, _Buf(array).ptr))
 
     @property
     def launches(self):

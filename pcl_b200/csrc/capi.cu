@@ -407,6 +407,39 @@ int pclb200_stream(pclb200_ctx* ctx, void** out_stream)
 
 void pclb200_free(void* p) { free(p); }
 
+int pclb200_host_register(pclb200_ctx* ctx, void* host_ptr, size_t bytes)
+{
+  return guarded([&] {
+    PCLB_REQUIRE(ctx && host_ptr && bytes, PCLB200_ERR_INVALID, "NULL argument or empty buffer");
+    std::lock_guard<std::recursive_mutex> lk(ctx->c.mu);
+    PCLB_CUDA(cudaSetDevice(ctx->c.device));
+    PCLB_REQUIRE(!is_device_ptr(host_ptr), PCLB200_ERR_INVALID, "pclb200_host_register: not a host pointer");
+    const cudaError_t e = cudaHostRegister(host_ptr, bytes, cudaHostRegisterPortable);
+    if (e == cudaErrorHostMemoryAlreadyRegistered) {
+      cudaGetLastError();
+      throw Error(PCLB200_ERR_INVALID, "pclb200_host_register: the buffer (or a part of it) is already registered");
+    }
+    PCLB_CUDA(e);
+  });
+}
+
+int pclb200_host_unregister(pclb200_ctx* ctx, void* host_ptr)
+{
+  return guarded([&] {
+    PCLB_REQUIRE(ctx && host_ptr, PCLB200_ERR_INVALID, "NULL argument");
+    std::lock_guard<std::recursive_mutex> lk(ctx->c.mu);
+    PCLB_CUDA(cudaSetDevice(ctx->c.device));
+    // nothing may still be copying out of it: wait for this context's stream
+    PCLB_CUDA(cudaStreamSynchronize(ctx->c.stream));
+    const cudaError_t e = cudaHostUnregister(host_ptr);
+    if (e == cudaErrorHostMemoryNotRegistered) {
+      cudaGetLastError();
+      throw Error(PCLB200_ERR_INVALID, "pclb200_host_unregister: the buffer is not registered");
+    }
+    PCLB_CUDA(e);
+  });
+}
+
 int pclb200_profile_enable(pclb200_ctx* ctx, int enable)
 {
   return guarded([&] {

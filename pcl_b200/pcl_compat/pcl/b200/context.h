@@ -74,6 +74,28 @@ private:
   pclb200_ctx* h_ = nullptr;
 };
 
+// Page-locks the storage of a cloud for as long as the object lives (the pinned reader — load the file,
+// pin once, and every setInputSource / setInputCloud / align() on that cloud moves it by DMA at PCIe rate instead of
+// through the pageable staging path; at 200 M points that is the difference between ~0.25 s and ~0.06 s per upload).
+// The cloud must not be resized or destroyed while pinned.
+template <typename CloudT>
+class PinnedCloud {
+public:
+  explicit PinnedCloud(CloudT& cloud) : p_(cloud.points.empty() ? nullptr : cloud.points.data())
+  {
+    if (p_) check(pclb200_host_register(Context::get(), p_, cloud.points.size() * sizeof(cloud.points[0])), "pclb200_host_register");
+  }
+  ~PinnedCloud()
+  {
+    if (p_) pclb200_host_unregister(Context::get(), p_);
+  }
+  PinnedCloud(const PinnedCloud&) = delete;
+  PinnedCloud& operator=(const PinnedCloud&) = delete;
+
+private:
+  void* p_;
+};
+
 // shared ownership of a device index (the LBVH) so trees can be handed between objects like PCL's KdTreePtr
 struct IndexHandle {
   pclb200_index* h = nullptr;

@@ -5,6 +5,7 @@
 #include <cmath>
 #include <cstdio>
 #include <limits>
+#include <memory>
 #include <vector>
 
 #include <pcl/common/io.h>
@@ -168,6 +169,25 @@ int main(int argc, char** argv)
     EXPECT_TRUE(st_off != Criteria::CONVERGENCE_CRITERIA_TRANSFORM);
     EXPECT_TRUE(it_off >= it_default);
     EXPECT_NEAR(c_off.getRotationThreshold(), 1.5, 1e-12);
+  }
+
+  {  // b200::PinnedCloud: the source's storage page-locked for the duration of the aligns — same matrix as unpinned
+    auto run = [&](bool pin) {
+      PointCloud<PointXYZ>::Ptr src(new PointCloud<PointXYZ>(cloud_source));
+      std::unique_ptr<b200::PinnedCloud<PointCloud<PointXYZ>>> guard;
+      if (pin) guard.reset(new b200::PinnedCloud<PointCloud<PointXYZ>>(*src));
+      IterativeClosestPoint<PointXYZ, PointXYZ> reg;
+      reg.setInputSource(src);
+      reg.setInputTarget(cloud_target.makeShared());
+      reg.setMaximumIterations(50);
+      reg.setTransformationEpsilon(1e-8);
+      reg.setMaxCorrespondenceDistance(0.05);
+      PointCloud<PointXYZ> out;
+      reg.align(out);
+      return reg.getFinalTransformation();
+    };
+    const Eigen::Matrix4f a = run(false), b = run(true);
+    EXPECT_TRUE(a == b);
   }
 
   {  // VoxelGrid::setSaveLeafLayout and the grid accessors (voxel_grid.h:296-425): every input point's cell maps to the

@@ -46,3 +46,34 @@ def test_icp_command_line_example(golden, tmp_path):
     def mean_nn(a):
         return np.sqrt(((a[:, None, :] - tgt[None, :, :]) ** 2).sum(-1).min(1)).mean()
     assert mean_nn(body[:, :3]) < mean_nn(np.asarray(golden["bun0"], dtype=np.float64)[:, :3])
+
+
+@pytest.mark.gpu
+def test_host_register_pinned_buffers(orc):
+    """pclb200_host_register / _unregister (the pinned-reader half of SURVEY.md §8f #3): a page-locked caller buffer gives the
+    same align as a pageable one; registering twice, unregistering an unknown buffer and registering a device pointer are
+    refused with PCLB200_ERR_INVALID."""
+    import numpy as np
+    import pcl_b200 as P
+    ctx = P.Context(0)
+    rng = np.random.default_rng(5)
+    tgt = P.xyz1(rng.random((200_000, 3), dtype=np.float32))
+    a = np.deg2rad(2.0)
+    R = np.array([[np.cos(a), -np.sin(a), 0], [np.sin(a), np.cos(a), 0], [0, 0, 1]])
+    src = P.xyz1((tgt[:, :3].astype(np.float64) @ R.T + [0.004, -0.003, 0.002]).astype(np.float32))
+    idx = P.Index(ctx, tgt)
+    kw = dict(max_iterations=20, max_correspondence_distance=0.05)
+    plain = P.icp_align(ctx, src.copy(), idx, **kw)
+    ctx.host_register(src)
+    try:
+        pinned = P.icp_align(ctx, src, idx, **kw)
+        with pytest.raises(P.Pclb200Error) as e:
+            ctx.host_register(src)
+        assert e.value.code == P.ERR_INVALID
+    finally:
+        ctx.host_unregister(src)
+    assert np.array_equal(plain["final"], pinned["final"]) and plain["iterations"] == pinned["iterations"]
+    with pytest.raises(P.Pclb200Error) as e:
+        ctx.host_unregister(src)
+    assert e.value.code == P.ERR_INVALID
+    ctx.close()
