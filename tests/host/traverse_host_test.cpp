@@ -1,0 +1,385 @@
+// traverse_host_test.cpp — the DEVICE traversal header (pcl_b200/csrc/traverse.cuh: walk, nearest1, the cell-table
+// look-ups and their conservative bounds) compiled for the host and run against brute force.
+//
+// Test infrastructure, CPU only: g++ sees the same source the kernels are built from; the CUDA intrinsics it uses are
+// supplied below with the same rounding (round-to-nearest without contraction, directed rounding through <cfenv>).  The
+// index (Morton-ordered padded leaves, 64-byte nodes holding both children's boxes, the (level, cell) -> subtree hash
+// table) is built here on the host to the invariants lbvh.cu documents:
+//   * leaves are whole radix-tree cells of <= 8 points; a node's two boxes bound its children's points exactly;
+//   * the table maps every occupied cell of levels 1..bmax to the deepest node / leaf that holds all its points
+//     (prefix_len(parent) < 3b <= prefix_len(child); a leaf that spans several level-b cells is entered for each).
+// What is checked: for every query, with and without a seed, with and without the TRACK visitor and an inflated ball,
+// nearest1 returns exactly the brute-force minimum of (d2, original index) under the library's distance expression and
+// gate; TRACK's lower bound never exceeds the true second-nearest distance.  Scenes: uniform volume, a thin surface,
+// duplicates beyond a leaf, a lattice full of exact ties, a degenerate line, far-away queries, tiny clouds.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cfenv>
+#include <cmath>
+#include <cstdint>
+#include <cstdio>
+#include <cstring>
+#include <random>
+#include <vector>
+
+// ---- the CUDA intrinsics traverse.cuh uses, for the host ---------------------------------------------------------
+template <typename T> static inline T __ldg(const T* p) { return *p; }
+static inline float __fadd_rn(float a, float b) { volatile float x = a, y = b; volatile float r = x + y; return r; }
+static inline float __fsub_rn(float a, float b) { volatile float x = a, y = b; volatile float r = x - y; return r; }
+static inline float __fmul_rn(float a, float b) { volatile float x = a, y = b; volatile float r = x * y; return r; }
+template <typename F> static inline float directed(int mode, F f)
+{
+  std::fesetround(mode);
+  volatile float r = f();
+  std::fesetround(FE_TONEAREST);
+  return r;
+}
+static inline float __fadd_rd(float a, float b) { volatile float x = a, y = b; return directed(FE_DOWNWARD, [&] { return x + y; }); }
+static inline float __fadd_ru(float a, float b) { volatile float x = a, y = b; return directed(FE_UPWARD, [&] { return x + y; }); }
+static inline float __fsub_rd(float a, float b) { volatile float x = a, y = b; return directed(FE_DOWNWARD, [&] { return x - y; }); }
+static inline float __fmul_rd(float a, float b) { volatile float x = a, y = b; return directed(FE_DOWNWARD, [&] { return x * y; }); }
+static inline float __fmul_ru(float a, float b) { volatile float x = a, y = b; return directed(FE_UPWARD, [&] { return x * y; }); }
+static inline float __fsqrt_ru(float a) { volatile float x = a; return directed(FE_UPWARD, [&] { return std::sqrt(x); }); }
+static inline unsigned max(unsigned a, unsigned b) { return a > b ? a : b; }   // CUDA's global integer max
+static inline int __clz(int x) { return x == 0 ? 32 : __builtin_clz(static_cast<unsigned>(x)); }
+static inline float __int_as_float(int i) { float f; std::memcpy(&f, &i, 4); return f; }
+static inline int __float_as_int(float f) { int i; std::memcpy(&i, &f, 4); return i; }
+
+#include "../../pcl_b200/csrc/traverse.cuh"
+
+using namespace pclb200;
+
+// ---- host-side index, to lbvh.cu's invariants --------------------------------------------------------------------
+struct HostIndex {
+  std::vector<float4> pts;       // leaves * kLeafSize, padded with +inf / sentinel
+  std::vector<BvhNode> nodes;
+  std::vector<uint2> slots;
+  int root = kDone;
+  float lo[3], hi[3], scale = 1.f, margin = 0.f;
+  int bmax = 0;
+  unsigned log2_slots = 0;
+  std::vector<float> xyz;        // original points (3 per point), for brute force
+  TreeView view(bool with_table) const
+  {
+    TreeView t;
+    t.nodes = nodes.data();
+    t.pts = pts.data();
+    t.root = root;
+    if (with_table && log2_slots) {
+      t.cells.slots = slots.data();
+      t.cells.shift = 32u - log2_slots;
+      t.cells.mask = (1u << log2_slots) - 1u;
+      t.cells.bmax = bmax;
+      for (int d = 0; d < 3; ++d) t.cells.lo[d] = lo[d];
+      t.cells.scale = scale;
+      t.cells.inv_scale = 1.f / scale;
+      t.cells.margin = margin;
+    }
+    return t;
+  }
+};
+
+static int prefix_len63(unsigned long long a, unsigned long long b)
+{
+  const unsigned long long x = a ^ b;
+  return x == 0 ? 63 : __builtin_clzll(x) - 1;
+}
+static unsigned compact21(unsigned long long v)   // every third bit of v
+{
+  unsigned r = 0;
+  for (int i = 0; i < 21; ++i) r |= static_cast<unsigned>((v >> (3 * i)) & 1ull) << i;
+  return r;
+}
+
+struct Builder {
+  HostIndex& I;
+  std::vector<unsigned long long> keys;   // sorted
+  std::vector<int> order;                 // sorted position -> original index
+  std::vector<int> leaf_of_first;         // leaf id by first sorted position
+  struct Box { float lo[3], hi[3]; };
+  std::vector<std::pair<unsigned, int>> entries;  // (cell key, reference)
+
+  void insert(int b, unsigned long long key, int ref)
+  {
+    const unsigned cx = compact21(key) >> (21 - b), cy = compact21(key >> 1) >> (21 - b), cz = compact21(key >> 2) >> (21 - b);
+    entries.emplace_back(cell_key(b, cx, cy, cz), ref);
+  }
+  Box box_of(int first, int last) const
+  {
+    Box b;
+    for (int d = 0; d < 3; ++d) { b.lo[d] = INFINITY; b.hi[d] = -INFINITY; }
+    for (int j = first; j <= last; ++j)
+      for (int d = 0; d < 3; ++d) {
+        const float v = I.xyz[3 * order[j] + d];
+        b.lo[d] = std::min(b.lo[d], v);
+        b.hi[d] = std::max(b.hi[d], v);
+      }
+    return b;
+  }
+  // returns the reference of the subtree over sorted positions [first, last]; l_parent = prefix length of its parent
+  int build(int first, int last, int l_parent)
+  {
+    const int count = last - first + 1;
+    const int l_self = prefix_len63(keys[first], keys[last]);
+    int ref;
+    if (count <= kLeafSize) {
+      const int leaf = static_cast<int>(I.pts.size() / kLeafSize);
+      for (int j = 0; j < kLeafSize; ++j) {
+        if (j < count) {
+          const int o = order[first + j];
+          I.pts.push_back(make_float4(I.xyz[3 * o], I.xyz[3 * o + 1], I.xyz[3 * o + 2], __int_as_float(o)));
+        }
+        else
+          I.pts.push_back(make_float4(INFINITY, INFINITY, INFINITY, __int_as_float(kSentinelIndex)));
+      }
+      ref = ~leaf;
+      for (int b = l_parent / 3 + 1; b <= I.bmax; ++b) {   // 3b > l_parent
+        if (3 * b <= l_self) insert(b, keys[first], ref);
+        else
+          for (int j = first; j <= last; ++j) insert(b, keys[j], ref);  // a leaf that spans several level-b cells
+      }
+      return ref;
+    }
+    const int id = static_cast<int>(I.nodes.size());
+    I.nodes.emplace_back();
+    int split;   // last position of the left child
+    if (l_self == 63) split = first + count / 2 - 1;   // a run of equal codes: any cut
+    else {
+      const unsigned long long bit = 1ull << (62 - l_self);
+      split = first;
+      while (split + 1 <= last && !(keys[split + 1] & bit)) ++split;
+    }
+    // prefix_len(parent) < 3b <= prefix_len(this): nodes cut INSIDE a run of equal codes have a parent of prefix 63 and
+    // never qualify, the top node of such a run does (lbvh.cu: k_link_cells)
+    for (int b = l_parent / 3 + 1; b <= I.bmax && 3 * b <= l_self; ++b) insert(b, keys[first], id);
+    const int l = build(first, split, l_self);
+    const int r = build(split + 1, last, l_self);
+    const Box a = box_of(first, split), c = box_of(split + 1, last);
+    BvhNode nd;
+    nd.a = make_float4(a.lo[0], a.lo[1], a.lo[2], a.hi[0]);
+    nd.b = make_float4(a.hi[1], a.hi[2], c.lo[0], c.lo[1]);
+    nd.c = make_float4(c.lo[2], c.hi[0], c.hi[1], c.hi[2]);
+    nd.d = make_int4(l, r, 0, 0);
+    I.nodes[id] = nd;
+    return id;
+  }
+};
+
+static void build_index(HostIndex& I, const std::vector<float>& xyz, int bmax)
+{
+  I = HostIndex();
+  I.xyz = xyz;
+  const int n = static_cast<int>(xyz.size() / 3);
+  for (int d = 0; d < 3; ++d) { I.lo[d] = INFINITY; I.hi[d] = -INFINITY; }
+  for (int i = 0; i < n; ++i)
+    for (int d = 0; d < 3; ++d) { I.lo[d] = std::min(I.lo[d], xyz[3 * i + d]); I.hi[d] = std::max(I.hi[d], xyz[3 * i + d]); }
+  float ext = 0.f;
+  for (int d = 0; d < 3; ++d) ext = std::max(ext, I.hi[d] - I.lo[d]);
+  I.scale = ext > 0.f ? 2097152.f / ext : 1.f;
+  if (!std::isfinite(I.scale)) I.scale = 1.f;
+  Builder B{I, {}, {}, {}, {}};
+  std::vector<std::pair<unsigned long long, int>> kv(n);
+  for (int i = 0; i < n; ++i) {
+    const unsigned long long k = (expand21(morton_cell(xyz[3 * i + 2], I.lo[2], I.scale)) << 2) |
+                                 (expand21(morton_cell(xyz[3 * i + 1], I.lo[1], I.scale)) << 1) |
+                                 expand21(morton_cell(xyz[3 * i], I.lo[0], I.scale));
+    kv[i] = {k, i};
+  }
+  std::sort(kv.begin(), kv.end());
+  B.keys.resize(n);
+  B.order.resize(n);
+  for (int i = 0; i < n; ++i) { B.keys[i] = kv[i].first; B.order[i] = kv[i].second; }
+  I.bmax = bmax;
+  float m = 0.f;
+  for (int d = 0; d < 3; ++d) m = std::max(m, std::max(std::fabs(I.lo[d]), std::fabs(I.hi[d])));
+  m = std::max(m, 2097152.f / I.scale);
+  I.margin = 2e-6f * m;
+  I.root = B.build(0, n - 1, -1);
+  if (bmax >= 1 && !B.entries.empty()) {
+    unsigned lg = 6;
+    while ((1ull << lg) < 2 * B.entries.size()) ++lg;
+    I.log2_slots = lg;
+    I.slots.assign(1u << lg, make_uint2(0u, 0u));
+    const unsigned shift = 32u - lg, mask = (1u << lg) - 1u;
+    for (const auto& e : B.entries) {
+      unsigned h = (e.first * 0x9E3779B1u) >> shift;
+      for (;;) {
+        if (I.slots[h].x == e.first) {
+          if (static_cast<int>(I.slots[h].y) != e.second) std::printf("BUILD ERROR: cell %u mapped to two subtrees\n", e.first);
+          break;
+        }
+        if (I.slots[h].x == 0u) { I.slots[h] = make_uint2(e.first, static_cast<unsigned>(e.second)); break; }
+        h = (h + 1u) & mask;
+      }
+    }
+  }
+}
+
+// ---- brute force under the library's own distance expression and tie rule --------------------------------------------
+struct Truth { float d1 = INFINITY, d2nd = INFINITY; int idx = kSentinelIndex; };
+static Truth brute(const std::vector<float>& xyz, const float q[3], float gate)
+{
+  Truth t;
+  const int n = static_cast<int>(xyz.size() / 3);
+  std::vector<float> all(n);
+  for (int i = 0; i < n; ++i) {
+    const float d = dist2_rn(q[0], q[1], q[2], xyz[3 * i], xyz[3 * i + 1], xyz[3 * i + 2]);
+    all[i] = d;
+    if (d <= gate && (d < t.d1 || (d == t.d1 && i < t.idx))) { t.d1 = d; t.idx = i; }
+  }
+  for (int i = 0; i < n; ++i)
+    if (i != t.idx) t.d2nd = std::min(t.d2nd, all[i]);
+  return t;
+}
+
+static long g_checks = 0, g_fail = 0;
+#define CHECK(c, ...) do { ++g_checks; if (!(c)) { if (++g_fail <= 20) { std::printf("FAIL %s:%d %s  ", __FILE__, __LINE__, #c); std::printf(__VA_ARGS__); std::printf("\n"); } } } while (0)
+
+static void run_scene(const char* name, const std::vector<float>& xyz, const std::vector<float>& queries, float gate, int bmax)
+{
+  const bool quiet = std::strncmp(name, "small cloud", 11) == 0;
+  HostIndex I;
+  build_index(I, xyz, bmax);
+  const int nq = static_cast<int>(queries.size() / 3);
+  const int n = static_cast<int>(xyz.size() / 3);
+  std::vector<int> pos_of(n, -1);
+  for (std::size_t p = 0; p < I.pts.size(); ++p) {
+    const int o = __float_as_int(I.pts[p].w);
+    if (o != kSentinelIndex) pos_of[o] = static_cast<int>(p);
+  }
+  std::mt19937 rng(99);
+  const float inf = INFINITY;
+  for (int with_table = 0; with_table < 2; ++with_table) {
+    const TreeView T = I.view(with_table != 0);
+    for (int i = 0; i < nq; ++i) {
+      const float* q = &queries[3 * i];
+      const Truth t = brute(xyz, q, gate);
+      for (int variant = 0; variant < 4; ++variant) {
+        // 0: no seed   1: seed = the true answer   2: seed = a random point (a "previous match" after a large motion)
+        // 3: TRACK visitor, inflated ball, random seed
+        int seed = -1;
+        if (variant == 1 && t.idx != kSentinelIndex) seed = pos_of[t.idx];
+        if (variant >= 2) seed = pos_of[static_cast<int>(rng() % n)];
+        WalkStats ws;
+        bool ok;
+        float best;
+        int best_idx, best_pos;
+        float lb2 = 0.f;
+        if (variant < 3) {
+          Nearest1T<false> v{q[0], q[1], q[2], gate, kSentinelIndex, -1, inf, inf, inf};
+          ok = nearest1<false>(T, q[0], q[1], q[2], v, seed, 1.00001f, ws);
+          best = v.best; best_idx = v.best_idx; best_pos = v.best_pos;
+        }
+        else {
+          Nearest1T<true> v{q[0], q[1], q[2], gate, kSentinelIndex, -1, inf, inf, inf};
+          ok = nearest1<true>(T, q[0], q[1], q[2], v, seed, 2.5f, ws);
+          best = v.best; best_idx = v.best_idx; best_pos = v.best_pos;
+          lb2 = v.lower_bound2();
+        }
+        CHECK(ok, "%s q%d v%d stack overflow", name, i, variant);
+        if (t.idx == kSentinelIndex) {
+          CHECK(best_pos < 0, "%s q%d v%d table%d: found %d beyond the gate", name, i, variant, with_table, best_idx);
+          continue;
+        }
+        CHECK(best_idx == t.idx && best == t.d1, "%s q%d v%d table%d: got (%g, %d) want (%g, %d)", name, i, variant, with_table,
+              (double)best, best_idx, (double)t.d1, t.idx);
+        CHECK(best_pos >= 0 && __float_as_int(I.pts[best_pos].w) == best_idx, "%s q%d v%d position", name, i, variant);
+        if (variant == 3)   // the bound the next iteration's skip test relies on: nothing but the match is closer than it
+          CHECK(lb2 <= t.d2nd, "%s q%d table%d: lower bound %g above the true second distance %g", name, i, with_table, (double)lb2, (double)t.d2nd);
+      }
+    }
+  }
+  if (!quiet)
+    std::printf("%-28s %6d points %6d queries  nodes %6zu leaves %6zu  bmax %d  table entries/slots %zu  ok so far: %ld checks, %ld failures\n",
+                name, n, nq, I.nodes.size(), I.pts.size() / kLeafSize, I.bmax, I.slots.size(), g_checks, g_fail);
+}
+
+int main(int argc, char** argv)
+{
+  const int scale = argc > 1 ? std::atoi(argv[1]) : 1;   // 1: seconds; larger: more points and queries
+  std::mt19937 rng(20250923);
+  std::uniform_real_distribution<float> U(0.f, 1.f);
+  std::normal_distribution<float> N(0.f, 1.f);
+  auto cloud = [&](int n, auto gen) { std::vector<float> v; v.reserve(3 * n); for (int i = 0; i < n; ++i) { float p[3]; gen(i, p); v.insert(v.end(), p, p + 3); } return v; };
+  auto near_queries = [&](const std::vector<float>& pts, int nq, float jitter, float far_frac) {
+    std::vector<float> q;
+    const int n = static_cast<int>(pts.size() / 3);
+    for (int i = 0; i < nq; ++i) {
+      if (U(rng) < far_frac) { for (int d = 0; d < 3; ++d) q.push_back(4.f * U(rng) - 1.5f); continue; }
+      const int j = static_cast<int>(rng() % n);
+      for (int d = 0; d < 3; ++d) q.push_back(pts[3 * j + d] + jitter * N(rng));
+    }
+    return q;
+  };
+  const float no_gate = INFINITY;
+  {
+    const auto pts = cloud(6000 * scale, [&](int, float* p) { p[0] = U(rng); p[1] = U(rng); p[2] = U(rng); });
+    run_scene("uniform volume", pts, near_queries(pts, 1500 * scale, 0.01f, 0.1f), no_gate, 4);
+    run_scene("uniform volume, gate", pts, near_queries(pts, 800 * scale, 0.02f, 0.2f), 0.02f * 0.02f, 4);
+    run_scene("uniform volume, bmax 1", pts, near_queries(pts, 400 * scale, 0.05f, 0.1f), no_gate, 1);
+  }
+  {
+    const auto pts = cloud(8000 * scale, [&](int, float* p) { p[0] = 10.f * U(rng); p[1] = 10.f * U(rng); p[2] = 0.5f * std::sin(p[0]) * std::cos(0.7f * p[1]) + 0.002f * N(rng); });
+    run_scene("surface", pts, near_queries(pts, 1500 * scale, 0.01f, 0.05f), no_gate, 6);
+    run_scene("surface, offset frame", cloud(4000 * scale, [&](int, float* p) { p[0] = 1000.f + 3.f * U(rng); p[1] = -500.f + 3.f * U(rng); p[2] = 20.f + 0.01f * N(rng); }),
+              cloud(600 * scale, [&](int, float* p) { p[0] = 1000.f + 3.f * U(rng); p[1] = -500.f + 3.f * U(rng); p[2] = 20.f + 0.05f * N(rng); }), no_gate, 5);
+  }
+  {
+    std::vector<float> base = cloud(400, [&](int, float* p) { p[0] = U(rng); p[1] = U(rng); p[2] = U(rng); });
+    std::vector<float> pts;
+    for (int rep = 0; rep < 12; ++rep) pts.insert(pts.end(), base.begin(), base.end());   // every point 12 times: runs of equal codes beyond a leaf
+    run_scene("duplicates x12", pts, near_queries(base, 500 * scale, 1e-4f, 0.1f), no_gate, 3);
+    std::vector<float> qd(base.begin(), base.begin() + 3 * 200);
+    run_scene("duplicates x12, exact hits", pts, qd, no_gate, 3);
+  }
+  {
+    std::vector<float> pts;
+    for (int x = 0; x < 13; ++x) for (int y = 0; y < 13; ++y) for (int z = 0; z < 13; ++z) { pts.push_back((float)x); pts.push_back((float)y); pts.push_back((float)z); }
+    std::vector<float> q;
+    for (int i = 0; i < 600 * scale; ++i) { q.push_back((rng() % 25) * 0.5f); q.push_back((rng() % 25) * 0.5f); q.push_back((rng() % 25) * 0.5f); }   // cell centres and faces: 2-, 4-, 8-way ties
+    run_scene("lattice, exact ties", pts, q, no_gate, 3);
+  }
+  {
+    const auto pts = cloud(1777, [&](int i, float* p) { p[0] = p[1] = p[2] = i / 1776.f; });
+    run_scene("collinear", pts, near_queries(pts, 500 * scale, 0.01f, 0.2f), no_gate, 5);
+    const auto flat = cloud(3000, [&](int, float* p) { p[0] = U(rng); p[1] = 0.25f; p[2] = U(rng); });   // zero extent along y
+    run_scene("planar, zero extent axis", flat, near_queries(flat, 500 * scale, 0.01f, 0.2f), no_gate, 5);
+  }
+  {
+    const auto tiny = cloud(5, [&](int, float* p) { p[0] = U(rng); p[1] = U(rng); p[2] = U(rng); });
+    run_scene("five points", tiny, near_queries(tiny, 100, 0.3f, 0.3f), no_gate, 1);
+    const auto one = cloud(1, [&](int, float* p) { p[0] = 0.3f; p[1] = 0.2f; p[2] = 0.1f; });
+    run_scene("single point", one, near_queries(one, 50, 0.3f, 0.3f), no_gate, 0);
+    const auto nine = cloud(9, [&](int, float* p) { p[0] = U(rng); p[1] = U(rng); p[2] = U(rng); });
+    run_scene("nine points", nine, near_queries(nine, 100, 0.3f, 0.3f), no_gate, 1);
+  }
+  {  // points and queries ON cell boundaries of a [0, 1]^3 frame (multiples of 1/64, one ulp either side): the places where
+     // the fp32 cell bound of cell_gap2 has to be conservative
+    std::vector<float> pts = {0.f, 0.f, 0.f, 1.f, 1.f, 1.f};
+    auto snap = [&](float v) {
+      const float g = std::round(v * 64.f) / 64.f;
+      const int k = static_cast<int>(rng() % 3);
+      return k == 0 ? g : k == 1 ? std::nextafter(g, 2.f) : std::max(0.f, std::nextafter(g, -1.f));
+    };
+    for (int i = 0; i < 3000 * scale; ++i) { pts.push_back(std::min(1.f, snap(U(rng)))); pts.push_back(std::min(1.f, snap(U(rng)))); pts.push_back(std::min(1.f, snap(U(rng)))); }
+    std::vector<float> q;
+    for (int i = 0; i < 1200 * scale; ++i) { q.push_back(snap(U(rng))); q.push_back(snap(U(rng))); q.push_back(snap(U(rng))); }
+    run_scene("on cell boundaries", pts, q, no_gate, 6);
+  }
+  for (int rep = 0; rep < 150 * scale; ++rep) {   // many small random clouds: every tree shape around the leaf size, every bmax
+    const int n = 1 + static_cast<int>(rng() % 120);
+    const int shape = static_cast<int>(rng() % 3);
+    const auto pts = cloud(n, [&](int, float* p) {
+      p[0] = U(rng); p[1] = shape == 1 ? 0.5f : U(rng); p[2] = shape == 2 ? std::floor(4.f * U(rng)) / 4.f : U(rng);
+    });
+    char name[64];
+    std::snprintf(name, sizeof name, "small cloud #%d", rep);
+    const long before = g_fail;
+    const int bmax = n >= 4 ? 1 + static_cast<int>(rng() % 4) : 0;
+    run_scene(name, pts, near_queries(pts, 40, 0.2f, 0.3f), rep % 3 == 0 ? 0.05f : no_gate, bmax);
+    if (g_fail != before) std::printf("  ^ failure in %s (n = %d, shape %d, bmax %d)\n", name, n, shape, bmax);
+  }
+  std::printf("%ld checks, %ld failures\n%s\n", g_checks, g_fail, g_fail ? "FAILED" : "PASSED");
+  return g_fail ? 1 : 0;
+}

@@ -1,0 +1,24 @@
+"""The device traversal header (pcl_b200/csrc/traverse.cuh: walk, nearest1, the cell-table look-ups and their conservative
+bounds) compiled for the HOST and run against brute force — tests/host/traverse_host_test.cpp.  CPU only: the CUDA
+intrinsics are supplied with the same rounding, the index is built on the host to lbvh.cu's invariants.  ~2e5 checks on
+nine scenes (ties, duplicates beyond a leaf, degenerate frames, gates, far queries), every query with and without the
+cell table, with no / the true / a random seed, and with the TRACK visitor whose lower bound the skip test relies on."""
+import os
+import shutil
+import subprocess
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+CUDA_INC = "/usr/local/cuda/include"
+
+
+@pytest.mark.skipif(not os.path.exists(os.path.join(CUDA_INC, "cuda_runtime.h")) or shutil.which("g++") is None,
+                    reason="needs g++ and the CUDA headers (vector types only; nothing is run on a device)")
+def test_device_traversal_header_on_the_host(tmp_path):
+    exe = str(tmp_path / "traverse_host_test")
+    subprocess.check_call(["g++", "-O1", "-std=c++17", "-frounding-math", "-ffp-contract=off", "-fno-fast-math",
+                           "-I" + CUDA_INC, "-I" + os.path.join(ROOT, "include"),
+                           os.path.join(ROOT, "tests", "host", "traverse_host_test.cpp"), "-o", exe])
+    r = subprocess.run([exe, "2"], capture_output=True, text=True)
+    assert r.returncode == 0 and "PASSED" in r.stdout, r.stdout[-3000:]
