@@ -433,4 +433,26 @@ __device__ __forceinline__ bool nearest1(const TreeView& T, float qx, float qy, 
   return walk(T.nodes, T.pts, stack_node, stack_dist, sp, kDone, qx, qy, qz, v, skip_a, skip_b, ws);
 }
 
+// ---- temporal coherence between ICP iterations (used by icp.cu: k_search<.., TRACK>) ------------------------------------
+constexpr float kRelMargin = 1e-5f;  // >> fp32 rounding of the distances involved (~2e-7): keeps the skip test exact
+// TRACK walks look at a ball kTrackInflate times wider than the candidate distance: every point they do not see is
+// then at least that much farther than the match, which is the head-room the next iteration's skip test lives on
+constexpr float kTrackInflate = 2.5f;
+
+// Temporal-coherence test.  Let m be the previous match at distance D1 from the old query position, L a lower
+// bound on the distance from the old position to every other point, and delta the distance the query moved.
+// Triangle inequality: the new distance to m is <= D1 + delta, the new distance to any other x is >= L - delta.
+// If D1 + delta < L - delta (with a relative safety margin far above fp32 round-off) m is still the UNIQUE nearest
+// neighbour, so the exact search result is (m, dist2(p_new, m)) and the tree walk can be skipped.
+__device__ __forceinline__ bool still_nearest(float prev_d2, float prev_lb, float delta, float* new_lb)
+{
+  if (!(prev_lb > 0.f))
+    return false;
+  const float D1 = sqrtf(prev_d2);
+  const float lhs = (D1 + 2.f * delta) * (1.f + kRelMargin);
+  const float rhs = prev_lb * (1.f - kRelMargin);
+  *new_lb = (prev_lb - delta * (1.f + kRelMargin)) * (1.f - kRelMargin);
+  return lhs < rhs && *new_lb > 0.f;
+}
+
 }  // namespace pclb200

@@ -295,6 +295,66 @@ static void run_scene(const char* name, const std::vector<float>& xyz, const std
                 name, n, nq, I.nodes.size(), I.pts.size() / kLeafSize, I.bmax, I.slots.size(), g_checks, g_fail);
 }
 
+// The temporal-coherence skip of icp.cu: k_search<.., TRACK>, replayed: a query drifts for a number of iterations; every
+// iteration either proves by still_nearest that the previous match is still the nearest neighbour (the walk is skipped,
+// the bound decays) or searches with the TRACK visitor and stores sqrt(lower_bound2).  Whatever the path, the result must
+// be the brute-force nearest neighbour — in particular a skip may never keep a match that stopped being the nearest.
+static void run_coherence(const char* name, const std::vector<float>& xyz, int n_queries, float step, float gate, int bmax, std::mt19937& rng)
+{
+  HostIndex I;
+  build_index(I, xyz, bmax);
+  const TreeView T = I.view(true);
+  const int n = static_cast<int>(xyz.size() / 3);
+  std::normal_distribution<float> N(0.f, 1.f);
+  const float inf = INFINITY;
+  long skips = 0, searches = 0;
+  for (int qi = 0; qi < n_queries; ++qi) {
+    const int j = static_cast<int>(rng() % n);
+    float p[3] = {xyz[3 * j] + 0.02f * N(rng), xyz[3 * j + 1] + 0.02f * N(rng), xyz[3 * j + 2] + 0.02f * N(rng)};
+    int seed = -1;          // Match::pos of the previous iteration (-1: none)
+    float prev_d2 = 0.f, lb = 0.f;
+    float s = step;
+    for (int it = 0; it < 14; ++it) {
+      const float old[3] = {p[0], p[1], p[2]};
+      for (int d = 0; d < 3; ++d) p[d] += s * N(rng);   // the increment of this iteration, shrinking like a converging ICP
+      s *= 0.6f;
+      const float delta = std::sqrt(dist2_rn(p[0], p[1], p[2], old[0], old[1], old[2]));
+      int pos = -1;
+      float d2 = 0.f, nlb = 0.f, lb_out = 0.f;
+      if (seed >= 0 && still_nearest(prev_d2, lb, delta, &nlb)) {
+        const float4 m = I.pts[seed];
+        d2 = dist2_rn(p[0], p[1], p[2], m.x, m.y, m.z);
+        pos = seed;   // (beyond the gate the kernel keeps the seed but marks the pair as not accepted)
+        lb_out = nlb;
+        ++skips;
+      }
+      else {
+        Nearest1T<true> v{p[0], p[1], p[2], gate, kSentinelIndex, -1, inf, inf, inf};
+        WalkStats ws;
+        CHECK(nearest1<true>(T, p[0], p[1], p[2], v, seed, kTrackInflate, ws), "%s stack", name);
+        if (v.best_pos >= 0) { pos = v.best_pos; d2 = v.best; lb_out = std::sqrt(v.lower_bound2()); }
+        ++searches;
+      }
+      const Truth t = brute(xyz, p, inf);
+      if (pos >= 0) {
+        const bool accepted = d2 <= gate;
+        if (accepted || seed >= 0)
+          CHECK(__float_as_int(I.pts[pos].w) == t.idx && d2 == t.d1, "%s q%d it%d: kept (%g, %d), nearest is (%g, %d)%s", name, qi, it, (double)d2,
+                __float_as_int(I.pts[pos].w), (double)t.d1, t.idx, seed >= 0 && lb_out == nlb ? " [skipped walk]" : "");
+        CHECK(lb_out * lb_out * 0.9999f <= t.d2nd || lb_out == 0.f, "%s q%d it%d: bound %g above the second distance %g", name, qi, it,
+              (double)lb_out, (double)std::sqrt(t.d2nd));
+      }
+      else
+        CHECK(!(t.d1 <= gate), "%s q%d it%d: nothing found but %d is inside the gate", name, qi, it, t.idx);
+      seed = pos;
+      prev_d2 = d2;
+      lb = lb_out;
+    }
+  }
+  std::printf("%-28s %6d points %6d drifting queries x 14 iterations: %ld walks skipped, %ld searched; ok so far: %ld checks, %ld failures\n", name, n,
+              n_queries, skips, searches, g_checks, g_fail);
+}
+
 int main(int argc, char** argv)
 {
   const int scale = argc > 1 ? std::atoi(argv[1]) : 1;   // 1: seconds; larger: more points and queries
@@ -353,6 +413,16 @@ int main(int argc, char** argv)
     run_scene("single point", one, near_queries(one, 50, 0.3f, 0.3f), no_gate, 0);
     const auto nine = cloud(9, [&](int, float* p) { p[0] = U(rng); p[1] = U(rng); p[2] = U(rng); });
     run_scene("nine points", nine, near_queries(nine, 100, 0.3f, 0.3f), no_gate, 1);
+  }
+  {  // temporal coherence: skipped walks must never change a result
+    const auto vol = cloud(5000 * scale, [&](int, float* p) { p[0] = U(rng); p[1] = U(rng); p[2] = U(rng); });
+    run_coherence("coherence, volume", vol, 400 * scale, 0.01f, no_gate, 4, rng);
+    run_coherence("coherence, volume, gate", vol, 300 * scale, 0.02f, 0.03f * 0.03f, 4, rng);
+    const auto surf = cloud(6000 * scale, [&](int, float* p) { p[0] = 4.f * U(rng); p[1] = 4.f * U(rng); p[2] = 0.3f * std::sin(2.f * p[0]) + 0.001f * N(rng); });
+    run_coherence("coherence, surface", surf, 400 * scale, 0.005f, no_gate, 6, rng);
+    std::vector<float> lat;
+    for (int x = 0; x < 12; ++x) for (int y = 0; y < 12; ++y) for (int z = 0; z < 12; ++z) { lat.push_back(0.1f * x); lat.push_back(0.1f * y); lat.push_back(0.1f * z); }
+    run_coherence("coherence, lattice (ties)", lat, 300 * scale, 0.02f, no_gate, 3, rng);
   }
   {  // points and queries ON cell boundaries of a [0, 1]^3 frame (multiples of 1/64, one ulp either side): the places where
      // the fp32 cell bound of cell_gap2 has to be conservative

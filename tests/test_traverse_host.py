@@ -1,8 +1,10 @@
 """The device traversal header (pcl_b200/csrc/traverse.cuh: walk, nearest1, the cell-table look-ups and their conservative
 bounds) compiled for the HOST and run against brute force — tests/host/traverse_host_test.cpp.  CPU only: the CUDA
 intrinsics are supplied with the same rounding, the index is built on the host to lbvh.cu's invariants.  ~2e5 checks on
-nine scenes (ties, duplicates beyond a leaf, degenerate frames, gates, far queries), every query with and without the
-cell table, with no / the true / a random seed, and with the TRACK visitor whose lower bound the skip test relies on."""
+eleven scene families (ties, duplicates beyond a leaf, points on cell boundaries, degenerate frames, gates, far queries, 300 random
+small clouds), every query with and without the
+cell table, with no / the true / a random seed, and with the TRACK visitor; plus the temporal-coherence chain of k_search
+(still_nearest + the TRACK bound over drifting queries): a skipped walk never keeps a match that stopped being the nearest."""
 import os
 import shutil
 import subprocess
