@@ -24,3 +24,21 @@ def test_device_traversal_header_on_the_host(tmp_path):
                            os.path.join(ROOT, "tests", "host", "traverse_host_test.cpp"), "-o", exe])
     r = subprocess.run([exe, "2"], capture_output=True, text=True)
     assert r.returncode == 0 and "PASSED" in r.stdout, r.stdout[-3000:]
+
+
+@pytest.mark.skipif(not os.path.exists(os.path.join(CUDA_INC, "cuda_runtime.h")) or shutil.which("g++") is None,
+                    reason="needs g++ and the CUDA headers (vector types only; nothing is run on a device)")
+def test_warp_knn_kernel_on_an_emulated_warp(tmp_path):
+    """pcl_b200/csrc/knn_warp.cuh (k_knn_warp<false|true>, the shuffled bitonic sort / merge, the ranked insertion, the
+    certification rule, the normals epilogue) compiled for the host and run on a lock-step emulation of one warp
+    (tests/host/warp_emu.h): every certified row equals brute force bit for bit, every normal equals the host
+    computePointNormal on the brute-force list, and the constructed shared-leaf scene — the bug the 10 M-row comparison
+    found on the device — passes (it fails on the kernel as it was before the fix)."""
+    exe = str(tmp_path / "knn_warp_host_test")
+    subprocess.check_call(["g++", "-O1", "-std=c++17", "-frounding-math", "-ffp-contract=off", "-fno-fast-math",
+                           "-I" + CUDA_INC, "-I" + os.path.join(ROOT, "include"), "-I" + os.path.join(ROOT, "tests", "host"),
+                           "-I" + os.path.join(ROOT, "pcl_b200", "pcl_compat"),
+                           os.path.join(ROOT, "tests", "host", "knn_warp_host_test.cpp"), "-o", exe])
+    r = subprocess.run([exe, "1"], capture_output=True, text=True)
+    assert r.returncode == 0 and "PASSED" in r.stdout, r.stdout[-3000:]
+    assert "shared leaf, constructed #5" in r.stdout
