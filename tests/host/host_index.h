@@ -33,6 +33,11 @@ static inline float __fmul_rd(float a, float b) { volatile float x = a, y = b; r
 static inline float __fmul_ru(float a, float b) { volatile float x = a, y = b; return directed(FE_UPWARD, [&] { return x * y; }); }
 static inline float __fsqrt_ru(float a) { volatile float x = a; return directed(FE_UPWARD, [&] { return std::sqrt(x); }); }
 static inline unsigned max(unsigned a, unsigned b) { return a > b ? a : b; }   // CUDA's global integer max
+static inline double __dadd_rn(double a, double b) { volatile double x = a, y = b; volatile double r = x + y; return r; }
+static inline double __dsub_rn(double a, double b) { volatile double x = a, y = b; volatile double r = x - y; return r; }
+static inline double __dmul_rn(double a, double b) { volatile double x = a, y = b; volatile double r = x * y; return r; }
+static inline double __longlong_as_double(long long v) { double d; std::memcpy(&d, &v, 8); return d; }
+static inline long long __double_as_longlong(double d) { long long v; std::memcpy(&v, &d, 8); return v; }
 static inline int __clz(int x) { return x == 0 ? 32 : __builtin_clz(static_cast<unsigned>(x)); }
 static inline float __int_as_float(int i) { float f; std::memcpy(&f, &i, 4); return f; }
 static inline int __float_as_int(float f) { int i; std::memcpy(&i, &f, 4); return i; }

@@ -1,0 +1,253 @@
+// icp_host_test.cpp — whole ICP iterations of the DEVICE code (pcl_b200/csrc/icp_kernels.cuh: k_search, k_accum_dmma on the
+// emulated fp64 tensor-core fragments, k_solve with the convergence criteria in its tail) compiled for the HOST, run on a
+// lock-step emulation of a 256-thread block (tests/host/warp_emu.h) and driven exactly like icp.cu's enqueue-ahead path
+// drives them — against the CPU oracle's IterativeClosestPoint (oracle/libpcl_oracle.so, linked: test infrastructure).
+// CPU only.  Checked: every iteration-0 correspondence against brute force, the accumulated normal equations against
+// plain fp64 sums, and iterations / convergence state / final transform of the whole align against the oracle for
+// Scalar = float and double, point-to-point (SVD, both formulas) and point-to-plane (LLS), gates, temporal tracking on.
+#define PCLB_HOST_EXTRA_SHIMS "warp_emu.h"
+#define PCLB_HOST_EMULATION 1
+#include "host_index.h"
+
+#include <cfloat>
+
+#include "../../pcl_b200/csrc/icp_kernels.cuh"
+
+// ---- the oracle's C entry points (oracle/pcl_oracle.cpp) ---------------------------------------------------------------
+struct orc_icp_params {
+  int32_t max_iterations, use_reciprocal, estimator, scalar_is_double, with_normals_transform, source_has_normals, is_dense, nthreads;
+  double max_correspondence_distance, transformation_epsilon, transformation_rotation_epsilon, euclidean_fitness_epsilon;
+  int32_t correspondence_kind, correspondence_k;
+};
+struct orc_icp_result {
+  double final_transformation[16], last_transformation[16];
+  int32_t converged, state, iterations, n_correspondences;
+  double mse;
+  long long total_correspondences;
+};
+extern "C" int orc_icp_align(const orc_icp_params* P, const float* src, size_t n_src, size_t stride_src, const int32_t* indices, size_t n_idx,
+                             const float* tgt, size_t n_tgt, size_t stride_tgt, const double* guess, orc_icp_result* R, float* out);
+
+static long g_checks = 0, g_fail = 0;
+#define CHECK(c, ...) do { ++g_checks; if (!(c)) { if (++g_fail <= 20) { std::printf("FAIL %s:%d %s  ", __FILE__, __LINE__, #c); std::printf(__VA_ARGS__); std::printf("\n"); } } } while (0)
+
+static float gate_from_max_dist(double max_dist)   // icp.cu: the largest float not above max_dist^2
+{
+  const double m2 = max_dist * max_dist;
+  if (!(m2 < (double)FLT_MAX)) return FLT_MAX;
+  float g = (float)m2;
+  if ((double)g > m2) g = std::nextafter(g, -INFINITY);
+  return g;
+}
+
+struct Scene {
+  std::vector<float> tgt;       // n x 8: xyz1 | normal 0
+  std::vector<float> src;       // n x 4
+};
+
+static void run_align(const char* name, const Scene& S, int estimator, bool scalar_double, double max_dist, double trans_eps, int max_iterations,
+                      int track_mode, bool svd_correlation)
+{
+  const std::size_t nt = S.tgt.size() / 8, ns = S.src.size() / 4;
+  std::vector<float> txyz(3 * nt);
+  for (std::size_t i = 0; i < nt; ++i) for (int d = 0; d < 3; ++d) txyz[3 * i + d] = S.tgt[8 * i + d];
+  HostIndex I;
+  build_index(I, txyz, 4);
+  const TreeView T = I.view(true);
+  std::vector<float4> tgt_normals(I.pts.size(), make_float4(0, 0, 0, 0));
+  for (std::size_t p = 0; p < I.pts.size(); ++p) {
+    const int o = __float_as_int(I.pts[p].w);
+    if (o != kSentinelIndex) tgt_normals[p] = make_float4(S.tgt[8 * o + 4], S.tgt[8 * o + 5], S.tgt[8 * o + 6], 0.f);
+  }
+  std::vector<float4> cur(ns);
+  for (std::size_t i = 0; i < ns; ++i) cur[i] = make_float4(S.src[4 * i], S.src[4 * i + 1], S.src[4 * i + 2], __int_as_float((int)i));
+  std::vector<Match> match(ns);
+  for (auto& m : match) { m.pos = -1; m.d2 = 0.f; }
+  std::vector<float> lbs(ns, 0.f);
+  Pending pending;
+  std::memset(&pending, 0, sizeof pending);
+  std::vector<double> partials2(128, 0.0), accum(kAccum, 0.0);
+  unsigned counter = 0;
+  int d_error = 0;
+  unsigned long long skip_count = 0;
+  LoopCtrl ctrl;
+  std::memset(&ctrl, 0, sizeof ctrl);
+  ctrl.prev_mse = std::numeric_limits<double>::max();
+  for (int i = 0; i < 16; ++i) ctrl.final_T[i] = ctrl.last_T[i] = (i % 5 == 0) ? 1.0 : 0.0;
+  ctrl.track_next = track_mode == PCLB200_TRACK_ON ? 1 : 0;
+  SolveOut solve_out;
+  std::memset(&solve_out, 0, sizeof solve_out);
+  CritParams crit;
+  crit.max_iterations = max_iterations;
+  crit.failure_after_max_iter = 0;
+  crit.max_iterations_similar = 0;
+  crit.scalar_is_double = scalar_double ? 1 : 0;
+  crit.track_mode = track_mode;
+  crit.rot_eps = 0.0;
+  crit.trans_eps = trans_eps;
+  crit.rel_mse = -std::numeric_limits<double>::max();
+  crit.abs_mse = 1e-12;
+  {
+    double rmax = 0.0;
+    for (int r = 0; r < 3; ++r) { const double m = std::max(std::fabs((double)I.lo[r]), std::fabs((double)I.hi[r])); rmax += m * m; }
+    crit.rmax = std::sqrt(rmax);
+  }
+  IterArgs a;
+  std::memset(&a, 0, sizeof a);
+  a.nodes = T.nodes; a.pts = T.pts; a.root = T.root;
+  a.tgt_normals = tgt_normals.data();
+  a.cur = cur.data();
+  a.n = ns;
+  a.pending = &pending;
+  a.gate = gate_from_max_dist(max_dist);
+  a.ox = 0.5f * (I.lo[0] + I.hi[0]); a.oy = 0.5f * (I.lo[1] + I.hi[1]); a.oz = 0.5f * (I.lo[2] + I.hi[2]);
+  a.partials2 = partials2.data();
+  a.counter = &counter;
+  a.accum = accum.data();
+  a.d_error = &d_error;
+  a.skip_count = &skip_count;
+  a.cells = T.cells;
+  a.ctrl = &ctrl;
+  a.peer.nranks = 0;
+  blockDim.x = 256;
+  long skipped_total = 0;
+  for (int it = 0; it < max_iterations; ++it) {
+    if (track_mode == PCLB200_TRACK_AUTO) {
+      a.track_sel = 1;
+      warp_emu::run_block(256, [&] { k_search<false, false>(a, match.data(), lbs.data()); });
+      warp_emu::run_block(256, [&] { k_search<false, true>(a, match.data(), lbs.data()); });
+    }
+    else if (track_mode == PCLB200_TRACK_ON)
+      warp_emu::run_block(256, [&] { k_search<false, true>(a, match.data(), lbs.data()); });
+    else
+      warp_emu::run_block(256, [&] { k_search<false, false>(a, match.data(), lbs.data()); });
+    if (!ctrl.done) {
+      // every match of this iteration against brute force on the (re-transformed) source the kernel left in `cur`
+      int bad = 0;
+      for (std::size_t i = 0; i < ns; ++i) {
+        const float q[3] = {cur[i].x, cur[i].y, cur[i].z};
+        const Truth t = brute(txyz, q, a.gate);
+        const Match m = match[i];
+        if (t.idx == kSentinelIndex) { if (match_accepted(m)) ++bad; continue; }
+        if (!match_accepted(m) || __float_as_int(I.pts[match_pos(m)].w) != t.idx || m.d2 != t.d1) ++bad;
+      }
+      CHECK(bad == 0, "%s iteration %d: %d correspondences differ from brute force", name, it, bad);
+      // the normal equations of the SAME pairs by plain fp64 sums (kAccum layout of icp_kernels.cuh)
+      if (estimator == PCLB200_EST_SVD)
+        warp_emu::run_block(256, [&] { k_accum_dmma<PCLB200_EST_SVD>(a, match.data()); });
+      else
+        warp_emu::run_block(256, [&] { k_accum_dmma<PCLB200_EST_POINT_TO_PLANE_LLS>(a, match.data()); });
+      double ref[kAccum] = {0};
+      for (std::size_t i = 0; i < ns; ++i) {
+        const Match m = match[i];
+        if (!match_accepted(m)) continue;
+        const float4 q = I.pts[match_pos(m)], p = cur[i];
+        ref[0] += 1.0;
+        ref[1] += (double)m.d2;
+        if (estimator == PCLB200_EST_SVD) {
+          const double P3[3] = {(double)p.x - a.ox, (double)p.y - a.oy, (double)p.z - a.oz}, Q3[3] = {(double)q.x - a.ox, (double)q.y - a.oy, (double)q.z - a.oz};
+          for (int d = 0; d < 3; ++d) { ref[2 + d] += P3[d]; ref[5 + d] += Q3[d]; }
+          for (int r = 0; r < 3; ++r) for (int c = 0; c < 3; ++c) ref[8 + 3 * r + c] += Q3[r] * P3[c];
+        }
+        else {
+          const float4 nn = tgt_normals[match_pos(m)];
+          const float sx = p.x, sy = p.y, sz = p.z, dx = q.x, dy = q.y, dz = q.z, nx = nn.x, ny = nn.y, nz = nn.z;
+          const float A = nz * sy - ny * sz, B = nx * sz - nz * sx, C = ny * sx - nx * sy;
+          const float D = nx * dx + ny * dy + nz * dz - nx * sx - ny * sy - nz * sz;
+          const double v[6] = {A, B, C, nx, ny, nz};
+          int k = 2;
+          for (int r = 0; r < 6; ++r)
+            for (int c = r; c < 6; ++c, ++k)
+              ref[k] += (r >= 3) ? (double)((float)v[r] * (float)v[c]) : v[r] * v[c];   // the normal-normal block adds FLOAT products
+          for (int r = 0; r < 6; ++r) ref[23 + r] += v[r] * (double)D;
+        }
+      }
+      double worst = 0.0;
+      const int used = estimator == PCLB200_EST_SVD ? kAccSvd : kAccLls;
+      for (int k = 0; k < used; ++k) worst = std::max(worst, std::fabs(accum[k] - ref[k]) / (1.0 + std::fabs(ref[k])));
+      CHECK(worst < 1e-11, "%s iteration %d: accumulated sums differ from plain fp64 sums by %g (relative)", name, it, worst);
+    }
+    else if (estimator == PCLB200_EST_SVD)   // the driver enqueues these regardless: they must return at once
+      warp_emu::run_block(256, [&] { k_accum_dmma<PCLB200_EST_SVD>(a, match.data()); });
+    warp_emu::run_block(32, [&] {
+      k_solve(accum.data(), estimator, scalar_double ? 1 : 0, 0, (double)a.ox, (double)a.oy, (double)a.oz, 3, &pending, &solve_out,
+              svd_correlation ? 1 : 0, &ctrl, crit);
+    });
+    skipped_total = (long)skip_count;
+    if (ctrl.done) break;
+  }
+  // the oracle's loop on the same clouds
+  orc_icp_params P;
+  std::memset(&P, 0, sizeof P);
+  P.max_iterations = max_iterations;
+  P.estimator = estimator == PCLB200_EST_SVD ? 0 : 1;
+  P.scalar_is_double = scalar_double ? 1 : 0;
+  P.is_dense = 1;
+  P.nthreads = 2;
+  P.max_correspondence_distance = max_dist;
+  P.transformation_epsilon = trans_eps;
+  P.euclidean_fitness_epsilon = -std::numeric_limits<double>::max();
+  orc_icp_result R;
+  std::memset(&R, 0, sizeof R);
+  orc_icp_align(&P, S.src.data(), ns, 4, nullptr, 0, S.tgt.data(), nt, 8, nullptr, &R, nullptr);
+  double dT = 0.0;
+  for (int i = 0; i < 16; ++i) dT += (ctrl.final_T[i] - R.final_transformation[i]) * (ctrl.final_T[i] - R.final_transformation[i]);
+  dT = std::sqrt(dT);
+  CHECK(ctrl.iterations == R.iterations && ctrl.state == R.state && (ctrl.converged != 0) == (R.converged != 0),
+        "%s: device loop %d iterations state %d converged %d, oracle %d / %d / %d", name, ctrl.iterations, ctrl.state, ctrl.converged, R.iterations,
+        R.state, R.converged);
+  CHECK(dT < (scalar_double ? 1e-9 : 1e-5), "%s: |T_device - T_oracle|_F = %g", name, dT);
+  CHECK((long long)ctrl.total_corr == R.total_correspondences && (int)ctrl.n_corr == R.n_correspondences, "%s: correspondence counts %lld / %d vs %lld / %d",
+        name, (long long)ctrl.total_corr, (int)ctrl.n_corr, R.total_correspondences, R.n_correspondences);
+  CHECK(d_error == 0, "%s: device error flag %d", name, d_error);
+  std::printf("%-44s %5zu -> %5zu points: %2d iterations, state %d, |dT| %.2e, %ld walks skipped; ok so far: %ld checks, %ld failures\n", name, ns, nt,
+              ctrl.iterations, ctrl.state, dT, skipped_total, g_checks, g_fail);
+}
+
+int main()
+{
+  std::mt19937 rng(77);
+  std::uniform_real_distribution<float> U(0.f, 1.f);
+  std::normal_distribution<float> N(0.f, 1.f);
+  auto rot = [](double ax, double ay, double az, double deg, double R[9]) {
+    const double n = std::sqrt(ax * ax + ay * ay + az * az), a = deg * M_PI / 180.0, c = std::cos(a), s = std::sin(a), x = ax / n, y = ay / n, z = az / n;
+    const double M[9] = {c + x * x * (1 - c), x * y * (1 - c) - z * s, x * z * (1 - c) + y * s, y * x * (1 - c) + z * s, c + y * y * (1 - c), y * z * (1 - c) - x * s,
+                         z * x * (1 - c) - y * s, z * y * (1 - c) + x * s, c + z * z * (1 - c)};
+    for (int i = 0; i < 9; ++i) R[i] = M[i];
+  };
+  // a bumpy sheet with analytic normals; the source is the same surface re-sampled, rotated and shifted
+  auto surface = [&](int n, Scene& S, int n_src, double deg, const double t[3]) {
+    auto f = [](float x, float y) { return 0.3f * std::sin(2.f * x) * std::cos(1.5f * y); };
+    S.tgt.assign(8 * (std::size_t)n, 0.f);
+    for (int i = 0; i < n; ++i) {
+      const float x = 3.f * U(rng), y = 3.f * U(rng), z = f(x, y) + 0.0005f * N(rng);
+      const float fx = 0.6f * std::cos(2.f * x) * std::cos(1.5f * y), fy = -0.45f * std::sin(2.f * x) * std::sin(1.5f * y);
+      const float inv = 1.f / std::sqrt(fx * fx + fy * fy + 1.f);
+      float* r = &S.tgt[8 * (std::size_t)i];
+      r[0] = x; r[1] = y; r[2] = z; r[3] = 1.f; r[4] = -fx * inv; r[5] = -fy * inv; r[6] = inv;
+    }
+    double R[9];
+    rot(0.2, -0.3, 1.0, deg, R);
+    S.src.assign(4 * (std::size_t)n_src, 1.f);
+    for (int i = 0; i < n_src; ++i) {
+      const float x = 0.2f + 2.6f * U(rng), y = 0.2f + 2.6f * U(rng), z = f(x, y) + 0.0005f * N(rng);
+      for (int r = 0; r < 3; ++r) S.src[4 * (std::size_t)i + r] = (float)(R[3 * r] * x + R[3 * r + 1] * y + R[3 * r + 2] * z + t[r]);
+    }
+  };
+  const double t1[3] = {0.01, -0.015, 0.008};
+  Scene A;
+  surface(4000, A, 1500, 1.5, t1);
+  run_align("SVD float, gate 0.2", A, PCLB200_EST_SVD, false, 0.2, 1e-9, 25, PCLB200_TRACK_OFF, false);
+  run_align("SVD double, gate 0.2", A, PCLB200_EST_SVD, true, 0.2, 1e-10, 25, PCLB200_TRACK_OFF, false);
+  run_align("SVD float, tracking on", A, PCLB200_EST_SVD, false, 0.2, 1e-9, 25, PCLB200_TRACK_ON, false);
+  run_align("SVD float, tracking automatic", A, PCLB200_EST_SVD, false, 0.2, 1e-9, 25, PCLB200_TRACK_AUTO, false);
+  run_align("point-to-plane LLS float", A, PCLB200_EST_POINT_TO_PLANE_LLS, false, 0.2, 1e-10, 20, PCLB200_TRACK_OFF, false);
+  run_align("point-to-plane LLS double, tracking on", A, PCLB200_EST_POINT_TO_PLANE_LLS, true, 0.2, 1e-12, 20, PCLB200_TRACK_ON, false);
+  run_align("SVD float, no gate, iteration limit", A, PCLB200_EST_SVD, false, std::sqrt(std::numeric_limits<double>::max()), 0.0, 6, PCLB200_TRACK_OFF, false);
+  Scene B;
+  const double t2[3] = {0.4, 0.3, -0.2};
+  surface(3000, B, 900, 4.0, t2);
+  run_align("SVD float, tight gate (few pairs)", B, PCLB200_EST_SVD, false, 0.02, 1e-9, 10, PCLB200_TRACK_OFF, false);
+  std::printf("%ld checks, %ld failures\n%s\n", g_checks, g_fail, g_fail ? "FAILED" : "PASSED");
+  return g_fail ? 1 : 0;
+}

@@ -1,5 +1,5 @@
-// warp_emu.h — a lock-step emulation of ONE CUDA warp for host-compiled device code: 32 fibers (ucontext), one per lane,
-// run round-robin; every warp-synchronous primitive (__shfl*_sync, __ballot_sync, __match_any_sync, __syncwarp) is a
+// warp_emu.h — a lock-step emulation of ONE CUDA thread block (up to 8 warps) for host-compiled device code: one fiber
+// (ucontext) per thread, run round-robin; every warp-synchronous primitive (__shfl*_sync, __ballot_sync, __match_any_sync, __syncwarp) is a
 // rendezvous of all 32 lanes: each lane deposits its operand, yields until the last lane has arrived, then reads what it
 // needs.  Deterministic and single-threaded.  The emulated code must execute the same sequence of primitives on every
 // lane (warp-uniform control flow around them), which is what the *_sync primitives with a full mask require on the
@@ -17,57 +17,74 @@
 
 namespace warp_emu {
 constexpr int kLanes = 32;
-struct Warp {
-  ucontext_t main_ctx, lane_ctx[kLanes];
-  std::vector<char> stacks[kLanes];
-  bool finished[kLanes];
+constexpr int kMaxThreads = 256;
+struct Block {
+  ucontext_t main_ctx, ctx[kMaxThreads];
+  std::vector<char> stacks[kMaxThreads];
+  bool finished[kMaxThreads];
+  int nthreads = 32;
   int current = -1;
-  unsigned generation = 0;
-  int arrived = 0;
-  std::uint64_t slot[kLanes];   // operands of the primitive in flight
+  // one rendezvous state per warp, one for the whole block
+  unsigned warp_generation[kMaxThreads / kLanes] = {0};
+  int warp_arrived[kMaxThreads / kLanes] = {0};
+  unsigned block_generation = 0;
+  int block_arrived = 0;
+  std::uint64_t slot[kMaxThreads];    // operands of the warp primitive in flight (per thread)
+  std::uint64_t slot2[kMaxThreads];
   long primitives = 0;
   std::function<void()> body;
 };
-inline Warp& W() { static Warp w; return w; }
+inline Block& W() { static Block w; return w; }
 
 inline void yield_lane()
 {
-  Warp& w = W();
+  Block& w = W();
   const int me = w.current;
-  for (int step = 1; step <= kLanes; ++step) {
-    const int next = (me + step) % kLanes;
-    if (!w.finished[next] || next == me) {
-      if (next == me) return;
+  for (int step = 1; step <= w.nthreads; ++step) {
+    const int next = (me + step) % w.nthreads;
+    if (next == me) return;
+    if (!w.finished[next]) {
       w.current = next;
-      swapcontext(&w.lane_ctx[me], &w.lane_ctx[next]);
+      swapcontext(&w.ctx[me], &w.ctx[next]);
       return;
     }
   }
 }
-// all 32 lanes meet here
+// the 32 lanes of the calling thread's warp meet here
 inline void rendezvous()
 {
-  Warp& w = W();
-  const unsigned gen = w.generation;
-  if (++w.arrived == kLanes) {
-    w.arrived = 0;
-    ++w.generation;
+  Block& w = W();
+  const int wid = w.current / kLanes;
+  const unsigned gen = w.warp_generation[wid];
+  if (++w.warp_arrived[wid] == kLanes) {
+    w.warp_arrived[wid] = 0;
+    ++w.warp_generation[wid];
     ++w.primitives;
   }
-  while (w.generation == gen) yield_lane();
+  while (w.warp_generation[wid] == gen) yield_lane();
+}
+// all threads of the block meet here (__syncthreads)
+inline void block_rendezvous()
+{
+  Block& w = W();
+  const unsigned gen = w.block_generation;
+  if (++w.block_arrived == w.nthreads) {
+    w.block_arrived = 0;
+    ++w.block_generation;
+  }
+  while (w.block_generation == gen) yield_lane();
 }
 inline void trampoline()
 {
-  Warp& w = W();
+  Block& w = W();
   const int me = w.current;
   w.body();
   w.finished[me] = true;
-  // hand over to a lane that still runs, or back to the caller
-  for (int step = 1; step < kLanes; ++step) {
-    const int next = (me + step) % kLanes;
+  for (int step = 1; step < w.nthreads; ++step) {   // hand over to a thread that still runs, or back to the caller
+    const int next = (me + step) % w.nthreads;
     if (!w.finished[next]) {
       w.current = next;
-      setcontext(&w.lane_ctx[next]);
+      setcontext(&w.ctx[next]);
     }
   }
   setcontext(&w.main_ctx);
@@ -77,13 +94,13 @@ inline void trampoline()
 // ---- what the device code sees -----------------------------------------------------------------------------------------
 struct EmuDim { unsigned x = 1, y = 1, z = 1; };
 struct EmuThreadIdx { operator int() const = delete; };
-namespace warp_emu { inline unsigned lane_id() { return static_cast<unsigned>(W().current); } }
+namespace warp_emu { inline unsigned lane_id() { return static_cast<unsigned>(W().current); } }   // = threadIdx.x
 struct EmuThreadIdxX { operator unsigned() const { return warp_emu::lane_id(); } };
 struct EmuThreadIdxT { EmuThreadIdxX x; };
 static EmuThreadIdxT threadIdx;
 static EmuDim blockIdx_storage{0, 0, 0};
 #define blockIdx blockIdx_storage
-static EmuDim blockDim{32, 1, 1}, gridDim{1, 1, 1};
+static EmuDim blockDim{32, 1, 1}, gridDim{1, 1, 1};   // a test sets blockDim.x to the size it passes to run_block
 
 #undef __global__
 #define __global__
@@ -97,45 +114,72 @@ template <typename T> static inline T emu_unpack(std::uint64_t u) { T v; std::me
 template <typename T> static inline T emu_exchange(T v, int src_lane)
 {
   auto& w = warp_emu::W();
+  const int base = w.current & ~31;
   w.slot[w.current] = emu_pack(v);
   warp_emu::rendezvous();
-  const T r = emu_unpack<T>(w.slot[src_lane & 31]);
+  const T r = emu_unpack<T>(w.slot[base + (src_lane & 31)]);
   warp_emu::rendezvous();   // nobody overwrites a slot before every lane has read
   return r;
 }
 template <typename T> static inline T __shfl_sync(unsigned, T v, int src) { return emu_exchange(v, src); }
-template <typename T> static inline T __shfl_xor_sync(unsigned, T v, int m) { return emu_exchange(v, warp_emu::W().current ^ m); }
+template <typename T> static inline T __shfl_xor_sync(unsigned, T v, int m) { return emu_exchange(v, (warp_emu::W().current & 31) ^ m); }
 template <typename T> static inline T __shfl_up_sync(unsigned, T v, unsigned d)
 {
-  const int me = warp_emu::W().current;
+  const int me = warp_emu::W().current & 31;
   return emu_exchange(v, me >= static_cast<int>(d) ? me - static_cast<int>(d) : me);
 }
 template <typename T> static inline T __shfl_down_sync(unsigned, T v, unsigned d)
 {
-  const int me = warp_emu::W().current;
+  const int me = warp_emu::W().current & 31;
   return emu_exchange(v, me + static_cast<int>(d) < 32 ? me + static_cast<int>(d) : me);
 }
 static inline unsigned __ballot_sync(unsigned, int pred)
 {
   auto& w = warp_emu::W();
+  const int base = w.current & ~31;
   w.slot[w.current] = pred ? 1u : 0u;
   warp_emu::rendezvous();
   unsigned m = 0;
-  for (int l = 0; l < 32; ++l) m |= static_cast<unsigned>(w.slot[l] & 1u) << l;
+  for (int l = 0; l < 32; ++l) m |= static_cast<unsigned>(w.slot[base + l] & 1u) << l;
   warp_emu::rendezvous();
   return m;
 }
 template <typename T> static inline unsigned __match_any_sync(unsigned, T v)
 {
   auto& w = warp_emu::W();
+  const int base = w.current & ~31;
   w.slot[w.current] = emu_pack(v);
   warp_emu::rendezvous();
   unsigned m = 0;
-  for (int l = 0; l < 32; ++l) m |= (w.slot[l] == w.slot[w.current] ? 1u : 0u) << l;
+  for (int l = 0; l < 32; ++l) m |= (w.slot[base + l] == w.slot[w.current] ? 1u : 0u) << l;
   warp_emu::rendezvous();
   return m;
 }
+// mma.sync.aligned.m8n8k4.row.col.f64: lane l feeds A[l / 4][l % 4] and B[l % 4][l / 4] and owns C[l / 4][2 (l % 4)], [.. + 1]
+static inline void emu_dmma884(double& c0, double& c1, double a, double b)
+{
+  auto& w = warp_emu::W();
+  const int base = w.current & ~31, lane = w.current & 31;
+  w.slot[w.current] = emu_pack(a);
+  w.slot2[w.current] = emu_pack(b);
+  warp_emu::rendezvous();
+  const int g = lane >> 2, t = lane & 3;
+  for (int k = 0; k < 4; ++k) {
+    const double A = emu_unpack<double>(w.slot[base + g * 4 + k]);
+    c0 = std::fma(A, emu_unpack<double>(w.slot2[base + (2 * t) * 4 + k]), c0);
+    c1 = std::fma(A, emu_unpack<double>(w.slot2[base + (2 * t + 1) * 4 + k]), c1);
+  }
+  warp_emu::rendezvous();
+}
 static inline void __syncwarp(unsigned = 0xffffffffu) { warp_emu::rendezvous(); }
+static inline void __syncthreads() { warp_emu::block_rendezvous(); }
+static inline void __threadfence() {}
+static inline void __threadfence_system() {}
+static inline long long clock64() { return 0; }
+template <typename T> static inline T __ldcg(const T* p) { return *p; }
+static inline unsigned atomicAdd(unsigned* p, unsigned v) { const unsigned o = *p; *p = o + v; return o; }          // fibers never run concurrently
+static inline unsigned long long atomicAdd(unsigned long long* p, unsigned long long v) { const unsigned long long o = *p; *p = o + v; return o; }
+static inline int atomicExch(int* p, int v) { const int o = *p; *p = v; return o; }
 static inline int __popc(unsigned v) { return __builtin_popcount(v); }
 static inline float __fdiv_rn(float a, float b) { volatile float x = a, y = b; volatile float r = x / y; return r; }
 static inline int max(int a, int b) { return a > b ? a : b; }
@@ -143,27 +187,31 @@ static inline int min(int a, int b) { return a < b ? a : b; }
 using std::isfinite;
 
 namespace warp_emu {
-// runs `kernel_body` once on each of the 32 lanes of the emulated warp, in lock step
-inline long run_warp(std::function<void()> kernel_body)
+// runs `kernel_body` once on each thread of an emulated block of `nthreads` (a multiple of 32) threads, in lock step
+inline long run_block(int nthreads, std::function<void()> kernel_body)
 {
-  Warp& w = W();
+  Block& w = W();
+  if (nthreads % kLanes != 0 || nthreads > kMaxThreads) { std::printf("warp_emu: unsupported block size %d\n", nthreads); std::exit(3); }
   w.body = std::move(kernel_body);
-  w.generation = 0;
-  w.arrived = 0;
+  w.nthreads = nthreads;
+  w.block_generation = 0;
+  w.block_arrived = 0;
   w.primitives = 0;
-  for (int l = 0; l < kLanes; ++l) {
+  for (int i = 0; i < kMaxThreads / kLanes; ++i) { w.warp_generation[i] = 0; w.warp_arrived[i] = 0; }
+  for (int l = 0; l < nthreads; ++l) {
     w.finished[l] = false;
-    if (w.stacks[l].empty()) w.stacks[l].resize(1 << 20);
-    getcontext(&w.lane_ctx[l]);
-    w.lane_ctx[l].uc_stack.ss_sp = w.stacks[l].data();
-    w.lane_ctx[l].uc_stack.ss_size = w.stacks[l].size();
-    w.lane_ctx[l].uc_link = nullptr;
-    makecontext(&w.lane_ctx[l], reinterpret_cast<void (*)()>(trampoline), 0);
+    if (w.stacks[l].empty()) w.stacks[l].resize(512 << 10);
+    getcontext(&w.ctx[l]);
+    w.ctx[l].uc_stack.ss_sp = w.stacks[l].data();
+    w.ctx[l].uc_stack.ss_size = w.stacks[l].size();
+    w.ctx[l].uc_link = nullptr;
+    makecontext(&w.ctx[l], reinterpret_cast<void (*)()>(trampoline), 0);
   }
   w.current = 0;
-  swapcontext(&w.main_ctx, &w.lane_ctx[0]);
-  for (int l = 0; l < kLanes; ++l)
-    if (!w.finished[l]) { std::printf("warp_emu: lane %d did not finish (divergent primitive sequence?)\n", l); std::exit(3); }
+  swapcontext(&w.main_ctx, &w.ctx[0]);
+  for (int l = 0; l < nthreads; ++l)
+    if (!w.finished[l]) { std::printf("warp_emu: thread %d did not finish (divergent primitive sequence?)\n", l); std::exit(3); }
   return w.primitives;
 }
+inline long run_warp(std::function<void()> kernel_body) { return run_block(kLanes, std::move(kernel_body)); }
 }  // namespace warp_emu

@@ -42,3 +42,25 @@ def test_warp_knn_kernel_on_an_emulated_warp(tmp_path):
     r = subprocess.run([exe, "1"], capture_output=True, text=True)
     assert r.returncode == 0 and "PASSED" in r.stdout, r.stdout[-3000:]
     assert "shared leaf, constructed #5" in r.stdout
+
+
+@pytest.mark.skipif(not os.path.exists(os.path.join(CUDA_INC, "cuda_runtime.h")) or shutil.which("g++") is None,
+                    reason="needs g++ and the CUDA headers (vector types only; nothing is run on a device)")
+def test_whole_icp_iterations_on_an_emulated_block(tmp_path):
+    """pcl_b200/csrc/icp_kernels.cuh — k_search, k_accum_dmma (the m8n8k4 fp64 MMA emulated fragment by fragment), k_solve
+    with the convergence criteria in its tail — compiled for the host, run on a lock-step emulation of a 256-thread block
+    and driven like icp.cu's enqueue-ahead path: every iteration's correspondences equal brute force, the accumulated
+    normal equations equal plain fp64 sums, and iterations / state / counts / final transform of eight aligns (SVD and
+    point-to-plane, float and double, gates, tracking off / on / automatic) equal the oracle's loop (1e-5 float, 1e-9
+    double)."""
+    import oracle
+    oracle.build()
+    odir = os.path.join(ROOT, "oracle")
+    exe = str(tmp_path / "icp_host_test")
+    subprocess.check_call(["g++", "-O1", "-std=c++17", "-frounding-math", "-ffp-contract=off", "-fno-fast-math",
+                           "-I" + CUDA_INC, "-I" + os.path.join(ROOT, "include"), "-I" + os.path.join(ROOT, "tests", "host"),
+                           os.path.join(ROOT, "tests", "host", "icp_host_test.cpp"), "-o", exe,
+                           "-L" + odir, "-lpcl_oracle", "-Wl,-rpath," + odir])
+    r = subprocess.run([exe], capture_output=True, text=True)
+    assert r.returncode == 0 and "PASSED" in r.stdout, r.stdout[-3000:]
+    assert "tracking automatic" in r.stdout and "point-to-plane LLS double" in r.stdout
