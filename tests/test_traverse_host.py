@@ -64,3 +64,18 @@ def test_whole_icp_iterations_on_an_emulated_block(tmp_path):
     r = subprocess.run([exe], capture_output=True, text=True)
     assert r.returncode == 0 and "PASSED" in r.stdout, r.stdout[-3000:]
     assert "tracking automatic" in r.stdout and "point-to-plane LLS double" in r.stdout
+
+
+@pytest.mark.skipif(not os.path.exists(os.path.join(CUDA_INC, "cuda_runtime.h")) or shutil.which("g++") is None,
+                    reason="needs g++ and the CUDA headers (vector types only; nothing is run on a device)")
+def test_per_thread_search_kernels_on_the_host(tmp_path):
+    """pcl_b200/csrc/search_kernels.cuh — k_knn<K> for every compiled list size, k_knn_any, k_knn_stats, k_radius_count /
+    k_radius_fill, k_normals<K> — compiled for the host and run block by block against brute force (lists bit for bit,
+    ties and duplicates included) and, for the normals, against the host computePointNormal."""
+    exe = str(tmp_path / "search_host_test")
+    subprocess.check_call(["g++", "-O1", "-std=c++17", "-frounding-math", "-ffp-contract=off", "-fno-fast-math",
+                           "-I" + CUDA_INC, "-I" + os.path.join(ROOT, "include"), "-I" + os.path.join(ROOT, "tests", "host"),
+                           "-I" + os.path.join(ROOT, "pcl_b200", "pcl_compat"),
+                           os.path.join(ROOT, "tests", "host", "search_host_test.cpp"), "-o", exe])
+    r = subprocess.run([exe, "2"], capture_output=True, text=True)
+    assert r.returncode == 0 and "PASSED" in r.stdout, r.stdout[-3000:]
