@@ -53,10 +53,15 @@ static float gate_from_max_dist(double max_dist)   // icp.cu: the largest float 
 struct Scene {
   std::vector<float> tgt;       // n x 8: xyz1 | normal 0
   std::vector<float> src;       // n x 4
+  std::vector<float> src_n;     // n x 8: xyz1 | normal 0 (the same points with normals, for the WithNormals / symmetric runs)
+};
+struct Extra {
+  bool reciprocal = false;        // setUseReciprocalCorrespondences: the source tree is rebuilt every iteration
+  bool with_normals = false;      // IterativeClosestPointWithNormals: the source normals are rotated with every increment
 };
 
 static void run_align(const char* name, const Scene& S, int estimator, bool scalar_double, double max_dist, double trans_eps, int max_iterations,
-                      int track_mode, bool svd_correlation)
+                      int track_mode, bool svd_correlation, Extra X = Extra())
 {
   const std::size_t nt = S.tgt.size() / 8, ns = S.src.size() / 4;
   std::vector<float> txyz(3 * nt);
@@ -69,8 +74,13 @@ static void run_align(const char* name, const Scene& S, int estimator, bool scal
     const int o = __float_as_int(I.pts[p].w);
     if (o != kSentinelIndex) tgt_normals[p] = make_float4(S.tgt[8 * o + 4], S.tgt[8 * o + 5], S.tgt[8 * o + 6], 0.f);
   }
-  std::vector<float4> cur(ns);
+  std::vector<float4> cur(ns), cur_normals;
   for (std::size_t i = 0; i < ns; ++i) cur[i] = make_float4(S.src[4 * i], S.src[4 * i + 1], S.src[4 * i + 2], __int_as_float((int)i));
+  if (X.with_normals) {
+    cur_normals.resize(ns);
+    for (std::size_t i = 0; i < ns; ++i) cur_normals[i] = make_float4(S.src_n[8 * i + 4], S.src_n[8 * i + 5], S.src_n[8 * i + 6], 0.f);
+  }
+  const int tmode = X.with_normals ? (scalar_double ? 2 : 1) : 0;   // icp.cu: transform_mode
   std::vector<Match> match(ns);
   for (auto& m : match) { m.pos = -1; m.d2 = 0.f; }
   std::vector<float> lbs(ns, 0.f);
@@ -117,12 +127,29 @@ static void run_align(const char* name, const Scene& S, int estimator, bool scal
   a.d_error = &d_error;
   a.skip_count = &skip_count;
   a.cells = T.cells;
+  a.cur_normals = X.with_normals ? cur_normals.data() : nullptr;
+  a.enforce_same_dir = 1;
   a.ctrl = &ctrl;
   a.peer.nranks = 0;
   blockDim.x = 256;
   long skipped_total = 0;
   for (int it = 0; it < max_iterations; ++it) {
-    if (track_mode == PCLB200_TRACK_AUTO) {
+    HostIndex SI;   // reciprocal: tree over the re-transformed source of THIS iteration (icp.cu: stage-by-stage path)
+    if (X.reciprocal) {
+      if (pending.apply) {
+        for (std::size_t i = 0; i < ns; ++i) {
+          apply_pending(pending, cur[i].x, cur[i].y, cur[i].z);
+          if (X.with_normals) apply_pending_normal(pending, cur_normals[i].x, cur_normals[i].y, cur_normals[i].z);
+        }
+        pending.apply = 0;
+      }
+      std::vector<float> sxyz(3 * ns);
+      for (std::size_t i = 0; i < ns; ++i) { sxyz[3 * i] = cur[i].x; sxyz[3 * i + 1] = cur[i].y; sxyz[3 * i + 2] = cur[i].z; }
+      build_index(SI, sxyz, 0);
+      a.s_nodes = SI.nodes.data(); a.s_pts = SI.pts.data(); a.s_root = SI.root;
+      if (!ctrl.done) warp_emu::run_block(256, [&] { k_search<true, false>(a, match.data(), lbs.data()); });
+    }
+    else if (track_mode == PCLB200_TRACK_AUTO) {
       a.track_sel = 1;
       warp_emu::run_block(256, [&] { k_search<false, false>(a, match.data(), lbs.data()); });
       warp_emu::run_block(256, [&] { k_search<false, true>(a, match.data(), lbs.data()); });
@@ -139,14 +166,31 @@ static void run_align(const char* name, const Scene& S, int estimator, bool scal
         const Truth t = brute(txyz, q, a.gate);
         const Match m = match[i];
         if (t.idx == kSentinelIndex) { if (match_accepted(m)) ++bad; continue; }
+        if (X.reciprocal) {   // kept only if the matched target point finds this source point back (first of equals by index)
+          const float* tp = &txyz[3 * t.idx];
+          float bd = INFINITY;
+          int bi = -1;
+          for (std::size_t j = 0; j < ns; ++j) {
+            const float d = dist2_rn(tp[0], tp[1], tp[2], cur[j].x, cur[j].y, cur[j].z);
+            if (d < bd) { bd = d; bi = (int)j; }
+          }
+          const bool keep = bd <= a.gate && bi == (int)i;
+          if (match_accepted(m) != keep) ++bad;
+          if (m.pos < 0 || __float_as_int(I.pts[match_pos(m)].w) != t.idx || m.d2 != t.d1) ++bad;
+          continue;
+        }
         if (!match_accepted(m) || __float_as_int(I.pts[match_pos(m)].w) != t.idx || m.d2 != t.d1) ++bad;
       }
       CHECK(bad == 0, "%s iteration %d: %d correspondences differ from brute force", name, it, bad);
       // the normal equations of the SAME pairs by plain fp64 sums (kAccum layout of icp_kernels.cuh)
+      std::vector<double> partials(kAccum, 0.0);
+      a.partials = partials.data();
       if (estimator == PCLB200_EST_SVD)
         warp_emu::run_block(256, [&] { k_accum_dmma<PCLB200_EST_SVD>(a, match.data()); });
-      else
+      else if (estimator == PCLB200_EST_POINT_TO_PLANE_LLS)
         warp_emu::run_block(256, [&] { k_accum_dmma<PCLB200_EST_POINT_TO_PLANE_LLS>(a, match.data()); });
+      else
+        warp_emu::run_block(256, [&] { k_accum<PCLB200_EST_SYMMETRIC_POINT_TO_PLANE_LLS>(a, match.data()); });
       double ref[kAccum] = {0};
       for (std::size_t i = 0; i < ns; ++i) {
         const Match m = match[i];
@@ -159,7 +203,7 @@ static void run_align(const char* name, const Scene& S, int estimator, bool scal
           for (int d = 0; d < 3; ++d) { ref[2 + d] += P3[d]; ref[5 + d] += Q3[d]; }
           for (int r = 0; r < 3; ++r) for (int c = 0; c < 3; ++c) ref[8 + 3 * r + c] += Q3[r] * P3[c];
         }
-        else {
+        else if (estimator == PCLB200_EST_POINT_TO_PLANE_LLS) {
           const float4 nn = tgt_normals[match_pos(m)];
           const float sx = p.x, sy = p.y, sz = p.z, dx = q.x, dy = q.y, dz = q.z, nx = nn.x, ny = nn.y, nz = nn.z;
           const float A = nz * sy - ny * sz, B = nx * sz - nz * sx, C = ny * sx - nx * sy;
@@ -173,14 +217,14 @@ static void run_align(const char* name, const Scene& S, int estimator, bool scal
         }
       }
       double worst = 0.0;
-      const int used = estimator == PCLB200_EST_SVD ? kAccSvd : kAccLls;
+      const int used = estimator == PCLB200_EST_SVD ? kAccSvd : estimator == PCLB200_EST_POINT_TO_PLANE_LLS ? kAccLls : 2;   // symmetric: count and sum only
       for (int k = 0; k < used; ++k) worst = std::max(worst, std::fabs(accum[k] - ref[k]) / (1.0 + std::fabs(ref[k])));
       CHECK(worst < 1e-11, "%s iteration %d: accumulated sums differ from plain fp64 sums by %g (relative)", name, it, worst);
     }
     else if (estimator == PCLB200_EST_SVD)   // the driver enqueues these regardless: they must return at once
       warp_emu::run_block(256, [&] { k_accum_dmma<PCLB200_EST_SVD>(a, match.data()); });
     warp_emu::run_block(32, [&] {
-      k_solve(accum.data(), estimator, scalar_double ? 1 : 0, 0, (double)a.ox, (double)a.oy, (double)a.oz, 3, &pending, &solve_out,
+      k_solve(accum.data(), estimator, scalar_double ? 1 : 0, tmode, (double)a.ox, (double)a.oy, (double)a.oz, 3, &pending, &solve_out,
               svd_correlation ? 1 : 0, &ctrl, crit);
     });
     skipped_total = (long)skip_count;
@@ -190,7 +234,10 @@ static void run_align(const char* name, const Scene& S, int estimator, bool scal
   orc_icp_params P;
   std::memset(&P, 0, sizeof P);
   P.max_iterations = max_iterations;
-  P.estimator = estimator == PCLB200_EST_SVD ? 0 : 1;
+  P.estimator = estimator == PCLB200_EST_SVD ? 0 : estimator == PCLB200_EST_POINT_TO_PLANE_LLS ? 1 : 2;
+  P.use_reciprocal = X.reciprocal ? 1 : 0;
+  P.with_normals_transform = X.with_normals ? 1 : 0;
+  P.source_has_normals = X.with_normals ? 1 : 0;
   P.scalar_is_double = scalar_double ? 1 : 0;
   P.is_dense = 1;
   P.nthreads = 2;
@@ -199,7 +246,8 @@ static void run_align(const char* name, const Scene& S, int estimator, bool scal
   P.euclidean_fitness_epsilon = -std::numeric_limits<double>::max();
   orc_icp_result R;
   std::memset(&R, 0, sizeof R);
-  orc_icp_align(&P, S.src.data(), ns, 4, nullptr, 0, S.tgt.data(), nt, 8, nullptr, &R, nullptr);
+  if (X.with_normals) orc_icp_align(&P, S.src_n.data(), ns, 8, nullptr, 0, S.tgt.data(), nt, 8, nullptr, &R, nullptr);
+  else orc_icp_align(&P, S.src.data(), ns, 4, nullptr, 0, S.tgt.data(), nt, 8, nullptr, &R, nullptr);
   double dT = 0.0;
   for (int i = 0; i < 16; ++i) dT += (ctrl.final_T[i] - R.final_transformation[i]) * (ctrl.final_T[i] - R.final_transformation[i]);
   dT = std::sqrt(dT);
@@ -321,9 +369,18 @@ int main()
     double R[9];
     rot(0.2, -0.3, 1.0, deg, R);
     S.src.assign(4 * (std::size_t)n_src, 1.f);
+    S.src_n.assign(8 * (std::size_t)n_src, 0.f);
     for (int i = 0; i < n_src; ++i) {
       const float x = 0.2f + 2.6f * U(rng), y = 0.2f + 2.6f * U(rng), z = f(x, y) + 0.0005f * N(rng);
-      for (int r = 0; r < 3; ++r) S.src[4 * (std::size_t)i + r] = (float)(R[3 * r] * x + R[3 * r + 1] * y + R[3 * r + 2] * z + t[r]);
+      const float fx = 0.6f * std::cos(2.f * x) * std::cos(1.5f * y), fy = -0.45f * std::sin(2.f * x) * std::sin(1.5f * y);
+      const float inv = 1.f / std::sqrt(fx * fx + fy * fy + 1.f);
+      const double nrm[3] = {-fx * inv, -fy * inv, inv};
+      for (int r = 0; r < 3; ++r) {
+        S.src[4 * (std::size_t)i + r] = (float)(R[3 * r] * x + R[3 * r + 1] * y + R[3 * r + 2] * z + t[r]);
+        S.src_n[8 * (std::size_t)i + r] = S.src[4 * (std::size_t)i + r];
+        S.src_n[8 * (std::size_t)i + 4 + r] = (float)(R[3 * r] * nrm[0] + R[3 * r + 1] * nrm[1] + R[3 * r + 2] * nrm[2]);
+      }
+      S.src_n[8 * (std::size_t)i + 3] = 1.f;
     }
   };
   const double t1[3] = {0.01, -0.015, 0.008};
@@ -336,6 +393,16 @@ int main()
   run_align("point-to-plane LLS float", A, PCLB200_EST_POINT_TO_PLANE_LLS, false, 0.2, 1e-10, 20, PCLB200_TRACK_OFF, false);
   run_align("point-to-plane LLS double, tracking on", A, PCLB200_EST_POINT_TO_PLANE_LLS, true, 0.2, 1e-12, 20, PCLB200_TRACK_ON, false);
   run_align("SVD float, no gate, iteration limit", A, PCLB200_EST_SVD, false, std::sqrt(std::numeric_limits<double>::max()), 0.0, 6, PCLB200_TRACK_OFF, false);
+  {
+    Extra recip;
+    recip.reciprocal = true;
+    run_align("SVD float, reciprocal correspondences", A, PCLB200_EST_SVD, false, 0.2, 1e-9, 12, PCLB200_TRACK_OFF, false, recip);
+    Extra wn;
+    wn.with_normals = true;
+    run_align("ICPWithNormals: LLS float, normals rotated", A, PCLB200_EST_POINT_TO_PLANE_LLS, false, 0.2, 1e-10, 20, PCLB200_TRACK_OFF, false, wn);
+    run_align("ICPWithNormals: LLS double", A, PCLB200_EST_POINT_TO_PLANE_LLS, true, 0.2, 1e-12, 20, PCLB200_TRACK_OFF, false, wn);
+    run_align("symmetric point-to-plane, double", A, PCLB200_EST_SYMMETRIC_POINT_TO_PLANE_LLS, true, 0.2, 1e-12, 20, PCLB200_TRACK_OFF, false, wn);
+  }
   Scene B;
   const double t2[3] = {0.4, 0.3, -0.2};
   surface(3000, B, 900, 4.0, t2);

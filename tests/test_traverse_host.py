@@ -50,9 +50,10 @@ def test_whole_icp_iterations_on_an_emulated_block(tmp_path):
     """pcl_b200/csrc/icp_kernels.cuh — k_search, k_accum_dmma (the m8n8k4 fp64 MMA emulated fragment by fragment), k_solve
     with the convergence criteria in its tail — compiled for the host, run on a lock-step emulation of a 256-thread block
     and driven like icp.cu's enqueue-ahead path: every iteration's correspondences equal brute force, the accumulated
-    normal equations equal plain fp64 sums, and iterations / state / counts / final transform of eight aligns (SVD and
-    point-to-plane, float and double, gates, tracking off / on / automatic) equal the oracle's loop (1e-5 float, 1e-9
-    double)."""
+    normal equations equal plain fp64 sums, and iterations / state / counts / final transform of twelve aligns (SVD,
+    point-to-plane, the symmetric objective, ICPWithNormals, reciprocal correspondences; float and double; gates; tracking
+    off / on / automatic) equal the oracle's loop (1e-5 float, 1e-9 double); the four stand-alone estimators against the
+    oracle's."""
     import oracle
     oracle.build()
     odir = os.path.join(ROOT, "oracle")
