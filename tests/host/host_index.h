@@ -80,12 +80,12 @@ struct HostIndex {
   }
 };
 
-static int prefix_len63(unsigned long long a, unsigned long long b)
+static int host_prefix_len63(unsigned long long a, unsigned long long b)
 {
   const unsigned long long x = a ^ b;
   return x == 0 ? 63 : __builtin_clzll(x) - 1;
 }
-static unsigned compact21(unsigned long long v)   // every third bit of v
+static unsigned host_compact21(unsigned long long v)   // every third bit of v
 {
   unsigned r = 0;
   for (int i = 0; i < 21; ++i) r |= static_cast<unsigned>((v >> (3 * i)) & 1ull) << i;
@@ -102,7 +102,7 @@ struct Builder {
 
   void insert(int b, unsigned long long key, int ref)
   {
-    const unsigned cx = compact21(key) >> (21 - b), cy = compact21(key >> 1) >> (21 - b), cz = compact21(key >> 2) >> (21 - b);
+    const unsigned cx = host_compact21(key) >> (21 - b), cy = host_compact21(key >> 1) >> (21 - b), cz = host_compact21(key >> 2) >> (21 - b);
     entries.emplace_back(cell_key(b, cx, cy, cz), ref);
   }
   Box box_of(int first, int last) const
@@ -121,7 +121,7 @@ struct Builder {
   int build(int first, int last, int l_parent)
   {
     const int count = last - first + 1;
-    const int l_self = prefix_len63(keys[first], keys[last]);
+    const int l_self = host_prefix_len63(keys[first], keys[last]);
     int ref;
     if (count <= kLeafSize) {
       const int leaf = static_cast<int>(I.pts.size() / kLeafSize);
@@ -169,7 +169,14 @@ struct Builder {
   }
 };
 
-static void build_index(HostIndex& I, const std::vector<float>& xyz, int bmax)
+static void build_index_reference(HostIndex& I, const std::vector<float>& xyz, int bmax);
+#ifdef PCLB_TEST_DEVICE_BUILD   // every test in this translation unit searches an index the DEVICE build kernels produced
+namespace device_build { inline void build(HostIndex& I, const std::vector<float>& xyz, bool build_cell_table); }
+static void build_index(HostIndex& I, const std::vector<float>& xyz, int /*bmax: the build decides*/) { device_build::build(I, xyz, true); }
+#else
+static void build_index(HostIndex& I, const std::vector<float>& xyz, int bmax) { build_index_reference(I, xyz, bmax); }
+#endif
+static void build_index_reference(HostIndex& I, const std::vector<float>& xyz, int bmax)
 {
   I = HostIndex();
   I.xyz = xyz;
@@ -236,3 +243,6 @@ static Truth brute(const std::vector<float>& xyz, const float q[3], float gate)
   return t;
 }
 
+#ifdef PCLB_TEST_DEVICE_BUILD
+#include "device_build.h"
+#endif

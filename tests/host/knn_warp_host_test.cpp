@@ -33,12 +33,15 @@ static void run_scene(const char* name, const std::vector<float>& xyz, const std
   build_index(I, xyz, bmax);
   if (I.node_leaves.size() < I.nodes.size()) I.node_leaves.resize(I.nodes.size());
   const TreeView T = I.view(true);
+  b_start = std::min(b_start, I.bmax);   // (an index built by the device kernels chooses its own finest level)
+  if (b_start < 1) { std::printf("%-34s skipped: this index has no cell table\n", name); return; }
   const std::size_t nq = queries.size() / 3;
   std::vector<float4> q(nq);
   for (std::size_t i = 0; i < nq; ++i) q[i] = make_float4(queries[3 * i], queries[3 * i + 1], queries[3 * i + 2], __int_as_float(static_cast<int>(i)));
   std::vector<int32_t> out_idx(nq * k, -7);
   std::vector<float> out_d2(nq * k, -7.f);
   std::vector<unsigned char> redo(nq, 0);
+  blockDim.x = 32;
   const long prims = warp_emu::run_warp([&] {
     k_knn_warp<false>(T, I.node_leaves.data(), b_start, r_first, q.data(), nq, k, out_idx.data(), out_d2.data(), 0.f, 0.f, 0.f, nullptr,
                       nullptr, redo.data());
@@ -79,12 +82,15 @@ static void run_normals(const char* name, const std::vector<float>& xyz, const s
   build_index(I, xyz, bmax);
   if (I.node_leaves.size() < I.nodes.size()) I.node_leaves.resize(I.nodes.size());
   const TreeView T = I.view(true);
+  b_start = std::min(b_start, I.bmax);
+  if (b_start < 1) { std::printf("%-34s skipped: this index has no cell table\n", name); return; }
   const std::size_t nq = queries.size() / 3;
   std::vector<float4> q(nq), out_n(nq, make_float4(-9.f, -9.f, -9.f, -9.f));
   for (std::size_t i = 0; i < nq; ++i) q[i] = make_float4(queries[3 * i], queries[3 * i + 1], queries[3 * i + 2], __int_as_float(static_cast<int>(i)));
   std::vector<unsigned char> redo(nq, 0);
   int not_dense = 0;
   const float vp[3] = {0.4f, 0.6f, 5.f};
+  blockDim.x = 32;
   warp_emu::run_warp([&] {
     k_knn_warp<true>(T, I.node_leaves.data(), b_start, 0.f, q.data(), nq, k, nullptr, nullptr, vp[0], vp[1], vp[2], out_n.data(), &not_dense,
                      redo.data());

@@ -180,6 +180,10 @@ template <typename T> static inline T __ldcg(const T* p) { return *p; }
 static inline unsigned atomicAdd(unsigned* p, unsigned v) { const unsigned o = *p; *p = o + v; return o; }          // fibers never run concurrently
 static inline unsigned long long atomicAdd(unsigned long long* p, unsigned long long v) { const unsigned long long o = *p; *p = o + v; return o; }
 static inline int atomicExch(int* p, int v) { const int o = *p; *p = v; return o; }
+static inline int atomicMin(int* p, int v) { const int o = *p; if (v < o) *p = v; return o; }
+static inline int atomicMax(int* p, int v) { const int o = *p; if (v > o) *p = v; return o; }
+static inline unsigned long long atomicCAS(unsigned long long* p, unsigned long long cmp, unsigned long long v) { const unsigned long long o = *p; if (o == cmp) *p = v; return o; }
+static inline int __clzll(long long x) { return x == 0 ? 64 : __builtin_clzll(static_cast<unsigned long long>(x)); }
 static inline int __popc(unsigned v) { return __builtin_popcount(v); }
 static inline float __fdiv_rn(float a, float b) { volatile float x = a, y = b; volatile float r = x / y; return r; }
 static inline int max(int a, int b) { return a > b ? a : b; }
