@@ -31,6 +31,7 @@ static inline float __fadd_ru(float a, float b) { volatile float x = a, y = b; r
 static inline float __fsub_rd(float a, float b) { volatile float x = a, y = b; return directed(FE_DOWNWARD, [&] { return x - y; }); }
 static inline float __fmul_rd(float a, float b) { volatile float x = a, y = b; return directed(FE_DOWNWARD, [&] { return x * y; }); }
 static inline float __fmul_ru(float a, float b) { volatile float x = a, y = b; return directed(FE_UPWARD, [&] { return x * y; }); }
+static inline float __fsqrt_rn(float a) { volatile float x = a; volatile float r = std::sqrt(x); return r; }
 static inline float __fsqrt_ru(float a) { volatile float x = a; return directed(FE_UPWARD, [&] { return std::sqrt(x); }); }
 static inline unsigned max(unsigned a, unsigned b) { return a > b ? a : b; }   // CUDA's global integer max
 static inline double __dadd_rn(double a, double b) { volatile double x = a, y = b; volatile double r = x + y; return r; }

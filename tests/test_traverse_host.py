@@ -1,7 +1,7 @@
 """The DEVICE code compiled for the HOST (tests/host/*.cpp) — CPU only; nothing runs on a GPU.
 
 g++ sees the same headers the kernels are built from (pcl_b200/csrc/traverse.cuh, knn_warp.cuh, search_kernels.cuh,
-icp_kernels.cuh, lbvh_kernels.cuh); the CUDA intrinsics are supplied with the same rounding, warp- and block-synchronous
+icp_kernels.cuh, lbvh_kernels.cuh, voxel_kernels.cuh); the CUDA intrinsics are supplied with the same rounding, warp- and block-synchronous
 primitives by a lock-step emulation of one thread block (tests/host/warp_emu.h: one fiber per thread, every *_sync
 primitive a rendezvous; the m8n8k4 fp64 MMA emulated fragment by fragment).  Each program checks against brute force
 under the library's own distance expression and tie rule, against the facade's host-side PCL functions, or against the
@@ -81,3 +81,15 @@ def test_whole_icp_iterations_on_an_emulated_block(tmp_path, device_built):
     odir = os.path.join(ROOT, "oracle")
     out = _run(tmp_path, "icp_host_test.cpp", (), DEVICE_BUILD if device_built else (), ["-L" + odir, "-lpcl_oracle", "-Wl,-rpath," + odir])
     assert "tracking automatic" in out and "point-to-plane LLS double" in out and "reciprocal" in out
+
+
+def test_voxelgrid_kernels_on_the_host(tmp_path):
+    """voxel_kernels.cuh in voxel.cu's sequence (bounds -> cell keys -> stable sort -> run heads -> runs -> minimum-points
+    filter -> centroids -> normal / curvature planes), against the oracle's VoxelGrid: the same voxels in the same order,
+    every centroid and every PointNormal plane bit for bit; anisotropic leaves, a far-from-origin sweep, non-finite points,
+    an index subset, the minimum-points filter, and the overflow guard."""
+    import oracle
+    oracle.build()
+    odir = os.path.join(ROOT, "oracle")
+    out = _run(tmp_path, "voxel_host_test.cpp", ["2"], (), ["-L" + odir, "-lpcl_oracle", "-Wl,-rpath," + odir])
+    assert "overflow guard" in out and "PointNormal, min 2 points" in out
