@@ -1604,11 +1604,23 @@ struct orc_icp_result {
   long long total_correspondences;   // summed over the iterations (throughput accounting in bench.py)
 };
 
+// The knobs of the loop that sit outside Registration's own setters: DefaultConvergenceCriteria's members
+// (default_convergence_criteria.h:148-152, 307-310), TransformationEstimationSVD(use_umeyama = false)
+// (transformation_estimation_svd.h:69) and setEnforceSameDirectionNormals (icp.h:402-418).  nullptr = the defaults.
+struct orc_icp_ext {
+  int32_t failure_after_max_iter;             // default 0
+  int32_t max_iterations_similar_transforms;  // default 0
+  int32_t svd_no_umeyama;                     // default 0
+  int32_t enforce_same_direction_normals;     // default 1
+  double mse_threshold_absolute;              // default 1e-12
+};
+
 template <typename S>
 static void icp_run(const orc_icp_params& P, const float* src, size_t n_s, size_t ss,
                     const int32_t* indices, size_t n_idx, const float* tgt, size_t n_t, size_t ts,
                     const double* guess, orc_icp_result& R, float* out_cloud, void* prebuilt_tree = nullptr,
-                    const orc_rejector* rejectors = nullptr, int n_rejectors = 0)
+                    const orc_rejector* rejectors = nullptr, int n_rejectors = 0, const orc_icp_ext* X = nullptr,
+                    orc_corr* last_corr = nullptr, size_t* n_last_corr = nullptr)
 {
   // Registration::align (registration/.../impl/registration.hpp:172-221) +
   // IterativeClosestPoint::computeTransformation (impl/icp.hpp:113-268)
@@ -1636,6 +1648,11 @@ static void icp_run(const orc_icp_params& P, const float* src, size_t n_s, size_
   conv.translation_threshold = P.transformation_epsilon;
   if (P.transformation_rotation_epsilon > 0)
     conv.rotation_threshold = P.transformation_rotation_epsilon;
+  if (X) {
+    conv.failure_after_max_iter = X->failure_after_max_iter != 0;
+    conv.max_iterations_similar_transforms = X->max_iterations_similar_transforms;
+    conv.mse_threshold_absolute = X->mse_threshold_absolute;
+  }
   std::vector<orc_corr> corr(indices ? n_idx : n_s);
   int iterations = 0;
   bool converged = false;
@@ -1686,12 +1703,15 @@ static void icp_run(const orc_icp_params& P, const float* src, size_t n_s, size_
       mse += corr[i].distance;
     }
     mse /= static_cast<double>(nc);
-    if (P.estimator == 0)
+    if (P.estimator == 0 && X && X->svd_no_umeyama)
+      correlation_svd<S>(cur.data(), ss, tgt, ts, qi.data(), mi.data(), nc, T);
+    else if (P.estimator == 0)
       umeyama<S>(cur.data(), ss, tgt, ts, qi.data(), mi.data(), nc, T);
     else if (P.estimator == 1)
       p2plane_lls<S>(cur.data(), ss, tgt, tgt + 4, ts, qi.data(), mi.data(), nc, T);
     else  // symmetric objective; setEnforceSameDirectionNormals(true) is the class default (icp.h:366-371)
-      sym_p2plane_lls<S>(cur.data(), cur.data() + 4, ss, tgt, tgt + 4, ts, qi.data(), mi.data(), nc, true, T);
+      sym_p2plane_lls<S>(cur.data(), cur.data() + 4, ss, tgt, tgt + 4, ts, qi.data(), mi.data(), nc,
+                         X ? X->enforce_same_direction_normals != 0 : true, T);
     transform_points<S>(cur.data(), n_s, ss, noff, T, tmode);
     mat4_mul<S>(T, final_T, final_T);
     ++iterations;
@@ -1707,6 +1727,10 @@ static void icp_run(const orc_icp_params& P, const float* src, size_t n_s, size_
   R.n_correspondences = (int32_t)nc;
   R.mse = mse;
   R.total_correspondences = total_nc;
+  if (last_corr) {  // Registration::correspondences_ after the loop: those of the last evaluated iteration
+    std::copy(corr.begin(), corr.begin() + nc, last_corr);
+    *n_last_corr = nc;
+  }
   if (out_cloud) {  // output = *input_; transformCloud(*input_, output, final) — icp.hpp:265-267
     std::memcpy(out_cloud, src, n_s * ss * sizeof(float));
     transform_points<S>(out_cloud, n_s, ss, noff, final_T, tmode);
@@ -1744,6 +1768,21 @@ ORC_API void orc_icp_align_rej(const orc_icp_params* P, const orc_rejector* rej,
     icp_run<double>(*P, src, n_s, sstride, nullptr, 0, tgt, n_t, tstride, nullptr, *R, nullptr, nullptr, rej, n_rej);
   else
     icp_run<float>(*P, src, n_s, sstride, nullptr, 0, tgt, n_t, tstride, nullptr, *R, nullptr, nullptr, rej, n_rej);
+}
+
+// Everything at once: rejector chain + kept target tree + source indices + guess + the criteria / estimator knobs, and
+// the correspondences of the last evaluated iteration (capacity: the number of indexed source points).
+ORC_API void orc_icp_align_full(const orc_icp_params* P, const orc_icp_ext* X, const orc_rejector* rej, int n_rej,
+                                void* h_tgt, const float* src, size_t n_s, size_t sstride, const int32_t* indices,
+                                size_t n_idx, const float* tgt, size_t n_t, size_t tstride, const double* guess,
+                                orc_icp_result* R, float* out_cloud, orc_corr* last_corr, size_t* n_last_corr)
+{
+  if (P->scalar_is_double)
+    icp_run<double>(*P, src, n_s, sstride, indices, n_idx, tgt, n_t, tstride, guess, *R, out_cloud, h_tgt, rej, n_rej, X,
+                    last_corr, n_last_corr);
+  else
+    icp_run<float>(*P, src, n_s, sstride, indices, n_idx, tgt, n_t, tstride, guess, *R, out_cloud, h_tgt, rej, n_rej, X,
+                   last_corr, n_last_corr);
 }
 
 // Registration::getFitnessScore — registration/.../impl/registration.hpp:134-168
