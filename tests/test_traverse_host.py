@@ -1,7 +1,7 @@
 """The DEVICE code compiled for the HOST (tests/host/*.cpp) — CPU only; nothing runs on a GPU.
 
 g++ sees the same headers the kernels are built from (pcl_b200/csrc/traverse.cuh, knn_warp.cuh, search_kernels.cuh,
-icp_kernels.cuh, lbvh_kernels.cuh, voxel_kernels.cuh); the CUDA intrinsics are supplied with the same rounding, warp- and block-synchronous
+icp_kernels.cuh, lbvh_kernels.cuh, voxel_kernels.cuh, reject_kernels.cuh); the CUDA intrinsics are supplied with the same rounding, warp- and block-synchronous
 primitives by a lock-step emulation of one thread block (tests/host/warp_emu.h: one fiber per thread, every *_sync
 primitive a rendezvous; the m8n8k4 fp64 MMA emulated fragment by fragment).  Each program checks against brute force
 under the library's own distance expression and tie rule, against the facade's host-side PCL functions, or against the
@@ -93,3 +93,14 @@ def test_voxelgrid_kernels_on_the_host(tmp_path):
     odir = os.path.join(ROOT, "oracle")
     out = _run(tmp_path, "voxel_host_test.cpp", ["2"], (), ["-L" + odir, "-lpcl_oracle", "-Wl,-rpath," + odir])
     assert "overflow guard" in out and "PointNormal, min 2 points" in out
+
+
+def test_rejector_kernels_on_the_host(tmp_path):
+    """reject_kernels.cuh in reject.cu's sequence (stable sorts where the driver calls CUB) against the oracle's rejectors:
+    survivors, their order and the median bit for bit for Distance / MedianDistance / OneToOne / Trimmed on eleven lists
+    (ties, shared and negative matches, 0 / 1 / 2 / 256 / 257 records) and three chains."""
+    import oracle
+    oracle.build()
+    odir = os.path.join(ROOT, "oracle")
+    out = _run(tmp_path, "reject_host_test.cpp", ["2"], (), ["-L" + odir, "-lpcl_oracle", "-Wl,-rpath," + odir])
+    assert "every distance equal" in out and "DIFFERS" not in out
