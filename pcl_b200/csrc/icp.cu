@@ -74,71 +74,6 @@ __global__ void k_scatter_xyz(const float4* __restrict__ src, size_t n, unsigned
     o[3] = w;
 }
 
-// correspondences by slot: match = original target index or -1
-template <bool RECIP>
-__global__ void __launch_bounds__(128)
-k_corr(const TreeView T, const float4* __restrict__ q,
-       size_t nq, float gate, const BvhNode* __restrict__ s_nodes, const float4* __restrict__ s_pts, int s_root,
-       const int32_t* __restrict__ src_orig, pclb200_corr* __restrict__ out, int* __restrict__ d_error)
-{
-  size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
-  if (i >= nq)
-    return;
-  const float4 p = __ldg(q + i);
-  const int slot = __float_as_int(p.w);
-  const int my_orig = src_orig ? src_orig[slot] : slot;
-  pclb200_corr r;
-  r.index_query = my_orig;
-  r.index_match = -1;
-  r.distance = 0.f;
-  if (isfinite(p.x) && isfinite(p.y) && isfinite(p.z)) {
-    Nearest1 v{p.x, p.y, p.z, gate, kSentinelIndex, -1};
-    WalkStats ws{};
-    if (!nearest1<false>(T, p.x, p.y, p.z, v, -1, 1.00001f, ws))
-      atomicExch(d_error, 1);
-    if (v.best_pos >= 0) {
-      bool keep = true;
-      if (RECIP) {
-        const float4 t = ldg4(T.pts + v.best_pos);
-        Nearest1 b{t.x, t.y, t.z, gate, kSentinelIndex, -1};
-        if (!traverse(s_nodes, s_pts, s_root, t.x, t.y, t.z, b))
-          atomicExch(d_error, 1);
-        keep = b.best_pos >= 0 && b.best_idx == my_orig;
-      }
-      if (keep) {
-        r.index_match = v.best_idx;
-        r.distance = v.best;
-      }
-    }
-  }
-  out[slot] = r;
-}
-
-
-// fitness: sum of d2 <= max_range and count (registration.hpp:146-163)
-__global__ void __launch_bounds__(256)
-k_fitness(const TreeView T, const float4* __restrict__ q, size_t nq, double max_range, IterArgs pub)
-{
-  double acc[2] = {0.0, 0.0};
-  bool overflow = false;
-  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < nq; i += (size_t)gridDim.x * blockDim.x) {
-    const float4 p = __ldg(q + i);
-    if (!(isfinite(p.x) && isfinite(p.y) && isfinite(p.z)))
-      continue;
-    Nearest1 v{p.x, p.y, p.z, __int_as_float(0x7f800000), kSentinelIndex, -1};
-    WalkStats ws{};
-    if (!nearest1<false>(T, p.x, p.y, p.z, v, -1, 1.00001f, ws))
-      overflow = true;
-    if (v.best_pos >= 0 && (double)v.best <= max_range) {
-      acc[0] += 1.0;
-      acc[1] += (double)v.best;
-    }
-  }
-  if (overflow)
-    atomicExch(pub.d_error, 1);
-  block_reduce_and_publish<2>(acc, pub);
-}
-
 // =============================================================================================================
 // host side
 // =============================================================================================================
@@ -149,52 +84,6 @@ static void check_device_error(Ctx& c);
 // of its k nearest neighbours relative to the point (float differences widened to double), mean removed, SVD, singular
 // values replaced by (1, 1, gicp_epsilon), reassembled from the columns of U.  One thread per point over the exact k-NN
 // rows of launch_knn; the 3x3 Jacobi SVD is k_solve's.
-__global__ void __launch_bounds__(128)
-k_gicp_cov(const float4* __restrict__ q, size_t n, const int32_t* __restrict__ rows, int k_rows, int k_div,
-           const float4* __restrict__ pts, const int32_t* __restrict__ pos_of_orig, double gicp_epsilon,
-           double* __restrict__ out)
-{
-  const size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
-  if (i >= n)
-    return;
-  const float4 qq = q[i];
-  double o[9] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
-  if (isfinite(qq.x) && isfinite(qq.y) && isfinite(qq.z)) {
-    double mean[3] = {0.0, 0.0, 0.0}, cov[9] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
-    const int32_t* row = rows + i * (size_t)k_rows;
-    for (int j = 0; j < k_rows; ++j) {
-      const int32_t oi = row[j];
-      if (oi < 0)
-        break;
-      const float4 p = ldg4(pts + pos_of_orig[oi]);
-      const double ptx = (double)__fsub_rn(p.x, qq.x), pty = (double)__fsub_rn(p.y, qq.y), ptz = (double)__fsub_rn(p.z, qq.z);
-      mean[0] += ptx; mean[1] += pty; mean[2] += ptz;
-      cov[0] += ptx * ptx;
-      cov[3] += pty * ptx; cov[4] += pty * pty;
-      cov[6] += ptz * ptx; cov[7] += ptz * pty; cov[8] += ptz * ptz;
-    }
-    const double kk = (double)k_div;
-    for (int d = 0; d < 3; ++d)
-      mean[d] /= kk;
-    for (int r = 0; r < 3; ++r)
-      for (int c = 0; c <= r; ++c) {
-        cov[3 * r + c] /= kk;
-        cov[3 * r + c] -= mean[r] * mean[c];
-        cov[3 * c + r] = cov[3 * r + c];
-      }
-    double U[9], sv[3], V[9];
-    svd3_dev(cov, U, sv, V);
-    for (int kc = 0; kc < 3; ++kc) {
-      const double v = kc == 2 ? gicp_epsilon : 1.0;
-      for (int r = 0; r < 3; ++r)
-        for (int c = 0; c < 3; ++c)
-          o[3 * r + c] += v * U[3 * r + kc] * U[3 * c + kc];
-    }
-  }
-  for (int e = 0; e < 9; ++e)
-    out[9 * i + e] = o[e];
-}
-
 void gicp_covariances(Ctx& c, Index& idx, const void* pts, size_t n, size_t stride, int k, double gicp_epsilon,
                       double* out)
 {

@@ -104,3 +104,15 @@ def test_rejector_kernels_on_the_host(tmp_path):
     odir = os.path.join(ROOT, "oracle")
     out = _run(tmp_path, "reject_host_test.cpp", ["2"], (), ["-L" + odir, "-lpcl_oracle", "-Wl,-rpath," + odir])
     assert "every distance equal" in out and "DIFFERS" not in out
+
+
+def test_searcher_consumer_kernels_on_the_host(tmp_path):
+    """icp_kernels.cuh: k_corr (pclb200_correspondences, plain and reciprocal), k_fitness (getFitnessScore) and k_gicp_cov on
+    the emulated block over the device-built index, against the oracle: correspondence lists bit for bit (gates incl. 0 and
+    none, a descending index subset, non-finite source points, duplicated target points), fitness to 1e-12 in float and
+    double, the regularised GICP covariances to 1e-9."""
+    import oracle
+    oracle.build()
+    odir = os.path.join(ROOT, "oracle")
+    out = _run(tmp_path, "consumers_host_test.cpp", (), DEVICE_BUILD, ["-L" + odir, "-lpcl_oracle", "-Wl,-rpath," + odir])
+    assert "reciprocal, index subset" in out and "GICP covariances" in out
