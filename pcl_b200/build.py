@@ -15,7 +15,7 @@ CSRC = os.path.join(HERE, "csrc")
 OBJ = os.path.join(HERE, "build")
 SO = os.path.join(HERE, "libpclb200.so")
 SOURCES = ["alloc.cu", "lbvh.cu", "search.cu", "icp.cu", "voxel.cu", "reject.cu", "normals_corr.cu", "cluster.cu", "comm.cu", "capi.cu"]
-HEADERS = ["internal.cuh", "traverse.cuh", "knn_warp.cuh", "search_kernels.cuh", "lbvh_kernels.cuh", "voxel_kernels.cuh", "reject_kernels.cuh", "icp_kernels.cuh", "corr_select.cuh", os.path.join("..", "..", "include", "pclb200.h")]
+HEADERS = ["internal.cuh", "traverse.cuh", "knn_warp.cuh", "search_kernels.cuh", "lbvh_kernels.cuh", "voxel_kernels.cuh", "reject_kernels.cuh", "normals_corr_kernels.cuh", "cluster_kernels.cuh", "icp_kernels.cuh", "corr_select.cuh", os.path.join("..", "..", "include", "pclb200.h")]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-fmad=false",
          "-Xcompiler", "-fPIC,-fvisibility=hidden", "-Xptxas", "-v", "--expt-relaxed-constexpr",

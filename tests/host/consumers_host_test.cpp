@@ -10,6 +10,8 @@
 #include <cfloat>
 
 #include "../../pcl_b200/csrc/icp_kernels.cuh"
+#include "../../pcl_b200/csrc/normals_corr_kernels.cuh"
+#include "../../pcl_b200/csrc/cluster_kernels.cuh"
 
 extern "C" {
 void* orc_index_build(const float* pts, size_t n, size_t stride, const int32_t* subset, size_t n_subset);
@@ -22,6 +24,12 @@ size_t orc_correspondences_reciprocal(void* h_tgt, void* h_src, const float* src
 double orc_fitness_score(void* h_tgt, const float* src, size_t n_s, size_t sstride, const int32_t* indices, size_t n_idx, int is_dense,
                          const double* final_T, int scalar_is_double, double max_range, int nthreads);
 void orc_gicp_covariances(void* h, const float* cloud, size_t n, size_t stride, int k, double gicp_epsilon, double* out, int nthreads);
+size_t orc_correspondences_normals(void* h_tgt, int kind, const float* src, size_t n_src, size_t sstride, const float* sn, size_t snstride,
+                                   const float* tgt, size_t tstride, const float* tn, size_t tnstride, const int32_t* indices, size_t n_idx,
+                                   int k, double max_distance, pclb200_corr* out, int nthreads);
+void orc_cluster_labels(void* h, size_t n_cloud, double tolerance, int32_t* out_labels);
+size_t orc_reject_surface_normal(const pclb200_corr* in, size_t n, const float* sn, size_t snstride, const float* tn, size_t tnstride,
+                                 double threshold, pclb200_corr* out);
 }
 
 static long g_checks = 0, g_fail = 0;
@@ -181,6 +189,98 @@ int main()
     for (std::size_t e = 0; e < got.size(); ++e) worst = std::max(worst, std::fabs(got[e] - wantc[e]));
     CHECK(worst < 1e-9, "GICP covariances: largest difference %.3g", worst);
     std::printf("GICP covariances k = 20: largest |difference| over %d matrices %.3g\n", nt, worst);
+  }
+  // ---- normal shooting / back projection over exact k-NN rows; the surface-normal rejector --------------------------------
+  {
+    auto unit_normals = [&](const std::vector<float>& c4, float tilt) {
+      std::vector<float> n(c4.size(), 0.f);
+      for (std::size_t i = 0; i < c4.size() / 4; ++i) {
+        float nx = -0.8f * std::cos(4.f * c4[4 * i]) + tilt * N(rng), ny = tilt * N(rng), nz = 1.f;
+        const float inv = 1.f / std::sqrt(nx * nx + ny * ny + nz * nz);
+        n[4 * i] = nx * inv; n[4 * i + 1] = ny * inv; n[4 * i + 2] = nz * inv;
+      }
+      return n;
+    };
+    const std::vector<float> sn = unit_normals(src, 0.05f), tn = unit_normals(tgt, 0.05f);
+    std::vector<int32_t> pos_of_orig(nt, -1);
+    for (std::size_t p = 0; p < IT.pts.size(); ++p) { const int o = __float_as_int(IT.pts[p].w); if (o != kSentinelIndex) pos_of_orig[o] = (int32_t)p; }
+    const float4* sn4 = reinterpret_cast<const float4*>(sn.data());
+    const float4* tn4 = reinterpret_cast<const float4*>(tn.data());
+    for (int kind : {PCLB200_CORR_NORMAL_SHOOTING, PCLB200_CORR_BACK_PROJECTION})
+      for (int k : {10, 3})
+        for (double md : {0.02, 0.0008})
+          for (int use_subset = 0; use_subset < 2; ++use_subset) {
+            const std::vector<int32_t>* ind = use_subset ? &subset : nullptr;
+            const std::size_t nq = ind ? ind->size() : (std::size_t)ns;
+            std::vector<float4> dense(nq);
+            std::vector<float> q4(4 * nq);
+            for (std::size_t i = 0; i < nq; ++i) {
+              const float* p = &src[4 * (ind ? (std::size_t)(*ind)[i] : i)];
+              dense[i] = make_float4(p[0], p[1], p[2], 1.f);
+              std::memcpy(&q4[4 * i], p, 16);
+            }
+            std::vector<int32_t> rows(nq * k);
+            std::vector<float> rd(nq * k);
+            orc_knn(ot, q4.data(), nq, 4, k, rows.data(), rd.data(), 2);
+            std::vector<pclb200_corr> by_slot(nq), got;
+            launch((unsigned)((nq + 127) / 128), 128, [&] {
+              k_corr_by_normals(dense.data(), nq, ind ? ind->data() : nullptr, sn4, kind, k, rows.data(), rd.data(), IT.pts.data(), pos_of_orig.data(), tn4, md, by_slot.data());
+            });
+            for (const pclb200_corr& c : by_slot) if (c.index_match >= 0) got.push_back(c);
+            want.resize(ns);
+            want.resize(orc_correspondences_normals(ot, kind, src.data(), ns, 4, sn.data(), 4, tgt.data(), 4, tn.data(), 4, ind ? ind->data() : nullptr, ind ? ind->size() : 0, k,
+                                                    md, want.data(), 2));
+            char name[128];
+            std::snprintf(name, sizeof name, "%s, k = %d, max distance %.3g%s", kind == PCLB200_CORR_NORMAL_SHOOTING ? "normal shooting" : "back projection", k, md,
+                          use_subset ? ", subset" : "");
+            compare_lists(name, got, want);
+          }
+    // CorrespondenceRejectorSurfaceNormal on the nearest-neighbour pairs, incl. out-of-range records
+    std::vector<pclb200_corr> pairs(ns);
+    pairs.resize(orc_correspondences(ot, src.data(), ns, 4, nullptr, 0, 1, 0.05, pairs.data(), 2));
+    for (double thr : {0.0, 0.9, 0.995, 1.0, -1.0}) {
+      std::vector<pclb200_corr> marked(pairs.size()), got;
+      launch((unsigned)((pairs.size() + 255) / 256), 256, [&] { k_mark_surface_normal(pairs.data(), pairs.size(), sn4, (size_t)ns, tn4, (size_t)nt, thr, marked.data()); });
+      for (const pclb200_corr& c : marked) if (c.index_match >= 0) got.push_back(c);
+      want.resize(pairs.size());
+      want.resize(orc_reject_surface_normal(pairs.data(), pairs.size(), sn.data(), 4, tn.data(), 4, thr, want.data()));
+      char name[96];
+      std::snprintf(name, sizeof name, "surface-normal rejector, threshold %g", thr);
+      compare_lists(name, got, want);
+    }
+  }
+  // ---- Euclidean clustering: union-find over the tolerance graph, label = smallest original index of the component -------
+  {
+    const int nb = 5000;
+    std::vector<float> blobs(4 * nb, 1.f);
+    for (int i = 0; i < nb; ++i) {
+      const int b = i % 23;
+      blobs[4 * i] = 0.31f * (b % 5) + 0.02f * N(rng);
+      blobs[4 * i + 1] = 0.29f * (b / 5) + 0.02f * N(rng);
+      blobs[4 * i + 2] = 0.01f * N(rng);
+    }
+    for (int i = 0; i < 60; ++i) std::memcpy(&blobs[4 * (nb - 1 - i)], &blobs[4 * (7 * i)], 12);   // exact duplicates (distance 0)
+    HostIndex IB;
+    build_index(IB, xyz_of(blobs), 4);
+    void* ob = orc_index_build(blobs.data(), nb, 4, nullptr, 0);
+    const std::size_t np = IB.pts.size();
+    for (double tol : {0.02, 0.008, 0.05, 0.2, 1e-9}) {
+      const double t = (double)(float)tol;
+      const float r2 = (float)(t * t), r2_below = std::nextafter(r2, -INFINITY);
+      std::vector<int> parent(np), min_orig(np);
+      std::vector<int32_t> labels(nb, -1), wantl(nb, -2);
+      int d_error = 0;
+      launch((unsigned)((np + 255) / 256), 256, [&] { k_cc_init(parent.data(), min_orig.data(), np); });
+      launch((unsigned)((np + 127) / 128), 128, [&] { k_cc_union(IB.nodes.data(), IB.pts.data(), IB.root, np, r2, r2_below, parent.data(), &d_error); });
+      launch((unsigned)((np + 255) / 256), 256, [&] { k_cc_min_orig(IB.pts.data(), np, parent.data(), min_orig.data()); });
+      launch((unsigned)((np + 255) / 256), 256, [&] { k_cc_labels(IB.pts.data(), np, parent.data(), min_orig.data(), labels.data()); });
+      orc_cluster_labels(ob, nb, tol, wantl.data());
+      int bad = 0, comps = 0;
+      for (int i = 0; i < nb; ++i) { bad += labels[i] != wantl[i]; comps += labels[i] == i; }
+      CHECK(bad == 0 && d_error == 0, "clustering, tolerance %g: %d labels differ from the oracle's", tol, bad);
+      std::printf("Euclidean clustering, tolerance %-8g %5d components over %d points, %d labels differ\n", tol, comps, nb, bad);
+    }
+    orc_index_free(ob);
   }
   orc_index_free(ot);
   orc_index_free(os);

@@ -182,6 +182,7 @@ static inline unsigned long long atomicAdd(unsigned long long* p, unsigned long 
 static inline int atomicExch(int* p, int v) { const int o = *p; *p = v; return o; }
 static inline int atomicMin(int* p, int v) { const int o = *p; if (v < o) *p = v; return o; }
 static inline int atomicMax(int* p, int v) { const int o = *p; if (v > o) *p = v; return o; }
+static inline int atomicCAS(int* p, int cmp, int v) { const int o = *p; if (o == cmp) *p = v; return o; }
 static inline unsigned long long atomicCAS(unsigned long long* p, unsigned long long cmp, unsigned long long v) { const unsigned long long o = *p; if (o == cmp) *p = v; return o; }
 static inline int __clzll(long long x) { return x == 0 ? 64 : __builtin_clzll(static_cast<unsigned long long>(x)); }
 static inline int __popc(unsigned v) { return __builtin_popcount(v); }

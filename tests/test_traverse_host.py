@@ -1,7 +1,7 @@
 """The DEVICE code compiled for the HOST (tests/host/*.cpp) — CPU only; nothing runs on a GPU.
 
 g++ sees the same headers the kernels are built from (pcl_b200/csrc/traverse.cuh, knn_warp.cuh, search_kernels.cuh,
-icp_kernels.cuh, lbvh_kernels.cuh, voxel_kernels.cuh, reject_kernels.cuh); the CUDA intrinsics are supplied with the same rounding, warp- and block-synchronous
+icp_kernels.cuh, lbvh_kernels.cuh, voxel_kernels.cuh, reject_kernels.cuh, normals_corr_kernels.cuh, cluster_kernels.cuh); the CUDA intrinsics are supplied with the same rounding, warp- and block-synchronous
 primitives by a lock-step emulation of one thread block (tests/host/warp_emu.h: one fiber per thread, every *_sync
 primitive a rendezvous; the m8n8k4 fp64 MMA emulated fragment by fragment).  Each program checks against brute force
 under the library's own distance expression and tie rule, against the facade's host-side PCL functions, or against the
@@ -107,12 +107,14 @@ def test_rejector_kernels_on_the_host(tmp_path):
 
 
 def test_searcher_consumer_kernels_on_the_host(tmp_path):
-    """icp_kernels.cuh: k_corr (pclb200_correspondences, plain and reciprocal), k_fitness (getFitnessScore) and k_gicp_cov on
-    the emulated block over the device-built index, against the oracle: correspondence lists bit for bit (gates incl. 0 and
-    none, a descending index subset, non-finite source points, duplicated target points), fitness to 1e-12 in float and
-    double, the regularised GICP covariances to 1e-9."""
+    """icp_kernels.cuh: k_corr (pclb200_correspondences, plain and reciprocal), k_fitness (getFitnessScore) and k_gicp_cov;
+    normals_corr_kernels.cuh: normal shooting / back projection over k-NN rows and the surface-normal rejector;
+    cluster_kernels.cuh: the union-find clustering — on the emulated block over the device-built index, against the oracle:
+    correspondence lists bit for bit (gates incl. 0 and none, a descending index subset, non-finite source points, duplicated
+    target points), fitness to 1e-12 in float and double, the regularised GICP covariances to 1e-9, cluster labels equal at
+    five tolerances (2 ... 4 940 components)."""
     import oracle
     oracle.build()
     odir = os.path.join(ROOT, "oracle")
     out = _run(tmp_path, "consumers_host_test.cpp", (), DEVICE_BUILD, ["-L" + odir, "-lpcl_oracle", "-Wl,-rpath," + odir])
-    assert "reciprocal, index subset" in out and "GICP covariances" in out
+    assert "reciprocal, index subset" in out and "GICP covariances" in out and "back projection" in out and "Euclidean clustering" in out
