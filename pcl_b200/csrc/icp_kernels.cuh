@@ -1121,6 +1121,74 @@ __global__ void k_solve(const double* __restrict__ accum, int est, int scalar_is
   }
 }
 
+// ---- the stages between search and accumulate (drivers: run_rejectors and the normal-based estimators in icp.cu) --------
+// Match array <-> flat rejector arrays (tie-break = slot = position in the source index list = the order of the
+// reference's correspondences_ vector; target identity = position in the Morton array)
+__global__ void k_match_to_arrays(const float4* __restrict__ cur, const Match* __restrict__ match, size_t n,
+                                  float* __restrict__ d2, int* __restrict__ mt, unsigned* __restrict__ tie, int* __restrict__ acc)
+{
+  size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+  if (i >= n)
+    return;
+  const Match m = match[i];
+  d2[i] = m.d2;
+  mt[i] = m.pos >= 0 ? match_pos(m) : -1;
+  tie[i] = (unsigned)__float_as_int(cur[i].w);
+  acc[i] = match_accepted(m) ? 1 : 0;
+}
+
+__global__ void k_arrays_to_match(const int* __restrict__ acc, size_t n, Match* __restrict__ match)
+{
+  size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+  if (i < n) {
+    const int pos = match[i].pos;
+    if (pos >= 0)
+      match[i].pos = acc[i] ? (pos & kPosMask) : (pos | kNotAccepted);
+  }
+}
+
+// CorrespondenceEstimationNormalShooting / ...BackProjection inside the loop: the candidate rows come from the
+// exact k-NN kernel (rows addressed by slot), the choice is corr_select.cuh's; the result is a Match like the 1-NN
+// search kernels produce, so the rejectors / accumulation / solve downstream are unchanged.
+__global__ void __launch_bounds__(128)
+k_select_match(const float4* __restrict__ cur, const float4* __restrict__ cur_normals, size_t n, int kind, int k,
+               const int32_t* __restrict__ nn_idx, const float* __restrict__ nn_d2, const float4* __restrict__ tgt_pts,
+               const int32_t* __restrict__ pos_of_orig, const float4* __restrict__ tgt_nrm_by_pos, double max_dist,
+               Match* __restrict__ match)
+{
+  const size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+  if (i >= n)
+    return;
+  const float4 p = cur[i];
+  Match m;
+  m.pos = -1;
+  m.d2 = 0.f;
+  if (isfinite(p.x) && isfinite(p.y) && isfinite(p.z)) {
+    const size_t slot = (size_t)(unsigned)__float_as_int(p.w);
+    const float4 nn = cur_normals[i];
+    const int32_t* row_idx = nn_idx + slot * (size_t)k;
+    const float* row_d2 = nn_d2 + slot * (size_t)k;
+    const int j = select_by_normals<true>(kind, k, row_idx, row_d2, p.x, p.y, p.z, nn.x, nn.y, nn.z, tgt_pts,
+                                          pos_of_orig, tgt_nrm_by_pos, max_dist);
+    if (j >= 0 && row_idx[j] >= 0) {
+      m.pos = pos_of_orig[row_idx[j]];
+      m.d2 = row_d2[j];
+    }
+  }
+  match[i] = m;
+}
+
+// CorrespondenceRejectorSurfaceNormal inside the loop: rotated source normal vs the matched target's normal
+__global__ void k_reject_surface_normal(const float4* __restrict__ cur_normals, const float4* __restrict__ tgt_nrm_by_pos,
+                                        const int* __restrict__ mt, size_t n, double threshold, int* __restrict__ acc)
+{
+  const size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+  if (i >= n || !acc[i])
+    return;
+  if (!surface_normal_keeps(cur_normals[i], tgt_nrm_by_pos[mt[i]], threshold))
+    acc[i] = 0;
+}
+
 // ---- consumers of the same searcher outside the loop (drivers in icp.cu) ------------------------------------------------
 // correspondences by slot: match = original target index or -1
 template <bool RECIP>

@@ -12,6 +12,7 @@
 #include <cfloat>
 
 #include "../../pcl_b200/csrc/icp_kernels.cuh"
+#include "reject_twin.h"
 
 // ---- the oracle's C entry points (oracle/pcl_oracle.cpp) ---------------------------------------------------------------
 struct orc_icp_params {
@@ -38,6 +39,17 @@ extern "C" int orc_estimate_point_to_plane_lls(const float* src, size_t sstride,
 extern "C" int orc_estimate_symmetric_lls(const float* src, const float* src_normals, size_t sstride, const float* tgt, const float* tgt_normals,
                                           size_t tstride, const orc_corr* corr, size_t n, int enforce_same_direction, int scalar_is_double, double* T_out);
 
+struct orc_icp_ext {
+  int32_t failure_after_max_iter, max_iterations_similar_transforms, svd_no_umeyama, enforce_same_direction_normals;
+  double mse_threshold_absolute;
+};
+extern "C" void orc_icp_align_full(const orc_icp_params* P, const orc_icp_ext* X, const pclb200_rejector* rej, int n_rej, void* h_tgt, const float* src, size_t n_s,
+                                   size_t sstride, const int32_t* indices, size_t n_idx, const float* tgt, size_t n_t, size_t tstride, const double* guess,
+                                   orc_icp_result* R, float* out_cloud, orc_corr* last_corr, size_t* n_last_corr);
+extern "C" void* orc_index_build(const float* pts, size_t n, size_t stride, const int32_t* subset, size_t n_subset);
+extern "C" void orc_index_free(void* h);
+extern "C" int orc_knn(void* h, const float* q, size_t nq, size_t qstride, int k, int32_t* out_idx, float* out_d2, int nthreads);
+
 static long g_checks = 0, g_fail = 0;
 #define CHECK(c, ...) do { ++g_checks; if (!(c)) { if (++g_fail <= 20) { std::printf("FAIL %s:%d %s  ", __FILE__, __LINE__, #c); std::printf(__VA_ARGS__); std::printf("\n"); } } } while (0)
 
@@ -58,6 +70,9 @@ struct Scene {
 struct Extra {
   bool reciprocal = false;        // setUseReciprocalCorrespondences: the source tree is rebuilt every iteration
   bool with_normals = false;      // IterativeClosestPointWithNormals: the source normals are rotated with every increment
+  std::vector<pclb200_rejector> rejectors;   // Registration::addCorrespondenceRejector chain, applied to every iteration's pairs (icp.cu: run_rejectors)
+  int corr_kind = PCLB200_CORR_NEAREST;      // setCorrespondenceEstimation(NormalShooting / BackProjection): k-NN rows + k_select_match
+  int corr_k = 10;
 };
 
 static void run_align(const char* name, const Scene& S, int estimator, bool scalar_double, double max_dist, double trans_eps, int max_iterations,
@@ -74,6 +89,9 @@ static void run_align(const char* name, const Scene& S, int estimator, bool scal
     const int o = __float_as_int(I.pts[p].w);
     if (o != kSentinelIndex) tgt_normals[p] = make_float4(S.tgt[8 * o + 4], S.tgt[8 * o + 5], S.tgt[8 * o + 6], 0.f);
   }
+  std::vector<int32_t> pos_of_orig(nt, -1);
+  for (std::size_t p = 0; p < I.pts.size(); ++p) { const int o = __float_as_int(I.pts[p].w); if (o != kSentinelIndex) pos_of_orig[o] = (int32_t)p; }
+  void* knn_tree = X.corr_kind != PCLB200_CORR_NEAREST ? orc_index_build(S.tgt.data(), nt, 8, nullptr, 0) : nullptr;
   std::vector<float4> cur(ns), cur_normals;
   for (std::size_t i = 0; i < ns; ++i) cur[i] = make_float4(S.src[4 * i], S.src[4 * i + 1], S.src[4 * i + 2], __int_as_float((int)i));
   if (X.with_normals) {
@@ -149,6 +167,35 @@ static void run_align(const char* name, const Scene& S, int estimator, bool scal
       a.s_nodes = SI.nodes.data(); a.s_pts = SI.pts.data(); a.s_root = SI.root;
       if (!ctrl.done) warp_emu::run_block(256, [&] { k_search<true, false>(a, match.data(), lbs.data()); });
     }
+    else if (X.corr_kind != PCLB200_CORR_NEAREST) {
+      // icp.cu: apply the pending increment, exact k-NN rows addressed by slot, then the normal-based choice
+      if (pending.apply) {
+        for (std::size_t i = 0; i < ns; ++i) {
+          apply_pending(pending, cur[i].x, cur[i].y, cur[i].z);
+          apply_pending_normal(pending, cur_normals[i].x, cur_normals[i].y, cur_normals[i].z);
+        }
+        pending.apply = 0;
+      }
+      if (!ctrl.done) {
+        const int k = X.corr_k;
+        std::vector<int32_t> nn_idx(ns * (std::size_t)k);
+        std::vector<float> nn_d2(ns * (std::size_t)k);
+        orc_knn(knn_tree, reinterpret_cast<const float*>(cur.data()), ns, 4, k, nn_idx.data(), nn_d2.data(), 2);   // rows by slot (slot i = query i here)
+        blockDim.x = 128;
+        for (unsigned b = 0; b < (ns + 127) / 128; ++b) {
+          blockIdx_storage.x = b;
+          warp_emu::run_block(128, [&] {
+            k_select_match(cur.data(), cur_normals.data(), ns, X.corr_kind, k, nn_idx.data(), nn_d2.data(), I.pts.data(), pos_of_orig.data(), tgt_normals.data(),
+                           max_dist, match.data());
+          });
+        }
+        blockIdx_storage.x = 0;
+        blockDim.x = 256;
+      }
+    }
+    else if (!X.rejectors.empty()) {
+      if (!ctrl.done) warp_emu::run_block(256, [&] { k_search<false, false>(a, match.data(), lbs.data()); });
+    }
     else if (track_mode == PCLB200_TRACK_AUTO) {
       a.track_sel = 1;
       warp_emu::run_block(256, [&] { k_search<false, false>(a, match.data(), lbs.data()); });
@@ -158,10 +205,27 @@ static void run_align(const char* name, const Scene& S, int estimator, bool scal
       warp_emu::run_block(256, [&] { k_search<false, true>(a, match.data(), lbs.data()); });
     else
       warp_emu::run_block(256, [&] { k_search<false, false>(a, match.data(), lbs.data()); });
+    if (!ctrl.done && !X.rejectors.empty()) {   // icp.cu: run_rejectors
+      Arrays ra;
+      ra.d2.resize(ns); ra.match.resize(ns); ra.tie.resize(ns); ra.acc.resize(ns);
+      launch((unsigned)((ns + 255) / 256), 256, [&] { k_match_to_arrays(cur.data(), match.data(), ns, ra.d2.data(), ra.match.data(), ra.tie.data(), ra.acc.data()); });
+      for (const pclb200_rejector& r : X.rejectors) {
+        if (r.kind == PCLB200_REJ_SURFACE_NORMAL) {
+          launch((unsigned)((ns + 255) / 256), 256, [&] { k_reject_surface_normal(cur_normals.data(), tgt_normals.data(), ra.match.data(), ns, r.p, ra.acc.data()); });
+          continue;
+        }
+        std::vector<int> perm(ns), keep_sorted(ns);
+        double info[2] = {0, 0};
+        int trimmed = 0;
+        apply_rejector(r, ra, perm, keep_sorted, info, trimmed);
+      }
+      launch((unsigned)((ns + 255) / 256), 256, [&] { k_arrays_to_match(ra.acc.data(), ns, match.data()); });
+      blockDim.x = 256;
+    }
     if (!ctrl.done) {
       // every match of this iteration against brute force on the (re-transformed) source the kernel left in `cur`
       int bad = 0;
-      for (std::size_t i = 0; i < ns; ++i) {
+      for (std::size_t i = 0; i < ns && X.rejectors.empty() && X.corr_kind == PCLB200_CORR_NEAREST; ++i) {
         const float q[3] = {cur[i].x, cur[i].y, cur[i].z};
         const Truth t = brute(txyz, q, a.gate);
         const Match m = match[i];
@@ -246,7 +310,17 @@ static void run_align(const char* name, const Scene& S, int estimator, bool scal
   P.euclidean_fitness_epsilon = -std::numeric_limits<double>::max();
   orc_icp_result R;
   std::memset(&R, 0, sizeof R);
-  if (X.with_normals) orc_icp_align(&P, S.src_n.data(), ns, 8, nullptr, 0, S.tgt.data(), nt, 8, nullptr, &R, nullptr);
+  P.correspondence_kind = X.corr_kind;
+  P.correspondence_k = X.corr_k;
+  if (knn_tree) orc_index_free(knn_tree);
+  if (!X.rejectors.empty() || X.corr_kind != PCLB200_CORR_NEAREST) {
+    void* ot = orc_index_build(S.tgt.data(), nt, 8, nullptr, 0);
+    const float* sp = X.with_normals ? S.src_n.data() : S.src.data();
+    orc_icp_align_full(&P, nullptr, X.rejectors.empty() ? nullptr : X.rejectors.data(), (int)X.rejectors.size(), ot, sp, ns, X.with_normals ? 8 : 4, nullptr, 0, S.tgt.data(), nt,
+                       8, nullptr, &R, nullptr, nullptr, nullptr);
+    orc_index_free(ot);
+  }
+  else if (X.with_normals) orc_icp_align(&P, S.src_n.data(), ns, 8, nullptr, 0, S.tgt.data(), nt, 8, nullptr, &R, nullptr);
   else orc_icp_align(&P, S.src.data(), ns, 4, nullptr, 0, S.tgt.data(), nt, 8, nullptr, &R, nullptr);
   double dT = 0.0;
   for (int i = 0; i < 16; ++i) dT += (ctrl.final_T[i] - R.final_transformation[i]) * (ctrl.final_T[i] - R.final_transformation[i]);
@@ -402,6 +476,25 @@ int main()
     run_align("ICPWithNormals: LLS float, normals rotated", A, PCLB200_EST_POINT_TO_PLANE_LLS, false, 0.2, 1e-10, 20, PCLB200_TRACK_OFF, false, wn);
     run_align("ICPWithNormals: LLS double", A, PCLB200_EST_POINT_TO_PLANE_LLS, true, 0.2, 1e-12, 20, PCLB200_TRACK_OFF, false, wn);
     run_align("symmetric point-to-plane, double", A, PCLB200_EST_SYMMETRIC_POINT_TO_PLANE_LLS, true, 0.2, 1e-12, 20, PCLB200_TRACK_OFF, false, wn);
+  }
+  {
+    Extra rj;
+    rj.rejectors = {{PCLB200_REJ_MEDIAN, 0, 1.5}, {PCLB200_REJ_ONE_TO_ONE, 0, 0.0}};
+    // double Scalar: in float the two loops' clouds differ by ~1e-7 after a few iterations (|dT| ~ 4e-6), enough to move one
+    // pair across the median threshold in one of 25 iterations (20 706 vs 20 705 pairs in total) — not a property of the kernels
+    run_align("SVD double, median + one-to-one rejectors", A, PCLB200_EST_SVD, true, 0.2, 1e-10, 25, PCLB200_TRACK_OFF, false, rj);
+    rj.rejectors = {{PCLB200_REJ_DISTANCE, 0, 0.05}, {PCLB200_REJ_TRIMMED, 10, 0.8}};
+    run_align("SVD double, distance + trimmed rejectors", A, PCLB200_EST_SVD, true, 0.2, 1e-10, 25, PCLB200_TRACK_OFF, false, rj);
+    rj.with_normals = true;
+    rj.rejectors = {{PCLB200_REJ_SURFACE_NORMAL, 0, 0.995}, {PCLB200_REJ_ONE_TO_ONE, 0, 0.0}};
+    run_align("LLS float, surface-normal + one-to-one rejectors", A, PCLB200_EST_POINT_TO_PLANE_LLS, false, 0.2, 1e-10, 20, PCLB200_TRACK_OFF, false, rj);
+    Extra ns_;
+    ns_.with_normals = true;
+    ns_.corr_kind = PCLB200_CORR_NORMAL_SHOOTING;
+    run_align("LLS float, normal-shooting correspondences", A, PCLB200_EST_POINT_TO_PLANE_LLS, false, 0.2, 1e-10, 20, PCLB200_TRACK_OFF, false, ns_);
+    ns_.corr_kind = PCLB200_CORR_BACK_PROJECTION;
+    ns_.corr_k = 6;
+    run_align("SVD double, back-projection correspondences", A, PCLB200_EST_SVD, true, 0.2, 1e-10, 20, PCLB200_TRACK_OFF, false, ns_);
   }
   Scene B;
   const double t2[3] = {0.4, 0.3, -0.2};

@@ -74,13 +74,14 @@ def test_whole_icp_iterations_on_an_emulated_block(tmp_path, device_built):
     convergence criteria in its tail — on an emulated 256-thread block, driven like icp.cu's enqueue-ahead path: every
     iteration's correspondences equal brute force, the accumulated normal equations equal plain fp64 sums, and iterations /
     state / counts / final transform of twelve aligns (SVD, point-to-plane, the symmetric objective, ICPWithNormals,
-    reciprocal correspondences; float and double; gates; tracking off / on / automatic) equal the oracle's loop (1e-5 float,
-    1e-9 double); the four stand-alone estimators against the oracle's."""
+    reciprocal correspondences; float and double; gates; tracking off / on / automatic; rejector chains inside the loop —
+    median + one-to-one, distance + trimmed, surface-normal + one-to-one; normal-shooting and back-projection
+    correspondences) equal the oracle's loop (1e-5 float, 1e-9 double); the four stand-alone estimators against the oracle's."""
     import oracle
     oracle.build()
     odir = os.path.join(ROOT, "oracle")
     out = _run(tmp_path, "icp_host_test.cpp", (), DEVICE_BUILD if device_built else (), ["-L" + odir, "-lpcl_oracle", "-Wl,-rpath," + odir])
-    assert "tracking automatic" in out and "point-to-plane LLS double" in out and "reciprocal" in out
+    assert "tracking automatic" in out and "point-to-plane LLS double" in out and "reciprocal" in out and "trimmed rejectors" in out and "back-projection" in out
 
 
 def test_voxelgrid_kernels_on_the_host(tmp_path):
