@@ -168,7 +168,64 @@ static void run_scene(const char* name, const std::vector<float>& xyz, const std
     }
     CHECK(bad == 0 && d_error == 0, "%s k_normals<10>: %d normals differ from the host computePointNormal", name, bad);
   }
-  std::printf("%-26s %6zu points %5zu queries: k_knn<1..32>, k_knn_any, radius, stats, normals; ok so far: %ld checks, %ld failures\n", name, xyz.size() / 3, nq,
+  {  // the list-based forms: statistics and normals from materialised k-NN rows (k > 32), normals from the radius search's
+     // sorted (d2, index) keys (NormalEstimation::setRadiusSearch)
+    const int k = 45;
+    const float vp[3] = {0.3f, 0.7f, 4.f};
+    std::vector<int32_t> pos_of_orig(I.xyz.size() / 3, -1);
+    for (std::size_t p = 0; p < I.pts.size(); ++p) { const int o = __float_as_int(I.pts[p].w); if (o != kSentinelIndex) pos_of_orig[o] = (int32_t)p; }
+    std::vector<int32_t> li(nq * k, -7);
+    std::vector<float> ld(nq * k, -7.f);
+    int d_error = 0, nd_lists = 0, nd_csr = 0;
+    for_blocks(nq, [&] { k_knn_any(I.nodes.data(), I.pts.data(), I.root, q.data(), nq, k, inf, li.data(), ld.data(), &d_error); });
+    std::vector<float> mean(nq, -1.f), kth(nq, -1.f);
+    for_blocks(nq, [&] { k_stats_from_lists(q.data(), nq, k, li.data(), ld.data(), mean.data(), kth.data()); });
+    std::vector<float4> out_l(nq, make_float4(-9.f, -9.f, -9.f, -9.f)), out_c(nq, make_float4(-9.f, -9.f, -9.f, -9.f));
+    for_blocks(nq, [&] { k_normals_from_lists(I.pts.data(), pos_of_orig.data(), q.data(), nq, k, li.data(), 0, vp[0], vp[1], vp[2], out_l.data(), &nd_lists); });
+    const float r2 = 0.0125f, r2_below = std::nextafter(r2, -INFINITY);
+    std::vector<unsigned long long> counts(nq, 0), offsets(nq + 1, 0);
+    for_blocks(nq, [&] { k_radius_count(I.nodes.data(), I.pts.data(), I.root, q.data(), nq, r2, r2_below, counts.data(), &d_error); });
+    for (std::size_t i = 0; i < nq; ++i) offsets[i + 1] = offsets[i] + counts[i];
+    std::vector<unsigned long long> keys(offsets[nq] + 1, 0);
+    for_blocks(nq, [&] { k_radius_fill(I.nodes.data(), I.pts.data(), I.root, q.data(), nq, r2, r2_below, offsets.data(), keys.data(), &d_error); });
+    for (std::size_t i = 0; i < nq; ++i) std::sort(keys.begin() + offsets[i], keys.begin() + offsets[i + 1]);   // cub::DeviceSegmentedSort in the driver
+    for_blocks(nq, [&] { k_normals_from_csr(I.pts.data(), pos_of_orig.data(), q.data(), nq, offsets.data(), keys.data(), vp[0], vp[1], vp[2], out_c.data(), &nd_csr); });
+    pcl::PointCloud<pcl::PointXYZ> cloud;
+    for (std::size_t i = 0; i < I.xyz.size() / 3; ++i) cloud.emplace_back(I.xyz[3 * i], I.xyz[3 * i + 1], I.xyz[3 * i + 2]);
+    auto same = [](float a, float b) { return std::memcmp(&a, &b, 4) == 0 || (std::isnan(a) && std::isnan(b)); };
+    auto host_normal = [&](const float* qq, int have, float4& r) {
+      if (have < 3) { r = make_float4(NAN, NAN, NAN, NAN); return; }
+      pcl::Indices idx;
+      for (int j = 0; j < have; ++j) idx.push_back(all[j].second);
+      Eigen::Vector4f plane;
+      float curv = 0.f;
+      pcl::computePointNormal(cloud, idx, plane, curv);
+      float nx = plane[0], ny = plane[1], nz = plane[2];
+      pcl::flipNormalTowardsViewpoint(pcl::PointXYZ(qq[0], qq[1], qq[2]), vp[0], vp[1], vp[2], nx, ny, nz);
+      r = make_float4(nx, ny, nz, curv);
+    };
+    int bad_stats = 0, bad_lists = 0, bad_csr = 0;
+    for (std::size_t i = 0; i < nq; ++i) {
+      const float qq[3] = {q[i].x, q[i].y, q[i].z};
+      if (!std::isfinite(qq[2])) { bad_stats += !(mean[i] == 0.f && std::isinf(kth[i])); bad_lists += !std::isnan(out_l[i].x); bad_csr += !std::isnan(out_c[i].x); continue; }
+      brute_all(I.xyz, qq, all);
+      const int have = std::min<int>(k, (int)all.size());
+      double sum = 0.0;
+      for (int j = 1; j < have; ++j) sum += std::sqrt((double)all[j].first);
+      const float m = have > 1 ? (float)(sum / (double)(have - 1)) : 0.f;
+      if (!(mean[i] == m && kth[i] == (have == k ? all[k - 1].first : INFINITY))) ++bad_stats;
+      float4 w;
+      host_normal(qq, have, w);
+      if (!(same(out_l[i].x, w.x) && same(out_l[i].y, w.y) && same(out_l[i].z, w.z) && same(out_l[i].w, w.w))) ++bad_lists;
+      int in_ball = 0;
+      while (in_ball < (int)all.size() && all[in_ball].first < r2) ++in_ball;
+      host_normal(qq, in_ball, w);
+      if (!(same(out_c[i].x, w.x) && same(out_c[i].y, w.y) && same(out_c[i].z, w.z) && same(out_c[i].w, w.w))) ++bad_csr;
+    }
+    CHECK(bad_stats == 0 && bad_lists == 0 && bad_csr == 0 && d_error == 0, "%s list-based forms: %d statistics, %d k-NN-list normals, %d radius normals differ", name, bad_stats,
+          bad_lists, bad_csr);
+  }
+  std::printf("%-26s %6zu points %5zu queries: k_knn<1..32>, k_knn_any, radius, stats, normals, list-based stats / normals (k-NN rows, radius keys); ok so far: %ld checks, %ld failures\n", name, xyz.size() / 3, nq,
               g_checks, g_fail);
 }
 

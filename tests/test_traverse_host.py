@@ -53,8 +53,9 @@ def test_device_traversal_header_on_the_host(tmp_path, device_built):
 @pytest.mark.parametrize("device_built", [False, True], ids=["reference-index", "device-built-index"])
 def test_per_thread_search_kernels_on_the_host(tmp_path, device_built):
     """search_kernels.cuh — k_knn<K> for every compiled list size, k_knn_any, k_knn_stats, k_radius_count / k_radius_fill,
-    k_normals<K> — block by block against brute force (lists bit for bit, ties and duplicates included) and, for the
-    normals, against the host computePointNormal."""
+    k_normals<K>, and the list-based forms k_stats_from_lists / k_normals_from_lists (k > 32) / k_normals_from_csr (radius
+    normals) — block by block against brute force (lists bit for bit, ties and duplicates included) and, for the normals,
+    against the host computePointNormal."""
     _run(tmp_path, "search_host_test.cpp", ["2"], DEVICE_BUILD if device_built else ())
 
 
