@@ -63,6 +63,9 @@ public:
   virtual bool requiresTargetNormals() const { return false; }
   virtual void setTargetNormals(pcl::PCLPointCloud2::ConstPtr /*cloud2*/) { notRequired("setTargetNormals", "input target normals"); }
   virtual pclb200_rejector abiRejector() const = 0;  // lets ICP run the chain inside the device loop
+  // false for a rejector that only exists on the host (CorrespondenceRejectorSampleConsensus): an ICP holding one runs the
+  // stage-by-stage loop and calls getRemainingCorrespondences between the device stages
+  virtual bool runsOnDevice() const { return true; }
 
 protected:
   void notRequired(const char* method, const char* what) const

@@ -17,6 +17,7 @@
 #include <vector>
 
 #include "correspondence_estimation.h"
+#include "../conversions.h"
 #include "correspondence_rejection.h"
 #include "transformation_estimation.h"
 
@@ -355,6 +356,14 @@ protected:
     int iterations_similar = 0;
     const double max_d2 = this->corr_dist_threshold_ * this->corr_dist_threshold_;
     pcl::Correspondences corr, tmp;
+    {  // impl/icp.hpp:142-155: rejectors that ask for the target cloud get it once, as a blob
+      pcl::PCLPointCloud2::Ptr target_blob;
+      for (const auto& rej : this->correspondence_rejectors_)
+        if (rej->requiresTargetPoints()) {
+          if (!target_blob) { target_blob.reset(new pcl::PCLPointCloud2); pcl::toPCLPointCloud2(*this->target_, *target_blob); }
+          rej->setTargetPoints(target_blob);
+        }
+    }
     do {
       this->previous_transformation_ = this->transformation_;
       // correspondences (impl/correspondence_estimation.hpp:145-218): one batch 1-NN for all source indices
@@ -377,9 +386,16 @@ protected:
         if (ki[j].empty() || static_cast<double>(kd[j][0]) > max_d2) continue;
         corr.emplace_back(i, ki[j][0], kd[j][0]);
       }
-      for (const auto& rej : this->correspondence_rejectors_) {  // impl/icp.hpp:187-201
-        rej->getRemainingCorrespondences(corr, tmp);
-        corr.swap(tmp);
+      {
+        pcl::PCLPointCloud2::Ptr moved_blob;  // impl/icp.hpp:166-170, 191-192: the transformed source of THIS iteration
+        for (const auto& rej : this->correspondence_rejectors_) {  // impl/icp.hpp:187-201
+          if (rej->requiresSourcePoints()) {
+            if (!moved_blob) { moved_blob.reset(new pcl::PCLPointCloud2); pcl::toPCLPointCloud2(moved, *moved_blob); }
+            rej->setSourcePoints(moved_blob);
+          }
+          rej->getRemainingCorrespondences(corr, tmp);
+          corr.swap(tmp);
+        }
       }
       if (corr.size() < 3) {  // impl/icp.hpp:204-213
         std::fprintf(stderr, "[pcl::%s::computeTransformation] Not enough correspondences found. Relax your threshold parameters.\n",
@@ -435,7 +451,9 @@ protected:
   // impl/icp.hpp:113-268 — the whole do-while runs on the device; the host only evaluates the convergence criteria
   void computeTransformation(PointCloudSource& output, const Matrix4& guess) override
   {
-    if (this->tree_->usesRepresentationVectors()) {
+    bool host_rejector = false;
+    for (const auto& r : this->correspondence_rejectors_) host_rejector = host_rejector || !r->runsOnDevice();
+    if (this->tree_->usesRepresentationVectors() || host_rejector) {
       computeTransformationStaged(output, guess);
       return;
     }

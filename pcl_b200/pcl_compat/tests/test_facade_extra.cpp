@@ -4,6 +4,10 @@
 // tests/test_zz_facade_extra_gpu.py) so the main program stays exactly what was verified.
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
+#include <fstream>
+#include <map>
+#include <string>
 #include <limits>
 #include <memory>
 #include <vector>
@@ -14,7 +18,10 @@
 #include <pcl/kdtree/kdtree_flann.h>
 #include <pcl/point_representation.h>
 #include <pcl/point_types.h>
+#include <pcl/common/transforms.h>
 #include <pcl/registration/correspondence_estimation.h>
+#include <pcl/registration/correspondence_rejection_median_distance.h>
+#include <pcl/registration/correspondence_rejection_sample_consensus.h>
 #include <pcl/registration/icp.h>
 
 using namespace pcl;
@@ -23,6 +30,45 @@ static int g_fail = 0, g_checks = 0;
 #define EXPECT_TRUE(c) do { ++g_checks; if (!(c)) { ++g_fail; std::printf("FAIL %s:%d  %s\n", __FILE__, __LINE__, #c); } } while (0)
 #define EXPECT_EQ(a, b) do { ++g_checks; if (!((a) == (b))) { ++g_fail; std::printf("FAIL %s:%d  %s == %s  (%g vs %g)\n", __FILE__, __LINE__, #a, #b, (double)(a), (double)(b)); } } while (0)
 #define EXPECT_NEAR(a, b, tol) do { ++g_checks; if (!(std::fabs((double)(a) - (double)(b)) <= (tol))) { ++g_fail; std::printf("FAIL %s:%d  |%s - %s| <= %g  (%.9g vs %.9g)\n", __FILE__, __LINE__, #a, #b, (double)(tol), (double)(a), (double)(b)); } } while (0)
+
+static std::map<std::string, std::vector<double>> load_golden(const char* path)
+{
+  std::map<std::string, std::vector<double>> g;
+  std::ifstream in(path);
+  std::string name;
+  std::size_t n;
+  while (in >> name >> n) {
+    std::vector<double> v(n);
+    for (auto& x : v) in >> x;
+    g[name] = v;
+  }
+  return g;
+}
+
+// test/registration/test_registration.cpp:322-334 sampleRandomTransform, with the axis / angle / translation drawn the same way
+static Eigen::Matrix4f sample_random_transform(float max_angle, float max_trans)
+{
+  float ax = static_cast<float>(std::rand()) / RAND_MAX, ay = static_cast<float>(std::rand()) / RAND_MAX, az = static_cast<float>(std::rand()) / RAND_MAX;
+  const float nrm = std::sqrt(ax * ax + ay * ay + az * az);
+  ax /= nrm; ay /= nrm; az /= nrm;
+  const float angle = static_cast<float>(std::rand()) / RAND_MAX * max_angle;
+  const float tx = static_cast<float>(std::rand()) / RAND_MAX * max_trans, ty = static_cast<float>(std::rand()) / RAND_MAX * max_trans,
+              tz = static_cast<float>(std::rand()) / RAND_MAX * max_trans;
+  const float c = std::cos(angle), s = std::sin(angle), t = 1.f - c;
+  Eigen::Matrix4f m = Eigen::Matrix4f::Identity();
+  m(0, 0) = c + ax * ax * t;      m(0, 1) = ax * ay * t - az * s; m(0, 2) = ax * az * t + ay * s; m(0, 3) = tx;
+  m(1, 0) = ay * ax * t + az * s; m(1, 1) = c + ay * ay * t;      m(1, 2) = ay * az * t - ax * s; m(1, 3) = ty;
+  m(2, 0) = az * ax * t - ay * s; m(2, 1) = az * ay * t + ax * s; m(2, 2) = c + az * az * t;      m(2, 3) = tz;
+  return m;
+}
+static Eigen::Matrix4f rigid_inverse(const Eigen::Matrix4f& m)
+{
+  Eigen::Matrix4f r = Eigen::Matrix4f::Identity();
+  for (int i = 0; i < 3; ++i)
+    for (int j = 0; j < 3; ++j) r(i, j) = m(j, i);
+  for (int i = 0; i < 3; ++i) r(i, 3) = -(r(i, 0) * m(0, 3) + r(i, 1) * m(1, 3) + r(i, 2) * m(2, 3));
+  return r;
+}
 
 int main(int argc, char** argv)
 {
@@ -223,6 +269,76 @@ int main(int argc, char** argv)
     far[0] = vg.getMinBoxCoordinates()[0]; far[1] = vg.getMinBoxCoordinates()[1]; far[2] = vg.getMaxBoxCoordinates()[2] + 5;  // past the last slab
     EXPECT_EQ(vg.getCentroidIndexAt(far), -1);
     EXPECT_TRUE(vg.getSaveLeafLayout() && vg.getDownsampleAllData() && !vg.getFilterLimitsNegative());
+  }
+
+  if (argc > 3) {  // TEST (PCL, CorrespondenceRejectorSampleConsensus) — test/registration/test_registration_api.cpp:225-263
+    auto G = load_golden(argv[3]);
+    const std::vector<double>& want = G["corr_rej_sac"];
+    const std::vector<double>& want_T = G["sac_transform"];
+    PointCloud<PointXYZ>::ConstPtr source(new PointCloud<PointXYZ>(cloud_source)), target(new PointCloud<PointXYZ>(cloud_target));
+    CorrespondencesPtr correspondences(new Correspondences);
+    registration::CorrespondenceEstimation<PointXYZ, PointXYZ> corr_est;
+    corr_est.setInputSource(source);
+    corr_est.setInputTarget(target);
+    corr_est.determineCorrespondences(*correspondences);
+    EXPECT_EQ(correspondences->size(), 397u);
+    Correspondences result;
+    registration::CorrespondenceRejectorSampleConsensus<PointXYZ> corr_rej_sac;
+    corr_rej_sac.setInputSource(source);
+    corr_rej_sac.setInputTarget(target);
+    corr_rej_sac.setInlierThreshold(0.01);    // rej_sac_max_dist, test_registration_api_data.h:816
+    corr_rej_sac.setMaximumIterations(1000);  // rej_sac_max_iter
+    corr_rej_sac.setInputCorrespondences(correspondences);
+    corr_rej_sac.getCorrespondences(result);
+    const Eigen::Matrix4f T = corr_rej_sac.getBestTransformation();
+    EXPECT_EQ(want.size(), 2u * 97u);
+    EXPECT_EQ(result.size(), want.size() / 2);
+    if (result.size() == want.size() / 2)
+      for (std::size_t i = 0; i < result.size(); ++i) {
+        EXPECT_EQ(result[i].index_query, (int)want[2 * i]);
+        EXPECT_EQ(result[i].index_match, (int)want[2 * i + 1]);
+      }
+    EXPECT_EQ(want_T.size(), 16u);
+    if (want_T.size() == 16)
+      for (int i = 0; i < 4; ++i)
+        for (int j = 0; j < 4; ++j) EXPECT_NEAR(T(i, j), want_T[4 * i + j], 1e-4);
+    EXPECT_TRUE(!corr_rej_sac.runsOnDevice() && corr_rej_sac.requiresSourcePoints() && corr_rej_sac.requiresTargetPoints());
+    EXPECT_NEAR(corr_rej_sac.getInlierThreshold(), 0.01, 0.0);
+    EXPECT_EQ(corr_rej_sac.getMaximumIterations(), 1000);
+    corr_rej_sac.setSaveInliers(true);
+    corr_rej_sac.getCorrespondences(result);
+    Indices inl;
+    corr_rej_sac.getInliersIndices(inl);
+    EXPECT_EQ(inl.size(), result.size());
+  }
+
+  {  // TEST (PCL, IterativeClosestPointWithRejectors) — test/registration/test_registration.cpp:336-382: a median-distance and
+     // a sample-consensus rejector, ten random offsets (<= 0.05) under ten random global poses (rotation <= 2 pi, |t| <= 10)
+    IterativeClosestPoint<PointXYZ, PointXYZ> reg;
+    reg.setMaximumIterations(50);
+    reg.setTransformationEpsilon(1e-8);
+    reg.setMaxCorrespondenceDistance(0.15);
+    registration::CorrespondenceRejectorMedianDistance::Ptr rej_med(new registration::CorrespondenceRejectorMedianDistance);
+    rej_med->setMedianFactor(4.0);
+    reg.addCorrespondenceRejector(rej_med);
+    registration::CorrespondenceRejectorSampleConsensus<PointXYZ>::Ptr rej_samp(new registration::CorrespondenceRejectorSampleConsensus<PointXYZ>);
+    reg.addCorrespondenceRejector(rej_samp);
+    std::srand(1);
+    for (int t = 0; t < 10; ++t) {
+      const Eigen::Matrix4f delta = sample_random_transform(0.f, 0.05f);
+      const Eigen::Matrix4f net = sample_random_transform(2.f * static_cast<float>(M_PI), 10.f);
+      PointCloud<PointXYZ>::Ptr source_trans(new PointCloud<PointXYZ>), target_trans(new PointCloud<PointXYZ>);
+      transformPointCloud(cloud_source, *source_trans, rigid_inverse(delta) * net);
+      transformPointCloud(cloud_source, *target_trans, net);
+      reg.setInputSource(source_trans);
+      reg.setInputTarget(target_trans);
+      PointCloud<PointXYZ> cloud_reg;
+      reg.align(cloud_reg);
+      const Eigen::Matrix4f trans_final = reg.getFinalTransformation();
+      for (int y = 0; y < 4; ++y) EXPECT_NEAR(trans_final(y, 3), delta(y, 3), 1e-2);
+      for (int y = 0; y < 4; ++y)
+        for (int x = 0; x < 3; ++x) EXPECT_NEAR(trans_final(y, x), delta(y, x), 1e-1);
+    }
   }
 
   std::printf("%d checks, %d failures\n%s\n", g_checks, g_fail, g_fail ? "FAILED" : "PASSED");

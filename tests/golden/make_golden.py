@@ -64,6 +64,10 @@ g["corr_rej_dist"] = c_int_pairs(hdr, "correspondences_dist")
 g["corr_rej_median"] = c_int_pairs(hdr, "correspondences_median_dist")
 g["corr_rej_one_to_one"] = c_int_pairs(hdr, "correspondences_one_to_one")
 g["corr_rej_trimmed"] = c_int_pairs(hdr, "correspondences_trimmed")
+# CorrespondenceRejectorSampleConsensus (test_registration_api.cpp:225-263): inlier threshold 0.01, 1000 iterations
+g["corr_rej_sac"] = c_int_pairs(hdr, "correspondences_sac")
+m = re.search(r"const float transform_from_SAC\[4\]\[4\] = \{(.*?)\};", hdr, re.S)
+g["sac_transform"] = np.asarray([float(v.rstrip("f")) for v in re.findall(r"-?\d+\.?\d*(?:e-?\d+)?f?", m.group(1))], dtype=np.float64).reshape(4, 4)
 
 xml = open(f"{REF}/test/kdtree/kdtree_unit_test_results.xml").read()
 offs, idx = [0], []

@@ -33,16 +33,21 @@ def test_facade_builds_on_cpu():
     assert os.path.exists(os.path.join(FACADE, "tests", "test_facade"))
 
 
+def _write_golden(path, golden):
+    """The golden vectors the facade programs compare against, as text: name, count, values."""
+    with open(path, "w") as f:
+        for k in ("corr_original", "corr_reciprocal", "icp_bun0_bun4", "svd_Tref", "normal_bun0", "corr_rej_dist",
+                  "corr_rej_median", "corr_rej_one_to_one", "corr_rej_trimmed", "corr_rej_sac", "sac_transform"):
+            v = np.asarray(golden[k], dtype=np.float64).ravel()
+            f.write(f"{k} {v.size}\n" + " ".join("%.17g" % x for x in v) + "\n")
+
+
 @pytest.mark.gpu
 def test_facade_reference_tests(golden, tmp_path):
     subprocess.check_call(["make", "-C", FACADE, "-s"])
     _write_ascii_pcd(tmp_path / "bun0.pcd", golden["bun0"])      # both PCD encodings go through the reader
     _write_binary_pcd(tmp_path / "bun4.pcd", golden["bun4"])
-    with open(tmp_path / "golden.txt", "w") as f:
-        for k in ("corr_original", "corr_reciprocal", "icp_bun0_bun4", "svd_Tref", "normal_bun0", "corr_rej_dist",
-                  "corr_rej_median", "corr_rej_one_to_one", "corr_rej_trimmed"):
-            v = np.asarray(golden[k], dtype=np.float64).ravel()
-            f.write(f"{k} {v.size}\n" + " ".join("%.17g" % x for x in v) + "\n")
+    _write_golden(tmp_path / "golden.txt", golden)
     r = subprocess.run([os.path.join(FACADE, "tests", "test_facade"), str(tmp_path / "bun0.pcd"),
                         str(tmp_path / "bun4.pcd"), str(tmp_path / "golden.txt")], capture_output=True, text=True)
     print(r.stdout[-3000:], r.stderr[-2000:])

@@ -14,7 +14,7 @@ import subprocess
 import numpy as np
 import pytest
 
-from test_facade_gpu import FACADE, ROOT, _write_ascii_pcd, _write_binary_pcd
+from test_facade_gpu import FACADE, ROOT, _write_ascii_pcd, _write_binary_pcd, _write_golden
 
 pytestmark = pytest.mark.skipif(shutil.which("g++") is None, reason="needs g++")
 
@@ -63,22 +63,23 @@ def test_reference_test_bodies_through_the_facade(double, golden, tmp_path):
     bodies written against the drop-in pcl:: classes, 8 600 checks incl. the reference's golden vectors."""
     _, _, program = double
     b0, b4 = _clouds(golden, tmp_path)
-    with open(tmp_path / "golden.txt", "w") as f:
-        for k in ("corr_original", "corr_reciprocal", "icp_bun0_bun4", "svd_Tref", "normal_bun0", "corr_rej_dist",
-                  "corr_rej_median", "corr_rej_one_to_one", "corr_rej_trimmed"):
-            v = np.asarray(golden[k], dtype=np.float64).ravel()
-            f.write(f"{k} {v.size}\n" + " ".join("%.17g" % x for x in v) + "\n")
+    _write_golden(tmp_path / "golden.txt", golden)
     r = subprocess.run([program("tests/test_facade.cpp"), b0, b4, str(tmp_path / "golden.txt")], capture_output=True, text=True)
     assert r.returncode == 0 and "PASSED" in r.stdout, r.stdout[-3000:] + r.stderr[-1500:]
 
 
 def test_extra_facade_program(double, golden, tmp_path):
     """pcl_compat/tests/test_facade_extra.cpp: Search<PointT> overloads, CorrespondenceEstimation under a point
-    representation, DefaultConvergenceCriteria thresholds, PinnedCloud, VoxelGrid leaf layout."""
+    representation, DefaultConvergenceCriteria thresholds, PinnedCloud, VoxelGrid leaf layout, and the host-side
+    CorrespondenceRejectorSampleConsensus: the reference's golden 97 inlier pairs in order and its transform to 1e-4
+    (test_registration_api.cpp:225-263), the reference's ICP with median + sample-consensus rejectors under ten random poses
+    (test_registration.cpp:336-382)."""
     _, _, program = double
     b0, b4 = _clouds(golden, tmp_path)
-    r = subprocess.run([program("tests/test_facade_extra.cpp"), b0, b4], capture_output=True, text=True)
+    _write_golden(tmp_path / "golden.txt", golden)
+    r = subprocess.run([program("tests/test_facade_extra.cpp"), b0, b4, str(tmp_path / "golden.txt")], capture_output=True, text=True)
     assert r.returncode == 0 and "PASSED" in r.stdout, r.stdout[-3000:] + r.stderr[-1500:]
+    assert int(r.stdout.split(" checks")[0].split()[-1]) > 400   # the golden block ran
 
 
 def test_icp_command_line_program(double, golden, tmp_path):
