@@ -7,6 +7,7 @@
 #include <cstdlib>
 #include <fstream>
 #include <map>
+#include <set>
 #include <string>
 #include <limits>
 #include <memory>
@@ -269,6 +270,121 @@ int main(int argc, char** argv)
     far[0] = vg.getMinBoxCoordinates()[0]; far[1] = vg.getMinBoxCoordinates()[1]; far[2] = vg.getMaxBoxCoordinates()[2] + 5;  // past the last slab
     EXPECT_EQ(vg.getCentroidIndexAt(far), -1);
     EXPECT_TRUE(vg.getSaveLeafLayout() && vg.getDownsampleAllData() && !vg.getFilterLimitsNegative());
+  }
+
+  {  // TEST (PCL, KdTreeFLANN_radiusSearch) and (PCL, KdTreeFLANN_nearestKSearch) — test/kdtree/test_kdtree.cpp:92-123, 161-205:
+     // an 11^3 lattice of a point type DERIVED from PointXYZ, against brute force (the timing loops assert nothing and are left out)
+    struct MyPoint : public PointXYZ {
+      MyPoint() = default;
+      MyPoint(float x_, float y_, float z_) { x = x_; y = y_; z = z_; }
+    };
+    PointCloud<MyPoint> cloud;
+    const float resolution = 0.1f;
+    for (float z = -0.5f; z <= 0.5f; z += resolution)
+      for (float y = -0.5f; y <= 0.5f; y += resolution)
+        for (float x = -0.5f; x <= 0.5f; x += resolution) cloud.push_back(MyPoint(x, y, z));
+    cloud.width = static_cast<std::uint32_t>(cloud.size());
+    cloud.height = 1;
+    auto dist = [](const PointXYZ& a, const PointXYZ& b) { return std::sqrt((a.x - b.x) * (a.x - b.x) + (a.y - b.y) * (a.y - b.y) + (a.z - b.z) * (a.z - b.z)); };
+    {
+      KdTreeFLANN<MyPoint> kdtree;
+      kdtree.setInputCloud(cloud.makeShared());
+      const MyPoint test_point(0.0f, 0.0f, 0.0f);
+      const double max_dist = 0.15;
+      std::set<int> brute_force_result;
+      for (std::size_t i = 0; i < cloud.size(); ++i)
+        if (dist(cloud[i], test_point) < max_dist) brute_force_result.insert(static_cast<int>(i));
+      EXPECT_TRUE(brute_force_result.size() > 1 && brute_force_result.size() < 100);
+      Indices k_indices;
+      std::vector<float> k_distances;
+      kdtree.radiusSearch(test_point, max_dist, k_indices, k_distances, 100);
+      for (const auto& k_index : k_indices) {
+        auto it = brute_force_result.find(k_index);
+        const bool ok = it != brute_force_result.end();
+        EXPECT_TRUE(ok);
+        if (ok) brute_force_result.erase(it);
+      }
+      EXPECT_TRUE(brute_force_result.empty());
+    }
+    {
+      KdTreeFLANN<MyPoint> kdtree;
+      kdtree.setInputCloud(cloud.makeShared());
+      const MyPoint test_point(0.01f, 0.01f, 0.01f);
+      const unsigned int no_of_neighbors = 20;
+      std::multimap<float, int> sorted_brute_force_result;
+      for (std::size_t i = 0; i < cloud.size(); ++i) sorted_brute_force_result.insert(std::make_pair(dist(cloud[i], test_point), static_cast<int>(i)));
+      float max_dist = 0.0f;
+      unsigned int counter = 0;
+      for (auto it = sorted_brute_force_result.begin(); it != sorted_brute_force_result.end() && counter < no_of_neighbors; ++it) {
+        max_dist = std::max(max_dist, it->first);
+        ++counter;
+      }
+      Indices k_indices(no_of_neighbors);
+      std::vector<float> k_distances(no_of_neighbors);
+      kdtree.nearestKSearch(test_point, no_of_neighbors, k_indices, k_distances);
+      EXPECT_EQ(k_indices.size(), no_of_neighbors);
+      for (const auto& k_index : k_indices) {
+        bool ok = dist(test_point, cloud[k_index]) <= max_dist;
+        if (!ok) ok = (std::abs(dist(test_point, cloud[k_index])) - max_dist) <= 1e-6;
+        EXPECT_TRUE(ok);
+      }
+    }
+  }
+
+  {  // TEST (CorrespondenceRejectors, CorrespondenceRejectionMedianDistance) — test/registration/test_correspondence_rejectors.cpp:53-73
+    CorrespondencesPtr corresps(new Correspondences());
+    for (int i = 0; i <= 10; ++i) {
+      Correspondence c;
+      c.distance = static_cast<float>(i * i);
+      corresps->push_back(c);
+    }
+    registration::CorrespondenceRejectorMedianDistance rejector;
+    rejector.setInputCorrespondences(corresps);
+    rejector.setMedianFactor(2.0);
+    Correspondences corresps_filtered;
+    rejector.getCorrespondences(corresps_filtered);
+    EXPECT_EQ(corresps_filtered.size(), 8u);
+    for (int i = 0; i < 8 && i < (int)corresps_filtered.size(); ++i) EXPECT_NEAR(corresps_filtered[i].distance, static_cast<float>(i * i), 1e-5);
+  }
+
+  {  // TYPED_TEST (CorrespondenceEstimationTestSuite, CorrespondenceEstimationSetSearchMethod) —
+     // test/registration/test_correspondence_estimation.cpp:139-174: trees handed over with force_no_recompute give the
+     // correspondences the estimator's own trees give (Scalar = double, PointXYZ -> PointXYZ and PointXYZ -> PointNormal)
+    auto body = [&](auto source_tag, auto target_tag) {
+      using PointSource = decltype(source_tag);
+      using PointTarget = decltype(target_tag);
+      auto cloud1 = std::make_shared<PointCloud<PointSource>>();
+      auto cloud2 = std::make_shared<PointCloud<PointTarget>>();
+      for (std::size_t i = 0; i < 50; i++) {
+        PointSource a;
+        PointTarget b;
+        a.x = static_cast<float>(std::rand()); a.y = static_cast<float>(std::rand()); a.z = static_cast<float>(std::rand());
+        b.x = static_cast<float>(std::rand()); b.y = static_cast<float>(std::rand()); b.z = static_cast<float>(std::rand());
+        cloud1->push_back(a);
+        cloud2->push_back(b);
+      }
+      auto tree1 = std::make_shared<pcl::search::KdTree<PointSource>>();
+      tree1->setInputCloud(cloud1);
+      auto tree2 = std::make_shared<pcl::search::KdTree<PointTarget>>();
+      tree2->setInputCloud(cloud2);
+      registration::CorrespondenceEstimation<PointSource, PointTarget, double> ce;
+      ce.setInputSource(cloud1);
+      ce.setInputTarget(cloud2);
+      Correspondences corr_orig;
+      ce.determineCorrespondences(corr_orig);
+      ce.setSearchMethodSource(tree1, true);
+      ce.setSearchMethodTarget(tree2, true);
+      Correspondences corr_cached;
+      ce.determineCorrespondences(corr_cached);
+      EXPECT_EQ(corr_orig.size(), 50u);
+      EXPECT_EQ(corr_orig.size(), corr_cached.size());
+      for (std::size_t i = 0; i < corr_orig.size() && i < corr_cached.size(); i++) {
+        EXPECT_EQ(corr_orig[i].index_query, corr_cached[i].index_query);
+        EXPECT_EQ(corr_orig[i].index_match, corr_cached[i].index_match);
+      }
+    };
+    body(PointXYZ(), PointXYZ());
+    body(PointXYZ(), PointNormal());
   }
 
   if (argc > 3) {  // TEST (PCL, CorrespondenceRejectorSampleConsensus) — test/registration/test_registration_api.cpp:225-263

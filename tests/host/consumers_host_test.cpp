@@ -143,6 +143,27 @@ int main()
     compare_lists("nearest, non-finite source points skipped", device_correspondences(IT, nullptr, holes, nullptr, 0.05), want);
   }
 
+  {  // the reference's CorrespondenceEstimationSetSearchMethod clouds: 50 points with coordinates static_cast<float>(rand()), up to 2^31
+    std::srand(7);
+    const int m = 50;
+    std::vector<float> a(4 * m, 1.f), b(4 * m, 1.f);
+    for (int i = 0; i < m; ++i)
+      for (int d = 0; d < 3; ++d) { a[4 * i + d] = static_cast<float>(std::rand()); b[4 * i + d] = static_cast<float>(std::rand()); }
+    HostIndex IB2, IA2;
+    build_index(IB2, xyz_of(b), 4);
+    build_index(IA2, xyz_of(a), 4);
+    void* ob2 = orc_index_build(b.data(), m, 4, nullptr, 0);
+    void* oa2 = orc_index_build(a.data(), m, 4, nullptr, 0);
+    want.resize(m);
+    want.resize(orc_correspondences(ob2, a.data(), m, 4, nullptr, 0, 1, std::sqrt(std::numeric_limits<double>::max()), want.data(), 1));
+    compare_lists("50 points with coordinates up to 2^31, nearest", device_correspondences(IB2, nullptr, a, nullptr, std::sqrt(std::numeric_limits<double>::max())), want);
+    want.resize(m);
+    want.resize(orc_correspondences_reciprocal(ob2, oa2, a.data(), m, 4, b.data(), 4, nullptr, 0, 1, std::sqrt(std::numeric_limits<double>::max()), want.data(), 1));
+    compare_lists("50 points with coordinates up to 2^31, reciprocal", device_correspondences(IB2, &IA2, a, nullptr, std::sqrt(std::numeric_limits<double>::max())), want);
+    orc_index_free(ob2);
+    orc_index_free(oa2);
+  }
+
   // ---- Registration::getFitnessScore: transform (float or double), 1-NN, mean of the squared distances <= max_range ----
   {
     const double a = 0.02, T[16] = {std::cos(a), -std::sin(a), 0, 0.004, std::sin(a), std::cos(a), 0, -0.003, 0, 0, 1, 0.001, 0, 0, 0, 1};
