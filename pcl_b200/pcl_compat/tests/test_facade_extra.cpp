@@ -24,6 +24,9 @@
 #include <pcl/registration/correspondence_rejection_median_distance.h>
 #include <pcl/registration/correspondence_rejection_sample_consensus.h>
 #include <pcl/registration/icp.h>
+#include <pcl/search/brute_force.h>
+#include <pcl/search/kdtree.h>
+#include <random>
 
 using namespace pcl;
 
@@ -385,6 +388,103 @@ int main(int argc, char** argv)
     };
     body(PointXYZ(), PointXYZ());
     body(PointXYZ(), PointNormal());
+  }
+
+  {  // test/search/test_search.cpp:293-451, 456-529 — the unorganized scenarios: the device searcher against pcl::search::BruteForce,
+     // k = 1, 8, 64, 512 and radius = 0.01 ... 0.08, on a dense cloud, a cloud with NaN points, a 10^3 grid; whole cloud and a shuffled
+     // ~10 % view; results unique, ascending, inside the view and finite, and equal under the reference's own rule
+     // (indices equal OR distances within 1e-6; a radius result may differ by the one point that sits on the sphere)
+    std::mt19937 rng;
+    std::uniform_int_distribution<unsigned> rand_uint(0, 10);
+    std::uniform_real_distribution<float> rand_float(0.0f, 1.0f);
+    const unsigned point_count = 1200, query_count = 100;
+    PointCloud<PointXYZ>::Ptr dense(new PointCloud<PointXYZ>), sparse(new PointCloud<PointXYZ>), grid(new PointCloud<PointXYZ>);
+    dense->resize(point_count); dense->height = 1; dense->width = point_count; dense->is_dense = true;
+    sparse->resize(point_count); sparse->height = 1; sparse->width = point_count; sparse->is_dense = false;
+    for (unsigned i = 0; i < point_count; ++i) {
+      PointXYZ point(rand_float(rng), rand_float(rng), rand_float(rng));
+      (*dense)[i] = point;
+      if (rand_uint(rng) == 0) (*sparse)[i].x = (*sparse)[i].y = (*sparse)[i].z = std::numeric_limits<float>::quiet_NaN();
+      else (*sparse)[i] = point;
+    }
+    grid->height = 1; grid->is_dense = true;
+    for (unsigned x = 0; x < 10; ++x)
+      for (unsigned y = 0; y < 10; ++y)
+        for (unsigned z = 0; z < 10; ++z) grid->push_back(PointXYZ(0.1f * static_cast<float>(x), 0.1f * static_cast<float>(y), 0.1f * static_cast<float>(z)));
+    Indices view;
+    for (unsigned idx = 0; idx < point_count; ++idx)
+      if (rand_uint(rng) == 0) view.push_back(static_cast<index_t>(idx));
+    {
+      std::uniform_int_distribution<> pick(0, static_cast<int>(view.size()) - 1);
+      for (unsigned idx = 0; idx < point_count - 1; ++idx) std::swap(view[pick(rng)], view[pick(rng)]);
+    }
+    auto query_indices = [&](const PointCloud<PointXYZ>& c) {
+      Indices q;
+      const unsigned skip = static_cast<unsigned>(c.size()) / query_count;
+      for (unsigned idx = 0; idx < c.size() && q.size() < query_count; ++idx)
+        if ((std::rand() % skip) == 0 && std::isfinite(c[idx].x)) q.push_back(static_cast<index_t>(idx));
+      return q;
+    };
+    pcl::search::BruteForce<PointXYZ> brute_force(true);
+    pcl::search::KdTree<PointXYZ> kdtree;
+    kdtree.setSortedResults(true);
+    std::vector<pcl::search::Search<PointXYZ>*> methods = {&brute_force, &kdtree};
+    auto unique = [](const Indices& v) { for (std::size_t a = 1; a < v.size(); ++a) for (std::size_t b = 0; b < a; ++b) if (v[a] == v[b]) return false; return true; };
+    auto ordered = [](const std::vector<float>& d) { for (std::size_t a = 1; a < d.size(); ++a) if (d[a - 1] > d[a]) return false; return true; };
+    auto same = [](const Indices& i1, const std::vector<float>& d1, const Indices& i2, const std::vector<float>& d2, float eps) {
+      if (i1.size() != i2.size()) return false;
+      for (std::size_t k = 0; k < i1.size(); ++k) if (i1[k] != i2[k] && std::abs(d1[k] - d2[k]) > eps) return false;
+      return true;
+    };
+    auto run = [&](const PointCloud<PointXYZ>::ConstPtr& cloud, const Indices& queries, const Indices& input_indices, bool radius_mode) {
+      std::vector<bool> in_view(cloud->size(), input_indices.empty()), finite(cloud->size(), true);
+      for (index_t i : input_indices) in_view[i] = true;
+      for (std::size_t i = 0; i < cloud->size(); ++i) finite[i] = std::isfinite((*cloud)[i].x) && std::isfinite((*cloud)[i].y) && std::isfinite((*cloud)[i].z);
+      IndicesPtr idx;
+      if (!input_indices.empty()) idx.reset(new Indices(input_indices));
+      for (auto* m : methods) m->setInputCloud(cloud, idx);
+      bool passed[2] = {true, true};
+      std::vector<Indices> ind(2);
+      std::vector<std::vector<float>> dst(2);
+      auto check = [&](float radius) {
+        for (int s = 0; s < 2; ++s) {
+          bool valid = true;
+          for (index_t i : ind[s]) valid = valid && in_view[i] && finite[i];
+          passed[s] = passed[s] && unique(ind[s]) && ordered(dst[s]) && valid;
+        }
+        if (!same(ind[0], dst[0], ind[1], dst[1], 1e-6f)) {
+          const bool on_sphere = radius > 0 && ((ind[0].size() + 1 == ind[1].size() && std::abs(dst[1].back() - radius * radius) < 1e-6) ||
+                                                (ind[1].size() + 1 == ind[0].size() && std::abs(dst[0].back() - radius * radius) < 1e-6));
+          if (!on_sphere) passed[1] = false;
+        }
+      };
+      if (radius_mode)
+        for (float radius = 0.01f; radius < 0.1f; radius *= 2.0f)
+          for (index_t q : queries) {
+            for (int s = 0; s < 2; ++s) methods[s]->radiusSearch((*cloud)[q], radius, ind[s], dst[s], 0);
+            check(radius);
+          }
+      else
+        for (unsigned knn = 1; knn <= 512; knn <<= 3)
+          for (index_t q : queries) {
+            for (int s = 0; s < 2; ++s) methods[s]->nearestKSearch((*cloud)[q], static_cast<int>(knn), ind[s], dst[s]);
+            check(0.f);
+          }
+      EXPECT_TRUE(passed[0]);
+      EXPECT_TRUE(passed[1]);
+    };
+    std::srand(3);
+    const Indices dense_q = query_indices(*dense), sparse_q = query_indices(*sparse), grid_q = query_indices(*grid);
+    EXPECT_TRUE(dense_q.size() > 20 && sparse_q.size() > 20 && grid_q.size() > 20 && view.size() > 50);
+    run(dense, dense_q, Indices(), false);    // unorganized_dense_cloud_Complete_KNN
+    run(dense, dense_q, view, false);         // unorganized_dense_cloud_View_KNN
+    run(sparse, sparse_q, Indices(), false);  // unorganized_sparse_cloud_Complete_KNN
+    run(sparse, sparse_q, view, false);       // unorganized_sparse_cloud_View_KNN
+    run(dense, dense_q, Indices(), true);     // unorganized_dense_cloud_Complete_Radius
+    run(grid, grid_q, Indices(), true);       // unorganized_grid_cloud_Complete_Radius
+    run(dense, dense_q, view, true);          // unorganized_dense_cloud_View_Radius
+    run(sparse, sparse_q, Indices(), true);   // unorganized_sparse_cloud_Complete_Radius
+    run(sparse, sparse_q, view, true);        // unorganized_sparse_cloud_View_Radius
   }
 
   if (argc > 3) {  // TEST (PCL, CorrespondenceRejectorSampleConsensus) — test/registration/test_registration_api.cpp:225-263
