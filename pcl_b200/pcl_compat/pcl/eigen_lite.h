@@ -13,6 +13,9 @@ template <typename S, int R, int C>
 struct Matrix {
   S m[R * C];  // column-major like Eigen's default
   Matrix() { for (int i = 0; i < R * C; ++i) m[i] = S(0); }
+  // fixed-size vectors from their coefficients (Eigen::Vector3i(0, 0, 1), Eigen::Vector4f(x, y, z, w))
+  Matrix(S a, S b, S c) { static_assert(R * C == 3, "three coefficients"); m[0] = a; m[1] = b; m[2] = c; }
+  Matrix(S a, S b, S c, S d) { static_assert(R * C == 4, "four coefficients"); m[0] = a; m[1] = b; m[2] = c; m[3] = d; }
   static Matrix Identity()
   {
     Matrix r;
@@ -71,6 +74,9 @@ struct MatrixXi {
   std::vector<int> v;
   MatrixXi() = default;
   MatrixXi(int rows_, int cols_) : r(rows_), c(cols_), v(static_cast<std::size_t>(rows_) * cols_, 0) {}
+  static MatrixXi Zero(int rows_, int cols_) { return MatrixXi(rows_, cols_); }
+  template <int R, int C>
+  MatrixXi(const Matrix<int, R, C>& f) : r(R), c(C), v(f.m, f.m + R * C) {}  // both column-major
   int rows() const { return r; }
   int cols() const { return c; }
   int& operator()(int i, int j) { return v[static_cast<std::size_t>(j) * r + i]; }

@@ -487,6 +487,94 @@ int main(int argc, char** argv)
     run(sparse, sparse_q, view, true);        // unorganized_sparse_cloud_View_Radius
   }
 
+  {  // TEST (VoxelGrid, Filters), the leaf-layout half — test/filters/test_filters.cpp:598-649 (the counts and centroids of
+     // :566-597 are in the main program)
+    PointCloud<PointXYZ>::Ptr cloud = cloud_source.makeShared();
+    PointCloud<PointXYZ> output;
+    VoxelGrid<PointXYZ> grid;
+    grid.setLeafSize(0.02f, 0.02f, 0.02f);
+    grid.setInputCloud(cloud);
+    grid.setFilterFieldName("z");
+    grid.setFilterLimits(0.05, 0.1);
+    grid.setFilterLimitsNegative(true);
+    grid.setSaveLeafLayout(true);
+    grid.filter(output);
+    EXPECT_EQ(output.size(), 100u);
+    EXPECT_EQ(output.width, 100u);
+    EXPECT_EQ(output.height, 1u);
+    EXPECT_TRUE(output.is_dense);
+    if (output.size() == 100) {
+      EXPECT_EQ(grid.getCentroidIndex(output[0]), 0);
+      EXPECT_EQ(grid.getCentroidIndex(output[99]), 99);
+      EXPECT_EQ(grid.getCentroidIndexAt(grid.getGridCoordinates(-1, -1, -1)), -1);
+      const int centroidIdx = grid.getCentroidIndex((*cloud)[195]);   // input point 195 [0.048722, 0.07376, 0.017434]
+      EXPECT_TRUE(centroidIdx >= 0 && centroidIdx < 100);
+      if (centroidIdx >= 0 && centroidIdx < 100) {
+        EXPECT_TRUE(std::abs(output[centroidIdx].x - (*cloud)[195].x) <= 0.02);
+        EXPECT_TRUE(std::abs(output[centroidIdx].y - (*cloud)[195].y) <= 0.02);
+        EXPECT_TRUE(std::abs(output[centroidIdx].z - (*cloud)[195].z) <= 0.02);
+        EXPECT_EQ(grid.getNeighborCentroidIndices(output[0], Eigen::MatrixXi::Zero(3, 1))[0], 0);
+        EXPECT_EQ(grid.getNeighborCentroidIndices(output[99], Eigen::MatrixXi::Zero(3, 1))[0], 99);
+        Eigen::MatrixXi directions = Eigen::Vector3i(0, 0, 1);
+        std::vector<int> neighbors = grid.getNeighborCentroidIndices((*cloud)[195], directions);
+        EXPECT_EQ(neighbors.size(), std::size_t(directions.cols()));
+        EXPECT_TRUE(neighbors.at(0) != -1);
+        if (neighbors.at(0) != -1) {
+          EXPECT_TRUE(std::abs(output[neighbors.at(0)].x - output[centroidIdx].x) <= 0.02);
+          EXPECT_TRUE(std::abs(output[neighbors.at(0)].y - output[centroidIdx].y) <= 0.02);
+          EXPECT_TRUE(output[neighbors.at(0)].z - output[centroidIdx].z <= 0.02 * 2);
+        }
+      }
+    }
+    // "indices must be handled correctly": the indices of the original cloud keep the hundred appended points out
+    auto indices = grid.getIndices();
+    auto cloud_copied = std::make_shared<PointCloud<PointXYZ>>();
+    *cloud_copied = *cloud;
+    for (int i = 0; i < 100; i++) cloud_copied->push_back(PointXYZ(100.f + i, 100.f + i, 100.f + i));
+    grid.setInputCloud(cloud_copied);
+    grid.setIndices(indices);
+    grid.filter(output);
+    EXPECT_EQ(output.size(), 100u);
+  }
+
+  {  // TEST (VoxelGridMinPoints, Filters) — test/filters/test_filters.cpp:1356-1406, the positions (the reference's cloud is
+     // PointXYZRGB; colour fields are outside this library): single points at 0 and 1, five points around 0.11, six around 0.31
+    PointCloud<PointXYZ>::Ptr input(new PointCloud<PointXYZ>());
+    input->push_back(PointXYZ(0.0f, 0.0f, 0.0f));
+    const float offsets[6] = {0.001f, 0.002f, 0.003f, -0.001f, -0.002f, -0.003f};
+    for (unsigned int i = 0; i < 5; ++i) {
+      input->push_back(PointXYZ(0.11f + offsets[i], 0.11f + offsets[i], 0.11f + offsets[i]));
+      input->push_back(PointXYZ(0.31f + offsets[i], 0.31f + offsets[i], 0.31f + offsets[i]));
+    }
+    input->push_back(PointXYZ(0.31f + offsets[5], 0.31f + offsets[5], 0.31f + offsets[5]));
+    input->push_back(PointXYZ(1.0f, 1.0f, 1.0f));
+    PointCloud<PointXYZ> outputMin4, outputMin6;
+    VoxelGrid<PointXYZ> grid;
+    grid.setLeafSize(0.02f, 0.02f, 0.02f);
+    grid.setInputCloud(input);
+    grid.setMinimumPointsNumberPerVoxel(4);
+    grid.setDownsampleAllData(true);
+    grid.filter(outputMin4);
+    EXPECT_EQ(outputMin4.size(), 2u);
+    if (outputMin4.size() == 2) {
+      EXPECT_NEAR(outputMin4[0].x, input->at(1).x, 1e-2);
+      EXPECT_NEAR(outputMin4[0].y, input->at(1).y, 1e-2);
+      EXPECT_NEAR(outputMin4[0].z, input->at(1).z, 1e-2);
+      EXPECT_NEAR(outputMin4[1].x, input->at(2).x, 1e-2);
+      EXPECT_NEAR(outputMin4[1].y, input->at(2).y, 1e-2);
+      EXPECT_NEAR(outputMin4[1].z, input->at(2).z, 1e-2);
+    }
+    grid.setMinimumPointsNumberPerVoxel(6);
+    grid.setDownsampleAllData(false);
+    grid.filter(outputMin6);
+    EXPECT_EQ(outputMin6.size(), 1u);
+    if (outputMin6.size() == 1) {
+      EXPECT_NEAR(outputMin6[0].x, input->at(2).x, 1e-2);
+      EXPECT_NEAR(outputMin6[0].y, input->at(2).y, 1e-2);
+      EXPECT_NEAR(outputMin6[0].z, input->at(2).z, 1e-2);
+    }
+  }
+
   if (argc > 3) {  // TEST (PCL, CorrespondenceRejectorSampleConsensus) — test/registration/test_registration_api.cpp:225-263
     auto G = load_golden(argv[3]);
     const std::vector<double>& want = G["corr_rej_sac"];
