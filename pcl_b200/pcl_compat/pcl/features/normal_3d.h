@@ -188,6 +188,18 @@ protected:
   float vp_[3] = {0.f, 0.f, 0.f};
   bool use_sensor_origin_ = true;
 };
+// features/include/pcl/features/normal_3d_omp.h:52-107: the same estimator with a thread count; on the device the batch is one
+// launch, so the count is accepted and kept, nothing more
 template <typename PointInT, typename PointOutT>
-using NormalEstimationOMP = NormalEstimation<PointInT, PointOutT>;
+class NormalEstimationOMP : public NormalEstimation<PointInT, PointOutT> {
+public:
+  using Ptr = std::shared_ptr<NormalEstimationOMP<PointInT, PointOutT>>;
+  using ConstPtr = std::shared_ptr<const NormalEstimationOMP<PointInT, PointOutT>>;
+  explicit NormalEstimationOMP(unsigned int nr_threads = 0, int /*chunk_size*/ = 256) { setNumberOfThreads(nr_threads); }
+  void setNumberOfThreads(unsigned int nr_threads = 0) { threads_ = nr_threads; }
+  unsigned int getNumberOfThreads() const { return threads_; }
+
+protected:
+  unsigned int threads_ = 0;
+};
 }  // namespace pcl

@@ -14,6 +14,7 @@
 #include <vector>
 
 #include <pcl/common/io.h>
+#include <pcl/features/normal_3d.h>
 #include <pcl/filters/voxel_grid.h>
 #include <pcl/io/pcd_io.h>
 #include <pcl/kdtree/kdtree_flann.h>
@@ -572,6 +573,125 @@ int main(int argc, char** argv)
       EXPECT_NEAR(outputMin6[0].x, input->at(2).x, 1e-2);
       EXPECT_NEAR(outputMin6[0].y, input->at(2).y, 1e-2);
       EXPECT_NEAR(outputMin6[0].z, input->at(2).z, 1e-2);
+    }
+  }
+
+  {  // TEST (PCL, TranslatedNormalEstimation), (NormalEstimation, FarFromOrigin), (PCL, NormalEstimationOpenMP) —
+     // test/features/test_normal_estimation.cpp:187-285, 287-316, 375-410 (cloud = bun0, indices = all of it)
+    const PointCloud<PointXYZ>& cloud = cloud_source;
+    Indices indices(cloud.size());
+    for (std::size_t i = 0; i < indices.size(); ++i) indices[i] = static_cast<index_t>(i);
+    search::KdTree<PointXYZ>::Ptr tree(new search::KdTree<PointXYZ>(false));
+    tree->setInputCloud(cloud.makeShared());
+    {
+      Eigen::Vector4f plane_parameters;
+      float curvature;
+      NormalEstimation<PointXYZ, Normal> n;
+      PointCloud<PointXYZ> translatedCloud(cloud);
+      for (auto& i : translatedCloud) { i.x += 100; i.y += 100; i.z += 100; }
+      computePointNormal(translatedCloud, indices, plane_parameters, curvature);
+      EXPECT_NEAR(std::abs(plane_parameters[0]), 0.035592, 1e-4);
+      EXPECT_NEAR(std::abs(plane_parameters[1]), 0.369596, 1e-4);
+      EXPECT_NEAR(std::abs(plane_parameters[2]), 0.928511, 1e-4);
+      EXPECT_NEAR(curvature, 0.0693136, 1e-4);
+      float nx, ny, nz;
+      n.computePointNormal(translatedCloud, indices, nx, ny, nz, curvature);
+      EXPECT_NEAR(std::abs(nx), 0.035592, 1e-4);
+      EXPECT_NEAR(std::abs(ny), 0.369596, 1e-4);
+      EXPECT_NEAR(std::abs(nz), 0.928511, 1e-4);
+      EXPECT_NEAR(curvature, 0.0693136, 1e-4);
+      computePointNormal(translatedCloud, plane_parameters, curvature);
+      EXPECT_NEAR(plane_parameters[0], 0.035592, 1e-4);
+      EXPECT_NEAR(plane_parameters[1], 0.369596, 1e-4);
+      EXPECT_NEAR(plane_parameters[2], 0.928511, 1e-4);
+      EXPECT_NEAR(curvature, 0.0693136, 1e-4);
+      flipNormalTowardsViewpoint(translatedCloud.points[0], 0, 0, 0, plane_parameters);
+      EXPECT_NEAR(plane_parameters[0], -0.035592, 1e-4);
+      EXPECT_NEAR(plane_parameters[1], -0.369596, 1e-4);
+      EXPECT_NEAR(plane_parameters[2], -0.928511, 1e-4);
+      flipNormalTowardsViewpoint(translatedCloud.points[0], 0, 0, 0, nx, ny, nz);
+      EXPECT_NEAR(nx, -0.035592, 1e-4);
+      EXPECT_NEAR(ny, -0.369596, 1e-4);
+      EXPECT_NEAR(nz, -0.928511, 1e-4);
+      PointCloud<Normal>::Ptr normals(new PointCloud<Normal>());
+      PointCloud<PointXYZ>::Ptr cloudptr = translatedCloud.makeShared();
+      n.setInputCloud(cloudptr);
+      EXPECT_TRUE(n.getInputCloud() == cloudptr);
+      IndicesPtr indicesptr(new Indices(indices));
+      n.setIndices(indicesptr);
+      EXPECT_TRUE(n.getIndices() == indicesptr);
+      n.setSearchMethod(tree);
+      EXPECT_TRUE(n.getSearchMethod() == tree);
+      n.setKSearch(static_cast<int>(indices.size()));
+      n.compute(*normals);
+      EXPECT_EQ(normals->size(), indices.size());
+      for (const auto& point : normals->points) {
+        EXPECT_NEAR(point.normal[0], -0.035592, 1e-4);
+        EXPECT_NEAR(point.normal[1], -0.369596, 1e-4);
+        EXPECT_NEAR(point.normal[2], -0.928511, 1e-4);
+        EXPECT_NEAR(point.curvature, 0.0693136, 1e-4);
+      }
+      PointCloud<PointXYZ>::Ptr surfaceptr = cloudptr;
+      n.setSearchSurface(surfaceptr);
+      EXPECT_TRUE(n.getSearchSurface() == surfaceptr);
+      // "Additional test for searchForNeighbors": a surface larger than the input, and no searcher given
+      surfaceptr.reset(new PointCloud<PointXYZ>);
+      *surfaceptr = *cloudptr;
+      surfaceptr->points.resize(640 * 480);
+      surfaceptr->width = 640;
+      surfaceptr->height = 480;
+      EXPECT_EQ(surfaceptr->size(), static_cast<std::size_t>(surfaceptr->width) * surfaceptr->height);
+      n.setSearchSurface(surfaceptr);
+      search::KdTree<PointXYZ>::Ptr none;
+      n.setSearchMethod(none);
+      n.compute(*normals);
+      EXPECT_EQ(normals->size(), indices.size());
+    }
+    {
+      NormalEstimation<PointXYZ, Normal> ne1;
+      ne1.setInputCloud(cloud.makeShared());
+      ne1.setKSearch(15);
+      PointCloud<Normal> normals1;
+      ne1.compute(normals1);
+      PointCloud<PointXYZ>::Ptr cloud_translated(new PointCloud<PointXYZ>(cloud));
+      for (auto& point : *cloud_translated) { point.x += 123.0f; point.y += -45.0f; point.z += 98.0f; }
+      NormalEstimation<PointXYZ, Normal> ne2;
+      ne2.setInputCloud(cloud_translated);
+      ne2.setKSearch(15);
+      ne2.setViewPoint(123.0f, -45.0f, 98.0f);
+      PointCloud<Normal> normals2;
+      ne2.compute(normals2);
+      EXPECT_EQ(normals1.size(), normals2.size());
+      EXPECT_EQ(normals1.size(), cloud.size());
+      int off = 0;
+      for (std::size_t i = 0; i < normals1.size() && i < normals2.size(); ++i) {
+        const float dot = normals1[i].normal_x * normals2[i].normal_x + normals1[i].normal_y * normals2[i].normal_y + normals1[i].normal_z * normals2[i].normal_z;
+        if (!(std::abs(std::abs(dot) - 1.0f) <= 1e-6f)) ++off;
+        if (!(std::abs(normals1[i].normal_x - normals2[i].normal_x) <= 5e-4f && std::abs(normals1[i].normal_y - normals2[i].normal_y) <= 5e-4f &&
+              std::abs(normals1[i].normal_z - normals2[i].normal_z) <= 5e-4f))
+          ++off;
+      }
+      EXPECT_EQ(off, 0);
+    }
+    {
+      NormalEstimationOMP<PointXYZ, Normal> n(4);
+      EXPECT_EQ(n.getNumberOfThreads(), 4u);
+      PointCloud<Normal>::Ptr normals(new PointCloud<Normal>());
+      PointCloud<PointXYZ>::Ptr cloudptr = cloud.makeShared();
+      n.setInputCloud(cloudptr);
+      IndicesPtr indicesptr(new Indices(indices));
+      n.setIndices(indicesptr);
+      tree->setInputCloud(cloudptr);
+      n.setSearchMethod(tree);
+      n.setKSearch(static_cast<int>(indices.size()));
+      n.compute(*normals);
+      EXPECT_EQ(normals->size(), indices.size());
+      for (const auto& point : normals->points) {
+        EXPECT_NEAR(point.normal[0], -0.035592, 1e-4);
+        EXPECT_NEAR(point.normal[1], -0.369596, 1e-4);
+        EXPECT_NEAR(point.normal[2], -0.928511, 1e-4);
+        EXPECT_NEAR(point.curvature, 0.0693136, 1e-4);
+      }
     }
   }
 

@@ -9,9 +9,12 @@
 
 #include <cfloat>
 
+static inline unsigned __float_as_uint(float f) { unsigned u; std::memcpy(&u, &f, 4); return u; }
+
 #include "../../pcl_b200/csrc/icp_kernels.cuh"
 #include "../../pcl_b200/csrc/normals_corr_kernels.cuh"
 #include "../../pcl_b200/csrc/cluster_kernels.cuh"
+#include "../../pcl_b200/csrc/search_kernels.cuh"
 
 extern "C" {
 void* orc_index_build(const float* pts, size_t n, size_t stride, const int32_t* subset, size_t n_subset);
@@ -302,6 +305,37 @@ int main()
       std::printf("Euclidean clustering, tolerance %-8g %5d components over %d points, %d labels differ\n", tol, comps, nb, bad);
     }
     orc_index_free(ob);
+  }
+  // ---- the reference's TranslatedNormalEstimation surface (test_normal_estimation.cpp:266-275): 397 real points and 306 803
+  //      default-constructed ones at the origin — one Morton code shared by 306 803 points: build, then k = 397 for every real point
+  {
+    const int real = 397, total = 640 * 480;
+    std::vector<float> xyz(3 * (std::size_t)total, 0.f);
+    for (int i = 0; i < real; ++i) { xyz[3 * i] = 100.f + 0.15f * U(rng); xyz[3 * i + 1] = 100.f + 0.15f * U(rng); xyz[3 * i + 2] = 100.f + 0.1f * U(rng); }
+    HostIndex IM;
+    build_index(IM, xyz, 0);
+    const int k = 397;
+    std::vector<float4> q(real);
+    for (int i = 0; i < real; ++i) q[i] = make_float4(xyz[3 * i], xyz[3 * i + 1], xyz[3 * i + 2], __int_as_float(i));
+    std::vector<int32_t> oi((std::size_t)real * k, -7);
+    std::vector<float> od((std::size_t)real * k, -7.f);
+    int d_error = 0;
+    launch((unsigned)((real + 127) / 128), 128, [&] { k_knn_any(IM.nodes.data(), IM.pts.data(), IM.root, q.data(), (size_t)real, k, INFINITY, oi.data(), od.data(), &d_error); });
+    int bad = 0;
+    std::vector<std::pair<float, int>> all(real);
+    for (int i = 0; i < real; ++i) {
+      for (int j = 0; j < real; ++j) all[j] = {dist2_rn(q[i].x, q[i].y, q[i].z, xyz[3 * j], xyz[3 * j + 1], xyz[3 * j + 2]), j};
+      std::sort(all.begin(), all.end());
+      for (int j = 0; j < k; ++j) if (oi[(std::size_t)i * k + j] != all[j].second || od[(std::size_t)i * k + j] != all[j].first) { ++bad; break; }
+    }
+    float4 qo = make_float4(0.f, 0.f, 0.f, __int_as_float(0));
+    std::vector<int32_t> o2(20, -7);
+    std::vector<float> d2(20, -7.f);
+    launch(1, 128, [&] { k_knn_any(IM.nodes.data(), IM.pts.data(), IM.root, &qo, (size_t)1, 20, INFINITY, o2.data(), d2.data(), &d_error); });
+    bool first_twenty = true;
+    for (int j = 0; j < 20; ++j) first_twenty = first_twenty && o2[j] == real + j && d2[j] == 0.f;
+    CHECK(bad == 0 && first_twenty && d_error == 0, "306 803 coincident points: %d of 397 k-NN rows differ, origin query ok %d, error flag %d", bad, (int)first_twenty, d_error);
+    std::printf("306 803 coincident points + 397 real ones: %zu leaf slots, %zu nodes; k = 397 rows differing from brute force: %d\n", IM.pts.size(), IM.nodes.size(), bad);
   }
   orc_index_free(ot);
   orc_index_free(os);
