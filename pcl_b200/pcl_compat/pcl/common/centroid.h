@@ -26,15 +26,15 @@ inline void forEachPoint(const pcl::PointCloud<PointT>& cloud, const Indices* in
 template <typename PointT, typename Scalar>
 inline unsigned int centroid3D(const pcl::PointCloud<PointT>& cloud, const Indices* indices, Eigen::Matrix<Scalar, 4, 1>& centroid)
 {
-  centroid = Eigen::Matrix<Scalar, 4, 1>::Zero();
+  Eigen::Matrix<Scalar, 4, 1> accumulator = Eigen::Matrix<Scalar, 4, 1>::Zero();
   unsigned int cp = 0;
   forEachPoint(cloud, indices, [&](const PointT& p) {
     if (!cloud.is_dense && !xyzFinite(p)) return;
-    centroid[0] += p.x; centroid[1] += p.y; centroid[2] += p.z;
+    accumulator[0] += p.x; accumulator[1] += p.y; accumulator[2] += p.z;
     ++cp;
   });
-  if (cp == 0) return 0;
-  for (int d = 0; d < 3; ++d) centroid[d] /= static_cast<Scalar>(cp);
+  if (cp == 0) return 0;  // impl/centroid.hpp:77-82: the caller's centroid is written only when a point was used
+  for (int d = 0; d < 3; ++d) centroid[d] = accumulator[d] / static_cast<Scalar>(cp);
   centroid[3] = Scalar(1);
   return cp;
 }
@@ -78,7 +78,7 @@ inline unsigned int meanAndCovariance(const pcl::PointCloud<PointT>& cloud, cons
 }
 }  // namespace detail
 
-// centroid of the finite points; returns how many were used (0: centroid untouched apart from being zeroed)
+// centroid of the finite points; returns how many were used (0: the caller's centroid is left as it was)
 template <typename PointT, typename Scalar>
 inline unsigned int compute3DCentroid(const pcl::PointCloud<PointT>& cloud, Eigen::Matrix<Scalar, 4, 1>& centroid)
 {

@@ -117,9 +117,124 @@ static int dump_normals(const char* pcd, const char* out_path)
   return 0;
 }
 
+// The bodies of the reference's test/common/test_centroid.cpp for the functions on the path: TEST (PCL, compute3DCentroidFloat)
+// :53-161, compute3DCentroidDouble :164-271, computeMeanAndCovariance :700-840, demeanPointCloud :1210-1236 (cloud = bun0.pcd).
+template <typename Scalar>
+static void centroid_body()
+{
+  using Vec4 = Eigen::Matrix<Scalar, 4, 1>;
+  Indices indices;
+  PointXYZ point;
+  PointCloud<PointXYZ> cloud;
+  Vec4 centroid;
+  centroid[0] = Scalar(0.125); centroid[1] = Scalar(-0.5); centroid[2] = Scalar(0.75); centroid[3] = Scalar(-0.25);   // "Random()"
+  const Vec4 old_centroid = centroid;
+  cloud.is_dense = true;    // empty and dense
+  CHECK(compute3DCentroid(cloud, centroid) == 0 && old_centroid == centroid);
+  cloud.is_dense = false;   // empty, not dense
+  CHECK(compute3DCentroid(cloud, centroid) == 0 && old_centroid == centroid);
+  point.x = point.y = point.z = std::numeric_limits<float>::quiet_NaN();   // only invalid points
+  cloud.push_back(point);
+  CHECK(compute3DCentroid(cloud, centroid) == 0 && old_centroid == centroid);
+  cloud.push_back(point);
+  indices.push_back(1);
+  CHECK(compute3DCentroid(cloud, indices, centroid) == 0 && old_centroid == centroid);
+  cloud.clear();
+  indices.clear();
+  for (point.x = -1; point.x < 2; point.x += 2)
+    for (point.y = -1; point.y < 2; point.y += 2)
+      for (point.z = -1; point.z < 2; point.z += 2) cloud.push_back(point);
+  cloud.is_dense = true;
+  auto reset = [&] { centroid[0] = -100; centroid[1] = -200; centroid[2] = -300; };
+  reset();
+  CHECK(compute3DCentroid(cloud, centroid) == 8 && centroid[0] == 0 && centroid[1] == 0 && centroid[2] == 0 && centroid[3] == 1);
+  reset();
+  indices = {2, 3, 6, 7};   // only positive y values
+  CHECK(compute3DCentroid(cloud, indices, centroid) == 4 && centroid[0] == 0 && centroid[1] == 1 && centroid[2] == 0 && centroid[3] == 1);
+  point.x = point.y = point.z = std::numeric_limits<float>::quiet_NaN();
+  cloud.push_back(point);
+  cloud.is_dense = false;
+  reset();
+  CHECK(compute3DCentroid(cloud, centroid) == 8 && centroid[0] == 0 && centroid[1] == 0 && centroid[2] == 0 && centroid[3] == 1);
+  reset();
+  indices.push_back(8);   // the NaN
+  CHECK(compute3DCentroid(cloud, indices, centroid) == 4 && centroid[0] == 0 && centroid[1] == 1 && centroid[2] == 0 && centroid[3] == 1);
+}
+
+static int reference_centroid_tests(const char* bun0_pcd)
+{
+  centroid_body<float>();
+  centroid_body<double>();
+  {  // computeMeanAndCovariance
+    PointCloud<PointXYZ> cloud;
+    PointXYZ point;
+    Indices indices;
+    Eigen::Matrix3f cov;
+    Eigen::Vector4f centroid;
+    for (int i = 0; i < 9; ++i) cov[i] = 0.1f * static_cast<float>(i) - 0.3f;
+    centroid[0] = 0.125f; centroid[1] = -0.5f; centroid[2] = 0.75f; centroid[3] = -0.25f;
+    const Eigen::Matrix3f old_cov = cov;
+    const Eigen::Vector4f old_centroid = centroid;
+    cloud.is_dense = true;
+    CHECK(computeMeanAndCovarianceMatrix(cloud, cov, centroid) == 0 && old_cov == cov && old_centroid == centroid);
+    cloud.is_dense = false;
+    CHECK(computeMeanAndCovarianceMatrix(cloud, cov, centroid) == 0 && old_cov == cov && old_centroid == centroid);
+    point.x = point.y = point.z = std::numeric_limits<float>::quiet_NaN();
+    cloud.push_back(point);
+    CHECK(computeMeanAndCovarianceMatrix(cloud, cov, centroid) == 0 && old_cov == cov && old_centroid == centroid);
+    cloud.push_back(point);
+    indices.push_back(1);
+    CHECK(computeMeanAndCovarianceMatrix(cloud, indices, cov, centroid) == 0 && old_cov == cov && old_centroid == centroid);
+    cloud.clear();
+    indices.clear();
+    for (point.x = -1; point.x < 2; point.x += 2)
+      for (point.y = -1; point.y < 2; point.y += 2)
+        for (point.z = -1; point.z < 2; point.z += 2) cloud.push_back(point);
+    cloud.is_dense = true;
+    auto reset = [&] { for (int i = 0; i < 9; ++i) cov[i] = -100.f - static_cast<float>(i); centroid[0] = -100; centroid[1] = -101; centroid[2] = -102; };
+    auto is_diag = [&](float a, float b, float c) {
+      return cov(0, 0) == a && cov(1, 1) == b && cov(2, 2) == c && cov(0, 1) == 0 && cov(0, 2) == 0 && cov(1, 0) == 0 && cov(1, 2) == 0 && cov(2, 0) == 0 && cov(2, 1) == 0;
+    };
+    reset();   // eight points with (0, 0, 0) as centroid and the identity as covariance
+    CHECK(computeMeanAndCovarianceMatrix(cloud, cov, centroid) == 8 && centroid[0] == 0 && centroid[1] == 0 && centroid[2] == 0 && is_diag(1, 1, 1));
+    indices = {2, 3, 6, 7};
+    reset();
+    CHECK(computeMeanAndCovarianceMatrix(cloud, indices, cov, centroid) == 4 && centroid[0] == 0 && centroid[1] == 1 && centroid[2] == 0 && is_diag(1, 0, 1));
+    point.x = point.y = point.z = std::numeric_limits<float>::quiet_NaN();
+    cloud.push_back(point);
+    cloud.is_dense = false;
+    reset();
+    CHECK(computeMeanAndCovarianceMatrix(cloud, cov, centroid) == 8 && centroid[0] == 0 && centroid[1] == 0 && centroid[2] == 0 && is_diag(1, 1, 1));
+    indices.push_back(8);
+    reset();
+    CHECK(computeMeanAndCovarianceMatrix(cloud, indices, cov, centroid) == 4 && centroid[0] == 0 && centroid[1] == 1 && centroid[2] == 0 && is_diag(1, 0, 1));
+  }
+  {  // demeanPointCloud on bun0
+    PointCloud<PointXYZ> cloud, cloud_demean;
+    if (io::loadPCDFile(bun0_pcd, cloud)) return 2;
+    Eigen::Vector4f centroid;
+    compute3DCentroid(cloud, centroid);
+    CHECK(std::fabs(centroid[0] + 0.0290809) < 1e-4 && std::fabs(centroid[1] - 0.102653) < 1e-4 && std::fabs(centroid[2] - 0.027302) < 1e-4 && std::fabs(centroid[3] - 1) < 1e-4);
+    auto near_xyz = [](const PointXYZ& p, float x, float y, float z) { return std::fabs(p.x - x) < 1e-4 && std::fabs(p.y - y) < 1e-4 && std::fabs(p.z - z) < 1e-4; };
+    demeanPointCloud(cloud, centroid, cloud_demean);
+    CHECK(cloud_demean.width == cloud.width && cloud_demean.height == cloud.height && cloud_demean.is_dense == cloud.is_dense && cloud_demean.size() == cloud.size());
+    CHECK(near_xyz(cloud_demean[0], 0.034503f, 0.010837f, 0.013447f));
+    CHECK(near_xyz(cloud_demean[cloud_demean.size() - 1], -0.048849f, 0.072507f, -0.071702f));
+    Indices indices(cloud.size());
+    for (int i = 0; i < static_cast<int>(indices.size()); ++i) indices[i] = i;
+    demeanPointCloud(cloud, indices, centroid, cloud_demean);
+    CHECK(cloud_demean.is_dense == cloud.is_dense && cloud_demean.width == indices.size() && cloud_demean.height == 1 && cloud_demean.size() == cloud.size());
+    CHECK(near_xyz(cloud_demean[0], 0.034503f, 0.010837f, 0.013447f));
+    CHECK(near_xyz(cloud_demean[cloud_demean.size() - 1], -0.048849f, 0.072507f, -0.071702f));
+  }
+  std::printf("%d checks, %d failures\n%s\n", g_checks, g_fail, g_fail ? "FAILED" : "PASSED");
+  return g_fail ? 1 : 0;
+}
+
 int main(int argc, char** argv)
 {
   if (argc == 4 && std::string(argv[1]) == "normals") return dump_normals(argv[2], argv[3]);
+  if (argc == 3 && std::string(argv[1]) == "centroid") return reference_centroid_tests(argv[2]);
   {  // organised or not is decided by height alone
     PointCloud<PointXYZ> c;
     c.width = 640; c.height = 480;

@@ -13,6 +13,18 @@ def test_point_cloud_container_and_host_classes():
     assert r.returncode == 0 and "PASSED" in r.stdout, r.stdout[-2000:]
 
 
+def test_reference_centroid_tests(golden, tmp_path):
+    """The bodies of the reference's test/common/test_centroid.cpp for the moment functions on the path: compute3DCentroid
+    (float, double; empty / all-NaN inputs leave the caller's centroid untouched), computeMeanAndCovarianceMatrix,
+    demeanPointCloud on bun0 with the reference's expected values."""
+    import numpy as np
+    from test_facade_gpu import _write_ascii_pcd
+    subprocess.check_call(["make", "-C", FACADE, "-s", "tests/test_host_api"])
+    _write_ascii_pcd(tmp_path / "bun0.pcd", np.asarray(golden["bun0"], dtype=np.float32))
+    r = subprocess.run([os.path.join(FACADE, "tests", "test_host_api"), "centroid", str(tmp_path / "bun0.pcd")], capture_output=True, text=True)
+    assert r.returncode == 0 and "PASSED" in r.stdout, r.stdout[-2000:]
+
+
 def test_facade_extra_program_builds():
     """the device-side extra program compiles against the C-ABI here (it runs under -m gpu)"""
     from pcl_b200 import build
