@@ -96,6 +96,30 @@ inline void transformPointCloudWithNormals(const pcl::PointCloud<PointT>& cloud_
     tf.so3(cloud_in[i].data_n, cloud_out[i].data_n);
   }
 }
+// transforms.h:260-300: the indexed form — output of indices.size() points, unorganized
+template <typename PointT, typename Scalar>
+inline void transformPointCloudWithNormals(const pcl::PointCloud<PointT>& cloud_in, const Indices& indices, pcl::PointCloud<PointT>& cloud_out,
+                                           const Eigen::Matrix<Scalar, 4, 4>& transform, bool copy_all_fields = true)
+{
+  const std::size_t n = indices.size();
+  pcl::PointCloud<PointT> out;
+  out.header = cloud_in.header;
+  out.is_dense = cloud_in.is_dense;
+  out.sensor_orientation_ = cloud_in.sensor_orientation_;
+  out.sensor_origin_ = cloud_in.sensor_origin_;
+  out.points.assign(n, PointT());
+  const detail::Transformer<Scalar> tf(transform);
+  for (std::size_t i = 0; i < n; ++i) {
+    const PointT& src = cloud_in[static_cast<std::size_t>(indices[i])];
+    if (copy_all_fields) out.points[i] = src;
+    if (!cloud_in.is_dense && !detail::finiteXYZ(src)) continue;
+    tf.se3(src.data, out.points[i].data);
+    tf.so3(src.data_n, out.points[i].data_n);
+  }
+  out.width = static_cast<std::uint32_t>(n);
+  out.height = 1;
+  cloud_out = std::move(out);
+}
 template <typename PointT, typename Scalar>
 inline PointT transformPoint(const PointT& point, const Eigen::Matrix<Scalar, 4, 4>& transform)
 {

@@ -6,6 +6,7 @@
 #include <cstdio>
 #include <limits>
 #include <map>
+#include <random>
 #include <set>
 #include <sstream>
 #include <vector>
@@ -161,10 +162,102 @@ static void centroid_body()
   CHECK(compute3DCentroid(cloud, indices, centroid) == 4 && centroid[0] == 0 && centroid[1] == 1 && centroid[2] == 0 && centroid[3] == 1);
 }
 
+// TYPED_TEST (Transforms, PointCloudXYZDense / DenseIndexed / Sparse / XYZRGBNormalDense / DenseIndexed) —
+// test/common/test_transforms.cpp:58-209 for the Matrix<float, 4, 4> and Matrix<double, 4, 4> instances (PointNormal stands in for
+// PointXYZRGBNormal; the expected values are the rigid transform applied in double and narrowed, the bound 10 epsilon of Scalar)
+template <typename Scalar>
+static void transforms_body(unsigned seed)
+{
+  std::mt19937 rng(seed);
+  std::uniform_real_distribution<double> U(-1.0, 1.0);
+  const double rx = U(rng), ry = U(rng), rz = U(rng), tx = U(rng), ty = U(rng), tz = U(rng);
+  // getTransformation (x, y, z, roll, pitch, yaw): R = Rz(yaw) Ry(pitch) Rx(roll)
+  const double A = std::cos(rz), B = std::sin(rz), C = std::cos(ry), D = std::sin(ry), E = std::cos(rx), F = std::sin(rx), DE = D * E, DF = D * F;
+  const double R[9] = {A * C, A * DF - B * E, B * F + A * DE, B * C, A * E + B * DF, B * DE - A * F, -D, C * F, C * E};
+  Eigen::Matrix<Scalar, 4, 4> tf = Eigen::Matrix<Scalar, 4, 4>::Identity();
+  for (int r = 0; r < 3; ++r) {
+    for (int c = 0; c < 3; ++c) tf(r, c) = static_cast<Scalar>(R[3 * r + c]);
+    tf(r, 3) = static_cast<Scalar>(r == 0 ? tx : r == 1 ? ty : tz);
+  }
+  const std::size_t CLOUD_SIZE = 100;
+  const double ABS_ERROR = static_cast<double>(std::numeric_limits<Scalar>::epsilon()) * 10;
+  PointCloud<PointXYZ> p_xyz, p_xyz_trans;
+  PointCloud<PointNormal> p_n, p_n_trans;
+  for (std::size_t i = 0; i < CLOUD_SIZE; ++i) {
+    const float v[3] = {static_cast<float>(U(rng)), static_cast<float>(U(rng)), static_cast<float>(U(rng))};
+    double nn[3] = {U(rng), U(rng), U(rng)};
+    const double nl = std::sqrt(nn[0] * nn[0] + nn[1] * nn[1] + nn[2] * nn[2]);
+    const float n[3] = {static_cast<float>(nn[0] / nl), static_cast<float>(nn[1] / nl), static_cast<float>(nn[2] / nl)};
+    PointNormal a, b;
+    a.x = v[0]; a.y = v[1]; a.z = v[2]; a.normal_x = n[0]; a.normal_y = n[1]; a.normal_z = n[2]; a.curvature = static_cast<float>(U(rng));
+    b = a;
+    float* bo[3] = {&b.x, &b.y, &b.z};
+    float* bn[3] = {&b.normal_x, &b.normal_y, &b.normal_z};
+    for (int r = 0; r < 3; ++r) {   // the expectation in the Scalar of the transform, as the reference's fixture computes it
+      *bo[r] = static_cast<float>(static_cast<Scalar>(static_cast<Scalar>(tf(r, 0)) * v[0] + static_cast<Scalar>(tf(r, 1)) * v[1] + static_cast<Scalar>(tf(r, 2)) * v[2] + tf(r, 3)));
+      *bn[r] = static_cast<float>(static_cast<Scalar>(static_cast<Scalar>(tf(r, 0)) * n[0] + static_cast<Scalar>(tf(r, 1)) * n[1] + static_cast<Scalar>(tf(r, 2)) * n[2]));
+    }
+    p_n.push_back(a);
+    p_n_trans.push_back(b);
+    p_xyz.push_back(PointXYZ(a.x, a.y, a.z));
+    p_xyz_trans.push_back(PointXYZ(b.x, b.y, b.z));
+  }
+  Indices indices(CLOUD_SIZE / 2);
+  for (std::size_t i = 0; i < indices.size(); ++i) indices[i] = static_cast<index_t>(i * 2);
+  auto xyz_near = [&](const auto& a, const auto& b) { return std::fabs(a.x - b.x) <= ABS_ERROR && std::fabs(a.y - b.y) <= ABS_ERROR && std::fabs(a.z - b.z) <= ABS_ERROR; };
+  auto n_near = [&](const PointNormal& a, const PointNormal& b) {
+    return std::fabs(a.normal_x - b.normal_x) <= ABS_ERROR && std::fabs(a.normal_y - b.normal_y) <= ABS_ERROR && std::fabs(a.normal_z - b.normal_z) <= ABS_ERROR;
+  };
+  {  // PointCloudXYZDense
+    PointCloud<PointXYZ> p;
+    transformPointCloud(p_xyz, p, tf);
+    CHECK(p.width == p_xyz.width && p.height == p_xyz.height && p.is_dense == p_xyz.is_dense && p.size() == p_xyz.size());
+    int bad = 0;
+    for (std::size_t i = 0; i < p.size(); ++i) bad += !xyz_near(p[i], p_xyz_trans[i]);
+    CHECK(bad == 0);
+  }
+  {  // PointCloudXYZDenseIndexed
+    PointCloud<PointXYZ> p;
+    transformPointCloud(p_xyz, indices, p, tf);
+    CHECK(p.size() == indices.size() && p.width == indices.size() && p.height == 1);
+    int bad = 0;
+    for (std::size_t i = 0; i < p.size(); ++i) bad += !xyz_near(p[i], p_xyz_trans[i * 2]);
+    CHECK(bad == 0);
+  }
+  {  // PointCloudXYZSparse
+    PointCloud<PointXYZ> sparse = p_xyz, p;
+    sparse.is_dense = false;
+    sparse[0].x = std::numeric_limits<float>::quiet_NaN();
+    transformPointCloud(sparse, p, tf);
+    CHECK(p.width == sparse.width && p.height == sparse.height && !p.is_dense && p.size() == sparse.size());
+    CHECK(!(std::isfinite(p[0].x) && std::isfinite(p[0].y) && std::isfinite(p[0].z)));
+    int bad = 0;
+    for (std::size_t i = 1; i < p.size(); ++i) bad += !(std::isfinite(p[i].x) && xyz_near(p[i], p_xyz_trans[i]));
+    CHECK(bad == 0);
+  }
+  {  // PointCloudXYZRGBNormalDense: coordinates and normals move, the other fields are carried
+    PointCloud<PointNormal> p;
+    transformPointCloudWithNormals(p_n, p, tf);
+    CHECK(p.width == p_n.width && p.height == p_n.height && p.size() == p_n.size());
+    int bad = 0;
+    for (std::size_t i = 0; i < p.size(); ++i) bad += !(xyz_near(p[i], p_n_trans[i]) && n_near(p[i], p_n_trans[i]) && p[i].curvature == p_n_trans[i].curvature);
+    CHECK(bad == 0);
+  }
+  {  // PointCloudXYZRGBNormalDenseIndexed
+    PointCloud<PointNormal> p;
+    transformPointCloudWithNormals(p_n, indices, p, tf);
+    CHECK(p.size() == indices.size() && p.width == indices.size() && p.height == 1);
+    int bad = 0;
+    for (std::size_t i = 0; i < p.size(); ++i) bad += !(xyz_near(p[i], p_n_trans[i * 2]) && n_near(p[i], p_n_trans[i * 2]) && p[i].curvature == p_n_trans[i * 2].curvature);
+    CHECK(bad == 0);
+  }
+}
+
 static int reference_centroid_tests(const char* bun0_pcd)
 {
   centroid_body<float>();
   centroid_body<double>();
+  for (unsigned seed = 1; seed <= 5; ++seed) { transforms_body<float>(seed); transforms_body<double>(seed); }
   {  // computeMeanAndCovariance
     PointCloud<PointXYZ> cloud;
     PointXYZ point;

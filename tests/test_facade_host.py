@@ -16,7 +16,8 @@ def test_point_cloud_container_and_host_classes():
 def test_reference_centroid_tests(golden, tmp_path):
     """The bodies of the reference's test/common/test_centroid.cpp for the moment functions on the path: compute3DCentroid
     (float, double; empty / all-NaN inputs leave the caller's centroid untouched), computeMeanAndCovarianceMatrix,
-    demeanPointCloud on bun0 with the reference's expected values."""
+    demeanPointCloud on bun0 with the reference's expected values; and of test/common/test_transforms.cpp: transformPointCloud
+    dense / indexed / with a NaN point, transformPointCloudWithNormals dense / indexed, Matrix4f and Matrix4d, 10 epsilon."""
     import numpy as np
     from test_facade_gpu import _write_ascii_pcd
     subprocess.check_call(["make", "-C", FACADE, "-s", "tests/test_host_api"])
