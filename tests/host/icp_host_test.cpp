@@ -9,6 +9,8 @@
 #define PCLB_HOST_EMULATION 1
 #include "host_index.h"
 
+#include <cstdlib>
+
 #include <cfloat>
 
 #include "../../pcl_b200/csrc/icp_kernels.cuh"
@@ -49,6 +51,13 @@ extern "C" void orc_icp_align_full(const orc_icp_params* P, const orc_icp_ext* X
 extern "C" void* orc_index_build(const float* pts, size_t n, size_t stride, const int32_t* subset, size_t n_subset);
 extern "C" void orc_index_free(void* h);
 extern "C" int orc_knn(void* h, const float* q, size_t nq, size_t qstride, int k, int32_t* out_idx, float* out_d2, int nthreads);
+
+// the fixed seed of the committed test, or PCLB_TEST_SEED for a fuzz run (tools/dev/fuzz_host_tests.sh)
+static unsigned test_seed(unsigned fixed)
+{
+  const char* e = std::getenv("PCLB_TEST_SEED");
+  return e && *e ? fixed ^ (2654435761u * static_cast<unsigned>(std::strtoul(e, nullptr, 10))) : fixed;
+}
 
 static long g_checks = 0, g_fail = 0;
 #define CHECK(c, ...) do { ++g_checks; if (!(c)) { if (++g_fail <= 20) { std::printf("FAIL %s:%d %s  ", __FILE__, __LINE__, #c); std::printf(__VA_ARGS__); std::printf("\n"); } } } while (0)
@@ -328,9 +337,18 @@ static void run_align(const char* name, const Scene& S, int estimator, bool scal
   CHECK(ctrl.iterations == R.iterations && ctrl.state == R.state && (ctrl.converged != 0) == (R.converged != 0),
         "%s: device loop %d iterations state %d converged %d, oracle %d / %d / %d", name, ctrl.iterations, ctrl.state, ctrl.converged, R.iterations,
         R.state, R.converged);
-  CHECK(dT < (scalar_double ? 1e-9 : 1e-5), "%s: |T_device - T_oracle|_F = %g", name, dT);
-  CHECK((long long)ctrl.total_corr == R.total_correspondences && (int)ctrl.n_corr == R.n_correspondences, "%s: correspondence counts %lld / %d vs %lld / %d",
-        name, (long long)ctrl.total_corr, (int)ctrl.n_corr, R.total_correspondences, R.n_correspondences);
+  // Scalar = float: the oracle restates the reference's FLOAT sums, the device accumulates in fp64 and rounds once; the two
+  // first estimates differ by ~1e-6, and on a scene where point-to-point ICP is still sliding when the iteration limit ends it
+  // that is enough to move a few of the 1 500 pairs to a neighbouring target point in the next iteration (measured with
+  // PCLB_TEST_SEED=1: 2.6e-6 after one iteration, 6.8e-5 after two, 5e-4 after five, shrinking again as both settle).  The
+  // committed scenes stay below 1e-5; a fuzz run (PCLB_TEST_SEED set) holds float to 2e-3 and double to 1e-9.
+  const double float_bar = std::getenv("PCLB_TEST_SEED") ? 2e-3 : 1e-5;
+  CHECK(dT < (scalar_double ? 1e-9 : float_bar), "%s: |T_device - T_oracle|_F = %g", name, dT);
+  {  // equal counts; in a float fuzz run the two trajectories may gate / pair a handful of points differently (see above): 0.5 %
+    const long long slack = (!scalar_double && std::getenv("PCLB_TEST_SEED")) ? std::max<long long>(2, R.total_correspondences / 200) : 0;
+    CHECK(std::llabs((long long)ctrl.total_corr - R.total_correspondences) <= slack && std::llabs((long long)ctrl.n_corr - (long long)R.n_correspondences) <= slack,
+          "%s: correspondence counts %lld / %d vs %lld / %d", name, (long long)ctrl.total_corr, (int)ctrl.n_corr, R.total_correspondences, R.n_correspondences);
+  }
   CHECK(d_error == 0, "%s: device error flag %d", name, d_error);
   std::printf("%-44s %5zu -> %5zu points: %2d iterations, state %d, |dT| %.2e, %ld walks skipped; ok so far: %ld checks, %ld failures\n", name, ns, nt,
               ctrl.iterations, ctrl.state, dT, skipped_total, g_checks, g_fail);
@@ -420,7 +438,7 @@ static void run_estimators(std::mt19937& rng)
 
 int main()
 {
-  std::mt19937 rng(77);
+  std::mt19937 rng(test_seed(77));
   std::uniform_real_distribution<float> U(0.f, 1.f);
   std::normal_distribution<float> N(0.f, 1.f);
   auto rot = [](double ax, double ay, double az, double deg, double R[9]) {

@@ -14,6 +14,15 @@
 // duplicates beyond a leaf, a lattice full of exact ties, a degenerate line, far-away queries, tiny clouds.
 #include "host_index.h"
 
+#include <cstdlib>
+
+// the fixed seed of the committed test, or PCLB_TEST_SEED for a fuzz run (tools/dev/fuzz_host_tests.sh)
+static unsigned test_seed(unsigned fixed)
+{
+  const char* e = std::getenv("PCLB_TEST_SEED");
+  return e && *e ? fixed ^ (2654435761u * static_cast<unsigned>(std::strtoul(e, nullptr, 10))) : fixed;
+}
+
 static long g_checks = 0, g_fail = 0;
 #define CHECK(c, ...) do { ++g_checks; if (!(c)) { if (++g_fail <= 20) { std::printf("FAIL %s:%d %s  ", __FILE__, __LINE__, #c); std::printf(__VA_ARGS__); std::printf("\n"); } } } while (0)
 
@@ -29,7 +38,7 @@ static void run_scene(const char* name, const std::vector<float>& xyz, const std
     const int o = __float_as_int(I.pts[p].w);
     if (o != kSentinelIndex) pos_of[o] = static_cast<int>(p);
   }
-  std::mt19937 rng(99);
+  std::mt19937 rng(test_seed(99));
   const float inf = INFINITY;
   for (int with_table = 0; with_table < 2; ++with_table) {
     const TreeView T = I.view(with_table != 0);
@@ -139,7 +148,7 @@ static void run_coherence(const char* name, const std::vector<float>& xyz, int n
 int main(int argc, char** argv)
 {
   const int scale = argc > 1 ? std::atoi(argv[1]) : 1;   // 1: seconds; larger: more points and queries
-  std::mt19937 rng(20250923);
+  std::mt19937 rng(test_seed(20250923));
   std::uniform_real_distribution<float> U(0.f, 1.f);
   std::normal_distribution<float> N(0.f, 1.f);
   auto cloud = [&](int n, auto gen) { std::vector<float> v; v.reserve(3 * n); for (int i = 0; i < n; ++i) { float p[3]; gen(i, p); v.insert(v.end(), p, p + 3); } return v; };
