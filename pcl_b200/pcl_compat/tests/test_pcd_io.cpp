@@ -157,6 +157,76 @@ static int selftest(const std::string& dir)
     EXPECT_EQ(io::loadPCDFile(dir + "/trunc.pcd", c), -1);
     EXPECT_EQ(io::loadPCDFile(dir + "/does_not_exist.pcd", c), -1);
   }
+  {  // TEST (PCL, EmptyCloudToPCD) — test/io/test_io.cpp:692-880: empty clouds through every writer and back, headers without
+     // WIDTH / HEIGHT, a non-numeric HEIGHT, blobs without fields
+    PointCloud<PointXYZ> cloud;
+    const std::string f = dir + "/empty.pcd";
+    for (int mode = 0; mode < 3; ++mode) {
+      const int res = mode == 0 ? io::savePCDFileASCII(f, cloud) : mode == 1 ? io::savePCDFileBinary(f, cloud) : io::savePCDFileBinaryCompressed(f, cloud);
+      EXPECT_EQ(res, 0);
+      PointCloud<PointXYZ> in;
+      in.width = 10;    // loadPCDFile must overwrite these
+      in.height = 10;
+      EXPECT_EQ(io::loadPCDFile(f, in), 0);
+      EXPECT_EQ(in.width, cloud.width);
+      EXPECT_EQ(in.height, cloud.height);
+      EXPECT_EQ(in.size(), 0u);
+      std::remove(f.c_str());
+    }
+    PCLPointCloud2 cloud2;
+    for (const char* name : {"x", "y", "z"}) {
+      PCLPointField fld;
+      fld.name = name;
+      fld.datatype = PCLPointField::FLOAT32;
+      cloud2.fields.push_back(fld);
+    }
+    cloud2.is_dense = true;
+    for (int mode = 0; mode < 3; ++mode) {
+      const int res = mode == 0 ? io::savePCDFile(f, cloud2, Eigen::Vector4f::Zero(), Eigen::Quaternionf::Identity())
+                      : mode == 1 ? io::savePCDFile(f, cloud2, Eigen::Vector4f::Zero(), Eigen::Quaternionf::Identity(), true)
+                                  : PCDWriter().writeBinaryCompressed(f, cloud2);
+      EXPECT_EQ(res, 0);
+      PCLPointCloud2 in2;
+      in2.width = 10;
+      in2.height = 10;
+      EXPECT_EQ(io::loadPCDFile(f, in2), 0);
+      EXPECT_EQ(in2.width, cloud2.width);
+      EXPECT_EQ(in2.height, cloud2.height);
+      std::remove(f.c_str());
+    }
+    auto write_text = [&](const char* text) { std::ofstream fs(f); fs << text; };
+    {  // WIDTH and HEIGHT not defined
+      write_text("# .PCD v0.5 - Point Cloud Data file format\nVERSION 0.5\nFIELDS x y z intensity\nSIZE 4 4 4 4\nTYPE F F F F\nCOUNT 1 1 1 1\nPOINTS 2\nDATA ascii\n1 2 3 4\n5 6 7 8");
+      PCLPointCloud2 in2;
+      EXPECT_EQ(io::loadPCDFile(f, in2), 0);
+      EXPECT_EQ(in2.width, 2u);
+      EXPECT_EQ(in2.height, 1u);
+      EXPECT_TRUE(in2.is_dense);
+      EXPECT_EQ(in2.data.size(), std::size_t(2 * 4 * 4));
+    }
+    {  // HEIGHT not defined
+      write_text("# .PCD v0.7 - Point Cloud Data file format\nVERSION 0.7\nFIELDS x y z intensity\nSIZE 4 4 4 4\nTYPE F F F F\nCOUNT 1 1 1 1\nWIDTH 2\nPOINTS 2\nDATA ascii\n1 2 3 4\n5 6 7 8");
+      PCLPointCloud2 in2;
+      EXPECT_EQ(io::loadPCDFile(f, in2), 0);
+      EXPECT_EQ(in2.width, 2u);
+      EXPECT_EQ(in2.height, 1u);
+      EXPECT_TRUE(in2.is_dense);
+      EXPECT_EQ(in2.data.size(), std::size_t(2 * 4 * 4));
+    }
+    {  // invalid height
+      write_text("# .PCD v0.7 - Point Cloud Data file format\nVERSION 0.7\nFIELDS x y z intensity\nSIZE 4 4 4 4\nTYPE F F F F\nCOUNT 1 1 1 1\nWIDTH 2\nHEIGHT a\nPOINTS 2\nDATA ascii\n1 2 3 4\n5 6 7 8");
+      PCLPointCloud2 in2;
+      EXPECT_EQ(io::loadPCDFile(f, in2), -1);
+    }
+    std::remove(f.c_str());
+    {  // no field data: every writer refuses
+      PCLPointCloud2 empty_cloud;
+      EXPECT_EQ(io::savePCDFile(f, empty_cloud, Eigen::Vector4f::Zero(), Eigen::Quaternionf::Identity()), -1);
+      EXPECT_EQ(io::savePCDFile(f, empty_cloud, Eigen::Vector4f::Zero(), Eigen::Quaternionf::Identity(), true), -1);
+      EXPECT_EQ(PCDWriter().writeBinaryCompressed(f, empty_cloud), -1);
+      std::remove(f.c_str());
+    }
+  }
   {  // the type-erased route: a blob with mixed field types, a COUNT > 1 field and padding survives all three encodings;
      // typed and blob readers agree; concatenateFields / getFieldsList / getFieldIndex (common/src/io.cpp)
     PCLPointCloud2 b;
