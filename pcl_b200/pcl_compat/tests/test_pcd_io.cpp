@@ -157,6 +157,46 @@ static int selftest(const std::string& dir)
     EXPECT_EQ(io::loadPCDFile(dir + "/trunc.pcd", c), -1);
     EXPECT_EQ(io::loadPCDFile(dir + "/does_not_exist.pcd", c), -1);
   }
+  {  // TEST (PCL, PCDReaderWriter) — test/io/test_io.cpp:879-946 with PointNormal in the place of PointXYZI: a 640 x 480 organised
+     // cloud -> blob (whole records, padding included) -> binary file -> blob -> cloud
+    PCLPointCloud2 cloud_blob;
+    PointCloud<PointNormal> cloud;
+    cloud.width = 640;
+    cloud.height = 480;
+    cloud.points.resize(static_cast<std::size_t>(cloud.width) * cloud.height);
+    cloud.is_dense = true;
+    const std::size_t nr_p = cloud.size();
+    for (std::size_t i = 0; i < nr_p; ++i) {
+      cloud[i].x = static_cast<float>(1024 * (rng() % 32768) / 32768.0);
+      cloud[i].y = static_cast<float>(1024 * (rng() % 32768) / 32768.0);
+      cloud[i].z = static_cast<float>(1024 * (rng() % 32768) / 32768.0);
+      cloud[i].normal_x = 0.f; cloud[i].normal_y = 0.6f; cloud[i].normal_z = 0.8f;
+      cloud[i].curvature = static_cast<float>(i);
+    }
+    const PointNormal first = cloud[0], last = cloud[nr_p - 1];
+    toPCLPointCloud2(cloud, cloud_blob);
+    EXPECT_EQ(cloud_blob.width, cloud.width);
+    EXPECT_EQ(cloud_blob.height, cloud.height);
+    EXPECT_EQ(bool(cloud_blob.is_dense), cloud.is_dense);
+    EXPECT_EQ(cloud_blob.data.size(), static_cast<std::size_t>(cloud_blob.width) * cloud_blob.height * sizeof(PointNormal));
+    const std::string f = dir + "/test_pcl_io.pcd";
+    PCDWriter writer;
+    EXPECT_EQ(writer.write(f, cloud_blob, Eigen::Vector4f::Zero(), Eigen::Quaternionf::Identity(), true), 0);
+    PCDReader reader;
+    EXPECT_EQ(reader.read(f, cloud_blob), 0);
+    EXPECT_EQ(cloud_blob.width, cloud.width);
+    EXPECT_EQ(cloud_blob.height, cloud.height);
+    EXPECT_EQ(bool(cloud_blob.is_dense), cloud.is_dense);
+    EXPECT_EQ(cloud_blob.data.size(), static_cast<std::size_t>(cloud_blob.width) * cloud_blob.height * sizeof(PointNormal));
+    fromPCLPointCloud2(cloud_blob, cloud);
+    EXPECT_EQ(cloud.width, cloud_blob.width);
+    EXPECT_EQ(cloud.height, cloud_blob.height);
+    EXPECT_EQ(cloud.is_dense, bool(cloud_blob.is_dense));
+    EXPECT_EQ(cloud.size(), nr_p);
+    EXPECT_TRUE(cloud[0].x == first.x && cloud[0].y == first.y && cloud[0].z == first.z && cloud[0].curvature == first.curvature && cloud[0].normal_z == first.normal_z);
+    EXPECT_TRUE(cloud[nr_p - 1].x == last.x && cloud[nr_p - 1].y == last.y && cloud[nr_p - 1].z == last.z && cloud[nr_p - 1].curvature == last.curvature);
+    std::remove(f.c_str());
+  }
   {  // TEST (PCL, EmptyCloudToPCD) — test/io/test_io.cpp:692-880: empty clouds through every writer and back, headers without
      // WIDTH / HEIGHT, a non-numeric HEIGHT, blobs without fields
     PointCloud<PointXYZ> cloud;
