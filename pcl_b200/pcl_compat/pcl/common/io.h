@@ -97,6 +97,35 @@ inline void copyPointCloud(const pcl::PointCloud<PointInT>& cloud_in, pcl::Point
   }
 }
 
+// common/include/pcl/common/impl/io.hpp:367-399: every field of the output type that one of the inputs has, by NAME — cloud1's
+// first, then cloud2's (so cloud2 wins where both have it); metadata of cloud1; dense only if both are
+template <typename PointIn1T, typename PointIn2T, typename PointOutT>
+inline void concatenateFields(const pcl::PointCloud<PointIn1T>& cloud1_in, const pcl::PointCloud<PointIn2T>& cloud2_in, pcl::PointCloud<PointOutT>& cloud_out)
+{
+  if (cloud1_in.size() != cloud2_in.size()) {
+    std::fprintf(stderr, "[pcl::concatenateFields] The number of points in the two input datasets differs!\n");
+    return;
+  }
+  cloud_out.points.resize(cloud1_in.size());
+  cloud_out.header = cloud1_in.header;
+  cloud_out.width = cloud1_in.width;
+  cloud_out.height = cloud1_in.height;
+  cloud_out.is_dense = cloud1_in.is_dense && cloud2_in.is_dense;
+  const auto out_fields = detail::blob_fields<PointOutT>::get();
+  auto copy_from = [&](const auto& in_fields, const unsigned char* src, unsigned char* dst) {
+    for (const auto& fi : in_fields)
+      for (const auto& fo : out_fields)
+        if (std::strcmp(fi.name, fo.name) == 0) std::memcpy(dst + fo.offset, src + fi.offset, 4);   // every field of these types is one FLOAT32
+  };
+  const auto f1 = detail::blob_fields<PointIn1T>::get();
+  const auto f2 = detail::blob_fields<PointIn2T>::get();
+  for (std::size_t i = 0; i < cloud_out.size(); ++i) {
+    unsigned char* dst = reinterpret_cast<unsigned char*>(&cloud_out.points[i]);
+    copy_from(f1, reinterpret_cast<const unsigned char*>(&cloud1_in.points[i]), dst);
+    copy_from(f2, reinterpret_cast<const unsigned char*>(&cloud2_in.points[i]), dst);
+  }
+}
+
 // cloud_out = the records of cloud2 followed, per point, by the fields of cloud1 that cloud2 does not have (by name;
 // "_" padding never carried over).  Each carried field keeps the room it had in cloud1 up to the next named field, the
 // slack zero-filled (common/src/io.cpp:69-210).  Both clouds must have the same width and height.

@@ -302,6 +302,45 @@ static int reference_centroid_tests(const char* bun0_pcd)
     reset();
     CHECK(computeMeanAndCovarianceMatrix(cloud, indices, cov, centroid) == 4 && centroid[0] == 0 && centroid[1] == 1 && centroid[2] == 0 && is_diag(1, 0, 1));
   }
+  {  // TEST (PCL, ConcatenatePoints) and (PCL, ConcatenateFields) — test/io/test_io.cpp:293-381
+    std::mt19937 rng(5);
+    auto rnd = [&] { return static_cast<float>(1024 * (rng() % 32768) / 32768.0); };
+    PointCloud<PointXYZ> cloud_a, cloud_b, cloud_c;
+    cloud_a.width = 5; cloud_b.width = 3;
+    cloud_a.height = cloud_b.height = 1;
+    cloud_a.points.resize(5); cloud_b.points.resize(3);
+    for (auto& p : cloud_a.points) { p.x = rnd(); p.y = rnd(); p.z = rnd(); }
+    for (auto& p : cloud_b.points) { p.x = rnd(); p.y = rnd(); p.z = rnd(); }
+    cloud_c = cloud_a;
+    cloud_c += cloud_b;
+    CHECK(cloud_c.size() == cloud_a.size() + cloud_b.size() && cloud_c.width == cloud_a.width + cloud_b.width && cloud_c.height == 1);
+    bool same = true;
+    for (std::size_t i = 0; i < cloud_a.size(); ++i) same = same && cloud_c[i].x == cloud_a[i].x && cloud_c[i].y == cloud_a[i].y && cloud_c[i].z == cloud_a[i].z;
+    for (std::size_t i = cloud_a.size(); i < cloud_c.size(); ++i) {
+      const PointXYZ& b = cloud_b[i - cloud_a.size()];
+      same = same && cloud_c[i].x == b.x && cloud_c[i].y == b.y && cloud_c[i].z == b.z;
+    }
+    CHECK(same);
+    PointCloud<PointXYZ> fa;
+    PointCloud<Normal> fb;
+    PointCloud<PointNormal> fc;
+    fa.width = fb.width = 5;
+    fa.height = fb.height = 1;
+    fa.points.resize(5); fb.points.resize(5);
+    for (auto& p : fa) { p.x = rnd(); p.y = rnd(); p.z = rnd(); }
+    for (auto& p : fb) { p.normal_x = rnd(); p.normal_y = rnd(); p.normal_z = rnd(); p.curvature = rnd(); }
+    concatenateFields(fa, fb, fc);
+    CHECK(fc.size() == fa.size() && fc.width == fa.width && fc.height == fa.height);
+    same = true;
+    for (std::size_t i = 0; i < fa.size() && i < fc.size(); ++i)
+      same = same && fc[i].x == fa[i].x && fc[i].y == fa[i].y && fc[i].z == fa[i].z && fc[i].normal[0] == fb[i].normal[0] && fc[i].normal[1] == fb[i].normal[1] &&
+             fc[i].normal[2] == fb[i].normal[2] && fc[i].curvature == fb[i].curvature;
+    CHECK(same);
+    fb.points.resize(4);   // sizes differ: refused, the output is left alone
+    PointCloud<PointNormal> untouched;
+    concatenateFields(fa, fb, untouched);
+    CHECK(untouched.empty());
+  }
   {  // demeanPointCloud on bun0
     PointCloud<PointXYZ> cloud, cloud_demean;
     if (io::loadPCDFile(bun0_pcd, cloud)) return 2;
