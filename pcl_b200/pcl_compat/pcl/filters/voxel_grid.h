@@ -16,6 +16,8 @@
 #include "../b200/context.h"
 #include "../point_cloud.h"
 #include "../point_types.h"
+#include "../PCLPointCloud2.h"
+#include "../common/io.h"
 
 namespace pcl {
 // voxel_grid.h:52-100: the 13 cells of the "upper half" of a cell's 26-neighbourhood, and all 26 + the cell itself
@@ -282,5 +284,151 @@ protected:
   std::string filter_field_name_;
   double filter_limit_min_ = std::numeric_limits<float>::lowest(), filter_limit_max_ = std::numeric_limits<float>::max();
   bool filter_limit_negative_ = false;
+};
+
+// VoxelGrid<pcl::PCLPointCloud2> (filters/include/pcl/filters/voxel_grid.h:507-870, filters/src/voxel_grid.cpp:211-545): the
+// type-erased form the PCL tutorials use.  The blob's x / y / z (FLOAT32) — and, when it carries them and all data is to be
+// downsampled, normal_x / normal_y / normal_z / curvature — go through the typed device filter above; the output blob holds
+// exactly those fields.  Other fields of the input (intensity, rgb, ...) are not carried: the reference averages them when
+// setDownsampleAllData(true), this class does not and says so once per filter() call.
+template <>
+class VoxelGrid<pcl::PCLPointCloud2> {
+public:
+  using PCLPointCloud2 = pcl::PCLPointCloud2;
+  using PCLPointCloud2Ptr = PCLPointCloud2::Ptr;
+  using PCLPointCloud2ConstPtr = PCLPointCloud2::ConstPtr;
+
+  void setInputCloud(const PCLPointCloud2ConstPtr& cloud) { input_ = cloud; }
+  PCLPointCloud2ConstPtr const getInputCloud() const { return input_; }
+  void setIndices(const IndicesPtr& indices) { indices_ = indices; }
+  void setIndices(const IndicesConstPtr& indices) { indices_.reset(new Indices(*indices)); }
+  IndicesPtr getIndices() { return indices_ ? indices_ : last_indices_; }   // without setIndices: the list the last filter() ran on
+  void setLeafSize(float lx, float ly, float lz) { xyz_.setLeafSize(lx, ly, lz); xyzn_.setLeafSize(lx, ly, lz); }
+  void setLeafSize(const Eigen::Vector4f& l) { setLeafSize(l[0], l[1], l[2]); }
+  Eigen::Vector3f getLeafSize() const { return xyz_.getLeafSize(); }
+  void setDownsampleAllData(bool v) { downsample_all_data_ = v; }
+  bool getDownsampleAllData() const { return downsample_all_data_; }
+  void setMinimumPointsNumberPerVoxel(unsigned int n) { xyz_.setMinimumPointsNumberPerVoxel(n); xyzn_.setMinimumPointsNumberPerVoxel(n); }
+  unsigned int getMinimumPointsNumberPerVoxel() const { return xyz_.getMinimumPointsNumberPerVoxel(); }
+  void setSaveLeafLayout(bool v) { xyz_.setSaveLeafLayout(v); xyzn_.setSaveLeafLayout(v); }
+  bool getSaveLeafLayout() const { return xyz_.getSaveLeafLayout(); }
+  void setFilterFieldName(const std::string& name) { xyz_.setFilterFieldName(name); xyzn_.setFilterFieldName(name); }
+  const std::string& getFilterFieldName() const { return xyz_.getFilterFieldName(); }
+  void setFilterLimits(const double& lo, const double& hi) { xyz_.setFilterLimits(lo, hi); xyzn_.setFilterLimits(lo, hi); }
+  void getFilterLimits(double& lo, double& hi) const { xyz_.getFilterLimits(lo, hi); }
+  void setFilterLimitsNegative(bool v) { xyz_.setFilterLimitsNegative(v); xyzn_.setFilterLimitsNegative(v); }
+  bool getFilterLimitsNegative() const { return xyz_.getFilterLimitsNegative(); }
+  Eigen::Vector3i getMinBoxCoordinates() const { return used_normals_ ? xyzn_.getMinBoxCoordinates() : xyz_.getMinBoxCoordinates(); }
+  Eigen::Vector3i getMaxBoxCoordinates() const { return used_normals_ ? xyzn_.getMaxBoxCoordinates() : xyz_.getMaxBoxCoordinates(); }
+  Eigen::Vector3i getNrDivisions() const { return used_normals_ ? xyzn_.getNrDivisions() : xyz_.getNrDivisions(); }
+  Eigen::Vector3i getDivisionMultiplier() const { return used_normals_ ? xyzn_.getDivisionMultiplier() : xyz_.getDivisionMultiplier(); }
+  std::vector<int> getLeafLayout() const { return used_normals_ ? xyzn_.getLeafLayout() : xyz_.getLeafLayout(); }
+  Eigen::Vector3i getGridCoordinates(float x, float y, float z) const { return xyz_.getGridCoordinates(x, y, z); }
+  int getCentroidIndexAt(const Eigen::Vector3i& ijk) const { return used_normals_ ? xyzn_.getCentroidIndexAt(ijk) : xyz_.getCentroidIndexAt(ijk); }
+  int getCentroidIndex(float x, float y, float z) const
+  {
+    return used_normals_ ? xyzn_.getCentroidIndex(PointNormal(x, y, z)) : xyz_.getCentroidIndex(PointXYZ(x, y, z));
+  }
+  std::vector<int> getNeighborCentroidIndices(float x, float y, float z, const Eigen::MatrixXi& relative_coordinates) const
+  {
+    return used_normals_ ? xyzn_.getNeighborCentroidIndices(PointNormal(x, y, z), relative_coordinates)
+                         : xyz_.getNeighborCentroidIndices(PointXYZ(x, y, z), relative_coordinates);
+  }
+
+  void filter(PCLPointCloud2& output)
+  {
+    output = PCLPointCloud2();
+    if (!input_) {
+      std::fprintf(stderr, "[pcl::VoxelGrid<pcl::PCLPointCloud2>::applyFilter] No input dataset given!\n");
+      return;
+    }
+    const int ix = getFieldIndex(*input_, "x"), iy = getFieldIndex(*input_, "y"), iz = getFieldIndex(*input_, "z");
+    auto is_float = [&](int i) { return i >= 0 && input_->fields[static_cast<std::size_t>(i)].datatype == PCLPointField::FLOAT32; };
+    if (!is_float(ix) || !is_float(iy) || !is_float(iz)) {
+      std::fprintf(stderr, "[pcl::VoxelGrid<pcl::PCLPointCloud2>::applyFilter] Input dataset doesn't have x-y-z coordinates!\n");
+      return;
+    }
+    const int inx = getFieldIndex(*input_, "normal_x"), iny = getFieldIndex(*input_, "normal_y"), inz = getFieldIndex(*input_, "normal_z"),
+              icv = getFieldIndex(*input_, "curvature");
+    used_normals_ = downsample_all_data_ && is_float(inx) && is_float(iny) && is_float(inz) && is_float(icv);
+    if (downsample_all_data_) {
+      std::size_t carried = used_normals_ ? 7 : 3, named = 0;
+      for (const auto& f : input_->fields) named += f.name != "_";
+      if (named > carried)
+        std::fprintf(stderr, "[pcl::VoxelGrid<pcl::PCLPointCloud2>::applyFilter] %zu field(s) besides x y z%s are not carried into the output.\n",
+                     named - carried, used_normals_ ? " normal_x normal_y normal_z curvature" : "");
+    }
+    const std::size_t n = static_cast<std::size_t>(input_->width) * input_->height;
+    auto at = [&](std::size_t i, int field) {
+      float v;
+      std::memcpy(&v, &input_->data[i * input_->point_step + input_->fields[static_cast<std::size_t>(field)].offset], 4);
+      return v;
+    };
+    auto run = [&](auto& grid, auto& cloud) {
+      using PointT = typename std::decay<decltype(cloud->points[0])>::type;
+      cloud->header = input_->header;
+      cloud->points.resize(n);
+      cloud->width = input_->width;
+      cloud->height = input_->height;
+      cloud->is_dense = input_->is_dense != 0;
+      for (std::size_t i = 0; i < n; ++i) {
+        PointT& p = cloud->points[i];
+        p.x = at(i, ix); p.y = at(i, iy); p.z = at(i, iz);
+      }
+      grid.setInputCloud(cloud);
+      if (indices_) grid.setIndices(indices_);
+      pcl::PointCloud<PointT> out;
+      grid.filter(out);
+      last_indices_ = grid.getIndices();   // the index list the filter ran on (PCLBase::initCompute)
+      toPCLPointCloud2(out, output);
+      // the output blob holds the downsampled fields only, tightly packed
+      PCLPointCloud2 packed;
+      packed.header = output.header;
+      packed.width = output.width;
+      packed.height = output.height;
+      packed.is_dense = output.is_dense;
+      packed.is_bigendian = 0;
+      std::uint32_t off = 0;
+      std::vector<std::uint32_t> src_off;
+      for (const auto& f : output.fields) {
+        if (f.name == "_") continue;
+        PCLPointField g = f;
+        src_off.push_back(f.offset);
+        g.offset = off;
+        off += 4;
+        packed.fields.push_back(g);
+      }
+      packed.point_step = off;
+      packed.row_step = off * packed.width;
+      packed.data.resize(static_cast<std::size_t>(packed.row_step) * packed.height);
+      const std::size_t m = static_cast<std::size_t>(output.width) * output.height;
+      for (std::size_t i = 0; i < m; ++i)
+        for (std::size_t k = 0; k < src_off.size(); ++k)
+          std::memcpy(&packed.data[i * off + 4 * k], &output.data[i * output.point_step + src_off[k]], 4);
+      output = std::move(packed);
+    };
+    if (used_normals_) {
+      auto cloud = std::make_shared<pcl::PointCloud<PointNormal>>();
+      cloud->points.resize(n);
+      for (std::size_t i = 0; i < n; ++i) {
+        PointNormal& p = cloud->points[i];
+        p.normal_x = at(i, inx); p.normal_y = at(i, iny); p.normal_z = at(i, inz); p.curvature = at(i, icv);
+      }
+      xyzn_.setDownsampleAllData(true);
+      run(xyzn_, cloud);
+    }
+    else {
+      auto cloud = std::make_shared<pcl::PointCloud<PointXYZ>>();
+      run(xyz_, cloud);
+    }
+  }
+
+protected:
+  PCLPointCloud2ConstPtr input_;
+  IndicesPtr indices_, last_indices_;
+  bool downsample_all_data_ = true;
+  bool used_normals_ = false;
+  VoxelGrid<PointXYZ> xyz_;
+  VoxelGrid<PointNormal> xyzn_;
 };
 }  // namespace pcl

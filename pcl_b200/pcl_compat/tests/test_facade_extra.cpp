@@ -538,6 +538,98 @@ int main(int argc, char** argv)
     EXPECT_EQ(output.size(), 100u);
   }
 
+  {  // TEST (VoxelGrid, Filters), "Test the pcl::PCLPointCloud2 method" — test/filters/test_filters.cpp:651-748
+    PCLPointCloud2::Ptr cloud_blob(new PCLPointCloud2);
+    toPCLPointCloud2(cloud_source, *cloud_blob);
+    PointCloud<PointXYZ> output;
+    VoxelGrid<PCLPointCloud2> grid2;
+    PCLPointCloud2 output_blob;
+    grid2.setLeafSize(0.02f, 0.02f, 0.02f);
+    grid2.setInputCloud(cloud_blob);
+    grid2.filter(output_blob);
+    fromPCLPointCloud2(output_blob, output);
+    EXPECT_EQ(output.size(), 103u);
+    EXPECT_EQ(output.width, 103u);
+    EXPECT_EQ(output.height, 1u);
+    EXPECT_TRUE(output.is_dense);
+    EXPECT_EQ(output_blob.point_step, 12u);
+    grid2.setFilterFieldName("z");
+    grid2.setFilterLimits(0.05, 0.1);
+    grid2.filter(output_blob);
+    fromPCLPointCloud2(output_blob, output);
+    EXPECT_EQ(output.size(), 14u);
+    EXPECT_EQ(output.width, 14u);
+    EXPECT_EQ(output.height, 1u);
+    EXPECT_TRUE(output.is_dense);
+    if (output.size() == 14) {
+      EXPECT_NEAR(output[0].x, -0.026125, 1e-4);
+      EXPECT_NEAR(output[0].y, 0.039788, 1e-4);
+      EXPECT_NEAR(output[0].z, 0.052827, 1e-4);
+      EXPECT_NEAR(output[13].x, -0.073202, 1e-4);
+      EXPECT_NEAR(output[13].y, 0.1296, 1e-4);
+      EXPECT_NEAR(output[13].z, 0.051333, 1e-4);
+    }
+    grid2.setFilterLimitsNegative(true);
+    grid2.setSaveLeafLayout(true);
+    grid2.filter(output_blob);
+    fromPCLPointCloud2(output_blob, output);
+    EXPECT_EQ(output.size(), 100u);
+    EXPECT_EQ(output.width, 100u);
+    EXPECT_EQ(output.height, 1u);
+    EXPECT_TRUE(output.is_dense);
+    if (output.size() == 100) {
+      EXPECT_EQ(grid2.getCentroidIndex(output[0].x, output[0].y, output[0].z), 0);
+      EXPECT_EQ(grid2.getCentroidIndex(output[99].x, output[99].y, output[99].z), 99);
+      EXPECT_EQ(grid2.getCentroidIndexAt(grid2.getGridCoordinates(-1, -1, -1)), -1);
+      const int centroidIdx2 = grid2.getCentroidIndex(0.048722f, 0.073760f, 0.017434f);
+      EXPECT_TRUE(centroidIdx2 != -1);
+      if (centroidIdx2 >= 0 && centroidIdx2 < 100) {
+        EXPECT_TRUE(std::abs(output[centroidIdx2].x - 0.048722) <= 0.02);
+        EXPECT_TRUE(std::abs(output[centroidIdx2].y - 0.073760) <= 0.02);
+        EXPECT_TRUE(std::abs(output[centroidIdx2].z - 0.017434) <= 0.02);
+        EXPECT_EQ(grid2.getNeighborCentroidIndices(output[0].x, output[0].y, output[0].z, Eigen::MatrixXi::Zero(3, 1))[0], 0);
+        EXPECT_EQ(grid2.getNeighborCentroidIndices(output[99].x, output[99].y, output[99].z, Eigen::MatrixXi::Zero(3, 1))[0], 99);
+        Eigen::MatrixXi directions2 = Eigen::Vector3i(0, 0, 1);
+        std::vector<int> neighbors2 = grid2.getNeighborCentroidIndices(0.048722f, 0.073760f, 0.017434f, directions2);
+        EXPECT_EQ(neighbors2.size(), std::size_t(directions2.cols()));
+        EXPECT_TRUE(neighbors2.at(0) != -1);
+        if (neighbors2.at(0) != -1) {
+          EXPECT_TRUE(std::abs(output[neighbors2.at(0)].x - output[centroidIdx2].x) <= 0.02);
+          EXPECT_TRUE(std::abs(output[neighbors2.at(0)].y - output[centroidIdx2].y) <= 0.02);
+          EXPECT_TRUE(output[neighbors2.at(0)].z - output[centroidIdx2].z <= 0.02 * 2);
+        }
+      }
+    }
+    auto indices2 = grid2.getIndices();   // original cloud indices
+    PointCloud<PointXYZ> cloud_copied = cloud_source;
+    for (int i = 0; i < 100; i++) cloud_copied.push_back(PointXYZ(100.f + i, 100.f + i, 100.f + i));
+    auto cloud_blob2 = std::make_shared<PCLPointCloud2>();
+    toPCLPointCloud2(cloud_copied, *cloud_blob2);
+    grid2.setInputCloud(cloud_blob2);
+    grid2.setIndices(indices2);
+    grid2.filter(output_blob);
+    fromPCLPointCloud2(output_blob, output);
+    EXPECT_EQ(output.size(), 100u);   // additional points are ignored
+    // a blob of PointNormal records: the normal and curvature planes come back too
+    PointCloud<PointNormal> pn;
+    for (const auto& p : cloud_source.points) pn.push_back(PointNormal(p.x, p.y, p.z, 0.f, 0.6f, 0.8f, 0.25f));
+    auto pn_blob = std::make_shared<PCLPointCloud2>();
+    toPCLPointCloud2(pn, *pn_blob);
+    VoxelGrid<PCLPointCloud2> grid3;
+    grid3.setLeafSize(0.02f, 0.02f, 0.02f);
+    grid3.setInputCloud(pn_blob);
+    grid3.filter(output_blob);
+    PointCloud<PointNormal> out_pn;
+    fromPCLPointCloud2(output_blob, out_pn);
+    EXPECT_EQ(out_pn.size(), 103u);
+    EXPECT_EQ(output_blob.point_step, 28u);
+    if (out_pn.size() == 103) {
+      EXPECT_NEAR(out_pn[5].normal_y, 0.6, 1e-6);
+      EXPECT_NEAR(out_pn[5].normal_z, 0.8, 1e-6);
+      EXPECT_NEAR(out_pn[5].curvature, 0.25, 1e-6);
+    }
+  }
+
   {  // TEST (VoxelGridMinPoints, Filters) — test/filters/test_filters.cpp:1356-1406, the positions (the reference's cloud is
      // PointXYZRGB; colour fields are outside this library): single points at 0 and 1, five points around 0.11, six around 0.31
     PointCloud<PointXYZ>::Ptr input(new PointCloud<PointXYZ>());
