@@ -7,6 +7,9 @@
 #else
 #include <cmath>
 #include <cstddef>
+#include <ostream>
+#include <sstream>
+#include <string>
 #include <vector>
 namespace Eigen {
 template <typename S, int R, int C>
@@ -60,6 +63,30 @@ struct Matrix {
     return r;
   }
 };
+// Eigen's default IOFormat: coefficients right-aligned to the widest one, columns separated by one space, rows by a newline
+template <typename S, int R, int C>
+std::ostream& operator<<(std::ostream& os, const Matrix<S, R, C>& m)
+{
+  std::string cell[R * C];
+  std::size_t width = 0;
+  for (int r = 0; r < R; ++r)
+    for (int c = 0; c < C; ++c) {
+      std::ostringstream one;
+      one.copyfmt(os);
+      one.width(0);
+      one << m(r, c);
+      cell[r * C + c] = one.str();
+      width = width > cell[r * C + c].size() ? width : cell[r * C + c].size();
+    }
+  for (int r = 0; r < R; ++r) {
+    if (r) os << "\n";
+    for (int c = 0; c < C; ++c) {
+      if (c) os << " ";
+      os << std::string(width - cell[r * C + c].size(), ' ') << cell[r * C + c];
+    }
+  }
+  return os;
+}
 using Matrix4f = Matrix<float, 4, 4>;
 using Matrix4d = Matrix<double, 4, 4>;
 using Matrix3f = Matrix<float, 3, 3>;

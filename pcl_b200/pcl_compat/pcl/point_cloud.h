@@ -6,11 +6,13 @@
 #include <initializer_list>
 #include <iterator>
 #include <memory>
+#include <ostream>
 #include <stdexcept>
 #include <string>
 #include <utility>
 #include <vector>
 
+#include "console/print.h"
 #include "eigen_lite.h"
 #include "types.h"
 
@@ -20,6 +22,15 @@ struct PCLHeader {
   std::uint64_t stamp = 0;
   std::string frame_id;
 };
+
+// PCLHeader.h:29-35
+inline std::ostream& operator<<(std::ostream& out, const PCLHeader& h)
+{
+  out << "seq: " << h.seq;
+  out << " stamp: " << h.stamp;
+  out << " frame_id: " << h.frame_id << std::endl;
+  return out;
+}
 
 // 2-D indexing of an unorganised cloud (common/include/pcl/exceptions.h: UnorganizedPointCloudException)
 struct UnorganizedPointCloudException : std::runtime_error {
@@ -295,6 +306,21 @@ private:
     if (static_cast<std::size_t>(width) * height != points.size()) unorganised();
   }
 };
+
+// point_cloud.h:904-923
+template <typename PointT>
+std::ostream& operator<<(std::ostream& s, const pcl::PointCloud<PointT>& p)
+{
+  s << "header: " << p.header << std::endl;
+  s << "points[]: " << p.size() << std::endl;
+  s << "width: " << p.width << std::endl;
+  s << "height: " << p.height << std::endl;
+  s << "is_dense: " << p.is_dense << std::endl;
+  s << "sensor origin (xyz): [" << p.sensor_origin_[0] << ", " << p.sensor_origin_[1] << ", " << p.sensor_origin_[2] << "] / orientation (xyzw): ["
+    << p.sensor_orientation_.x() << ", " << p.sensor_orientation_.y() << ", " << p.sensor_orientation_.z() << ", " << p.sensor_orientation_.w() << "]"
+    << std::endl;
+  return s;
+}
 
 template <typename PointT>
 class PCLBase {

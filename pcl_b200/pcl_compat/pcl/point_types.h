@@ -4,6 +4,7 @@
 #pragma once
 #include <cstddef>
 #include <cmath>
+#include <ostream>
 namespace pcl {
 struct alignas(16) PointXYZ {
   union {
@@ -58,4 +59,20 @@ template <typename PointT> inline bool isXYZFinite(const PointT& p)
   return std::isfinite(p.x) && std::isfinite(p.y) && std::isfinite(p.z);
 }
 template <typename PointT> inline bool isFinite(const PointT& p) { return isXYZFinite(p); }
+// common/src/point_types.cpp:41-46, 168-173, 189-194
+inline std::ostream& operator<<(std::ostream& os, const PointXYZ& p)
+{
+  os << "(" << p.x << "," << p.y << "," << p.z << ")";
+  return os;
+}
+inline std::ostream& operator<<(std::ostream& os, const Normal& p)
+{
+  os << "(" << p.normal[0] << "," << p.normal[1] << "," << p.normal[2] << " - " << p.curvature << ")";
+  return os;
+}
+inline std::ostream& operator<<(std::ostream& os, const PointNormal& p)
+{
+  os << "(" << p.x << "," << p.y << "," << p.z << " - " << p.normal[0] << "," << p.normal[1] << "," << p.normal[2] << " - " << p.curvature << ")";
+  return os;
+}
 }  // namespace pcl

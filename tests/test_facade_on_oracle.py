@@ -100,3 +100,37 @@ def test_icp_command_line_program(double, golden, tmp_path):
     def mean_nn(a):
         return np.sqrt(((a[:, None, :] - tgt[None, :, :]) ** 2).sum(-1).min(1)).mean()
     assert mean_nn(body[:, :3]) < 0.5 * mean_nn(np.asarray(golden["bun0"], dtype=np.float64)[:, :3])
+
+
+TUTORIALS = "/root/reference/doc/tutorials/content/sources"
+
+
+@pytest.mark.skipif(not os.path.isdir(TUTORIALS), reason="the reference checkout (its tutorial sources) is not on this machine")
+def test_reference_tutorials_compile_unchanged(double, tmp_path):
+    """The reference's own tutorial programs for the path — iterative_closest_point, kdtree_search, voxel_grid (the
+    PCLPointCloud2 form), pcd_read, pcd_write, concatenate_clouds / _fields / _points, statistical_removal,
+    radius_outlier_removal — compiled UNCHANGED, from where they lie in the reference checkout, against the facade headers;
+    the ones that need no data file are run (on the test double): the ICP tutorial converges and prints the 0.7 shift."""
+    _, lib, _ = double
+    built = {}
+    for name in ("iterative_closest_point", "kdtree_search", "voxel_grid", "pcd_read", "pcd_write", "concatenate_clouds",
+                 "concatenate_fields", "concatenate_points", "statistical_removal", "radius_outlier_removal"):
+        src = os.path.join(TUTORIALS, name, name + ".cpp")
+        exe = str(tmp_path / name)
+        subprocess.check_call(["g++", "-O1", "-std=c++17", "-I" + FACADE, "-I" + os.path.join(ROOT, "include"), src, "-o", exe, lib,
+                               "-Wl,-rpath," + os.path.dirname(lib), "-pthread"])
+        built[name] = exe
+    r = subprocess.run([built["iterative_closest_point"]], capture_output=True, text=True, cwd=tmp_path)
+    assert r.returncode == 0 and "has converged" in r.stdout, r.stdout[-1500:] + r.stderr[-500:]
+    rows = [ln.split() for ln in r.stdout.strip().splitlines()[-4:]]
+    T = np.array([[float(v) for v in row] for row in rows])
+    assert T.shape == (4, 4) and abs(T[0, 3] - 0.7) < 1e-5 and np.allclose(T[:3, :3], np.eye(3), atol=1e-5) and np.allclose(T[1:3, 3], 0, atol=1e-5)
+    r = subprocess.run([built["kdtree_search"]], capture_output=True, text=True, cwd=tmp_path)
+    assert r.returncode == 0 and "K nearest neighbor search" in r.stdout and "Neighbors within radius search" in r.stdout
+    d2 = [float(ln.split("squared distance:")[1].strip(" )\n")) for ln in r.stdout.splitlines() if "squared distance" in ln][:10]
+    assert len(d2) == 10 and d2 == sorted(d2)
+    assert subprocess.run([built["pcd_write"]], capture_output=True, text=True, cwd=tmp_path).returncode == 0
+    r = subprocess.run([built["pcd_read"]], capture_output=True, text=True, cwd=tmp_path)
+    assert r.returncode == 0 and "Loaded" in r.stdout and len(r.stdout.strip().splitlines()) >= 6
+    r = subprocess.run([built["concatenate_clouds"], "-f"], capture_output=True, text=True, cwd=tmp_path)
+    assert r.returncode == 0 and len(r.stderr.strip().splitlines()[-1].split()) == 6     # x y z + the three normal components
