@@ -38,6 +38,49 @@ inline void print(VERBOSITY_LEVEL level, FILE* stream, const char* format, ...)
   std::vfprintf(stream, format, ap);
   va_end(ap);
 }
+// print.h:121-290: the named forms a command-line tool prints with (no colours here); each also exists with a FILE* first
+#define PCLB_PRINT_FN(name, lvl, dflt)                                  \
+  inline void name(const char* format, ...)                             \
+  {                                                                     \
+    if (!isVerbosityLevelEnabled(lvl)) return;                          \
+    va_list ap;                                                         \
+    va_start(ap, format);                                               \
+    std::vfprintf(dflt, format, ap);                                    \
+    va_end(ap);                                                         \
+  }                                                                     \
+  inline void name(FILE* stream, const char* format, ...)               \
+  {                                                                     \
+    if (!isVerbosityLevelEnabled(lvl)) return;                          \
+    va_list ap;                                                         \
+    va_start(ap, format);                                               \
+    std::vfprintf(stream, format, ap);                                  \
+    va_end(ap);                                                         \
+  }
+PCLB_PRINT_FN(print_info, L_INFO, stdout)
+PCLB_PRINT_FN(print_value, L_INFO, stdout)
+PCLB_PRINT_FN(print_error, L_ERROR, stderr)
+PCLB_PRINT_FN(print_warn, L_WARN, stderr)
+PCLB_PRINT_FN(print_debug, L_DEBUG, stdout)
+#undef PCLB_PRINT_FN
+// print_highlight prefixes "> " (print.cpp:150-172)
+inline void print_highlight(const char* format, ...)
+{
+  if (!isVerbosityLevelEnabled(L_ALWAYS)) return;
+  std::fputs("> ", stdout);
+  va_list ap;
+  va_start(ap, format);
+  std::vfprintf(stdout, format, ap);
+  va_end(ap);
+}
+inline void print_highlight(FILE* stream, const char* format, ...)
+{
+  if (!isVerbosityLevelEnabled(L_ALWAYS)) return;
+  std::fputs("> ", stream);
+  va_list ap;
+  va_start(ap, format);
+  std::vfprintf(stream, format, ap);
+  va_end(ap);
+}
 }  // namespace console
 }  // namespace pcl
 

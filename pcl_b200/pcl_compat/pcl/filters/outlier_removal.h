@@ -12,7 +12,9 @@
 
 #include "../point_cloud.h"
 #include "../point_types.h"
+#include "../PointIndices.h"
 #include "../search/kdtree.h"
+#include "filter.h"
 
 namespace pcl {
 
@@ -24,9 +26,13 @@ public:
   : removed_indices_(new Indices), extract_removed_indices_(extract_removed_indices) {}
   void setNegative(bool negative) { negative_ = negative; }
   bool getNegative() const { return negative_; }
-  void setKeepOrganized(bool) {}
+  // filter_indices.h:120-170: the output keeps the input's size and structure, removed points get the user filter value (NaN)
+  void setKeepOrganized(bool keep_organized) { keep_organized_ = keep_organized; }
+  bool getKeepOrganized() const { return keep_organized_; }
+  void setUserFilterValue(float value) { user_filter_value_ = value; }
   void setNumberOfThreads(unsigned int) {}
   IndicesConstPtr getRemovedIndices() const { return removed_indices_; }
+  void getRemovedIndices(PointIndices& pi) const { pi.indices = *removed_indices_; }   // filter.h:100-104
   void setSearchMethod(const typename pcl::search::KdTree<PointT>::Ptr& tree) { searcher_ = tree; }
   // statistical_outlier_removal.h:88,150 / radius_outlier_removal.h:79,146: SearcherPtr = pcl::search::Search<PointT>::Ptr
   void setSearchMethod(const typename pcl::search::Search<PointT>::Ptr& searcher)
@@ -56,6 +62,20 @@ public:
   }
   void filter(PointCloud& output)
   {
+    if (keep_organized_ && this->input_) {  // impl/filter_indices.hpp:47-63
+      const bool temp = extract_removed_indices_;
+      extract_removed_indices_ = true;
+      Indices ind;
+      filter(ind);
+      extract_removed_indices_ = temp;
+      output = *this->input_;
+      for (index_t rii : *removed_indices_) {
+        PointT& p = output.points[static_cast<std::size_t>(rii)];
+        p.x = p.y = p.z = user_filter_value_;
+      }
+      if (!std::isfinite(user_filter_value_)) output.is_dense = false;
+      return;
+    }
     Indices ind;
     filter(ind);
     output.header = this->input_ ? this->input_->header : PCLHeader();
@@ -80,6 +100,8 @@ protected:
   IndicesPtr removed_indices_;
   bool extract_removed_indices_;
   bool negative_ = false;
+  bool keep_organized_ = false;
+  float user_filter_value_ = std::numeric_limits<float>::quiet_NaN();
   const char* name_ = "Filter";
 };
 

@@ -3,7 +3,10 @@
 // correspondence_rejection_distance.h, …_median_distance.h, …_one_to_one.h, …_trimmed.h and their src/*.cpp.
 #pragma once
 #include <cmath>
+#include <algorithm>
 #include <cstdio>
+#include <functional>
+#include <vector>
 #include <limits>
 #include <memory>
 #include <string>
@@ -11,6 +14,7 @@
 #include "../PCLPointCloud2.h"
 #include "../b200/context.h"
 #include "../correspondence.h"
+#include "../point_cloud.h"
 
 namespace pcl {
 namespace registration {
@@ -97,9 +101,53 @@ public:
   double getMedianFactor() const { return factor_; }
   double getMedianDistance() const { return last_median_; }
   pclb200_rejector abiRejector() const override { return pclb200_rejector{PCLB200_REJ_MEDIAN, 0, factor_}; }
+  // correspondence_rejection_median_distance.h:100-130: with a source AND a target cloud the score of a pair is the squared
+  // distance of the two POINTS (DataContainer::getCorrespondenceScore), not Correspondence::distance; the stored distances
+  // are what an ICP loop keeps current, so inside ICP the two agree and the device form is used; stand-alone the scored form
+  // runs on the host (src/correspondence_rejection_median_distance.cpp:44-70)
+  template <typename PointT>
+  void setInputSource(const typename pcl::PointCloud<PointT>::ConstPtr& cloud)
+  {
+    source_ = cloud;
+    rescore<PointT>();
+  }
+  template <typename PointT>
+  void setInputTarget(const typename pcl::PointCloud<PointT>::ConstPtr& cloud)
+  {
+    target_ = cloud;
+    rescore<PointT>();
+  }
+  void getRemainingCorrespondences(const pcl::Correspondences& in, pcl::Correspondences& out) override
+  {
+    if (!score_) { CorrespondenceRejector::getRemainingCorrespondences(in, out); return; }
+    out.clear();
+    if (in.empty()) return;
+    std::vector<double> dists(in.size());
+    for (std::size_t i = 0; i < in.size(); ++i) dists[i] = score_(in[i]);
+    std::vector<double> nth(dists);
+    std::nth_element(nth.begin(), nth.begin() + static_cast<std::ptrdiff_t>(nth.size() / 2), nth.end());
+    last_median_ = nth[nth.size() / 2];
+    for (std::size_t i = 0; i < in.size(); ++i)
+      if (dists[i] <= last_median_ * factor_) out.push_back(in[i]);
+  }
 
 protected:
+  template <typename PointT>
+  void rescore()
+  {
+    auto s = std::static_pointer_cast<const pcl::PointCloud<PointT>>(source_);
+    auto t = std::static_pointer_cast<const pcl::PointCloud<PointT>>(target_);
+    if (!s || !t) { score_ = nullptr; return; }
+    score_ = [s, t](const pcl::Correspondence& c) {
+      const PointT& a = (*s)[static_cast<std::size_t>(c.index_query)];
+      const PointT& b = (*t)[static_cast<std::size_t>(c.index_match)];
+      const float dx = a.x - b.x, dy = a.y - b.y, dz = a.z - b.z;
+      return static_cast<double>(dx * dx + dy * dy + dz * dz);
+    };
+  }
   double factor_ = 1.0;
+  std::shared_ptr<const void> source_, target_;
+  std::function<double(const pcl::Correspondence&)> score_;
 };
 
 class CorrespondenceRejectorOneToOne : public CorrespondenceRejector {

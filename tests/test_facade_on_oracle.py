@@ -134,3 +134,51 @@ def test_reference_tutorials_compile_unchanged(double, tmp_path):
     assert r.returncode == 0 and "Loaded" in r.stdout and len(r.stdout.strip().splitlines()) >= 6
     r = subprocess.run([built["concatenate_clouds"], "-f"], capture_output=True, text=True, cwd=tmp_path)
     assert r.returncode == 0 and len(r.stderr.strip().splitlines()[-1].split()) == 6     # x y z + the three normal components
+
+
+TOOLS = "/root/reference/tools"
+
+
+@pytest.mark.skipif(not os.path.isdir(TOOLS), reason="the reference checkout (its tools/) is not on this machine")
+def test_reference_command_line_tools_compile_unchanged_and_run(double, golden, tmp_path):
+    """The reference's own command-line tools for the path — tools/iterative_closest_point.cpp, voxel_grid.cpp, outlier_removal.cpp,
+    cluster_extraction.cpp — compiled UNCHANGED from the reference checkout against the facade headers (pcl/console/{print,parse,
+    time}.h, blob PCD I/O, VoxelGrid<PCLPointCloud2>, ExtractIndices, the rejector family, TransformationEstimationLM, ...) and run on
+    bun0 / bun4 (on the test double): ICP converges and moves bun0 onto bun4, VoxelGrid at 0.02 gives the reference's 103 points."""
+    _, lib, _ = double
+    b0, b4 = _clouds(golden, tmp_path)
+    exe = {}
+    for name in ("iterative_closest_point", "voxel_grid", "outlier_removal", "cluster_extraction"):
+        exe[name] = str(tmp_path / ("tool_" + name))
+        subprocess.check_call(["g++", "-O1", "-std=c++17", "-I" + FACADE, "-I" + os.path.join(ROOT, "include"), os.path.join(TOOLS, name + ".cpp"),
+                               "-o", exe[name], lib, "-Wl,-rpath," + os.path.dirname(lib), "-pthread"])
+
+    def points_of(path):
+        lines = open(path, "rb").read().split(b"\n")
+        n = [int(ln.split()[1]) for ln in lines[:12] if ln.startswith(b"POINTS")][0]
+        return n
+
+    out = tmp_path / "aligned.pcd"
+    r = subprocess.run([exe["iterative_closest_point"], b0, b4, str(out), "-debug", "1"], capture_output=True, text=True)
+    assert r.returncode == 0 and "has converged: 1" in r.stdout, r.stdout[-1500:] + r.stderr[-800:]
+    rows = r.stdout.split("Transformation is:")[1].strip().splitlines()[:4]
+    T = np.array([[float(v) for v in row.split()] for row in rows])
+    assert T.shape == (4, 4) and abs(np.linalg.det(T[:3, :3]) - 1) < 1e-4 and 0.4 < T[2, 0] < 0.7   # the ~30 degree turn about y between the two scans
+    text = out.read_text().splitlines()
+    body = np.array([[float(t) for t in ln.split()] for ln in text[11:] if ln.strip()])
+    tgt = np.asarray(golden["bun4"], dtype=np.float64)[:, :3]
+
+    def mean_nn(a):
+        return np.sqrt(((a[:, None, :] - tgt[None, :, :]) ** 2).sum(-1).min(1)).mean()
+    assert body.shape[0] == 397 and mean_nn(body[:, :3]) < 0.5 * mean_nn(np.asarray(golden["bun0"], dtype=np.float64)[:, :3])
+
+    r = subprocess.run([exe["voxel_grid"], b0, str(tmp_path / "vg.pcd"), "-leaf", "0.02,0.02,0.02"], capture_output=True, text=True)
+    assert r.returncode == 0 and points_of(tmp_path / "vg.pcd") == 103, r.stdout[-800:] + r.stderr[-400:]
+    r = subprocess.run([exe["outlier_removal"], b0, str(tmp_path / "sor.pcd"), "-method", "statistical", "-mean_k", "8", "-std_dev_mul", "1.0"],
+                       capture_output=True, text=True)
+    assert r.returncode == 0 and 200 < points_of(tmp_path / "sor.pcd") < 397, r.stdout[-800:] + r.stderr[-400:]
+    r = subprocess.run([exe["outlier_removal"], b0, str(tmp_path / "ror.pcd"), "-method", "radius", "-radius", "0.01", "-min_pts", "4"],
+                       capture_output=True, text=True)
+    assert r.returncode == 0 and 100 < points_of(tmp_path / "ror.pcd") < 397
+    r = subprocess.run([exe["cluster_extraction"], b0, str(tmp_path / "cl.pcd"), "-tolerance", "0.01", "-min", "5"], capture_output=True, text=True)
+    assert r.returncode == 0 and "clusters]" in r.stdout and os.path.exists(tmp_path / "cl0.pcd") and points_of(tmp_path / "cl0.pcd") > 300
