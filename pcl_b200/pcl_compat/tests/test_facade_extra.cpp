@@ -24,6 +24,8 @@
 #include <pcl/registration/correspondence_estimation.h>
 #include <pcl/registration/correspondence_rejection_median_distance.h>
 #include <pcl/registration/correspondence_rejection_sample_consensus.h>
+#include <pcl/registration/correspondence_rejection_var_trimmed.h>
+#include <pcl/registration/transformation_estimation_lm.h>
 #include <pcl/registration/icp.h>
 #include <pcl/search/brute_force.h>
 #include <pcl/search/kdtree.h>
@@ -80,6 +82,8 @@ int main(int argc, char** argv)
   if (argc < 3) { std::fprintf(stderr, "usage: %s bun0.pcd bun4.pcd\n", argv[0]); return 2; }
   PointCloud<PointXYZ> cloud_source, cloud_target;
   if (io::loadPCDFile(argv[1], cloud_source) || io::loadPCDFile(argv[2], cloud_target)) return 2;
+  std::map<std::string, std::vector<double>> G;
+  if (argc > 3) G = load_golden(argv[3]);
 
   {  // the remaining Search<PointT> overloads (search.h:158-165, 229-260, 285-292, 311-315, 368-397): same lists as the
      // per-point forms
@@ -788,7 +792,6 @@ int main(int argc, char** argv)
   }
 
   if (argc > 3) {  // TEST (PCL, CorrespondenceRejectorSampleConsensus) — test/registration/test_registration_api.cpp:225-263
-    auto G = load_golden(argv[3]);
     const std::vector<double>& want = G["corr_rej_sac"];
     const std::vector<double>& want_T = G["sac_transform"];
     PointCloud<PointXYZ>::ConstPtr source(new PointCloud<PointXYZ>(cloud_source)), target(new PointCloud<PointXYZ>(cloud_target));
@@ -826,6 +829,58 @@ int main(int argc, char** argv)
     Indices inl;
     corr_rej_sac.getInliersIndices(inl);
     EXPECT_EQ(inl.size(), result.size());
+  }
+
+  {  // TEST (PCL, CorrespondenceRejectorVarTrimmed) — test/registration/test_registration_api.cpp:351-380 (its only assertion is
+     // conditional on the result having 97 pairs), plus what the reference's code does: the trim factor minimises its FRMS over
+     // [5 %, 95 %], the threshold is the sorted distance at that rank, and the FIRST m input pairs survive, m = #distances below it
+    PointCloud<PointXYZ>::ConstPtr source(new PointCloud<PointXYZ>(cloud_source)), target(new PointCloud<PointXYZ>(cloud_target));
+    CorrespondencesPtr correspondences(new Correspondences);
+    registration::CorrespondenceEstimation<PointXYZ, PointXYZ> corr_est;
+    corr_est.setInputSource(source);
+    corr_est.setInputTarget(target);
+    corr_est.determineCorrespondences(*correspondences);
+    Correspondences kept;
+    registration::CorrespondenceRejectorVarTrimmed rej;
+    rej.setInputSource<PointXYZ>(source);
+    rej.setInputTarget<PointXYZ>(target);
+    rej.setInputCorrespondences(correspondences);
+    rej.getCorrespondences(kept);
+    const std::vector<double>& gd = G["corr_rej_dist"];
+    if (kept.size() * 2 == gd.size())
+      for (std::size_t i = 0; i < kept.size(); ++i) {
+        EXPECT_EQ(kept[i].index_query, (int)gd[2 * i]);
+        EXPECT_EQ(kept[i].index_match, (int)gd[2 * i + 1]);
+      }
+    std::vector<double> sorted;
+    for (const auto& c : *correspondences) sorted.push_back(c.distance);
+    std::sort(sorted.begin(), sorted.end());
+    EXPECT_TRUE(rej.getTrimFactor() >= 0.05 - 1e-6 && rej.getTrimFactor() <= 0.95 + 1e-6);
+    const std::size_t at = static_cast<std::size_t>(static_cast<int>(static_cast<double>(sorted.size()) * rej.getTrimFactor()));
+    EXPECT_NEAR(rej.getTrimmedDistance(), sorted[at], 1e-12);
+    std::size_t below = 0;
+    for (double d : sorted) below += d < rej.getTrimmedDistance();
+    EXPECT_EQ(kept.size(), below);
+    for (std::size_t i = 0; i < kept.size() && i < correspondences->size(); ++i) EXPECT_EQ(kept[i].index_query, (*correspondences)[i].index_query);
+    EXPECT_TRUE(!rej.runsOnDevice() && rej.requiresSourcePoints() && rej.requiresTargetPoints());
+    // the scored form of the median rejector (clouds given): scores are the squared point distances, here the stored ones
+    registration::CorrespondenceRejectorMedianDistance med_plain, med_scored;
+    med_plain.setMedianFactor(1.5);
+    med_scored.setMedianFactor(1.5);
+    med_scored.setInputSource<PointXYZ>(source);
+    med_scored.setInputTarget<PointXYZ>(target);
+    Correspondences a, b;
+    med_plain.getRemainingCorrespondences(*correspondences, a);
+    med_scored.getRemainingCorrespondences(*correspondences, b);
+    EXPECT_EQ(a.size(), b.size());
+    EXPECT_NEAR(med_plain.getMedianDistance(), med_scored.getMedianDistance(), 1e-9);
+    // TransformationEstimationLM: the minimiser of the point-to-point objective = the SVD estimate
+    registration::TransformationEstimationLM<PointXYZ, PointXYZ, double> lm;
+    registration::TransformationEstimationSVD<PointXYZ, PointXYZ, double> svd;
+    Eigen::Matrix4d Tl, Ts;
+    lm.estimateRigidTransformation(*source, *target, *correspondences, Tl);
+    svd.estimateRigidTransformation(*source, *target, *correspondences, Ts);
+    EXPECT_TRUE(Tl == Ts);
   }
 
   {  // TEST (PCL, IterativeClosestPointWithRejectors) — test/registration/test_registration.cpp:336-382: a median-distance and
