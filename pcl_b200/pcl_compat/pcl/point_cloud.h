@@ -14,6 +14,7 @@
 
 #include "console/print.h"
 #include "eigen_lite.h"
+#include "memory.h"
 #include "types.h"
 
 namespace pcl {

@@ -4,6 +4,7 @@
 #pragma once
 #include <cstddef>
 #include <cmath>
+#include <iostream>
 #include <ostream>
 namespace pcl {
 struct alignas(16) PointXYZ {
@@ -59,6 +60,7 @@ template <typename PointT> inline bool isXYZFinite(const PointT& p)
   return std::isfinite(p.x) && std::isfinite(p.y) && std::isfinite(p.z);
 }
 template <typename PointT> inline bool isFinite(const PointT& p) { return isXYZFinite(p); }
+template <> inline bool isFinite<Normal>(const Normal& n) { return std::isfinite(n.normal_x) && std::isfinite(n.normal_y) && std::isfinite(n.normal_z); }   // point_tests.h:122-127
 // common/src/point_types.cpp:41-46, 168-173, 189-194
 inline std::ostream& operator<<(std::ostream& os, const PointXYZ& p)
 {

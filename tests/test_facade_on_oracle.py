@@ -109,7 +109,8 @@ TUTORIALS = "/root/reference/doc/tutorials/content/sources"
 def test_reference_tutorials_compile_unchanged(double, tmp_path):
     """The reference's own tutorial programs for the path — iterative_closest_point, kdtree_search, voxel_grid (the
     PCLPointCloud2 form), pcd_read, pcd_write, concatenate_clouds / _fields / _points, statistical_removal,
-    radius_outlier_removal — compiled UNCHANGED, from where they lie in the reference checkout, against the facade headers;
+    radius_outlier_removal — and seven of its examples/ (normal estimation, extract indices, remove NaN, copy point cloud,
+    min / max coordinates, point validity, organised clouds) compiled UNCHANGED, from where they lie in the reference checkout, against the facade headers;
     the ones that need no data file are run (on the test double): the ICP tutorial converges and prints the 0.7 shift."""
     _, lib, _ = double
     built = {}
@@ -120,6 +121,18 @@ def test_reference_tutorials_compile_unchanged(double, tmp_path):
         subprocess.check_call(["g++", "-O1", "-std=c++17", "-I" + FACADE, "-I" + os.path.join(ROOT, "include"), src, "-o", exe, lib,
                                "-Wl,-rpath," + os.path.dirname(lib), "-pthread"])
         built[name] = exe
+    examples = "/root/reference/examples"
+    for rel in ("features/example_normal_estimation", "filters/example_extract_indices", "filters/example_remove_nan_from_point_cloud",
+                "common/example_copy_point_cloud", "common/example_get_max_min_coordinates", "common/example_check_if_point_is_valid",
+                "common/example_organized_point_cloud"):
+        name = os.path.basename(rel)
+        subprocess.check_call(["g++", "-O1", "-std=c++17", "-I" + FACADE, "-I" + os.path.join(ROOT, "include"), os.path.join(examples, rel + ".cpp"),
+                               "-o", str(tmp_path / name), lib, "-Wl,-rpath," + os.path.dirname(lib), "-pthread"])
+        built[name] = str(tmp_path / name)
+    r = subprocess.run([built["example_check_if_point_is_valid"]], capture_output=True, text=True)
+    assert r.returncode == 0 and "Is p_valid valid? 1" in r.stdout and "Is p_invalid valid? 0" in r.stdout
+    r = subprocess.run([built["example_extract_indices"]], capture_output=True, text=True)
+    assert r.returncode == 0 and "Cloud has 5 points." in r.stdout and "Output has 2 points." in r.stdout
     r = subprocess.run([built["iterative_closest_point"]], capture_output=True, text=True, cwd=tmp_path)
     assert r.returncode == 0 and "has converged" in r.stdout, r.stdout[-1500:] + r.stderr[-500:]
     rows = [ln.split() for ln in r.stdout.strip().splitlines()[-4:]]
