@@ -11,6 +11,8 @@
 #include <algorithm>
 #include <cmath>
 #include <functional>
+#include <typeindex>
+#include <typeinfo>
 #include <vector>
 
 #include "../conversions.h"
@@ -58,9 +60,9 @@ private:
   std::pair<typename pcl::PointCloud<PointT>::ConstPtr, typename pcl::PointCloud<PointT>::ConstPtr>& holder()
   {
     using Pair = std::pair<typename pcl::PointCloud<PointT>::ConstPtr, typename pcl::PointCloud<PointT>::ConstPtr>;
-    if (!store_ || tag_ != &typeTag<PointT>) {
+    if (!store_ || tag_ != std::type_index(typeid(PointT))) {
       store_ = std::make_shared<Pair>();
-      tag_ = &typeTag<PointT>;
+      tag_ = std::type_index(typeid(PointT));
     }
     return *std::static_pointer_cast<Pair>(store_);
   }
@@ -71,9 +73,8 @@ private:
     if (slot.first && slot.second) score = pairScore<PointT>(slot.first, slot.second);
     else score = nullptr;
   }
-  template <typename PointT> static void typeTag() {}
   std::shared_ptr<void> store_;
-  void (*tag_)() = nullptr;
+  std::type_index tag_ = std::type_index(typeid(void));
 };
 }  // namespace detail
 
