@@ -15,6 +15,8 @@
 
 #include <pcl/common/io.h>
 #include <pcl/features/normal_3d.h>
+#include <pcl/filters/extract_indices.h>
+#include <pcl/filters/radius_outlier_removal.h>
 #include <pcl/filters/voxel_grid.h>
 #include <pcl/io/pcd_io.h>
 #include <pcl/kdtree/kdtree_flann.h>
@@ -632,6 +634,52 @@ int main(int argc, char** argv)
       EXPECT_NEAR(out_pn[5].normal_z, 0.8, 1e-6);
       EXPECT_NEAR(out_pn[5].curvature, 0.25, 1e-6);
     }
+  }
+
+  {  // FilterIndices::setKeepOrganized (impl/filter_indices.hpp:47-63) on RadiusOutlierRemoval, and ExtractIndices mapping the removed
+     // indices back onto a blob the way tools/outlier_removal.cpp does
+    PointCloud<PointXYZ>::Ptr cloud = cloud_source.makeShared();
+    RadiusOutlierRemoval<PointXYZ> plain(true), organized(true);
+    for (auto* f : {&plain, &organized}) {
+      f->setInputCloud(cloud);
+      f->setRadiusSearch(0.01);
+      f->setMinNeighborsInRadius(4);
+    }
+    organized.setKeepOrganized(true);
+    PointCloud<PointXYZ> kept, same_size;
+    plain.filter(kept);
+    organized.filter(same_size);
+    PointIndices removed;
+    plain.getRemovedIndices(removed);
+    EXPECT_TRUE(!kept.empty() && kept.size() < cloud->size());
+    EXPECT_EQ(kept.size() + removed.indices.size(), cloud->size());
+    EXPECT_EQ(same_size.size(), cloud->size());
+    EXPECT_EQ(same_size.width, cloud->width);
+    EXPECT_TRUE(!same_size.is_dense);
+    std::size_t nan_points = 0;
+    for (const auto& p : same_size.points) nan_points += !std::isfinite(p.x);
+    EXPECT_EQ(nan_points, removed.indices.size());
+    for (index_t r : removed.indices) EXPECT_TRUE(std::isnan(same_size[static_cast<std::size_t>(r)].x) && std::isnan(same_size[static_cast<std::size_t>(r)].z));
+    PCLPointCloud2::Ptr blob(new PCLPointCloud2);
+    toPCLPointCloud2(*cloud, *blob);
+    ExtractIndices<PCLPointCloud2> ei;
+    ei.setInputCloud(blob);
+    ei.setIndices(std::make_shared<const PointIndices>(removed));
+    ei.setNegative(true);
+    PCLPointCloud2 survivors;
+    ei.filter(survivors);
+    PointCloud<PointXYZ> back;
+    fromPCLPointCloud2(survivors, back);
+    EXPECT_EQ(back.size(), kept.size());
+    bool same = back.size() == kept.size();
+    for (std::size_t i = 0; same && i < back.size(); ++i) same = back[i].x == kept[i].x && back[i].y == kept[i].y && back[i].z == kept[i].z;
+    EXPECT_TRUE(same);
+    ExtractIndices<PointXYZ> et;
+    et.setInputCloud(cloud);
+    et.setIndices(std::make_shared<const PointIndices>(removed));
+    PointCloud<PointXYZ> only_removed;
+    et.filter(only_removed);
+    EXPECT_EQ(only_removed.size(), removed.indices.size());
   }
 
   {  // TEST (VoxelGridMinPoints, Filters) — test/filters/test_filters.cpp:1356-1406, the positions (the reference's cloud is
