@@ -12,6 +12,8 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <algorithm>
+#include <cstdlib>
 #include <functional>
 #include <vector>
 
@@ -36,12 +38,27 @@ struct Block {
 };
 inline Block& W() { static Block w; return w; }
 
+// The order in which the threads of a block get to run between two synchronisation points is a free choice of the hardware; the
+// emulation makes one: PCLB_EMU_ORDER unset = ascending thread index, "reverse" = descending, a number = a stride co-prime with the
+// block size (a fixed pseudo-random permutation).  Code that is correct only under one order — a missing __syncthreads /
+// __syncwarp between a write and another thread's read — gives different results under the others (tools/dev/racecheck_host_kernels.sh).
+inline int schedule_stride(int nthreads)
+{
+  static const char* e = std::getenv("PCLB_EMU_ORDER");
+  if (!e || !*e) return 1;
+  if (e[0] == 'r') return nthreads - 1;                       // me - 1 (mod n)
+  long k = std::strtol(e, nullptr, 10);
+  int s = static_cast<int>((k * 2 + 1) % nthreads);            // odd: co-prime with the power-of-two-multiple block sizes used here
+  while (s > 1 && std::__gcd(s, nthreads) != 1) s -= 2;
+  return s < 1 ? 1 : s;
+}
 inline void yield_lane()
 {
   Block& w = W();
   const int me = w.current;
+  const int stride = schedule_stride(w.nthreads);
   for (int step = 1; step <= w.nthreads; ++step) {
-    const int next = (me + step) % w.nthreads;
+    const int next = static_cast<int>((me + static_cast<long>(step) * stride) % w.nthreads);
     if (next == me) return;
     if (!w.finished[next]) {
       w.current = next;
@@ -80,8 +97,9 @@ inline void trampoline()
   const int me = w.current;
   w.body();
   w.finished[me] = true;
+  const int stride = schedule_stride(w.nthreads);
   for (int step = 1; step < w.nthreads; ++step) {   // hand over to a thread that still runs, or back to the caller
-    const int next = (me + step) % w.nthreads;
+    const int next = static_cast<int>((me + static_cast<long>(step) * stride) % w.nthreads);
     if (!w.finished[next]) {
       w.current = next;
       setcontext(&w.ctx[next]);
@@ -212,8 +230,8 @@ inline long run_block(int nthreads, std::function<void()> kernel_body)
     w.ctx[l].uc_link = nullptr;
     makecontext(&w.ctx[l], reinterpret_cast<void (*)()>(trampoline), 0);
   }
-  w.current = 0;
-  swapcontext(&w.main_ctx, &w.ctx[0]);
+  w.current = schedule_stride(nthreads) == 1 ? 0 : nthreads - 1;   // another first thread under the other orders
+  swapcontext(&w.main_ctx, &w.ctx[w.current]);
   for (int l = 0; l < nthreads; ++l)
     if (!w.finished[l]) { std::printf("warp_emu: thread %d did not finish (divergent primitive sequence?)\n", l); std::exit(3); }
   return w.primitives;
